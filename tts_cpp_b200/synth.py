@@ -1,0 +1,238 @@
+"""Synthetic Kokoro-82M-shaped GGUF writer (no real weights exist offline).
+
+Writes a GGUF file in the exact tensor-name / metadata schema the reference loader
+consumes (reference py-gguf/tts_encoders/kokoro_gguf_encoder.py:146-487 defines the
+schema; src/models/kokoro/model.cpp:413-773 routes the names, :841-930 reads the KV),
+with random fp16-representable weights.  Used by the parity tests, bench.py and
+__graft_entry__.smoke(); both the reference (oracle/_ref) and the CUDA path load
+the same file, so parity is on identical weights.
+
+dtype policy "f16" mirrors `quantize --quantized-type F16 --convert-non-quantized-to-f16`
+(reference examples/quantize/quantize_impl.cpp:14-18,264-278): every tensor whose name
+has no voice_tensors/bias/gamma/beta/alpha and does not end in embd/norm is stored F16 --
+EXCEPT the ConvTranspose1d kernels (ups.N.weight, pool_weight), which stay F32 because the
+reference's F16 ConvTranspose1d CPU kernel is mis-indexed (ggml-cpu.c:10091 vs :10189).
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+STYLE = 128
+HID = 512
+N_VOICE_ROWS = 510
+
+
+def _f16_ok(name: str) -> bool:
+    if any(s in name for s in ("voice_tensors", "bias", "gamma", "beta", "alpha")):
+        return False
+    if name.endswith("embd") or name.endswith("norm"):
+        return False
+    if name.endswith("pool_weight") or (".ups." in name and name.endswith(".weight")):
+        return False  # ConvTranspose1d kernels: keep F32 (reference F16 kernel bug)
+    return True
+
+
+class _Spec:
+    """Collects (name, array) pairs; all randomness flows from one seeded generator."""
+
+    def __init__(self, seed: int):
+        self.rng = np.random.default_rng(seed)
+        self.items: list[tuple[str, np.ndarray]] = []
+
+    def rand(self, name, shape, scale=None):
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        s = (1.0 / np.sqrt(max(fan_in, 1))) if scale is None else scale
+        a = (self.rng.standard_normal(shape).astype(np.float32) * np.float32(s))
+        a = a.astype(np.float16).astype(np.float32)  # fp16-representable in every storage dtype
+        self.items.append(("kokoro." + name, a))
+
+    def const(self, name, shape, v):
+        self.items.append(("kokoro." + name, np.full(shape, v, dtype=np.float32)))
+
+    # -- composite blocks -------------------------------------------------
+    def lstm(self, base, n_in, hid=256):
+        for part in ("weights", "reverse_weights"):
+            for g in range(4):
+                self.rand(f"{base}.0.{part}.{2 * g}", (hid, n_in))
+                self.rand(f"{base}.0.{part}.{2 * g + 1}", (hid, hid))
+        for part in ("biases", "reverse_biases"):
+            for i in range(8):
+                self.rand(f"{base}.0.{part}.{i}", (hid,), 0.05)
+
+    def adain_block(self, base, cin, cout, up=False):
+        self.rand(f"{base}.conv1_weight", (cout, cin, 3))
+        self.rand(f"{base}.conv1_bias", (cout,), 0.02)
+        self.rand(f"{base}.conv2_weight", (cout, cout, 3))
+        self.rand(f"{base}.conv2_bias", (cout,), 0.02)
+        for nm, c in (("norm1", cin), ("norm2", cout)):
+            for gb in ("gamma", "beta"):
+                self.rand(f"{base}.{nm}_{gb}_weight", (c, STYLE))
+                self.rand(f"{base}.{nm}_{gb}_bias", (c,), 0.02)
+        if up:
+            self.rand(f"{base}.pool_weight", (cin, 1, 3))
+            self.rand(f"{base}.pool_bias", (cin,), 0.02)
+        if cin != cout:
+            self.rand(f"{base}.conv1x1_weight", (cout, cin, 1))
+
+    def gen_resblock(self, base, ch, k):
+        for i in range(3):
+            for j in ("1", "2"):
+                self.rand(f"{base}.{i}.gamma{j}_weight", (ch, STYLE))
+                self.rand(f"{base}.{i}.gamma{j}_bias", (ch,), 0.02)
+                self.rand(f"{base}.{i}.beta{j}_weight", (ch, STYLE))
+                self.rand(f"{base}.{i}.beta{j}_bias", (ch,), 0.02)
+                self.rand(f"{base}.{i}.convs{j}_weight", (ch, ch, k))
+                self.rand(f"{base}.{i}.convs{j}_bias", (ch,), 0.02)
+                alpha = (1.0 + 0.25 * self.rng.standard_normal((1, ch, 1))).clip(0.3, 2.0)
+                self.items.append((f"kokoro.{base}.{i}.alpha{j}", alpha.astype(np.float16).astype(np.float32)))
+
+
+def kokoro_tensors(seed: int = 0, dur_sigma: float = 0.01, dur_bias: float = -2.75, f0_bias: float = 120.0):
+    """All Kokoro tensors as float32 numpy arrays (numpy shape = reversed ggml ne)."""
+    s = _Spec(seed)
+    # ALBERT (duration predictor front-end)
+    s.rand("albert.token_embd", (178, 128), 0.5)
+    s.rand("albert.position_embd", (512, 128), 0.1)
+    s.rand("albert.token_type_embd", (128,), 0.1)
+    s.const("albert.norm", (128,), 1.0)
+    s.const("albert.norm_bias", (128,), 0.0)
+    s.rand("albert.embd", (768, 128))
+    s.rand("albert.embd_bias", (768,), 0.02)
+    for nm in "qkvo":
+        s.rand(f"albert.layer.0.{nm}", (768, 768))
+        s.rand(f"albert.layer.0.{nm}_bias", (768,), 0.02)
+    s.rand("albert.layer.0.ffn", (2048, 768))
+    s.rand("albert.layer.0.ffn_bias", (2048,), 0.02)
+    s.rand("albert.layer.0.ffn_out", (768, 2048))
+    s.rand("albert.layer.0.ffn_out_bias", (768,), 0.02)
+    for nm in ("attn_norm", "ffn_norm"):
+        s.items.append((f"kokoro.albert.layer.0.{nm}", (1.0 + 0.1 * s.rng.standard_normal(768)).astype(np.float32)))
+        s.rand(f"albert.layer.0.{nm}_bias", (768,), 0.05)
+    # duration / prosody predictor
+    s.rand("duration_predictor.encode", (HID, 768))
+    s.rand("duration_predictor.encode_bias", (HID,), 0.02)
+    for i in range(3):
+        s.lstm(f"duration_predictor.layers.{2 * i}.lstm", HID + STYLE)
+        for gb in ("gamma", "beta"):
+            s.rand(f"duration_predictor.layers.{2 * i + 1}.{gb}_weight", (HID, STYLE))
+            s.rand(f"duration_predictor.layers.{2 * i + 1}.{gb}_bias", (HID,), 0.02)
+    s.lstm("duration_predictor.duration_lstm", HID + STYLE)
+    s.lstm("duration_predictor.shared_lstm", HID + STYLE)
+    s.rand("duration_predictor.duration_proj", (50, HID), dur_sigma)
+    s.const("duration_predictor.duration_proj_bias", (50,), dur_bias)
+    for br in ("f0", "n"):
+        s.adain_block(f"duration_predictor.{br}_blocks.0", 512, 512)
+        s.adain_block(f"duration_predictor.{br}_blocks.1", 512, 256, up=True)
+        s.adain_block(f"duration_predictor.{br}_blocks.2", 256, 256)
+        s.rand(f"duration_predictor.{br}_proj_kernel", (1, 256, 1))
+        s.const(f"duration_predictor.{br}_proj_bias", (1,), f0_bias if br == "f0" else 0.0)
+    # text encoder
+    s.rand("text_encoder.embedding_weight", (178, 512), 0.5)
+    for i in range(3):
+        s.rand(f"text_encoder.layers.{i}.weight", (512, 512, 5))
+        s.rand(f"text_encoder.layers.{i}.bias", (512,), 0.02)
+        s.items.append((f"kokoro.text_encoder.layers.{i}.gamma", (1.0 + 0.1 * s.rng.standard_normal(512)).astype(np.float32)))
+        s.rand(f"text_encoder.layers.{i}.beta", (512,), 0.05)
+    s.lstm("text_encoder.lstm", 512)
+    # decoder
+    for br in ("f0", "n"):
+        s.rand(f"decoder.{br}_conv_weight", (1, 1, 3))
+        s.rand(f"decoder.{br}_conv_bias", (1,), 0.02)
+    s.rand("decoder.asr_conv_weight", (64, 512, 1))
+    s.rand("decoder.asr_conv_bias", (64,), 0.02)
+    s.adain_block("decoder.encoder_block", 514, 1024)
+    for i in range(3):
+        s.adain_block(f"decoder.decoder_blocks.{i}", 1090, 1024)
+    s.adain_block("decoder.decoder_blocks.3", 1090, 512, up=True)
+    g = "decoder.generator"
+    s.rand(f"{g}.m_source_weight", (1, 9))
+    s.const(f"{g}.m_source_bias", (1,), 0.0)
+    s.rand(f"{g}.ups.0.weight", (512, 256, 20))
+    s.rand(f"{g}.ups.0.bias", (256,), 0.02)
+    s.rand(f"{g}.ups.1.weight", (256, 128, 12))
+    s.rand(f"{g}.ups.1.bias", (128,), 0.02)
+    s.rand(f"{g}.noise_blocks.0.conv_weight", (256, 22, 12))
+    s.rand(f"{g}.noise_blocks.0.conv_bias", (256,), 0.02)
+    s.rand(f"{g}.noise_blocks.1.conv_weight", (128, 22, 1))
+    s.rand(f"{g}.noise_blocks.1.conv_bias", (128,), 0.02)
+    s.gen_resblock(f"{g}.noise_blocks.0.resblock", 256, 7)
+    s.gen_resblock(f"{g}.noise_blocks.1.resblock", 128, 11)
+    for i, (ch, k) in enumerate([(256, 3), (256, 7), (256, 11), (128, 3), (128, 7), (128, 11)]):
+        s.gen_resblock(f"{g}.resblocks.{i}", ch, k)
+    s.rand(f"{g}.conv_post_weight", (22, 128, 7), 0.01)
+    s.const(f"{g}.conv_post_bias", (22,), 0.0)
+    s.rand("voice_tensors.af_heart", (N_VOICE_ROWS, 256), 0.1)
+    return s.items
+
+
+def kokoro_metadata(ctx_len: int = 512):
+    """(key, value) uint32 metadata the reference reads (model.cpp:841-930,264-298)."""
+    a = "kokoro.duration_predictor.albert"
+    kv = [(f"{a}.context_length", ctx_len), (f"{a}.layers", 1), (f"{a}.attn_heads", 12), (f"{a}.hidden_size", 768),
+          (f"{a}.recurrence", 12), ("kokoro.duration_predictor.hidden_size", 512), ("kokoro.duration_predictor.layers", 3),
+          ("kokoro.duration_predictor.f0_n_blocks", 3), ("kokoro.text_encoder.layers", 3)]
+    G = "kokoro.decoder.generator"
+    for k, v in dict(up_sampling_factor=600, kernels=3, upsamples=2, layers=4, padding=3, n_fft=20, hop=5).items():
+        kv.append((f"{G}.{k}", v))
+    for i, k in enumerate((7, 11)):
+        for ii, d in enumerate((1, 3, 5)):
+            kv.append((f"{G}.noise_blocks.{i}.res_block.{ii}.padding", (k * d - d) // 2))
+            kv.append((f"{G}.noise_blocks.{i}.res_block.{ii}.dilation", d))
+    kv += [(f"{G}.noise_blocks.0.stride", 6), (f"{G}.noise_blocks.0.padding", 3),
+           (f"{G}.noise_blocks.1.stride", 1), (f"{G}.noise_blocks.1.padding", 0)]
+    for i, k in enumerate((3, 7, 11, 3, 7, 11)):
+        for ii, d in enumerate((1, 3, 5)):
+            kv.append((f"{G}.res_blocks.{i}.{ii}.padding", (k * d - d) // 2))
+            kv.append((f"{G}.res_blocks.{i}.{ii}.dilation", d))
+    kv += [(f"{G}.up_convs.0.padding", 5), (f"{G}.up_convs.0.stride", 10),
+           (f"{G}.up_convs.1.padding", 3), (f"{G}.up_convs.1.stride", 6)]
+    return kv
+
+
+def write_kokoro_gguf(path: str, seed: int = 0, dtype: str = "f16", ctx_len: int = 512, **kw) -> dict:
+    """Write the synthetic model; returns {"tensors": n, "params": n, "bytes": n}."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="kokoro")
+    n_params = 0
+    items = kokoro_tensors(seed=seed, **kw)
+    for name, arr in items:
+        n_params += arr.size
+        if dtype == "f16" and _f16_ok(name):
+            w.add_tensor(name, arr.astype(np.float16))
+        else:
+            w.add_tensor(name, arr.astype(np.float32))
+    for k, v in kokoro_metadata(ctx_len):
+        w.add_uint32(k, v)
+    # the reference loader aborts without a (possibly trivial) rule phonemizer and tokenizer vocabulary
+    w.add_uint32("phonemizer.type", 0)
+    w.add_uint32("phonemizer.phoneme_type", 1)
+    w.add_array("phonemizer.graphemes", ["a", "b"])
+    w.add_array("phonemizer.rules.keys", ["a"])
+    w.add_array("phonemizer.rules.phonemes", ["a"])
+    w.add_array("phonemizer.dictionary.keys", ["a"])
+    w.add_array("phonemizer.dictionary.values", ["a"])
+    w.add_array("tokenizer.ggml.tokens", [""] + [chr(0x100 + i) for i in range(177)])
+    w.add_array("kokoro.voices", ["af_heart"])
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
+    """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
+    out = []
+    for i in range(batch):
+        r = np.random.default_rng(seed0 + i)
+        out.append([0] + [int(v) for v in r.integers(1, 178, size=n_phonemes)] + [0])
+    return out
+
+
+if __name__ == "__main__":
+    import sys
+    print(write_kokoro_gguf(sys.argv[1], dtype=sys.argv[2] if len(sys.argv) > 2 else "f16",
+                            ctx_len=int(sys.argv[3]) if len(sys.argv) > 3 else 512))
