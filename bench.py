@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: audio-seconds/sec for Kokoro-82M fp16, batch 32 synthetic 64-char prompts per B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path (duration pass + generation pass of the whole batch) through the public C-ABI call
+(b2tts_kokoro_run_batch) with HOST buffers in and out.  N > 1: launched by torchrun, one rank per GPU, each rank runs its own
+batch of 32 independent utterances (weak scaling, no data-path collective); NCCL is used for the barrier, the max-over-ranks
+of the timings and the gather of PCM to rank 0 (inside the e2e region).
+
+  value      : audio-s/s from CUDA-event device time of the forward (events on the library's launching stream)
+  e2e.value  : audio-s/s from wall time of the same calls incl. H2D of tokens and D2H of PCM into pinned host memory
+  roofline   : the dominant kernel (conv_gemm, tensor-bound): algorithmic FLOPs / CUDA-event time of its launches, live
+  cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref/kokoro_ref, built from /root/reference by
+               oracle/Makefile) on the host cores, as P worker processes x 8 ggml threads (its own server's
+               n-parallelism model, examples/server/server.cpp:225-321), on a bounded sample of the same prompts.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32
+N_PHON = 64
+CTX_LEN = 128           # GGUF context_length (>= 66 tokens); keeps the reference's worst-case graph reservation small
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "kokoro_ref")
+
+
+def _gguf():
+    from tts_cpp_b200.synth import cached_gguf
+    return cached_gguf("f16", CTX_LEN, 0)
+
+
+def _prompts(rank: int):
+    from tts_cpp_b200.synth import synthetic_prompts
+    return synthetic_prompts(BATCH, N_PHON, seed0=1234 + rank * BATCH)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", 1400.0)), float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, threads: int = 8):
+    """Run the reference CPU path: `workers` processes x `threads` ggml threads, one prompt each, (n_warm + n_timed) repetitions."""
+    if not os.path.exists(REF_BIN):
+        return None, "oracle/_ref/kokoro_ref missing (run `make -C oracle ref` where /root/reference exists)"
+    ncpu = os.cpu_count() or 8
+    threads = max(1, min(threads, ncpu))
+    workers = workers or max(1, ncpu // threads)
+    gguf = _gguf()
+    prompts = _prompts(0)
+    tmp = tempfile.mkdtemp(prefix="b2ref_")
+    procs = []
+    for w in range(workers):
+        tok = os.path.join(tmp, f"tok{w}.txt")
+        with open(tok, "w") as f:
+            f.write(" ".join(map(str, prompts[w % len(prompts)])) + "\n")
+        cmd = [REF_BIN, gguf, tok, os.path.join(tmp, f"o{w}"), "--threads", str(threads), "--reps", str(n_warm + n_timed), "--warm", str(n_warm), "--quiet"]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    audio, wall = 0.0, 0.0
+    for p in procs:
+        out, err = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("SUMMARY"):
+                s = json.loads(line[len("SUMMARY "):])
+                audio += s["audio_s"]; wall = max(wall, s["wall_s"])
+    if wall <= 0:
+        return None, "reference run produced no SUMMARY"
+    return {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
+            "sample": f"{workers} worker processes x {threads} ggml threads, each {n_timed} timed run(s) of one 66-token prompt "
+                      f"(~4.95 s audio) after {n_warm} warm-up; throughput = total audio / slowest worker's wall; x86-64-v3 build"}, None
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base, why = reference_throughput(n_timed=max(1, args.steps), n_warm=max(1, min(args.warmup, 1)))
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+        return 0
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": base["value"], "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 weights / f32 activations (GGML CPU)", "data": "synthetic",
+        "config": {"workload": "Kokoro-82M fp16 GGUF (synthetic weights), 64-char (66-token) prompts, reference CPU GGML path, sequential per worker"},
+        "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from tts_cpp_b200.binding import Context, runner_from_file, lib
+    import ctypes as C
+
+    gguf = _gguf() if rank == 0 else None
+    if dist is not None:
+        dist.barrier()
+        gguf = _gguf()
+    ctx = Context(local)
+    runner = runner_from_file(gguf, ctx=ctx)
+    prompts = _prompts(rank)
+    h2d_bytes = sum(len(p) for p in prompts) * 4
+
+    def step():
+        pcms, durs = runner.run_batch(prompts)
+        if dist is not None:   # gather PCM to rank 0 over NCCL/NVLink (e2e only)
+            flat = torch.from_numpy(np.concatenate(pcms)).cuda(non_blocking=True)
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
+            dist.gather(torch.tensor([flat.numel()], dtype=torch.int64, device="cuda"), sizes, dst=0)
+            if rank == 0:
+                bufs = [torch.empty(int(s.item()), dtype=torch.float32, device="cuda") for s in sizes]
+                dist.gather(flat, bufs, dst=0)
+                _ = [b.cpu() for b in bufs]
+            else:
+                dist.gather(flat, None, dst=0)
+        return pcms
+
+    for _ in range(max(args.warmup, 3)):
+        pcms = step()
+    audio_s = sum(p.shape[0] for p in pcms) / 24000.0
+    d2h_bytes = sum(p.shape[0] for p in pcms) * 4
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib().b2tts_prof_enable(ctx.h, 1)
+    l0 = ctx.launches()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        tm = runner.timings()
+        dev_ms += tm["duration_ms"] + tm["generation_ms"]
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    prof = {}
+    for kind, name in ((0, "conv_gemm"), (1, "bilstm"), (2, "norm_adain"), (3, "conv_transpose")):
+        ms, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+        lib().b2tts_prof_read(ctx.h, kind, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n))
+        prof[name] = {"ms": ms.value, "flops": fl.value, "bytes": by.value, "launches": n.value}
+    lib().b2tts_prof_enable(ctx.h, 0)
+
+    if dist is not None:
+        t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, dev_ms = float(t[0]), float(t[1])
+        a = torch.tensor([audio_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        audio_total = float(a[0])
+    else:
+        audio_total = audio_s
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak_tf, peak_gbs, peak_src = _peaks()
+    g = prof["conv_gemm"]
+    ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    line = {
+        "metric": "audio_seconds_per_second", "value": audio_total * args.steps / (dev_ms * 1e-3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate / activations",
+        "data": "synthetic",
+        "config": {"workload": "Kokoro-82M fp16 GGUF (synthetic weights, 81.3 M params), batch 32 x 64-char (66-token) prompts per GPU, greedy durations, 24 kHz",
+                   "batch_per_gpu": BATCH, "audio_s_per_step_per_gpu": audio_s, "l2": "activations (GBs per step) and weights (164 MB) exceed the 126 MB L2; no flush needed",
+                   "value_timing": "CUDA events on the library stream around duration+generation passes (incl. the mid-forward host sync for durations)"},
+        "e2e": {"value": audio_total * args.steps / wall, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
+                "note": "host token ids in, PCM in pinned host memory out, through b2tts_kokoro_run_batch" + ("; plus NCCL gather of PCM to rank 0" if world > 1 else "")},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM Conv1d/Linear, fp16 mma.sync, fp32 accumulate)", "achieved": ach, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "launches_per_step": g["launches"] / args.steps,
+                     "share_of_device_time": g["ms"] / dev_ms if dev_ms else None},
+        "kernel_classes_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+        "device_ms_per_step": dev_ms / args.steps,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        base, why = reference_throughput(n_timed=1, n_warm=1)
+        line["cpu_baseline"] = base if base else {"value": None, "unavailable": why}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,131 @@
+/* b2tts.h -- C-ABI of the B200-native TTS hot path (libb2tts.so).
+ *
+ * The reference (mmwillet/TTS.cpp) has no FFI: its seam is the C++ API of static lib `tts`
+ * (include/common.h:68-94, src/models/loaders.h:7-20).  This header is the thin C boundary the
+ * reference's runners would call instead of building + computing GGML graphs; every entry point
+ * names the reference function it replaces (file:line relative to the TTS.cpp tree).  Plain C
+ * types only; all pointers are HOST memory owned by the caller unless stated; device memory
+ * never crosses this ABI.  Every function returns 0 on success, non-zero on error
+ * (b2tts_last_error() gives the text); the C++ shim (tts_cpp_b200/host) maps errors to the
+ * reference's abort() convention (src/util.cpp:14-22).
+ *
+ * A context is one CUDA device + stream; one in-flight call per context (the reference's
+ * runners are not re-entrant either: examples/server/server.cpp:316-321 gives each worker its own).
+ */
+#ifndef B2TTS_H
+#define B2TTS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2tts_ctx    b2tts_ctx;
+typedef struct b2tts_kokoro b2tts_kokoro;
+
+/* ggml type ids used by the weight hand-off (ggml/include/ggml.h enum ggml_type) */
+enum { B2TTS_TYPE_F32 = 0, B2TTS_TYPE_F16 = 1 };
+
+/* ---- context (replaces runner_context: src/tts_model.h:16-44, src/tts_model.cpp:38-67) ---- */
+int          b2tts_ctx_create(int device, b2tts_ctx ** out);
+void         b2tts_ctx_destroy(b2tts_ctx * ctx);
+const char * b2tts_last_error(void);
+/* number of kernels this library launched on the context since creation (bench.py "gpu_launches") */
+uint64_t     b2tts_launch_count(const b2tts_ctx * ctx);
+/* raw CUDA stream handle (cudaStream_t) so a host harness can record events on the launching stream */
+void *       b2tts_stream(const b2tts_ctx * ctx);
+/* per-kernel-class timing with CUDA events on the launching stream (bench.py's live roofline accounting; off by default).
+ * kinds: 0 = conv_gemm (tensor-core contractions), 1 = cluster bi-LSTM, 2 = InstanceNorm/AdaIN passes, 3 = ConvTranspose1d.
+ * b2tts_prof_enable(ctx, on) clears the records; b2tts_prof_read sums device ms / algorithmic flops / bytes / launches of a kind. */
+int          b2tts_prof_enable(b2tts_ctx * ctx, int on);
+int          b2tts_prof_read(b2tts_ctx * ctx, int kind, double * total_ms, double * flops, double * bytes, uint64_t * launches);
+
+/* ---- Kokoro model: weight hand-off --------------------------------------------------------
+ * b2tts_kokoro_create       <- kokoro_model::setup_from_file / prep_constants (src/models/kokoro/model.h:297-314, model.cpp:841-930)
+ *                              `kv_keys/kv_vals` are the uint32 GGUF metadata (generator paddings/dilations/strides, recurrence ...)
+ * b2tts_kokoro_assign_weight<- tts_generation_runner::assign_weight -> kokoro_model::assign_weight (model.cpp:1327-1332, 413-427);
+ *                              `name` is the GGUF tensor name (with the "kokoro." prefix), `ne` the ggml dims (ne[0] fastest)
+ * b2tts_kokoro_prepare      <- kokoro_runner::prepare_post_load (model.cpp:1244-1252, 310-392): repacks weights for the
+ *                              tensor-core kernels, builds the constants (Hann window, harmonic factors, window^2 table)
+ * b2tts_kokoro_load_gguf    <- runner_from_file (src/models/loaders.cpp:34-95) for arch "kokoro": does all three from a file
+ */
+int  b2tts_kokoro_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_kokoro ** out);
+int  b2tts_kokoro_assign_weight(b2tts_kokoro * m, const char * name, int ggml_type, int n_dims, const int64_t * ne,
+                                const void * data, size_t nbytes);
+int  b2tts_kokoro_prepare(b2tts_kokoro * m);
+int  b2tts_kokoro_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_kokoro ** out);
+void b2tts_kokoro_free(b2tts_kokoro * m);
+/* voices (tts_generation_runner::list_voices, model.cpp:1452-1455): returns count; names[i] valid for the model's life */
+int  b2tts_kokoro_n_voices(const b2tts_kokoro * m);
+const char * b2tts_kokoro_voice_name(const b2tts_kokoro * m, int i);
+/* bytes of weights resident in HBM (for the roofline accounting) */
+size_t b2tts_kokoro_weight_bytes(const b2tts_kokoro * m);
+
+/* ---- Kokoro forward ------------------------------------------------------------------------
+ * b2tts_kokoro_run_batch <- kokoro_runner::run (model.cpp:1277-1325), batched over independent utterances:
+ *   duration pass (kokoro_duration_runner::run, model.cpp:1069-1123) -> host sum of durations -> generation pass.
+ *   tokens      : concatenated token ids of all utterances (each already wrapped with BOS/EOS, as tokenize_chunks does)
+ *   n_tokens[b] : tokens per utterance (3 <= n <= 512)
+ *   voice       : voice name (NULL -> "af_heart", model.cpp:1390-1393); style row = n_tokens-3 (model.cpp:1013,1213)
+ *   noise_skip[b]: how many draws of the reference's process-wide uniform engine (src/util.cpp:66-72) precede this
+ *                 utterance's 9*600*T noise values (0 = first generate() of a fresh process); NULL -> all 0
+ *   Outputs are borrowed pointers into context-owned pinned host buffers, valid until the next call on this model
+ *   (same lifetime rule as tts_response.data, model.cpp:1299):
+ *   pcm[b]      : float32 PCM @24 kHz, n_samples[b] = 600 * sum(durations)
+ *   durations   : (optional, may be NULL) receives a pointer to sum(n_tokens) floats: the integral frame counts
+ */
+int b2tts_kokoro_run_batch(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice,
+                           const uint64_t * noise_skip, const float ** pcm, int64_t * n_samples, const float ** durations);
+
+/* Stage timings of the last run_batch in milliseconds (CUDA events on the launching stream):
+ * [0] duration pass, [1] generation pass (device), [2] whole call incl. H2D/D2H.  */
+int b2tts_kokoro_last_timings(const b2tts_kokoro * m, float ms[3]);
+
+/* ---- test taps (teacher forcing / stage parity; no effect on the product path unless used) ----
+ * Named stage buffers of the LAST run (batch-major, padded to the longest utterance, channels-last fp32):
+ * "albert","d","lens","en","shared","f0","n","t_en","asr","dec","har","har_spec","gen_out0","gen_out1","spec","pcm", ...
+ * b2tts_kokoro_tap_info  : rows = batch*padded_len, cols = channels
+ * b2tts_kokoro_tap_read  : copy the buffer to host
+ * b2tts_kokoro_override  : for the NEXT runs, overwrite the named buffer with host data right after it is produced
+ *                          (count floats must match); count==0 clears the override
+ */
+int b2tts_kokoro_set_taps(b2tts_kokoro * m, int enable);
+int b2tts_kokoro_tap_info(b2tts_kokoro * m, const char * name, int64_t * rows, int64_t * cols, int64_t * padded_len);
+int b2tts_kokoro_tap_read(b2tts_kokoro * m, const char * name, float * dst, size_t count);
+int b2tts_kokoro_override(b2tts_kokoro * m, const char * name, const float * src, size_t count);
+
+/* ---- the patched ggml ops as stand-alone device kernels (host buffers in/out) -------------------
+ * These replace the ops the reference adds to its ggml fork (constructors ggml/src/ggml.c:2204-2345,3847-3945,4223-4233;
+ * CPU kernels ggml/src/ggml-cpu/ggml-cpu.c:5526-5720,8476-8860,10004-10220,10849-10984) and the util.cpp wrappers
+ * (src/util.cpp:86-137).  Layouts follow ggml: x[c][l] = data[c*L + l] ("ne = [L, C]").
+ */
+/* ggml_conv_transpose_1d(kernel[K,Cout/g,Cin], x[L,Cin], s, p, d=1, op, g): y[Lout,Cout], Lout=(L-1)s-2p+(K-1)+op+1; fp32 math */
+int b2tts_op_conv_transpose_1d(b2tts_ctx * ctx, const float * kernel, int K, int cout_per_group, int cin, const float * x, int L,
+                               int stride, int pad, int out_pad, int groups, float * y);
+/* ggml_conv_1d (im2col + mul_mat): kernel[K,Cin,Cout]; f16_kernel!=0 re-rounds kernel and activations to fp16 like the reference */
+int b2tts_op_conv_1d(b2tts_ctx * ctx, const float * kernel, int K, int cin, int cout, const float * x, int L, int stride, int pad,
+                     int dil, int f16_kernel, float * y);
+int b2tts_op_cumsum(b2tts_ctx * ctx, const float * x, int L, int rows, float * y);            /* ggml_cumsum along ne0 */
+int b2tts_op_mod(b2tts_ctx * ctx, const float * x, int64_t n, float mod_val, float * y);      /* ggml_mod: fmod */
+int b2tts_op_round(b2tts_ctx * ctx, const float * x, int64_t n, float * y);                   /* ggml_round: (float)(int)(x+0.5f) */
+int b2tts_op_reciprocal(b2tts_ctx * ctx, const float * x, int64_t n, float * y);              /* ggml_reciprocal */
+int b2tts_op_upscale_linear(b2tts_ctx * ctx, const float * x, int L, int rows, int factor, float * y); /* ggml_upscale_linear */
+int b2tts_op_snake(b2tts_ctx * ctx, const float * alpha, int C, const float * x, int L, float * y);    /* snake_1d */
+/* stft(x[L], hann(n_fft), n_fft, hop, abs_and_angle=1, one_sided=1): mag,phase [frames][n_fft/2+1], frames = L/hop+1 */
+int b2tts_op_stft(b2tts_ctx * ctx, const float * x, int L, int n_fft, int hop, float * mag, float * phase);
+/* istft(mag,phase [frames][bins]) / window_sq_sum  -> y[(frames-1)*hop] */
+int b2tts_op_istft(b2tts_ctx * ctx, const float * mag, const float * phase, int frames, int n_fft, int hop, float * y);
+/* the reference's static uniform generator (src/util.cpp:66-72): draws skip+1 .. skip+count */
+int b2tts_op_uniform(b2tts_ctx * ctx, uint64_t skip, int64_t count, float * y);
+/* bidirectional LSTM (src/models/kokoro/model.cpp:35-86) on a ragged batch, used by the stage parity tests:
+ * w_ih[2][4*H][In], w_hh[2][4*H][H], b_ih[2][4*H], b_hh[2][4*H] (dir 0 = forward; gate order i,f,g,o; fp16-representable values),
+ * x[B][Lmax][In], len[B] -> y[B][Lmax][2H];  H must be 256 */
+int b2tts_op_bilstm(b2tts_ctx * ctx, const float * w_ih, const float * w_hh, const float * b_ih, const float * b_hh, int In, int H,
+                    const float * x, int B, int Lmax, const int32_t * len, float * y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2TTS_H */

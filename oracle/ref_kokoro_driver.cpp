@@ -80,12 +80,13 @@ static void dump_all(std::vector<dump_req> & reqs, const std::string & prefix, c
 int main(int argc, char ** argv) {
     if (argc < 4) { fprintf(stderr, "usage: %s model.gguf tokens.txt out_prefix [opts]\n", argv[0]); return 2; }
     std::string model_path = argv[1], tok_path = argv[2], out_prefix = argv[3];
-    int n_threads = 1, reps = 1; bool list = false, quiet = false;
+    int n_threads = 1, reps = 1, warm = -1; bool list = false, quiet = false;
     std::vector<dump_req> ddur, dgen;
     for (int i = 4; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--threads" && i + 1 < argc) n_threads = atoi(argv[++i]);
         else if (a == "--reps" && i + 1 < argc) reps = atoi(argv[++i]);
+        else if (a == "--warm" && i + 1 < argc) warm = atoi(argv[++i]);   // leading repetitions excluded from SUMMARY (default: 1 if reps > 1)
         else if (a == "--dump-dur" && i + 1 < argc) { for (auto & s : split_csv(argv[++i])) ddur.push_back({s}); }
         else if (a == "--dump-gen" && i + 1 < argc) { for (auto & s : split_csv(argv[++i])) dgen.push_back({s}); }
         else if (a == "--list-nodes") list = true;
@@ -178,7 +179,7 @@ int main(int argc, char ** argv) {
                 printf("UTT rep=%d u=%zu n_tokens=%zu T=%u samples=%zu ms=%.1f dur_ms=%.1f rms=%.6g max=%.6g\n", rep, u, toks.size(),
                        total_length, n_out, ms, dur_ms, rms, mx);
             }
-            if (rep > 0 || reps == 1) { total_audio_s += n_out / 24000.0; total_ms += ms; total_dur_ms += dur_ms; }
+            if (rep >= (warm >= 0 ? warm : (reps > 1 ? 1 : 0))) { total_audio_s += n_out / 24000.0; total_ms += ms; total_dur_ms += dur_ms; }
         }
     }
     printf("SUMMARY {\"threads\": %d, \"audio_s\": %.4f, \"wall_s\": %.4f, \"duration_graph_s\": %.4f, \"audio_s_per_s\": %.5f}\n", n_threads,

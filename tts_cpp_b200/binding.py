@@ -1,0 +1,218 @@
+"""ctypes binding of libb2tts.so -- the host-side mirror (for tests / bench) of the reference interface.
+
+Names follow the reference (src/models/loaders.h:19-20, include/common.h:68-94, src/models/kokoro/model.h:430-468):
+`runner_from_file(path)` returns a `KokoroRunner` whose `run(tokens)` is kokoro_runner::run (token-id entry, below the
+phonemizer) and `run_batch` its batched form.  There is NO CPU fallback: a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2tts.so")
+_lib = None
+
+
+class B2TTSError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2TTSError(f"{LIB_PATH} is missing: run `python -m tts_cpp_b200.build` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.b2tts_last_error.restype = C.c_char_p
+        _lib.b2tts_launch_count.restype = C.c_uint64
+        _lib.b2tts_stream.restype = C.c_void_p
+        _lib.b2tts_kokoro_voice_name.restype = C.c_char_p
+        _lib.b2tts_kokoro_weight_bytes.restype = C.c_size_t
+    return _lib
+
+
+def _chk(rc: int):
+    if rc != 0:
+        raise B2TTSError(lib().b2tts_last_error().decode())
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.h = C.c_void_p()
+        _chk(lib().b2tts_ctx_create(C.c_int(device), C.byref(self.h)))
+
+    def launches(self) -> int:
+        return int(lib().b2tts_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(lib().b2tts_stream(self.h) or 0)
+
+    def close(self):
+        if self.h:
+            lib().b2tts_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # ---- the patched ggml ops (ggml layout x[c][l]) -------------------------------------------------
+    def conv_transpose_1d(self, kernel, x, stride, pad, out_pad=0, groups=1):
+        k = np.ascontiguousarray(kernel, np.float32)      # numpy [Cin, Cout/g, K]
+        xx = np.ascontiguousarray(x, np.float32)          # [Cin, L]
+        cin, coutg, K = k.shape
+        L = xx.shape[1]
+        lout = (L - 1) * stride - 2 * pad + (K - 1) + out_pad + 1
+        y = np.empty((coutg * groups, lout), np.float32)
+        _chk(lib().b2tts_op_conv_transpose_1d(self.h, _fp(k), K, coutg, cin, _fp(xx), L, stride, pad, out_pad, groups, _fp(y)))
+        return y
+
+    def conv_1d(self, kernel, x, stride=1, pad=0, dil=1):
+        k = np.ascontiguousarray(kernel, np.float32)      # numpy [Cout, Cin, K]
+        xx = np.ascontiguousarray(x, np.float32)
+        cout, cin, K = k.shape
+        L = xx.shape[1]
+        lout = (L + 2 * pad - dil * (K - 1) - 1) // stride + 1
+        y = np.empty((cout, lout), np.float32)
+        _chk(lib().b2tts_op_conv_1d(self.h, _fp(k), K, cin, cout, _fp(xx), L, stride, pad, dil, 1, _fp(y)))
+        return y
+
+    def cumsum(self, x):
+        xx = np.ascontiguousarray(x, np.float32); y = np.empty_like(xx)
+        _chk(lib().b2tts_op_cumsum(self.h, _fp(xx), xx.shape[-1], int(xx.size // xx.shape[-1]), _fp(y)))
+        return y
+
+    def _unary(self, fn, x, *args):
+        xx = np.ascontiguousarray(x, np.float32); y = np.empty_like(xx)
+        _chk(fn(self.h, _fp(xx), C.c_int64(xx.size), *args, _fp(y)))
+        return y
+
+    def mod(self, x, v):
+        return self._unary(lib().b2tts_op_mod, x, C.c_float(v))
+
+    def round(self, x):
+        return self._unary(lib().b2tts_op_round, x)
+
+    def reciprocal(self, x):
+        return self._unary(lib().b2tts_op_reciprocal, x)
+
+    def upscale_linear(self, x, factor):
+        xx = np.ascontiguousarray(x, np.float32)
+        y = np.empty(xx.shape[:-1] + (xx.shape[-1] * factor,), np.float32)
+        _chk(lib().b2tts_op_upscale_linear(self.h, _fp(xx), xx.shape[-1], int(xx.size // xx.shape[-1]), factor, _fp(y)))
+        return y
+
+    def snake(self, alpha, x):
+        a = np.ascontiguousarray(alpha, np.float32).ravel(); xx = np.ascontiguousarray(x, np.float32); y = np.empty_like(xx)
+        _chk(lib().b2tts_op_snake(self.h, _fp(a), xx.shape[0], _fp(xx), xx.shape[1], _fp(y)))
+        return y
+
+    def stft(self, x, n_fft=20, hop=5):
+        xx = np.ascontiguousarray(x, np.float32)
+        fr = xx.shape[0] // hop + 1
+        mag = np.empty((fr, n_fft // 2 + 1), np.float32); ph = np.empty_like(mag)
+        _chk(lib().b2tts_op_stft(self.h, _fp(xx), xx.shape[0], n_fft, hop, _fp(mag), _fp(ph)))
+        return mag, ph
+
+    def istft(self, mag, ph, n_fft=20, hop=5):
+        m = np.ascontiguousarray(mag, np.float32); p = np.ascontiguousarray(ph, np.float32)
+        y = np.empty((m.shape[0] - 1) * hop, np.float32)
+        _chk(lib().b2tts_op_istft(self.h, _fp(m), _fp(p), m.shape[0], n_fft, hop, _fp(y)))
+        return y
+
+    def uniform(self, count, skip=0):
+        y = np.empty(count, np.float32)
+        _chk(lib().b2tts_op_uniform(self.h, C.c_uint64(skip), C.c_int64(count), _fp(y)))
+        return y
+
+    def bilstm(self, w_ih, w_hh, b_ih, b_hh, x, lens):
+        w_ih = np.ascontiguousarray(w_ih, np.float32); w_hh = np.ascontiguousarray(w_hh, np.float32)
+        b_ih = np.ascontiguousarray(b_ih, np.float32); b_hh = np.ascontiguousarray(b_hh, np.float32)
+        xx = np.ascontiguousarray(x, np.float32); ln = np.ascontiguousarray(lens, np.int32)
+        B, Lmax, In = xx.shape
+        H = w_hh.shape[-1]
+        y = np.empty((B, Lmax, 2 * H), np.float32)
+        _chk(lib().b2tts_op_bilstm(self.h, _fp(w_ih), _fp(w_hh), _fp(b_ih), _fp(b_hh), In, H, _fp(xx), B, Lmax,
+                                   ln.ctypes.data_as(C.POINTER(C.c_int32)), _fp(y)))
+        return y
+
+
+class KokoroRunner:
+    """kokoro_runner (src/models/kokoro/model.h:430-468) on a B200."""
+    sampling_rate = 24000.0
+    supports_voices = True
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    def list_voices(self):
+        n = lib().b2tts_kokoro_n_voices(self.h)
+        return [lib().b2tts_kokoro_voice_name(self.h, i).decode() for i in range(n)]
+
+    def weight_bytes(self) -> int:
+        return int(lib().b2tts_kokoro_weight_bytes(self.h))
+
+    def run_batch(self, utterances, voice: str | None = None, noise_skip=None):
+        """utterances: list of token-id lists (BOS/EOS included).  Returns (list of pcm arrays, list of duration arrays)."""
+        B = len(utterances)
+        ntok = np.array([len(u) for u in utterances], np.int32)
+        toks = np.ascontiguousarray(np.concatenate([np.asarray(u, np.uint32) for u in utterances]))
+        pcm = (C.POINTER(C.c_float) * B)()
+        ns = (C.c_int64 * B)()
+        dur = C.POINTER(C.c_float)()
+        skip = None
+        if noise_skip is not None:
+            skip = np.ascontiguousarray(noise_skip, np.uint64).ctypes.data_as(C.POINTER(C.c_uint64))
+        _chk(lib().b2tts_kokoro_run_batch(self.h, B, toks.ctypes.data_as(C.POINTER(C.c_uint32)), ntok.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          voice.encode() if voice else None, skip, pcm, ns, C.byref(dur)))
+        outs, durs, off = [], [], 0
+        for b in range(B):
+            outs.append(np.ctypeslib.as_array(pcm[b], shape=(int(ns[b]),)).copy() if ns[b] else np.zeros(0, np.float32))
+            durs.append(np.ctypeslib.as_array(dur, shape=(int(ntok.sum()),))[off:off + int(ntok[b])].copy())
+            off += int(ntok[b])
+        return outs, durs
+
+    def run(self, tokens, voice: str | None = None, noise_skip: int = 0):
+        p, d = self.run_batch([tokens], voice, [noise_skip])
+        return p[0], d[0]
+
+    def timings(self):
+        ms = (C.c_float * 3)()
+        lib().b2tts_kokoro_last_timings(self.h, ms)
+        return {"duration_ms": ms[0], "generation_ms": ms[1], "total_ms": ms[2]}
+
+    # ---- test taps
+    def set_taps(self, on=True):
+        _chk(lib().b2tts_kokoro_set_taps(self.h, int(on)))
+
+    def tap(self, name: str) -> np.ndarray:
+        r, c, p = C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(lib().b2tts_kokoro_tap_info(self.h, name.encode(), C.byref(r), C.byref(c), C.byref(p)))
+        a = np.empty((r.value, c.value), np.float32)
+        _chk(lib().b2tts_kokoro_tap_read(self.h, name.encode(), _fp(a), C.c_size_t(a.size)))
+        if p.value > 0 and p.value != c.value and r.value % p.value == 0:
+            return a.reshape(r.value // p.value, p.value, c.value)   # [utterance][padded time][channels]
+        return a                                                      # [utterance][samples]
+
+    def override(self, name: str, arr=None):
+        if arr is None:
+            _chk(lib().b2tts_kokoro_override(self.h, name.encode(), None, C.c_size_t(0)))
+        else:
+            a = np.ascontiguousarray(arr, np.float32)
+            _chk(lib().b2tts_kokoro_override(self.h, name.encode(), _fp(a), C.c_size_t(a.size)))
+
+    def close(self):
+        if self.h:
+            lib().b2tts_kokoro_free(self.h)
+            self.h = None
+
+
+def runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> KokoroRunner:
+    """runner_from_file (src/models/loaders.cpp:34-95) for general.architecture == "kokoro"."""
+    ctx = ctx or Context(device)
+    h = C.c_void_p()
+    _chk(lib().b2tts_kokoro_load_gguf(ctx.h, path.encode(), C.byref(h)))
+    return KokoroRunner(ctx, h)

@@ -1,0 +1,254 @@
+// capi.cu -- extern "C" boundary of libb2tts.so (declared in include/b2tts.h).
+#include "../../include/b2tts.h"
+#include "kokoro.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace b2 {
+static thread_local char g_err[1024] = "";
+void set_error(const char * fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace b2
+
+using namespace b2;
+
+struct b2tts_ctx { Ctx c; };
+struct b2tts_kokoro { Kokoro k; };
+
+namespace {
+// RAII device scratch for the op-level entry points
+struct Dev {
+    std::vector<void *> ptrs;
+    ~Dev() { for (void * p : ptrs) cudaFree(p); }
+    template <class T> T * get(size_t n) { void * p = nullptr; if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed"); return nullptr; } ptrs.push_back(p); return (T *) p; }
+    template <class T> T * put(const T * h, size_t n) { T * d = get<T>(n); if (d && n) cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice); return d; }
+};
+int finish(Ctx * c, void * dst, const void * src, size_t bytes) {
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int b2tts_ctx_create(int device, b2tts_ctx ** out) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); set_error("no CUDA device visible: libb2tts has no CPU fallback"); return 1; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return 1; }
+    B2_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return 1; }
+    b2tts_ctx * c = new b2tts_ctx();
+    c->c.device = device;
+    B2_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+void b2tts_ctx_destroy(b2tts_ctx * ctx) {
+    if (!ctx) return;
+    if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+const char * b2tts_last_error(void) { return g_err; }
+uint64_t b2tts_launch_count(const b2tts_ctx * ctx) { return ctx ? ctx->c.launches : 0; }
+void * b2tts_stream(const b2tts_ctx * ctx) { return ctx ? (void *) ctx->c.stream : nullptr; }
+int b2tts_prof_enable(b2tts_ctx * ctx, int on) {
+    Ctx & c = ctx->c;
+    for (auto & r : c.recs) { c.pool.push_back(r.a); c.pool.push_back(r.b); }
+    c.recs.clear();
+    c.prof = on != 0;
+    return 0;
+}
+int b2tts_prof_read(b2tts_ctx * ctx, int kind, double * total_ms, double * flops, double * bytes, uint64_t * launches) {
+    Ctx & c = ctx->c;
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    double ms = 0, fl = 0, by = 0; uint64_t n = 0;
+    for (auto & r : c.recs) {
+        if (r.kind != kind) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        ms += t; fl += r.flops; by += r.bytes; n++;
+    }
+    if (total_ms) *total_ms = ms; if (flops) *flops = fl; if (bytes) *bytes = by; if (launches) *launches = n;
+    return 0;
+}
+
+int b2tts_kokoro_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_kokoro ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    b2tts_kokoro * m = new b2tts_kokoro();
+    m->k.ctx = &ctx->c;
+    for (int i = 0; i < n_kv; i++) m->k.kv[kv_keys[i]] = kv_vals[i];
+    *out = m;
+    return 0;
+}
+int b2tts_kokoro_assign_weight(b2tts_kokoro * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
+    return m->k.assign(name, ggml_type, n_dims, ne, data, nbytes);
+}
+int b2tts_kokoro_prepare(b2tts_kokoro * m) { B2_CUDA(cudaSetDevice(m->k.ctx->device)); return m->k.prepare(); }
+int b2tts_kokoro_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_kokoro ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_kokoro * m = new b2tts_kokoro();
+    m->k.ctx = &ctx->c;
+    if (load_gguf_into(&m->k, path)) { m->k.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_kokoro_free(b2tts_kokoro * m) { if (m) { m->k.free_all(); delete m; } }
+int b2tts_kokoro_n_voices(const b2tts_kokoro * m) { return (int) m->k.voice_names.size(); }
+const char * b2tts_kokoro_voice_name(const b2tts_kokoro * m, int i) { return (i >= 0 && i < (int) m->k.voice_names.size()) ? m->k.voice_names[i].c_str() : nullptr; }
+size_t b2tts_kokoro_weight_bytes(const b2tts_kokoro * m) { return m->k.weight_bytes; }
+
+int b2tts_kokoro_run_batch(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, const uint64_t * noise_skip,
+                           const float ** pcm, int64_t * n_samples, const float ** durations) {
+    B2_CUDA(cudaSetDevice(m->k.ctx->device));
+    return m->k.run_batch(batch, tokens, n_tokens, voice, noise_skip, pcm, n_samples, durations);
+}
+int b2tts_kokoro_last_timings(const b2tts_kokoro * m, float ms[3]) { for (int i = 0; i < 3; i++) ms[i] = m->k.timings[i]; return 0; }
+
+int b2tts_kokoro_set_taps(b2tts_kokoro * m, int enable) { m->k.taps_on = enable != 0; return 0; }
+int b2tts_kokoro_tap_info(b2tts_kokoro * m, const char * name, int64_t * rows, int64_t * cols, int64_t * padded_len) {
+    auto it = m->k.taps.find(name);
+    if (it == m->k.taps.end()) { set_error("no tap named '%s' (enable taps and run first)", name); return 1; }
+    if (rows) *rows = it->second.rows; if (cols) *cols = it->second.cols; if (padded_len) *padded_len = it->second.padded;
+    return 0;
+}
+int b2tts_kokoro_tap_read(b2tts_kokoro * m, const char * name, float * dst, size_t count) {
+    auto it = m->k.taps.find(name);
+    if (it == m->k.taps.end()) { set_error("no tap named '%s'", name); return 1; }
+    const Tap & t = it->second;
+    if ((int64_t) count != t.rows * t.cols) { set_error("tap '%s' holds %lld floats, asked for %zu", name, (long long) (t.rows * t.cols), count); return 1; }
+    B2_CUDA(cudaSetDevice(m->k.ctx->device));
+    B2_CUDA(cudaMemcpy2D(dst, t.cols * 4, t.ptr, t.ld * 4, t.cols * 4, t.rows, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int b2tts_kokoro_override(b2tts_kokoro * m, const char * name, const float * src, size_t count) {
+    if (count == 0) { m->k.overrides.erase(name); return 0; }
+    m->k.overrides[name] = std::vector<float>(src, src + count);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ op-level entry points
+int b2tts_op_conv_transpose_1d(b2tts_ctx * ctx, const float * kernel, int K, int coutg, int cin, const float * x, int L, int stride, int pad, int out_pad,
+                               int groups, float * y) {
+    Ctx * c = &ctx->c; Dev d;
+    const int Lout = (L - 1) * stride - 2 * pad + (K - 1) + out_pad + 1;
+    float * dk = d.put(kernel, (size_t) K * coutg * cin); float * dx = d.put(x, (size_t) L * cin); float * dy = d.get<float>((size_t) Lout * coutg * groups);
+    if (!dk || !dx || !dy) return 1;
+    if (op_conv_transpose_1d(c, dk, K, coutg, cin, dx, L, stride, pad, out_pad, groups, dy, Lout)) return 1;
+    return finish(c, y, dy, (size_t) Lout * coutg * groups * 4);
+}
+
+int b2tts_op_conv_1d(b2tts_ctx * ctx, const float * kernel, int K, int cin, int cout, const float * x, int L, int stride, int pad, int dil, int f16_kernel,
+                     float * y) {
+    if (!f16_kernel) { set_error("b2tts_op_conv_1d: only the F16-kernel path (fp16 operands, fp32 accumulate) is implemented"); return 1; }
+    Ctx * c = &ctx->c; Dev d;
+    const int Lout = (L + 2 * pad - dil * (K - 1) - 1) / stride + 1;
+    const int cp = round_up(cin, 32), np = round_up(cout, 64);
+    std::vector<__half> w((size_t) np * K * cp, __float2half(0.f)), a((size_t) L * cp, __float2half(0.f));
+    for (int co = 0; co < cout; co++) for (int ci = 0; ci < cin; ci++) for (int k = 0; k < K; k++) w[((size_t) co * K + k) * cp + ci] = __float2half(kernel[((size_t) co * cin + ci) * K + k]);
+    for (int ci = 0; ci < cin; ci++) for (int t = 0; t < L; t++) a[(size_t) t * cp + ci] = __float2half(x[(size_t) ci * L + t]);
+    __half * dw = d.put(w.data(), w.size()); __half * da = d.put(a.data(), a.size()); float * dy = d.get<float>((size_t) Lout * cout);
+    if (!dw || !da || !dy) return 1;
+    ConvGemmParams p;
+    p.A = da; p.lda = cp; p.W = dw; p.outF = dy; p.ldo = cout; p.B = 1; p.LmaxIn = L; p.LmaxOut = Lout; p.N = cout; p.Npad = np; p.KW = K; p.CinPad = cp;
+    p.stride = stride; p.dil = dil; p.pad = pad;
+    if (conv_gemm(c, p)) return 1;
+    std::vector<float> t((size_t) Lout * cout);
+    if (finish(c, t.data(), dy, t.size() * 4)) return 1;
+    for (int co = 0; co < cout; co++) for (int o = 0; o < Lout; o++) y[(size_t) co * Lout + o] = t[(size_t) o * cout + co];
+    return 0;
+}
+
+int b2tts_op_cumsum(b2tts_ctx * ctx, const float * x, int L, int rows, float * y) {
+    Ctx * c = &ctx->c; Dev d; float * dx = d.put(x, (size_t) L * rows); float * dy = d.get<float>((size_t) L * rows);
+    if (!dx || !dy || op_cumsum(c, dx, L, rows, dy)) return 1;
+    return finish(c, y, dy, (size_t) L * rows * 4);
+}
+static int unary(b2tts_ctx * ctx, int which, const float * x, int64_t n, float arg, float * y) {
+    Ctx * c = &ctx->c; Dev d; float * dx = d.put(x, (size_t) n); float * dy = d.get<float>((size_t) n);
+    if (!dx || !dy || op_unary(c, which, dx, n, arg, dy)) return 1;
+    return finish(c, y, dy, (size_t) n * 4);
+}
+int b2tts_op_mod(b2tts_ctx * ctx, const float * x, int64_t n, float mod_val, float * y) { return unary(ctx, 0, x, n, mod_val, y); }
+int b2tts_op_round(b2tts_ctx * ctx, const float * x, int64_t n, float * y) { return unary(ctx, 1, x, n, 0.f, y); }
+int b2tts_op_reciprocal(b2tts_ctx * ctx, const float * x, int64_t n, float * y) { return unary(ctx, 2, x, n, 0.f, y); }
+int b2tts_op_upscale_linear(b2tts_ctx * ctx, const float * x, int L, int rows, int factor, float * y) {
+    Ctx * c = &ctx->c; Dev d; float * dx = d.put(x, (size_t) L * rows); float * dy = d.get<float>((size_t) L * rows * factor);
+    if (!dx || !dy || op_upscale_linear(c, dx, L, rows, factor, dy)) return 1;
+    return finish(c, y, dy, (size_t) L * rows * factor * 4);
+}
+int b2tts_op_snake(b2tts_ctx * ctx, const float * alpha, int C, const float * x, int L, float * y) {
+    Ctx * c = &ctx->c; Dev d; float * da = d.put(alpha, (size_t) C); float * dx = d.put(x, (size_t) C * L); float * dy = d.get<float>((size_t) C * L);
+    if (!da || !dx || !dy || op_snake(c, da, C, dx, L, dy)) return 1;
+    return finish(c, y, dy, (size_t) C * L * 4);
+}
+int b2tts_op_stft(b2tts_ctx * ctx, const float * x, int L, int n_fft, int hop, float * mag, float * phase) {
+    if (n_fft != 20 || hop != 5) { set_error("b2tts_op_stft: only n_fft=20 hop=5 (Kokoro's iSTFTNet) is implemented"); return 1; }
+    Ctx * c = &ctx->c; Dev d;
+    const int frames = L / hop + 1, one = L;
+    float * dx = d.put(x, (size_t) L); float * df = d.get<float>((size_t) frames * 22); int * dl = d.put(&one, 1);
+    if (!dx || !df || !dl || stft20(c, dx, L, 1, dl, frames, nullptr, 0, 0, df, 22)) return 1;
+    std::vector<float> t((size_t) frames * 22);
+    if (finish(c, t.data(), df, t.size() * 4)) return 1;
+    for (int f = 0; f < frames; f++) for (int k = 0; k < 11; k++) { mag[(size_t) f * 11 + k] = t[(size_t) f * 22 + k]; phase[(size_t) f * 11 + k] = t[(size_t) f * 22 + 11 + k]; }
+    return 0;
+}
+int b2tts_op_istft(b2tts_ctx * ctx, const float * mag, const float * phase, int frames, int n_fft, int hop, float * y) {
+    if (n_fft != 20 || hop != 5) { set_error("b2tts_op_istft: only n_fft=20 hop=5 is implemented"); return 1; }
+    Ctx * c = &ctx->c; Dev d;
+    std::vector<float> t((size_t) frames * 22);
+    for (int f = 0; f < frames; f++) for (int k = 0; k < 11; k++) { t[(size_t) f * 22 + k] = mag[(size_t) f * 11 + k]; t[(size_t) f * 22 + 11 + k] = phase[(size_t) f * 11 + k]; }
+    const int S = (frames - 1) * hop;
+    float * ds = d.put(t.data(), t.size()); float * dy = d.get<float>((size_t) S); int * dl = d.put(&frames, 1);
+    if (!ds || !dy || !dl || istft20(c, ds, 22, 1, dl, frames, dy, S)) return 1;
+    return finish(c, y, dy, (size_t) S * 4);
+}
+int b2tts_op_uniform(b2tts_ctx * ctx, uint64_t skip, int64_t count, float * y) {
+    Ctx * c = &ctx->c; Dev d; float * dy = d.get<float>((size_t) count);
+    if (!dy || op_uniform(c, skip, count, dy)) return 1;
+    return finish(c, y, dy, (size_t) count * 4);
+}
+
+int b2tts_op_bilstm(b2tts_ctx * ctx, const float * w_ih, const float * w_hh, const float * b_ih, const float * b_hh, int In, int H, const float * x, int B,
+                    int Lmax, const int32_t * len, float * y) {
+    if (H != 256) { set_error("b2tts_op_bilstm: hidden size must be 256"); return 1; }
+    Ctx * c = &ctx->c; Dev d;
+    const int ip = round_up(In, 32);
+    std::vector<__half> wih((size_t) 2048 * ip, __float2half(0.f)), whh((size_t) 2 * 1024 * 256), xa((size_t) B * Lmax * ip, __float2half(0.f));
+    std::vector<float> bih(2048), bhh(2048);
+    for (int dd = 0; dd < 2; dd++) for (int g = 0; g < 4; g++) for (int u = 0; u < H; u++) {
+        const size_t src = (size_t) dd * 4 * H + g * H + u, row = (size_t) dd * 4 * H + (size_t) u * 4 + g;
+        for (int k = 0; k < In; k++) wih[row * ip + k] = __float2half(w_ih[src * In + k]);
+        for (int k = 0; k < H; k++) whh[src * H + k] = __float2half(w_hh[src * H + k]);
+        bih[row] = b_ih[src]; bhh[src] = b_hh[src];
+    }
+    int maxLen = 0;
+    for (int b = 0; b < B; b++) { maxLen = std::max(maxLen, (int) len[b]); for (int t = 0; t < Lmax; t++) for (int k = 0; k < In; k++) xa[((size_t) b * Lmax + t) * ip + k] = __float2half(x[((size_t) b * Lmax + t) * In + k]); }
+    __half * dwih = d.put(wih.data(), wih.size()); __half * dwhh = d.put(whh.data(), whh.size()); __half * dx = d.put(xa.data(), xa.size());
+    float * dbih = d.put(bih.data(), bih.size()); float * dbhh = d.put(bhh.data(), bhh.size());
+    std::vector<int> l32(len, len + B); int * dl = d.put(l32.data(), (size_t) B);
+    float * xp = d.get<float>((size_t) B * Lmax * 2048); float * dy = d.get<float>((size_t) B * Lmax * 512);
+    if (!dwih || !dwhh || !dx || !dbih || !dbhh || !dl || !xp || !dy) return 1;
+    B2_CUDA(cudaMemset(dy, 0, (size_t) B * Lmax * 512 * 4));
+    ConvGemmParams p;
+    p.A = dx; p.lda = ip; p.W = dwih; p.bias = dbih; p.outF = xp; p.ldo = 2048; p.B = B; p.LmaxIn = Lmax; p.LmaxOut = Lmax; p.lenIn = dl; p.lenOut = dl;
+    p.N = 2048; p.Npad = 2048; p.KW = 1; p.CinPad = ip;
+    if (conv_gemm(c, p)) return 1;
+    LstmParams lp;
+    lp.xp = xp; lp.whh = dwhh; lp.bhh = dbhh; lp.out = dy; lp.ldo = 512; lp.len = dl; lp.B = B; lp.Lmax = Lmax; lp.maxLen = maxLen;
+    if (bilstm(c, lp)) return 1;
+    return finish(c, y, dy, (size_t) B * Lmax * 512 * 4);
+}
+
+}  // extern "C"

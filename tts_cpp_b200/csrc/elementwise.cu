@@ -1,0 +1,499 @@
+// elementwise.cu -- normalisation, activation, gather and small-matrix kernels of the Kokoro forward (sm_100a).
+// Everything here is HBM/L2-bound: channels-last rows are read/written with consecutive threads on consecutive
+// channels (coalesced), per-channel parameters live in registers, and each kernel fuses the chain of GGML nodes the
+// reference spends separate passes on (norm -> mul -> add -> add -> leaky_relu/snake -> cont(transpose) -> fp16 im2col).
+#include "kernels.cuh"
+#include <math.h>
+
+namespace b2 {
+namespace {
+
+constexpr int KMAX = 5;  // channels per thread (C <= 1280)
+
+__device__ __forceinline__ float lrelu(float v, float ns) { return (v > 0.f ? v : 0.f) + ns * (v < 0.f ? v : 0.f); }  // ggml_vec_leaky_relu_f32
+
+// ---------------------------------------------------------------- InstanceNorm statistics
+__global__ void inorm_stats_kernel(const float * __restrict__ x, int ldx, int C, int Lmax, const int * __restrict__ len, double * sums,
+                                   int rows_per_block) {
+    const int b = blockIdx.y;
+    const int L = len[b];
+    const int t0 = blockIdx.x * rows_per_block;
+    if (t0 >= L) return;
+    const int t1 = min(L, t0 + rows_per_block);
+    const int tx = threadIdx.x, ty = threadIdx.y, nx = blockDim.x, ny = blockDim.y;
+    double s[KMAX], q[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) s[k] = q[k] = 0.0;
+    const float * xb = x + (size_t) b * Lmax * ldx;
+    for (int t = t0 + ty; t < t1; t += ny) {
+        const float * row = xb + (size_t) t * ldx;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            const int c = tx + k * nx;
+            if (c < C) { const double v = (double) row[c]; s[k] += v; q[k] += v * v; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+        const int c = tx + k * nx;
+        if (c < C) {
+            atomicAdd(&sums[((size_t) b * C + c) * 2 + 0], s[k]);
+            atomicAdd(&sums[((size_t) b * C + c) * 2 + 1], q[k]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- AdaIN apply + activation
+__global__ void adain_apply_kernel(const AdainParams p, int rows_per_block) {
+    const int b = blockIdx.y;
+    const int L = p.len[b];
+    const int t0 = blockIdx.x * rows_per_block;
+    if (t0 >= L) return;
+    const int t1 = min(L, t0 + rows_per_block);
+    const int tx = threadIdx.x, ty = threadIdx.y, nx = blockDim.x, ny = blockDim.y;
+    float mean[KMAX], rstd[KMAX], gam[KMAX], bet[KMAX], al[KMAX], ial[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+        const int c = tx + k * nx;
+        mean[k] = 0.f; rstd[k] = 0.f; gam[k] = 0.f; bet[k] = 0.f; al[k] = 1.f; ial[k] = 1.f;
+        if (c < p.C) {
+            const double s = p.sums[((size_t) b * p.C + c) * 2], q = p.sums[((size_t) b * p.C + c) * 2 + 1];
+            const double m = s / (double) L;
+            double var = q / (double) L - m * m;
+            if (var < 0.0) var = 0.0;
+            mean[k] = (float) m;
+            rstd[k] = 1.0f / sqrtf((float) var + 1e-5f);
+            gam[k]  = p.gb[(size_t) b * p.ldgb + p.goff + c];
+            bet[k]  = p.gb[(size_t) b * p.ldgb + p.boff + c];
+            if (p.act == NACT_SNAKE) { al[k] = p.alpha[c]; ial[k] = 1.0f / al[k]; }
+        }
+    }
+    const float * xb = p.x + (size_t) b * p.Lmax * p.ldx;
+    for (int t = t0 + ty; t < t1; t += ny) {
+        const float * row = xb + (size_t) t * p.ldx;
+        const size_t orow = (size_t) b * p.Lmax + t;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            const int c = tx + k * nx;
+            if (c < p.C) {
+                const float n = (row[c] - mean[k]) * rstd[k];
+                float v = (n + n * gam[k]) + bet[k];                       // model.cpp:99-100 / :148
+                if (p.act == NACT_LRELU02) v = lrelu(v, 0.2f);
+                else if (p.act == NACT_SNAKE) { const float sn = sinf(v * al[k]); v = v + (sn * sn) * ial[k]; }   // util.cpp:99-101
+                if (p.outH) p.outH[orow * p.ldoh + c] = __float2half_rn(v);
+                if (p.outF) p.outF[orow * p.ldof + c] = v;
+            } else if (c < p.Cpad && p.outH) {
+                p.outH[orow * p.ldoh + c] = __float2half_rn(0.f);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- depthwise ConvTranspose1d k3 s2 p1 op1 ("pool")
+__global__ void pool_convt_kernel(const float * __restrict__ x, int ldx, int C, int Lmax, const int * __restrict__ len,
+                                  const float * __restrict__ w3, const float * __restrict__ bias, __half * outH, int ldoh, int Cpad) {
+    const int b = blockIdx.y;
+    const int L = len[b];
+    const int o = blockIdx.x * blockDim.y + threadIdx.y;   // output position in [0, 2L)
+    if (o >= 2 * L) return;
+    const float * xb = x + (size_t) b * Lmax * ldx;
+    const size_t orow = (size_t) b * (2 * Lmax) + o;
+    const int q = o >> 1;
+    for (int c = threadIdx.x; c < Cpad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < C) {
+            // dst is zero-initialised and accumulated in (t, k) order (ggml-cpu.c:10180-10195); kernel layout w3[c*3 + k]
+            if ((o & 1) == 0) {
+                v = 0.f + xb[(size_t) q * ldx + c] * w3[c * 3 + 1];
+            } else {
+                v = 0.f + xb[(size_t) q * ldx + c] * w3[c * 3 + 2];
+                if (q + 1 < L) v = v + xb[(size_t) (q + 1) * ldx + c] * w3[c * 3 + 0];
+            }
+            v = v + bias[c];
+        }
+        outH[orow * ldoh + c] = __float2half_rn(v);
+    }
+}
+
+// ---------------------------------------------------------------- row LayerNorm (one warp per row)
+__global__ void row_norm_kernel(const RowNormParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int b = warp / p.Lmax, t = warp - b * p.Lmax;
+    if (b >= p.B || t >= p.len[b]) return;
+    const float * row = p.x + ((size_t) b * p.Lmax + t) * p.ldx;
+    double s = 0.0;
+    for (int c = lane; c < p.C; c += 32) s += (double) row[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = (float) (s / (double) p.C);
+    double q = 0.0;
+    for (int c = lane; c < p.C; c += 32) { const float v = row[c] - mean; q += (double) (v * v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float var = (float) (q / (double) p.C);
+    const float scale = 1.0f / sqrtf(var + p.eps);
+    const size_t orow = (size_t) b * p.Lmax + t;
+    for (int c = lane; c < p.C; c += 32) {
+        const float n = (row[c] - mean) * scale;
+        float v;
+        if (p.mode == LN_AFFINE) v = n * p.w[c] + p.bias[c];
+        else v = (n + n * p.gb[(size_t) b * p.ldgb + p.goff + c]) + p.gb[(size_t) b * p.ldgb + p.boff + c];
+        if (p.lrelu02) v = lrelu(v, 0.2f);
+        if (p.outF) p.outF[orow * p.ldof + p.coff + c] = v;
+        if (p.outH) p.outH[orow * p.ldoh + p.coffh + c] = __float2half_rn(v);
+    }
+}
+
+// ---------------------------------------------------------------- helpers
+__global__ void cast_rows_kernel(const float * __restrict__ x, int ldx, int C, int LmaxIn, const int * __restrict__ lenOut, int LmaxOut, int up2,
+                                 float ns, __half * outH, int ldoh, int Cpad) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= lenOut[b]) return;
+    const int ts = up2 ? (t >> 1) : t;
+    const float * row = x + ((size_t) b * LmaxIn + ts) * ldx;
+    __half * orow = outH + ((size_t) b * LmaxOut + t) * ldoh;
+    for (int c = threadIdx.x; c < Cpad; c += blockDim.x) orow[c] = __float2half_rn(c < C ? lrelu(row[c], ns) : 0.f);
+}
+
+__global__ void copy_cols_kernel(const float * __restrict__ src, int lds, int scoff, float * dst, int ldd, int dcoff, int C, int Lmax,
+                                 const int * __restrict__ len) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= len[b]) return;
+    const size_t r = (size_t) b * Lmax + t;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) dst[r * ldd + dcoff + c] = src[r * lds + scoff + c];
+}
+
+__global__ void bcast_cols_kernel(const float * __restrict__ v, int ldv, int C, int Lmax, const int * __restrict__ len, float * dstF, int ldf,
+                                  int cofff, __half * dstH, int ldh, int coffh) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= len[b]) return;
+    const size_t r = (size_t) b * Lmax + t;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float val = v[(size_t) b * ldv + c];
+        if (dstF) dstF[r * ldf + cofff + c] = val;
+        if (dstH) dstH[r * ldh + coffh + c] = __float2half_rn(val);
+    }
+}
+
+__global__ void gather_rows_kernel(const float * __restrict__ src, int lds, int LmaxSrc, const int * __restrict__ idx, int C, int Lmax,
+                                   const int * __restrict__ len, float * dstF, int ldf, __half * dstH, int ldh, int Cpad) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= len[b]) return;
+    const int j = idx[(size_t) b * Lmax + t];
+    const float * row = src + ((size_t) b * LmaxSrc + j) * lds;
+    const size_t r = (size_t) b * Lmax + t;
+    for (int c = threadIdx.x; c < Cpad; c += blockDim.x) {
+        const float val = c < C ? row[c] : 0.f;
+        if (dstF && c < C) dstF[r * ldf + c] = val;
+        if (dstH) dstH[r * ldh + c] = __float2half_rn(val);
+    }
+}
+
+__global__ void linear_f32_kernel(const float * __restrict__ x, int ldx, const float * __restrict__ W, const float * __restrict__ bias, int rows,
+                                  int K, int N, float * y, int ldy) {
+    // one warp per (row, 32 outputs): lanes stride over K for each output -> coalesced W reads, shuffle reduce
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (N + 31) / 32;
+    const int r = warp / ngroups, g = warp - r * ngroups;
+    if (r >= rows) return;
+    const float * xr = x + (size_t) r * ldx;
+    for (int j = 0; j < 32; j++) {
+        const int n = g * 32 + j;
+        if (n >= N) break;
+        const float * wr = W + (size_t) n * K;
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc = fmaf(xr[k], wr[k], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[(size_t) r * ldy + n] = acc + (bias ? bias[n] : 0.f);
+    }
+}
+
+__global__ void albert_embed_kernel(const int * __restrict__ tokens, const int * __restrict__ tok_off, const float * __restrict__ tok_embd,
+                                    const float * __restrict__ pos_embd, const float * __restrict__ type_embd, const float * __restrict__ nw,
+                                    const float * __restrict__ nb, int B, int Lmax, const int * __restrict__ len, float * out, int ldo) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int b = warp / Lmax, t = warp - b * Lmax;
+    if (b >= B || t >= len[b]) return;
+    const int tok = tokens[tok_off[b] + t];
+    float v[4];
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = lane + k * 32;
+        v[k] = (tok_embd[(size_t) tok * 128 + c] + pos_embd[(size_t) t * 128 + c]) + type_embd[c];
+        s += (double) v[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = (float) (s / 128.0);
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = v[k] - mean; q += (double) (v[k] * v[k]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float scale = 1.0f / sqrtf((float) (q / 128.0) + 1e-12f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = lane + k * 32;
+        out[((size_t) b * Lmax + t) * ldo + c] = (v[k] * scale) * nw[c] + nb[c];
+    }
+}
+
+__global__ void embed_rows_h_kernel(const int * __restrict__ tokens, const int * __restrict__ tok_off, const __half * __restrict__ table, int C,
+                                    int Lmax, const int * __restrict__ len, __half * outH, int ldoh) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= len[b]) return;
+    const int tok = tokens[tok_off[b] + t];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) outH[((size_t) b * Lmax + t) * ldoh + c] = table[(size_t) tok * C + c];
+}
+
+// ---------------------------------------------------------------- ALBERT attention (fp32)
+// one block per (query tile of 8, head, utterance); scores kept in shared memory
+__global__ void albert_attention_kernel(const float * __restrict__ qkv, int Lmax, const int * __restrict__ len, int heads, int hd, float scale,
+                                        __half * outH, int ldoh) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 8;
+    const int n = len[b];
+    if (q0 >= n) return;
+    const int D = heads * hd;
+    float * sq = sm;                 // [8][hd]
+    float * sc = sm + 8 * hd;        // [8][n]
+    const int nq = min(8, n - q0);
+    const float * base = qkv + (size_t) b * Lmax * 3 * D;
+    for (int i = threadIdx.x; i < nq * hd; i += blockDim.x) sq[i] = base[(size_t) (q0 + i / hd) * 3 * D + h * hd + (i % hd)];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    // scores: warp per key
+    for (int j = warp; j < n; j += nw) {
+        const float * kr = base + (size_t) j * 3 * D + D + h * hd;
+        float kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) kv[u] = (lane + u * 32 < hd) ? kr[lane + u * 32] : 0.f;
+        for (int qi = 0; qi < nq; qi++) {
+            float a = 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (lane + u * 32 < hd) a = fmaf(sq[qi * hd + lane + u * 32], kv[u], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) sc[qi * n + j] = a * scale;
+        }
+    }
+    __syncthreads();
+    // softmax: warp per query (ggml_compute_forward_soft_max_f32: max, exp, double sum, scale)
+    for (int qi = warp; qi < nq; qi += nw) {
+        float mx = -INFINITY;
+        for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sc[qi * n + j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double sum = 0.0;
+        for (int j = lane; j < n; j += 32) { const float e = expf(sc[qi * n + j] - mx); sc[qi * n + j] = e; sum += (double) e; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = (float) (1.0 / sum);
+        for (int j = lane; j < n; j += 32) sc[qi * n + j] *= inv;
+    }
+    __syncthreads();
+    // PV: thread per (query, dim)
+    for (int i = threadIdx.x; i < nq * hd; i += blockDim.x) {
+        const int qi = i / hd, d = i % hd;
+        const float * vr = base + 2 * D + h * hd + d;
+        float a = 0.f;
+        for (int j = 0; j < n; j++) a = fmaf(sc[qi * n + j], vr[(size_t) j * 3 * D], a);
+        outH[((size_t) b * Lmax + q0 + qi) * ldoh + h * hd + d] = __float2half_rn(a);
+    }
+}
+
+__global__ void duration_tail_kernel(const float * __restrict__ logits, int ldl, int n_bins, int B, int Lmax, const int * __restrict__ len,
+                                     float * lens_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = i / Lmax, t = i - b * Lmax;
+    if (b >= B || t >= len[b]) return;
+    const float * row = logits + ((size_t) b * Lmax + t) * ldl;
+    double s = 0.0;                                       // ggml_compute_forward_sum_rows -> ggml_vec_sum_f32 accumulates in ggml_float
+    for (int j = 0; j < n_bins; j++) s += (double) (1.0f / (1.0f + expf(-row[j])));
+    float v = (float) s;
+    v = (float) ((int) (v + 0.5f));                       // ggml_round (ggml-cpu.c:1797)
+    v = fminf(fmaxf(v, 1.0f), 50.0f);                     // ggml_clamp [1,50] (model.cpp:1040)
+    lens_out[(size_t) b * Lmax + t] = v;
+}
+
+__global__ void build_alignment_kernel(const float * __restrict__ lens, int B, int LmaxTok, const int * __restrict__ ntok, int LmaxFrames,
+                                       int * idx, int * T) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int pos = 0;
+    for (int i = 0; i < ntok[b]; i++) {
+        const int d = (int) (unsigned) lens[(size_t) b * LmaxTok + i];     // (uint32_t) cast, model.cpp:1286
+        if (idx) for (int k = 0; k < d && pos + k < LmaxFrames; k++) idx[(size_t) b * LmaxFrames + pos + k] = i;
+        pos += d;
+    }
+    T[b] = pos;
+}
+
+__global__ void curve_conv_s2_kernel(const float * __restrict__ x, int ldx, int B, const int * __restrict__ lenOut, int LmaxOut,
+                                     const int * __restrict__ lenIn, float w0, float w1, float w2, float bias, float * dst, int ldd, int coff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = i / LmaxOut, t = i - b * LmaxOut;
+    if (b >= B || t >= lenOut[b]) return;
+    const float * xb = x + (size_t) b * ldx;
+    const int Li = lenIn[b];
+    // F16 kernel -> im2col in fp16 (ggml.c:3878): activations re-rounded to fp16, fp32 accumulate over the 3 taps
+    float a = 0.f;
+    const int p0 = 2 * t - 1;
+    const float ws[3] = { w0, w1, w2 };
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int ps = p0 + k;
+        const float xv = (ps >= 0 && ps < Li) ? __half2float(__float2half_rn(xb[ps])) : 0.f;
+        a = fmaf(xv, ws[k], a);
+    }
+    dst[((size_t) b * LmaxOut + t) * ldd + coff] = a + bias;
+}
+
+static dim3 row_block(int Cpad, int & rows_per_blk) {
+    int nx = Cpad >= 256 ? 256 : (Cpad <= 32 ? 32 : round_up(Cpad, 32));
+    if (nx > 256) nx = 256;
+    int ny = 256 / nx;
+    if (ny < 1) ny = 1;
+    rows_per_blk = ny;
+    return dim3(nx, ny);
+}
+
+}  // namespace
+
+int inorm_stats(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, const int * len, double * sums) {
+    if (C > KMAX * 256) { set_error("inorm_stats: C=%d too large", C); return 1; }
+    B2_CUDA(cudaMemsetAsync(sums, 0, (size_t) B * C * 2 * sizeof(double), ctx->stream));
+    int rpb; dim3 blk = row_block(C, rpb);
+    const int rows_per_block = 128;
+    dim3 grid(cdiv(Lmax, rows_per_block), B);
+    ctx->prof_begin(PROF_NORM, 0.0, (double) B * Lmax * C * 4.0);
+    inorm_stats_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, Lmax, len, sums, rows_per_block);
+    ctx->prof_end();
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int adain_apply(Ctx * ctx, const AdainParams & p) {
+    if (p.C > KMAX * 256 || p.Cpad > KMAX * 256) { set_error("adain_apply: C=%d too large", p.C); return 1; }
+    int rpb; dim3 blk = row_block(p.outH ? p.Cpad : p.C, rpb);
+    const int rows_per_block = 32;
+    dim3 grid(cdiv(p.Lmax, rows_per_block), p.B);
+    ctx->prof_begin(PROF_NORM, 0.0, (double) p.B * p.Lmax * p.C * (4.0 + (p.outH ? 2.0 : 0.0) + (p.outF ? 4.0 : 0.0)));
+    adain_apply_kernel<<<grid, blk, 0, ctx->stream>>>(p, rows_per_block);
+    ctx->prof_end();
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int pool_convt(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, const int * len, const float * w3, const float * bias, __half * outH,
+               int ldoh, int Cpad) {
+    int rpb; dim3 blk = row_block(Cpad, rpb);
+    dim3 grid(cdiv(2 * Lmax, rpb), B);
+    pool_convt_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, Lmax, len, w3, bias, outH, ldoh, Cpad);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int row_norm(Ctx * ctx, const RowNormParams & p) {
+    const int64_t warps = (int64_t) p.B * p.Lmax;
+    row_norm_kernel<<<cdiv(warps * 32, 256), 256, 0, ctx->stream>>>(p);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int cast_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, const int * lenOut, int LmaxOut, int up2, float ns, __half * outH,
+              int ldoh, int Cpad) {
+    int rpb; dim3 blk = row_block(Cpad, rpb);
+    dim3 grid(cdiv(LmaxOut, rpb), B);
+    cast_rows_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, LmaxIn, lenOut, LmaxOut, up2, ns, outH, ldoh, Cpad);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int copy_cols(Ctx * ctx, const float * src, int lds, int scoff, float * dst, int ldd, int dcoff, int C, int B, int Lmax, const int * len) {
+    int rpb; dim3 blk = row_block(C, rpb);
+    dim3 grid(cdiv(Lmax, rpb), B);
+    copy_cols_kernel<<<grid, blk, 0, ctx->stream>>>(src, lds, scoff, dst, ldd, dcoff, C, Lmax, len);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int bcast_cols(Ctx * ctx, const float * v, int ldv, int C, int B, int Lmax, const int * len, float * dstF, int ldf, int cofff, __half * dstH,
+               int ldh, int coffh) {
+    int rpb; dim3 blk = row_block(C, rpb);
+    dim3 grid(cdiv(Lmax, rpb), B);
+    bcast_cols_kernel<<<grid, blk, 0, ctx->stream>>>(v, ldv, C, Lmax, len, dstF, ldf, cofff, dstH, ldh, coffh);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int gather_rows(Ctx * ctx, const float * src, int lds, int LmaxSrc, const int * idx, int C, int B, int Lmax, const int * len, float * dstF, int ldf,
+                __half * dstH, int ldh, int Cpad) {
+    int rpb; dim3 blk = row_block(Cpad, rpb);
+    dim3 grid(cdiv(Lmax, rpb), B);
+    gather_rows_kernel<<<grid, blk, 0, ctx->stream>>>(src, lds, LmaxSrc, idx, C, Lmax, len, dstF, ldf, dstH, ldh, Cpad);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int linear_f32(Ctx * ctx, const float * x, int ldx, const float * W, const float * bias, int rows, int K, int N, float * y, int ldy) {
+    const int64_t warps = (int64_t) rows * ((N + 31) / 32);
+    linear_f32_kernel<<<cdiv(warps * 32, 256), 256, 0, ctx->stream>>>(x, ldx, W, bias, rows, K, N, y, ldy);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int albert_embed(Ctx * ctx, const int * tokens, const int * tok_off, const float * tok_embd, const float * pos_embd, const float * type_embd,
+                 const float * nw, const float * nb, int B, int Lmax, const int * len, float * out, int ldo) {
+    const int64_t warps = (int64_t) B * Lmax;
+    albert_embed_kernel<<<cdiv(warps * 32, 256), 256, 0, ctx->stream>>>(tokens, tok_off, tok_embd, pos_embd, type_embd, nw, nb, B, Lmax, len, out, ldo);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int embed_rows_h(Ctx * ctx, const int * tokens, const int * tok_off, const __half * table, int C, int B, int Lmax, const int * len, __half * outH,
+                 int ldoh) {
+    int rpb; dim3 blk = row_block(C, rpb);
+    dim3 grid(cdiv(Lmax, rpb), B);
+    embed_rows_h_kernel<<<grid, blk, 0, ctx->stream>>>(tokens, tok_off, table, C, Lmax, len, outH, ldoh);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int albert_attention(Ctx * ctx, const float * qkv, int B, int Lmax, const int * len, int heads, int hd, float scale, __half * outH, int ldoh) {
+    if (hd > 128) { set_error("albert_attention: head dim %d > 128", hd); return 1; }
+    const size_t smem = (size_t) (8 * hd + 8 * Lmax) * sizeof(float);
+    dim3 grid(cdiv(Lmax, 8), heads, B);
+    albert_attention_kernel<<<grid, 256, smem, ctx->stream>>>(qkv, Lmax, len, heads, hd, scale, outH, ldoh);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int duration_tail(Ctx * ctx, const float * logits, int ldl, int n_bins, int B, int Lmax, const int * len, float * lens_out) {
+    duration_tail_kernel<<<cdiv((int64_t) B * Lmax, 128), 128, 0, ctx->stream>>>(logits, ldl, n_bins, B, Lmax, len, lens_out);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int build_alignment(Ctx * ctx, const float * lens, int B, int LmaxTok, const int * ntok, int LmaxFrames, int * idx, int * T) {
+    build_alignment_kernel<<<cdiv(B, 32), 32, 0, ctx->stream>>>(lens, B, LmaxTok, ntok, LmaxFrames, idx, T);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int curve_conv_s2(Ctx * ctx, const float * x, int ldx, int B, const int * lenOut, int LmaxOut, const int * lenIn, const float * w3,
+                  const float * bias, float * dst, int ldd, int coff) {
+    curve_conv_s2_kernel<<<cdiv((int64_t) B * LmaxOut, 128), 128, 0, ctx->stream>>>(x, ldx, B, lenOut, LmaxOut, lenIn, w3[0], w3[1], w3[2], bias[0],
+                                                                                    dst, ldd, coff);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,124 @@
+// gguf_reader.cpp -- minimal GGUF v2/v3 reader (host side of the drop-in boundary).
+//
+// Replaces, for the hot path, what runner_from_file does with llama_mmap + gguf_init_from_file + the tensor iterator
+// (reference src/models/loaders.cpp:34-95, ggml-patches/llama-mmap.cpp, ggml-patches/ggml-iterator.h): mmap the file, walk the
+// metadata and tensor directory, and stream every (name, type, ne, data) to Kokoro::assign -- the analogue of
+// tts_generation_runner::assign_weight -- followed by prepare() (prepare_post_load).  Written from the GGUF format
+// specification; no ggml code is linked.
+#include "kokoro.h"
+
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace b2 {
+namespace {
+
+struct Cursor {
+    const uint8_t * p; const uint8_t * end; bool ok = true;
+    template <class T> T rd() {
+        T v{};
+        if (p + sizeof(T) > end) { ok = false; return v; }
+        memcpy(&v, p, sizeof(T)); p += sizeof(T);
+        return v;
+    }
+    std::string str() {
+        uint64_t n = rd<uint64_t>();
+        if (!ok || p + n > end) { ok = false; return std::string(); }
+        std::string s((const char *) p, (size_t) n); p += n;
+        return s;
+    }
+};
+
+size_t scalar_size(uint32_t t) {
+    switch (t) {
+        case 0: case 1: case 7: return 1;
+        case 2: case 3: return 2;
+        case 4: case 5: case 6: return 4;
+        case 10: case 11: case 12: return 8;
+        default: return 0;
+    }
+}
+
+// skips (or captures) one metadata value of GGUF type `t`
+bool read_value(Cursor & c, uint32_t t, uint32_t * u32_out, std::string * str_out, std::vector<std::string> * arr_out) {
+    if (t == 8) { std::string s = c.str(); if (str_out) *str_out = s; return c.ok; }
+    if (t == 9) {
+        uint32_t et = c.rd<uint32_t>(); uint64_t n = c.rd<uint64_t>();
+        for (uint64_t i = 0; i < n && c.ok; i++) {
+            if (et == 8) { std::string s = c.str(); if (arr_out) arr_out->push_back(s); }
+            else { size_t sz = scalar_size(et); if (!sz) return false; c.p += sz; if (c.p > c.end) c.ok = false; }
+        }
+        return c.ok;
+    }
+    size_t sz = scalar_size(t);
+    if (!sz) return false;
+    if (t == 4 && u32_out) { *u32_out = c.rd<uint32_t>(); return c.ok; }
+    c.p += sz;
+    if (c.p > c.end) c.ok = false;
+    return c.ok;
+}
+
+}  // namespace
+
+int load_gguf_into(Kokoro * m, const char * path) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_error("cannot open '%s'", path); return 1; }
+    struct stat st;
+    fstat(fd, &st);
+    void * map = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) { set_error("mmap of '%s' failed", path); return 1; }
+    const uint8_t * base = (const uint8_t *) map;
+    Cursor c{base, base + st.st_size};
+    int rc = 1;
+    do {
+        if (c.rd<uint32_t>() != 0x46554747u) { set_error("%s: not a GGUF file", path); break; }
+        uint32_t ver = c.rd<uint32_t>();
+        if (ver < 2 || ver > 3) { set_error("%s: unsupported GGUF version %u", path, ver); break; }
+        uint64_t n_tensors = c.rd<uint64_t>(), n_kv = c.rd<uint64_t>();
+        uint32_t alignment = 32;
+        std::string arch;
+        bool bad = false;
+        for (uint64_t i = 0; i < n_kv && !bad; i++) {
+            std::string key = c.str();
+            uint32_t t = c.rd<uint32_t>();
+            uint32_t u = 0; bool is_u32 = (t == 4); std::string s;
+            if (!read_value(c, t, &u, &s, nullptr)) { bad = true; break; }
+            if (is_u32) { m->kv[key] = u; if (key == "general.alignment") alignment = u; }
+            if (key == "general.architecture") arch = s;
+        }
+        if (bad || !c.ok) { set_error("%s: corrupt GGUF metadata", path); break; }
+        if (arch != "kokoro") { set_error("%s: general.architecture is '%s', this loader handles 'kokoro'", path, arch.c_str()); break; }
+        struct TI { std::string name; int nd; int64_t ne[4]; uint32_t type; uint64_t off; };
+        std::vector<TI> tis((size_t) n_tensors);
+        for (auto & t : tis) {
+            t.name = c.str(); t.nd = (int) c.rd<uint32_t>();
+            if (t.nd > 4) { bad = true; break; }
+            for (int d = 0; d < 4; d++) t.ne[d] = 1;
+            for (int d = 0; d < t.nd; d++) t.ne[d] = (int64_t) c.rd<uint64_t>();
+            t.type = c.rd<uint32_t>(); t.off = c.rd<uint64_t>();
+        }
+        if (bad || !c.ok) { set_error("%s: corrupt GGUF tensor directory", path); break; }
+        size_t data0 = (size_t) (c.p - base);
+        data0 = (data0 + alignment - 1) / alignment * alignment;
+        for (auto & t : tis) {
+            if (t.name.rfind("kokoro.", 0) != 0) continue;
+            int64_t n = 1; for (int d = 0; d < t.nd; d++) n *= t.ne[d];
+            size_t esz = t.type == 0 ? 4 : t.type == 1 ? 2 : 0;
+            if (!esz) { set_error("%s: tensor '%s' has ggml type %u; only F32/F16 Kokoro files are supported", path, t.name.c_str(), t.type); bad = true; break; }
+            if (data0 + t.off + (size_t) n * esz > (size_t) st.st_size) { set_error("%s: tensor '%s' runs past the end of the file", path, t.name.c_str()); bad = true; break; }
+            if (m->assign(t.name.c_str(), (int) t.type, t.nd, t.ne, base + data0 + t.off, (size_t) n * esz)) { bad = true; break; }
+        }
+        if (bad) break;
+        rc = m->prepare();
+    } while (false);
+    munmap(map, (size_t) st.st_size);
+    return rc;
+}
+
+}  // namespace b2

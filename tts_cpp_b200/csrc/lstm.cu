@@ -1,0 +1,195 @@
+// lstm.cu -- persistent thread-block-cluster bi-LSTM for sm_100a (hidden size 256).
+//
+// Replaces build_lstm / build_lstm_run (reference src/models/kokoro/model.cpp:35-86), which unrolls every
+// time step into 26 GGML nodes per direction (each followed by a thread-pool barrier).  Here one cluster of
+// 8 CTAs per (direction, batch tile of 32 utterances) runs the whole sequence:
+//   * the hidden-side weights W_hh (fp16, 1024x256) stay resident in shared memory, 128 gate rows per CTA
+//     (4 gates x 32 hidden units);
+//   * every step is one tensor-core contraction  G[128 x 32] = W_hh_slice[128 x 256] . h^T[256 x 32]
+//     (h re-rounded to fp16 exactly like ggml does for an F16 weight, ggml-cpu.c:262-267);
+//   * gate math (sigmoid/tanh, c = f*c + i*g, h = o*tanh(c), model.cpp:63-76) happens in registers, the cell
+//     state never leaves them;
+//   * the new h slice is broadcast to the 8 CTAs' shared memory through DSMEM and one cluster barrier ends the step.
+// The input-side projections W_ih x + b_ih for all steps come from conv_gemm (they are one big GEMM), laid out
+// [b][t][dir][unit][gate] so a thread fetches its 4 gate pre-activations with one 16-byte load.
+// Ragged batches: utterance b is active for len[b] steps; the reverse direction walks t = len[b]-1-s.
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace b2 {
+namespace {
+
+constexpr int H = 256, CL = 8, UNITS = 32, NBT = 32;  // hidden, cluster size, units per CTA, utterances per cluster
+constexpr int LDW = 264;                              // smem row stride (halves): 528 B -> conflict-free ldmatrix
+constexpr int SW_BYTES = 128 * LDW * 2;
+constexpr int SH_BYTES = 2 * NBT * LDW * 2;
+constexpr int ST_BYTES = NBT * UNITS * 2;
+constexpr int LSTM_SMEM = SW_BYTES + SH_BYTES + ST_BYTES;
+
+__device__ __forceinline__ void ldsm_x4(unsigned & r0, unsigned & r1, unsigned & r2, unsigned & r3, const void * p) {
+    unsigned s = (unsigned) __cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(s));
+}
+__device__ __forceinline__ void mma16816(float * c, const unsigned * a, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }  // ggml_vec_sigmoid_f32
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(const LstmParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half * sW  = reinterpret_cast<__half *>(smem_raw);                       // [128][LDW]
+    __half * sH  = reinterpret_cast<__half *>(smem_raw + SW_BYTES);            // [2][NBT][LDW]
+    __half * sSt = reinterpret_cast<__half *>(smem_raw + SW_BYTES + SH_BYTES); // [NBT][UNITS]
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int) cluster.block_rank();
+    const int dir  = blockIdx.y;
+    const int b0   = blockIdx.z * NBT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ug = warp & 3, nh = warp >> 2;
+
+    // ---- resident weights: local row lr = ug*32 + tile*16 + r ; gate = tile*2 + (r>=8) ; unit = ug*8 + (r&7)
+    const __half * Wd = p.whh + (size_t) dir * 4 * H * H;
+    for (int idx = tid; idx < 128 * (H / 8); idx += 256) {
+        const int lr = idx / (H / 8), ch = idx % (H / 8);
+        const int g4 = lr >> 5, tile = (lr >> 4) & 1, r = lr & 15;
+        const int gate = tile * 2 + (r >> 3);
+        const int unit = rank * UNITS + g4 * 8 + (r & 7);
+        const int4 v = *reinterpret_cast<const int4 *>(Wd + (size_t) (gate * H + unit) * H + ch * 8);
+        *reinterpret_cast<int4 *>(sW + lr * LDW + ch * 8) = v;
+    }
+    for (int idx = tid; idx < 2 * NBT * LDW / 2; idx += 256) reinterpret_cast<unsigned *>(sH)[idx] = 0u;
+
+    // ---- per-thread ownership: unit ul (local), utterances u[ni][e]
+    const int ul = ug * 8 + (lane >> 2);
+    const int unit_g = rank * UNITS + ul;
+    int   ub[2][2], ulen[2][2];
+    float cst[2][2];
+    int nsteps = 0;
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int u = nh * 16 + ni * 8 + (lane & 3) * 2 + e;
+            ub[ni][e]   = b0 + u;
+            ulen[ni][e] = (ub[ni][e] < p.B) ? p.len[ub[ni][e]] : 0;
+            cst[ni][e]  = 0.f;
+        }
+    for (int u = 0; u < NBT; u++)
+        if (b0 + u < p.B) nsteps = max(nsteps, p.len[b0 + u]);
+    float bh[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) bh[g] = p.bhh[dir * 4 * H + g * H + unit_g];
+
+    __syncthreads();
+    cluster.sync();
+
+    for (int s = 0; s < nsteps; s++) {
+        const __half * hcur = sH + (size_t) (s & 1) * NBT * LDW;
+        __half *       hnxt = sH + (size_t) ((s + 1) & 1) * NBT * LDW;
+
+        // 1. input-side pre-activations for this step (one float4 = gates i,f,g,o of (b, t, dir, unit))
+        float4 xp[2][2];
+        int    tt[2][2];
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const bool act = s < ulen[ni][e];
+                tt[ni][e]      = dir == 0 ? s : ulen[ni][e] - 1 - s;
+                if (act) {
+                    const size_t row = (size_t) ub[ni][e] * p.Lmax + tt[ni][e];
+                    xp[ni][e] = *reinterpret_cast<const float4 *>(p.xp + ((row * 2 + dir) * H + unit_g) * 4);
+                } else {
+                    xp[ni][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+
+        // 2. G = W_hh_slice . h^T on tensor cores: 2 m16 tiles (i|f , g|o) x 2 n8 tiles per warp
+        float acc[2][2][4];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[a][b][e] = 0.f;
+#pragma unroll 4
+        for (int ks = 0; ks < H / 16; ks++) {
+            unsigned af[2][4], bf[4];
+#pragma unroll
+            for (int tl = 0; tl < 2; tl++) {
+                const int r = ug * 32 + tl * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                ldsm_x4(af[tl][0], af[tl][1], af[tl][2], af[tl][3], sW + r * LDW + ks * 16 + (lane >> 4) * 8);
+            }
+            {
+                const int r = nh * 16 + (lane & 7) + (lane >> 4) * 8;
+                ldsm_x4(bf[0], bf[1], bf[2], bf[3], hcur + r * LDW + ks * 16 + ((lane >> 3) & 1) * 8);
+            }
+#pragma unroll
+            for (int tl = 0; tl < 2; tl++) {
+                mma16816(acc[tl][0], af[tl], bf[0], bf[1]);
+                mma16816(acc[tl][1], af[tl], bf[2], bf[3]);
+            }
+        }
+
+        // 3. gates in registers.  acc[0][ni][e] = i, acc[0][ni][2+e] = f, acc[1][ni][e] = g, acc[1][ni][2+e] = o
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int  u   = nh * 16 + ni * 8 + (lane & 3) * 2 + e;
+                const bool act = s < ulen[ni][e];
+                float hval = 0.f;
+                if (act) {
+                    const float4 x = xp[ni][e];
+                    const float gi = sigmoidf_ref(x.x + (acc[0][ni][e] + bh[0]));       // model.cpp:64 association
+                    const float gf = sigmoidf_ref(x.y + (acc[0][ni][2 + e] + bh[1]));
+                    const float gg = tanhf(x.z + (acc[1][ni][e] + bh[2]));
+                    const float go = sigmoidf_ref(x.w + (acc[1][ni][2 + e] + bh[3]));
+                    const float c  = gf * cst[ni][e] + gi * gg;
+                    cst[ni][e]     = c;
+                    hval           = tanhf(c) * go;
+                    const size_t row = (size_t) ub[ni][e] * p.Lmax + tt[ni][e];
+                    p.out[row * p.ldo + p.coff + dir * H + unit_g] = hval;
+                    if (p.outH) p.outH[row * p.ldoh + p.coffh + dir * H + unit_g] = __float2half_rn(hval);
+                }
+                sSt[u * UNITS + ul] = __float2half_rn(hval);
+            }
+        __syncthreads();
+
+        // 4. broadcast the 32x32 fp16 slice into every CTA's next-step h buffer (DSMEM, 16 B stores)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = tid + j * 256;
+            const int dest = q >> 7, rem = q & 127, u = rem >> 2, part = rem & 3;
+            const int4 v = *reinterpret_cast<const int4 *>(sSt + u * UNITS + part * 8);
+            __half * dst_local = hnxt + u * LDW + rank * UNITS + part * 8;
+            int4 * dst = reinterpret_cast<int4 *>(cluster.map_shared_rank(dst_local, dest));
+            *dst = v;
+        }
+        cluster.sync();
+    }
+}
+
+}  // namespace
+
+int bilstm(Ctx * ctx, const LstmParams & p) {
+    if (p.B <= 0 || p.maxLen <= 0) return 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+        B2_CUDA(cudaFuncSetAttribute(bilstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
+        attr_done = true;
+    }
+    dim3 grid(CL, 2, cdiv(p.B, NBT));
+    ctx->prof_begin(PROF_LSTM, 2.0 * p.B * p.maxLen * 2.0 * 1024.0 * 256.0, 0.0);
+    bilstm_kernel<<<grid, 256, LSTM_SMEM, ctx->stream>>>(p);
+    ctx->prof_end();
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // namespace b2

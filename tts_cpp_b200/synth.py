@@ -223,6 +223,19 @@ def write_kokoro_gguf(path: str, seed: int = 0, dtype: str = "f16", ctx_len: int
     return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
 
 
+def cached_gguf(dtype: str = "f16", ctx_len: int = 128, seed: int = 0, cache_dir: str | None = None, **kw) -> str:
+    """Synthetic Kokoro GGUF cached on disk (deterministic in its arguments); safe under concurrent callers."""
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    tag = "_".join(f"{k}{v}" for k, v in sorted(kw.items()))
+    path = os.path.join(cache_dir, f"kokoro_{dtype}_c{ctx_len}_s{seed}_{tag}.gguf")
+    if not os.path.exists(path):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_kokoro_gguf(tmp, seed=seed, dtype=dtype, ctx_len=ctx_len, **kw)
+        os.replace(tmp, path)
+    return path
+
+
 def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
     """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
     out = []
