@@ -91,13 +91,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, threads: int = 8):
-    """Run the reference CPU path: `workers` processes x `threads` ggml threads, one prompt each, (n_warm + n_timed) repetitions."""
+def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, threads: int = 4):
+    """Run the reference CPU path: `workers` processes x `threads` ggml threads, one prompt each, (n_warm + n_timed) repetitions.
+    Default split = the best of the (workers, threads) grid measured on the GPU box (2 x Xeon 8562Y+, 128 logical CPUs):
+    1x8 2.1 | 1x32 1.5 | 4x8 3.5 | 8x8 3.1 | 16x8 1.8 | 16x4 4.0 | 32x4 2.6 | 8x16 0.9 audio-s/s -> ncpu/8 workers x 4 threads
+    (one ggml thread per physical core; its spin-wait barriers and memory traffic make wider splits slower)."""
     if not os.path.exists(REF_BIN):
         return None, "oracle/_ref/kokoro_ref missing (run `make -C oracle ref` where /root/reference exists)"
     ncpu = os.cpu_count() or 8
     threads = max(1, min(threads, ncpu))
-    workers = workers or max(1, ncpu // threads)
+    workers = workers or max(1, ncpu // (2 * threads))
     gguf = _gguf()
     prompts = _prompts(0)
     tmp = tempfile.mkdtemp(prefix="b2ref_")

@@ -1,0 +1,116 @@
+"""Generate tests/golden/*.npz from the compiled UNMODIFIED reference (oracle/_ref, built by oracle/Makefile).
+
+Run in the build container (where /root/reference exists):   python tests/golden/make_golden.py
+The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, through it, the CUDA path.
+
+  kokoro_stage_vectors.npz : one 8-token utterance on the deterministic synthetic GGUF (seed 0, f16 policy, ctx 128):
+      tokens, lens, hidden (duration_hidden_states), f0, n, dec (generator input), har_spec (STFT of the harmonic source),
+      pcm -- all dumped from the reference's own GGML graph nodes by oracle/ref_kokoro_driver.cpp
+  op_vectors.npz           : known-answer vectors of the patched ggml ops from oracle/ref_ops_driver.cpp
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = os.path.join(ROOT, "oracle", "_ref")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return r.stdout
+
+
+def kokoro_vectors():
+    from tts_cpp_b200.synth import cached_gguf, synthetic_prompts
+    gguf = cached_gguf("f16", 128, 0)
+    toks = synthetic_prompts(1, n_phonemes=6, seed0=4242)[0]
+    tmp = tempfile.mkdtemp()
+    tokf = os.path.join(tmp, "tok.txt")
+    open(tokf, "w").write(" ".join(map(str, toks)) + "\n")
+    pre = os.path.join(tmp, "g")
+    listing = run([os.path.join(REF, "kokoro_ref"), gguf, tokf, pre, "--threads", "4", "--list-nodes"])
+    lens = np.fromfile(pre + ".u0.lens.f32", np.float32)
+    T = int(lens.sum())
+    nodes = [(int(m.group(1)), int(m.group(2)), [int(v) for v in m.group(3).split(",")])
+             for m in re.finditer(r"NODE gen (\d+) op=(\d+) name=\S* ne=\[([\d,]+)\]", listing)]
+    OP_DIV, OP_CONCAT, OP_LRELU = 7, 20, 60
+    first_lrelu = min(i for i, op, ne in nodes if op == OP_LRELU and ne[:2] == [512, 2 * T])
+    dec_idx = max(i for i, op, ne in nodes if op == OP_DIV and ne[:2] == [2 * T, 512] and i < first_lrelu)
+    har_idx = min(i for i, op, ne in nodes if op == OP_CONCAT and ne[:2] == [22, 120 * T + 1])
+    run([os.path.join(REF, "kokoro_ref"), gguf, tokf, pre, "--threads", "4", "--dump-gen", f"#{dec_idx},#{har_idx},f0_out,n_out"])
+    rd = lambda n: np.fromfile(f"{pre}.u0.{n}.f32", np.float32)
+    np.savez_compressed(os.path.join(OUT, "kokoro_stage_vectors.npz"),
+                        tokens=np.array(toks, np.int32), lens=lens, hidden=rd("hidden").reshape(len(toks), 640),
+                        f0=rd("gen.f0_out"), n=rd("gen.n_out"), dec=rd(f"gen.n{dec_idx}").reshape(512, 2 * T),
+                        har_spec=rd(f"gen.n{har_idx}").reshape(120 * T + 1, 22), pcm=rd("pcm"),
+                        meta=np.array([dec_idx, har_idx, T], np.int64))
+    print("kokoro vectors: T =", T, "dec node", dec_idx, "har node", har_idx)
+
+
+def op_vectors():
+    tmp = tempfile.mkdtemp()
+    ops = os.path.join(REF, "ops_ref")
+    rng = np.random.default_rng(2024)
+    out = {}
+
+    def call(op, name, *args):
+        o = os.path.join(tmp, name + ".f32")
+        run([ops, op, o] + [str(a) for a in args])
+        return np.fromfile(o, np.float32)
+
+    def put(name, arr):
+        p = os.path.join(tmp, name + ".in.f32")
+        np.asarray(arr, np.float32).tofile(p)
+        return p
+
+    out["uniform_first_4096"] = call("uniform", "uni", 4096)
+    out["wss_20_5_37"] = call("wss", "wss", 20, 5, 37)
+    x = np.tanh(0.3 * np.sin(np.arange(615) * 0.031) + 0.01 * rng.standard_normal(615)).astype(np.float32)
+    out["stft_in"] = x
+    out["stft_out"] = call("stft", "stft", put("stft", x), 615, 20, 5, 1, 1).reshape(2, 124, 11)      # [mag|phase][frames][bins]
+    mp = np.stack([np.exp(0.5 * rng.standard_normal((124, 11))), np.sin(rng.standard_normal((124, 11)))]).astype(np.float32)
+    out["istft_in"] = mp
+    out["istft_out"] = call("istft", "istft", put("istft", mp), 11, 124, 20, 5)
+    cs = (rng.standard_normal((9, 40)) * 3).astype(np.float32)
+    out["cumsum_in"] = cs
+    out["cumsum_out"] = call("cumsum", "cumsum", put("cumsum", cs), 40, 9).reshape(9, 40)
+    out["mod_out"] = call("mod", "mod", put("mod", cs), cs.size, 1.0).reshape(9, 40)
+    out["round_out"] = call("round", "round", put("round", cs), cs.size).reshape(9, 40)
+    out["upscale_linear_out"] = call("upscale_linear", "ul", put("ul", np.cumsum(np.abs(cs), axis=1) * 100), 40, 9, 300).reshape(9, 12000)
+    out["upscale_linear_in"] = (np.cumsum(np.abs(cs), axis=1) * 100).astype(np.float32)
+    al = rng.uniform(0.3, 2.0, 12).astype(np.float32)
+    sx = (rng.standard_normal((12, 50)) * 2).astype(np.float32)
+    out["snake_alpha"], out["snake_in"] = al, sx
+    out["snake_out"] = call("snake", "snake", put("sa", al), 12, put("sx", sx), 50).reshape(12, 50)
+    g = (rng.standard_normal(512) * 3).astype(np.float32)
+    out["gelu_in"] = g
+    out["gelu_out"] = call("gelu", "gelu", put("gelu", g), 512)
+    # ConvTranspose1d: the generator's two shapes (scaled down) and the depthwise "pool"
+    for tag, (K, cout, cin, L, s, p, op_, grp) in {"ct_up0": (20, 8, 16, 9, 10, 5, 0, 1), "ct_up1": (12, 4, 8, 7, 6, 3, 0, 1), "ct_pool": (3, 6, 6, 5, 2, 1, 1, 6)}.items():
+        W = rng.standard_normal((cin, cout // grp, K)).astype(np.float32)
+        xx = rng.standard_normal((cin, L)).astype(np.float32)
+        lout = (L - 1) * s - 2 * p + (K - 1) + op_ + 1
+        out[tag + "_w"], out[tag + "_x"] = W, xx
+        out[tag + "_cfg"] = np.array([K, cout, cin, L, s, p, op_, grp], np.int32)
+        out[tag + "_y"] = call("convt1d", tag, put(tag + "w", W), K, cout // grp, cin, put(tag + "x", xx), L, s, p, op_, grp, 0).reshape(cout, lout)
+    # F16 conv1d (im2col in fp16): dilated k7
+    W = (rng.standard_normal((16, 32, 7)) / 15).astype(np.float16).astype(np.float32)
+    xx = rng.standard_normal((32, 60)).astype(np.float32)
+    out["conv_w"], out["conv_x"] = W, xx
+    out["conv_y"] = call("conv1d", "conv", put("cw", W), 7, 32, 16, put("cx", xx), 60, 1, 9, 3, 1).reshape(16, 60)
+    np.savez_compressed(os.path.join(OUT, "op_vectors.npz"), **out)
+    print("op vectors:", sorted(out))
+
+
+if __name__ == "__main__":
+    kokoro_vectors()
+    op_vectors()

@@ -203,7 +203,7 @@ __global__ void istft_ola_kernel(const float * __restrict__ reim, int ld, const 
     for (int g = g_lo; g < n_frames + 2; g++) {
         const int ii = n + 10 - 5 * g;
         if (ii < 0) break;
-        if (ii < 20) wss = wss + c_hann20sq[ii];
+        if (ii < 20) wss = fmaf(c_hann20[ii], c_hann20[ii], wss);   // `tgt += powf(w, 2)` is one FMA in the reference build
     }
     pcm[(size_t) b * Smax + n] = acc / wss;
 }
