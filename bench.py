@@ -248,7 +248,7 @@ def main():
                    "value_timing": "CUDA events on the library stream around duration+generation passes (incl. the mid-forward host sync for durations)"},
         "e2e": {"value": audio_total * args.steps / wall, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
                 "note": "host token ids in, PCM in pinned host memory out, through b2tts_kokoro_run_batch" + ("; plus NCCL gather of PCM to rank 0" if world > 1 else "")},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "gemm_dispatch": dict(zip(("tcgen05_tma", "mma_sync_fallback"), ctx.gemm_launches())),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM Conv1d/Linear, fp16 mma.sync, fp32 accumulate)", "achieved": ach, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "launches_per_step": g["launches"] / args.steps,

@@ -39,6 +39,8 @@ void *       b2tts_stream(const b2tts_ctx * ctx);
 /* per-kernel-class timing with CUDA events on the launching stream (bench.py's live roofline accounting; off by default).
  * kinds: 0 = conv_gemm (tensor-core contractions), 1 = cluster bi-LSTM, 2 = InstanceNorm/AdaIN passes, 3 = ConvTranspose1d.
  * b2tts_prof_enable(ctx, on) clears the records; b2tts_prof_read sums device ms / algorithmic flops / bytes / launches of a kind. */
+/* conv/linear dispatch counters: which = 0 -> launches of the tcgen05 + TMA kernel, 1 -> launches of the mma.sync fallback */
+uint64_t     b2tts_gemm_launches(const b2tts_ctx * ctx, int which);
 int          b2tts_prof_enable(b2tts_ctx * ctx, int on);
 int          b2tts_prof_read(b2tts_ctx * ctx, int kind, double * total_ms, double * flops, double * bytes, uint64_t * launches);
 

@@ -50,6 +50,12 @@ class Context:
     def launches(self) -> int:
         return int(lib().b2tts_launch_count(self.h))
 
+    def gemm_launches(self) -> tuple[int, int]:
+        """(tcgen05+TMA kernel launches, mma.sync fallback launches) since the context was created."""
+        f = lib().b2tts_gemm_launches
+        f.restype = C.c_uint64
+        return int(f(self.h, 0)), int(f(self.h, 1))
+
     def stream(self) -> int:
         return int(lib().b2tts_stream(self.h) or 0)
 

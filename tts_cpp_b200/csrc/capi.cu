@@ -62,6 +62,7 @@ void b2tts_ctx_destroy(b2tts_ctx * ctx) {
 const char * b2tts_last_error(void) { return g_err; }
 uint64_t b2tts_launch_count(const b2tts_ctx * ctx) { return ctx ? ctx->c.launches : 0; }
 void * b2tts_stream(const b2tts_ctx * ctx) { return ctx ? (void *) ctx->c.stream : nullptr; }
+uint64_t b2tts_gemm_launches(const b2tts_ctx * ctx, int which) { return which == 0 ? ctx->c.umma_launches : ctx->c.mma_sync_launches; }
 int b2tts_prof_enable(b2tts_ctx * ctx, int on) {
     Ctx & c = ctx->c;
     for (auto & r : c.recs) { c.pool.push_back(r.a); c.pool.push_back(r.b); }
@@ -154,7 +155,7 @@ int b2tts_op_conv_1d(b2tts_ctx * ctx, const float * kernel, int K, int cin, int 
     if (!f16_kernel) { set_error("b2tts_op_conv_1d: only the F16-kernel path (fp16 operands, fp32 accumulate) is implemented"); return 1; }
     Ctx * c = &ctx->c; Dev d;
     const int Lout = (L + 2 * pad - dil * (K - 1) - 1) / stride + 1;
-    const int cp = round_up(cin, 32), np = round_up(cout, 64);
+    const int cp = round_up(cin, 64), np = cout > 64 ? round_up(cout, 128) : 64;
     std::vector<__half> w((size_t) np * K * cp, __float2half(0.f)), a((size_t) L * cp, __float2half(0.f));
     for (int co = 0; co < cout; co++) for (int ci = 0; ci < cin; ci++) for (int k = 0; k < K; k++) w[((size_t) co * K + k) * cp + ci] = __float2half(kernel[((size_t) co * cin + ci) * K + k]);
     for (int ci = 0; ci < cin; ci++) for (int t = 0; t < L; t++) a[(size_t) t * cp + ci] = __float2half(x[(size_t) ci * L + t]);
@@ -224,7 +225,7 @@ int b2tts_op_bilstm(b2tts_ctx * ctx, const float * w_ih, const float * w_hh, con
                     int Lmax, const int32_t * len, float * y) {
     if (H != 256) { set_error("b2tts_op_bilstm: hidden size must be 256"); return 1; }
     Ctx * c = &ctx->c; Dev d;
-    const int ip = round_up(In, 32);
+    const int ip = round_up(In, 64);
     std::vector<__half> wih((size_t) 2048 * ip, __float2half(0.f)), whh((size_t) 2 * 1024 * 256), xa((size_t) B * Lmax * ip, __float2half(0.f));
     std::vector<float> bih(2048), bhh(2048);
     for (int dd = 0; dd < 2; dd++) for (int g = 0; g < 4; g++) for (int u = 0; u < H; u++) {

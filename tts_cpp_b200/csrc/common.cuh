@@ -18,6 +18,7 @@ struct Ctx {
     int          device   = 0;
     cudaStream_t stream   = nullptr;
     uint64_t     launches = 0;   // kernels launched by this library on this context
+    uint64_t     umma_launches = 0, mma_sync_launches = 0;   // conv_gemm dispatch: tcgen05 kernel vs mma.sync fallback
     bool                     prof = false;
     std::vector<ProfRec>     recs;
     std::vector<cudaEvent_t> pool;
@@ -85,6 +86,7 @@ struct ConvGemmParams {
     int64_t        validRows = 0;       // sum of lenOut (roofline accounting only; 0 -> B*LmaxOut)
 };
 int conv_gemm(Ctx * ctx, const ConvGemmParams & p);
+int conv_umma(Ctx * ctx, const ConvGemmParams & p);   // gemm_umma.cu: 0 launched, 1 error, 2 shape unsupported (fallback)
 
 // ---------------------------------------------------------------------------------------------
 // Persistent cluster bi-LSTM (lstm.cu).  Hidden size 256.

@@ -81,7 +81,7 @@ struct Prep {
     float * f32v(const std::vector<float> & v) { return (float *) dev(v.data(), v.size() * 4); }
     // [N][Cin][K] (numpy order) -> fp16 [Npad][K][CinPad]
     W16 w16_from(const std::vector<float> & src, int N, int Cin, int K) {
-        W16 w; w.N = N; w.Cin = Cin; w.KW = K; w.CinPad = round_up(Cin, 32); w.Npad = round_up(N, 64);
+        W16 w; w.N = N; w.Cin = Cin; w.KW = K; w.CinPad = round_up(Cin, 64); w.Npad = N > 64 ? round_up(N, 128) : 64;
         std::vector<__half> h((size_t) w.Npad * K * w.CinPad, __float2half(0.f));
         for (int n = 0; n < N; n++)
             for (int ci = 0; ci < Cin; ci++)
@@ -617,7 +617,8 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
 
     // B5: harmonic source + STFT (model.cpp:173-206)
     const int Fmax = L4;
-    float * har = Gf.al<float>((size_t) B * S); __half * hs16 = Gf.al<__half>((size_t) B * Fmax * 32);
+    const int hsp = nconv[0].w.CinPad;   // 22 channels padded for the GEMM operand
+    float * har = Gf.al<float>((size_t) B * S); __half * hs16 = Gf.al<__half>((size_t) B * Fmax * hsp);
     float * phase = Gf.al<float>((size_t) B * 9 * L2);
     float * hsF = taps_on || overrides.count("har_spec") ? Gf.al<float>((size_t) B * Fmax * 22) : nullptr;
     if (Gf.fail) return 1;
@@ -627,10 +628,10 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         sp.phase = phase; sp.har = har; sp.Smax = S;
         if (source_har(ctx, sp)) return 1;
         if (Gf.tap("har", har, B, S, S, S)) return 1;
-        if (stft20(ctx, har, S, B, lS, Fmax, hs16, 32, 32, hsF, 22)) return 1;
+        if (stft20(ctx, har, S, B, lS, Fmax, hs16, hsp, hsp, hsF, 22)) return 1;
         if (hsF) {
             if (Gf.tap("har_spec", hsF, (int64_t) B * Fmax, 22, 22, Fmax)) return 1;
-            if (overrides.count("har_spec")) { if (cast_rows(ctx, hsF, 22, 22, B, Fmax, l120, Fmax, 0, 1.0f, hs16, 32, 32)) return 1; }
+            if (overrides.count("har_spec")) { if (cast_rows(ctx, hsF, 22, 22, B, Fmax, l120, Fmax, 0, 1.0f, hs16, hsp, hsp)) return 1; }
         }
     }
 
@@ -646,7 +647,7 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         __half * a16 = Gf.al<__half>((size_t) B * Lo * Cp); double * sums = Gf.al<double>((size_t) B * C * 2);
         if (Gf.fail) return 1;
         if (convt_cl(ctx, gin, ups[i].Cin, ups[i].Cin, B, gin_L, gin_len, ups[i].w, ups[i].b, ups[i].K, C, ups[i].stride, ups[i].pad, 0.1f, i == 1 ? 1 : 0, u, C, Lo, lo_len)) return 1;
-        if (Gf.gemm(hs16, 32, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
+        if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
         if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums)) return 1;       // cur = up + x_source
         if (Gf.tap(i == 0 ? "gen_in0" : "gen_in1", curg, (int64_t) B * Lo, C, C, Lo)) return 1;
         for (int j = 0; j < 3; j++) {
