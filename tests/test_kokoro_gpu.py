@@ -66,7 +66,8 @@ def test_stagewise_teacher_forced(runner, port):
         "t_en": pad([r[2]["t_en"].numpy() for r in ref], nmax, 512),
         "dec": pad([_cl(r[2]["dec"]) for r in ref], 2 * tmax, 512),
         "har_spec": pad([np.concatenate([r[2]["mag"].numpy(), r[2]["ph"].numpy()], axis=1) for r in ref], 120 * tmax + 1, 22),
-        "gen_out0": pad([_cl(r[2]["gen_out0"]) for r in ref], 20 * tmax, 256),
+        # generator stage buffers use the polyphase ConvTranspose pitch: (2*Tmax + 1) * 10 rows per utterance
+        "gen_out0": pad([_cl(r[2]["gen_out0"]) for r in ref], (2 * tmax + 1) * 10, 256),
     }
     har = np.zeros((B, 600 * tmax), np.float32)
     for b, r in enumerate(ref):

@@ -156,6 +156,21 @@ __global__ void cast_rows_kernel(const float * __restrict__ x, int ldx, int C, i
     for (int c = threadIdx.x; c < Cpad; c += blockDim.x) orow[c] = __float2half_rn(c < C ? lrelu(row[c], ns) : 0.f);
 }
 
+__global__ void split3_rows_kernel(const float * __restrict__ x, int ldx, int C, int LmaxIn, const int * __restrict__ len, float ns, __half * outH, int Lq) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.y + threadIdx.y;
+    if (q >= Lq) return;
+    __half * orow = outH + ((size_t) b * Lq + q) * (3 * C);
+    const bool live = q < len[b];
+    const float * row = x + ((size_t) b * LmaxIn + (live ? q : 0)) * ldx;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = live ? lrelu(row[c], ns) : 0.f;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        orow[c] = hi; orow[C + c] = lo; orow[2 * C + c] = hi;
+    }
+}
+
 __global__ void copy_cols_kernel(const float * __restrict__ src, int lds, int scoff, float * dst, int ldd, int dcoff, int C, int Lmax,
                                  const int * __restrict__ len) {
     const int b = blockIdx.y;
@@ -413,6 +428,14 @@ int cast_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, con
     int rpb; dim3 blk = row_block(Cpad, rpb);
     dim3 grid(cdiv(LmaxOut, rpb), B);
     cast_rows_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, LmaxIn, lenOut, LmaxOut, up2, ns, outH, ldoh, Cpad);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int split3_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, const int * len, float ns, __half * outH, int Lq) {
+    int rpb; dim3 blk = row_block(C, rpb);
+    dim3 grid(cdiv(Lq, rpb), B);
+    split3_rows_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, LmaxIn, len, ns, outH, Lq);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -47,6 +47,9 @@ int row_norm(Ctx * ctx, const RowNormParams & p);
 // fp32 -> fp16 operand copy with optional nearest x2 upsample along time (ggml_upscale_ext, model.cpp:127) and channel padding
 int cast_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, const int * lenOut, int LmaxOut, int up2, float ns, __half * outH,
               int ldoh, int Cpad);   // ns: leaky-relu slope applied before the cast (1.0f = identity)
+// split-fp16 operand for fp32-faithful tensor-core products: out[b][q][0:C] = hi(v), [C:2C] = lo(v), [2C:3C] = hi(v) with
+// v = leaky_relu(x[b][q][c], ns), hi = fp16(v), lo = fp16(v - hi); rows q >= len[b] (up to Lq) are written as zeros
+int split3_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, const int * len, float ns, __half * outH, int Lq);
 // copy channel slice of fp32 rows: dst[b][t][dcoff + c] = src[b][t][scoff + c], c < C
 int copy_cols(Ctx * ctx, const float * src, int lds, int scoff, float * dst, int ldd, int dcoff, int C, int B, int Lmax, const int * len);
 // broadcast a per-utterance vector into channel slice: dstF/dstH[b][t][coff + c] = v[b*ldv + c]

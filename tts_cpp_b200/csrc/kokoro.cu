@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace b2 {
 
@@ -253,6 +254,32 @@ int Kokoro::prepare() {
         auto sk = kv.find(G + "up_convs." + std::to_string(i) + ".stride"), pk = kv.find(G + "up_convs." + std::to_string(i) + ".padding");
         if (sk == kv.end() || pk == kv.end()) { set_error("both padding and stride keys must be assigned in order to initialize a kokoro upsample block."); return 1; }
         u.stride = (int) sk->second; u.pad = (int) pk->second;
+        if (u.K == 2 * u.stride && u.pad < u.stride && (3 * u.Cin) % 64 == 0 && getenv("B2TTS_NO_POLY_CONVT") == nullptr) {
+            // ConvTranspose1d(K = 2s) == s interleaved 2-tap convolutions (one per output phase r = (o + p) mod s):
+            //   out[q*s + r - p] = x[q] . W[:, :, r] + x[q-1] . W[:, :, r+s]
+            // run as ONE tensor-core GEMM with N = s*Cout.  The F32 kernel semantics are kept by splitting both operands
+            // into fp16 hi + lo parts (x = hi + lo, W = Whi + Wlo; hi*Whi + lo*Whi + hi*Wlo, error ~2^-22): K = 2 taps x 3*Cin.
+            const int s = u.stride, C3 = 3 * u.Cin, N = s * u.Cout;
+            std::vector<float> src((size_t) N * C3 * 2), brep((size_t) N);
+            auto bt = P.get(g + "ups." + std::to_string(i) + ".bias");
+            if (!bt) return 1;
+            for (int r = 0; r < s; r++)
+                for (int co = 0; co < u.Cout; co++) {
+                    const size_t n = (size_t) r * u.Cout + co;
+                    brep[n] = bt->v[co];
+                    for (int ci = 0; ci < u.Cin; ci++)
+                        for (int k = 0; k < 2; k++) {
+                            const float wv = t->v[((size_t) ci * u.Cout + co) * u.K + (k == 0 ? r + s : r)];   // tap 0 reads x[q-1]
+                            const float whi = __half2float(__float2half(wv)), wlo = wv - whi;
+                            src[(n * C3 + ci) * 2 + k] = whi;                 // x hi * W hi
+                            src[(n * C3 + u.Cin + ci) * 2 + k] = whi;         // x lo * W hi
+                            src[(n * C3 + 2 * u.Cin + ci) * 2 + k] = wlo;     // x hi * W lo
+                        }
+                }
+            u.w3 = P.w16_from(src, N, C3, 2);
+            u.b_rep = P.f32v(brep);
+            u.poly = true;
+        }
         nconv[i].w = P.w16(g + "noise_blocks." + std::to_string(i) + ".conv_weight");
         nconv[i].b = P.f32(g + "noise_blocks." + std::to_string(i) + ".conv_bias");
         auto ns = kv.find(G + "noise_blocks." + std::to_string(i) + ".stride"), np = kv.find(G + "noise_blocks." + std::to_string(i) + ".padding");
@@ -526,21 +553,29 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     if (durations) *durations = dur_out;
 
     // ================================================================ pass 2: generation (model.cpp:1141-1242)
-    const int L1 = Tmax, L2 = 2 * Tmax, L3 = 20 * Tmax, L4 = 120 * Tmax + 1, S = 600 * Tmax;
+    const int L1 = Tmax, L2 = 2 * Tmax, L4 = 120 * Tmax + 1, S = 600 * Tmax;
+    // row pitches of the two generator stages.  The polyphase ConvTranspose GEMM writes [q][phase][Cout] rows, i.e. the stage
+    // tensor shifted by `pad` rows inside a buffer of (Lin_pitch + 1) * stride rows per utterance; every buffer of a stage shares it.
+    const int P0 = ups[0].poly ? (L2 + 1) * ups[0].stride : 20 * Tmax;
+    const int P1 = ups[1].poly ? (P0 + 1) * ups[1].stride : L4;
     {
-        const size_t big = (size_t) B * L4 * 128 * 4;     // one fp32 generator activation at full rate
+        const size_t big = (size_t) B * P1 * 128 * 4;     // one fp32 generator activation at full rate
         const size_t need = big * 14 + (size_t) B * L1 * (640 * 6 + 2048 * 4 + 1090 * 4 * 3 + 1024 * 8) + (size_t) B * S * 4 * 3 + (256 << 20);
         if (a2.reserve(need)) return 1;
     }
     Fwd Gf{this, ctx, &a2, B};
-    std::vector<int> hl(5 * (size_t) B);
-    for (int b = 0; b < B; b++) { hl[b] = T[b]; hl[B + b] = 2 * T[b]; hl[2 * B + b] = 20 * T[b]; hl[3 * B + b] = 120 * T[b] + 1; hl[4 * B + b] = 600 * T[b]; }
-    int * d_len = Gf.al<int>(5 * (size_t) B);
+    std::vector<int> hl(7 * (size_t) B);
+    for (int b = 0; b < B; b++) {
+        hl[b] = T[b]; hl[B + b] = 2 * T[b]; hl[2 * B + b] = 20 * T[b]; hl[3 * B + b] = 120 * T[b] + 1; hl[4 * B + b] = 600 * T[b];
+        hl[5 * B + b] = 2 * T[b] + 1; hl[6 * B + b] = 20 * T[b] + 1;      // polyphase GEMM rows per utterance (Lin + 1)
+    }
+    int * d_len = Gf.al<int>(7 * (size_t) B);
     int * d_idx = Gf.al<int>((size_t) B * L1);
     if (Gf.fail) return 1;
     B2_CUDA(cudaMemcpyAsync(d_len, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaStreamSynchronize(st));
     const int * lT = d_len, * l2T = d_len + B, * l20 = d_len + 2 * B, * l120 = d_len + 3 * B, * lS = d_len + 4 * B;
+    const int * lq[2] = {d_len + 5 * B, d_len + 6 * B};
     if (build_alignment(ctx, d_lens, B, Nmax, d_ntok, L1, d_idx, d_T)) return 1;
 
     // B0/B1: en = gather(d) -> shared bi-LSTM
@@ -639,14 +674,28 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     const float * gin = dec; int gin_L = L2; const int * gin_len = l2T;
     float * stage_out = nullptr;
     for (int i = 0; i < 2; i++) {
-        const int Lo = i == 0 ? L3 : L4; const int * lo_len = i == 0 ? l20 : l120; const int C = ups[i].Cout;
+        const int Lo = i == 0 ? P0 : P1; const int * lo_len = i == 0 ? l20 : l120; const int C = ups[i].Cout;
         const int Cp = res[3 * i].c1[0].CinPad;
-        float * u = Gf.al<float>((size_t) B * Lo * C); float * xs = Gf.al<float>((size_t) B * Lo * C); float * curg = Gf.al<float>((size_t) B * Lo * C);
+        float * ubuf = Gf.al<float>((size_t) B * Lo * C + 64 * C); float * xs = Gf.al<float>((size_t) B * Lo * C); float * curg = Gf.al<float>((size_t) B * Lo * C);
+        float * u = ubuf;
         float * scr[3] = {Gf.al<float>((size_t) B * Lo * C), Gf.al<float>((size_t) B * Lo * C), Gf.al<float>((size_t) B * Lo * C)};
         float * acc[2] = {Gf.al<float>((size_t) B * Lo * C), Gf.al<float>((size_t) B * Lo * C)};
         __half * a16 = Gf.al<__half>((size_t) B * Lo * Cp); double * sums = Gf.al<double>((size_t) B * C * 2);
         if (Gf.fail) return 1;
-        if (convt_cl(ctx, gin, ups[i].Cin, ups[i].Cin, B, gin_L, gin_len, ups[i].w, ups[i].b, ups[i].K, C, ups[i].stride, ups[i].pad, 0.1f, i == 1 ? 1 : 0, u, C, Lo, lo_len)) return 1;
+        if (ups[i].poly) {
+            // lrelu(0.1) -> split fp16 hi/lo -> one tensor-core GEMM over all `stride` output phases (see Kokoro::prepare)
+            const int Lq = gin_L + 1, s = ups[i].stride, refl = i == 1 ? 1 : 0;
+            const size_t mk = a2.off;
+            __half * a3 = Gf.al<__half>((size_t) B * Lq * 3 * ups[i].Cin);
+            if (Gf.fail) return 1;
+            if (split3_rows(ctx, gin, ups[i].Cin, ups[i].Cin, B, gin_L, gin_len, 0.1f, a3, Lq)) return 1;
+            if (Gf.gemm(a3, 3 * ups[i].Cin, ups[i].w3, ups[i].b_rep, Lq, Lq, gin_len, lq[i], 1, 1, 1, ubuf, s * C, 0)) return 1;
+            a2.off = mk;
+            u = ubuf + (size_t) (ups[i].pad - refl) * C;          // out[o] = Y[o + pad]; with the 1-sample left reflect pad out'[o] = out[o-1]
+            if (refl) B2_CUDA(cudaMemcpy2DAsync(u, (size_t) Lo * C * 4, u + 2 * (size_t) C, (size_t) Lo * C * 4, (size_t) C * 4, B, cudaMemcpyDeviceToDevice, st));   // out'[0] = out[1]
+        } else {
+            if (convt_cl(ctx, gin, ups[i].Cin, ups[i].Cin, B, gin_L, gin_len, ups[i].w, ups[i].b, ups[i].K, C, ups[i].stride, ups[i].pad, 0.1f, i == 1 ? 1 : 0, u, C, Lo, lo_len)) return 1;
+        }
         if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
         if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums)) return 1;       // cur = up + x_source
         if (Gf.tap(i == 0 ? "gen_in0" : "gen_in1", curg, (int64_t) B * Lo, C, C, Lo)) return 1;
@@ -659,13 +708,13 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         gin = stage_out; gin_L = Lo; gin_len = lo_len;
     }
     // B8: conv_post -> exp / sin -> iSTFT (model.cpp:232-241)
-    __half * p16 = Gf.al<__half>((size_t) B * L4 * conv_post.CinPad); float * specph = Gf.al<float>((size_t) B * L4 * 22);
+    __half * p16 = Gf.al<__half>((size_t) B * P1 * conv_post.CinPad); float * specph = Gf.al<float>((size_t) B * P1 * 22);
     float * pcm_d = Gf.al<float>((size_t) B * S);
     if (Gf.fail) return 1;
-    if (cast_rows(ctx, stage_out, 128, 128, B, L4, l120, L4, 0, 0.01f, p16, conv_post.CinPad, conv_post.CinPad)) return 1;
-    if (Gf.gemm(p16, conv_post.CinPad, conv_post, conv_post_b, L4, L4, l120, l120, 1, 1, post_pad, specph, 22, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, 0.f, ACT_EXP_SIN_11)) return 1;
-    if (Gf.tap("spec", specph, (int64_t) B * L4, 22, 22, L4)) return 1;
-    if (istft20(ctx, specph, 22, B, l120, L4, pcm_d, S)) return 1;
+    if (cast_rows(ctx, stage_out, 128, 128, B, P1, l120, P1, 0, 0.01f, p16, conv_post.CinPad, conv_post.CinPad)) return 1;
+    if (Gf.gemm(p16, conv_post.CinPad, conv_post, conv_post_b, P1, P1, l120, l120, 1, 1, post_pad, specph, 22, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, 0.f, ACT_EXP_SIN_11)) return 1;
+    if (Gf.tap("spec", specph, (int64_t) B * P1, 22, 22, P1)) return 1;
+    if (istft20(ctx, specph, 22, B, l120, P1, pcm_d, S)) return 1;
     if (Gf.tap("pcm", pcm_d, B, S, S, S)) return 1;
     B2_CUDA(cudaEventRecord(ev[2], st));
 

@@ -81,7 +81,11 @@ struct Kokoro {
     AdaBlock enc_block, dec_blocks[4];
     // generator
     float m_src_w[9]; float m_src_b = 0.f;
-    struct Up { float * w = nullptr, * b = nullptr; int K = 0, Cin = 0, Cout = 0, stride = 0, pad = 0; } ups[2];
+    struct Up {
+        float * w = nullptr, * b = nullptr; int K = 0, Cin = 0, Cout = 0, stride = 0, pad = 0;
+        // polyphase tensor-core form (K == 2*stride): N = stride*Cout phases, 2 taps, 3*Cin split-fp16 channels
+        bool poly = false; W16 w3; float * b_rep = nullptr;
+    } ups[2];
     struct NoiseConv { W16 w; float * b = nullptr; int stride = 1, pad = 0; } nconv[2];
     GenResBlock nres[2], res[6];
     W16 conv_post; float * conv_post_b = nullptr; int post_pad = 3;
