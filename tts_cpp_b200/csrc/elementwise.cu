@@ -89,6 +89,117 @@ __global__ void adain_apply_kernel(const AdainParams p, int rows_per_block) {
     }
 }
 
+// ---------------------------------------------------------------- vectorised variants (C % 4 == 0): one thread = 4 channels,
+// 16-byte loads, 8-byte fp16 stores, 4 rows in flight per thread -> these passes run at HBM speed instead of latency-bound.
+constexpr int V4_ROWS = 64;   // rows per block
+
+__global__ void __launch_bounds__(256) inorm_stats4_kernel(const float * __restrict__ x, int ldx, int C, int Lmax, const int * __restrict__ len, double * sums) {
+    const int b = blockIdx.y;
+    const int L = len[b];
+    const int t0 = blockIdx.x * V4_ROWS;
+    if (t0 >= L) return;
+    const int t1 = min(L, t0 + V4_ROWS);
+    const int c4 = threadIdx.x, ny = blockDim.y;
+    if (c4 * 4 >= C) return;
+    const float * xb = x + (size_t) b * Lmax * ldx + c4 * 4;
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    for (int t = t0 + threadIdx.y; t < t1; t += 4 * ny) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int tt = t + u * ny;
+            v[u] = tt < t1 ? *reinterpret_cast<const float4 *>(xb + (size_t) tt * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // fp32 partial over 4 rows, then into the double accumulators (ggml accumulates in double: ggml-cpu.c:7138-7152)
+        float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            ps[0] += v[u].x; ps[1] += v[u].y; ps[2] += v[u].z; ps[3] += v[u].w;
+            pq[0] = fmaf(v[u].x, v[u].x, pq[0]); pq[1] = fmaf(v[u].y, v[u].y, pq[1]); pq[2] = fmaf(v[u].z, v[u].z, pq[2]); pq[3] = fmaf(v[u].w, v[u].w, pq[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { s[k] += (double) ps[k]; q[k] += (double) pq[k]; }
+    }
+    // combine the ny row-lanes of the block through shared memory, then one atomic per channel per block
+    __shared__ double sh[256 * 8];
+    double * mine = sh + (threadIdx.y * blockDim.x + c4) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { mine[k] = s[k]; mine[4 + k] = q[k]; }
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        for (int y = 1; y < ny; y++) {
+            const double * o = sh + (y * blockDim.x + c4) * 8;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { s[k] += o[k]; q[k] += o[4 + k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            atomicAdd(&sums[((size_t) b * C + c4 * 4 + k) * 2 + 0], s[k]);
+            atomicAdd(&sums[((size_t) b * C + c4 * 4 + k) * 2 + 1], q[k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p) {
+    const int b = blockIdx.y;
+    const int L = p.len[b];
+    const int t0 = blockIdx.x * V4_ROWS;
+    if (t0 >= L) return;
+    const int t1 = min(L, t0 + V4_ROWS);
+    const int c0 = threadIdx.x * 4, ny = blockDim.y;
+    if (c0 >= (p.outH ? p.Cpad : p.C)) return;
+    const bool live = c0 < p.C;
+    float mean[4], rstd[4], gam[4], bet[4], al[4], ial[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        mean[k] = 0.f; rstd[k] = 0.f; gam[k] = 0.f; bet[k] = 0.f; al[k] = 1.f; ial[k] = 1.f;
+        if (live) {
+            const int c = c0 + k;
+            const double s = p.sums[((size_t) b * p.C + c) * 2], q = p.sums[((size_t) b * p.C + c) * 2 + 1];
+            const double m = s / (double) L;
+            double var = q / (double) L - m * m;
+            if (var < 0.0) var = 0.0;
+            mean[k] = (float) m;
+            rstd[k] = 1.0f / sqrtf((float) var + 1e-5f);
+            gam[k]  = p.gb[(size_t) b * p.ldgb + p.goff + c];
+            bet[k]  = p.gb[(size_t) b * p.ldgb + p.boff + c];
+            if (p.act == NACT_SNAKE) { al[k] = p.alpha[c]; ial[k] = 1.0f / al[k]; }
+        }
+    }
+    const float * xb = p.x + (size_t) b * p.Lmax * p.ldx + c0;
+    for (int t = t0 + threadIdx.y; t < t1; t += 4 * ny) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int tt = t + u * ny;
+            v[u] = (live && tt < t1) ? *reinterpret_cast<const float4 *>(xb + (size_t) tt * p.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int tt = t + u * ny;
+            if (tt >= t1) continue;
+            float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float n = (f[k] - mean[k]) * rstd[k];
+                    float w = (n + n * gam[k]) + bet[k];
+                    if (p.act == NACT_LRELU02) w = lrelu(w, 0.2f);
+                    else if (p.act == NACT_SNAKE) { const float sn = sinf(w * al[k]); w = w + (sn * sn) * ial[k]; }
+                    f[k] = w;
+                }
+            }
+            const size_t orow = (size_t) b * p.Lmax + tt;
+            if (p.outH) {
+                __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+                uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                *reinterpret_cast<uint2 *>(p.outH + orow * p.ldoh + c0) = pk;
+            }
+            if (p.outF && live) *reinterpret_cast<float4 *>(p.outF + orow * p.ldof + c0) = make_float4(f[0], f[1], f[2], f[3]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- depthwise ConvTranspose1d k3 s2 p1 op1 ("pool")
 __global__ void pool_convt_kernel(const float * __restrict__ x, int ldx, int C, int Lmax, const int * __restrict__ len,
                                   const float * __restrict__ w3, const float * __restrict__ bias, __half * outH, int ldoh, int Cpad) {
@@ -385,6 +496,15 @@ static dim3 row_block(int Cpad, int & rows_per_blk) {
 int inorm_stats(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, const int * len, double * sums) {
     if (C > KMAX * 256) { set_error("inorm_stats: C=%d too large", C); return 1; }
     B2_CUDA(cudaMemsetAsync(sums, 0, (size_t) B * C * 2 * sizeof(double), ctx->stream));
+    if (C % 4 == 0 && ldx % 4 == 0 && C / 4 <= 256 && (((uintptr_t) x) & 15) == 0) {
+        const int bx = C / 4, by = 256 / bx > 0 ? 256 / bx : 1;
+        dim3 grid(cdiv(Lmax, V4_ROWS), B), blk(bx, by);
+        ctx->prof_begin(PROF_NORM, 0.0, (double) B * Lmax * C * 4.0);
+        inorm_stats4_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, Lmax, len, sums);
+        ctx->prof_end();
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     int rpb; dim3 blk = row_block(C, rpb);
     const int rows_per_block = 128;
     dim3 grid(cdiv(Lmax, rows_per_block), B);
@@ -397,6 +517,20 @@ int inorm_stats(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, con
 
 int adain_apply(Ctx * ctx, const AdainParams & p) {
     if (p.C > KMAX * 256 || p.Cpad > KMAX * 256) { set_error("adain_apply: C=%d too large", p.C); return 1; }
+    {
+        const int cw = p.outH ? p.Cpad : p.C;
+        const bool al = (((uintptr_t) p.x) & 15) == 0 && (p.outH == nullptr || ((((uintptr_t) p.outH) & 7) == 0 && p.ldoh % 4 == 0)) &&
+                        (p.outF == nullptr || ((((uintptr_t) p.outF) & 15) == 0 && p.ldof % 4 == 0));
+        if (p.C % 4 == 0 && cw % 4 == 0 && p.ldx % 4 == 0 && cw / 4 <= 256 && al) {
+            const int bx = cw / 4, by = 256 / bx > 0 ? 256 / bx : 1;
+            dim3 grid(cdiv(p.Lmax, V4_ROWS), p.B), blk(bx, by);
+            ctx->prof_begin(PROF_NORM, 0.0, (double) p.B * p.Lmax * p.C * (4.0 + (p.outH ? 2.0 : 0.0) + (p.outF ? 4.0 : 0.0)));
+            adain_apply4_kernel<<<grid, blk, 0, ctx->stream>>>(p);
+            ctx->prof_end();
+            B2_LAUNCH_CHECK(ctx);
+            return 0;
+        }
+    }
     int rpb; dim3 blk = row_block(p.outH ? p.Cpad : p.C, rpb);
     const int rows_per_block = 32;
     dim3 grid(cdiv(p.Lmax, rows_per_block), p.B);
