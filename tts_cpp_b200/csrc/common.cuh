@@ -84,6 +84,8 @@ struct ConvGemmParams {
     int            N = 0, Npad = 0, KW = 1, CinPad = 0, lda = 0, stride = 1, dil = 1, pad = 0;
     int            CinTrue = 0;         // un-padded input channels (roofline accounting only; 0 -> CinPad)
     int64_t        validRows = 0;       // sum of lenOut (roofline accounting only; 0 -> B*LmaxOut)
+    float *        statsPart = nullptr; // optional [B][ceil(LmaxOut/128)][N][2]: per-tile (sum, sum of squares) of the stored values over valid rows
+                                        // (tcgen05 kernel only; the caller checks Ctx::umma_launches to know it was produced)
 };
 int conv_gemm(Ctx * ctx, const ConvGemmParams & p);
 int conv_umma(Ctx * ctx, const ConvGemmParams & p);   // gemm_umma.cu: 0 launched, 1 error, 2 shape unsupported (fallback)

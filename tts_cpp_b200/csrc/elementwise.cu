@@ -93,6 +93,16 @@ __global__ void adain_apply_kernel(const AdainParams p, int rows_per_block) {
 // 16-byte loads, 8-byte fp16 stores, 4 rows in flight per thread -> these passes run at HBM speed instead of latency-bound.
 constexpr int V4_ROWS = 64;   // rows per block
 
+// sin for the snake activation: 2-term Cody-Waite reduction to [-pi, pi] + the SFU sine (abs error ~5e-7 here, i.e. ~1e-3 of
+// an fp16 ulp of the value this feeds -- the result is re-rounded to fp16 for the next conv).  libm-grade sinf made this
+// HBM-bound pass issue-bound.
+__device__ __forceinline__ float sin_snake(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484556000744883e-7f, r);
+    return __sinf(r);
+}
+
 __global__ void __launch_bounds__(256) inorm_stats4_kernel(const float * __restrict__ x, int ldx, int C, int Lmax, const int * __restrict__ len, double * sums) {
     const int b = blockIdx.y;
     const int L = len[b];
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p) 
                     const float n = (f[k] - mean[k]) * rstd[k];
                     float w = (n + n * gam[k]) + bet[k];
                     if (p.act == NACT_LRELU02) w = lrelu(w, 0.2f);
-                    else if (p.act == NACT_SNAKE) { const float sn = sinf(w * al[k]); w = w + (sn * sn) * ial[k]; }
+                    else if (p.act == NACT_SNAKE) { const float sn = sin_snake(w * al[k]); w = w + (sn * sn) * ial[k]; }
                     f[k] = w;
                 }
             }
@@ -562,6 +572,24 @@ int cast_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, con
     int rpb; dim3 blk = row_block(Cpad, rpb);
     dim3 grid(cdiv(LmaxOut, rpb), B);
     cast_rows_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, LmaxIn, lenOut, LmaxOut, up2, ns, outH, ldoh, Cpad);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+__global__ void stats_finalize_kernel(const float * __restrict__ part, int n_mt, int C, double * sums) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    const float * p = part + ((size_t) b * n_mt * C + c) * 2;
+    for (int m = 0; m < n_mt; m++) { const float2 v = *reinterpret_cast<const float2 *>(p + (size_t) m * C * 2); s += (double) v.x; q += (double) v.y; }
+    sums[((size_t) b * C + c) * 2] = s;
+    sums[((size_t) b * C + c) * 2 + 1] = q;
+}
+
+int stats_finalize(Ctx * ctx, const float * part, int B, int n_mt, int C, double * sums) {
+    dim3 grid(cdiv(C, 128), B);
+    stats_finalize_kernel<<<grid, 128, 0, ctx->stream>>>(part, n_mt, C, sums);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -118,6 +118,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
     uint64_t * a_full = bars, * a_empty = bars + 2, * b_full = bars + 4, * b_empty = bars + 4 + NSTAGE;
     uint64_t * acc_full = bars + 4 + 2 * NSTAGE, * acc_empty = acc_full + 2;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float * red = reinterpret_cast<float *>(sA + 2 * A_BUF_BYTES + 256);   // [4 epilogue warps][NT][2]: per-tile column sums for the fused InstanceNorm statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_cc = p.CinPad / BKC;
@@ -222,78 +223,113 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
             for (int c0 = 0; c0 < NT; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t) c0, v);
-                if (!valid) continue;
                 const int cb = n0 + c0;
-                if (cb >= p.N) continue;
+                const bool on = valid && cb < p.N;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-                if (e.vec4 && cb + 32 <= p.N) {
-                    if (p.bias) {
+                const bool vec = e.vec4 && cb + 32 <= p.N;
+                if (on) {
+                    if (vec) {
+                        if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) { const float4 bb = *reinterpret_cast<const float4 *>(p.bias + cb + j); f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w; }
+                            for (int j = 0; j < 32; j += 4) { const float4 bb = *reinterpret_cast<const float4 *>(p.bias + cb + j); f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w; }
+                        }
+                        if (p.add1) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) { const float4 a = *reinterpret_cast<const float4 *>(p.add1 + r * p.ldadd1 + cb + j); f[j] = a.x + f[j]; f[j + 1] = a.y + f[j + 1]; f[j + 2] = a.z + f[j + 2]; f[j + 3] = a.w + f[j + 3]; }
+                        }
+                        if (p.add2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) { const float4 a = *reinterpret_cast<const float4 *>(p.add2 + r * p.ldadd2 + cb + j); f[j] = a.x + f[j]; f[j + 1] = a.y + f[j + 1]; f[j + 2] = a.z + f[j + 2]; f[j + 3] = a.w + f[j + 3]; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int c = cb + j;
+                            if (c < p.N) {
+                                if (p.bias) f[j] = f[j] + p.bias[c];
+                                if (p.add1) f[j] = p.add1[r * p.ldadd1 + c] + f[j];
+                                if (p.add2) f[j] = p.add2[r * p.ldadd2 + c] + f[j];
+                            }
+                        }
                     }
-                    if (p.add1) {
+                    if (p.div != 0.f) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) { const float4 a = *reinterpret_cast<const float4 *>(p.add1 + r * p.ldadd1 + cb + j); f[j] = a.x + f[j]; f[j + 1] = a.y + f[j + 1]; f[j + 2] = a.z + f[j + 2]; f[j + 3] = a.w + f[j + 3]; }
+                        for (int j = 0; j < 32; j++) f[j] = __fdiv_rn(f[j], p.div);
                     }
-                    if (p.add2) {
+                    if (p.act == ACT_GELU_F16LUT) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) { const float4 a = *reinterpret_cast<const float4 *>(p.add2 + r * p.ldadd2 + cb + j); f[j] = a.x + f[j]; f[j + 1] = a.y + f[j + 1]; f[j + 2] = a.z + f[j + 2]; f[j + 3] = a.w + f[j + 3]; }
+                        for (int j = 0; j < 32; j++) f[j] = gelu_f16lut_u(f[j]);
+                    } else if (p.act == ACT_LRELU_02) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = (f[j] > 0.f ? f[j] : 0.f) + 0.2f * (f[j] < 0.f ? f[j] : 0.f);
+                    } else if (p.act == ACT_EXP_SIN_11) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = (cb + j < 11) ? expf(f[j]) : sinf(f[j]);
                     }
-                } else {
+                    if (vec) {
+                        if (p.outF) {
+                            float * o = p.outF + r * p.ldo + p.coff + cb;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int c = cb + j;
-                        if (c < p.N) {
-                            if (p.bias) f[j] = f[j] + p.bias[c];
-                            if (p.add1) f[j] = p.add1[r * p.ldadd1 + c] + f[j];
-                            if (p.add2) f[j] = p.add2[r * p.ldadd2 + c] + f[j];
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                        if (p.outH) {
+                            __half * o = p.outH + r * p.ldoh + p.coffh + cb;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                                uint4 u;
+                                u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+                                u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
+                                *reinterpret_cast<uint4 *>(o + j) = u;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int c = cb + j;
+                            if (c < p.N) {
+                                if (p.outF) p.outF[r * p.ldo + p.coff + c] = f[j];
+                                if (p.outH) p.outH[r * p.ldoh + p.coffh + c] = __float2half_rn(f[j]);
+                            }
                         }
                     }
                 }
-                if (p.div != 0.f) {
+                if (p.statsPart) {
+                    // fused InstanceNorm statistics: column sums of the stored values over this warp's 32 rows (butterfly
+                    // reduce-scatter: 31 shuffles leave lane l with column l), staged per warp for the cross-warp combine below
+                    float sq[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = __fdiv_rn(f[j], p.div);
-                }
-                if (p.act == ACT_GELU_F16LUT) {
+                    for (int j = 0; j < 32; j++) { if (!on || cb + j >= p.N) f[j] = 0.f; sq[j] = f[j] * f[j]; }
 #pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = gelu_f16lut_u(f[j]);
-                } else if (p.act == ACT_LRELU_02) {
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = (f[j] > 0.f ? f[j] : 0.f) + 0.2f * (f[j] < 0.f ? f[j] : 0.f);
-                } else if (p.act == ACT_EXP_SIN_11) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = (cb + j < 11) ? expf(f[j]) : sinf(f[j]);
-                }
-                if (e.vec4 && cb + 32 <= p.N) {
-                    if (p.outF) {
-                        float * o = p.outF + r * p.ldo + p.coff + cb;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                    if (p.outH) {
-                        __half * o = p.outH + r * p.ldoh + p.coffh + cb;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                            __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
-                            u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
-                            *reinterpret_cast<uint4 *>(o + j) = u;
+                        for (int i = 0; i < off; i++) {
+                            const float send = up ? f[i] : f[i + off], keep = up ? f[i + off] : f[i];
+                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            const float send2 = up ? sq[i] : sq[i + off], keep2 = up ? sq[i + off] : sq[i];
+                            sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
                         }
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int c = cb + j;
-                        if (c < p.N) {
-                            if (p.outF) p.outF[r * p.ldo + p.coff + c] = f[j];
-                            if (p.outH) p.outH[r * p.ldoh + p.coffh + c] = __float2half_rn(f[j]);
-                        }
+                    red[((warp - 2) * NT + c0 + lane) * 2 + 0] = f[0];
+                    red[((warp - 2) * NT + c0 + lane) * 2 + 1] = sq[0];
+                }
+            }
+            if (p.statsPart) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int te = threadIdx.x - 64;
+                for (int c = te; c < NT; c += 128) {
+                    if (n0 + c < p.N) {
+                        const float s0 = (red[(0 * NT + c) * 2] + red[(1 * NT + c) * 2]) + (red[(2 * NT + c) * 2] + red[(3 * NT + c) * 2]);
+                        const float s1 = (red[(0 * NT + c) * 2 + 1] + red[(1 * NT + c) * 2 + 1]) + (red[(2 * NT + c) * 2 + 1] + red[(3 * NT + c) * 2 + 1]);
+                        float * dst = p.statsPart + (((size_t) b * e.n_mt + mt) * p.N + n0 + c) * 2;
+                        dst[0] = s0; dst[1] = s1;
                     }
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
@@ -339,7 +375,7 @@ int umma_init() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    constexpr int smem256 = NSTAGE * 256 * 128 + 2 * A_BUF_BYTES + 256, smem128 = NSTAGE * 128 * 128 + 2 * A_BUF_BYTES + 256;
+    constexpr int smem256 = NSTAGE * 256 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 256 * 8, smem128 = NSTAGE * 128 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 128 * 8;
     if (cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem256) != cudaSuccess ||
         cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128) != cudaSuccess) {
         cudaGetLastError();
@@ -400,10 +436,10 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p) {
         ctx->prof_begin(PROF_GEMM, 2.0 * rows * p.N * p.KW * cin, rows * cin * 2.0 + (double) p.N * p.KW * cin * 2.0 + rows * p.N * 4.0);
     }
     if (NT == 256) {
-        constexpr int smem = NSTAGE * 256 * 128 + 2 * A_BUF_BYTES + 256;
+        constexpr int smem = NSTAGE * 256 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 256 * 8;
         conv_umma_kernel<256><<<grid, UMMA_THREADS, smem, ctx->stream>>>(p, e, tmA, tmB);
     } else {
-        constexpr int smem = NSTAGE * 128 * 128 + 2 * A_BUF_BYTES + 256;
+        constexpr int smem = NSTAGE * 128 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 128 * 8;
         conv_umma_kernel<128><<<grid, UMMA_THREADS, smem, ctx->stream>>>(p, e, tmA, tmB);
     }
     ctx->prof_end();

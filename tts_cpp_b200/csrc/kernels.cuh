@@ -10,6 +10,9 @@ namespace b2 {
 // sums[b][c][2] (double): sum, sum of squares over t < len[b]   (zeroed by the launcher)
 int inorm_stats(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, const int * len, double * sums);
 
+// per-tile partials written by the tcgen05 GEMM epilogue ([B][n_mt][C][2] fp32) -> sums[b][c][2] (double), same format as inorm_stats
+int stats_finalize(Ctx * ctx, const float * part, int B, int n_mt, int C, double * sums);
+
 enum { NACT_LRELU02 = 0, NACT_SNAKE = 1, NACT_NONE = 2 };
 struct AdainParams {
     const float *  x = nullptr;   int ldx = 0;

@@ -351,6 +351,21 @@ struct Fwd {
         return conv_gemm(ctx, p);
     }
 
+    // conv_gemm whose fp32 result (ld == N) is InstanceNorm'ed next: the statistics come out of the tcgen05 epilogue
+    // (per-tile partials + a tiny finalize); if the shape fell back to the mma.sync kernel, a separate pass computes them.
+    int gemm_stats(const __half * A, int lda, const W16 & W, const float * bias, int L, const int * len, int dil, int pad, float * outF,
+                   const float * add1, const float * add2, float div, float * part, double * sums_out) {
+        ConvGemmParams p;
+        p.A = A; p.lda = lda; p.W = W.w; p.bias = bias; p.outF = outF; p.ldo = W.N; p.add1 = add1; p.ldadd1 = W.N; p.add2 = add2; p.ldadd2 = W.N; p.div = div;
+        p.B = B; p.LmaxIn = L; p.LmaxOut = L; p.lenIn = len; p.lenOut = len;
+        p.N = W.N; p.Npad = W.Npad; p.KW = W.KW; p.CinPad = W.CinPad; p.CinTrue = W.Cin; p.stride = 1; p.dil = dil; p.pad = pad;
+        p.statsPart = part;
+        const uint64_t before = ctx->umma_launches;
+        if (conv_gemm(ctx, p)) return 1;
+        if (ctx->umma_launches != before) return stats_finalize(ctx, part, B, cdiv(L, 128), W.N, sums_out);
+        return inorm_stats(ctx, outF, W.N, W.N, B, L, len, sums_out);
+    }
+
     // bi-LSTM over a16 [B][Lmax][CinPad] -> out fp32 (ldo/coff) (+ fp16 copy)
     int lstm(const Lstm & L, const __half * a16, int lda, int Lmax, const int * len, int maxLen, float * out, int ldo, int coff, __half * outH, int ldoh,
              int coffh) {
@@ -406,26 +421,32 @@ struct Fwd {
     }
 
     // generator residual block (model.cpp:136-165): x [B][L][C] -> out = (x_final [+ add2]) [/ div]
+    // generator residual block (model.cpp:136-165): x [B][L][C] -> out = (x_final [+ add2]) [/ div].
+    // sums_x: InstanceNorm statistics of x if the caller already has them (nullptr -> computed here);
+    // sums_out: if non-null, receives the statistics of `out` (fused into the last conv's epilogue).
     int gen_resblock(const GenResBlock & r, const float * gb, int ldgb, const float * x, int L, const int * len, float * out, const float * add2, float div,
-                     float * scratch[3], __half * a16, double * sums) {
+                     float * scratch[3], __half * a16, double * sums2[3], float * part, const double * sums_x, double * sums_out) {
         const float * inp = x;
         const int C = r.C, Cp = r.c1[0].CinPad;
+        const double * s_in = sums_x;
+        if (!s_in) { if (inorm_stats(ctx, inp, C, C, B, L, len, sums2[0])) return 1; s_in = sums2[0]; }
         for (int i = 0; i < 3; i++) {
             float * h = scratch[2];
             float * nxt = (i == 2) ? out : scratch[i & 1];
-            if (inorm_stats(ctx, inp, C, C, B, L, len, sums)) return 1;
             AdainParams ap;
-            ap.x = inp; ap.ldx = C; ap.C = C; ap.B = B; ap.Lmax = L; ap.len = len; ap.sums = sums; ap.gb = gb; ap.ldgb = ldgb;
+            ap.x = inp; ap.ldx = C; ap.C = C; ap.B = B; ap.Lmax = L; ap.len = len; ap.sums = s_in; ap.gb = gb; ap.ldgb = ldgb;
             ap.goff = r.s1[i].goff; ap.boff = r.s1[i].boff; ap.act = NACT_SNAKE; ap.alpha = r.a1[i]; ap.outH = a16; ap.ldoh = Cp; ap.Cpad = Cp;
             if (adain_apply(ctx, ap)) return 1;
-            if (gemm(a16, Cp, r.c1[i], r.b1[i], L, L, len, len, 1, r.dil[i], r.pad[i], h, C, 0)) return 1;
-            if (inorm_stats(ctx, h, C, C, B, L, len, sums)) return 1;
-            ap.x = h; ap.goff = r.s2[i].goff; ap.boff = r.s2[i].boff; ap.alpha = r.a2[i];
+            if (gemm_stats(a16, Cp, r.c1[i], r.b1[i], L, len, r.dil[i], r.pad[i], h, nullptr, nullptr, 0.f, part, sums2[1])) return 1;
+            ap.x = h; ap.sums = sums2[1]; ap.goff = r.s2[i].goff; ap.boff = r.s2[i].boff; ap.alpha = r.a2[i];
             if (adain_apply(ctx, ap)) return 1;
-            if (gemm(a16, Cp, r.c2[i], r.b2[i], L, L, len, len, 1, 1, r.pad[0], nxt, C, 0, nullptr, 0, 0, inp, C, (i == 2) ? add2 : nullptr, C,
-                     (i == 2) ? div : 0.f))
-                return 1;
-            inp = nxt;
+            double * s_next = (i == 2) ? sums_out : sums2[2 - (i & 1) * 2];   // ping-pong between sums2[2] and sums2[0] (s_in may alias sums2[0] only at i == 0)
+            if (s_next) {
+                if (gemm_stats(a16, Cp, r.c2[i], r.b2[i], L, len, 1, r.pad[0], nxt, inp, (i == 2) ? add2 : nullptr, (i == 2) ? div : 0.f, part, s_next)) return 1;
+            } else {
+                if (gemm(a16, Cp, r.c2[i], r.b2[i], L, L, len, len, 1, 1, r.pad[0], nxt, C, 0, nullptr, 0, 0, inp, C, (i == 2) ? add2 : nullptr, C, (i == 2) ? div : 0.f)) return 1;
+            }
+            inp = nxt; s_in = s_next;
         }
         return 0;
     }
@@ -680,7 +701,10 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         float * u = ubuf;
         float * scr[3] = {Gf.al<float>((size_t) B * Lo * C), Gf.al<float>((size_t) B * Lo * C), Gf.al<float>((size_t) B * Lo * C)};
         float * acc[2] = {Gf.al<float>((size_t) B * Lo * C), Gf.al<float>((size_t) B * Lo * C)};
-        __half * a16 = Gf.al<__half>((size_t) B * Lo * Cp); double * sums = Gf.al<double>((size_t) B * C * 2);
+        __half * a16 = Gf.al<__half>((size_t) B * Lo * Cp);
+        double * sums2[3] = {Gf.al<double>((size_t) B * C * 2), Gf.al<double>((size_t) B * C * 2), Gf.al<double>((size_t) B * C * 2)};
+        double * sums_cur = Gf.al<double>((size_t) B * C * 2);
+        float * part = Gf.al<float>((size_t) B * cdiv(Lo, 128) * C * 2);
         if (Gf.fail) return 1;
         if (ups[i].poly) {
             // lrelu(0.1) -> split fp16 hi/lo -> one tensor-core GEMM over all `stride` output phases (see Kokoro::prepare)
@@ -697,11 +721,12 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
             if (convt_cl(ctx, gin, ups[i].Cin, ups[i].Cin, B, gin_L, gin_len, ups[i].w, ups[i].b, ups[i].K, C, ups[i].stride, ups[i].pad, 0.1f, i == 1 ? 1 : 0, u, C, Lo, lo_len)) return 1;
         }
         if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
-        if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums)) return 1;       // cur = up + x_source
+        if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums2, part, nullptr, sums_cur)) return 1;   // cur = up + x_source
         if (Gf.tap(i == 0 ? "gen_in0" : "gen_in1", curg, (int64_t) B * Lo, C, C, Lo)) return 1;
         for (int j = 0; j < 3; j++) {
             float * dst = acc[j & 1];
-            if (Gf.gen_resblock(res[3 * i + j], gbD, sty_n[1], curg, Lo, lo_len, dst, j == 0 ? nullptr : acc[(j + 1) & 1], j == 2 ? 3.0f : 0.f, scr, a16, sums)) return 1;
+            if (Gf.gen_resblock(res[3 * i + j], gbD, sty_n[1], curg, Lo, lo_len, dst, j == 0 ? nullptr : acc[(j + 1) & 1], j == 2 ? 3.0f : 0.f, scr, a16, sums2, part,
+                                overrides.count(i == 0 ? "gen_in0" : "gen_in1") ? nullptr : sums_cur, nullptr)) return 1;
         }
         stage_out = acc[0];   // j == 2 writes acc[0]
         if (Gf.tap(i == 0 ? "gen_out0" : "gen_out1", stage_out, (int64_t) B * Lo, C, C, Lo)) return 1;
