@@ -74,12 +74,16 @@ int b2tts_prof_read(b2tts_ctx * ctx, int kind, double * total_ms, double * flops
     Ctx & c = ctx->c;
     B2_CUDA(cudaStreamSynchronize(c.stream));
     double ms = 0, fl = 0, by = 0; uint64_t n = 0;
+    const char * dump = getenv("B2TTS_PROF_DUMP");   // diagnostics: append one line per profiled launch of this kind
+    FILE * df = dump ? fopen(dump, "a") : nullptr;
     for (auto & r : c.recs) {
         if (r.kind != kind) continue;
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
         ms += t; fl += r.flops; by += r.bytes; n++;
+        if (df) fprintf(df, "%d %.4f %.4g %.4g %s\n", r.kind, t, r.flops, r.bytes, r.tag);
     }
+    if (df) fclose(df);
     if (total_ms) *total_ms = ms; if (flops) *flops = fl; if (bytes) *bytes = by; if (launches) *launches = n;
     return 0;
 }

@@ -12,7 +12,7 @@ void set_error(const char * fmt, ...);
 
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline accounting)
 enum { PROF_GEMM = 0, PROF_LSTM = 1, PROF_NORM = 2, PROF_CONVT = 3, PROF_KINDS = 4 };
-struct ProfRec { cudaEvent_t a, b; int kind; double flops, bytes; };
+struct ProfRec { cudaEvent_t a, b; int kind; double flops, bytes; char tag[48]; };
 
 struct Ctx {
     int          device   = 0;
@@ -20,11 +20,14 @@ struct Ctx {
     uint64_t     launches = 0;   // kernels launched by this library on this context
     uint64_t     umma_launches = 0, mma_sync_launches = 0;   // conv_gemm dispatch: tcgen05 kernel vs mma.sync fallback
     bool                     prof = false;
+    char                     tag[48] = "";   // optional label of the next profiled launch (B2TTS_PROF_DUMP diagnostics)
     std::vector<ProfRec>     recs;
     std::vector<cudaEvent_t> pool;
     void prof_begin(int kind, double flops, double bytes) {
         if (!prof) return;
         ProfRec r; r.kind = kind; r.flops = flops; r.bytes = bytes;
+        for (int i = 0; i < 48; i++) r.tag[i] = tag[i];
+        tag[0] = 0;
         for (cudaEvent_t * e : { &r.a, &r.b }) {
             if (!pool.empty()) { *e = pool.back(); pool.pop_back(); } else cudaEventCreate(e);
         }
@@ -84,10 +87,11 @@ struct ConvGemmParams {
     int            N = 0, Npad = 0, KW = 1, CinPad = 0, lda = 0, stride = 1, dil = 1, pad = 0;
     int            CinTrue = 0;         // un-padded input channels (roofline accounting only; 0 -> CinPad)
     int64_t        validRows = 0;       // sum of lenOut (roofline accounting only; 0 -> B*LmaxOut)
-    float *        statsPart = nullptr; // optional [B][ceil(LmaxOut/128)][N][2]: per-tile (sum, sum of squares) of the stored values over valid rows
+    float *        statsPart = nullptr; // optional [B][ceil(LmaxOut/conv_umma_tile_m)][N][2]: per-tile (sum, sum of squares) of the stored values over valid rows
                                         // (tcgen05 kernel only; the caller checks Ctx::umma_launches to know it was produced)
 };
 int conv_gemm(Ctx * ctx, const ConvGemmParams & p);
+int conv_umma_tile_m(const ConvGemmParams & p);   // rows per tcgen05 work item for this shape (128 or 256; 0 = unsupported): statsPart is [B][ceil(LmaxOut / tile_m)][N][2]
 int conv_umma(Ctx * ctx, const ConvGemmParams & p);   // gemm_umma.cu: 0 launched, 1 error, 2 shape unsupported (fallback)
 
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 // Tile 128(M = time) x BN(N = Cout) x 32(K), 8 warps, 4-stage cp.async pipeline, ldmatrix + mma.sync.m16n8k16.
 // (Round-1 tensor path; the tcgen05/TMA version of this kernel is the round-2 item -- see DESIGN.md.)
 #include "common.cuh"
+#include <cstdio>
 
 namespace b2 {
 
@@ -203,6 +204,7 @@ int conv_gemm(Ctx * ctx, const ConvGemmParams & p) {
     {
         const double rows = (double) (p.validRows ? p.validRows : M), cin = (double) (p.CinTrue ? p.CinTrue : p.CinPad);
         // algorithmic work of this launch: 2*rows*N*KW*Cin flops; bytes = fp16 operand once + weights once + fp32 result once
+        snprintf(ctx->tag, sizeof(ctx->tag), "%s N%d K%d C%d L%d B%d d%d", "mmasync", p.N, p.KW, p.CinPad, p.LmaxOut, p.B, p.dil);
         ctx->prof_begin(PROF_GEMM, 2.0 * rows * p.N * p.KW * cin, rows * cin * 2.0 + (double) p.N * p.KW * cin * 2.0 + rows * p.N * 4.0);
     }
     if (p.N > 64) {

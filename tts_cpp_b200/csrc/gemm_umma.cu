@@ -4,35 +4,64 @@
 // fp16 operands, fp32 accumulation -- the reference's ggml_conv_1d / ggml_mul_mat with F16 weights (ggml/src/ggml.c:3870-3894,
 // ggml/src/ggml-cpu/ggml-cpu.c:262-267) -- for stride-1 layers with Cin % 64 == 0 and Cout % 128 == 0 (all the heavy ones).
 //
-// Blackwell mapping:
-//   * one CTA per SM, persistent over (utterance, 128-row time tile, Cout tile) work items;
-//   * warp 0  = TMA producer: per 64-channel chunk it loads the activation rows ONCE, with the conv halo
-//               (128 + (K-1)*dil rows), as 8 un-swizzled [rows][16 B] core-matrix columns; every tap then reads the same
-//               shared-memory chunk at a row offset (descriptor start address + tap*dil*16 B) -- no im2col, no re-load per tap.
-//               Weight tiles [Cout_tile][64] stream through a 4-stage 128B-swizzled ring, one per (chunk, tap);
-//   * warp 1  = MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128|256, K=16) into a TMEM accumulator;
-//               tcgen05.commit releases smem stages / publishes the accumulator through mbarriers;
-//   * warps 2-5 = epilogue: tcgen05.ld the accumulator (double-buffered in TMEM, so the next tile's MMAs overlap), apply
-//               bias / residual adds / divide / activation, store fp32 and/or fp16 rows.
+// Blackwell mapping (one CTA per SM, persistent over (utterance, 256-row time tile, 128-column Cout tile) work items):
+//   * warp 0  = TMA producer.  Per 64-channel chunk the activation rows are loaded ONCE with the conv halo
+//               (256 + (K-1)*dil rows) as 8 un-swizzled [rows][16 B] core-matrix columns; every tap then reads the same
+//               shared-memory chunk at a row offset (descriptor start address + tap*dil*16 B): no im2col, no reload per tap.
+//               Weight tiles [128][64] (128B-swizzled) stream through a 6-stage ring, one per (chunk, tap).
+//   * warp 1  = MMA issuer: one elected thread issues tcgen05.mma M=128 N=128 K=16.  Each weight stage feeds TWO 128-row
+//               accumulators (rows 0-127 and 128-255 of the tile): measured on B200 the kernel is bound by L2->SM traffic of
+//               the weight tiles (an ablation with MMAs, stores and loads removed still took 2/3 of the time), so every weight
+//               byte fetched is used for 256 output rows.  tcgen05.commit releases smem stages / publishes accumulators.
+//   * warps 2-9 = epilogue: 8 warps = 2 row-halves x 4 TMEM lane quarters; tcgen05.ld the accumulator (double-buffered in
+//               TMEM: 2 x 2 x 128 columns, so the next tile's MMAs overlap), bias / residual adds / divide / activation, fused
+//               InstanceNorm statistics (column sums via a shuffle reduce-scatter), and row-contiguous global accesses
+//               staged through a per-warp shared-memory tile.
 //   * activations outside [0, len_b) must read as zero: TMA zero-fills out-of-range rows, and zero_tail_rows() clears the
 //     first rows past each utterance's end for ragged batches.
 #include "common.cuh"
+#include <cstdio>
 #include <cuda.h>
 #include <cstdlib>
 
 namespace b2 {
 namespace {
 
-constexpr int UM = 128, BKC = 64, RA_MAX = 192, NSTAGE = 4;
-constexpr int A_BUF_BYTES = 8 * RA_MAX * 16;   // 8 core-matrix columns x RA_MAX rows x 16 B
-constexpr int UMMA_THREADS = 192;
+constexpr int UM = 128, BKC = 64;
+constexpr int RA_MAX = 320;                            // tile rows + (K-1)*dil, rounded up to 16
+// Two tile configurations (template <NT, NH>):
+//   Cout % 256 == 0 : NT = 256, NH = 1 -> 128 rows x 256 columns per work item, one accumulator (largest MMA, N = 256)
+//   otherwise       : NT = 128, NH = 2 -> 256 rows x 128 columns: each 16 KB weight stage feeds two 128-row accumulators
+// Either way a weight byte fetched from L2 is used for 128*256 MACs per K element and TMEM holds 2 x 256 columns (double buffer).
+__host__ __device__ constexpr int nstage_for(int nt) { return nt == 256 ? 4 : 6; }   // weight-tile ring (4 x 32 KB or 6 x 16 KB)
+constexpr int STAGE_PITCH = 36;                        // floats per staged row (32 + 4: conflict-free 16 B accesses both ways)
+constexpr int STAGE_WARP_BYTES = 32 * STAGE_PITCH * 4;
+constexpr int UMMA_THREADS = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int RED_BYTES = 8 * 128 * 8;                 // [slabs][NT][2] floats: 8 x 128 or 4 x 256 columns
+__host__ __device__ constexpr int fixed_bytes(int nt) { return nstage_for(nt) * nt * 128 + 256 + RED_BYTES + 8 * STAGE_WARP_BYTES; }
+constexpr int UMMA_SMEM_TOTAL = 232448;                // 227 KB: all the opt-in shared memory of an SM
+constexpr int MAX_ABUF = 4;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// exactly one lane of a fully converged warp: the compiler then knows the guarded code runs on a single lane and keeps the
+// tcgen05 operands in uniform registers (an `if (lane == 0)` guard made it wrap every MMA in an R2UR + ELECT + BRA.U.ANY
+// "uniformisation" loop, ~150 cycles per instruction: the issuing thread, not the tensor core, was the bottleneck)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes) {
+    if (elect_one())
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
@@ -50,16 +79,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void * dst, const CUtensorMap * tm, uint64_t * bar, int c0, int c1) {
+    if (elect_one())
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void * dst, const CUtensorMap * tm, uint64_t * bar, int c0, int c1, int c2) {
+    if (elect_one())
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one())
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -68,6 +100,7 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t * bar) {
+    if (elect_one())
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t * r) {
@@ -80,7 +113,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t * r) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// shared-memory matrix descriptor (K-major operand).  layout_type: 0 = no swizzle, 2 = 128B swizzle; version field = 1 on sm_100
+// shared-memory matrix descriptor (K-major operand).  layout_type: 0 = no swizzle, 2 = 128B swizzle; version field = 1 on sm_100.
+// (Row-shifted 128B-swizzled descriptors via base_offset were tried for the activation operand and give wrong tap shifts
+//  for dil = 3 on sm_100a, so the activation chunk uses the un-swizzled core-matrix layout, where a row shift is start + 16 B.)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t) ((addr & 0x3FFFFu) >> 4);
@@ -100,37 +135,43 @@ __device__ __forceinline__ float gelu_f16lut_u(float x) {   // ggml-cpu.c:1816-1
 }
 
 struct UmmaExtra {
-    int RA;            // activation rows staged per chunk (128 + (KW-1)*dil rounded up to 8)
-    int n_mt;          // 128-row tiles per utterance
-    int n_nt;          // Cout tiles
+    int RA;            // activation rows staged per chunk: TM + (KW-1)*dil rounded up to 16 (loaded as two TMA boxes of RA/2 rows)
+    int n_abuf;        // activation chunk buffers in the ring
+    int n_mt;          // TM-row tiles per utterance
+    int n_nt;          // NT-column Cout tiles
     int total_tiles;
     int vec4;          // epilogue may use 16-byte accesses
+    int dbg;           // B2TTS_UMMA_DBG ablation bits (timing experiments only; results are wrong when set)
 };
 
-template <int NT>
+template <int NT, int NH>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
-    constexpr int B_STAGE_BYTES = NT * 128;
+    constexpr int TM = UM * NH, NSTAGE = nstage_for(NT), B_STAGE_BYTES = NT * 128, FIXED_BYTES = fixed_bytes(NT);
+    constexpr int NSLAB = 4 * NH;                 // row slabs of 32 rows that own a distinct set of tile rows
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char * sB = smem;                                        // [NSTAGE][NT][128 B], 128B-swizzled by TMA
-    unsigned char * sA = smem + NSTAGE * B_STAGE_BYTES;               // [2][8][RA][16 B]
-    uint64_t * bars = reinterpret_cast<uint64_t *>(sA + 2 * A_BUF_BYTES);
-    uint64_t * a_full = bars, * a_empty = bars + 2, * b_full = bars + 4, * b_empty = bars + 4 + NSTAGE;
-    uint64_t * acc_full = bars + 4 + 2 * NSTAGE, * acc_empty = acc_full + 2;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smem + NSTAGE * B_STAGE_BYTES);
+    uint64_t * a_full = bars, * a_empty = bars + MAX_ABUF, * b_full = bars + 2 * MAX_ABUF, * b_empty = b_full + NSTAGE;
+    uint64_t * acc_full = b_empty + NSTAGE, * acc_empty = acc_full + 2;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    float * red = reinterpret_cast<float *>(sA + 2 * A_BUF_BYTES + 256);   // [4 epilogue warps][NT][2]: per-tile column sums for the fused InstanceNorm statistics
+    float * red = reinterpret_cast<float *>(smem + NSTAGE * B_STAGE_BYTES + 256);       // [8 slabs][NT][2]
+    float * stage_all = red + RED_BYTES / 4;                                               // [8 epilogue warps][32][STAGE_PITCH]
+    unsigned char * sA = smem + FIXED_BYTES;                                            // [n_abuf][8][RA][16 B]
+    const int a_buf_bytes = e.RA * 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_cc = p.CinPad / BKC;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < MAX_ABUF; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < NSTAGE; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: 2 accumulators of NT fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * NT) : "memory");
+    if (warp == 1) {   // TMEM: 2 (double buffer) x NH accumulators x NT fp32 columns = all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -139,25 +180,30 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================================================================= TMA producer
-        if (lane == 0) {
+        // ================================================================= TMA producer (whole warp runs the loop; one elected lane issues)
+        {
             uint32_t a_it = 0, b_it = 0;
+            const int RAh = e.RA / 2;
             for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
                 const int nt = tile % e.n_nt, rest = tile / e.n_nt, mt = rest % e.n_mt, b = rest / e.n_mt;
-                const int t0 = mt * UM, n0 = nt * NT;
+                const int t0 = mt * TM, n0 = nt * NT;
                 for (int cc = 0; cc < n_cc; cc++) {
-                    const int ab = a_it & 1;
-                    mbar_wait(&a_empty[ab], ((a_it >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&a_full[ab], (uint32_t) e.RA * 128u);
+                    const int ab = a_it % e.n_abuf;
+                    mbar_wait(&a_empty[ab], ((a_it / e.n_abuf) & 1) ^ 1);
+                    mbar_expect_tx(&a_full[ab], (e.dbg & 1) ? 0u : (uint32_t) e.RA * 128u);
 #pragma unroll
-                    for (int kc = 0; kc < 8; kc++)
-                        tma_load_3d(sA + ab * A_BUF_BYTES + kc * e.RA * 16, &tmA, &a_full[ab], cc * BKC + kc * 8, t0 - p.pad, b);
+                    for (int kc = 0; kc < 8; kc++) {
+                        if (e.dbg & 1) break;
+                        unsigned char * dst = sA + ab * a_buf_bytes + kc * e.RA * 16;
+                        tma_load_3d(dst, &tmA, &a_full[ab], cc * BKC + kc * 8, t0 - p.pad, b);
+                        tma_load_3d(dst + RAh * 16, &tmA, &a_full[ab], cc * BKC + kc * 8, t0 - p.pad + RAh, b);
+                    }
                     a_it++;
                     for (int tap = 0; tap < p.KW; tap++) {
                         const int s = b_it % NSTAGE;
                         mbar_wait(&b_empty[s], ((b_it / NSTAGE) & 1) ^ 1);
-                        mbar_expect_tx(&b_full[s], (uint32_t) B_STAGE_BYTES);
-                        tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &b_full[s], tap * p.CinPad + cc * BKC, n0);
+                        mbar_expect_tx(&b_full[s], (e.dbg & 2) ? 0u : (uint32_t) B_STAGE_BYTES);
+                        if (!(e.dbg & 2)) tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &b_full[s], tap * p.CinPad + cc * BKC, n0);
                         b_it++;
                     }
                 }
@@ -166,29 +212,37 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
     } else if (warp == 1) {
         // ================================================================= MMA issuer
         const uint32_t idesc = (1u << 4) | ((uint32_t) (NT >> 3) << 17) | ((uint32_t) (UM >> 4) << 24);   // F32 accum, F16 x F16, K-major A and B
+        // descriptor templates (everything but the 14-bit start address, which is added per MMA in 16-byte units)
+        const uint64_t bdesc_t = ((uint64_t) (16u >> 4) << 16) | ((uint64_t) (1024u >> 4) << 32) | ((uint64_t) 1 << 46) | ((uint64_t) 2 << 61);   // 128B swizzle
+        const uint64_t adesc_t = ((uint64_t) ((uint32_t) e.RA & 0x3FFFu) << 16) | ((uint64_t) (128u >> 4) << 32) | ((uint64_t) 1 << 46);          // LBO = RA*16 B, SBO = 128 B
+        const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+        const uint32_t abuf16 = (uint32_t) a_buf_bytes >> 4;
         uint32_t a_it = 0, b_it = 0, acc_it = 0;
         for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
             const int acb = acc_it & 1;
             mbar_wait(&acc_empty[acb], ((acc_it >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t) (acb * NT);
+            const uint32_t d_tmem = tmem_base + (uint32_t) (acb * 256);
             uint32_t accumulate = 0;
             for (int cc = 0; cc < n_cc; cc++) {
-                const int ab = a_it & 1;
-                mbar_wait(&a_full[ab], (a_it >> 1) & 1);
-                const uint32_t a_base = smem_u32(sA + ab * A_BUF_BYTES);
+                const int ab = a_it % e.n_abuf;
+                mbar_wait(&a_full[ab], (a_it / e.n_abuf) & 1);
+                const uint32_t a16 = sA16 + (uint32_t) ab * abuf16;
                 for (int tap = 0; tap < p.KW; tap++) {
                     const int s = b_it % NSTAGE;
                     mbar_wait(&b_full[s], (b_it / NSTAGE) & 1);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t b_base = smem_u32(sB + s * B_STAGE_BYTES);
-                        const uint32_t a_tap = a_base + (uint32_t) (tap * p.dil) * 16u;
+                    {
+                        const uint32_t b16 = sB16 + (uint32_t) s * (B_STAGE_BYTES >> 4);
+                        const uint32_t at16 = a16 + (uint32_t) (tap * p.dil);
 #pragma unroll
                         for (int j = 0; j < BKC / 16; j++) {
-                            const uint64_t ad = smem_desc(a_tap + (uint32_t) (2 * j * e.RA) * 16u, (uint32_t) e.RA * 16u, 128u, 0u);
-                            const uint64_t bd = smem_desc(b_base + (uint32_t) j * 32u, 16u, 1024u, 2u);
-                            umma_f16(d_tmem, ad, bd, idesc, accumulate);
+                            const uint64_t bd = bdesc_t | (uint64_t) (b16 + 2u * j);
+#pragma unroll
+                            for (int h = 0; h < NH; h++) {   // the same weight stage feeds every 128-row accumulator of the tile
+                                const uint64_t ad = adesc_t | (uint64_t) (at16 + (uint32_t) (2 * j * e.RA + h * UM));
+                                if (!(e.dbg & 4)) umma_f16(d_tmem + (uint32_t) (h * NT), ad, bd, idesc, accumulate);
+                            }
                             accumulate = 1;
                         }
                         umma_commit(&b_empty[s]);
@@ -196,140 +250,165 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                     __syncwarp();
                     b_it++;
                 }
-                if (lane == 0) umma_commit(&a_empty[ab]);
+                umma_commit(&a_empty[ab]);
                 __syncwarp();
                 a_it++;
             }
-            if (lane == 0) umma_commit(&acc_full[acb]);
+            umma_commit(&acc_full[acb]);
             __syncwarp();
             acc_it++;
         }
     } else {
-        // ================================================================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
+        // ================================================================= epilogue: warp -> (row half mh, TMEM lane quarter q)
+        // A thread owns one accumulator ROW, but rows are >= 512 B apart in global memory, so global accesses are staged through
+        // a per-warp shared-memory tile and issued row-contiguous (one instruction = 4 rows x 128 B).  The residual chunk for the
+        // next iteration is loaded one chunk ahead.
+        const int q = warp & 3, g = (warp - 2) >> 2;
+        const int mh = NH == 2 ? g : 0;                       // NH == 2: the two warp groups take the two row halves, all columns
+        const int c_lo = NH == 2 ? 0 : g * (NT / 2), c_hi = NH == 2 ? NT : (g + 1) * (NT / 2);   // NH == 1: they split the columns
+        const int slab = mh * 4 + q;
+        const int rloc = mh * UM + q * 32;                    // first row (within the tile) of this warp's 32-row slab
+        float * stg = stage_all + (warp - 2) * (32 * STAGE_PITCH);
+        const int cr = lane >> 3, cc4 = (lane & 7) * 4;      // row-contiguous pattern: step i covers rows 4i + cr, columns cc4..cc4+3
+        const bool do_f = p.outF != nullptr, do_h = p.outH != nullptr, has1 = p.add1 != nullptr, has2 = p.add2 != nullptr;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
             const int nt = tile % e.n_nt, rest = tile / e.n_nt, mt = rest % e.n_mt, b = rest / e.n_mt;
-            const int t = mt * UM + row, n0 = nt * NT;
-            const int lo = p.lenOut ? p.lenOut[b] : p.LmaxOut;
-            const bool valid = t < lo && t < p.LmaxOut;
-            const size_t r = (size_t) b * p.LmaxOut + t;
+            const int n0 = nt * NT;
+            const int tq = mt * TM + rloc;
+            const int lo = min(p.lenOut ? p.lenOut[b] : p.LmaxOut, p.LmaxOut);
+            const int nrows = lo - tq - cr;                          // step i is a valid output row iff 4 * i < nrows
+            const size_t rq = (size_t) b * p.LmaxOut + tq;
+            // per-tile row pointers of the row-contiguous pattern (advanced by 4 rows per step, by 32 columns per chunk)
+            const float * a1p = has1 ? p.add1 + (rq + cr) * p.ldadd1 + n0 + cc4 : nullptr;
+            const float * a2p = has2 ? p.add2 + (rq + cr) * p.ldadd2 + n0 + cc4 : nullptr;
+            float *       ofp = do_f ? p.outF + (rq + cr) * p.ldo + p.coff + n0 + cc4 : nullptr;
+            __half *      ohp = do_h ? p.outH + (rq + cr) * p.ldoh + p.coffh + n0 + cc4 : nullptr;
+            const size_t s1 = 4 * (size_t) p.ldadd1, s2 = 4 * (size_t) p.ldadd2, sf = 4 * (size_t) p.ldo, sh = 4 * (size_t) p.ldoh;
             const int acb = acc_it & 1;
-            mbar_wait(&acc_full[acb], (acc_it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acb * NT);
+            bool waited = false;
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acb * 256 + mh * NT);
 #pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t) c0, v);
+            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                if (e.dbg & 8) break;
                 const int cb = n0 + c0;
-                const bool on = valid && cb < p.N;
-                float f[32];
+                if (e.vec4 && cb + 32 <= p.N) {
+                    // ---- residual rows of this chunk: issued first, they do not depend on the accumulator
+                    float4 r1[8], r2[8];
+                    if (has1) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-                const bool vec = e.vec4 && cb + 32 <= p.N;
-                if (on) {
-                    if (vec) {
-                        if (p.bias) {
+                        for (int i = 0; i < 8; i++) r1[i] = (4 * i < nrows) ? __ldg(reinterpret_cast<const float4 *>(a1p + i * s1 + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (has2) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) { const float4 bb = *reinterpret_cast<const float4 *>(p.bias + cb + j); f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w; }
+                        for (int i = 0; i < 8; i++) r2[i] = (4 * i < nrows) ? __ldg(reinterpret_cast<const float4 *>(a2p + i * s2 + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + cb + cc4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!waited) { mbar_wait(&acc_full[acb], (acc_it >> 1) & 1); tc_fence_after(); waited = true; }
+                    // ---- accumulator rows (one per thread) -> shared tile, then everything below works row-contiguous:
+                    //      one warp instruction = 4 rows x 128 B
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + (uint32_t) c0, v);
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(stg + lane * STAGE_PITCH + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        __syncwarp();
+                    }
+                    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float4 x4 = *reinterpret_cast<const float4 *>(stg + (4 * i + cr) * STAGE_PITCH + cc4);
+                        float x[4] = {x4.x, x4.y, x4.z, x4.w};
+                        if (p.bias) { x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w; }
+                        if (has1) { x[0] = r1[i].x + x[0]; x[1] = r1[i].y + x[1]; x[2] = r1[i].z + x[2]; x[3] = r1[i].w + x[3]; }
+                        if (has2) { x[0] = r2[i].x + x[0]; x[1] = r2[i].y + x[1]; x[2] = r2[i].z + x[2]; x[3] = r2[i].w + x[3]; }
+                        if (p.div != 0.f) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) x[k] = __fdiv_rn(x[k], p.div);
                         }
-                        if (p.add1) {
+                        if (p.act == ACT_GELU_F16LUT) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) { const float4 a = *reinterpret_cast<const float4 *>(p.add1 + r * p.ldadd1 + cb + j); f[j] = a.x + f[j]; f[j + 1] = a.y + f[j + 1]; f[j + 2] = a.z + f[j + 2]; f[j + 3] = a.w + f[j + 3]; }
+                            for (int k = 0; k < 4; k++) x[k] = gelu_f16lut_u(x[k]);
+                        } else if (p.act == ACT_LRELU_02) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) x[k] = (x[k] > 0.f ? x[k] : 0.f) + 0.2f * (x[k] < 0.f ? x[k] : 0.f);
+                        } else if (p.act == ACT_EXP_SIN_11) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) x[k] = (cb + cc4 + k < 11) ? expf(x[k]) : sinf(x[k]);
                         }
-                        if (p.add2) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) { const float4 a = *reinterpret_cast<const float4 *>(p.add2 + r * p.ldadd2 + cb + j); f[j] = a.x + f[j]; f[j + 1] = a.y + f[j + 1]; f[j + 2] = a.z + f[j + 2]; f[j + 3] = a.w + f[j + 3]; }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int c = cb + j;
-                            if (c < p.N) {
-                                if (p.bias) f[j] = f[j] + p.bias[c];
-                                if (p.add1) f[j] = p.add1[r * p.ldadd1 + c] + f[j];
-                                if (p.add2) f[j] = p.add2[r * p.ldadd2 + c] + f[j];
+                        if (4 * i < nrows) {
+                            if (do_f) *reinterpret_cast<float4 *>(ofp + i * sf + c0) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (do_h) {
+                                const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+                                uint2 u;
+                                u.x = *reinterpret_cast<const uint32_t *>(&h0); u.y = *reinterpret_cast<const uint32_t *>(&h1);
+                                *reinterpret_cast<uint2 *>(ohp + i * sh + c0) = u;
                             }
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { cs[k] += x[k]; cq[k] += x[k] * x[k]; }
                         }
                     }
-                    if (p.div != 0.f) {
+                    if (p.statsPart) {
+                        // fused InstanceNorm statistics: per-thread column sums over its 8 rows, then across the 4 row groups of the warp
 #pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = __fdiv_rn(f[j], p.div);
-                    }
-                    if (p.act == ACT_GELU_F16LUT) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = gelu_f16lut_u(f[j]);
-                    } else if (p.act == ACT_LRELU_02) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = (f[j] > 0.f ? f[j] : 0.f) + 0.2f * (f[j] < 0.f ? f[j] : 0.f);
-                    } else if (p.act == ACT_EXP_SIN_11) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = (cb + j < 11) ? expf(f[j]) : sinf(f[j]);
-                    }
-                    if (vec) {
-                        if (p.outF) {
-                            float * o = p.outF + r * p.ldo + p.coff + cb;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        for (int k = 0; k < 4; k++) {
+                            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);  cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 8);
+                            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16); cq[k] += __shfl_xor_sync(0xffffffffu, cq[k], 16);
                         }
-                        if (p.outH) {
-                            __half * o = p.outH + r * p.ldoh + p.coffh + cb;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                                uint4 u;
-                                u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
-                                u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
-                                *reinterpret_cast<uint4 *>(o + j) = u;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int c = cb + j;
-                            if (c < p.N) {
-                                if (p.outF) p.outF[r * p.ldo + p.coff + c] = f[j];
-                                if (p.outH) p.outH[r * p.ldoh + p.coffh + c] = __float2half_rn(f[j]);
-                            }
+                        if (lane < 8) {
+                            float4 * dst = reinterpret_cast<float4 *>(red + (slab * NT + c0 + cc4) * 2);
+                            dst[0] = make_float4(cs[0], cq[0], cs[1], cq[1]);
+                            dst[1] = make_float4(cs[2], cq[2], cs[3], cq[3]);
                         }
                     }
-                }
-                if (p.statsPart) {
-                    // fused InstanceNorm statistics: column sums of the stored values over this warp's 32 rows (butterfly
-                    // reduce-scatter: 31 shuffles leave lane l with column l), staged per warp for the cross-warp combine below
-                    float sq[32];
+                } else {
+                    // ---- generic path (unaligned rows or a ragged last column chunk): lane = column, loop over the 32 rows
+                    if (!waited) { mbar_wait(&acc_full[acb], (acc_it >> 1) & 1); tc_fence_after(); waited = true; }
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + (uint32_t) c0, v);
+                        __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; j++) { if (!on || cb + j >= p.N) f[j] = 0.f; sq[j] = f[j] * f[j]; }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; i++) {
-                            const float send = up ? f[i] : f[i + off], keep = up ? f[i + off] : f[i];
-                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                            const float send2 = up ? sq[i] : sq[i + off], keep2 = up ? sq[i + off] : sq[i];
-                            sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                        for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(stg + lane * STAGE_PITCH + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        __syncwarp();
+                    }
+                    const int c = cb + lane;
+                    const bool cok = c < p.N;
+                    const float bs = (p.bias && cok) ? p.bias[c] : 0.f;
+                    float s0 = 0.f, q0 = 0.f;
+                    const int rmax = min(32, lo - tq);
+#pragma unroll 4
+                    for (int r = 0; r < rmax; r++) {
+                        float x = stg[r * STAGE_PITCH + lane];
+                        if (cok) {
+                            const size_t row = rq + r;
+                            x = x + bs;
+                            if (has1) x = p.add1[row * p.ldadd1 + c] + x;
+                            if (has2) x = p.add2[row * p.ldadd2 + c] + x;
+                            if (p.div != 0.f) x = __fdiv_rn(x, p.div);
+                            if (p.act == ACT_GELU_F16LUT) x = gelu_f16lut_u(x);
+                            else if (p.act == ACT_LRELU_02) x = (x > 0.f ? x : 0.f) + 0.2f * (x < 0.f ? x : 0.f);
+                            else if (p.act == ACT_EXP_SIN_11) x = (c < 11) ? expf(x) : sinf(x);
+                            if (do_f) p.outF[row * p.ldo + p.coff + c] = x;
+                            if (do_h) p.outH[row * p.ldoh + p.coffh + c] = __float2half_rn(x);
+                            s0 += x; q0 += x * x;
                         }
                     }
-                    red[((warp - 2) * NT + c0 + lane) * 2 + 0] = f[0];
-                    red[((warp - 2) * NT + c0 + lane) * 2 + 1] = sq[0];
+                    if (p.statsPart) *reinterpret_cast<float2 *>(red + (slab * NT + c0 + lane) * 2) = make_float2(s0, q0);
                 }
             }
+            if (!waited) { mbar_wait(&acc_full[acb], (acc_it >> 1) & 1); tc_fence_after(); }
             if (p.statsPart) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int te = threadIdx.x - 64;
-                for (int c = te; c < NT; c += 128) {
-                    if (n0 + c < p.N) {
-                        const float s0 = (red[(0 * NT + c) * 2] + red[(1 * NT + c) * 2]) + (red[(2 * NT + c) * 2] + red[(3 * NT + c) * 2]);
-                        const float s1 = (red[(0 * NT + c) * 2 + 1] + red[(1 * NT + c) * 2 + 1]) + (red[(2 * NT + c) * 2 + 1] + red[(3 * NT + c) * 2 + 1]);
-                        float * dst = p.statsPart + (((size_t) b * e.n_mt + mt) * p.N + n0 + c) * 2;
-                        dst[0] = s0; dst[1] = s1;
-                    }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int c = threadIdx.x - 64;
+                if (c < NT && n0 + c < p.N) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int sl = 0; sl < NSLAB; sl++) { const float2 a = *reinterpret_cast<const float2 *>(red + (sl * NT + c) * 2); s0 += a.x; s1 += a.y; }
+                    *reinterpret_cast<float2 *>(p.statsPart + (((size_t) b * e.n_mt + mt) * p.N + n0 + c) * 2) = make_float2(s0, s1);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
@@ -342,7 +421,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * NT) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
@@ -375,9 +454,8 @@ int umma_init() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    constexpr int smem256 = NSTAGE * 256 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 256 * 8, smem128 = NSTAGE * 128 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 128 * 8;
-    if (cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem256) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_TOTAL) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_TOTAL) != cudaSuccess) {
         cudaGetLastError();
         return g_umma_state;
     }
@@ -387,22 +465,33 @@ int umma_init() {
 
 }  // namespace
 
+// rows per work item the kernel will use for these params (layout of statsPart); 0 if the shape is not supported
+int conv_umma_tile_m(const ConvGemmParams & p) {
+    if (p.stride != 1 || p.CinPad % BKC != 0 || p.N < 128 || p.Npad % 128 != 0) return 0;
+    return (p.Npad % 256 == 0) ? 128 : 256;
+}
+
 // returns 0 = launched, 1 = error, 2 = shape not supported here (caller falls back to the mma.sync kernel)
 int conv_umma(Ctx * ctx, const ConvGemmParams & p) {
-    if (p.stride != 1 || p.CinPad % BKC != 0 || p.lda % 8 != 0 || p.N < 128) return 2;
-    const int NT = (p.Npad % 256 == 0 && p.N > 128) ? 256 : (p.Npad % 128 == 0 ? 128 : 0);
-    if (!NT) return 2;
-    const int RA = round_up(UM + (p.KW - 1) * p.dil, 8);
+    if (p.stride != 1 || p.CinPad % BKC != 0 || p.lda % 8 != 0 || p.N < 128 || p.Npad % 128 != 0) return 2;
+    const int NT = (p.Npad % 256 == 0) ? 256 : 128, NH = NT == 256 ? 1 : 2, TM = UM * NH;
+    const int FIXED_BYTES = fixed_bytes(NT);
+    const int RA = round_up(TM + (p.KW - 1) * p.dil, 16);
     if (RA > RA_MAX) return 2;
     if (p.LmaxIn != p.LmaxOut && p.KW > 1) return 2;
     if (umma_init() != 1) return 2;
     if (((uintptr_t) p.A & 15) || ((uintptr_t) p.W & 15)) return 2;
+    UmmaExtra e;
+    e.RA = RA;
+    e.n_abuf = (UMMA_SMEM_TOTAL - FIXED_BYTES - 1024) / (RA * 128);
+    if (e.n_abuf > MAX_ABUF) e.n_abuf = MAX_ABUF;
+    if (e.n_abuf < 2) return 2;
 
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[3] = {(cuuint64_t) p.CinPad, (cuuint64_t) p.LmaxIn, (cuuint64_t) p.B};
         cuuint64_t strides[2] = {(cuuint64_t) p.lda * 2, (cuuint64_t) p.LmaxIn * p.lda * 2};
-        cuuint32_t box[3] = {8, (cuuint32_t) RA, 1};
+        cuuint32_t box[3] = {8, (cuuint32_t) (RA / 2), 1};
         cuuint32_t es[3] = {1, 1, 1};
         if (g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *) p.A, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -422,9 +511,8 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p) {
         zero_tail_rows_kernel<<<grid, 128, 0, ctx->stream>>>(const_cast<__half *>(p.A), p.lda, p.CinPad, p.LmaxIn, p.lenIn, 32);
         B2_LAUNCH_CHECK(ctx);
     }
-    UmmaExtra e;
-    e.RA = RA;
-    e.n_mt = cdiv(p.LmaxOut, UM);
+    { static const int dbg_env = getenv("B2TTS_UMMA_DBG") ? atoi(getenv("B2TTS_UMMA_DBG")) : 0; static const int dbg_lo = getenv("B2TTS_UMMA_DBG_LO") ? atoi(getenv("B2TTS_UMMA_DBG_LO")) : 4096; static const int dbg_hi = getenv("B2TTS_UMMA_DBG_HI") ? atoi(getenv("B2TTS_UMMA_DBG_HI")) : (1 << 30); e.dbg = (p.LmaxOut >= dbg_lo && p.LmaxOut < dbg_hi) ? dbg_env : 0; }
+    e.n_mt = cdiv(p.LmaxOut, TM);
     e.n_nt = cdiv(p.N, NT);
     e.total_tiles = p.B * e.n_mt * e.n_nt;
     auto al4 = [](const void * q, int ld, int off) { return q == nullptr || ((((uintptr_t) q) & 15) == 0 && ld % 4 == 0 && off % 4 == 0); };
@@ -433,15 +521,11 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p) {
     const int grid = e.total_tiles < g_num_sms ? e.total_tiles : g_num_sms;
     {
         const double rows = (double) (p.validRows ? p.validRows : (int64_t) p.B * p.LmaxOut), cin = (double) (p.CinTrue ? p.CinTrue : p.CinPad);
+        snprintf(ctx->tag, sizeof(ctx->tag), "%s N%d K%d C%d L%d B%d d%d", "umma", p.N, p.KW, p.CinPad, p.LmaxOut, p.B, p.dil);
         ctx->prof_begin(PROF_GEMM, 2.0 * rows * p.N * p.KW * cin, rows * cin * 2.0 + (double) p.N * p.KW * cin * 2.0 + rows * p.N * 4.0);
     }
-    if (NT == 256) {
-        constexpr int smem = NSTAGE * 256 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 256 * 8;
-        conv_umma_kernel<256><<<grid, UMMA_THREADS, smem, ctx->stream>>>(p, e, tmA, tmB);
-    } else {
-        constexpr int smem = NSTAGE * 128 * 128 + 2 * A_BUF_BYTES + 256 + 4 * 128 * 8;
-        conv_umma_kernel<128><<<grid, UMMA_THREADS, smem, ctx->stream>>>(p, e, tmA, tmB);
-    }
+    if (NT == 256) conv_umma_kernel<256, 1><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
+    else           conv_umma_kernel<128, 2><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
     ctx->prof_end();
     ctx->umma_launches++;
     B2_LAUNCH_CHECK(ctx);

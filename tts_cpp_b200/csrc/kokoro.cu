@@ -362,7 +362,7 @@ struct Fwd {
         p.statsPart = part;
         const uint64_t before = ctx->umma_launches;
         if (conv_gemm(ctx, p)) return 1;
-        if (ctx->umma_launches != before) return stats_finalize(ctx, part, B, cdiv(L, 128), W.N, sums_out);
+        if (ctx->umma_launches != before) return stats_finalize(ctx, part, B, cdiv(L, conv_umma_tile_m(p)), W.N, sums_out);
         return inorm_stats(ctx, outF, W.N, W.N, B, L, len, sums_out);
     }
 
