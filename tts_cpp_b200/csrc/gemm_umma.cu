@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cuda.h>
 #include <cstdlib>
+#include <type_traits>
 
 namespace b2 {
 namespace {
@@ -270,6 +271,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
         const int rloc = mh * UM + q * 32;                    // first row (within the tile) of this warp's 32-row slab
         float * stg = stage_all + (warp - 2) * (32 * STAGE_PITCH);
         const int cr = lane >> 3, cc4 = (lane & 7) * 4;      // row-contiguous pattern: step i covers rows 4i + cr, columns cc4..cc4+3
+        const bool plain = p.div == 0.f && p.act == ACT_NONE;
         const bool do_f = p.outF != nullptr, do_h = p.outH != nullptr, has1 = p.add1 != nullptr, has2 = p.add2 != nullptr;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
@@ -309,13 +311,15 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                     //      one warp instruction = 4 rows x 128 B
                     {
                         uint32_t v[32];
-                        tmem_ld32(taddr + (uint32_t) c0, v);
+                        if (!(e.dbg & 32)) tmem_ld32(taddr + (uint32_t) c0, v);
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(stg + lane * STAGE_PITCH + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         __syncwarp();
                     }
                     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+                    auto steps = [&](auto plain_tag) {
+                    constexpr bool PLAIN = decltype(plain_tag)::value;   // no division, no activation: the resblock convs
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const float4 x4 = *reinterpret_cast<const float4 *>(stg + (4 * i + cr) * STAGE_PITCH + cc4);
@@ -323,22 +327,24 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                         if (p.bias) { x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w; }
                         if (has1) { x[0] = r1[i].x + x[0]; x[1] = r1[i].y + x[1]; x[2] = r1[i].z + x[2]; x[3] = r1[i].w + x[3]; }
                         if (has2) { x[0] = r2[i].x + x[0]; x[1] = r2[i].y + x[1]; x[2] = r2[i].z + x[2]; x[3] = r2[i].w + x[3]; }
-                        if (p.div != 0.f) {
+                        if constexpr (!PLAIN) {
+                            if (p.div != 0.f) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = __fdiv_rn(x[k], p.div);
-                        }
-                        if (p.act == ACT_GELU_F16LUT) {
+                                for (int k = 0; k < 4; k++) x[k] = __fdiv_rn(x[k], p.div);
+                            }
+                            if (p.act == ACT_GELU_F16LUT) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = gelu_f16lut_u(x[k]);
-                        } else if (p.act == ACT_LRELU_02) {
+                                for (int k = 0; k < 4; k++) x[k] = gelu_f16lut_u(x[k]);
+                            } else if (p.act == ACT_LRELU_02) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = (x[k] > 0.f ? x[k] : 0.f) + 0.2f * (x[k] < 0.f ? x[k] : 0.f);
-                        } else if (p.act == ACT_EXP_SIN_11) {
+                                for (int k = 0; k < 4; k++) x[k] = (x[k] > 0.f ? x[k] : 0.f) + 0.2f * (x[k] < 0.f ? x[k] : 0.f);
+                            } else if (p.act == ACT_EXP_SIN_11) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = (cb + cc4 + k < 11) ? expf(x[k]) : sinf(x[k]);
+                                for (int k = 0; k < 4; k++) x[k] = (cb + cc4 + k < 11) ? expf(x[k]) : sinf(x[k]);
+                            }
                         }
                         if (4 * i < nrows) {
-                            if (do_f) *reinterpret_cast<float4 *>(ofp + i * sf + c0) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (do_f && !(e.dbg & 16)) *reinterpret_cast<float4 *>(ofp + i * sf + c0) = make_float4(x[0], x[1], x[2], x[3]);
                             if (do_h) {
                                 const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
                                 uint2 u;
@@ -349,7 +355,9 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                             for (int k = 0; k < 4; k++) { cs[k] += x[k]; cq[k] += x[k] * x[k]; }
                         }
                     }
-                    if (p.statsPart) {
+                    };
+                    if (plain) steps(std::true_type{}); else steps(std::false_type{});
+                    if (p.statsPart && !(e.dbg & 64)) {
                         // fused InstanceNorm statistics: per-thread column sums over its 8 rows, then across the 4 row groups of the warp
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
