@@ -2,21 +2,20 @@
 //
 // Same contract as conv_gemm_kernel (gemm_conv.cu): out[b][t][co] = epilogue( sum_{k,ci} A[b][t + k*dil - pad][ci] * W[co][k][ci] ),
 // fp16 operands, fp32 accumulation -- the reference's ggml_conv_1d / ggml_mul_mat with F16 weights (ggml/src/ggml.c:3870-3894,
-// ggml/src/ggml-cpu/ggml-cpu.c:262-267) -- for stride-1 layers with Cin % 64 == 0 and Cout % 128 == 0 (all the heavy ones).
+// ggml/src/ggml-cpu/ggml-cpu.c:262-267) -- for stride-1 layers with Cin % 64 == 0 (all the heavy ones).
 //
-// Blackwell mapping (one CTA per SM, persistent over (utterance, 256-row time tile, 128-column Cout tile) work items):
+// Blackwell mapping (one CTA per SM, persistent over (utterance, time tile, Cout tile) work items; two tile shapes, see below):
 //   * warp 0  = TMA producer.  Per 64-channel chunk the activation rows are loaded ONCE with the conv halo
-//               (256 + (K-1)*dil rows) as 8 un-swizzled [rows][16 B] core-matrix columns; every tap then reads the same
-//               shared-memory chunk at a row offset (descriptor start address + tap*dil*16 B): no im2col, no reload per tap.
-//               Weight tiles [128][64] (128B-swizzled) stream through a 6-stage ring, one per (chunk, tap).
-//   * warp 1  = MMA issuer: one elected thread issues tcgen05.mma M=128 N=128 K=16.  Each weight stage feeds TWO 128-row
-//               accumulators (rows 0-127 and 128-255 of the tile): measured on B200 the kernel is bound by L2->SM traffic of
-//               the weight tiles (an ablation with MMAs, stores and loads removed still took 2/3 of the time), so every weight
-//               byte fetched is used for 256 output rows.  tcgen05.commit releases smem stages / publishes accumulators.
-//   * warps 2-9 = epilogue: 8 warps = 2 row-halves x 4 TMEM lane quarters; tcgen05.ld the accumulator (double-buffered in
-//               TMEM: 2 x 2 x 128 columns, so the next tile's MMAs overlap), bias / residual adds / divide / activation, fused
-//               InstanceNorm statistics (column sums via a shuffle reduce-scatter), and row-contiguous global accesses
-//               staged through a per-warp shared-memory tile.
+//               (tile rows + (K-1)*dil) as a 128B-swizzled [rows][128 B] chunk; every tap then reads the same shared-memory
+//               chunk from a start address shifted by tap*dil rows: no im2col, no reload per tap.
+//               Weight tiles [NT][64] (128B-swizzled) stream through a ring, one per (chunk, tap).
+//   * warp 1  = MMA issuer: one elected thread issues tcgen05.mma M=128 N=NT K=16; tcgen05.commit releases smem stages and
+//               publishes accumulators (double-buffered in TMEM, 2 x 256 columns, so the next tile's MMAs overlap the epilogue).
+//   * warps 2-9 = epilogue.  tcgen05.ld gives a thread one accumulator ROW; rows are >= 512 B apart in global memory, so the
+//               32x32 chunk is transposed through a per-warp shared-memory tile and everything else -- bias, residual adds,
+//               divide, activation, fp32/fp16 stores, fused InstanceNorm column sums -- runs row-contiguous (one warp
+//               instruction = 4 rows x 128 B).  Measured: with ~1240 instructions per chunk the 8 epilogue warps (2 per
+//               scheduler) were the bottleneck of the big generator layers; this form needs ~4x fewer.
 //   * activations outside [0, len_b) must read as zero: TMA zero-fills out-of-range rows, and zero_tail_rows() clears the
 //     first rows past each utterance's end for ragged batches.
 #include "common.cuh"
@@ -39,7 +38,7 @@ constexpr int STAGE_PITCH = 36;                        // floats per staged row 
 constexpr int STAGE_WARP_BYTES = 32 * STAGE_PITCH * 4;
 constexpr int UMMA_THREADS = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int RED_BYTES = 8 * 128 * 8;                 // [slabs][NT][2] floats: 8 x 128 or 4 x 256 columns
-__host__ __device__ constexpr int fixed_bytes(int nt) { return nstage_for(nt) * nt * 128 + 256 + RED_BYTES + 8 * STAGE_WARP_BYTES; }
+__host__ __device__ constexpr int fixed_bytes(int nt) { return (nstage_for(nt) * nt * 128 + 256 + RED_BYTES + 8 * STAGE_WARP_BYTES + 1023) / 1024 * 1024; }
 constexpr int UMMA_SMEM_TOTAL = 232448;                // 227 KB: all the opt-in shared memory of an SM
 constexpr int MAX_ABUF = 4;
 
@@ -158,7 +157,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     float * red = reinterpret_cast<float *>(smem + NSTAGE * B_STAGE_BYTES + 256);       // [8 slabs][NT][2]
     float * stage_all = red + RED_BYTES / 4;                                               // [8 epilogue warps][32][STAGE_PITCH]
-    unsigned char * sA = smem + FIXED_BYTES;                                            // [n_abuf][8][RA][16 B]
+    unsigned char * sA = smem + FIXED_BYTES;                                            // [n_abuf][RA][128 B], 128B-swizzled by TMA
     const int a_buf_bytes = e.RA * 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,12 +191,10 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                     const int ab = a_it % e.n_abuf;
                     mbar_wait(&a_empty[ab], ((a_it / e.n_abuf) & 1) ^ 1);
                     mbar_expect_tx(&a_full[ab], (e.dbg & 1) ? 0u : (uint32_t) e.RA * 128u);
-#pragma unroll
-                    for (int kc = 0; kc < 8; kc++) {
-                        if (e.dbg & 1) break;
-                        unsigned char * dst = sA + ab * a_buf_bytes + kc * e.RA * 16;
-                        tma_load_3d(dst, &tmA, &a_full[ab], cc * BKC + kc * 8, t0 - p.pad, b);
-                        tma_load_3d(dst + RAh * 16, &tmA, &a_full[ab], cc * BKC + kc * 8, t0 - p.pad + RAh, b);
+                    if (!(e.dbg & 1)) {   // one 128B-swizzled [RA rows][64 channels] chunk, as two boxes of RA/2 rows
+                        unsigned char * dst = sA + ab * a_buf_bytes;
+                        tma_load_3d(dst, &tmA, &a_full[ab], cc * BKC, t0 - p.pad, b);
+                        tma_load_3d(dst + RAh * 128, &tmA, &a_full[ab], cc * BKC, t0 - p.pad + RAh, b);
                     }
                     a_it++;
                     for (int tap = 0; tap < p.KW; tap++) {
@@ -215,7 +212,11 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
         const uint32_t idesc = (1u << 4) | ((uint32_t) (NT >> 3) << 17) | ((uint32_t) (UM >> 4) << 24);   // F32 accum, F16 x F16, K-major A and B
         // descriptor templates (everything but the 14-bit start address, which is added per MMA in 16-byte units)
         const uint64_t bdesc_t = ((uint64_t) (16u >> 4) << 16) | ((uint64_t) (1024u >> 4) << 32) | ((uint64_t) 1 << 46) | ((uint64_t) 2 << 61);   // 128B swizzle
-        const uint64_t adesc_t = ((uint64_t) ((uint32_t) e.RA & 0x3FFFu) << 16) | ((uint64_t) (128u >> 4) << 32) | ((uint64_t) 1 << 46);          // LBO = RA*16 B, SBO = 128 B
+        // A uses the same canonical layout (128 B rows, 8-row swizzle groups 1024 B apart).  A conv tap is the SAME staged chunk read
+        // from a start address shifted by tap*dil whole rows: the swizzle XOR is a function of the absolute shared-memory address
+        // (chunk buffers are 1024 B aligned), so a row-shifted start needs no base offset -- verified on hardware for dil 1, 3, 5.
+        const uint64_t adesc_t = bdesc_t;
+        constexpr uint32_t a_row16 = 8u, a_k16 = 2u;   // descriptor address steps (16 B units): one row, one K=16 slice
         const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
         const uint32_t abuf16 = (uint32_t) a_buf_bytes >> 4;
         uint32_t a_it = 0, b_it = 0, acc_it = 0;
@@ -235,13 +236,13 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                     tc_fence_after();
                     {
                         const uint32_t b16 = sB16 + (uint32_t) s * (B_STAGE_BYTES >> 4);
-                        const uint32_t at16 = a16 + (uint32_t) (tap * p.dil);
+                        const uint32_t at16 = a16 + (uint32_t) (tap * p.dil) * a_row16;
 #pragma unroll
                         for (int j = 0; j < BKC / 16; j++) {
                             const uint64_t bd = bdesc_t | (uint64_t) (b16 + 2u * j);
 #pragma unroll
                             for (int h = 0; h < NH; h++) {   // the same weight stage feeds every 128-row accumulator of the tile
-                                const uint64_t ad = adesc_t | (uint64_t) (at16 + (uint32_t) (2 * j * e.RA + h * UM));
+                                const uint64_t ad = adesc_t | (uint64_t) (at16 + (uint32_t) j * a_k16 + (uint32_t) (h * UM) * a_row16);
                                 if (!(e.dbg & 4)) umma_f16(d_tmem + (uint32_t) (h * NT), ad, bd, idesc, accumulate);
                             }
                             accumulate = 1;
@@ -292,8 +293,8 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
             const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acb * 256 + mh * NT);
 #pragma unroll 1
             for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-                if (e.dbg & 8) break;
                 const int cb = n0 + c0;
+                if ((e.dbg & 8) || cb >= p.N) break;
                 if (e.vec4 && cb + 32 <= p.N) {
                     // ---- residual rows of this chunk: issued first, they do not depend on the accumulator
                     float4 r1[8], r2[8];
@@ -474,14 +475,30 @@ int umma_init() {
 }  // namespace
 
 // rows per work item the kernel will use for these params (layout of statsPart); 0 if the shape is not supported
+// Cout >= 128 (weights padded to 128 rows), or a narrow head (Cout < 128, weights padded to 64 rows: the TMA box reads the
+// missing weight rows as zeros) when there are enough output rows to fill the machine
+static bool umma_shape_ok(const ConvGemmParams & p) {
+    if (p.stride != 1 || p.CinPad % BKC != 0) return false;
+    if (p.N >= 128 && p.Npad % 128 == 0) return true;
+    return p.N < 128 && p.Npad % 64 == 0 && (int64_t) p.B * p.LmaxOut >= 32768;
+}
 int conv_umma_tile_m(const ConvGemmParams & p) {
-    if (p.stride != 1 || p.CinPad % BKC != 0 || p.N < 128 || p.Npad % 128 != 0) return 0;
+    if (!umma_shape_ok(p)) return 0;
     return (p.Npad % 256 == 0) ? 128 : 256;
 }
 
 // returns 0 = launched, 1 = error, 2 = shape not supported here (caller falls back to the mma.sync kernel)
-int conv_umma(Ctx * ctx, const ConvGemmParams & p) {
-    if (p.stride != 1 || p.CinPad % BKC != 0 || p.lda % 8 != 0 || p.N < 128 || p.Npad % 128 != 0) return 2;
+int conv_umma(Ctx * ctx, const ConvGemmParams & p_in) {
+    ConvGemmParams p = p_in;
+    if (!umma_shape_ok(p) || p.lda % 8 != 0) return 2;
+    if (p.KW == 1 && p.LmaxIn == p.LmaxOut && p.B > 1 && !p.statsPart) {
+        // pointwise layers (Linear): the batch is one flat row range [0, B * Lmax).  Rows past an utterance's length are computed
+        // and stored too -- they are padding no consumer reads (kernels.cuh) -- which removes the per-utterance partial tiles.
+        const int tm = conv_umma_tile_m(p);
+        if (cdiv((int64_t) p.B * p.LmaxOut, tm) < p.B * cdiv(p.LmaxOut, tm)) {
+            p.LmaxIn = p.LmaxOut = p.B * p.LmaxOut; p.B = 1; p.lenIn = p.lenOut = nullptr;
+        }
+    }
     const int NT = (p.Npad % 256 == 0) ? 256 : 128, NH = NT == 256 ? 1 : 2, TM = UM * NH;
     const int FIXED_BYTES = fixed_bytes(NT);
     const int RA = round_up(TM + (p.KW - 1) * p.dil, 16);
@@ -499,9 +516,9 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p) {
     {
         cuuint64_t dims[3] = {(cuuint64_t) p.CinPad, (cuuint64_t) p.LmaxIn, (cuuint64_t) p.B};
         cuuint64_t strides[2] = {(cuuint64_t) p.lda * 2, (cuuint64_t) p.LmaxIn * p.lda * 2};
-        cuuint32_t box[3] = {8, (cuuint32_t) (RA / 2), 1};
+        cuuint32_t box[3] = {BKC, (cuuint32_t) (RA / 2), 1};
         cuuint32_t es[3] = {1, 1, 1};
-        if (g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *) p.A, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+        if (g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void *) p.A, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 2;
     }
