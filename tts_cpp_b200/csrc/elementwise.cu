@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(256) inorm_stats4_kernel(const float * __restr
     }
 }
 
-__global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p) {
+__global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p, const int rows_per_block) {
     const int b = blockIdx.y;
     const int L = p.len[b];
-    const int t0 = blockIdx.x * V4_ROWS;
+    const int t0 = blockIdx.x * rows_per_block;
     if (t0 >= L) return;
-    const int t1 = min(L, t0 + V4_ROWS);
+    const int t1 = min(L, t0 + rows_per_block);
     const int c0 = threadIdx.x * 4, ny = blockDim.y;
     if (c0 >= (p.outH ? p.Cpad : p.C)) return;
     const bool live = c0 < p.C;
@@ -445,6 +445,85 @@ __global__ void albert_attention_kernel(const float * __restrict__ qkv, int Lmax
     }
 }
 
+// head dim 64 (Kokoro's ALBERT): one block per (tile of 16 queries, head, utterance), 128 threads.  Keys / values stream through
+// shared memory in tiles of 64; a thread owns one key (scores) or one output dim (PV) for 8 queries, so every shared-memory read is
+// either a broadcast or conflict-free and there are no shuffle reductions in the inner loops.
+constexpr int ATT_Q = 16, ATT_K = 64, ATT_HD = 64;
+__global__ void __launch_bounds__(128) albert_attention64_kernel(const float * __restrict__ qkv, int Lmax, const int * __restrict__ len, int heads,
+                                                                 float scale, __half * outH, int ldoh, int n_pad) {
+    extern __shared__ float sm[];
+    float * sQ = sm;                               // [16][64]
+    float * sK = sQ + ATT_Q * ATT_HD;              // [64][65]   (keys, later values [64][64])
+    float * sS = sK + ATT_K * (ATT_HD + 1);        // [16][n_pad]
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_Q;
+    const int n = len[b];
+    if (q0 >= n) return;
+    const int D = heads * ATT_HD, tid = threadIdx.x;
+    const int nq = min(ATT_Q, n - q0);
+    const float * base = qkv + (size_t) b * Lmax * 3 * D + h * ATT_HD;
+    for (int i = tid; i < ATT_Q * ATT_HD; i += 128) {
+        const int qi = i >> 6, d = i & 63;
+        sQ[i] = qi < nq ? base[(size_t) (q0 + qi) * 3 * D + d] : 0.f;
+    }
+    const int jj = tid & 63, qg = (tid >> 6) * 8;
+    // ---- scores
+    for (int k0 = 0; k0 < n; k0 += ATT_K) {
+        __syncthreads();
+        for (int i = tid; i < ATT_K * ATT_HD; i += 128) {
+            const int j = i >> 6, d = i & 63;
+            sK[j * (ATT_HD + 1) + d] = (k0 + j < n) ? base[(size_t) (k0 + j) * 3 * D + D + d] : 0.f;
+        }
+        __syncthreads();
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int d = 0; d < ATT_HD; d++) {
+            const float kv = sK[jj * (ATT_HD + 1) + d];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc[u] = fmaf(sQ[(qg + u) * ATT_HD + d], kv, acc[u]);
+        }
+        if (k0 + jj < n) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) sS[(qg + u) * n_pad + k0 + jj] = acc[u] * scale;
+        }
+    }
+    __syncthreads();
+    // ---- softmax: warp per query (ggml_compute_forward_soft_max_f32: max, exp, double sum, scale)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int qi = warp; qi < nq; qi += 4) {
+            float mx = -INFINITY;
+            for (int j = lane; j < n; j += 32) mx = fmaxf(mx, sS[qi * n_pad + j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            double sum = 0.0;
+            for (int j = lane; j < n; j += 32) { const float e = expf(sS[qi * n_pad + j] - mx); sS[qi * n_pad + j] = e; sum += (double) e; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float inv = (float) (1.0 / sum);
+            for (int j = lane; j < n; j += 32) sS[qi * n_pad + j] *= inv;
+        }
+    }
+    // ---- PV: thread = output dim jj for queries qg..qg+7
+    float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < n; k0 += ATT_K) {
+        __syncthreads();
+        for (int i = tid; i < ATT_K * ATT_HD; i += 128) {
+            const int j = i >> 6, d = i & 63;
+            sK[j * ATT_HD + d] = (k0 + j < n) ? base[(size_t) (k0 + j) * 3 * D + 2 * D + d] : 0.f;
+        }
+        __syncthreads();
+        const int kn = min(ATT_K, n - k0);
+        for (int j = 0; j < kn; j++) {
+            const float vv = sK[j * ATT_HD + jj];
+#pragma unroll
+            for (int u = 0; u < 8; u++) out[u] = fmaf(sS[(qg + u) * n_pad + k0 + j], vv, out[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+        if (qg + u < nq) outH[((size_t) b * Lmax + q0 + qg + u) * ldoh + h * ATT_HD + jj] = __float2half_rn(out[u]);
+}
+
 __global__ void duration_tail_kernel(const float * __restrict__ logits, int ldl, int n_bins, int B, int Lmax, const int * __restrict__ len,
                                      float * lens_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,9 +612,11 @@ int adain_apply(Ctx * ctx, const AdainParams & p) {
                         (p.outF == nullptr || ((((uintptr_t) p.outF) & 15) == 0 && p.ldof % 4 == 0));
         if (p.C % 4 == 0 && cw % 4 == 0 && p.ldx % 4 == 0 && cw / 4 <= 256 && al) {
             const int bx = cw / 4, by = 256 / bx > 0 ? 256 / bx : 1;
-            dim3 grid(cdiv(p.Lmax, V4_ROWS), p.B), blk(bx, by);
+            // long sequences: 256 rows per block so the per-block statistics preamble (double-precision mean / variance) is amortised
+            const int rpb4 = p.Lmax >= 8192 ? 256 : V4_ROWS;
+            dim3 grid(cdiv(p.Lmax, rpb4), p.B), blk(bx, by);
             ctx->prof_begin(PROF_NORM, 0.0, (double) p.B * p.Lmax * p.C * (4.0 + (p.outH ? 2.0 : 0.0) + (p.outF ? 4.0 : 0.0)));
-            adain_apply4_kernel<<<grid, blk, 0, ctx->stream>>>(p);
+            adain_apply4_kernel<<<grid, blk, 0, ctx->stream>>>(p, rpb4);
             ctx->prof_end();
             B2_LAUNCH_CHECK(ctx);
             return 0;
@@ -654,6 +735,18 @@ int embed_rows_h(Ctx * ctx, const int * tokens, const int * tok_off, const __hal
 
 int albert_attention(Ctx * ctx, const float * qkv, int B, int Lmax, const int * len, int heads, int hd, float scale, __half * outH, int ldoh) {
     if (hd > 128) { set_error("albert_attention: head dim %d > 128", hd); return 1; }
+    if (hd == ATT_HD) {
+        const int n_pad = Lmax + 1;
+        const size_t smem64 = (size_t) (ATT_Q * ATT_HD + ATT_K * (ATT_HD + 1) + ATT_Q * n_pad) * sizeof(float);
+        if (smem64 <= 200 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(albert_attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+            dim3 grid64(cdiv(Lmax, ATT_Q), heads, B);
+            albert_attention64_kernel<<<grid64, 128, smem64, ctx->stream>>>(qkv, Lmax, len, heads, scale, outH, ldoh, n_pad);
+            B2_LAUNCH_CHECK(ctx);
+            return 0;
+        }
+    }
     const size_t smem = (size_t) (8 * hd + 8 * Lmax) * sizeof(float);
     dim3 grid(cdiv(Lmax, 8), heads, B);
     albert_attention_kernel<<<grid, 256, smem, ctx->stream>>>(qkv, Lmax, len, heads, hd, scale, outH, ldoh);
