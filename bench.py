@@ -5,14 +5,14 @@
 
 One "step" = one pass of the hot path (duration pass + generation pass of the whole batch) through the public C-ABI call
 (b2tts_kokoro_run_batch) with HOST buffers in and out.  N > 1: launched by torchrun, one rank per GPU, each rank runs its own
-batch of 32 independent utterances (weak scaling, no data-path collective); NCCL is used for the barrier, the max-over-ranks
-of the timings and the gather of PCM to rank 0 (inside the e2e region).
+batch of 32 independent utterances (weak scaling, no data-path collective: every rank returns its own shard's audio); NCCL is
+used only for the barrier and the max-over-ranks of the timings.
 
   value      : audio-s/s from CUDA-event device time of the forward (events on the library's launching stream)
   e2e.value  : audio-s/s from wall time of the same calls incl. H2D of tokens and D2H of PCM into pinned host memory
   roofline   : the dominant kernel (conv_gemm, tensor-bound): algorithmic FLOPs / CUDA-event time of its launches, live
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref/kokoro_ref, built from /root/reference by
-               oracle/Makefile) on the host cores, as P worker processes x 8 ggml threads (its own server's
+               oracle/Makefile) on the host cores, as P worker processes x 4 ggml threads (its own server's
                n-parallelism model, examples/server/server.cpp:225-321), on a bounded sample of the same prompts.
 """
 from __future__ import annotations
@@ -56,39 +56,79 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 10 ms (nvidia-smi -lms fallback)."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
         self.gpu = gpu_index
+        self.sm, self.mx, self.reasons = [], 0.0, set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
 
-    def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu), "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.01)
+
+    def _smi_loop(self, proc):
+        for line in proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[0])); self.mx = max(self.mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, args=(self.proc,), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.source = None
+
+    def stop(self):
+        self.stop_flag.set()
+        if getattr(self, "proc", None):
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        sm = list(self.sm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, threads: int = 4):
@@ -175,17 +215,7 @@ def main():
     h2d_bytes = sum(len(p) for p in prompts) * 4
 
     def step():
-        pcms, durs = runner.run_batch(prompts)
-        if dist is not None:   # gather PCM to rank 0 over NCCL/NVLink (e2e only)
-            flat = torch.from_numpy(np.concatenate(pcms)).cuda(non_blocking=True)
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)] if rank == 0 else None
-            dist.gather(torch.tensor([flat.numel()], dtype=torch.int64, device="cuda"), sizes, dst=0)
-            if rank == 0:
-                bufs = [torch.empty(int(s.item()), dtype=torch.float32, device="cuda") for s in sizes]
-                dist.gather(flat, bufs, dst=0)
-                _ = [b.cpu() for b in bufs]
-            else:
-                dist.gather(flat, None, dst=0)
+        pcms, durs = runner.run_batch(prompts, copy=False)   # PCM stays in the runner's pinned host buffers
         return pcms
 
     for _ in range(max(args.warmup, 3)):
@@ -240,17 +270,18 @@ def main():
     ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     line = {
         "metric": "audio_seconds_per_second", "value": audio_total * args.steps / (dev_ms * 1e-3), "unit": "audio-s/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall * 1e3 / args.steps,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate / activations",
         "data": "synthetic",
         "config": {"workload": "Kokoro-82M fp16 GGUF (synthetic weights, 81.3 M params), batch 32 x 64-char (66-token) prompts per GPU, greedy durations, 24 kHz",
                    "batch_per_gpu": BATCH, "audio_s_per_step_per_gpu": audio_s, "l2": "activations (GBs per step) and weights (164 MB) exceed the 126 MB L2; no flush needed",
-                   "value_timing": "CUDA events on the library stream around duration+generation passes (incl. the mid-forward host sync for durations)"},
+                   "value_timing": "CUDA events on the library stream around duration+generation passes (incl. the mid-forward host sync for durations), max over ranks; ms_per_step is this device time"},
         "e2e": {"value": audio_total * args.steps / wall, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
-                "note": "host token ids in, PCM in pinned host memory out, through b2tts_kokoro_run_batch" + ("; plus NCCL gather of PCM to rank 0" if world > 1 else "")},
+                "ms_per_step": wall * 1e3 / args.steps,
+                "note": "wall clock, max over ranks: host token ids in, PCM in pinned host memory out, through b2tts_kokoro_run_batch (each rank keeps its own shard's audio)"},
         "gpu_launches": int(launches), "gemm_dispatch": dict(zip(("tcgen05_tma", "mma_sync_fallback"), ctx.gemm_launches())),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (implicit-GEMM Conv1d/Linear, fp16 mma.sync, fp32 accumulate)", "achieved": ach, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (persistent tcgen05 + TMA implicit-GEMM Conv1d/Linear, fp16 operands, fp32 TMEM accumulators; all conv_gemm launches incl. the few mma.sync fallbacks)", "achieved": ach, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "launches_per_step": g["launches"] / args.steps,
                      "share_of_device_time": g["ms"] / dev_ms if dev_ms else None},
         "kernel_classes_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},

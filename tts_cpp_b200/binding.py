@@ -161,8 +161,10 @@ class KokoroRunner:
     def weight_bytes(self) -> int:
         return int(lib().b2tts_kokoro_weight_bytes(self.h))
 
-    def run_batch(self, utterances, voice: str | None = None, noise_skip=None):
-        """utterances: list of token-id lists (BOS/EOS included).  Returns (list of pcm arrays, list of duration arrays)."""
+    def run_batch(self, utterances, voice: str | None = None, noise_skip=None, copy: bool = True):
+        """utterances: list of token-id lists (BOS/EOS included).  Returns (list of pcm arrays, list of duration arrays).
+        copy=False returns views of the runner's pinned host buffers, valid until its next call -- the lifetime the reference
+        gives tts_response::data (include/common.h), and what a server would hand to its encoder."""
         B = len(utterances)
         ntok = np.array([len(u) for u in utterances], np.int32)
         toks = np.ascontiguousarray(np.concatenate([np.asarray(u, np.uint32) for u in utterances]))
@@ -176,7 +178,8 @@ class KokoroRunner:
                                           voice.encode() if voice else None, skip, pcm, ns, C.byref(dur)))
         outs, durs, off = [], [], 0
         for b in range(B):
-            outs.append(np.ctypeslib.as_array(pcm[b], shape=(int(ns[b]),)).copy() if ns[b] else np.zeros(0, np.float32))
+            a = np.ctypeslib.as_array(pcm[b], shape=(int(ns[b]),)) if ns[b] else np.zeros(0, np.float32)
+            outs.append(a.copy() if copy else a)
             durs.append(np.ctypeslib.as_array(dur, shape=(int(ntok.sum()),))[off:off + int(ntok[b])].copy())
             off += int(ntok[b])
         return outs, durs

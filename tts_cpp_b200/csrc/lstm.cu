@@ -88,13 +88,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
     __syncthreads();
     cluster.sync();
 
-    for (int s = 0; s < nsteps; s++) {
-        const __half * hcur = sH + (size_t) (s & 1) * NBT * LDW;
-        __half *       hnxt = sH + (size_t) ((s + 1) & 1) * NBT * LDW;
-
-        // 1. input-side pre-activations for this step (one float4 = gates i,f,g,o of (b, t, dir, unit))
-        float4 xp[2][2];
-        int    tt[2][2];
+    // input-side pre-activations of a step (one float4 = gates i,f,g,o of (b, t, dir, unit)); loaded one step ahead, while the
+    // cluster barrier of the previous step is in flight, so their L2 latency is off the recurrence's critical path
+    float4 xp[2][2];
+    int    tt[2][2];
+    auto load_xp = [&](int s) {
 #pragma unroll
         for (int ni = 0; ni < 2; ni++)
 #pragma unroll
@@ -108,6 +106,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
                     xp[ni][e] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+    };
+    load_xp(0);
+
+    for (int s = 0; s < nsteps; s++) {
+        const __half * hcur = sH + (size_t) (s & 1) * NBT * LDW;
+        __half *       hnxt = sH + (size_t) ((s + 1) & 1) * NBT * LDW;
 
         // 2. G = W_hh_slice . h^T on tensor cores: 2 m16 tiles (i|f , g|o) x 2 n8 tiles per warp
         float acc[2][2][4];
@@ -171,7 +175,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
             int4 * dst = reinterpret_cast<int4 *>(cluster.map_shared_rank(dst_local, dest));
             *dst = v;
         }
-        cluster.sync();
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        if (s + 1 < nsteps) load_xp(s + 1);
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 }
 
