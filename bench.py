@@ -232,11 +232,13 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     dev_ms = 0.0
+    pass_ms = [0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
         tm = runner.timings()
         dev_ms += tm["duration_ms"] + tm["generation_ms"]
+        pass_ms[0] += tm["duration_ms"]; pass_ms[1] += tm["generation_ms"]
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -286,6 +288,7 @@ def main():
                      "share_of_device_time": g["ms"] / dev_ms if dev_ms else None},
         "kernel_classes_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         "device_ms_per_step": dev_ms / args.steps,
+        "pass_ms_per_step": {"duration_pass": pass_ms[0] / args.steps, "generation_pass": pass_ms[1] / args.steps},
     }
     if world == 1 and not args.no_cpu_baseline:
         base, why = reference_throughput(n_timed=1, n_warm=1)

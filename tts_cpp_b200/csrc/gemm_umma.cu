@@ -272,7 +272,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
         const int rloc = mh * UM + q * 32;                    // first row (within the tile) of this warp's 32-row slab
         float * stg = stage_all + (warp - 2) * (32 * STAGE_PITCH);
         const int cr = lane >> 3, cc4 = (lane & 7) * 4;      // row-contiguous pattern: step i covers rows 4i + cr, columns cc4..cc4+3
-        const bool plain = p.div == 0.f && p.act == ACT_NONE;
+        const int emode = (p.div == 0.f && p.act == ACT_NONE) ? 0 : (p.act == ACT_NONE ? 1 : ((p.div == 0.f && p.act == ACT_GELU_F16LUT) ? 2 : 3));
         const bool do_f = p.outF != nullptr, do_h = p.outH != nullptr, has1 = p.add1 != nullptr, has2 = p.add2 != nullptr;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
@@ -319,8 +319,10 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                         __syncwarp();
                     }
                     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-                    auto steps = [&](auto plain_tag) {
-                    constexpr bool PLAIN = decltype(plain_tag)::value;   // no division, no activation: the resblock convs
+                    auto steps = [&](auto mode_tag) {
+                    // compile-time epilogue flavour: 0 plain (no division, no activation: the resblock convs), 1 division only
+                    // (AdaIN decoder blocks), 2 GELU only (ALBERT FFN), 3 anything
+                    constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const float4 x4 = *reinterpret_cast<const float4 *>(stg + (4 * i + cr) * STAGE_PITCH + cc4);
@@ -328,7 +330,13 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                         if (p.bias) { x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w; }
                         if (has1) { x[0] = r1[i].x + x[0]; x[1] = r1[i].y + x[1]; x[2] = r1[i].z + x[2]; x[3] = r1[i].w + x[3]; }
                         if (has2) { x[0] = r2[i].x + x[0]; x[1] = r2[i].y + x[1]; x[2] = r2[i].z + x[2]; x[3] = r2[i].w + x[3]; }
-                        if constexpr (!PLAIN) {
+                        if constexpr (MODE == 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) x[k] = __fdiv_rn(x[k], p.div);
+                        } else if constexpr (MODE == 2) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) x[k] = gelu_f16lut_u(x[k]);
+                        } else if constexpr (MODE == 3) {
                             if (p.div != 0.f) {
 #pragma unroll
                                 for (int k = 0; k < 4; k++) x[k] = __fdiv_rn(x[k], p.div);
@@ -357,7 +365,10 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                         }
                     }
                     };
-                    if (plain) steps(std::true_type{}); else steps(std::false_type{});
+                    if (emode == 0) steps(std::integral_constant<int, 0>{});
+                    else if (emode == 1) steps(std::integral_constant<int, 1>{});
+                    else if (emode == 2) steps(std::integral_constant<int, 2>{});
+                    else steps(std::integral_constant<int, 3>{});
                     if (p.statsPart && !(e.dbg & 64)) {
                         // fused InstanceNorm statistics: per-thread column sums over its 8 rows, then across the 4 row groups of the warp
 #pragma unroll

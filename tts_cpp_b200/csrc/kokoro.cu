@@ -393,11 +393,12 @@ struct Fwd {
         ap.goff = k.n1.goff; ap.boff = k.n1.boff; ap.act = NACT_LRELU02;
         if (k.pool) {
             if (Lout != 2 * Lin) { set_error("ada_block: pool expects Lout == 2*Lin"); return 1; }
-            float * tmp = al<float>((size_t) B * Lin * k.cin);
+            const int ldt = round_up(k.cin, 4);
+            float * tmp = al<float>((size_t) B * Lin * ldt);
             if (fail) return 1;
-            ap.outF = tmp; ap.ldof = k.cin;
+            ap.outF = tmp; ap.ldof = ldt;
             if (adain_apply(ctx, ap)) return 1;
-            if (pool_convt(ctx, tmp, k.cin, k.cin, B, Lin, lenIn, k.poolw, k.poolb, a16, k.conv1.CinPad, k.conv1.CinPad)) return 1;
+            if (pool_convt(ctx, tmp, ldt, k.cin, B, Lin, lenIn, k.poolw, k.poolb, a16, k.conv1.CinPad, k.conv1.CinPad)) return 1;
         } else {
             ap.outH = a16; ap.ldoh = k.conv1.CinPad; ap.Cpad = k.conv1.CinPad;
             if (adain_apply(ctx, ap)) return 1;
@@ -648,23 +649,26 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     float * dec = Gf.al<float>((size_t) B * L2 * 512);
     {
         const size_t mark = a2.off;
-        float * x0 = Gf.al<float>((size_t) B * L1 * 514); __half * asr16 = Gf.al<__half>((size_t) B * L1 * 512);
+        // concat buffers are padded to a row pitch that is a multiple of 4 floats (514 -> 516, 1090 -> 1092) so every kernel takes its
+        // 16-byte path; the pad columns are never read as channels
+        constexpr int LD514 = 516, LD1090 = 1092;
+        float * x0 = Gf.al<float>((size_t) B * L1 * LD514); __half * asr16 = Gf.al<__half>((size_t) B * L1 * 512);
         float * side = Gf.al<float>((size_t) B * L1 * 66);
-        float * xin[2] = {Gf.al<float>((size_t) B * L1 * 1090), Gf.al<float>((size_t) B * L1 * 1090)};
+        float * xin[2] = {Gf.al<float>((size_t) B * L1 * LD1090), Gf.al<float>((size_t) B * L1 * LD1090)};
         if (Gf.fail) return 1;
-        if (gather_rows(ctx, t_en, 512, Nmax, d_idx, 512, B, L1, lT, x0, 514, asr16, 512, 512)) return 1;        // asr = t_en . mask
+        if (gather_rows(ctx, t_en, 512, Nmax, d_idx, 512, B, L1, lT, x0, LD514, asr16, 512, 512)) return 1;        // asr = t_en . mask
         if (curve_conv_s2(ctx, f0, L2, B, lT, L1, l2T, f0_conv_w, f0_conv_b, side, 66, 64)) return 1;
         if (curve_conv_s2(ctx, nc, L2, B, lT, L1, l2T, n_conv_w, n_conv_b, side, 66, 65)) return 1;
         if (Gf.gemm(asr16, 512, asr_conv, asr_conv_b, L1, L1, lT, lT, 1, 1, 0, side, 66, 0)) return 1;            // asr_res
-        if (copy_cols(ctx, side, 66, 64, x0, 514, 512, 2, B, L1, lT)) return 1;
-        if (Gf.tap("dec_in", x0, (int64_t) B * L1, 514, 514, L1)) return 1;
-        if (copy_cols(ctx, side, 66, 0, xin[0], 1090, 1024, 66, B, L1, lT)) return 1;
-        if (copy_cols(ctx, side, 66, 0, xin[1], 1090, 1024, 66, B, L1, lT)) return 1;
-        if (Gf.ada_block(enc_block, gbD, sty_n[1], x0, 514, L1, lT, L1, lT, xin[0], 1090, 0)) return 1;
+        if (copy_cols(ctx, side, 66, 64, x0, LD514, 512, 2, B, L1, lT)) return 1;
+        if (Gf.tap("dec_in", x0, (int64_t) B * L1, 514, LD514, L1)) return 1;
+        if (copy_cols(ctx, side, 66, 0, xin[0], LD1090, 1024, 66, B, L1, lT)) return 1;
+        if (copy_cols(ctx, side, 66, 0, xin[1], LD1090, 1024, 66, B, L1, lT)) return 1;
+        if (Gf.ada_block(enc_block, gbD, sty_n[1], x0, LD514, L1, lT, L1, lT, xin[0], LD1090, 0)) return 1;
         for (int i = 0; i < 4; i++) {
             const size_t mk2 = a2.off;
-            if (i < 3) { if (Gf.ada_block(dec_blocks[i], gbD, sty_n[1], xin[i & 1], 1090, L1, lT, L1, lT, xin[(i + 1) & 1], 1090, 0)) return 1; }
-            else       { if (Gf.ada_block(dec_blocks[i], gbD, sty_n[1], xin[i & 1], 1090, L1, lT, L2, l2T, dec, 512, 0)) return 1; }
+            if (i < 3) { if (Gf.ada_block(dec_blocks[i], gbD, sty_n[1], xin[i & 1], LD1090, L1, lT, L1, lT, xin[(i + 1) & 1], LD1090, 0)) return 1; }
+            else       { if (Gf.ada_block(dec_blocks[i], gbD, sty_n[1], xin[i & 1], LD1090, L1, lT, L2, l2T, dec, 512, 0)) return 1; }
             a2.off = mk2;
         }
         a2.off = mark;
