@@ -3,6 +3,7 @@
 // channels (coalesced), per-channel parameters live in registers, and each kernel fuses the chain of GGML nodes the
 // reference spends separate passes on (norm -> mul -> add -> add -> leaky_relu/snake -> cont(transpose) -> fp16 im2col).
 #include "kernels.cuh"
+#include <type_traits>
 #include <math.h>
 
 namespace b2 {
@@ -154,7 +155,9 @@ __global__ void __launch_bounds__(256) inorm_stats4_kernel(const float * __restr
 
 // RAGGED: C is not a multiple of 4 (rows padded to ldx % 4 == 0): per-channel liveness checks, kept out of the common instantiation
 // because a per-element test in the inner loop cost 18 % on the 585 MB generator tensors
-template <bool RAGGED>
+// ACT (NACT_*) and the output flavour are template constants so that the 4 x 4 unrolled element chains of an iteration form one
+// basic block and interleave (runtime-uniform `if`s inside the loop ended a block per element and serialised them)
+template <bool RAGGED, int ACT, bool OUTH, bool OUTF>
 __global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p, const int rows_per_block) {
     const int b = blockIdx.y;
     const int L = p.len[b];
@@ -192,26 +195,23 @@ __global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p, 
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int tt = t + u * ny;
-            if (tt >= t1) continue;
+            const bool ok = tt < t1;
             float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            if (live) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (RAGGED && c0 + k >= p.C) { f[k] = 0.f; continue; }
-                    const float n = (f[k] - mean[k]) * rstd[k];
-                    float w = (n + n * gam[k]) + bet[k];
-                    if (p.act == NACT_LRELU02) w = lrelu(w, 0.2f);
-                    else if (p.act == NACT_SNAKE) { const float sn = sin_snake(w * al[k]); w = w + (sn * sn) * ial[k]; }
-                    f[k] = w;
-                }
+            for (int k = 0; k < 4; k++) {
+                const float n = (f[k] - mean[k]) * rstd[k];
+                float w = (n + n * gam[k]) + bet[k];
+                if constexpr (ACT == NACT_LRELU02) w = lrelu(w, 0.2f);
+                else if constexpr (ACT == NACT_SNAKE) { const float sn = sin_snake(w * al[k]); w = w + (sn * sn) * ial[k]; }
+                f[k] = (RAGGED ? (c0 + k < p.C) : live) ? w : 0.f;     // pad channels of the fp16 operand are zeros
             }
             const size_t orow = (size_t) b * p.Lmax + tt;
-            if (p.outH) {
+            if constexpr (OUTH) {
                 __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
                 uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                *reinterpret_cast<uint2 *>(p.outH + orow * p.ldoh + c0) = pk;
+                if (ok) *reinterpret_cast<uint2 *>(p.outH + orow * p.ldoh + c0) = pk;
             }
-            if (p.outF && live) *reinterpret_cast<float4 *>(p.outF + orow * p.ldof + c0) = make_float4(f[0], f[1], f[2], f[3]);
+            if constexpr (OUTF) { if (ok && live) *reinterpret_cast<float4 *>(p.outF + orow * p.ldof + c0) = make_float4(f[0], f[1], f[2], f[3]); }
         }
     }
 }
@@ -612,6 +612,7 @@ int inorm_stats(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, con
 
 int adain_apply(Ctx * ctx, const AdainParams & p) {
     if (p.C > KMAX * 256 || p.Cpad > KMAX * 256) { set_error("adain_apply: C=%d too large", p.C); return 1; }
+    if (!p.outH && !p.outF) { set_error("adain_apply: no output"); return 1; }
     {
         const int cw = p.outH ? p.Cpad : p.C;
         const bool al = (((uintptr_t) p.x) & 15) == 0 && (p.outH == nullptr || ((((uintptr_t) p.outH) & 7) == 0 && p.ldoh % 4 == 0)) &&
@@ -622,8 +623,21 @@ int adain_apply(Ctx * ctx, const AdainParams & p) {
             const int rpb4 = p.Lmax >= 8192 ? 256 : V4_ROWS;
             dim3 grid(cdiv(p.Lmax, rpb4), p.B, cdiv(groups, bx)), blk(bx, by);
             ctx->prof_begin(PROF_NORM, 0.0, (double) p.B * p.Lmax * p.C * (4.0 + (p.outH ? 2.0 : 0.0) + (p.outF ? 4.0 : 0.0)));
-            if (p.C % 4 == 0) adain_apply4_kernel<false><<<grid, blk, 0, ctx->stream>>>(p, rpb4);
-            else              adain_apply4_kernel<true><<<grid, blk, 0, ctx->stream>>>(p, rpb4);
+            // the generator's snake applies (fp16 operand only) get the fully specialised instantiation; the decoder's leaky-relu ones too
+            auto launch = [&](auto ragged, auto act, auto oh, auto of) {
+                adain_apply4_kernel<decltype(ragged)::value, decltype(act)::value, decltype(oh)::value, decltype(of)::value><<<grid, blk, 0, ctx->stream>>>(p, rpb4);
+            };
+            using T = std::true_type; using F = std::false_type;
+            const bool rg = p.C % 4 != 0, oh = p.outH != nullptr, of = p.outF != nullptr;
+            auto by_out = [&](auto ragged, auto act) {
+                if (oh && !of) launch(ragged, act, T{}, F{}); else if (!oh && of) launch(ragged, act, F{}, T{}); else launch(ragged, act, T{}, T{});
+            };
+            auto by_act = [&](auto ragged) {
+                if (p.act == NACT_SNAKE) by_out(ragged, std::integral_constant<int, NACT_SNAKE>{});
+                else if (p.act == NACT_LRELU02) by_out(ragged, std::integral_constant<int, NACT_LRELU02>{});
+                else by_out(ragged, std::integral_constant<int, NACT_NONE>{});
+            };
+            if (rg) by_act(T{}); else by_act(F{});
             ctx->prof_end();
             B2_LAUNCH_CHECK(ctx);
             return 0;
