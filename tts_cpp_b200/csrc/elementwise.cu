@@ -272,6 +272,35 @@ __global__ void row_norm_kernel(const RowNormParams p) {
 }
 
 // ---------------------------------------------------------------- helpers
+// 16-byte flavour of cast_rows (C % 4 == 0, aligned rows): thread = 4 channels x 4 rows in flight
+__global__ void __launch_bounds__(256) cast_rows4_kernel(const float * __restrict__ x, int ldx, int C, int LmaxIn, const int * __restrict__ lenOut, int LmaxOut,
+                                                         int up2, float ns, __half * outH, int ldoh, int Cpad, int rows_per_block) {
+    const int b = blockIdx.y;
+    const int L = lenOut[b];
+    const int t0 = blockIdx.x * rows_per_block;
+    if (t0 >= L) return;
+    const int t1 = min(L, t0 + rows_per_block);
+    const int c0 = threadIdx.x * 4, ny = blockDim.y;
+    if (c0 >= Cpad) return;
+    const bool live = c0 < C;
+    const float * xb = x + (size_t) b * LmaxIn * ldx + c0;
+    for (int t = t0 + threadIdx.y; t < t1; t += 4 * ny) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int tt = t + u * ny;
+            v[u] = (live && tt < t1) ? *reinterpret_cast<const float4 *>(xb + (size_t) (up2 ? (tt >> 1) : tt) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int tt = t + u * ny;
+            const __half2 h0 = __floats2half2_rn(lrelu(v[u].x, ns), lrelu(v[u].y, ns)), h1 = __floats2half2_rn(lrelu(v[u].z, ns), lrelu(v[u].w, ns));
+            uint2 pk; pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+            if (tt < t1) *reinterpret_cast<uint2 *>(outH + ((size_t) b * LmaxOut + tt) * ldoh + c0) = pk;
+        }
+    }
+}
+
 __global__ void cast_rows_kernel(const float * __restrict__ x, int ldx, int C, int LmaxIn, const int * __restrict__ lenOut, int LmaxOut, int up2,
                                  float ns, __half * outH, int ldoh, int Cpad) {
     const int b = blockIdx.y;
@@ -671,6 +700,14 @@ int row_norm(Ctx * ctx, const RowNormParams & p) {
 
 int cast_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, const int * lenOut, int LmaxOut, int up2, float ns, __half * outH,
               int ldoh, int Cpad) {
+    if (C % 4 == 0 && Cpad % 4 == 0 && ldx % 4 == 0 && ldoh % 4 == 0 && Cpad / 4 <= 256 && ((((uintptr_t) x) & 15) == 0) && ((((uintptr_t) outH) & 7) == 0)) {
+        const int bx = Cpad / 4, by = 256 / bx > 0 ? 256 / bx : 1;
+        const int rows = LmaxOut >= 8192 ? 256 : 64;
+        dim3 grid4(cdiv(LmaxOut, rows), B), blk4(bx, by);
+        cast_rows4_kernel<<<grid4, blk4, 0, ctx->stream>>>(x, ldx, C, LmaxIn, lenOut, LmaxOut, up2, ns, outH, ldoh, Cpad, rows);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     int rpb; dim3 blk = row_block(Cpad, rpb);
     dim3 grid(cdiv(LmaxOut, rpb), B);
     cast_rows_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, LmaxIn, lenOut, LmaxOut, up2, ns, outH, ldoh, Cpad);

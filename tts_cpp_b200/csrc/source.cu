@@ -84,6 +84,15 @@ __global__ void f0_phase_kernel(const float * __restrict__ f0, int L2max, const 
 }
 
 // ---------------------------------------------------------------- harmonic source: upsample, sin, uv/noise, m_source linear, tanh
+// sine of the (large: up to ~4e5 rad) accumulated phase.  sinf() takes its slow Payne-Hanek path above 1e5; reducing in double
+// (x - k*2pi with 2pi split hi/lo, error < 1e-10) and calling sinf on the small remainder is as accurate and several times cheaper.
+__device__ __forceinline__ float sin_phase(float x) {
+    const double xd = (double) x;
+    const double k = rint(xd * 0.15915494309189535);
+    double r = fma(-k, 6.283185307179586, xd);
+    r = fma(-k, 2.4492935982947064e-16, r);
+    return sinf((float) r);
+}
 constexpr int SRC_RUN = 16;  // consecutive samples per thread (amortises the LCG jump-ahead)
 __global__ void source_har_kernel(const SourceParams p) {
     const int b = blockIdx.y;
@@ -112,7 +121,7 @@ __global__ void source_har_kernel(const SourceParams p) {
                 const bool voiced = fv > 10.0f;
                 const float uv = voiced ? 0.1f : 0.0f;
                 const float nz = voiced ? 0.003f * u : (0.1f / 3.0f) * u;
-                const float sv = sinf(upscale_linear_at(ph, L2, 300, j)) * uv + nz;
+                const float sv = sin_phase(upscale_linear_at(ph, L2, 300, j)) * uv + nz;
                 if (p.sing) p.sing[((size_t) b * p.Smax + j) * 9 + h] = sv;
                 // m_source_weight is stored F16 -> activation re-rounded to fp16; ggml_vec_dot_f16 tail accumulates in double
                 acc[r] += (double) (__half2float(__float2half_rn(sv)) * wh);
@@ -143,6 +152,7 @@ __global__ void stft20_kernel(const float * __restrict__ har, int Smax, const in
         fr[i] = x[ai] * c_hann20[i];
     }
     const size_t row = (size_t) b * Fmax + f;
+    float mg[11], an[11];
 #pragma unroll
     for (int k = 0; k <= 10; k++) {
         float re = 0.f, im = 0.f;
@@ -155,10 +165,33 @@ __global__ void stft20_kernel(const float * __restrict__ har, int Smax, const in
         if (k == 0 || k == 10) im = 0.0f;   // the reference's radix-2/DFT yields exactly +0.0 here for a real frame
         const float mag = sqrtf(re * re + im * im);
         const float ang = atan2f(im, re);
-        if (outH) { outH[row * ldoh + k] = __float2half_rn(mag); outH[row * ldoh + 11 + k] = __float2half_rn(ang); }
+        mg[k] = mag; an[k] = ang;
         if (outF) { outF[row * ldof + k] = mag; outF[row * ldof + 11 + k] = ang; }
     }
-    if (outH) for (int c = 22; c < Cpad; c++) outH[row * ldoh + c] = __float2half_rn(0.f);
+    if (outH) {
+        __half * o = outH + row * ldoh;
+        if (Cpad % 8 == 0 && Cpad >= 24 && ldoh % 8 == 0 && ((((uintptr_t) outH) & 15) == 0)) {
+            // the operand row (22 values + zero pad channels) leaves as 16-byte stores: a row is one or two full 64-byte sectors
+            __half hv[24];
+#pragma unroll
+            for (int k = 0; k < 11; k++) { hv[k] = __float2half_rn(mg[k]); hv[11 + k] = __float2half_rn(an[k]); }
+            hv[22] = hv[23] = __float2half_rn(0.f);
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                uint4 u;
+                u.x = (uint32_t) __half_as_ushort(hv[8 * q]) | ((uint32_t) __half_as_ushort(hv[8 * q + 1]) << 16);
+                u.y = (uint32_t) __half_as_ushort(hv[8 * q + 2]) | ((uint32_t) __half_as_ushort(hv[8 * q + 3]) << 16);
+                u.z = (uint32_t) __half_as_ushort(hv[8 * q + 4]) | ((uint32_t) __half_as_ushort(hv[8 * q + 5]) << 16);
+                u.w = (uint32_t) __half_as_ushort(hv[8 * q + 6]) | ((uint32_t) __half_as_ushort(hv[8 * q + 7]) << 16);
+                *reinterpret_cast<uint4 *>(o + 8 * q) = u;
+            }
+            for (int c = 24; c < Cpad; c += 8) *reinterpret_cast<uint4 *>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 11; k++) { o[k] = __float2half_rn(mg[k]); o[11 + k] = __float2half_rn(an[k]); }
+            for (int c = 22; c < Cpad; c++) o[c] = __float2half_rn(0.f);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- iSTFT: (mag, phase) -> (re, im) in place, then overlap-add / window^2 sum
