@@ -268,6 +268,15 @@ def main():
         return 0
 
     peak_tf, peak_gbs, peak_src = _peaks()
+    traffic, traffic_src = None, None   # DRAM bytes per conv_umma launch from the committed ncu capture of this same command (profiles/)
+    try:
+        import glob
+        cand = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_conv_umma_traffic.json")))
+        if cand:
+            tj = json.load(open(cand[-1]))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d launches (%s)" % (tj["launches"], os.path.basename(cand[-1]))
+    except Exception:
+        pass
     g = prof["conv_gemm"]
     ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     line = {
@@ -284,7 +293,9 @@ def main():
         "gpu_launches": int(launches), "gemm_dispatch": dict(zip(("tcgen05_tma", "mma_sync_fallback"), ctx.gemm_launches())),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (persistent tcgen05 + TMA implicit-GEMM Conv1d/Linear, fp16 operands, fp32 TMEM accumulators; all conv_gemm launches incl. the few mma.sync fallbacks)", "achieved": ach, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "launches_per_step": g["launches"] / args.steps,
+                     "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1), "algorithmic_flops_per_launch": g["flops"] / max(g["launches"], 1),
+                     "peak_source": peak_src, "launches_per_step": g["launches"] / args.steps,
                      "share_of_device_time": g["ms"] / dev_ms if dev_ms else None},
         "kernel_classes_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         "device_ms_per_step": dev_ms / args.steps,

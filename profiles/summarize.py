@@ -14,12 +14,23 @@ def launches(src, dst, steps=4):
     r = csv.reader(lines)
     hdr = next(r)
     ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    mi, ui = hdr.index("Metric Name"), hdr.index("Metric Unit")
     agg = collections.defaultdict(lambda: [0, 0.0])
+    dram = collections.defaultdict(lambda: [0, 0.0])   # kernel -> [launches, DRAM bytes read + written]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     n = 0
     for row in r:
         try:
             v = float(row[vi].replace(",", ""))
         except ValueError:
+            continue
+        if row[mi].startswith("dram__bytes"):
+            nm = row[ki].split("(")[0].replace("void ", "").replace("unnamed>::", "")
+            dram[nm][1] += v * scale.get(row[ui], 1.0)
+            if row[mi] == "dram__bytes_read.sum":
+                dram[nm][0] += 1
+            continue
+        if row[mi] != "gpu__time_duration.sum":
             continue
         name = row[ki].split("(")[0].replace("void ", "").replace("unnamed>::", "")
         agg[name][0] += 1
@@ -33,6 +44,15 @@ def launches(src, dst, steps=4):
         f.write(f"{'kernel':40s} {'launches':>9s} {'total_ms':>10s} {'ms/forward':>11s} {'share':>7s}\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:40]:40s} {v[0]:9d} {v[1] / 1e6:10.3f} {v[1] / 1e6 / steps:11.3f} {v[1] / tot:7.1%}\n")
+        if dram:
+            f.write("\n# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch, same capture\n")
+            for k, v in sorted(dram.items(), key=lambda kv: -kv[1][1])[:12]:
+                f.write(f"{k[:40]:40s} launches {v[0]:6d}  total {v[1] / 1e9:9.3f} GB  per launch {v[1] / max(v[0], 1) / 1e6:10.3f} MB\n")
+    if dram:
+        import json
+        um = [(k, v) for k, v in dram.items() if "conv_umma" in k]
+        nl = sum(v[0] for _, v in um); by = sum(v[1] for _, v in um)
+        json.dump({"kernel": "conv_umma_kernel", "launches": nl, "dram_bytes_per_launch": by / max(nl, 1), "source": dst}, open(dst.replace("_launches_summary.txt", "_conv_umma_traffic.json"), "w"))
     print(open(dst).read())
 
 
