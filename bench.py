@@ -160,7 +160,7 @@ def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, 
                 audio += s["audio_s"]; wall = max(wall, s["wall_s"])
     if wall <= 0:
         return None, "reference run produced no SUMMARY"
-    return {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
+    return {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference", "wall_s": wall, "timed_runs_per_worker": n_timed,
             "sample": f"{workers} worker processes x {threads} ggml threads, each {n_timed} timed run(s) of one 66-token prompt "
                       f"(~4.95 s audio) after {n_warm} warm-up; throughput = total audio / slowest worker's wall; x86-64-v3 build"}, None
 
@@ -169,13 +169,16 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    base, why = reference_throughput(n_timed=max(1, args.steps), n_warm=max(1, min(args.warmup, 1)))
+    # a step of this arm = every worker synthesising one prompt (a bounded sample of the batch-32 step: 16 of its prompts on this
+    # box); capped at 6 timed repetitions so that any --steps finishes within a few minutes
+    base, why = reference_throughput(n_timed=max(1, min(args.steps, 6)), n_warm=max(1, min(args.warmup, 1)))
     if base is None:
         print(json.dumps({"impl": "reference", "unavailable": why}))
         return 0
     line = {
         "impl": "reference", "metric": "audio_seconds_per_second", "value": base["value"], "unit": "audio-s/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps": base["timed_runs_per_worker"], "warmup": max(1, min(args.warmup, 1)), "ms_per_step": base["wall_s"] * 1e3 / base["timed_runs_per_worker"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 weights / f32 activations (GGML CPU)", "data": "synthetic",
         "config": {"workload": "Kokoro-82M fp16 GGUF (synthetic weights), 64-char (66-token) prompts, reference CPU GGML path, sequential per worker"},
         "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
