@@ -87,6 +87,7 @@ struct ConvGemmParams {
     int            N = 0, Npad = 0, KW = 1, CinPad = 0, lda = 0, stride = 1, dil = 1, pad = 0;
     int            CinTrue = 0;         // un-padded input channels (roofline accounting only; 0 -> CinPad)
     int64_t        validRows = 0;       // sum of lenOut (roofline accounting only; 0 -> B*LmaxOut)
+    bool           tailClean = false;   // the producer of A (adain_apply) already zeroed the rows past each utterance's end: skip zero_tail_rows
     float *        statsPart = nullptr; // optional [B][ceil(LmaxOut/conv_umma_tile_m)][N][2]: per-tile (sum, sum of squares) of the stored values over valid rows
                                         // (tcgen05 kernel only; the caller checks Ctx::umma_launches to know it was produced)
 };

@@ -45,6 +45,8 @@ __global__ void inorm_stats_kernel(const float * __restrict__ x, int ldx, int C,
 }
 
 // ---------------------------------------------------------------- AdaIN apply + activation
+constexpr int TAIL_ROWS = 32;   // rows past an utterance's end that a conv may read as padding: (K-1)*dil - pad <= 25 for every Kokoro layer
+
 __global__ void adain_apply_kernel(const AdainParams p, int rows_per_block) {
     const int b = blockIdx.y;
     const int L = p.len[b];
@@ -88,6 +90,9 @@ __global__ void adain_apply_kernel(const AdainParams p, int rows_per_block) {
             }
         }
     }
+    if (p.outH && t1 == L)   // clear the rows past the utterance's end (see adain_apply4_kernel)
+        for (int t = L + ty; t < min(L + TAIL_ROWS, p.Lmax); t += ny)
+            for (int c = tx; c < p.Cpad; c += nx) p.outH[((size_t) b * p.Lmax + t) * p.ldoh + c] = __float2half_rn(0.f);
 }
 
 // ---------------------------------------------------------------- vectorised variants (C % 4 == 0): one thread = 4 channels,
@@ -214,6 +219,13 @@ __global__ void __launch_bounds__(256) adain_apply4_kernel(const AdainParams p, 
             if constexpr (OUTF) { if (ok && live) *reinterpret_cast<float4 *>(p.outF + orow * p.ldof + c0) = make_float4(f[0], f[1], f[2], f[3]); }
         }
     }
+    if constexpr (OUTH) {
+        // the block that holds the utterance's last row also clears the TAIL_ROWS rows past it: the conv that consumes this operand
+        // must read zeros there (ragged batches), which saves it a separate clearing launch (ConvGemmParams::tailClean)
+        if (t1 == L)
+            for (int tt = L + threadIdx.y; tt < min(L + TAIL_ROWS, p.Lmax); tt += ny)
+                *reinterpret_cast<uint2 *>(p.outH + ((size_t) b * p.Lmax + tt) * p.ldoh + c0) = make_uint2(0u, 0u);
+    }
 }
 
 // ---------------------------------------------------------------- depthwise ConvTranspose1d k3 s2 p1 op1 ("pool")
@@ -247,21 +259,29 @@ __global__ void row_norm_kernel(const RowNormParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int b = warp / p.Lmax, t = warp - b * p.Lmax;
     if (b >= p.B || t >= p.len[b]) return;
-    const float * row = p.x + ((size_t) b * p.Lmax + t) * p.ldx;
+    const float * grow = p.x + ((size_t) b * p.Lmax + t) * p.ldx;
+    float row_r[32];                                       // the row, read once (C <= 1024: 32 values per lane)
+#pragma unroll
+    for (int k = 0; k < 32; k++) { const int c = lane + 32 * k; row_r[k] = c < p.C ? grow[c] : 0.f; }
     double s = 0.0;
-    for (int c = lane; c < p.C; c += 32) s += (double) row[c];
+#pragma unroll
+    for (int k = 0; k < 32; k++) { if (lane + 32 * k < p.C) s += (double) row_r[k]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = (float) (s / (double) p.C);
     double q = 0.0;
-    for (int c = lane; c < p.C; c += 32) { const float v = row[c] - mean; q += (double) (v * v); }
+#pragma unroll
+    for (int k = 0; k < 32; k++) { if (lane + 32 * k < p.C) { const float v = row_r[k] - mean; q += (double) (v * v); } }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float var = (float) (q / (double) p.C);
     const float scale = 1.0f / sqrtf(var + p.eps);
     const size_t orow = (size_t) b * p.Lmax + t;
-    for (int c = lane; c < p.C; c += 32) {
-        const float n = (row[c] - mean) * scale;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const int c = lane + 32 * k;
+        if (c >= p.C) break;
+        const float n = (row_r[k] - mean) * scale;
         float v;
         if (p.mode == LN_AFFINE) v = n * p.w[c] + p.bias[c];
         else v = (n + n * p.gb[(size_t) b * p.ldgb + p.goff + c]) + p.gb[(size_t) b * p.ldgb + p.boff + c];
@@ -692,6 +712,7 @@ int pool_convt(Ctx * ctx, const float * x, int ldx, int C, int B, int Lmax, cons
 }
 
 int row_norm(Ctx * ctx, const RowNormParams & p) {
+    if (p.C > 1024) { set_error("row_norm: C=%d > 1024", p.C); return 1; }
     const int64_t warps = (int64_t) p.B * p.Lmax;
     row_norm_kernel<<<cdiv(warps * 32, 256), 256, 0, ctx->stream>>>(p);
     B2_LAUNCH_CHECK(ctx);
@@ -715,20 +736,30 @@ int cast_rows(Ctx * ctx, const float * x, int ldx, int C, int B, int LmaxIn, con
     return 0;
 }
 
-__global__ void stats_finalize_kernel(const float * __restrict__ part, int n_mt, int C, double * sums) {
+// block = 32 channels x 8 partial groups: group g sums tiles g, g+8, ...; the 8 group sums are combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float * __restrict__ part, int n_mt, int C, double * sums) {
+    __shared__ double sh[8][32][2];
     const int b = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     double s = 0.0, q = 0.0;
-    const float * p = part + ((size_t) b * n_mt * C + c) * 2;
-    for (int m = 0; m < n_mt; m++) { const float2 v = *reinterpret_cast<const float2 *>(p + (size_t) m * C * 2); s += (double) v.x; q += (double) v.y; }
-    sums[((size_t) b * C + c) * 2] = s;
-    sums[((size_t) b * C + c) * 2 + 1] = q;
+    if (c < C) {
+        const float * p = part + ((size_t) b * n_mt * C + c) * 2;
+        for (int m = g; m < n_mt; m += 8) { const float2 v = *reinterpret_cast<const float2 *>(p + (size_t) m * C * 2); s += (double) v.x; q += (double) v.y; }
+    }
+    sh[g][cx][0] = s; sh[g][cx][1] = q;
+    __syncthreads();
+    if (g == 0 && c < C) {
+#pragma unroll
+        for (int k = 1; k < 8; k++) { s += sh[k][cx][0]; q += sh[k][cx][1]; }
+        sums[((size_t) b * C + c) * 2] = s;
+        sums[((size_t) b * C + c) * 2 + 1] = q;
+    }
 }
 
 int stats_finalize(Ctx * ctx, const float * part, int B, int n_mt, int C, double * sums) {
-    dim3 grid(cdiv(C, 128), B);
-    stats_finalize_kernel<<<grid, 128, 0, ctx->stream>>>(part, n_mt, C, sums);
+    dim3 grid(cdiv(C, 32), B);
+    stats_finalize_kernel<<<grid, 256, 0, ctx->stream>>>(part, n_mt, C, sums);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

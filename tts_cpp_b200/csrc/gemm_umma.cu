@@ -565,7 +565,7 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p_in) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return 2;
     }
-    if (p.KW > 1 && p.lenIn) {   // ragged batches: clear the halo rows past each utterance's end
+    if (p.KW > 1 && p.lenIn && !p.tailClean) {   // ragged batches: clear the halo rows past each utterance's end
         dim3 grid(32, p.B);
         zero_tail_rows_kernel<<<grid, 128, 0, ctx->stream>>>(const_cast<__half *>(p.A), p.lda, p.CinPad, p.LmaxIn, p.lenIn, 32);
         B2_LAUNCH_CHECK(ctx);

@@ -342,8 +342,9 @@ struct Fwd {
 
     int gemm(const __half * A, int lda, const W16 & W, const float * bias, int Lin, int Lout, const int * lenIn, const int * lenOut, int stride, int dil,
              int pad, float * outF, int ldo, int coff, __half * outH = nullptr, int ldoh = 0, int coffh = 0, const float * add1 = nullptr, int ldadd1 = 0,
-             const float * add2 = nullptr, int ldadd2 = 0, float div = 0.f, int act = ACT_NONE, int Bn = -1) {
+             const float * add2 = nullptr, int ldadd2 = 0, float div = 0.f, int act = ACT_NONE, int Bn = -1, bool tailClean = false) {
         ConvGemmParams p;
+        p.tailClean = tailClean;
         p.A = A; p.lda = lda; p.W = W.w; p.bias = bias; p.outF = outF; p.ldo = ldo; p.coff = coff; p.outH = outH; p.ldoh = ldoh; p.coffh = coffh;
         p.add1 = add1; p.ldadd1 = ldadd1; p.add2 = add2; p.ldadd2 = ldadd2; p.div = div; p.act = act;
         p.B = Bn < 0 ? B : Bn; p.LmaxIn = Lin; p.LmaxOut = Lout; p.lenIn = lenIn; p.lenOut = lenOut;
@@ -356,6 +357,7 @@ struct Fwd {
     int gemm_stats(const __half * A, int lda, const W16 & W, const float * bias, int L, const int * len, int dil, int pad, float * outF,
                    const float * add1, const float * add2, float div, float * part, double * sums_out) {
         ConvGemmParams p;
+        p.tailClean = true;   // gen_resblock: the operand always comes straight from adain_apply
         p.A = A; p.lda = lda; p.W = W.w; p.bias = bias; p.outF = outF; p.ldo = W.N; p.add1 = add1; p.ldadd1 = W.N; p.add2 = add2; p.ldadd2 = W.N; p.div = div;
         p.B = B; p.LmaxIn = L; p.LmaxOut = L; p.lenIn = len; p.lenOut = len;
         p.N = W.N; p.Npad = W.Npad; p.KW = W.KW; p.CinPad = W.CinPad; p.CinTrue = W.Cin; p.stride = 1; p.dil = dil; p.pad = pad;
@@ -403,7 +405,7 @@ struct Fwd {
             ap.outH = a16; ap.ldoh = k.conv1.CinPad; ap.Cpad = k.conv1.CinPad;
             if (adain_apply(ctx, ap)) return 1;
         }
-        if (gemm(a16, k.conv1.CinPad, k.conv1, k.b1, Lout, Lout, lenOut, lenOut, 1, 1, 1, h, k.cout, 0)) return 1;
+        if (gemm(a16, k.conv1.CinPad, k.conv1, k.b1, Lout, Lout, lenOut, lenOut, 1, 1, 1, h, k.cout, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, 0.f, ACT_NONE, -1, !k.pool)) return 1;
         if (inorm_stats(ctx, h, k.cout, k.cout, B, Lout, lenOut, sums)) return 1;
         AdainParams ap2;
         ap2.x = h; ap2.ldx = k.cout; ap2.C = k.cout; ap2.B = B; ap2.Lmax = Lout; ap2.len = lenOut; ap2.sums = sums; ap2.gb = gb; ap2.ldgb = ldgb;
@@ -418,7 +420,7 @@ struct Fwd {
             if (gemm(sc16, k.conv1x1.CinPad, k.conv1x1, nullptr, Lout, Lout, lenOut, lenOut, 1, 1, 0, scf, k.cout, 0)) return 1;   // bias never applied: model.cpp:129
             sc = scf; ldsc = k.cout;
         }
-        return gemm(h16, k.conv2.CinPad, k.conv2, k.b2, Lout, Lout, lenOut, lenOut, 1, 1, 1, out, ldo, coff, nullptr, 0, 0, sc, ldsc, nullptr, 0, sqrtf(2.0f));
+        return gemm(h16, k.conv2.CinPad, k.conv2, k.b2, Lout, Lout, lenOut, lenOut, 1, 1, 1, out, ldo, coff, nullptr, 0, 0, sc, ldsc, nullptr, 0, sqrtf(2.0f), ACT_NONE, -1, true);
     }
 
     // generator residual block (model.cpp:136-165): x [B][L][C] -> out = (x_final [+ add2]) [/ div]
@@ -445,7 +447,7 @@ struct Fwd {
             if (s_next) {
                 if (gemm_stats(a16, Cp, r.c2[i], r.b2[i], L, len, 1, r.pad[0], nxt, inp, (i == 2) ? add2 : nullptr, (i == 2) ? div : 0.f, part, s_next)) return 1;
             } else {
-                if (gemm(a16, Cp, r.c2[i], r.b2[i], L, L, len, len, 1, 1, r.pad[0], nxt, C, 0, nullptr, 0, 0, inp, C, (i == 2) ? add2 : nullptr, C, (i == 2) ? div : 0.f)) return 1;
+                if (gemm(a16, Cp, r.c2[i], r.b2[i], L, L, len, len, 1, 1, r.pad[0], nxt, C, 0, nullptr, 0, 0, inp, C, (i == 2) ? add2 : nullptr, C, (i == 2) ? div : 0.f, ACT_NONE, -1, true)) return 1;
             }
             inp = nxt; s_in = s_next;
         }
