@@ -273,7 +273,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
         float * stg = stage_all + (warp - 2) * (32 * STAGE_PITCH);
         const int cr = lane >> 3, cc4 = (lane & 7) * 4;      // row-contiguous pattern: step i covers rows 4i + cr, columns cc4..cc4+3
         const int emode = (p.div == 0.f && p.act == ACT_NONE) ? 0 : (p.act == ACT_NONE ? 1 : ((p.div == 0.f && p.act == ACT_GELU_F16LUT) ? 2 : 3));
-        const bool efast = emode == 0 && p.bias != nullptr && p.outF != nullptr && p.outH == nullptr && p.add2 == nullptr && !(e.dbg & 16);
+        const bool efast = emode <= 1 && p.bias != nullptr && p.outF != nullptr && p.outH == nullptr && !(e.dbg & 16);
         const bool do_f = p.outF != nullptr, do_h = p.outH != nullptr, has1 = p.add1 != nullptr, has2 = p.add2 != nullptr;
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
@@ -369,13 +369,18 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                     // branch-free body for the generator's resblock convs (bias, fp32 result, <= 1 residual, no fp16 copy): with every
                     // launch-uniform flag a template constant the 8 unrolled steps are ONE basic block, so their independent
                     // LDS -> FADD -> STG chains interleave (each runtime-uniform `if` used to end a block and serialise them)
-                    auto fast = [&](auto has1_tag, auto stats_tag) {
-                        constexpr bool HAS1 = decltype(has1_tag)::value, STATS = decltype(stats_tag)::value;
+                    auto fast = [&](auto has1_tag, auto has2_tag, auto div_tag, auto stats_tag) {
+                        constexpr bool HAS1 = decltype(has1_tag)::value, HAS2 = decltype(has2_tag)::value, DIV = decltype(div_tag)::value, STATS = decltype(stats_tag)::value;
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const float4 x4 = *reinterpret_cast<const float4 *>(stg + (4 * i + cr) * STAGE_PITCH + cc4);
                             float x[4] = {x4.x + b4.x, x4.y + b4.y, x4.z + b4.z, x4.w + b4.w};
                             if constexpr (HAS1) { x[0] = r1[i].x + x[0]; x[1] = r1[i].y + x[1]; x[2] = r1[i].z + x[2]; x[3] = r1[i].w + x[3]; }
+                            if constexpr (HAS2) { x[0] = r2[i].x + x[0]; x[1] = r2[i].y + x[1]; x[2] = r2[i].z + x[2]; x[3] = r2[i].w + x[3]; }
+                            if constexpr (DIV) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) x[k] = __fdiv_rn(x[k], p.div);
+                            }
                             const bool rv = 4 * i < nrows;
                             if (rv) *reinterpret_cast<float4 *>(ofp + i * sf + c0) = make_float4(x[0], x[1], x[2], x[3]);
                             if constexpr (STATS) {
@@ -385,8 +390,11 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                         }
                     };
                     if (efast) {
-                        if (has1) { if (p.statsPart) fast(std::true_type{}, std::true_type{}); else fast(std::true_type{}, std::false_type{}); }
-                        else      { if (p.statsPart) fast(std::false_type{}, std::true_type{}); else fast(std::false_type{}, std::false_type{}); }
+                        using T = std::true_type; using F = std::false_type;
+                        auto d4 = [&](auto a, auto b, auto c) { if (p.statsPart) fast(a, b, c, T{}); else fast(a, b, c, F{}); };
+                        auto d3 = [&](auto a, auto b) { if (emode == 1) d4(a, b, T{}); else d4(a, b, F{}); };
+                        auto d2 = [&](auto a) { if (has2) d3(a, T{}); else d3(a, F{}); };
+                        if (has1) d2(T{}); else d2(F{});
                     }
                     else if (emode == 0) steps(std::integral_constant<int, 0>{});
                     else if (emode == 1) steps(std::integral_constant<int, 1>{});
