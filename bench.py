@@ -292,7 +292,7 @@ def main():
                    "value_timing": "CUDA events on the library stream around duration+generation passes (incl. the mid-forward host sync for durations), max over ranks; ms_per_step is this device time"},
         "e2e": {"value": audio_total * args.steps / wall, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
                 "ms_per_step": wall * 1e3 / args.steps,
-                "note": "wall clock, max over ranks: host token ids in, PCM in pinned host memory out, through b2tts_kokoro_run_batch (each rank keeps its own shard's audio)"},
+                "note": "wall clock, max over ranks: host token ids in, PCM in pinned host memory out, through b2tts_kokoro_run_batch (each rank keeps its own shard's audio; the PCM leaves the device as one padded [B][S] block when padding < 25 %, d2h_bytes_per_step counts the audio itself)"},
         "gpu_launches": int(launches), "gemm_dispatch": dict(zip(("tcgen05_tma", "mma_sync_fallback"), ctx.gemm_launches())),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (persistent tcgen05 + TMA implicit-GEMM Conv1d/Linear, fp16 operands, fp32 TMEM accumulators; all conv_gemm launches incl. the few mma.sync fallbacks)", "achieved": ach, "peak": peak_tf,

@@ -98,7 +98,11 @@ def test_conv_transpose_1d(gpu_ctx):
 
 def test_conv_1d_f16(gpu_ctx):
     rng = np.random.default_rng(6)
-    for (K, cin, cout, L, s, p, dl) in ((3, 64, 96, 50, 1, 1, 1), (7, 128, 128, 300, 1, 9, 3), (11, 128, 128, 257, 1, 25, 5), (12, 22, 256, 601, 6, 3, 1), (5, 512, 512, 66, 1, 2, 1), (1, 514, 1024, 33, 1, 0, 1)):
+    for (K, cin, cout, L, s, p, dl) in ((3, 64, 96, 50, 1, 1, 1), (7, 128, 128, 300, 1, 9, 3), (11, 128, 128, 257, 1, 25, 5), (12, 22, 256, 601, 6, 3, 1), (5, 512, 512, 66, 1, 2, 1), (1, 514, 1024, 33, 1, 0, 1),
+                                      # tcgen05 kernel corners: 128x256 tiles with dilation, 256x128 tiles over several row tiles, an unaligned Cout
+                                      # (generic epilogue), a narrow head (Cout < 128, weight rows zero-filled by TMA) and a long pointwise layer
+                                      (7, 256, 256, 700, 1, 9, 3), (3, 128, 128, 900, 1, 1, 1), (3, 64, 130, 300, 1, 1, 1), (7, 128, 22, 33000, 1, 3, 1),
+                                      (1, 768, 2048, 400, 1, 0, 1)):
         W = (rng.standard_normal((cout, cin, K)) / np.sqrt(cin * K)).astype(np.float16).astype(np.float32)
         x = rng.standard_normal((cin, L)).astype(np.float32)
         xh = torch.from_numpy(x).half().float()

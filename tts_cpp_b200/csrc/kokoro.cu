@@ -750,16 +750,22 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     B2_CUDA(cudaEventRecord(ev[2], st));
 
     // ---- D2H into the runner-owned pinned buffer (borrowed by the caller until the next call, like tts_response.data)
-    if (pcm_pinned_cap < Ssum) {
+    // one copy of the padded [B][S] block when the padding is small (a copy per utterance costs ~10 us of launch overhead each);
+    // ragged batches whose padding would add > 25 % bytes are copied utterance by utterance, packed
+    const bool one_copy = (size_t) B * S <= Ssum + Ssum / 4;
+    const size_t need_pinned = one_copy ? (size_t) B * S : Ssum;
+    if (pcm_pinned_cap < need_pinned) {
         if (pcm_pinned) cudaFreeHost(pcm_pinned);
         pcm_pinned = nullptr; pcm_pinned_cap = 0;
-        B2_CUDA(cudaMallocHost(&pcm_pinned, std::max<size_t>(Ssum, 1) * 4));
-        pcm_pinned_cap = Ssum;
+        B2_CUDA(cudaMallocHost(&pcm_pinned, std::max<size_t>(need_pinned, 1) * 4));
+        pcm_pinned_cap = need_pinned;
     }
+    if (one_copy) B2_CUDA(cudaMemcpyAsync(pcm_pinned, pcm_d, (size_t) B * S * 4, cudaMemcpyDeviceToHost, st));
     size_t offp = 0;
     for (int b = 0; b < B; b++) {
         const size_t n = (size_t) T[b] * 600;
-        if (n) B2_CUDA(cudaMemcpyAsync(pcm_pinned + offp, pcm_d + (size_t) b * S, n * 4, cudaMemcpyDeviceToHost, st));
+        if (one_copy) offp = (size_t) b * S;
+        else if (n) B2_CUDA(cudaMemcpyAsync(pcm_pinned + offp, pcm_d + (size_t) b * S, n * 4, cudaMemcpyDeviceToHost, st));
         if (pcm) pcm[b] = pcm_pinned + offp;
         if (n_samples) n_samples[b] = (int64_t) n;
         offp += n;
