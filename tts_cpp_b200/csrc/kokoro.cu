@@ -355,11 +355,12 @@ struct Fwd {
     // conv_gemm whose fp32 result (ld == N) is InstanceNorm'ed next: the statistics come out of the tcgen05 epilogue
     // (per-tile partials + a tiny finalize); if the shape fell back to the mma.sync kernel, a separate pass computes them.
     int gemm_stats(const __half * A, int lda, const W16 & W, const float * bias, int L, const int * len, int dil, int pad, float * outF,
-                   const float * add1, const float * add2, float div, float * part, double * sums_out) {
+                   const float * add1, const float * add2, float div, float * part, double * sums_out, int Lin = 0, const int * lenInP = nullptr,
+                   bool tailClean = true) {
         ConvGemmParams p;
-        p.tailClean = true;   // gen_resblock: the operand always comes straight from adain_apply
+        p.tailClean = tailClean;   // gen_resblock: the operand always comes straight from adain_apply
         p.A = A; p.lda = lda; p.W = W.w; p.bias = bias; p.outF = outF; p.ldo = W.N; p.add1 = add1; p.ldadd1 = W.N; p.add2 = add2; p.ldadd2 = W.N; p.div = div;
-        p.B = B; p.LmaxIn = L; p.LmaxOut = L; p.lenIn = len; p.lenOut = len;
+        p.B = B; p.LmaxIn = Lin ? Lin : L; p.LmaxOut = L; p.lenIn = lenInP ? lenInP : len; p.lenOut = len;
         p.N = W.N; p.Npad = W.Npad; p.KW = W.KW; p.CinPad = W.CinPad; p.CinTrue = W.Cin; p.stride = 1; p.dil = dil; p.pad = pad;
         p.statsPart = part;
         const uint64_t before = ctx->umma_launches;
@@ -726,8 +727,13 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         } else {
             if (convt_cl(ctx, gin, ups[i].Cin, ups[i].Cin, B, gin_L, gin_len, ups[i].w, ups[i].b, ups[i].K, C, ups[i].stride, ups[i].pad, 0.1f, i == 1 ? 1 : 0, u, C, Lo, lo_len)) return 1;
         }
-        if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
-        if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums2, part, nullptr, sums_cur)) return 1;   // cur = up + x_source
+        // noise conv; where it is a stride-1 layer its epilogue also yields the InstanceNorm statistics the noise resblock starts with
+        const bool xs_stats = nconv[i].stride == 1 && nconv[i].w.KW == 1;
+        double * sums_xs = xs_stats ? Gf.al<double>((size_t) B * C * 2) : nullptr;
+        if (Gf.fail) return 1;
+        if (xs_stats) { if (Gf.gemm_stats(hs16, hsp, nconv[i].w, nconv[i].b, Lo, lo_len, 1, nconv[i].pad, xs, nullptr, nullptr, 0.f, part, sums_xs, Fmax, l120, false)) return 1; }
+        else if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
+        if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums2, part, sums_xs, sums_cur)) return 1;   // cur = up + x_source
         if (Gf.tap(i == 0 ? "gen_in0" : "gen_in1", curg, (int64_t) B * Lo, C, C, Lo)) return 1;
         for (int j = 0; j < 3; j++) {
             float * dst = acc[j & 1];

@@ -2,10 +2,10 @@
 //
 // Replaces build_lstm / build_lstm_run (reference src/models/kokoro/model.cpp:35-86), which unrolls every
 // time step into 26 GGML nodes per direction (each followed by a thread-pool barrier).  Here one cluster of
-// 8 CTAs per (direction, batch tile of 32 utterances) runs the whole sequence:
+// 8 CTAs per (direction, batch tile of 16 utterances) runs the whole sequence:
 //   * the hidden-side weights W_hh (fp16, 1024x256) stay resident in shared memory, 128 gate rows per CTA
 //     (4 gates x 32 hidden units);
-//   * every step is one tensor-core contraction  G[128 x 32] = W_hh_slice[128 x 256] . h^T[256 x 32]
+//   * every step is one tensor-core contraction  G[128 x 16] = W_hh_slice[128 x 256] . h^T[256 x 16]
 //     (h re-rounded to fp16 exactly like ggml does for an F16 weight, ggml-cpu.c:262-267);
 //   * gate math (sigmoid/tanh, c = f*c + i*g, h = o*tanh(c), model.cpp:63-76) happens in registers, the cell
 //     state never leaves them;
@@ -21,7 +21,9 @@ namespace cg = cooperative_groups;
 namespace b2 {
 namespace {
 
-constexpr int H = 256, CL = 8, UNITS = 32, NBT = 32;  // hidden, cluster size, units per CTA, utterances per cluster
+// utterances per cluster: 16 (not 32) -- the step is a latency chain (HMMA accumulator chain, MUFU-heavy gate math, cluster barrier), so
+// halving the per-thread work per step and running twice as many clusters shortens it; one n8 MMA tile per warp
+constexpr int H = 256, CL = 8, UNITS = 32, NBT = 16, NI = NBT / 16;  // hidden, cluster size, units per CTA, utterances per cluster, n8 tiles per warp
 constexpr int LDW = 264;                              // smem row stride (halves): 528 B -> conflict-free ldmatrix
 constexpr int SW_BYTES = 128 * LDW * 2;
 constexpr int SH_BYTES = 2 * NBT * LDW * 2;
@@ -31,6 +33,10 @@ constexpr int LSTM_SMEM = SW_BYTES + SH_BYTES + ST_BYTES;
 __device__ __forceinline__ void ldsm_x4(unsigned & r0, unsigned & r1, unsigned & r2, unsigned & r3, const void * p) {
     unsigned s = (unsigned) __cvta_generic_to_shared(p);
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(s));
+}
+__device__ __forceinline__ void ldsm_x2(unsigned & r0, unsigned & r1, const void * p) {
+    unsigned s = (unsigned) __cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(s));
 }
 __device__ __forceinline__ void mma16816(float * c, const unsigned * a, unsigned b0, unsigned b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -67,14 +73,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
     // ---- per-thread ownership: unit ul (local), utterances u[ni][e]
     const int ul = ug * 8 + (lane >> 2);
     const int unit_g = rank * UNITS + ul;
-    int   ub[2][2], ulen[2][2];
-    float cst[2][2];
+    int   ub[NI][2], ulen[NI][2];
+    float cst[NI][2];
     int nsteps = 0;
 #pragma unroll
-    for (int ni = 0; ni < 2; ni++)
+    for (int ni = 0; ni < NI; ni++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int u = nh * 16 + ni * 8 + (lane & 3) * 2 + e;
+            const int u = nh * (8 * NI) + ni * 8 + (lane & 3) * 2 + e;
             ub[ni][e]   = b0 + u;
             ulen[ni][e] = (ub[ni][e] < p.B) ? p.len[ub[ni][e]] : 0;
             cst[ni][e]  = 0.f;
@@ -90,11 +96,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
 
     // input-side pre-activations of a step (one float4 = gates i,f,g,o of (b, t, dir, unit)); loaded one step ahead, while the
     // cluster barrier of the previous step is in flight, so their L2 latency is off the recurrence's critical path
-    float4 xp[2][2];
-    int    tt[2][2];
+    float4 xp[NI][2];
+    int    tt[NI][2];
     auto load_xp = [&](int s) {
 #pragma unroll
-        for (int ni = 0; ni < 2; ni++)
+        for (int ni = 0; ni < NI; ni++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const bool act = s < ulen[ni][e];
@@ -114,11 +120,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
         __half *       hnxt = sH + (size_t) ((s + 1) & 1) * NBT * LDW;
 
         // 2. G = W_hh_slice . h^T on tensor cores: 2 m16 tiles (i|f , g|o) x 2 n8 tiles per warp
-        float acc[2][2][4];
+        float acc[2][NI][4];
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
-            for (int b = 0; b < 2; b++)
+            for (int b = 0; b < NI; b++)
 #pragma unroll
                 for (int e = 0; e < 4; e++) acc[a][b][e] = 0.f;
 #pragma unroll 4
@@ -129,23 +135,27 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
                 const int r = ug * 32 + tl * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 ldsm_x4(af[tl][0], af[tl][1], af[tl][2], af[tl][3], sW + r * LDW + ks * 16 + (lane >> 4) * 8);
             }
-            {
+            if constexpr (NI == 2) {
                 const int r = nh * 16 + (lane & 7) + (lane >> 4) * 8;
                 ldsm_x4(bf[0], bf[1], bf[2], bf[3], hcur + r * LDW + ks * 16 + ((lane >> 3) & 1) * 8);
+            } else {
+                const int r = nh * 8 + (lane & 7);
+                ldsm_x2(bf[0], bf[1], hcur + r * LDW + ks * 16 + ((lane >> 3) & 1) * 8);
+                bf[2] = bf[3] = 0u;
             }
 #pragma unroll
             for (int tl = 0; tl < 2; tl++) {
                 mma16816(acc[tl][0], af[tl], bf[0], bf[1]);
-                mma16816(acc[tl][1], af[tl], bf[2], bf[3]);
+                if constexpr (NI == 2) mma16816(acc[tl][NI - 1], af[tl], bf[2], bf[3]);
             }
         }
 
         // 3. gates in registers.  acc[0][ni][e] = i, acc[0][ni][2+e] = f, acc[1][ni][e] = g, acc[1][ni][2+e] = o
 #pragma unroll
-        for (int ni = 0; ni < 2; ni++)
+        for (int ni = 0; ni < NI; ni++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int  u   = nh * 16 + ni * 8 + (lane & 3) * 2 + e;
+                const int  u   = nh * (8 * NI) + ni * 8 + (lane & 3) * 2 + e;
                 const bool act = s < ulen[ni][e];
                 float hval = 0.f;
                 if (act) {
@@ -167,9 +177,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
 
         // 4. broadcast the 32x32 fp16 slice into every CTA's next-step h buffer (DSMEM, 16 B stores)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NBT / 8; j++) {
             const int q = tid + j * 256;
-            const int dest = q >> 7, rem = q & 127, u = rem >> 2, part = rem & 3;
+            const int dest = q / (NBT * 4), rem = q % (NBT * 4), u = rem >> 2, part = rem & 3;
             const int4 v = *reinterpret_cast<const int4 *>(sSt + u * UNITS + part * 8);
             __half * dst_local = hnxt + u * LDW + rank * UNITS + part * 8;
             int4 * dst = reinterpret_cast<int4 *>(cluster.map_shared_rank(dst_local, dest));
