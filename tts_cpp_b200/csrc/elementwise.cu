@@ -404,6 +404,41 @@ __global__ void linear_f32_kernel(const float * __restrict__ x, int ldx, const f
     }
 }
 
+// K == 128 flavour (the AdaIN gamma/beta projections: 32 style rows x ~30 K outputs, and ALBERT's embedding projection): a block
+// stages 32 rows of x in shared memory, a warp owns one output n at a time: its lanes hold W[n][4l..4l+3] (one coalesced 512 B read,
+// W is read ONCE, not once per row), form the 32 row partials and a shuffle reduce-scatter leaves lane r with y[r][n].
+__global__ void __launch_bounds__(256) linear_f32_k128_kernel(const float * __restrict__ x, int ldx, const float * __restrict__ W,
+                                                              const float * __restrict__ bias, int rows, int N, float * y, int ldy, int n_per_block) {
+    __shared__ float4 xs[32][32];
+    const int r0 = blockIdx.y * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        const int r = i >> 5, k4 = i & 31;
+        xs[r][k4] = (r0 + r < rows) ? *reinterpret_cast<const float4 *>(x + (size_t) (r0 + r) * ldx + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int n_lo = blockIdx.x * n_per_block, n_hi = min(N, n_lo + n_per_block);
+    for (int n = n_lo + warp; n < n_hi; n += 8) {
+        const float4 w = *reinterpret_cast<const float4 *>(W + (size_t) n * 128 + 4 * lane);
+        float p[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const float4 xv = xs[r][lane];
+            p[r] = fmaf(xv.w, w.w, fmaf(xv.z, w.z, fmaf(xv.y, w.y, xv.x * w.x)));
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; i++) {
+                const float send = up ? p[i] : p[i + off], keep = up ? p[i + off] : p[i];
+                p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        if (r0 + lane < rows) y[(size_t) (r0 + lane) * ldy + n] = p[0] + (bias ? bias[n] : 0.f);
+    }
+}
+
 __global__ void albert_embed_kernel(const int * __restrict__ tokens, const int * __restrict__ tok_off, const float * __restrict__ tok_embd,
                                     const float * __restrict__ pos_embd, const float * __restrict__ type_embd, const float * __restrict__ nw,
                                     const float * __restrict__ nb, int B, int Lmax, const int * __restrict__ len, float * out, int ldo) {
@@ -799,6 +834,13 @@ int gather_rows(Ctx * ctx, const float * src, int lds, int LmaxSrc, const int * 
 }
 
 int linear_f32(Ctx * ctx, const float * x, int ldx, const float * W, const float * bias, int rows, int K, int N, float * y, int ldy) {
+    if (K == 128 && ldx % 4 == 0 && ((((uintptr_t) x) | ((uintptr_t) W)) & 15) == 0) {
+        const int npb = 64;
+        dim3 grid(cdiv(N, npb), cdiv(rows, 32));
+        linear_f32_k128_kernel<<<grid, 256, 0, ctx->stream>>>(x, ldx, W, bias, rows, N, y, ldy, npb);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     const int64_t warps = (int64_t) rows * ((N + 31) / 32);
     linear_f32_kernel<<<cdiv(warps * 32, 256), 256, 0, ctx->stream>>>(x, ldx, W, bias, rows, K, N, y, ldy);
     B2_LAUNCH_CHECK(ctx);
