@@ -792,6 +792,21 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float * __res
     }
 }
 
+__global__ void zero_rows_past_end_kernel(__half * A, int lda, int C, int Lmax, const int * __restrict__ len) {
+    const int b = blockIdx.y;
+    const int nrow = Lmax - len[b];
+    for (int r = blockIdx.x; r < nrow; r += gridDim.x) {
+        __half * row = A + ((size_t) b * Lmax + len[b] + r) * lda;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) row[c] = __float2half_rn(0.f);
+    }
+}
+int zero_rows_past_end(Ctx * ctx, __half * A, int lda, int C, int B, int Lmax, const int * len) {
+    dim3 grid(64, B);
+    zero_rows_past_end_kernel<<<grid, 64, 0, ctx->stream>>>(A, lda, C, Lmax, len);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int stats_finalize(Ctx * ctx, const float * part, int B, int n_mt, int C, double * sums) {
     dim3 grid(cdiv(C, 32), B);
     stats_finalize_kernel<<<grid, 256, 0, ctx->stream>>>(part, n_mt, C, sums);

@@ -545,7 +545,6 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p_in) {
     const int FIXED_BYTES = fixed_bytes(NT);
     const int RA = round_up(TM + (p.KW - 1) * p.dil, 16);
     if (RA > RA_MAX) return 2;
-    if (p.LmaxIn != p.LmaxOut && p.KW > 1) return 2;
     if (umma_init() != 1) return 2;
     if (((uintptr_t) p.A & 15) || ((uintptr_t) p.W & 15)) return 2;
     UmmaExtra e;

@@ -94,7 +94,11 @@ struct SourceParams {
 };
 int source_har(Ctx * ctx, const SourceParams & p);
 // har[b][S] -> fp16 operand [b][frame][Cpad] (mag 0..10, phase 11..21) and optional fp32 tap; frames = S/5+1
-int stft20(Ctx * ctx, const float * har, int Smax, int B, const int * lenS, int Fmax, __half * outH, int ldoh, int Cpad, float * outF, int ldof);
+// FpitchH: rows per utterance of the fp16 operand (>= Fmax; 0 -> Fmax): the strided noise conv wants a multiple of its stride
+int stft20(Ctx * ctx, const float * har, int Smax, int B, const int * lenS, int Fmax, __half * outH, int ldoh, int Cpad, float * outF, int ldof,
+           int FpitchH = 0);
+// rows [len_b, Lmax) of every utterance of a fp16 operand cleared (what a conv must read as zero padding past the end)
+int zero_rows_past_end(Ctx * ctx, __half * A, int lda, int C, int B, int Lmax, const int * len);
 // spec/phase [b][frame][22] (exp'd magnitude, sin'd phase) -> pcm[b][S]
 int istft20(Ctx * ctx, float * specph, int ld, int B, const int * lenF, int Fmax, float * pcm, int Smax);
 // stand-alone pieces for the op-level ABI

@@ -285,6 +285,27 @@ int Kokoro::prepare() {
         auto ns = kv.find(G + "noise_blocks." + std::to_string(i) + ".stride"), np = kv.find(G + "noise_blocks." + std::to_string(i) + ".padding");
         if (ns == kv.end() || np == kv.end()) { set_error("both padding and stride keys must be assigned in order to initialize a kokoro noise block."); return 1; }
         nconv[i].stride = (int) ns->second; nconv[i].pad = (int) np->second;
+        if (nconv[i].stride > 1) {
+            // out[t] = sum_k x[t*s + k - pad] w[k].  View the (channels-last, 64-half rows) input as rows of s frames, X'[r][j*64 + c] =
+            // x[r*s + j][c] -- a pure reinterpretation when the per-utterance pitch is a multiple of s -- and shift the taps by
+            // sh = (s - pad % s) % s:  out[t] = sum_m sum_{j,c} X'[t - pad' + m][j*64 + c] w'[m][j*64 + c],  w'[m][j] = w[m*s + j - sh]
+            // (zero outside [0, K)), pad' = pad / s + (sh != 0).  A stride-1 conv with K' = ceil((K + sh) / s) taps: tcgen05-eligible.
+            auto t = P.get(g + "noise_blocks." + std::to_string(i) + ".conv_weight");
+            const int s = nconv[i].stride, N = nconv[i].w.N, Cin = nconv[i].w.Cin, K = nconv[i].w.KW, CX = nconv[i].w.CinPad;
+            const int sh = (s - nconv[i].pad % s) % s, Kp = (K + sh + s - 1) / s, Cp = s * CX;
+            std::vector<float> src((size_t) N * Cp * Kp, 0.f);
+            for (int n = 0; n < N; n++)
+                for (int m = 0; m < Kp; m++)
+                    for (int j = 0; j < s; j++) {
+                        const int k = m * s + j - sh;
+                        if (k < 0 || k >= K) continue;
+                        for (int c = 0; c < Cin; c++) src[((size_t) n * Cp + j * CX + c) * Kp + m] = t->v[((size_t) n * Cin + c) * K + k];
+                    }
+            nconv[i].wp = P.w16_from(src, N, Cp, Kp);
+            nconv[i].wp.Cin = K * Cin / Kp;   // roofline accounting counts the conv's own K*Cin products, not the zero-padded polyphase ones
+            nconv[i].padp = nconv[i].pad / s + (sh ? 1 : 0);
+            nconv[i].poly = true;
+        }
         nres[i] = P.gres(g + "noise_blocks." + std::to_string(i) + ".resblock", G + "noise_blocks." + std::to_string(i) + ".res_block");
     }
     for (int i = 0; i < 6; i++) res[i] = P.gres(g + "resblocks." + std::to_string(i), G + "res_blocks." + std::to_string(i));
@@ -681,7 +702,11 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     // B5: harmonic source + STFT (model.cpp:173-206)
     const int Fmax = L4;
     const int hsp = nconv[0].w.CinPad;   // 22 channels padded for the GEMM operand
-    float * har = Gf.al<float>((size_t) B * S); __half * hs16 = Gf.al<__half>((size_t) B * Fmax * hsp);
+    // fp16 STFT operand: per-utterance pitch Fp = Fmax rounded up to the strided noise conv's stride (its polyphase view needs whole rows)
+    int fp_mult = 1;
+    for (int i = 0; i < 2; i++) if (nconv[i].poly) fp_mult = fp_mult * nconv[i].stride / std::__gcd(fp_mult, nconv[i].stride);
+    const int Fp = round_up(Fmax, fp_mult);
+    float * har = Gf.al<float>((size_t) B * S); __half * hs16 = Gf.al<__half>((size_t) B * Fp * hsp);
     float * phase = Gf.al<float>((size_t) B * 9 * L2);
     float * hsF = taps_on || overrides.count("har_spec") ? Gf.al<float>((size_t) B * Fmax * 22) : nullptr;
     if (Gf.fail) return 1;
@@ -691,11 +716,12 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         sp.phase = phase; sp.har = har; sp.Smax = S;
         if (source_har(ctx, sp)) return 1;
         if (Gf.tap("har", har, B, S, S, S)) return 1;
-        if (stft20(ctx, har, S, B, lS, Fmax, hs16, hsp, hsp, hsF, 22)) return 1;
+        if (stft20(ctx, har, S, B, lS, Fmax, hs16, hsp, hsp, hsF, 22, Fp)) return 1;
         if (hsF) {
             if (Gf.tap("har_spec", hsF, (int64_t) B * Fmax, 22, 22, Fmax)) return 1;
-            if (overrides.count("har_spec")) { if (cast_rows(ctx, hsF, 22, 22, B, Fmax, l120, Fmax, 0, 1.0f, hs16, hsp, hsp)) return 1; }
+            if (overrides.count("har_spec")) { if (cast_rows(ctx, hsF, 22, 22, B, Fmax, l120, Fp, 0, 1.0f, hs16, hsp, hsp)) return 1; }
         }
+        if (fp_mult > 1 && zero_rows_past_end(ctx, hs16, hsp, hsp, B, Fp, l120)) return 1;   // the polyphase conv cannot mask rows per utterance
     }
 
     // B6/B7: generator stages (model.cpp:208-230)
@@ -731,8 +757,11 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
         const bool xs_stats = nconv[i].stride == 1 && nconv[i].w.KW == 1;
         double * sums_xs = xs_stats ? Gf.al<double>((size_t) B * C * 2) : nullptr;
         if (Gf.fail) return 1;
-        if (xs_stats) { if (Gf.gemm_stats(hs16, hsp, nconv[i].w, nconv[i].b, Lo, lo_len, 1, nconv[i].pad, xs, nullptr, nullptr, 0.f, part, sums_xs, Fmax, l120, false)) return 1; }
-        else if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fmax, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
+        if (xs_stats) { if (Gf.gemm_stats(hs16, hsp, nconv[i].w, nconv[i].b, Lo, lo_len, 1, nconv[i].pad, xs, nullptr, nullptr, 0.f, part, sums_xs, Fp, l120, false)) return 1; }
+        else if (nconv[i].poly && Fp % nconv[i].stride == 0) {
+            if (Gf.gemm(hs16, nconv[i].stride * hsp, nconv[i].wp, nconv[i].b, Fp / nconv[i].stride, Lo, nullptr, lo_len, 1, 1, nconv[i].padp, xs, C, 0, nullptr, 0, 0, nullptr, 0,
+                        nullptr, 0, 0.f, ACT_NONE, -1, true)) return 1;
+        } else if (Gf.gemm(hs16, hsp, nconv[i].w, nconv[i].b, Fp, Lo, l120, lo_len, nconv[i].stride, 1, nconv[i].pad, xs, C, 0)) return 1;
         if (Gf.gen_resblock(nres[i], gbD, sty_n[1], xs, Lo, lo_len, curg, u, 0.f, scr, a16, sums2, part, sums_xs, sums_cur)) return 1;   // cur = up + x_source
         if (Gf.tap(i == 0 ? "gen_in0" : "gen_in1", curg, (int64_t) B * Lo, C, C, Lo)) return 1;
         for (int j = 0; j < 3; j++) {

@@ -86,7 +86,8 @@ struct Kokoro {
         // polyphase tensor-core form (K == 2*stride): N = stride*Cout phases, 2 taps, 3*Cin split-fp16 channels
         bool poly = false; W16 w3; float * b_rep = nullptr;
     } ups[2];
-    struct NoiseConv { W16 w; float * b = nullptr; int stride = 1, pad = 0; } nconv[2];
+    // strided noise conv: `wp` is its polyphase form (stride 1 over rows of `stride` input frames, see Kokoro::prepare) for the tcgen05 kernel
+    struct NoiseConv { W16 w, wp; float * b = nullptr; int stride = 1, pad = 0, padp = 0; bool poly = false; } nconv[2];
     GenResBlock nres[2], res[6];
     W16 conv_post; float * conv_post_b = nullptr; int post_pad = 3;
     // style projections (F32): kind 0 = prosody style (voice[:,128:256]), 1 = decoder style (voice[:,0:128])

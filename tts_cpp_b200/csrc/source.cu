@@ -137,7 +137,7 @@ __global__ void source_har_kernel(const SourceParams p) {
 
 // ---------------------------------------------------------------- STFT n_fft=20 hop=5, centre reflect, |X| and angle
 __global__ void stft20_kernel(const float * __restrict__ har, int Smax, const int * __restrict__ lenS, int Fmax, __half * outH, int ldoh, int Cpad,
-                              float * outF, int ldof) {
+                              float * outF, int ldof, int FpitchH) {
     const int b = blockIdx.y;
     const int S = lenS[b];
     const int nfr = S / 5 + 1;
@@ -169,7 +169,7 @@ __global__ void stft20_kernel(const float * __restrict__ har, int Smax, const in
         if (outF) { outF[row * ldof + k] = mag; outF[row * ldof + 11 + k] = ang; }
     }
     if (outH) {
-        __half * o = outH + row * ldoh;
+        __half * o = outH + ((size_t) b * FpitchH + f) * ldoh;
         if (Cpad % 8 == 0 && Cpad >= 24 && ldoh % 8 == 0 && ((((uintptr_t) outH) & 15) == 0)) {
             // the operand row (22 values + zero pad channels) leaves as 16-byte stores: a row is one or two full 64-byte sectors
             __half hv[24];
@@ -353,10 +353,10 @@ int source_har(Ctx * ctx, const SourceParams & p) {
     return 0;
 }
 
-int stft20(Ctx * ctx, const float * har, int Smax, int B, const int * lenS, int Fmax, __half * outH, int ldoh, int Cpad, float * outF, int ldof) {
+int stft20(Ctx * ctx, const float * har, int Smax, int B, const int * lenS, int Fmax, __half * outH, int ldoh, int Cpad, float * outF, int ldof, int FpitchH) {
     if (ensure_tables()) return 1;
     dim3 grid(cdiv(Fmax, 128), B);
-    stft20_kernel<<<grid, 128, 0, ctx->stream>>>(har, Smax, lenS, Fmax, outH, ldoh, Cpad, outF, ldof);
+    stft20_kernel<<<grid, 128, 0, ctx->stream>>>(har, Smax, lenS, Fmax, outH, ldoh, Cpad, outF, ldof, FpitchH > 0 ? FpitchH : Fmax);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
