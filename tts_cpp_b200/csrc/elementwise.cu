@@ -538,7 +538,7 @@ __global__ void albert_attention_kernel(const float * __restrict__ qkv, int Lmax
 // head dim 64 (Kokoro's ALBERT): one block per (tile of 16 queries, head, utterance), 128 threads.  Keys / values stream through
 // shared memory in tiles of 64; a thread owns one key (scores) or one output dim (PV) for 8 queries, so every shared-memory read is
 // either a broadcast or conflict-free and there are no shuffle reductions in the inner loops.
-constexpr int ATT_Q = 16, ATT_K = 64, ATT_HD = 64;
+constexpr int ATT_Q = 16, ATT_K = 128, ATT_HD = 64;   // key / value tile of 128 rows: a 66-token prompt is one tile (two with 64 wasted a pass)
 __global__ void __launch_bounds__(128) albert_attention64_kernel(const float * __restrict__ qkv, int Lmax, const int * __restrict__ len, int heads,
                                                                  float scale, __half * outH, int ldoh, int n_pad) {
     extern __shared__ float sm[];
@@ -559,21 +559,29 @@ __global__ void __launch_bounds__(128) albert_attention64_kernel(const float * _
     // ---- scores
     for (int k0 = 0; k0 < n; k0 += ATT_K) {
         __syncthreads();
-        for (int i = tid; i < ATT_K * ATT_HD; i += 128) {
+        const int kn = min(ATT_K, n - k0);
+        for (int i = tid; i < kn * ATT_HD; i += 128) {
             const int j = i >> 6, d = i & 63;
-            sK[j * (ATT_HD + 1) + d] = (k0 + j < n) ? base[(size_t) (k0 + j) * 3 * D + D + d] : 0.f;
+            sK[j * (ATT_HD + 1) + d] = base[(size_t) (k0 + j) * 3 * D + D + d];
         }
         __syncthreads();
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // a thread scores key jj and, where the tile has that many, key jj + 64 (the test is warp-uniform: 32 consecutive keys per warp)
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            const int kj = jj + 64 * half;
+            if ((kj & ~31) >= kn) break;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int kr = kj < kn ? kj : 0;
 #pragma unroll 8
-        for (int d = 0; d < ATT_HD; d++) {
-            const float kv = sK[jj * (ATT_HD + 1) + d];
+            for (int d = 0; d < ATT_HD; d++) {
+                const float kv = sK[kr * (ATT_HD + 1) + d];
 #pragma unroll
-            for (int u = 0; u < 8; u++) acc[u] = fmaf(sQ[(qg + u) * ATT_HD + d], kv, acc[u]);
-        }
-        if (k0 + jj < n) {
+                for (int u = 0; u < 8; u++) acc[u] = fmaf(sQ[(qg + u) * ATT_HD + d], kv, acc[u]);
+            }
+            if (kj < kn) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) sS[(qg + u) * n_pad + k0 + jj] = acc[u] * scale;
+                for (int u = 0; u < 8; u++) sS[(qg + u) * n_pad + k0 + kj] = acc[u] * scale;
+            }
         }
     }
     __syncthreads();
@@ -597,12 +605,12 @@ __global__ void __launch_bounds__(128) albert_attention64_kernel(const float * _
     float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < n; k0 += ATT_K) {
         __syncthreads();
-        for (int i = tid; i < ATT_K * ATT_HD; i += 128) {
+        const int kn = min(ATT_K, n - k0);
+        for (int i = tid; i < kn * ATT_HD; i += 128) {
             const int j = i >> 6, d = i & 63;
-            sK[j * ATT_HD + d] = (k0 + j < n) ? base[(size_t) (k0 + j) * 3 * D + 2 * D + d] : 0.f;
+            sK[j * ATT_HD + d] = base[(size_t) (k0 + j) * 3 * D + 2 * D + d];
         }
         __syncthreads();
-        const int kn = min(ATT_K, n - k0);
         for (int j = 0; j < kn; j++) {
             const float vv = sK[j * ATT_HD + jj];
 #pragma unroll

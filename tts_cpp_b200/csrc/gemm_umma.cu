@@ -506,6 +506,7 @@ int umma_init() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaFuncSetAttribute(conv_umma_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_TOTAL) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_TOTAL) != cudaSuccess ||
         cudaFuncSetAttribute(conv_umma_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_TOTAL) != cudaSuccess) {
         cudaGetLastError();
         return g_umma_state;
@@ -524,6 +525,14 @@ static bool umma_shape_ok(const ConvGemmParams & p) {
     if (p.N >= 128 && p.Npad % 128 == 0) return true;
     return p.N < 128 && p.Npad % 64 == 0 && (int64_t) p.B * p.LmaxOut >= 32768;
 }
+// tile shape: Cout % 256 == 0 -> 128 x 256 (or 128 x 128 when that would leave more than half of the SMs without a tile: small
+// pointwise layers); otherwise 256 x 128
+static void umma_config(const ConvGemmParams & p, int & NT, int & NH) {
+    if (p.Npad % 256 == 0) {
+        const int64_t tiles256 = (int64_t) p.B * cdiv(p.LmaxOut, 128) * cdiv(p.N, 256);
+        NT = (2 * tiles256 <= g_num_sms && !p.statsPart) ? 128 : 256; NH = 1;
+    } else { NT = 128; NH = 2; }
+}
 int conv_umma_tile_m(const ConvGemmParams & p) {
     if (!umma_shape_ok(p)) return 0;
     return (p.Npad % 256 == 0) ? 128 : 256;
@@ -541,7 +550,9 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p_in) {
             p.LmaxIn = p.LmaxOut = p.B * p.LmaxOut; p.B = 1; p.lenIn = p.lenOut = nullptr;
         }
     }
-    const int NT = (p.Npad % 256 == 0) ? 256 : 128, NH = NT == 256 ? 1 : 2, TM = UM * NH;
+    int NT, NH;
+    umma_config(p, NT, NH);
+    const int TM = UM * NH;
     const int FIXED_BYTES = fixed_bytes(NT);
     const int RA = round_up(TM + (p.KW - 1) * p.dil, 16);
     if (RA > RA_MAX) return 2;
@@ -590,8 +601,9 @@ int conv_umma(Ctx * ctx, const ConvGemmParams & p_in) {
         snprintf(ctx->tag, sizeof(ctx->tag), "%s N%d K%d C%d L%d B%d d%d", "umma", p.N, p.KW, p.CinPad, p.LmaxOut, p.B, p.dil);
         ctx->prof_begin(PROF_GEMM, 2.0 * rows * p.N * p.KW * cin, rows * cin * 2.0 + (double) p.N * p.KW * cin * 2.0 + rows * p.N * 4.0);
     }
-    if (NT == 256) conv_umma_kernel<256, 1><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
-    else           conv_umma_kernel<128, 2><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
+    if (NT == 256)    conv_umma_kernel<256, 1><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
+    else if (NH == 1) conv_umma_kernel<128, 1><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
+    else              conv_umma_kernel<128, 2><<<grid, UMMA_THREADS, UMMA_SMEM_TOTAL, ctx->stream>>>(p, e, tmA, tmB);
     ctx->prof_end();
     ctx->umma_launches++;
     B2_LAUNCH_CHECK(ctx);
