@@ -572,11 +572,14 @@ __global__ void __launch_bounds__(128) albert_attention64_kernel(const float * _
             if ((kj & ~31) >= kn) break;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const int kr = kj < kn ? kj : 0;
-#pragma unroll 8
-            for (int d = 0; d < ATT_HD; d++) {
-                const float kv = sK[kr * (ATT_HD + 1) + d];
+#pragma unroll 4
+            for (int d = 0; d < ATT_HD; d += 4) {      // 4 key values + 8 broadcast 16-byte query loads per 32 FMAs
+                const float k0v = sK[kr * (ATT_HD + 1) + d], k1v = sK[kr * (ATT_HD + 1) + d + 1], k2v = sK[kr * (ATT_HD + 1) + d + 2], k3v = sK[kr * (ATT_HD + 1) + d + 3];
 #pragma unroll
-                for (int u = 0; u < 8; u++) acc[u] = fmaf(sQ[(qg + u) * ATT_HD + d], kv, acc[u]);
+                for (int u = 0; u < 8; u++) {
+                    const float4 q4 = *reinterpret_cast<const float4 *>(sQ + (qg + u) * ATT_HD + d);
+                    acc[u] = fmaf(q4.w, k3v, fmaf(q4.z, k2v, fmaf(q4.y, k1v, fmaf(q4.x, k0v, acc[u]))));
+                }
             }
             if (kj < kn) {
 #pragma unroll
@@ -611,7 +614,16 @@ __global__ void __launch_bounds__(128) albert_attention64_kernel(const float * _
             sK[j * ATT_HD + d] = base[(size_t) (k0 + j) * 3 * D + 2 * D + d];
         }
         __syncthreads();
-        for (int j = 0; j < kn; j++) {
+        int j = 0;
+        for (; j + 4 <= kn; j += 4) {                  // n_pad % 4 == 0 and k0 % 4 == 0: the probability rows are 16-byte readable
+            const float v0 = sK[j * ATT_HD + jj], v1 = sK[(j + 1) * ATT_HD + jj], v2 = sK[(j + 2) * ATT_HD + jj], v3 = sK[(j + 3) * ATT_HD + jj];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float4 p4 = *reinterpret_cast<const float4 *>(sS + (qg + u) * n_pad + k0 + j);
+                out[u] = fmaf(p4.w, v3, fmaf(p4.z, v2, fmaf(p4.y, v1, fmaf(p4.x, v0, out[u]))));
+            }
+        }
+        for (; j < kn; j++) {
             const float vv = sK[j * ATT_HD + jj];
 #pragma unroll
             for (int u = 0; u < 8; u++) out[u] = fmaf(sS[(qg + u) * n_pad + k0 + j], vv, out[u]);
@@ -890,7 +902,7 @@ int embed_rows_h(Ctx * ctx, const int * tokens, const int * tok_off, const __hal
 int albert_attention(Ctx * ctx, const float * qkv, int B, int Lmax, const int * len, int heads, int hd, float scale, __half * outH, int ldoh) {
     if (hd > 128) { set_error("albert_attention: head dim %d > 128", hd); return 1; }
     if (hd == ATT_HD) {
-        const int n_pad = Lmax + 1;
+        const int n_pad = round_up(Lmax, 4) + 4;   // multiple of 4 floats (16-byte row reads), not of 32 (bank spread)
         const size_t smem64 = (size_t) (ATT_Q * ATT_HD + ATT_K * (ATT_HD + 1) + ATT_Q * n_pad) * sizeof(float);
         if (smem64 <= 200 * 1024) {
             static bool attr_set = false;

@@ -16,7 +16,13 @@ namespace {
 
 // ---------------------------------------------------------------- minstd_rand0 with jump-ahead
 constexpr unsigned long long LCG_M = 2147483647ull, LCG_A = 16807ull;
-__device__ __forceinline__ unsigned long long mulmod(unsigned long long a, unsigned long long b) { return (a * b) % LCG_M; }
+// (a * b) mod (2^31 - 1) for a, b < 2^31: Mersenne folding (2^31 == 1 mod M) instead of a 64-bit remainder
+__device__ __forceinline__ unsigned long long mulmod(unsigned long long a, unsigned long long b) {
+    const unsigned long long p = a * b;                                   // < 2^62
+    unsigned long long r = (p & LCG_M) + (p >> 31);                       // < 2^32
+    r = (r & LCG_M) + (r >> 31);                                          // <= M + 1
+    return r >= LCG_M ? r - LCG_M : r;
+}
 __device__ unsigned long long lcg_state(unsigned long long k) {   // A^k mod M == state after k draws from seed 1
     unsigned long long r = 1, a = LCG_A;
     k %= (LCG_M - 1);
@@ -25,7 +31,7 @@ __device__ unsigned long long lcg_state(unsigned long long k) {   // A^k mod M =
 }
 __device__ __forceinline__ float lcg_to_uniform(unsigned long long x) {
     // libstdc++ generate_canonical<float,24> over minstd_rand0: (float)(x - 1) / (float)2147483646  [== 2^31 in fp32], clamp < 1
-    float u = __fdiv_rn((float) (x - 1ull), 2147483648.0f);
+    float u = (float) (x - 1ull) * 4.656612873077392578125e-10f;   // / 2^31: a power of two, so the product is the exactly rounded quotient
     return u >= 1.0f ? 0.99999994f : u;
 }
 
