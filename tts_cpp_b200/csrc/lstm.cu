@@ -9,11 +9,13 @@
 //     (h re-rounded to fp16 exactly like ggml does for an F16 weight, ggml-cpu.c:262-267);
 //   * gate math (sigmoid/tanh, c = f*c + i*g, h = o*tanh(c), model.cpp:63-76) happens in registers, the cell
 //     state never leaves them;
-//   * the new h slice is broadcast to the 8 CTAs' shared memory through DSMEM and one cluster barrier ends the step.
+//   * the new h slice is broadcast to the 8 CTAs' shared memory through DSMEM as st.async stores that complete a transaction count
+//     on each destination's mbarrier: a CTA waits only for its own buffer to fill, there is no cluster-wide barrier per step.
 // The input-side projections W_ih x + b_ih for all steps come from conv_gemm (they are one big GEMM), laid out
 // [b][t][dir][unit][gate] so a thread fetches its 4 gate pre-activations with one 16-byte load.
 // Ragged batches: utterance b is active for len[b] steps; the reverse direction walks t = len[b]-1-s.
 #include "common.cuh"
+#include <cstdlib>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -28,7 +30,8 @@ constexpr int LDW = 264;                              // smem row stride (halves
 constexpr int SW_BYTES = 128 * LDW * 2;
 constexpr int SH_BYTES = 2 * NBT * LDW * 2;
 constexpr int ST_BYTES = NBT * UNITS * 2;
-constexpr int LSTM_SMEM = SW_BYTES + SH_BYTES + ST_BYTES;
+constexpr int LSTM_SMEM = SW_BYTES + SH_BYTES + ST_BYTES + 16;   // + two mbarriers (the asynchronous h exchange)
+constexpr unsigned STEP_BYTES = CL * NBT * UNITS * 2;         // bytes a CTA receives per step: a [NBT][UNITS] fp16 slice from each of the CL CTAs
 
 __device__ __forceinline__ void ldsm_x4(unsigned & r0, unsigned & r1, unsigned & r2, unsigned & r3, const void * p) {
     unsigned s = (unsigned) __cvta_generic_to_shared(p);
@@ -45,11 +48,13 @@ __device__ __forceinline__ void mma16816(float * c, const unsigned * a, unsigned
 }
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }  // ggml_vec_sigmoid_f32
 
+template <bool ASYNC>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(const LstmParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half * sW  = reinterpret_cast<__half *>(smem_raw);                       // [128][LDW]
     __half * sH  = reinterpret_cast<__half *>(smem_raw + SW_BYTES);            // [2][NBT][LDW]
     __half * sSt = reinterpret_cast<__half *>(smem_raw + SW_BYTES + SH_BYTES); // [NBT][UNITS]
+    unsigned long long * hbar = reinterpret_cast<unsigned long long *>(smem_raw + SW_BYTES + SH_BYTES + ST_BYTES);   // [2]: one per h buffer
 
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int) cluster.block_rank();
@@ -91,6 +96,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
 #pragma unroll
     for (int g = 0; g < 4; g++) bh[g] = p.bhh[dir * 4 * H + g * H + unit_g];
 
+    // ASYNC: the step's h slices travel as st.async (remote shared-memory stores that complete a transaction count on the DESTINATION
+    // CTA's mbarrier); a CTA just waits for its own barrier to have received all CL slices.  No cluster-wide barrier and no release
+    // fence per step: ncu showed 22 % of the stall samples of the barrier version on the ERRBAR of barrier.cluster.arrive.release.
+    // Double buffering is enough: a CTA sends D(s+2) only after it received everybody's D(s+1), which each sender produced after
+    // it had finished reading D(s) -- so nobody overwrites a buffer (or runs a barrier phase) that is still in use.
+    const unsigned hbar_s = (unsigned) __cvta_generic_to_shared(hbar);
+    if (ASYNC && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hbar_s));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hbar_s + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // arm both buffers: D(0) lands in buffer 1, D(1) in buffer 0
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hbar_s), "r"(STEP_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hbar_s + 8), "r"(STEP_BYTES) : "memory");
+    }
+    unsigned hphase0 = 0u, hphase1 = 0u;
     __syncthreads();
     cluster.sync();
 
@@ -182,13 +202,44 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256) bilstm_kernel(
             const int dest = q / (NBT * 4), rem = q % (NBT * 4), u = rem >> 2, part = rem & 3;
             const int4 v = *reinterpret_cast<const int4 *>(sSt + u * UNITS + part * 8);
             __half * dst_local = hnxt + u * LDW + rank * UNITS + part * 8;
-            int4 * dst = reinterpret_cast<int4 *>(cluster.map_shared_rank(dst_local, dest));
-            *dst = v;
+            if constexpr (ASYNC) {
+                if (s + 1 < nsteps) {   // the last step's h is never consumed
+                    unsigned ra, rb;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((unsigned) __cvta_generic_to_shared(dst_local)), "r"(dest));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(hbar_s + 8u * ((s + 1) & 1)), "r"(dest));
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                 ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rb) : "memory");
+                }
+            } else {
+                int4 * dst = reinterpret_cast<int4 *>(cluster.map_shared_rank(dst_local, dest));
+                *dst = v;
+            }
         }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        if (s + 1 < nsteps) load_xp(s + 1);
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if constexpr (ASYNC) {
+            if (s + 1 < nsteps) {
+                load_xp(s + 1);
+                const int bi = (s + 1) & 1;
+                const unsigned bar = hbar_s + 8u * bi, par = bi ? hphase1 : hphase0;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred P1;\n\t"
+                    "LAB_WAIT:\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                    "@P1 bra DONE;\n\t"
+                    "bra LAB_WAIT;\n\t"
+                    "DONE:\n\t"
+                    "}" ::"r"(bar), "r"(par) : "memory");
+                if (bi) hphase1 ^= 1u; else hphase0 ^= 1u;
+                // re-arm this buffer's barrier for D(s+2) (its data cannot arrive before every thread here has passed the wait above)
+                if (tid == 0 && s + 3 < nsteps + 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STEP_BYTES) : "memory");
+            }
+        } else {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            if (s + 1 < nsteps) load_xp(s + 1);
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
     }
+    if constexpr (ASYNC) cluster.sync();   // nobody leaves while a peer might still address its shared memory
 }
 
 }  // namespace
@@ -197,12 +248,15 @@ int bilstm(Ctx * ctx, const LstmParams & p) {
     if (p.B <= 0 || p.maxLen <= 0) return 0;
     static bool attr_done = false;
     if (!attr_done) {
-        B2_CUDA(cudaFuncSetAttribute(bilstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
+        B2_CUDA(cudaFuncSetAttribute(bilstm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
+        B2_CUDA(cudaFuncSetAttribute(bilstm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
         attr_done = true;
     }
     dim3 grid(CL, 2, cdiv(p.B, NBT));
     ctx->prof_begin(PROF_LSTM, 2.0 * p.B * p.maxLen * 2.0 * 1024.0 * 256.0, 0.0);
-    bilstm_kernel<<<grid, 256, LSTM_SMEM, ctx->stream>>>(p);
+    static const bool use_async = getenv("B2TTS_LSTM_BARRIER") == nullptr;   // default: st.async exchange; the cluster-barrier form is kept for A/B runs
+    if (use_async) bilstm_kernel<true><<<grid, 256, LSTM_SMEM, ctx->stream>>>(p);
+    else           bilstm_kernel<false><<<grid, 256, LSTM_SMEM, ctx->stream>>>(p);
     ctx->prof_end();
     B2_LAUNCH_CHECK(ctx);
     return 0;
