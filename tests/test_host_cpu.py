@@ -108,3 +108,36 @@ def test_scatter_gather_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_polyphase_identity_of_the_strided_noise_conv():
+    """The strided noise conv (K = 12, stride 6, pad 3) runs on the tcgen05 kernel as a stride-1 conv over rows of `stride` input
+    frames (tts_cpp_b200/csrc/kokoro.cu, Kokoro::prepare).  This restates that re-indexing in numpy and checks it against the plain
+    strided conv, for the model's shape and for shapes that exercise pad % stride == 0 and K not a multiple of the stride."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(3)
+    for (K, s, pad, Cin, N, L) in ((12, 6, 3, 22, 8, 121), (12, 6, 6, 5, 3, 66), (7, 3, 2, 4, 2, 40), (10, 5, 0, 3, 2, 35)):
+        x = rng.standard_normal((Cin, L)).astype(np.float64)
+        w = rng.standard_normal((N, Cin, K)).astype(np.float64)
+        want = F.conv1d(torch.from_numpy(x)[None], torch.from_numpy(w), None, stride=s, padding=pad)[0].numpy()
+        sh = (s - pad % s) % s
+        Kp = (K + sh + s - 1) // s
+        padp = pad // s + (1 if sh else 0)
+        Lp = -(-L // s) * s                       # per-utterance pitch rounded up to the stride, rows past the end are zeros
+        xp = np.zeros((Cin, Lp)); xp[:, :L] = x
+        X = xp.reshape(Cin, Lp // s, s)           # X[c][r][j] = x[c][r*s + j]
+        wp = np.zeros((N, Kp, s, Cin))
+        for m in range(Kp):
+            for j in range(s):
+                k = m * s + j - sh
+                if 0 <= k < K:
+                    wp[:, m, j, :] = w[:, :, k]
+        Lout = want.shape[1]
+        got = np.zeros((N, Lout))
+        for t in range(Lout):
+            for m in range(Kp):
+                r = t - padp + m
+                if 0 <= r < Lp // s:
+                    got[:, t] += np.einsum("njc,cj->n", wp[:, m], X[:, r, :])
+        assert np.allclose(got, want, atol=1e-10), (K, s, pad)
