@@ -7,6 +7,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       tokens, lens, hidden (duration_hidden_states), f0, n, dec (generator input), har_spec (STFT of the harmonic source),
       pcm -- all dumped from the reference's own GGML graph nodes by oracle/ref_kokoro_driver.cpp
   op_vectors.npz           : known-answer vectors of the patched ggml ops from oracle/ref_ops_driver.cpp
+  dac_vectors.npz          : two 24-frame utterances of codebook indices and the PCM the reference's dac_runner produces for them
+      on the deterministic synthetic DAC GGUF (seed 0, all F32), from oracle/ref_dac_driver.cpp
 """
 import os
 import re
@@ -111,6 +113,22 @@ def op_vectors():
     print("op vectors:", sorted(out))
 
 
+def dac_vectors():
+    from tts_cpp_b200.synth import cached_dac_gguf, synthetic_codes
+    gguf = cached_dac_gguf(seed=0, max_frames=64)
+    codes = synthetic_codes(2, 24)
+    tmp = tempfile.mkdtemp()
+    cf = os.path.join(tmp, "codes.txt")
+    open(cf, "w").write("\n".join(" ".join(map(str, c.reshape(-1))) for c in codes) + "\n")
+    pre = os.path.join(tmp, "d")
+    run([os.path.join(REF, "dac_ref"), gguf, cf, pre, "--threads", "4", "--quiet"])
+    pcm = np.stack([np.fromfile(f"{pre}.u{u}.pcm.f32", np.float32) for u in range(2)])
+    np.savez_compressed(os.path.join(OUT, "dac_vectors.npz"), codes=np.stack(codes).astype(np.int32), pcm=pcm)
+    print("dac vectors:", pcm.shape, "rms", float(np.sqrt((pcm ** 2).mean())))
+
+
 if __name__ == "__main__":
-    kokoro_vectors()
-    op_vectors()
+    which = sys.argv[1:] or ["kokoro", "ops", "dac"]
+    if "kokoro" in which: kokoro_vectors()
+    if "ops" in which: op_vectors()
+    if "dac" in which: dac_vectors()

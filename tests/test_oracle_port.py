@@ -110,3 +110,16 @@ def test_free_running_pcm_is_at_the_reference_build_to_build_floor(port, kv):
     assert np.array_equal(lens, kv["lens"])
     assert pcm.shape == kv["pcm"].shape
     assert 0.8 < rms(pcm) / rms(kv["pcm"]) < 1.25
+
+
+def test_dac_port_against_reference():
+    """oracle/dac_port.py vs the PCM the compiled reference's dac_runner produced for the same codes (tests/golden/dac_vectors.npz)."""
+    from oracle.dac_port import DacPort
+    from tts_cpp_b200.synth import cached_dac_gguf
+    g = np.load(os.path.join(GOLD, "dac_vectors.npz"))
+    port = DacPort(cached_dac_gguf(seed=0, max_frames=64))
+    for u in range(g["codes"].shape[0]):
+        got = port.decode(g["codes"][u].astype(np.uint32))
+        d = rms(got - g["pcm"][u])
+        print(f"dac utterance {u}: rms diff {d:.3e} (signal rms {rms(g['pcm'][u]):.3f})")
+        assert got.shape == g["pcm"][u].shape and d < 5e-6          # fp32 summation-order differences only

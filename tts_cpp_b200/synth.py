@@ -236,6 +236,95 @@ def cached_gguf(dtype: str = "f16", ctx_len: int = 128, seed: int = 0, cache_dir
     return path
 
 
+# ------------------------------------------------------------------------------------------ DAC codec decoder
+DAC_RATES = (8, 8, 4, 2)          # descript-audio-codec 44 kHz decoder: 1536 -> 768 -> 384 -> 192 -> 96 channels, 512 samples per frame
+
+
+def dac_tensors(seed: int = 0, d_model: int = 1536, n_heads: int = 9, codebook: int = 1024, cb_dim: int = 8, latent: int = 1024,
+                rates=DAC_RATES):
+    """Synthetic weights in the reference's DAC schema (py-gguf/tts_encoders/dac_gguf_encoder.py:7-100, names after the
+    "audio_encoder." prefix as dac_model::assign_weight sees them, src/decoder/dac_model.cpp:60-98).  Shapes are PyTorch order."""
+    rng = np.random.default_rng(seed)
+    items: list[tuple[str, np.ndarray]] = []
+
+    def rand(name, shape, fan_in, scale=None):
+        s = (1.0 / np.sqrt(max(fan_in, 1))) if scale is None else scale
+        a = (rng.standard_normal(shape).astype(np.float32) * np.float32(s)).astype(np.float16).astype(np.float32)
+        items.append(("audio_encoder." + name, a))
+
+    def alpha(name, c):
+        a = rng.uniform(0.5, 1.5, size=(1, c, 1)).astype(np.float32).astype(np.float16).astype(np.float32)
+        items.append(("audio_encoder." + name, a))
+
+    for i in range(n_heads):
+        rand(f"quantizers.{i}.codebook.weight", (codebook, cb_dim), 1, 1.0)
+        rand(f"quantizers.{i}.out_proj.weight", (latent, cb_dim, 1), cb_dim * n_heads)
+        rand(f"quantizers.{i}.out_proj.bias", (latent,), 1, 0.02)
+    rand("initial.weight", (d_model, latent, 7), latent * 7)
+    rand("initial.bias", (d_model,), 1, 0.02)
+    c = d_model
+    for l, s in enumerate(rates, start=1):
+        co = c // 2
+        alpha(f"decoder_block.{l}.final.alpha", c)
+        rand(f"decoder_block.{l}.final.weight", (c, co, 2 * s), c * 2)        # ConvTranspose1d kernel [Cin][Cout][K]; 2 taps reach an output
+        rand(f"decoder_block.{l}.final.bias", (co,), 1, 0.02)
+        for i in range(3):
+            b = f"decoder_block.{l}.residual_unit.{i}.res"
+            alpha(f"{b}.initial.alpha", co)
+            rand(f"{b}.initial.weight", (co, co, 7), co * 7 * 4)                # small residual branch keeps the stack well-conditioned
+            rand(f"{b}.initial.bias", (co,), 1, 0.02)
+            alpha(f"{b}.final.alpha", co)
+            rand(f"{b}.final.weight", (co, co, 1), co * 4)
+            rand(f"{b}.final.bias", (co,), 1, 0.02)
+        c = co
+    alpha("final.alpha", c)
+    rand("final.weight", (1, c, 7), c * 7 * 400)                                # keeps the tanh output un-saturated (std ~ 0.3)
+    rand("final.bias", (1,), 1, 0.02)
+    return items
+
+
+def write_dac_gguf(path: str, seed: int = 0, max_frames: int = 128, **kw) -> dict:
+    """Synthetic DAC decoder GGUF, all tensors F32 (the reference's quantizer leaves audio_encoder.* in F32 unless
+    --convert-dac-to-f16 is given, examples/quantize/quantize_impl.cpp:44,265)."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="dac")
+    items = dac_tensors(seed=seed, **kw)
+    n_params = 0
+    for name, arr in items:
+        n_params += arr.size
+        w.add_tensor(name, arr.astype(np.float32))
+    rates = kw.get("rates", DAC_RATES)
+    for i, s in enumerate(rates):
+        w.add_uint32(f"dac.dac_layer_stride_{i}", int(s))
+        w.add_uint32(f"dac.dac_layer_padding_{i}", int((s + 1) // 2))           # DAC: padding = ceil(stride / 2)
+    w.add_uint32("dac.up_sampling_factor", int(np.prod(rates)))
+    w.add_uint32("output_heads", int(kw.get("n_heads", 9)))
+    w.add_uint32("max_generation", int(max_frames))
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def cached_dac_gguf(seed: int = 0, max_frames: int = 128, cache_dir: str | None = None) -> str:
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, f"dac_f32_m{max_frames}_s{seed}.gguf")
+    if not os.path.exists(path):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_dac_gguf(tmp, seed=seed, max_frames=max_frames)
+        os.replace(tmp, path)
+    return path
+
+
+def synthetic_codes(batch: int, frames: int, n_heads: int = 9, codebook: int = 1024, seed0: int = 4321) -> list[np.ndarray]:
+    """Utterance i: frames x n_heads codebook indices, frame-major (the layout dac_runner::run takes), from default_rng(seed0 + i)."""
+    return [np.random.default_rng(seed0 + i).integers(0, codebook, size=(frames, n_heads)).astype(np.uint32) for i in range(batch)]
+
+
 def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
     """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
     out = []
