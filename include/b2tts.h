@@ -127,6 +127,23 @@ int b2tts_op_uniform(b2tts_ctx * ctx, uint64_t skip, int64_t count, float * y);
 int b2tts_op_bilstm(b2tts_ctx * ctx, const float * w_ih, const float * w_hh, const float * b_ih, const float * b_hh, int In, int H,
                     const float * x, int B, int Lmax, const int32_t * len, float * y);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * DAC neural audio codec decoder: codebook indices -> PCM, batched over independent utterances.
+ *   b2tts_dac_load_gguf  : dac_model::setup_from_file + the assign_weight loop over the "audio_encoder.*" tensors + prepare_post_load
+ *                          (reference src/decoder/dac_model.h:40-44, src/decoder/dac_model.cpp:14-98,139-144; src/models/parler/loader.cpp:12-20,
+ *                          src/models/loaders.cpp:79-89).  Works on a Parler / Dia GGUF or on a file holding only the codec.
+ *   b2tts_dac_decode_batch : dac_runner::run (src/decoder/dac_model.cpp:172-212) for n_utterances at once.  codes[b] = frames[b] * n_heads
+ *                          indices, frame-major (index of head h at frame t is codes[b][t*n_heads + h], the layout the reference takes);
+ *                          pcm[b] = frames[b] * up_sampling_factor samples in a runner-owned pinned host buffer, valid until the next call
+ *                          on this model (the lifetime of tts_response.data, dac_model.cpp:191).
+ * All return 0 on success; on failure b2tts_last_error() holds the message (the reference would TTS_ABORT). */
+typedef struct b2tts_dac b2tts_dac;
+int   b2tts_dac_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dac ** out);
+void  b2tts_dac_free(b2tts_dac * m);
+int   b2tts_dac_info(const b2tts_dac * m, int * n_heads, int * up_sampling_factor, int * codebook_size);
+int   b2tts_dac_decode_batch(b2tts_dac * m, int n_utterances, const uint32_t * const * codes, const int32_t * frames, const float ** pcm, int64_t * n_samples);
+float b2tts_dac_last_ms(const b2tts_dac * m);   /* device time of the last decode_batch (CUDA events), for bench / tests */
+
 #ifdef __cplusplus
 }
 #endif

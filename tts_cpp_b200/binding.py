@@ -225,3 +225,51 @@ def runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> 
     h = C.c_void_p()
     _chk(lib().b2tts_kokoro_load_gguf(ctx.h, path.encode(), C.byref(h)))
     return KokoroRunner(ctx, h)
+
+
+class DacRunner:
+    """dac_runner (reference src/decoder/dac_model.h:78-97): codebook indices -> PCM, batched over independent utterances."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        nh, up, cb = C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().b2tts_dac_info(self.h, C.byref(nh), C.byref(up), C.byref(cb)))
+        self.n_heads, self.up_sampling_factor, self.codebook_size = nh.value, up.value, cb.value
+
+    def run_batch(self, codes, copy: bool = True):
+        """codes: list of [frames, n_heads] integer arrays (frame-major, the layout dac_runner::run takes).  Returns list of PCM arrays
+        (copy=False: views of the runner's pinned host buffer, valid until its next call)."""
+        B = len(codes)
+        arrs = [np.ascontiguousarray(np.asarray(c, np.uint32).reshape(-1, self.n_heads)) for c in codes]
+        frames = np.array([a.shape[0] for a in arrs], np.int32)
+        ptrs = (C.POINTER(C.c_uint32) * B)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        pcm = (C.POINTER(C.c_float) * B)()
+        ns = (C.c_int64 * B)()
+        _chk(lib().b2tts_dac_decode_batch(self.h, B, ptrs, frames.ctypes.data_as(C.POINTER(C.c_int32)), pcm, ns))
+        outs = []
+        for b in range(B):
+            a = np.ctypeslib.as_array(pcm[b], shape=(int(ns[b]),))
+            outs.append(a.copy() if copy else a)
+        return outs
+
+    def run(self, codes):
+        return self.run_batch([codes])[0]
+
+    def last_ms(self) -> float:
+        lib().b2tts_dac_last_ms.restype = C.c_float
+        return float(lib().b2tts_dac_last_ms(self.h))
+
+    def close(self):
+        if self.h:
+            lib().b2tts_dac_free(self.h)
+            self.h = None
+
+
+def dac_runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> DacRunner:
+    """The audio decoder half of the reference's Parler / Dia loaders (src/models/parler/loader.cpp:12-20): reads the "audio_encoder.*"
+    tensors of a GGUF."""
+    ctx = ctx or Context(device)
+    h = C.c_void_p()
+    _chk(lib().b2tts_dac_load_gguf(ctx.h, path.encode(), C.byref(h)))
+    return DacRunner(ctx, h)

@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" boundary of libb2tts.so (declared in include/b2tts.h).
 #include "../../include/b2tts.h"
 #include "kokoro.h"
+#include "dac.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -22,6 +23,7 @@ using namespace b2;
 
 struct b2tts_ctx { Ctx c; };
 struct b2tts_kokoro { Kokoro k; };
+struct b2tts_dac { Dac d; };
 
 namespace {
 // RAII device scratch for the op-level entry points
@@ -110,6 +112,30 @@ int b2tts_kokoro_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_kokoro ** o
     return 0;
 }
 void b2tts_kokoro_free(b2tts_kokoro * m) { if (m) { m->k.free_all(); delete m; } }
+
+// ---- DAC codec decoder
+int b2tts_dac_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dac ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_dac * m = new b2tts_dac();
+    m->d.ctx = &ctx->c;
+    if (load_gguf_into(&m->d, path)) { m->d.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_dac_free(b2tts_dac * m) { if (m) { m->d.free_all(); delete m; } }
+int b2tts_dac_info(const b2tts_dac * m, int * n_heads, int * up_sampling_factor, int * codebook_size) {
+    if (!m) { set_error("null model"); return 1; }
+    if (n_heads) *n_heads = m->d.n_heads;
+    if (up_sampling_factor) *up_sampling_factor = m->d.up_factor;
+    if (codebook_size) *codebook_size = m->d.n_codes;
+    return 0;
+}
+int b2tts_dac_decode_batch(b2tts_dac * m, int n_utterances, const uint32_t * const * codes, const int32_t * frames, const float ** pcm, int64_t * n_samples) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->d.decode_batch(n_utterances, codes, frames, pcm, n_samples);
+}
+float b2tts_dac_last_ms(const b2tts_dac * m) { return m ? m->d.timing_ms : 0.f; }
 int b2tts_kokoro_n_voices(const b2tts_kokoro * m) { return (int) m->k.voice_names.size(); }
 const char * b2tts_kokoro_voice_name(const b2tts_kokoro * m, int i) { return (i >= 0 && i < (int) m->k.voice_names.size()) ? m->k.voice_names[i].c_str() : nullptr; }
 size_t b2tts_kokoro_weight_bytes(const b2tts_kokoro * m) { return m->k.weight_bytes; }

@@ -69,7 +69,7 @@ static inline int round_up(int a, int m) { return (a + m - 1) / m * m; }
 // The reference computes these contractions as ggml_mul_mat / im2col+mul_mat with F16 weights: activations
 // re-rounded to fp16, products accumulated in fp32 (ggml-cpu.c:262-267, ggml.c:3870-3894).
 // ---------------------------------------------------------------------------------------------
-enum { ACT_NONE = 0, ACT_GELU_F16LUT = 1, ACT_EXP_SIN_11 = 2, ACT_LRELU_02 = 3 };
+enum { ACT_NONE = 0, ACT_GELU_F16LUT = 1, ACT_EXP_SIN_11 = 2, ACT_LRELU_02 = 3, ACT_TANH = 4 };
 
 struct ConvGemmParams {
     const __half * A       = nullptr;

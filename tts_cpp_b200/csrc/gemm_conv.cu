@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemmParams p) 
                     if (p.div != 0.f) v = __fdiv_rn(v, p.div);
                     if (p.act == ACT_GELU_F16LUT) v = gelu_f16lut(v);
                     else if (p.act == ACT_EXP_SIN_11) v = (c < 11) ? expf(v) : sinf(v);
+                    else if (p.act == ACT_TANH) v = tanhf(v);
                     else if (p.act == ACT_LRELU_02) v = (v > 0.f ? v : 0.f) + 0.2f * (v < 0.f ? v : 0.f);
                     if (p.outF) p.outF[(size_t) r * p.ldo + p.coff + c] = v;
                     if (p.outH) p.outH[(size_t) r * p.ldoh + p.coffh + c] = __float2half_rn(v);

@@ -351,6 +351,9 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                             } else if (p.act == ACT_EXP_SIN_11) {
 #pragma unroll
                                 for (int k = 0; k < 4; k++) x[k] = (cb + cc4 + k < 11) ? expf(x[k]) : sinf(x[k]);
+                            } else if (p.act == ACT_TANH) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) x[k] = tanhf(x[k]);
                             }
                         }
                         if (4 * i < nrows) {
@@ -441,6 +444,7 @@ conv_umma_kernel(const ConvGemmParams p, const UmmaExtra e, const __grid_constan
                             if (p.act == ACT_GELU_F16LUT) x = gelu_f16lut_u(x);
                             else if (p.act == ACT_LRELU_02) x = (x > 0.f ? x : 0.f) + 0.2f * (x < 0.f ? x : 0.f);
                             else if (p.act == ACT_EXP_SIN_11) x = (c < 11) ? expf(x) : sinf(x);
+                            else if (p.act == ACT_TANH) x = tanhf(x);
                             if (do_f) p.outF[row * p.ldo + p.coff + c] = x;
                             if (do_h) p.outH[row * p.ldoh + p.coffh + c] = __float2half_rn(x);
                             s0 += x; q0 += x * x;

@@ -6,6 +6,9 @@
 // tts_generation_runner::assign_weight -- followed by prepare() (prepare_post_load).  Written from the GGUF format
 // specification; no ggml code is linked.
 #include "kokoro.h"
+#include "dac.h"
+
+#include <functional>
 
 #include <cstdio>
 #include <cstring>
@@ -65,7 +68,12 @@ bool read_value(Cursor & c, uint32_t t, uint32_t * u32_out, std::string * str_ou
 
 }  // namespace
 
-int load_gguf_into(Kokoro * m, const char * path) {
+namespace {
+
+// walks the file: u32 metadata into `kv`, every F32/F16 tensor whose name starts with `prefix` to `on_tensor`; `arch` (if given) must
+// match general.architecture
+int read_gguf(const char * path, const char * prefix, const char * arch_required, std::map<std::string, uint32_t> & kv,
+              const std::function<int(const char *, int, int, const int64_t *, const void *, size_t)> & on_tensor) {
     int fd = open(path, O_RDONLY);
     if (fd < 0) { set_error("cannot open '%s'", path); return 1; }
     struct stat st;
@@ -89,11 +97,11 @@ int load_gguf_into(Kokoro * m, const char * path) {
             uint32_t t = c.rd<uint32_t>();
             uint32_t u = 0; bool is_u32 = (t == 4); std::string s;
             if (!read_value(c, t, &u, &s, nullptr)) { bad = true; break; }
-            if (is_u32) { m->kv[key] = u; if (key == "general.alignment") alignment = u; }
+            if (is_u32) { kv[key] = u; if (key == "general.alignment") alignment = u; }
             if (key == "general.architecture") arch = s;
         }
         if (bad || !c.ok) { set_error("%s: corrupt GGUF metadata", path); break; }
-        if (arch != "kokoro") { set_error("%s: general.architecture is '%s', this loader handles 'kokoro'", path, arch.c_str()); break; }
+        if (arch_required && arch != arch_required) { set_error("%s: general.architecture is '%s', this loader handles '%s'", path, arch.c_str(), arch_required); break; }
         struct TI { std::string name; int nd; int64_t ne[4]; uint32_t type; uint64_t off; };
         std::vector<TI> tis((size_t) n_tensors);
         for (auto & t : tis) {
@@ -107,18 +115,31 @@ int load_gguf_into(Kokoro * m, const char * path) {
         size_t data0 = (size_t) (c.p - base);
         data0 = (data0 + alignment - 1) / alignment * alignment;
         for (auto & t : tis) {
-            if (t.name.rfind("kokoro.", 0) != 0) continue;
+            if (t.name.rfind(prefix, 0) != 0) continue;
             int64_t n = 1; for (int d = 0; d < t.nd; d++) n *= t.ne[d];
             size_t esz = t.type == 0 ? 4 : t.type == 1 ? 2 : 0;
-            if (!esz) { set_error("%s: tensor '%s' has ggml type %u; only F32/F16 Kokoro files are supported", path, t.name.c_str(), t.type); bad = true; break; }
+            if (!esz) { set_error("%s: tensor '%s' has ggml type %u; only F32/F16 files are supported", path, t.name.c_str(), t.type); bad = true; break; }
             if (data0 + t.off + (size_t) n * esz > (size_t) st.st_size) { set_error("%s: tensor '%s' runs past the end of the file", path, t.name.c_str()); bad = true; break; }
-            if (m->assign(t.name.c_str(), (int) t.type, t.nd, t.ne, base + data0 + t.off, (size_t) n * esz)) { bad = true; break; }
+            if (on_tensor(t.name.c_str(), (int) t.type, t.nd, t.ne, base + data0 + t.off, (size_t) n * esz)) { bad = true; break; }
         }
         if (bad) break;
-        rc = m->prepare();
+        rc = 0;
     } while (false);
     munmap(map, (size_t) st.st_size);
     return rc;
+}
+
+}  // namespace
+
+int load_gguf_into(Kokoro * m, const char * path) {
+    if (read_gguf(path, "kokoro.", "kokoro", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
+}
+
+// the codec decoder's tensors live under "audio_encoder." in Parler / Dia GGUFs (reference src/decoder/dac_model.h:40-44)
+int load_gguf_into(Dac * m, const char * path) {
+    if (read_gguf(path, "audio_encoder.", nullptr, m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
 }
 
 }  // namespace b2
