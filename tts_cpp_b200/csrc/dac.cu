@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace b2 {
 
@@ -137,11 +138,58 @@ __global__ void dac_operand_kernel(const float * __restrict__ x, int ldx, int C,
     for (int c = CW + threadIdx.x; c < ldo; c += blockDim.x) orow[c] = __float2half_rn(0.f);
 }
 
+// 16-byte flavour (C % 4 == 0, 16-byte aligned rows): a thread converts 4 channels of a row (one float4 load, three 8-byte stores in
+// split mode); blockDim = (64 channel groups, 4 rows), each thread walks the row's groups with stride 64 and 4 rows per block pass
+__global__ void __launch_bounds__(256) dac_operand4_kernel(const float * __restrict__ x, int ldx, int C, int Lmax, const int * __restrict__ len,
+                                                           const float * __restrict__ alpha, int split, __half * outH, int ldo, int Lq) {
+    const int b = blockIdx.y;
+    const int L = len[b];
+    const int CW = split ? 3 * C : C;
+    for (int u = 0; u < 4; u++) {
+        const int q = (blockIdx.x * 4 + u) * 4 + threadIdx.y;
+        if (q >= Lq || q >= L + DAC_TAIL) continue;
+        __half * orow = outH + ((size_t) b * Lq + q) * ldo;
+        if (q >= L) { for (int c = threadIdx.x * 4; c < ldo; c += 256) *reinterpret_cast<uint2 *>(orow + c) = make_uint2(0u, 0u); continue; }
+        const float * row = x + ((size_t) b * Lmax + q) * ldx;
+        for (int c = threadIdx.x * 4; c < C; c += 256) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(row + c);
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            if (alpha) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(alpha + c);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const float s = sinf(v[k] * a[k]); v[k] = v[k] + (s * s) * (1.0f / a[k]); }
+            }
+            __half hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { hi[k] = __float2half_rn(v[k]); lo[k] = __float2half_rn(v[k] - __half2float(hi[k])); }
+            uint2 ph, pl;
+            ph.x = (uint32_t) __half_as_ushort(hi[0]) | ((uint32_t) __half_as_ushort(hi[1]) << 16);
+            ph.y = (uint32_t) __half_as_ushort(hi[2]) | ((uint32_t) __half_as_ushort(hi[3]) << 16);
+            *reinterpret_cast<uint2 *>(orow + c) = ph;
+            if (split) {
+                pl.x = (uint32_t) __half_as_ushort(lo[0]) | ((uint32_t) __half_as_ushort(lo[1]) << 16);
+                pl.y = (uint32_t) __half_as_ushort(lo[2]) | ((uint32_t) __half_as_ushort(lo[3]) << 16);
+                *reinterpret_cast<uint2 *>(orow + C + c) = pl;
+                *reinterpret_cast<uint2 *>(orow + 2 * C + c) = ph;
+            }
+        }
+        for (int c = CW + threadIdx.x * 4; c < ldo; c += 256) *reinterpret_cast<uint2 *>(orow + c) = make_uint2(0u, 0u);
+    }
+}
+
 struct DacFwd {
     Dac * m; Ctx * ctx; int B; bool fail = false;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
 
     int operand(const float * x, int ldx, int C, int Lmax, const int * len, const float * alpha, bool split, __half * out, int ldo, int Lq) {
+        if (C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ((((uintptr_t) x) | ((uintptr_t) alpha)) & 15) == 0 && (((uintptr_t) out) & 7) == 0 &&
+            !getenv("B2TTS_DAC_SCALAR_OPERAND")) {
+            dim3 blk4(64, 4), grid4(cdiv(Lq, 16), B);
+            dac_operand4_kernel<<<grid4, blk4, 0, ctx->stream>>>(x, ldx, C, Lmax, len, alpha, split ? 1 : 0, out, ldo, Lq);
+            B2_LAUNCH_CHECK(ctx);
+            return 0;
+        }
         dim3 blk(128, 2), grid(cdiv(Lq, 2), B);
         dac_operand_kernel<<<grid, blk, 0, ctx->stream>>>(x, ldx, C, Lmax, len, alpha, split ? 1 : 0, out, ldo, Lq);
         B2_LAUNCH_CHECK(ctx);
