@@ -9,6 +9,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
   op_vectors.npz           : known-answer vectors of the patched ggml ops from oracle/ref_ops_driver.cpp
   dac_vectors.npz          : two 24-frame utterances of codebook indices and the PCM the reference's dac_runner produces for them
       on the deterministic synthetic DAC GGUF (seed 0, all F32), from oracle/ref_dac_driver.cpp
+  snac_vectors.npz         : two utterances (16 fine frames: 4 + 8 + 16 indices) decoded IN ONE PROCESS by the reference's snac_runner
+      (its std::normal_distribution noise stream carries over from the first to the second), from oracle/ref_snac_driver.cpp
 """
 import os
 import re
@@ -127,8 +129,23 @@ def dac_vectors():
     print("dac vectors:", pcm.shape, "rms", float(np.sqrt((pcm ** 2).mean())))
 
 
+def snac_vectors():
+    from tts_cpp_b200.synth import cached_snac_gguf, synthetic_snac_codes
+    gguf = cached_snac_gguf(seed=0, max_frames=64)
+    codes = synthetic_snac_codes(2, 16)
+    tmp = tempfile.mkdtemp()
+    cf = os.path.join(tmp, "codes.txt")
+    open(cf, "w").write("\n".join(" ".join(map(str, np.concatenate(c))) for c in codes) + "\n")
+    pre = os.path.join(tmp, "s")
+    run([os.path.join(REF, "snac_ref"), gguf, cf, pre, "--threads", "4", "--quiet"])
+    pcm = np.stack([np.fromfile(f"{pre}.u{u}.pcm.f32", np.float32) for u in range(2)])
+    np.savez_compressed(os.path.join(OUT, "snac_vectors.npz"), codes=np.stack([np.concatenate(c) for c in codes]).astype(np.int32), pcm=pcm)
+    print("snac vectors:", pcm.shape, "rms", float(np.sqrt((pcm ** 2).mean())))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac"]
+    if "snac" in which: snac_vectors()
     if "kokoro" in which: kokoro_vectors()
     if "ops" in which: op_vectors()
     if "dac" in which: dac_vectors()

@@ -123,3 +123,19 @@ def test_dac_port_against_reference():
         d = rms(got - g["pcm"][u])
         print(f"dac utterance {u}: rms diff {d:.3e} (signal rms {rms(g['pcm'][u]):.3f})")
         assert got.shape == g["pcm"][u].shape and d < 5e-6          # fp32 summation-order differences only
+
+
+def test_snac_port_against_reference_including_its_noise_stream():
+    """oracle/snac_port.py vs the PCM of the compiled reference's snac_runner for two utterances decoded in one process: the port's
+    restatement of libstdc++'s normal_distribution over minstd_rand0 must reproduce the injected noise, and carry its state across calls."""
+    from oracle.snac_port import SnacPort
+    from tts_cpp_b200.synth import cached_snac_gguf
+    g = np.load(os.path.join(GOLD, "snac_vectors.npz"))
+    port = SnacPort(cached_snac_gguf(seed=0, max_frames=64))
+    for u in range(g["codes"].shape[0]):
+        c = g["codes"][u].astype(np.uint32)
+        L = c.size * 4 // 7
+        got = port.decode([c[:L // 4], c[L // 4:L // 4 + L // 2], c[L // 4 + L // 2:]])
+        d = rms(got - g["pcm"][u])
+        print(f"snac utterance {u}: rms diff {d:.3e} (signal rms {rms(g['pcm'][u]):.3f})")
+        assert got.shape == g["pcm"][u].shape and d < 5e-6

@@ -325,6 +325,104 @@ def synthetic_codes(batch: int, frames: int, n_heads: int = 9, codebook: int = 1
     return [np.random.default_rng(seed0 + i).integers(0, codebook, size=(frames, n_heads)).astype(np.uint32) for i in range(batch)]
 
 
+# ------------------------------------------------------------------------------------------ SNAC codec decoder
+SNAC_RATES = (8, 8, 4, 2)         # snac_24khz decoder: 768 latent -> 1024 -> 512 -> 256 -> 128 -> 64 channels, 512 samples per fine frame
+
+
+def snac_tensors(seed: int = 0, latent: int = 768, d_model: int = 1024, codebook: int = 4096, cb_dim: int = 8, rates=SNAC_RATES):
+    """Synthetic weights in the reference's SNAC schema (py-gguf/tts_encoders/orpheus_gguf_encoder.py:89-142; names after the "snac."
+    prefix as snac_model::assign_weight sees them, src/decoder/snac_model.cpp:52-84).  Shapes are PyTorch order."""
+    rng = np.random.default_rng(seed)
+    items: list[tuple[str, np.ndarray]] = []
+
+    def rand(name, shape, fan_in, scale=None):
+        s = (1.0 / np.sqrt(max(fan_in, 1))) if scale is None else scale
+        a = (rng.standard_normal(shape).astype(np.float32) * np.float32(s)).astype(np.float16).astype(np.float32)
+        items.append(("snac." + name, a))
+
+    def alpha(name, c):
+        a = rng.uniform(0.5, 1.5, size=(1, c, 1)).astype(np.float32).astype(np.float16).astype(np.float32)
+        items.append(("snac." + name, a))
+
+    for i in range(3):
+        rand(f"quantizers.{i}.codebook.weight", (codebook, cb_dim), 1, 1.0)
+        rand(f"quantizers.{i}.out_proj.weight", (latent, cb_dim, 1), cb_dim * 3)
+        rand(f"quantizers.{i}.out_proj.bias", (latent,), 1, 0.02)
+    rand("in.weight", (latent, 1, 7), 7)                       # depthwise
+    rand("in.bias", (latent,), 1, 0.02)
+    rand("up.weight", (d_model, latent, 1), latent)
+    rand("up.bias", (d_model,), 1, 0.02)
+    c = d_model
+    for l, s in enumerate(rates):
+        co = c // 2
+        alpha(f"layers.{l}.alpha", c)
+        rand(f"layers.{l}.weight", (c, co, 2 * s), c * 2)       # ConvTranspose1d [Cin][Cout][K]
+        rand(f"layers.{l}.bias", (co,), 1, 0.02)
+        rand(f"layers.{l}.noise_weight", (co, co, 1), co * 16)  # NoiseBlock linear (no bias)
+        for i in range(3):
+            b = f"layers.{l}.residual_unit.{i}.res"
+            alpha(f"{b}.initial.alpha", co)
+            rand(f"{b}.initial.weight", (co, 1, 7), 7 * 4)       # depthwise k7, dilation 3^i
+            rand(f"{b}.initial.bias", (co,), 1, 0.02)
+            alpha(f"{b}.final.alpha", co)
+            rand(f"{b}.final.weight", (co, co, 1), co * 4)
+            rand(f"{b}.final.bias", (co,), 1, 0.02)
+        c = co
+    alpha("alpha_out", c)
+    rand("final.weight", (1, c, 7), c * 7 * 400)
+    rand("final.bias", (1,), 1, 0.02)
+    return items
+
+
+def write_snac_gguf(path: str, seed: int = 0, max_frames: int = 64, **kw) -> dict:
+    """Synthetic SNAC decoder GGUF, all tensors F32 (the reference's quantizer never converts snac.* : it only handles orpheus.* for Orpheus)."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="snac")
+    items = snac_tensors(seed=seed, **kw)
+    n_params = 0
+    for name, arr in items:
+        n_params += arr.size
+        w.add_tensor(name, arr.astype(np.float32))
+    rates = kw.get("rates", SNAC_RATES)
+    c = kw.get("d_model", 1024)
+    for i, s in enumerate(rates):
+        c //= 2
+        w.add_uint32(f"snac.snac_layer_stride_{i}", int(s))
+        w.add_uint32(f"snac.snac_layer_padding_{i}", int((s + 1) // 2))
+        w.add_uint32(f"snac.snac_layer_grouping_{i}", int(c))      # depthwise residual units: groups == channels
+    w.add_uint32("snac.audio_token_channels", 3)
+    w.add_uint32("snac.up_sampling_factor", int(np.prod(rates)))
+    w.add_uint32("snac.max_generation_size", int(max_frames))
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def cached_snac_gguf(seed: int = 0, max_frames: int = 64, cache_dir: str | None = None) -> str:
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, f"snac_f32_m{max_frames}_s{seed}.gguf")
+    if not os.path.exists(path):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_snac_gguf(tmp, seed=seed, max_frames=max_frames)
+        os.replace(tmp, path)
+    return path
+
+
+def synthetic_snac_codes(batch: int, fine_frames: int, codebook: int = 4096, seed0: int = 8765) -> list[list[np.ndarray]]:
+    """Utterance i: three streams of L/4, L/2 and L indices (what snac_runner::run takes), from default_rng(seed0 + i); L % 4 == 0."""
+    assert fine_frames % 4 == 0
+    out = []
+    for i in range(batch):
+        r = np.random.default_rng(seed0 + i)
+        out.append([r.integers(0, codebook, size=fine_frames // d).astype(np.uint32) for d in (4, 2, 1)])
+    return out
+
+
 def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
     """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
     out = []
