@@ -144,6 +144,23 @@ int   b2tts_dac_info(const b2tts_dac * m, int * n_heads, int * up_sampling_facto
 int   b2tts_dac_decode_batch(b2tts_dac * m, int n_utterances, const uint32_t * const * codes, const int32_t * frames, const float ** pcm, int64_t * n_samples);
 float b2tts_dac_last_ms(const b2tts_dac * m);   /* device time of the last decode_batch (CUDA events), for bench / tests */
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SNAC neural audio codec decoder, batched.  NOT YET VALIDATED ON A B200 (written after round 1's GPU budget ran out;
+ * its oracle, oracle/snac_port.py, is pinned to the reference).
+ *   b2tts_snac_load_gguf   : snac_model::setup_from_file + assign_weight loop over the "snac.*" tensors + prepare_post_load
+ *                            (reference src/decoder/snac_model.h:41-46, snac_model.cpp:3-84,124-127; src/models/orpheus/loader.cpp:12-18)
+ *   b2tts_snac_decode_batch: snac_runner::run (snac_model.cpp:181-208).  codes[b] = the three vectors the reference takes, concatenated:
+ *                            L/4 coarse, L/2 medium, L fine indices, L = fine_frames[b] (a multiple of 4); pcm[b] = L * 512 samples in a
+ *                            runner-owned pinned buffer.  The injected noise is the reference's process-wide normal generator
+ *                            (src/util.cpp:74-80): utterance b of a call continues the stream where utterance b-1 (or the previous call) left it;
+ *   b2tts_snac_reset_noise : rewinds that stream to the state of a fresh process. */
+typedef struct b2tts_snac b2tts_snac;
+int   b2tts_snac_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_snac ** out);
+void  b2tts_snac_free(b2tts_snac * m);
+int   b2tts_snac_info(const b2tts_snac * m, int * up_sampling_factor, int * codebook_size);
+int   b2tts_snac_decode_batch(b2tts_snac * m, int n_utterances, const uint32_t * const * codes, const int32_t * fine_frames, const float ** pcm, int64_t * n_samples);
+int   b2tts_snac_reset_noise(b2tts_snac * m);
+
 #ifdef __cplusplus
 }
 #endif

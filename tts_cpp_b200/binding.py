@@ -273,3 +273,44 @@ def dac_runner_from_file(path: str, device: int = 0, ctx: Context | None = None)
     h = C.c_void_p()
     _chk(lib().b2tts_dac_load_gguf(ctx.h, path.encode(), C.byref(h)))
     return DacRunner(ctx, h)
+
+
+class SnacRunner:
+    """snac_runner (reference src/decoder/snac_model.h:65-86): three code streams -> PCM, batched over independent utterances."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        up, cb = C.c_int(), C.c_int()
+        _chk(lib().b2tts_snac_info(self.h, C.byref(up), C.byref(cb)))
+        self.up_sampling_factor, self.codebook_size = up.value, cb.value
+
+    def run_batch(self, codes, copy: bool = True):
+        """codes: list of [coarse L/4, medium L/2, fine L] index arrays per utterance (what snac_runner::run takes)."""
+        B = len(codes)
+        arrs = [np.ascontiguousarray(np.concatenate([np.asarray(s, np.uint32) for s in c])) for c in codes]
+        fine = np.array([len(c[2]) for c in codes], np.int32)
+        ptrs = (C.POINTER(C.c_uint32) * B)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        pcm = (C.POINTER(C.c_float) * B)()
+        ns = (C.c_int64 * B)()
+        _chk(lib().b2tts_snac_decode_batch(self.h, B, ptrs, fine.ctypes.data_as(C.POINTER(C.c_int32)), pcm, ns))
+        outs = []
+        for b in range(B):
+            a = np.ctypeslib.as_array(pcm[b], shape=(int(ns[b]),))
+            outs.append(a.copy() if copy else a)
+        return outs
+
+    def reset_noise(self):
+        _chk(lib().b2tts_snac_reset_noise(self.h))
+
+    def close(self):
+        if self.h:
+            lib().b2tts_snac_free(self.h)
+            self.h = None
+
+
+def snac_runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> SnacRunner:
+    ctx = ctx or Context(device)
+    h = C.c_void_p()
+    _chk(lib().b2tts_snac_load_gguf(ctx.h, path.encode(), C.byref(h)))
+    return SnacRunner(ctx, h)

@@ -24,6 +24,7 @@ using namespace b2;
 struct b2tts_ctx { Ctx c; };
 struct b2tts_kokoro { Kokoro k; };
 struct b2tts_dac { Dac d; };
+struct b2tts_snac { Snac s; };
 
 namespace {
 // RAII device scratch for the op-level entry points
@@ -136,6 +137,29 @@ int b2tts_dac_decode_batch(b2tts_dac * m, int n_utterances, const uint32_t * con
     return m->d.decode_batch(n_utterances, codes, frames, pcm, n_samples);
 }
 float b2tts_dac_last_ms(const b2tts_dac * m) { return m ? m->d.timing_ms : 0.f; }
+
+// ---- SNAC codec decoder
+int b2tts_snac_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_snac ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_snac * m = new b2tts_snac();
+    m->s.ctx = &ctx->c;
+    if (load_gguf_into(&m->s, path)) { m->s.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_snac_free(b2tts_snac * m) { if (m) { m->s.free_all(); delete m; } }
+int b2tts_snac_info(const b2tts_snac * m, int * up_sampling_factor, int * codebook_size) {
+    if (!m) { set_error("null model"); return 1; }
+    if (up_sampling_factor) *up_sampling_factor = m->s.up_factor;
+    if (codebook_size) *codebook_size = m->s.n_codes;
+    return 0;
+}
+int b2tts_snac_decode_batch(b2tts_snac * m, int n_utterances, const uint32_t * const * codes, const int32_t * fine_frames, const float ** pcm, int64_t * n_samples) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->s.decode_batch(n_utterances, codes, fine_frames, pcm, n_samples);
+}
+int b2tts_snac_reset_noise(b2tts_snac * m) { if (!m) { set_error("null model"); return 1; } m->s.reset_noise(); return 0; }
 int b2tts_kokoro_n_voices(const b2tts_kokoro * m) { return (int) m->k.voice_names.size(); }
 const char * b2tts_kokoro_voice_name(const b2tts_kokoro * m, int i) { return (i >= 0 && i < (int) m->k.voice_names.size()) ? m->k.voice_names[i].c_str() : nullptr; }
 size_t b2tts_kokoro_weight_bytes(const b2tts_kokoro * m) { return m->k.weight_bytes; }

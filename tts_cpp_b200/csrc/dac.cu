@@ -17,10 +17,10 @@ namespace b2 {
 
 static inline float h2f_(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
 
-int Dac::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
-    if (prepared) { set_error("dac: assign_weight after prepare"); return 1; }
+static int assign_host(std::map<std::string, HostTensor> & host, const char * prefix, const char * name, int type, int n_dims, const int64_t * ne,
+                       const void * data, size_t nbytes) {
     std::string nm(name);
-    if (nm.rfind("audio_encoder.", 0) == 0) nm = nm.substr(14);
+    if (nm.rfind(prefix, 0) == 0) nm = nm.substr(strlen(prefix));
     HostTensor t;
     int64_t n = 1;
     for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
@@ -41,10 +41,20 @@ int Dac::assign(const char * name, int type, int n_dims, const int64_t * ne, con
     return 0;
 }
 
+int Dac::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
+    if (prepared) { set_error("dac: assign_weight after prepare"); return 1; }
+    return assign_host(host, "audio_encoder.", name, type, n_dims, ne, data, nbytes);
+}
+int Snac::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
+    if (prepared) { set_error("snac: assign_weight after prepare"); return 1; }
+    return assign_host(host, "snac.", name, type, n_dims, ne, data, nbytes);
+}
+
 namespace {
 
-struct DacPrep {
-    Dac * m;
+template <class M>
+struct PrepT {
+    M * m;
     bool ok = true;
     const HostTensor * get(const std::string & n) {
         auto it = m->host.find(n);
@@ -178,8 +188,9 @@ __global__ void __launch_bounds__(256) dac_operand4_kernel(const float * __restr
     }
 }
 
-struct DacFwd {
-    Dac * m; Ctx * ctx; int B; bool fail = false;
+template <class M>
+struct FwdT {
+    M * m; Ctx * ctx; int B; bool fail = false;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
 
     int operand(const float * x, int ldx, int C, int Lmax, const int * len, const float * alpha, bool split, __half * out, int ldo, int Lq) {
@@ -220,7 +231,7 @@ struct DacFwd {
 int Dac::prepare() {
     if (prepared) return 0;
     B2_CUDA(cudaSetDevice(ctx->device));
-    DacPrep P{this};
+    PrepT<Dac> P{this};
     auto kvget = [&](std::initializer_list<const char *> keys, uint32_t dflt) { for (auto k : keys) { auto it = kv.find(k); if (it != kv.end()) return it->second; } return dflt; };
     n_heads = (int) kvget({"parler-tts.decoder.output_heads", "output_heads", "dia.decoder.output_heads"}, 9);     // dac_model.cpp:15-18
     up_factor = (int) kvget({"dac.up_sampling_factor", "up_sampling_factor"}, 512);                               // dac_model.cpp:20-23
@@ -333,7 +344,7 @@ int Dac::decode_batch(int B, const uint32_t * const * codes, const int32_t * fra
     }
     need += (size_t) B * P[4] * (final_conv.w.CinPad * 2 + 4) + (16 << 20);
     if (arena.reserve(need)) return 1;
-    DacFwd F{this, ctx, B};
+    FwdT<Dac> F{this, ctx, B};
 
     // ---- inputs
     std::vector<uint32_t> hc((size_t) B * Fmax * n_heads, 0u);
@@ -415,6 +426,317 @@ int Dac::decode_batch(int B, const uint32_t * const * codes, const int32_t * fra
     for (int b = 0; b < B; b++) {
         const size_t n = (size_t) frames[b] * up_factor;
         if ((int64_t) n > (int64_t) P[4]) { set_error("dac: up_sampling_factor %d does not match the layer strides", up_factor); return 1; }
+        B2_CUDA(cudaMemcpyAsync(pcm_pinned + off, pcm_d + (size_t) b * P[4], n * 4, cudaMemcpyDeviceToHost, st));
+        if (pcm) pcm[b] = pcm_pinned + off;
+        if (n_samples) n_samples[b] = (int64_t) n;
+        off += n;
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&timing_ms, ev[0], ev[1]);
+    return 0;
+}
+
+}  // namespace b2
+
+// ============================================================================================ SNAC
+#include <random>
+
+namespace b2 {
+namespace {
+
+// the reference's static generator (src/util.cpp:74-80): libstdc++'s own engine and distribution, so the stream is identical by construction
+struct NormalGen {
+    std::default_random_engine e;
+    std::normal_distribution<float> dis{0.0f, 1.0f};
+};
+
+// quantizer: x[b][t][c] = T0[c0[t/4]][c] + T1[c1[t/2]][c] + T2[c2[t]][c]   (snac_build_audio_inputs, snac_model.cpp:86-109)
+__global__ void snac_embed_kernel(const uint32_t * __restrict__ codes, const int * __restrict__ code_off, const float * __restrict__ tables, int n_codes,
+                                  int latent, int Lmax, const int * __restrict__ len, float * __restrict__ out) {
+    const int b = blockIdx.y, t = blockIdx.x;
+    const int L = len[b];
+    if (t >= L) return;
+    const uint32_t * cd = codes + code_off[b];
+    const uint32_t c0 = cd[t >> 2], c1 = cd[(L >> 2) + (t >> 1)], c2 = cd[(L >> 2) + (L >> 1) + t];
+    float * o = out + ((size_t) b * Lmax + t) * latent;
+    for (int c = threadIdx.x; c < latent; c += blockDim.x) {
+        float acc = tables[((size_t) 0 * n_codes + c0) * latent + c];
+        acc = acc + tables[((size_t) 1 * n_codes + c1) * latent + c];
+        acc = acc + tables[((size_t) 2 * n_codes + c2) * latent + c];
+        o[c] = acc;
+    }
+}
+
+// depthwise Conv1d k7 (ggml_conv_1d_dw: F32 im2col + mul_mat, the 7-tap dot accumulated in a double like ggml_vec_dot_f32's leftovers,
+// ggml.c:3847-3868), optional snake on the input, + bias.  x, y: [b][t][C]
+__global__ void snac_dwconv7_kernel(const float * __restrict__ x, int C, int Lmax, const int * __restrict__ len, const float * __restrict__ alpha,
+                                    const float * __restrict__ w, const float * __restrict__ bias, int dil, float * __restrict__ y) {
+    const int b = blockIdx.y;
+    const int L = len[b];
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= L) return;
+    const float * xb = x + (size_t) b * Lmax * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float a = alpha ? alpha[c] : 0.f;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const int tt = t + (k - 3) * dil;
+            float v = 0.f;
+            if (tt >= 0 && tt < L) {
+                v = xb[(size_t) tt * C + c];
+                if (alpha) { const float sn = sinf(v * a); v = v + (sn * sn) * (1.0f / a); }
+            }
+            s += (double) (v * w[c * 7 + k]);
+        }
+        y[((size_t) b * Lmax + t) * C + c] = (float) s + bias[c];
+    }
+}
+
+// noise block: x[b][t][c] += nx[b][t][c] * noise[b][t]   (general_neural_audio_codec.cpp:153-157)
+__global__ void snac_noise_add_kernel(float * x, const float * __restrict__ nx, const float * __restrict__ noise, int C, int Lmax, const int * __restrict__ len) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= len[b]) return;
+    const float n = noise[(size_t) b * Lmax + t];
+    const size_t row = ((size_t) b * Lmax + t) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) x[row + c] = x[row + c] + nx[row + c] * n;
+}
+
+}  // namespace
+
+int Snac::prepare() {
+    if (prepared) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    PrepT<Snac> P{this};
+    auto kvget = [&](const std::string & k, uint32_t dflt) { auto it = kv.find(k); return it != kv.end() ? it->second : dflt; };
+    up_factor = (int) kvget("snac.up_sampling_factor", 512);
+    if (kvget("snac.audio_token_channels", 3) != 3) { set_error("snac: audio_token_channels must be 3"); return 1; }
+    {
+        auto cb0 = P.get("quantizers.0.codebook.weight"), w0 = P.get("quantizers.0.out_proj.weight");
+        if (!cb0 || !w0) return 1;
+        n_codes = (int) cb0->shape[0]; const int cbd = (int) cb0->shape[1]; latent = (int) w0->shape[0];
+        std::vector<float> tab((size_t) 3 * n_codes * latent);
+        for (int h = 0; h < 3; h++) {
+            auto cb = P.get("quantizers." + std::to_string(h) + ".codebook.weight"), w = P.get("quantizers." + std::to_string(h) + ".out_proj.weight"),
+                 bs = P.get("quantizers." + std::to_string(h) + ".out_proj.bias");
+            if (!cb || !w || !bs) return 1;
+            for (int code = 0; code < n_codes; code++)
+                for (int c = 0; c < latent; c++) {
+                    double s = 0.0;
+                    for (int d = 0; d < cbd; d++) s += (double) (cb->v[(size_t) code * cbd + d] * w->v[(size_t) c * cbd + d]);
+                    tab[((size_t) h * n_codes + code) * latent + c] = (float) s + bs->v[c];
+                }
+        }
+        tables = P.f32v(tab);
+    }
+    { auto t = P.get("in.weight"); if (!t) return 1; if (t->shape.size() != 3 || t->shape[1] != 1 || t->shape[2] != 7) { set_error("snac.in.weight must be a depthwise k7 kernel"); return 1; } }
+    in_w = P.f32("in.weight"); in_b = P.f32("in.bias");
+    up = P.conv("up", 1, 0);
+    for (int l = 0; l < 4; l++) {
+        SnacLayer & L = layers[l];
+        const std::string b = "layers." + std::to_string(l);
+        const uint32_t sk = kvget("snac.snac_layer_stride_" + std::to_string(l), 0), pk = kvget("snac.snac_layer_padding_" + std::to_string(l), 0xffffffffu);
+        if (sk == 0 || pk == 0xffffffffu) { set_error("key snac.snac_layer_stride_%d must be specified in gguf file inorder to initialize the SNAC audio decoder.", l); return 1; }
+        L.stride = (int) sk; L.pad = (int) pk;
+        L.alpha = P.f32(b + ".alpha");
+        auto t = P.get(b + ".weight"), bt = P.get(b + ".bias");
+        if (!t || !bt) return 1;
+        if (t->f16) { set_error("snac %s.weight: F16 ConvTranspose1d kernels are not supported; keep them F32", b.c_str()); return 1; }
+        L.Cin = (int) t->shape[0]; L.Cout = (int) t->shape[1];
+        const int K = (int) t->shape[2], s = L.stride;
+        if (K != 2 * s || L.pad >= s) { set_error("snac %s: ConvTranspose1d K=%d stride=%d pad=%d is outside the polyphase form", b.c_str(), K, s, L.pad); return 1; }
+        const int C3 = 3 * L.Cin, N = s * L.Cout;
+        std::vector<float> src((size_t) N * C3 * 2), brep((size_t) N);
+        for (int r = 0; r < s; r++)
+            for (int co = 0; co < L.Cout; co++) {
+                const size_t n = (size_t) r * L.Cout + co;
+                brep[n] = bt->v[co];
+                for (int ci = 0; ci < L.Cin; ci++)
+                    for (int k = 0; k < 2; k++) {
+                        const float wv = t->v[((size_t) ci * L.Cout + co) * K + (k == 0 ? r + s : r)];
+                        const float whi = __half2float(__float2half(wv)), wlo = wv - whi;
+                        src[(n * C3 + ci) * 2 + k] = whi;
+                        src[(n * C3 + L.Cin + ci) * 2 + k] = whi;
+                        src[(n * C3 + 2 * L.Cin + ci) * 2 + k] = wlo;
+                    }
+            }
+        L.w3 = P.w16_from(src, N, C3, 2);
+        L.w3.Cin = L.Cin;
+        L.b_rep = P.f32v(brep);
+        {   // noise block kernel: 1x1, no bias
+            auto nt = P.get(b + ".noise_weight");
+            if (!nt) return 1;
+            host[b + ".noise.weight"] = *nt;
+            HostTensor zb; zb.shape = {(int64_t) L.Cout}; zb.v.assign((size_t) L.Cout, 0.f);
+            host[b + ".noise.bias"] = zb;
+            L.noise = P.conv(b + ".noise", 1, 0);
+            L.noise.b = nullptr;
+        }
+        for (int i = 0; i < 3; i++) {
+            const std::string r = b + ".residual_unit." + std::to_string(i) + ".res";
+            auto dw = P.get(r + ".initial.weight");
+            if (!dw) return 1;
+            if (dw->shape.size() != 3 || dw->shape[1] != 1 || dw->shape[2] != 7) { set_error("snac %s.initial.weight must be a depthwise k7 kernel (grouping == channels)", r.c_str()); return 1; }
+            L.res[i].dil = (int) std::lround(std::pow(3.0, i));
+            L.res[i].a1 = P.f32(r + ".initial.alpha"); L.res[i].dw_w = P.f32(r + ".initial.weight"); L.res[i].dw_b = P.f32(r + ".initial.bias");
+            L.res[i].a2 = P.f32(r + ".final.alpha");   L.res[i].c2 = P.conv(r + ".final", 1, 0);
+        }
+    }
+    final_alpha = P.f32("alpha_out");
+    final_conv = P.conv("final", 1, 3);
+    if (!P.ok) return 1;
+    for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+    noise_engine = new NormalGen();
+    host.clear();
+    prepared = true;
+    return 0;
+}
+
+void Snac::reset_noise() { if (noise_engine) { delete (NormalGen *) noise_engine; noise_engine = new NormalGen(); } }
+
+void Snac::free_all() {
+    for (void * p : dev_allocs) cudaFree(p);
+    dev_allocs.clear();
+    arena.release();
+    if (pcm_pinned) cudaFreeHost(pcm_pinned);
+    if (noise_engine) { delete (NormalGen *) noise_engine; noise_engine = nullptr; }
+    for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+}
+
+int Snac::decode_batch(int B, const uint32_t * const * codes, const int32_t * fine_frames, const float ** pcm, int64_t * n_samples) {
+    if (!prepared) { set_error("snac: model not prepared"); return 1; }
+    if (B <= 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int Fmax = 0; size_t n_codes_total = 0;
+    for (int b = 0; b < B; b++) {
+        if (fine_frames[b] <= 0 || fine_frames[b] % 4) { set_error("snac: utterance %d has %d fine frames (must be a positive multiple of 4)", b, fine_frames[b]); return 1; }
+        Fmax = std::max(Fmax, (int) fine_frames[b]);
+        n_codes_total += (size_t) fine_frames[b] / 4 * 7;
+    }
+    int P[5]; P[0] = Fmax;
+    for (int l = 0; l < 4; l++) P[l + 1] = (P[l] + 1) * layers[l].stride;
+    size_t need = n_codes_total * 4 + (size_t) B * Fmax * ((size_t) latent * 8 + up.w.CinPad * 2 + up.Cout * 4) + (64 << 20);
+    for (int l = 0; l < 4; l++) {
+        const SnacLayer & L = layers[l];
+        need += (size_t) B * (P[l] + 1) * L.w3.CinPad * 2;
+        need += ((size_t) B * P[l + 1] + 64) * L.Cout * 4 * 4 + (size_t) B * P[l + 1] * 4;
+        need += (size_t) B * P[l + 1] * (size_t) std::max(L.noise.w.CinPad, L.res[0].c2.w.CinPad) * 2 + (4 << 20);
+    }
+    need += (size_t) B * P[4] * (final_conv.w.CinPad * 2 + 4) + (16 << 20);
+    if (arena.reserve(need)) return 1;
+    FwdT<Snac> F{this, ctx, B};
+
+    // ---- inputs: codes, lengths per level, and the noise every utterance would have seen had they been decoded one after another
+    std::vector<uint32_t> hc(n_codes_total);
+    std::vector<int> hoff((size_t) B), hl((size_t) 9 * B);
+    size_t o = 0;
+    for (int b = 0; b < B; b++) {
+        const size_t n = (size_t) fine_frames[b] / 4 * 7;
+        for (size_t i = 0; i < n; i++) {
+            if (codes[b][i] >= (uint32_t) n_codes) { set_error("snac: utterance %d code %u >= codebook size %d", b, codes[b][i], n_codes); return 1; }
+            hc[o + i] = codes[b][i];
+        }
+        hoff[(size_t) b] = (int) o; o += n;
+        int L = fine_frames[b];
+        for (int l = 0; l <= 4; l++) { hl[(size_t) l * B + b] = L; if (l < 4) { hl[(size_t) (5 + l) * B + b] = L + 1; L *= layers[l].stride; } }
+    }
+    std::vector<std::vector<float>> hnoise(4);
+    for (int l = 0; l < 4; l++) hnoise[(size_t) l].assign((size_t) B * P[l + 1], 0.f);
+    {
+        NormalGen * g = (NormalGen *) noise_engine;
+        for (int b = 0; b < B; b++)            // snac_runner::set_inputs: one random_normal_gen(840 * L) per run, consumed layer by layer
+            for (int l = 0; l < 4; l++) {
+                float * dst = hnoise[(size_t) l].data() + (size_t) b * P[l + 1];
+                const int n = noise_steps[l] * fine_frames[b];
+                if (n > P[l + 1]) { set_error("snac: noise_steps do not match the layer strides"); return 1; }
+                for (int i = 0; i < n; i++) dst[i] = g->dis(g->e);
+            }
+    }
+    uint32_t * d_codes = F.al<uint32_t>(hc.size());
+    int * d_off = F.al<int>(hoff.size());
+    int * d_len = F.al<int>(hl.size());
+    float * d_noise[4];
+    for (int l = 0; l < 4; l++) d_noise[l] = F.al<float>(hnoise[(size_t) l].size());
+    if (F.fail) return 1;
+    B2_CUDA(cudaEventRecord(ev[0], st));
+    B2_CUDA(cudaMemcpyAsync(d_codes, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(d_off, hoff.data(), hoff.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(d_len, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, st));
+    for (int l = 0; l < 4; l++) B2_CUDA(cudaMemcpyAsync(d_noise[l], hnoise[(size_t) l].data(), hnoise[(size_t) l].size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+
+    // ---- quantizer -> depthwise k7 -> 1x1 up (snac_model.cpp:136-140)
+    float * emb = F.al<float>((size_t) B * Fmax * latent);
+    float * e2 = F.al<float>((size_t) B * Fmax * latent);
+    float * h = F.al<float>((size_t) B * Fmax * up.Cout);
+    if (F.fail) return 1;
+    {
+        dim3 grid(Fmax, B);
+        snac_embed_kernel<<<grid, 256, 0, st>>>(d_codes, d_off, tables, n_codes, latent, Fmax, d_len, emb);
+        B2_LAUNCH_CHECK(ctx);
+        dim3 blk(128, 2), g2(cdiv(Fmax, 2), B);
+        snac_dwconv7_kernel<<<g2, blk, 0, st>>>(emb, latent, Fmax, d_len, nullptr, in_w, in_b, 1, e2);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    if (F.snake_conv(up, nullptr, e2, Fmax, d_len, h, nullptr)) return 1;
+
+    const float * x = h;
+    for (int l = 0; l < 4; l++) {
+        const SnacLayer & L = layers[l];
+        const int Lq = P[l] + 1, Pn = P[l + 1], C = L.Cout;
+        const int * len_in = d_len + (size_t) l * B, * len_q = d_len + (size_t) (5 + l) * B, * len_out = d_len + (size_t) (l + 1) * B;
+        __half * a3 = F.al<__half>((size_t) B * Lq * L.w3.CinPad);
+        float * ubuf = F.al<float>(((size_t) B * Pn + 64) * C);
+        float * y = F.al<float>((size_t) B * Pn * C);
+        float * alt = F.al<float>((size_t) B * Pn * C);
+        if (F.fail) return 1;
+        if (F.operand(x, L.Cin, L.Cin, P[l], len_in, L.alpha, true, a3, L.w3.CinPad, Lq)) return 1;
+        {
+            ConvGemmParams p;
+            p.A = a3; p.lda = L.w3.CinPad; p.W = L.w3.w; p.bias = L.b_rep; p.outF = ubuf; p.ldo = L.stride * C;
+            p.B = B; p.LmaxIn = Lq; p.LmaxOut = Lq; p.lenIn = len_in; p.lenOut = len_q;
+            p.N = L.w3.N; p.Npad = L.w3.Npad; p.KW = 2; p.CinPad = L.w3.CinPad; p.CinTrue = L.w3.Cin; p.stride = 1; p.dil = 1; p.pad = 1;
+            p.tailClean = true;
+            if (conv_gemm(ctx, p)) return 1;
+        }
+        float * cur = ubuf + (size_t) L.pad * C;
+        // noise block: cur += conv1x1(cur) * noise[t]
+        if (F.snake_conv(L.noise, nullptr, cur, Pn, len_out, y, nullptr)) return 1;
+        {
+            dim3 blk(128, 2), grid(cdiv(Pn, 2), B);
+            snac_noise_add_kernel<<<grid, blk, 0, st>>>(cur, y, d_noise[l], C, Pn, len_out);
+            B2_LAUNCH_CHECK(ctx);
+        }
+        for (int i = 0; i < 3; i++) {
+            const SnacLayer::Unit & U = L.res[i];
+            float * nxt = (cur == alt) ? ubuf : alt;
+            dim3 blk(128, 2), grid(cdiv(Pn, 2), B);
+            snac_dwconv7_kernel<<<grid, blk, 0, st>>>(cur, C, Pn, len_out, U.a1, U.dw_w, U.dw_b, U.dil, y);
+            B2_LAUNCH_CHECK(ctx);
+            if (F.snake_conv(U.c2, U.a2, y, Pn, len_out, nxt, cur)) return 1;
+            cur = nxt;
+        }
+        x = cur;
+    }
+    float * pcm_d = F.al<float>((size_t) B * P[4]);
+    if (F.fail) return 1;
+    if (F.snake_conv(final_conv, final_alpha, x, P[4], d_len + (size_t) 4 * B, pcm_d, nullptr, ACT_TANH)) return 1;
+    B2_CUDA(cudaEventRecord(ev[1], st));
+
+    size_t total = 0;
+    for (int b = 0; b < B; b++) total += (size_t) fine_frames[b] * up_factor;
+    if (pcm_pinned_cap < total) {
+        if (pcm_pinned) cudaFreeHost(pcm_pinned);
+        pcm_pinned = nullptr; pcm_pinned_cap = 0;
+        B2_CUDA(cudaMallocHost(&pcm_pinned, total * 4));
+        pcm_pinned_cap = total;
+    }
+    size_t off = 0;
+    for (int b = 0; b < B; b++) {
+        const size_t n = (size_t) fine_frames[b] * up_factor;
+        if ((int64_t) n > (int64_t) P[4]) { set_error("snac: up_sampling_factor %d does not match the layer strides", up_factor); return 1; }
         B2_CUDA(cudaMemcpyAsync(pcm_pinned + off, pcm_d + (size_t) b * P[4], n * 4, cudaMemcpyDeviceToHost, st));
         if (pcm) pcm[b] = pcm_pinned + off;
         if (n_samples) n_samples[b] = (int64_t) n;

@@ -142,4 +142,10 @@ int load_gguf_into(Dac * m, const char * path) {
     return m->prepare();
 }
 
+// the SNAC decoder's tensors live under "snac." in Orpheus GGUFs (reference src/decoder/snac_model.h:41-46, src/models/orpheus/model.cpp:440-441)
+int load_gguf_into(Snac * m, const char * path) {
+    if (read_gguf(path, "snac.", nullptr, m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
+}
+
 }  // namespace b2
