@@ -11,6 +11,9 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       on the deterministic synthetic DAC GGUF (seed 0, all F32), from oracle/ref_dac_driver.cpp
   snac_vectors.npz         : two utterances (16 fine frames: 4 + 8 + 16 indices) decoded IN ONE PROCESS by the reference's snac_runner
       (its std::normal_distribution noise stream carries over from the first to the second), from oracle/ref_snac_driver.cpp
+  orpheus_vectors.npz      : two prompts (7 and 12 token ids) and, for 6 greedy decode steps each, the tokens the reference's decode loop +
+      sampler produced and the logits of every step, on the small synthetic Orpheus GGUF (2 layers, 6/2 heads x 64, vocab 2048, F32),
+      from oracle/ref_orpheus_driver.cpp
 """
 import os
 import re
@@ -143,8 +146,29 @@ def snac_vectors():
     print("snac vectors:", pcm.shape, "rms", float(np.sqrt((pcm ** 2).mean())))
 
 
+def orpheus_vectors():
+    from tts_cpp_b200.synth import cached_orpheus_gguf
+    gguf = cached_orpheus_gguf(seed=0)
+    rng = np.random.default_rng(5)
+    prompts = [rng.integers(2, 2000, size=n) for n in (7, 12)]
+    tmp = tempfile.mkdtemp()
+    pf = os.path.join(tmp, "prompts.txt")
+    open(pf, "w").write("\n".join(" ".join(map(str, q)) for q in prompts) + "\n")
+    pre = os.path.join(tmp, "o")
+    steps = 6
+    run([os.path.join(REF, "orpheus_ref"), gguf, pf, pre, "--steps", str(steps), "--threads", "4", "--quiet"])
+    out = {}
+    for u, q in enumerate(prompts):
+        out[f"prompt{u}"] = np.asarray(q, np.int32)
+        out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32)
+        out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, -1)
+    np.savez_compressed(os.path.join(OUT, "orpheus_vectors.npz"), **out)
+    print("orpheus vectors:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus"]
+    if "orpheus" in which: orpheus_vectors()
     if "snac" in which: snac_vectors()
     if "kokoro" in which: kokoro_vectors()
     if "ops" in which: op_vectors()

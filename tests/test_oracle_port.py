@@ -139,3 +139,17 @@ def test_snac_port_against_reference_including_its_noise_stream():
         d = rms(got - g["pcm"][u])
         print(f"snac utterance {u}: rms diff {d:.3e} (signal rms {rms(g['pcm'][u]):.3f})")
         assert got.shape == g["pcm"][u].shape and d < 5e-6
+
+
+def test_orpheus_port_against_reference_decode_loop():
+    """oracle/orpheus_port.py vs the reference's decode loop + greedy sampler: identical token ids, logits to fp32 rounding."""
+    from oracle.orpheus_port import OrpheusPort
+    from tts_cpp_b200.synth import cached_orpheus_gguf
+    g = np.load(os.path.join(GOLD, "orpheus_vectors.npz"))
+    port = OrpheusPort(cached_orpheus_gguf(seed=0))
+    for u in range(2):
+        toks, logits = port.greedy(g[f"prompt{u}"], g[f"tokens{u}"].size)
+        d = float(np.abs(logits - g[f"logits{u}"]).max())
+        print(f"orpheus prompt {u}: tokens {toks.tolist()}  max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
+        assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact token ids at temperature 0 (the north star's bar)
+        assert d < 1e-4

@@ -423,6 +423,89 @@ def synthetic_snac_codes(batch: int, fine_frames: int, codebook: int = 4096, see
     return out
 
 
+# ------------------------------------------------------------------------------------------ Orpheus AR decoder
+def orpheus_tensors(seed: int = 0, layers: int = 2, heads: int = 6, kv_heads: int = 2, head_dim: int = 64, ffn: int = 1024, vocab: int = 2048):
+    """Synthetic llama-3-style weights in the reference's Orpheus schema (py-gguf/tts_encoders/orpheus_gguf_encoder.py:118-122, names after
+    the "orpheus." prefix as orpheus_model::assign_weight sees them, src/models/orpheus/model.cpp:11-61).  heads == 3 * kv_heads: the
+    reference hard-codes the GQA repeat of 3 (model.cpp:251)."""
+    assert heads == 3 * kv_heads
+    rng = np.random.default_rng(seed)
+    hidden, kvh = heads * head_dim, kv_heads * head_dim
+    items: list[tuple[str, np.ndarray]] = []
+
+    def rand(name, shape, fan_in, scale=None):
+        s = (1.0 / np.sqrt(max(fan_in, 1))) if scale is None else scale
+        a = (rng.standard_normal(shape).astype(np.float32) * np.float32(s)).astype(np.float16).astype(np.float32)
+        items.append(("orpheus." + name, a))
+
+    def norm(name, c):
+        items.append(("orpheus." + name, (1.0 + 0.1 * rng.standard_normal(c)).astype(np.float32).astype(np.float16).astype(np.float32)))
+
+    rand("embed_tokens", (vocab, hidden), 1, 1.0)
+    for l in range(layers):
+        b = f"layers.{l}"
+        norm(b + ".input_layernorm", hidden)
+        rand(b + ".self_attn.q_proj", (hidden, hidden), hidden)
+        rand(b + ".self_attn.k_proj", (kvh, hidden), hidden)
+        rand(b + ".self_attn.v_proj", (kvh, hidden), hidden)
+        rand(b + ".self_attn.o_proj", (hidden, hidden), hidden)
+        norm(b + ".post_attention_layernorm", hidden)
+        rand(b + ".mlp.gate_proj", (ffn, hidden), hidden)
+        rand(b + ".mlp.up_proj", (ffn, hidden), hidden)
+        rand(b + ".mlp.down_proj", (hidden, ffn), ffn)
+    norm("norm", hidden)
+    rand("lm_head", (vocab, hidden), hidden, 4.0 / np.sqrt(hidden))          # spread logits: greedy decoding far from ties
+    # llama-3 rope frequency factors (ggml_rope_ext's `c` operand): 1 for the high frequencies, growing towards 8 for the low ones
+    ff = np.ones(head_dim // 2, np.float32)
+    ff[head_dim // 4:] = np.linspace(1.0, 8.0, head_dim // 2 - head_dim // 4).astype(np.float32)
+    items.append(("orpheus.rope_frequencies", ff))
+    return items
+
+
+def write_orpheus_gguf(path: str, seed: int = 0, layers: int = 2, heads: int = 6, kv_heads: int = 2, head_dim: int = 64, ffn: int = 1024,
+                       vocab: int = 2048) -> dict:
+    """Small synthetic Orpheus GGUF (all F32: the only dtype the reference supports for Orpheus, README.md:25), with the SNAC decoder
+    tensors the reference's loader also needs."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="orpheus")
+    items = orpheus_tensors(seed, layers, heads, kv_heads, head_dim, ffn, vocab) + snac_tensors(seed=seed)
+    n_params = 0
+    for name, arr in items:
+        n_params += arr.size
+        w.add_tensor(name, arr.astype(np.float32))
+    for k, v in (("orpheus.vocab_size", vocab), ("orpheus.attn_heads", heads), ("orpheus.kv_attn_heads", kv_heads), ("orpheus.head_dim", head_dim),
+                 ("orpheus.layers", layers), ("orpheus.hidden_size", heads * head_dim), ("orpheus.kv_hidden_size", kv_heads * head_dim),
+                 ("orpheus.stopping_token_id", vocab - 1), ("tokenizer.ggml.eos_token_id", vocab - 2), ("tokenizer.ggml.bos_token_id", 1)):
+        w.add_uint32(k, int(v))
+    c = 1024
+    for i, s in enumerate(SNAC_RATES):
+        c //= 2
+        w.add_uint32(f"snac.snac_layer_stride_{i}", int(s))
+        w.add_uint32(f"snac.snac_layer_padding_{i}", int((s + 1) // 2))
+        w.add_uint32(f"snac.snac_layer_grouping_{i}", int(c))
+    w.add_uint32("snac.audio_token_channels", 3)
+    w.add_uint32("snac.max_generation_size", 64)
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def cached_orpheus_gguf(seed: int = 0, cache_dir: str | None = None, **kw) -> str:
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    tag = "_".join(f"{k}{v}" for k, v in sorted(kw.items()))
+    path = os.path.join(cache_dir, f"orpheus_f32_s{seed}_{tag}.gguf")
+    if not os.path.exists(path):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_orpheus_gguf(tmp, seed=seed, **kw)
+        os.replace(tmp, path)
+    return path
+
+
 def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
     """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
     out = []
