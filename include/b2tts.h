@@ -160,6 +160,23 @@ int   b2tts_snac_info(const b2tts_snac * m, int * up_sampling_factor, int * code
 int   b2tts_snac_decode_batch(b2tts_snac * m, int n_utterances, const uint32_t * const * codes, const int32_t * fine_frames, const float ** pcm, int64_t * n_samples);
 int   b2tts_snac_reset_noise(b2tts_snac * m);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Orpheus autoregressive decode, FIRST CORRECT PATH: fp32 CUDA-core GEMVs, compact GQA KV cache, device argmax.
+ * NOT YET VALIDATED ON A B200 (written after round 1's GPU budget was spent; its oracle, oracle/orpheus_port.py, reproduces the reference's
+ * greedy token ids exactly).  No performance claims are made for it.
+ *   b2tts_orpheus_load_gguf      : orpheus_model::setup_from_file + assign_weight loop over "orpheus.*" (reference
+ *                                  src/models/orpheus/model.h:59-63, model.cpp:11-120; loader.cpp:8-23)
+ *   b2tts_orpheus_generate_greedy: generate_from_batch's decode + sampler loop (model.cpp:230-353,389-398; sampler::max) for n_sequences
+ *                                  independent prompts of token ids, n_steps tokens each, without the stop condition.
+ *                                  out_tokens [n_sequences][n_steps]; out_logits (may be NULL) [n_sequences][n_steps][vocab]. */
+typedef struct b2tts_orpheus b2tts_orpheus;
+int   b2tts_orpheus_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_orpheus ** out);
+void  b2tts_orpheus_free(b2tts_orpheus * m);
+int   b2tts_orpheus_info(const b2tts_orpheus * m, int * vocab_size, int * n_layers, int * hidden_size);
+int   b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
+                                    int32_t * out_tokens, float * out_logits);
+float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
+
 #ifdef __cplusplus
 }
 #endif

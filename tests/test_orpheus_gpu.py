@@ -1,0 +1,42 @@
+"""GPU: the Orpheus decode loop (tts_cpp_b200/csrc/orpheus.cu) against the token ids and logits the compiled UNMODIFIED reference produced
+(tests/golden/orpheus_vectors.npz: two prompts, 6 greedy steps each, small synthetic Orpheus GGUF).
+
+This path was written after round 1's GPU budget was spent and has never run on a B200, hence xfail(strict=False): the test reports
+XPASS / XFAIL without gating the suite, and it runs the check in a CHILD PROCESS so that a fault in the unvalidated kernels cannot poison
+the CUDA context of the tests that follow.  Round 2 removes both once validated."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="Orpheus decode path not yet validated on a B200 (round 1 GPU budget exhausted)")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import orpheus_runner_from_file
+from tts_cpp_b200.synth import cached_orpheus_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "orpheus_vectors.npz"))
+orph = orpheus_runner_from_file(cached_orpheus_gguf(seed=0))
+prompts = [g["prompt0"], g["prompt1"]]
+steps = g["tokens0"].size
+toks, logits = orph.generate_greedy(prompts, steps, want_logits=True)         # one ragged batch of both prompts
+ok = True
+for u in range(2):
+    d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
+    print(f"PARITY orpheus prompt {u}: tokens {toks[u].tolist()} vs {g[f'tokens{u}'].tolist()}  max |logit diff| {d:.3e}")
+    ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < 1e-3          # bit-exact token ids at temperature 0
+single = orph.generate_greedy([prompts[1]], steps)
+ok &= bool(np.array_equal(single[0], toks[1]))                                  # batching does not change a sequence
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_orpheus_greedy_tokens_and_logits_match_reference():
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=240)
+    print(r.stdout[-2000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0

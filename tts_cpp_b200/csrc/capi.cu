@@ -2,6 +2,7 @@
 #include "../../include/b2tts.h"
 #include "kokoro.h"
 #include "dac.h"
+#include "orpheus.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -25,6 +26,7 @@ struct b2tts_ctx { Ctx c; };
 struct b2tts_kokoro { Kokoro k; };
 struct b2tts_dac { Dac d; };
 struct b2tts_snac { Snac s; };
+struct b2tts_orpheus { Orpheus o; };
 
 namespace {
 // RAII device scratch for the op-level entry points
@@ -159,6 +161,31 @@ int b2tts_snac_decode_batch(b2tts_snac * m, int n_utterances, const uint32_t * c
     if (!m) { set_error("null model"); return 1; }
     return m->s.decode_batch(n_utterances, codes, fine_frames, pcm, n_samples);
 }
+// ---- Orpheus AR decode (first correct path)
+int b2tts_orpheus_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_orpheus ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_orpheus * m = new b2tts_orpheus();
+    m->o.ctx = &ctx->c;
+    if (load_gguf_into(&m->o, path)) { m->o.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_orpheus_free(b2tts_orpheus * m) { if (m) { m->o.free_all(); delete m; } }
+int b2tts_orpheus_info(const b2tts_orpheus * m, int * vocab_size, int * n_layers, int * hidden_size) {
+    if (!m) { set_error("null model"); return 1; }
+    if (vocab_size) *vocab_size = m->o.vocab;
+    if (n_layers) *n_layers = m->o.n_layers;
+    if (hidden_size) *hidden_size = m->o.hidden;
+    return 0;
+}
+int b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens,
+                                  float * out_logits) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->o.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
+}
+float b2tts_orpheus_last_ms(const b2tts_orpheus * m) { return m ? m->o.timing_ms : 0.f; }
+
 int b2tts_snac_reset_noise(b2tts_snac * m) { if (!m) { set_error("null model"); return 1; } m->s.reset_noise(); return 0; }
 int b2tts_kokoro_n_voices(const b2tts_kokoro * m) { return (int) m->k.voice_names.size(); }
 const char * b2tts_kokoro_voice_name(const b2tts_kokoro * m, int i) { return (i >= 0 && i < (int) m->k.voice_names.size()) ? m->k.voice_names[i].c_str() : nullptr; }

@@ -7,6 +7,7 @@
 // specification; no ggml code is linked.
 #include "kokoro.h"
 #include "dac.h"
+#include "orpheus.h"
 
 #include <functional>
 
@@ -145,6 +146,11 @@ int load_gguf_into(Dac * m, const char * path) {
 // the SNAC decoder's tensors live under "snac." in Orpheus GGUFs (reference src/decoder/snac_model.h:41-46, src/models/orpheus/model.cpp:440-441)
 int load_gguf_into(Snac * m, const char * path) {
     if (read_gguf(path, "snac.", nullptr, m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
+}
+
+int load_gguf_into(Orpheus * m, const char * path) {
+    if (read_gguf(path, "orpheus.", "orpheus", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
     return m->prepare();
 }
 

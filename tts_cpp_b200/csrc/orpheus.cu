@@ -1,0 +1,341 @@
+// orpheus.cu -- Orpheus autoregressive decode (llama-3 style), first correct CUDA path.  See orpheus.h for what it replaces and why it is plain.
+#include "orpheus.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace b2 {
+
+static inline float oh2f(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
+
+int Orpheus::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
+    if (prepared) { set_error("orpheus: assign_weight after prepare"); return 1; }
+    std::string nm(name);
+    if (nm.rfind("orpheus.", 0) == 0) nm = nm.substr(8);
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
+    t.v.resize((size_t) n);
+    if (type == 0) {
+        if (nbytes < (size_t) n * 4) { set_error("tensor %s: short data", name); return 1; }
+        memcpy(t.v.data(), data, (size_t) n * 4);
+    } else if (type == 1) {
+        if (nbytes < (size_t) n * 2) { set_error("tensor %s: short data", name); return 1; }
+        const uint16_t * s = (const uint16_t *) data;
+        for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = oh2f(s[i]);
+        t.f16 = true;
+    } else {
+        set_error("tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
+        return 1;
+    }
+    host[nm] = std::move(t);
+    return 0;
+}
+
+int Orpheus::prepare() {
+    if (prepared) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    auto kvreq = [&](const char * k, int & out) { auto it = kv.find(k); if (it == kv.end()) { set_error("the '%s' key must be specified in the GGUF file.", k); return 1; } out = (int) it->second; return 0; };
+    if (kvreq("orpheus.layers", n_layers) || kvreq("orpheus.vocab_size", vocab) || kvreq("orpheus.attn_heads", heads) || kvreq("orpheus.kv_attn_heads", kv_heads) ||
+        kvreq("orpheus.head_dim", head_dim) || kvreq("orpheus.hidden_size", hidden) || kvreq("orpheus.kv_hidden_size", kv_hidden)) return 1;
+    { auto it = kv.find("orpheus.stopping_token_id"); stopping_token = it != kv.end() ? (int) it->second : 128258; }
+    if (hidden != heads * head_dim || kv_hidden != kv_heads * head_dim || heads % kv_heads || head_dim % 2 || hidden % 4) { set_error("orpheus: inconsistent head configuration"); return 1; }
+    bool ok = true;
+    auto up = [&](const std::string & n, int64_t expect) -> float * {
+        auto it = host.find(n);
+        if (it == host.end()) { set_error("missing tensor orpheus.%s", n.c_str()); ok = false; return nullptr; }
+        if (expect && (int64_t) it->second.v.size() != expect) { set_error("tensor orpheus.%s has %zu elements, expected %lld", n.c_str(), it->second.v.size(), (long long) expect); ok = false; return nullptr; }
+        void * d = nullptr;
+        if (cudaMalloc(&d, it->second.v.size() * 4) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed for orpheus.%s", n.c_str()); ok = false; return nullptr; }
+        cudaMemcpy(d, it->second.v.data(), it->second.v.size() * 4, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += it->second.v.size() * 4;
+        return (float *) d;
+    };
+    embed = up("embed_tokens", (int64_t) vocab * hidden);
+    out_norm = up("norm", hidden);
+    head = up("lm_head", (int64_t) vocab * hidden);
+    rope_ff = up("rope_frequencies", head_dim / 2);
+    {
+        auto it = host.find("layers.0.mlp.gate_proj");
+        if (it == host.end()) { set_error("missing tensor orpheus.layers.0.mlp.gate_proj"); return 1; }
+        ffn = (int) it->second.shape[0];
+        if (ffn % 4) { set_error("orpheus: ffn size %d must be a multiple of 4", ffn); return 1; }
+    }
+    layers.resize((size_t) n_layers);
+    for (int l = 0; l < n_layers && ok; l++) {
+        const std::string b = "layers." + std::to_string(l);
+        OrpheusLayer & L = layers[(size_t) l];
+        L.in_norm = up(b + ".input_layernorm", hidden);  L.post_norm = up(b + ".post_attention_layernorm", hidden);
+        L.wq = up(b + ".self_attn.q_proj", (int64_t) hidden * hidden);    L.wk = up(b + ".self_attn.k_proj", (int64_t) kv_hidden * hidden);
+        L.wv = up(b + ".self_attn.v_proj", (int64_t) kv_hidden * hidden); L.wo = up(b + ".self_attn.o_proj", (int64_t) hidden * hidden);
+        L.wgate = up(b + ".mlp.gate_proj", (int64_t) ffn * hidden);       L.wup = up(b + ".mlp.up_proj", (int64_t) ffn * hidden);
+        L.wdown = up(b + ".mlp.down_proj", (int64_t) hidden * ffn);
+    }
+    if (!ok) return 1;
+    for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+    host.clear();
+    prepared = true;
+    return 0;
+}
+
+void Orpheus::free_all() {
+    for (void * p : dev_allocs) cudaFree(p);
+    dev_allocs.clear();
+    arena.release();
+    for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+}
+
+namespace {
+
+// rows of a step: (sequence, position, token).  Decode steps have one row per sequence, built on the device from the last argmax.
+__global__ void decode_rows_kernel(const int * __restrict__ n_prompt, const int * __restrict__ cur_tok, int B, int step, int * row_seq, int * row_pos, int * row_tok) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    row_seq[b] = b; row_pos[b] = n_prompt[b] + step - 1; row_tok[b] = cur_tok[b];
+}
+
+__global__ void embed_kernel(const int * __restrict__ row_tok, const float * __restrict__ embed, int H, float * __restrict__ x) {   // ggml_get_rows
+    const int r = blockIdx.x;
+    const float * src = embed + (size_t) row_tok[r] * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) x[(size_t) r * H + c] = src[c];
+}
+
+// ggml_rms_norm (float squares accumulated in a double, scale = 1/sqrtf(mean + eps)) followed by the weight multiply (model.cpp:122-125)
+__global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __restrict__ w, int H, int R, float * __restrict__ y) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float * row = x + (size_t) r * H;
+    double s = 0.0;
+    for (int c = lane; c < H; c += 32) s += (double) (row[c] * row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = (float) (s / (double) H);
+    const float scale = 1.0f / sqrtf(mean + 1e-5f);
+    for (int c = lane; c < H; c += 32) y[(size_t) r * H + c] = (row[c] * scale) * w[c];
+}
+
+// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]): one warp per output n, the weight row is read once per chunk of 8 rows
+// (ggml_mul_mat with F32 weights and activations; K % 4 == 0)
+constexpr int GR = 8;
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
+                                                        const float * __restrict__ res, float * __restrict__ Y, int ldy) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const float * wrow = W + (size_t) n * K;
+    for (int r0 = 0; r0 < R; r0 += GR) {
+        float acc[GR];
+#pragma unroll
+        for (int j = 0; j < GR; j++) acc[j] = 0.f;
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(wrow + k);
+#pragma unroll
+            for (int j = 0; j < GR; j++) {
+                if (r0 + j < R) {
+                    const float4 x4 = *reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + k);
+                    acc[j] = fmaf(x4.w, w4.w, fmaf(x4.z, w4.z, fmaf(x4.y, w4.y, fmaf(x4.x, w4.x, acc[j]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GR; j++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? acc[j] + res[(size_t) (r0 + j) * ldy + n] : acc[j];
+        }
+    }
+}
+
+// NeoX RoPE over the whole head with per-pair frequency factors (ggml_rope_ext mode 2, theta base 5e5, ggml-cpu rope cache: theta starts at
+// the position and is multiplied by theta_scale pair after pair), applied to q in place and to k on its way into the cache; v is copied
+// (orpheus_build_kv_store, model.cpp:196-228 -- here the cache is compact: the 3x head expansion is done by indexing in the attention)
+__global__ void rope_append_kernel(float * q, const float * __restrict__ k, const float * __restrict__ v, const float * __restrict__ ff, const int * __restrict__ row_seq,
+                                   const int * __restrict__ row_pos, int heads, int kv_heads, int hd, float theta_scale, float * Kc, float * Vc, int Tmax) {
+    const int r = blockIdx.x, h = blockIdx.y;                  // h < heads: a query head; h >= heads: kv head h - heads
+    const int b = row_seq[r], pos = row_pos[r], half = hd >> 1;
+    const int KV = kv_heads * hd, H = heads * hd;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float theta = (float) pos;
+        for (int j = 0; j < i; j++) theta *= theta_scale;
+        const float th = theta / ff[i];
+        const float c = cosf(th), s = sinf(th);
+        if (h < heads) {
+            float * p = q + (size_t) r * H + (size_t) h * hd;
+            const float x0 = p[i], x1 = p[i + half];
+            p[i] = x0 * c - x1 * s; p[i + half] = x0 * s + x1 * c;
+        } else {
+            const int kh = h - heads;
+            const float * p = k + (size_t) r * KV + (size_t) kh * hd;
+            float * d = Kc + ((size_t) b * Tmax + pos) * KV + (size_t) kh * hd;
+            const float x0 = p[i], x1 = p[i + half];
+            d[i] = x0 * c - x1 * s; d[i + half] = x0 * s + x1 * c;
+            const float * pv = v + (size_t) r * KV + (size_t) kh * hd;
+            float * dv = Vc + ((size_t) b * Tmax + pos) * KV + (size_t) kh * hd;
+            dv[i] = pv[i]; dv[i + half] = pv[i + half];
+        }
+    }
+}
+
+// causal attention of one new row against its sequence's cache: softmax(q.K^T / sqrt(hd)) V with ggml_soft_max's double-accumulated sum
+// (model.cpp:268-276; ggml-cpu.c soft_max: max, expf, ggml_float sum, scale by (float)(1/sum))
+__global__ void __launch_bounds__(128) attention_kernel(const float * __restrict__ q, const float * __restrict__ Kc, const float * __restrict__ Vc,
+                                                        const int * __restrict__ row_seq, const int * __restrict__ row_pos, int heads, int kv_heads, int hd,
+                                                        int Tmax, float scale, float * __restrict__ out) {
+    extern __shared__ float sc[];          // [T] scores, then 128 floats + 128 doubles of reduction scratch behind them
+    const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    const int b = row_seq[r], T = row_pos[r] + 1;
+    const int KV = kv_heads * hd, H = heads * hd, kh = h / (heads / kv_heads);
+    float * redf = sc + ((Tmax + 1) & ~1);      // keeps the double scratch behind it 8-byte aligned
+    double * redd = reinterpret_cast<double *>(redf + 128);
+    const float * qv = q + (size_t) r * H + (size_t) h * hd;
+    float mx = -INFINITY;
+    for (int t = tid; t < T; t += 128) {
+        const float * kr = Kc + ((size_t) b * Tmax + t) * KV + (size_t) kh * hd;
+        float a = 0.f;
+        for (int d = 0; d < hd; d++) a = fmaf(qv[d], kr[d], a);
+        a *= scale;
+        sc[t] = a;
+        mx = fmaxf(mx, a);
+    }
+    redf[tid] = mx;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) { if (tid < o) redf[tid] = fmaxf(redf[tid], redf[tid + o]); __syncthreads(); }
+    mx = redf[0];
+    double sum = 0.0;
+    for (int t = tid; t < T; t += 128) { const float e = expf(sc[t] - mx); sc[t] = e; sum += (double) e; }
+    redd[tid] = sum;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) { if (tid < o) redd[tid] += redd[tid + o]; __syncthreads(); }
+    const float inv = (float) (1.0 / redd[0]);
+    for (int d = tid; d < hd; d += 128) {
+        float a = 0.f;
+        for (int t = 0; t < T; t++) a = fmaf(sc[t] * inv, Vc[((size_t) b * Tmax + t) * KV + (size_t) kh * hd + d], a);
+        out[(size_t) r * H + (size_t) h * hd + d] = a;
+    }
+}
+
+__global__ void silu_mul_kernel(float * g, const float * __restrict__ u, size_t n) {      // ggml_silu (x / (1 + expf(-x))) * up
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float x = g[i]; g[i] = (x / (1.0f + expf(-x))) * u[i]; }
+}
+
+__global__ void gather_rows_f32_kernel(const float * __restrict__ x, const int * __restrict__ idx, int H, float * __restrict__ y) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) y[(size_t) b * H + c] = x[(size_t) idx[b] * H + c];
+}
+
+// sampler::max: the first maximum wins
+__global__ void __launch_bounds__(256) argmax_kernel(const float * __restrict__ logits, int V, int * cur_tok, int * out_tokens, int n_steps, int step) {
+    __shared__ float sv[256]; __shared__ int si[256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float * lg = logits + (size_t) b * V;
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += 256) { const float v = lg[i]; if (v > best) { best = v; bi = i; } }
+    sv[tid] = best; si[tid] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
+        __syncthreads();
+    }
+    if (tid == 0) { cur_tok[b] = si[0]; out_tokens[(size_t) b * n_steps + step] = si[0]; }
+}
+
+struct OFwd {
+    Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false;
+    template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
+    int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+};
+
+}  // namespace
+
+int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
+    if (!prepared) { set_error("orpheus: model not prepared"); return 1; }
+    if (B <= 0 || n_steps <= 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int R0 = 0, Pmax = 0;
+    for (int b = 0; b < B; b++) {
+        if (n_prompt[b] <= 0) { set_error("orpheus: prompt %d is empty", b); return 1; }
+        for (int i = 0; i < n_prompt[b]; i++) if (prompts[b][i] >= (uint32_t) vocab) { set_error("orpheus: prompt %d token %u >= vocab %d", b, prompts[b][i], vocab); return 1; }
+        R0 += n_prompt[b]; Pmax = std::max(Pmax, (int) n_prompt[b]);
+    }
+    const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, KV = kv_hidden, F = ffn;
+    const size_t cache = (size_t) n_layers * B * Tmax * KV * 4;
+    const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
+                        (size_t) Rmax * 16 + (size_t) B * 16 + (32 << 20);
+    if (arena.reserve(need)) return 1;
+    OFwd Fw{this, ctx, st};
+    float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * KV), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * KV);
+    float * x = Fw.al<float>((size_t) Rmax * H), * xn = Fw.al<float>((size_t) Rmax * H), * q = Fw.al<float>((size_t) Rmax * H), * att = Fw.al<float>((size_t) Rmax * H);
+    float * kbuf = Fw.al<float>((size_t) Rmax * KV), * vbuf = Fw.al<float>((size_t) Rmax * KV);
+    float * g = Fw.al<float>((size_t) Rmax * F), * u = Fw.al<float>((size_t) Rmax * F);
+    float * last = Fw.al<float>((size_t) B * H), * logits = Fw.al<float>((size_t) B * vocab);
+    int * row_seq = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_tok = Fw.al<int>((size_t) Rmax);
+    int * d_np = Fw.al<int>((size_t) B), * d_last = Fw.al<int>((size_t) B), * cur_tok = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) B * n_steps);
+    if (Fw.fail) return 1;
+
+    std::vector<int> hs((size_t) R0), hp((size_t) R0), ht((size_t) R0), hnp((size_t) B), hlast((size_t) B);
+    {
+        int r = 0;
+        for (int b = 0; b < B; b++) {
+            hnp[(size_t) b] = n_prompt[b];
+            for (int i = 0; i < n_prompt[b]; i++, r++) { hs[(size_t) r] = b; hp[(size_t) r] = i; ht[(size_t) r] = (int) prompts[b][i]; }
+            hlast[(size_t) b] = r - 1;
+        }
+    }
+    B2_CUDA(cudaEventRecord(ev[0], st));
+    B2_CUDA(cudaMemcpyAsync(row_seq, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_pos, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_tok, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(d_np, hnp.data(), hnp.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(d_last, hlast.data(), hlast.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
+
+    const float theta_scale = powf(500000.0f, -2.0f / (float) head_dim);
+    const float scale = 1.0f / sqrtf((float) head_dim);
+    const size_t att_smem = (size_t) ((Tmax + 1) & ~1) * 4 + 128 * 4 + 128 * 8;
+    if (att_smem > 200 * 1024) { set_error("orpheus: context of %d positions exceeds the v1 attention kernel's shared memory", Tmax); return 1; }
+    B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
+
+    for (int s = 0; s < n_steps; s++) {
+        const int R = s == 0 ? R0 : B;
+        if (s > 0) { decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, s, row_seq, row_pos, row_tok); B2_LAUNCH_CHECK(ctx); }
+        embed_kernel<<<R, 256, 0, st>>>(row_tok, embed, H, x);
+        B2_LAUNCH_CHECK(ctx);
+        for (int l = 0; l < n_layers; l++) {
+            const OrpheusLayer & L = layers[(size_t) l];
+            float * Kl = Kc + (size_t) l * B * Tmax * KV, * Vl = Vc + (size_t) l * B * Tmax * KV;
+            rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, L.in_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
+            if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
+            if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
+            if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
+            { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax); B2_LAUNCH_CHECK(ctx); }
+            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_seq, row_pos, heads, kv_heads, head_dim, Tmax, scale, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                        // xn = attn_out + residual(x)
+            rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
+            if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;
+            if (Fw.gemv(q, H, L.wup, H, F, R, nullptr, u, F)) return 1;
+            { const size_t n = (size_t) R * F; silu_mul_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, u, n); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(g, F, L.wdown, F, H, R, xn, x, H)) return 1;                         // x = mlp + residual(xn)
+        }
+        rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, out_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
+        const float * lastp = xn;
+        if (s == 0) { gather_rows_f32_kernel<<<B, 256, 0, st>>>(xn, d_last, H, last); B2_LAUNCH_CHECK(ctx); lastp = last; }   // logits of the last position only
+        if (Fw.gemv(lastp, H, head, H, vocab, B, nullptr, logits, vocab)) return 1;
+        argmax_kernel<<<B, 256, 0, st>>>(logits, vocab, cur_tok, d_out, n_steps, s); B2_LAUNCH_CHECK(ctx);
+        if (out_logits)
+            for (int b = 0; b < B; b++)
+                B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * vocab, logits + (size_t) b * vocab, (size_t) vocab * 4, cudaMemcpyDeviceToHost, st));
+    }
+    B2_CUDA(cudaEventRecord(ev[1], st));
+    B2_CUDA(cudaMemcpyAsync(out_tokens, d_out, (size_t) B * n_steps * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&timing_ms, ev[0], ev[1]);
+    return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,45 @@
+// orpheus.h -- Orpheus (llama-3 style) autoregressive decode on the B200, first correct path.
+//
+// Replaces orpheus_runner::build_orpheus_graph / decode / set_inputs / orpheus_build_kv_store / generate_from_batch's token loop
+// (reference src/models/orpheus/model.cpp:196-353,389-398) and sampler::max (src/sampler.cpp) for a batch of independent sequences.
+// v1 is deliberately plain: fp32 weights (the only dtype the reference supports for Orpheus), fp32 CUDA-core GEMVs that stream each
+// weight matrix once per step for the whole batch, a compact (un-expanded) GQA KV cache, softmax with the reference's double-accumulated
+// sum, argmax on the device.  Written after round 1's GPU budget was spent: parity tests are xfail(strict=False) until validated.
+#pragma once
+#include "kokoro.h"   // HostTensor, Arena
+
+namespace b2 {
+
+struct OrpheusLayer {
+    float * in_norm = nullptr, * post_norm = nullptr;
+    float * wq = nullptr, * wk = nullptr, * wv = nullptr, * wo = nullptr, * wgate = nullptr, * wup = nullptr, * wdown = nullptr;
+};
+
+struct Orpheus {
+    Ctx * ctx = nullptr;
+    std::map<std::string, uint32_t>   kv;
+    std::map<std::string, HostTensor> host;
+    bool prepared = false;
+    size_t weight_bytes = 0;
+    std::vector<void *> dev_allocs;
+
+    int vocab = 0, heads = 0, kv_heads = 0, head_dim = 0, hidden = 0, kv_hidden = 0, ffn = 0, n_layers = 0;
+    int stopping_token = -1;
+    float * embed = nullptr, * out_norm = nullptr, * head = nullptr, * rope_ff = nullptr;
+    std::vector<OrpheusLayer> layers;
+
+    Arena arena;
+    float timing_ms = 0.f;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    int assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+    int prepare();
+    // greedy continuation of B prompts for n_steps tokens each (generate_from_batch's loop without the stop condition):
+    // out_tokens [B][n_steps]; out_logits (optional) [B][n_steps][vocab]
+    int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits);
+    void free_all();
+};
+
+int load_gguf_into(Orpheus * m, const char * path);   // gguf_reader.cpp
+
+}  // namespace b2
