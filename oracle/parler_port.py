@@ -1,0 +1,105 @@
+"""oracle/parler_port.py -- TEST INFRASTRUCTURE.  CPU restatement of the reference Parler-TTS decode loop.
+
+The checker for a future CUDA path (never imported by the product): what parler_tts_runner::decode computes per call (reference
+src/models/parler/model.cpp:387-470,520-614) and the token loop of generate_from_batch with its delay pattern (model.cpp:762-786) under
+the greedy sampler (src/sampler.cpp: per-head argmax, first maximum wins), in CPU torch fp32 with an explicit KV cache.
+Pinned against oracle/_ref/parler_ref by tests/golden/make_golden.py + tests/test_oracle_port.py.
+
+Reference semantics restated: learned positional embeddings added to the prompt / summed codebook embeddings; pre-LayerNorm blocks
+(ggml_norm eps 1e-5, double-accumulated, weight and bias); bias-free MHA with a causal -inf mask inside the softmax, scale 1/sqrt(head);
+cross-attention over K/V computed once from the stored text encoding (prep_cross_key_values, model.cpp:110-173) with an all-zero mask;
+fc1 -> GELU (ggml's fp16 table) -> fc2; nine output heads; head i is fed BOS until step i + 1 (the delay pattern).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from kokoro_port import gelu_f16_lut, ggml_norm   # same ggml numerics (ggml-cpu.c:1816-1830, 7114-7163)
+
+
+class ParlerPort:
+    def __init__(self, gguf_path: str, threads: int = 8):
+        import gguf
+        torch.set_num_threads(threads)
+        rd = gguf.GGUFReader(gguf_path)
+        self.w = {}
+        for t in rd.tensors:
+            if t.name.startswith("decoder."):
+                self.w[t.name[len("decoder."):]] = torch.from_numpy(np.array(t.data).astype(np.float32))
+        self.kv = {}
+        for k, f in rd.fields.items():
+            if len(f.data) == 1 and f.types and f.types[0].name in ("UINT32",):
+                self.kv[k] = int(f.parts[f.data[0]][0])
+        a = "parler-tts.decoder"
+        self.layers = self.kv[f"{a}.num_hidden_layers"]; self.heads = self.kv[f"{a}.attention.head_count"]
+        self.hidden = self.kv[f"{a}.hidden_size"]; self.hd = self.hidden // self.heads
+        self.n_out = self.kv[f"{a}.output_heads"]; self.vocab = self.kv[f"{a}.out_vocab_size"]
+        self.bos = self.kv["audio.bos_token_id"]; self.eos = self.kv["audio.eos_token_id"]
+        enc = self.w["text_encoding"]
+        self.ck = [enc @ self.w[f"layers.{l}.encoder_attn.k_proj.weight"].t() for l in range(self.layers)]
+        self.cv = [enc @ self.w[f"layers.{l}.encoder_attn.v_proj.weight"].t() for l in range(self.layers)]
+        self.reset()
+
+    def reset(self):
+        self.k = [None] * self.layers; self.v = [None] * self.layers
+        self.pos = 0
+
+    def ln(self, x, base):
+        return ggml_norm(x, 1e-5) * self.w[base + ".weight"] + self.w[base + ".bias"]
+
+    def attend(self, q, K, V, mask):
+        n, T = q.shape[0], K.shape[0]
+        qh = q.reshape(n, self.heads, self.hd); Kh = K.reshape(T, self.heads, self.hd); Vh = V.reshape(T, self.heads, self.hd)
+        s = torch.einsum("nhd,thd->hnt", qh, Kh) * (1.0 / np.sqrt(np.float32(self.hd)))
+        p = torch.softmax((s + mask[None]).double(), dim=-1).float()
+        return torch.einsum("hnt,thd->nhd", p, Vh).reshape(n, self.hidden)
+
+    def step(self, x) -> torch.Tensor:
+        """x [n, hidden]: input embeddings (positions self.pos .. self.pos + n - 1 already added); returns logits [n_out, n, vocab]."""
+        n = x.shape[0]
+        for l in range(self.layers):
+            b = f"layers.{l}"
+            res = x
+            cur = self.ln(x, b + ".self_attn_layer_norm")
+            q = cur @ self.w[b + ".self_attn.q_proj.weight"].t()
+            k = cur @ self.w[b + ".self_attn.k_proj.weight"].t()
+            v = cur @ self.w[b + ".self_attn.v_proj.weight"].t()
+            self.k[l] = k if self.k[l] is None else torch.cat([self.k[l], k], 0)
+            self.v[l] = v if self.v[l] is None else torch.cat([self.v[l], v], 0)
+            T = self.k[l].shape[0]
+            mask = torch.zeros(n, T)
+            for i in range(n):
+                mask[i, self.pos + i + 1:] = float("-inf")
+            x = self.attend(q, self.k[l], self.v[l], mask) @ self.w[b + ".self_attn.out_proj.weight"].t() + res
+            res = x
+            cur = self.ln(x, b + ".encoder_attn_layer_norm")
+            q = cur @ self.w[b + ".encoder_attn.q_proj.weight"].t()
+            x = self.attend(q, self.ck[l], self.cv[l], torch.zeros(n, self.ck[l].shape[0])) @ self.w[b + ".encoder_attn.out_proj.weight"].t() + res
+            res = x
+            cur = self.ln(x, b + ".final_layer_norm")
+            cur = gelu_f16_lut(cur @ self.w[b + ".fc1.weight"].t())
+            x = cur @ self.w[b + ".fc2.weight"].t() + res
+        x = self.ln(x, "layer_norm")
+        self.pos += n
+        return torch.stack([x @ self.w[f"lm_heads.{i}.weight.head"].t() for i in range(self.n_out)])
+
+    def greedy(self, prompt, steps: int):
+        """Returns (tokens [steps, n_out], logits [steps, n_out, vocab]) like oracle/_ref/parler_ref."""
+        self.reset()
+        tok = torch.from_numpy(np.asarray(prompt).astype(np.int64))
+        x = self.w["embed_prompts"][tok] + self.w["positional_embed"][torch.arange(tok.numel())]
+        self.step(x)
+        toks, logits = [], []
+        last = None
+        for s in range(steps):                       # the audio batch built after decode number s has current_step == s
+            ids = [int(last[i]) if s > i else self.bos for i in range(self.n_out)]
+            x = None
+            for i in range(self.n_out):              # embds[0][id0], then embds[i][id_i] + accumulated (parler_build_inp_embd)
+                e = self.w[f"embed_tokens.{i}.weight"][ids[i]]
+                x = e if x is None else e + x
+            x = (x + self.w["positional_embed"][self.pos])[None, :]
+            lg = self.step(x)[:, 0, :].numpy()
+            last = lg.argmax(axis=1)                 # numpy argmax returns the first maximum, like sampler::max
+            toks.append(last.astype(np.int32)); logits.append(lg)
+        return np.stack(toks), np.stack(logits)

@@ -14,6 +14,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
   orpheus_vectors.npz      : two prompts (7 and 12 token ids) and, for 6 greedy decode steps each, the tokens the reference's decode loop +
       sampler produced and the logits of every step, on the small synthetic Orpheus GGUF (2 layers, 6/2 heads x 64, vocab 2048, F32),
       from oracle/ref_orpheus_driver.cpp
+  parler_vectors.npz       : two prompts (5 and 9 ids) and, for 5 greedy audio steps each, the 9 codebook tokens per step and their logits
+      from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
 """
 import os
 import re
@@ -166,8 +168,29 @@ def orpheus_vectors():
     print("orpheus vectors:", {k: v.shape for k, v in out.items()})
 
 
+def parler_vectors():
+    from tts_cpp_b200.synth import cached_parler_gguf
+    gguf = cached_parler_gguf(seed=0)
+    rng = np.random.default_rng(7)
+    prompts = [rng.integers(1, 500, size=n) for n in (5, 9)]
+    tmp = tempfile.mkdtemp()
+    pf = os.path.join(tmp, "prompts.txt")
+    open(pf, "w").write("\n".join(" ".join(map(str, q)) for q in prompts) + "\n")
+    pre = os.path.join(tmp, "p")
+    steps = 5
+    run([os.path.join(REF, "parler_ref"), gguf, pf, pre, "--steps", str(steps), "--threads", "4", "--quiet"])
+    out = {}
+    for u, q in enumerate(prompts):
+        out[f"prompt{u}"] = np.asarray(q, np.int32)
+        out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
+        out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
+    np.savez_compressed(os.path.join(OUT, "parler_vectors.npz"), **out)
+    print("parler vectors:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler"]
+    if "parler" in which: parler_vectors()
     if "orpheus" in which: orpheus_vectors()
     if "snac" in which: snac_vectors()
     if "kokoro" in which: kokoro_vectors()

@@ -1,6 +1,7 @@
 """CPU: pin the oracle restatement (oracle/kokoro_port.py) against vectors produced by the compiled UNMODIFIED reference
 (tests/golden/make_golden.py ran oracle/_ref/{kokoro_ref,ops_ref} in the build container)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -153,3 +154,19 @@ def test_orpheus_port_against_reference_decode_loop():
         print(f"orpheus prompt {u}: tokens {toks.tolist()}  max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
         assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact token ids at temperature 0 (the north star's bar)
         assert d < 1e-4
+
+
+def test_parler_port_against_reference_decode_loop():
+    """oracle/parler_port.py vs the reference's Parler decode loop (cross-attention, delay pattern, 9-head greedy sampler): identical
+    codebook tokens; logits to the resolution ggml's fp16 GELU table leaves (a last-bit change before the table moves a logit by ~1e-3)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "oracle"))
+    from parler_port import ParlerPort
+    from tts_cpp_b200.synth import cached_parler_gguf
+    g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
+    port = ParlerPort(cached_parler_gguf(seed=0))
+    for u in range(2):
+        toks, logits = port.greedy(g[f"prompt{u}"], g[f"tokens{u}"].shape[0])
+        d = float(np.abs(logits - g[f"logits{u}"]).max())
+        print(f"parler prompt {u}: max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
+        assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact codebook indices at temperature 0
+        assert d < 1e-2

@@ -506,6 +506,85 @@ def cached_orpheus_gguf(seed: int = 0, cache_dir: str | None = None, **kw) -> st
     return path
 
 
+# ------------------------------------------------------------------------------------------ Parler-TTS decoder
+def parler_tensors(seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, out_vocab: int = 1088, n_heads: int = 9,
+                   prompt_vocab: int = 512, n_enc: int = 12, ctx: int = 4096):
+    """Synthetic weights in the reference's Parler schema (py-gguf/tts_encoders/parler_tts_gguf_encoder.py:85-131; names after the
+    "decoder." prefix as assign_to_decoder sees them, src/models/parler/model.cpp:3-28,271-318)."""
+    rng = np.random.default_rng(seed)
+    hidden = heads * head_dim
+    items: list[tuple[str, np.ndarray]] = []
+
+    def rand(name, shape, fan_in, scale=None):
+        s = (1.0 / np.sqrt(max(fan_in, 1))) if scale is None else scale
+        items.append(("decoder." + name, (rng.standard_normal(shape).astype(np.float32) * np.float32(s)).astype(np.float16).astype(np.float32)))
+
+    def norm(base, c):
+        items.append(("decoder." + base + ".weight", (1.0 + 0.1 * rng.standard_normal(c)).astype(np.float32).astype(np.float16).astype(np.float32)))
+        items.append(("decoder." + base + ".bias", (0.05 * rng.standard_normal(c)).astype(np.float32).astype(np.float16).astype(np.float32)))
+
+    rand("embed_prompts", (prompt_vocab, hidden), 1, 1.0)
+    rand("text_encoding", (n_enc, hidden), 1, 1.0)
+    rand("positional_embed", (ctx, hidden), 1, 0.5)
+    for i in range(n_heads):
+        rand(f"embed_tokens.{i}.weight", (out_vocab + 1, hidden), 1, 0.5)
+    for l in range(layers):
+        b = f"layers.{l}"
+        norm(b + ".self_attn_layer_norm", hidden)
+        for part in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            rand(f"{b}.self_attn.{part}.weight", (hidden, hidden), hidden)
+        norm(b + ".encoder_attn_layer_norm", hidden)
+        for part in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            rand(f"{b}.encoder_attn.{part}.weight", (hidden, hidden), hidden)
+        norm(b + ".final_layer_norm", hidden)
+        rand(f"{b}.fc1.weight", (ffn, hidden), hidden)
+        rand(f"{b}.fc2.weight", (hidden, ffn), ffn)
+    norm("layer_norm", hidden)
+    for i in range(n_heads):
+        rand(f"lm_heads.{i}.weight.head", (out_vocab, hidden), hidden, 4.0 / np.sqrt(hidden))
+    return items
+
+
+def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12) -> dict:
+    """Small synthetic Parler-TTS GGUF (F32) with a matching small DAC decoder (the reference's loader needs both).  32 heads x 8 layers is
+    the smallest shape the reference loads: prep_cross_key_values sizes its metadata pool from n_attn_heads * 2 * n_layers tensors but
+    allocates a 4096-node graph in it (src/models/parler/model.cpp:117-129)."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="parler-tts")
+    dac_rates = (2, 2, 2, 2)
+    items = parler_tensors(seed, layers, heads, head_dim, ffn, n_enc=n_enc) + dac_tensors(seed=seed, d_model=64, latent=32, rates=dac_rates)
+    n_params = 0
+    for name, arr in items:
+        n_params += arr.size
+        w.add_tensor(name, arr.astype(np.float32))
+    a = "parler-tts.decoder"
+    for k, v in ((f"{a}.encode_length", n_enc), (f"{a}.hidden_size", heads * head_dim), (f"{a}.output_heads", 9), (f"{a}.context_length", 4096),
+                 (f"{a}.attention.head_count", heads), (f"{a}.max_generation", 64), (f"{a}.out_vocab_size", 1088), (f"{a}.audio_vocab_size", 1024),
+                 (f"{a}.num_hidden_layers", layers), ("audio.bos_token_id", 1025), ("audio.eos_token_id", 1024)):
+        w.add_uint32(k, int(v))
+    for i, s in enumerate(dac_rates):
+        w.add_uint32(f"dac.dac_layer_stride_{i}", int(s))
+        w.add_uint32(f"dac.dac_layer_padding_{i}", int((s + 1) // 2))
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None) -> str:
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, f"parler_f32_s{seed}.gguf")
+    if not os.path.exists(path):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_parler_gguf(tmp, seed=seed)
+        os.replace(tmp, path)
+    return path
+
+
 def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
     """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
     out = []
