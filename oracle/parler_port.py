@@ -15,7 +15,10 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from kokoro_port import gelu_f16_lut, ggml_norm   # same ggml numerics (ggml-cpu.c:1816-1830, 7114-7163)
+try:                                              # same ggml numerics (ggml-cpu.c:1816-1830, 7114-7163)
+    from .kokoro_port import gelu_f16_lut, ggml_norm
+except ImportError:                               # imported as a top-level module (oracle/ on sys.path)
+    from kokoro_port import gelu_f16_lut, ggml_norm
 
 
 class ParlerPort:

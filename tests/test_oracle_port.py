@@ -159,8 +159,7 @@ def test_orpheus_port_against_reference_decode_loop():
 def test_parler_port_against_reference_decode_loop():
     """oracle/parler_port.py vs the reference's Parler decode loop (cross-attention, delay pattern, 9-head greedy sampler): identical
     codebook tokens; logits to the resolution ggml's fp16 GELU table leaves (a last-bit change before the table moves a logit by ~1e-3)."""
-    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "oracle"))
-    from parler_port import ParlerPort
+    from oracle.parler_port import ParlerPort
     from tts_cpp_b200.synth import cached_parler_gguf
     g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
     port = ParlerPort(cached_parler_gguf(seed=0))
