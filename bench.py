@@ -187,8 +187,47 @@ def run_reference_arm(args):
     return 0
 
 
+def run_dac_reference(args, threads: int = 4):
+    """The reference's dac_runner (oracle/_ref/dac_ref) on the host cores: W worker processes x `threads` ggml threads, each decoding one
+    861-frame utterance (10 s of audio) of the same synthetic GGUF -- a bounded sample of the batch-16 step."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    ref = os.path.join(ROOT, "oracle", "_ref", "dac_ref")
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "workload": "dac", "unavailable": "oracle/_ref/dac_ref missing (run `make -C oracle ref` where /root/reference exists)"}))
+        return 0
+    from tts_cpp_b200.synth import cached_dac_gguf, synthetic_codes
+    gguf = cached_dac_gguf(seed=0, max_frames=870)
+    ncpu = os.cpu_count() or 8
+    workers = max(1, min(16, ncpu // (2 * threads)))
+    tmp = tempfile.mkdtemp(prefix="b2dac_")
+    procs = []
+    for w, c in enumerate(synthetic_codes(workers, 861)):
+        cf = os.path.join(tmp, f"c{w}.txt")
+        open(cf, "w").write(" ".join(map(str, c.reshape(-1))) + "\n")
+        procs.append(subprocess.Popen([ref, gguf, cf, os.path.join(tmp, f"o{w}"), "--threads", str(threads), "--quiet"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    audio, wall = 0.0, 0.0
+    for p in procs:
+        out, _ = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("SUMMARY"):
+                sm = json.loads(line[len("SUMMARY "):])
+                audio += sm["audio_s"]; wall = max(wall, sm["wall_s"])
+    if wall <= 0:
+        print(json.dumps({"impl": "reference", "workload": "dac", "unavailable": "dac_ref produced no SUMMARY"}))
+        return 0
+    print(json.dumps({"impl": "reference", "metric": "audio_seconds_per_second", "workload": "DAC codec decode, 861-frame utterances (10 s @ 44.1 kHz), reference CPU GGML path",
+                      "value": audio / wall, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": 1, "ms_per_step": wall * 1e3,
+                      "cpu_baseline": {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
+                                       "sample": f"{workers} worker processes x {threads} ggml threads, one 10 s utterance each; throughput = total audio / slowest worker"},
+                      "e2e": {"value": audio / wall, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "data": "synthetic"}))
+    return 0
+
+
 def run_dac(args):
     """Secondary line (not the headline): DAC codec decode, batch 16 x 861 frames (10 s @ 44.1 kHz each), synthetic F32 DAC GGUF."""
+    if args.impl == "reference":
+        return run_dac_reference(args)
     import torch  # noqa: F401  (device context / first-import cost, like the main arm)
     from tts_cpp_b200.binding import Context, dac_runner_from_file
     from tts_cpp_b200.synth import cached_dac_gguf, synthetic_codes
