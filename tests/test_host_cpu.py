@@ -141,3 +141,15 @@ def test_polyphase_identity_of_the_strided_noise_conv():
                 if 0 <= r < Lp // s:
                     got[:, t] += np.einsum("njc,cj->n", wp[:, m], X[:, r, :])
         assert np.allclose(got, want, atol=1e-10), (K, s, pad)
+
+
+def test_reference_side_binding_type_checks_against_the_reference_headers():
+    """integration/kokoro_b200_runner.cpp (the tts_generation_runner subclass + loader a TTS.cpp maintainer adds) must compile against the
+    reference's own headers and include/b2tts.h.  Only possible where the reference checkout exists (the build container)."""
+    import shutil
+    import subprocess
+    if not os.path.isdir("/root/reference/src") or shutil.which("g++") is None:
+        pytest.skip("reference checkout not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "oracle"), "binding_check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
