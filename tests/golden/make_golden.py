@@ -16,6 +16,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       from oracle/ref_orpheus_driver.cpp
   parler_vectors.npz       : two prompts (5 and 9 ids) and, for 5 greedy audio steps each, the 9 codebook tokens per step and their logits
       from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
+  dia_vectors.npz          : two byte-token prompts (10 and 18 tokens, the second after the first in the same process) and, for 5 greedy steps
+      each, the 9 codebook tokens and the CFG-combined logits from the reference's Dia encoder + decode loop, from oracle/ref_dia_driver.cpp
 """
 import os
 import re
@@ -188,8 +190,29 @@ def parler_vectors():
     print("parler vectors:", {k: v.shape for k, v in out.items()})
 
 
+def dia_vectors():
+    from tts_cpp_b200.synth import cached_dia_gguf
+    gguf = cached_dia_gguf(seed=0)
+    rng = np.random.default_rng(11)
+    prompts = [np.concatenate([[1], rng.integers(32, 127, size=n)]) for n in (9, 17)]      # [S1] + printable bytes
+    tmp = tempfile.mkdtemp()
+    pf = os.path.join(tmp, "prompts.txt")
+    open(pf, "w").write("\n".join(" ".join(map(str, q)) for q in prompts) + "\n")
+    pre = os.path.join(tmp, "d")
+    steps = 5
+    run([os.path.join(REF, "dia_ref"), gguf, pf, pre, "--steps", str(steps), "--threads", "4", "--quiet"])
+    out = {}
+    for u, q in enumerate(prompts):
+        out[f"prompt{u}"] = np.asarray(q, np.int32)
+        out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
+        out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
+    np.savez_compressed(os.path.join(OUT, "dia_vectors.npz"), **out)
+    print("dia vectors:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "dia"]
+    if "dia" in which: dia_vectors()
     if "parler" in which: parler_vectors()
     if "orpheus" in which: orpheus_vectors()
     if "snac" in which: snac_vectors()

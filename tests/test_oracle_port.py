@@ -169,3 +169,18 @@ def test_parler_port_against_reference_decode_loop():
         print(f"parler prompt {u}: max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
         assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact codebook indices at temperature 0
         assert d < 1e-2
+
+
+def test_dia_port_against_reference_decode_loop():
+    """oracle/dia_port.py vs the reference's Dia encoder pass + CFG-paired decode loop: identical codebook tokens; logits (std ~13: no
+    1/sqrt(d) in Dia's softmax and a 4x CFG amplification) to 3e-4 relative."""
+    from oracle.dia_port import DiaPort
+    from tts_cpp_b200.synth import cached_dia_gguf
+    g = np.load(os.path.join(GOLD, "dia_vectors.npz"))
+    port = DiaPort(cached_dia_gguf(seed=0))
+    for u in range(2):
+        toks, logits = port.greedy(g[f"prompt{u}"], g[f"tokens{u}"].shape[0])
+        d = float(np.abs(logits - g[f"logits{u}"]).max())
+        print(f"dia prompt {u}: max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
+        assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact codebook indices at temperature 0
+        assert d < 2e-2

@@ -585,6 +585,89 @@ def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None) -> str:
     return path
 
 
+# ------------------------------------------------------------------------------------------ Dia encoder + decoder
+def dia_tensors(seed: int = 0, enc_layers: int = 2, dec_layers: int = 2, head_dim: int = 32, heads: int = 4, query_heads: int = 2, ffn: int = 256,
+                vocab: int = 1028, n_heads: int = 9):
+    """Synthetic weights in the reference's Dia schema (names exactly as dia_model::assign_weight splits them, src/models/dia/model.cpp:3-132).
+    The encoder width is the reference's hard-coded 1024 (src/models/dia/model.h:69: no GGUF key overrides it); encoder heads * head_dim ==
+    decoder heads * head_dim == decoder width (the reference reshapes attention outputs to decoder_hidden_size in both stacks)."""
+    rng = np.random.default_rng(seed)
+    EH, D, KVD = 1024, heads * head_dim, (heads // query_heads) * head_dim
+    items: list[tuple[str, np.ndarray]] = []
+
+    def rand(name, shape, fan_in, scale=None):
+        s = (1.0 / np.sqrt(max(fan_in, 1))) if scale is None else scale
+        items.append(("dia." + name, (rng.standard_normal(shape).astype(np.float32) * np.float32(s)).astype(np.float16).astype(np.float32)))
+
+    def norm(name, c):
+        items.append(("dia." + name, (1.0 + 0.1 * rng.standard_normal(c)).astype(np.float32).astype(np.float16).astype(np.float32)))
+
+    rand("encoder.embedding", (256, EH), 1, 1.0)
+    for l in range(enc_layers):
+        b = f"encoder.layers.{l}"
+        norm(b + ".pre_sa_norm", EH)
+        rand(b + ".q_proj", (D, EH), EH, 2.0 / np.sqrt(EH)); rand(b + ".k_proj", (D, EH), EH, 2.0 / np.sqrt(EH)); rand(b + ".v_proj", (D, EH), EH)
+        rand(b + ".o_proj", (EH, D), D)
+        norm(b + ".post_sa_norm", EH)
+        rand(b + ".gate", (ffn, EH), EH); rand(b + ".up", (ffn, EH), EH); rand(b + ".wo", (EH, ffn), ffn)
+    norm("encoder.norm", EH)
+    for i in range(n_heads):
+        rand(f"decoder.embeddings.{i}", (vocab, D), 1, 0.5)
+    for l in range(dec_layers):
+        b = f"decoder.layers.{l}"
+        norm(b + ".pre_sa_norm", D)
+        rand(b + ".self_q_proj", (D, D), D, 2.0 / np.sqrt(D)); rand(b + ".self_k_proj", (KVD, D), D, 2.0 / np.sqrt(D)); rand(b + ".self_v_proj", (KVD, D), D)
+        rand(b + ".self_o_proj", (D, D), D)
+        norm(b + ".pre_ca_norm", D)
+        rand(b + ".cross_q_proj", (D, D), D, 2.0 / np.sqrt(D)); rand(b + ".cross_k_proj", (D, EH), EH, 2.0 / np.sqrt(EH)); rand(b + ".cross_v_proj", (D, EH), EH)
+        rand(b + ".cross_o_proj", (D, D), D)
+        norm(b + ".pre_mlp_norm", D)
+        rand(b + ".gate", (ffn, D), D); rand(b + ".up", (ffn, D), D); rand(b + ".wo", (D, ffn), ffn)
+    norm("decoder.norm", D)
+    for i in range(n_heads):
+        rand(f"decoder.heads.{i}", (vocab, D), D, 4.0 / np.sqrt(D))
+    return items
+
+
+def write_dia_gguf(path: str, seed: int = 0, enc_layers: int = 2, dec_layers: int = 2, head_dim: int = 32, heads: int = 4, query_heads: int = 2,
+                   ffn: int = 256, max_ctx: int = 32) -> dict:
+    """Small synthetic Dia GGUF (F32) with a matching small DAC decoder."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="dia")
+    dac_rates = (2, 2, 2, 2)
+    items = dia_tensors(seed, enc_layers, dec_layers, head_dim, heads, query_heads, ffn) + dac_tensors(seed=seed, d_model=64, latent=32, rates=dac_rates)
+    n_params = 0
+    for name, arr in items:
+        n_params += arr.size
+        w.add_tensor(name, arr.astype(np.float32))
+    for k, v in (("dia.decoder.output_heads", 9), ("dia.decoder.layers", dec_layers), ("dia.encoder.layers", enc_layers), ("dia.decoder.hidden_size", heads * head_dim),
+                 ("dia.decoder.attn_heads", heads), ("dia.decoder.query_heads", query_heads), ("dia.encoder.attn_heads", heads), ("dia.attn_head_size", head_dim),
+                 ("dia.eos_token_id", 1024), ("dia.bos_token_id", 1026), ("dia.pad_token_id", 1025), ("dia.encoder.max_context_length", max_ctx),
+                 ("dia.decoder.output_vocab_size", 1028), ("dia.decoder.audio_vocab_size", 1024), ("dia.decoder.max_generation_size", 64), ("dia.max_delay", 15)):
+        w.add_uint32(k, int(v))
+    for i, s in enumerate(dac_rates):
+        w.add_uint32(f"dac.dac_layer_stride_{i}", int(s))
+        w.add_uint32(f"dac.dac_layer_padding_{i}", int((s + 1) // 2))
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def cached_dia_gguf(seed: int = 0, cache_dir: str | None = None) -> str:
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, f"dia_f32_s{seed}.gguf")
+    if not os.path.exists(path):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        write_dia_gguf(tmp, seed=seed)
+        os.replace(tmp, path)
+    return path
+
+
 def synthetic_prompts(batch: int, n_phonemes: int = 64, seed0: int = 1234) -> list[list[int]]:
     """Utterance i = BOS(0) + n_phonemes ids ~ U[1,177] from default_rng(seed0+i) + EOS(0)  (SURVEY 8d config 2)."""
     out = []
