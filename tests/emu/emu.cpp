@@ -1,0 +1,176 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE ONLY: the fiber scheduler behind tests/emu/include/cuda_runtime.h, plus the host-side pieces of
+// the library the emulated translation units expect (error string, workspace arena, stubs for the models that are not emulated).
+#include "kokoro.h"
+#include "dac.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+extern "C" void b2emu_switch(void ** save_sp, void * load_sp);
+// x86-64 SysV: callee-saved registers on the old stack, swap stack pointers, restore from the new stack
+asm(R"(
+.text
+.globl b2emu_switch
+.type b2emu_switch,@function
+b2emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size b2emu_switch,.-b2emu_switch
+)");
+
+namespace b2emu {
+
+Fiber * g_cur = nullptr;
+dim3 g_blockIdx, g_blockDim, g_gridDim;
+uint64_t g_launches = 0, g_blocks = 0;
+
+namespace {
+constexpr size_t STACK = 96 * 1024;
+void * g_sched_sp = nullptr;
+const std::function<void()> * g_body = nullptr;
+std::vector<Fiber> g_fibers;
+std::vector<char *> g_stacks;
+int g_alive = 0, g_arrived = 0; uint64_t g_gen = 0, g_progress = 0;
+struct Warp { int alive = 0, arrived = 0; uint64_t gen = 0; uint64_t slot[32]; };
+std::vector<Warp> g_warps;
+std::vector<char> g_dyn;
+
+void yield() { Fiber * f = g_cur; b2emu_switch(&f->sp, g_sched_sp); }
+int linear_tid(const Fiber * f) { return (int) (f - g_fibers.data()); }
+
+void release_if_complete() {      // a thread that exits while others wait at a barrier completes that barrier (CUDA leaves this undefined; be lenient)
+    if (g_alive > 0 && g_arrived == g_alive) { g_arrived = 0; g_gen++; }
+}
+
+void fiber_entry() {
+    (*g_body)();
+    Fiber * f = g_cur;
+    f->done = true; g_progress++;
+    g_alive--;
+    Warp & w = g_warps[(size_t) linear_tid(f) >> 5];
+    w.alive--;
+    if (w.alive > 0 && w.arrived == w.alive) { w.arrived = 0; w.gen++; }
+    release_if_complete();
+    yield();
+    abort();   // a finished fiber is never resumed
+}
+
+void warp_barrier() {
+    Warp & w = g_warps[(size_t) linear_tid(g_cur) >> 5];
+    const uint64_t gen = w.gen; g_progress++;
+    if (++w.arrived == w.alive) { w.arrived = 0; w.gen++; return; }
+    while (w.gen == gen) yield();
+}
+}  // namespace
+
+void sync_block() {
+    const uint64_t gen = g_gen; g_progress++;
+    if (++g_arrived == g_alive) { g_arrived = 0; g_gen++; return; }
+    while (g_gen == gen) yield();
+}
+
+uint64_t shfl(uint64_t v, int src_lane) {
+    const int t = linear_tid(g_cur);
+    Warp & w = g_warps[(size_t) t >> 5];
+    w.slot[t & 31] = v;
+    warp_barrier();
+    const uint64_t r = w.slot[src_lane & 31];
+    warp_barrier();
+    return r;
+}
+
+void * dyn_smem() { return g_dyn.data(); }
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body) {
+    if (g_cur) { fprintf(stderr, "b2emu: nested launch\n"); abort(); }
+    const int nt = (int) (block.x * block.y * block.z);
+    if (nt <= 0 || nt > 1024) { fprintf(stderr, "b2emu: %d threads per block\n", nt); abort(); }
+    if (smem > 227 * 1024) { fprintf(stderr, "b2emu: %zu bytes of dynamic shared memory\n", smem); abort(); }
+    g_launches++;
+    g_body = &body; g_blockDim = block; g_gridDim = grid;
+    while ((int) g_stacks.size() < nt) g_stacks.push_back((char *) aligned_alloc(64, STACK));
+    g_fibers.assign((size_t) nt, Fiber{});
+    g_dyn.assign(smem + 64, 0);
+    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+        g_blockIdx = dim3(bx, by, bz); g_blocks++;
+        g_alive = nt; g_arrived = 0;
+        g_warps.assign((size_t) (nt + 31) / 32, Warp{});
+        for (int t = 0; t < nt; t++) {
+            Fiber & f = g_fibers[(size_t) t];
+            f.tid = uint3{(unsigned) t % block.x, (unsigned) t / block.x % block.y, (unsigned) t / (block.x * block.y)};
+            f.done = false; f.stack = g_stacks[(size_t) t];
+            g_warps[(size_t) t >> 5].alive++;
+            void ** sp = (void **) (f.stack + STACK - 64);   // 6 callee-saved slots, then the entry address `ret` pops: rsp % 16 == 8 at entry
+            for (int i = 0; i < 6; i++) sp[i] = nullptr;
+            sp[6] = (void *) &fiber_entry; sp[7] = nullptr;
+            f.sp = sp;
+        }
+        int live = nt;
+        while (live > 0) {
+            const uint64_t before = g_progress;
+            for (int t = 0; t < nt; t++) {
+                Fiber & f = g_fibers[(size_t) t];
+                if (f.done) continue;
+                g_cur = &f;
+                b2emu_switch(&g_sched_sp, f.sp);
+                g_cur = nullptr;
+                if (f.done) live--;
+            }
+            if (live > 0 && g_progress == before) { fprintf(stderr, "b2emu: deadlock -- %d threads of block (%u,%u,%u) wait at a barrier not all reach\n", live, bx, by, bz); abort(); }
+        }
+    }
+    g_body = nullptr;
+}
+
+}  // namespace b2emu
+
+namespace b2 {
+
+static char g_err[1024] = "";
+void set_error(const char * fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+const char * emu_last_error() { return g_err; }
+
+int Arena::reserve(size_t bytes) {
+    if (bytes <= cap) { off = 0; return 0; }
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0; off = 0;
+    if (cudaMalloc(&base, bytes) != cudaSuccess) { set_error("emu: workspace allocation failed"); return 1; }
+    memset(base, 0xff, bytes);   // NaN-fill: reads of never-written workspace show up in the comparison
+    cap = bytes;
+    return 0;
+}
+void * Arena::alloc(size_t bytes) {
+    const size_t a = (off + 255) & ~(size_t) 255;
+    if (a + bytes > cap) { set_error("workspace arena exhausted (%zu + %zu > %zu)", a, bytes, cap); return nullptr; }
+    off = a + bytes;
+    return base + a;
+}
+void Arena::release() { if (base) cudaFree(base); base = nullptr; cap = off = 0; }
+
+// models whose kernels need hardware features the emulation does not have: the GGUF reader references them, nothing calls them here
+#ifndef B2EMU_HAVE_KOKORO
+int Kokoro::assign(const char *, int, int, const int64_t *, const void *, size_t) { return 1; }
+int Kokoro::prepare() { return 1; }
+#endif
+#ifndef B2EMU_HAVE_DAC
+int Dac::assign(const char *, int, int, const int64_t *, const void *, size_t) { return 1; }
+int Dac::prepare() { return 1; }
+int Snac::assign(const char *, int, int, const int64_t *, const void *, size_t) { return 1; }
+int Snac::prepare() { return 1; }
+#endif
+
+}  // namespace b2

@@ -1,0 +1,103 @@
+// tests/emu/include/cuda_runtime.h -- TEST INFRASTRUCTURE ONLY.
+//
+// A functional CPU emulation of the small CUDA subset the plain (CUDA-core) kernels of this library use, so that their LOGIC -- indexing,
+// reductions, barriers, host-side orchestration -- can be checked against the golden vectors in the GPU-less build container
+// (tests/test_emu_cpu.py).  A kernel launch runs its blocks one after another; the threads of a block are cooperative fibers, so
+// __syncthreads() and warp shuffles have their real meaning.  Nothing in the product links or includes this; it says nothing about
+// performance, memory coalescing or hardware-only features (tcgen05, TMA, mbarriers, clusters are not emulated).
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static
+#define __launch_bounds__(...)
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    dim3() {}
+    dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+    dim3(int a) : x((unsigned) a) {}
+    dim3(long a) : x((unsigned) a) {}
+    dim3(size_t a) : x((unsigned) a) {}
+};
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+typedef struct b2emu_stream * cudaStream_t;
+typedef struct b2emu_event * cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyHostToHost };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char * cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaMalloc(void ** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t) 255); return *p ? 0 : 2; }
+template <class T> static inline cudaError_t cudaMalloc(T ** p, size_t n) { return cudaMalloc((void **) p, n); }
+static inline cudaError_t cudaFree(void * p) { free(p); return 0; }
+static inline cudaError_t cudaMallocHost(void ** p, size_t n) { return cudaMalloc(p, n); }
+template <class T> static inline cudaError_t cudaMallocHost(T ** p, size_t n) { return cudaMalloc((void **) p, n); }
+static inline cudaError_t cudaFreeHost(void * p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpy(void * d, const void * s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void * d, const void * s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemset(void * d, int v, size_t n) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void * d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t * e) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float * ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+
+namespace b2emu {
+struct Fiber { uint3 tid; void * sp; char * stack; bool done; };
+extern Fiber * g_cur;
+extern dim3 g_blockIdx, g_blockDim, g_gridDim;
+extern uint64_t g_launches, g_blocks;
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body);
+void sync_block();
+uint64_t shfl(uint64_t v, int src_lane);   // every live lane of the warp calls it; returns the value lane src_lane passed
+void * dyn_smem();
+}  // namespace b2emu
+
+#define threadIdx (b2emu::g_cur->tid)
+#define blockIdx  (b2emu::g_blockIdx)
+#define blockDim  (b2emu::g_blockDim)
+#define gridDim   (b2emu::g_gridDim)
+
+static inline void __syncthreads() { b2emu::sync_block(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { (void) b2emu::shfl(0, 0); }
+static inline int b2emu_lane() { return (int) ((threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y) & 31); }
+template <class T> static inline T b2emu_shfl_t(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of a wide type");
+    uint64_t u = 0; memcpy(&u, &v, sizeof(T));
+    u = b2emu::shfl(u, src & 31);
+    T r; memcpy(&r, &u, sizeof(T));
+    return r;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return b2emu_shfl_t(v, b2emu_lane() ^ o); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return b2emu_shfl_t(v, src); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { const int l = b2emu_lane(); return b2emu_shfl_t(v, l + d < 32 ? l + d : l); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { const int l = b2emu_lane(); return b2emu_shfl_t(v, l - d >= 0 ? l - d : l); }
+#define __expf(x) expf(x)
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __ldg(const float * p) { return *p; }
+static inline int __ldg(const int * p) { return *p; }
