@@ -162,8 +162,9 @@ int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Orpheus autoregressive decode, FIRST CORRECT PATH: fp32 CUDA-core GEMVs, compact GQA KV cache, device argmax.
- * NOT YET VALIDATED ON A B200 (written after round 1's GPU budget was spent; its oracle, oracle/orpheus_port.py, reproduces the reference's
- * greedy token ids exactly).  No performance claims are made for it.
+ * NOT YET RUN ON A B200 (written after round 1's GPU budget was spent).  Its logic is checked in the build container: the unmodified .cu file,
+ * compiled against a CPU emulation of the CUDA subset it uses (tests/emu), reproduces the reference's greedy token ids exactly and its logits
+ * to 4.5e-6 (tests/test_emu_cpu.py).  No performance claims are made for it.
  *   b2tts_orpheus_load_gguf      : orpheus_model::setup_from_file + assign_weight loop over "orpheus.*" (reference
  *                                  src/models/orpheus/model.h:59-63, model.cpp:11-120; loader.cpp:8-23)
  *   b2tts_orpheus_generate_greedy: generate_from_batch's decode + sampler loop (model.cpp:230-353,389-398; sampler::max) for n_sequences
@@ -176,6 +177,23 @@ int   b2tts_orpheus_info(const b2tts_orpheus * m, int * vocab_size, int * n_laye
 int   b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
                                     int32_t * out_tokens, float * out_logits);
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Parler-TTS autoregressive decode, FIRST CORRECT PATH, same status as Orpheus above (emulation-checked: identical token
+ * ids, logits within 1.7e-3 of the reference at a logit std of 4 -- ggml's fp16 GELU table; NOT YET RUN ON A B200).
+ *   b2tts_parler_load_gguf      : parler_tts_model::setup_from_file + assign_weight loop over "decoder.*" + prep_cross_key_values (reference
+ *                                 src/models/parler/model.cpp:3-28,110-173,271-318; parler/loader.cpp)
+ *   b2tts_parler_generate_greedy: generate_from_batch's prompt decode, then the audio decode + sampler loop with the delay pattern
+ *                                 (model.cpp:387-470,520-614,762-786; sampler::max per output head) for n_sequences independent prompts of token
+ *                                 ids sharing the model's stored conditional-prompt encoding, n_steps frames each, without check_stopping.
+ *                                 out_tokens [n_sequences][n_steps][n_heads]; out_logits (may be NULL) [n_sequences][n_steps][n_heads][out_vocab]. */
+typedef struct b2tts_parler b2tts_parler;
+int   b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out);
+void  b2tts_parler_free(b2tts_parler * m);
+int   b2tts_parler_info(const b2tts_parler * m, int * n_heads, int * out_vocab, int * n_layers, int * hidden_size);
+int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
+                                   int32_t * out_tokens, float * out_logits);
+float b2tts_parler_last_ms(const b2tts_parler * m);
 
 #ifdef __cplusplus
 }

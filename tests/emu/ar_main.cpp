@@ -1,0 +1,48 @@
+// tests/emu/ar_main.cpp -- TEST INFRASTRUCTURE ONLY: drive a model's generate_greedy (tts_cpp_b200/csrc/{orpheus,parler,dia}.cu compiled against the
+// CPU emulation in tests/emu/include) on the prompts of the golden vectors and dump token ids + logits for the Python test.
+//   ar_emu <orpheus|parler> <model.gguf> <prompts.bin> <out.bin>
+// prompts.bin: int32 B, int32 n_steps, then per prompt int32 n, n x uint32.
+// out.bin: int32 W (tokens per step), int32 V (logits per step), int32 tokens [B][n_steps][W], float logits [B][n_steps][V]
+#include "orpheus.h"
+#include "parler.h"
+#include <cstring>
+#include <cstdio>
+#include <vector>
+
+namespace b2 { const char * emu_last_error(); }
+
+static int out_width(const b2::Orpheus &) { return 1; }
+static int out_logits(const b2::Orpheus & m) { return m.vocab; }
+template <class M> static int out_width(const M & m) { return m.n_out; }
+template <class M> static int out_logits(const M & m) { return m.n_out * m.vocab; }
+
+template <class M> static int run(int argc, char ** argv) {
+    b2::Ctx ctx;
+    M m; m.ctx = &ctx;
+    if (b2::load_gguf_into(&m, argv[2])) { fprintf(stderr, "load: %s\n", b2::emu_last_error()); return 1; }
+    FILE * f = fopen(argv[3], "rb");
+    if (!f) return 2;
+    int32_t B = 0, steps = 0;
+    if (fread(&B, 4, 1, f) != 1 || fread(&steps, 4, 1, f) != 1) return 2;
+    std::vector<std::vector<uint32_t>> pr((size_t) B);
+    std::vector<const uint32_t *> pp; std::vector<int32_t> np;
+    for (auto & p : pr) { int32_t n = 0; if (fread(&n, 4, 1, f) != 1) return 2; p.resize((size_t) n); if (fread(p.data(), 4, (size_t) n, f) != (size_t) n) return 2; pp.push_back(p.data()); np.push_back(n); }
+    fclose(f);
+    const int32_t W = out_width(m), V = out_logits(m);
+    std::vector<int32_t> tok((size_t) B * steps * W);
+    std::vector<float> logits((size_t) B * steps * V);
+    if (m.generate_greedy(B, pp.data(), np.data(), steps, tok.data(), logits.data())) { fprintf(stderr, "generate: %s\n", b2::emu_last_error()); return 1; }
+    f = fopen(argv[4], "wb");
+    fwrite(&W, 4, 1, f); fwrite(&V, 4, 1, f);
+    fwrite(tok.data(), 4, tok.size(), f); fwrite(logits.data(), 4, logits.size(), f);
+    fclose(f);
+    fprintf(stderr, "emulated %llu launches, %llu blocks\n", (unsigned long long) b2emu::g_launches, (unsigned long long) b2emu::g_blocks);
+    return 0;
+}
+
+int main(int argc, char ** argv) {
+    if (argc < 5) return 2;
+    if (!strcmp(argv[1], "orpheus")) return run<b2::Orpheus>(argc, argv);
+    if (!strcmp(argv[1], "parler")) return run<b2::Parler>(argc, argv);
+    return 2;
+}

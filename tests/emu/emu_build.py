@@ -16,6 +16,11 @@ def build(name, cu_sources, cpp_sources, defines=()):
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, name)
     srcs = []
+    for h in os.listdir(CSRC):                      # headers with device code are converted too; BUILD is searched first (same directory as the converted sources)
+        if h.endswith(".cuh"):
+            text = open(os.path.join(CSRC, h)).read()
+            if "<<<" in text or "extern __shared__" in text:
+                open(os.path.join(BUILD, h), "w").write('#line 1 "%s"\n' % os.path.join(CSRC, h) + prep.convert(text))
     for cu in cu_sources:
         out = os.path.join(BUILD, os.path.basename(cu)[:-3] + ".cpp")
         open(out, "w").write('#line 1 "%s"\n' % os.path.join(CSRC, cu) + prep.convert(open(os.path.join(CSRC, cu)).read()))
@@ -24,7 +29,7 @@ def build(name, cu_sources, cpp_sources, defines=()):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))]
     if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps if not d.startswith(BUILD)):
         return exe
-    cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(HERE, "include"), "-I" + CSRC] + ["-D" + d for d in defines] + ["-o", exe] + srcs
+    cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(HERE, "include"), "-I" + BUILD, "-I" + CSRC] + ["-D" + d for d in defines] + ["-o", exe] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError("emulation build failed:\n" + r.stderr[-4000:])

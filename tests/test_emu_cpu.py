@@ -16,26 +16,36 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 import emu_build  # noqa: E402
 
-from tts_cpp_b200.synth import cached_orpheus_gguf  # noqa: E402
+from tts_cpp_b200.synth import cached_orpheus_gguf, cached_parler_gguf  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def _run_orpheus(tmp_path, prompts, steps, tag):
-    exe = emu_build.build("orpheus_emu", ["orpheus.cu"], ["orpheus_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
+AR_SOURCES = ["orpheus.cu", "parler.cu"]
+
+
+def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag):
+    """-> (tokens [B][steps][W], logits [B][steps][V]) from the library's generate_greedy under emulation"""
+    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
     pin, pout = str(tmp_path / f"p{tag}.bin"), str(tmp_path / f"o{tag}.bin")
     with open(pin, "wb") as f:
         f.write(struct.pack("ii", len(prompts), steps))
         for p in prompts:
             f.write(struct.pack("i", p.size))
             f.write(np.asarray(p, np.uint32).tobytes())
-    r = subprocess.run([exe, cached_orpheus_gguf(seed=0), pin, pout], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, model, gguf_path, pin, pout], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     raw = open(pout, "rb").read()
+    W, V = struct.unpack("ii", raw[:8])
     n = len(prompts) * steps
-    tok = np.frombuffer(raw[:n * 4], np.int32).reshape(len(prompts), steps)
-    logits = np.frombuffer(raw[n * 4:], np.float32).reshape(len(prompts), steps, -1)
+    tok = np.frombuffer(raw[8:8 + n * W * 4], np.int32).reshape(len(prompts), steps, W)
+    logits = np.frombuffer(raw[8 + n * W * 4:], np.float32).reshape(len(prompts), steps, V)
     return tok, logits
+
+
+def _run_orpheus(tmp_path, prompts, steps, tag):
+    tok, logits = _run_ar(tmp_path, "orpheus", cached_orpheus_gguf(seed=0), prompts, steps, tag)
+    return tok[:, :, 0], logits
 
 
 def test_orpheus_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path):
@@ -52,3 +62,18 @@ def test_orpheus_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path
         assert d < 1e-3      # same tolerance as tests/test_orpheus_gpu.py (measured 4.5e-6: fp32 throughout, summation order differs)
     single, _ = _run_orpheus(tmp_path, [prompts[1]], steps, "s")
     assert np.array_equal(single[0], tok[1])         # batching does not change a sequence
+
+
+def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path):
+    """Parler::generate_greedy (parler.cu: prompt pass, delay-pattern codebook embedding, causal self-attention over the cache, cross-attention
+    over the stored text encoding, GELU table, nine heads + per-head argmax) under emulation against tests/golden/parler_vectors.npz."""
+    g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0), prompts, steps, "b")
+    for u in range(2):
+        ref = g[f"logits{u}"].reshape(steps, -1)
+        d = float(np.abs(logits[u] - ref).max())
+        print(f"PARITY(emulated) parler prompt {u}: tokens {tok[u].tolist()}  max |logit diff| {d:.3e}  (logit std {ref.std():.2f})")
+        assert np.array_equal(tok[u], g[f"tokens{u}"])
+        assert d < 1e-2      # ggml's GELU is an fp16 table: an activation that lands on the other side of a rounding boundary moves a logit by ~1e-3

@@ -349,3 +349,39 @@ def orpheus_runner_from_file(path: str, device: int = 0, ctx: Context | None = N
     h = C.c_void_p()
     _chk(lib().b2tts_orpheus_load_gguf(ctx.h, path.encode(), C.byref(h)))
     return OrpheusRunner(ctx, h)
+
+
+class ParlerRunner:
+    """The decode loop of parler_tts_runner (reference src/models/parler/model.cpp:762-786) below the tokenizer, batched, greedy."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        nh, v, l, hd = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().b2tts_parler_info(self.h, C.byref(nh), C.byref(v), C.byref(l), C.byref(hd)))
+        self.n_heads, self.out_vocab, self.n_layers, self.hidden_size = nh.value, v.value, l.value, hd.value
+
+    def generate_greedy(self, prompts, n_steps: int, want_logits: bool = False):
+        """-> tokens [B][n_steps][n_heads] (and logits [B][n_steps][n_heads][out_vocab])"""
+        B = len(prompts)
+        arrs = [np.ascontiguousarray(np.asarray(p, np.uint32)) for p in prompts]
+        npr = np.array([a.size for a in arrs], np.int32)
+        ptrs = (C.POINTER(C.c_uint32) * B)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        toks = np.empty((B, n_steps, self.n_heads), np.int32)
+        logits = np.empty((B, n_steps, self.n_heads, self.out_vocab), np.float32) if want_logits else None
+        _chk(lib().b2tts_parler_generate_greedy(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps),
+                                                toks.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None))
+        return (toks, logits) if want_logits else toks
+
+    def close(self):
+        if self.h:
+            lib().b2tts_parler_free(self.h)
+            self.h = None
+
+
+def parler_runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> ParlerRunner:
+    ctx = ctx or Context(device)
+    h = C.c_void_p()
+    _chk(lib().b2tts_parler_load_gguf(ctx.h, path.encode(), C.byref(h)))
+    return ParlerRunner(ctx, h)

@@ -3,6 +3,7 @@
 #include "kokoro.h"
 #include "dac.h"
 #include "orpheus.h"
+#include "parler.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -27,6 +28,7 @@ struct b2tts_kokoro { Kokoro k; };
 struct b2tts_dac { Dac d; };
 struct b2tts_snac { Snac s; };
 struct b2tts_orpheus { Orpheus o; };
+struct b2tts_parler { Parler p; };
 
 namespace {
 // RAII device scratch for the op-level entry points
@@ -185,6 +187,31 @@ int b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const uint
     return m->o.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
 }
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m) { return m ? m->o.timing_ms : 0.f; }
+// ---- Parler AR decode (first correct path)
+int b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_parler * m = new b2tts_parler();
+    m->p.ctx = &ctx->c;
+    if (load_gguf_into(&m->p, path)) { m->p.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_parler_free(b2tts_parler * m) { if (m) { m->p.free_all(); delete m; } }
+int b2tts_parler_info(const b2tts_parler * m, int * n_heads, int * out_vocab, int * n_layers, int * hidden_size) {
+    if (!m) { set_error("null model"); return 1; }
+    if (n_heads) *n_heads = m->p.n_out;
+    if (out_vocab) *out_vocab = m->p.vocab;
+    if (n_layers) *n_layers = m->p.n_layers;
+    if (hidden_size) *hidden_size = m->p.hidden;
+    return 0;
+}
+int b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens,
+                                 float * out_logits) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->p.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
+}
+float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
 
 int b2tts_snac_reset_noise(b2tts_snac * m) { if (!m) { set_error("null model"); return 1; } m->s.reset_noise(); return 0; }
 int b2tts_kokoro_n_voices(const b2tts_kokoro * m) { return (int) m->k.voice_names.size(); }

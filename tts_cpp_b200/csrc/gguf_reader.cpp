@@ -8,6 +8,7 @@
 #include "kokoro.h"
 #include "dac.h"
 #include "orpheus.h"
+#include "parler.h"
 
 #include <functional>
 
@@ -151,6 +152,12 @@ int load_gguf_into(Snac * m, const char * path) {
 
 int load_gguf_into(Orpheus * m, const char * path) {
     if (read_gguf(path, "orpheus.", "orpheus", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
+}
+
+// Parler's decoder tensors live under "decoder." (reference src/models/parler/model.cpp:3-28 assign_to_decoder); its DAC under "audio_encoder."
+int load_gguf_into(Parler * m, const char * path) {
+    if (read_gguf(path, "decoder.", "parler-tts", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
     return m->prepare();
 }
 

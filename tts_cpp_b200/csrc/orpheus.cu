@@ -1,5 +1,6 @@
 // orpheus.cu -- Orpheus autoregressive decode (llama-3 style), first correct CUDA path.  See orpheus.h for what it replaces and why it is plain.
 #include "orpheus.h"
+#include "ar_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -88,158 +89,6 @@ void Orpheus::free_all() {
 
 namespace {
 
-// rows of a step: (sequence, position, token).  Decode steps have one row per sequence, built on the device from the last argmax.
-__global__ void decode_rows_kernel(const int * __restrict__ n_prompt, const int * __restrict__ cur_tok, int B, int step, int * row_seq, int * row_pos, int * row_tok) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    row_seq[b] = b; row_pos[b] = n_prompt[b] + step - 1; row_tok[b] = cur_tok[b];
-}
-
-__global__ void embed_kernel(const int * __restrict__ row_tok, const float * __restrict__ embed, int H, float * __restrict__ x) {   // ggml_get_rows
-    const int r = blockIdx.x;
-    const float * src = embed + (size_t) row_tok[r] * H;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) x[(size_t) r * H + c] = src[c];
-}
-
-// ggml_rms_norm (float squares accumulated in a double, scale = 1/sqrtf(mean + eps)) followed by the weight multiply (model.cpp:122-125)
-__global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __restrict__ w, int H, int R, float * __restrict__ y) {
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (r >= R) return;
-    const float * row = x + (size_t) r * H;
-    double s = 0.0;
-    for (int c = lane; c < H; c += 32) s += (double) (row[c] * row[c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = (float) (s / (double) H);
-    const float scale = 1.0f / sqrtf(mean + 1e-5f);
-    for (int c = lane; c < H; c += 32) y[(size_t) r * H + c] = (row[c] * scale) * w[c];
-}
-
-// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]): one warp per output n, the weight row is read once per chunk of 8 rows
-// (ggml_mul_mat with F32 weights and activations; K % 4 == 0)
-constexpr int GR = 8;
-__global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
-                                                        const float * __restrict__ res, float * __restrict__ Y, int ldy) {
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const float * wrow = W + (size_t) n * K;
-    for (int r0 = 0; r0 < R; r0 += GR) {
-        float acc[GR];
-#pragma unroll
-        for (int j = 0; j < GR; j++) acc[j] = 0.f;
-        for (int k = lane * 4; k < K; k += 128) {
-            const float4 w4 = *reinterpret_cast<const float4 *>(wrow + k);
-#pragma unroll
-            for (int j = 0; j < GR; j++) {
-                if (r0 + j < R) {
-                    const float4 x4 = *reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + k);
-                    acc[j] = fmaf(x4.w, w4.w, fmaf(x4.z, w4.z, fmaf(x4.y, w4.y, fmaf(x4.x, w4.x, acc[j]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < GR; j++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-            if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? acc[j] + res[(size_t) (r0 + j) * ldy + n] : acc[j];
-        }
-    }
-}
-
-// NeoX RoPE over the whole head with per-pair frequency factors (ggml_rope_ext mode 2, theta base 5e5, ggml-cpu rope cache: theta starts at
-// the position and is multiplied by theta_scale pair after pair), applied to q in place and to k on its way into the cache; v is copied
-// (orpheus_build_kv_store, model.cpp:196-228 -- here the cache is compact: the 3x head expansion is done by indexing in the attention)
-__global__ void rope_append_kernel(float * q, const float * __restrict__ k, const float * __restrict__ v, const float * __restrict__ ff, const int * __restrict__ row_seq,
-                                   const int * __restrict__ row_pos, int heads, int kv_heads, int hd, float theta_scale, float * Kc, float * Vc, int Tmax) {
-    const int r = blockIdx.x, h = blockIdx.y;                  // h < heads: a query head; h >= heads: kv head h - heads
-    const int b = row_seq[r], pos = row_pos[r], half = hd >> 1;
-    const int KV = kv_heads * hd, H = heads * hd;
-    for (int i = threadIdx.x; i < half; i += blockDim.x) {
-        float theta = (float) pos;
-        for (int j = 0; j < i; j++) theta *= theta_scale;
-        const float th = theta / ff[i];
-        const float c = cosf(th), s = sinf(th);
-        if (h < heads) {
-            float * p = q + (size_t) r * H + (size_t) h * hd;
-            const float x0 = p[i], x1 = p[i + half];
-            p[i] = x0 * c - x1 * s; p[i + half] = x0 * s + x1 * c;
-        } else {
-            const int kh = h - heads;
-            const float * p = k + (size_t) r * KV + (size_t) kh * hd;
-            float * d = Kc + ((size_t) b * Tmax + pos) * KV + (size_t) kh * hd;
-            const float x0 = p[i], x1 = p[i + half];
-            d[i] = x0 * c - x1 * s; d[i + half] = x0 * s + x1 * c;
-            const float * pv = v + (size_t) r * KV + (size_t) kh * hd;
-            float * dv = Vc + ((size_t) b * Tmax + pos) * KV + (size_t) kh * hd;
-            dv[i] = pv[i]; dv[i + half] = pv[i + half];
-        }
-    }
-}
-
-// causal attention of one new row against its sequence's cache: softmax(q.K^T / sqrt(hd)) V with ggml_soft_max's double-accumulated sum
-// (model.cpp:268-276; ggml-cpu.c soft_max: max, expf, ggml_float sum, scale by (float)(1/sum))
-__global__ void __launch_bounds__(128) attention_kernel(const float * __restrict__ q, const float * __restrict__ Kc, const float * __restrict__ Vc,
-                                                        const int * __restrict__ row_seq, const int * __restrict__ row_pos, int heads, int kv_heads, int hd,
-                                                        int Tmax, float scale, float * __restrict__ out) {
-    extern __shared__ float sc[];          // [T] scores, then 128 floats + 128 doubles of reduction scratch behind them
-    const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-    const int b = row_seq[r], T = row_pos[r] + 1;
-    const int KV = kv_heads * hd, H = heads * hd, kh = h / (heads / kv_heads);
-    float * redf = sc + ((Tmax + 1) & ~1);      // keeps the double scratch behind it 8-byte aligned
-    double * redd = reinterpret_cast<double *>(redf + 128);
-    const float * qv = q + (size_t) r * H + (size_t) h * hd;
-    float mx = -INFINITY;
-    for (int t = tid; t < T; t += 128) {
-        const float * kr = Kc + ((size_t) b * Tmax + t) * KV + (size_t) kh * hd;
-        float a = 0.f;
-        for (int d = 0; d < hd; d++) a = fmaf(qv[d], kr[d], a);
-        a *= scale;
-        sc[t] = a;
-        mx = fmaxf(mx, a);
-    }
-    redf[tid] = mx;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) { if (tid < o) redf[tid] = fmaxf(redf[tid], redf[tid + o]); __syncthreads(); }
-    mx = redf[0];
-    double sum = 0.0;
-    for (int t = tid; t < T; t += 128) { const float e = expf(sc[t] - mx); sc[t] = e; sum += (double) e; }
-    redd[tid] = sum;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) { if (tid < o) redd[tid] += redd[tid + o]; __syncthreads(); }
-    const float inv = (float) (1.0 / redd[0]);
-    for (int d = tid; d < hd; d += 128) {
-        float a = 0.f;
-        for (int t = 0; t < T; t++) a = fmaf(sc[t] * inv, Vc[((size_t) b * Tmax + t) * KV + (size_t) kh * hd + d], a);
-        out[(size_t) r * H + (size_t) h * hd + d] = a;
-    }
-}
-
-__global__ void silu_mul_kernel(float * g, const float * __restrict__ u, size_t n) {      // ggml_silu (x / (1 + expf(-x))) * up
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { const float x = g[i]; g[i] = (x / (1.0f + expf(-x))) * u[i]; }
-}
-
-__global__ void gather_rows_f32_kernel(const float * __restrict__ x, const int * __restrict__ idx, int H, float * __restrict__ y) {
-    const int b = blockIdx.x;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) y[(size_t) b * H + c] = x[(size_t) idx[b] * H + c];
-}
-
-// sampler::max: the first maximum wins
-__global__ void __launch_bounds__(256) argmax_kernel(const float * __restrict__ logits, int V, int * cur_tok, int * out_tokens, int n_steps, int step) {
-    __shared__ float sv[256]; __shared__ int si[256];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const float * lg = logits + (size_t) b * V;
-    float best = -INFINITY; int bi = 0x7fffffff;
-    for (int i = tid; i < V; i += 256) { const float v = lg[i]; if (v > best) { best = v; bi = i; } }
-    sv[tid] = best; si[tid] = bi;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
-        __syncthreads();
-    }
-    if (tid == 0) { cur_tok[b] = si[0]; out_tokens[(size_t) b * n_steps + step] = si[0]; }
-}
-
 struct OFwd {
     Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
@@ -266,7 +115,7 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, KV = kv_hidden, F = ffn;
     const size_t cache = (size_t) n_layers * B * Tmax * KV * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
-                        (size_t) Rmax * 16 + (size_t) B * 16 + (32 << 20);
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20);
     if (arena.reserve(need)) return 1;
     OFwd Fw{this, ctx, st};
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * KV), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * KV);
@@ -275,15 +124,16 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     float * g = Fw.al<float>((size_t) Rmax * F), * u = Fw.al<float>((size_t) Rmax * F);
     float * last = Fw.al<float>((size_t) B * H), * logits = Fw.al<float>((size_t) B * vocab);
     int * row_seq = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_tok = Fw.al<int>((size_t) Rmax);
+    int * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax);
     int * d_np = Fw.al<int>((size_t) B), * d_last = Fw.al<int>((size_t) B), * cur_tok = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) B * n_steps);
     if (Fw.fail) return 1;
 
-    std::vector<int> hs((size_t) R0), hp((size_t) R0), ht((size_t) R0), hnp((size_t) B), hlast((size_t) B);
+    std::vector<int> hs((size_t) R0), hp((size_t) R0), ht((size_t) R0), hb((size_t) R0), hl((size_t) R0), hnp((size_t) B), hlast((size_t) B);
     {
         int r = 0;
         for (int b = 0; b < B; b++) {
             hnp[(size_t) b] = n_prompt[b];
-            for (int i = 0; i < n_prompt[b]; i++, r++) { hs[(size_t) r] = b; hp[(size_t) r] = i; ht[(size_t) r] = (int) prompts[b][i]; }
+            for (int i = 0; i < n_prompt[b]; i++, r++) { hs[(size_t) r] = b; hp[(size_t) r] = i; ht[(size_t) r] = (int) prompts[b][i]; hb[(size_t) r] = b * (Pmax + n_steps); hl[(size_t) r] = i + 1; }
             hlast[(size_t) b] = r - 1;
         }
     }
@@ -291,19 +141,21 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     B2_CUDA(cudaMemcpyAsync(row_seq, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(row_pos, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(row_tok, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_base, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_len, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(d_np, hnp.data(), hnp.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(d_last, hlast.data(), hlast.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float theta_scale = powf(500000.0f, -2.0f / (float) head_dim);
     const float scale = 1.0f / sqrtf((float) head_dim);
-    const size_t att_smem = (size_t) ((Tmax + 1) & ~1) * 4 + 128 * 4 + 128 * 8;
+    const size_t att_smem = attention_smem_bytes(Tmax);
     if (att_smem > 200 * 1024) { set_error("orpheus: context of %d positions exceeds the v1 attention kernel's shared memory", Tmax); return 1; }
     B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
 
     for (int s = 0; s < n_steps; s++) {
         const int R = s == 0 ? R0 : B;
-        if (s > 0) { decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, s, row_seq, row_pos, row_tok); B2_LAUNCH_CHECK(ctx); }
+        if (s > 0) { decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, s, Tmax, row_seq, row_pos, row_tok, row_base, row_len); B2_LAUNCH_CHECK(ctx); }
         embed_kernel<<<R, 256, 0, st>>>(row_tok, embed, H, x);
         B2_LAUNCH_CHECK(ctx);
         for (int l = 0; l < n_layers; l++) {
@@ -314,7 +166,7 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
             if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
             if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
             { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax); B2_LAUNCH_CHECK(ctx); }
-            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_seq, row_pos, heads, kv_heads, head_dim, Tmax, scale, att); B2_LAUNCH_CHECK(ctx); }
+            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_base, row_len, heads, kv_heads, head_dim, Tmax, scale, att); B2_LAUNCH_CHECK(ctx); }
             if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                        // xn = attn_out + residual(x)
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
             if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;

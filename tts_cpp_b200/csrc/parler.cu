@@ -1,0 +1,240 @@
+// parler.cu -- Parler-TTS autoregressive decode, first correct CUDA path.  See parler.h for what it replaces.
+#include "parler.h"
+#include "ar_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace b2 {
+
+static inline float ph2f(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
+
+int Parler::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
+    if (prepared) { set_error("parler: assign_weight after prepare"); return 1; }
+    std::string nm(name);
+    if (nm.rfind("decoder.", 0) == 0) nm = nm.substr(8);
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
+    t.v.resize((size_t) n);
+    if (type == 0) {
+        if (nbytes < (size_t) n * 4) { set_error("tensor %s: short data", name); return 1; }
+        memcpy(t.v.data(), data, (size_t) n * 4);
+    } else if (type == 1) {
+        if (nbytes < (size_t) n * 2) { set_error("tensor %s: short data", name); return 1; }
+        const uint16_t * s = (const uint16_t *) data;
+        for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = ph2f(s[i]);
+        t.f16 = true;
+    } else {
+        set_error("tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
+        return 1;
+    }
+    host[nm] = std::move(t);
+    return 0;
+}
+
+namespace {
+struct PFwd {
+    Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false;
+    template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
+    int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    int ln(const float * x, const float * w, const float * b, int H, int R, float * y) {
+        layernorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, w, b, H, R, 1e-5f, y);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+};
+}  // namespace
+
+int Parler::prepare() {
+    if (prepared) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    const std::string a = "parler-tts.decoder.";
+    auto kvreq = [&](const std::string & k, int & out) { auto it = kv.find(k); if (it == kv.end()) { set_error("the '%s' key must be specified in the GGUF file.", k.c_str()); return 1; } out = (int) it->second; return 0; };
+    if (kvreq(a + "num_hidden_layers", n_layers) || kvreq(a + "attention.head_count", heads) || kvreq(a + "hidden_size", hidden) || kvreq(a + "output_heads", n_out) ||
+        kvreq(a + "out_vocab_size", vocab) || kvreq(a + "encode_length", n_enc) || kvreq(a + "context_length", max_ctx)) return 1;
+    { auto it = kv.find("audio.bos_token_id"); if (it != kv.end()) bos = (int) it->second; it = kv.find("audio.eos_token_id"); if (it != kv.end()) eos = (int) it->second; }
+    if (heads <= 0 || hidden % heads || hidden % 4) { set_error("parler: inconsistent head configuration"); return 1; }
+    head_dim = hidden / heads;
+    bool ok = true;
+    auto find = [&](const std::string & n, int64_t expect) -> const HostTensor * {
+        auto it = host.find(n);
+        if (it == host.end()) { set_error("missing tensor decoder.%s", n.c_str()); ok = false; return nullptr; }
+        if (expect && (int64_t) it->second.v.size() != expect) { set_error("tensor decoder.%s has %zu elements, expected %lld", n.c_str(), it->second.v.size(), (long long) expect); ok = false; return nullptr; }
+        return &it->second;
+    };
+    auto dev = [&](const float * src, size_t n) -> float * {
+        void * d = nullptr;
+        if (cudaMalloc(&d, n * 4) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", n * 4); ok = false; return nullptr; }
+        if (src) cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += n * 4;
+        return (float *) d;
+    };
+    auto up = [&](const std::string & n, int64_t expect) -> float * { const HostTensor * t = find(n, expect); return t ? dev(t->v.data(), t->v.size()) : nullptr; };
+
+    embed_prompts = up("embed_prompts", 0);
+    { const HostTensor * t = find("embed_prompts", 0); if (t) prompt_vocab = (int) (t->v.size() / (size_t) hidden); }
+    pos_embed = up("positional_embed", 0);
+    { const HostTensor * t = find("positional_embed", 0); if (t) max_ctx = std::min<int>(max_ctx, (int) (t->v.size() / (size_t) hidden)); }
+    ln_w = up("layer_norm.weight", hidden); ln_b = up("layer_norm.bias", hidden);
+    {   // the n_out codebook tables and output heads, each family in one buffer
+        std::vector<float> tab, hw;
+        for (int i = 0; i < n_out && ok; i++) {
+            const HostTensor * t = find("embed_tokens." + std::to_string(i) + ".weight", 0);
+            const HostTensor * h = find("lm_heads." + std::to_string(i) + ".weight.head", (int64_t) vocab * hidden);
+            if (!t || !h) break;
+            const int rows = (int) (t->v.size() / (size_t) hidden);
+            if (i == 0) tab_rows = rows;
+            if (rows != tab_rows || t->v.size() % (size_t) hidden) { set_error("parler: codebook table %d has %d rows, table 0 has %d", i, rows, tab_rows); ok = false; break; }
+            tab.insert(tab.end(), t->v.begin(), t->v.end());
+            hw.insert(hw.end(), h->v.begin(), h->v.end());
+        }
+        if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev(hw.data(), hw.size()); }
+    }
+    {
+        const HostTensor * t = find("layers.0.fc1.weight", 0);
+        if (t) { ffn = (int) t->shape[0]; if (ffn % 4) { set_error("parler: ffn size %d must be a multiple of 4", ffn); return 1; } }
+    }
+    const HostTensor * enc = find("text_encoding", (int64_t) n_enc * hidden);
+    float * d_enc = enc ? dev(enc->v.data(), enc->v.size()) : nullptr;
+    layers.resize((size_t) n_layers);
+    PFwd Fw{this, ctx, ctx->stream};
+    for (int l = 0; l < n_layers && ok; l++) {
+        const std::string b = "layers." + std::to_string(l);
+        ParlerLayer & L = layers[(size_t) l];
+        const int64_t HH = (int64_t) hidden * hidden;
+        L.ln1_w = up(b + ".self_attn_layer_norm.weight", hidden);    L.ln1_b = up(b + ".self_attn_layer_norm.bias", hidden);
+        L.wq = up(b + ".self_attn.q_proj.weight", HH); L.wk = up(b + ".self_attn.k_proj.weight", HH); L.wv = up(b + ".self_attn.v_proj.weight", HH); L.wo = up(b + ".self_attn.out_proj.weight", HH);
+        L.ln2_w = up(b + ".encoder_attn_layer_norm.weight", hidden); L.ln2_b = up(b + ".encoder_attn_layer_norm.bias", hidden);
+        L.cq = up(b + ".encoder_attn.q_proj.weight", HH); L.co = up(b + ".encoder_attn.out_proj.weight", HH);
+        L.ln3_w = up(b + ".final_layer_norm.weight", hidden);        L.ln3_b = up(b + ".final_layer_norm.bias", hidden);
+        L.fc1 = up(b + ".fc1.weight", (int64_t) ffn * hidden);       L.fc2 = up(b + ".fc2.weight", (int64_t) hidden * ffn);
+        // prep_cross_key_values (model.cpp:110-173): K and V of the stored text encoding, once per model
+        float * wck = up(b + ".encoder_attn.k_proj.weight", HH), * wcv = up(b + ".encoder_attn.v_proj.weight", HH);
+        L.cross_k = dev(nullptr, (size_t) n_enc * hidden); L.cross_v = dev(nullptr, (size_t) n_enc * hidden);
+        if (!ok) break;
+        if (Fw.gemv(d_enc, hidden, wck, hidden, hidden, n_enc, nullptr, L.cross_k, hidden)) return 1;
+        if (Fw.gemv(d_enc, hidden, wcv, hidden, hidden, n_enc, nullptr, L.cross_v, hidden)) return 1;
+    }
+    if (!ok) return 1;
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+    host.clear();
+    prepared = true;
+    return 0;
+}
+
+void Parler::free_all() {
+    for (void * p : dev_allocs) cudaFree(p);
+    dev_allocs.clear();
+    arena.release();
+    for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+}
+
+int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
+    if (!prepared) { set_error("parler: model not prepared"); return 1; }
+    if (B <= 0 || n_steps <= 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int R0 = 0, Pmax = 0;
+    for (int b = 0; b < B; b++) {
+        if (n_prompt[b] <= 0) { set_error("parler: prompt %d is empty", b); return 1; }
+        for (int i = 0; i < n_prompt[b]; i++) if (prompts[b][i] >= (uint32_t) prompt_vocab) { set_error("parler: prompt %d token %u >= prompt vocabulary %d", b, prompts[b][i], prompt_vocab); return 1; }
+        R0 += n_prompt[b]; Pmax = std::max(Pmax, (int) n_prompt[b]);
+    }
+    const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, F = ffn, NV = n_out * vocab;
+    if (Tmax > max_ctx) { set_error("parler: %d positions exceed the model's context of %d", Tmax, max_ctx); return 1; }
+    const size_t cache = (size_t) n_layers * B * Tmax * H * 4;
+    const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 6 * H + F) * 4 + (size_t) B * NV * 4 + (size_t) n_steps * B * n_out * 4 + (size_t) B * n_out * 4 +
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20);
+    if (arena.reserve(need)) return 1;
+    PFwd Fw{this, ctx, st};
+    float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * H);
+    float * x = Fw.al<float>((size_t) Rmax * H), * xn = Fw.al<float>((size_t) Rmax * H), * q = Fw.al<float>((size_t) Rmax * H), * att = Fw.al<float>((size_t) Rmax * H);
+    float * kbuf = Fw.al<float>((size_t) Rmax * H), * vbuf = Fw.al<float>((size_t) Rmax * H), * g = Fw.al<float>((size_t) Rmax * F);
+    float * logits = Fw.al<float>((size_t) B * NV);
+    int * row_tok = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax), * row_dst = Fw.al<int>((size_t) Rmax);
+    int * cross_base = Fw.al<int>((size_t) Rmax), * cross_len = Fw.al<int>((size_t) Rmax);
+    int * d_np = Fw.al<int>((size_t) B), * ids = Fw.al<int>((size_t) B * n_out), * d_out = Fw.al<int>((size_t) n_steps * B * n_out);
+    if (Fw.fail) return 1;
+
+    std::vector<int> ht((size_t) R0), hp((size_t) R0), hb((size_t) R0), hl((size_t) R0), hd((size_t) R0), hcb((size_t) Rmax, 0), hcl((size_t) Rmax, n_enc), hnp((size_t) B);
+    {
+        int r = 0;
+        for (int b = 0; b < B; b++) {
+            hnp[(size_t) b] = n_prompt[b];
+            for (int i = 0; i < n_prompt[b]; i++, r++) { ht[(size_t) r] = (int) prompts[b][i]; hp[(size_t) r] = i; hb[(size_t) r] = b * Tmax; hl[(size_t) r] = i + 1; hd[(size_t) r] = b * Tmax + i; }
+        }
+    }
+    B2_CUDA(cudaEventRecord(ev[0], st));
+    B2_CUDA(cudaMemcpyAsync(row_tok, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_pos, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_base, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_len, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(row_dst, hd.data(), hd.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(cross_base, hcb.data(), hcb.size() * 4, cudaMemcpyHostToDevice, st));   // every row attends to the whole stored encoding (all-zero cross mask)
+    B2_CUDA(cudaMemcpyAsync(cross_len, hcl.data(), hcl.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(d_np, hnp.data(), hnp.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
+
+    const float scale = 1.0f / sqrtf((float) head_dim);
+    const size_t att_smem = attention_smem_bytes(std::max(Tmax, n_enc));
+    if (att_smem > 200 * 1024) { set_error("parler: context of %d positions exceeds the v1 attention kernel's shared memory", Tmax); return 1; }
+    B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
+    const int Tcap = std::max(Tmax, n_enc);
+
+    // pass -1 is the prompt pass (its logits are never read: generate_from_batch only samples after audio decodes); passes 0 .. n_steps-1 are audio steps
+    for (int s = -1; s < n_steps; s++) {
+        const int R = s < 0 ? R0 : B;
+        if (s < 0) {
+            embed_pos_kernel<<<R, 256, 0, st>>>(row_tok, row_pos, embed_prompts, pos_embed, H, x); B2_LAUNCH_CHECK(ctx);
+        } else {
+            const int * last = s > 0 ? d_out + (size_t) (s - 1) * B * n_out : nullptr;
+            delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(last, d_np, B, n_out, s, bos, Tmax, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
+            codebook_embed_kernel<<<R, 256, 0, st>>>(ids, n_out, tables, (size_t) tab_rows * H, pos_embed, row_pos, H, x); B2_LAUNCH_CHECK(ctx);
+        }
+        for (int l = 0; l < n_layers; l++) {
+            const ParlerLayer & L = layers[(size_t) l];
+            float * Kl = Kc + (size_t) l * B * Tmax * H, * Vl = Vc + (size_t) l * B * Tmax * H;
+            if (Fw.ln(x, L.ln1_w, L.ln1_b, H, R, xn)) return 1;
+            if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
+            if (Fw.gemv(xn, H, L.wk, H, H, R, nullptr, kbuf, H)) return 1;
+            if (Fw.gemv(xn, H, L.wv, H, H, R, nullptr, vbuf, H)) return 1;
+            store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, H, Kl, Vl); B2_LAUNCH_CHECK(ctx);
+            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_base, row_len, heads, heads, head_dim, Tcap, scale, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                            // xn = self-attention + residual(x)
+            if (Fw.ln(xn, L.ln2_w, L.ln2_b, H, R, x)) return 1;
+            if (Fw.gemv(x, H, L.cq, H, H, R, nullptr, q, H)) return 1;
+            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, L.cross_k, L.cross_v, cross_base, cross_len, heads, heads, head_dim, Tcap, scale, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(att, H, L.co, H, H, R, xn, x, H)) return 1;                            // x = cross-attention + residual(xn)
+            if (Fw.ln(x, L.ln3_w, L.ln3_b, H, R, xn)) return 1;
+            if (Fw.gemv(xn, H, L.fc1, H, F, R, nullptr, g, F)) return 1;
+            { const size_t n = (size_t) R * F; gelu_f16lut_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, n); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(g, F, L.fc2, F, H, R, x, xn, H)) return 1;                             // xn = mlp + residual(x)
+            std::swap(x, xn);
+        }
+        if (s < 0) continue;
+        if (Fw.ln(x, ln_w, ln_b, H, R, xn)) return 1;
+        if (Fw.gemv(xn, H, heads_w, H, NV, B, nullptr, logits, NV)) return 1;                  // the n_out heads as one [n_out * vocab][hidden] matrix
+        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out + (size_t) s * B * n_out); B2_LAUNCH_CHECK(ctx);
+        if (out_logits)
+            for (int b = 0; b < B; b++)
+                B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+    }
+    B2_CUDA(cudaEventRecord(ev[1], st));
+    std::vector<int32_t> tmp((size_t) n_steps * B * n_out);
+    B2_CUDA(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_steps; s++)
+        for (int b = 0; b < B; b++)
+            for (int i = 0; i < n_out; i++) out_tokens[((size_t) b * n_steps + s) * n_out + i] = tmp[((size_t) s * B + b) * n_out + i];
+    cudaEventElapsedTime(&timing_ms, ev[0], ev[1]);
+    return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,47 @@
+// parler.h -- Parler-TTS autoregressive decode on the B200, first correct path.
+//
+// Replaces parler_tts_runner::build_parler_graph / decode / set_inputs / parler_build_kv_store / prep_cross_key_values and the token loop of
+// generate_from_batch with its delay pattern (reference src/models/parler/model.cpp:110-173,387-470,520-614,762-786) under sampler::max
+// (src/sampler.cpp), for a batch of independent prompts that share the model's stored conditional-prompt encoding.
+// Same plain design as orpheus.h (fp32 CUDA-core kernels from ar_kernels.cuh, one launch per op); logic checked under tests/emu, not yet run
+// on a GPU.
+#pragma once
+#include "kokoro.h"   // HostTensor, Arena
+
+namespace b2 {
+
+struct ParlerLayer {
+    float * ln1_w = nullptr, * ln1_b = nullptr, * wq = nullptr, * wk = nullptr, * wv = nullptr, * wo = nullptr;
+    float * ln2_w = nullptr, * ln2_b = nullptr, * cq = nullptr, * co = nullptr, * cross_k = nullptr, * cross_v = nullptr;   // cross_k / cross_v [n_enc][hidden]
+    float * ln3_w = nullptr, * ln3_b = nullptr, * fc1 = nullptr, * fc2 = nullptr;
+};
+
+struct Parler {
+    Ctx * ctx = nullptr;
+    std::map<std::string, uint32_t>   kv;
+    std::map<std::string, HostTensor> host;
+    bool prepared = false;
+    size_t weight_bytes = 0;
+    std::vector<void *> dev_allocs;
+
+    int n_layers = 0, heads = 0, head_dim = 0, hidden = 0, ffn = 0, n_out = 0, vocab = 0, n_enc = 0, max_ctx = 0, tab_rows = 0, prompt_vocab = 0;
+    int bos = 1025, eos = 1024;
+    float * embed_prompts = nullptr, * pos_embed = nullptr, * tables = nullptr /* [n_out][tab_rows][hidden] */, * heads_w = nullptr /* [n_out * vocab][hidden] */;
+    float * ln_w = nullptr, * ln_b = nullptr;
+    std::vector<ParlerLayer> layers;
+
+    Arena arena;
+    float timing_ms = 0.f;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    int assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+    int prepare();
+    // greedy generation of n_steps audio frames for B prompts (generate_from_batch's loop with a step cap instead of check_stopping):
+    // out_tokens [B][n_steps][n_out]; out_logits (optional) [B][n_steps][n_out][vocab]
+    int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits);
+    void free_all();
+};
+
+int load_gguf_into(Parler * m, const char * path);   // gguf_reader.cpp
+
+}  // namespace b2
