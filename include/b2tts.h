@@ -195,6 +195,25 @@ int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint
                                    int32_t * out_tokens, float * out_logits);
 float b2tts_parler_last_ms(const b2tts_parler * m);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Dia autoregressive decode, FIRST CORRECT PATH, same status as Orpheus / Parler above (emulation-checked: identical token
+ * ids, CFG-combined logits within 2.4e-3 of the reference at a logit std of 13; NOT YET RUN ON A B200).
+ *   b2tts_dia_load_gguf      : dia_model::setup_from_file + assign_weight loop over "dia.*" (reference src/models/dia/model.cpp:3-132,200-262;
+ *                              dia/loader.cpp:8-22)
+ *   b2tts_dia_generate_greedy: dia_runner::decode -- the encoder pass over the conditional and the all-zero unconditional sequence, the cross K/V
+ *                              store, then the CFG-paired decoder step with cfg_scale (model.cpp:324-637,705-737; src/util.cpp:175-200) -- inside
+ *                              generate_from_batch's loop with check_stopping (model.cpp:806-864; sampler::max per output head), for n_sequences
+ *                              independent prompts of byte tokens, at most n_steps frames each.  n_generated[b] (may be NULL) is where
+ *                              check_stopping ended utterance b; rows past it are zero.
+ *                              out_tokens [n_sequences][n_steps][n_heads]; out_logits (may be NULL) [n_sequences][n_steps][n_heads][out_vocab]. */
+typedef struct b2tts_dia b2tts_dia;
+int   b2tts_dia_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dia ** out);
+void  b2tts_dia_free(b2tts_dia * m);
+int   b2tts_dia_info(const b2tts_dia * m, int * n_heads, int * out_vocab, int * encoder_context, int * max_generation);
+int   b2tts_dia_generate_greedy(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
+                                int32_t * out_tokens, float * out_logits, int32_t * n_generated);
+float b2tts_dia_last_ms(const b2tts_dia * m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,10 +1,11 @@
 // tests/emu/ar_main.cpp -- TEST INFRASTRUCTURE ONLY: drive a model's generate_greedy (tts_cpp_b200/csrc/{orpheus,parler,dia}.cu compiled against the
 // CPU emulation in tests/emu/include) on the prompts of the golden vectors and dump token ids + logits for the Python test.
-//   ar_emu <orpheus|parler> <model.gguf> <prompts.bin> <out.bin>
+//   ar_emu <orpheus|parler|dia> <model.gguf> <prompts.bin> <out.bin>
 // prompts.bin: int32 B, int32 n_steps, then per prompt int32 n, n x uint32.
 // out.bin: int32 W (tokens per step), int32 V (logits per step), int32 tokens [B][n_steps][W], float logits [B][n_steps][V]
 #include "orpheus.h"
 #include "parler.h"
+#include "dia.h"
 #include <cstring>
 #include <cstdio>
 #include <vector>
@@ -44,5 +45,6 @@ int main(int argc, char ** argv) {
     if (argc < 5) return 2;
     if (!strcmp(argv[1], "orpheus")) return run<b2::Orpheus>(argc, argv);
     if (!strcmp(argv[1], "parler")) return run<b2::Parler>(argc, argv);
+    if (!strcmp(argv[1], "dia")) return run<b2::Dia>(argc, argv);
     return 2;
 }

@@ -45,7 +45,7 @@ const std::function<void()> * g_body = nullptr;
 std::vector<Fiber> g_fibers;
 std::vector<char *> g_stacks;
 int g_alive = 0, g_arrived = 0; uint64_t g_gen = 0, g_progress = 0;
-struct Warp { int alive = 0, arrived = 0; uint64_t gen = 0; uint64_t slot[32]; };
+struct Warp { int alive = 0, arrived = 0; uint64_t gen = 0; uint64_t slot[2][32]; };
 std::vector<Warp> g_warps;
 std::vector<char> g_dyn;
 
@@ -86,11 +86,12 @@ void sync_block() {
 uint64_t shfl(uint64_t v, int src_lane) {
     const int t = linear_tid(g_cur);
     Warp & w = g_warps[(size_t) t >> 5];
-    w.slot[t & 31] = v;
+    // double-buffered by barrier generation: a lane can only overwrite a buffer two shuffles later, after every lane has passed the barrier in between
+    // (and read its value before arriving there), so one barrier per shuffle is enough
+    const int buf = (int) (w.gen & 1);
+    w.slot[buf][t & 31] = v;
     warp_barrier();
-    const uint64_t r = w.slot[src_lane & 31];
-    warp_barrier();
-    return r;
+    return w.slot[buf][src_lane & 31];
 }
 
 void * dyn_smem() { return g_dyn.data(); }

@@ -16,6 +16,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       from oracle/ref_orpheus_driver.cpp
   parler_vectors.npz       : two prompts (5 and 9 ids) and, for 5 greedy audio steps each, the 9 codebook tokens per step and their logits
       from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
+  dia_stop_vectors.npz     : one byte-token prompt run until the reference's check_stopping ends the loop (64 frames of 9 tokens, the logits of the
+      last frame), from oracle/ref_dia_driver.cpp with a step cap of 80
   dia_vectors.npz          : two byte-token prompts (10 and 18 tokens, the second after the first in the same process) and, for 5 greedy steps
       each, the 9 codebook tokens and the CFG-combined logits from the reference's Dia encoder + decode loop, from oracle/ref_dia_driver.cpp
 """
@@ -210,8 +212,27 @@ def dia_vectors():
     print("dia vectors:", {k: v.shape for k, v in out.items()})
 
 
+def dia_stop_vectors():
+    """The whole of generate_from_batch's loop: with dia.decoder.max_generation_size = 64 and max_delay = 15 check_stopping starts the end-of-stream
+    countdown at position 49 (EOS / PAD injected head by head along the delay pattern) and ends the loop after 64 frames."""
+    from tts_cpp_b200.synth import cached_dia_gguf
+    gguf = cached_dia_gguf(seed=0)
+    rng = np.random.default_rng(12)
+    q = np.concatenate([[1], rng.integers(32, 127, size=13)])
+    tmp = tempfile.mkdtemp()
+    pf = os.path.join(tmp, "prompts.txt")
+    open(pf, "w").write(" ".join(map(str, q)) + "\n")
+    pre = os.path.join(tmp, "d")
+    run([os.path.join(REF, "dia_ref"), gguf, pf, pre, "--steps", "80", "--threads", "4", "--quiet"])
+    toks = np.fromfile(f"{pre}.u0.tokens.i32", np.int32).reshape(-1, 9)
+    lg = np.fromfile(f"{pre}.u0.logits.f32", np.float32).reshape(toks.shape[0], 9, -1)
+    np.savez_compressed(os.path.join(OUT, "dia_stop_vectors.npz"), prompt0=np.asarray(q, np.int32), tokens0=toks, logits_last0=lg[-1], step_cap=np.int32(80))
+    print("dia stop vectors:", toks.shape)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "dia"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "dia", "dia_stop"]
+    if "dia_stop" in which: dia_stop_vectors()
     if "dia" in which: dia_vectors()
     if "parler" in which: parler_vectors()
     if "orpheus" in which: orpheus_vectors()

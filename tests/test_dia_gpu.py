@@ -1,0 +1,42 @@
+"""GPU: the Dia decode loop (tts_cpp_b200/csrc/dia.cu) against the token ids and logits the compiled UNMODIFIED reference produced
+(tests/golden/dia_vectors.npz: two byte-token prompts, 5 greedy frames of 9 codebooks each with the CFG-combined logits, small synthetic Dia GGUF).
+
+Written after round 1's GPU budget was spent: never run on a B200 (its logic is checked under the CPU emulation, tests/test_emu_cpu.py), hence
+xfail(strict=False) and a CHILD PROCESS, so that a fault in an unvalidated kernel cannot poison the CUDA context of the tests that follow.
+Round 2 removes both once it has passed on hardware."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="Dia decode path not yet run on a B200 (round 1 GPU budget exhausted)")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import dia_runner_from_file
+from tts_cpp_b200.synth import cached_dia_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "dia_vectors.npz"))
+par = dia_runner_from_file(cached_dia_gguf(seed=0))
+prompts = [g["prompt0"], g["prompt1"]]
+steps = g["tokens0"].shape[0]
+toks, ngen, logits = par.generate_greedy(prompts, steps, want_logits=True)           # one ragged batch of both prompts
+ok = True
+for u in range(2):
+    d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
+    print(f"PARITY dia prompt {u}: tokens {toks[u].tolist()}  max |logit diff| {d:.3e}")
+    ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < 2e-2            # bit-exact ids at temperature 0; logits: CFG multiplies fp32 summation noise by 4 at std ~13
+single, _ = par.generate_greedy([prompts[1]], steps)
+ok &= bool(np.array_equal(single[0], toks[1])) and bool((ngen == steps).all())                                   # batching does not change a sequence
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_dia_greedy_tokens_and_logits_match_reference():
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=240)
+    print(r.stdout[-2000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0

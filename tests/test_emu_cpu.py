@@ -16,12 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 import emu_build  # noqa: E402
 
-from tts_cpp_b200.synth import cached_orpheus_gguf, cached_parler_gguf  # noqa: E402
+from tts_cpp_b200.synth import cached_dia_gguf, cached_orpheus_gguf, cached_parler_gguf  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-AR_SOURCES = ["orpheus.cu", "parler.cu"]
+AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu"]
 
 
 def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag):
@@ -77,3 +77,34 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path)
         print(f"PARITY(emulated) parler prompt {u}: tokens {tok[u].tolist()}  max |logit diff| {d:.3e}  (logit std {ref.std():.2f})")
         assert np.array_equal(tok[u], g[f"tokens{u}"])
         assert d < 1e-2      # ggml's GELU is an fp16 table: an activation that lands on the other side of a rounding boundary moves a logit by ~1e-3
+
+
+def test_dia_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path):
+    """Dia::generate_greedy (dia.cu: two-sequence encoder pass with its block mask, RoPE'd cross keys for the prompt positions only, GQA decoder
+    self-attention, cross-attention, cfg_scale, nine heads + per-head argmax) under emulation against tests/golden/dia_vectors.npz."""
+    g = np.load(os.path.join(GOLD, "dia_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    tok, logits = _run_ar(tmp_path, "dia", cached_dia_gguf(seed=0), prompts, steps, "b")
+    for u in range(2):
+        ref = g[f"logits{u}"].reshape(steps, -1)
+        d = float(np.abs(logits[u] - ref).max())
+        print(f"PARITY(emulated) dia prompt {u}: tokens {tok[u].tolist()}  max |logit diff| {d:.3e}  (logit std {ref.std():.2f})")
+        assert np.array_equal(tok[u], g[f"tokens{u}"])
+        assert d < 2e-2      # CFG multiplies the fp32 summation-order noise of both passes by 4 at a logit std of ~13
+
+
+def test_dia_cuda_path_emulated_check_stopping(tmp_path):
+    """generate_from_batch's whole loop: the end-of-stream countdown (EOS / PAD injected along the delay pattern from position max_generation - max_delay)
+    and the frame count at which check_stopping ends it, against the reference run to completion (tests/golden/dia_stop_vectors.npz: 63 frames)."""
+    g = np.load(os.path.join(GOLD, "dia_stop_vectors.npz"))
+    ref = g["tokens0"]
+    cap = int(g["step_cap"])
+    tok, logits = _run_ar(tmp_path, "dia", cached_dia_gguf(seed=0), [g["prompt0"]], cap, "stop")
+    n_gen = ref.shape[0]
+    assert n_gen < cap
+    assert np.array_equal(tok[0, :n_gen], ref)
+    assert not tok[0, n_gen:].any() and not logits[0, n_gen:].any()        # rows past the stop are zero
+    d = float(np.abs(logits[0, n_gen - 1] - g["logits_last0"].reshape(-1)).max())
+    print(f"PARITY(emulated) dia run to check_stopping: {n_gen} frames, last-frame max |logit diff| {d:.3e}")
+    assert d < 2e-2

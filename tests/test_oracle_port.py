@@ -184,3 +184,16 @@ def test_dia_port_against_reference_decode_loop():
         print(f"dia prompt {u}: max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
         assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact codebook indices at temperature 0
         assert d < 2e-2
+
+
+def test_dia_port_check_stopping_against_reference():
+    """oracle/dia_port.py run until check_stopping ends the loop (reference src/models/dia/model.cpp:806-823,849-864): same 63 frames as the
+    reference, including the steps that are fed the injected EOS / PAD tokens."""
+    from oracle.dia_port import DiaPort
+    from tts_cpp_b200.synth import cached_dia_gguf
+    g = np.load(os.path.join(GOLD, "dia_stop_vectors.npz"))
+    port = DiaPort(cached_dia_gguf(seed=0))
+    toks, logits = port.greedy(g["prompt0"], int(g["step_cap"]))
+    assert toks.shape == g["tokens0"].shape and toks.shape[0] < int(g["step_cap"])
+    assert np.array_equal(toks, g["tokens0"])
+    assert float(np.abs(logits[-1] - g["logits_last0"]).max()) < 2e-2

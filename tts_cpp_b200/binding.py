@@ -385,3 +385,41 @@ def parler_runner_from_file(path: str, device: int = 0, ctx: Context | None = No
     h = C.c_void_p()
     _chk(lib().b2tts_parler_load_gguf(ctx.h, path.encode(), C.byref(h)))
     return ParlerRunner(ctx, h)
+
+
+class DiaRunner:
+    """dia_runner::decode inside generate_from_batch's loop (reference src/models/dia/model.cpp:705-737,806-864) below the tokenizer, batched, greedy."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        nh, v, c, mg = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().b2tts_dia_info(self.h, C.byref(nh), C.byref(v), C.byref(c), C.byref(mg)))
+        self.n_heads, self.out_vocab, self.encoder_context, self.max_generation = nh.value, v.value, c.value, mg.value
+
+    def generate_greedy(self, prompts, n_steps: int, want_logits: bool = False):
+        """-> tokens [B][n_steps][n_heads], n_generated [B] (and the CFG-combined logits [B][n_steps][n_heads][out_vocab])"""
+        B = len(prompts)
+        arrs = [np.ascontiguousarray(np.asarray(p, np.uint32)) for p in prompts]
+        npr = np.array([a.size for a in arrs], np.int32)
+        ptrs = (C.POINTER(C.c_uint32) * B)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        toks = np.empty((B, n_steps, self.n_heads), np.int32)
+        ngen = np.empty(B, np.int32)
+        logits = np.empty((B, n_steps, self.n_heads, self.out_vocab), np.float32) if want_logits else None
+        _chk(lib().b2tts_dia_generate_greedy(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps),
+                                             toks.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None,
+                                             ngen.ctypes.data_as(C.POINTER(C.c_int32))))
+        return (toks, ngen, logits) if want_logits else (toks, ngen)
+
+    def close(self):
+        if self.h:
+            lib().b2tts_dia_free(self.h)
+            self.h = None
+
+
+def dia_runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> DiaRunner:
+    ctx = ctx or Context(device)
+    h = C.c_void_p()
+    _chk(lib().b2tts_dia_load_gguf(ctx.h, path.encode(), C.byref(h)))
+    return DiaRunner(ctx, h)

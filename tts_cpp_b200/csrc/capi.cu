@@ -4,6 +4,7 @@
 #include "dac.h"
 #include "orpheus.h"
 #include "parler.h"
+#include "dia.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -29,6 +30,7 @@ struct b2tts_dac { Dac d; };
 struct b2tts_snac { Snac s; };
 struct b2tts_orpheus { Orpheus o; };
 struct b2tts_parler { Parler p; };
+struct b2tts_dia { Dia d; };
 
 namespace {
 // RAII device scratch for the op-level entry points
@@ -212,6 +214,31 @@ int b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32
     return m->p.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
 }
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
+// ---- Dia AR decode (first correct path)
+int b2tts_dia_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dia ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_dia * m = new b2tts_dia();
+    m->d.ctx = &ctx->c;
+    if (load_gguf_into(&m->d, path)) { m->d.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_dia_free(b2tts_dia * m) { if (m) { m->d.free_all(); delete m; } }
+int b2tts_dia_info(const b2tts_dia * m, int * n_heads, int * out_vocab, int * encoder_context, int * max_generation) {
+    if (!m) { set_error("null model"); return 1; }
+    if (n_heads) *n_heads = m->d.n_out;
+    if (out_vocab) *out_vocab = m->d.vocab;
+    if (encoder_context) *encoder_context = m->d.enc_ctx;
+    if (max_generation) *max_generation = m->d.max_gen;
+    return 0;
+}
+int b2tts_dia_generate_greedy(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens,
+                              float * out_logits, int32_t * n_generated) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->d.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits, n_generated);
+}
+float b2tts_dia_last_ms(const b2tts_dia * m) { return m ? m->d.timing_ms : 0.f; }
 
 int b2tts_snac_reset_noise(b2tts_snac * m) { if (!m) { set_error("null model"); return 1; } m->s.reset_noise(); return 0; }
 int b2tts_kokoro_n_voices(const b2tts_kokoro * m) { return (int) m->k.voice_names.size(); }

@@ -1,0 +1,325 @@
+// dia.cu -- Dia autoregressive decode (encoder pass + CFG-paired decoder loop), first correct CUDA path.  See dia.h for what it replaces.
+#include "dia.h"
+#include "ar_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace b2 {
+
+static inline float dh2f(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
+
+int Dia::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
+    if (prepared) { set_error("dia: assign_weight after prepare"); return 1; }
+    std::string nm(name);
+    if (nm.rfind("dia.", 0) == 0) nm = nm.substr(4);
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
+    t.v.resize((size_t) n);
+    if (type == 0) {
+        if (nbytes < (size_t) n * 4) { set_error("tensor %s: short data", name); return 1; }
+        memcpy(t.v.data(), data, (size_t) n * 4);
+    } else if (type == 1) {
+        if (nbytes < (size_t) n * 2) { set_error("tensor %s: short data", name); return 1; }
+        const uint16_t * s = (const uint16_t *) data;
+        for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = dh2f(s[i]);
+        t.f16 = true;
+    } else {
+        set_error("tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
+        return 1;
+    }
+    host[nm] = std::move(t);
+    return 0;
+}
+
+int Dia::prepare() {
+    if (prepared) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    auto kvreq = [&](const char * k, int & out) { auto it = kv.find(k); if (it == kv.end()) { set_error("the '%s' key must be specified in the GGUF file.", k); return 1; } out = (int) it->second; return 0; };
+    auto kvopt = [&](const char * k, int & out) { auto it = kv.find(k); if (it != kv.end()) out = (int) it->second; };
+    if (kvreq("dia.encoder.layers", enc_layers) || kvreq("dia.decoder.layers", dec_layers) || kvreq("dia.decoder.attn_heads", heads) || kvreq("dia.decoder.query_heads", rep) ||
+        kvreq("dia.encoder.attn_heads", enc_heads) || kvreq("dia.attn_head_size", head_dim) || kvreq("dia.encoder.max_context_length", enc_ctx) ||
+        kvreq("dia.decoder.output_heads", n_out) || kvreq("dia.decoder.output_vocab_size", vocab) || kvreq("dia.decoder.max_generation_size", max_gen)) return 1;
+    kvopt("dia.bos_token_id", bos); kvopt("dia.eos_token_id", eos); kvopt("dia.pad_token_id", pad); kvopt("dia.max_delay", max_delay);
+    { auto it = kv.find("dia.cfg_scale#f32"); if (it != kv.end()) memcpy(&cfg, &it->second, 4); }
+    if (heads <= 0 || rep <= 0 || heads % rep || head_dim % 2 || n_out > 9) { set_error("dia: inconsistent head configuration"); return 1; }
+    hidden = heads * head_dim; kv_hidden = heads / rep * head_dim; enc_inner = enc_heads * head_dim;
+    bool ok = true;
+    auto find = [&](const std::string & n, int64_t expect) -> const HostTensor * {
+        auto it = host.find(n);
+        if (it == host.end()) { set_error("missing tensor dia.%s", n.c_str()); ok = false; return nullptr; }
+        if (expect && (int64_t) it->second.v.size() != expect) { set_error("tensor dia.%s has %zu elements, expected %lld", n.c_str(), it->second.v.size(), (long long) expect); ok = false; return nullptr; }
+        return &it->second;
+    };
+    auto dev = [&](const float * src, size_t n) -> float * {
+        void * d = nullptr;
+        if (cudaMalloc(&d, n * 4) != cudaSuccess) { cudaGetLastError(); set_error("dia: cudaMalloc of %zu bytes failed", n * 4); ok = false; return nullptr; }
+        cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += n * 4;
+        return (float *) d;
+    };
+    auto up = [&](const std::string & n, int64_t expect) -> float * { const HostTensor * t = find(n, expect); return t ? dev(t->v.data(), t->v.size()) : nullptr; };
+
+    {   // the encoder width is not in the metadata (the reference hard-codes 1024, model.h:68): take it from the embedding table
+        const HostTensor * t = find("encoder.embedding", 0);
+        if (!t || t->shape.size() != 2) { if (ok) set_error("dia: encoder.embedding must be 2-D"); return 1; }
+        enc_vocab = (int) t->shape[0]; enc_hidden = (int) t->shape[1];
+        const HostTensor * g = find("encoder.layers.0.gate", 0), * gd = find("decoder.layers.0.gate", 0);
+        if (!g || !gd) return 1;
+        enc_ffn = (int) g->shape[0]; ffn = (int) gd->shape[0];
+        if (enc_hidden % 4 || hidden % 4 || enc_ffn % 4 || ffn % 4 || enc_inner % 4 || kv_hidden % 4) { set_error("dia: layer widths must be multiples of 4"); return 1; }
+    }
+    enc_embed = up("encoder.embedding", 0);
+    enc_norm = up("encoder.norm", enc_hidden);
+    dec_norm = up("decoder.norm", hidden);
+    enc.resize((size_t) enc_layers); dec.resize((size_t) dec_layers);
+    for (int l = 0; l < enc_layers && ok; l++) {
+        const std::string b = "encoder.layers." + std::to_string(l);
+        DiaEncLayer & L = enc[(size_t) l];
+        L.pre_sa = up(b + ".pre_sa_norm", enc_hidden); L.post_sa = up(b + ".post_sa_norm", enc_hidden);
+        L.wq = up(b + ".q_proj", (int64_t) enc_inner * enc_hidden); L.wk = up(b + ".k_proj", (int64_t) enc_inner * enc_hidden); L.wv = up(b + ".v_proj", (int64_t) enc_inner * enc_hidden);
+        L.wo = up(b + ".o_proj", (int64_t) enc_hidden * enc_inner);
+        L.gate = up(b + ".gate", (int64_t) enc_ffn * enc_hidden); L.up = up(b + ".up", (int64_t) enc_ffn * enc_hidden); L.down = up(b + ".wo", (int64_t) enc_hidden * enc_ffn);
+    }
+    for (int l = 0; l < dec_layers && ok; l++) {
+        const std::string b = "decoder.layers." + std::to_string(l);
+        DiaDecLayer & L = dec[(size_t) l];
+        const int64_t DD = (int64_t) hidden * hidden;
+        L.pre_sa = up(b + ".pre_sa_norm", hidden); L.pre_ca = up(b + ".pre_ca_norm", hidden); L.pre_mlp = up(b + ".pre_mlp_norm", hidden);
+        L.sq = up(b + ".self_q_proj", DD); L.sk = up(b + ".self_k_proj", (int64_t) kv_hidden * hidden); L.sv = up(b + ".self_v_proj", (int64_t) kv_hidden * hidden); L.so = up(b + ".self_o_proj", DD);
+        L.cq = up(b + ".cross_q_proj", DD); L.ck = up(b + ".cross_k_proj", (int64_t) hidden * enc_hidden); L.cv = up(b + ".cross_v_proj", (int64_t) hidden * enc_hidden); L.co = up(b + ".cross_o_proj", DD);
+        L.gate = up(b + ".gate", (int64_t) ffn * hidden); L.up = up(b + ".up", (int64_t) ffn * hidden); L.down = up(b + ".wo", (int64_t) hidden * ffn);
+    }
+    if (ok) {   // the n_out codebook tables and output heads, each family in one buffer
+        std::vector<float> tab, hw;
+        for (int i = 0; i < n_out && ok; i++) {
+            const HostTensor * t = find("decoder.embeddings." + std::to_string(i), (int64_t) vocab * hidden);
+            const HostTensor * h = find("decoder.heads." + std::to_string(i), (int64_t) vocab * hidden);
+            if (!t || !h) break;
+            tab.insert(tab.end(), t->v.begin(), t->v.end());
+            hw.insert(hw.end(), h->v.begin(), h->v.end());
+        }
+        if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev(hw.data(), hw.size()); }
+    }
+    if (!ok) return 1;
+    for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+    host.clear();
+    prepared = true;
+    return 0;
+}
+
+void Dia::free_all() {
+    for (void * p : dev_allocs) cudaFree(p);
+    dev_allocs.clear();
+    arena.release();
+    for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+}
+
+namespace {
+
+// cross-attention keys exist only for the prompt's positions: the rest of the enc_ctx-long key store stays zero and is attended to unmasked
+// (build_dia_cross_kv_store, model.cpp:392-424 stores sentence_length rows of K but all rows of V)
+__global__ void zero_key_tail_kernel(float * K, const int * __restrict__ seq_len, int C, int D) {
+    const int r = blockIdx.x, seq = r / C, n = r % C;
+    if (n < seq_len[seq]) return;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) K[(size_t) r * D + c] = 0.f;
+}
+
+// the decoder rows of one step.  Both sequences of an utterance are fed the same audio tokens: head i gets BOS until the decode position exceeds i,
+// then the token it produced one step earlier (generate_from_batch, model.cpp:843-858), with check_stopping's end-of-stream injection on top
+// (model.cpp:806-823: `delay` is dia_context::delay_steps; `stopped` records the step at which the reference's loop would have ended).
+__global__ void dia_step_rows_kernel(const int * __restrict__ last, int B, int n_out, int step, int bos, int eos, int pad, int max_gen, int max_delay, int Tmax,
+                                     int * delay, int * stopped, int * ids, int * row_pos, int * row_base, int * row_len, int * row_dst) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B) return;
+    const int pattern[9] = {0, 8, 9, 10, 11, 12, 13, 14, 15};     // dia_model::delay_pattern (model.h:85)
+    int audio[9];
+    for (int i = 0; i < n_out; i++) audio[i] = step > i ? last[u * n_out + i] : bos;
+    int d = delay[u];
+    if (d == -1 && (audio[0] == eos || step >= max_gen - max_delay)) d = max_delay;
+    if (d > 0) {
+        const int after = max_delay - d;
+        for (int i = 0; i < n_out; i++) {
+            if (after == pattern[i]) audio[i] = eos;
+            else if (after > pattern[i]) audio[i] = pad;
+        }
+        d -= 1;
+    }
+    delay[u] = d;
+    if (d == 0 && stopped[u] < 0) stopped[u] = step;
+    for (int q = 0; q < 2; q++) {
+        const int r = 2 * u + q;
+        for (int i = 0; i < n_out; i++) ids[r * n_out + i] = audio[i];
+        row_pos[r] = step; row_base[r] = r * Tmax; row_len[r] = step + 1; row_dst[r] = r * Tmax + step;
+    }
+}
+
+// cfg_scale (src/util.cpp:175-200): out = cond + scale * (cond - uncond); the "-inf above max_output" store is overwritten by it and has no effect
+__global__ void cfg_combine_kernel(const float * __restrict__ logits2, int NV, float scale, float * __restrict__ out) {
+    const int u = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= NV) return;
+    const float cr = logits2[(size_t) (2 * u) * NV + j], ur = logits2[(size_t) (2 * u + 1) * NV + j];
+    out[(size_t) u * NV + j] = cr + scale * (cr - ur);
+}
+
+struct DFwd {
+    Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false;
+    template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
+    int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    int rms(const float * x, const float * w, int H, int R, float * y) { rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, w, H, R, y); B2_LAUNCH_CHECK(ctx); return 0; }
+    int rope(float * x, const int * pos, int R, int nh, int hd, float theta_scale) { dim3 grid(R, nh); rope_rows_kernel<<<grid, 64, 0, st>>>(x, pos, nh, hd, theta_scale); B2_LAUNCH_CHECK(ctx); return 0; }
+    int swiglu(float * g, const float * u, size_t n) { silu_mul_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, u, n); B2_LAUNCH_CHECK(ctx); return 0; }
+};
+
+}  // namespace
+
+int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits, int32_t * n_generated) {
+    if (!prepared) { set_error("dia: model not prepared"); return 1; }
+    if (B <= 0 || n_steps <= 0) return 0;
+    B2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int C = enc_ctx, S2 = 2 * B, RE = S2 * C, EH = enc_hidden, EI = enc_inner, D = hidden, KVD = kv_hidden, NV = n_out * vocab, Tmax = n_steps;
+    for (int b = 0; b < B; b++) {
+        if (n_prompt[b] <= 0 || n_prompt[b] > C) { set_error("dia: prompt %d has %d tokens (1 .. %d supported)", b, n_prompt[b], C); return 1; }
+        for (int i = 0; i < n_prompt[b]; i++) if (prompts[b][i] >= (uint32_t) enc_vocab) { set_error("dia: prompt %d token %u >= encoder vocabulary %d", b, prompts[b][i], enc_vocab); return 1; }
+    }
+    const size_t enc_ws = (size_t) RE * ((size_t) 3 * EH + 4 * EI + 2 * enc_ffn) * 4;
+    const size_t cross = (size_t) 2 * dec_layers * RE * D * 4;
+    const size_t self_cache = (size_t) 2 * dec_layers * S2 * Tmax * KVD * 4;
+    const size_t dec_ws = (size_t) S2 * ((size_t) 4 * D + 2 * KVD + 2 * ffn + NV) * 4 + (size_t) B * NV * 4;
+    const size_t need = enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20);
+    if (arena.reserve(need)) return 1;
+    DFwd Fw{this, ctx, st};
+    // ---- buffers
+    float * ck = Fw.al<float>((size_t) dec_layers * RE * D), * cv = Fw.al<float>((size_t) dec_layers * RE * D);
+    float * Kc = Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD), * Vc = Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD);
+    int * e_tok = Fw.al<int>((size_t) RE), * e_pos = Fw.al<int>((size_t) RE), * e_base = Fw.al<int>((size_t) RE), * e_len = Fw.al<int>((size_t) RE);
+    int * seq_len = Fw.al<int>((size_t) S2), * cross_base = Fw.al<int>((size_t) S2), * cross_len = Fw.al<int>((size_t) S2);
+    int * ids = Fw.al<int>((size_t) S2 * n_out), * row_pos = Fw.al<int>((size_t) S2), * row_base = Fw.al<int>((size_t) S2), * row_len = Fw.al<int>((size_t) S2), * row_dst = Fw.al<int>((size_t) S2);
+    int * delay = Fw.al<int>((size_t) B), * stopped = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) n_steps * B * n_out);
+    if (Fw.fail) return 1;
+
+    std::vector<int> htok((size_t) RE, 0), hpos((size_t) RE), hbase((size_t) RE), hlen((size_t) RE), hseq((size_t) S2), hcb((size_t) S2), hcl((size_t) S2, C), hm1((size_t) B, -1);
+    for (int s = 0; s < S2; s++) {
+        const int u = s >> 1, S = n_prompt[u];
+        hseq[(size_t) s] = S;                   // one mask for both sequences of the pair: the conditional prompt's length (model.cpp:352-366)
+        hcb[(size_t) s] = s * C;
+        for (int n = 0; n < C; n++) {
+            const size_t r = (size_t) s * C + n;
+            if (!(s & 1) && n < S) htok[r] = (int) prompts[u][n];      // the unconditional sequence is all zeros
+            hpos[r] = n;
+            hbase[r] = s * C + (n < S ? 0 : S);                       // prompt positions see each other, padded positions see each other
+            hlen[r] = n < S ? S : C - S;
+        }
+    }
+    B2_CUDA(cudaEventRecord(ev[0], st));
+    B2_CUDA(cudaMemcpyAsync(e_tok, htok.data(), htok.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(e_pos, hpos.data(), hpos.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(e_base, hbase.data(), hbase.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(e_len, hlen.data(), hlen.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(seq_len, hseq.data(), hseq.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(cross_base, hcb.data(), hcb.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(cross_len, hcl.data(), hcl.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(delay, hm1.data(), hm1.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemcpyAsync(stopped, hm1.data(), hm1.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
+
+    const float theta_scale = powf(10000.0f, -2.0f / (float) head_dim);
+    const int Tcap = std::max(Tmax, C);
+    const size_t att_smem = attention_smem_bytes(Tcap);
+    if (att_smem > 200 * 1024) { set_error("dia: context of %d positions exceeds the v1 attention kernel's shared memory", Tcap); return 1; }
+    B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
+
+    // ---- encoder pass over both sequences of every utterance (build_dia_encoder, model.cpp:440-500); softmax scale 1.0
+    {
+        float * x = Fw.al<float>((size_t) RE * EH), * xn = Fw.al<float>((size_t) RE * EH), * enc_out = Fw.al<float>((size_t) RE * EH);
+        float * q = Fw.al<float>((size_t) RE * EI), * k = Fw.al<float>((size_t) RE * EI), * v = Fw.al<float>((size_t) RE * EI), * att = Fw.al<float>((size_t) RE * EI);
+        float * g = Fw.al<float>((size_t) RE * enc_ffn), * up = Fw.al<float>((size_t) RE * enc_ffn);
+        if (Fw.fail) return 1;
+        embed_kernel<<<RE, 256, 0, st>>>(e_tok, enc_embed, EH, x); B2_LAUNCH_CHECK(ctx);
+        for (int l = 0; l < enc_layers; l++) {
+            const DiaEncLayer & L = enc[(size_t) l];
+            if (Fw.rms(x, L.pre_sa, EH, RE, xn)) return 1;
+            if (Fw.gemv(xn, EH, L.wq, EH, EI, RE, nullptr, q, EI) || Fw.gemv(xn, EH, L.wk, EH, EI, RE, nullptr, k, EI) || Fw.gemv(xn, EH, L.wv, EH, EI, RE, nullptr, v, EI)) return 1;
+            if (Fw.rope(q, e_pos, RE, enc_heads, head_dim, theta_scale) || Fw.rope(k, e_pos, RE, enc_heads, head_dim, theta_scale)) return 1;
+            { dim3 grid(RE, enc_heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, k, v, e_base, e_len, enc_heads, enc_heads, head_dim, Tcap, 1.0f, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(att, EI, L.wo, EI, EH, RE, x, xn, EH)) return 1;                    // xn = attention + residual(x)
+            if (Fw.rms(xn, L.post_sa, EH, RE, x)) return 1;
+            if (Fw.gemv(x, EH, L.gate, EH, enc_ffn, RE, nullptr, g, enc_ffn) || Fw.gemv(x, EH, L.up, EH, enc_ffn, RE, nullptr, up, enc_ffn)) return 1;
+            if (Fw.swiglu(g, up, (size_t) RE * enc_ffn)) return 1;
+            if (Fw.gemv(g, enc_ffn, L.down, enc_ffn, EH, RE, xn, x, EH)) return 1;           // x = mlp + residual(xn)
+        }
+        if (Fw.rms(x, enc_norm, EH, RE, enc_out)) return 1;
+        for (int l = 0; l < dec_layers; l++) {                                               // cross K (RoPE'd, prompt positions only) and V (all positions)
+            const DiaDecLayer & L = dec[(size_t) l];
+            float * ckl = ck + (size_t) l * RE * D, * cvl = cv + (size_t) l * RE * D;
+            if (Fw.gemv(enc_out, EH, L.ck, EH, D, RE, nullptr, ckl, D) || Fw.gemv(enc_out, EH, L.cv, EH, D, RE, nullptr, cvl, D)) return 1;
+            if (Fw.rope(ckl, e_pos, RE, heads, head_dim, theta_scale)) return 1;
+            zero_key_tail_kernel<<<RE, 128, 0, st>>>(ckl, seq_len, C, D); B2_LAUNCH_CHECK(ctx);
+        }
+    }
+    // ---- decoder loop
+    float * x = Fw.al<float>((size_t) S2 * D), * xn = Fw.al<float>((size_t) S2 * D), * q = Fw.al<float>((size_t) S2 * D), * att = Fw.al<float>((size_t) S2 * D);
+    float * kbuf = Fw.al<float>((size_t) S2 * KVD), * vbuf = Fw.al<float>((size_t) S2 * KVD), * g = Fw.al<float>((size_t) S2 * ffn), * up = Fw.al<float>((size_t) S2 * ffn);
+    float * logits2 = Fw.al<float>((size_t) S2 * NV), * logits = Fw.al<float>((size_t) B * NV);
+    if (Fw.fail) return 1;
+    for (int s = 0; s < n_steps; s++) {
+        const int R = S2;
+        const int * last = s > 0 ? d_out + (size_t) (s - 1) * B * n_out : nullptr;
+        dia_step_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(last, B, n_out, s, bos, eos, pad, max_gen, max_delay, Tmax, delay, stopped, ids, row_pos, row_base, row_len, row_dst);
+        B2_LAUNCH_CHECK(ctx);
+        codebook_embed_kernel<<<R, 256, 0, st>>>(ids, n_out, tables, (size_t) vocab * D, nullptr, row_pos, D, x); B2_LAUNCH_CHECK(ctx);
+        for (int l = 0; l < dec_layers; l++) {
+            const DiaDecLayer & L = dec[(size_t) l];
+            float * Kl = Kc + (size_t) l * S2 * Tmax * KVD, * Vl = Vc + (size_t) l * S2 * Tmax * KVD;
+            const float * ckl = ck + (size_t) l * RE * D, * cvl = cv + (size_t) l * RE * D;
+            if (Fw.rms(x, L.pre_sa, D, R, xn)) return 1;
+            if (Fw.gemv(xn, D, L.sq, D, D, R, nullptr, q, D) || Fw.gemv(xn, D, L.sk, D, KVD, R, nullptr, kbuf, KVD) || Fw.gemv(xn, D, L.sv, D, KVD, R, nullptr, vbuf, KVD)) return 1;
+            if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale) || Fw.rope(kbuf, row_pos, R, heads / rep, head_dim, theta_scale)) return 1;
+            store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, KVD, Kl, Vl); B2_LAUNCH_CHECK(ctx);
+            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_base, row_len, heads, heads / rep, head_dim, Tcap, 1.0f, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(att, D, L.so, D, D, R, x, xn, D)) return 1;                          // xn = self-attention + residual(x)
+            if (Fw.rms(xn, L.pre_ca, D, R, x)) return 1;
+            if (Fw.gemv(x, D, L.cq, D, D, R, nullptr, q, D)) return 1;
+            if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale)) return 1;              // the cross query is RoPE'd with the decode position
+            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, ckl, cvl, cross_base, cross_len, heads, heads, head_dim, Tcap, 1.0f, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.gemv(att, D, L.co, D, D, R, xn, x, D)) return 1;                          // x = cross-attention + residual(xn)
+            if (Fw.rms(x, L.pre_mlp, D, R, xn)) return 1;
+            if (Fw.gemv(xn, D, L.gate, D, ffn, R, nullptr, g, ffn) || Fw.gemv(xn, D, L.up, D, ffn, R, nullptr, up, ffn)) return 1;
+            if (Fw.swiglu(g, up, (size_t) R * ffn)) return 1;
+            if (Fw.gemv(g, ffn, L.down, ffn, D, R, x, xn, D)) return 1;                      // xn = mlp + residual(x)
+            std::swap(x, xn);
+        }
+        if (Fw.rms(x, dec_norm, D, R, xn)) return 1;
+        if (Fw.gemv(xn, D, heads_w, D, NV, R, nullptr, logits2, NV)) return 1;
+        { dim3 grid(cdiv(NV, 256), B); cfg_combine_kernel<<<grid, 256, 0, st>>>(logits2, NV, cfg, logits); B2_LAUNCH_CHECK(ctx); }
+        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out + (size_t) s * B * n_out); B2_LAUNCH_CHECK(ctx);
+        if (out_logits)
+            for (int b = 0; b < B; b++)
+                B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+    }
+    B2_CUDA(cudaEventRecord(ev[1], st));
+    std::vector<int32_t> tmp((size_t) n_steps * B * n_out), hstop((size_t) B);
+    B2_CUDA(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(hstop.data(), stopped, hstop.size() * 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; b++) {
+        const int n_gen = hstop[(size_t) b] >= 0 ? hstop[(size_t) b] : n_steps;
+        if (n_generated) n_generated[b] = n_gen;
+        for (int s = 0; s < n_steps; s++) {
+            for (int i = 0; i < n_out; i++) out_tokens[((size_t) b * n_steps + s) * n_out + i] = s < n_gen ? tmp[((size_t) s * B + b) * n_out + i] : 0;
+            if (out_logits && s >= n_gen) memset(out_logits + ((size_t) b * n_steps + s) * NV, 0, (size_t) NV * 4);
+        }
+    }
+    cudaEventElapsedTime(&timing_ms, ev[0], ev[1]);
+    return 0;
+}
+
+}  // namespace b2

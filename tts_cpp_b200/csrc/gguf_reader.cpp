@@ -9,6 +9,7 @@
 #include "dac.h"
 #include "orpheus.h"
 #include "parler.h"
+#include "dia.h"
 
 #include <functional>
 
@@ -62,7 +63,7 @@ bool read_value(Cursor & c, uint32_t t, uint32_t * u32_out, std::string * str_ou
     }
     size_t sz = scalar_size(t);
     if (!sz) return false;
-    if (t == 4 && u32_out) { *u32_out = c.rd<uint32_t>(); return c.ok; }
+    if ((t == 4 || t == 6) && u32_out) { *u32_out = c.rd<uint32_t>(); return c.ok; }   // f32 values are captured as their bit pattern
     c.p += sz;
     if (c.p > c.end) c.ok = false;
     return c.ok;
@@ -98,8 +99,10 @@ int read_gguf(const char * path, const char * prefix, const char * arch_required
             std::string key = c.str();
             uint32_t t = c.rd<uint32_t>();
             uint32_t u = 0; bool is_u32 = (t == 4); std::string s;
+            const bool is_f32 = (t == 6);
             if (!read_value(c, t, &u, &s, nullptr)) { bad = true; break; }
             if (is_u32) { kv[key] = u; if (key == "general.alignment") alignment = u; }
+            if (is_f32) kv[key + "#f32"] = u;   // e.g. dia.cfg_scale: the bit pattern of the float under a suffixed key
             if (key == "general.architecture") arch = s;
         }
         if (bad || !c.ok) { set_error("%s: corrupt GGUF metadata", path); break; }
@@ -158,6 +161,12 @@ int load_gguf_into(Orpheus * m, const char * path) {
 // Parler's decoder tensors live under "decoder." (reference src/models/parler/model.cpp:3-28 assign_to_decoder); its DAC under "audio_encoder."
 int load_gguf_into(Parler * m, const char * path) {
     if (read_gguf(path, "decoder.", "parler-tts", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
+}
+
+// Dia's encoder + decoder tensors live under "dia." (reference src/models/dia/model.cpp:3-132); its DAC under "audio_encoder."
+int load_gguf_into(Dia * m, const char * path) {
+    if (read_gguf(path, "dia.", "dia", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
     return m->prepare();
 }
 
