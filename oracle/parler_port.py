@@ -27,9 +27,12 @@ class ParlerPort:
         torch.set_num_threads(threads)
         rd = gguf.GGUFReader(gguf_path)
         self.w = {}
+        self.f16 = set()          # F16 matrices: ggml_mul_mat rounds the activations to fp16 before the product (ggml-cpu.c: vec_dot_type of F16 is F16)
         for t in rd.tensors:
             if t.name.startswith("decoder."):
                 self.w[t.name[len("decoder."):]] = torch.from_numpy(np.array(t.data).astype(np.float32))
+                if t.tensor_type.name == "F16":
+                    self.f16.add(t.name[len("decoder."):])
         self.kv = {}
         for k, f in rd.fields.items():
             if len(f.data) == 1 and f.types and f.types[0].name in ("UINT32",):
@@ -40,9 +43,15 @@ class ParlerPort:
         self.n_out = self.kv[f"{a}.output_heads"]; self.vocab = self.kv[f"{a}.out_vocab_size"]
         self.bos = self.kv["audio.bos_token_id"]; self.eos = self.kv["audio.eos_token_id"]
         enc = self.w["text_encoding"]
-        self.ck = [enc @ self.w[f"layers.{l}.encoder_attn.k_proj.weight"].t() for l in range(self.layers)]
-        self.cv = [enc @ self.w[f"layers.{l}.encoder_attn.v_proj.weight"].t() for l in range(self.layers)]
+        self.ck = [self.mm(enc, f"layers.{l}.encoder_attn.k_proj.weight") for l in range(self.layers)]
+        self.cv = [self.mm(enc, f"layers.{l}.encoder_attn.v_proj.weight") for l in range(self.layers)]
         self.reset()
+
+    def mm(self, x, name):
+        """ggml_mul_mat(weight, x): exact products of fp16-rounded activations with F16 weights, fp32 accumulation; plain fp32 for F32 weights."""
+        if name in self.f16:
+            x = x.half().float()
+        return x @ self.w[name].t()
 
     def reset(self):
         self.k = [None] * self.layers; self.v = [None] * self.layers
@@ -65,27 +74,27 @@ class ParlerPort:
             b = f"layers.{l}"
             res = x
             cur = self.ln(x, b + ".self_attn_layer_norm")
-            q = cur @ self.w[b + ".self_attn.q_proj.weight"].t()
-            k = cur @ self.w[b + ".self_attn.k_proj.weight"].t()
-            v = cur @ self.w[b + ".self_attn.v_proj.weight"].t()
+            q = self.mm(cur, b + ".self_attn.q_proj.weight")
+            k = self.mm(cur, b + ".self_attn.k_proj.weight")
+            v = self.mm(cur, b + ".self_attn.v_proj.weight")
             self.k[l] = k if self.k[l] is None else torch.cat([self.k[l], k], 0)
             self.v[l] = v if self.v[l] is None else torch.cat([self.v[l], v], 0)
             T = self.k[l].shape[0]
             mask = torch.zeros(n, T)
             for i in range(n):
                 mask[i, self.pos + i + 1:] = float("-inf")
-            x = self.attend(q, self.k[l], self.v[l], mask) @ self.w[b + ".self_attn.out_proj.weight"].t() + res
+            x = self.mm(self.attend(q, self.k[l], self.v[l], mask), b + ".self_attn.out_proj.weight") + res
             res = x
             cur = self.ln(x, b + ".encoder_attn_layer_norm")
-            q = cur @ self.w[b + ".encoder_attn.q_proj.weight"].t()
-            x = self.attend(q, self.ck[l], self.cv[l], torch.zeros(n, self.ck[l].shape[0])) @ self.w[b + ".encoder_attn.out_proj.weight"].t() + res
+            q = self.mm(cur, b + ".encoder_attn.q_proj.weight")
+            x = self.mm(self.attend(q, self.ck[l], self.cv[l], torch.zeros(n, self.ck[l].shape[0])), b + ".encoder_attn.out_proj.weight") + res
             res = x
             cur = self.ln(x, b + ".final_layer_norm")
-            cur = gelu_f16_lut(cur @ self.w[b + ".fc1.weight"].t())
-            x = cur @ self.w[b + ".fc2.weight"].t() + res
+            cur = gelu_f16_lut(self.mm(cur, b + ".fc1.weight"))
+            x = self.mm(cur, b + ".fc2.weight") + res
         x = self.ln(x, "layer_norm")
         self.pos += n
-        return torch.stack([x @ self.w[f"lm_heads.{i}.weight.head"].t() for i in range(self.n_out)])
+        return torch.stack([self.mm(x, f"lm_heads.{i}.weight.head") for i in range(self.n_out)])
 
     def greedy(self, prompt, steps: int):
         """Returns (tokens [steps, n_out], logits [steps, n_out, vocab]) like oracle/_ref/parler_ref."""

@@ -16,6 +16,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       from oracle/ref_orpheus_driver.cpp
   parler_vectors.npz       : two prompts (5 and 9 ids) and, for 5 greedy audio steps each, the 9 codebook tokens per step and their logits
       from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
+  parler_f16_vectors.npz   : as parler_vectors.npz for the GGUF `quantize --quantized-type F16` would write (decoder matrices and codebook tables F16: the
+      reference then rounds the activations to fp16 before every such product)
   dia_stop_vectors.npz     : one byte-token prompt run until the reference's check_stopping ends the loop (64 frames of 9 tokens, the logits of the
       last frame), from oracle/ref_dia_driver.cpp with a step cap of 80
   dia_vectors.npz          : two byte-token prompts (10 and 18 tokens, the second after the first in the same process) and, for 5 greedy steps
@@ -172,9 +174,9 @@ def orpheus_vectors():
     print("orpheus vectors:", {k: v.shape for k, v in out.items()})
 
 
-def parler_vectors():
+def parler_vectors(f16: bool = False):
     from tts_cpp_b200.synth import cached_parler_gguf
-    gguf = cached_parler_gguf(seed=0)
+    gguf = cached_parler_gguf(seed=0, f16=f16)
     rng = np.random.default_rng(7)
     prompts = [rng.integers(1, 500, size=n) for n in (5, 9)]
     tmp = tempfile.mkdtemp()
@@ -188,8 +190,8 @@ def parler_vectors():
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
-    np.savez_compressed(os.path.join(OUT, "parler_vectors.npz"), **out)
-    print("parler vectors:", {k: v.shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(OUT, "parler_f16_vectors.npz" if f16 else "parler_vectors.npz"), **out)
+    print("parler f16 vectors:" if f16 else "parler vectors:", {k: v.shape for k, v in out.items()})
 
 
 def dia_vectors():
@@ -231,8 +233,9 @@ def dia_stop_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "dia", "dia_stop"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "dia", "dia_stop"]
     if "dia_stop" in which: dia_stop_vectors()
+    if "parler_f16" in which: parler_vectors(f16=True)
     if "dia" in which: dia_vectors()
     if "parler" in which: parler_vectors()
     if "orpheus" in which: orpheus_vectors()

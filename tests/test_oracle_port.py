@@ -156,19 +156,21 @@ def test_orpheus_port_against_reference_decode_loop():
         assert d < 1e-4
 
 
-def test_parler_port_against_reference_decode_loop():
+@pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])
+def test_parler_port_against_reference_decode_loop(f16):
     """oracle/parler_port.py vs the reference's Parler decode loop (cross-attention, delay pattern, 9-head greedy sampler): identical
-    codebook tokens; logits to the resolution ggml's fp16 GELU table leaves (a last-bit change before the table moves a logit by ~1e-3)."""
+    codebook tokens; logits to the resolution ggml's fp16 GELU table leaves (a last-bit change before the table moves a logit by ~1e-3).
+    f16: the F16 GGUF of the quantize tool -- activations rounded to fp16 before every F16 product; the rounding boundaries raise the floor to ~7e-3."""
     from oracle.parler_port import ParlerPort
     from tts_cpp_b200.synth import cached_parler_gguf
-    g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
-    port = ParlerPort(cached_parler_gguf(seed=0))
+    g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz" if f16 else "parler_vectors.npz"))
+    port = ParlerPort(cached_parler_gguf(seed=0, f16=f16))
     for u in range(2):
         toks, logits = port.greedy(g[f"prompt{u}"], g[f"tokens{u}"].shape[0])
         d = float(np.abs(logits - g[f"logits{u}"]).max())
         print(f"parler prompt {u}: max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
         assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact codebook indices at temperature 0
-        assert d < 1e-2
+        assert d < (3e-2 if f16 else 1e-2)
 
 
 def test_dia_port_against_reference_decode_loop():

@@ -19,8 +19,9 @@ import numpy as np
 sys.path.insert(0, sys.argv[1])
 from tts_cpp_b200.binding import parler_runner_from_file
 from tts_cpp_b200.synth import cached_parler_gguf
-g = np.load(os.path.join(sys.argv[1], "tests", "golden", "parler_vectors.npz"))
-par = parler_runner_from_file(cached_parler_gguf(seed=0))
+f16 = sys.argv[2] == "f16"
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "parler_f16_vectors.npz" if f16 else "parler_vectors.npz"))
+par = parler_runner_from_file(cached_parler_gguf(seed=0, f16=f16))
 prompts = [g["prompt0"], g["prompt1"]]
 steps = g["tokens0"].shape[0]
 toks, logits = par.generate_greedy(prompts, steps, want_logits=True)           # one ragged batch of both prompts
@@ -28,15 +29,19 @@ ok = True
 for u in range(2):
     d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
     print(f"PARITY parler prompt {u}: tokens {toks[u].tolist()}  max |logit diff| {d:.3e}")
-    ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < 1e-2            # bit-exact ids at temperature 0; logits: ggml's fp16 GELU table
+    ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < (3e-2 if f16 else 1e-2)   # bit-exact ids at temperature 0; logits: ggml's fp16 GELU table (+ fp16 activation rounding for F16 weights)
 single = par.generate_greedy([prompts[1]], steps)
 ok &= bool(np.array_equal(single[0], toks[1]))                                   # batching does not change a sequence
 sys.exit(0 if ok else 1)
 '''
 
 
-def test_parler_greedy_tokens_and_logits_match_reference():
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=240)
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_parler_greedy_tokens_and_logits_match_reference(dtype):
+    """f16: the GGUF `quantize --quantized-type F16` writes (decoder matrices F16, activations rounded to fp16 before each such product).  Two runs
+    of that model that differ only in summation order already differ by 1.5e-3 RMS / 6e-3 max in the logits (rounding boundaries), so the bar there
+    is identical token ids + 3e-2."""
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=240)
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0

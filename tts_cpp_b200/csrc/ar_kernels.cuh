@@ -70,6 +70,39 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict
     }
 }
 
+// the same product for an F16 weight matrix: ggml_mul_mat converts the activation rows to fp16 first (the vec_dot_type of F16 is F16, ggml-cpu.c
+// mul_mat from_float) and accumulates the exact fp16 x fp16 products in fp32 -- also what halves the bytes streamed per step
+__global__ void __launch_bounds__(256) gemv_rows_h_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, int K, int N, int R,
+                                                          const float * __restrict__ res, float * __restrict__ Y, int ldy) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const __half * wrow = W + (size_t) n * K;
+    for (int r0 = 0; r0 < R; r0 += GR) {
+        float acc[GR];
+#pragma unroll
+        for (int j = 0; j < GR; j++) acc[j] = 0.f;
+        for (int k = lane * 4; k < K; k += 128) {
+            const __half2 * wp = reinterpret_cast<const __half2 *>(wrow + k);
+            const float2 w01 = __half22float2(wp[0]), w23 = __half22float2(wp[1]);
+#pragma unroll
+            for (int j = 0; j < GR; j++) {
+                if (r0 + j < R) {
+                    const float4 x4 = *reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + k);
+                    const float x0 = __half2float(__float2half_rn(x4.x)), x1 = __half2float(__float2half_rn(x4.y));
+                    const float x2 = __half2float(__float2half_rn(x4.z)), x3 = __half2float(__float2half_rn(x4.w));
+                    acc[j] = fmaf(x3, w23.y, fmaf(x2, w23.x, fmaf(x1, w01.y, fmaf(x0, w01.x, acc[j]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GR; j++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? acc[j] + res[(size_t) (r0 + j) * ldy + n] : acc[j];
+        }
+    }
+}
+
 // NeoX RoPE over the whole head with per-pair frequency factors (ggml_rope_ext mode 2, theta base 5e5, ggml-cpu rope cache: theta starts at
 // the position and is multiplied by theta_scale pair after pair), applied to q in place and to k on its way into the cache; v is copied
 // (orpheus_build_kv_store, model.cpp:196-228 -- here the cache is compact: the 3x head expansion is done by indexing in the attention)

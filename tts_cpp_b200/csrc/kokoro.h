@@ -18,6 +18,11 @@ struct W16 {                    // fp16 GEMM weight [Npad][KW][CinPad]
     int N = 0, Npad = 0, KW = 1, Cin = 0, CinPad = 0;
 };
 
+struct ArW {                    // a weight matrix [N][K] of the autoregressive decode paths: fp32, or fp16 when the GGUF stores it as F16
+    const void * p = nullptr;
+    bool f16 = false;
+};
+
 struct Lstm {
     W16      wih;               // N = 2048 rows ordered (dir, unit, gate)
     float *  bih = nullptr;     // [2048] same order

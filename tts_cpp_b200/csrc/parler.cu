@@ -38,8 +38,9 @@ namespace {
 struct PFwd {
     Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
-    int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
+    int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (W.f16) gemv_rows_h_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, (const __half *) W.p, K, N, R, res, Y, ldy);
+        else       gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, (const float *) W.p, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -76,6 +77,19 @@ int Parler::prepare() {
         return (float *) d;
     };
     auto up = [&](const std::string & n, int64_t expect) -> float * { const HostTensor * t = find(n, expect); return t ? dev(t->v.data(), t->v.size()) : nullptr; };
+    auto dev_mat = [&](const float * src, size_t n, bool f16) -> ArW {      // F16 tensors go to HBM as fp16 (their fp32 host copies are exact widenings)
+        ArW w; w.f16 = f16;
+        if (!f16) { w.p = dev(src, n); return w; }
+        std::vector<__half> h(n);
+        for (size_t i = 0; i < n; i++) h[i] = __float2half_rn(src[i]);
+        void * d = nullptr;
+        if (cudaMalloc(&d, n * 2) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", n * 2); ok = false; return w; }
+        cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += n * 2;
+        w.p = d;
+        return w;
+    };
+    auto upw = [&](const std::string & n, int64_t expect) -> ArW { const HostTensor * t = find(n, expect); return t ? dev_mat(t->v.data(), t->v.size(), t->f16) : ArW(); };
 
     embed_prompts = up("embed_prompts", 0);
     { const HostTensor * t = find("embed_prompts", 0); if (t) prompt_vocab = (int) (t->v.size() / (size_t) hidden); }
@@ -84,6 +98,7 @@ int Parler::prepare() {
     ln_w = up("layer_norm.weight", hidden); ln_b = up("layer_norm.bias", hidden);
     {   // the n_out codebook tables and output heads, each family in one buffer
         std::vector<float> tab, hw;
+        bool heads_f16 = true, heads_any_f16 = false;
         for (int i = 0; i < n_out && ok; i++) {
             const HostTensor * t = find("embed_tokens." + std::to_string(i) + ".weight", 0);
             const HostTensor * h = find("lm_heads." + std::to_string(i) + ".weight.head", (int64_t) vocab * hidden);
@@ -93,8 +108,10 @@ int Parler::prepare() {
             if (rows != tab_rows || t->v.size() % (size_t) hidden) { set_error("parler: codebook table %d has %d rows, table 0 has %d", i, rows, tab_rows); ok = false; break; }
             tab.insert(tab.end(), t->v.begin(), t->v.end());
             hw.insert(hw.end(), h->v.begin(), h->v.end());
+            heads_f16 = heads_f16 && h->f16; heads_any_f16 = heads_any_f16 || h->f16;
         }
-        if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev(hw.data(), hw.size()); }
+        if (ok && heads_any_f16 != heads_f16) { set_error("parler: the output heads mix F16 and F32 tensors"); ok = false; }
+        if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev_mat(hw.data(), hw.size(), heads_f16); }   // tables: ggml_get_rows widens F16 rows to fp32 exactly
     }
     {
         const HostTensor * t = find("layers.0.fc1.weight", 0);
@@ -109,13 +126,13 @@ int Parler::prepare() {
         ParlerLayer & L = layers[(size_t) l];
         const int64_t HH = (int64_t) hidden * hidden;
         L.ln1_w = up(b + ".self_attn_layer_norm.weight", hidden);    L.ln1_b = up(b + ".self_attn_layer_norm.bias", hidden);
-        L.wq = up(b + ".self_attn.q_proj.weight", HH); L.wk = up(b + ".self_attn.k_proj.weight", HH); L.wv = up(b + ".self_attn.v_proj.weight", HH); L.wo = up(b + ".self_attn.out_proj.weight", HH);
+        L.wq = upw(b + ".self_attn.q_proj.weight", HH); L.wk = upw(b + ".self_attn.k_proj.weight", HH); L.wv = upw(b + ".self_attn.v_proj.weight", HH); L.wo = upw(b + ".self_attn.out_proj.weight", HH);
         L.ln2_w = up(b + ".encoder_attn_layer_norm.weight", hidden); L.ln2_b = up(b + ".encoder_attn_layer_norm.bias", hidden);
-        L.cq = up(b + ".encoder_attn.q_proj.weight", HH); L.co = up(b + ".encoder_attn.out_proj.weight", HH);
+        L.cq = upw(b + ".encoder_attn.q_proj.weight", HH); L.co = upw(b + ".encoder_attn.out_proj.weight", HH);
         L.ln3_w = up(b + ".final_layer_norm.weight", hidden);        L.ln3_b = up(b + ".final_layer_norm.bias", hidden);
-        L.fc1 = up(b + ".fc1.weight", (int64_t) ffn * hidden);       L.fc2 = up(b + ".fc2.weight", (int64_t) hidden * ffn);
+        L.fc1 = upw(b + ".fc1.weight", (int64_t) ffn * hidden);      L.fc2 = upw(b + ".fc2.weight", (int64_t) hidden * ffn);
         // prep_cross_key_values (model.cpp:110-173): K and V of the stored text encoding, once per model
-        float * wck = up(b + ".encoder_attn.k_proj.weight", HH), * wcv = up(b + ".encoder_attn.v_proj.weight", HH);
+        const ArW wck = upw(b + ".encoder_attn.k_proj.weight", HH), wcv = upw(b + ".encoder_attn.v_proj.weight", HH);
         L.cross_k = dev(nullptr, (size_t) n_enc * hidden); L.cross_v = dev(nullptr, (size_t) n_enc * hidden);
         if (!ok) break;
         if (Fw.gemv(d_enc, hidden, wck, hidden, hidden, n_enc, nullptr, L.cross_k, hidden)) return 1;

@@ -3,17 +3,17 @@
 // Replaces parler_tts_runner::build_parler_graph / decode / set_inputs / parler_build_kv_store / prep_cross_key_values and the token loop of
 // generate_from_batch with its delay pattern (reference src/models/parler/model.cpp:110-173,387-470,520-614,762-786) under sampler::max
 // (src/sampler.cpp), for a batch of independent prompts that share the model's stored conditional-prompt encoding.
-// Same plain design as orpheus.h (fp32 CUDA-core kernels from ar_kernels.cuh, one launch per op); logic checked under tests/emu, not yet run
-// on a GPU.
+// Same plain design as orpheus.h (CUDA-core kernels from ar_kernels.cuh, one launch per op); F32 and F16 matrices (the GGUFs `quantize
+// --quantized-type F16` writes) with the reference's numerics for each.  Logic checked under tests/emu, not yet run on a GPU.
 #pragma once
 #include "kokoro.h"   // HostTensor, Arena
 
 namespace b2 {
 
 struct ParlerLayer {
-    float * ln1_w = nullptr, * ln1_b = nullptr, * wq = nullptr, * wk = nullptr, * wv = nullptr, * wo = nullptr;
-    float * ln2_w = nullptr, * ln2_b = nullptr, * cq = nullptr, * co = nullptr, * cross_k = nullptr, * cross_v = nullptr;   // cross_k / cross_v [n_enc][hidden]
-    float * ln3_w = nullptr, * ln3_b = nullptr, * fc1 = nullptr, * fc2 = nullptr;
+    float * ln1_w = nullptr, * ln1_b = nullptr; ArW wq, wk, wv, wo;
+    float * ln2_w = nullptr, * ln2_b = nullptr; ArW cq, co; float * cross_k = nullptr, * cross_v = nullptr;   // cross_k / cross_v [n_enc][hidden]
+    float * ln3_w = nullptr, * ln3_b = nullptr; ArW fc1, fc2;
 };
 
 struct Parler {
@@ -26,7 +26,8 @@ struct Parler {
 
     int n_layers = 0, heads = 0, head_dim = 0, hidden = 0, ffn = 0, n_out = 0, vocab = 0, n_enc = 0, max_ctx = 0, tab_rows = 0, prompt_vocab = 0;
     int bos = 1025, eos = 1024;
-    float * embed_prompts = nullptr, * pos_embed = nullptr, * tables = nullptr /* [n_out][tab_rows][hidden] */, * heads_w = nullptr /* [n_out * vocab][hidden] */;
+    float * embed_prompts = nullptr, * pos_embed = nullptr, * tables = nullptr /* [n_out][tab_rows][hidden] */;
+    ArW heads_w;   // [n_out * vocab][hidden]
     float * ln_w = nullptr, * ln_b = nullptr;
     std::vector<ParlerLayer> layers;
 

@@ -545,7 +545,17 @@ def parler_tensors(seed: int = 0, layers: int = 8, heads: int = 32, head_dim: in
     return items
 
 
-def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12) -> dict:
+def parler_f16_tensor(name: str) -> bool:
+    """Which tensors `quantize --quantized-type F16` turns into F16 with its default flags (reference examples/quantize/quantize_impl.cpp:51-67:
+    parler_is_quanitizable): every decoder matrix and the codebook tables; norms, positional_embed, text_encoding, embed_prompts, the output heads
+    and the cross-attention k / v projections stay F32, and so does the DAC."""
+    if name.startswith("audio_encoder") or name.endswith(("norm.weight", "norm.bias", "text_encoding", "positional_embed", "weight.head", "embed_prompts",
+                                                           "encoder_attn.k_proj.weight", "encoder_attn.v_proj.weight")):
+        return False
+    return True
+
+
+def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12, f16: bool = False) -> dict:
     """Small synthetic Parler-TTS GGUF (F32) with a matching small DAC decoder (the reference's loader needs both).  32 heads x 8 layers is
     the smallest shape the reference loads: prep_cross_key_values sizes its metadata pool from n_attn_heads * 2 * n_layers tensors but
     allocates a 4096-node graph in it (src/models/parler/model.cpp:117-129)."""
@@ -558,7 +568,7 @@ def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32
     n_params = 0
     for name, arr in items:
         n_params += arr.size
-        w.add_tensor(name, arr.astype(np.float32))
+        w.add_tensor(name, arr.astype(np.float16 if f16 and parler_f16_tensor(name) else np.float32))
     a = "parler-tts.decoder"
     for k, v in ((f"{a}.encode_length", n_enc), (f"{a}.hidden_size", heads * head_dim), (f"{a}.output_heads", 9), (f"{a}.context_length", 4096),
                  (f"{a}.attention.head_count", heads), (f"{a}.max_generation", 64), (f"{a}.out_vocab_size", 1088), (f"{a}.audio_vocab_size", 1024),
@@ -574,13 +584,13 @@ def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32
     return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
 
 
-def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None) -> str:
+def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False) -> str:
     cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, f"parler_f32_s{seed}.gguf")
+    path = os.path.join(cache_dir, f"parler_{'f16' if f16 else 'f32'}_s{seed}.gguf")
     if not os.path.exists(path):
         tmp = f"{path}.{os.getpid()}.tmp"
-        write_parler_gguf(tmp, seed=seed)
+        write_parler_gguf(tmp, seed=seed, f16=f16)
         os.replace(tmp, path)
     return path
 
