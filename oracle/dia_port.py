@@ -30,9 +30,12 @@ class DiaPort:
         torch.set_num_threads(threads)
         rd = gguf.GGUFReader(gguf_path)
         self.w = {}
+        self.f16 = set()          # F16 matrices: ggml_mul_mat rounds the activations to fp16 before the product
         for t in rd.tensors:
             if t.name.startswith("dia."):
                 self.w[t.name[len("dia."):]] = torch.from_numpy(np.array(t.data).astype(np.float32))
+                if t.tensor_type.name == "F16":
+                    self.f16.add(t.name[len("dia."):])
         self.kv = {}
         for k, f in rd.fields.items():
             if len(f.data) == 1 and f.types and f.types[0].name in ("UINT32",):
@@ -43,6 +46,12 @@ class DiaPort:
         self.hd = g["dia.attn_head_size"]; self.C = g["dia.encoder.max_context_length"]; self.n_out = g["dia.decoder.output_heads"]
         self.vocab = g["dia.decoder.output_vocab_size"]; self.bos = g["dia.bos_token_id"]; self.eos = g["dia.eos_token_id"]; self.pad = g["dia.pad_token_id"]
         self.max_gen = g["dia.decoder.max_generation_size"]
+
+    def mm(self, x, name):
+        """ggml_mul_mat(weight, x): exact products of fp16-rounded activations with F16 weights, fp32 accumulation; plain fp32 for F32 weights."""
+        if name in self.f16:
+            x = x.half().float()
+        return x @ self.w[name].t()
 
     @staticmethod
     def rms(x, w):
@@ -80,26 +89,26 @@ class DiaPort:
             b = f"encoder.layers.{l}"
             res = x
             cur = self.rms(x, self.w[b + ".pre_sa_norm"])
-            q = self.rope((cur @ self.w[b + ".q_proj"].t()).reshape(2, C, H, hd), pos)
-            k = self.rope((cur @ self.w[b + ".k_proj"].t()).reshape(2, C, H, hd), pos)
-            v = (cur @ self.w[b + ".v_proj"].t()).reshape(2, C, H, hd)
+            q = self.rope((self.mm(cur, b + ".q_proj")).reshape(2, C, H, hd), pos)
+            k = self.rope((self.mm(cur, b + ".k_proj")).reshape(2, C, H, hd), pos)
+            v = (self.mm(cur, b + ".v_proj")).reshape(2, C, H, hd)
             p = self.softmax(torch.einsum("bnhd,bthd->bhnt", q, k) + mask[None, None])
             o = torch.einsum("bhnt,bthd->bnhd", p, v).reshape(2, C, H * hd)
-            x = o @ self.w[b + ".o_proj"].t() + res
+            x = self.mm(o, b + ".o_proj") + res
             res = x
             cur = self.rms(x, self.w[b + ".post_sa_norm"])
-            gte = cur @ self.w[b + ".gate"].t()
-            cur = (gte / (1.0 + torch.exp(-gte))) * (cur @ self.w[b + ".up"].t())
-            x = cur @ self.w[b + ".wo"].t() + res
+            gte = self.mm(cur, b + ".gate")
+            cur = (gte / (1.0 + torch.exp(-gte))) * (self.mm(cur, b + ".up"))
+            x = self.mm(cur, b + ".wo") + res
         enc = self.rms(x, self.w["encoder.norm"])
         self.ck, self.cv = [], []
         H = self.heads
         for l in range(self.dec_layers):
             b = f"decoder.layers.{l}"
             k = torch.zeros(2, C, H, hd)
-            k[:, :S] = self.rope((enc[:, :S] @ self.w[b + ".cross_k_proj"].t()).reshape(2, S, H, hd), list(range(S)))
+            k[:, :S] = self.rope((self.mm(enc[:, :S], b + ".cross_k_proj")).reshape(2, S, H, hd), list(range(S)))
             self.ck.append(k)
-            self.cv.append((enc @ self.w[b + ".cross_v_proj"].t()).reshape(2, C, H, hd))
+            self.cv.append((self.mm(enc, b + ".cross_v_proj")).reshape(2, C, H, hd))
         self.k = [None] * self.dec_layers; self.v = [None] * self.dec_layers
         self.pos = 0
 
@@ -115,27 +124,27 @@ class DiaPort:
             b = f"decoder.layers.{l}"
             res = x
             cur = self.rms(x, self.w[b + ".pre_sa_norm"])
-            q = self.rope((cur @ self.w[b + ".self_q_proj"].t()).reshape(2, 1, H, hd), [self.pos])
-            k = self.rope((cur @ self.w[b + ".self_k_proj"].t()).reshape(2, 1, H // rep, hd), [self.pos]).repeat_interleave(rep, dim=2)
-            v = (cur @ self.w[b + ".self_v_proj"].t()).reshape(2, 1, H // rep, hd).repeat_interleave(rep, dim=2)
+            q = self.rope((self.mm(cur, b + ".self_q_proj")).reshape(2, 1, H, hd), [self.pos])
+            k = self.rope((self.mm(cur, b + ".self_k_proj")).reshape(2, 1, H // rep, hd), [self.pos]).repeat_interleave(rep, dim=2)
+            v = (self.mm(cur, b + ".self_v_proj")).reshape(2, 1, H // rep, hd).repeat_interleave(rep, dim=2)
             self.k[l] = k if self.k[l] is None else torch.cat([self.k[l], k], 1)
             self.v[l] = v if self.v[l] is None else torch.cat([self.v[l], v], 1)
             p = self.softmax(torch.einsum("bnhd,bthd->bhnt", q, self.k[l]))
             o = torch.einsum("bhnt,bthd->bnhd", p, self.v[l]).reshape(2, H * hd)
-            x = o @ self.w[b + ".self_o_proj"].t() + res
+            x = self.mm(o, b + ".self_o_proj") + res
             res = x
             cur = self.rms(x, self.w[b + ".pre_ca_norm"])
-            q = self.rope((cur @ self.w[b + ".cross_q_proj"].t()).reshape(2, 1, H, hd), [self.pos])
+            q = self.rope((self.mm(cur, b + ".cross_q_proj")).reshape(2, 1, H, hd), [self.pos])
             p = self.softmax(torch.einsum("bnhd,bthd->bhnt", q, self.ck[l]))
             o = torch.einsum("bhnt,bthd->bnhd", p, self.cv[l]).reshape(2, H * hd)
-            x = o @ self.w[b + ".cross_o_proj"].t() + res
+            x = self.mm(o, b + ".cross_o_proj") + res
             res = x
             cur = self.rms(x, self.w[b + ".pre_mlp_norm"])
-            gte = cur @ self.w[b + ".gate"].t()
-            cur = (gte / (1.0 + torch.exp(-gte))) * (cur @ self.w[b + ".up"].t())
-            x = cur @ self.w[b + ".wo"].t() + res
+            gte = self.mm(cur, b + ".gate")
+            cur = (gte / (1.0 + torch.exp(-gte))) * (self.mm(cur, b + ".up"))
+            x = self.mm(cur, b + ".wo") + res
         x = self.rms(x, self.w["decoder.norm"])
-        lg = torch.stack([x @ self.w[f"decoder.heads.{i}"].t() for i in range(self.n_out)])    # [n_out, 2, vocab]
+        lg = torch.stack([self.mm(x, f"decoder.heads.{i}") for i in range(self.n_out)])    # [n_out, 2, vocab]
         cond, uncond = lg[:, 0], lg[:, 1]
         self.pos += 1
         return (cond + 3.0 * (cond - uncond)).numpy()

@@ -18,6 +18,7 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
   parler_f16_vectors.npz   : as parler_vectors.npz for the GGUF `quantize --quantized-type F16` would write (decoder matrices and codebook tables F16: the
       reference then rounds the activations to fp16 before every such product)
+  dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
   dia_stop_vectors.npz     : one byte-token prompt run until the reference's check_stopping ends the loop (64 frames of 9 tokens, the logits of the
       last frame), from oracle/ref_dia_driver.cpp with a step cap of 80
   dia_vectors.npz          : two byte-token prompts (10 and 18 tokens, the second after the first in the same process) and, for 5 greedy steps
@@ -194,9 +195,9 @@ def parler_vectors(f16: bool = False):
     print("parler f16 vectors:" if f16 else "parler vectors:", {k: v.shape for k, v in out.items()})
 
 
-def dia_vectors():
+def dia_vectors(f16: bool = False):
     from tts_cpp_b200.synth import cached_dia_gguf
-    gguf = cached_dia_gguf(seed=0)
+    gguf = cached_dia_gguf(seed=0, f16=f16)
     rng = np.random.default_rng(11)
     prompts = [np.concatenate([[1], rng.integers(32, 127, size=n)]) for n in (9, 17)]      # [S1] + printable bytes
     tmp = tempfile.mkdtemp()
@@ -210,8 +211,8 @@ def dia_vectors():
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
-    np.savez_compressed(os.path.join(OUT, "dia_vectors.npz"), **out)
-    print("dia vectors:", {k: v.shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(OUT, "dia_f16_vectors.npz" if f16 else "dia_vectors.npz"), **out)
+    print("dia f16 vectors:" if f16 else "dia vectors:", {k: v.shape for k, v in out.items()})
 
 
 def dia_stop_vectors():
@@ -233,9 +234,10 @@ def dia_stop_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "dia", "dia_stop"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "dia", "dia_f16", "dia_stop"]
     if "dia_stop" in which: dia_stop_vectors()
     if "parler_f16" in which: parler_vectors(f16=True)
+    if "dia_f16" in which: dia_vectors(f16=True)
     if "dia" in which: dia_vectors()
     if "parler" in which: parler_vectors()
     if "orpheus" in which: orpheus_vectors()

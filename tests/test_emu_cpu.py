@@ -83,19 +83,25 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path,
         assert d < (3e-2 if f16 else 1e-2)
 
 
-def test_dia_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path):
+@pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])
+def test_dia_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path, f16):
     """Dia::generate_greedy (dia.cu: two-sequence encoder pass with its block mask, RoPE'd cross keys for the prompt positions only, GQA decoder
-    self-attention, cross-attention, cfg_scale, nine heads + per-head argmax) under emulation against tests/golden/dia_vectors.npz."""
-    g = np.load(os.path.join(GOLD, "dia_vectors.npz"))
+    self-attention, cross-attention, cfg_scale, nine heads + per-head argmax) under emulation against tests/golden/dia[_f16]_vectors.npz.
+    f16: the quantize tool's F16 GGUF (every matrix but the output heads F16, activations rounded to fp16 before each such product)."""
+    g = np.load(os.path.join(GOLD, "dia_f16_vectors.npz" if f16 else "dia_vectors.npz"))
     prompts = [g["prompt0"], g["prompt1"]]
     steps = int(g["tokens0"].shape[0])
-    tok, logits = _run_ar(tmp_path, "dia", cached_dia_gguf(seed=0), prompts, steps, "b")
+    tok, logits = _run_ar(tmp_path, "dia", cached_dia_gguf(seed=0, f16=f16), prompts, steps, "b")
     for u in range(2):
         ref = g[f"logits{u}"].reshape(steps, -1)
         d = float(np.abs(logits[u] - ref).max())
-        print(f"PARITY(emulated) dia prompt {u}: tokens {tok[u].tolist()}  max |logit diff| {d:.3e}  (logit std {ref.std():.2f})")
+        rms = float(np.sqrt(((logits[u] - ref) ** 2).mean()))
+        print(f"PARITY(emulated) dia {'f16' if f16 else 'f32'} prompt {u}: tokens {tok[u].tolist()}  logit diff max {d:.3e} rms {rms:.3e}  (logit std {ref.std():.2f})")
         assert np.array_equal(tok[u], g[f"tokens{u}"])
-        assert d < 2e-2      # CFG multiplies the fp32 summation-order noise of both passes by 4 at a logit std of ~13
+        # F32: CFG multiplies the fp32 summation-order noise of both passes by 4 at a logit std of ~13.
+        # F16: rounding-boundary flips in every product, a softmax without 1/sqrt(d) and the 4x CFG gain: the reference's own F16 and F32 logits differ by
+        # 0.03-0.19 RMS; the restated rounding model stays within 0.05 RMS of the F16 reference (and reproduces its tokens, which differ from the F32 ones)
+        assert (rms < 0.1 and d < 1.0) if f16 else d < 2e-2
 
 
 def test_dia_cuda_path_emulated_check_stopping(tmp_path):

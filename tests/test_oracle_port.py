@@ -173,19 +173,23 @@ def test_parler_port_against_reference_decode_loop(f16):
         assert d < (3e-2 if f16 else 1e-2)
 
 
-def test_dia_port_against_reference_decode_loop():
+@pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])
+def test_dia_port_against_reference_decode_loop(f16):
     """oracle/dia_port.py vs the reference's Dia encoder pass + CFG-paired decode loop: identical codebook tokens; logits (std ~13: no
     1/sqrt(d) in Dia's softmax and a 4x CFG amplification) to 3e-4 relative."""
     from oracle.dia_port import DiaPort
     from tts_cpp_b200.synth import cached_dia_gguf
-    g = np.load(os.path.join(GOLD, "dia_vectors.npz"))
-    port = DiaPort(cached_dia_gguf(seed=0))
+    g = np.load(os.path.join(GOLD, "dia_f16_vectors.npz" if f16 else "dia_vectors.npz"))
+    port = DiaPort(cached_dia_gguf(seed=0, f16=f16))
     for u in range(2):
         toks, logits = port.greedy(g[f"prompt{u}"], g[f"tokens{u}"].shape[0])
         d = float(np.abs(logits - g[f"logits{u}"]).max())
-        print(f"dia prompt {u}: max |logit diff| {d:.3e} (logit std {g[f'logits{u}'].std():.2f})")
+        rms = float(np.sqrt(((logits - g[f"logits{u}"]) ** 2).mean()))
+        print(f"dia {'f16' if f16 else 'f32'} prompt {u}: logit diff max {d:.3e} rms {rms:.3e} (logit std {g[f'logits{u}'].std():.2f})")
         assert np.array_equal(toks, g[f"tokens{u}"])          # bit-exact codebook indices at temperature 0
-        assert d < 2e-2
+        # f16 (the quantize tool's F16 GGUF): activations rounded to fp16 before every F16 product; the reference's own F16 and F32 logits differ by
+        # 0.03-0.19 RMS (and in tokens for prompt 1), the restated rounding model stays within 0.05 RMS and reproduces the F16 tokens
+        assert (rms < 0.1 and d < 1.0) if f16 else d < 2e-2
 
 
 def test_dia_port_check_stopping_against_reference():

@@ -61,6 +61,19 @@ int Dia::prepare() {
         return (float *) d;
     };
     auto up = [&](const std::string & n, int64_t expect) -> float * { const HostTensor * t = find(n, expect); return t ? dev(t->v.data(), t->v.size()) : nullptr; };
+    auto dev_mat = [&](const float * src, size_t n, bool f16) -> ArW {      // F16 tensors go to HBM as fp16 (their fp32 host copies are exact widenings)
+        ArW w; w.f16 = f16;
+        if (!f16) { w.p = dev(src, n); return w; }
+        std::vector<__half> h(n);
+        for (size_t i = 0; i < n; i++) h[i] = __float2half_rn(src[i]);
+        void * d = nullptr;
+        if (cudaMalloc(&d, n * 2) != cudaSuccess) { cudaGetLastError(); set_error("dia: cudaMalloc of %zu bytes failed", n * 2); ok = false; return w; }
+        cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += n * 2;
+        w.p = d;
+        return w;
+    };
+    auto upw = [&](const std::string & n, int64_t expect) -> ArW { const HostTensor * t = find(n, expect); return t ? dev_mat(t->v.data(), t->v.size(), t->f16) : ArW(); };
 
     {   // the encoder width is not in the metadata (the reference hard-codes 1024, model.h:68): take it from the embedding table
         const HostTensor * t = find("encoder.embedding", 0);
@@ -79,29 +92,32 @@ int Dia::prepare() {
         const std::string b = "encoder.layers." + std::to_string(l);
         DiaEncLayer & L = enc[(size_t) l];
         L.pre_sa = up(b + ".pre_sa_norm", enc_hidden); L.post_sa = up(b + ".post_sa_norm", enc_hidden);
-        L.wq = up(b + ".q_proj", (int64_t) enc_inner * enc_hidden); L.wk = up(b + ".k_proj", (int64_t) enc_inner * enc_hidden); L.wv = up(b + ".v_proj", (int64_t) enc_inner * enc_hidden);
-        L.wo = up(b + ".o_proj", (int64_t) enc_hidden * enc_inner);
-        L.gate = up(b + ".gate", (int64_t) enc_ffn * enc_hidden); L.up = up(b + ".up", (int64_t) enc_ffn * enc_hidden); L.down = up(b + ".wo", (int64_t) enc_hidden * enc_ffn);
+        L.wq = upw(b + ".q_proj", (int64_t) enc_inner * enc_hidden); L.wk = upw(b + ".k_proj", (int64_t) enc_inner * enc_hidden); L.wv = upw(b + ".v_proj", (int64_t) enc_inner * enc_hidden);
+        L.wo = upw(b + ".o_proj", (int64_t) enc_hidden * enc_inner);
+        L.gate = upw(b + ".gate", (int64_t) enc_ffn * enc_hidden); L.up = upw(b + ".up", (int64_t) enc_ffn * enc_hidden); L.down = upw(b + ".wo", (int64_t) enc_hidden * enc_ffn);
     }
     for (int l = 0; l < dec_layers && ok; l++) {
         const std::string b = "decoder.layers." + std::to_string(l);
         DiaDecLayer & L = dec[(size_t) l];
         const int64_t DD = (int64_t) hidden * hidden;
         L.pre_sa = up(b + ".pre_sa_norm", hidden); L.pre_ca = up(b + ".pre_ca_norm", hidden); L.pre_mlp = up(b + ".pre_mlp_norm", hidden);
-        L.sq = up(b + ".self_q_proj", DD); L.sk = up(b + ".self_k_proj", (int64_t) kv_hidden * hidden); L.sv = up(b + ".self_v_proj", (int64_t) kv_hidden * hidden); L.so = up(b + ".self_o_proj", DD);
-        L.cq = up(b + ".cross_q_proj", DD); L.ck = up(b + ".cross_k_proj", (int64_t) hidden * enc_hidden); L.cv = up(b + ".cross_v_proj", (int64_t) hidden * enc_hidden); L.co = up(b + ".cross_o_proj", DD);
-        L.gate = up(b + ".gate", (int64_t) ffn * hidden); L.up = up(b + ".up", (int64_t) ffn * hidden); L.down = up(b + ".wo", (int64_t) hidden * ffn);
+        L.sq = upw(b + ".self_q_proj", DD); L.sk = upw(b + ".self_k_proj", (int64_t) kv_hidden * hidden); L.sv = upw(b + ".self_v_proj", (int64_t) kv_hidden * hidden); L.so = upw(b + ".self_o_proj", DD);
+        L.cq = upw(b + ".cross_q_proj", DD); L.ck = upw(b + ".cross_k_proj", (int64_t) hidden * enc_hidden); L.cv = upw(b + ".cross_v_proj", (int64_t) hidden * enc_hidden); L.co = upw(b + ".cross_o_proj", DD);
+        L.gate = upw(b + ".gate", (int64_t) ffn * hidden); L.up = upw(b + ".up", (int64_t) ffn * hidden); L.down = upw(b + ".wo", (int64_t) hidden * ffn);
     }
     if (ok) {   // the n_out codebook tables and output heads, each family in one buffer
         std::vector<float> tab, hw;
+        bool heads_f16 = true, heads_any_f16 = false;
         for (int i = 0; i < n_out && ok; i++) {
             const HostTensor * t = find("decoder.embeddings." + std::to_string(i), (int64_t) vocab * hidden);
             const HostTensor * h = find("decoder.heads." + std::to_string(i), (int64_t) vocab * hidden);
             if (!t || !h) break;
             tab.insert(tab.end(), t->v.begin(), t->v.end());
             hw.insert(hw.end(), h->v.begin(), h->v.end());
+            heads_f16 = heads_f16 && h->f16; heads_any_f16 = heads_any_f16 || h->f16;
         }
-        if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev(hw.data(), hw.size()); }
+        if (ok && heads_any_f16 != heads_f16) { set_error("dia: the output heads mix F16 and F32 tensors"); ok = false; }
+        if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev_mat(hw.data(), hw.size(), heads_f16); }   // tables: ggml_get_rows widens F16 rows to fp32 exactly
     }
     if (!ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
@@ -168,8 +184,9 @@ __global__ void cfg_combine_kernel(const float * __restrict__ logits2, int NV, f
 struct DFwd {
     Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
-    int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
+    int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (W.f16) gemv_rows_h_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, (const __half *) W.p, K, N, R, res, Y, ldy);
+        else       gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, (const float *) W.p, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }

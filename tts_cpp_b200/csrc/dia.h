@@ -3,18 +3,17 @@
 // Replaces dia_runner::build_dia_graph / decode / set_inputs (encoder pass, cross K/V store, CFG-paired decoder step, cfg_scale) and the token
 // loop of generate_from_batch with check_stopping (reference src/models/dia/model.cpp:324-637,705-737,806-864; src/util.cpp:175-200) under
 // sampler::max, for a batch of independent prompts.  Every utterance is TWO sequences throughout, like the reference: the conditional prompt and
-// an all-zero unconditional one.  Same plain design as orpheus.h / parler.h (fp32 CUDA-core kernels from ar_kernels.cuh); logic checked under
-// tests/emu, not yet run on a GPU.
+// an all-zero unconditional one.  Same plain design as orpheus.h / parler.h (CUDA-core kernels from ar_kernels.cuh; F32 and F16 matrices with the
+// reference's numerics for each); logic checked under tests/emu, not yet run on a GPU.
 #pragma once
 #include "kokoro.h"   // HostTensor, Arena
 
 namespace b2 {
 
-struct DiaEncLayer { float * pre_sa = nullptr, * wq = nullptr, * wk = nullptr, * wv = nullptr, * wo = nullptr, * post_sa = nullptr, * gate = nullptr, * up = nullptr, * down = nullptr; };
+struct DiaEncLayer { float * pre_sa = nullptr, * post_sa = nullptr; ArW wq, wk, wv, wo, gate, up, down; };
 struct DiaDecLayer {
-    float * pre_sa = nullptr, * sq = nullptr, * sk = nullptr, * sv = nullptr, * so = nullptr;
-    float * pre_ca = nullptr, * cq = nullptr, * ck = nullptr, * cv = nullptr, * co = nullptr;
-    float * pre_mlp = nullptr, * gate = nullptr, * up = nullptr, * down = nullptr;
+    float * pre_sa = nullptr, * pre_ca = nullptr, * pre_mlp = nullptr;
+    ArW sq, sk, sv, so, cq, ck, cv, co, gate, up, down;
 };
 
 struct Dia {
@@ -29,7 +28,8 @@ struct Dia {
     int enc_hidden = 0, hidden = 0, kv_hidden = 0, enc_inner = 0, enc_ffn = 0, ffn = 0, enc_vocab = 0;
     int bos = 1026, eos = 1024, pad = 1025;
     float cfg = 3.0f;
-    float * enc_embed = nullptr, * enc_norm = nullptr, * tables = nullptr /* [n_out][vocab][hidden] */, * dec_norm = nullptr, * heads_w = nullptr /* [n_out * vocab][hidden] */;
+    float * enc_embed = nullptr, * enc_norm = nullptr, * tables = nullptr /* [n_out][vocab][hidden] */, * dec_norm = nullptr;
+    ArW heads_w;   // [n_out * vocab][hidden]
     std::vector<DiaEncLayer> enc;
     std::vector<DiaDecLayer> dec;
 
