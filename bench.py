@@ -187,15 +187,11 @@ def run_reference_arm(args):
     return 0
 
 
-def run_dac_reference(args, threads: int = 4):
-    """The reference's dac_runner (oracle/_ref/dac_ref) on the host cores: W worker processes x `threads` ggml threads, each decoding one
-    861-frame utterance (10 s of audio) of the same synthetic GGUF -- a bounded sample of the batch-16 step."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return 0
+def _dac_reference_sample(threads: int = 4):
+    """-> (audio_s, wall_s, workers) of oracle/_ref/dac_ref decoding one 861-frame utterance per worker process, or None"""
     ref = os.path.join(ROOT, "oracle", "_ref", "dac_ref")
     if not os.path.exists(ref):
-        print(json.dumps({"impl": "reference", "workload": "dac", "unavailable": "oracle/_ref/dac_ref missing (run `make -C oracle ref` where /root/reference exists)"}))
-        return 0
+        return None
     from tts_cpp_b200.synth import cached_dac_gguf, synthetic_codes
     gguf = cached_dac_gguf(seed=0, max_frames=870)
     ncpu = os.cpu_count() or 8
@@ -213,14 +209,70 @@ def run_dac_reference(args, threads: int = 4):
             if line.startswith("SUMMARY"):
                 sm = json.loads(line[len("SUMMARY "):])
                 audio += sm["audio_s"]; wall = max(wall, sm["wall_s"])
-    if wall <= 0:
-        print(json.dumps({"impl": "reference", "workload": "dac", "unavailable": "dac_ref produced no SUMMARY"}))
+    return (audio, wall, workers) if wall > 0 else None
+
+
+def run_dac_reference(args, threads: int = 4):
+    """The reference's dac_runner (oracle/_ref/dac_ref) on the host cores: W worker processes x `threads` ggml threads, each decoding one
+    861-frame utterance (10 s of audio) of the same synthetic GGUF -- a bounded sample of the batch-16 step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
+    r = _dac_reference_sample(threads)
+    if r is None:
+        print(json.dumps({"impl": "reference", "workload": "dac", "unavailable": "oracle/_ref/dac_ref missing or silent (run `make -C oracle ref` where /root/reference exists)"}))
+        return 0
+    audio, wall, workers = r
     print(json.dumps({"impl": "reference", "metric": "audio_seconds_per_second", "workload": "DAC codec decode, 861-frame utterances (10 s @ 44.1 kHz), reference CPU GGML path",
                       "value": audio / wall, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": 1, "ms_per_step": wall * 1e3,
                       "cpu_baseline": {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
                                        "sample": f"{workers} worker processes x {threads} ggml threads, one 10 s utterance each; throughput = total audio / slowest worker"},
                       "e2e": {"value": audio / wall, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "data": "synthetic"}))
+    return 0
+
+
+def run_parler_reference(args, threads: int = 4, sample_steps: int = 60):
+    """The reference's Parler decode loop (oracle/_ref/parler_ref) + DAC decode (dac_ref) on the host cores, a bounded sample of config 3: every worker
+    process generates `sample_steps` frames of one utterance; the DAC rate comes from the 10 s-utterance sample of run_dac_reference.  The two stages run one
+    after the other in the reference, so the pipeline rate is the harmonic combination of the stage rates."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    ref = os.path.join(ROOT, "oracle", "_ref", "parler_ref")
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "workload": "parler", "unavailable": "oracle/_ref/parler_ref missing (run `make -C oracle ref` where /root/reference exists)"}))
+        return 0
+    import numpy as np
+    from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_parler_gguf
+    gguf = cached_parler_gguf(seed=0, f16=True, **PARLER_MINI_SHAPE)
+    ncpu = os.cpu_count() or 8
+    workers = max(1, min(16, ncpu // (2 * threads)))
+    tmp = tempfile.mkdtemp(prefix="b2par_")
+    rng = np.random.default_rng(5)
+    procs = []
+    for w in range(workers):
+        pf = os.path.join(tmp, f"p{w}.txt")
+        open(pf, "w").write(" ".join(map(str, rng.integers(1, 500, size=24))) + "\n")
+        procs.append(subprocess.Popen([ref, gguf, pf, os.path.join(tmp, f"o{w}"), "--steps", str(sample_steps), "--threads", str(threads), "--quiet"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    frames, wall = 0, 0.0
+    for p in procs:
+        out, _ = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("SUMMARY"):
+                sm = json.loads(line[len("SUMMARY "):])
+                frames += sm["steps"]; wall = max(wall, sm["wall_s"])
+    dac = _dac_reference_sample(threads)
+    if wall <= 0 or dac is None:
+        print(json.dumps({"impl": "reference", "workload": "parler", "unavailable": "parler_ref / dac_ref produced no SUMMARY"}))
+        return 0
+    ar_rate = (frames * 512 / 44100.0) / wall                     # audio-seconds of frames generated per second (the prompt pass is inside wall)
+    dac_rate = dac[0] / dac[1]
+    rate = 1.0 / (1.0 / ar_rate + 1.0 / dac_rate)
+    print(json.dumps({"impl": "reference", "metric": "audio_seconds_per_second", "workload": "Parler-TTS-Mini-sized F16 decoder (synthetic) greedy AR decode + DAC decode, reference CPU GGML path",
+                      "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": 1, "ms_per_step": wall * 1e3, "ar_audio_s_per_s": ar_rate, "dac_audio_s_per_s": dac_rate,
+                      "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
+                                       "sample": f"{workers} worker processes x {threads} ggml threads: {sample_steps} decode steps of one utterance each (KV cache shorter than at 861 steps), "
+                                                 "then one 10 s DAC decode each; stage rates combined harmonically"},
+                      "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "data": "synthetic"}))
     return 0
 
 
@@ -253,6 +305,59 @@ def run_dac(args):
     return 0
 
 
+def run_parler(args):
+    """Secondary line (not the headline; written before it could be run on a B200): BASELINE config 3's shape -- a Parler-TTS-Mini-sized F16 decoder
+    (synthetic weights), batch 16, 10 s of audio per utterance (861 DAC frames + the 8-step delay tail), greedy, then the DAC decode of the frames.
+    Random weights emit special ids at random, which the reference would drop frame by frame: they are folded into the codebook range here so that every
+    utterance decodes its full 10 s (said in `config`)."""
+    if args.impl == "reference":
+        return run_parler_reference(args)
+    import numpy as np
+    import torch  # noqa: F401  (device context / first-import cost, like the main arm)
+    from tts_cpp_b200.ar_host import parler_adjust_output_tokens
+    from tts_cpp_b200.binding import Context, dac_runner_from_file, parler_runner_from_file
+    from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_dac_gguf, cached_parler_gguf
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    par = parler_runner_from_file(cached_parler_gguf(seed=0, f16=True, **PARLER_MINI_SHAPE), ctx=ctx)
+    dac = dac_runner_from_file(cached_dac_gguf(seed=0, max_frames=64), ctx=ctx)
+    B, frames = 16, 861
+    n_steps = frames + par.n_heads - 1
+    rng = np.random.default_rng(5)
+    prompts = [rng.integers(1, 500, size=24).astype(np.uint32) for _ in range(B)]
+
+    def step():
+        toks = par.generate_greedy(prompts, n_steps)
+        t_ar = par.last_ms()
+        codes = [parler_adjust_output_tokens(t % 1024, 1024) for t in toks]
+        pcm = dac.run_batch(codes, copy=False)
+        return t_ar, dac.last_ms(), sum(p.shape[0] for p in pcm) / 44100.0
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    l0 = ctx.launches()
+    ar_ms = dac_ms = audio_s = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, d, au = step()
+        ar_ms += a; dac_ms += d; audio_s += au
+    wall = time.perf_counter() - t0
+    dev_ms = ar_ms + dac_ms
+    wb = par.weight_bytes()
+    _, hbm, peak_src = _peaks()
+    per_step_ms = ar_ms / args.steps / n_steps
+    print(json.dumps({
+        "metric": "audio_seconds_per_second", "workload": "Parler-TTS-Mini-sized F16 decoder (synthetic), batch 16 x 10 s, greedy AR decode + DAC decode (BASELINE config 3)",
+        "value": audio_s / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dev_ms / args.steps,
+        "ar_ms_per_step": ar_ms / args.steps, "dac_ms_per_step": dac_ms / args.steps, "decode_step_ms": per_step_ms,
+        "e2e": {"value": audio_s / wall, "unit": "audio-s/s", "ms_per_step": wall * 1e3 / args.steps},
+        "roofline": {"bound": "hbm", "achieved": wb / (per_step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": wb / (per_step_ms * 1e-3) / 1e9 / hbm,
+                     "traffic": None, "peak_source": peak_src, "note": "algorithmic bytes of one decode step = the resident weights streamed once for the whole batch (KV cache reads excluded)"},
+        "gpu_launches": int(ctx.launches() - l0), "dtype": "f16 matrices x fp16-rounded activations, f32 accumulate (the reference's numerics for an F16 GGUF)",
+        "data": "synthetic", "config": {"workload": "parler-mini F16 (24 layers x 1024, 9 codebooks), batch 16, 869 decode steps -> 861 frames, special ids folded mod 1024, DAC 44.1 kHz decode",
+                                         "status": "plain first path (one launch per op, no CUDA graph); see DESIGN 7.1"}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,11 +365,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac"],
-                    help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line")
+    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "parler"],
+                    help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
+                         "parler: config 3 end to end (AR decode + DAC), plain first path")
     args = ap.parse_args()
     if args.workload == "dac":
         return run_dac(args)
+    if args.workload == "parler":
+        return run_parler(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 

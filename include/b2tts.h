@@ -194,6 +194,7 @@ int   b2tts_parler_info(const b2tts_parler * m, int * n_heads, int * out_vocab, 
 int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
                                    int32_t * out_tokens, float * out_logits);
 float b2tts_parler_last_ms(const b2tts_parler * m);
+size_t b2tts_parler_weight_bytes(const b2tts_parler * m);   /* bytes of the matrices, tables and norms resident in HBM (F16 matrices count 2 bytes) */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dia autoregressive decode, FIRST CORRECT PATH, same status as Orpheus / Parler above (emulation-checked: identical token

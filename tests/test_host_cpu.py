@@ -153,3 +153,33 @@ def test_reference_side_binding_type_checks_against_the_reference_headers():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run(["make", "-C", os.path.join(root, "oracle"), "binding_check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_delay_pattern_undo_matches_the_reference_indexing():
+    """ar_host.{parler,dia}_adjust_output_tokens against a literal restatement of the reference's flat-index loops
+    (parler model.cpp:734-760, dia model.cpp:825-847) on random token streams with special ids mixed in."""
+    from tts_cpp_b200.ar_host import DIA_DELAY_PATTERN, dia_adjust_output_tokens, parler_adjust_output_tokens
+    rng = np.random.default_rng(3)
+    H, V = 9, 1024
+    for steps in (8, 9, 10, 40):
+        t = rng.integers(0, 1040, size=(steps, H))          # ~1.5 % special ids per token
+        flat = t.reshape(-1)
+        want = []
+        for i in range(steps):                               # parler: next_index = i*H + ii*H + ii
+            idx = [i * H + ii * H + ii for ii in range(H)]
+            if any(j >= flat.size or flat[j] >= V for j in idx):
+                continue
+            want.append([flat[j] for j in idx])
+        got = parler_adjust_output_tokens(t, V)
+        assert got.shape == (len(want), H) and (len(want) == 0 or np.array_equal(got, np.asarray(want)))
+    for steps in (15, 16, 30, 80):
+        t = rng.integers(0, 1030, size=(steps, H))
+        flat = t.reshape(-1)
+        want = []
+        for i in range(steps - 15):                          # dia: next_index = i*H + delay[ii]*H + ii
+            idx = [i * H + DIA_DELAY_PATTERN[ii] * H + ii for ii in range(H)]
+            if any(flat[j] >= V for j in idx):
+                continue
+            want.append([flat[j] for j in idx])
+        got = dia_adjust_output_tokens(t, V)
+        assert got.shape == (len(want), H) and (len(want) == 0 or np.array_equal(got, np.asarray(want)))

@@ -374,6 +374,14 @@ class ParlerRunner:
                                                 logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None))
         return (toks, logits) if want_logits else toks
 
+    def last_ms(self) -> float:
+        lib().b2tts_parler_last_ms.restype = C.c_float
+        return float(lib().b2tts_parler_last_ms(self.h))
+
+    def weight_bytes(self) -> int:
+        lib().b2tts_parler_weight_bytes.restype = C.c_size_t
+        return int(lib().b2tts_parler_weight_bytes(self.h))
+
     def close(self):
         if self.h:
             lib().b2tts_parler_free(self.h)

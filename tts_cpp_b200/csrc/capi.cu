@@ -214,6 +214,7 @@ int b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32
     return m->p.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
 }
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
+size_t b2tts_parler_weight_bytes(const b2tts_parler * m) { return m ? m->p.weight_bytes : 0; }
 // ---- Dia AR decode (first correct path)
 int b2tts_dia_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dia ** out) {
     if (!ctx) { set_error("null context"); return 1; }

@@ -555,7 +555,8 @@ def parler_f16_tensor(name: str) -> bool:
     return True
 
 
-def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12, f16: bool = False) -> dict:
+def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12, f16: bool = False,
+                      max_generation: int = 64) -> dict:
     """Small synthetic Parler-TTS GGUF (F32) with a matching small DAC decoder (the reference's loader needs both).  32 heads x 8 layers is
     the smallest shape the reference loads: prep_cross_key_values sizes its metadata pool from n_attn_heads * 2 * n_layers tensors but
     allocates a 4096-node graph in it (src/models/parler/model.cpp:117-129)."""
@@ -571,7 +572,7 @@ def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32
         w.add_tensor(name, arr.astype(np.float16 if f16 and parler_f16_tensor(name) else np.float32))
     a = "parler-tts.decoder"
     for k, v in ((f"{a}.encode_length", n_enc), (f"{a}.hidden_size", heads * head_dim), (f"{a}.output_heads", 9), (f"{a}.context_length", 4096),
-                 (f"{a}.attention.head_count", heads), (f"{a}.max_generation", 64), (f"{a}.out_vocab_size", 1088), (f"{a}.audio_vocab_size", 1024),
+                 (f"{a}.attention.head_count", heads), (f"{a}.max_generation", max_generation), (f"{a}.out_vocab_size", 1088), (f"{a}.audio_vocab_size", 1024),
                  (f"{a}.num_hidden_layers", layers), ("audio.bos_token_id", 1025), ("audio.eos_token_id", 1024)):
         w.add_uint32(k, int(v))
     for i, s in enumerate(dac_rates):
@@ -584,13 +585,17 @@ def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32
     return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
 
 
-def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False) -> str:
+PARLER_MINI_SHAPE = dict(layers=24, heads=16, head_dim=64, ffn=4096, n_enc=32, max_generation=1024)     # parler-tts-mini-v1's decoder: hidden 1024, 24 layers, 9 codebooks
+
+
+def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, **shape) -> str:
     cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, f"parler_{'f16' if f16 else 'f32'}_s{seed}.gguf")
+    tag = "".join(f"_{k}{v}" for k, v in sorted(shape.items()))
+    path = os.path.join(cache_dir, f"parler_{'f16' if f16 else 'f32'}_s{seed}{tag}.gguf")
     if not os.path.exists(path):
         tmp = f"{path}.{os.getpid()}.tmp"
-        write_parler_gguf(tmp, seed=seed, f16=f16)
+        write_parler_gguf(tmp, seed=seed, f16=f16, **shape)
         os.replace(tmp, path)
     return path
 
