@@ -6,6 +6,7 @@
 #include "orpheus.h"
 #include "parler.h"
 #include "dia.h"
+#include <cstdlib>
 #include <cstring>
 #include <cstdio>
 #include <vector>
@@ -32,12 +33,13 @@ template <class M> static int run(int argc, char ** argv) {
     const int32_t W = out_width(m), V = out_logits(m);
     std::vector<int32_t> tok((size_t) B * steps * W);
     std::vector<float> logits((size_t) B * steps * V);
-    if (m.generate_greedy(B, pp.data(), np.data(), steps, tok.data(), logits.data())) { fprintf(stderr, "generate: %s\n", b2::emu_last_error()); return 1; }
+    const bool want_logits = !getenv("B2EMU_NO_LOGITS");      // without logits the decode loops may replay a captured CUDA graph (B2TTS_AR_GRAPH=1)
+    if (m.generate_greedy(B, pp.data(), np.data(), steps, tok.data(), want_logits ? logits.data() : nullptr)) { fprintf(stderr, "generate: %s\n", b2::emu_last_error()); return 1; }
     f = fopen(argv[4], "wb");
     fwrite(&W, 4, 1, f); fwrite(&V, 4, 1, f);
     fwrite(tok.data(), 4, tok.size(), f); fwrite(logits.data(), 4, logits.size(), f);
     fclose(f);
-    fprintf(stderr, "emulated %llu launches, %llu blocks\n", (unsigned long long) b2emu::g_launches, (unsigned long long) b2emu::g_blocks);
+    fprintf(stderr, "emulated %llu launches, %llu blocks, %llu graph replays\n", (unsigned long long) b2emu::g_launches, (unsigned long long) b2emu::g_blocks, (unsigned long long) b2emu::g_replays);
     return 0;
 }
 

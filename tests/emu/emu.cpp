@@ -96,8 +96,16 @@ uint64_t shfl(uint64_t v, int src_lane) {
 
 void * dyn_smem() { return g_dyn.data(); }
 
+struct Recorded { dim3 grid, block; size_t smem; std::function<void()> body; };
+}  // namespace b2emu
+struct b2emu_graph { std::vector<b2emu::Recorded> nodes; int refs = 1; };
+namespace b2emu {
+static b2emu_graph * g_capture = nullptr;
+uint64_t g_replays = 0;
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body) {
     if (g_cur) { fprintf(stderr, "b2emu: nested launch\n"); abort(); }
+    if (g_capture) { g_capture->nodes.push_back(Recorded{grid, block, smem, body}); return; }   // captured, not executed -- like a real stream capture
     const int nt = (int) (block.x * block.y * block.z);
     if (nt <= 0 || nt > 1024) { fprintf(stderr, "b2emu: %d threads per block\n", nt); abort(); }
     if (smem > 227 * 1024) { fprintf(stderr, "b2emu: %zu bytes of dynamic shared memory\n", smem); abort(); }
@@ -138,6 +146,17 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & bo
 }
 
 }  // namespace b2emu
+
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { if (b2emu::g_capture) return 1; b2emu::g_capture = new b2emu_graph(); return 0; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t * g) { if (!b2emu::g_capture) return 1; *g = b2emu::g_capture; b2emu::g_capture = nullptr; return 0; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t * e, cudaGraph_t g, unsigned long long) { g->refs++; *e = g; return 0; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+    b2emu::g_replays++;
+    for (const auto & n : e->nodes) b2emu::launch(n.grid, n.block, n.smem, n.body);
+    return 0;
+}
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { if (--e->refs == 0) delete e; return 0; }
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { if (--g->refs == 0) delete g; return 0; }
 
 namespace b2 {
 

@@ -66,11 +66,22 @@ static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float * ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 
+// stream capture: launches issued between Begin/EndCapture are recorded (closures own their arguments, like kernel parameters) and replayed by cudaGraphLaunch
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+typedef struct b2emu_graph * cudaGraph_t;
+typedef struct b2emu_graph * cudaGraphExec_t;
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode);
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t * g);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t * e, cudaGraph_t g, unsigned long long flags);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e);
+cudaError_t cudaGraphDestroy(cudaGraph_t g);
+
 namespace b2emu {
 struct Fiber { uint3 tid; void * sp; char * stack; bool done; };
 extern Fiber * g_cur;
 extern dim3 g_blockIdx, g_blockDim, g_gridDim;
-extern uint64_t g_launches, g_blocks;
+extern uint64_t g_launches, g_blocks, g_replays;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body);
 void sync_block();
 uint64_t shfl(uint64_t v, int src_lane);   // every live lane of the warp calls it; returns the value lane src_lane passed

@@ -1,7 +1,8 @@
 """tests/emu/prep.py -- TEST INFRASTRUCTURE ONLY: rewrite the two pieces of CUDA syntax a host compiler cannot parse, so that an unmodified
 .cu file of the library compiles against tests/emu/include:
 
-    kernel<<<grid, block, smem, stream>>>(args);   ->  b2emu::launch(grid, block, smem, [&]() { kernel(args); });
+    kernel<<<grid, block, smem, stream>>>(args);   ->  b2emu::launch(grid, block, smem, [=]() { kernel(args); });     (by value, like kernel parameters:
+                                                    a launch recorded during stream capture can be replayed after the caller's locals are gone)
     extern __shared__ T name[];                    ->  T * name = (T *) b2emu::dyn_smem();
 """
 import re
@@ -57,7 +58,7 @@ def convert(src):
         e = _match(src, k, "(", ")")
         grid, block = cfg[0], cfg[1]
         smem = cfg[2] if len(cfg) > 2 else "0"
-        out += src[pos:kstart] + "b2emu::launch(%s, %s, %s, [&]() { %s%s; })" % (grid, block, smem, m.group(1), src[k:e + 1])
+        out += src[pos:kstart] + "b2emu::launch(%s, %s, %s, [=]() { %s%s; })" % (grid, block, smem, m.group(1), src[k:e + 1])
         pos = e + 1
     return out + src[pos:]
 

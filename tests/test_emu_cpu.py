@@ -24,7 +24,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu"]
 
 
-def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag):
+def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag, env=None, want_stderr=False):
     """-> (tokens [B][steps][W], logits [B][steps][V]) from the library's generate_greedy under emulation"""
     exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
     pin, pout = str(tmp_path / f"p{tag}.bin"), str(tmp_path / f"o{tag}.bin")
@@ -33,14 +33,14 @@ def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag):
         for p in prompts:
             f.write(struct.pack("i", p.size))
             f.write(np.asarray(p, np.uint32).tobytes())
-    r = subprocess.run([exe, model, gguf_path, pin, pout], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([exe, model, gguf_path, pin, pout], capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stderr[-2000:]
     raw = open(pout, "rb").read()
     W, V = struct.unpack("ii", raw[:8])
     n = len(prompts) * steps
     tok = np.frombuffer(raw[8:8 + n * W * 4], np.int32).reshape(len(prompts), steps, W)
     logits = np.frombuffer(raw[8 + n * W * 4:], np.float32).reshape(len(prompts), steps, V)
-    return tok, logits
+    return (tok, logits, r.stderr) if want_stderr else (tok, logits)
 
 
 def _run_orpheus(tmp_path, prompts, steps, tag):
@@ -81,6 +81,18 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path,
         # F32: ggml's GELU is an fp16 table -- an activation that lands on the other side of a rounding boundary moves a logit by ~1e-3.
         # F16: every matrix input is rounded to fp16 as well, so summation-order noise flips roundings in all 64 products: ~7e-3 at a logit std of 4
         assert d < (3e-2 if f16 else 1e-2)
+
+
+def test_parler_cuda_graph_replay_emulated(tmp_path):
+    """B2TTS_AR_GRAPH=1: one audio step is captured into a CUDA graph and replayed, the step number being device-resident.  Under emulation a capture
+    records the launches (closures owning their arguments, like kernel parameters) and cudaGraphLaunch replays them: same tokens as the reference."""
+    g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    tok, _, err = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0), prompts, steps, "g", env={"B2TTS_AR_GRAPH": "1", "B2EMU_NO_LOGITS": "1"}, want_stderr=True)
+    assert f"{steps} graph replays" in err, err[-300:]
+    for u in range(2):
+        assert np.array_equal(tok[u], g[f"tokens{u}"])
 
 
 @pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])

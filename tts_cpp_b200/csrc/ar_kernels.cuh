@@ -39,11 +39,12 @@ __global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __res
     for (int c = lane; c < H; c += 32) y[(size_t) r * H + c] = (row[c] * scale) * w[c];
 }
 
-// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]): one warp per output n, the weight row is read once per chunk of 8 rows
+// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]; res may alias Y: each element is read and written by the same thread): one warp per output n,
+// the weight row is read once per chunk of 8 rows
 // (ggml_mul_mat with F32 weights and activations; K % 4 == 0)
 constexpr int GR = 8;
 __global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
-                                                        const float * __restrict__ res, float * __restrict__ Y, int ldy) {
+                                                        const float * res, float * Y, int ldy) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     const float * wrow = W + (size_t) n * K;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict
 // the same product for an F16 weight matrix: ggml_mul_mat converts the activation rows to fp16 first (the vec_dot_type of F16 is F16, ggml-cpu.c
 // mul_mat from_float) and accumulates the exact fp16 x fp16 products in fp32 -- also what halves the bytes streamed per step
 __global__ void __launch_bounds__(256) gemv_rows_h_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, int K, int N, int R,
-                                                          const float * __restrict__ res, float * __restrict__ Y, int ldy) {
+                                                          const float * res, float * Y, int ldy) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     const __half * wrow = W + (size_t) n * K;
@@ -280,8 +281,8 @@ __global__ void gelu_f16lut_kernel(float * g, size_t n) {
     g[i] = y;
 }
 
-// sampler::max over rows of V logits: the first maximum wins.  row -> out[row]
-__global__ void __launch_bounds__(256) argmax_rows_kernel(const float * __restrict__ logits, int V, int * __restrict__ out) {
+// sampler::max over rows of V logits: the first maximum wins.  row -> out[step * gridDim.x + row], step = *d_step (0 when d_step is null)
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float * __restrict__ logits, int V, int * __restrict__ out, const int * __restrict__ d_step) {
     __shared__ float sv[256]; __shared__ int si[256];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float * lg = logits + (size_t) b * V;
@@ -293,19 +294,23 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float * __restri
         if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
         __syncthreads();
     }
-    if (tid == 0) out[b] = si[0];
+    if (tid == 0) out[(size_t) (d_step ? *d_step : 0) * gridDim.x + b] = si[0];
 }
 
 // rows of an audio decode step under the delay pattern (parler generate_from_batch, model.cpp:762-786; dia model.cpp:843-858): output head i is fed BOS
-// until step i + 1, then the token it produced in the previous step.  One row per sequence at position first_pos[b] + step (first_pos == nullptr: step).
-__global__ void delay_rows_kernel(const int * __restrict__ last, const int * __restrict__ first_pos, int B, int n_out, int step, int bos, int Tmax,
+// until step i + 1, then the token it produced in the previous step (d_out [steps][B][n_out]).  One row per sequence at position first_pos[b] + step.
+// The step number lives in device memory (d_step, advanced by step_advance_kernel) so that one captured CUDA graph of a step can be replayed for every step.
+__global__ void delay_rows_kernel(const int * __restrict__ d_out, const int * __restrict__ first_pos, int B, int n_out, const int * __restrict__ d_step, int bos, int Tmax,
                                   int * ids, int * row_pos, int * row_base, int * row_len, int * row_dst) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int step = *d_step;
     const int pos = (first_pos ? first_pos[b] : 0) + step;
-    for (int i = 0; i < n_out; i++) ids[b * n_out + i] = step > i ? last[b * n_out + i] : bos;
+    for (int i = 0; i < n_out; i++) ids[b * n_out + i] = step > i ? d_out[((size_t) (step - 1) * B + b) * n_out + i] : bos;
     row_pos[b] = pos; row_base[b] = b * Tmax; row_len[b] = pos + 1; row_dst[b] = b * Tmax + pos;
 }
+
+__global__ void step_advance_kernel(int * d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_step += 1; }
 
 }  // namespace
 }  // namespace b2

@@ -146,10 +146,12 @@ __global__ void zero_key_tail_kernel(float * K, const int * __restrict__ seq_len
 // the decoder rows of one step.  Both sequences of an utterance are fed the same audio tokens: head i gets BOS until the decode position exceeds i,
 // then the token it produced one step earlier (generate_from_batch, model.cpp:843-858), with check_stopping's end-of-stream injection on top
 // (model.cpp:806-823: `delay` is dia_context::delay_steps; `stopped` records the step at which the reference's loop would have ended).
-__global__ void dia_step_rows_kernel(const int * __restrict__ last, int B, int n_out, int step, int bos, int eos, int pad, int max_gen, int max_delay, int Tmax,
+__global__ void dia_step_rows_kernel(const int * __restrict__ d_out, int B, int n_out, const int * __restrict__ d_step, int bos, int eos, int pad, int max_gen, int max_delay, int Tmax,
                                      int * delay, int * stopped, int * ids, int * row_pos, int * row_base, int * row_len, int * row_dst) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= B) return;
+    const int step = *d_step;                                      // device-resident so that a captured graph of one step can be replayed
+    const int * last = d_out + (size_t) (step > 0 ? step - 1 : 0) * B * n_out;
     const int pattern[9] = {0, 8, 9, 10, 11, 12, 13, 14, 15};     // dia_model::delay_pattern (model.h:85)
     int audio[9];
     for (int i = 0; i < n_out; i++) audio[i] = step > i ? last[u * n_out + i] : bos;
@@ -220,7 +222,7 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
     int * e_tok = Fw.al<int>((size_t) RE), * e_pos = Fw.al<int>((size_t) RE), * e_base = Fw.al<int>((size_t) RE), * e_len = Fw.al<int>((size_t) RE);
     int * seq_len = Fw.al<int>((size_t) S2), * cross_base = Fw.al<int>((size_t) S2), * cross_len = Fw.al<int>((size_t) S2);
     int * ids = Fw.al<int>((size_t) S2 * n_out), * row_pos = Fw.al<int>((size_t) S2), * row_base = Fw.al<int>((size_t) S2), * row_len = Fw.al<int>((size_t) S2), * row_dst = Fw.al<int>((size_t) S2);
-    int * delay = Fw.al<int>((size_t) B), * stopped = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) n_steps * B * n_out);
+    int * delay = Fw.al<int>((size_t) B), * stopped = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
     if (Fw.fail) return 1;
 
     std::vector<int> htok((size_t) RE, 0), hpos((size_t) RE), hbase((size_t) RE), hlen((size_t) RE), hseq((size_t) S2), hcb((size_t) S2), hcl((size_t) S2, C), hm1((size_t) B, -1);
@@ -246,6 +248,7 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
     B2_CUDA(cudaMemcpyAsync(cross_len, hcl.data(), hcl.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(delay, hm1.data(), hm1.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(stopped, hm1.data(), hm1.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemsetAsync(d_step, 0, 4, st));
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float theta_scale = powf(10000.0f, -2.0f / (float) head_dim);
@@ -289,8 +292,7 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
     if (Fw.fail) return 1;
     for (int s = 0; s < n_steps; s++) {
         const int R = S2;
-        const int * last = s > 0 ? d_out + (size_t) (s - 1) * B * n_out : nullptr;
-        dia_step_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(last, B, n_out, s, bos, eos, pad, max_gen, max_delay, Tmax, delay, stopped, ids, row_pos, row_base, row_len, row_dst);
+        dia_step_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, B, n_out, d_step, bos, eos, pad, max_gen, max_delay, Tmax, delay, stopped, ids, row_pos, row_base, row_len, row_dst);
         B2_LAUNCH_CHECK(ctx);
         codebook_embed_kernel<<<R, 256, 0, st>>>(ids, n_out, tables, (size_t) vocab * D, nullptr, row_pos, D, x); B2_LAUNCH_CHECK(ctx);
         for (int l = 0; l < dec_layers; l++) {
@@ -317,7 +319,8 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
         if (Fw.rms(x, dec_norm, D, R, xn)) return 1;
         if (Fw.gemv(xn, D, heads_w, D, NV, R, nullptr, logits2, NV)) return 1;
         { dim3 grid(cdiv(NV, 256), B); cfg_combine_kernel<<<grid, 256, 0, st>>>(logits2, NV, cfg, logits); B2_LAUNCH_CHECK(ctx); }
-        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out + (size_t) s * B * n_out); B2_LAUNCH_CHECK(ctx);
+        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx);
+        step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
         if (out_logits)
             for (int b = 0; b < B; b++)
                 B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2 {
@@ -177,7 +178,7 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
     float * logits = Fw.al<float>((size_t) B * NV);
     int * row_tok = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax), * row_dst = Fw.al<int>((size_t) Rmax);
     int * cross_base = Fw.al<int>((size_t) Rmax), * cross_len = Fw.al<int>((size_t) Rmax);
-    int * d_np = Fw.al<int>((size_t) B), * ids = Fw.al<int>((size_t) B * n_out), * d_out = Fw.al<int>((size_t) n_steps * B * n_out);
+    int * d_np = Fw.al<int>((size_t) B), * ids = Fw.al<int>((size_t) B * n_out), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
     if (Fw.fail) return 1;
 
     std::vector<int> ht((size_t) R0), hp((size_t) R0), hb((size_t) R0), hl((size_t) R0), hd((size_t) R0), hcb((size_t) Rmax, 0), hcl((size_t) Rmax, n_enc), hnp((size_t) B);
@@ -197,6 +198,7 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
     B2_CUDA(cudaMemcpyAsync(cross_base, hcb.data(), hcb.size() * 4, cudaMemcpyHostToDevice, st));   // every row attends to the whole stored encoding (all-zero cross mask)
     B2_CUDA(cudaMemcpyAsync(cross_len, hcl.data(), hcl.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(d_np, hnp.data(), hnp.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemsetAsync(d_step, 0, 4, st));
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float scale = 1.0f / sqrtf((float) head_dim);
@@ -205,16 +207,8 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
     B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
     const int Tcap = std::max(Tmax, n_enc);
 
-    // pass -1 is the prompt pass (its logits are never read: generate_from_batch only samples after audio decodes); passes 0 .. n_steps-1 are audio steps
-    for (int s = -1; s < n_steps; s++) {
-        const int R = s < 0 ? R0 : B;
-        if (s < 0) {
-            embed_pos_kernel<<<R, 256, 0, st>>>(row_tok, row_pos, embed_prompts, pos_embed, H, x); B2_LAUNCH_CHECK(ctx);
-        } else {
-            const int * last = s > 0 ? d_out + (size_t) (s - 1) * B * n_out : nullptr;
-            delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(last, d_np, B, n_out, s, bos, Tmax, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
-            codebook_embed_kernel<<<R, 256, 0, st>>>(ids, n_out, tables, (size_t) tab_rows * H, pos_embed, row_pos, H, x); B2_LAUNCH_CHECK(ctx);
-        }
+    // one pass over the layers for R rows whose inputs are already in x; leaves the result in x
+    auto run_layers = [&](int R) -> int {
         for (int l = 0; l < n_layers; l++) {
             const ParlerLayer & L = layers[(size_t) l];
             float * Kl = Kc + (size_t) l * B * Tmax * H, * Vl = Vc + (size_t) l * B * Tmax * H;
@@ -232,16 +226,48 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
             if (Fw.ln(x, L.ln3_w, L.ln3_b, H, R, xn)) return 1;
             if (Fw.gemv(xn, H, L.fc1, H, F, R, nullptr, g, F)) return 1;
             { const size_t n = (size_t) R * F; gelu_f16lut_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, n); B2_LAUNCH_CHECK(ctx); }
-            if (Fw.gemv(g, F, L.fc2, F, H, R, x, xn, H)) return 1;                             // xn = mlp + residual(x)
-            std::swap(x, xn);
+            if (Fw.gemv(g, F, L.fc2, F, H, R, x, x, H)) return 1;                              // x = mlp + residual(x), in place
         }
-        if (s < 0) continue;
-        if (Fw.ln(x, ln_w, ln_b, H, R, xn)) return 1;
+        return 0;
+    };
+    // the prompt pass: its logits are never read (generate_from_batch only samples after audio decodes)
+    embed_pos_kernel<<<R0, 256, 0, st>>>(row_tok, row_pos, embed_prompts, pos_embed, H, x); B2_LAUNCH_CHECK(ctx);
+    if (run_layers(R0)) return 1;
+    // one audio step; the step number is device-resident (d_step), so the launches are identical for every step
+    auto run_step = [&]() -> int {
+        delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, d_np, B, n_out, d_step, bos, Tmax, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
+        codebook_embed_kernel<<<B, 256, 0, st>>>(ids, n_out, tables, (size_t) tab_rows * H, pos_embed, row_pos, H, x); B2_LAUNCH_CHECK(ctx);
+        if (run_layers(B)) return 1;
+        if (Fw.ln(x, ln_w, ln_b, H, B, xn)) return 1;
         if (Fw.gemv(xn, H, heads_w, H, NV, B, nullptr, logits, NV)) return 1;                  // the n_out heads as one [n_out * vocab][hidden] matrix
-        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out + (size_t) s * B * n_out); B2_LAUNCH_CHECK(ctx);
-        if (out_logits)
-            for (int b = 0; b < B; b++)
-                B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx);
+        step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    // B2TTS_AR_GRAPH=1: capture one step into a CUDA graph and replay it (an audio step is ~15 launches per layer of microsecond kernels: launch-bound
+    // otherwise).  Off by default until it has run on hardware; not used when the caller wants every step's logits (a host copy per step).
+    const char * ge = getenv("B2TTS_AR_GRAPH");
+    const bool use_graph = ge && ge[0] == '1' && !out_logits;
+    const uint64_t launches_before_step = ctx->launches;
+    if (use_graph) {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_step();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("parler: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("parler: cudaGraphInstantiate failed"); return 1; }
+        cudaError_t le = cudaSuccess;
+        for (int s = 0; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
+        ctx->launches += (uint64_t) (n_steps - 1) * (uint64_t) (ctx->launches - launches_before_step);   // the captured launches, replayed
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        if (le != cudaSuccess) { set_error("parler: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
+    } else {
+        for (int s = 0; s < n_steps; s++) {
+            if (run_step()) return 1;
+            if (out_logits)
+                for (int b = 0; b < B; b++)
+                    B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+        }
     }
     B2_CUDA(cudaEventRecord(ev[1], st));
     std::vector<int32_t> tmp((size_t) n_steps * B * n_out);
