@@ -45,7 +45,7 @@ const std::function<void()> * g_body = nullptr;
 std::vector<Fiber> g_fibers;
 std::vector<char *> g_stacks;
 int g_alive = 0, g_arrived = 0; uint64_t g_gen = 0, g_progress = 0;
-struct Warp { int alive = 0, arrived = 0; uint64_t gen = 0; uint64_t slot[2][32]; };
+struct Warp { int alive = 0, arrived = 0; uint64_t gen = 0; uint64_t slot[2][32]; unsigned wide[2][32][8]; };
 std::vector<Warp> g_warps;
 std::vector<char> g_dyn;
 
@@ -95,6 +95,16 @@ uint64_t shfl(uint64_t v, int src_lane) {
 }
 
 void * dyn_smem() { return g_dyn.data(); }
+
+void warp_exchange(const unsigned * mine, int nwords, unsigned * all) {
+    if (nwords > 8) { fprintf(stderr, "b2emu: warp_exchange of %d words\n", nwords); abort(); }
+    const int t = linear_tid(g_cur);
+    Warp & w = g_warps[(size_t) t >> 5];
+    const int buf = (int) (w.gen & 1);
+    for (int i = 0; i < nwords; i++) w.wide[buf][t & 31][i] = mine[i];
+    warp_barrier();
+    for (int l = 0; l < 32; l++) for (int i = 0; i < nwords; i++) all[l * nwords + i] = w.wide[buf][l][i];
+}
 
 struct Recorded { dim3 grid, block; size_t smem; std::function<void()> body; };
 }  // namespace b2emu

@@ -86,6 +86,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & bo
 void sync_block();
 uint64_t shfl(uint64_t v, int src_lane);   // every live lane of the warp calls it; returns the value lane src_lane passed
 void * dyn_smem();
+void warp_exchange(const unsigned * mine, int nwords, unsigned * all /* [32][nwords] */);   // every live lane publishes nwords and receives the whole warp's
 }  // namespace b2emu
 
 #define threadIdx (b2emu::g_cur->tid)
@@ -110,5 +111,6 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { const 
 #define __expf(x) expf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+template <class T> static inline T __ldcs(const T * p) { return *p; }
 static inline float __ldg(const float * p) { return *p; }
 static inline int __ldg(const int * p) { return *p; }

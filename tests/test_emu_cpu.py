@@ -83,6 +83,23 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path,
         assert d < (3e-2 if f16 else 1e-2)
 
 
+@pytest.mark.parametrize("model", ["parler", "dia"])
+def test_tensor_core_gemv_emulated_f16(tmp_path, model):
+    """B2TTS_AR_MMA=1: F16 matrices through gemv_mma_h_kernel (mma.sync.m16n8k16 with the batch as M, K split over the warps of a block, the k index permuted
+    consistently on both operands).  Under emulation the instruction is a functional model of the PTX fragment layout; the tokens must be the F16 reference's."""
+    g = np.load(os.path.join(GOLD, f"{model}_f16_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    gguf = cached_parler_gguf(seed=0, f16=True) if model == "parler" else cached_dia_gguf(seed=0, f16=True)
+    tok, logits = _run_ar(tmp_path, model, gguf, prompts, steps, "m", env={"B2TTS_AR_MMA": "1"})
+    for u in range(2):
+        ref = g[f"logits{u}"].reshape(steps, -1)
+        rms = float(np.sqrt(((logits[u] - ref) ** 2).mean()))
+        print(f"PARITY(emulated, mma gemv) {model} f16 prompt {u}: logit diff rms {rms:.3e} max {float(np.abs(logits[u] - ref).max()):.3e}")
+        assert np.array_equal(tok[u], g[f"tokens{u}"])
+        assert rms < (0.1 if model == "dia" else 5e-3)
+
+
 def test_parler_cuda_graph_replay_emulated(tmp_path):
     """B2TTS_AR_GRAPH=1: one audio step is captured into a CUDA graph and replayed, the step number being device-resident.  Under emulation a capture
     records the launches (closures owning their arguments, like kernel parameters) and cudaGraphLaunch replays them: same tokens as the reference."""

@@ -5,6 +5,7 @@
 // the -m gpu tests are the parity gate.  Included into each model's translation unit (internal linkage).
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b2 {
 namespace {
@@ -101,6 +102,96 @@ __global__ void __launch_bounds__(256) gemv_rows_h_kernel(const float * __restri
             for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
             if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? acc[j] + res[(size_t) (r0 + j) * ldy + n] : acc[j];
         }
+    }
+}
+
+// ---- tensor-core batched GEMV for F16 matrices: the decode step of a batch of <= 16 sequences.
+// At batch 16 an F16 weight byte carries 16 flops: 6.6 TB/s of weights would need ~105 TFLOP/s of fp32 FMA, above what the CUDA cores deliver, and the plain
+// kernel above issues 8 activation loads per weight load.  Here the batch IS the M = 16 of mma.sync.m16n8k16 (exact fp16 products, fp32 accumulation -- the
+// reference's numerics for an F16 matrix): a block owns 8 output rows and splits K over its 8 warps; every lane streams 16 contiguous bytes of its weight row per
+// step (8 rows x 64 B per warp instruction, whole sectors), the activations sit in shared memory as fp16 (rounded once per block), and the warps' partial
+// 16 x 8 tiles are summed in a fixed order.  The k index is permuted consistently on both operands (a dot product does not care): the 8 halves a lane loads
+// are k-slots {2t, 2t+1, 2t+8, 2t+9} of two consecutive k16 steps, so no ldmatrix / transposition is needed.  tcgen05 would bring nothing here: its M is 64+.
+#ifdef B2EMU
+static inline void mma16816_f16f32(float * c, const unsigned * a, unsigned b0, unsigned b1) {      // functional model of the PTX fragment layout (tests/emu)
+    unsigned mine[6] = {a[0], a[1], a[2], a[3], b0, b1}, all[32][6];
+    b2emu::warp_exchange(mine, 6, &all[0][0]);
+    const int lane = b2emu_lane(), g = lane >> 2, t = lane & 3;
+    auto h = [](unsigned v, int i) { __half_raw r; r.x = (unsigned short) (i ? v >> 16 : v & 0xffff); return __half2float(__half(r)); };
+    for (int ci = 0; ci < 4; ci++) {
+        const int row = g + (ci >> 1) * 8, col = 2 * t + (ci & 1);
+        float acc = c[ci];
+        for (int tp = 0; tp < 4; tp++)                          // k = 2tp, 2tp+1 (a0/a1, b0) and 2tp+8, 2tp+9 (a2/a3, b1)
+            for (int hi = 0; hi < 2; hi++)
+                for (int i = 0; i < 2; i++) {
+                    const unsigned av = all[(row & 7) * 4 + tp][(row >> 3) + 2 * hi], bv = all[col * 4 + tp][4 + hi];
+                    acc = fmaf(h(av, i), h(bv, i), acc);
+                }
+        c[ci] = acc;
+    }
+}
+#else
+__device__ __forceinline__ void mma16816_f16f32(float * c, const unsigned * a, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#endif
+
+constexpr int GM_PAD = 8;      // halves of padding per activation row in shared memory: consecutive rows start 4 banks apart
+static inline bool gemv_mma_ok(int K, int N, int R) { return R <= 16 && K % 256 == 0 && N % 8 == 0 && (size_t) 16 * (K + GM_PAD) * 2 + 8 * 16 * 8 * 4 <= 200 * 1024; }
+static inline size_t gemv_mma_smem(int K) { return (size_t) 16 * (K + GM_PAD) * 2 + 8 * 16 * 8 * 4; }
+// off until it has run on hardware (B2TTS_AR_MMA=1 turns it on): the plain kernels are the emulation- and (from round 2) GPU-checked baseline
+static inline bool gemv_mma_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_MMA"); return e && e[0] == '1'; }(); return on; }
+
+// D k-steps of 32: all D weight loads are issued before the first mma so that a lane keeps D x 16 B of the weight stream in flight (read once: streaming hint)
+template <int D> __device__ __forceinline__ void gm_chunk(float * c, const __half * w, const __half * xa, const __half * xb) {
+    uint4 wv[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) wv[j] = __ldcs(reinterpret_cast<const uint4 *>(w + 32 * j));
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(xa + 32 * j), b = *reinterpret_cast<const uint4 *>(xb + 32 * j);
+        const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
+        mma16816_f16f32(c, f0, wv[j].x, wv[j].y);
+        mma16816_f16f32(c, f1, wv[j].z, wv[j].w);
+    }
+}
+
+__global__ void __launch_bounds__(256) gemv_mma_h_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, int K, int N, int R,
+                                                         const float * res, float * Y, int ldy) {
+    extern __shared__ __align__(16) float gm_smem[];
+    __half * sX = reinterpret_cast<__half *>(gm_smem);                                   // [16][K + GM_PAD] fp16-rounded activations (rows >= R are zero)
+    const int pitch = K + GM_PAD;
+    float * red = reinterpret_cast<float *>(sX + (size_t) 16 * pitch);                    // [8 warps][16][8] partial tiles
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int n0 = blockIdx.x * 8;
+    for (int i = tid * 4; i < 16 * K; i += 256 * 4) {
+        const int r = i / K, k = i - r * K;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < R) v = *reinterpret_cast<const float4 *>(X + (size_t) r * ldx + k);
+        __half2 * d = reinterpret_cast<__half2 *>(sX + (size_t) r * pitch + k);
+        d[0] = __floats2half2_rn(v.x, v.y); d[1] = __floats2half2_rn(v.z, v.w);
+    }
+    __syncthreads();
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ks = K >> 3, kbeg = warp * ks;                                              // this warp's K slice (a multiple of 32)
+    const __half * wrow = W + (size_t) (n0 + g) * K + t * 8;
+    const __half * xa = sX + (size_t) g * pitch + t * 8, * xb = sX + (size_t) (g + 8) * pitch + t * 8;
+    const int kend = kbeg + ks;
+    int k = kbeg;
+    for (; k + 256 <= kend; k += 256) gm_chunk<8>(c, wrow + k, xa + k, xb + k);          // 8 x 16 B of weights in flight per lane
+    for (; k + 128 <= kend; k += 128) gm_chunk<4>(c, wrow + k, xa + k, xb + k);
+    for (; k < kend; k += 32) gm_chunk<1>(c, wrow + k, xa + k, xb + k);
+    float * my = red + warp * 128;                                                       // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8
+    my[g * 8 + 2 * t] = c[0]; my[g * 8 + 2 * t + 1] = c[1]; my[(g + 8) * 8 + 2 * t] = c[2]; my[(g + 8) * 8 + 2 * t + 1] = c[3];
+    __syncthreads();
+    if (tid < 128) {
+        const int r = tid >> 3, col = tid & 7;
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) a += red[w * 128 + tid];
+        if (r < R && n0 + col < N) Y[(size_t) r * ldy + n0 + col] = res ? a + res[(size_t) r * ldy + n0 + col] : a;
     }
 }
 
