@@ -100,16 +100,19 @@ def test_tensor_core_gemv_emulated_f16(tmp_path, model):
         assert rms < (0.1 if model == "dia" else 5e-3)
 
 
-def test_parler_cuda_graph_replay_emulated(tmp_path):
-    """B2TTS_AR_GRAPH=1: one audio step is captured into a CUDA graph and replayed, the step number being device-resident.  Under emulation a capture
+@pytest.mark.parametrize("model", ["orpheus", "parler", "dia"])
+def test_cuda_graph_replay_emulated(tmp_path, model):
+    """B2TTS_AR_GRAPH=1: one decode step is captured into a CUDA graph and replayed, the step number being device-resident.  Under emulation a capture
     records the launches (closures owning their arguments, like kernel parameters) and cudaGraphLaunch replays them: same tokens as the reference."""
-    g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
+    g = np.load(os.path.join(GOLD, f"{model}_vectors.npz"))
     prompts = [g["prompt0"], g["prompt1"]]
     steps = int(g["tokens0"].shape[0])
-    tok, _, err = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0), prompts, steps, "g", env={"B2TTS_AR_GRAPH": "1", "B2EMU_NO_LOGITS": "1"}, want_stderr=True)
-    assert f"{steps} graph replays" in err, err[-300:]
+    gguf = {"orpheus": cached_orpheus_gguf, "parler": cached_parler_gguf, "dia": cached_dia_gguf}[model](seed=0)
+    tok, _, err = _run_ar(tmp_path, model, gguf, prompts, steps, "g", env={"B2TTS_AR_GRAPH": "1", "B2EMU_NO_LOGITS": "1"}, want_stderr=True)
+    replays = steps - 1 if model == "orpheus" else steps          # Orpheus' step 0 is the prompt pass itself
+    assert f"{replays} graph replays" in err, err[-300:]
     for u in range(2):
-        assert np.array_equal(tok[u], g[f"tokens{u}"])
+        assert np.array_equal(tok[u].reshape(g[f"tokens{u}"].shape), g[f"tokens{u}"])
 
 
 @pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])

@@ -11,11 +11,11 @@ namespace b2 {
 namespace {
 
 // rows of a step: (sequence, position, token).  Decode steps have one row per sequence, built on the device from the last argmax.
-__global__ void decode_rows_kernel(const int * __restrict__ n_prompt, const int * __restrict__ cur_tok, int B, int step, int Tmax, int * row_seq, int * row_pos, int * row_tok,
-                                   int * row_base, int * row_len) {
+__global__ void decode_rows_kernel(const int * __restrict__ n_prompt, const int * __restrict__ cur_tok, int B, const int * __restrict__ d_step, int Tmax, int * row_seq, int * row_pos,
+                                   int * row_tok, int * row_base, int * row_len) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const int pos = n_prompt[b] + step - 1;
+    const int pos = n_prompt[b] + *d_step - 1;          // the step number is device-resident so that one captured graph of a step can be replayed
     row_seq[b] = b; row_pos[b] = pos; row_tok[b] = cur_tok[b];
     row_base[b] = b * Tmax; row_len[b] = pos + 1;      // causal: the new row sees its sequence's cache up to and including itself
 }
@@ -278,7 +278,7 @@ __global__ void gather_rows_f32_kernel(const float * __restrict__ x, const int *
 }
 
 // sampler::max: the first maximum wins
-__global__ void __launch_bounds__(256) argmax_kernel(const float * __restrict__ logits, int V, int * cur_tok, int * out_tokens, int n_steps, int step) {
+__global__ void __launch_bounds__(256) argmax_kernel(const float * __restrict__ logits, int V, int * cur_tok, int * out_tokens, int n_steps, const int * __restrict__ d_step) {
     __shared__ float sv[256]; __shared__ int si[256];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float * lg = logits + (size_t) b * V;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float * __restrict__ 
         if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
         __syncthreads();
     }
-    if (tid == 0) { cur_tok[b] = si[0]; out_tokens[(size_t) b * n_steps + step] = si[0]; }
+    if (tid == 0) { cur_tok[b] = si[0]; out_tokens[(size_t) b * n_steps + *d_step] = si[0]; }
 }
 
 

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2 {
@@ -300,8 +301,8 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
     float * kbuf = Fw.al<float>((size_t) S2 * KVD), * vbuf = Fw.al<float>((size_t) S2 * KVD), * g = Fw.al<float>((size_t) S2 * ffn), * up = Fw.al<float>((size_t) S2 * ffn);
     float * logits2 = Fw.al<float>((size_t) S2 * NV), * logits = Fw.al<float>((size_t) B * NV);
     if (Fw.fail) return 1;
-    for (int s = 0; s < n_steps; s++) {
-        const int R = S2;
+    const int R = S2;
+    auto run_step = [&]() -> int {
         dia_step_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, B, n_out, d_step, bos, eos, pad, max_gen, max_delay, Tmax, delay, stopped, ids, row_pos, row_base, row_len, row_dst);
         B2_LAUNCH_CHECK(ctx);
         codebook_embed_kernel<<<R, 256, 0, st>>>(ids, n_out, tables, (size_t) vocab * D, nullptr, row_pos, D, x); B2_LAUNCH_CHECK(ctx);
@@ -323,17 +324,37 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
             if (Fw.rms(x, L.pre_mlp, D, R, xn)) return 1;
             if (Fw.gemv(xn, D, L.gate, D, ffn, R, nullptr, g, ffn) || Fw.gemv(xn, D, L.up, D, ffn, R, nullptr, up, ffn)) return 1;
             if (Fw.swiglu(g, up, (size_t) R * ffn)) return 1;
-            if (Fw.gemv(g, ffn, L.down, ffn, D, R, x, xn, D)) return 1;                      // xn = mlp + residual(x)
-            std::swap(x, xn);
+            if (Fw.gemv(g, ffn, L.down, ffn, D, R, x, x, D)) return 1;                       // x = mlp + residual(x), in place
         }
         if (Fw.rms(x, dec_norm, D, R, xn)) return 1;
         if (Fw.gemv(xn, D, heads_w, D, NV, R, nullptr, logits2, NV)) return 1;
         { dim3 grid(cdiv(NV, 256), B); cfg_combine_kernel<<<grid, 256, 0, st>>>(logits2, NV, cfg, logits); B2_LAUNCH_CHECK(ctx); }
         argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx);
         step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
-        if (out_logits)
-            for (int b = 0; b < B; b++)
-                B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    // B2TTS_AR_GRAPH=1: capture one decoder step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
+    const char * ge = getenv("B2TTS_AR_GRAPH");
+    if (ge && ge[0] == '1' && !out_logits) {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        const uint64_t l0 = ctx->launches;
+        B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_step();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("dia: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("dia: cudaGraphInstantiate failed"); return 1; }
+        cudaError_t le = cudaSuccess;
+        for (int s = 0; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
+        ctx->launches += (uint64_t) (n_steps - 1) * (ctx->launches - l0);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        if (le != cudaSuccess) { set_error("dia: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
+    } else {
+        for (int s = 0; s < n_steps; s++) {
+            if (run_step()) return 1;
+            if (out_logits)
+                for (int b = 0; b < B; b++)
+                    B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits + (size_t) b * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+        }
     }
     B2_CUDA(cudaEventRecord(ev[1], st));
     std::vector<int32_t> tmp((size_t) n_steps * B * n_out), hstop((size_t) B);

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2 {
@@ -125,7 +126,7 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     float * last = Fw.al<float>((size_t) B * H), * logits = Fw.al<float>((size_t) B * vocab);
     int * row_seq = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_tok = Fw.al<int>((size_t) Rmax);
     int * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax);
-    int * d_np = Fw.al<int>((size_t) B), * d_last = Fw.al<int>((size_t) B), * cur_tok = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) B * n_steps);
+    int * d_np = Fw.al<int>((size_t) B), * d_last = Fw.al<int>((size_t) B), * cur_tok = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) B * n_steps), * d_step = Fw.al<int>(1);
     if (Fw.fail) return 1;
 
     std::vector<int> hs((size_t) R0), hp((size_t) R0), ht((size_t) R0), hb((size_t) R0), hl((size_t) R0), hnp((size_t) B), hlast((size_t) B);
@@ -145,6 +146,7 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     B2_CUDA(cudaMemcpyAsync(row_len, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(d_np, hnp.data(), hnp.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(d_last, hlast.data(), hlast.size() * 4, cudaMemcpyHostToDevice, st));
+    B2_CUDA(cudaMemsetAsync(d_step, 0, 4, st));
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float theta_scale = powf(500000.0f, -2.0f / (float) head_dim);
@@ -153,9 +155,8 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     if (att_smem > 200 * 1024) { set_error("orpheus: context of %d positions exceeds the v1 attention kernel's shared memory", Tmax); return 1; }
     B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
 
-    for (int s = 0; s < n_steps; s++) {
-        const int R = s == 0 ? R0 : B;
-        if (s > 0) { decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, s, Tmax, row_seq, row_pos, row_tok, row_base, row_len); B2_LAUNCH_CHECK(ctx); }
+    // one pass: R rows already described by row_* -> logits of B rows -> argmax into d_out[.][*d_step] and cur_tok; advances d_step
+    auto run_pass = [&](int R, bool prefill) -> int {
         embed_kernel<<<R, 256, 0, st>>>(row_tok, embed, H, x);
         B2_LAUNCH_CHECK(ctx);
         for (int l = 0; l < n_layers; l++) {
@@ -176,12 +177,40 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
         }
         rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, out_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
         const float * lastp = xn;
-        if (s == 0) { gather_rows_f32_kernel<<<B, 256, 0, st>>>(xn, d_last, H, last); B2_LAUNCH_CHECK(ctx); lastp = last; }   // logits of the last position only
+        if (prefill) { gather_rows_f32_kernel<<<B, 256, 0, st>>>(xn, d_last, H, last); B2_LAUNCH_CHECK(ctx); lastp = last; }   // logits of the last position only
         if (Fw.gemv(lastp, H, head, H, vocab, B, nullptr, logits, vocab)) return 1;
-        argmax_kernel<<<B, 256, 0, st>>>(logits, vocab, cur_tok, d_out, n_steps, s); B2_LAUNCH_CHECK(ctx);
+        argmax_kernel<<<B, 256, 0, st>>>(logits, vocab, cur_tok, d_out, n_steps, d_step); B2_LAUNCH_CHECK(ctx);
+        step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    auto copy_logits = [&](int s) -> int {
         if (out_logits)
             for (int b = 0; b < B; b++)
                 B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * vocab, logits + (size_t) b * vocab, (size_t) vocab * 4, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    auto run_decode = [&]() -> int {
+        decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, d_step, Tmax, row_seq, row_pos, row_tok, row_base, row_len); B2_LAUNCH_CHECK(ctx);
+        return run_pass(B, false);
+    };
+    if (run_pass(R0, true) || copy_logits(0)) return 1;                                   // step 0: the whole ragged batch of prompts
+    // B2TTS_AR_GRAPH=1: capture one decode step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
+    const char * ge = getenv("B2TTS_AR_GRAPH");
+    if (ge && ge[0] == '1' && !out_logits && n_steps > 1) {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        const uint64_t l0 = ctx->launches;
+        B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_decode();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("orpheus: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("orpheus: cudaGraphInstantiate failed"); return 1; }
+        cudaError_t le = cudaSuccess;
+        for (int s = 1; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
+        ctx->launches += (uint64_t) (n_steps - 2) * (ctx->launches - l0);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        if (le != cudaSuccess) { set_error("orpheus: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
+    } else {
+        for (int s = 1; s < n_steps; s++) if (run_decode() || copy_logits(s)) return 1;
     }
     B2_CUDA(cudaEventRecord(ev[1], st));
     B2_CUDA(cudaMemcpyAsync(out_tokens, d_out, (size_t) B * n_steps * 4, cudaMemcpyDeviceToHost, st));
