@@ -19,6 +19,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
   parler_f16_vectors.npz   : as parler_vectors.npz for the GGUF `quantize --quantized-type F16` would write (decoder matrices and codebook tables F16: the
       reference then rounds the activations to fp16 before every such product)
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
+  sampler_vectors.npz      : the reference sampler (src/sampler.cpp) on fixed logits under four configurations: nucleus, probabilities, max_head_probs and a
+      histogram of 20 000 draws each, from oracle/ref_sampler_driver.cpp
   dia_stop_vectors.npz     : one byte-token prompt run until the reference's check_stopping ends the loop (64 frames of 9 tokens, the logits of the
       last frame), from oracle/ref_dia_driver.cpp with a step cap of 80
   dia_vectors.npz          : two byte-token prompts (10 and 18 tokens, the second after the first in the same process) and, for 5 greedy steps
@@ -233,9 +235,39 @@ def dia_stop_vectors():
     print("dia stop vectors:", toks.shape)
 
 
+def sampler_vectors():
+    """The reference sampler's nucleus / probabilities / max_head_probs and a histogram of 20 000 of its draws for four configurations on fixed logits."""
+    import struct
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_port import SAMPLER_CFGS
+    rng = np.random.default_rng(21)
+    H, V, n_draws = 3, 300, 20000
+    logits = (rng.standard_normal((H, V)) * 2.5).astype(np.float32)
+    last = np.array([int(np.argmax(logits[0])), 5, -1], np.int32); counts = np.array([2, 1, 0], np.uint32)     # head 0: the penalty hits its best token
+    out = {"logits": logits, "last": last, "counts": counts, "n_draws": np.int32(n_draws)}
+    tmp = tempfile.mkdtemp()
+    for name, cfg in SAMPLER_CFGS.items():
+        pin, pout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+        with open(pin, "wb") as f:
+            f.write(struct.pack("<IIfIff", H, V, cfg["temperature"], cfg["top_k"], cfg["top_p"], cfg["rp"]))
+            f.write(last.tobytes()); f.write(counts.tobytes()); f.write(struct.pack("<I", n_draws)); f.write(logits.tobytes())
+        run([os.path.join(REF, "sampler_ref"), pin, pout])
+        raw = open(pout, "rb").read()
+        off = 0
+        for i in range(H):
+            n = struct.unpack_from("<I", raw, off)[0]; off += 4
+            out[f"{name}.picks{i}"] = np.frombuffer(raw, np.uint32, n, off).copy(); off += 4 * n
+            out[f"{name}.probs{i}"] = np.frombuffer(raw, np.float32, n, off).copy(); off += 4 * n
+            out[f"{name}.mh{i}"] = np.float32(struct.unpack_from("<f", raw, off)[0]); off += 4
+        out[f"{name}.hist"] = np.frombuffer(raw, np.uint32, H * V, off).reshape(H, V).copy()
+    np.savez_compressed(os.path.join(OUT, "sampler_vectors.npz"), **out)
+    print("sampler vectors:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "dia", "dia_f16", "dia_stop"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "dia", "dia_f16", "dia_stop", "sampler"]
     if "dia_stop" in which: dia_stop_vectors()
+    if "sampler" in which: sampler_vectors()
     if "parler_f16" in which: parler_vectors(f16=True)
     if "dia_f16" in which: dia_vectors(f16=True)
     if "dia" in which: dia_vectors()

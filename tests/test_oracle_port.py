@@ -203,3 +203,39 @@ def test_dia_port_check_stopping_against_reference():
     assert toks.shape == g["tokens0"].shape and toks.shape[0] < int(g["step_cap"])
     assert np.array_equal(toks, g["tokens0"])
     assert float(np.abs(logits[-1] - g["logits_last0"]).max()) < 2e-2
+
+
+SAMPLER_CFGS = {"default_top50": dict(temperature=1.0, top_k=50, top_p=1.0, rp=1.0),          # the reference's default generation_configuration
+                "temp_rep": dict(temperature=0.7, top_k=20, top_p=1.0, rp=1.3),
+                "topk_topp": dict(temperature=1.3, top_k=40, top_p=0.9, rp=1.0),
+                "topp_only": dict(temperature=0.9, top_k=0, top_p=0.8, rp=1.1)}
+
+
+@pytest.mark.parametrize("name", list(SAMPLER_CFGS))
+def test_sampler_port_against_reference(name):
+    """oracle/sampler_port.py vs the reference sampler (tests/golden/sampler_vectors.npz, from oracle/ref_sampler_driver.cpp): the nucleus (picks in order),
+    its probabilities and max_head_probs stage by stage, and the distribution of 20 000 of the reference's own draws (its generator is seeded from
+    std::random_device, so only a histogram can be compared) against the port's draw() rule."""
+    from oracle.sampler_port import SamplerPort
+    g = np.load(os.path.join(GOLD, "sampler_vectors.npz"))
+    cfg = SAMPLER_CFGS[name]
+    logits, last, counts, n_draws = g["logits"], g["last"], g["counts"], int(g["n_draws"])
+    H, V = logits.shape
+    port = SamplerPort(H, V, cfg["temperature"], cfg["top_k"], cfg["top_p"], cfg["rp"])
+    port.last[:] = last; port.counts[:] = counts
+    nuc = port.nucleus(logits)
+    for i in range(H):
+        picks, probs, mh = nuc[i]
+        assert np.array_equal(picks, g[f"{name}.picks{i}"].astype(np.int64)), f"head {i}: nucleus differs"
+        assert np.allclose(probs, g[f"{name}.probs{i}"], rtol=2e-6, atol=1e-9)
+        assert abs(float(mh) - float(g[f"{name}.mh{i}"])) < 1e-6
+        # the draw rule: token picks[n] is returned for u*mh in (c[n-1], c[n]], the last pick also absorbs everything above
+        c = np.cumsum(probs.astype(np.float64)); lo = np.concatenate([[0.0], c[:-1]])
+        p = (np.minimum(c, float(mh)) - np.minimum(lo, float(mh))) / float(mh)
+        p[-1] += max(0.0, 1.0 - p.sum())
+        expect = np.zeros(V); expect[picks] = p * n_draws
+        got = g[f"{name}.hist"][i].astype(np.float64)
+        assert got[expect == 0].sum() == 0                                          # never outside the nucleus
+        m = expect > 5
+        chi2 = float((((got - expect) ** 2)[m] / expect[m]).sum()); dof = int(m.sum())
+        assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, f"head {i}: chi2 {chi2:.1f} for {dof} bins"
