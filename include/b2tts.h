@@ -110,6 +110,13 @@ int b2tts_op_conv_transpose_1d(b2tts_ctx * ctx, const float * kernel, int K, int
 int b2tts_op_conv_1d(b2tts_ctx * ctx, const float * kernel, int K, int cin, int cout, const float * x, int L, int stride, int pad,
                      int dil, int f16_kernel, float * y);
 int b2tts_op_cumsum(b2tts_ctx * ctx, const float * x, int L, int rows, float * y);            /* ggml_cumsum along ne0 */
+/* sampler::sample / sampler::max (reference src/sampler.cpp:3-70,187-204) for `rows` independent heads of `vocab` logits: repetition penalty, temperature,
+ * top-k (<= 1024), top-p, one draw each.  do_sample == 0 is sampler::max.  The reference seeds a fresh generator from std::random_device per call; here row r
+ * draws the uniform b2tts_sample_uniform(seed, r, step).  last_ids / rep_counts (may be NULL when repetition_penalty == 1): sampler::last_token_ids /
+ * repetition_counts, updated in place (-1 / 0 after sampler::reset). */
+int   b2tts_op_sample(b2tts_ctx * ctx, const float * logits, int rows, int vocab, int do_sample, int top_k, float top_p, float temperature, float repetition_penalty,
+                      int32_t * last_ids, int32_t * rep_counts, uint64_t seed, int step, int32_t * tokens);
+float b2tts_sample_uniform(uint64_t seed, uint64_t row, uint64_t step);
 int b2tts_op_mod(b2tts_ctx * ctx, const float * x, int64_t n, float mod_val, float * y);      /* ggml_mod: fmod */
 int b2tts_op_round(b2tts_ctx * ctx, const float * x, int64_t n, float * y);                   /* ggml_round: (float)(int)(x+0.5f) */
 int b2tts_op_reciprocal(b2tts_ctx * ctx, const float * x, int64_t n, float * y);              /* ggml_reciprocal */
@@ -170,12 +177,19 @@ int   b2tts_snac_reset_noise(b2tts_snac * m);
  *   b2tts_orpheus_generate_greedy: generate_from_batch's decode + sampler loop (model.cpp:230-353,389-398; sampler::max) for n_sequences
  *                                  independent prompts of token ids, n_steps tokens each, without the stop condition.
  *                                  out_tokens [n_sequences][n_steps]; out_logits (may be NULL) [n_sequences][n_steps][vocab]. */
+/* sampler settings of one generate call: generation_configuration's sample / top_k / top_p / temperature / repetition_penalty (reference include/common.h:45-66).
+ * do_sample == 0 is sampler::max.  seed: head r of step s draws the uniform b2tts_sample_uniform(seed, r, s) (see b2tts_op_sample). */
+typedef struct b2tts_sampling { int32_t do_sample; int32_t top_k; float top_p; float temperature; float repetition_penalty; uint64_t seed; } b2tts_sampling;
+
 typedef struct b2tts_orpheus b2tts_orpheus;
 int   b2tts_orpheus_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_orpheus ** out);
 void  b2tts_orpheus_free(b2tts_orpheus * m);
 int   b2tts_orpheus_info(const b2tts_orpheus * m, int * vocab_size, int * n_layers, int * hidden_size);
 int   b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
                                     int32_t * out_tokens, float * out_logits);
+/* the same loop under the reference sampler's settings (sampler.cpp on the device, sampler.cu); sampling == NULL is the greedy call above */
+int   b2tts_orpheus_generate(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
+                             int32_t * out_tokens, float * out_logits);
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -193,6 +207,8 @@ void  b2tts_parler_free(b2tts_parler * m);
 int   b2tts_parler_info(const b2tts_parler * m, int * n_heads, int * out_vocab, int * n_layers, int * hidden_size);
 int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
                                    int32_t * out_tokens, float * out_logits);
+int   b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
+                            int32_t * out_tokens, float * out_logits);
 float b2tts_parler_last_ms(const b2tts_parler * m);
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m);   /* bytes of the matrices, tables and norms resident in HBM (F16 matrices count 2 bytes) */
 
@@ -213,6 +229,8 @@ void  b2tts_dia_free(b2tts_dia * m);
 int   b2tts_dia_info(const b2tts_dia * m, int * n_heads, int * out_vocab, int * encoder_context, int * max_generation);
 int   b2tts_dia_generate_greedy(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
                                 int32_t * out_tokens, float * out_logits, int32_t * n_generated);
+int   b2tts_dia_generate(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
+                         int32_t * out_tokens, float * out_logits, int32_t * n_generated);
 float b2tts_dia_last_ms(const b2tts_dia * m);
 
 #ifdef __cplusplus

@@ -92,3 +92,13 @@ class SamplerPort:
                 self.counts[i] += 1
             toks[i] = tok
         return toks
+
+
+def uniform_from_counter(seed: int, row: int, step: int) -> np.float32:
+    """The uniform the device sampler derives for (seed, row, step) (tts_cpp_b200/csrc/sampler.cu: a splitmix64 finaliser over a mixed counter, 24 bits)."""
+    M = (1 << 64) - 1
+    x = (seed + 0x9E3779B97F4A7C15 * (row + 1) + 0xD1B54A32D192ED03 * (step + 1)) & M
+    x ^= x >> 30; x = (x * 0xBF58476D1CE4E5B9) & M
+    x ^= x >> 27; x = (x * 0x94D049BB133111EB) & M
+    x ^= x >> 31
+    return np.float32(x >> 40) * np.float32(1.0 / 16777216.0)

@@ -18,6 +18,9 @@ static int out_logits(const b2::Orpheus & m) { return m.vocab; }
 template <class M> static int out_width(const M & m) { return m.n_out; }
 template <class M> static int out_logits(const M & m) { return m.n_out * m.vocab; }
 
+template <class M> static int gen(M & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) { return m.generate(B, pp, np, steps, s, tok, lg); }
+static int gen(b2::Dia & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) { return m.generate(B, pp, np, steps, s, tok, lg, nullptr); }
+
 template <class M> static int run(int argc, char ** argv) {
     b2::Ctx ctx;
     M m; m.ctx = &ctx;
@@ -33,8 +36,14 @@ template <class M> static int run(int argc, char ** argv) {
     const int32_t W = out_width(m), V = out_logits(m);
     std::vector<int32_t> tok((size_t) B * steps * W);
     std::vector<float> logits((size_t) B * steps * V);
+    b2::ArSampling samp;                                          // B2EMU_SAMPLE="top_k top_p temperature repetition_penalty seed": the stochastic sampler
+    if (const char * e = getenv("B2EMU_SAMPLE")) {
+        unsigned long long sd = 0;
+        if (sscanf(e, "%d %f %f %f %llu", &samp.top_k, &samp.top_p, &samp.temperature, &samp.repetition_penalty, &sd) != 5) return 2;
+        samp.seed = sd; samp.do_sample = 1;
+    }
     const bool want_logits = !getenv("B2EMU_NO_LOGITS");      // without logits the decode loops may replay a captured CUDA graph (B2TTS_AR_GRAPH=1)
-    if (m.generate_greedy(B, pp.data(), np.data(), steps, tok.data(), want_logits ? logits.data() : nullptr)) { fprintf(stderr, "generate: %s\n", b2::emu_last_error()); return 1; }
+    if (gen(m, B, pp.data(), np.data(), steps, &samp, tok.data(), want_logits ? logits.data() : nullptr)) { fprintf(stderr, "generate: %s\n", b2::emu_last_error()); return 1; }
     f = fopen(argv[4], "wb");
     fwrite(&W, 4, 1, f); fwrite(&V, 4, 1, f);
     fwrite(tok.data(), 4, tok.size(), f); fwrite(logits.data(), 4, logits.size(), f);

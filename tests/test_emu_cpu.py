@@ -21,7 +21,7 @@ from tts_cpp_b200.synth import cached_dia_gguf, cached_orpheus_gguf, cached_parl
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu"]
+AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "sampler.cu"]
 
 
 def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag, env=None, want_stderr=False):
@@ -150,3 +150,82 @@ def test_dia_cuda_path_emulated_check_stopping(tmp_path):
     d = float(np.abs(logits[0, n_gen - 1] - g["logits_last0"].reshape(-1)).max())
     print(f"PARITY(emulated) dia run to check_stopping: {n_gen} frames, last-frame max |logit diff| {d:.3e}")
     assert d < 2e-2
+
+
+SAMPLER_CFGS = {"greedy": dict(do_sample=0, temperature=1.0, top_k=0, top_p=1.0, rp=1.0),
+                "default_top50": dict(do_sample=1, temperature=1.0, top_k=50, top_p=1.0, rp=1.0),      # the reference's default generation_configuration
+                "temp_rep": dict(do_sample=1, temperature=0.7, top_k=20, top_p=1.0, rp=1.3),
+                "topk_topp": dict(do_sample=1, temperature=1.3, top_k=40, top_p=0.9, rp=1.0),
+                "topp_only": dict(do_sample=1, temperature=0.9, top_k=0, top_p=0.8, rp=1.1),
+                "full_vocab": dict(do_sample=1, temperature=1.1, top_k=0, top_p=1.0, rp=1.2)}
+
+
+@pytest.mark.parametrize("name", list(SAMPLER_CFGS))
+def test_sampler_kernel_emulated_matches_port(tmp_path, name):
+    """sample_rows (sampler.cu) under emulation against oracle/sampler_port.py (itself pinned to the reference sampler) over 6 consecutive steps with the
+    repetition state carried along: the port is fed the same uniforms the kernel derives from (seed, row, step); tokens and state must be identical."""
+    sys.path.insert(0, ROOT)
+    from oracle.sampler_port import SamplerPort
+    cfg = SAMPLER_CFGS[name]
+    exe = emu_build.build("sampler_emu", ["sampler.cu"], ["sampler_main.cpp"])
+    rng = np.random.default_rng(33)
+    rows, V, steps, seed = 5, 300, 6, 0x1234ABCD5678
+    logits = (rng.standard_normal((steps, rows, V)) * 2.5).astype(np.float32)
+    logits[:, :, 7] += 6.0                                    # a dominant token: repeated picks exercise the repetition counts
+    logits[2:, 1, 40] = logits[2:, 1, 41]                      # exact ties inside the nucleus: lower id first
+    pin, pout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(pin, "wb") as f:
+        f.write(struct.pack("<iiiifffQi", rows, V, cfg["do_sample"], cfg["top_k"], cfg["top_p"], cfg["temperature"], cfg["rp"], seed, steps))
+        f.write(np.full(rows, -1, np.int32).tobytes()); f.write(np.zeros(rows, np.int32).tobytes()); f.write(logits.tobytes())
+    r = subprocess.run([exe, pin, pout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = open(pout, "rb").read()
+    n = steps * rows
+    toks = np.frombuffer(raw, np.int32, n, 0).reshape(steps, rows)
+    us = np.frombuffer(raw, np.float32, n, 4 * n).reshape(steps, rows)
+    last = np.frombuffer(raw, np.int32, rows, 8 * n); counts = np.frombuffer(raw, np.int32, rows, 8 * n + 4 * rows)
+    assert us.min() >= 0.0 and us.max() < 1.0 and len(np.unique(us)) == n
+    from oracle.sampler_port import uniform_from_counter
+    assert all(us[s_, r_] == uniform_from_counter(seed, r_, s_) for s_ in range(steps) for r_ in range(rows))      # the Python mirror of the counter hash
+    port = SamplerPort(rows, V, cfg["temperature"], cfg["top_k"], cfg["top_p"], cfg["rp"])
+    for s in range(steps):
+        if cfg["do_sample"]:
+            want = port.draw(logits[s], us[s])
+        else:
+            want = np.array([int(np.argmax(port._eff(logits[s][i], i))) for i in range(rows)])
+        assert np.array_equal(toks[s], want), f"step {s}: {toks[s]} vs {want}"
+    if cfg["do_sample"] and cfg["rp"] != 1.0:
+        assert np.array_equal(last, port.last) and np.array_equal(counts, port.counts)
+
+
+def test_parler_sampling_loop_emulated_matches_port(tmp_path):
+    """Parler::generate with the reference's default sampler settings (top_k 50, temperature 1) under emulation, against oracle/parler_port.py stepping with
+    oracle/sampler_port.py on the same uniforms: the whole loop -- logits, nucleus, draw, delay-pattern feedback of SAMPLED tokens -- must give the same ids."""
+    sys.path.insert(0, ROOT)
+    from oracle.parler_port import ParlerPort
+    from oracle.sampler_port import SamplerPort, uniform_from_counter
+    import torch
+    g = np.load(os.path.join(GOLD, "parler_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps, seed, top_k, temp = 5, 77, 50, 1.0
+    tok, _ = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0), prompts, steps, "smp", env={"B2EMU_SAMPLE": f"{top_k} 1.0 {temp} 1.0 {seed}"})
+    port = ParlerPort(cached_parler_gguf(seed=0))
+    H = port.n_out
+    for u, prompt in enumerate(prompts):
+        samp = SamplerPort(H, port.vocab, temp, top_k, 1.0, 1.0)
+        port.reset()
+        t = torch.from_numpy(np.asarray(prompt).astype(np.int64))
+        port.step(port.w["embed_prompts"][t] + port.w["positional_embed"][torch.arange(t.numel())])
+        last, want = None, []
+        for s in range(steps):
+            ids = [int(last[i]) if s > i else port.bos for i in range(H)]
+            x = None
+            for i in range(H):
+                e = port.w[f"embed_tokens.{i}.weight"][ids[i]]
+                x = e if x is None else e + x
+            lg = port.step((x + port.w["positional_embed"][port.pos])[None, :])[:, 0, :].numpy()
+            us = np.array([uniform_from_counter(seed, u * H + i, s) for i in range(H)], np.float32)      # row = sequence * heads + head
+            last = samp.draw(lg, us)
+            want.append(last.astype(np.int32))
+        assert np.array_equal(tok[u], np.stack(want)), f"prompt {u}: {tok[u].tolist()} vs {np.stack(want).tolist()}"
+    assert not np.array_equal(tok[0], g["tokens0"])          # and it is not the greedy stream

@@ -316,6 +316,29 @@ def snac_runner_from_file(path: str, device: int = 0, ctx: Context | None = None
     return SnacRunner(ctx, h)
 
 
+class Sampling(C.Structure):
+    """b2tts_sampling: generation_configuration's sample / top_k / top_p / temperature / repetition_penalty (reference include/common.h:45-66) + a seed."""
+    _fields_ = [("do_sample", C.c_int32), ("top_k", C.c_int32), ("top_p", C.c_float), ("temperature", C.c_float), ("repetition_penalty", C.c_float), ("seed", C.c_uint64)]
+
+    def __init__(self, do_sample=True, top_k=50, top_p=1.0, temperature=1.0, repetition_penalty=1.0, seed=0):
+        super().__init__(int(bool(do_sample)), int(top_k), float(top_p), float(temperature), float(repetition_penalty), int(seed))
+
+
+def sample_uniform(seed: int, row: int, step: int) -> float:
+    """the uniform head `row` draws at step `step` (b2tts_sample_uniform)"""
+    lib().b2tts_sample_uniform.restype = C.c_float
+    lib().b2tts_sample_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    return float(lib().b2tts_sample_uniform(seed, row, step))
+
+
+def _prompt_args(prompts):
+    B = len(prompts)
+    arrs = [np.ascontiguousarray(np.asarray(p, np.uint32)) for p in prompts]
+    npr = np.array([a.size for a in arrs], np.int32)
+    ptrs = (C.POINTER(C.c_uint32) * B)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+    return B, arrs, npr, ptrs
+
+
 class OrpheusRunner:
     """The token loop of orpheus_runner (reference src/models/orpheus/model.cpp:389-398) below the tokenizer, batched, greedy."""
 
@@ -337,6 +360,14 @@ class OrpheusRunner:
                                                  toks.ctypes.data_as(C.POINTER(C.c_int32)),
                                                  logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None))
         return (toks, logits) if want_logits else toks
+
+    def generate(self, prompts, n_steps: int, sampling: "Sampling | None" = None):
+        """-> tokens [B][n_steps] under the reference sampler's settings (None: greedy)"""
+        B, arrs, npr, ptrs = _prompt_args(prompts)
+        toks = np.empty((B, n_steps), np.int32)
+        _chk(lib().b2tts_orpheus_generate(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps), C.byref(sampling) if sampling is not None else None,
+                                          toks.ctypes.data_as(C.POINTER(C.c_int32)), None))
+        return toks
 
     def close(self):
         if self.h:
@@ -373,6 +404,14 @@ class ParlerRunner:
                                                 toks.ctypes.data_as(C.POINTER(C.c_int32)),
                                                 logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None))
         return (toks, logits) if want_logits else toks
+
+    def generate(self, prompts, n_steps: int, sampling: "Sampling | None" = None):
+        """-> tokens [B][n_steps][n_heads] under the reference sampler's settings (None: greedy)"""
+        B, arrs, npr, ptrs = _prompt_args(prompts)
+        toks = np.empty((B, n_steps, self.n_heads), np.int32)
+        _chk(lib().b2tts_parler_generate(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps), C.byref(sampling) if sampling is not None else None,
+                                         toks.ctypes.data_as(C.POINTER(C.c_int32)), None))
+        return toks
 
     def last_ms(self) -> float:
         lib().b2tts_parler_last_ms.restype = C.c_float
@@ -419,6 +458,15 @@ class DiaRunner:
                                              logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else None,
                                              ngen.ctypes.data_as(C.POINTER(C.c_int32))))
         return (toks, ngen, logits) if want_logits else (toks, ngen)
+
+    def generate(self, prompts, n_steps: int, sampling: "Sampling | None" = None):
+        """-> (tokens [B][n_steps][n_heads], n_generated [B]) under the reference sampler's settings (None: greedy)"""
+        B, arrs, npr, ptrs = _prompt_args(prompts)
+        toks = np.empty((B, n_steps, self.n_heads), np.int32)
+        ngen = np.empty(B, np.int32)
+        _chk(lib().b2tts_dia_generate(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps), C.byref(sampling) if sampling is not None else None,
+                                      toks.ctypes.data_as(C.POINTER(C.c_int32)), None, ngen.ctypes.data_as(C.POINTER(C.c_int32))))
+        return toks, ngen
 
     def close(self):
         if self.h:

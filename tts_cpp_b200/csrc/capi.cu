@@ -188,6 +188,17 @@ int b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const uint
     if (!m) { set_error("null model"); return 1; }
     return m->o.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
 }
+static ArSampling to_sampling(const b2tts_sampling * s) {
+    ArSampling a;
+    if (s) { a.do_sample = s->do_sample; a.top_k = s->top_k; a.top_p = s->top_p; a.temperature = s->temperature; a.repetition_penalty = s->repetition_penalty; a.seed = s->seed; }
+    return a;
+}
+int b2tts_orpheus_generate(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
+                           int32_t * out_tokens, float * out_logits) {
+    if (!m) { set_error("null model"); return 1; }
+    const ArSampling a = to_sampling(sampling);
+    return m->o.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits);
+}
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m) { return m ? m->o.timing_ms : 0.f; }
 // ---- Parler AR decode (first correct path)
 int b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out) {
@@ -212,6 +223,12 @@ int b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32
                                  float * out_logits) {
     if (!m) { set_error("null model"); return 1; }
     return m->p.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
+}
+int b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
+                          int32_t * out_tokens, float * out_logits) {
+    if (!m) { set_error("null model"); return 1; }
+    const ArSampling a = to_sampling(sampling);
+    return m->p.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits);
 }
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m) { return m ? m->p.weight_bytes : 0; }
@@ -238,6 +255,12 @@ int b2tts_dia_generate_greedy(b2tts_dia * m, int n_sequences, const uint32_t * c
                               float * out_logits, int32_t * n_generated) {
     if (!m) { set_error("null model"); return 1; }
     return m->d.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits, n_generated);
+}
+int b2tts_dia_generate(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
+                       int32_t * out_tokens, float * out_logits, int32_t * n_generated) {
+    if (!m) { set_error("null model"); return 1; }
+    const ArSampling a = to_sampling(sampling);
+    return m->d.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits, n_generated);
 }
 float b2tts_dia_last_ms(const b2tts_dia * m) { return m ? m->d.timing_ms : 0.f; }
 
@@ -304,6 +327,25 @@ int b2tts_op_conv_1d(b2tts_ctx * ctx, const float * kernel, int K, int cin, int 
     std::vector<float> t((size_t) Lout * cout);
     if (finish(c, t.data(), dy, t.size() * 4)) return 1;
     for (int co = 0; co < cout; co++) for (int o = 0; o < Lout; o++) y[(size_t) co * Lout + o] = t[(size_t) o * cout + co];
+    return 0;
+}
+
+float b2tts_sample_uniform(uint64_t seed, uint64_t row, uint64_t step) { return sample_uniform_host(seed, row, step); }
+int b2tts_op_sample(b2tts_ctx * ctx, const float * logits, int rows, int vocab, int do_sample, int top_k, float top_p, float temperature, float repetition_penalty,
+                    int32_t * last_ids, int32_t * rep_counts, uint64_t seed, int step, int32_t * tokens) {
+    Ctx * c = &ctx->c; Dev d;
+    SampleParams p;
+    p.rows = rows; p.V = vocab; p.do_sample = do_sample; p.top_k = top_k; p.top_p = top_p; p.temperature = temperature; p.repetition_penalty = repetition_penalty; p.seed = seed;
+    p.logits = d.put(logits, (size_t) rows * vocab);
+    p.scratch = d.get<float>((size_t) rows * vocab);
+    std::vector<int> hstep(1, step);
+    int * dstep = d.put(hstep.data(), 1);
+    p.d_step = dstep;
+    p.out = d.get<int>((size_t) rows * (step + 1));
+    if (last_ids && rep_counts) { p.last_ids = d.put((const int *) last_ids, (size_t) rows); p.rep_counts = d.put((const int *) rep_counts, (size_t) rows); }
+    if (!p.logits || !p.scratch || !dstep || !p.out || sample_rows(c, p)) return 1;
+    if (finish(c, tokens, p.out + (size_t) step * rows, (size_t) rows * 4)) return 1;
+    if (last_ids && rep_counts) { if (finish(c, last_ids, p.last_ids, (size_t) rows * 4) || finish(c, rep_counts, p.rep_counts, (size_t) rows * 4)) return 1; }
     return 0;
 }
 

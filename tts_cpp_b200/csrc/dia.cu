@@ -210,7 +210,8 @@ struct DFwd {
 
 }  // namespace
 
-int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits, int32_t * n_generated) {
+int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits, int32_t * n_generated) {
+    const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("dia: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
     B2_CUDA(cudaSetDevice(ctx->device));
@@ -224,7 +225,8 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
     const size_t cross = (size_t) 2 * dec_layers * RE * D * 4;
     const size_t self_cache = (size_t) 2 * dec_layers * S2 * Tmax * KVD * 4;
     const size_t dec_ws = (size_t) S2 * ((size_t) 4 * D + 2 * KVD + 2 * ffn + NV) * 4 + (size_t) B * NV * 4;
-    const size_t need = enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20);
+    const size_t need = enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20) +
+                        (size_t) B * n_out * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
     DFwd Fw{this, ctx, st};
     // ---- buffers
@@ -234,7 +236,11 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
     int * seq_len = Fw.al<int>((size_t) S2), * cross_base = Fw.al<int>((size_t) S2), * cross_len = Fw.al<int>((size_t) S2);
     int * ids = Fw.al<int>((size_t) S2 * n_out), * row_pos = Fw.al<int>((size_t) S2), * row_base = Fw.al<int>((size_t) S2), * row_len = Fw.al<int>((size_t) S2), * row_dst = Fw.al<int>((size_t) S2);
     int * delay = Fw.al<int>((size_t) B), * stopped = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
+    int * s_last = Fw.al<int>((size_t) B * n_out), * s_cnt = Fw.al<int>((size_t) B * n_out);
+    float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * NV) : nullptr;
     if (Fw.fail) return 1;
+    B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * n_out * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
+    B2_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t) B * n_out * 4, st));
 
     std::vector<int> htok((size_t) RE, 0), hpos((size_t) RE), hbase((size_t) RE), hlen((size_t) RE), hseq((size_t) S2), hcb((size_t) S2), hcl((size_t) S2, C), hm1((size_t) B, -1);
     for (int s = 0; s < S2; s++) {
@@ -329,7 +335,8 @@ int Dia::generate_greedy(int B, const uint32_t * const * prompts, const int32_t 
         if (Fw.rms(x, dec_norm, D, R, xn)) return 1;
         if (Fw.gemv(xn, D, heads_w, D, NV, R, nullptr, logits2, NV)) return 1;
         { dim3 grid(cdiv(NV, 256), B); cfg_combine_kernel<<<grid, 256, 0, st>>>(logits2, NV, cfg, logits); B2_LAUNCH_CHECK(ctx); }
-        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx);
+        if (samp.do_sample) { if (sample_rows(ctx, make_sample_params(samp, logits, B * n_out, vocab, s_last, s_cnt, s_scratch, d_step, d_out))) return 1; }
+        else { argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx); }
         step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
         return 0;
     };

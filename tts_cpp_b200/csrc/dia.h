@@ -42,7 +42,11 @@ struct Dia {
     // greedy generation for B prompts of byte tokens (each at most enc_ctx long), at most n_steps frames each; an utterance stops early exactly where
     // check_stopping would end the reference's loop: n_generated[b] (may be NULL) is the number of frames it produced, rows past that are zero.
     // out_tokens [B][n_steps][n_out]; out_logits (optional) [B][n_steps][n_out][vocab] (the CFG-combined logits)
-    int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits, int32_t * n_generated = nullptr);
+    int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits, int32_t * n_generated = nullptr) {
+        return generate(B, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits, n_generated);
+    }
+    // the same loop under the reference sampler's settings (sampler.cu): sampling == nullptr or do_sample == 0 is the greedy sampler::max
+    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits, int32_t * n_generated);
     void free_all();
 };
 

@@ -114,4 +114,35 @@ int op_conv_transpose_1d(Ctx * ctx, const float * w, int K, int coutg, int cin, 
 int convt_cl(Ctx * ctx, const float * x, int ldx, int Cin, int B, int LmaxIn, const int * lenIn, const float * w, const float * bias, int K,
              int Cout, int stride, int pad, float ns, int reflect1, float * y, int ldy, int LmaxOut, const int * lenOut);
 
+// sampler.cu -- the reference sampler (src/sampler.cpp) on the device for `rows` independent heads: repetition penalty, temperature, top-k, top-p, one draw each.
+// temperature <= 0 or do_sample == 0 is sampler::max.  The uniform of a row comes from (seed, row, *d_step) by a counter-based hash, so a captured graph of a
+// decode step can be replayed; out[*d_step * rows + row] receives the token (d_step == nullptr: step 0).
+struct SampleParams {
+    const float * logits = nullptr;   // [rows][V]
+    int rows = 0, V = 0;
+    int do_sample = 0, top_k = 0;
+    float temperature = 1.f, top_p = 1.f, repetition_penalty = 1.f;
+    int * last_ids = nullptr;         // [rows], -1 initially (sampler::reset); only used when repetition_penalty != 1
+    int * rep_counts = nullptr;       // [rows], 0 initially
+    float * scratch = nullptr;        // [rows][V] workspace, needed when top_p < 1 (the full-vocabulary softmax)
+    unsigned long long seed = 0;
+    const int * d_step = nullptr;
+    int * out = nullptr;
+    int * cur_tok = nullptr;          // optional [rows]: also receives the token (Orpheus feeds it straight back)
+    int out_stride_steps = 0;         // 0: out[step * rows + row]; else out[row * out_stride_steps + step] (Orpheus' [B][n_steps] layout)
+};
+int sample_rows(Ctx * ctx, const SampleParams & p);
+float sample_uniform_host(unsigned long long seed, unsigned long long row, unsigned long long step);   // the uniform row `row` draws at step `step`
+constexpr int SAMPLE_MAX_TOP_K = 1024;
+// the sampler settings of one generate call (generation_configuration's temperature / top_k / top_p / repetition_penalty / sample, include/common.h:45-66)
+struct ArSampling { int do_sample = 0, top_k = 0; float top_p = 1.f, temperature = 1.f, repetition_penalty = 1.f; unsigned long long seed = 0; };
+// fills SampleParams' sampling fields and state pointers for `rows` heads of V logits; state / scratch come from the caller's arena (may be null when unused)
+static inline SampleParams make_sample_params(const ArSampling & a, const float * logits, int rows, int V, int * last_ids, int * rep_counts, float * scratch, const int * d_step, int * out) {
+    SampleParams p;
+    p.logits = logits; p.rows = rows; p.V = V; p.do_sample = a.do_sample; p.top_k = a.top_k; p.top_p = a.top_p; p.temperature = a.temperature;
+    p.repetition_penalty = a.repetition_penalty; p.seed = a.seed; p.last_ids = last_ids; p.rep_counts = rep_counts; p.scratch = scratch; p.d_step = d_step; p.out = out;
+    return p;
+}
+static inline bool sampling_needs_scratch(const ArSampling & a, int V) { return a.do_sample && (a.top_p < 1.f || !(a.top_k > 0 && a.top_k < V)); }
+
 }  // namespace b2

@@ -102,7 +102,8 @@ struct OFwd {
 
 }  // namespace
 
-int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
+int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits) {
+    const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("orpheus: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
     B2_CUDA(cudaSetDevice(ctx->device));
@@ -116,7 +117,7 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, KV = kv_hidden, F = ffn;
     const size_t cache = (size_t) n_layers * B * Tmax * KV * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
-                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20);
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * vocab * 4 : 0);
     if (arena.reserve(need)) return 1;
     OFwd Fw{this, ctx, st};
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * KV), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * KV);
@@ -127,7 +128,11 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
     int * row_seq = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_tok = Fw.al<int>((size_t) Rmax);
     int * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax);
     int * d_np = Fw.al<int>((size_t) B), * d_last = Fw.al<int>((size_t) B), * cur_tok = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) B * n_steps), * d_step = Fw.al<int>(1);
+    int * s_last = Fw.al<int>((size_t) B), * s_cnt = Fw.al<int>((size_t) B);
+    float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * vocab) : nullptr;
     if (Fw.fail) return 1;
+    B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
+    B2_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t) B * 4, st));
 
     std::vector<int> hs((size_t) R0), hp((size_t) R0), ht((size_t) R0), hb((size_t) R0), hl((size_t) R0), hnp((size_t) B), hlast((size_t) B);
     {
@@ -179,7 +184,11 @@ int Orpheus::generate_greedy(int B, const uint32_t * const * prompts, const int3
         const float * lastp = xn;
         if (prefill) { gather_rows_f32_kernel<<<B, 256, 0, st>>>(xn, d_last, H, last); B2_LAUNCH_CHECK(ctx); lastp = last; }   // logits of the last position only
         if (Fw.gemv(lastp, H, head, H, vocab, B, nullptr, logits, vocab)) return 1;
-        argmax_kernel<<<B, 256, 0, st>>>(logits, vocab, cur_tok, d_out, n_steps, d_step); B2_LAUNCH_CHECK(ctx);
+        if (samp.do_sample) {
+            SampleParams sp = make_sample_params(samp, logits, B, vocab, s_last, s_cnt, s_scratch, d_step, d_out);
+            sp.cur_tok = cur_tok; sp.out_stride_steps = n_steps;
+            if (sample_rows(ctx, sp)) return 1;
+        } else { argmax_kernel<<<B, 256, 0, st>>>(logits, vocab, cur_tok, d_out, n_steps, d_step); B2_LAUNCH_CHECK(ctx); }
         step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
         return 0;
     };

@@ -36,7 +36,11 @@ struct Orpheus {
     int prepare();
     // greedy continuation of B prompts for n_steps tokens each (generate_from_batch's loop without the stop condition):
     // out_tokens [B][n_steps]; out_logits (optional) [B][n_steps][vocab]
-    int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits);
+    int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
+        return generate(B, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits);
+    }
+    // the same loop under the reference sampler's settings (sampler.cu): sampling == nullptr or do_sample == 0 is the greedy sampler::max
+    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits);
     void free_all();
 };
 

@@ -164,7 +164,8 @@ void Parler::free_all() {
     for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
 }
 
-int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
+int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits) {
+    const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("parler: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
     B2_CUDA(cudaSetDevice(ctx->device));
@@ -179,7 +180,7 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
     if (Tmax > max_ctx) { set_error("parler: %d positions exceed the model's context of %d", Tmax, max_ctx); return 1; }
     const size_t cache = (size_t) n_layers * B * Tmax * H * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 6 * H + F) * 4 + (size_t) B * NV * 4 + (size_t) n_steps * B * n_out * 4 + (size_t) B * n_out * 4 +
-                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20);
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
     PFwd Fw{this, ctx, st};
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * H);
@@ -189,7 +190,11 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
     int * row_tok = Fw.al<int>((size_t) Rmax), * row_pos = Fw.al<int>((size_t) Rmax), * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax), * row_dst = Fw.al<int>((size_t) Rmax);
     int * cross_base = Fw.al<int>((size_t) Rmax), * cross_len = Fw.al<int>((size_t) Rmax);
     int * d_np = Fw.al<int>((size_t) B), * ids = Fw.al<int>((size_t) B * n_out), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
+    int * s_last = Fw.al<int>((size_t) B * n_out), * s_cnt = Fw.al<int>((size_t) B * n_out);
+    float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * NV) : nullptr;
     if (Fw.fail) return 1;
+    B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * n_out * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
+    B2_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t) B * n_out * 4, st));
 
     std::vector<int> ht((size_t) R0), hp((size_t) R0), hb((size_t) R0), hl((size_t) R0), hd((size_t) R0), hcb((size_t) Rmax, 0), hcl((size_t) Rmax, n_enc), hnp((size_t) B);
     {
@@ -250,7 +255,8 @@ int Parler::generate_greedy(int B, const uint32_t * const * prompts, const int32
         if (run_layers(B)) return 1;
         if (Fw.ln(x, ln_w, ln_b, H, B, xn)) return 1;
         if (Fw.gemv(xn, H, heads_w, H, NV, B, nullptr, logits, NV)) return 1;                  // the n_out heads as one [n_out * vocab][hidden] matrix
-        argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx);
+        if (samp.do_sample) { if (sample_rows(ctx, make_sample_params(samp, logits, B * n_out, vocab, s_last, s_cnt, s_scratch, d_step, d_out))) return 1; }
+        else { argmax_rows_kernel<<<B * n_out, 256, 0, st>>>(logits, vocab, d_out, d_step); B2_LAUNCH_CHECK(ctx); }
         step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
         return 0;
     };

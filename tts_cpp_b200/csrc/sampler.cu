@@ -1,0 +1,163 @@
+// sampler.cu -- the reference sampler on the device ("sampler.cpp hot loop").
+//
+// Restates sampler::sample (reference src/sampler.cpp:3-70) for many heads at once, one block per head: sampler::max (first maximum; also the stabiliser of
+// the softmax), the repetition penalty (the last sampled token's logit divided by penalty^count, in double like std::pow), temperature, top-k (sorted by
+// value, ties to the lower id), the softmax with its sequential fp32 denominator, top-p trimming WITHOUT renormalisation (the uniform is scaled by
+// min(prob_sum, top_p) instead) and the cumulative draw.  The reference draws its uniform from a std::minstd_rand freshly seeded from std::random_device on
+// every call, so nothing about its random stream can be reproduced: here the uniform is a counter-based hash of (seed, row, step), which makes runs
+// repeatable and lets a captured CUDA graph of a decode step be replayed.  oracle/sampler_port.py is the checker (pinned to the reference stage by stage
+// and, for the draw rule, by a histogram of the reference's own draws).
+//
+// First correct version: top-k by k rounds of block arg-max over the row (k x V reads: fine for the 1 088-wide codebook heads, the first thing to replace
+// by a radix select for Orpheus' 156 k-wide vocabulary); the sequential fp32 sums that fix the rounding of the reference are done by one thread.
+#include "kernels.cuh"
+
+#include <cmath>
+
+namespace b2 {
+namespace {
+
+__device__ __host__ inline float uniform_from_counter(unsigned long long seed, unsigned long long row, unsigned long long step) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (row + 1) + 0xD1B54A32D192ED03ull * (step + 1);      // splitmix64 finaliser over a mixed counter
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float) (x >> 40) * (1.0f / 16777216.0f);                                                           // 24 bits -> [0, 1)
+}
+
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+// block-wide (value, index) maximum, ties to the lower index; every thread gets the result
+__device__ ArgMax block_argmax(float v, int i, float * sv, int * si) {
+    const int tid = threadIdx.x;
+    sv[tid] = v; si[tid] = i;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o && better(sv[tid + o], si[tid + o], sv[tid], si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; }
+        __syncthreads();
+    }
+    ArgMax r{sv[0], si[0]};
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) sample_rows_kernel(const SampleParams p) {
+    __shared__ float sv[256]; __shared__ int si[256];
+    __shared__ int pick_idx[SAMPLE_MAX_TOP_K]; __shared__ float pick_val[SAMPLE_MAX_TOP_K];
+    __shared__ int s_n, s_tok; __shared__ float s_mh;
+    const int row = blockIdx.x, tid = threadIdx.x, V = p.V;
+    const float * lg = p.logits + (size_t) row * V;
+    const int step = p.d_step ? *p.d_step : 0;
+    const bool has_rp = p.repetition_penalty != 1.0f;
+    const int last = has_rp ? p.last_ids[row] : -1;
+    double pen_d = 1.0;                                   // applied as float(v / pow(penalty, count)): the double division of the reference
+    if (has_rp && last >= 0) pen_d = pow((double) p.repetition_penalty, (double) p.rep_counts[row]);
+    auto eff = [&](int ii) -> float { const float v = lg[ii]; return (has_rp && ii == last) ? (float) ((double) v / pen_d) : v; };
+
+    // sampler::max
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int ii = tid; ii < V; ii += 256) { const float v = eff(ii); if (better(v, ii, bv, bi)) { bv = v; bi = ii; } }
+    const ArgMax mx = block_argmax(bv, bi, sv, si);
+    int tok = mx.i;
+    if (p.do_sample) {
+        const bool has_t = p.temperature != 1.0f;
+        const float max_val = has_t ? mx.v / p.temperature : mx.v;
+        const bool nucleus_k = p.top_k > 0 && p.top_k < V;
+        const float u = uniform_from_counter(p.seed, (unsigned long long) row, (unsigned long long) step);
+        float * probs_all = p.scratch ? p.scratch + (size_t) row * V : nullptr;
+        if (p.top_p < 1.0f) {
+            // softmax over the whole vocabulary first, then the picks in order of probability until top_k or top_p is reached
+            for (int ii = tid; ii < V; ii += 256) { float v = eff(ii); if (has_t) v /= p.temperature; probs_all[ii] = expf(v - max_val); }
+            __syncthreads();
+            if (tid == 0) { float s = 0.f; for (int ii = 0; ii < V; ii++) s += probs_all[ii]; s_mh = s; }
+            __syncthreads();
+            const float denom = s_mh;
+            __syncthreads();
+            for (int ii = tid; ii < V; ii += 256) probs_all[ii] = probs_all[ii] / denom;
+            __syncthreads();
+            const int kmax = nucleus_k ? p.top_k : (V < SAMPLE_MAX_TOP_K ? V : SAMPLE_MAX_TOP_K);
+            float prob_sum = 0.f; int n = 0; bool done = false;
+            while (n < kmax && !done) {
+                float cv = -INFINITY; int ci = 0x7fffffff;
+                for (int ii = tid; ii < V; ii += 256) { const float v = probs_all[ii]; if (v >= 0.f && better(v, ii, cv, ci)) { cv = v; ci = ii; } }
+                const ArgMax a = block_argmax(cv, ci, sv, si);
+                if (tid == 0) { pick_idx[n] = a.i; pick_val[n] = a.v; probs_all[a.i] = -1.0f; }      // negative marks "already picked"
+                prob_sum += a.v; n++;
+                if (prob_sum >= p.top_p) done = true;
+                __syncthreads();
+            }
+            if (tid == 0) { s_n = n; s_mh = fminf(prob_sum, p.top_p); }
+        } else if (nucleus_k) {
+            // top-k by value, then the softmax over the picks
+            float pv = INFINITY; int pi = -1;                                        // the previous pick: later picks are strictly "worse" in (value desc, id asc) order
+            for (int n = 0; n < p.top_k; n++) {
+                float cv = -INFINITY; int ci = 0x7fffffff;
+                for (int ii = tid; ii < V; ii += 256) {
+                    const float v = eff(ii);
+                    const bool after = v < pv || (v == pv && ii > pi);
+                    if (after && better(v, ii, cv, ci)) { cv = v; ci = ii; }
+                }
+                const ArgMax a = block_argmax(cv, ci, sv, si);
+                if (tid == 0) { pick_idx[n] = a.i; pick_val[n] = a.v; }
+                pv = a.v; pi = a.i;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float s = 0.f;
+                for (int n = 0; n < p.top_k; n++) { float v = pick_val[n]; if (has_t) v /= p.temperature; v = expf(v - max_val); pick_val[n] = v; s += v; }
+                for (int n = 0; n < p.top_k; n++) pick_val[n] = pick_val[n] / s;
+                s_n = p.top_k; s_mh = 1.0f;
+            }
+        } else {
+            // no nucleus: the softmax over the whole vocabulary, drawn in index order
+            for (int ii = tid; ii < V; ii += 256) { float v = eff(ii); if (has_t) v /= p.temperature; probs_all[ii] = expf(v - max_val); }
+            __syncthreads();
+            if (tid == 0) {
+                float s = 0.f;
+                for (int ii = 0; ii < V; ii++) s += probs_all[ii];
+                float c = 0.f; int t = V - 1;
+                for (int ii = 0; ii < V; ii++) { c += probs_all[ii] / s; if (u <= c) { t = ii; break; } }
+                s_tok = t; s_n = 0;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && s_n > 0) {
+            const float a = p.top_p < 1.0f ? u * s_mh : u;
+            float c = 0.f; int t = pick_idx[s_n - 1];
+            for (int n = 0; n < s_n; n++) { c += pick_val[n]; if (a <= c || n >= s_n - 1) { t = pick_idx[n]; break; } }
+            s_tok = t;
+        }
+        __syncthreads();
+        tok = s_tok;
+    }
+    if (tid == 0) {
+        if (has_rp && p.do_sample) {                      // sampler::sample's repetition bookkeeping (sampler::max does none)
+            int cnt = p.rep_counts[row];
+            if (last != tok) cnt = 0;
+            p.last_ids[row] = tok; p.rep_counts[row] = cnt + 1;
+        }
+        if (p.out_stride_steps) p.out[(size_t) row * p.out_stride_steps + step] = tok;
+        else p.out[(size_t) step * p.rows + row] = tok;
+        if (p.cur_tok) p.cur_tok[row] = tok;
+    }
+}
+
+}  // namespace
+
+float sample_uniform_host(unsigned long long seed, unsigned long long row, unsigned long long step) { return uniform_from_counter(seed, row, step); }
+
+int sample_rows(Ctx * ctx, const SampleParams & p) {
+    if (p.rows <= 0) return 0;
+    if (p.do_sample) {
+        if (p.top_k > SAMPLE_MAX_TOP_K) { set_error("sampler: top_k %d > %d", p.top_k, SAMPLE_MAX_TOP_K); return 1; }
+        const bool nucleus_k = p.top_k > 0 && p.top_k < p.V;
+        if ((p.top_p < 1.0f || !nucleus_k) && !p.scratch) { set_error("sampler: top_p < 1 or top_k == 0 needs the [rows][V] scratch buffer"); return 1; }
+        if (p.repetition_penalty != 1.0f && (!p.last_ids || !p.rep_counts)) { set_error("sampler: repetition penalty needs the last_ids / rep_counts state"); return 1; }
+    }
+    sample_rows_kernel<<<p.rows, 256, 0, ctx->stream>>>(p);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+}  // namespace b2
