@@ -207,8 +207,10 @@ void  b2tts_parler_free(b2tts_parler * m);
 int   b2tts_parler_info(const b2tts_parler * m, int * n_heads, int * out_vocab, int * n_layers, int * hidden_size);
 int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
                                    int32_t * out_tokens, float * out_logits);
+/* n_generated != NULL turns on the reference's stop rule (eos_seen feeding + check_stopping, model.cpp:715-732,795-832): n_generated[b] = frames before the
+ * reference's loop would have ended (position >= max_generation, or every head has produced EOS), rows past it are zero.  NULL: fixed-length generation. */
 int   b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
-                            int32_t * out_tokens, float * out_logits);
+                            int32_t * out_tokens, float * out_logits, int32_t * n_generated);
 float b2tts_parler_last_ms(const b2tts_parler * m);
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m);   /* bytes of the matrices, tables and norms resident in HBM (F16 matrices count 2 bytes) */
 

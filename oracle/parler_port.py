@@ -96,16 +96,25 @@ class ParlerPort:
         self.pos += n
         return torch.stack([self.mm(x, f"lm_heads.{i}.weight.head") for i in range(self.n_out)])
 
-    def greedy(self, prompt, steps: int):
-        """Returns (tokens [steps, n_out], logits [steps, n_out, vocab]) like oracle/_ref/parler_ref."""
+    def greedy(self, prompt, steps: int, stop: bool = False):
+        """Returns (tokens [steps', n_out], logits [steps', n_out, vocab]) like oracle/_ref/parler_ref.  stop: with the reference's stop rule
+        (parler_context::eos_seen feeding + check_stopping, model.cpp:715-732,795-832) instead of a plain step cap."""
         self.reset()
         tok = torch.from_numpy(np.asarray(prompt).astype(np.int64))
         x = self.w["embed_prompts"][tok] + self.w["positional_embed"][torch.arange(tok.numel())]
         self.step(x)
         toks, logits = [], []
         last = None
+        seen = [False] * self.n_out                  # eos_seen: updated by check_stopping at the top of an iteration, i.e. AFTER the next batch was built
+        max_gen = self.kv["parler-tts.decoder.max_generation"]
         for s in range(steps):                       # the audio batch built after decode number s has current_step == s
-            ids = [int(last[i]) if s > i else self.bos for i in range(self.n_out)]
+            ids = [(self.eos if seen[i] else int(last[i])) if s > i else self.bos for i in range(self.n_out)]
+            if stop and s >= 1:                      # check_stopping before this decode
+                if self.pos >= max_gen:
+                    break
+                seen = [seen[i] or int(last[i]) == self.eos for i in range(self.n_out)]
+                if all(seen):
+                    break
             x = None
             for i in range(self.n_out):              # embds[0][id0], then embds[i][id_i] + accumulated (parler_build_inp_embd)
                 e = self.w[f"embed_tokens.{i}.weight"][ids[i]]

@@ -5,7 +5,7 @@
 // audio steps (9 codebook tokens each) and the logits of every step out.  Loading follows parler_model_loader::from_file and
 // runner_from_file's weight loop (src/models/parler/loader.cpp:8-23, src/models/loaders.cpp:79-89) without a tokenizer.
 //
-// usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet]
+// usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet] [--stop]
 //   writes <out_prefix>.u<k>.tokens.i32 ([N][heads] generated ids) and <out_prefix>.u<k>.logits.f32 ([N][heads][output_vocab])
 #include "models/parler/model.h"
 #include "ggml.h"
@@ -22,12 +22,13 @@
 using clk = std::chrono::steady_clock;
 
 int main(int argc, char ** argv) {
-    if (argc < 4) { fprintf(stderr, "usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet]\n"); return 2; }
-    int threads = 4, steps = 6; bool quiet = false;
+    if (argc < 4) { fprintf(stderr, "usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet] [--stop]\n"); return 2; }
+    int threads = 4, steps = 6; bool quiet = false, use_stop = false;
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--quiet")) quiet = true;
+        else if (!strcmp(argv[i], "--stop")) use_stop = true;
     }
     ggml_context * weight_ctx = nullptr;
     gguf_init_params gp; gp.no_alloc = false; gp.ctx = &weight_ctx;
@@ -72,7 +73,7 @@ int main(int argc, char ** argv) {
         std::vector<float> all_logits;
         auto t0 = clk::now();
         int audio_steps = 0;
-        while (audio_steps < steps) {               // generate_from_batch's loop (model.cpp:762-786) with a step cap instead of check_stopping
+        while (audio_steps < steps && !(use_stop && runner->check_stopping())) {   // generate_from_batch's loop (model.cpp:762-786); --stop: with check_stopping, else a step cap only
             if (runner->decode(batch)) return 3;
             if (!batch.audio_generation) pctx->prompt_end_position += batch.sequence_length;
             if (batch.audio_generation) {

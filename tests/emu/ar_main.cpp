@@ -18,7 +18,12 @@ static int out_logits(const b2::Orpheus & m) { return m.vocab; }
 template <class M> static int out_width(const M & m) { return m.n_out; }
 template <class M> static int out_logits(const M & m) { return m.n_out * m.vocab; }
 
+static std::vector<int32_t> g_ngen;      // B2EMU_STOP=1: the reference's stop rule; n_generated is appended to out.bin
 template <class M> static int gen(M & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) { return m.generate(B, pp, np, steps, s, tok, lg); }
+static int gen(b2::Parler & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) {
+    if (getenv("B2EMU_STOP")) g_ngen.assign((size_t) B, 0);
+    return m.generate(B, pp, np, steps, s, tok, lg, g_ngen.empty() ? nullptr : g_ngen.data());
+}
 static int gen(b2::Dia & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) { return m.generate(B, pp, np, steps, s, tok, lg, nullptr); }
 
 template <class M> static int run(int argc, char ** argv) {
@@ -47,6 +52,7 @@ template <class M> static int run(int argc, char ** argv) {
     f = fopen(argv[4], "wb");
     fwrite(&W, 4, 1, f); fwrite(&V, 4, 1, f);
     fwrite(tok.data(), 4, tok.size(), f); fwrite(logits.data(), 4, logits.size(), f);
+    if (!g_ngen.empty()) fwrite(g_ngen.data(), 4, g_ngen.size(), f);
     fclose(f);
     fprintf(stderr, "emulated %llu launches, %llu blocks, %llu graph replays\n", (unsigned long long) b2emu::g_launches, (unsigned long long) b2emu::g_blocks, (unsigned long long) b2emu::g_replays);
     return 0;

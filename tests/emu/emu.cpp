@@ -4,6 +4,7 @@
 #include "dac.h"
 
 #include <cstdarg>
+#include <algorithm>
 #include <cstdio>
 #include <vector>
 
@@ -52,6 +53,21 @@ std::vector<char> g_dyn;
 void yield() { Fiber * f = g_cur; b2emu_switch(&f->sp, g_sched_sp); }
 int linear_tid(const Fiber * f) { return (int) (f - g_fibers.data()); }
 
+// A thread that has to wait hands the CPU straight to the next live thread of its group (warp or block) instead of going through the scheduler: in lockstep code
+// every lane then costs one context switch per barrier.  After a few fruitless rounds (divergent code) it falls back to the round-robin scheduler.
+void wait_pass_on(int lo, int hi, int & tries) {
+    Fiber * f = g_cur;
+    if (tries++ < 3 * (hi - lo)) {
+        int t = linear_tid(f);
+        for (int k = 1; k < hi - lo; k++) {
+            const int c = lo + (t - lo + k) % (hi - lo);
+            Fiber * n = &g_fibers[(size_t) c];
+            if (!n->done) { g_cur = n; b2emu_switch(&f->sp, n->sp); return; }
+        }
+    }
+    yield();
+}
+
 void release_if_complete() {      // a thread that exits while others wait at a barrier completes that barrier (CUDA leaves this undefined; be lenient)
     if (g_alive > 0 && g_arrived == g_alive) { g_arrived = 0; g_gen++; }
 }
@@ -73,14 +89,17 @@ void warp_barrier() {
     Warp & w = g_warps[(size_t) linear_tid(g_cur) >> 5];
     const uint64_t gen = w.gen; g_progress++;
     if (++w.arrived == w.alive) { w.arrived = 0; w.gen++; return; }
-    while (w.gen == gen) yield();
+    const int lo = linear_tid(g_cur) & ~31, hi = std::min(lo + 32, (int) g_fibers.size());
+    int tries = 0;
+    while (w.gen == gen) wait_pass_on(lo, hi, tries);
 }
 }  // namespace
 
 void sync_block() {
     const uint64_t gen = g_gen; g_progress++;
     if (++g_arrived == g_alive) { g_arrived = 0; g_gen++; return; }
-    while (g_gen == gen) yield();
+    int tries = 0;
+    while (g_gen == gen) wait_pass_on(0, (int) g_fibers.size(), tries);
 }
 
 uint64_t shfl(uint64_t v, int src_lane) {
@@ -147,8 +166,9 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & bo
                 g_cur = &f;
                 b2emu_switch(&g_sched_sp, f.sp);
                 g_cur = nullptr;
-                if (f.done) live--;
             }
+            live = 0;                                           // threads hand the CPU to each other directly, so any of them may have finished in this round
+            for (int t = 0; t < nt; t++) if (!g_fibers[(size_t) t].done) live++;
             if (live > 0 && g_progress == before) { fprintf(stderr, "b2emu: deadlock -- %d threads of block (%u,%u,%u) wait at a barrier not all reach\n", live, bx, by, bz); abort(); }
         }
     }

@@ -18,6 +18,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
   parler_f16_vectors.npz   : as parler_vectors.npz for the GGUF `quantize --quantized-type F16` would write (decoder matrices and codebook tables F16: the
       reference then rounds the activations to fp16 before every such product)
+  parler_stop_vectors.npz  : the Parler loop run to completion under the reference's stop rule (eos_seen feeding + check_stopping) on two EOS-boosted synthetic
+      GGUFs: one ends at max_generation, one because every head produced EOS; from oracle/ref_parler_driver.cpp --stop
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
   sampler_vectors.npz      : the reference sampler (src/sampler.cpp) on fixed logits under four configurations: nucleus, probabilities, max_head_probs and a
       histogram of 20 000 draws each, from oracle/ref_sampler_driver.cpp
@@ -197,6 +199,27 @@ def parler_vectors(f16: bool = False):
     print("parler f16 vectors:" if f16 else "parler vectors:", {k: v.shape for k, v in out.items()})
 
 
+def parler_stop_vectors():
+    """The reference's Parler loop run to completion with its stop rule (ref_parler_driver --stop) on GGUFs whose EOS logit row is boosted so that greedy
+    decoding emits EOS.  x6, 7-token prompt: heads are fed EOS once they have produced one and the loop ends when every head has (13 frames).  x3, 55-token
+    prompt: the loop ends at max_generation (64 positions) with some heads pinned to EOS (kept short so that the emulated CUDA path can replay it quickly)."""
+    from tts_cpp_b200.synth import cached_parler_gguf
+    rng = np.random.default_rng(7)
+    tmp = tempfile.mkdtemp()
+    out = {"step_cap": np.int32(40)}
+    for name, boost, n_prompt in (("all_eos", 6.0, 7), ("max_generation", 3.0, 55)):
+        q = rng.integers(1, 500, size=n_prompt)
+        pf = os.path.join(tmp, f"{name}.txt")
+        open(pf, "w").write(" ".join(map(str, q)) + "\n")
+        pre = os.path.join(tmp, name)
+        run([os.path.join(REF, "parler_ref"), cached_parler_gguf(seed=0, eos_boost=boost), pf, pre, "--steps", "40", "--threads", "4", "--quiet", "--stop"])
+        out[f"{name}.prompt"] = np.asarray(q, np.int32)
+        out[f"{name}.boost"] = np.float32(boost)
+        out[f"{name}.tokens"] = np.fromfile(f"{pre}.u0.tokens.i32", np.int32).reshape(-1, 9)
+    np.savez_compressed(os.path.join(OUT, "parler_stop_vectors.npz"), **out)
+    print("parler stop vectors:", {k: v.shape for k, v in out.items()})
+
+
 def dia_vectors(f16: bool = False):
     from tts_cpp_b200.synth import cached_dia_gguf
     gguf = cached_dia_gguf(seed=0, f16=f16)
@@ -265,8 +288,9 @@ def sampler_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "dia", "dia_f16", "dia_stop", "sampler"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_stop", "dia", "dia_f16", "dia_stop", "sampler"]
     if "dia_stop" in which: dia_stop_vectors()
+    if "parler_stop" in which: parler_stop_vectors()
     if "sampler" in which: sampler_vectors()
     if "parler_f16" in which: parler_vectors(f16=True)
     if "dia_f16" in which: dia_vectors(f16=True)

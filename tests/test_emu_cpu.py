@@ -229,3 +229,26 @@ def test_parler_sampling_loop_emulated_matches_port(tmp_path):
             want.append(last.astype(np.int32))
         assert np.array_equal(tok[u], np.stack(want)), f"prompt {u}: {tok[u].tolist()} vs {np.stack(want).tolist()}"
     assert not np.array_equal(tok[0], g["tokens0"])          # and it is not the greedy stream
+
+
+@pytest.mark.parametrize("case", ["all_eos", "max_generation"])
+def test_parler_stop_rule_emulated(tmp_path, case):
+    """Parler::generate with n_generated (the reference's stop rule on the device: eos_seen per head, check_stopping per sequence) under emulation against the
+    reference run to completion (tests/golden/parler_stop_vectors.npz): same frame count, same tokens, zero rows past the stop."""
+    g = np.load(os.path.join(GOLD, "parler_stop_vectors.npz"))
+    ref = g[f"{case}.tokens"]
+    prompt, boost = g[f"{case}.prompt"], float(g[f"{case}.boost"])
+    cap = ref.shape[0] + 3                                     # the device loop has no early exit (no host sync per step): keep the emulated run short
+    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
+    pin, pout = str(tmp_path / "p.bin"), str(tmp_path / "o.bin")
+    with open(pin, "wb") as f:
+        f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompt.size)); f.write(prompt.astype(np.uint32).tobytes())
+    r = subprocess.run([exe, "parler", cached_parler_gguf(seed=0, eos_boost=boost), pin, pout], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = open(pout, "rb").read()
+    W, V = struct.unpack("ii", raw[:8])
+    tok = np.frombuffer(raw, np.int32, cap * W, 8).reshape(cap, W)
+    n_gen = int(np.frombuffer(raw[-4:], np.int32)[0])
+    assert n_gen == ref.shape[0]
+    assert np.array_equal(tok[:n_gen], ref) and not tok[n_gen:].any()

@@ -239,3 +239,18 @@ def test_sampler_port_against_reference(name):
         m = expect > 5
         chi2 = float((((got - expect) ** 2)[m] / expect[m]).sum()); dof = int(m.sum())
         assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, f"head {i}: chi2 {chi2:.1f} for {dof} bins"
+
+
+@pytest.mark.parametrize("case", ["all_eos", "max_generation"])
+def test_parler_port_stop_rule_against_reference(case):
+    """oracle/parler_port.py under the reference's stop rule (eos_seen feeding + check_stopping, parler model.cpp:715-732,795-832) on EOS-boosted GGUFs:
+    one case ends because every head produced EOS, the other at max_generation with heads pinned to EOS -- same frames as the reference."""
+    from oracle.parler_port import ParlerPort
+    from tts_cpp_b200.synth import cached_parler_gguf
+    g = np.load(os.path.join(GOLD, "parler_stop_vectors.npz"))
+    port = ParlerPort(cached_parler_gguf(seed=0, eos_boost=float(g[f"{case}.boost"])))
+    toks, _ = port.greedy(g[f"{case}.prompt"], int(g["step_cap"]), stop=True)
+    ref = g[f"{case}.tokens"]
+    assert toks.shape == ref.shape and toks.shape[0] < int(g["step_cap"])
+    assert np.array_equal(toks, ref)
+    assert (ref == 1024).any()

@@ -53,3 +53,31 @@ def test_parler_tensor_core_gemv_f16_matches_reference_tokens():
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
+
+
+STOP_CHILD = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import parler_runner_from_file
+from tts_cpp_b200.synth import cached_parler_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "parler_stop_vectors.npz"))
+ok = True
+for case in ("all_eos", "max_generation"):
+    par = parler_runner_from_file(cached_parler_gguf(seed=0, eos_boost=float(g[f"{case}.boost"])))
+    ref = g[f"{case}.tokens"]
+    toks, ngen = par.generate([g[f"{case}.prompt"]], int(g["step_cap"]))            # greedy, with the reference's stop rule
+    good = int(ngen[0]) == ref.shape[0] and bool(np.array_equal(toks[0, :ref.shape[0]], ref)) and not toks[0, ref.shape[0]:].any()
+    print(f"PARITY parler stop rule {case}: frames {int(ngen[0])} vs {ref.shape[0]} ->", good)
+    ok &= good
+    par.close()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_parler_stop_rule_matches_reference():
+    """eos_seen feeding + check_stopping on the device against the reference run to completion (tests/golden/parler_stop_vectors.npz)."""
+    r = subprocess.run([sys.executable, "-c", STOP_CHILD, ROOT], capture_output=True, text=True, timeout=240)
+    print(r.stdout[-2000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0

@@ -406,12 +406,13 @@ class ParlerRunner:
         return (toks, logits) if want_logits else toks
 
     def generate(self, prompts, n_steps: int, sampling: "Sampling | None" = None):
-        """-> tokens [B][n_steps][n_heads] under the reference sampler's settings (None: greedy)"""
+        """-> (tokens [B][n_steps][n_heads], n_generated [B]) under the reference sampler's settings (None: greedy) and its stop rule"""
         B, arrs, npr, ptrs = _prompt_args(prompts)
         toks = np.empty((B, n_steps, self.n_heads), np.int32)
+        ngen = np.empty(B, np.int32)
         _chk(lib().b2tts_parler_generate(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps), C.byref(sampling) if sampling is not None else None,
-                                         toks.ctypes.data_as(C.POINTER(C.c_int32)), None))
-        return toks
+                                         toks.ctypes.data_as(C.POINTER(C.c_int32)), None, ngen.ctypes.data_as(C.POINTER(C.c_int32))))
+        return toks, ngen
 
     def last_ms(self) -> float:
         lib().b2tts_parler_last_ms.restype = C.c_float

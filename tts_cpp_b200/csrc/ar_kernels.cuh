@@ -388,16 +388,29 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float * __restri
     if (tid == 0) out[(size_t) (d_step ? *d_step : 0) * gridDim.x + b] = si[0];
 }
 
-// rows of an audio decode step under the delay pattern (parler generate_from_batch, model.cpp:762-786; dia model.cpp:843-858): output head i is fed BOS
-// until step i + 1, then the token it produced in the previous step (d_out [steps][B][n_out]).  One row per sequence at position first_pos[b] + step.
+// rows of an audio decode step under the delay pattern (parler generate_audio_tokens, model.cpp:795-832): output head i is fed BOS until step i + 1, then the
+// token it produced in the previous step (d_out [steps][B][n_out]) -- or EOS for good once an EOS of that head is two or more steps old (eos_seen is
+// updated by check_stopping at the top of an iteration, after the next batch was already built).  One row per sequence at position first_pos[b] + step.
+// seen / stopped (may be null: fixed-length generation): parler_context::eos_seen per head and the step at which check_stopping (model.cpp:715-732: position
+// >= max_generation, or every head has produced EOS) would have ended the reference's loop for sequence b.
 // The step number lives in device memory (d_step, advanced by step_advance_kernel) so that one captured CUDA graph of a step can be replayed for every step.
-__global__ void delay_rows_kernel(const int * __restrict__ d_out, const int * __restrict__ first_pos, int B, int n_out, const int * __restrict__ d_step, int bos, int Tmax,
-                                  int * ids, int * row_pos, int * row_base, int * row_len, int * row_dst) {
+__global__ void delay_rows_kernel(const int * __restrict__ d_out, const int * __restrict__ first_pos, int B, int n_out, const int * __restrict__ d_step, int bos, int eos, int max_gen,
+                                  int Tmax, int * seen, int * stopped, int * ids, int * row_pos, int * row_base, int * row_len, int * row_dst) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int step = *d_step;
     const int pos = (first_pos ? first_pos[b] : 0) + step;
-    for (int i = 0; i < n_out; i++) ids[b * n_out + i] = step > i ? d_out[((size_t) (step - 1) * B + b) * n_out + i] : bos;
+    const int * last = d_out + ((size_t) (step > 0 ? step - 1 : 0) * B + b) * n_out;
+    if (seen && step >= 1 && stopped[b] < 0) {                       // check_stopping at the top of this iteration
+        bool stop = pos >= max_gen;
+        if (!stop) { stop = true; for (int i = 0; i < n_out; i++) stop = stop && (seen[b * n_out + i] || last[i] == eos); }
+        if (stop) stopped[b] = step;
+    }
+    for (int i = 0; i < n_out; i++) {
+        const bool s = seen && seen[b * n_out + i];                  // as of the outputs up to step - 2
+        ids[b * n_out + i] = step > i ? (s ? eos : last[i]) : bos;
+        if (seen && step >= 1 && last[i] == eos) seen[b * n_out + i] = 1;
+    }
     row_pos[b] = pos; row_base[b] = b * Tmax; row_len[b] = pos + 1; row_dst[b] = b * Tmax + pos;
 }
 

@@ -225,10 +225,10 @@ int b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint32
     return m->p.generate_greedy(n_sequences, prompts, n_prompt, n_steps, out_tokens, out_logits);
 }
 int b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
-                          int32_t * out_tokens, float * out_logits) {
+                          int32_t * out_tokens, float * out_logits, int32_t * n_generated) {
     if (!m) { set_error("null model"); return 1; }
     const ArSampling a = to_sampling(sampling);
-    return m->p.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits);
+    return m->p.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits, n_generated);
 }
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m) { return m ? m->p.weight_bytes : 0; }

@@ -69,7 +69,7 @@ int Parler::prepare() {
     const std::string a = "parler-tts.decoder.";
     auto kvreq = [&](const std::string & k, int & out) { auto it = kv.find(k); if (it == kv.end()) { set_error("the '%s' key must be specified in the GGUF file.", k.c_str()); return 1; } out = (int) it->second; return 0; };
     if (kvreq(a + "num_hidden_layers", n_layers) || kvreq(a + "attention.head_count", heads) || kvreq(a + "hidden_size", hidden) || kvreq(a + "output_heads", n_out) ||
-        kvreq(a + "out_vocab_size", vocab) || kvreq(a + "encode_length", n_enc) || kvreq(a + "context_length", max_ctx)) return 1;
+        kvreq(a + "out_vocab_size", vocab) || kvreq(a + "encode_length", n_enc) || kvreq(a + "context_length", max_ctx) || kvreq(a + "max_generation", max_generation)) return 1;
     { auto it = kv.find("audio.bos_token_id"); if (it != kv.end()) bos = (int) it->second; it = kv.find("audio.eos_token_id"); if (it != kv.end()) eos = (int) it->second; }
     if (heads <= 0 || hidden % heads || hidden % 4) { set_error("parler: inconsistent head configuration"); return 1; }
     head_dim = hidden / heads;
@@ -164,7 +164,8 @@ void Parler::free_all() {
     for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
 }
 
-int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits) {
+int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits,
+                     int32_t * n_generated) {
     const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("parler: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
@@ -180,7 +181,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     if (Tmax > max_ctx) { set_error("parler: %d positions exceed the model's context of %d", Tmax, max_ctx); return 1; }
     const size_t cache = (size_t) n_layers * B * Tmax * H * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 6 * H + F) * 4 + (size_t) B * NV * 4 + (size_t) n_steps * B * n_out * 4 + (size_t) B * n_out * 4 +
-                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 12 + (size_t) B * 4 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
     PFwd Fw{this, ctx, st};
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * H);
@@ -191,10 +192,12 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     int * cross_base = Fw.al<int>((size_t) Rmax), * cross_len = Fw.al<int>((size_t) Rmax);
     int * d_np = Fw.al<int>((size_t) B), * ids = Fw.al<int>((size_t) B * n_out), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
     int * s_last = Fw.al<int>((size_t) B * n_out), * s_cnt = Fw.al<int>((size_t) B * n_out);
+    int * seen = n_generated ? Fw.al<int>((size_t) B * n_out) : nullptr, * stopped = n_generated ? Fw.al<int>((size_t) B) : nullptr;
     float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * NV) : nullptr;
     if (Fw.fail) return 1;
     B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * n_out * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
     B2_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t) B * n_out * 4, st));
+    if (n_generated) { B2_CUDA(cudaMemsetAsync(seen, 0, (size_t) B * n_out * 4, st)); B2_CUDA(cudaMemsetAsync(stopped, 0xff, (size_t) B * 4, st)); }
 
     std::vector<int> ht((size_t) R0), hp((size_t) R0), hb((size_t) R0), hl((size_t) R0), hd((size_t) R0), hcb((size_t) Rmax, 0), hcl((size_t) Rmax, n_enc), hnp((size_t) B);
     {
@@ -250,7 +253,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     if (run_layers(R0)) return 1;
     // one audio step; the step number is device-resident (d_step), so the launches are identical for every step
     auto run_step = [&]() -> int {
-        delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, d_np, B, n_out, d_step, bos, Tmax, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
+        delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, d_np, B, n_out, d_step, bos, eos, max_generation, Tmax, seen, stopped, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
         codebook_embed_kernel<<<B, 256, 0, st>>>(ids, n_out, tables, (size_t) tab_rows * H, pos_embed, row_pos, H, x); B2_LAUNCH_CHECK(ctx);
         if (run_layers(B)) return 1;
         if (Fw.ln(x, ln_w, ln_b, H, B, xn)) return 1;
@@ -286,12 +289,18 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
         }
     }
     B2_CUDA(cudaEventRecord(ev[1], st));
-    std::vector<int32_t> tmp((size_t) n_steps * B * n_out);
+    std::vector<int32_t> tmp((size_t) n_steps * B * n_out), hstop((size_t) B, -1);
     B2_CUDA(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
+    if (n_generated) B2_CUDA(cudaMemcpyAsync(hstop.data(), stopped, hstop.size() * 4, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
-    for (int s = 0; s < n_steps; s++)
-        for (int b = 0; b < B; b++)
-            for (int i = 0; i < n_out; i++) out_tokens[((size_t) b * n_steps + s) * n_out + i] = tmp[((size_t) s * B + b) * n_out + i];
+    for (int b = 0; b < B; b++) {
+        const int n_gen = hstop[(size_t) b] >= 0 ? hstop[(size_t) b] : n_steps;
+        if (n_generated) n_generated[b] = n_gen;
+        for (int s = 0; s < n_steps; s++) {
+            for (int i = 0; i < n_out; i++) out_tokens[((size_t) b * n_steps + s) * n_out + i] = s < n_gen ? tmp[((size_t) s * B + b) * n_out + i] : 0;
+            if (out_logits && s >= n_gen) memset(out_logits + ((size_t) b * n_steps + s) * NV, 0, (size_t) NV * 4);
+        }
+    }
     cudaEventElapsedTime(&timing_ms, ev[0], ev[1]);
     return 0;
 }

@@ -40,10 +40,14 @@ struct Parler {
     // greedy generation of n_steps audio frames for B prompts (generate_from_batch's loop with a step cap instead of check_stopping):
     // out_tokens [B][n_steps][n_out]; out_logits (optional) [B][n_steps][n_out][vocab]
     int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
-        return generate(B, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits);
+        return generate(B, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits, nullptr);
     }
     // the same loop under the reference sampler's settings (sampler.cu): sampling == nullptr or do_sample == 0 is the greedy sampler::max
-    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits);
+    // n_generated != nullptr turns on the reference's stop rule (parler_context::eos_seen feeding + check_stopping, model.cpp:715-732,795-832): n_generated[b] is
+    // the number of frames sequence b produced before the reference's loop would have ended, rows past it are zero; nullptr: fixed-length generation
+    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits,
+                 int32_t * n_generated);
+    int max_generation = 0;
     void free_all();
 };
 

@@ -508,7 +508,7 @@ def cached_orpheus_gguf(seed: int = 0, cache_dir: str | None = None, **kw) -> st
 
 # ------------------------------------------------------------------------------------------ Parler-TTS decoder
 def parler_tensors(seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, out_vocab: int = 1088, n_heads: int = 9,
-                   prompt_vocab: int = 512, n_enc: int = 12, ctx: int = 4096):
+                   prompt_vocab: int = 512, n_enc: int = 12, ctx: int = 4096, eos_boost: float = 1.0):
     """Synthetic weights in the reference's Parler schema (py-gguf/tts_encoders/parler_tts_gguf_encoder.py:85-131; names after the
     "decoder." prefix as assign_to_decoder sees them, src/models/parler/model.cpp:3-28,271-318)."""
     rng = np.random.default_rng(seed)
@@ -542,6 +542,10 @@ def parler_tensors(seed: int = 0, layers: int = 8, heads: int = 32, head_dim: in
     norm("layer_norm", hidden)
     for i in range(n_heads):
         rand(f"lm_heads.{i}.weight.head", (out_vocab, hidden), hidden, 4.0 / np.sqrt(hidden))
+        if eos_boost != 1.0:            # make the EOS logit (row 1024) win now and then, so that a greedy run exercises eos_seen / check_stopping
+            name, arr = items[-1]
+            arr = arr.copy(); arr[1024] = (arr[1024] * np.float32(eos_boost)).astype(np.float16).astype(np.float32)
+            items[-1] = (name, arr)
     return items
 
 
@@ -556,7 +560,7 @@ def parler_f16_tensor(name: str) -> bool:
 
 
 def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12, f16: bool = False,
-                      max_generation: int = 64) -> dict:
+                      max_generation: int = 64, eos_boost: float = 1.0) -> dict:
     """Small synthetic Parler-TTS GGUF (F32) with a matching small DAC decoder (the reference's loader needs both).  32 heads x 8 layers is
     the smallest shape the reference loads: prep_cross_key_values sizes its metadata pool from n_attn_heads * 2 * n_layers tensors but
     allocates a 4096-node graph in it (src/models/parler/model.cpp:117-129)."""
@@ -565,7 +569,7 @@ def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     w = gguf.GGUFWriter(path, arch="parler-tts")
     dac_rates = (2, 2, 2, 2)
-    items = parler_tensors(seed, layers, heads, head_dim, ffn, n_enc=n_enc) + dac_tensors(seed=seed, d_model=64, latent=32, rates=dac_rates)
+    items = parler_tensors(seed, layers, heads, head_dim, ffn, n_enc=n_enc, eos_boost=eos_boost) + dac_tensors(seed=seed, d_model=64, latent=32, rates=dac_rates)
     n_params = 0
     for name, arr in items:
         n_params += arr.size
