@@ -183,3 +183,21 @@ def test_delay_pattern_undo_matches_the_reference_indexing():
             want.append([flat[j] for j in idx])
         got = dia_adjust_output_tokens(t, V)
         assert got.shape == (len(want), H) and (len(want) == 0 or np.array_equal(got, np.asarray(want)))
+
+
+def test_orpheus_stream_to_snac_codes():
+    """ar_host.orpheus_{n_generated,prepare_output_tokens}: the stopping rule and the 7-token frame -> three SNAC levels mapping (orpheus model.cpp:371-398)."""
+    from tts_cpp_b200.ar_host import orpheus_n_generated, orpheus_prepare_output_tokens
+    base = 128266
+    frames = 5
+    stream = []
+    for f in range(frames):
+        stream += [base + ii * 4096 + (100 * f + ii) for ii in range(7)]
+    stream_stop = stream + [128258, 11, 12]
+    assert orpheus_n_generated(stream_stop) == len(stream) + 1 and orpheus_n_generated(stream) == len(stream) and orpheus_n_generated(stream, max_generation=9) == 9
+    kept = np.asarray(stream_stop[:orpheus_n_generated(stream_stop)])
+    c, m, fine = orpheus_prepare_output_tokens(kept)                  # the trailing stop token does not fill a frame and is dropped
+    assert c.tolist() == [100 * f for f in range(frames)]
+    assert m.tolist() == sum(([100 * f + 1, 100 * f + 4] for f in range(frames)), [])
+    assert fine.tolist() == sum(([100 * f + 2, 100 * f + 3, 100 * f + 5, 100 * f + 6] for f in range(frames)), [])
+    assert len(m) == 2 * len(c) and len(fine) == 4 * len(c)             # the L/4, L/2, L layout snac_runner::run / b2tts_snac_decode_batch takes
