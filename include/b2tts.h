@@ -233,7 +233,30 @@ int   b2tts_dia_generate_greedy(b2tts_dia * m, int n_sequences, const uint32_t *
                                 int32_t * out_tokens, float * out_logits, int32_t * n_generated);
 int   b2tts_dia_generate(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
                          int32_t * out_tokens, float * out_logits, int32_t * n_generated);
+/* generation_configuration::max_tokens (dia_runner::generate, model.cpp:873-879): replaces the model's max_generation_size in check_stopping when > max_delay */
+int   b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens);
 float b2tts_dia_last_ms(const b2tts_dia * m);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Piecewise weight hand-off for the codec and autoregressive models, the same three steps as b2tts_kokoro_{create,assign_weight,prepare}: what the reference's
+ * runner_from_file drives through tts_model_loader::from_file (uint32 metadata), tts_generation_runner::assign_weight (every tensor, full GGUF name, ggml type
+ * 0 = F32 / 1 = F16, ggml dims) and prepare_post_load (reference src/models/loaders.cpp:79-89).  A Parler or Dia runner hands "audio_encoder.*" tensors to its
+ * b2tts_dac and the rest to the decoder; an Orpheus runner "snac.*" to its b2tts_snac (parler/model.cpp:271-318, dia/model.cpp:3-132, orpheus/model.cpp:436-447). */
+int   b2tts_dac_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_dac ** out);
+int   b2tts_dac_assign_weight(b2tts_dac * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+int   b2tts_dac_prepare(b2tts_dac * m);
+int   b2tts_snac_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_snac ** out);
+int   b2tts_snac_assign_weight(b2tts_snac * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+int   b2tts_snac_prepare(b2tts_snac * m);
+int   b2tts_orpheus_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_orpheus ** out);
+int   b2tts_orpheus_assign_weight(b2tts_orpheus * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+int   b2tts_orpheus_prepare(b2tts_orpheus * m);
+int   b2tts_parler_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_parler ** out);
+int   b2tts_parler_assign_weight(b2tts_parler * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+int   b2tts_parler_prepare(b2tts_parler * m);
+int   b2tts_dia_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_dia ** out);
+int   b2tts_dia_assign_weight(b2tts_dia * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
+int   b2tts_dia_prepare(b2tts_dia * m);
 
 #ifdef __cplusplus
 }

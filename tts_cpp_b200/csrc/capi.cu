@@ -120,6 +120,29 @@ int b2tts_kokoro_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_kokoro ** o
 }
 void b2tts_kokoro_free(b2tts_kokoro * m) { if (m) { m->k.free_all(); delete m; } }
 
+// ---- piecewise weight hand-off for the other models: what runner_from_file drives through tts_model_loader::from_file (metadata), assign_weight (every
+// tensor of the GGUF; names outside the model's prefix are ignored by the caller) and prepare_post_load (reference src/models/loaders.cpp:79-89)
+#define B2TTS_HANDOFF(NAME, FIELD)                                                                                                                                   \
+    int b2tts_##NAME##_create(b2tts_ctx * ctx, int n_kv, const char * const * kv_keys, const uint32_t * kv_vals, b2tts_##NAME ** out) {                               \
+        if (!ctx) { set_error("null context"); return 1; }                                                                                                            \
+        b2tts_##NAME * m = new b2tts_##NAME();                                                                                                                        \
+        m->FIELD.ctx = &ctx->c;                                                                                                                                       \
+        for (int i = 0; i < n_kv; i++) m->FIELD.kv[kv_keys[i]] = kv_vals[i];                                                                                          \
+        *out = m;                                                                                                                                                     \
+        return 0;                                                                                                                                                     \
+    }                                                                                                                                                                 \
+    int b2tts_##NAME##_assign_weight(b2tts_##NAME * m, const char * name, int ggml_type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {          \
+        if (!m) { set_error("null model"); return 1; }                                                                                                                \
+        return m->FIELD.assign(name, ggml_type, n_dims, ne, data, nbytes);                                                                                            \
+    }                                                                                                                                                                 \
+    int b2tts_##NAME##_prepare(b2tts_##NAME * m) { if (!m) { set_error("null model"); return 1; } B2_CUDA(cudaSetDevice(m->FIELD.ctx->device)); return m->FIELD.prepare(); }
+B2TTS_HANDOFF(dac, d)
+B2TTS_HANDOFF(snac, s)
+B2TTS_HANDOFF(orpheus, o)
+B2TTS_HANDOFF(parler, p)
+B2TTS_HANDOFF(dia, d)
+#undef B2TTS_HANDOFF
+
 // ---- DAC codec decoder
 int b2tts_dac_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dac ** out) {
     if (!ctx) { set_error("null context"); return 1; }
@@ -261,6 +284,11 @@ int b2tts_dia_generate(b2tts_dia * m, int n_sequences, const uint32_t * const * 
     if (!m) { set_error("null model"); return 1; }
     const ArSampling a = to_sampling(sampling);
     return m->d.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits, n_generated);
+}
+int b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens) {
+    if (!m) { set_error("null model"); return 1; }
+    if (max_tokens > m->d.max_delay) m->d.max_gen = max_tokens;
+    return 0;
 }
 float b2tts_dia_last_ms(const b2tts_dia * m) { return m ? m->d.timing_ms : 0.f; }
 
