@@ -29,7 +29,7 @@ sys.exit(0 if ok else 1)
 
 @pytest.mark.parametrize("model", ["orpheus", "parler", "dia"])
 def test_cuda_graph_replay_matches_reference_tokens(model):
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, model], capture_output=True, text=True, timeout=240, env=dict(os.environ, B2TTS_AR_GRAPH="1"))
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, model], capture_output=True, text=True, timeout=150, env=dict(os.environ, B2TTS_AR_GRAPH="1"))
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0

@@ -38,7 +38,7 @@ sys.exit(0 if ok else 1)
 
 @pytest.mark.parametrize("dtype", ["f32", "f16"])
 def test_dia_greedy_tokens_and_logits_match_reference(dtype):
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=150)
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0

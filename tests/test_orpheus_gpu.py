@@ -36,7 +36,7 @@ sys.exit(0 if ok else 1)
 
 
 def test_orpheus_greedy_tokens_and_logits_match_reference():
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=150)
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0

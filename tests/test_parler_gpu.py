@@ -41,7 +41,7 @@ def test_parler_greedy_tokens_and_logits_match_reference(dtype):
     """f16: the GGUF `quantize --quantized-type F16` writes (decoder matrices F16, activations rounded to fp16 before each such product).  Two runs
     of that model that differ only in summation order already differ by 1.5e-3 RMS / 6e-3 max in the logits (rounding boundaries), so the bar there
     is identical token ids + 3e-2."""
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=150)
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
@@ -49,7 +49,7 @@ def test_parler_greedy_tokens_and_logits_match_reference(dtype):
 
 def test_parler_tensor_core_gemv_f16_matches_reference_tokens():
     """B2TTS_AR_MMA=1: the F16 matrices through gemv_mma_h_kernel (mma.sync with the batch as M) -- same token ids as the F16 reference."""
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, "f16"], capture_output=True, text=True, timeout=240, env=dict(os.environ, B2TTS_AR_MMA="1"))
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, "f16"], capture_output=True, text=True, timeout=150, env=dict(os.environ, B2TTS_AR_MMA="1"))
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
@@ -77,7 +77,7 @@ sys.exit(0 if ok else 1)
 
 def test_parler_stop_rule_matches_reference():
     """eos_seen feeding + check_stopping on the device against the reference run to completion (tests/golden/parler_stop_vectors.npz)."""
-    r = subprocess.run([sys.executable, "-c", STOP_CHILD, ROOT], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([sys.executable, "-c", STOP_CHILD, ROOT], capture_output=True, text=True, timeout=150)
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0

@@ -49,7 +49,7 @@ sys.exit(0 if ok else 1)
 
 
 def test_sampler_matches_port_over_steps():
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=150)
     print(r.stdout[-3000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
