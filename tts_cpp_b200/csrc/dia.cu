@@ -45,7 +45,7 @@ int Dia::prepare() {
         kvreq("dia.decoder.output_heads", n_out) || kvreq("dia.decoder.output_vocab_size", vocab) || kvreq("dia.decoder.max_generation_size", max_gen)) return 1;
     kvopt("dia.bos_token_id", bos); kvopt("dia.eos_token_id", eos); kvopt("dia.pad_token_id", pad); kvopt("dia.max_delay", max_delay);
     { auto it = kv.find("dia.cfg_scale#f32"); if (it != kv.end()) memcpy(&cfg, &it->second, 4); }
-    if (heads <= 0 || rep <= 0 || heads % rep || head_dim % 2 || n_out > 9) { set_error("dia: inconsistent head configuration"); return 1; }
+    if (heads <= 0 || rep <= 0 || heads % rep || head_dim % 4 || n_out > 9) { set_error("dia: inconsistent head configuration"); return 1; }
     hidden = heads * head_dim; kv_hidden = heads / rep * head_dim; enc_inner = enc_heads * head_dim;
     bool ok = true;
     auto find = [&](const std::string & n, int64_t expect) -> const HostTensor * {

@@ -42,7 +42,7 @@ int Orpheus::prepare() {
     if (kvreq("orpheus.layers", n_layers) || kvreq("orpheus.vocab_size", vocab) || kvreq("orpheus.attn_heads", heads) || kvreq("orpheus.kv_attn_heads", kv_heads) ||
         kvreq("orpheus.head_dim", head_dim) || kvreq("orpheus.hidden_size", hidden) || kvreq("orpheus.kv_hidden_size", kv_hidden)) return 1;
     { auto it = kv.find("orpheus.stopping_token_id"); stopping_token = it != kv.end() ? (int) it->second : 128258; }
-    if (hidden != heads * head_dim || kv_hidden != kv_heads * head_dim || heads % kv_heads || head_dim % 2 || hidden % 4) { set_error("orpheus: inconsistent head configuration"); return 1; }
+    if (hidden != heads * head_dim || kv_hidden != kv_heads * head_dim || heads % kv_heads || head_dim % 4 || hidden % 4) { set_error("orpheus: inconsistent head configuration"); return 1; }
     bool ok = true;
     auto up = [&](const std::string & n, int64_t expect) -> float * {
         auto it = host.find(n);

@@ -71,7 +71,7 @@ int Parler::prepare() {
     if (kvreq(a + "num_hidden_layers", n_layers) || kvreq(a + "attention.head_count", heads) || kvreq(a + "hidden_size", hidden) || kvreq(a + "output_heads", n_out) ||
         kvreq(a + "out_vocab_size", vocab) || kvreq(a + "encode_length", n_enc) || kvreq(a + "context_length", max_ctx) || kvreq(a + "max_generation", max_generation)) return 1;
     { auto it = kv.find("audio.bos_token_id"); if (it != kv.end()) bos = (int) it->second; it = kv.find("audio.eos_token_id"); if (it != kv.end()) eos = (int) it->second; }
-    if (heads <= 0 || hidden % heads || hidden % 4) { set_error("parler: inconsistent head configuration"); return 1; }
+    if (heads <= 0 || hidden % heads || hidden % 4 || (hidden / heads) % 4) { set_error("parler: inconsistent head configuration (head size must be a multiple of 4)"); return 1; }
     head_dim = hidden / heads;
     bool ok = true;
     auto find = [&](const std::string & n, int64_t expect) -> const HostTensor * {
