@@ -43,8 +43,8 @@ def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag, env=None, want_stde
     return (tok, logits, r.stderr) if want_stderr else (tok, logits)
 
 
-def _run_orpheus(tmp_path, prompts, steps, tag):
-    tok, logits = _run_ar(tmp_path, "orpheus", cached_orpheus_gguf(seed=0), prompts, steps, tag)
+def _run_orpheus(tmp_path, prompts, steps, tag, env=None):
+    tok, logits = _run_ar(tmp_path, "orpheus", cached_orpheus_gguf(seed=0), prompts, steps, tag, env=env)
     return tok[:, :, 0], logits
 
 
@@ -62,6 +62,8 @@ def test_orpheus_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path
         assert d < 1e-3      # same tolerance as tests/test_orpheus_gpu.py (measured 4.5e-6: fp32 throughout, summation order differs)
     single, _ = _run_orpheus(tmp_path, [prompts[1]], steps, "s")
     assert np.array_equal(single[0], tok[1])         # batching does not change a sequence
+    plain, lp = _run_orpheus(tmp_path, prompts, steps, "p", env={"B2TTS_AR_ATT": "plain"})      # one block per query head instead of per kv-head group
+    assert np.array_equal(plain, tok) and float(np.abs(lp - logits).max()) < 1e-4
 
 
 @pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])

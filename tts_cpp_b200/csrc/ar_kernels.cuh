@@ -268,6 +268,94 @@ __global__ void __launch_bounds__(128) attention_kernel(const float * __restrict
         out[(size_t) r * H + (size_t) h * hd + d] = a;
     }
 }
+// The same attention for ALL the query heads that share one kv head (grid: rows x kv_heads): every K and V row of the compact cache is read from HBM once per
+// kv head instead of once per query head (3x less cache traffic for Orpheus' 24 / 8 heads, 4x for Dia), and the P.V product uses the whole block (16 threads x
+// 16 B cover a V row, 8 slices of positions reduced in a fixed order).  Scores, maxima and the double-accumulated softmax sums are computed exactly as in
+// attention_kernel (same per-thread order, same trees); only the P.V summation order differs.  REP = heads / kv_heads <= 8, hd % 4 == 0, hd <= 128.
+constexpr int ATT_MAX_REP = 8;
+__global__ void __launch_bounds__(128) attention_gqa_kernel(const float * __restrict__ q, const float * __restrict__ Kc, const float * __restrict__ Vc,
+                                                            const int * __restrict__ row_base, const int * __restrict__ row_len, int heads, int kv_heads, int hd,
+                                                            int Tcap, float scale, float * __restrict__ out) {
+    extern __shared__ __align__(16) float ag_smem[];
+    const int rep = heads / kv_heads, Tp = (Tcap + 3) & ~3;
+    float * sc = ag_smem;                                      // [rep][Tp] scores, then probabilities
+    float * sq = sc + (size_t) rep * Tp;                        // [rep][hd] the query heads of this group
+    float * redf = sq + (size_t) rep * hd;                      // [128] floats
+    double * redd = reinterpret_cast<double *>(redf + 128);     // [128] doubles (8-byte aligned: every segment above is a multiple of 4 floats, and rep*Tp, rep*hd even)
+    float * pv = reinterpret_cast<float *>(redd + 128);         // [8 slices][rep][hd] partial outputs
+    const int r = blockIdx.x, kh = blockIdx.y, tid = threadIdx.x;
+    const size_t base = (size_t) row_base[r];
+    const int T = row_len[r];
+    const int KV = kv_heads * hd, H = heads * hd;
+    for (int i = tid; i < rep * hd; i += 128) sq[i] = q[(size_t) r * H + (size_t) kh * rep * hd + i];      // query heads kh*rep .. kh*rep+rep-1 are contiguous
+    __syncthreads();
+    for (int t = tid; t < T; t += 128) {
+        const float * kr = Kc + (base + t) * KV + (size_t) kh * hd;
+        float a[ATT_MAX_REP];
+#pragma unroll
+        for (int j = 0; j < ATT_MAX_REP; j++) a[j] = 0.f;
+        for (int d = 0; d < hd; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4 *>(kr + d);
+#pragma unroll
+            for (int j = 0; j < ATT_MAX_REP; j++)
+                if (j < rep) { const float * qj = sq + j * hd + d; a[j] = fmaf(qj[3], k4.w, fmaf(qj[2], k4.z, fmaf(qj[1], k4.y, fmaf(qj[0], k4.x, a[j])))); }
+        }
+#pragma unroll
+        for (int j = 0; j < ATT_MAX_REP; j++) if (j < rep) sc[(size_t) j * Tp + t] = a[j] * scale;
+    }
+    for (int j = 0; j < rep; j++) {                             // per query head: max, exp, double sum -- the reductions of attention_kernel
+        float mloc = -INFINITY;
+        for (int t = tid; t < T; t += 128) mloc = fmaxf(mloc, sc[(size_t) j * Tp + t]);      // a thread re-reads the scores it wrote itself
+        redf[tid] = mloc;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) { if (tid < o) redf[tid] = fmaxf(redf[tid], redf[tid + o]); __syncthreads(); }
+        const float m = redf[0];
+        double sum = 0.0;
+        for (int t = tid; t < T; t += 128) { const float e = expf(sc[(size_t) j * Tp + t] - m); sc[(size_t) j * Tp + t] = e; sum += (double) e; }
+        redd[tid] = sum;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) { if (tid < o) redd[tid] += redd[tid + o]; __syncthreads(); }
+        const float inv = (float) (1.0 / redd[0]);
+        __syncthreads();
+        for (int t = tid; t < T; t += 128) sc[(size_t) j * Tp + t] *= inv;
+    }
+    __syncthreads();
+    // P.V: thread (slice, d4) walks positions slice, slice + 8, ... and 4 consecutive channels; a V row is read once for all rep heads
+    const int nd4 = hd >> 2, d4 = tid % 16, slice = tid / 16;   // 16 x 8 threads; channels beyond 64 are covered by looping d4 in steps of 16
+    for (int dd = d4; dd < nd4; dd += 16) {
+        float acc[ATT_MAX_REP][4];
+#pragma unroll
+        for (int j = 0; j < ATT_MAX_REP; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+        for (int t = slice; t < T; t += 8) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(Vc + (base + t) * KV + (size_t) kh * hd + dd * 4);
+#pragma unroll
+            for (int j = 0; j < ATT_MAX_REP; j++)
+                if (j < rep) {
+                    const float p = sc[(size_t) j * Tp + t];
+                    acc[j][0] = fmaf(p, v4.x, acc[j][0]); acc[j][1] = fmaf(p, v4.y, acc[j][1]); acc[j][2] = fmaf(p, v4.z, acc[j][2]); acc[j][3] = fmaf(p, v4.w, acc[j][3]);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < ATT_MAX_REP; j++)
+            if (j < rep) { float * d = pv + ((size_t) slice * rep + j) * hd + dd * 4; d[0] = acc[j][0]; d[1] = acc[j][1]; d[2] = acc[j][2]; d[3] = acc[j][3]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < rep * hd; i += 128) {
+        float a = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < 8; sl++) a += pv[(size_t) sl * rep * hd + i];
+        out[(size_t) r * H + (size_t) kh * rep * hd + i] = a;
+    }
+}
+static inline size_t attention_gqa_smem_bytes(int Tcap, int rep, int hd) { return ((size_t) rep * ((Tcap + 3) & ~3) + (size_t) rep * hd + 128) * 4 + 128 * 8 + (size_t) 8 * rep * hd * 4; }
+static inline bool attention_gqa_ok(int heads, int kv_heads, int hd, int Tcap) {
+    return kv_heads > 0 && heads % kv_heads == 0 && heads / kv_heads <= ATT_MAX_REP && hd % 4 == 0 && hd <= 128 && ((heads / kv_heads) * hd) % 2 == 0 &&
+           attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd) <= 200 * 1024;
+}
+
+// B2TTS_AR_ATT=plain selects attention_kernel (one block per query head) for A/B runs; the grouped kernel is the default
+static inline bool attention_gqa_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_ATT"); return !(e && e[0] == 'p'); }(); return on; }
+
 static inline size_t attention_smem_bytes(int Tcap) { return (size_t) ((Tcap + 1) & ~1) * 4 + 128 * 4 + 128 * 8; }
 
 __global__ void silu_mul_kernel(float * g, const float * __restrict__ u, size_t n) {      // ggml_silu (x / (1 + expf(-x))) * up

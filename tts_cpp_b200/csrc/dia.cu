@@ -187,6 +187,24 @@ __global__ void cfg_combine_kernel(const float * __restrict__ logits2, int NV, f
 struct DFwd {
     Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
+    size_t att_smem_set = 0, gqa_smem_set = 0;
+    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
+    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
+        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
+            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
+            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
+            dim3 grid(R, kv_heads);
+            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        } else {
+            const size_t smem = attention_smem_bytes(Tcap);
+            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
+            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
+            dim3 grid(R, heads);
+            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
         if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {      // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
             const size_t smem = gemv_mma_smem(K);
@@ -286,7 +304,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
             if (Fw.rms(x, L.pre_sa, EH, RE, xn)) return 1;
             if (Fw.gemv(xn, EH, L.wq, EH, EI, RE, nullptr, q, EI) || Fw.gemv(xn, EH, L.wk, EH, EI, RE, nullptr, k, EI) || Fw.gemv(xn, EH, L.wv, EH, EI, RE, nullptr, v, EI)) return 1;
             if (Fw.rope(q, e_pos, RE, enc_heads, head_dim, theta_scale) || Fw.rope(k, e_pos, RE, enc_heads, head_dim, theta_scale)) return 1;
-            { dim3 grid(RE, enc_heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, k, v, e_base, e_len, enc_heads, enc_heads, head_dim, Tcap, 1.0f, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, k, v, e_base, e_len, RE, enc_heads, enc_heads, head_dim, Tcap, 1.0f, att)) return 1;
             if (Fw.gemv(att, EI, L.wo, EI, EH, RE, x, xn, EH)) return 1;                    // xn = attention + residual(x)
             if (Fw.rms(xn, L.post_sa, EH, RE, x)) return 1;
             if (Fw.gemv(x, EH, L.gate, EH, enc_ffn, RE, nullptr, g, enc_ffn) || Fw.gemv(x, EH, L.up, EH, enc_ffn, RE, nullptr, up, enc_ffn)) return 1;
@@ -320,12 +338,12 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
             if (Fw.gemv(xn, D, L.sq, D, D, R, nullptr, q, D) || Fw.gemv(xn, D, L.sk, D, KVD, R, nullptr, kbuf, KVD) || Fw.gemv(xn, D, L.sv, D, KVD, R, nullptr, vbuf, KVD)) return 1;
             if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale) || Fw.rope(kbuf, row_pos, R, heads / rep, head_dim, theta_scale)) return 1;
             store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, KVD, Kl, Vl); B2_LAUNCH_CHECK(ctx);
-            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_base, row_len, heads, heads / rep, head_dim, Tcap, 1.0f, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, heads / rep, head_dim, Tcap, 1.0f, att)) return 1;
             if (Fw.gemv(att, D, L.so, D, D, R, x, xn, D)) return 1;                          // xn = self-attention + residual(x)
             if (Fw.rms(xn, L.pre_ca, D, R, x)) return 1;
             if (Fw.gemv(x, D, L.cq, D, D, R, nullptr, q, D)) return 1;
             if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale)) return 1;              // the cross query is RoPE'd with the decode position
-            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, ckl, cvl, cross_base, cross_len, heads, heads, head_dim, Tcap, 1.0f, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, ckl, cvl, cross_base, cross_len, R, heads, heads, head_dim, Tcap, 1.0f, att)) return 1;
             if (Fw.gemv(att, D, L.co, D, D, R, xn, x, D)) return 1;                          // x = cross-attention + residual(xn)
             if (Fw.rms(x, L.pre_mlp, D, R, xn)) return 1;
             if (Fw.gemv(xn, D, L.gate, D, ffn, R, nullptr, g, ffn) || Fw.gemv(xn, D, L.up, D, ffn, R, nullptr, up, ffn)) return 1;

@@ -93,6 +93,24 @@ namespace {
 struct OFwd {
     Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
+    size_t att_smem_set = 0, gqa_smem_set = 0;
+    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
+    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
+        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
+            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
+            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
+            dim3 grid(R, kv_heads);
+            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        } else {
+            const size_t smem = attention_smem_bytes(Tcap);
+            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
+            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
+            dim3 grid(R, heads);
+            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
         gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
@@ -172,7 +190,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
             if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
             if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
             { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax); B2_LAUNCH_CHECK(ctx); }
-            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_base, row_len, heads, kv_heads, head_dim, Tmax, scale, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, kv_heads, head_dim, Tmax, scale, att)) return 1;
             if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                        // xn = attn_out + residual(x)
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
             if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;

@@ -39,6 +39,24 @@ namespace {
 struct PFwd {
     Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
+    size_t att_smem_set = 0, gqa_smem_set = 0;
+    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
+    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
+        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
+            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
+            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
+            dim3 grid(R, kv_heads);
+            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        } else {
+            const size_t smem = attention_smem_bytes(Tcap);
+            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
+            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
+            dim3 grid(R, heads);
+            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
         if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {      // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
             const size_t smem = gemv_mma_smem(K);
@@ -235,11 +253,11 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
             if (Fw.gemv(xn, H, L.wk, H, H, R, nullptr, kbuf, H)) return 1;
             if (Fw.gemv(xn, H, L.wv, H, H, R, nullptr, vbuf, H)) return 1;
             store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, H, Kl, Vl); B2_LAUNCH_CHECK(ctx);
-            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, Kl, Vl, row_base, row_len, heads, heads, head_dim, Tcap, scale, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, heads, head_dim, Tcap, scale, att)) return 1;
             if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                            // xn = self-attention + residual(x)
             if (Fw.ln(xn, L.ln2_w, L.ln2_b, H, R, x)) return 1;
             if (Fw.gemv(x, H, L.cq, H, H, R, nullptr, q, H)) return 1;
-            { dim3 grid(R, heads); attention_kernel<<<grid, 128, att_smem, st>>>(q, L.cross_k, L.cross_v, cross_base, cross_len, heads, heads, head_dim, Tcap, scale, att); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, L.cross_k, L.cross_v, cross_base, cross_len, R, heads, heads, head_dim, Tcap, scale, att)) return 1;
             if (Fw.gemv(att, H, L.co, H, H, R, xn, x, H)) return 1;                            // x = cross-attention + residual(xn)
             if (Fw.ln(x, L.ln3_w, L.ln3_b, H, R, xn)) return 1;
             if (Fw.gemv(xn, H, L.fc1, H, F, R, nullptr, g, F)) return 1;
