@@ -369,6 +369,10 @@ def main():
                     help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
                          "parler: config 3 end to end (AR decode + DAC), plain first path")
     args = ap.parse_args()
+    if args.workload != "kokoro" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("RANK", "0")) == 0:       # the secondary lines are single-GPU measurements; the headline workload is the one that shards
+            print(json.dumps({"workload": args.workload, "unavailable": "secondary workloads are measured on one GPU (run without torchrun)"}))
+        return 0
     if args.workload == "dac":
         return run_dac(args)
     if args.workload == "parler":
