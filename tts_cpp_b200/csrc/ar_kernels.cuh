@@ -40,70 +40,70 @@ __global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __res
     for (int c = lane; c < H; c += 32) y[(size_t) r * H + c] = (row[c] * scale) * w[c];
 }
 
-// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]; res may alias Y: each element is read and written by the same thread): one warp per output n,
-// the weight row is read once per chunk of 8 rows
-// (ggml_mul_mat with F32 weights and activations; K % 4 == 0)
-constexpr int GR = 8;
-__global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
-                                                        const float * res, float * Y, int ldy) {
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const float * wrow = W + (size_t) n * K;
+// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]; res may alias Y: each element is read and written by the same thread).  A warp owns GN = 4 output rows
+// and walks K in lane-strided 16-byte steps; every activation load is reused for the 4 weight rows and every weight load for the 8 batch rows of a chunk
+// (2 activation loads per weight load instead of 8: the plain one-row-per-warp form is LSU-bound long before HBM).  Per output the summation order is
+// lane-strided k, then the xor-shuffle tree -- independent of GN.  ggml_mul_mat with F32 weights and activations; K % 4 == 0.
+constexpr int GR = 8, GN = 4;
+template <typename WT, bool ROUND_X>
+__device__ __forceinline__ void gemv_rows_body(const float * __restrict__ X, int ldx, const WT * __restrict__ W, int K, int N, int R, const float * res, float * Y, int ldy) {
+    const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GN, lane = threadIdx.x & 31;
+    if (n0 >= N) return;
     for (int r0 = 0; r0 < R; r0 += GR) {
-        float acc[GR];
+        float acc[GN][GR];
 #pragma unroll
-        for (int j = 0; j < GR; j++) acc[j] = 0.f;
+        for (int i = 0; i < GN; i++)
+#pragma unroll
+            for (int j = 0; j < GR; j++) acc[i][j] = 0.f;
         for (int k = lane * 4; k < K; k += 128) {
-            const float4 w4 = *reinterpret_cast<const float4 *>(wrow + k);
+            float w[GN][4];
+#pragma unroll
+            for (int i = 0; i < GN; i++) {
+                const int n = n0 + i < N ? n0 + i : N - 1;                 // rows past N recompute the last row and are not stored
+                if constexpr (sizeof(WT) == 4) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(W + (size_t) n * K + k);
+                    w[i][0] = w4.x; w[i][1] = w4.y; w[i][2] = w4.z; w[i][3] = w4.w;
+                } else {
+                    const __half2 * wp = reinterpret_cast<const __half2 *>(W + (size_t) n * K + k);
+                    const float2 w01 = __half22float2(wp[0]), w23 = __half22float2(wp[1]);
+                    w[i][0] = w01.x; w[i][1] = w01.y; w[i][2] = w23.x; w[i][3] = w23.y;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < GR; j++) {
                 if (r0 + j < R) {
-                    const float4 x4 = *reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + k);
-                    acc[j] = fmaf(x4.w, w4.w, fmaf(x4.z, w4.z, fmaf(x4.y, w4.y, fmaf(x4.x, w4.x, acc[j]))));
+                    float4 x4 = *reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + k);
+                    if constexpr (ROUND_X) {                               // F16 matrix: ggml_mul_mat rounds the activations to fp16 first
+                        x4.x = __half2float(__float2half_rn(x4.x)); x4.y = __half2float(__float2half_rn(x4.y));
+                        x4.z = __half2float(__float2half_rn(x4.z)); x4.w = __half2float(__float2half_rn(x4.w));
+                    }
+#pragma unroll
+                    for (int i = 0; i < GN; i++) acc[i][j] = fmaf(x4.w, w[i][3], fmaf(x4.z, w[i][2], fmaf(x4.y, w[i][1], fmaf(x4.x, w[i][0], acc[i][j]))));
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < GR; j++) {
+        for (int i = 0; i < GN; i++)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-            if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? acc[j] + res[(size_t) (r0 + j) * ldy + n] : acc[j];
-        }
+            for (int j = 0; j < GR; j++) {
+                float a = acc[i][j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0 && r0 + j < R && n0 + i < N) Y[(size_t) (r0 + j) * ldy + n0 + i] = res ? a + res[(size_t) (r0 + j) * ldy + n0 + i] : a;
+            }
     }
 }
-
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
+                                                        const float * res, float * Y, int ldy) {
+    gemv_rows_body<float, false>(X, ldx, W, K, N, R, res, Y, ldy);
+}
 // the same product for an F16 weight matrix: ggml_mul_mat converts the activation rows to fp16 first (the vec_dot_type of F16 is F16, ggml-cpu.c
 // mul_mat from_float) and accumulates the exact fp16 x fp16 products in fp32 -- also what halves the bytes streamed per step
 __global__ void __launch_bounds__(256) gemv_rows_h_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, int K, int N, int R,
                                                           const float * res, float * Y, int ldy) {
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const __half * wrow = W + (size_t) n * K;
-    for (int r0 = 0; r0 < R; r0 += GR) {
-        float acc[GR];
-#pragma unroll
-        for (int j = 0; j < GR; j++) acc[j] = 0.f;
-        for (int k = lane * 4; k < K; k += 128) {
-            const __half2 * wp = reinterpret_cast<const __half2 *>(wrow + k);
-            const float2 w01 = __half22float2(wp[0]), w23 = __half22float2(wp[1]);
-#pragma unroll
-            for (int j = 0; j < GR; j++) {
-                if (r0 + j < R) {
-                    const float4 x4 = *reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + k);
-                    const float x0 = __half2float(__float2half_rn(x4.x)), x1 = __half2float(__float2half_rn(x4.y));
-                    const float x2 = __half2float(__float2half_rn(x4.z)), x3 = __half2float(__float2half_rn(x4.w));
-                    acc[j] = fmaf(x3, w23.y, fmaf(x2, w23.x, fmaf(x1, w01.y, fmaf(x0, w01.x, acc[j]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < GR; j++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-            if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? acc[j] + res[(size_t) (r0 + j) * ldy + n] : acc[j];
-        }
-    }
+    gemv_rows_body<__half, true>(X, ldx, W, K, N, R, res, Y, ldy);
 }
+static inline int gemv_rows_grid(int N) { return cdiv(N, 8 * GN); }
 
 // ---- tensor-core batched GEMV for F16 matrices: the decode step of a batch of <= 16 sequences.
 // At batch 16 an F16 weight byte carries 16 flops: 6.6 TB/s of weights would need ~105 TFLOP/s of fp32 FMA, above what the CUDA cores deliver, and the plain

@@ -216,8 +216,8 @@ struct DFwd {
             }
             return 0;
         }
-        if (W.f16) gemv_rows_h_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, (const __half *) W.p, K, N, R, res, Y, ldy);
-        else       gemv_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>(X, ldx, (const float *) W.p, K, N, R, res, Y, ldy);
+        if (W.f16) gemv_rows_h_kernel<<<gemv_rows_grid(N), 256, 0, st>>>(X, ldx, (const __half *) W.p, K, N, R, res, Y, ldy);
+        else       gemv_rows_kernel<<<gemv_rows_grid(N), 256, 0, st>>>(X, ldx, (const float *) W.p, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }
