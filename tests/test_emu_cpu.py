@@ -64,6 +64,9 @@ def test_orpheus_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path
     assert np.array_equal(single[0], tok[1])         # batching does not change a sequence
     plain, lp = _run_orpheus(tmp_path, prompts, steps, "p", env={"B2TTS_AR_ATT": "plain"})      # one block per query head instead of per kv-head group
     assert np.array_equal(plain, tok) and float(np.abs(lp - logits).max()) < 1e-4
+    for gn in (1, 2, 4):                              # output rows per warp of the plain GEMV: the per-output summation order does not depend on it
+        t2, l2 = _run_orpheus(tmp_path, prompts, steps, f"g{gn}", env={"B2TTS_GEMV_GN": str(gn)})
+        assert np.array_equal(t2, tok) and np.array_equal(l2, logits)
 
 
 @pytest.mark.parametrize("f16", [False, True], ids=["f32", "f16"])

@@ -40,12 +40,13 @@ __global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __res
     for (int c = lane; c < H; c += 32) y[(size_t) r * H + c] = (row[c] * scale) * w[c];
 }
 
-// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]; res may alias Y: each element is read and written by the same thread).  A warp owns GN = 4 output rows
+// Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]; res may alias Y: each element is read and written by the same thread).  A warp owns GN (1, 2 or 4) output rows
 // and walks K in lane-strided 16-byte steps; every activation load is reused for the 4 weight rows and every weight load for the 8 batch rows of a chunk
-// (2 activation loads per weight load instead of 8: the plain one-row-per-warp form is LSU-bound long before HBM).  Per output the summation order is
+// (GN = 4: 2 activation loads per weight load instead of 8 -- the one-row-per-warp form is LSU-bound long before HBM; GN shrinks for small N so that the grid
+// still covers the 148 SMs).  Per output the summation order is
 // lane-strided k, then the xor-shuffle tree -- independent of GN.  ggml_mul_mat with F32 weights and activations; K % 4 == 0.
-constexpr int GR = 8, GN = 4;
-template <typename WT, bool ROUND_X>
+constexpr int GR = 8;
+template <typename WT, bool ROUND_X, int GN>
 __device__ __forceinline__ void gemv_rows_body(const float * __restrict__ X, int ldx, const WT * __restrict__ W, int K, int N, int R, const float * res, float * Y, int ldy) {
     const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GN, lane = threadIdx.x & 31;
     if (n0 >= N) return;
@@ -93,17 +94,38 @@ __device__ __forceinline__ void gemv_rows_body(const float * __restrict__ X, int
             }
     }
 }
+template <int GN>
 __global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
                                                         const float * res, float * Y, int ldy) {
-    gemv_rows_body<float, false>(X, ldx, W, K, N, R, res, Y, ldy);
+    gemv_rows_body<float, false, GN>(X, ldx, W, K, N, R, res, Y, ldy);
 }
 // the same product for an F16 weight matrix: ggml_mul_mat converts the activation rows to fp16 first (the vec_dot_type of F16 is F16, ggml-cpu.c
 // mul_mat from_float) and accumulates the exact fp16 x fp16 products in fp32 -- also what halves the bytes streamed per step
+template <int GN>
 __global__ void __launch_bounds__(256) gemv_rows_h_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, int K, int N, int R,
                                                           const float * res, float * Y, int ldy) {
-    gemv_rows_body<__half, true>(X, ldx, W, K, N, R, res, Y, ldy);
+    gemv_rows_body<__half, true, GN>(X, ldx, W, K, N, R, res, Y, ldy);
 }
-static inline int gemv_rows_grid(int N) { return cdiv(N, 8 * GN); }
+// rows per warp for N outputs: as many as still give every SM a block (148 SMs x 8 warps)
+static inline int gemv_rows_gn(int N) {
+    static const int forced = [] { const char * e = getenv("B2TTS_GEMV_GN"); return e ? atoi(e) : 0; }();      // 1 / 2 / 4: A/B runs and tests
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    return N >= 148 * 8 * 4 ? 4 : (N >= 148 * 8 * 2 ? 2 : 1);
+}
+static inline void gemv_rows_launch(cudaStream_t st, const float * X, int ldx, const void * W, bool f16, int K, int N, int R, const float * res, float * Y, int ldy) {
+    const int gn = gemv_rows_gn(N), grid = cdiv(N, 8 * gn);
+    if (f16) {
+        const __half * w = (const __half *) W;
+        if (gn == 4) gemv_rows_h_kernel<4><<<grid, 256, 0, st>>>(X, ldx, w, K, N, R, res, Y, ldy);
+        else if (gn == 2) gemv_rows_h_kernel<2><<<grid, 256, 0, st>>>(X, ldx, w, K, N, R, res, Y, ldy);
+        else gemv_rows_h_kernel<1><<<grid, 256, 0, st>>>(X, ldx, w, K, N, R, res, Y, ldy);
+    } else {
+        const float * w = (const float *) W;
+        if (gn == 4) gemv_rows_kernel<4><<<grid, 256, 0, st>>>(X, ldx, w, K, N, R, res, Y, ldy);
+        else if (gn == 2) gemv_rows_kernel<2><<<grid, 256, 0, st>>>(X, ldx, w, K, N, R, res, Y, ldy);
+        else gemv_rows_kernel<1><<<grid, 256, 0, st>>>(X, ldx, w, K, N, R, res, Y, ldy);
+    }
+}
 
 // ---- tensor-core batched GEMV for F16 matrices: the decode step of a batch of <= 16 sequences.
 // At batch 16 an F16 weight byte carries 16 flops: 6.6 TB/s of weights would need ~105 TFLOP/s of fp32 FMA, above what the CUDA cores deliver, and the plain

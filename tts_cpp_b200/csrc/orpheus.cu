@@ -112,7 +112,7 @@ struct OFwd {
         return 0;
     }
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        gemv_rows_kernel<<<gemv_rows_grid(N), 256, 0, st>>>(X, ldx, W, K, N, R, res, Y, ldy);
+        gemv_rows_launch(st, X, ldx, W, false, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }

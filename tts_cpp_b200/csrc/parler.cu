@@ -68,8 +68,7 @@ struct PFwd {
             }
             return 0;
         }
-        if (W.f16) gemv_rows_h_kernel<<<gemv_rows_grid(N), 256, 0, st>>>(X, ldx, (const __half *) W.p, K, N, R, res, Y, ldy);
-        else       gemv_rows_kernel<<<gemv_rows_grid(N), 256, 0, st>>>(X, ldx, (const float *) W.p, K, N, R, res, Y, ldy);
+        gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }
