@@ -55,12 +55,16 @@ int linear_tid(const Fiber * f) { return (int) (f - g_fibers.data()); }
 
 // A thread that has to wait hands the CPU straight to the next live thread of its group (warp or block) instead of going through the scheduler: in lockstep code
 // every lane then costs one context switch per barrier.  After a few fruitless rounds (divergent code) it falls back to the round-robin scheduler.
+// B2EMU_REVERSE=1 runs the threads of a block (and hands over at barriers) in descending order instead of ascending: a kernel whose result depends on the
+// order in which threads reach a barrier-free region -- a missing __syncthreads, a race on shared memory -- gives a different answer under the two schedules.
+const bool g_reverse = [] { const char * e = getenv("B2EMU_REVERSE"); return e && e[0] == '1'; }();
+
 void wait_pass_on(int lo, int hi, int & tries) {
     Fiber * f = g_cur;
     if (tries++ < 3 * (hi - lo)) {
         int t = linear_tid(f);
         for (int k = 1; k < hi - lo; k++) {
-            const int c = lo + (t - lo + k) % (hi - lo);
+            const int c = lo + (t - lo + (g_reverse ? (hi - lo) - k : k)) % (hi - lo);
             Fiber * n = &g_fibers[(size_t) c];
             if (!n->done) { g_cur = n; b2emu_switch(&f->sp, n->sp); return; }
         }
@@ -160,7 +164,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & bo
         int live = nt;
         while (live > 0) {
             const uint64_t before = g_progress;
-            for (int t = 0; t < nt; t++) {
+            for (int tt = 0; tt < nt; tt++) {
+                const int t = g_reverse ? nt - 1 - tt : tt;
                 Fiber & f = g_fibers[(size_t) t];
                 if (f.done) continue;
                 g_cur = &f;

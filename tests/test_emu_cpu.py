@@ -64,6 +64,8 @@ def test_orpheus_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path
     assert np.array_equal(single[0], tok[1])         # batching does not change a sequence
     plain, lp = _run_orpheus(tmp_path, prompts, steps, "p", env={"B2TTS_AR_ATT": "plain"})      # one block per query head instead of per kv-head group
     assert np.array_equal(plain, tok) and float(np.abs(lp - logits).max()) < 1e-4
+    rev, lr = _run_orpheus(tmp_path, prompts, steps, "r", env={"B2EMU_REVERSE": "1"})             # threads scheduled in descending order: a result that depends on
+    assert np.array_equal(rev, tok) and np.array_equal(lr, logits)                                  # the order threads reach a barrier-free region (a race) would differ
     for gn in (1, 2, 4):                              # output rows per warp of the plain GEMV: the per-output summation order does not depend on it
         t2, l2 = _run_orpheus(tmp_path, prompts, steps, f"g{gn}", env={"B2TTS_GEMV_GN": str(gn)})
         assert np.array_equal(t2, tok) and np.array_equal(l2, logits)
