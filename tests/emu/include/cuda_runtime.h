@@ -38,7 +38,7 @@ static inline float4 make_float4(float a, float b, float c, float d) { return fl
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorUnknown = 999 };
 typedef struct b2emu_stream * cudaStream_t;
 typedef struct b2emu_event * cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyHostToHost };

@@ -245,14 +245,22 @@ def test_parler_stop_rule_emulated(tmp_path, case):
     g = np.load(os.path.join(GOLD, "parler_stop_vectors.npz"))
     ref = g[f"{case}.tokens"]
     prompt, boost = g[f"{case}.prompt"], float(g[f"{case}.boost"])
-    cap = ref.shape[0] + 3                                     # the device loop has no early exit (no host sync per step): keep the emulated run short
+    cap = ref.shape[0] + 8                                     # a few steps past the stop: the early exit (stop flags read back every 4 steps here) skips most of them
     exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
     pin, pout = str(tmp_path / "p.bin"), str(tmp_path / "o.bin")
     with open(pin, "wb") as f:
         f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompt.size)); f.write(prompt.astype(np.uint32).tobytes())
     r = subprocess.run([exe, "parler", cached_parler_gguf(seed=0, eos_boost=boost), pin, pout], capture_output=True, text=True, timeout=900,
-                       env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1"))
+                       env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1", B2TTS_AR_EXIT_EVERY="4"))
     assert r.returncode == 0, r.stderr[-2000:]
+    launches = int(r.stderr.split("emulated ")[1].split(" launches")[0])
+    if case == "all_eos":                                       # the stop flags are read back every 4 steps here: the batch stops stepping once every sequence has ended
+        r2 = subprocess.run([exe, "parler", cached_parler_gguf(seed=0, eos_boost=boost), pin, pout + ".noexit"], capture_output=True, text=True, timeout=900,
+                            env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1", B2TTS_AR_EXIT_EVERY="1000"))
+        assert r2.returncode == 0, r2.stderr[-2000:]
+        full = int(r2.stderr.split("emulated ")[1].split(" launches")[0])
+        assert full - launches >= 3 * 100, (full, launches)      # at least three ~126-launch steps skipped
+        assert open(pout + ".noexit", "rb").read() == open(pout, "rb").read()
     raw = open(pout, "rb").read()
     W, V = struct.unpack("ii", raw[:8])
     tok = np.frombuffer(raw, np.int32, cap * W, 8).reshape(cap, W)

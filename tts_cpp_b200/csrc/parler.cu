@@ -280,6 +280,16 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
         step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
         return 0;
     };
+    // every `exit_every` steps the per-sequence stop flags are read back (one small sync): when the reference's loop would have ended for EVERY sequence of the
+    // batch the remaining steps are skipped
+    const int exit_every = [] { const char * e = getenv("B2TTS_AR_EXIT_EVERY"); const int v = e ? atoi(e) : 32; return v > 0 ? v : 32; }();
+    const bool track_stop = n_generated != nullptr;
+    std::vector<int32_t> hflags((size_t) B);
+    auto all_stopped = [&]() -> int {          // 1 all stopped, 0 not yet, -1 error
+        if (cudaMemcpyAsync(hflags.data(), stopped, (size_t) B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { set_error("parler: reading the stop flags failed"); return -1; }
+        for (int b = 0; b < B; b++) if (hflags[(size_t) b] < 0) return 0;
+        return 1;
+    };
     // B2TTS_AR_GRAPH=1: capture one step into a CUDA graph and replay it (an audio step is ~15 launches per layer of microsecond kernels: launch-bound
     // otherwise).  Off by default until it has run on hardware; not used when the caller wants every step's logits (a host copy per step).
     const char * ge = getenv("B2TTS_AR_GRAPH");
@@ -293,12 +303,16 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
         if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("parler: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
         if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("parler: cudaGraphInstantiate failed"); return 1; }
         cudaError_t le = cudaSuccess;
-        for (int s = 0; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
+        for (int s = 0; s < n_steps && le == cudaSuccess; s++) {
+            le = cudaGraphLaunch(exec, st);
+            if (track_stop && le == cudaSuccess && (s + 1) % exit_every == 0 && s + 1 < n_steps) { const int a = all_stopped(); if (a < 0) { le = cudaErrorUnknown; } else if (a) break; }
+        }
         ctx->launches += (uint64_t) (n_steps - 1) * (uint64_t) (ctx->launches - launches_before_step);   // the captured launches, replayed
         cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
         if (le != cudaSuccess) { set_error("parler: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
     } else {
         for (int s = 0; s < n_steps; s++) {
+            if (track_stop && s > 0 && s % exit_every == 0) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
             if (run_step()) return 1;
             if (out_logits)
                 for (int b = 0; b < B; b++)
