@@ -21,6 +21,7 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
   parler_stop_vectors.npz  : the Parler loop run to completion under the reference's stop rule (eos_seen feeding + check_stopping) on two EOS-boosted synthetic
       GGUFs: one ends at max_generation, one because every head produced EOS; from oracle/ref_parler_driver.cpp --stop
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
+  orpheus_wide_vectors.npz : as orpheus_vectors.npz for a GGUF with head size 128 (hidden 768)
   sampler_vectors.npz      : the reference sampler (src/sampler.cpp) on fixed logits under four configurations: nucleus, probabilities, max_head_probs and a
       histogram of 20 000 draws each, from oracle/ref_sampler_driver.cpp
   dia_stop_vectors.npz     : one byte-token prompt run until the reference's check_stopping ends the loop (64 frames of 9 tokens, the logits of the
@@ -159,9 +160,10 @@ def snac_vectors():
     print("snac vectors:", pcm.shape, "rms", float(np.sqrt((pcm ** 2).mean())))
 
 
-def orpheus_vectors():
+def orpheus_vectors(wide: bool = False):
+    """wide: head size 128 (hidden 768, a multiple of 256): the shape the tensor-core GEMV of the CUDA path accepts for every matrix"""
     from tts_cpp_b200.synth import cached_orpheus_gguf
-    gguf = cached_orpheus_gguf(seed=0)
+    gguf = cached_orpheus_gguf(seed=0, head_dim=128) if wide else cached_orpheus_gguf(seed=0)
     rng = np.random.default_rng(5)
     prompts = [rng.integers(2, 2000, size=n) for n in (7, 12)]
     tmp = tempfile.mkdtemp()
@@ -175,8 +177,8 @@ def orpheus_vectors():
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, -1)
-    np.savez_compressed(os.path.join(OUT, "orpheus_vectors.npz"), **out)
-    print("orpheus vectors:", {k: v.shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(OUT, "orpheus_wide_vectors.npz" if wide else "orpheus_vectors.npz"), **out)
+    print("orpheus wide vectors:" if wide else "orpheus vectors:", {k: v.shape for k, v in out.items()})
 
 
 def parler_vectors(f16: bool = False):
@@ -288,10 +290,11 @@ def sampler_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_stop", "dia", "dia_f16", "dia_stop", "sampler"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_stop", "dia", "dia_f16", "dia_stop", "sampler", "orpheus_wide"]
     if "dia_stop" in which: dia_stop_vectors()
     if "parler_stop" in which: parler_stop_vectors()
     if "sampler" in which: sampler_vectors()
+    if "orpheus_wide" in which: orpheus_vectors(wide=True)
     if "parler_f16" in which: parler_vectors(f16=True)
     if "dia_f16" in which: dia_vectors(f16=True)
     if "dia" in which: dia_vectors()

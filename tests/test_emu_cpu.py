@@ -267,3 +267,19 @@ def test_parler_stop_rule_emulated(tmp_path, case):
     n_gen = int(np.frombuffer(raw[-4:], np.int32)[0])
     assert n_gen == ref.shape[0]
     assert np.array_equal(tok[:n_gen], ref) and not tok[n_gen:].any()
+
+
+@pytest.mark.parametrize("mma", [False, True], ids=["plain", "split_mma"])
+def test_orpheus_wide_emulated(tmp_path, mma):
+    """Orpheus with head size 128 (hidden 768: every matrix has K % 256 == 0).  split_mma: B2TTS_AR_MMA=1 sends the F32 matrices through gemv_mma_kernel<true>
+    -- W and x as fp16 (hi, lo) pairs, x.W ~ xh.Wh + (xl.Wh + xh.Wl), three tensor-core products instead of an fp32 FMA chain -- which has to stay
+    fp32-faithful: same greedy tokens as the reference and logits within 1e-4 (the plain fp32 path sits at ~6e-6)."""
+    g = np.load(os.path.join(GOLD, "orpheus_wide_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].size)
+    tok, logits = _run_ar(tmp_path, "orpheus", cached_orpheus_gguf(seed=0, head_dim=128), prompts, steps, "w", env={"B2TTS_AR_MMA": "1"} if mma else None)
+    for u in range(2):
+        d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
+        print(f"PARITY(emulated) orpheus wide {'split mma' if mma else 'plain'} prompt {u}: max |logit diff| {d:.3e}")
+        assert np.array_equal(tok[u, :, 0], g[f"tokens{u}"])
+        assert d < 1e-4

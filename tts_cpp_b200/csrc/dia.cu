@@ -185,7 +185,7 @@ __global__ void cfg_combine_kernel(const float * __restrict__ logits2, int NV, f
 }
 
 struct DFwd {
-    Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set = 0;
+    Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set = 0, mma_smem_set_s = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     size_t att_smem_set = 0, gqa_smem_set = 0;
     // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
@@ -206,16 +206,8 @@ struct DFwd {
         return 0;
     }
     int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {      // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
-            const size_t smem = gemv_mma_smem(K);
-            if (smem > mma_smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_mma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); mma_smem_set = smem; }
-            for (int r0 = 0; r0 < R; r0 += 16) {
-                gemv_mma_h_kernel<<<N / 8, 256, smem, st>>>(X + (size_t) r0 * ldx, ldx, (const __half *) W.p, K, N, R - r0 < 16 ? R - r0 : 16, res ? res + (size_t) r0 * ldy : nullptr,
-                                                         Y + (size_t) r0 * ldy, ldy);
-                B2_LAUNCH_CHECK(ctx);
-            }
-            return 0;
-        }
+        if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
+            return gemv_mma_launch(ctx, st, mma_smem_set, mma_smem_set_s, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
         gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;

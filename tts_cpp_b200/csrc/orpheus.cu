@@ -52,6 +52,16 @@ int Orpheus::prepare() {
         if (cudaMalloc(&d, it->second.v.size() * 4) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed for orpheus.%s", n.c_str()); ok = false; return nullptr; }
         cudaMemcpy(d, it->second.v.data(), it->second.v.size() * 4, cudaMemcpyHostToDevice);
         dev_allocs.push_back(d); weight_bytes += it->second.v.size() * 4;
+        if (gemv_mma_enabled() && it->second.shape.size() == 2) {                     // the split copy of a matrix: W = hi + lo, lo carried scaled by 2^11
+            const size_t cnt = it->second.v.size();
+            std::vector<__half> hi(cnt), lo(cnt);
+            for (size_t i = 0; i < cnt; i++) { const float w = it->second.v[i]; hi[i] = __float2half_rn(w); lo[i] = __float2half_rn((w - __half2float(hi[i])) * GM_LO_SCALE); }
+            void * dh = nullptr, * dl = nullptr;
+            if (cudaMalloc(&dh, cnt * 2) != cudaSuccess || cudaMalloc(&dl, cnt * 2) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed for the split of orpheus.%s", n.c_str()); ok = false; return nullptr; }
+            cudaMemcpy(dh, hi.data(), cnt * 2, cudaMemcpyHostToDevice); cudaMemcpy(dl, lo.data(), cnt * 2, cudaMemcpyHostToDevice);
+            dev_allocs.push_back(dh); dev_allocs.push_back(dl); weight_bytes += cnt * 4;
+            split[(const float *) d] = {dh, dl};
+        }
         return (float *) d;
     };
     embed = up("embed_tokens", (int64_t) vocab * hidden);
@@ -91,7 +101,7 @@ void Orpheus::free_all() {
 namespace {
 
 struct OFwd {
-    Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false;
+    Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set = 0, mma_smem_set_s = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     size_t att_smem_set = 0, gqa_smem_set = 0;
     // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
@@ -112,6 +122,10 @@ struct OFwd {
         return 0;
     }
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
+            auto it = m->split.find(W);
+            if (it != m->split.end()) return gemv_mma_launch(ctx, st, mma_smem_set, mma_smem_set_s, X, ldx, (const __half *) it->second.first, (const __half *) it->second.second, K, N, R, res, Y, ldy);
+        }
         gemv_rows_launch(st, X, ldx, W, false, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;

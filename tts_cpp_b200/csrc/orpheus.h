@@ -27,6 +27,8 @@ struct Orpheus {
     int stopping_token = -1;
     float * embed = nullptr, * out_norm = nullptr, * head = nullptr, * rope_ff = nullptr;
     std::vector<OrpheusLayer> layers;
+    // B2TTS_AR_MMA=1: fp16 (hi, 2^11-scaled lo) splits of the F32 matrices for the tensor-core batched GEMV (ar_kernels.cuh gemv_mma_kernel<true>), keyed by the fp32 pointer
+    std::map<const float *, std::pair<const void *, const void *>> split;
 
     Arena arena;
     float timing_ms = 0.f;
