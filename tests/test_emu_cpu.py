@@ -92,7 +92,7 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path,
 
 @pytest.mark.parametrize("model", ["parler", "dia"])
 def test_tensor_core_gemv_emulated_f16(tmp_path, model):
-    """B2TTS_AR_MMA=1: F16 matrices through gemv_mma_h_kernel (mma.sync.m16n8k16 with the batch as M, K split over the warps of a block, the k index permuted
+    """B2TTS_AR_MMA=1: F16 matrices through gemv_mma_kernel<false> (mma.sync.m16n8k16 with the batch as M, K split over the warps of a block, the k index permuted
     consistently on both operands).  Under emulation the instruction is a functional model of the PTX fragment layout; the tokens must be the F16 reference's."""
     g = np.load(os.path.join(GOLD, f"{model}_f16_vectors.npz"))
     prompts = [g["prompt0"], g["prompt1"]]

@@ -40,3 +40,31 @@ def test_orpheus_greedy_tokens_and_logits_match_reference():
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
+
+
+WIDE_CHILD = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import orpheus_runner_from_file
+from tts_cpp_b200.synth import cached_orpheus_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "orpheus_wide_vectors.npz"))
+orph = orpheus_runner_from_file(cached_orpheus_gguf(seed=0, head_dim=128))
+prompts = [g["prompt0"], g["prompt1"]]
+toks, logits = orph.generate_greedy(prompts, g["tokens0"].size, want_logits=True)
+ok = True
+for u in range(2):
+    d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
+    print(f"PARITY orpheus wide ({os.environ.get('B2TTS_AR_MMA', '0')}) prompt {u}: max |logit diff| {d:.3e}")
+    ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < 1e-4
+sys.exit(0 if ok else 1)
+'''
+
+
+@pytest.mark.parametrize("mma", ["0", "1"], ids=["plain", "split_mma"])
+def test_orpheus_wide_tokens_and_logits_match_reference(mma):
+    """hidden 768 (every matrix eligible for the tensor-core GEMV); split_mma: the fp32-faithful three-product path over fp16 (hi, lo) pairs."""
+    r = subprocess.run([sys.executable, "-c", WIDE_CHILD, ROOT], capture_output=True, text=True, timeout=150, env=dict(os.environ, B2TTS_AR_MMA=mma))
+    print(r.stdout[-2000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0

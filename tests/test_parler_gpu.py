@@ -48,7 +48,7 @@ def test_parler_greedy_tokens_and_logits_match_reference(dtype):
 
 
 def test_parler_tensor_core_gemv_f16_matches_reference_tokens():
-    """B2TTS_AR_MMA=1: the F16 matrices through gemv_mma_h_kernel (mma.sync with the batch as M) -- same token ids as the F16 reference."""
+    """B2TTS_AR_MMA=1: the F16 matrices through gemv_mma_kernel<false> (mma.sync with the batch as M) -- same token ids as the F16 reference."""
     r = subprocess.run([sys.executable, "-c", CHILD, ROOT, "f16"], capture_output=True, text=True, timeout=150, env=dict(os.environ, B2TTS_AR_MMA="1"))
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
