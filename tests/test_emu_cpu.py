@@ -283,3 +283,16 @@ def test_orpheus_wide_emulated(tmp_path, mma):
         print(f"PARITY(emulated) orpheus wide {'split mma' if mma else 'plain'} prompt {u}: max |logit diff| {d:.3e}")
         assert np.array_equal(tok[u, :, 0], g[f"tokens{u}"])
         assert d < 1e-4
+
+
+def test_tensor_core_gemv_multi_tile_emulated(tmp_path):
+    """A batch of 18 sequences through the split-operand tensor-core GEMV: the decode steps use two m16 tiles per block (18 rows), the 171-row prompt pass four
+    (chunks of 64) -- the weight fragment of a k-step is reused for every tile, so a large batch still streams each matrix once.  Every sequence must produce the
+    reference's tokens for its prompt, whatever its position in the batch."""
+    g = np.load(os.path.join(GOLD, "orpheus_wide_vectors.npz"))
+    prompts = [g[f"prompt{u % 2}"] for u in range(18)]
+    steps = 3
+    tok, logits = _run_ar(tmp_path, "orpheus", cached_orpheus_gguf(seed=0, head_dim=128), prompts, steps, "mt", env={"B2TTS_AR_MMA": "1"})
+    for u in range(18):
+        assert np.array_equal(tok[u, :, 0], g[f"tokens{u % 2}"][:steps]), u
+        assert float(np.abs(logits[u] - g[f"logits{u % 2}"][:steps]).max()) < 1e-4

@@ -163,55 +163,65 @@ __device__ __forceinline__ void mma16816_f16f32(float * c, const unsigned * a, u
 constexpr int GM_PAD = 8;      // halves of padding per activation row in shared memory: consecutive rows start 4 banks apart
 constexpr int GM_KC  = 2048;   // activations are staged through shared memory in K chunks of this many columns (16 rows x 2048 x fp16 = 64 KB; twice that for SPLIT)
 constexpr float GM_LO_SCALE = 2048.0f;   // SPLIT: the low halves are carried scaled by 2^11 so that they stay in fp16's normal range
-static inline bool gemv_mma_ok(int K, int N, int R) { return R <= 16 && K % 256 == 0 && N % 8 == 0; }
-static inline size_t gemv_mma_smem(int K, bool split) { return (size_t) 16 * ((K < GM_KC ? K : GM_KC) + GM_PAD) * 2 * (split ? 2 : 1) + 8 * 16 * 8 * 4; }
+static inline bool gemv_mma_ok(int K, int N, int R) { (void) R; return K % 256 == 0 && N % 8 == 0; }
+// MT = m16 tiles per block (batch rows / 16): the weight fragment of a k-step is reused for all of them, so a batch of 64 still streams W once
+static inline int gemv_mma_kc(int K, int mt) { const int kc = GM_KC / mt; return K < kc ? K : kc; }
+static inline size_t gemv_mma_smem(int K, bool split, int mt) { return (size_t) 16 * mt * (gemv_mma_kc(K, mt) + GM_PAD) * 2 * (split ? 2 : 1) + (size_t) 8 * 16 * mt * 8 * 4; }
 // off until it has run on hardware (B2TTS_AR_MMA=1 turns it on): the plain kernels are the emulation- and (from round 2) GPU-checked baseline
 static inline bool gemv_mma_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_MMA"); return e && e[0] == '1'; }(); return on; }
 
 // D k-steps of 32: all D weight loads are issued before the first mma so that a lane keeps D x 16 B (SPLIT: 2 x D x 16 B) of the weight stream in flight
 // (read once: streaming hint).  SPLIT: the fp32-faithful product of an F32 matrix -- x = xh + xl, W = Wh + Wl in fp16 pairs, x.W ~ xh.Wh + (xl.Wh + xh.Wl)
 // with the two cross terms in their own accumulator (scaled by 2^11); the dropped xl.Wl term and the rounding of the low halves are ~2^-22 relative.
-template <int D, bool SPLIT> __device__ __forceinline__ void gm_chunk(float * c, float * cl, const __half * w, const __half * wl, const __half * xa, const __half * xb,
-                                                                      const __half * xla, const __half * xlb) {
+// tile: halves between the activation rows of consecutive m16 tiles in shared memory.
+template <int D, bool SPLIT, int MT> __device__ __forceinline__ void gm_chunk(float (*c)[4], float (*cl)[4], const __half * w, const __half * wl, const __half * xa, const __half * xb,
+                                                                              const __half * xla, const __half * xlb, size_t tile) {
     uint4 wv[D], wlv[SPLIT ? D : 1];
 #pragma unroll
     for (int j = 0; j < D; j++) { wv[j] = __ldcs(reinterpret_cast<const uint4 *>(w + 32 * j)); if constexpr (SPLIT) wlv[j] = __ldcs(reinterpret_cast<const uint4 *>(wl + 32 * j)); }
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(xa + 32 * j), b = *reinterpret_cast<const uint4 *>(xb + 32 * j);
-        const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
-        mma16816_f16f32(c, f0, wv[j].x, wv[j].y);
-        mma16816_f16f32(c, f1, wv[j].z, wv[j].w);
-        if constexpr (SPLIT) {
-            const uint4 la = *reinterpret_cast<const uint4 *>(xla + 32 * j), lb = *reinterpret_cast<const uint4 *>(xlb + 32 * j);
-            const unsigned l0[4] = {la.x, lb.x, la.y, lb.y}, l1[4] = {la.z, lb.z, la.w, lb.w};
-            mma16816_f16f32(cl, l0, wv[j].x, wv[j].y);      // xl . Wh
-            mma16816_f16f32(cl, l1, wv[j].z, wv[j].w);
-            mma16816_f16f32(cl, f0, wlv[j].x, wlv[j].y);    // xh . Wl
-            mma16816_f16f32(cl, f1, wlv[j].z, wlv[j].w);
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(xa + m * tile + 32 * j), b = *reinterpret_cast<const uint4 *>(xb + m * tile + 32 * j);
+            const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
+            mma16816_f16f32(c[m], f0, wv[j].x, wv[j].y);
+            mma16816_f16f32(c[m], f1, wv[j].z, wv[j].w);
+            if constexpr (SPLIT) {
+                const uint4 la = *reinterpret_cast<const uint4 *>(xla + m * tile + 32 * j), lb = *reinterpret_cast<const uint4 *>(xlb + m * tile + 32 * j);
+                const unsigned l0[4] = {la.x, lb.x, la.y, lb.y}, l1[4] = {la.z, lb.z, la.w, lb.w};
+                mma16816_f16f32(cl[m], l0, wv[j].x, wv[j].y);      // xl . Wh
+                mma16816_f16f32(cl[m], l1, wv[j].z, wv[j].w);
+                mma16816_f16f32(cl[m], f0, wlv[j].x, wlv[j].y);    // xh . Wl
+                mma16816_f16f32(cl[m], f1, wlv[j].z, wlv[j].w);
+            }
         }
     }
 }
 
-template <bool SPLIT>
+template <bool SPLIT, int MT>
 __global__ void __launch_bounds__(256) gemv_mma_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, const __half * __restrict__ Wl, int K, int N, int R,
                                                        const float * res, float * Y, int ldy) {
     extern __shared__ __align__(16) float gm_smem[];
-    const int kc = K < GM_KC ? K : GM_KC, pitch = kc + GM_PAD;
-    __half * sX = reinterpret_cast<__half *>(gm_smem);                                   // [16][kc + GM_PAD] fp16-rounded activations of the current K chunk (rows >= R are zero)
-    __half * sXl = sX + (SPLIT ? (size_t) 16 * pitch : 0);                                // SPLIT: their low halves, scaled by 2^11
-    float * red = reinterpret_cast<float *>(sX + (size_t) 16 * pitch * (SPLIT ? 2 : 1));  // [8 warps][16][8] partial tiles
+    constexpr int ROWS = 16 * MT;
+    const int kc = K < GM_KC / MT ? K : GM_KC / MT, pitch = kc + GM_PAD;
+    __half * sX = reinterpret_cast<__half *>(gm_smem);                                   // [ROWS][kc + GM_PAD] fp16-rounded activations of the current K chunk (rows >= R are zero)
+    __half * sXl = sX + (SPLIT ? (size_t) ROWS * pitch : 0);                              // SPLIT: their low halves, scaled by 2^11
+    float * red = reinterpret_cast<float *>(sX + (size_t) ROWS * pitch * (SPLIT ? 2 : 1));  // [8 warps][ROWS][8] partial tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int n0 = blockIdx.x * 8;
-    float c[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
+    float c[MT][4], cl[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; m++) { c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f; cl[m][0] = cl[m][1] = cl[m][2] = cl[m][3] = 0.f; }
     const __half * wrow = W + (size_t) (n0 + g) * K + t * 8;
     const __half * wlrow = SPLIT ? Wl + (size_t) (n0 + g) * K + t * 8 : nullptr;
     const __half * xa = sX + (size_t) g * pitch + t * 8, * xb = sX + (size_t) (g + 8) * pitch + t * 8;
     const __half * xla = sXl + (size_t) g * pitch + t * 8, * xlb = sXl + (size_t) (g + 8) * pitch + t * 8;
+    const size_t tile = (size_t) 16 * pitch;
     for (int k0 = 0; k0 < K; k0 += kc) {
-        const int kn = K - k0 < kc ? K - k0 : kc;                                         // a multiple of 256, like K and GM_KC
+        const int kn = K - k0 < kc ? K - k0 : kc;                                         // a multiple of 256, like K and GM_KC / MT
         if (k0) __syncthreads();                                                         // every warp is done with the previous chunk
-        for (int i = tid * 4; i < 16 * kn; i += 256 * 4) {
+        for (int i = tid * 4; i < ROWS * kn; i += 256 * 4) {
             const int r = i / kn, k = i - r * kn;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < R) v = *reinterpret_cast<const float4 *>(X + (size_t) r * ldx + k0 + k);
@@ -228,40 +238,52 @@ __global__ void __launch_bounds__(256) gemv_mma_kernel(const float * __restrict_
         __syncthreads();
         const int ks = kn >> 3, kbeg = warp * ks, kend = kbeg + ks;                        // this warp's slice of the chunk (a multiple of 32)
         int k = kbeg;
-        if constexpr (!SPLIT) for (; k + 256 <= kend; k += 256) gm_chunk<8, false>(c, cl, wrow + k0 + k, nullptr, xa + k, xb + k, nullptr, nullptr);   // 8 x 16 B in flight per lane
-        for (; k + 128 <= kend; k += 128) gm_chunk<4, SPLIT>(c, cl, wrow + k0 + k, SPLIT ? wlrow + k0 + k : nullptr, xa + k, xb + k, xla + k, xlb + k);
-        for (; k < kend; k += 32) gm_chunk<1, SPLIT>(c, cl, wrow + k0 + k, SPLIT ? wlrow + k0 + k : nullptr, xa + k, xb + k, xla + k, xlb + k);
+        if constexpr (!SPLIT && MT == 1) for (; k + 256 <= kend; k += 256) gm_chunk<8, false, 1>(c, cl, wrow + k0 + k, nullptr, xa + k, xb + k, nullptr, nullptr, tile);   // 8 x 16 B in flight per lane
+        if constexpr (MT <= 2) for (; k + 128 <= kend; k += 128) gm_chunk<4, SPLIT, MT>(c, cl, wrow + k0 + k, SPLIT ? wlrow + k0 + k : nullptr, xa + k, xb + k, xla + k, xlb + k, tile);
+        for (; k + 64 <= kend; k += 64) gm_chunk<2, SPLIT, MT>(c, cl, wrow + k0 + k, SPLIT ? wlrow + k0 + k : nullptr, xa + k, xb + k, xla + k, xlb + k, tile);
+        for (; k < kend; k += 32) gm_chunk<1, SPLIT, MT>(c, cl, wrow + k0 + k, SPLIT ? wlrow + k0 + k : nullptr, xa + k, xb + k, xla + k, xlb + k, tile);
     }
-    if constexpr (SPLIT) { for (int i = 0; i < 4; i++) c[i] += cl[i] * (1.0f / GM_LO_SCALE); }
-    float * my = red + warp * 128;                                                       // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8
-    my[g * 8 + 2 * t] = c[0]; my[g * 8 + 2 * t + 1] = c[1]; my[(g + 8) * 8 + 2 * t] = c[2]; my[(g + 8) * 8 + 2 * t + 1] = c[3];
+    float * my = red + (size_t) warp * ROWS * 8;                                         // c0,c1: row g, cols 2t,2t+1;  c2,c3: row g+8 (of tile m)
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+        if constexpr (SPLIT) { for (int i = 0; i < 4; i++) c[m][i] += cl[m][i] * (1.0f / GM_LO_SCALE); }
+        float * mm = my + m * 128;
+        mm[g * 8 + 2 * t] = c[m][0]; mm[g * 8 + 2 * t + 1] = c[m][1]; mm[(g + 8) * 8 + 2 * t] = c[m][2]; mm[(g + 8) * 8 + 2 * t + 1] = c[m][3];
+    }
     __syncthreads();
-    if (tid < 128) {
-        const int r = tid >> 3, col = tid & 7;
+    for (int i = tid; i < ROWS * 8; i += 256) {
+        const int r = i >> 3, col = i & 7;
         float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; w++) a += red[w * 128 + tid];
+        for (int w = 0; w < 8; w++) a += red[(size_t) w * ROWS * 8 + i];
         if (r < R && n0 + col < N) Y[(size_t) r * ldy + n0 + col] = res ? a + res[(size_t) r * ldy + n0 + col] : a;
     }
 }
 
-// R rows (any number: chunks of 16) of X against an F16 matrix (Wl == nullptr) or the fp16 (hi, scaled lo) split of an F32 matrix; 0 launched, 1 error
-static inline int gemv_mma_launch(Ctx * ctx, cudaStream_t st, size_t & smem_set_h, size_t & smem_set_s, const float * X, int ldx, const __half * W, const __half * Wl, int K, int N, int R,
+template <bool SPLIT, int MT>
+static inline int gemv_mma_launch_t(Ctx * ctx, cudaStream_t st, size_t & smem_set, const float * X, int ldx, const __half * W, const __half * Wl, int K, int N, int R, const float * res, float * Y,
+                                    int ldy) {
+    const size_t smem = gemv_mma_smem(K, SPLIT, MT);
+    if (smem > smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_mma_kernel<SPLIT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); smem_set = smem; }
+    gemv_mma_kernel<SPLIT, MT><<<N / 8, 256, smem, st>>>(X, ldx, W, Wl, K, N, R, res, Y, ldy);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// R rows (any number: chunks of up to 64) of X against an F16 matrix (Wl == nullptr) or the fp16 (hi, scaled lo) split of an F32 matrix; 0 launched, 1 error.
+// smem_set: six counters of the caller (one per kernel instantiation) remembering the dynamic shared memory already opted into.
+static inline int gemv_mma_launch(Ctx * ctx, cudaStream_t st, size_t * smem_set, const float * X, int ldx, const __half * W, const __half * Wl, int K, int N, int R,
                                   const float * res, float * Y, int ldy) {
     const bool split = Wl != nullptr;
-    const size_t smem = gemv_mma_smem(K, split);
-    size_t & set = split ? smem_set_s : smem_set_h;
-    if (smem > set) {
-        if (split) B2_CUDA(cudaFuncSetAttribute(gemv_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        else       B2_CUDA(cudaFuncSetAttribute(gemv_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        set = smem;
-    }
-    for (int r0 = 0; r0 < R; r0 += 16) {
-        const int rn = R - r0 < 16 ? R - r0 : 16;
-        const float * rs = res ? res + (size_t) r0 * ldy : nullptr;
-        if (split) gemv_mma_kernel<true><<<N / 8, 256, smem, st>>>(X + (size_t) r0 * ldx, ldx, W, Wl, K, N, rn, rs, Y + (size_t) r0 * ldy, ldy);
-        else       gemv_mma_kernel<false><<<N / 8, 256, smem, st>>>(X + (size_t) r0 * ldx, ldx, W, Wl, K, N, rn, rs, Y + (size_t) r0 * ldy, ldy);
-        B2_LAUNCH_CHECK(ctx);
+    for (int r0 = 0; r0 < R; r0 += 64) {
+        const int rn = R - r0 < 64 ? R - r0 : 64;
+        const float * x = X + (size_t) r0 * ldx, * rs = res ? res + (size_t) r0 * ldy : nullptr;
+        float * y = Y + (size_t) r0 * ldy;
+        int rc;
+        if (rn <= 16)      rc = split ? gemv_mma_launch_t<true, 1>(ctx, st, smem_set[0], x, ldx, W, Wl, K, N, rn, rs, y, ldy) : gemv_mma_launch_t<false, 1>(ctx, st, smem_set[1], x, ldx, W, Wl, K, N, rn, rs, y, ldy);
+        else if (rn <= 32) rc = split ? gemv_mma_launch_t<true, 2>(ctx, st, smem_set[2], x, ldx, W, Wl, K, N, rn, rs, y, ldy) : gemv_mma_launch_t<false, 2>(ctx, st, smem_set[3], x, ldx, W, Wl, K, N, rn, rs, y, ldy);
+        else               rc = split ? gemv_mma_launch_t<true, 4>(ctx, st, smem_set[4], x, ldx, W, Wl, K, N, rn, rs, y, ldy) : gemv_mma_launch_t<false, 4>(ctx, st, smem_set[5], x, ldx, W, Wl, K, N, rn, rs, y, ldy);
+        if (rc) return 1;
     }
     return 0;
 }

@@ -101,7 +101,7 @@ void Orpheus::free_all() {
 namespace {
 
 struct OFwd {
-    Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set = 0, mma_smem_set_s = 0;
+    Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0};
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     size_t att_smem_set = 0, gqa_smem_set = 0;
     // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
@@ -124,7 +124,7 @@ struct OFwd {
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
         if (gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
             auto it = m->split.find(W);
-            if (it != m->split.end()) return gemv_mma_launch(ctx, st, mma_smem_set, mma_smem_set_s, X, ldx, (const __half *) it->second.first, (const __half *) it->second.second, K, N, R, res, Y, ldy);
+            if (it != m->split.end()) return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) it->second.first, (const __half *) it->second.second, K, N, R, res, Y, ldy);
         }
         gemv_rows_launch(st, X, ldx, W, false, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
