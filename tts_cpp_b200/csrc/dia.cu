@@ -361,8 +361,9 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     };
     // B2TTS_AR_GRAPH=1: capture one decoder step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    if (ge && ge[0] == '1' && !out_logits) {
+    if (ge && ge[0] == '1' && !out_logits && n_steps > 1) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        if (run_step()) return 1;                               // step 0 runs directly: every kernel instantiation has its attributes set before the capture
         const uint64_t l0 = ctx->launches;
         B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int rc = run_step();
@@ -370,11 +371,11 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("dia: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
         if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("dia: cudaGraphInstantiate failed"); return 1; }
         cudaError_t le = cudaSuccess;
-        for (int s = 0; s < n_steps && le == cudaSuccess; s++) {
+        for (int s = 1; s < n_steps && le == cudaSuccess; s++) {
             le = cudaGraphLaunch(exec, st);
             if (track_stop && le == cudaSuccess && (s + 1) % exit_every == 0 && s + 1 < n_steps) { const int a = all_stopped(); if (a < 0) { le = cudaErrorUnknown; } else if (a) break; }
         }
-        ctx->launches += (uint64_t) (n_steps - 1) * (ctx->launches - l0);
+        ctx->launches += (uint64_t) (n_steps - 2) * (ctx->launches - l0);
         cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
         if (le != cudaSuccess) { set_error("dia: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
     } else {

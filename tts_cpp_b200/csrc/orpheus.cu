@@ -237,8 +237,9 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     if (run_pass(R0, true) || copy_logits(0)) return 1;                                   // step 0: the whole ragged batch of prompts
     // B2TTS_AR_GRAPH=1: capture one decode step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    if (ge && ge[0] == '1' && !out_logits && n_steps > 1) {
+    if (ge && ge[0] == '1' && !out_logits && n_steps > 2) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        if (run_decode()) return 1;                             // step 1 runs directly: every kernel instantiation has its attributes set before the capture
         const uint64_t l0 = ctx->launches;
         B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int rc = run_decode();
@@ -246,8 +247,8 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("orpheus: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
         if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("orpheus: cudaGraphInstantiate failed"); return 1; }
         cudaError_t le = cudaSuccess;
-        for (int s = 1; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
-        ctx->launches += (uint64_t) (n_steps - 2) * (ctx->launches - l0);
+        for (int s = 2; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
+        ctx->launches += (uint64_t) (n_steps - 3) * (ctx->launches - l0);
         cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
         if (le != cudaSuccess) { set_error("orpheus: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
     } else {

@@ -287,19 +287,20 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     const char * ge = getenv("B2TTS_AR_GRAPH");
     const bool use_graph = ge && ge[0] == '1' && !out_logits;
     const uint64_t launches_before_step = ctx->launches;
-    if (use_graph) {
+    if (use_graph && n_steps > 1) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        if (run_step()) return 1;                               // step 0 runs directly: every kernel instantiation has its attributes set before the capture
         B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int rc = run_step();
         const cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("parler: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
         if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("parler: cudaGraphInstantiate failed"); return 1; }
         cudaError_t le = cudaSuccess;
-        for (int s = 0; s < n_steps && le == cudaSuccess; s++) {
+        for (int s = 1; s < n_steps && le == cudaSuccess; s++) {
             le = cudaGraphLaunch(exec, st);
             if (track_stop && le == cudaSuccess && (s + 1) % exit_every == 0 && s + 1 < n_steps) { const int a = all_stopped(); if (a < 0) { le = cudaErrorUnknown; } else if (a) break; }
         }
-        ctx->launches += (uint64_t) (n_steps - 1) * (uint64_t) (ctx->launches - launches_before_step);   // the captured launches, replayed
+        ctx->launches += (uint64_t) (n_steps - 2) * (uint64_t) ((ctx->launches - launches_before_step) / 2);   // direct step + captured step counted so far; the replays
         cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
         if (le != cudaSuccess) { set_error("parler: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
     } else {
