@@ -211,6 +211,11 @@ int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint
  * reference's loop would have ended (position >= max_generation, or every head has produced EOS), rows past it are zero.  NULL: fixed-length generation. */
 int   b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
                             int32_t * out_tokens, float * out_logits, int32_t * n_generated);
+/* parity helper: greedy, fixed length, but the tokens fed back through the delay pattern are `teacher` ([n_sequences][n_steps][n_heads], e.g. the reference's own
+ * output) instead of the produced ones; out_tokens / out_logits are still what this library produced at every step.  Block-quantised models (Q4_0 / Q5_0 / Q8_0
+ * matrices: activations re-quantised per 32 columns) flip near-tied tokens on summation-order noise and then diverge; teacher forcing keeps every step comparable. */
+int   b2tts_parler_generate_teacher_forced(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
+                                           const int32_t * teacher, int32_t * out_tokens, float * out_logits);
 float b2tts_parler_last_ms(const b2tts_parler * m);
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m);   /* bytes of the matrices, tables and norms resident in HBM (F16 matrices count 2 bytes) */
 

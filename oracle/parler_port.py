@@ -21,6 +21,28 @@ except ImportError:                               # imported as a top-level modu
     from kokoro_port import gelu_f16_lut, ggml_norm
 
 
+def unpack_blocks(raw: np.ndarray, kind: str):
+    """GGUF rows of Q8_0 / Q5_0 / Q4_0 blocks (ggml-common.h block_q8_0 / block_q5_0 / block_q4_0) -> (scales [N, nb] fp32, integer values [N, nb, 32] fp32)."""
+    N = raw.shape[0]
+    bs = {"Q8_0": 34, "Q5_0": 22, "Q4_0": 18}[kind]
+    b = raw.reshape(N, -1, bs)
+    d = b[:, :, :2].copy().view(np.float16)[:, :, 0].astype(np.float32)
+    if kind == "Q8_0":
+        q = b[:, :, 2:].copy().view(np.int8).astype(np.float32)
+    else:
+        qs = b[:, :, bs - 16:].astype(np.int32)
+        lo, hi = qs & 0x0F, qs >> 4                                   # elements 0..15 and 16..31 of the block
+        if kind == "Q5_0":
+            qh = b[:, :, 2:6].copy().view(np.uint32)[:, :, 0].astype(np.int64)
+            j = np.arange(16)
+            lo = lo | (((qh[:, :, None] >> j) & 1) << 4)
+            hi = hi | (((qh[:, :, None] >> (j + 16)) & 1) << 4)
+            q = np.concatenate([lo, hi], axis=2).astype(np.float32) - 16.0
+        else:
+            q = np.concatenate([lo, hi], axis=2).astype(np.float32) - 8.0
+    return d, q
+
+
 class ParlerPort:
     def __init__(self, gguf_path: str, threads: int = 8):
         import gguf
@@ -28,11 +50,18 @@ class ParlerPort:
         rd = gguf.GGUFReader(gguf_path)
         self.w = {}
         self.f16 = set()          # F16 matrices: ggml_mul_mat rounds the activations to fp16 before the product (ggml-cpu.c: vec_dot_type of F16 is F16)
+        self.q = {}               # quantised matrices (Q8_0 / Q5_0 / Q4_0): name -> (block scales [N, nb] fp32, integer values [N, nb, 32] fp32)
         for t in rd.tensors:
             if t.name.startswith("decoder."):
-                self.w[t.name[len("decoder."):]] = torch.from_numpy(np.array(t.data).astype(np.float32))
+                name = t.name[len("decoder."):]
+                if t.tensor_type.name in ("Q8_0", "Q5_0", "Q4_0"):
+                    d, qv = unpack_blocks(np.array(t.data), t.tensor_type.name)
+                    self.q[name] = (torch.from_numpy(d), torch.from_numpy(qv))
+                    self.w[name] = torch.from_numpy((d[:, :, None] * qv).reshape(d.shape[0], -1))       # dequantize_row: what ggml_get_rows returns
+                    continue
+                self.w[name] = torch.from_numpy(np.array(t.data).astype(np.float32))
                 if t.tensor_type.name == "F16":
-                    self.f16.add(t.name[len("decoder."):])
+                    self.f16.add(name)
         self.kv = {}
         for k, f in rd.fields.items():
             if len(f.data) == 1 and f.types and f.types[0].name in ("UINT32",):
@@ -49,6 +78,16 @@ class ParlerPort:
 
     def mm(self, x, name):
         """ggml_mul_mat(weight, x): exact products of fp16-rounded activations with F16 weights, fp32 accumulation; plain fp32 for F32 weights."""
+        if name in self.q:        # ggml_mul_mat with a quantised matrix: the activations are quantised to Q8_0 per 32 columns (vec_dot_type), integer dot products per block
+            d, qv = self.q[name]
+            n, K = x.shape
+            xb = x.reshape(n, K // 32, 32)
+            amax = xb.abs().amax(dim=2)
+            idv = torch.where(amax > 0, np.float32(127.0) / amax, torch.zeros_like(amax))
+            xq = torch.round(xb * idv[:, :, None])                              # AVX2 quantize_row_q8_0: _mm256_round_ps, nearest-even, scale 127 / amax
+            dx = (amax / np.float32(127.0)).half().float()                       # the block scale is stored as fp16
+            sumi = torch.einsum("nbk,Nbk->nNb", xq.double(), qv.double())        # exact integers
+            return (sumi.float() * (d[None, :, :] * dx[:, None, :])).sum(dim=2)
         if name in self.f16:
             x = x.half().float()
         return x @ self.w[name].t()
@@ -96,9 +135,10 @@ class ParlerPort:
         self.pos += n
         return torch.stack([self.mm(x, f"lm_heads.{i}.weight.head") for i in range(self.n_out)])
 
-    def greedy(self, prompt, steps: int, stop: bool = False):
+    def greedy(self, prompt, steps: int, stop: bool = False, teacher=None):
         """Returns (tokens [steps', n_out], logits [steps', n_out, vocab]) like oracle/_ref/parler_ref.  stop: with the reference's stop rule
-        (parler_context::eos_seen feeding + check_stopping, model.cpp:715-732,795-832) instead of a plain step cap."""
+        (parler_context::eos_seen feeding + check_stopping, model.cpp:715-732,795-832) instead of a plain step cap.
+        teacher [steps, n_out]: tokens fed back instead of the produced ones (teacher-forced comparison; the outputs are still the produced tokens)."""
         self.reset()
         tok = torch.from_numpy(np.asarray(prompt).astype(np.int64))
         x = self.w["embed_prompts"][tok] + self.w["positional_embed"][torch.arange(tok.numel())]
@@ -123,4 +163,6 @@ class ParlerPort:
             lg = self.step(x)[:, 0, :].numpy()
             last = lg.argmax(axis=1)                 # numpy argmax returns the first maximum, like sampler::max
             toks.append(last.astype(np.int32)); logits.append(lg)
+            if teacher is not None:
+                last = np.asarray(teacher[s])
         return np.stack(toks), np.stack(logits)

@@ -112,5 +112,8 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { const 
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 template <class T> static inline T __ldcs(const T * p) { return *p; }
+static inline int __dp4a(int a, int b, int c) { for (int i = 0; i < 4; i++) c += (int) (int8_t) (a >> (8 * i)) * (int) (int8_t) (b >> (8 * i)); return c; }
+static inline unsigned __vsub4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i); return r; }
+static inline int __float2int_rn(float x) { return (int) nearbyintf(x); }      // round-to-nearest-even (the default rounding mode)
 static inline float __ldg(const float * p) { return *p; }
 static inline int __ldg(const int * p) { return *p; }

@@ -18,6 +18,8 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       from the reference's Parler decode loop (delay pattern included) on the small synthetic Parler GGUF, from oracle/ref_parler_driver.cpp
   parler_f16_vectors.npz   : as parler_vectors.npz for the GGUF `quantize --quantized-type F16` would write (decoder matrices and codebook tables F16: the
       reference then rounds the activations to fp16 before every such product)
+  parler_q{8,5,4}_0_vectors.npz : as parler_vectors.npz for the GGUFs `quantize --quantized-type Q8_0 / Q5_0 / Q4_0` would write (decoder matrices and codebook
+      tables as ggml blocks; the reference re-quantises the activations to Q8_0 per 32 columns before every such product)
   parler_stop_vectors.npz  : the Parler loop run to completion under the reference's stop rule (eos_seen feeding + check_stopping) on two EOS-boosted synthetic
       GGUFs: one ends at max_generation, one because every head produced EOS; from oracle/ref_parler_driver.cpp --stop
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
@@ -181,9 +183,9 @@ def orpheus_vectors(wide: bool = False):
     print("orpheus wide vectors:" if wide else "orpheus vectors:", {k: v.shape for k, v in out.items()})
 
 
-def parler_vectors(f16: bool = False):
+def parler_vectors(f16: bool = False, quant: str | None = None):
     from tts_cpp_b200.synth import cached_parler_gguf
-    gguf = cached_parler_gguf(seed=0, f16=f16)
+    gguf = cached_parler_gguf(seed=0, f16=f16, quant=quant)
     rng = np.random.default_rng(7)
     prompts = [rng.integers(1, 500, size=n) for n in (5, 9)]
     tmp = tempfile.mkdtemp()
@@ -197,8 +199,9 @@ def parler_vectors(f16: bool = False):
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
-    np.savez_compressed(os.path.join(OUT, "parler_f16_vectors.npz" if f16 else "parler_vectors.npz"), **out)
-    print("parler f16 vectors:" if f16 else "parler vectors:", {k: v.shape for k, v in out.items()})
+    tag = f"_{quant.lower()}" if quant else ("_f16" if f16 else "")
+    np.savez_compressed(os.path.join(OUT, f"parler{tag}_vectors.npz"), **out)
+    print(f"parler{tag} vectors:", {k: v.shape for k, v in out.items()})
 
 
 def parler_stop_vectors():
@@ -290,12 +293,14 @@ def sampler_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_stop", "dia", "dia_f16", "dia_stop", "sampler", "orpheus_wide"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_q8_0", "parler_q5_0", "parler_q4_0", "parler_stop", "dia", "dia_f16", "dia_stop", "sampler", "orpheus_wide"]
     if "dia_stop" in which: dia_stop_vectors()
     if "parler_stop" in which: parler_stop_vectors()
     if "sampler" in which: sampler_vectors()
     if "orpheus_wide" in which: orpheus_vectors(wide=True)
     if "parler_f16" in which: parler_vectors(f16=True)
+    for q in ("Q8_0", "Q5_0", "Q4_0"):
+        if f"parler_{q.lower()}" in which: parler_vectors(quant=q)
     if "dia_f16" in which: dia_vectors(f16=True)
     if "dia" in which: dia_vectors()
     if "parler" in which: parler_vectors()

@@ -296,3 +296,24 @@ def test_tensor_core_gemv_multi_tile_emulated(tmp_path):
     for u in range(18):
         assert np.array_equal(tok[u, :, 0], g[f"tokens{u % 2}"][:steps]), u
         assert float(np.abs(logits[u] - g[f"logits{u % 2}"][:steps]).max()) < 1e-4
+
+
+@pytest.mark.parametrize("quant", ["Q8_0", "Q5_0", "Q4_0"])
+def test_parler_quantised_emulated_teacher_forced(tmp_path, quant):
+    """parler.cu on block-quantised GGUFs (gemv_rows_q_kernel: activations quantised to Q8_0 per 32 columns in shared memory, dp4a over the ggml blocks as they are
+    in the file) under emulation, teacher-forced on the reference's tokens (see test_parler_port_quantised_teacher_forced for why): logits within 0.1 RMS of the
+    reference at every step and the same token wherever the reference's top-2 gap exceeds 0.5."""
+    g = np.load(os.path.join(GOLD, f"parler_{quant.lower()}_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    tf = str(tmp_path / "teacher.bin")
+    np.stack([g["tokens0"], g["tokens1"]]).astype(np.int32).tofile(tf)
+    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, quant=quant), prompts, steps, "q", env={"B2EMU_TEACHER": tf})
+    for u in range(2):
+        ref_t, ref_l = g[f"tokens{u}"], g[f"logits{u}"].reshape(steps, -1)
+        rms = np.sqrt(((logits[u] - ref_l) ** 2).mean(axis=1))
+        top2 = np.sort(g[f"logits{u}"], axis=2)[:, :, -2:]
+        clear = (top2[:, :, 1] - top2[:, :, 0]) > 0.5
+        print(f"PARITY(emulated) parler {quant} prompt {u}: per-step logit rms {np.round(rms, 4).tolist()}, tokens equal {int((tok[u] == ref_t).sum())}/{ref_t.size}")
+        assert float(rms.max()) < 0.1
+        assert np.array_equal(tok[u][clear], ref_t[clear])

@@ -254,3 +254,25 @@ def test_parler_port_stop_rule_against_reference(case):
     assert toks.shape == ref.shape and toks.shape[0] < int(g["step_cap"])
     assert np.array_equal(toks, ref)
     assert (ref == 1024).any()
+
+
+@pytest.mark.parametrize("quant", ["Q8_0", "Q5_0", "Q4_0"])
+def test_parler_port_quantised_teacher_forced(quant):
+    """oracle/parler_port.py on block-quantised GGUFs (decoder matrices and codebook tables as Q8_0 / Q5_0 / Q4_0 blocks; activations re-quantised to Q8_0 per 32
+    columns, integer dot products per block) against the reference, TEACHER-FORCED on the reference's tokens: re-quantisation turns 1e-7 summation-order noise into
+    whole quantisation steps, so the logits of two correct implementations differ by ~0.04 RMS (logit std 4) and near-tied tokens flip, after which free-running
+    sequences diverge.  Bar: logits within 0.1 RMS at every step, and the same token wherever the reference's own top-2 gap exceeds 0.5."""
+    from oracle.parler_port import ParlerPort
+    from tts_cpp_b200.synth import cached_parler_gguf
+    g = np.load(os.path.join(GOLD, f"parler_{quant.lower()}_vectors.npz"))
+    port = ParlerPort(cached_parler_gguf(seed=0, quant=quant))
+    assert len(port.q) == 73
+    for u in range(2):
+        ref_t, ref_l = g[f"tokens{u}"], g[f"logits{u}"]
+        toks, logits = port.greedy(g[f"prompt{u}"], ref_t.shape[0], teacher=ref_t)
+        rms = np.sqrt(((logits - ref_l) ** 2).mean(axis=(1, 2)))
+        top2 = np.sort(ref_l, axis=2)[:, :, -2:]
+        clear = (top2[:, :, 1] - top2[:, :, 0]) > 0.5
+        print(f"parler {quant} prompt {u}: per-step logit rms {np.round(rms, 4).tolist()}, tokens equal {int((toks == ref_t).sum())}/{toks.size}, clear-cut {int(clear.sum())}")
+        assert float(rms.max()) < 0.1
+        assert np.array_equal(toks[clear], ref_t[clear])

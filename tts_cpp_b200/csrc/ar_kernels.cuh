@@ -127,6 +127,90 @@ static inline void gemv_rows_launch(cudaStream_t st, const float * X, int ldx, c
     }
 }
 
+// ---- block-quantised matrices (Q4_0 / Q5_0 / Q8_0; the reference's `quantize` tool, its perf battery runs Parler as Q5_0 / Q8_0).  ggml_mul_mat quantises the
+// activation rows to Q8_0 first (vec_dot_type): per 32 columns d = amax / 127 (stored as fp16), q = round-to-nearest-even(x * 127 / amax) (the AVX2
+// quantize_row_q8_0), then per block an exact integer dot product scaled by d_w * d_x (ggml_vec_dot_q{4,5,8}_0_q8_0).  Here: stage 1 quantises the 8 rows of a
+// chunk into shared memory once per block; stage 2 is a warp per output row, a lane per weight block, dp4a over the eight 4-byte words of a block.
+// First version (2-byte loads of the unaligned 34 / 22 / 18-byte blocks); the weight stream is a quarter to an eighth of the fp32 one.
+static inline size_t gemv_q_smem(int K) { return (size_t) GR * K + (size_t) GR * (K / 32) * 4; }
+__device__ __forceinline__ unsigned ld_u16x2(const uint8_t * p) { return (unsigned) *reinterpret_cast<const uint16_t *>(p) | ((unsigned) *reinterpret_cast<const uint16_t *>(p + 2) << 16); }
+__global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restrict__ X, int ldx, const uint8_t * __restrict__ W, int qtype, int K, int N, int R,
+                                                          const float * res, float * Y, int ldy) {
+    extern __shared__ __align__(16) float gq_smem[];
+    const int nb = K >> 5, blk = qtype == 8 ? 34 : (qtype == 6 ? 22 : 18);
+    int * xq = reinterpret_cast<int *>(gq_smem);                    // [GR][K / 4] packed int8 activations
+    float * xd = gq_smem + (size_t) GR * (K >> 2);                   // [GR][nb] block scales (fp16-rounded)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.x * 8 + warp;
+    for (int r0 = 0; r0 < R; r0 += GR) {
+        if (r0) __syncthreads();
+        for (int i = tid; i < GR * nb; i += 256) {                   // stage 1: one thread quantises one (row, block)
+            const int j = i / nb, b = i - j * nb;
+            int * q = xq + (size_t) j * (K >> 2) + b * 8;
+            if (r0 + j >= R) { for (int w = 0; w < 8; w++) q[w] = 0; xd[j * nb + b] = 0.f; continue; }
+            const float4 * src = reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + b * 32);
+            float4 v[8];
+            float amax = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { v[w] = src[w]; amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[w].x), fabsf(v[w].y)), fmaxf(fabsf(v[w].z), fabsf(v[w].w)))); }
+            const float id = amax != 0.f ? 127.f / amax : 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const int a0 = __float2int_rn(v[w].x * id), a1 = __float2int_rn(v[w].y * id), a2 = __float2int_rn(v[w].z * id), a3 = __float2int_rn(v[w].w * id);
+                q[w] = (a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24);
+            }
+            xd[j * nb + b] = __half2float(__float2half_rn(amax / 127.f));
+        }
+        __syncthreads();
+        if (n < N) {
+            float acc[GR];
+#pragma unroll
+            for (int j = 0; j < GR; j++) acc[j] = 0.f;
+            for (int b = lane; b < nb; b += 32) {
+                const uint8_t * p = W + ((size_t) n * nb + b) * blk;
+                __half_raw hr; hr.x = *reinterpret_cast<const uint16_t *>(p);
+                const float dw = __half2float(__half(hr));
+                int wq[8];
+                if (qtype == 8) {
+#pragma unroll
+                    for (int w = 0; w < 8; w++) wq[w] = (int) ld_u16x2(p + 2 + 4 * w);
+                } else {
+                    const uint8_t * qs = p + (qtype == 6 ? 6 : 2);
+                    const unsigned qh = qtype == 6 ? ld_u16x2(p + 2) : 0u;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {                    // bytes 4w .. 4w+3 of qs: low nibbles are elements 4w.., high nibbles elements 16 + 4w..
+                        const unsigned q4 = ld_u16x2(qs + 4 * w);
+                        unsigned lo = q4 & 0x0F0F0F0Fu, hi = (q4 >> 4) & 0x0F0F0F0Fu;
+                        if (qtype == 6) {
+                            const unsigned bl = (qh >> (4 * w)) & 0xFu, bh = (qh >> (16 + 4 * w)) & 0xFu;
+                            lo |= ((bl & 1u) << 4) | ((bl & 2u) << 11) | ((bl & 4u) << 18) | ((bl & 8u) << 25);
+                            hi |= ((bh & 1u) << 4) | ((bh & 2u) << 11) | ((bh & 4u) << 18) | ((bh & 8u) << 25);
+                            wq[w] = (int) __vsub4(lo, 0x10101010u); wq[w + 4] = (int) __vsub4(hi, 0x10101010u);
+                        } else {
+                            wq[w] = (int) __vsub4(lo, 0x08080808u); wq[w + 4] = (int) __vsub4(hi, 0x08080808u);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < GR; j++) {
+                    const int * q = xq + (size_t) j * (K >> 2) + b * 8;
+                    int sumi = 0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) sumi = __dp4a(wq[w], q[w], sumi);
+                    acc[j] = fmaf((float) sumi, dw * xd[j * nb + b], acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < GR; j++) {
+                float a = acc[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? a + res[(size_t) (r0 + j) * ldy + n] : a;
+            }
+        }
+    }
+}
+
 // ---- tensor-core batched GEMV for F16 matrices: the decode step of a batch of <= 16 sequences.
 // At batch 16 an F16 weight byte carries 16 flops: 6.6 TB/s of weights would need ~105 TFLOP/s of fp32 FMA, above what the CUDA cores deliver, and the plain
 // kernel above issues 8 activation loads per weight load.  Here the batch IS the M = 16 of mma.sync.m16n8k16 (exact fp16 products, fp32 accumulation -- the

@@ -253,6 +253,12 @@ int b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * co
     const ArSampling a = to_sampling(sampling);
     return m->p.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits, n_generated);
 }
+int b2tts_parler_generate_teacher_forced(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const int32_t * teacher,
+                                         int32_t * out_tokens, float * out_logits) {
+    if (!m) { set_error("null model"); return 1; }
+    if (!teacher) { set_error("null teacher tokens"); return 1; }
+    return m->p.generate(n_sequences, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits, nullptr, teacher);
+}
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m) { return m ? m->p.weight_bytes : 0; }
 // ---- Dia AR decode (first correct path)

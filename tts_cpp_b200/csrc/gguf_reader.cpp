@@ -122,10 +122,13 @@ int read_gguf(const char * path, const char * prefix, const char * arch_required
         for (auto & t : tis) {
             if (t.name.rfind(prefix, 0) != 0) continue;
             int64_t n = 1; for (int d = 0; d < t.nd; d++) n *= t.ne[d];
-            size_t esz = t.type == 0 ? 4 : t.type == 1 ? 2 : 0;
-            if (!esz) { set_error("%s: tensor '%s' has ggml type %u; only F32/F16 files are supported", path, t.name.c_str(), t.type); bad = true; break; }
-            if (data0 + t.off + (size_t) n * esz > (size_t) st.st_size) { set_error("%s: tensor '%s' runs past the end of the file", path, t.name.c_str()); bad = true; break; }
-            if (on_tensor(t.name.c_str(), (int) t.type, t.nd, t.ne, base + data0 + t.off, (size_t) n * esz)) { bad = true; break; }
+            // F32, F16, or 32-value blocks: Q4_0 (18 bytes), Q5_0 (22), Q8_0 (34) -- ggml-common.h; the model decides whether it accepts a quantised tensor
+            const size_t blk = t.type == 2 ? 18 : t.type == 6 ? 22 : t.type == 8 ? 34 : 0;
+            size_t nbytes = t.type == 0 ? (size_t) n * 4 : t.type == 1 ? (size_t) n * 2 : 0;
+            if (blk) { if (t.ne[0] % 32) { set_error("%s: quantised tensor '%s' has a row length that is not a multiple of 32", path, t.name.c_str()); bad = true; break; } nbytes = (size_t) n / 32 * blk; }
+            if (!nbytes) { set_error("%s: tensor '%s' has ggml type %u; F32, F16, Q4_0, Q5_0 and Q8_0 are supported", path, t.name.c_str(), t.type); bad = true; break; }
+            if (data0 + t.off + nbytes > (size_t) st.st_size) { set_error("%s: tensor '%s' runs past the end of the file", path, t.name.c_str()); bad = true; break; }
+            if (on_tensor(t.name.c_str(), (int) t.type, t.nd, t.ne, base + data0 + t.off, nbytes)) { bad = true; break; }
         }
         if (bad) break;
         rc = 0;

@@ -11,6 +11,8 @@ struct HostTensor {             // fp32 host copy of one GGUF tensor (numpy shap
     std::vector<float>   v;
     std::vector<int64_t> shape; // outermost first
     bool                 f16 = false;
+    int                  qtype = 0;   // ggml type of a block-quantised tensor (2 Q4_0, 6 Q5_0, 8 Q8_0): `raw` holds its blocks, `v` the dequantised values
+    std::vector<uint8_t> raw;
 };
 
 struct W16 {                    // fp16 GEMM weight [Npad][KW][CinPad]
@@ -18,9 +20,10 @@ struct W16 {                    // fp16 GEMM weight [Npad][KW][CinPad]
     int N = 0, Npad = 0, KW = 1, Cin = 0, CinPad = 0;
 };
 
-struct ArW {                    // a weight matrix [N][K] of the autoregressive decode paths: fp32, or fp16 when the GGUF stores it as F16
+struct ArW {                    // a weight matrix [N][K] of the autoregressive decode paths: fp32, fp16 when the GGUF stores it as F16, or ggml blocks (qtype 2 / 6 / 8)
     const void * p = nullptr;
     bool f16 = false;
+    int  qtype = 0;
 };
 
 struct Lstm {

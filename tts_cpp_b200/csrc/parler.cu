@@ -27,8 +27,30 @@ int Parler::assign(const char * name, int type, int n_dims, const int64_t * ne, 
         const uint16_t * s = (const uint16_t *) data;
         for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = ph2f(s[i]);
         t.f16 = true;
+    } else if (type == 2 || type == 6 || type == 8) {          // Q4_0 / Q5_0 / Q8_0 blocks: keep them, and dequantise like dequantize_row_q*_0 (ggml-quants.c) for ggml_get_rows users
+        const size_t blk = type == 2 ? 18 : type == 6 ? 22 : 34;
+        if (n % 32 || nbytes < (size_t) n / 32 * blk) { set_error("tensor %s: short or ragged quantised data", name); return 1; }
+        t.qtype = type;
+        t.raw.assign((const uint8_t *) data, (const uint8_t *) data + (size_t) n / 32 * blk);
+        for (int64_t b = 0; b < n / 32; b++) {
+            const uint8_t * p = t.raw.data() + (size_t) b * blk;
+            uint16_t dh; memcpy(&dh, p, 2);
+            const float d = ph2f(dh);
+            float * y = t.v.data() + (size_t) b * 32;
+            if (type == 8) { for (int j = 0; j < 32; j++) y[j] = (float) (int8_t) p[2 + j] * d; }
+            else {
+                uint32_t qh = 0; if (type == 6) memcpy(&qh, p + 2, 4);
+                const uint8_t * qs = p + (type == 6 ? 6 : 2);
+                for (int j = 0; j < 16; j++) {
+                    int x0 = qs[j] & 0x0F, x1 = qs[j] >> 4;
+                    if (type == 6) { x0 = (x0 | (int) (((qh >> j) & 1u) << 4)) - 16; x1 = (x1 | (int) (((qh >> (j + 16)) & 1u) << 4)) - 16; }
+                    else { x0 -= 8; x1 -= 8; }
+                    y[j] = (float) x0 * d; y[j + 16] = (float) x1 * d;
+                }
+            }
+        }
     } else {
-        set_error("tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
+        set_error("tensor %s: ggml type %d not supported (F32, F16, Q4_0, Q5_0, Q8_0)", name, type);
         return 1;
     }
     host[nm] = std::move(t);
@@ -37,7 +59,7 @@ int Parler::assign(const char * name, int type, int n_dims, const int64_t * ne, 
 
 namespace {
 struct PFwd {
-    Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0};
+    Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0}, q_smem_set = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     size_t att_smem_set = 0, gqa_smem_set = 0;
     // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
@@ -58,6 +80,14 @@ struct PFwd {
         return 0;
     }
     int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (W.qtype) {                                              // Q4_0 / Q5_0 / Q8_0: activations quantised to Q8_0 per 32 columns, integer dot products per block
+            if (K % 32 || (size_t) GR * K + (size_t) GR * (K / 32) * 4 > 200 * 1024) { set_error("parler: quantised matrix with K = %d is not supported", K); return 1; }
+            const size_t smem = gemv_q_smem(K);
+            if (smem > q_smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_rows_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); q_smem_set = smem; }
+            gemv_rows_q_kernel<<<cdiv(N, 8), 256, smem, st>>>(X, ldx, (const uint8_t *) W.p, W.qtype, K, N, R, res, Y, ldy);
+            B2_LAUNCH_CHECK(ctx);
+            return 0;
+        }
         if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
             return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
         gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
@@ -109,7 +139,18 @@ int Parler::prepare() {
         w.p = d;
         return w;
     };
-    auto upw = [&](const std::string & n, int64_t expect) -> ArW { const HostTensor * t = find(n, expect); return t ? dev_mat(t->v.data(), t->v.size(), t->f16) : ArW(); };
+    auto upw = [&](const std::string & n, int64_t expect) -> ArW {
+        const HostTensor * t = find(n, expect);
+        if (!t) return ArW();
+        if (!t->qtype) return dev_mat(t->v.data(), t->v.size(), t->f16);
+        ArW w; w.qtype = t->qtype;                                  // block-quantised matrix: the blocks go to HBM as they are in the file
+        void * d = nullptr;
+        if (cudaMalloc(&d, t->raw.size()) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", t->raw.size()); ok = false; return w; }
+        cudaMemcpy(d, t->raw.data(), t->raw.size(), cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += t->raw.size();
+        w.p = d;
+        return w;
+    };
 
     embed_prompts = up("embed_prompts", 0);
     { const HostTensor * t = find("embed_prompts", 0); if (t) prompt_vocab = (int) (t->v.size() / (size_t) hidden); }
@@ -129,6 +170,7 @@ int Parler::prepare() {
             tab.insert(tab.end(), t->v.begin(), t->v.end());
             hw.insert(hw.end(), h->v.begin(), h->v.end());
             heads_f16 = heads_f16 && h->f16; heads_any_f16 = heads_any_f16 || h->f16;
+            if (h->qtype) { set_error("parler: block-quantised output heads (quantize --quantize-output-heads) are not supported"); ok = false; break; }
         }
         if (ok && heads_any_f16 != heads_f16) { set_error("parler: the output heads mix F16 and F32 tensors"); ok = false; }
         if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev_mat(hw.data(), hw.size(), heads_f16); }   // tables: ggml_get_rows widens F16 rows to fp32 exactly
@@ -174,7 +216,7 @@ void Parler::free_all() {
 }
 
 int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits,
-                     int32_t * n_generated) {
+                     int32_t * n_generated, const int32_t * teacher) {
     const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("parler: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
@@ -190,7 +232,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     if (Tmax > max_ctx) { set_error("parler: %d positions exceed the model's context of %d", Tmax, max_ctx); return 1; }
     const size_t cache = (size_t) n_layers * B * Tmax * H * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 6 * H + F) * 4 + (size_t) B * NV * 4 + (size_t) n_steps * B * n_out * 4 + (size_t) B * n_out * 4 +
-                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 12 + (size_t) B * 4 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 12 + (size_t) B * 4 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
     PFwd Fw{this, ctx, st};
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * H);
@@ -202,6 +244,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     int * d_np = Fw.al<int>((size_t) B), * ids = Fw.al<int>((size_t) B * n_out), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
     int * s_last = Fw.al<int>((size_t) B * n_out), * s_cnt = Fw.al<int>((size_t) B * n_out);
     int * seen = n_generated ? Fw.al<int>((size_t) B * n_out) : nullptr, * stopped = n_generated ? Fw.al<int>((size_t) B) : nullptr;
+    int * d_teacher = teacher ? Fw.al<int>((size_t) n_steps * B * n_out) : nullptr;
     float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * NV) : nullptr;
     if (Fw.fail) return 1;
     B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * n_out * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
@@ -226,6 +269,12 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     B2_CUDA(cudaMemcpyAsync(cross_len, hcl.data(), hcl.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(d_np, hnp.data(), hnp.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemsetAsync(d_step, 0, 4, st));
+    std::vector<int> hteach;
+    if (teacher) {                                                  // [B][n_steps][n_out] -> the device's [n_steps][B][n_out]
+        hteach.resize((size_t) n_steps * B * n_out);
+        for (int b = 0; b < B; b++) for (int s2 = 0; s2 < n_steps; s2++) for (int i = 0; i < n_out; i++) hteach[((size_t) s2 * B + b) * n_out + i] = teacher[((size_t) b * n_steps + s2) * n_out + i];
+        B2_CUDA(cudaMemcpyAsync(d_teacher, hteach.data(), hteach.size() * 4, cudaMemcpyHostToDevice, st));
+    }
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float scale = 1.0f / sqrtf((float) head_dim);
@@ -262,7 +311,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     if (run_layers(R0)) return 1;
     // one audio step; the step number is device-resident (d_step), so the launches are identical for every step
     auto run_step = [&]() -> int {
-        delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, d_np, B, n_out, d_step, bos, eos, max_generation, Tmax, seen, stopped, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
+        delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_teacher ? d_teacher : d_out, d_np, B, n_out, d_step, bos, eos, max_generation, Tmax, seen, stopped, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
         codebook_embed_kernel<<<B, 256, 0, st>>>(ids, n_out, tables, (size_t) tab_rows * H, pos_embed, row_pos, H, x); B2_LAUNCH_CHECK(ctx);
         if (run_layers(B)) return 1;
         if (Fw.ln(x, ln_w, ln_b, H, B, xn)) return 1;

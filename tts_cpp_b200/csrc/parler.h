@@ -45,8 +45,10 @@ struct Parler {
     // the same loop under the reference sampler's settings (sampler.cu): sampling == nullptr or do_sample == 0 is the greedy sampler::max
     // n_generated != nullptr turns on the reference's stop rule (parler_context::eos_seen feeding + check_stopping, model.cpp:715-732,795-832): n_generated[b] is
     // the number of frames sequence b produced before the reference's loop would have ended, rows past it are zero; nullptr: fixed-length generation
+    // teacher (optional, [B][n_steps][n_out]): the tokens fed back through the delay pattern instead of the produced ones (outputs are still the produced tokens
+    // and their logits) -- teacher-forced parity checks: block-quantised models flip near-tied tokens on summation-order noise and then diverge
     int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits,
-                 int32_t * n_generated);
+                 int32_t * n_generated, const int32_t * teacher = nullptr);
     int max_generation = 0;
     void free_all();
 };

@@ -560,7 +560,7 @@ def parler_f16_tensor(name: str) -> bool:
 
 
 def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32, head_dim: int = 8, ffn: int = 1024, n_enc: int = 12, f16: bool = False,
-                      max_generation: int = 64, eos_boost: float = 1.0) -> dict:
+                      max_generation: int = 64, eos_boost: float = 1.0, quant: str | None = None) -> dict:
     """Small synthetic Parler-TTS GGUF (F32) with a matching small DAC decoder (the reference's loader needs both).  32 heads x 8 layers is
     the smallest shape the reference loads: prep_cross_key_values sizes its metadata pool from n_attn_heads * 2 * n_layers tensors but
     allocates a 4096-node graph in it (src/models/parler/model.cpp:117-129)."""
@@ -573,7 +573,11 @@ def write_parler_gguf(path: str, seed: int = 0, layers: int = 8, heads: int = 32
     n_params = 0
     for name, arr in items:
         n_params += arr.size
-        w.add_tensor(name, arr.astype(np.float16 if f16 and parler_f16_tensor(name) else np.float32))
+        if quant and parler_f16_tensor(name) and arr.ndim == 2 and arr.shape[1] % 32 == 0:     # the tensors `quantize --quantized-type <quant>` converts (same rule as for F16)
+            qt = getattr(gguf.GGMLQuantizationType, quant)
+            w.add_tensor(name, gguf.quants.quantize(arr.astype(np.float32), qt), raw_dtype=qt)
+        else:
+            w.add_tensor(name, arr.astype(np.float16 if f16 and parler_f16_tensor(name) else np.float32))
     a = "parler-tts.decoder"
     for k, v in ((f"{a}.encode_length", n_enc), (f"{a}.hidden_size", heads * head_dim), (f"{a}.output_heads", 9), (f"{a}.context_length", 4096),
                  (f"{a}.attention.head_count", heads), (f"{a}.max_generation", max_generation), (f"{a}.out_vocab_size", 1088), (f"{a}.audio_vocab_size", 1024),
@@ -595,7 +599,7 @@ PARLER_MINI_SHAPE = dict(layers=24, heads=16, head_dim=64, ffn=4096, n_enc=32, m
 def cached_parler_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, **shape) -> str:
     cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
     os.makedirs(cache_dir, exist_ok=True)
-    tag = "".join(f"_{k}{v}" for k, v in sorted(shape.items()))
+    tag = "".join(f"_{k}{v}" for k, v in sorted(shape.items()) if v is not None)
     path = os.path.join(cache_dir, f"parler_{'f16' if f16 else 'f32'}_s{seed}{tag}.gguf")
     if not os.path.exists(path):
         tmp = f"{path}.{os.getpid()}.tmp"
