@@ -242,7 +242,8 @@ def run_parler_reference(args, threads: int = 4, sample_steps: int = 60):
         return 0
     import numpy as np
     from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_parler_gguf
-    gguf = cached_parler_gguf(seed=0, f16=True, **PARLER_MINI_SHAPE)
+    quant = None if args.parler_dtype == "f16" else args.parler_dtype.upper()
+    gguf = cached_parler_gguf(seed=0, f16=quant is None, quant=quant, **PARLER_MINI_SHAPE)
     ncpu = os.cpu_count() or 8
     workers = max(1, min(16, ncpu // (2 * threads)))
     tmp = tempfile.mkdtemp(prefix="b2par_")
@@ -267,7 +268,7 @@ def run_parler_reference(args, threads: int = 4, sample_steps: int = 60):
     ar_rate = (frames * 512 / 44100.0) / wall                     # audio-seconds of frames generated per second (the prompt pass is inside wall)
     dac_rate = dac[0] / dac[1]
     rate = 1.0 / (1.0 / ar_rate + 1.0 / dac_rate)
-    print(json.dumps({"impl": "reference", "metric": "audio_seconds_per_second", "workload": "Parler-TTS-Mini-sized F16 decoder (synthetic) greedy AR decode + DAC decode, reference CPU GGML path",
+    print(json.dumps({"impl": "reference", "metric": "audio_seconds_per_second", "workload": f"Parler-TTS-Mini-sized {args.parler_dtype} decoder (synthetic) greedy AR decode + DAC decode, reference CPU GGML path",
                       "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": 1, "ms_per_step": wall * 1e3, "ar_audio_s_per_s": ar_rate, "dac_audio_s_per_s": dac_rate,
                       "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
                                        "sample": f"{workers} worker processes x {threads} ggml threads: {sample_steps} decode steps of one utterance each (KV cache shorter than at 861 steps), "
@@ -318,7 +319,8 @@ def run_parler(args):
     from tts_cpp_b200.binding import Context, dac_runner_from_file, parler_runner_from_file
     from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_dac_gguf, cached_parler_gguf
     ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
-    par = parler_runner_from_file(cached_parler_gguf(seed=0, f16=True, **PARLER_MINI_SHAPE), ctx=ctx)
+    quant = None if args.parler_dtype == "f16" else args.parler_dtype.upper()
+    par = parler_runner_from_file(cached_parler_gguf(seed=0, f16=quant is None, quant=quant, **PARLER_MINI_SHAPE), ctx=ctx)
     dac = dac_runner_from_file(cached_dac_gguf(seed=0, max_frames=64), ctx=ctx)
     B, frames = 16, 861
     n_steps = frames + par.n_heads - 1
@@ -346,14 +348,14 @@ def run_parler(args):
     _, hbm, peak_src = _peaks()
     per_step_ms = ar_ms / args.steps / n_steps
     print(json.dumps({
-        "metric": "audio_seconds_per_second", "workload": "Parler-TTS-Mini-sized F16 decoder (synthetic), batch 16 x 10 s, greedy AR decode + DAC decode (BASELINE config 3)",
+        "metric": "audio_seconds_per_second", "workload": f"Parler-TTS-Mini-sized {args.parler_dtype} decoder (synthetic), batch 16 x 10 s, greedy AR decode + DAC decode (BASELINE config 3)",
         "value": audio_s / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dev_ms / args.steps,
         "ar_ms_per_step": ar_ms / args.steps, "dac_ms_per_step": dac_ms / args.steps, "decode_step_ms": per_step_ms,
         "e2e": {"value": audio_s / wall, "unit": "audio-s/s", "ms_per_step": wall * 1e3 / args.steps},
         "roofline": {"bound": "hbm", "achieved": wb / (per_step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": wb / (per_step_ms * 1e-3) / 1e9 / hbm,
                      "traffic": None, "peak_source": peak_src, "note": "algorithmic bytes of one decode step = the resident weights streamed once for the whole batch (KV cache reads excluded)"},
-        "gpu_launches": int(ctx.launches() - l0), "dtype": "f16 matrices x fp16-rounded activations, f32 accumulate (the reference's numerics for an F16 GGUF)",
-        "data": "synthetic", "config": {"workload": "parler-mini F16 (24 layers x 1024, 9 codebooks), batch 16, 869 decode steps -> 861 frames, special ids folded mod 1024, DAC 44.1 kHz decode",
+        "gpu_launches": int(ctx.launches() - l0), "dtype": ("f16 matrices x fp16-rounded activations, f32 accumulate" if quant is None else f"{quant} blocks x Q8_0-requantised activations, int32 block dots, f32 accumulate") + " (the reference's numerics for this GGUF)",
+        "data": "synthetic", "config": {"workload": f"parler-mini {args.parler_dtype} (24 layers x 1024, 9 codebooks), batch 16, 869 decode steps -> 861 frames, special ids folded mod 1024, DAC 44.1 kHz decode",
                                          "status": "plain first path (one launch per op, no CUDA graph); see DESIGN 7.1"}}))
     return 0
 
@@ -365,6 +367,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parler-dtype", default="f16", choices=["f16", "q8_0", "q5_0", "q4_0"],
+                    help="--workload parler: dtype of the decoder matrices (f16 = BASELINE config 3; q5_0 is what the reference's published Parler numbers use)")
     ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "parler"],
                     help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
                          "parler: config 3 end to end (AR decode + DAC), plain first path")
