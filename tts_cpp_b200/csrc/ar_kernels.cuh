@@ -131,13 +131,13 @@ static inline void gemv_rows_launch(cudaStream_t st, const float * X, int ldx, c
 // activation rows to Q8_0 first (vec_dot_type): per 32 columns d = amax / 127 (stored as fp16), q = round-to-nearest-even(x * 127 / amax) (the AVX2
 // quantize_row_q8_0), then per block an exact integer dot product scaled by d_w * d_x (ggml_vec_dot_q{4,5,8}_0_q8_0).  Here: stage 1 quantises the 8 rows of a
 // chunk into shared memory once per block; stage 2 is a warp per output row, a lane per weight block, dp4a over the eight 4-byte words of a block.
-// First version (2-byte loads of the unaligned 34 / 22 / 18-byte blocks); the weight stream is a quarter to an eighth of the fp32 one.
+// The matrix lives in HBM as planes (values / fp16 scales / Q5_0 fifth bits, split at load time from ggml's unaligned 34 / 22 / 18-byte blocks): a lane fetches a
+// block's values with aligned 16-byte loads; the weight stream is a quarter to an eighth of the fp32 one.
 static inline size_t gemv_q_smem(int K) { return (size_t) GR * K + (size_t) GR * (K / 32) * 4; }
-__device__ __forceinline__ unsigned ld_u16x2(const uint8_t * p) { return (unsigned) *reinterpret_cast<const uint16_t *>(p) | ((unsigned) *reinterpret_cast<const uint16_t *>(p + 2) << 16); }
-__global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restrict__ X, int ldx, const uint8_t * __restrict__ W, int qtype, int K, int N, int R,
-                                                          const float * res, float * Y, int ldy) {
+__global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restrict__ X, int ldx, const uint8_t * __restrict__ W, const __half * __restrict__ Ws,
+                                                          const unsigned * __restrict__ Wh, int qtype, int K, int N, int R, const float * res, float * Y, int ldy) {
     extern __shared__ __align__(16) float gq_smem[];
-    const int nb = K >> 5, blk = qtype == 8 ? 34 : (qtype == 6 ? 22 : 18);
+    const int nb = K >> 5;
     int * xq = reinterpret_cast<int *>(gq_smem);                    // [GR][K / 4] packed int8 activations
     float * xd = gq_smem + (size_t) GR * (K >> 2);                   // [GR][nb] block scales (fp16-rounded)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -167,19 +167,19 @@ __global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restri
 #pragma unroll
             for (int j = 0; j < GR; j++) acc[j] = 0.f;
             for (int b = lane; b < nb; b += 32) {
-                const uint8_t * p = W + ((size_t) n * nb + b) * blk;
-                __half_raw hr; hr.x = *reinterpret_cast<const uint16_t *>(p);
-                const float dw = __half2float(__half(hr));
+                const size_t bi = (size_t) n * nb + b;
+                const float dw = __half2float(Ws[bi]);
                 int wq[8];
                 if (qtype == 8) {
-#pragma unroll
-                    for (int w = 0; w < 8; w++) wq[w] = (int) ld_u16x2(p + 2 + 4 * w);
+                    const uint4 v0 = *reinterpret_cast<const uint4 *>(W + bi * 32), v1 = *reinterpret_cast<const uint4 *>(W + bi * 32 + 16);
+                    wq[0] = (int) v0.x; wq[1] = (int) v0.y; wq[2] = (int) v0.z; wq[3] = (int) v0.w; wq[4] = (int) v1.x; wq[5] = (int) v1.y; wq[6] = (int) v1.z; wq[7] = (int) v1.w;
                 } else {
-                    const uint8_t * qs = p + (qtype == 6 ? 6 : 2);
-                    const unsigned qh = qtype == 6 ? ld_u16x2(p + 2) : 0u;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(W + bi * 16);
+                    const unsigned q4s[4] = {v.x, v.y, v.z, v.w};
+                    const unsigned qh = qtype == 6 ? Wh[bi] : 0u;
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {                    // bytes 4w .. 4w+3 of qs: low nibbles are elements 4w.., high nibbles elements 16 + 4w..
-                        const unsigned q4 = ld_u16x2(qs + 4 * w);
+                    for (int w = 0; w < 4; w++) {                    // bytes 4w .. 4w+3 of the block: low nibbles are elements 4w.., high nibbles elements 16 + 4w..
+                        const unsigned q4 = q4s[w];
                         unsigned lo = q4 & 0x0F0F0F0Fu, hi = (q4 >> 4) & 0x0F0F0F0Fu;
                         if (qtype == 6) {
                             const unsigned bl = (qh >> (4 * w)) & 0xFu, bh = (qh >> (16 + 4 * w)) & 0xFu;

@@ -20,10 +20,12 @@ struct W16 {                    // fp16 GEMM weight [Npad][KW][CinPad]
     int N = 0, Npad = 0, KW = 1, Cin = 0, CinPad = 0;
 };
 
-struct ArW {                    // a weight matrix [N][K] of the autoregressive decode paths: fp32, fp16 when the GGUF stores it as F16, or ggml blocks (qtype 2 / 6 / 8)
-    const void * p = nullptr;
+struct ArW {                    // a weight matrix [N][K] of the autoregressive decode paths: fp32, fp16 when the GGUF stores it as F16, or block-quantised (qtype 2 / 6 / 8)
+    const void * p = nullptr;   // fp32 / fp16 values; quantised: the 4- or 8-bit plane, rows of K/2 (Q4_0, Q5_0: byte j of a block = elements j | j+16) or K (Q8_0) bytes
     bool f16 = false;
     int  qtype = 0;
+    const void * scales = nullptr;   // quantised: [N][K/32] fp16 block scales
+    const void * qh = nullptr;       // Q5_0: [N][K/32] uint32, the fifth bits
 };
 
 struct Lstm {

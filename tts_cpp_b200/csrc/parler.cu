@@ -84,7 +84,7 @@ struct PFwd {
             if (K % 32 || (size_t) GR * K + (size_t) GR * (K / 32) * 4 > 200 * 1024) { set_error("parler: quantised matrix with K = %d is not supported", K); return 1; }
             const size_t smem = gemv_q_smem(K);
             if (smem > q_smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_rows_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); q_smem_set = smem; }
-            gemv_rows_q_kernel<<<cdiv(N, 8), 256, smem, st>>>(X, ldx, (const uint8_t *) W.p, W.qtype, K, N, R, res, Y, ldy);
+            gemv_rows_q_kernel<<<cdiv(N, 8), 256, smem, st>>>(X, ldx, (const uint8_t *) W.p, (const __half *) W.scales, (const unsigned *) W.qh, W.qtype, K, N, R, res, Y, ldy);
             B2_LAUNCH_CHECK(ctx);
             return 0;
         }
@@ -143,12 +143,26 @@ int Parler::prepare() {
         const HostTensor * t = find(n, expect);
         if (!t) return ArW();
         if (!t->qtype) return dev_mat(t->v.data(), t->v.size(), t->f16);
-        ArW w; w.qtype = t->qtype;                                  // block-quantised matrix: the blocks go to HBM as they are in the file
-        void * d = nullptr;
-        if (cudaMalloc(&d, t->raw.size()) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", t->raw.size()); ok = false; return w; }
-        cudaMemcpy(d, t->raw.data(), t->raw.size(), cudaMemcpyHostToDevice);
-        dev_allocs.push_back(d); weight_bytes += t->raw.size();
-        w.p = d;
+        // block-quantised matrix: the ggml blocks (fp16 scale | [4 bytes of fifth bits] | 16 or 32 bytes of values, 18 / 22 / 34 bytes, unaligned) are split into
+        // planes -- values, scales, fifth bits -- so that a lane reads a block's values with one aligned 16-byte (two for Q8_0) load; same bytes in total
+        ArW w; w.qtype = t->qtype;
+        const size_t nblk = t->v.size() / 32, blk = t->qtype == 2 ? 18 : t->qtype == 6 ? 22 : 34, vb = t->qtype == 8 ? 32 : 16;
+        std::vector<uint8_t> vals(nblk * vb); std::vector<uint16_t> sc(nblk); std::vector<uint32_t> hb(t->qtype == 6 ? nblk : 0);
+        for (size_t b = 0; b < nblk; b++) {
+            const uint8_t * p = t->raw.data() + b * blk;
+            memcpy(&sc[b], p, 2);
+            if (t->qtype == 6) memcpy(&hb[b], p + 2, 4);
+            memcpy(&vals[b * vb], p + (t->qtype == 6 ? 6 : 2), vb);
+        }
+        auto put = [&](const void * src, size_t bytes) -> void * {
+            void * d = nullptr;
+            if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", bytes); ok = false; return nullptr; }
+            cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+            dev_allocs.push_back(d); weight_bytes += bytes;
+            return d;
+        };
+        w.p = put(vals.data(), vals.size()); w.scales = put(sc.data(), sc.size() * 2);
+        if (t->qtype == 6) w.qh = put(hb.data(), hb.size() * 4);
         return w;
     };
 
