@@ -238,6 +238,9 @@ int   b2tts_dia_generate_greedy(b2tts_dia * m, int n_sequences, const uint32_t *
                                 int32_t * out_tokens, float * out_logits, int32_t * n_generated);
 int   b2tts_dia_generate(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
                          int32_t * out_tokens, float * out_logits, int32_t * n_generated);
+/* parity helper, as b2tts_parler_generate_teacher_forced */
+int   b2tts_dia_generate_teacher_forced(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps,
+                                        const int32_t * teacher, int32_t * out_tokens, float * out_logits);
 /* generation_configuration::max_tokens (dia_runner::generate, model.cpp:873-879): replaces the model's max_generation_size in check_stopping when > max_delay */
 int   b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens);
 float b2tts_dia_last_ms(const b2tts_dia * m);

@@ -20,6 +20,11 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+try:
+    from .parler_port import quant_mm, unpack_blocks
+except ImportError:                               # imported as a top-level module (oracle/ on sys.path)
+    from parler_port import quant_mm, unpack_blocks
+
 
 class DiaPort:
     MAX_DELAY = 15
@@ -31,11 +36,18 @@ class DiaPort:
         rd = gguf.GGUFReader(gguf_path)
         self.w = {}
         self.f16 = set()          # F16 matrices: ggml_mul_mat rounds the activations to fp16 before the product
+        self.q = {}               # block-quantised matrices: name -> (scales [N, nb], integer values [N, nb, 32]) (see parler_port.unpack_blocks)
         for t in rd.tensors:
             if t.name.startswith("dia."):
-                self.w[t.name[len("dia."):]] = torch.from_numpy(np.array(t.data).astype(np.float32))
+                name = t.name[len("dia."):]
+                if t.tensor_type.name in ("Q8_0", "Q5_0", "Q4_0"):
+                    d, qv = unpack_blocks(np.array(t.data), t.tensor_type.name)
+                    self.q[name] = (torch.from_numpy(d), torch.from_numpy(qv))
+                    self.w[name] = torch.from_numpy((d[:, :, None] * qv).reshape(d.shape[0], -1))       # dequantize_row: what ggml_get_rows returns
+                    continue
+                self.w[name] = torch.from_numpy(np.array(t.data).astype(np.float32))
                 if t.tensor_type.name == "F16":
-                    self.f16.add(t.name[len("dia."):])
+                    self.f16.add(name)
         self.kv = {}
         for k, f in rd.fields.items():
             if len(f.data) == 1 and f.types and f.types[0].name in ("UINT32",):
@@ -49,6 +61,8 @@ class DiaPort:
 
     def mm(self, x, name):
         """ggml_mul_mat(weight, x): exact products of fp16-rounded activations with F16 weights, fp32 accumulation; plain fp32 for F32 weights."""
+        if name in self.q:
+            return quant_mm(x, *self.q[name])
         if name in self.f16:
             x = x.half().float()
         return x @ self.w[name].t()
@@ -149,7 +163,7 @@ class DiaPort:
         self.pos += 1
         return (cond + 3.0 * (cond - uncond)).numpy()
 
-    def greedy(self, prompt, steps: int):
+    def greedy(self, prompt, steps: int, teacher=None):
         self.encode(prompt)
         audio = [self.bos] * self.n_out
         toks, logits = [], []
@@ -169,5 +183,7 @@ class DiaPort:
             lg = self.step(audio)
             last = lg.argmax(axis=1)
             toks.append(last.astype(np.int32)); logits.append(lg)
+            if teacher is not None:                  # teacher-forced comparison: feed the given tokens back, keep reporting the produced ones
+                last = np.asarray(teacher[len(toks) - 1])
             audio = [int(last[i]) if self.pos > i else self.bos for i in range(self.n_out)]
         return np.stack(toks), np.stack(logits)

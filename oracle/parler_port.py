@@ -43,6 +43,20 @@ def unpack_blocks(raw: np.ndarray, kind: str):
     return d, q
 
 
+def quant_mm(x: torch.Tensor, d: torch.Tensor, qv: torch.Tensor) -> torch.Tensor:
+    """ggml_mul_mat with a block-quantised matrix (scales d [N, nb], integer values qv [N, nb, 32]): the activations (any leading shape, K last) are quantised to
+    Q8_0 per 32 columns (vec_dot_type), integer dot products per block, scaled by d_w * d_x."""
+    lead, K = x.shape[:-1], x.shape[-1]
+    xb = x.reshape(-1, K // 32, 32)
+    amax = xb.abs().amax(dim=2)
+    idv = torch.where(amax > 0, np.float32(127.0) / amax, torch.zeros_like(amax))
+    xq = torch.round(xb * idv[:, :, None])                              # AVX2 quantize_row_q8_0: _mm256_round_ps, nearest-even, scale 127 / amax
+    dx = (amax / np.float32(127.0)).half().float()                       # the block scale is stored as fp16
+    sumi = torch.einsum("nbk,Nbk->nNb", xq.double(), qv.double())        # exact integers
+    y = (sumi.float() * (d[None, :, :] * dx[:, None, :])).sum(dim=2)
+    return y.reshape(*lead, d.shape[0])
+
+
 class ParlerPort:
     def __init__(self, gguf_path: str, threads: int = 8):
         import gguf
@@ -78,16 +92,8 @@ class ParlerPort:
 
     def mm(self, x, name):
         """ggml_mul_mat(weight, x): exact products of fp16-rounded activations with F16 weights, fp32 accumulation; plain fp32 for F32 weights."""
-        if name in self.q:        # ggml_mul_mat with a quantised matrix: the activations are quantised to Q8_0 per 32 columns (vec_dot_type), integer dot products per block
-            d, qv = self.q[name]
-            n, K = x.shape
-            xb = x.reshape(n, K // 32, 32)
-            amax = xb.abs().amax(dim=2)
-            idv = torch.where(amax > 0, np.float32(127.0) / amax, torch.zeros_like(amax))
-            xq = torch.round(xb * idv[:, :, None])                              # AVX2 quantize_row_q8_0: _mm256_round_ps, nearest-even, scale 127 / amax
-            dx = (amax / np.float32(127.0)).half().float()                       # the block scale is stored as fp16
-            sumi = torch.einsum("nbk,Nbk->nNb", xq.double(), qv.double())        # exact integers
-            return (sumi.float() * (d[None, :, :] * dx[:, None, :])).sum(dim=2)
+        if name in self.q:
+            return quant_mm(x, *self.q[name])
         if name in self.f16:
             x = x.half().float()
         return x @ self.w[name].t()

@@ -31,7 +31,16 @@ static int gen(b2::Parler & m, int B, const uint32_t * const * pp, const int32_t
     }
     return m.generate(B, pp, np, steps, s, tok, lg, g_ngen.empty() ? nullptr : g_ngen.data(), teacher.empty() ? nullptr : teacher.data());
 }
-static int gen(b2::Dia & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) { return m.generate(B, pp, np, steps, s, tok, lg, nullptr); }
+static int gen(b2::Dia & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) {
+    std::vector<int32_t> teacher;                                  // B2EMU_TEACHER=<file of int32 [B][steps][n_out]>: teacher-forced feedback
+    if (const char * tf = getenv("B2EMU_TEACHER")) {
+        teacher.resize((size_t) B * steps * m.n_out);
+        FILE * f = fopen(tf, "rb");
+        if (!f || fread(teacher.data(), 4, teacher.size(), f) != teacher.size()) return 2;
+        fclose(f);
+    }
+    return m.generate(B, pp, np, steps, s, tok, lg, nullptr, teacher.empty() ? nullptr : teacher.data());
+}
 
 template <class M> static int run(int argc, char ** argv) {
     b2::Ctx ctx;

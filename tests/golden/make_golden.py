@@ -26,6 +26,7 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
   orpheus_wide_vectors.npz : as orpheus_vectors.npz for a GGUF with head size 128 (hidden 768)
   sampler_vectors.npz      : the reference sampler (src/sampler.cpp) on fixed logits under four configurations: nucleus, probabilities, max_head_probs and a
       histogram of 20 000 draws each, from oracle/ref_sampler_driver.cpp
+  dia_q8_0_vectors.npz     : as dia_vectors.npz for the Q8_0 GGUF of the quantize tool
   dia_stop_vectors.npz     : one byte-token prompt run until the reference's check_stopping ends the loop (64 frames of 9 tokens, the logits of the
       last frame), from oracle/ref_dia_driver.cpp with a step cap of 80
   dia_vectors.npz          : two byte-token prompts (10 and 18 tokens, the second after the first in the same process) and, for 5 greedy steps
@@ -225,9 +226,9 @@ def parler_stop_vectors():
     print("parler stop vectors:", {k: v.shape for k, v in out.items()})
 
 
-def dia_vectors(f16: bool = False):
+def dia_vectors(f16: bool = False, quant: str | None = None):
     from tts_cpp_b200.synth import cached_dia_gguf
-    gguf = cached_dia_gguf(seed=0, f16=f16)
+    gguf = cached_dia_gguf(seed=0, f16=f16, quant=quant)
     rng = np.random.default_rng(11)
     prompts = [np.concatenate([[1], rng.integers(32, 127, size=n)]) for n in (9, 17)]      # [S1] + printable bytes
     tmp = tempfile.mkdtemp()
@@ -241,8 +242,9 @@ def dia_vectors(f16: bool = False):
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
-    np.savez_compressed(os.path.join(OUT, "dia_f16_vectors.npz" if f16 else "dia_vectors.npz"), **out)
-    print("dia f16 vectors:" if f16 else "dia vectors:", {k: v.shape for k, v in out.items()})
+    tag = f"_{quant.lower()}" if quant else ("_f16" if f16 else "")
+    np.savez_compressed(os.path.join(OUT, f"dia{tag}_vectors.npz"), **out)
+    print(f"dia{tag} vectors:", {k: v.shape for k, v in out.items()})
 
 
 def dia_stop_vectors():
@@ -293,7 +295,7 @@ def sampler_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_q8_0", "parler_q5_0", "parler_q4_0", "parler_stop", "dia", "dia_f16", "dia_stop", "sampler", "orpheus_wide"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_q8_0", "parler_q5_0", "parler_q4_0", "parler_stop", "dia", "dia_f16", "dia_q8_0", "dia_stop", "sampler", "orpheus_wide"]
     if "dia_stop" in which: dia_stop_vectors()
     if "parler_stop" in which: parler_stop_vectors()
     if "sampler" in which: sampler_vectors()
@@ -302,6 +304,7 @@ if __name__ == "__main__":
     for q in ("Q8_0", "Q5_0", "Q4_0"):
         if f"parler_{q.lower()}" in which: parler_vectors(quant=q)
     if "dia_f16" in which: dia_vectors(f16=True)
+    if "dia_q8_0" in which: dia_vectors(quant="Q8_0")
     if "dia" in which: dia_vectors()
     if "parler" in which: parler_vectors()
     if "orpheus" in which: orpheus_vectors()

@@ -42,3 +42,30 @@ def test_dia_greedy_tokens_and_logits_match_reference(dtype):
     print(r.stdout[-2000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
+
+
+QUANT_CHILD = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import dia_runner_from_file
+from tts_cpp_b200.synth import cached_dia_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "dia_q8_0_vectors.npz"))
+dia = dia_runner_from_file(cached_dia_gguf(seed=0, quant="Q8_0"))
+toks, logits = dia.generate_teacher_forced([g["prompt0"], g["prompt1"]], np.stack([g["tokens0"], g["tokens1"]]))
+ok = True
+for u in range(2):
+    rms = np.sqrt(((logits[u] - g[f"logits{u}"]) ** 2).mean(axis=(1, 2)))
+    agree = float((toks[u] == g[f"tokens{u}"]).mean())
+    print(f"PARITY dia Q8_0 prompt {u}: per-step logit rms {np.round(rms, 3).tolist()}, tokens equal {agree:.2f}")
+    ok &= float(rms.max()) < 4.0 and agree >= 0.8
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_dia_quantised_teacher_forced():
+    """Q8_0 matrices (gemv_rows_q_kernel), teacher-forced on the reference's tokens; smoke-level bar (Dia amplifies re-quantisation noise: see tests/test_emu_cpu.py)."""
+    r = subprocess.run([sys.executable, "-c", QUANT_CHILD, ROOT], capture_output=True, text=True, timeout=150)
+    print(r.stdout[-2000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0

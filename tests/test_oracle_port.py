@@ -276,3 +276,17 @@ def test_parler_port_quantised_teacher_forced(quant):
         print(f"parler {quant} prompt {u}: per-step logit rms {np.round(rms, 4).tolist()}, tokens equal {int((toks == ref_t).sum())}/{toks.size}, clear-cut {int(clear.sum())}")
         assert float(rms.max()) < 0.1
         assert np.array_equal(toks[clear], ref_t[clear])
+
+
+def test_dia_port_quantised_teacher_forced():
+    """oracle/dia_port.py on the Q8_0 GGUF, teacher-forced (see test_dia_quantised_emulated_teacher_forced in test_emu_cpu.py for the bar and why it is loose)."""
+    from oracle.dia_port import DiaPort
+    from tts_cpp_b200.synth import cached_dia_gguf
+    g = np.load(os.path.join(GOLD, "dia_q8_0_vectors.npz"))
+    port = DiaPort(cached_dia_gguf(seed=0, quant="Q8_0"))
+    assert len(port.q) == 46
+    for u in range(2):
+        toks, logits = port.greedy(g[f"prompt{u}"], g[f"tokens{u}"].shape[0], teacher=g[f"tokens{u}"])
+        rms = np.sqrt(((logits - g[f"logits{u}"]) ** 2).mean(axis=(1, 2)))
+        print(f"dia Q8_0 prompt {u}: per-step logit rms {np.round(rms, 3).tolist()}, tokens equal {int((toks == g[f'tokens{u}']).sum())}/{toks.size}")
+        assert float(rms.max()) < 4.0 and float((toks == g[f"tokens{u}"]).mean()) >= 0.8

@@ -480,6 +480,17 @@ class DiaRunner:
                                       toks.ctypes.data_as(C.POINTER(C.c_int32)), None, ngen.ctypes.data_as(C.POINTER(C.c_int32))))
         return toks, ngen
 
+    def generate_teacher_forced(self, prompts, teacher):
+        """teacher [B][n_steps][n_heads]: the tokens fed back instead of the produced ones -> (produced tokens, CFG-combined logits)"""
+        B, arrs, npr, ptrs = _prompt_args(prompts)
+        teacher = np.ascontiguousarray(np.asarray(teacher, np.int32))
+        n_steps = teacher.shape[1]
+        toks = np.empty((B, n_steps, self.n_heads), np.int32)
+        logits = np.empty((B, n_steps, self.n_heads, self.out_vocab), np.float32)
+        _chk(lib().b2tts_dia_generate_teacher_forced(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps), teacher.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     toks.ctypes.data_as(C.POINTER(C.c_int32)), logits.ctypes.data_as(C.POINTER(C.c_float))))
+        return toks, logits
+
     def close(self):
         if self.h:
             lib().b2tts_dia_free(self.h)

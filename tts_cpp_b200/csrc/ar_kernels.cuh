@@ -4,8 +4,9 @@
 // Each kernel states the ggml op it restates.  Their LOGIC is checked under the CPU emulation in tests/emu (tests/test_emu_cpu.py);
 // the -m gpu tests are the parity gate.  Included into each model's translation unit (internal linkage).
 #pragma once
-#include "common.cuh"
+#include "kokoro.h"   // HostTensor, ArW
 #include <cstdlib>
+#include <cstring>
 
 namespace b2 {
 namespace {
@@ -683,6 +684,71 @@ __global__ void delay_rows_kernel(const int * __restrict__ d_out, const int * __
 }
 
 __global__ void step_advance_kernel(int * d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_step += 1; }
+
+// ---- host helpers for block-quantised tensors (shared by parler.cu and dia.cu)
+
+// a GGUF tensor of Q4_0 / Q5_0 / Q8_0 blocks -> HostTensor: keeps the blocks in `raw` and dequantises them like dequantize_row_q{4,5,8}_0 (ggml-quants.c) into `v`
+// (what ggml_get_rows hands to the embedding users).  0 ok, 1 error (message set).
+static inline int host_tensor_from_blocks(HostTensor & t, const char * name, int type, int64_t n, const void * data, size_t nbytes) {
+    const size_t blk = type == 2 ? 18 : type == 6 ? 22 : 34;
+    if (n % 32 || nbytes < (size_t) n / 32 * blk) { set_error("tensor %s: short or ragged quantised data", name); return 1; }
+    t.qtype = type;
+    t.raw.assign((const uint8_t *) data, (const uint8_t *) data + (size_t) n / 32 * blk);
+    t.v.resize((size_t) n);
+    for (int64_t b = 0; b < n / 32; b++) {
+        const uint8_t * p = t.raw.data() + (size_t) b * blk;
+        __half_raw hr; memcpy(&hr.x, p, 2);
+        const float d = __half2float(__half(hr));
+        float * y = t.v.data() + (size_t) b * 32;
+        if (type == 8) { for (int j = 0; j < 32; j++) y[j] = (float) (int8_t) p[2 + j] * d; }
+        else {
+            uint32_t qh = 0; if (type == 6) memcpy(&qh, p + 2, 4);
+            const uint8_t * qs = p + (type == 6 ? 6 : 2);
+            for (int j = 0; j < 16; j++) {
+                int x0 = qs[j] & 0x0F, x1 = qs[j] >> 4;
+                if (type == 6) { x0 = (x0 | (int) (((qh >> j) & 1u) << 4)) - 16; x1 = (x1 | (int) (((qh >> (j + 16)) & 1u) << 4)) - 16; }
+                else { x0 -= 8; x1 -= 8; }
+                y[j] = (float) x0 * d; y[j + 16] = (float) x1 * d;
+            }
+        }
+    }
+    return 0;
+}
+
+// the planes of a block-quantised matrix in HBM: the ggml blocks (fp16 scale | [4 bytes of fifth bits] | 16 or 32 bytes of values, 18 / 22 / 34 bytes, unaligned) split
+// into values, scales and fifth bits so that a lane reads a block's values with one aligned 16-byte (two for Q8_0) load; same bytes in total.  false on cudaMalloc failure.
+static inline bool upload_quant_planes(const HostTensor & t, ArW & w, std::vector<void *> & dev_allocs, size_t & weight_bytes) {
+    w = ArW(); w.qtype = t.qtype;
+    const size_t nblk = t.v.size() / 32, blk = t.qtype == 2 ? 18 : t.qtype == 6 ? 22 : 34, vb = t.qtype == 8 ? 32 : 16;
+    std::vector<uint8_t> vals(nblk * vb); std::vector<uint16_t> sc(nblk); std::vector<uint32_t> hb(t.qtype == 6 ? nblk : 0);
+    for (size_t b = 0; b < nblk; b++) {
+        const uint8_t * p = t.raw.data() + b * blk;
+        memcpy(&sc[b], p, 2);
+        if (t.qtype == 6) memcpy(&hb[b], p + 2, 4);
+        memcpy(&vals[b * vb], p + (t.qtype == 6 ? 6 : 2), vb);
+    }
+    bool ok = true;
+    auto put = [&](const void * src, size_t bytes) -> void * {
+        void * d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %zu bytes failed", bytes); ok = false; return nullptr; }
+        cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += bytes;
+        return d;
+    };
+    w.p = put(vals.data(), vals.size()); w.scales = put(sc.data(), sc.size() * 2);
+    if (t.qtype == 6) w.qh = put(hb.data(), hb.size() * 4);
+    return ok;
+}
+
+// Y = X . W^T (+ res) for a block-quantised W: 0 launched, 1 error
+static inline int gemv_q_launch(Ctx * ctx, cudaStream_t st, size_t & smem_set, const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+    if (K % 32 || gemv_q_smem(K) > 200 * 1024) { set_error("quantised matrix with K = %d is not supported", K); return 1; }
+    const size_t smem = gemv_q_smem(K);
+    if (smem > smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_rows_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); smem_set = smem; }
+    gemv_rows_q_kernel<<<cdiv(N, 8), 256, smem, st>>>(X, ldx, (const uint8_t *) W.p, (const __half *) W.scales, (const unsigned *) W.qh, W.qtype, K, N, R, res, Y, ldy);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 }  // namespace
 }  // namespace b2

@@ -291,6 +291,12 @@ int b2tts_dia_generate(b2tts_dia * m, int n_sequences, const uint32_t * const * 
     const ArSampling a = to_sampling(sampling);
     return m->d.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits, n_generated);
 }
+int b2tts_dia_generate_teacher_forced(b2tts_dia * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const int32_t * teacher,
+                                      int32_t * out_tokens, float * out_logits) {
+    if (!m) { set_error("null model"); return 1; }
+    if (!teacher) { set_error("null teacher tokens"); return 1; }
+    return m->d.generate(n_sequences, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits, nullptr, teacher);
+}
 int b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens) {
     if (!m) { set_error("null model"); return 1; }
     if (max_tokens > m->d.max_delay) m->d.max_gen = max_tokens;

@@ -27,8 +27,10 @@ int Dia::assign(const char * name, int type, int n_dims, const int64_t * ne, con
         const uint16_t * s = (const uint16_t *) data;
         for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = dh2f(s[i]);
         t.f16 = true;
+    } else if (type == 2 || type == 6 || type == 8) {          // Q4_0 / Q5_0 / Q8_0 blocks
+        if (host_tensor_from_blocks(t, name, type, n, data, nbytes)) return 1;
     } else {
-        set_error("tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
+        set_error("tensor %s: ggml type %d not supported (F32, F16, Q4_0, Q5_0, Q8_0)", name, type);
         return 1;
     }
     host[nm] = std::move(t);
@@ -74,7 +76,14 @@ int Dia::prepare() {
         w.p = d;
         return w;
     };
-    auto upw = [&](const std::string & n, int64_t expect) -> ArW { const HostTensor * t = find(n, expect); return t ? dev_mat(t->v.data(), t->v.size(), t->f16) : ArW(); };
+    auto upw = [&](const std::string & n, int64_t expect) -> ArW {
+        const HostTensor * t = find(n, expect);
+        if (!t) return ArW();
+        if (!t->qtype) return dev_mat(t->v.data(), t->v.size(), t->f16);
+        ArW w;                                                      // block-quantised matrix: value / scale / fifth-bit planes (ar_kernels.cuh)
+        if (!upload_quant_planes(*t, w, dev_allocs, weight_bytes)) ok = false;
+        return w;
+    };
 
     {   // the encoder width is not in the metadata (the reference hard-codes 1024, model.h:68): take it from the embedding table
         const HostTensor * t = find("encoder.embedding", 0);
@@ -116,6 +125,7 @@ int Dia::prepare() {
             tab.insert(tab.end(), t->v.begin(), t->v.end());
             hw.insert(hw.end(), h->v.begin(), h->v.end());
             heads_f16 = heads_f16 && h->f16; heads_any_f16 = heads_any_f16 || h->f16;
+            if (h->qtype) { set_error("dia: block-quantised output heads (quantize --quantize-output-heads) are not supported"); ok = false; break; }
         }
         if (ok && heads_any_f16 != heads_f16) { set_error("dia: the output heads mix F16 and F32 tensors"); ok = false; }
         if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev_mat(hw.data(), hw.size(), heads_f16); }   // tables: ggml_get_rows widens F16 rows to fp32 exactly
@@ -185,7 +195,7 @@ __global__ void cfg_combine_kernel(const float * __restrict__ logits2, int NV, f
 }
 
 struct DFwd {
-    Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0};
+    Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0}, q_smem_set = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     size_t att_smem_set = 0, gqa_smem_set = 0;
     // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
@@ -206,6 +216,7 @@ struct DFwd {
         return 0;
     }
     int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (W.qtype) return gemv_q_launch(ctx, st, q_smem_set, X, ldx, W, K, N, R, res, Y, ldy);      // Q4_0 / Q5_0 / Q8_0: Q8_0-requantised activations, dp4a per block
         if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
             return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
         gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
@@ -219,7 +230,8 @@ struct DFwd {
 
 }  // namespace
 
-int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits, int32_t * n_generated) {
+int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits, int32_t * n_generated,
+                  const int32_t * teacher) {
     const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("dia: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
@@ -235,7 +247,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     const size_t self_cache = (size_t) 2 * dec_layers * S2 * Tmax * KVD * 4;
     const size_t dec_ws = (size_t) S2 * ((size_t) 4 * D + 2 * KVD + 2 * ffn + NV) * 4 + (size_t) B * NV * 4;
     const size_t need = enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20) +
-                        (size_t) B * n_out * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
+                        (size_t) B * n_out * 8 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
     DFwd Fw{this, ctx, st};
     // ---- buffers
@@ -246,6 +258,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     int * ids = Fw.al<int>((size_t) S2 * n_out), * row_pos = Fw.al<int>((size_t) S2), * row_base = Fw.al<int>((size_t) S2), * row_len = Fw.al<int>((size_t) S2), * row_dst = Fw.al<int>((size_t) S2);
     int * delay = Fw.al<int>((size_t) B), * stopped = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) n_steps * B * n_out), * d_step = Fw.al<int>(1);
     int * s_last = Fw.al<int>((size_t) B * n_out), * s_cnt = Fw.al<int>((size_t) B * n_out);
+    int * d_teacher = teacher ? Fw.al<int>((size_t) n_steps * B * n_out) : nullptr;
     float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * NV) : nullptr;
     if (Fw.fail) return 1;
     B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * n_out * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
@@ -275,6 +288,12 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     B2_CUDA(cudaMemcpyAsync(delay, hm1.data(), hm1.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemcpyAsync(stopped, hm1.data(), hm1.size() * 4, cudaMemcpyHostToDevice, st));
     B2_CUDA(cudaMemsetAsync(d_step, 0, 4, st));
+    std::vector<int> hteach;
+    if (teacher) {                                                  // [B][n_steps][n_out] -> the device's [n_steps][B][n_out]
+        hteach.resize((size_t) n_steps * B * n_out);
+        for (int b = 0; b < B; b++) for (int s2 = 0; s2 < n_steps; s2++) for (int i = 0; i < n_out; i++) hteach[((size_t) s2 * B + b) * n_out + i] = teacher[((size_t) b * n_steps + s2) * n_out + i];
+        B2_CUDA(cudaMemcpyAsync(d_teacher, hteach.data(), hteach.size() * 4, cudaMemcpyHostToDevice, st));
+    }
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float theta_scale = powf(10000.0f, -2.0f / (float) head_dim);
@@ -318,7 +337,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     if (Fw.fail) return 1;
     const int R = S2;
     auto run_step = [&]() -> int {
-        dia_step_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_out, B, n_out, d_step, bos, eos, pad, max_gen, max_delay, Tmax, delay, stopped, ids, row_pos, row_base, row_len, row_dst);
+        dia_step_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_teacher ? d_teacher : d_out, B, n_out, d_step, bos, eos, pad, max_gen, max_delay, Tmax, delay, stopped, ids, row_pos, row_base, row_len, row_dst);
         B2_LAUNCH_CHECK(ctx);
         codebook_embed_kernel<<<R, 256, 0, st>>>(ids, n_out, tables, (size_t) vocab * D, nullptr, row_pos, D, x); B2_LAUNCH_CHECK(ctx);
         for (int l = 0; l < dec_layers; l++) {

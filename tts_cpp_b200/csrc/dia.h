@@ -46,7 +46,9 @@ struct Dia {
         return generate(B, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits, n_generated);
     }
     // the same loop under the reference sampler's settings (sampler.cu): sampling == nullptr or do_sample == 0 is the greedy sampler::max
-    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits, int32_t * n_generated);
+    // teacher (optional, [B][n_steps][n_out]): tokens fed back instead of the produced ones (teacher-forced parity checks, see parler.h)
+    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits, int32_t * n_generated,
+                 const int32_t * teacher = nullptr);
     void free_all();
 };
 

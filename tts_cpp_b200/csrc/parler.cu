@@ -27,28 +27,8 @@ int Parler::assign(const char * name, int type, int n_dims, const int64_t * ne, 
         const uint16_t * s = (const uint16_t *) data;
         for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = ph2f(s[i]);
         t.f16 = true;
-    } else if (type == 2 || type == 6 || type == 8) {          // Q4_0 / Q5_0 / Q8_0 blocks: keep them, and dequantise like dequantize_row_q*_0 (ggml-quants.c) for ggml_get_rows users
-        const size_t blk = type == 2 ? 18 : type == 6 ? 22 : 34;
-        if (n % 32 || nbytes < (size_t) n / 32 * blk) { set_error("tensor %s: short or ragged quantised data", name); return 1; }
-        t.qtype = type;
-        t.raw.assign((const uint8_t *) data, (const uint8_t *) data + (size_t) n / 32 * blk);
-        for (int64_t b = 0; b < n / 32; b++) {
-            const uint8_t * p = t.raw.data() + (size_t) b * blk;
-            uint16_t dh; memcpy(&dh, p, 2);
-            const float d = ph2f(dh);
-            float * y = t.v.data() + (size_t) b * 32;
-            if (type == 8) { for (int j = 0; j < 32; j++) y[j] = (float) (int8_t) p[2 + j] * d; }
-            else {
-                uint32_t qh = 0; if (type == 6) memcpy(&qh, p + 2, 4);
-                const uint8_t * qs = p + (type == 6 ? 6 : 2);
-                for (int j = 0; j < 16; j++) {
-                    int x0 = qs[j] & 0x0F, x1 = qs[j] >> 4;
-                    if (type == 6) { x0 = (x0 | (int) (((qh >> j) & 1u) << 4)) - 16; x1 = (x1 | (int) (((qh >> (j + 16)) & 1u) << 4)) - 16; }
-                    else { x0 -= 8; x1 -= 8; }
-                    y[j] = (float) x0 * d; y[j + 16] = (float) x1 * d;
-                }
-            }
-        }
+    } else if (type == 2 || type == 6 || type == 8) {          // Q4_0 / Q5_0 / Q8_0 blocks
+        if (host_tensor_from_blocks(t, name, type, n, data, nbytes)) return 1;
     } else {
         set_error("tensor %s: ggml type %d not supported (F32, F16, Q4_0, Q5_0, Q8_0)", name, type);
         return 1;
@@ -80,14 +60,7 @@ struct PFwd {
         return 0;
     }
     int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        if (W.qtype) {                                              // Q4_0 / Q5_0 / Q8_0: activations quantised to Q8_0 per 32 columns, integer dot products per block
-            if (K % 32 || (size_t) GR * K + (size_t) GR * (K / 32) * 4 > 200 * 1024) { set_error("parler: quantised matrix with K = %d is not supported", K); return 1; }
-            const size_t smem = gemv_q_smem(K);
-            if (smem > q_smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_rows_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); q_smem_set = smem; }
-            gemv_rows_q_kernel<<<cdiv(N, 8), 256, smem, st>>>(X, ldx, (const uint8_t *) W.p, (const __half *) W.scales, (const unsigned *) W.qh, W.qtype, K, N, R, res, Y, ldy);
-            B2_LAUNCH_CHECK(ctx);
-            return 0;
-        }
+        if (W.qtype) return gemv_q_launch(ctx, st, q_smem_set, X, ldx, W, K, N, R, res, Y, ldy);      // Q4_0 / Q5_0 / Q8_0: Q8_0-requantised activations, dp4a per block
         if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
             return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
         gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
@@ -143,26 +116,8 @@ int Parler::prepare() {
         const HostTensor * t = find(n, expect);
         if (!t) return ArW();
         if (!t->qtype) return dev_mat(t->v.data(), t->v.size(), t->f16);
-        // block-quantised matrix: the ggml blocks (fp16 scale | [4 bytes of fifth bits] | 16 or 32 bytes of values, 18 / 22 / 34 bytes, unaligned) are split into
-        // planes -- values, scales, fifth bits -- so that a lane reads a block's values with one aligned 16-byte (two for Q8_0) load; same bytes in total
-        ArW w; w.qtype = t->qtype;
-        const size_t nblk = t->v.size() / 32, blk = t->qtype == 2 ? 18 : t->qtype == 6 ? 22 : 34, vb = t->qtype == 8 ? 32 : 16;
-        std::vector<uint8_t> vals(nblk * vb); std::vector<uint16_t> sc(nblk); std::vector<uint32_t> hb(t->qtype == 6 ? nblk : 0);
-        for (size_t b = 0; b < nblk; b++) {
-            const uint8_t * p = t->raw.data() + b * blk;
-            memcpy(&sc[b], p, 2);
-            if (t->qtype == 6) memcpy(&hb[b], p + 2, 4);
-            memcpy(&vals[b * vb], p + (t->qtype == 6 ? 6 : 2), vb);
-        }
-        auto put = [&](const void * src, size_t bytes) -> void * {
-            void * d = nullptr;
-            if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", bytes); ok = false; return nullptr; }
-            cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
-            dev_allocs.push_back(d); weight_bytes += bytes;
-            return d;
-        };
-        w.p = put(vals.data(), vals.size()); w.scales = put(sc.data(), sc.size() * 2);
-        if (t->qtype == 6) w.qh = put(hb.data(), hb.size() * 4);
+        ArW w;                                                      // block-quantised matrix: value / scale / fifth-bit planes (ar_kernels.cuh)
+        if (!upload_quant_planes(*t, w, dev_allocs, weight_bytes)) ok = false;
         return w;
     };
 

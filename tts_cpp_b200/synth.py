@@ -659,7 +659,7 @@ def dia_f16_tensor(name: str) -> bool:
 
 
 def write_dia_gguf(path: str, seed: int = 0, enc_layers: int = 2, dec_layers: int = 2, head_dim: int = 32, heads: int = 4, query_heads: int = 2,
-                   ffn: int = 256, max_ctx: int = 32, f16: bool = False) -> dict:
+                   ffn: int = 256, max_ctx: int = 32, f16: bool = False, quant: str | None = None) -> dict:
     """Small synthetic Dia GGUF (F32) with a matching small DAC decoder."""
     import gguf
 
@@ -670,7 +670,11 @@ def write_dia_gguf(path: str, seed: int = 0, enc_layers: int = 2, dec_layers: in
     n_params = 0
     for name, arr in items:
         n_params += arr.size
-        w.add_tensor(name, arr.astype(np.float16 if f16 and dia_f16_tensor(name) else np.float32))
+        if quant and dia_f16_tensor(name) and arr.ndim == 2 and arr.shape[1] % 32 == 0:        # the tensors `quantize --quantized-type <quant>` converts
+            qt = getattr(gguf.GGMLQuantizationType, quant)
+            w.add_tensor(name, gguf.quants.quantize(arr.astype(np.float32), qt), raw_dtype=qt)
+        else:
+            w.add_tensor(name, arr.astype(np.float16 if f16 and dia_f16_tensor(name) else np.float32))
     for k, v in (("dia.decoder.output_heads", 9), ("dia.decoder.layers", dec_layers), ("dia.encoder.layers", enc_layers), ("dia.decoder.hidden_size", heads * head_dim),
                  ("dia.decoder.attn_heads", heads), ("dia.decoder.query_heads", query_heads), ("dia.encoder.attn_heads", heads), ("dia.attn_head_size", head_dim),
                  ("dia.eos_token_id", 1024), ("dia.bos_token_id", 1026), ("dia.pad_token_id", 1025), ("dia.encoder.max_context_length", max_ctx),
@@ -686,13 +690,13 @@ def write_dia_gguf(path: str, seed: int = 0, enc_layers: int = 2, dec_layers: in
     return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
 
 
-def cached_dia_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False) -> str:
+def cached_dia_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, quant: str | None = None) -> str:
     cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, f"dia_{'f16' if f16 else 'f32'}_s{seed}.gguf")
+    path = os.path.join(cache_dir, f"dia_{quant.lower() if quant else ('f16' if f16 else 'f32')}_s{seed}.gguf")
     if not os.path.exists(path):
         tmp = f"{path}.{os.getpid()}.tmp"
-        write_dia_gguf(tmp, seed=seed, f16=f16)
+        write_dia_gguf(tmp, seed=seed, f16=f16, quant=quant)
         os.replace(tmp, path)
     return path
 
