@@ -9,8 +9,10 @@
 // loader registry (src/models/loaders.cpp:11-31,79-89), unigram_tokenizer (src/tokenizer.h:35-53).  Behaviour mirrored: parler_model_loader::from_file
 // (src/models/parler/loader.cpp:8-26), batch_from_sentence (model.cpp:473-498: tokens + EOS), parler_tts_runner::generate / generate_from_batch /
 // adjust_output_tokens (model.cpp:734-792,838-861), assign_weight's routing of "audio_encoder.*" to the DAC (model.cpp:499-512).
-// Not supported here: update_conditional_prompt / use_cross_attn = false (they need the T5 encoder, a "next" row).
+// update_conditional_prompt runs the reference's own T5 encoder on the host and hands its output to b2tts_parler_set_text_encoding (cross K / V recomputed on the
+// device).  Not supported: use_cross_attn = false.
 #include "models/loaders.h"
+#include "models/parler/t5/model.h"
 #include "tokenizer.h"
 #include "util.h"
 
@@ -27,6 +29,7 @@ struct parler_b200_runner : tts_generation_runner {
     b2tts_dac *         dac       = nullptr;
     unigram_tokenizer * tokenizer = nullptr;
     uint32_t n_output_heads = 9, audio_vocab_size = 1024, max_generation = 2580;
+    int n_threads = 4;
 
     parler_b200_runner(const tts_model_loader & loader, unigram_tokenizer * t) : tts_generation_runner{ loader }, tokenizer{ t } {
         sampling_rate = 44100.0f;
@@ -50,8 +53,14 @@ struct parler_b200_runner : tts_generation_runner {
     void prepare_post_load() override {
         if (b2tts_parler_prepare(decoder) || b2tts_dac_prepare(dac)) TTS_ABORT("%s\n", b2tts_last_error());
     }
-    void update_conditional_prompt(const char *, const char *) override {
-        TTS_ABORT("parler_b200_runner: conditional prompts need the T5 encoder, which is not on the B200 path yet; the GGUF's stored text encoding is used.\n");
+    // the reference's own T5 encoder pass on the host (parler_tts_runner::update_conditional_prompt, model.cpp:510-518; the T5 encoder is a "next" row of the B200
+    // path), then the cross-attention K / V of every layer recomputed on the device from its output
+    void update_conditional_prompt(const char * file_path, const char * prompt) override {
+        t5_runner *    text_encoder = text_encoder_from_file(file_path, n_threads, tokenizer, /*cpu_only*/ true);
+        tts_response * response     = nullptr;
+        text_encoder->generate(prompt, response);
+        if (!response || b2tts_parler_set_text_encoding(decoder, response->data, (int) response->n_outputs)) TTS_ABORT("%s\n", b2tts_last_error());
+        delete text_encoder;
     }
 
     // parler_tts_runner::adjust_output_tokens (model.cpp:734-760): undo the delay pattern (head h lags h steps) and drop frames holding a special id
@@ -96,10 +105,11 @@ struct parler_b200_runner : tts_generation_runner {
 // so this object has to be linked ahead of the stock parler loader or replace it when TTS_B200 is on
 struct parler_b200_loader final : tts_model_loader {
     parler_b200_loader() : tts_model_loader{ "parler-tts" } {}
-    unique_ptr<tts_generation_runner> from_file(gguf_context * meta, ggml_context *, int, bool, const generation_configuration &) const override {
+    unique_ptr<tts_generation_runner> from_file(gguf_context * meta, ggml_context *, int n_threads, bool, const generation_configuration &) const override {
         unigram_tokenizer * ut = unigram_tokenizer_from_gguf(meta);
         ut->initialize_tokenizer();
         auto r = make_unique<parler_b200_runner>(*this, ut);
+        r->n_threads = n_threads;
         std::vector<const char *> keys;
         std::vector<uint32_t>     vals;
         for (int i = 0; i < gguf_get_n_kv(meta); i++) {

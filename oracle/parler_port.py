@@ -98,6 +98,12 @@ class ParlerPort:
             x = x.half().float()
         return x @ self.w[name].t()
 
+    def set_text_encoding(self, enc):
+        """parler_tts_model::prep_cross_key_values with a replacement conditional-prompt encoding [rows, hidden] (update_conditional_prompt, model.cpp:510-518)"""
+        enc = torch.from_numpy(np.asarray(enc, np.float32))
+        self.ck = [self.mm(enc, f"layers.{l}.encoder_attn.k_proj.weight") for l in range(self.layers)]
+        self.cv = [self.mm(enc, f"layers.{l}.encoder_attn.v_proj.weight") for l in range(self.layers)]
+
     def reset(self):
         self.k = [None] * self.layers; self.v = [None] * self.layers
         self.pos = 0

@@ -5,7 +5,7 @@
 // audio steps (9 codebook tokens each) and the logits of every step out.  Loading follows parler_model_loader::from_file and
 // runner_from_file's weight loop (src/models/parler/loader.cpp:8-23, src/models/loaders.cpp:79-89) without a tokenizer.
 //
-// usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet] [--stop]
+// usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet] [--stop] [--encoding f32file rows]
 //   writes <out_prefix>.u<k>.tokens.i32 ([N][heads] generated ids) and <out_prefix>.u<k>.logits.f32 ([N][heads][output_vocab])
 #include "models/parler/model.h"
 #include "ggml.h"
@@ -22,13 +22,15 @@
 using clk = std::chrono::steady_clock;
 
 int main(int argc, char ** argv) {
-    if (argc < 4) { fprintf(stderr, "usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet] [--stop]\n"); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: parler_ref <model.gguf> <prompts.txt> <out_prefix> [--steps N] [--threads T] [--quiet] [--stop] [--encoding f32file rows]\n"); return 2; }
     int threads = 4, steps = 6; bool quiet = false, use_stop = false;
+    const char * enc_file = nullptr; int enc_rows = 0;      // --encoding <f32 file> <rows>: a replacement conditional-prompt encoding (what update_conditional_prompt's T5 pass yields)
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--quiet")) quiet = true;
         else if (!strcmp(argv[i], "--stop")) use_stop = true;
+        else if (!strcmp(argv[i], "--encoding") && i + 2 < argc) { enc_file = argv[++i]; enc_rows = atoi(argv[++i]); }
     }
     ggml_context * weight_ctx = nullptr;
     gguf_init_params gp; gp.no_alloc = false; gp.ctx = &weight_ctx;
@@ -51,6 +53,15 @@ int main(int argc, char ** argv) {
         runner->assign_weight(cur->name, *cur);
     }
     runner->prepare_post_load();
+    std::vector<float> enc_data;
+    if (enc_file) {                                         // parler_tts_runner::update_conditional_prompt's second half (model.cpp:516) with a given encoding
+        enc_data.resize((size_t) enc_rows * model->hidden_size);
+        FILE * ef = fopen(enc_file, "rb");
+        if (!ef || fread(enc_data.data(), 4, enc_data.size(), ef) != enc_data.size()) { fprintf(stderr, "cannot read %s\n", enc_file); return 2; }
+        fclose(ef);
+        tts_response resp; resp.data = enc_data.data(); resp.n_outputs = (size_t) enc_rows; resp.hidden_size = model->hidden_size;
+        model->prep_cross_key_values(threads, &resp);
+    }
     samp->do_sample = false;           // greedy: sampler::max per head, first maximum wins
     samp->repetition_penalty = 1.0f;
     const uint32_t H = model->n_output_heads, V = model->output_vocab_size;

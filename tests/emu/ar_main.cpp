@@ -22,6 +22,15 @@ static std::vector<int32_t> g_ngen;      // B2EMU_STOP=1: the reference's stop r
 template <class M> static int gen(M & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) { return m.generate(B, pp, np, steps, s, tok, lg); }
 static int gen(b2::Parler & m, int B, const uint32_t * const * pp, const int32_t * np, int steps, const b2::ArSampling * s, int32_t * tok, float * lg) {
     if (getenv("B2EMU_STOP")) g_ngen.assign((size_t) B, 0);
+    if (const char * ef = getenv("B2EMU_ENCODING")) {             // "<f32 file> <rows>": replace the stored conditional-prompt encoding first
+        char path[512]; int rows = 0;
+        if (sscanf(ef, "%511s %d", path, &rows) != 2) return 2;
+        std::vector<float> enc((size_t) rows * m.hidden);
+        FILE * f = fopen(path, "rb");
+        if (!f || fread(enc.data(), 4, enc.size(), f) != enc.size()) return 2;
+        fclose(f);
+        if (m.set_text_encoding(enc.data(), rows)) return 1;
+    }
     std::vector<int32_t> teacher;                                  // B2EMU_TEACHER=<file of int32 [B][steps][n_out]>: teacher-forced feedback
     if (const char * tf = getenv("B2EMU_TEACHER")) {
         teacher.resize((size_t) B * steps * m.n_out);

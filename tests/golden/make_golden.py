@@ -20,6 +20,7 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       reference then rounds the activations to fp16 before every such product)
   parler_q{8,5,4}_0_vectors.npz : as parler_vectors.npz for the GGUFs `quantize --quantized-type Q8_0 / Q5_0 / Q4_0` would write (decoder matrices and codebook
       tables as ggml blocks; the reference re-quantises the activations to Q8_0 per 32 columns before every such product)
+  parler_encoding_vectors.npz : the Parler loop after the stored conditional-prompt encoding was replaced (update_conditional_prompt's prep_cross_key_values call)
   parler_stop_vectors.npz  : the Parler loop run to completion under the reference's stop rule (eos_seen feeding + check_stopping) on two EOS-boosted synthetic
       GGUFs: one ends at max_generation, one because every head produced EOS; from oracle/ref_parler_driver.cpp --stop
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
@@ -205,6 +206,24 @@ def parler_vectors(f16: bool = False, quant: str | None = None):
     print(f"parler{tag} vectors:", {k: v.shape for k, v in out.items()})
 
 
+def parler_encoding_vectors():
+    """update_conditional_prompt's second half: the Parler loop after the stored text encoding (12 rows) was replaced by another one (7 rows) through
+    prep_cross_key_values(n_threads, response) -- ref_parler_driver --encoding."""
+    from tts_cpp_b200.synth import cached_parler_gguf
+    rng = np.random.default_rng(41)
+    enc = rng.standard_normal((7, 256)).astype(np.float32)
+    q = rng.integers(1, 500, size=6)
+    tmp = tempfile.mkdtemp()
+    ef, pf, pre = os.path.join(tmp, "enc.f32"), os.path.join(tmp, "prompts.txt"), os.path.join(tmp, "e")
+    enc.tofile(ef)
+    open(pf, "w").write(" ".join(map(str, q)) + "\n")
+    steps = 5
+    run([os.path.join(REF, "parler_ref"), cached_parler_gguf(seed=0), pf, pre, "--steps", str(steps), "--threads", "4", "--quiet", "--encoding", ef, "7"])
+    np.savez_compressed(os.path.join(OUT, "parler_encoding_vectors.npz"), encoding=enc, prompt0=np.asarray(q, np.int32),
+                        tokens0=np.fromfile(f"{pre}.u0.tokens.i32", np.int32).reshape(steps, 9), logits0=np.fromfile(f"{pre}.u0.logits.f32", np.float32).reshape(steps, 9, -1))
+    print("parler encoding vectors written")
+
+
 def parler_stop_vectors():
     """The reference's Parler loop run to completion with its stop rule (ref_parler_driver --stop) on GGUFs whose EOS logit row is boosted so that greedy
     decoding emits EOS.  x6, 7-token prompt: heads are fed EOS once they have produced one and the loop ends when every head has (13 frames).  x3, 55-token
@@ -295,9 +314,10 @@ def sampler_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_q8_0", "parler_q5_0", "parler_q4_0", "parler_stop", "dia", "dia_f16", "dia_q8_0", "dia_stop", "sampler", "orpheus_wide"]
+    which = sys.argv[1:] or ["kokoro", "ops", "dac", "snac", "orpheus", "parler", "parler_f16", "parler_q8_0", "parler_q5_0", "parler_q4_0", "parler_stop", "parler_encoding", "dia", "dia_f16", "dia_q8_0", "dia_stop", "sampler", "orpheus_wide"]
     if "dia_stop" in which: dia_stop_vectors()
     if "parler_stop" in which: parler_stop_vectors()
+    if "parler_encoding" in which: parler_encoding_vectors()
     if "sampler" in which: sampler_vectors()
     if "orpheus_wide" in which: orpheus_vectors(wide=True)
     if "parler_f16" in which: parler_vectors(f16=True)

@@ -335,3 +335,15 @@ def test_dia_quantised_emulated_teacher_forced(tmp_path):
         agree = float((tok[u] == ref_t).mean())
         print(f"PARITY(emulated) dia Q8_0 prompt {u}: per-step logit rms {np.round(rms, 3).tolist()}, tokens equal {agree:.2f}")
         assert float(rms.max()) < 4.0 and agree >= 0.8
+
+
+def test_parler_replacement_text_encoding_emulated(tmp_path):
+    """Parler::set_text_encoding (the cross K / V of every layer recomputed on the device from a 7-row encoding instead of the stored 12 rows -- what
+    update_conditional_prompt does after its T5 pass) under emulation against the reference run with the same replacement."""
+    g = np.load(os.path.join(GOLD, "parler_encoding_vectors.npz"))
+    ef = str(tmp_path / "enc.f32")
+    g["encoding"].astype(np.float32).tofile(ef)
+    steps = int(g["tokens0"].shape[0])
+    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0), [g["prompt0"]], steps, "e", env={"B2EMU_ENCODING": f"{ef} {g['encoding'].shape[0]}"})
+    assert np.array_equal(tok[0], g["tokens0"])
+    assert float(np.abs(logits[0] - g["logits0"].reshape(steps, -1)).max()) < 1e-2

@@ -290,3 +290,14 @@ def test_dia_port_quantised_teacher_forced():
         rms = np.sqrt(((logits - g[f"logits{u}"]) ** 2).mean(axis=(1, 2)))
         print(f"dia Q8_0 prompt {u}: per-step logit rms {np.round(rms, 3).tolist()}, tokens equal {int((toks == g[f'tokens{u}']).sum())}/{toks.size}")
         assert float(rms.max()) < 4.0 and float((toks == g[f"tokens{u}"]).mean()) >= 0.8
+
+
+def test_parler_port_replacement_text_encoding():
+    """oracle/parler_port.py after set_text_encoding (prep_cross_key_values with a 7-row encoding instead of the stored 12 rows) against the reference."""
+    from oracle.parler_port import ParlerPort
+    from tts_cpp_b200.synth import cached_parler_gguf
+    g = np.load(os.path.join(GOLD, "parler_encoding_vectors.npz"))
+    port = ParlerPort(cached_parler_gguf(seed=0))
+    port.set_text_encoding(g["encoding"])
+    toks, logits = port.greedy(g["prompt0"], g["tokens0"].shape[0])
+    assert np.array_equal(toks, g["tokens0"]) and float(np.abs(logits - g["logits0"]).max()) < 1e-2

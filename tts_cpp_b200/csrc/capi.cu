@@ -259,6 +259,10 @@ int b2tts_parler_generate_teacher_forced(b2tts_parler * m, int n_sequences, cons
     if (!teacher) { set_error("null teacher tokens"); return 1; }
     return m->p.generate(n_sequences, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits, nullptr, teacher);
 }
+int b2tts_parler_set_text_encoding(b2tts_parler * m, const float * encoding, int n_rows) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->p.set_text_encoding(encoding, n_rows);
+}
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m) { return m ? m->p.weight_bytes : 0; }
 // ---- Dia AR decode (first correct path)

@@ -163,11 +163,11 @@ int Parler::prepare() {
         L.ln3_w = up(b + ".final_layer_norm.weight", hidden);        L.ln3_b = up(b + ".final_layer_norm.bias", hidden);
         L.fc1 = upw(b + ".fc1.weight", (int64_t) ffn * hidden);      L.fc2 = upw(b + ".fc2.weight", (int64_t) hidden * ffn);
         // prep_cross_key_values (model.cpp:110-173): K and V of the stored text encoding, once per model
-        const ArW wck = upw(b + ".encoder_attn.k_proj.weight", HH), wcv = upw(b + ".encoder_attn.v_proj.weight", HH);
+        L.wck = upw(b + ".encoder_attn.k_proj.weight", HH); L.wcv = upw(b + ".encoder_attn.v_proj.weight", HH);
         L.cross_k = dev(nullptr, (size_t) n_enc * hidden); L.cross_v = dev(nullptr, (size_t) n_enc * hidden);
         if (!ok) break;
-        if (Fw.gemv(d_enc, hidden, wck, hidden, hidden, n_enc, nullptr, L.cross_k, hidden)) return 1;
-        if (Fw.gemv(d_enc, hidden, wcv, hidden, hidden, n_enc, nullptr, L.cross_v, hidden)) return 1;
+        if (Fw.gemv(d_enc, hidden, L.wck, hidden, hidden, n_enc, nullptr, L.cross_k, hidden)) return 1;
+        if (Fw.gemv(d_enc, hidden, L.wcv, hidden, hidden, n_enc, nullptr, L.cross_v, hidden)) return 1;
     }
     if (!ok) return 1;
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -175,6 +175,29 @@ int Parler::prepare() {
     host.clear();
     prepared = true;
     return 0;
+}
+
+int Parler::set_text_encoding(const float * enc, int n_rows) {
+    if (!prepared) { set_error("parler: model not prepared"); return 1; }
+    if (!enc || n_rows <= 0) { set_error("parler: empty text encoding"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->device));
+    float * d_enc = nullptr;
+    B2_CUDA(cudaMalloc(&d_enc, (size_t) n_rows * hidden * 4));
+    B2_CUDA(cudaMemcpy(d_enc, enc, (size_t) n_rows * hidden * 4, cudaMemcpyHostToDevice));
+    PFwd Fw{this, ctx, ctx->stream};
+    int rc = 0;
+    for (int l = 0; l < n_layers && !rc; l++) {
+        ParlerLayer & L = layers[(size_t) l];
+        float * nk = nullptr, * nv = nullptr;
+        if (cudaMalloc(&nk, (size_t) n_rows * hidden * 4) != cudaSuccess || cudaMalloc(&nv, (size_t) n_rows * hidden * 4) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc failed for the cross K / V"); rc = 1; break; }
+        dev_allocs.push_back(nk); dev_allocs.push_back(nv);          // the previous stores stay allocated until free_all (a few MB per call)
+        rc = Fw.gemv(d_enc, hidden, L.wck, hidden, hidden, n_rows, nullptr, nk, hidden) || Fw.gemv(d_enc, hidden, L.wcv, hidden, hidden, n_rows, nullptr, nv, hidden);
+        L.cross_k = nk; L.cross_v = nv;
+    }
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("parler: recomputing the cross K / V failed"); rc = 1; }
+    cudaFree(d_enc);
+    if (!rc) n_enc = n_rows;
+    return rc;
 }
 
 void Parler::free_all() {

@@ -12,7 +12,7 @@ namespace b2 {
 
 struct ParlerLayer {
     float * ln1_w = nullptr, * ln1_b = nullptr; ArW wq, wk, wv, wo;
-    float * ln2_w = nullptr, * ln2_b = nullptr; ArW cq, co; float * cross_k = nullptr, * cross_v = nullptr;   // cross_k / cross_v [n_enc][hidden]
+    float * ln2_w = nullptr, * ln2_b = nullptr; ArW cq, co, wck, wcv; float * cross_k = nullptr, * cross_v = nullptr;   // cross_k / cross_v [n_enc][hidden] = encoding . wck^T / wcv^T
     float * ln3_w = nullptr, * ln3_b = nullptr; ArW fc1, fc2;
 };
 
@@ -37,6 +37,9 @@ struct Parler {
 
     int assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
     int prepare();
+    // replace the stored conditional-prompt encoding ([n_rows][hidden], e.g. the T5 encoder's output for a new description) and recompute the cross K / V of every
+    // layer: parler_tts_model::prep_cross_key_values(n_threads, response) as update_conditional_prompt calls it (reference model.cpp:110-173,510-518)
+    int set_text_encoding(const float * enc, int n_rows);
     // greedy generation of n_steps audio frames for B prompts (generate_from_batch's loop with a step cap instead of check_stopping):
     // out_tokens [B][n_steps][n_out]; out_logits (optional) [B][n_steps][n_out][vocab]
     int generate_greedy(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, int32_t * out_tokens, float * out_logits) {
