@@ -199,22 +199,26 @@ static char g_err[1024] = "";
 void set_error(const char * fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
 const char * emu_last_error() { return g_err; }
 
+// The emulated workspace arena hands out separately malloc'd blocks (NaN-filled) instead of slices of one allocation: under AddressSanitizer
+// (tests/test_emu_cpu.py::test_address_sanitizer_*) every workspace buffer then has its own red zones, so a kernel that indexes past the end of one is caught
+// even when the neighbouring slice would have absorbed the access on a real device.
+static std::vector<void *> g_arena_blocks;
+static void arena_drop() { for (void * p : g_arena_blocks) free(p); g_arena_blocks.clear(); }
 int Arena::reserve(size_t bytes) {
-    if (bytes <= cap) { off = 0; return 0; }
-    if (base) cudaFree(base);
-    base = nullptr; cap = 0; off = 0;
-    if (cudaMalloc(&base, bytes) != cudaSuccess) { set_error("emu: workspace allocation failed"); return 1; }
-    memset(base, 0xff, bytes);   // NaN-fill: reads of never-written workspace show up in the comparison
-    cap = bytes;
+    arena_drop();
+    base = (char *) 1; cap = bytes; off = 0;                      // only the budget is tracked; `base` is never dereferenced
     return 0;
 }
 void * Arena::alloc(size_t bytes) {
-    const size_t a = (off + 255) & ~(size_t) 255;
-    if (a + bytes > cap) { set_error("workspace arena exhausted (%zu + %zu > %zu)", a, bytes, cap); return nullptr; }
-    off = a + bytes;
-    return base + a;
+    if (off + bytes > cap) { set_error("workspace arena exhausted (%zu + %zu > %zu)", off, bytes, cap); return nullptr; }
+    off += (bytes + 255) & ~(size_t) 255;
+    void * p = nullptr;                                           // exact size: the sanitizer's red zone starts right behind the last element
+    if (posix_memalign(&p, 256, bytes ? bytes : 1)) { set_error("emu: workspace allocation failed"); return nullptr; }
+    memset(p, 0xff, bytes);                                       // NaN-fill: reads of never-written workspace show up in the comparison
+    g_arena_blocks.push_back(p);
+    return p;
 }
-void Arena::release() { if (base) cudaFree(base); base = nullptr; cap = off = 0; }
+void Arena::release() { arena_drop(); base = nullptr; cap = off = 0; }
 
 // models whose kernels need hardware features the emulation does not have: the GGUF reader references them, nothing calls them here
 #ifndef B2EMU_HAVE_KOKORO

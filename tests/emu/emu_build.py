@@ -11,7 +11,7 @@ sys.path.insert(0, HERE)
 import prep  # noqa: E402
 
 
-def build(name, cu_sources, cpp_sources, defines=()):
+def build(name, cu_sources, cpp_sources, defines=(), asan=False):
     """-> path of the executable; rebuilt when any input is newer"""
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, name)
@@ -29,7 +29,8 @@ def build(name, cu_sources, cpp_sources, defines=()):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))]
     if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps if not d.startswith(BUILD)):
         return exe
-    cmd = ["g++", "-O3", "-march=native", "-fno-plt", "-std=c++17", "-DB2EMU", "-I" + os.path.join(HERE, "include"), "-I" + BUILD, "-I" + CSRC] + ["-D" + d for d in defines] + ["-o", exe] + srcs
+    opt = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O3", "-march=native", "-fno-plt"]
+    cmd = ["g++"] + opt + ["-std=c++17", "-DB2EMU", "-I" + os.path.join(HERE, "include"), "-I" + BUILD, "-I" + CSRC] + ["-D" + d for d in defines] + ["-o", exe] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError("emulation build failed:\n" + r.stderr[-4000:])

@@ -47,7 +47,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char * cudaGetErrorString(cudaError_t) { return "emulated"; }
-static inline cudaError_t cudaMalloc(void ** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t) 255); return *p ? 0 : 2; }
+static inline cudaError_t cudaMalloc(void ** p, size_t n) { *p = nullptr; return posix_memalign(p, 256, n ? n : 1) ? 2 : 0; }   // exact size (sanitizer red zones)
 template <class T> static inline cudaError_t cudaMalloc(T ** p, size_t n) { return cudaMalloc((void **) p, n); }
 static inline cudaError_t cudaFree(void * p) { free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void ** p, size_t n) { return cudaMalloc(p, n); }

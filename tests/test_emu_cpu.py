@@ -347,3 +347,32 @@ def test_parler_replacement_text_encoding_emulated(tmp_path):
     tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0), [g["prompt0"]], steps, "e", env={"B2EMU_ENCODING": f"{ef} {g['encoding'].shape[0]}"})
     assert np.array_equal(tok[0], g["tokens0"])
     assert float(np.abs(logits[0] - g["logits0"].reshape(steps, -1)).max()) < 1e-2
+
+
+ASAN_CASES = {
+    "orpheus_plain": ("orpheus", lambda: cached_orpheus_gguf(seed=0), "orpheus_vectors", {}),
+    "orpheus_split_mma_graph": ("orpheus", lambda: cached_orpheus_gguf(seed=0, head_dim=128), "orpheus_wide_vectors", {"B2TTS_AR_MMA": "1", "B2TTS_AR_GRAPH": "1", "B2EMU_NO_LOGITS": "1"}),
+    "parler_f16_mma_sampling_stop": ("parler", lambda: cached_parler_gguf(seed=0, f16=True), "parler_f16_vectors", {"B2TTS_AR_MMA": "1", "B2EMU_SAMPLE": "20 0.9 0.8 1.2 5", "B2EMU_STOP": "1"}),
+    "parler_q5_0": ("parler", lambda: cached_parler_gguf(seed=0, quant="Q5_0"), "parler_q5_0_vectors", {}),
+    "dia_f32": ("dia", lambda: cached_dia_gguf(seed=0), "dia_vectors", {}),
+    "dia_q8_0_plain_attention": ("dia", lambda: cached_dia_gguf(seed=0, quant="Q8_0"), "dia_q8_0_vectors", {"B2TTS_AR_ATT": "plain"}),
+}
+
+
+@pytest.mark.parametrize("case", list(ASAN_CASES))
+def test_address_sanitizer_emulated(tmp_path, case):
+    """The emulated decode paths under AddressSanitizer: "device" memory is the host heap and the workspace arena hands out one allocation per buffer, so a kernel
+    that reads or writes past the end of a weight matrix, a KV cache or a workspace buffer aborts here (on a GPU it would fault, or silently corrupt a neighbour)."""
+    model, gguf, gold, env = ASAN_CASES[case]
+    exe = emu_build.build("ar_emu_asan", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")], asan=True)
+    g = np.load(os.path.join(GOLD, gold + ".npz"))
+    pin, pout = str(tmp_path / "p.bin"), str(tmp_path / "o.bin")
+    steps = 3
+    with open(pin, "wb") as f:
+        f.write(struct.pack("ii", 2, steps))
+        for p in (g["prompt0"], g["prompt1"]):
+            f.write(struct.pack("i", p.size)); f.write(p.astype(np.uint32).tobytes())
+    r = subprocess.run([exe, model, gguf(), pin, pout], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0", **env))
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "AddressSanitizer" not in r.stderr
