@@ -29,7 +29,7 @@ def build(name, cu_sources, cpp_sources, defines=(), asan=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))]
     if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps if not d.startswith(BUILD)):
         return exe
-    opt = ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O3", "-march=native", "-fno-plt"]
+    opt = ["-O1", "-g", "-fsanitize=address,alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer"] if asan else ["-O3", "-march=native", "-fno-plt"]
     cmd = ["g++"] + opt + ["-std=c++17", "-DB2EMU", "-I" + os.path.join(HERE, "include"), "-I" + BUILD, "-I" + CSRC] + ["-D" + d for d in defines] + ["-o", exe] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
