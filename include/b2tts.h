@@ -190,6 +190,7 @@ int   b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const ui
 /* the same loop under the reference sampler's settings (sampler.cpp on the device, sampler.cu); sampling == NULL is the greedy call above */
 int   b2tts_orpheus_generate(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
                              int32_t * out_tokens, float * out_logits);
+size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m);   /* bytes resident in HBM (B2TTS_AR_MMA=1 adds the fp16 split copies of the matrices) */
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -247,6 +248,7 @@ int   b2tts_dia_generate_teacher_forced(b2tts_dia * m, int n_sequences, const ui
                                         const int32_t * teacher, int32_t * out_tokens, float * out_logits);
 /* generation_configuration::max_tokens (dia_runner::generate, model.cpp:873-879): replaces the model's max_generation_size in check_stopping when > max_delay */
 int   b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens);
+size_t b2tts_dia_weight_bytes(const b2tts_dia * m);
 float b2tts_dia_last_ms(const b2tts_dia * m);
 
 /* ------------------------------------------------------------------------------------------------------------------

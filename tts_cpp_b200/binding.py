@@ -369,6 +369,14 @@ class OrpheusRunner:
                                           toks.ctypes.data_as(C.POINTER(C.c_int32)), None))
         return toks
 
+    def last_ms(self) -> float:
+        lib().b2tts_orpheus_last_ms.restype = C.c_float
+        return float(lib().b2tts_orpheus_last_ms(self.h))
+
+    def weight_bytes(self) -> int:
+        lib().b2tts_orpheus_weight_bytes.restype = C.c_size_t
+        return int(lib().b2tts_orpheus_weight_bytes(self.h))
+
     def close(self):
         if self.h:
             lib().b2tts_orpheus_free(self.h)
@@ -490,6 +498,14 @@ class DiaRunner:
         _chk(lib().b2tts_dia_generate_teacher_forced(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(n_steps), teacher.ctypes.data_as(C.POINTER(C.c_int32)),
                                                      toks.ctypes.data_as(C.POINTER(C.c_int32)), logits.ctypes.data_as(C.POINTER(C.c_float))))
         return toks, logits
+
+    def last_ms(self) -> float:
+        lib().b2tts_dia_last_ms.restype = C.c_float
+        return float(lib().b2tts_dia_last_ms(self.h))
+
+    def weight_bytes(self) -> int:
+        lib().b2tts_dia_weight_bytes.restype = C.c_size_t
+        return int(lib().b2tts_dia_weight_bytes(self.h))
 
     def close(self):
         if self.h:

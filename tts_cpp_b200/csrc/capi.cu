@@ -222,6 +222,7 @@ int b2tts_orpheus_generate(b2tts_orpheus * m, int n_sequences, const uint32_t * 
     const ArSampling a = to_sampling(sampling);
     return m->o.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits);
 }
+size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m) { return m ? m->o.weight_bytes : 0; }
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m) { return m ? m->o.timing_ms : 0.f; }
 // ---- Parler AR decode (first correct path)
 int b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out) {
@@ -306,6 +307,7 @@ int b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens) {
     if (max_tokens > m->d.max_delay) m->d.max_gen = max_tokens;
     return 0;
 }
+size_t b2tts_dia_weight_bytes(const b2tts_dia * m) { return m ? m->d.weight_bytes : 0; }
 float b2tts_dia_last_ms(const b2tts_dia * m) { return m ? m->d.timing_ms : 0.f; }
 
 int b2tts_snac_reset_noise(b2tts_snac * m) { if (!m) { set_error("null model"); return 1; } m->s.reset_noise(); return 0; }

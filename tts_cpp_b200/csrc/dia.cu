@@ -298,9 +298,6 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
 
     const float theta_scale = powf(10000.0f, -2.0f / (float) head_dim);
     const int Tcap = std::max(Tmax, C);
-    const size_t att_smem = attention_smem_bytes(Tcap);
-    if (att_smem > 200 * 1024) { set_error("dia: context of %d positions exceeds the v1 attention kernel's shared memory", Tcap); return 1; }
-    B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
 
     // ---- encoder pass over both sequences of every utterance (build_dia_encoder, model.cpp:440-500); softmax scale 1.0
     {

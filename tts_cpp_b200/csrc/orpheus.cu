@@ -188,9 +188,6 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
 
     const float theta_scale = powf(500000.0f, -2.0f / (float) head_dim);
     const float scale = 1.0f / sqrtf((float) head_dim);
-    const size_t att_smem = attention_smem_bytes(Tmax);
-    if (att_smem > 200 * 1024) { set_error("orpheus: context of %d positions exceeds the v1 attention kernel's shared memory", Tmax); return 1; }
-    B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
 
     // one pass: R rows already described by row_* -> logits of B rows -> argmax into d_out[.][*d_step] and cur_tok; advances d_step
     auto run_pass = [&](int R, bool prefill) -> int {

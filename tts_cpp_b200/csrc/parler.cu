@@ -270,9 +270,6 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     B2_CUDA(cudaStreamSynchronize(st));   // the host vectors above are stack-owned
 
     const float scale = 1.0f / sqrtf((float) head_dim);
-    const size_t att_smem = attention_smem_bytes(std::max(Tmax, n_enc));
-    if (att_smem > 200 * 1024) { set_error("parler: context of %d positions exceeds the v1 attention kernel's shared memory", Tmax); return 1; }
-    B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) att_smem));
     const int Tcap = std::max(Tmax, n_enc);
 
     // one pass over the layers for R rows whose inputs are already in x; leaves the result in x
