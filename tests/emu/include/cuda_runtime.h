@@ -115,5 +115,10 @@ template <class T> static inline T __ldcs(const T * p) { return *p; }
 static inline int __dp4a(int a, int b, int c) { for (int i = 0; i < 4; i++) c += (int) (int8_t) (a >> (8 * i)) * (int) (int8_t) (b >> (8 * i)); return c; }
 static inline unsigned __vsub4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i); return r; }
 static inline int __float2int_rn(float x) { return (int) nearbyintf(x); }      // round-to-nearest-even (the default rounding mode)
+// fibers are cooperative (a thread runs until its next barrier / shuffle), so a read-modify-write is atomic as it stands
+static inline unsigned atomicAdd(unsigned * p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int * p, int v) { const int o = *p; *p = o + v; return o; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __ldg(const float * p) { return *p; }
 static inline int __ldg(const int * p) { return *p; }

@@ -164,22 +164,42 @@ SAMPLER_CFGS = {"greedy": dict(do_sample=0, temperature=1.0, top_k=0, top_p=1.0,
                 "temp_rep": dict(do_sample=1, temperature=0.7, top_k=20, top_p=1.0, rp=1.3),
                 "topk_topp": dict(do_sample=1, temperature=1.3, top_k=40, top_p=0.9, rp=1.0),
                 "topp_only": dict(do_sample=1, temperature=0.9, top_k=0, top_p=0.8, rp=1.1),
-                "full_vocab": dict(do_sample=1, temperature=1.1, top_k=0, top_p=1.0, rp=1.2)}
+                "full_vocab": dict(do_sample=1, temperature=1.1, top_k=0, top_p=1.0, rp=1.2),
+                "top1000_flat": dict(do_sample=1, temperature=4.0, top_k=1000, top_p=1.0, rp=1.0)}      # draws land deep inside a 1 000-entry nucleus
 
 
-@pytest.mark.parametrize("name", list(SAMPLER_CFGS))
-def test_sampler_kernel_emulated_matches_port(tmp_path, name):
-    """sample_rows (sampler.cu) under emulation against oracle/sampler_port.py (itself pinned to the reference sampler) over 6 consecutive steps with the
+def _sampler_case(shape):
+    """(rows, V, steps, logits) of a sampler test: `small` = codebook-sized rows; `wide_ties` = a wide vocabulary on a coarse grid of values (signed zeros
+    included), so that the nucleus boundary falls inside a run of exactly equal logits -- the radix select's ordered tie path; `wide` = wide, no ties."""
+    rng = np.random.default_rng(33)
+    if shape == "small":
+        rows, V, steps = 5, 300, 6
+        logits = (rng.standard_normal((steps, rows, V)) * 2.5).astype(np.float32)
+        logits[:, :, 7] += 6.0                                # a dominant token: repeated picks exercise the repetition counts
+        logits[2:, 1, 40] = logits[2:, 1, 41]                  # exact ties inside the nucleus: lower id first
+    else:
+        rows, V, steps = 8, 20011, 6
+        logits = (rng.standard_normal((steps, rows, V)) * 2.0).astype(np.float32)
+        if shape.startswith("wide_ties"):
+            logits = (np.round(logits * 2.0) / 2.0).astype(np.float32)      # multiples of 0.5: hundreds of equal entries per value, +0.0 and -0.0 both present
+            assert np.signbit(logits[logits == 0]).any() and not np.signbit(logits[logits == 0]).all()
+        logits[:, :, 11] += 3.0
+        if shape == "wide_ties_peaked":                        # top-p without top-k is capped at SAMPLE_MAX_TOP_K = 1 024 picks: keep the 0.8 nucleus below that
+            logits = (np.round(logits * 2.0) * 1.5).astype(np.float32)
+    return rows, V, steps, logits
+
+
+@pytest.mark.parametrize("name,shape", [(n, "small") for n in SAMPLER_CFGS if n != "top1000_flat"] + [("top1000_flat", "wide_ties"), ("top1000_flat", "wide")] +
+                         [("default_top50", "wide_ties"), ("temp_rep", "wide_ties"), ("topk_topp", "wide_ties"), ("topp_only", "wide_ties_peaked"), ("default_top50", "wide")])
+def test_sampler_kernel_emulated_matches_port(tmp_path, name, shape):
+    """sample_rows (sampler.cu) under emulation against oracle/sampler_port.py (itself pinned to the reference sampler) over consecutive steps with the
     repetition state carried along: the port is fed the same uniforms the kernel derives from (seed, row, step); tokens and state must be identical."""
     sys.path.insert(0, ROOT)
     from oracle.sampler_port import SamplerPort
     cfg = SAMPLER_CFGS[name]
     exe = emu_build.build("sampler_emu", ["sampler.cu"], ["sampler_main.cpp"])
-    rng = np.random.default_rng(33)
-    rows, V, steps, seed = 5, 300, 6, 0x1234ABCD5678
-    logits = (rng.standard_normal((steps, rows, V)) * 2.5).astype(np.float32)
-    logits[:, :, 7] += 6.0                                    # a dominant token: repeated picks exercise the repetition counts
-    logits[2:, 1, 40] = logits[2:, 1, 41]                      # exact ties inside the nucleus: lower id first
+    seed = 0x1234ABCD5678
+    rows, V, steps, logits = _sampler_case(shape)
     pin, pout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(pin, "wb") as f:
         f.write(struct.pack("<iiiifffQi", rows, V, cfg["do_sample"], cfg["top_k"], cfg["top_p"], cfg["temperature"], cfg["rp"], seed, steps))
@@ -187,6 +207,18 @@ def test_sampler_kernel_emulated_matches_port(tmp_path, name):
     r = subprocess.run([exe, pin, pout], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     raw = open(pout, "rb").read()
+    if shape != "small":
+        # the same run with the threads of a block scheduled in descending order (the slots of the unordered collection change, the result must not), and under
+        # AddressSanitizer + the alignment sanitizer (shared-memory pick / histogram arrays are statics there: an index past their end is reported)
+        r = subprocess.run([exe, pin, pout + ".rev"], capture_output=True, text=True, timeout=600, env=dict(os.environ, B2EMU_REVERSE="1"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert open(pout + ".rev", "rb").read() == raw
+        if name in ("default_top50", "topp_only"):
+            exe_asan = emu_build.build("sampler_emu_asan", ["sampler.cu"], ["sampler_main.cpp"], asan=True)
+            r = subprocess.run([exe_asan, pin, pout + ".asan"], capture_output=True, text=True, timeout=900,
+                               env=dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0"))      # (the fiber stacks are a pool kept until exit)
+            assert r.returncode == 0, r.stderr[-3000:]
+            assert open(pout + ".asan", "rb").read() == raw
     n = steps * rows
     toks = np.frombuffer(raw, np.int32, n, 0).reshape(steps, rows)
     us = np.frombuffer(raw, np.float32, n, 4 * n).reshape(steps, rows)

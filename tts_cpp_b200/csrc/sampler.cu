@@ -8,8 +8,10 @@
 // repeatable and lets a captured CUDA graph of a decode step be replayed.  oracle/sampler_port.py is the checker (pinned to the reference stage by stage
 // and, for the draw rule, by a histogram of the reference's own draws).
 //
-// First correct version: top-k by k rounds of block arg-max over the row (k x V reads: fine for the 1 088-wide codebook heads, the first thing to replace
-// by a radix select for Orpheus' 156 k-wide vocabulary); the sequential fp32 sums that fix the rounding of the reference are done by one thread.
+// The nucleus (the k best entries in (value descending, id ascending) order -- the reference's std::sort with a stable tie rule) comes from a radix select:
+// four 8-bit histogram passes over an order-preserving integer key find the k-th largest key and how many entries equal to it belong to the nucleus, one more
+// pass collects them (ties at the threshold: lowest ids first), and the <= 1 024 picks are put in order by rank counting in shared memory -- 5 reads of the row
+// instead of k (Orpheus: V = 156 940, k = 50).  The sequential fp32 sums that fix the rounding of the reference are done by one thread.
 #include "kernels.cuh"
 
 #include <cmath>
@@ -42,9 +44,97 @@ __device__ ArgMax block_argmax(float v, int i, float * sv, int * si) {
     return r;
 }
 
+// order-preserving key of a float (larger value <-> larger key; -0 and +0 share a key like `==` says; NaN, which `better` never picks, sorts below -inf)
+__device__ __forceinline__ unsigned order_key(float v) {
+    if (v != v) return 0u;
+    const unsigned b = __float_as_uint(v + 0.0f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// The k best of val(0 .. V-1) in (value descending, id ascending) order -> pick_idx / pick_val[0 .. k), 1 <= k <= min(V, SAMPLE_MAX_TOP_K); 256 threads.
+// hist: [8 warps][256] counters, tmp_*: [SAMPLE_MAX_TOP_K] unordered picks, misc: [4] ints -- all shared memory.  Every thread must call it (barriers inside).
+template <class F>
+__device__ void block_topk(F val, int V, int k, int * pick_idx, float * pick_val, int * tmp_idx, float * tmp_val, unsigned * hist, int * misc) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned prefix = 0u, mask = 0u;
+    int need = k;                                              // entries still to be found among those whose key matches `prefix` under `mask`
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 8 * 256; i += 256) hist[i] = 0u;
+        __syncthreads();
+        for (int ii = tid; ii < V; ii += 256) {
+            const unsigned key = order_key(val(ii));
+            if ((key & mask) == prefix) atomicAdd(&hist[warp * 256 + ((key >> shift) & 255u)], 1u);      // a histogram per warp: 8x less contention
+        }
+        __syncthreads();
+        unsigned c = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; w++) c += hist[w * 256 + tid];
+        __syncthreads();
+        hist[tid] = c;                                         // row 0 becomes the digit histogram, then its suffix sums S[d] = #entries with digit >= d
+        hist[256 + tid] = c;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const unsigned v = tid + o < 256 ? hist[tid + o] : 0u;
+            __syncthreads();
+            hist[tid] += v;
+            __syncthreads();
+        }
+        {   // the digit d with S[d] >= need > S[d+1]: exactly one thread sees it (S[0] >= need by construction)
+            const unsigned above = tid < 255 ? hist[tid + 1] : 0u;
+            if (hist[tid] >= (unsigned) need && above < (unsigned) need) { misc[0] = tid; misc[1] = need - (int) above; misc[2] = (int) hist[256 + tid]; }
+        }
+        __syncthreads();
+        prefix |= (unsigned) misc[0] << shift; mask |= 255u << shift; need = misc[1];
+        __syncthreads();
+    }
+    // prefix = the k-th largest key T; `need` of the misc[2] entries equal to T belong to the nucleus, together with the k - need entries above T
+    const unsigned T = prefix;
+    const int n_eq = misc[2], n_gt = k - need;
+    if (tid == 0) misc[3] = 0;
+    __syncthreads();
+    if (n_eq == need) {                                        // no tie across the boundary (the usual case): everything >= T, in any order
+        for (int ii = tid; ii < V; ii += 256) {
+            const float v = val(ii);
+            if (order_key(v) >= T) { const int slot = atomicAdd(&misc[3], 1); tmp_idx[slot] = ii; tmp_val[slot] = v; }
+        }
+    } else {                                                   // ties at the threshold: the `need` lowest ids among them
+        for (int ii = tid; ii < V; ii += 256) {
+            const float v = val(ii);
+            if (order_key(v) > T) { const int slot = atomicAdd(&misc[3], 1); tmp_idx[slot] = ii; tmp_val[slot] = v; }
+        }
+        const int chunk = (V + 255) / 256, lo = tid * chunk, hi = lo + chunk < V ? lo + chunk : V;      // thread t owns ids [t * chunk, (t + 1) * chunk)
+        unsigned mine = 0u;
+        for (int ii = lo; ii < hi; ii++) mine += order_key(val(ii)) == T ? 1u : 0u;
+        __syncthreads();                                       // (hist is free again: everyone left the select loop)
+        hist[tid] = mine;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {                    // inclusive prefix sums over the threads
+            const unsigned v = tid >= o ? hist[tid - o] : 0u;
+            __syncthreads();
+            hist[tid] += v;
+            __syncthreads();
+        }
+        int rank = (int) (hist[tid] - mine);                   // equal entries with lower ids
+        for (int ii = lo; ii < hi && rank < need; ii++) {
+            const float v = val(ii);
+            if (order_key(v) == T) { tmp_idx[n_gt + rank] = ii; tmp_val[n_gt + rank] = v; rank++; }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += 256) {                        // rank counting: (value, id) pairs are distinct, so the ranks are a permutation of 0 .. k-1
+        const float v = tmp_val[i]; const int id = tmp_idx[i];
+        int rank = 0;
+        for (int j = 0; j < k; j++) rank += better(tmp_val[j], tmp_idx[j], v, id) ? 1 : 0;
+        pick_idx[rank] = id; pick_val[rank] = v;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleParams p) {
     __shared__ float sv[256]; __shared__ int si[256];
     __shared__ int pick_idx[SAMPLE_MAX_TOP_K]; __shared__ float pick_val[SAMPLE_MAX_TOP_K];
+    __shared__ int tmp_idx[SAMPLE_MAX_TOP_K]; __shared__ float tmp_val[SAMPLE_MAX_TOP_K];
+    __shared__ unsigned hist[8 * 256]; __shared__ int misc[4];
     __shared__ int s_n, s_tok; __shared__ float s_mh;
     const int row = blockIdx.x, tid = threadIdx.x, V = p.V;
     const float * lg = p.logits + (size_t) row * V;
@@ -77,32 +167,13 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleParams p) 
             for (int ii = tid; ii < V; ii += 256) probs_all[ii] = probs_all[ii] / denom;
             __syncthreads();
             const int kmax = nucleus_k ? p.top_k : (V < SAMPLE_MAX_TOP_K ? V : SAMPLE_MAX_TOP_K);
-            float prob_sum = 0.f; int n = 0; bool done = false;
-            while (n < kmax && !done) {
-                float cv = -INFINITY; int ci = 0x7fffffff;
-                for (int ii = tid; ii < V; ii += 256) { const float v = probs_all[ii]; if (v >= 0.f && better(v, ii, cv, ci)) { cv = v; ci = ii; } }
-                const ArgMax a = block_argmax(cv, ci, sv, si);
-                if (tid == 0) { pick_idx[n] = a.i; pick_val[n] = a.v; probs_all[a.i] = -1.0f; }      // negative marks "already picked"
-                prob_sum += a.v; n++;
-                if (prob_sum >= p.top_p) done = true;
-                __syncthreads();
-            }
+            block_topk([&](int ii) { return probs_all[ii]; }, V, kmax, pick_idx, pick_val, tmp_idx, tmp_val, hist, misc);
+            float prob_sum = 0.f; int n = 0;
+            while (n < kmax) { prob_sum += pick_val[n]; n++; if (prob_sum >= p.top_p) break; }      // every thread walks the same sorted picks
             if (tid == 0) { s_n = n; s_mh = fminf(prob_sum, p.top_p); }
         } else if (nucleus_k) {
             // top-k by value, then the softmax over the picks
-            float pv = INFINITY; int pi = -1;                                        // the previous pick: later picks are strictly "worse" in (value desc, id asc) order
-            for (int n = 0; n < p.top_k; n++) {
-                float cv = -INFINITY; int ci = 0x7fffffff;
-                for (int ii = tid; ii < V; ii += 256) {
-                    const float v = eff(ii);
-                    const bool after = v < pv || (v == pv && ii > pi);
-                    if (after && better(v, ii, cv, ci)) { cv = v; ci = ii; }
-                }
-                const ArgMax a = block_argmax(cv, ci, sv, si);
-                if (tid == 0) { pick_idx[n] = a.i; pick_val[n] = a.v; }
-                pv = a.v; pi = a.i;
-            }
-            __syncthreads();
+            block_topk(eff, V, p.top_k, pick_idx, pick_val, tmp_idx, tmp_val, hist, misc);
             if (tid == 0) {
                 float s = 0.f;
                 for (int n = 0; n < p.top_k; n++) { float v = pick_val[n]; if (has_t) v /= p.temperature; v = expf(v - max_val); pick_val[n] = v; s += v; }
