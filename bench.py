@@ -306,6 +306,38 @@ def run_dac(args):
     return 0
 
 
+def run_snac(args):
+    """Secondary line (not the headline): SNAC codec decode (Orpheus' codec), batch 16 x 468 fine frames (9.98 s @ 24 kHz each), synthetic F32 SNAC
+    GGUF.  The reference's process-wide normal-noise stream is part of the call (generated on the host inside decode_batch, like snac_runner::set_inputs)."""
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "workload": "snac", "unavailable": "no reference arm for the SNAC line yet (oracle/_ref/snac_ref decodes one utterance per process)"}))
+        return 0
+    import torch  # noqa: F401  (device context / first-import cost, like the main arm)
+    from tts_cpp_b200.binding import Context, snac_runner_from_file
+    from tts_cpp_b200.synth import cached_snac_gguf, synthetic_snac_codes
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    snac = snac_runner_from_file(cached_snac_gguf(seed=0, max_frames=64), ctx=ctx)
+    B, fine = 16, 468
+    codes = synthetic_snac_codes(B, fine, codebook=snac.codebook_size)
+    for _ in range(max(args.warmup, 2)):
+        pcm = snac.run_batch(codes, copy=False)
+    audio_s = sum(p.shape[0] for p in pcm) / 24000.0
+    l0 = ctx.launches()
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        snac.run_batch(codes, copy=False)
+        dev_ms += snac.last_ms()
+    wall = time.perf_counter() - t0
+    print(json.dumps({
+        "metric": "audio_seconds_per_second", "workload": "SNAC codec decode (SURVEY 8a-C), batch 16 x 468 fine frames (9.98 s @ 24 kHz), synthetic F32 SNAC GGUF",
+        "value": audio_s * args.steps / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": dev_ms / args.steps,
+        "e2e": {"value": audio_s * args.steps / wall, "unit": "audio-s/s", "ms_per_step": wall * 1e3 / args.steps,
+                "note": "includes the host-side libstdc++-compatible normal noise stream (840 floats per fine frame)"},
+        "gpu_launches": int(ctx.launches() - l0), "gemm_dispatch": dict(zip(("tcgen05_tma", "mma_sync_fallback"), ctx.gemm_launches())),
+        "dtype": "split-fp16 operands (fp32-faithful), f32 accumulate / activations", "data": "synthetic"}))
+    return 0
+
+
 def run_parler(args):
     """Secondary line (not the headline; written before it could be run on a B200): BASELINE config 3's shape -- a Parler-TTS-Mini-sized F16 decoder
     (synthetic weights), batch 16, 10 s of audio per utterance (861 DAC frames + the 8-step delay tail), greedy, then the DAC decode of the frames.
@@ -369,7 +401,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parler-dtype", default="f16", choices=["f16", "q8_0", "q5_0", "q4_0"],
                     help="--workload parler: dtype of the decoder matrices (f16 = BASELINE config 3; q5_0 is what the reference's published Parler numbers use)")
-    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "parler"],
+    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "snac", "parler"],
                     help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
                          "parler: config 3 end to end (AR decode + DAC), plain first path")
     args = ap.parse_args()
@@ -377,6 +409,8 @@ def main():
         if int(os.environ.get("RANK", "0")) == 0:       # the secondary lines are single-GPU measurements; the headline workload is the one that shards
             print(json.dumps({"workload": args.workload, "unavailable": "secondary workloads are measured on one GPU (run without torchrun)"}))
         return 0
+    if args.workload == "snac":
+        return run_snac(args)
     if args.workload == "dac":
         return run_dac(args)
     if args.workload == "parler":

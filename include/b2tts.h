@@ -165,6 +165,7 @@ int   b2tts_snac_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_snac ** out
 void  b2tts_snac_free(b2tts_snac * m);
 int   b2tts_snac_info(const b2tts_snac * m, int * up_sampling_factor, int * codebook_size);
 int   b2tts_snac_decode_batch(b2tts_snac * m, int n_utterances, const uint32_t * const * codes, const int32_t * fine_frames, const float ** pcm, int64_t * n_samples);
+float b2tts_snac_last_ms(const b2tts_snac * m);   /* device time of the last decode_batch (CUDA events on the context's stream), like b2tts_dac_last_ms */
 int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -22,10 +22,18 @@ cfgs = {"greedy": (0, 1.0, 0, 1.0, 1.0), "default_top50": (1, 1.0, 50, 1.0, 1.0)
         "topp_only": (1, 0.9, 0, 0.8, 1.1), "full_vocab": (1, 1.1, 0, 1.0, 1.2)}
 ctx = Context(0)
 rng = np.random.default_rng(33)
-rows, V, steps, seed = 18, 1088, 6, 0x1234ABCD5678
-logits = (rng.standard_normal((steps, rows, V)) * 2.5).astype(np.float32)
-logits[:, :, 7] += 6.0
-logits[2:, 1, 40] = logits[2:, 1, 41]
+seed = 0x1234ABCD5678
+if sys.argv[2] == "wide":       # Orpheus' vocabulary on a coarse grid of values: the nucleus boundary falls inside a run of equal logits (the radix select's ordered tie path)
+    rows, V, steps = 6, 156940, 3
+    logits = (np.round(rng.standard_normal((steps, rows, V)) * 4.0) / 2.0).astype(np.float32)
+    logits[:, :, 11] += 3.0
+    cfgs = {k: cfgs[k] for k in ("default_top50", "temp_rep", "topk_topp")}
+    cfgs["top1000_flat"] = (1, 4.0, 1000, 1.0, 1.0)
+else:
+    rows, V, steps = 18, 1088, 6
+    logits = (rng.standard_normal((steps, rows, V)) * 2.5).astype(np.float32)
+    logits[:, :, 7] += 6.0
+    logits[2:, 1, 40] = logits[2:, 1, 41]
 ok = True
 for name, (do_sample, temp, top_k, top_p, rp) in cfgs.items():
     port = SamplerPort(rows, V, temp, top_k, top_p, rp)
@@ -48,8 +56,9 @@ sys.exit(0 if ok else 1)
 '''
 
 
-def test_sampler_matches_port_over_steps():
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], capture_output=True, text=True, timeout=150)
+@pytest.mark.parametrize("shape", ["small", "wide"])
+def test_sampler_matches_port_over_steps(shape):
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, shape], capture_output=True, text=True, timeout=150)
     print(r.stdout[-3000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0

@@ -303,6 +303,10 @@ class SnacRunner:
     def reset_noise(self):
         _chk(lib().b2tts_snac_reset_noise(self.h))
 
+    def last_ms(self) -> float:
+        lib().b2tts_snac_last_ms.restype = C.c_float
+        return float(lib().b2tts_snac_last_ms(self.h))
+
     def close(self):
         if self.h:
             lib().b2tts_snac_free(self.h)

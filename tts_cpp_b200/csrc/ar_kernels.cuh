@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restri
                                                           const unsigned * __restrict__ Wh, int qtype, int K, int N, int R, const float * res, float * Y, int ldy) {
     extern __shared__ __align__(16) float gq_smem[];
     const int nb = K >> 5;
-    int * xq = reinterpret_cast<int *>(gq_smem);                    // [GR][K / 4] packed int8 activations
+    int * xq = reinterpret_cast<int *>(gq_smem);                    // [GR][2 planes][nb][4] packed int8 activations (plane p = words 4p .. 4p+3 of every block)
     float * xd = gq_smem + (size_t) GR * (K >> 2);                   // [GR][nb] block scales (fp16-rounded)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = blockIdx.x * 8 + warp;
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restri
         if (r0) __syncthreads();
         for (int i = tid; i < GR * nb; i += 256) {                   // stage 1: one thread quantises one (row, block)
             const int j = i / nb, b = i - j * nb;
-            int * q = xq + (size_t) j * (K >> 2) + b * 8;
-            if (r0 + j >= R) { for (int w = 0; w < 8; w++) q[w] = 0; xd[j * nb + b] = 0.f; continue; }
+            int * q = xq + (size_t) j * (K >> 2) + b * 4;             // words 0..3 of block b; words 4..7 sit nb * 4 further (second plane)
+            if (r0 + j >= R) { for (int w = 0; w < 8; w++) q[(w >> 2) * nb * 4 + (w & 3)] = 0; xd[j * nb + b] = 0.f; continue; }
             const float4 * src = reinterpret_cast<const float4 *>(X + (size_t) (r0 + j) * ldx + b * 32);
             float4 v[8];
             float amax = 0.f;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restri
 #pragma unroll
             for (int w = 0; w < 8; w++) {
                 const int a0 = __float2int_rn(v[w].x * id), a1 = __float2int_rn(v[w].y * id), a2 = __float2int_rn(v[w].z * id), a3 = __float2int_rn(v[w].w * id);
-                q[w] = (a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24);
+                q[(w >> 2) * nb * 4 + (w & 3)] = (a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24);
             }
             xd[j * nb + b] = __half2float(__float2half_rn(amax / 127.f));
         }
@@ -194,10 +194,11 @@ __global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restri
                 }
 #pragma unroll
                 for (int j = 0; j < GR; j++) {
-                    const int * q = xq + (size_t) j * (K >> 2) + b * 8;
-                    int sumi = 0;
-#pragma unroll
-                    for (int w = 0; w < 8; w++) sumi = __dp4a(wq[w], q[w], sumi);
+                    // two 16-byte loads per (row, block); consecutive lanes read consecutive 16 B of a plane: no bank conflicts (block-major, 32 B per lane, was 8-way)
+                    const int4 q0 = *reinterpret_cast<const int4 *>(xq + (size_t) j * (K >> 2) + b * 4), q1 = *reinterpret_cast<const int4 *>(xq + (size_t) j * (K >> 2) + nb * 4 + b * 4);
+                    int sumi = __dp4a(wq[0], q0.x, 0);
+                    sumi = __dp4a(wq[1], q0.y, sumi); sumi = __dp4a(wq[2], q0.z, sumi); sumi = __dp4a(wq[3], q0.w, sumi);
+                    sumi = __dp4a(wq[4], q1.x, sumi); sumi = __dp4a(wq[5], q1.y, sumi); sumi = __dp4a(wq[6], q1.z, sumi); sumi = __dp4a(wq[7], q1.w, sumi);
                     acc[j] = fmaf((float) sumi, dw * xd[j * nb + b], acc[j]);
                 }
             }
@@ -245,7 +246,8 @@ __device__ __forceinline__ void mma16816_f16f32(float * c, const unsigned * a, u
 }
 #endif
 
-constexpr int GM_PAD = 8;      // halves of padding per activation row in shared memory: consecutive rows start 4 banks apart
+constexpr int GM_PAD = 32;     // halves of padding per activation row in shared memory: consecutive rows start 16 banks apart, so the 8 lanes of a quarter warp
+                               // (rows g, g+1 x 4 lanes x 16 B) cover all 32 banks once per 128-bit load (8 halves = 4 banks made every such load a 2-way conflict)
 constexpr int GM_KC  = 2048;   // activations are staged through shared memory in K chunks of this many columns (16 rows x 2048 x fp16 = 64 KB; twice that for SPLIT)
 constexpr float GM_LO_SCALE = 2048.0f;   // SPLIT: the low halves are carried scaled by 2^11 so that they stay in fp16's normal range
 static inline bool gemv_mma_ok(int K, int N, int R) { (void) R; return K % 256 == 0 && N % 8 == 0; }

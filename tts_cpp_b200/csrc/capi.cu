@@ -188,6 +188,7 @@ int b2tts_snac_decode_batch(b2tts_snac * m, int n_utterances, const uint32_t * c
     if (!m) { set_error("null model"); return 1; }
     return m->s.decode_batch(n_utterances, codes, fine_frames, pcm, n_samples);
 }
+float b2tts_snac_last_ms(const b2tts_snac * m) { return m ? m->s.timing_ms : 0.f; }
 // ---- Orpheus AR decode (first correct path)
 int b2tts_orpheus_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_orpheus ** out) {
     if (!ctx) { set_error("null context"); return 1; }
