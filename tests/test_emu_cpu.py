@@ -90,6 +90,26 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path,
         assert d < (3e-2 if f16 else 1e-2)
 
 
+@pytest.mark.parametrize("kind", ["f32", "f16", "f16_mma", "q5_0"])
+def test_parler_fused_launches_bit_identical(tmp_path, kind):
+    """The fused launches of the decode step (default: q / k / v as ONE grouped GEMV whose k / v rows go straight into the cache, GELU in fc1's epilogue) against
+    B2TTS_AR_FUSE=0 (three launches + store_kv_kernel + gelu_f16lut_kernel): the same per-output arithmetic, so tokens AND logits must be bit-identical, for every
+    storage kind of the matrices -- and the fused path must issue 4 launches per layer and pass fewer."""
+    g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz" if kind.startswith("f16") else "parler_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    gguf = cached_parler_gguf(seed=0, quant="Q5_0") if kind == "q5_0" else cached_parler_gguf(seed=0, f16=kind.startswith("f16"))
+    env = {"B2TTS_AR_MMA": "1"} if kind == "f16_mma" else {}
+    tok_f, log_f, err_f = _run_ar(tmp_path, "parler", gguf, prompts, steps, "fu", env=env, want_stderr=True)
+    tok_u, log_u, err_u = _run_ar(tmp_path, "parler", gguf, prompts, steps, "un", env=dict(env, B2TTS_AR_FUSE="0"), want_stderr=True)
+    assert np.array_equal(tok_f, tok_u) and np.array_equal(log_f.view(np.uint32), log_u.view(np.uint32))
+    import re
+    n_f, n_u = (int(re.search(r"(\d+) launches", e).group(1)) for e in (err_f, err_u))
+    layers = 8                                                   # cached_parler_gguf's default shape
+    print(f"PARITY(emulated) parler {kind}: fused == unfused bit for bit; launches {n_u} -> {n_f}")
+    assert n_u - n_f == 4 * layers * (steps + 1)                 # (steps decode passes + the prompt pass) x 4 launches per layer
+
+
 @pytest.mark.parametrize("model", ["parler", "dia"])
 def test_tensor_core_gemv_emulated_f16(tmp_path, model):
     """B2TTS_AR_MMA=1: F16 matrices through gemv_mma_kernel<false> (mma.sync.m16n8k16 with the batch as M, K split over the warps of a block, the k index permuted

@@ -41,6 +41,30 @@ __global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __res
     for (int c = lane; c < H; c += 32) y[(size_t) r * H + c] = (row[c] * scale) * w[c];
 }
 
+// ggml's GELU for F32 tensors: an fp16 lookup table of the tanh approximation (ggml-cpu.c:1816-1830)
+__device__ __forceinline__ float gelu_f16lut(float x) {
+    if (x <= -10.0f) return 0.0f;
+    if (x >= 10.0f) return x;
+    const float xh = __half2float(__float2half_rn(x));
+    return __half2float(__float2half_rn(0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh)))));
+}
+
+// where a GEMV puts its results.  act = 1: ggml_gelu on the product (the op that follows fc1); row_dst: output row r goes to row row_dst[r] of Y (the K / V
+// projections write straight into their cache slots: ggml_cpy into the cache views); res (indexed by r, may alias Y when there is no row_dst) is added last.
+struct GemvOut { const float * res; float * Y; const int * row_dst; int ldy; int act; };
+__device__ __forceinline__ void gemv_store(const GemvOut & o, int r, int n, float a) {
+    if (o.act == 1) a = gelu_f16lut(a);
+    const size_t row = o.row_dst ? (size_t) o.row_dst[r] : (size_t) r;
+    o.Y[row * o.ldy + n] = o.res ? a + o.res[(size_t) r * o.ldy + n] : a;
+}
+// up to three matrices of one dtype against the same activation rows in ONE launch (q / k / v, gate / up): segment j owns the blocks [blk0_j, blk0_j+1)
+struct GemvSeg { const void * W; const void * W2; const void * W3; GemvOut o; int N; int blk0; };      // W2 / W3: split low halves (tensor-core F32) or quantised scales / fifth bits
+struct GemvGroup { GemvSeg s[3]; int n; };
+__device__ __forceinline__ GemvSeg gemv_group_pick(const GemvGroup & g, int blk) {
+    const int j = (g.n > 2 && blk >= g.s[2].blk0) ? 2 : ((g.n > 1 && blk >= g.s[1].blk0) ? 1 : 0);
+    return j == 2 ? g.s[2] : (j == 1 ? g.s[1] : g.s[0]);
+}
+
 // Y[r][n] = sum_k X[r][k] * W[n][k] (+ res[r][n]; res may alias Y: each element is read and written by the same thread).  A warp owns GN (1, 2 or 4) output rows
 // and walks K in lane-strided 16-byte steps; every activation load is reused for the 4 weight rows and every weight load for the 8 batch rows of a chunk
 // (GN = 4: 2 activation loads per weight load instead of 8 -- the one-row-per-warp form is LSU-bound long before HBM; GN shrinks for small N so that the grid
@@ -48,8 +72,8 @@ __global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __res
 // lane-strided k, then the xor-shuffle tree -- independent of GN.  ggml_mul_mat with F32 weights and activations; K % 4 == 0.
 constexpr int GR = 8;
 template <typename WT, bool ROUND_X, int GN>
-__device__ __forceinline__ void gemv_rows_body(const float * __restrict__ X, int ldx, const WT * __restrict__ W, int K, int N, int R, const float * res, float * Y, int ldy) {
-    const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GN, lane = threadIdx.x & 31;
+__device__ __forceinline__ void gemv_rows_body(const float * __restrict__ X, int ldx, const WT * __restrict__ W, int K, int N, int R, const GemvOut out, int blk) {
+    const int n0 = (blk * 8 + (threadIdx.x >> 5)) * GN, lane = threadIdx.x & 31;
     if (n0 >= N) return;
     for (int r0 = 0; r0 < R; r0 += GR) {
         float acc[GN][GR];
@@ -91,21 +115,26 @@ __device__ __forceinline__ void gemv_rows_body(const float * __restrict__ X, int
                 float a = acc[i][j];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (lane == 0 && r0 + j < R && n0 + i < N) Y[(size_t) (r0 + j) * ldy + n0 + i] = res ? a + res[(size_t) (r0 + j) * ldy + n0 + i] : a;
+                if (lane == 0 && r0 + j < R && n0 + i < N) gemv_store(out, r0 + j, n0 + i, a);
             }
     }
 }
 template <int GN>
 __global__ void __launch_bounds__(256) gemv_rows_kernel(const float * __restrict__ X, int ldx, const float * __restrict__ W, int K, int N, int R,
                                                         const float * res, float * Y, int ldy) {
-    gemv_rows_body<float, false, GN>(X, ldx, W, K, N, R, res, Y, ldy);
+    gemv_rows_body<float, false, GN>(X, ldx, W, K, N, R, GemvOut{res, Y, nullptr, ldy, 0}, (int) blockIdx.x);
 }
 // the same product for an F16 weight matrix: ggml_mul_mat converts the activation rows to fp16 first (the vec_dot_type of F16 is F16, ggml-cpu.c
 // mul_mat from_float) and accumulates the exact fp16 x fp16 products in fp32 -- also what halves the bytes streamed per step
 template <int GN>
 __global__ void __launch_bounds__(256) gemv_rows_h_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, int K, int N, int R,
                                                           const float * res, float * Y, int ldy) {
-    gemv_rows_body<__half, true, GN>(X, ldx, W, K, N, R, res, Y, ldy);
+    gemv_rows_body<__half, true, GN>(X, ldx, W, K, N, R, GemvOut{res, Y, nullptr, ldy, 0}, (int) blockIdx.x);
+}
+template <typename WT, bool ROUND_X, int GN>
+__global__ void __launch_bounds__(256) gemv_rows_group_kernel(const float * __restrict__ X, int ldx, int K, int R, const GemvGroup g) {
+    const GemvSeg s = gemv_group_pick(g, (int) blockIdx.x);
+    gemv_rows_body<WT, ROUND_X, GN>(X, ldx, (const WT *) s.W, K, s.N, R, s.o, (int) blockIdx.x - s.blk0);
 }
 // rows per warp for N outputs: as many as still give every SM a block (148 SMs x 8 warps)
 static inline int gemv_rows_gn(int N) {
@@ -135,14 +164,14 @@ static inline void gemv_rows_launch(cudaStream_t st, const float * X, int ldx, c
 // The matrix lives in HBM as planes (values / fp16 scales / Q5_0 fifth bits, split at load time from ggml's unaligned 34 / 22 / 18-byte blocks): a lane fetches a
 // block's values with aligned 16-byte loads; the weight stream is a quarter to an eighth of the fp32 one.
 static inline size_t gemv_q_smem(int K) { return (size_t) GR * K + (size_t) GR * (K / 32) * 4; }
-__global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restrict__ X, int ldx, const uint8_t * __restrict__ W, const __half * __restrict__ Ws,
-                                                          const unsigned * __restrict__ Wh, int qtype, int K, int N, int R, const float * res, float * Y, int ldy) {
+__device__ __forceinline__ void gemv_rows_q_body(const float * __restrict__ X, int ldx, const uint8_t * __restrict__ W, const __half * __restrict__ Ws,
+                                                 const unsigned * __restrict__ Wh, int qtype, int K, int N, int R, const GemvOut out, int blk) {
     extern __shared__ __align__(16) float gq_smem[];
     const int nb = K >> 5;
     int * xq = reinterpret_cast<int *>(gq_smem);                    // [GR][2 planes][nb][4] packed int8 activations (plane p = words 4p .. 4p+3 of every block)
     float * xd = gq_smem + (size_t) GR * (K >> 2);                   // [GR][nb] block scales (fp16-rounded)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = blockIdx.x * 8 + warp;
+    const int n = blk * 8 + warp;
     for (int r0 = 0; r0 < R; r0 += GR) {
         if (r0) __syncthreads();
         for (int i = tid; i < GR * nb; i += 256) {                   // stage 1: one thread quantises one (row, block)
@@ -207,10 +236,18 @@ __global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restri
                 float a = acc[j];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (lane == 0 && r0 + j < R) Y[(size_t) (r0 + j) * ldy + n] = res ? a + res[(size_t) (r0 + j) * ldy + n] : a;
+                if (lane == 0 && r0 + j < R) gemv_store(out, r0 + j, n, a);
             }
         }
     }
+}
+__global__ void __launch_bounds__(256) gemv_rows_q_kernel(const float * __restrict__ X, int ldx, const uint8_t * __restrict__ W, const __half * __restrict__ Ws,
+                                                          const unsigned * __restrict__ Wh, int qtype, int K, int N, int R, const float * res, float * Y, int ldy) {
+    gemv_rows_q_body(X, ldx, W, Ws, Wh, qtype, K, N, R, GemvOut{res, Y, nullptr, ldy, 0}, (int) blockIdx.x);
+}
+__global__ void __launch_bounds__(256) gemv_rows_q_group_kernel(const float * __restrict__ X, int ldx, int qtype, int K, int R, const GemvGroup g) {
+    const GemvSeg s = gemv_group_pick(g, (int) blockIdx.x);
+    gemv_rows_q_body(X, ldx, (const uint8_t *) s.W, (const __half *) s.W2, (const unsigned *) s.W3, qtype, K, s.N, R, s.o, (int) blockIdx.x - s.blk0);
 }
 
 // ---- tensor-core batched GEMV for F16 matrices: the decode step of a batch of <= 16 sequences.
@@ -287,8 +324,8 @@ template <int D, bool SPLIT, int MT> __device__ __forceinline__ void gm_chunk(fl
 }
 
 template <bool SPLIT, int MT>
-__global__ void __launch_bounds__(256) gemv_mma_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, const __half * __restrict__ Wl, int K, int N, int R,
-                                                       const float * res, float * Y, int ldy) {
+__device__ __forceinline__ void gemv_mma_body(const float * __restrict__ X, int ldx, const __half * __restrict__ W, const __half * __restrict__ Wl, int K, int N, int R,
+                                              const GemvOut out, int blk) {
     extern __shared__ __align__(16) float gm_smem[];
     constexpr int ROWS = 16 * MT;
     const int kc = K < GM_KC / MT ? K : GM_KC / MT, pitch = kc + GM_PAD;
@@ -296,7 +333,7 @@ __global__ void __launch_bounds__(256) gemv_mma_kernel(const float * __restrict_
     __half * sXl = sX + (SPLIT ? (size_t) ROWS * pitch : 0);                              // SPLIT: their low halves, scaled by 2^11
     float * red = reinterpret_cast<float *>(sX + (size_t) ROWS * pitch * (SPLIT ? 2 : 1));  // [8 warps][ROWS][8] partial tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int n0 = blockIdx.x * 8;
+    const int n0 = blk * 8;
     float c[MT][4], cl[MT][4];
 #pragma unroll
     for (int m = 0; m < MT; m++) { c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f; cl[m][0] = cl[m][1] = cl[m][2] = cl[m][3] = 0.f; }
@@ -343,8 +380,18 @@ __global__ void __launch_bounds__(256) gemv_mma_kernel(const float * __restrict_
         float a = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; w++) a += red[(size_t) w * ROWS * 8 + i];
-        if (r < R && n0 + col < N) Y[(size_t) r * ldy + n0 + col] = res ? a + res[(size_t) r * ldy + n0 + col] : a;
+        if (r < R && n0 + col < N) gemv_store(out, r, n0 + col, a);
     }
+}
+template <bool SPLIT, int MT>
+__global__ void __launch_bounds__(256) gemv_mma_kernel(const float * __restrict__ X, int ldx, const __half * __restrict__ W, const __half * __restrict__ Wl, int K, int N, int R,
+                                                       const float * res, float * Y, int ldy) {
+    gemv_mma_body<SPLIT, MT>(X, ldx, W, Wl, K, N, R, GemvOut{res, Y, nullptr, ldy, 0}, (int) blockIdx.x);
+}
+template <bool SPLIT, int MT>
+__global__ void __launch_bounds__(256) gemv_mma_group_kernel(const float * __restrict__ X, int ldx, int K, int R, const GemvGroup g) {
+    const GemvSeg s = gemv_group_pick(g, (int) blockIdx.x);
+    gemv_mma_body<SPLIT, MT>(X, ldx, (const __half *) s.W, (const __half *) s.W2, K, s.N, R, s.o, (int) blockIdx.x - s.blk0);
 }
 
 template <bool SPLIT, int MT>
@@ -628,19 +675,10 @@ __global__ void store_kv_kernel(const float * __restrict__ k, const float * __re
     for (int c = threadIdx.x; c < KV; c += blockDim.x) { Kc[d + c] = k[(size_t) r * KV + c]; if (v) Vc[d + c] = v[(size_t) r * KV + c]; }
 }
 
-// ggml's GELU for F32 tensors: an fp16 lookup table of the tanh approximation (ggml-cpu.c:1816-1830), in place
+// ggml_gelu in place (the stand-alone pass; the decode paths apply it in fc1's GEMV epilogue, GemvOut::act)
 __global__ void gelu_f16lut_kernel(float * g, size_t n) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = g[i];
-    float y;
-    if (x <= -10.0f) y = 0.0f;
-    else if (x >= 10.0f) y = x;
-    else {
-        const float xh = __half2float(__float2half_rn(x));
-        y = __half2float(__float2half_rn(0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh)))));
-    }
-    g[i] = y;
+    if (i < n) g[i] = gelu_f16lut(g[i]);
 }
 
 // sampler::max over rows of V logits: the first maximum wins.  row -> out[step * gridDim.x + row], step = *d_step (0 when d_step is null)
@@ -749,6 +787,91 @@ static inline int gemv_q_launch(Ctx * ctx, cudaStream_t st, size_t & smem_set, c
     if (smem > smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_rows_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); smem_set = smem; }
     gemv_rows_q_kernel<<<cdiv(N, 8), 256, smem, st>>>(X, ldx, (const uint8_t *) W.p, (const __half *) W.scales, (const unsigned *) W.qh, W.qtype, K, N, R, res, Y, ldy);
     B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ---- grouped launches: up to three matrices of ONE storage kind against the same activation rows (q / k / v, gate / up), each with its own epilogue (GemvOut).
+// The per-output arithmetic is the single-matrix kernels' (same bodies): results are bit-identical to separate launches.
+enum GemvKind { GEMV_F32 = 0, GEMV_F16 = 1, GEMV_F16_MMA = 2, GEMV_SPLIT_MMA = 3, GEMV_QUANT = 4 };
+struct GemvItem { const void * W; const void * W2; const void * W3; int N; GemvOut o; };      // W2 / W3 as in GemvSeg
+struct GemvGroupSmem { size_t mma[6] = {0, 0, 0, 0, 0, 0}; size_t q = 0; };                 // dynamic shared memory already opted into, per group-kernel instantiation
+
+template <bool SPLIT, int MT>
+static inline int gemv_mma_group_launch_t(Ctx * ctx, cudaStream_t st, size_t & smem_set, const float * X, int ldx, int K, int R, const GemvGroup & g, int blocks) {
+    const size_t smem = gemv_mma_smem(K, SPLIT, MT);
+    if (smem > smem_set) { B2_CUDA(cudaFuncSetAttribute(gemv_mma_group_kernel<SPLIT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); smem_set = smem; }
+    gemv_mma_group_kernel<SPLIT, MT><<<blocks, 256, smem, st>>>(X, ldx, K, R, g);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+template <typename WT, bool ROUND_X>
+static inline void gemv_rows_group_launch_t(cudaStream_t st, int gn, int blocks, const float * X, int ldx, int K, int R, const GemvGroup & g) {
+    if (gn == 4) gemv_rows_group_kernel<WT, ROUND_X, 4><<<blocks, 256, 0, st>>>(X, ldx, K, R, g);
+    else if (gn == 2) gemv_rows_group_kernel<WT, ROUND_X, 2><<<blocks, 256, 0, st>>>(X, ldx, K, R, g);
+    else gemv_rows_group_kernel<WT, ROUND_X, 1><<<blocks, 256, 0, st>>>(X, ldx, K, R, g);
+}
+
+// B2TTS_AR_FUSE=0 turns the fused launches of the decode paths off (separate q / k / v launches, stand-alone KV store and activation passes) for A/B runs
+static inline bool ar_fuse_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_FUSE"); return !(e && e[0] == '0'); }(); return on; }
+
+// kind: the storage / kernel family of ALL n items (the caller checks that they agree); qtype for GEMV_QUANT.  0 launched, 1 error.
+static inline int gemv_group_launch(Ctx * ctx, cudaStream_t st, GemvGroupSmem & sm, int kind, int qtype, const float * X, int ldx, int K, int R, const GemvItem * it, int n) {
+    if (n < 1 || n > 3) { set_error("gemv group of %d matrices", n); return 1; }
+    GemvGroup g; g.n = n;
+    int total_n = 0;
+    for (int i = 0; i < n; i++) total_n += it[i].N;
+    auto fill = [&](int rows_per_block, int r0) {             // segments for the row chunk starting at r0; returns the number of blocks
+        int blk = 0;
+        for (int i = 0; i < n; i++) {
+            GemvOut o = it[i].o;
+            if (r0) { if (o.res) o.res += (size_t) r0 * o.ldy; if (o.row_dst) o.row_dst += r0; else o.Y += (size_t) r0 * o.ldy; }
+            g.s[i] = GemvSeg{it[i].W, it[i].W2, it[i].W3, o, it[i].N, blk};
+            blk += cdiv(it[i].N, rows_per_block);
+        }
+        for (int i = n; i < 3; i++) g.s[i] = g.s[0];
+        return blk;
+    };
+    if (kind == GEMV_QUANT) {
+        if (K % 32 || gemv_q_smem(K) > 200 * 1024) { set_error("quantised matrix with K = %d is not supported", K); return 1; }
+        const size_t smem = gemv_q_smem(K);
+        if (smem > sm.q) { B2_CUDA(cudaFuncSetAttribute(gemv_rows_q_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); sm.q = smem; }
+        const int blocks = fill(8, 0);
+        gemv_rows_q_group_kernel<<<blocks, 256, smem, st>>>(X, ldx, qtype, K, R, g);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    if (kind == GEMV_F16_MMA || kind == GEMV_SPLIT_MMA) {
+        const bool split = kind == GEMV_SPLIT_MMA;
+        for (int r0 = 0; r0 < R; r0 += 64) {                  // row chunks of up to 64 (4 m16 tiles), like gemv_mma_launch
+            const int rn = R - r0 < 64 ? R - r0 : 64, blocks = fill(8, r0);
+            const float * x = X + (size_t) r0 * ldx;
+            int rc;
+            if (rn <= 16)      rc = split ? gemv_mma_group_launch_t<true, 1>(ctx, st, sm.mma[0], x, ldx, K, rn, g, blocks) : gemv_mma_group_launch_t<false, 1>(ctx, st, sm.mma[1], x, ldx, K, rn, g, blocks);
+            else if (rn <= 32) rc = split ? gemv_mma_group_launch_t<true, 2>(ctx, st, sm.mma[2], x, ldx, K, rn, g, blocks) : gemv_mma_group_launch_t<false, 2>(ctx, st, sm.mma[3], x, ldx, K, rn, g, blocks);
+            else               rc = split ? gemv_mma_group_launch_t<true, 4>(ctx, st, sm.mma[4], x, ldx, K, rn, g, blocks) : gemv_mma_group_launch_t<false, 4>(ctx, st, sm.mma[5], x, ldx, K, rn, g, blocks);
+            if (rc) return 1;
+        }
+        return 0;
+    }
+    const int gn = gemv_rows_gn(total_n), blocks = fill(8 * gn, 0);
+    if (kind == GEMV_F16) gemv_rows_group_launch_t<__half, true>(st, gn, blocks, X, ldx, K, R, g);
+    else gemv_rows_group_launch_t<float, false>(st, gn, blocks, X, ldx, K, R, g);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// up to 3 ArW matrices against the same rows: one launch when they share a storage kind, else one launch each
+static inline int gemv_group_arw(Ctx * ctx, cudaStream_t st, GemvGroupSmem & sm, const float * X, int ldx, int K, int R, const ArW * const * W, const int * N, const GemvOut * o, int n) {
+    auto kind_of = [&](const ArW & w, int Nw) -> int { return w.qtype ? GEMV_QUANT : (w.f16 ? ((gemv_mma_enabled() && gemv_mma_ok(K, Nw, 16)) ? GEMV_F16_MMA : GEMV_F16) : GEMV_F32); };
+    GemvItem it[3];
+    bool same = true;
+    const int k0 = kind_of(*W[0], N[0]);
+    for (int i = 0; i < n; i++) {
+        it[i] = GemvItem{W[i]->p, W[i]->scales, W[i]->qh, N[i], o[i]};
+        same = same && kind_of(*W[i], N[i]) == k0 && W[i]->qtype == W[0]->qtype;
+    }
+    if (same) return gemv_group_launch(ctx, st, sm, k0, W[0]->qtype, X, ldx, K, R, it, n);
+    for (int i = 0; i < n; i++) if (gemv_group_launch(ctx, st, sm, kind_of(*W[i], N[i]), W[i]->qtype, X, ldx, K, R, it + i, 1)) return 1;
     return 0;
 }
 

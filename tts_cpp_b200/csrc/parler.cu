@@ -42,6 +42,8 @@ struct PFwd {
     Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0}, q_smem_set = 0;
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     size_t att_smem_set = 0, gqa_smem_set = 0;
+    GemvGroupSmem group_smem;
+    int gemv_group(const float * X, int ldx, int K, int R, const ArW * const * W, const int * N, const GemvOut * o, int n) { return gemv_group_arw(ctx, st, group_smem, X, ldx, K, R, W, N, o, n); }
     // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
     int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
         if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
@@ -273,15 +275,22 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     const int Tcap = std::max(Tmax, n_enc);
 
     // one pass over the layers for R rows whose inputs are already in x; leaves the result in x
+    const bool fuse = ar_fuse_enabled();
     auto run_layers = [&](int R) -> int {
         for (int l = 0; l < n_layers; l++) {
             const ParlerLayer & L = layers[(size_t) l];
             float * Kl = Kc + (size_t) l * B * Tmax * H, * Vl = Vc + (size_t) l * B * Tmax * H;
             if (Fw.ln(x, L.ln1_w, L.ln1_b, H, R, xn)) return 1;
-            if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
-            if (Fw.gemv(xn, H, L.wk, H, H, R, nullptr, kbuf, H)) return 1;
-            if (Fw.gemv(xn, H, L.wv, H, H, R, nullptr, vbuf, H)) return 1;
-            store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, H, Kl, Vl); B2_LAUNCH_CHECK(ctx);
+            if (fuse) {                                                                        // q, k, v in one launch; the k / v rows go straight to their cache slots
+                const ArW * W3[3] = {&L.wq, &L.wk, &L.wv}; const int N3[3] = {H, H, H};
+                const GemvOut o3[3] = {GemvOut{nullptr, q, nullptr, H, 0}, GemvOut{nullptr, Kl, row_dst, H, 0}, GemvOut{nullptr, Vl, row_dst, H, 0}};
+                if (Fw.gemv_group(xn, H, H, R, W3, N3, o3, 3)) return 1;
+            } else {
+                if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
+                if (Fw.gemv(xn, H, L.wk, H, H, R, nullptr, kbuf, H)) return 1;
+                if (Fw.gemv(xn, H, L.wv, H, H, R, nullptr, vbuf, H)) return 1;
+                store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, H, Kl, Vl); B2_LAUNCH_CHECK(ctx);
+            }
             if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, heads, head_dim, Tcap, scale, att)) return 1;
             if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                            // xn = self-attention + residual(x)
             if (Fw.ln(xn, L.ln2_w, L.ln2_b, H, R, x)) return 1;
@@ -289,8 +298,13 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
             if (Fw.attend(q, L.cross_k, L.cross_v, cross_base, cross_len, R, heads, heads, head_dim, Tcap, scale, att)) return 1;
             if (Fw.gemv(att, H, L.co, H, H, R, xn, x, H)) return 1;                            // x = cross-attention + residual(xn)
             if (Fw.ln(x, L.ln3_w, L.ln3_b, H, R, xn)) return 1;
-            if (Fw.gemv(xn, H, L.fc1, H, F, R, nullptr, g, F)) return 1;
-            { const size_t n = (size_t) R * F; gelu_f16lut_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, n); B2_LAUNCH_CHECK(ctx); }
+            if (fuse) {                                                                        // fc1 with ggml_gelu in its epilogue
+                const ArW * W1[1] = {&L.fc1}; const int N1[1] = {F}; const GemvOut o1[1] = {GemvOut{nullptr, g, nullptr, F, 1}};
+                if (Fw.gemv_group(xn, H, H, R, W1, N1, o1, 1)) return 1;
+            } else {
+                if (Fw.gemv(xn, H, L.fc1, H, F, R, nullptr, g, F)) return 1;
+                { const size_t n = (size_t) R * F; gelu_f16lut_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, n); B2_LAUNCH_CHECK(ctx); }
+            }
             if (Fw.gemv(g, F, L.fc2, F, H, R, x, x, H)) return 1;                              // x = mlp + residual(x), in place
         }
         return 0;
