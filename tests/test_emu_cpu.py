@@ -90,24 +90,32 @@ def test_parler_cuda_path_emulated_matches_reference_tokens_and_logits(tmp_path,
         assert d < (3e-2 if f16 else 1e-2)
 
 
-@pytest.mark.parametrize("kind", ["f32", "f16", "f16_mma", "q5_0"])
-def test_parler_fused_launches_bit_identical(tmp_path, kind):
-    """The fused launches of the decode step (default: q / k / v as ONE grouped GEMV whose k / v rows go straight into the cache, GELU in fc1's epilogue) against
-    B2TTS_AR_FUSE=0 (three launches + store_kv_kernel + gelu_f16lut_kernel): the same per-output arithmetic, so tokens AND logits must be bit-identical, for every
-    storage kind of the matrices -- and the fused path must issue 4 launches per layer and pass fewer."""
-    g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz" if kind.startswith("f16") else "parler_vectors.npz"))
+@pytest.mark.parametrize("model,kind", [("parler", "f32"), ("parler", "f16"), ("parler", "f16_mma"), ("parler", "q5_0"),
+                                        ("orpheus", "f32"), ("dia", "f32"), ("dia", "f16_mma"), ("dia", "q8_0")])
+def test_fused_launches_bit_identical(tmp_path, model, kind):
+    """The fused launches of the decode step (default) against B2TTS_AR_FUSE=0: q / k / v (gate / up, Dia's cross k / v) as ONE grouped GEMV launch; for Parler the
+    k / v rows also go straight into the cache and GELU sits in fc1's epilogue (three launches + store_kv_kernel + gelu_f16lut_kernel before).  The per-output
+    arithmetic is the same, so tokens AND logits must be bit-identical for every storage kind of the matrices, with the expected number of launches saved."""
+    import re
+    gname = {"f32": f"{model}_vectors.npz", "f16": f"{model}_f16_vectors.npz", "f16_mma": f"{model}_f16_vectors.npz", "q5_0": f"{model}_vectors.npz", "q8_0": f"{model}_vectors.npz"}[kind]
+    g = np.load(os.path.join(GOLD, gname))
     prompts = [g["prompt0"], g["prompt1"]]
     steps = int(g["tokens0"].shape[0])
-    gguf = cached_parler_gguf(seed=0, quant="Q5_0") if kind == "q5_0" else cached_parler_gguf(seed=0, f16=kind.startswith("f16"))
+    cached = {"parler": cached_parler_gguf, "orpheus": cached_orpheus_gguf, "dia": cached_dia_gguf}[model]
+    gguf = cached(seed=0, quant=kind.upper()) if kind.startswith("q") else (cached(seed=0, f16=True) if kind.startswith("f16") else cached(seed=0))
     env = {"B2TTS_AR_MMA": "1"} if kind == "f16_mma" else {}
-    tok_f, log_f, err_f = _run_ar(tmp_path, "parler", gguf, prompts, steps, "fu", env=env, want_stderr=True)
-    tok_u, log_u, err_u = _run_ar(tmp_path, "parler", gguf, prompts, steps, "un", env=dict(env, B2TTS_AR_FUSE="0"), want_stderr=True)
+    tok_f, log_f, err_f = _run_ar(tmp_path, model, gguf, prompts, steps, "fu", env=env, want_stderr=True)
+    tok_u, log_u, err_u = _run_ar(tmp_path, model, gguf, prompts, steps, "un", env=dict(env, B2TTS_AR_FUSE="0"), want_stderr=True)
     assert np.array_equal(tok_f, tok_u) and np.array_equal(log_f.view(np.uint32), log_u.view(np.uint32))
-    import re
     n_f, n_u = (int(re.search(r"(\d+) launches", e).group(1)) for e in (err_f, err_u))
-    layers = 8                                                   # cached_parler_gguf's default shape
-    print(f"PARITY(emulated) parler {kind}: fused == unfused bit for bit; launches {n_u} -> {n_f}")
-    assert n_u - n_f == 4 * layers * (steps + 1)                 # (steps decode passes + the prompt pass) x 4 launches per layer
+    print(f"PARITY(emulated) {model} {kind}: fused == unfused bit for bit; launches {n_u} -> {n_f}")
+    want = {"parler": 4 * 8 * (steps + 1),                        # 8 layers x (decode passes + the prompt pass) x (q/k/v: 2, KV store: 1, GELU: 1)
+            "orpheus": 3 * 2 * steps,                              # 2 layers x passes (step 0 is the prompt pass) x (q/k/v: 2, gate/up: 1)
+            "dia": 3 * 2 * steps + 3 * 2 + 2}[model]               # 2 decoder layers x steps x 3, 2 encoder layers x 3 once, cross k/v of 2 decoder layers once
+    if model == "dia" and kind == "f16_mma":                      # the tensor-core kernel takes the encoder's rows in chunks of 64: every saved GEMV there is several launches
+        assert n_u - n_f >= want, (n_u, n_f, want)
+    else:
+        assert n_u - n_f == want, (n_u, n_f, want)
 
 
 @pytest.mark.parametrize("model", ["parler", "dia"])

@@ -223,6 +223,14 @@ struct DFwd {
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }
+    GemvGroupSmem group_smem;
+    // 2 or 3 matrices against the same rows (q / k / v, gate / up, cross k / v): one grouped launch by default, separate launches with B2TTS_AR_FUSE=0
+    int gemv_n(const float * X, int ldx, int K, int R, int n, const ArW * const * W, const int * N, float * const * Y) {
+        if (!ar_fuse_enabled()) { for (int i = 0; i < n; i++) if (gemv(X, ldx, *W[i], K, N[i], R, nullptr, Y[i], N[i])) return 1; return 0; }
+        GemvOut o[3];
+        for (int i = 0; i < n; i++) o[i] = GemvOut{nullptr, Y[i], nullptr, N[i], 0};
+        return gemv_group_arw(ctx, st, group_smem, X, ldx, K, R, W, N, o, n);
+    }
     int rms(const float * x, const float * w, int H, int R, float * y) { rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, w, H, R, y); B2_LAUNCH_CHECK(ctx); return 0; }
     int rope(float * x, const int * pos, int R, int nh, int hd, float theta_scale) { dim3 grid(R, nh); rope_rows_kernel<<<grid, 64, 0, st>>>(x, pos, nh, hd, theta_scale); B2_LAUNCH_CHECK(ctx); return 0; }
     int swiglu(float * g, const float * u, size_t n) { silu_mul_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, u, n); B2_LAUNCH_CHECK(ctx); return 0; }
@@ -309,12 +317,12 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         for (int l = 0; l < enc_layers; l++) {
             const DiaEncLayer & L = enc[(size_t) l];
             if (Fw.rms(x, L.pre_sa, EH, RE, xn)) return 1;
-            if (Fw.gemv(xn, EH, L.wq, EH, EI, RE, nullptr, q, EI) || Fw.gemv(xn, EH, L.wk, EH, EI, RE, nullptr, k, EI) || Fw.gemv(xn, EH, L.wv, EH, EI, RE, nullptr, v, EI)) return 1;
+            { const ArW * W3[3] = {&L.wq, &L.wk, &L.wv}; const int N3[3] = {EI, EI, EI}; float * Y3[3] = {q, k, v}; if (Fw.gemv_n(xn, EH, EH, RE, 3, W3, N3, Y3)) return 1; }
             if (Fw.rope(q, e_pos, RE, enc_heads, head_dim, theta_scale) || Fw.rope(k, e_pos, RE, enc_heads, head_dim, theta_scale)) return 1;
             if (Fw.attend(q, k, v, e_base, e_len, RE, enc_heads, enc_heads, head_dim, Tcap, 1.0f, att)) return 1;
             if (Fw.gemv(att, EI, L.wo, EI, EH, RE, x, xn, EH)) return 1;                    // xn = attention + residual(x)
             if (Fw.rms(xn, L.post_sa, EH, RE, x)) return 1;
-            if (Fw.gemv(x, EH, L.gate, EH, enc_ffn, RE, nullptr, g, enc_ffn) || Fw.gemv(x, EH, L.up, EH, enc_ffn, RE, nullptr, up, enc_ffn)) return 1;
+            { const ArW * W2[2] = {&L.gate, &L.up}; const int N2[2] = {enc_ffn, enc_ffn}; float * Y2[2] = {g, up}; if (Fw.gemv_n(x, EH, EH, RE, 2, W2, N2, Y2)) return 1; }
             if (Fw.swiglu(g, up, (size_t) RE * enc_ffn)) return 1;
             if (Fw.gemv(g, enc_ffn, L.down, enc_ffn, EH, RE, xn, x, EH)) return 1;           // x = mlp + residual(xn)
         }
@@ -322,7 +330,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         for (int l = 0; l < dec_layers; l++) {                                               // cross K (RoPE'd, prompt positions only) and V (all positions)
             const DiaDecLayer & L = dec[(size_t) l];
             float * ckl = ck + (size_t) l * RE * D, * cvl = cv + (size_t) l * RE * D;
-            if (Fw.gemv(enc_out, EH, L.ck, EH, D, RE, nullptr, ckl, D) || Fw.gemv(enc_out, EH, L.cv, EH, D, RE, nullptr, cvl, D)) return 1;
+            { const ArW * W2[2] = {&L.ck, &L.cv}; const int N2[2] = {D, D}; float * Y2[2] = {ckl, cvl}; if (Fw.gemv_n(enc_out, EH, EH, RE, 2, W2, N2, Y2)) return 1; }
             if (Fw.rope(ckl, e_pos, RE, heads, head_dim, theta_scale)) return 1;
             zero_key_tail_kernel<<<RE, 128, 0, st>>>(ckl, seq_len, C, D); B2_LAUNCH_CHECK(ctx);
         }
@@ -342,7 +350,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
             float * Kl = Kc + (size_t) l * S2 * Tmax * KVD, * Vl = Vc + (size_t) l * S2 * Tmax * KVD;
             const float * ckl = ck + (size_t) l * RE * D, * cvl = cv + (size_t) l * RE * D;
             if (Fw.rms(x, L.pre_sa, D, R, xn)) return 1;
-            if (Fw.gemv(xn, D, L.sq, D, D, R, nullptr, q, D) || Fw.gemv(xn, D, L.sk, D, KVD, R, nullptr, kbuf, KVD) || Fw.gemv(xn, D, L.sv, D, KVD, R, nullptr, vbuf, KVD)) return 1;
+            { const ArW * W3[3] = {&L.sq, &L.sk, &L.sv}; const int N3[3] = {D, KVD, KVD}; float * Y3[3] = {q, kbuf, vbuf}; if (Fw.gemv_n(xn, D, D, R, 3, W3, N3, Y3)) return 1; }
             if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale) || Fw.rope(kbuf, row_pos, R, heads / rep, head_dim, theta_scale)) return 1;
             store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, KVD, Kl, Vl); B2_LAUNCH_CHECK(ctx);
             if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, heads / rep, head_dim, Tcap, 1.0f, att)) return 1;
@@ -353,7 +361,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
             if (Fw.attend(q, ckl, cvl, cross_base, cross_len, R, heads, heads, head_dim, Tcap, 1.0f, att)) return 1;
             if (Fw.gemv(att, D, L.co, D, D, R, xn, x, D)) return 1;                          // x = cross-attention + residual(xn)
             if (Fw.rms(x, L.pre_mlp, D, R, xn)) return 1;
-            if (Fw.gemv(xn, D, L.gate, D, ffn, R, nullptr, g, ffn) || Fw.gemv(xn, D, L.up, D, ffn, R, nullptr, up, ffn)) return 1;
+            { const ArW * W2[2] = {&L.gate, &L.up}; const int N2[2] = {ffn, ffn}; float * Y2[2] = {g, up}; if (Fw.gemv_n(xn, D, D, R, 2, W2, N2, Y2)) return 1; }
             if (Fw.swiglu(g, up, (size_t) R * ffn)) return 1;
             if (Fw.gemv(g, ffn, L.down, ffn, D, R, x, x, D)) return 1;                       // x = mlp + residual(x), in place
         }

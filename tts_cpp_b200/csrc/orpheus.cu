@@ -121,6 +121,18 @@ struct OFwd {
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }
+    GemvGroupSmem group_smem;
+    // up to 3 F32 matrices against the same rows in one launch (tensor-core path: when every one of them has its fp16 split and an eligible shape)
+    int gemv_group(const float * X, int ldx, int K, int R, const float * const * W, const int * N, float * const * Y, int n) {
+        GemvItem it[3];
+        bool mma = gemv_mma_enabled();
+        for (int i = 0; i < n && mma; i++) mma = gemv_mma_ok(K, N[i], 16) && m->split.find(W[i]) != m->split.end();
+        for (int i = 0; i < n; i++) {
+            it[i] = GemvItem{W[i], nullptr, nullptr, N[i], GemvOut{nullptr, Y[i], nullptr, N[i], 0}};
+            if (mma) { const auto & sp = m->split.find(W[i])->second; it[i].W = sp.first; it[i].W2 = sp.second; }
+        }
+        return gemv_group_launch(ctx, st, group_smem, mma ? GEMV_SPLIT_MMA : GEMV_F32, 0, X, ldx, K, R, it, n);
+    }
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
         if (gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
             auto it = m->split.find(W);
@@ -190,6 +202,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     const float scale = 1.0f / sqrtf((float) head_dim);
 
     // one pass: R rows already described by row_* -> logits of B rows -> argmax into d_out[.][*d_step] and cur_tok; advances d_step
+    const bool fuse = ar_fuse_enabled();
     auto run_pass = [&](int R, bool prefill) -> int {
         embed_kernel<<<R, 256, 0, st>>>(row_tok, embed, H, x);
         B2_LAUNCH_CHECK(ctx);
@@ -197,15 +210,25 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
             const OrpheusLayer & L = layers[(size_t) l];
             float * Kl = Kc + (size_t) l * B * Tmax * KV, * Vl = Vc + (size_t) l * B * Tmax * KV;
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, L.in_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
-            if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
-            if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
-            if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
+            if (fuse) {                                                                        // q, k, v in one launch
+                const float * W3[3] = {L.wq, L.wk, L.wv}; const int N3[3] = {H, KV, KV}; float * Y3[3] = {q, kbuf, vbuf};
+                if (Fw.gemv_group(xn, H, H, R, W3, N3, Y3, 3)) return 1;
+            } else {
+                if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
+                if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
+                if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
+            }
             { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax); B2_LAUNCH_CHECK(ctx); }
             if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, kv_heads, head_dim, Tmax, scale, att)) return 1;
             if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                        // xn = attn_out + residual(x)
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
-            if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;
-            if (Fw.gemv(q, H, L.wup, H, F, R, nullptr, u, F)) return 1;
+            if (fuse) {                                                                        // gate and up in one launch
+                const float * W2[2] = {L.wgate, L.wup}; const int N2[2] = {F, F}; float * Y2[2] = {g, u};
+                if (Fw.gemv_group(q, H, H, R, W2, N2, Y2, 2)) return 1;
+            } else {
+                if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;
+                if (Fw.gemv(q, H, L.wup, H, F, R, nullptr, u, F)) return 1;
+            }
             { const size_t n = (size_t) R * F; silu_mul_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, u, n); B2_LAUNCH_CHECK(ctx); }
             if (Fw.gemv(g, F, L.wdown, F, H, R, xn, x, H)) return 1;                         // x = mlp + residual(xn)
         }
