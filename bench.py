@@ -306,17 +306,54 @@ def run_dac(args):
     return 0
 
 
+def run_snac_reference(args, threads: int = 4):
+    """The reference's snac_runner (oracle/_ref/snac_ref) on the host cores: W worker processes x `threads` ggml threads, each decoding one 468-fine-frame
+    utterance (9.98 s of audio) of the same synthetic GGUF -- a bounded sample of the batch-16 step."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    ref = os.path.join(ROOT, "oracle", "_ref", "snac_ref")
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "workload": "snac", "unavailable": "oracle/_ref/snac_ref missing (run `make -C oracle ref` where /root/reference exists)"}))
+        return 0
+    import numpy as np
+    from tts_cpp_b200.synth import cached_snac_gguf, synthetic_snac_codes
+    gguf = cached_snac_gguf(seed=0, max_frames=480)
+    ncpu = os.cpu_count() or 8
+    workers = max(1, min(16, ncpu // (2 * threads)))
+    tmp = tempfile.mkdtemp(prefix="b2snac_")
+    procs = []
+    for w, c in enumerate(synthetic_snac_codes(workers, 468)):
+        cf = os.path.join(tmp, f"c{w}.txt")
+        open(cf, "w").write(" ".join(map(str, np.concatenate(c))) + "\n")
+        procs.append(subprocess.Popen([ref, gguf, cf, os.path.join(tmp, f"o{w}"), "--threads", str(threads), "--quiet"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    audio, wall = 0.0, 0.0
+    for p in procs:
+        out, _ = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("SUMMARY"):
+                sm = json.loads(line[len("SUMMARY "):])
+                audio += sm["audio_s"]; wall = max(wall, sm["wall_s"])
+    if wall <= 0:
+        print(json.dumps({"impl": "reference", "workload": "snac", "unavailable": "snac_ref produced no SUMMARY"}))
+        return 0
+    print(json.dumps({"impl": "reference", "metric": "audio_seconds_per_second", "workload": "SNAC codec decode, 468-fine-frame utterances (9.98 s @ 24 kHz), reference CPU GGML path",
+                      "value": audio / wall, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": 1, "ms_per_step": wall * 1e3,
+                      "cpu_baseline": {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference",
+                                       "sample": f"{workers} worker processes x {threads} ggml threads, one 9.98 s utterance each; throughput = total audio / slowest worker"},
+                      "e2e": {"value": audio / wall, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "data": "synthetic"}))
+    return 0
+
+
 def run_snac(args):
     """Secondary line (not the headline): SNAC codec decode (Orpheus' codec), batch 16 x 468 fine frames (9.98 s @ 24 kHz each), synthetic F32 SNAC
     GGUF.  The reference's process-wide normal-noise stream is part of the call (generated on the host inside decode_batch, like snac_runner::set_inputs)."""
     if args.impl == "reference":
-        print(json.dumps({"impl": "reference", "workload": "snac", "unavailable": "no reference arm for the SNAC line yet (oracle/_ref/snac_ref decodes one utterance per process)"}))
-        return 0
+        return run_snac_reference(args)
     import torch  # noqa: F401  (device context / first-import cost, like the main arm)
     from tts_cpp_b200.binding import Context, snac_runner_from_file
     from tts_cpp_b200.synth import cached_snac_gguf, synthetic_snac_codes
     ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
-    snac = snac_runner_from_file(cached_snac_gguf(seed=0, max_frames=64), ctx=ctx)
+    snac = snac_runner_from_file(cached_snac_gguf(seed=0, max_frames=480), ctx=ctx)
     B, fine = 16, 468
     codes = synthetic_snac_codes(B, fine, codebook=snac.codebook_size)
     for _ in range(max(args.warmup, 2)):

@@ -45,5 +45,9 @@ run ncu_parler_full 900 ncu --set full --clock-control none --import-source on -
 run bench_kokoro 600 python bench.py
 run bench_dac 600 python bench.py --workload dac
 run bench_snac 600 python bench.py --workload snac
+# 6. the reference's CPU arms on this box's host cores (the denominators of the lines above)
+run bench_parler_ref 900 python bench.py --workload parler --impl reference
+run bench_dac_ref 600 python bench.py --workload dac --impl reference
+run bench_snac_ref 600 python bench.py --workload snac --impl reference
 grep -h '^{' "$OUT"/bench_*.log > "$OUT/bench_lines.jsonl" 2>/dev/null
 tail -n 40 "$OUT/index.log"

@@ -425,15 +425,18 @@ static inline int gemv_mma_launch(Ctx * ctx, cudaStream_t st, size_t * smem_set,
 // NeoX RoPE over the whole head with per-pair frequency factors (ggml_rope_ext mode 2, theta base 5e5, ggml-cpu rope cache: theta starts at
 // the position and is multiplied by theta_scale pair after pair), applied to q in place and to k on its way into the cache; v is copied
 // (orpheus_build_kv_store, model.cpp:196-228 -- here the cache is compact: the 3x head expansion is done by indexing in the attention)
+// ff may be null (no frequency factors: Dia); the cache row of r is row_dst[r] when given, else row_seq[r] * Tmax + row_pos[r].
 __global__ void rope_append_kernel(float * q, const float * __restrict__ k, const float * __restrict__ v, const float * __restrict__ ff, const int * __restrict__ row_seq,
-                                   const int * __restrict__ row_pos, int heads, int kv_heads, int hd, float theta_scale, float * Kc, float * Vc, int Tmax) {
+                                   const int * __restrict__ row_pos, int heads, int kv_heads, int hd, float theta_scale, float * Kc, float * Vc, int Tmax,
+                                   const int * __restrict__ row_dst) {
     const int r = blockIdx.x, h = blockIdx.y;                  // h < heads: a query head; h >= heads: kv head h - heads
-    const int b = row_seq[r], pos = row_pos[r], half = hd >> 1;
+    const int pos = row_pos[r], half = hd >> 1;
+    const size_t dst = row_dst ? (size_t) row_dst[r] : (size_t) row_seq[r] * Tmax + pos;
     const int KV = kv_heads * hd, H = heads * hd;
     for (int i = threadIdx.x; i < half; i += blockDim.x) {
         float theta = (float) pos;
         for (int j = 0; j < i; j++) theta *= theta_scale;
-        const float th = theta / ff[i];
+        const float th = ff ? theta / ff[i] : theta;
         const float c = cosf(th), s = sinf(th);
         if (h < heads) {
             float * p = q + (size_t) r * H + (size_t) h * hd;
@@ -442,11 +445,11 @@ __global__ void rope_append_kernel(float * q, const float * __restrict__ k, cons
         } else {
             const int kh = h - heads;
             const float * p = k + (size_t) r * KV + (size_t) kh * hd;
-            float * d = Kc + ((size_t) b * Tmax + pos) * KV + (size_t) kh * hd;
+            float * d = Kc + dst * KV + (size_t) kh * hd;
             const float x0 = p[i], x1 = p[i + half];
             d[i] = x0 * c - x1 * s; d[i + half] = x0 * s + x1 * c;
             const float * pv = v + (size_t) r * KV + (size_t) kh * hd;
-            float * dv = Vc + ((size_t) b * Tmax + pos) * KV + (size_t) kh * hd;
+            float * dv = Vc + dst * KV + (size_t) kh * hd;
             dv[i] = pv[i]; dv[i + half] = pv[i + half];
         }
     }

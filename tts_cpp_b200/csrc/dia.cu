@@ -351,8 +351,13 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
             const float * ckl = ck + (size_t) l * RE * D, * cvl = cv + (size_t) l * RE * D;
             if (Fw.rms(x, L.pre_sa, D, R, xn)) return 1;
             { const ArW * W3[3] = {&L.sq, &L.sk, &L.sv}; const int N3[3] = {D, KVD, KVD}; float * Y3[3] = {q, kbuf, vbuf}; if (Fw.gemv_n(xn, D, D, R, 3, W3, N3, Y3)) return 1; }
-            if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale) || Fw.rope(kbuf, row_pos, R, heads / rep, head_dim, theta_scale)) return 1;
-            store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, KVD, Kl, Vl); B2_LAUNCH_CHECK(ctx);
+            if (ar_fuse_enabled()) {                                                         // RoPE of q (in place) and of k on its way into the cache, v copied: one launch instead of three
+                dim3 grid(R, heads + heads / rep);
+                rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, nullptr, nullptr, row_pos, heads, heads / rep, head_dim, theta_scale, Kl, Vl, Tmax, row_dst); B2_LAUNCH_CHECK(ctx);
+            } else {
+                if (Fw.rope(q, row_pos, R, heads, head_dim, theta_scale) || Fw.rope(kbuf, row_pos, R, heads / rep, head_dim, theta_scale)) return 1;
+                store_kv_kernel<<<R, 256, 0, st>>>(kbuf, vbuf, row_dst, KVD, Kl, Vl); B2_LAUNCH_CHECK(ctx);
+            }
             if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, heads / rep, head_dim, Tcap, 1.0f, att)) return 1;
             if (Fw.gemv(att, D, L.so, D, D, R, x, xn, D)) return 1;                          // xn = self-attention + residual(x)
             if (Fw.rms(xn, L.pre_ca, D, R, x)) return 1;

@@ -218,7 +218,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
                 if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
                 if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
             }
-            { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax); B2_LAUNCH_CHECK(ctx); }
+            { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax, nullptr); B2_LAUNCH_CHECK(ctx); }
             if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, kv_heads, head_dim, Tmax, scale, att)) return 1;
             if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                        // xn = attn_out + residual(x)
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
