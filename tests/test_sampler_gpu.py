@@ -27,7 +27,7 @@ if sys.argv[2] == "wide":       # Orpheus' vocabulary on a coarse grid of values
     rows, V, steps = 6, 156940, 3
     logits = (np.round(rng.standard_normal((steps, rows, V)) * 4.0) / 2.0).astype(np.float32)
     logits[:, :, 11] += 3.0
-    cfgs = {k: cfgs[k] for k in ("default_top50", "temp_rep", "topk_topp")}
+    cfgs = {k: cfgs[k] for k in ("default_top50", "temp_rep", "topk_topp", "topp_only")}      # topp_only: a nucleus of tens of thousands of entries, produced in chunks of 1 024
     cfgs["top1000_flat"] = (1, 4.0, 1000, 1.0, 1.0)
 else:
     rows, V, steps = 18, 1088, 6

@@ -878,5 +878,39 @@ static inline int gemv_group_arw(Ctx * ctx, cudaStream_t st, GemvGroupSmem & sm,
     return 0;
 }
 
+// ---- the launch helpers the three decode paths share (each model's forward context derives from this)
+struct ArLaunch {
+    Ctx * ctx = nullptr; cudaStream_t st = nullptr;
+    size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0}, q_smem_set = 0, att_smem_set = 0, gqa_smem_set = 0;      // dynamic shared memory already opted into, per kernel instantiation
+    GemvGroupSmem group_smem;
+    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
+    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
+        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
+            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
+            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
+            dim3 grid(R, kv_heads);
+            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        } else {
+            const size_t smem = attention_smem_bytes(Tcap);
+            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
+            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
+            dim3 grid(R, heads);
+            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    // Y = X . W^T (+ res) for a matrix in any of its storage kinds
+    int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (W.qtype) return gemv_q_launch(ctx, st, q_smem_set, X, ldx, W, K, N, R, res, Y, ldy);      // Q4_0 / Q5_0 / Q8_0: Q8_0-requantised activations, dp4a per block
+        if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
+            return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
+        gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    int gemv_group(const float * X, int ldx, int K, int R, const ArW * const * W, const int * N, const GemvOut * o, int n) { return gemv_group_arw(ctx, st, group_smem, X, ldx, K, R, W, N, o, n); }
+};
+
 }  // namespace
 }  // namespace b2

@@ -194,42 +194,16 @@ __global__ void cfg_combine_kernel(const float * __restrict__ logits2, int NV, f
     out[(size_t) u * NV + j] = cr + scale * (cr - ur);
 }
 
-struct DFwd {
-    Dia * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0}, q_smem_set = 0;
+struct DFwd : ArLaunch {
+    Dia * m; bool fail = false;
+    DFwd(Dia * m_, Ctx * c, cudaStream_t s) : m(m_) { ctx = c; st = s; }
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
-    size_t att_smem_set = 0, gqa_smem_set = 0;
-    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
-    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
-        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
-            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
-            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
-            dim3 grid(R, kv_heads);
-            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
-        } else {
-            const size_t smem = attention_smem_bytes(Tcap);
-            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
-            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
-            dim3 grid(R, heads);
-            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
-        }
-        B2_LAUNCH_CHECK(ctx);
-        return 0;
-    }
-    int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        if (W.qtype) return gemv_q_launch(ctx, st, q_smem_set, X, ldx, W, K, N, R, res, Y, ldy);      // Q4_0 / Q5_0 / Q8_0: Q8_0-requantised activations, dp4a per block
-        if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
-            return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
-        gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
-        B2_LAUNCH_CHECK(ctx);
-        return 0;
-    }
-    GemvGroupSmem group_smem;
     // 2 or 3 matrices against the same rows (q / k / v, gate / up, cross k / v): one grouped launch by default, separate launches with B2TTS_AR_FUSE=0
     int gemv_n(const float * X, int ldx, int K, int R, int n, const ArW * const * W, const int * N, float * const * Y) {
         if (!ar_fuse_enabled()) { for (int i = 0; i < n; i++) if (gemv(X, ldx, *W[i], K, N[i], R, nullptr, Y[i], N[i])) return 1; return 0; }
         GemvOut o[3];
         for (int i = 0; i < n; i++) o[i] = GemvOut{nullptr, Y[i], nullptr, N[i], 0};
-        return gemv_group_arw(ctx, st, group_smem, X, ldx, K, R, W, N, o, n);
+        return gemv_group(X, ldx, K, R, W, N, o, n);
     }
     int rms(const float * x, const float * w, int H, int R, float * y) { rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, w, H, R, y); B2_LAUNCH_CHECK(ctx); return 0; }
     int rope(float * x, const int * pos, int R, int nh, int hd, float theta_scale) { dim3 grid(R, nh); rope_rows_kernel<<<grid, 64, 0, st>>>(x, pos, nh, hd, theta_scale); B2_LAUNCH_CHECK(ctx); return 0; }
@@ -257,7 +231,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     const size_t need = enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20) +
                         (size_t) B * n_out * 8 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
-    DFwd Fw{this, ctx, st};
+    DFwd Fw(this, ctx, st);
     // ---- buffers
     float * ck = Fw.al<float>((size_t) dec_layers * RE * D), * cv = Fw.al<float>((size_t) dec_layers * RE * D);
     float * Kc = Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD), * Vc = Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD);

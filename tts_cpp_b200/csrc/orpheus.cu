@@ -100,30 +100,12 @@ void Orpheus::free_all() {
 
 namespace {
 
-struct OFwd {
-    Orpheus * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0};
+struct OFwd : ArLaunch {
+    Orpheus * m; bool fail = false;
+    OFwd(Orpheus * m_, Ctx * c, cudaStream_t s) : m(m_) { ctx = c; st = s; }
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
-    size_t att_smem_set = 0, gqa_smem_set = 0;
-    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
-    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
-        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
-            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
-            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
-            dim3 grid(R, kv_heads);
-            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
-        } else {
-            const size_t smem = attention_smem_bytes(Tcap);
-            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
-            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
-            dim3 grid(R, heads);
-            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
-        }
-        B2_LAUNCH_CHECK(ctx);
-        return 0;
-    }
-    GemvGroupSmem group_smem;
     // up to 3 F32 matrices against the same rows in one launch (tensor-core path: when every one of them has its fp16 split and an eligible shape)
-    int gemv_group(const float * X, int ldx, int K, int R, const float * const * W, const int * N, float * const * Y, int n) {
+    int gemv_group_f32(const float * X, int ldx, int K, int R, const float * const * W, const int * N, float * const * Y, int n) {
         GemvItem it[3];
         bool mma = gemv_mma_enabled();
         for (int i = 0; i < n && mma; i++) mma = gemv_mma_ok(K, N[i], 16) && m->split.find(W[i]) != m->split.end();
@@ -133,6 +115,7 @@ struct OFwd {
         }
         return gemv_group_launch(ctx, st, group_smem, mma ? GEMV_SPLIT_MMA : GEMV_F32, 0, X, ldx, K, R, it, n);
     }
+    // an F32 matrix by its device pointer (fp32-faithful tensor-core path when its fp16 split exists)
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
         if (gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
             auto it = m->split.find(W);
@@ -163,7 +146,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
                         (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * vocab * 4 : 0);
     if (arena.reserve(need)) return 1;
-    OFwd Fw{this, ctx, st};
+    OFwd Fw(this, ctx, st);
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * KV), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * KV);
     float * x = Fw.al<float>((size_t) Rmax * H), * xn = Fw.al<float>((size_t) Rmax * H), * q = Fw.al<float>((size_t) Rmax * H), * att = Fw.al<float>((size_t) Rmax * H);
     float * kbuf = Fw.al<float>((size_t) Rmax * KV), * vbuf = Fw.al<float>((size_t) Rmax * KV);
@@ -212,7 +195,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, L.in_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
             if (fuse) {                                                                        // q, k, v in one launch
                 const float * W3[3] = {L.wq, L.wk, L.wv}; const int N3[3] = {H, KV, KV}; float * Y3[3] = {q, kbuf, vbuf};
-                if (Fw.gemv_group(xn, H, H, R, W3, N3, Y3, 3)) return 1;
+                if (Fw.gemv_group_f32(xn, H, H, R, W3, N3, Y3, 3)) return 1;
             } else {
                 if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
                 if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
@@ -224,7 +207,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
             if (fuse) {                                                                        // gate and up in one launch
                 const float * W2[2] = {L.wgate, L.wup}; const int N2[2] = {F, F}; float * Y2[2] = {g, u};
-                if (Fw.gemv_group(q, H, H, R, W2, N2, Y2, 2)) return 1;
+                if (Fw.gemv_group_f32(q, H, H, R, W2, N2, Y2, 2)) return 1;
             } else {
                 if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;
                 if (Fw.gemv(q, H, L.wup, H, F, R, nullptr, u, F)) return 1;

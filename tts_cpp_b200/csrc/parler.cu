@@ -38,37 +38,10 @@ int Parler::assign(const char * name, int type, int n_dims, const int64_t * ne, 
 }
 
 namespace {
-struct PFwd {
-    Parler * m; Ctx * ctx; cudaStream_t st; bool fail = false; size_t mma_smem_set[6] = {0, 0, 0, 0, 0, 0}, q_smem_set = 0;
+struct PFwd : ArLaunch {
+    Parler * m; bool fail = false;
+    PFwd(Parler * m_, Ctx * c, cudaStream_t s) : m(m_) { ctx = c; st = s; }
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
-    size_t att_smem_set = 0, gqa_smem_set = 0;
-    GemvGroupSmem group_smem;
-    int gemv_group(const float * X, int ldx, int K, int R, const ArW * const * W, const int * N, const GemvOut * o, int n) { return gemv_group_arw(ctx, st, group_smem, X, ldx, K, R, W, N, o, n); }
-    // softmax(q K^T * scale) V for R rows over their cache ranges: grouped by kv head when the shape allows (K / V read once per kv head), else one block per query head
-    int attend(const float * q, const float * Kc, const float * Vc, const int * row_base, const int * row_len, int R, int heads, int kv_heads, int hd, int Tcap, float scale, float * out) {
-        if (attention_gqa_enabled() && attention_gqa_ok(heads, kv_heads, hd, Tcap)) {
-            const size_t smem = attention_gqa_smem_bytes(Tcap, heads / kv_heads, hd);
-            if (smem > gqa_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); gqa_smem_set = smem; }
-            dim3 grid(R, kv_heads);
-            attention_gqa_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
-        } else {
-            const size_t smem = attention_smem_bytes(Tcap);
-            if (smem > 200 * 1024) { set_error("context of %d positions exceeds the attention kernel's shared memory", Tcap); return 1; }
-            if (smem > att_smem_set) { B2_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); att_smem_set = smem; }
-            dim3 grid(R, heads);
-            attention_kernel<<<grid, 128, smem, st>>>(q, Kc, Vc, row_base, row_len, heads, kv_heads, hd, Tcap, scale, out);
-        }
-        B2_LAUNCH_CHECK(ctx);
-        return 0;
-    }
-    int gemv(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        if (W.qtype) return gemv_q_launch(ctx, st, q_smem_set, X, ldx, W, K, N, R, res, Y, ldy);      // Q4_0 / Q5_0 / Q8_0: Q8_0-requantised activations, dp4a per block
-        if (W.f16 && gemv_mma_enabled() && gemv_mma_ok(K, N, 16))         // tensor-core path: chunks of 16 rows (a decode step of <= 16 sequences is one chunk)
-            return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) W.p, nullptr, K, N, R, res, Y, ldy);
-        gemv_rows_launch(st, X, ldx, W.p, W.f16, K, N, R, res, Y, ldy);
-        B2_LAUNCH_CHECK(ctx);
-        return 0;
-    }
     int ln(const float * x, const float * w, const float * b, int H, int R, float * y) {
         layernorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, w, b, H, R, 1e-5f, y);
         B2_LAUNCH_CHECK(ctx);
@@ -228,7 +201,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 6 * H + F) * 4 + (size_t) B * NV * 4 + (size_t) n_steps * B * n_out * 4 + (size_t) B * n_out * 4 +
                         (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 12 + (size_t) B * 4 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
-    PFwd Fw{this, ctx, st};
+    PFwd Fw(this, ctx, st);
     float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * H);
     float * x = Fw.al<float>((size_t) Rmax * H), * xn = Fw.al<float>((size_t) Rmax * H), * q = Fw.al<float>((size_t) Rmax * H), * att = Fw.al<float>((size_t) Rmax * H);
     float * kbuf = Fw.al<float>((size_t) Rmax * H), * vbuf = Fw.al<float>((size_t) Rmax * H), * g = Fw.al<float>((size_t) Rmax * F);

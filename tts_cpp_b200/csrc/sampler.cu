@@ -53,9 +53,13 @@ __device__ __forceinline__ unsigned order_key(float v) {
 
 // The k best of val(0 .. V-1) in (value descending, id ascending) order -> pick_idx / pick_val[0 .. k), 1 <= k <= min(V, SAMPLE_MAX_TOP_K); 256 threads.
 // hist: [8 warps][256] counters, tmp_*: [SAMPLE_MAX_TOP_K] unordered picks, misc: [4] ints -- all shared memory.  Every thread must call it (barriers inside).
+// have_prev: only the entries strictly AFTER (prev_key, prev_id) in that order take part -- the continuation of an earlier call whose last pick that was, so that a
+// nucleus of more than SAMPLE_MAX_TOP_K entries is produced chunk by chunk (k <= the number of such entries).
 template <class F>
-__device__ void block_topk(F val, int V, int k, int * pick_idx, float * pick_val, int * tmp_idx, float * tmp_val, unsigned * hist, int * misc) {
+__device__ void block_topk(F val, int V, int k, int * pick_idx, float * pick_val, int * tmp_idx, float * tmp_val, unsigned * hist, int * misc,
+                           bool have_prev = false, unsigned prev_key = 0u, int prev_id = -1) {
     const int tid = threadIdx.x, warp = tid >> 5;
+    auto live = [&](unsigned key, int id) -> bool { return !have_prev || key < prev_key || (key == prev_key && id > prev_id); };
     unsigned prefix = 0u, mask = 0u;
     int need = k;                                              // entries still to be found among those whose key matches `prefix` under `mask`
     for (int shift = 24; shift >= 0; shift -= 8) {
@@ -63,7 +67,7 @@ __device__ void block_topk(F val, int V, int k, int * pick_idx, float * pick_val
         __syncthreads();
         for (int ii = tid; ii < V; ii += 256) {
             const unsigned key = order_key(val(ii));
-            if ((key & mask) == prefix) atomicAdd(&hist[warp * 256 + ((key >> shift) & 255u)], 1u);      // a histogram per warp: 8x less contention
+            if ((key & mask) == prefix && live(key, ii)) atomicAdd(&hist[warp * 256 + ((key >> shift) & 255u)], 1u);      // a histogram per warp: 8x less contention
         }
         __syncthreads();
         unsigned c = 0u;
@@ -95,16 +99,18 @@ __device__ void block_topk(F val, int V, int k, int * pick_idx, float * pick_val
     if (n_eq == need) {                                        // no tie across the boundary (the usual case): everything >= T, in any order
         for (int ii = tid; ii < V; ii += 256) {
             const float v = val(ii);
-            if (order_key(v) >= T) { const int slot = atomicAdd(&misc[3], 1); tmp_idx[slot] = ii; tmp_val[slot] = v; }
+            const unsigned key = order_key(v);
+            if (key >= T && live(key, ii)) { const int slot = atomicAdd(&misc[3], 1); tmp_idx[slot] = ii; tmp_val[slot] = v; }
         }
     } else {                                                   // ties at the threshold: the `need` lowest ids among them
         for (int ii = tid; ii < V; ii += 256) {
             const float v = val(ii);
-            if (order_key(v) > T) { const int slot = atomicAdd(&misc[3], 1); tmp_idx[slot] = ii; tmp_val[slot] = v; }
+            const unsigned key = order_key(v);
+            if (key > T && live(key, ii)) { const int slot = atomicAdd(&misc[3], 1); tmp_idx[slot] = ii; tmp_val[slot] = v; }
         }
         const int chunk = (V + 255) / 256, lo = tid * chunk, hi = lo + chunk < V ? lo + chunk : V;      // thread t owns ids [t * chunk, (t + 1) * chunk)
         unsigned mine = 0u;
-        for (int ii = lo; ii < hi; ii++) mine += order_key(val(ii)) == T ? 1u : 0u;
+        for (int ii = lo; ii < hi; ii++) mine += (order_key(val(ii)) == T && live(T, ii)) ? 1u : 0u;
         __syncthreads();                                       // (hist is free again: everyone left the select loop)
         hist[tid] = mine;
         __syncthreads();
@@ -117,7 +123,7 @@ __device__ void block_topk(F val, int V, int k, int * pick_idx, float * pick_val
         int rank = (int) (hist[tid] - mine);                   // equal entries with lower ids
         for (int ii = lo; ii < hi && rank < need; ii++) {
             const float v = val(ii);
-            if (order_key(v) == T) { tmp_idx[n_gt + rank] = ii; tmp_val[n_gt + rank] = v; rank++; }
+            if (order_key(v) == T && live(T, ii)) { tmp_idx[n_gt + rank] = ii; tmp_val[n_gt + rank] = v; rank++; }
         }
     }
     __syncthreads();
@@ -166,11 +172,35 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleParams p) 
             __syncthreads();
             for (int ii = tid; ii < V; ii += 256) probs_all[ii] = probs_all[ii] / denom;
             __syncthreads();
-            const int kmax = nucleus_k ? p.top_k : (V < SAMPLE_MAX_TOP_K ? V : SAMPLE_MAX_TOP_K);
-            block_topk([&](int ii) { return probs_all[ii]; }, V, kmax, pick_idx, pick_val, tmp_idx, tmp_val, hist, misc);
-            float prob_sum = 0.f; int n = 0;
-            while (n < kmax) { prob_sum += pick_val[n]; n++; if (prob_sum >= p.top_p) break; }      // every thread walks the same sorted picks
-            if (tid == 0) { s_n = n; s_mh = fminf(prob_sum, p.top_p); }
+            // the picks come in chunks of up to SAMPLE_MAX_TOP_K, each the continuation of the one before (one chunk whenever top_k is set, and for any peaked distribution)
+            const int ktotal = nucleus_k ? p.top_k : V;
+            auto prob = [&](int ii) { return probs_all[ii]; };
+            float prob_sum = 0.f; int n = 0, chunks = 0; bool done = false;      // the same in every thread: all of them walk the sorted picks
+            unsigned prev_key = 0u; int prev_id = -1;
+            while (!done && n < ktotal) {
+                const int k = ktotal - n < SAMPLE_MAX_TOP_K ? ktotal - n : SAMPLE_MAX_TOP_K;
+                block_topk(prob, V, k, pick_idx, pick_val, tmp_idx, tmp_val, hist, misc, chunks > 0, prev_key, prev_id);
+                for (int j = 0; j < k; j++) { prob_sum += pick_val[j]; n++; if (prob_sum >= p.top_p) { done = true; break; } }
+                chunks++;
+                if (!done && n < ktotal) { prev_key = order_key(pick_val[k - 1]); prev_id = pick_idx[k - 1]; __syncthreads(); }      // (the next call overwrites the picks)
+            }
+            const float mh = fminf(prob_sum, p.top_p);
+            if (chunks == 1) {
+                if (tid == 0) { s_n = n; s_mh = mh; }                              // the nucleus is in shared memory: the common draw below
+            } else {
+                // a nucleus of several chunks: produce them once more for the cumulative draw (same picks, same order)
+                __syncthreads();
+                const float a = u * mh;
+                float c = 0.f; int t = -1, seen = 0, ch = 0;
+                while (t < 0) {
+                    const int k = n - seen < SAMPLE_MAX_TOP_K ? n - seen : SAMPLE_MAX_TOP_K;
+                    block_topk(prob, V, k, pick_idx, pick_val, tmp_idx, tmp_val, hist, misc, ch > 0, prev_key, prev_id);
+                    for (int j = 0; j < k; j++) { c += pick_val[j]; seen++; if (a <= c || seen >= n) { t = pick_idx[j]; break; } }
+                    ch++;
+                    if (t < 0) { prev_key = order_key(pick_val[k - 1]); prev_id = pick_idx[k - 1]; __syncthreads(); }
+                }
+                if (tid == 0) { s_tok = t; s_n = 0; }
+            }
         } else if (nucleus_k) {
             // top-k by value, then the softmax over the picks
             block_topk(eff, V, p.top_k, pick_idx, pick_val, tmp_idx, tmp_val, hist, misc);
