@@ -425,7 +425,8 @@ def run_parler(args):
                      "traffic": None, "peak_source": peak_src, "note": "algorithmic bytes of one decode step = the resident weights streamed once for the whole batch (KV cache reads excluded)"},
         "gpu_launches": int(ctx.launches() - l0), "dtype": ("f16 matrices x fp16-rounded activations, f32 accumulate" if quant is None else f"{quant} blocks x Q8_0-requantised activations, int32 block dots, f32 accumulate") + " (the reference's numerics for this GGUF)",
         "data": "synthetic", "config": {"workload": f"parler-mini {args.parler_dtype} (24 layers x 1024, 9 codebooks), batch 16, 869 decode steps -> 861 frames, special ids folded mod 1024, DAC 44.1 kHz decode",
-                                         "status": "plain first path (one launch per op, no CUDA graph); see DESIGN 7.1"}}))
+                                         "switches": {k: os.environ.get(k, d) for k, d in (("B2TTS_AR_FUSE", "1"), ("B2TTS_AR_GRAPH", "0"), ("B2TTS_AR_MMA", "0"), ("B2TTS_AR_ATT", "gqa"))},
+                                         "status": "first path: grouped GEMV launches by default, CUDA-graph replay and the tensor-core GEMV behind switches; see DESIGN 7.1"}}))
     return 0
 
 

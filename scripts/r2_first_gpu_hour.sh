@@ -27,7 +27,7 @@ if grep -q "XFAIL" "$OUT/tests_gpu.log"; then
 fi
 
 # 3. A/B matrix on BASELINE config 3 (Parler-Mini F16, batch 16 x 10 s + DAC decode); 2 timed steps each (a step = 869 decode steps)
-for cfg in "plain:" "graph:B2TTS_AR_GRAPH=1" "mma:B2TTS_AR_MMA=1" "graph_mma:B2TTS_AR_GRAPH=1 B2TTS_AR_MMA=1" "graph_mma_plainatt:B2TTS_AR_GRAPH=1 B2TTS_AR_MMA=1 B2TTS_AR_ATT=plain"; do
+for cfg in "plain:" "unfused:B2TTS_AR_FUSE=0" "graph:B2TTS_AR_GRAPH=1" "mma:B2TTS_AR_MMA=1" "graph_mma:B2TTS_AR_GRAPH=1 B2TTS_AR_MMA=1" "graph_mma_plainatt:B2TTS_AR_GRAPH=1 B2TTS_AR_MMA=1 B2TTS_AR_ATT=plain"; do
     name=${cfg%%:*}; envs=${cfg#*:}
     run "bench_parler_$name" 600 env $envs python bench.py --workload parler --steps 2 --warmup 1
 done
