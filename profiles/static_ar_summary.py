@@ -37,7 +37,7 @@ def main():
         if r.returncode:
             sys.exit(r.stderr)
         objs[src] = obj
-        ents = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers(?:, used \d+ barriers)?(?:, (\d+) bytes smem)?", r.stderr)
+        ents = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers(?:, used \d+ barriers)?(?:, \d+ bytes cumulative stack size)?(?:, (\d+) bytes smem)?", r.stderr)
         names = demangle([e[0] for e in ents])
         for n, e in sorted(zip(names, ents)):
             print(f"{n:<52} {e[4]:>3} regs   stack {e[1]} B, spills {e[2]}/{e[3]} B" + (f", static smem {e[5]} B" if e[5] else ""))
