@@ -10,7 +10,9 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="Dia decode path not yet run on a B200 (round 1 GPU budget exhausted)")]
+pytestmark = pytest.mark.gpu
+# the F32 model on the default path (fused launches) has run on a B200 (profiles/r1i_rowb_first_contact.log: reference tokens, logits 3.5e-3); the other variants have not
+UNRUN = pytest.mark.xfail(strict=False, reason="this variant of the Dia decode path has not run on a B200 yet (round 1 GPU budget exhausted)")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CHILD = r'''
@@ -36,7 +38,7 @@ sys.exit(0 if ok else 1)
 '''
 
 
-@pytest.mark.parametrize("dtype", ["f32", "f16"])
+@pytest.mark.parametrize("dtype", ["f32", pytest.param("f16", marks=UNRUN)])
 def test_dia_greedy_tokens_and_logits_match_reference(dtype):
     r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=150)
     print(r.stdout[-2000:])
@@ -63,6 +65,7 @@ sys.exit(0 if ok else 1)
 '''
 
 
+@UNRUN
 def test_dia_quantised_teacher_forced():
     """Q8_0 matrices (gemv_rows_q_kernel), teacher-forced on the reference's tokens; smoke-level bar (Dia amplifies re-quantisation noise: see tests/test_emu_cpu.py)."""
     r = subprocess.run([sys.executable, "-c", QUANT_CHILD, ROOT], capture_output=True, text=True, timeout=150)

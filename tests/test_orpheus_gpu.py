@@ -10,7 +10,9 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="Orpheus decode path not yet validated on a B200 (round 1 GPU budget exhausted)")]
+pytestmark = pytest.mark.gpu
+# the default (plain fp32, fused launches) path has run on a B200 (profiles/r1i_rowb_first_contact.log: reference tokens, logits 5e-6); the variants below it have not
+UNRUN = pytest.mark.xfail(strict=False, reason="this variant of the Orpheus decode path has not run on a B200 yet (round 1 GPU budget exhausted)")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CHILD = r'''
@@ -61,6 +63,7 @@ sys.exit(0 if ok else 1)
 '''
 
 
+@UNRUN
 @pytest.mark.parametrize("mma", ["0", "1"], ids=["plain", "split_mma"])
 def test_orpheus_wide_tokens_and_logits_match_reference(mma):
     """hidden 768 (every matrix eligible for the tensor-core GEMV); split_mma: the fp32-faithful three-product path over fp16 (hi, lo) pairs."""

@@ -10,7 +10,9 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="Parler decode path not yet run on a B200 (round 1 GPU budget exhausted)")]
+pytestmark = pytest.mark.gpu
+# the F32 model on the default path (fused launches) has run on a B200 (profiles/r1i_rowb_first_contact.log: reference tokens, logits 1.5e-3); the other variants have not
+UNRUN = pytest.mark.xfail(strict=False, reason="this variant of the Parler decode path has not run on a B200 yet (round 1 GPU budget exhausted)")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CHILD = r'''
@@ -36,7 +38,7 @@ sys.exit(0 if ok else 1)
 '''
 
 
-@pytest.mark.parametrize("dtype", ["f32", "f16"])
+@pytest.mark.parametrize("dtype", ["f32", pytest.param("f16", marks=UNRUN)])
 def test_parler_greedy_tokens_and_logits_match_reference(dtype):
     """f16: the GGUF `quantize --quantized-type F16` writes (decoder matrices F16, activations rounded to fp16 before each such product).  Two runs
     of that model that differ only in summation order already differ by 1.5e-3 RMS / 6e-3 max in the logits (rounding boundaries), so the bar there
@@ -47,6 +49,7 @@ def test_parler_greedy_tokens_and_logits_match_reference(dtype):
     assert r.returncode == 0
 
 
+@UNRUN
 def test_parler_tensor_core_gemv_f16_matches_reference_tokens():
     """B2TTS_AR_MMA=1: the F16 matrices through gemv_mma_kernel<false> (mma.sync with the batch as M) -- same token ids as the F16 reference."""
     r = subprocess.run([sys.executable, "-c", CHILD, ROOT, "f16"], capture_output=True, text=True, timeout=150, env=dict(os.environ, B2TTS_AR_MMA="1"))
@@ -75,6 +78,7 @@ sys.exit(0 if ok else 1)
 '''
 
 
+@UNRUN
 def test_parler_stop_rule_matches_reference():
     """eos_seen feeding + check_stopping on the device against the reference run to completion (tests/golden/parler_stop_vectors.npz)."""
     r = subprocess.run([sys.executable, "-c", STOP_CHILD, ROOT], capture_output=True, text=True, timeout=150)
@@ -107,6 +111,7 @@ sys.exit(0 if ok else 1)
 '''
 
 
+@UNRUN
 @pytest.mark.parametrize("quant", ["Q8_0", "Q5_0", "Q4_0"])
 def test_parler_quantised_teacher_forced(quant):
     """Block-quantised decoder matrices (gemv_rows_q_kernel), teacher-forced on the reference's tokens: logits within 0.1 RMS at every step, the same token wherever

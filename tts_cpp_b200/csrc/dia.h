@@ -4,7 +4,7 @@
 // loop of generate_from_batch with check_stopping (reference src/models/dia/model.cpp:324-637,705-737,806-864; src/util.cpp:175-200) under
 // sampler::max, for a batch of independent prompts.  Every utterance is TWO sequences throughout, like the reference: the conditional prompt and
 // an all-zero unconditional one.  Same plain design as orpheus.h / parler.h (CUDA-core kernels from ar_kernels.cuh; F32 and F16 matrices with the
-// reference's numerics for each); logic checked under tests/emu, not yet run on a GPU.
+// reference's numerics for each); logic checked under tests/emu; on a B200 the F32 greedy path reproduces the reference's tokens (profiles/r1i_rowb_first_contact.log).
 #pragma once
 #include "kokoro.h"   // HostTensor, Arena
 

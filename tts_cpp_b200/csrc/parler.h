@@ -4,7 +4,7 @@
 // generate_from_batch with its delay pattern (reference src/models/parler/model.cpp:110-173,387-470,520-614,762-786) under sampler::max
 // (src/sampler.cpp), for a batch of independent prompts that share the model's stored conditional-prompt encoding.
 // Same plain design as orpheus.h (CUDA-core kernels from ar_kernels.cuh, one launch per op); F32 and F16 matrices (the GGUFs `quantize
-// --quantized-type F16` writes) with the reference's numerics for each.  Logic checked under tests/emu, not yet run on a GPU.
+// --quantized-type F16` writes) with the reference's numerics for each.  Logic checked under tests/emu; on a B200 the F32 greedy path reproduces the reference's tokens (profiles/r1i_rowb_first_contact.log).
 #pragma once
 #include "kokoro.h"   // HostTensor, Arena
 
