@@ -350,6 +350,19 @@ def test_tensor_core_gemv_multi_tile_emulated(tmp_path):
         assert float(np.abs(logits[u] - g[f"logits{u % 2}"][:steps]).max()) < 1e-4
 
 
+def test_parler_tensor_core_prompt_pass_row_chunks_emulated(tmp_path):
+    """Parler F16 through the tensor-core GEMV with a prompt pass of more than 64 rows: the grouped q / k / v launch then runs in row chunks of 64 and the k / v rows of
+    the later chunks must still land in THEIR cache slots (GemvOut::row_dst advanced per chunk).  Every sequence of the batch must give the reference's tokens."""
+    g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz"))
+    n = 2 * (64 // int(g["prompt0"].size + g["prompt1"].size) + 1)
+    prompts = [g[f"prompt{u % 2}"] for u in range(n)]
+    assert sum(p.size for p in prompts) > 64
+    steps = 3
+    tok, _ = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "rc", env={"B2TTS_AR_MMA": "1"})
+    for u in range(n):
+        assert np.array_equal(tok[u], g[f"tokens{u % 2}"][:steps]), u
+
+
 @pytest.mark.parametrize("quant", ["Q8_0", "Q5_0", "Q4_0"])
 def test_parler_quantised_emulated_teacher_forced(tmp_path, quant):
     """parler.cu on block-quantised GGUFs (gemv_rows_q_kernel: activations quantised to Q8_0 per 32 columns in shared memory, dp4a over the ggml blocks as they are
