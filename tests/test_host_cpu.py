@@ -201,3 +201,15 @@ def test_orpheus_stream_to_snac_codes():
     assert m.tolist() == sum(([100 * f + 1, 100 * f + 4] for f in range(frames)), [])
     assert fine.tolist() == sum(([100 * f + 2, 100 * f + 3, 100 * f + 5, 100 * f + 6] for f in range(frames)), [])
     assert len(m) == 2 * len(c) and len(fine) == 4 * len(c)             # the L/4, L/2, L layout snac_runner::run / b2tts_snac_decode_batch takes
+
+
+def test_scripts_parse():
+    """scripts/ is what the first GPU call of the next round runs: the shell script must parse and the Python ones must compile (no GPU needed for either)."""
+    import glob
+    import py_compile
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for sh in glob.glob(os.path.join(root, "scripts", "*.sh")):
+        assert subprocess.run(["bash", "-n", sh]).returncode == 0, sh
+    for py in glob.glob(os.path.join(root, "scripts", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py"), os.path.join(root, "profiles", "static_ar_summary.py")]:
+        py_compile.compile(py, doraise=True)

@@ -758,6 +758,29 @@ static inline int host_tensor_from_blocks(HostTensor & t, const char * name, int
     return 0;
 }
 
+// one GGUF tensor (ggml type 0 = F32, 1 = F16; with allow_quant also 2 / 6 / 8 = Q4_0 / Q5_0 / Q8_0 blocks) -> HostTensor: fp32 values in `v` (F16 widened exactly,
+// blocks dequantised like ggml), outermost dimension first in `shape`.  The assign_weight of all three decode paths.  0 ok, 1 error (message set).
+static inline int host_tensor_from_gguf(HostTensor & t, const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes, bool allow_quant) {
+    int64_t n = 1;
+    for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
+    t.v.resize((size_t) n);
+    if (type == 0) {
+        if (nbytes < (size_t) n * 4) { set_error("tensor %s: short data", name); return 1; }
+        memcpy(t.v.data(), data, (size_t) n * 4);
+    } else if (type == 1) {
+        if (nbytes < (size_t) n * 2) { set_error("tensor %s: short data", name); return 1; }
+        const uint16_t * s = (const uint16_t *) data;
+        for (int64_t i = 0; i < n; i++) { __half_raw r; r.x = s[i]; t.v[(size_t) i] = __half2float(__half(r)); }
+        t.f16 = true;
+    } else if (allow_quant && (type == 2 || type == 6 || type == 8)) {
+        if (host_tensor_from_blocks(t, name, type, n, data, nbytes)) return 1;
+    } else {
+        set_error(allow_quant ? "tensor %s: ggml type %d not supported (F32, F16, Q4_0, Q5_0, Q8_0)" : "tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
+        return 1;
+    }
+    return 0;
+}
+
 // the planes of a block-quantised matrix in HBM: the ggml blocks (fp16 scale | [4 bytes of fifth bits] | 16 or 32 bytes of values, 18 / 22 / 34 bytes, unaligned) split
 // into values, scales and fifth bits so that a lane reads a block's values with one aligned 16-byte (two for Q8_0) load; same bytes in total.  false on cudaMalloc failure.
 static inline bool upload_quant_planes(const HostTensor & t, ArW & w, std::vector<void *> & dev_allocs, size_t & weight_bytes) {

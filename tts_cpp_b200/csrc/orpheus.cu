@@ -9,28 +9,12 @@
 
 namespace b2 {
 
-static inline float oh2f(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
-
 int Orpheus::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
     if (prepared) { set_error("orpheus: assign_weight after prepare"); return 1; }
     std::string nm(name);
     if (nm.rfind("orpheus.", 0) == 0) nm = nm.substr(8);
     HostTensor t;
-    int64_t n = 1;
-    for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
-    t.v.resize((size_t) n);
-    if (type == 0) {
-        if (nbytes < (size_t) n * 4) { set_error("tensor %s: short data", name); return 1; }
-        memcpy(t.v.data(), data, (size_t) n * 4);
-    } else if (type == 1) {
-        if (nbytes < (size_t) n * 2) { set_error("tensor %s: short data", name); return 1; }
-        const uint16_t * s = (const uint16_t *) data;
-        for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = oh2f(s[i]);
-        t.f16 = true;
-    } else {
-        set_error("tensor %s: ggml type %d not supported (F32/F16 only)", name, type);
-        return 1;
-    }
+    if (host_tensor_from_gguf(t, name, type, n_dims, ne, data, nbytes, false)) return 1;
     host[nm] = std::move(t);
     return 0;
 }

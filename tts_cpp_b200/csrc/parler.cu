@@ -9,30 +9,12 @@
 
 namespace b2 {
 
-static inline float ph2f(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
-
 int Parler::assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes) {
     if (prepared) { set_error("parler: assign_weight after prepare"); return 1; }
     std::string nm(name);
     if (nm.rfind("decoder.", 0) == 0) nm = nm.substr(8);
     HostTensor t;
-    int64_t n = 1;
-    for (int i = n_dims - 1; i >= 0; i--) { t.shape.push_back(ne[i]); n *= ne[i]; }
-    t.v.resize((size_t) n);
-    if (type == 0) {
-        if (nbytes < (size_t) n * 4) { set_error("tensor %s: short data", name); return 1; }
-        memcpy(t.v.data(), data, (size_t) n * 4);
-    } else if (type == 1) {
-        if (nbytes < (size_t) n * 2) { set_error("tensor %s: short data", name); return 1; }
-        const uint16_t * s = (const uint16_t *) data;
-        for (int64_t i = 0; i < n; i++) t.v[(size_t) i] = ph2f(s[i]);
-        t.f16 = true;
-    } else if (type == 2 || type == 6 || type == 8) {          // Q4_0 / Q5_0 / Q8_0 blocks
-        if (host_tensor_from_blocks(t, name, type, n, data, nbytes)) return 1;
-    } else {
-        set_error("tensor %s: ggml type %d not supported (F32, F16, Q4_0, Q5_0, Q8_0)", name, type);
-        return 1;
-    }
+    if (host_tensor_from_gguf(t, name, type, n_dims, ne, data, nbytes, true)) return 1;
     host[nm] = std::move(t);
     return 0;
 }
