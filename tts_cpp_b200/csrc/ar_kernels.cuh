@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float * __restrict__ 
         if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
         __syncthreads();
     }
-    if (tid == 0) { cur_tok[b] = si[0]; out_tokens[(size_t) b * n_steps + *d_step] = si[0]; }
+    if (tid == 0) { const int t = si[0] == 0x7fffffff ? 0 : si[0]; cur_tok[b] = t; out_tokens[(size_t) b * n_steps + *d_step] = t; }      // (all-NaN logits: token 0, never an out-of-range id)
 }
 
 
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float * __restri
         if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
         __syncthreads();
     }
-    if (tid == 0) out[(size_t) (d_step ? *d_step : 0) * gridDim.x + b] = si[0];
+    if (tid == 0) out[(size_t) (d_step ? *d_step : 0) * gridDim.x + b] = si[0] == 0x7fffffff ? 0 : si[0];                                 // (all-NaN logits: token 0)
 }
 
 // rows of an audio decode step under the delay pattern (parler generate_audio_tokens, model.cpp:795-832): output head i is fed BOS until step i + 1, then the

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleParams p) 
     float bv = -INFINITY; int bi = 0x7fffffff;
     for (int ii = tid; ii < V; ii += 256) { const float v = eff(ii); if (better(v, ii, bv, bi)) { bv = v; bi = ii; } }
     const ArgMax mx = block_argmax(bv, bi, sv, si);
-    int tok = mx.i;
+    int tok = mx.i == 0x7fffffff ? 0 : mx.i;               // (all-NaN logits: token 0, never an out-of-range id)
     if (p.do_sample) {
         const bool has_t = p.temperature != 1.0f;
         const float max_val = has_t ? mx.v / p.temperature : mx.v;
