@@ -170,7 +170,8 @@ int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Orpheus autoregressive decode, FIRST CORRECT PATH: fp32 CUDA-core GEMVs, compact GQA KV cache, device argmax.
- * NOT YET RUN ON A B200 (written after round 1's GPU budget was spent).  Its logic is checked in the build container: the unmodified .cu file,
+ * On a B200 its default greedy path reproduces the reference's token ids exactly, logits 5.2e-6 (one short run at the end of round 1,
+ * profiles/r1i_rowb_first_contact.log; the tensor-core and graph-replay variants have not run on hardware).  Its logic is checked in the build container: the unmodified .cu file,
  * compiled against a CPU emulation of the CUDA subset it uses (tests/emu), reproduces the reference's greedy token ids exactly and its logits
  * to 4.5e-6 (tests/test_emu_cpu.py).  No performance claims are made for it.
  *   b2tts_orpheus_load_gguf      : orpheus_model::setup_from_file + assign_weight loop over "orpheus.*" (reference
@@ -196,7 +197,8 @@ float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Parler-TTS autoregressive decode, FIRST CORRECT PATH, same status as Orpheus above (emulation-checked: identical token
- * ids, logits within 1.7e-3 of the reference at a logit std of 4 -- ggml's fp16 GELU table; NOT YET RUN ON A B200).
+ * ids, logits within 1.7e-3 of the reference at a logit std of 4 -- ggml's fp16 GELU table; on a B200: the F32 greedy path gives the reference's
+ * token ids, logits 1.5e-3 -- the F16 / quantised / graph-replay / tensor-core variants have not run on hardware).
  *   b2tts_parler_load_gguf      : parler_tts_model::setup_from_file + assign_weight loop over "decoder.*" + prep_cross_key_values (reference
  *                                 src/models/parler/model.cpp:3-28,110-173,271-318; parler/loader.cpp)
  *   b2tts_parler_generate_greedy: generate_from_batch's prompt decode, then the audio decode + sampler loop with the delay pattern
@@ -227,7 +229,8 @@ size_t b2tts_parler_weight_bytes(const b2tts_parler * m);   /* bytes of the matr
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dia autoregressive decode, FIRST CORRECT PATH, same status as Orpheus / Parler above (emulation-checked: identical token
- * ids, CFG-combined logits within 2.4e-3 of the reference at a logit std of 13; NOT YET RUN ON A B200).
+ * ids, CFG-combined logits within 2.4e-3 of the reference at a logit std of 13; on a B200: the F32 greedy path gives the reference's token ids,
+ * logits 3.5e-3 -- the other variants have not run on hardware).
  *   b2tts_dia_load_gguf      : dia_model::setup_from_file + assign_weight loop over "dia.*" (reference src/models/dia/model.cpp:3-132,200-262;
  *                              dia/loader.cpp:8-22)
  *   b2tts_dia_generate_greedy: dia_runner::decode -- the encoder pass over the conditional and the all-zero unconditional sequence, the cross K/V
