@@ -16,6 +16,11 @@ run() { local name=$1 t=$2; shift 2; echo "=== $name" | tee -a "$OUT/index.log";
 
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/gpu.csv" 2>&1
 
+# 0. four seconds each: the small models of all three decode paths against the reference's tokens / logits, default path and two switches
+run contact_default 120 python scripts/rowb_first_contact.py
+run contact_unfused 120 env B2TTS_AR_FUSE=0 python scripts/rowb_first_contact.py
+run contact_mma 120 env B2TTS_AR_MMA=1 python scripts/rowb_first_contact.py
+
 # 1. every -m gpu test, row B included (xfail(strict=False) in child processes): XPASS = works on hardware
 run tests_gpu 900 python -m pytest tests -m gpu -q -rxXs -p no:cacheprovider
 
