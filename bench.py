@@ -34,6 +34,57 @@ sys.path.insert(0, ROOT)
 BATCH = 32
 N_PHON = 64
 CTX_LEN = 128           # GGUF context_length (>= 66 tokens); keeps the reference's worst-case graph reservation small
+
+
+def host_cpus():
+    """What this process may actually use: the affinity mask and the cgroup CPU quota (os.cpu_count() reports the machine, not the lease)."""
+    logical = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = logical
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return {"logical": logical, "affinity": aff, "cgroup_quota_cpus": quota, "usable": usable, "model": model}
+
+
+def ref_bin(name: str):
+    """-> (path, build) of a reference binary for TIMING: the -march=native build of oracle/Makefile's ref_native target when this host's CPU has every ISA
+    extension that build was compiled with (it was built on a Sapphire-Rapids-class Xeon; the GPU boxes are Xeon 8562Y+), else the portable x86-64-v3 build
+    the golden vectors come from."""
+    nat = os.path.join(ROOT, "oracle", "_ref", "native", name)
+    macros = os.path.join(ROOT, "oracle", "_ref", "native", "isa_macros.txt")
+    if os.path.exists(nat) and os.path.exists(macros):
+        need = {"__AVX512F__": "avx512f", "__AVX512BW__": "avx512bw", "__AVX512VL__": "avx512vl", "__AVX512DQ__": "avx512dq", "__AVX512CD__": "avx512cd", "__AVX512VNNI__": "avx512_vnni",
+                "__AVX512BF16__": "avx512_bf16", "__AVX512FP16__": "avx512_fp16", "__AVX512VBMI__": "avx512vbmi", "__AVX512VBMI2__": "avx512_vbmi2", "__AVX512IFMA__": "avx512ifma",
+                "__AVX512BITALG__": "avx512_bitalg", "__AVX512VPOPCNTDQ__": "avx512_vpopcntdq", "__AMX_TILE__": "amx_tile", "__AMX_INT8__": "amx_int8", "__AMX_BF16__": "amx_bf16",
+                "__AVX2__": "avx2", "__FMA__": "fma", "__F16C__": "f16c"}
+        try:
+            flags = set()
+            for ln in open("/proc/cpuinfo"):
+                if ln.startswith("flags"):
+                    flags = set(ln.split(":", 1)[1].split()); break
+            want = [need[m.split()[1]] for m in open(macros) if m.split()[1] in need]
+            if all(f in flags for f in want):
+                return nat, "-march=native build (AVX-512/VNNI/BF16/AMX host)"
+        except Exception:
+            pass
+    return os.path.join(ROOT, "oracle", "_ref", name), "x86-64-v3 build"
+
+
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "kokoro_ref")
 
 
@@ -136,9 +187,11 @@ def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, 
     Default split = the best of the (workers, threads) grid measured on the GPU box (2 x Xeon 8562Y+, 128 logical CPUs):
     1x8 2.1 | 1x32 1.5 | 4x8 3.5 | 8x8 3.1 | 16x8 1.8 | 16x4 4.0 | 32x4 2.6 | 8x16 0.9 audio-s/s -> ncpu/8 workers x 4 threads
     (one ggml thread per physical core; its spin-wait barriers and memory traffic make wider splits slower)."""
-    if not os.path.exists(REF_BIN):
+    binp, build = ref_bin("kokoro_ref")
+    if not os.path.exists(binp):
         return None, "oracle/_ref/kokoro_ref missing (run `make -C oracle ref` where /root/reference exists)"
-    ncpu = os.cpu_count() or 8
+    hc = host_cpus()
+    ncpu = hc["usable"]
     threads = max(1, min(threads, ncpu))
     workers = workers or max(1, ncpu // (2 * threads))
     gguf = _gguf()
@@ -149,7 +202,7 @@ def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, 
         tok = os.path.join(tmp, f"tok{w}.txt")
         with open(tok, "w") as f:
             f.write(" ".join(map(str, prompts[w % len(prompts)])) + "\n")
-        cmd = [REF_BIN, gguf, tok, os.path.join(tmp, f"o{w}"), "--threads", str(threads), "--reps", str(n_warm + n_timed), "--warm", str(n_warm), "--quiet"]
+        cmd = [binp, gguf, tok, os.path.join(tmp, f"o{w}"), "--threads", str(threads), "--reps", str(n_warm + n_timed), "--warm", str(n_warm), "--quiet"]
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     audio, wall = 0.0, 0.0
     for p in procs:
@@ -161,8 +214,10 @@ def reference_throughput(n_timed: int, n_warm: int, workers: int | None = None, 
     if wall <= 0:
         return None, "reference run produced no SUMMARY"
     return {"value": audio / wall, "unit": "audio-s/s", "cores": workers * threads, "kind": "reference", "wall_s": wall, "timed_runs_per_worker": n_timed,
-            "sample": f"{workers} worker processes x {threads} ggml threads, each {n_timed} timed run(s) of one 66-token prompt "
-                      f"(~4.95 s audio) after {n_warm} warm-up; throughput = total audio / slowest worker's wall; x86-64-v3 build"}, None
+            "workers": workers, "threads_per_worker": threads, "host": hc, "build": build,
+            "sample": f"{workers} worker processes x {threads} ggml threads (of {hc['usable']} usable logical CPUs: affinity {hc['affinity']}, cgroup quota {hc['cgroup_quota_cpus']}, {hc['model']}), "
+                      f"each {n_timed} timed run(s) of one 66-token prompt (~4.95 s audio, one of the batch's 32 prompts; the reference has no batching) after {n_warm} warm-up; "
+                      f"throughput = total audio / slowest worker's wall; {build}"}, None
 
 
 def run_reference_arm(args):
@@ -171,7 +226,19 @@ def run_reference_arm(args):
         return 0
     # a step of this arm = every worker synthesising one prompt (a bounded sample of the batch-32 step: 16 of its prompts on this
     # box); capped at 6 timed repetitions so that any --steps finishes within a few minutes
-    base, why = reference_throughput(n_timed=max(1, min(args.steps, 6)), n_warm=max(1, min(args.warmup, 1)))
+    # the worker x thread split is swept on THIS box first (one timed run each, ~10 s per point), then the best split is timed
+    ncpu = host_cpus()["usable"]
+    grid = sorted({(max(1, ncpu // (2 * t)), t) for t in (2, 4, 8)} | {(max(1, ncpu // 4), 4)})
+    sweep, best = [], None
+    for w, t in grid:
+        r, _ = reference_throughput(n_timed=1, n_warm=1, workers=w, threads=t)
+        if r:
+            sweep.append({"workers": w, "threads": t, "audio_s_per_s": round(r["value"], 3)})
+            if best is None or r["value"] > best[0]:
+                best = (r["value"], w, t)
+    base, why = reference_throughput(n_timed=max(1, min(args.steps, 6)), n_warm=max(1, min(args.warmup, 1)), workers=best[1] if best else None, threads=best[2] if best else 4)
+    if base is not None:
+        base["split_sweep"] = sweep
     if base is None:
         print(json.dumps({"impl": "reference", "unavailable": why}))
         return 0
@@ -180,7 +247,8 @@ def run_reference_arm(args):
         "steps": base["timed_runs_per_worker"], "warmup": max(1, min(args.warmup, 1)), "ms_per_step": base["wall_s"] * 1e3 / base["timed_runs_per_worker"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 weights / f32 activations (GGML CPU)", "data": "synthetic",
-        "config": {"workload": "Kokoro-82M fp16 GGUF (synthetic weights), 64-char (66-token) prompts, reference CPU GGML path, sequential per worker"},
+        "config": {"workload": "Kokoro-82M fp16 GGUF (synthetic weights), 64-char (66-token) prompts, reference CPU GGML path, sequential per worker",
+                   "sample_note": "a step of this arm = every worker synthesising ONE prompt of the batch-32 workload (the reference has no batching); at most 6 timed repetitions; same GGUF and prompts as the CUDA arm"},
         "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -189,12 +257,12 @@ def run_reference_arm(args):
 
 def _dac_reference_sample(threads: int = 4):
     """-> (audio_s, wall_s, workers) of oracle/_ref/dac_ref decoding one 861-frame utterance per worker process, or None"""
-    ref = os.path.join(ROOT, "oracle", "_ref", "dac_ref")
+    ref, _build = ref_bin("dac_ref")
     if not os.path.exists(ref):
         return None
     from tts_cpp_b200.synth import cached_dac_gguf, synthetic_codes
     gguf = cached_dac_gguf(seed=0, max_frames=870)
-    ncpu = os.cpu_count() or 8
+    ncpu = host_cpus()["usable"]
     workers = max(1, min(16, ncpu // (2 * threads)))
     tmp = tempfile.mkdtemp(prefix="b2dac_")
     procs = []
@@ -236,7 +304,7 @@ def run_parler_reference(args, threads: int = 4, sample_steps: int = 60):
     after the other in the reference, so the pipeline rate is the harmonic combination of the stage rates."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    ref = os.path.join(ROOT, "oracle", "_ref", "parler_ref")
+    ref, _build = ref_bin("parler_ref")
     if not os.path.exists(ref):
         print(json.dumps({"impl": "reference", "workload": "parler", "unavailable": "oracle/_ref/parler_ref missing (run `make -C oracle ref` where /root/reference exists)"}))
         return 0
@@ -244,7 +312,7 @@ def run_parler_reference(args, threads: int = 4, sample_steps: int = 60):
     from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_parler_gguf
     quant = None if args.parler_dtype == "f16" else args.parler_dtype.upper()
     gguf = cached_parler_gguf(seed=0, f16=quant is None, quant=quant, **PARLER_MINI_SHAPE)
-    ncpu = os.cpu_count() or 8
+    ncpu = host_cpus()["usable"]
     workers = max(1, min(16, ncpu // (2 * threads)))
     tmp = tempfile.mkdtemp(prefix="b2par_")
     rng = np.random.default_rng(5)
@@ -311,14 +379,14 @@ def run_snac_reference(args, threads: int = 4):
     utterance (9.98 s of audio) of the same synthetic GGUF -- a bounded sample of the batch-16 step."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    ref = os.path.join(ROOT, "oracle", "_ref", "snac_ref")
+    ref, _build = ref_bin("snac_ref")
     if not os.path.exists(ref):
         print(json.dumps({"impl": "reference", "workload": "snac", "unavailable": "oracle/_ref/snac_ref missing (run `make -C oracle ref` where /root/reference exists)"}))
         return 0
     import numpy as np
     from tts_cpp_b200.synth import cached_snac_gguf, synthetic_snac_codes
     gguf = cached_snac_gguf(seed=0, max_frames=480)
-    ncpu = os.cpu_count() or 8
+    ncpu = host_cpus()["usable"]
     workers = max(1, min(16, ncpu // (2 * threads)))
     tmp = tempfile.mkdtemp(prefix="b2snac_")
     procs = []

@@ -186,6 +186,8 @@ int Kokoro::prepare() {
     heads = (int) kvget("kokoro.duration_predictor.albert.attn_heads", 12);
     // ALBERT
     tok_embd = P.f32("albert.token_embd"); pos_embd = P.f32("albert.position_embd"); type_embd = P.f32("albert.token_type_embd");
+    if (auto t = P.get("albert.token_embd")) n_vocab = (int) (t->v.size() / 128);        // rows of the two token tables: run_batch rejects ids beyond either
+    if (auto t = P.get("albert.position_embd")) n_positions = (int) (t->v.size() / 128);
     in_nw = P.f32("albert.norm"); in_nb = P.f32("albert.norm_bias");
     embd_w = P.f32("albert.embd"); embd_b = P.f32("albert.embd_bias");
     {
@@ -220,6 +222,7 @@ int Kokoro::prepare() {
     n_proj = P.w16("duration_predictor.n_proj_kernel"); n_proj_b = P.f32("duration_predictor.n_proj_bias");
     // text encoder
     if (auto t = P.get("text_encoder.embedding_weight")) {
+        n_vocab = std::min(n_vocab, (int) (t->v.size() / 512));
         std::vector<__half> h(t->v.size());
         for (size_t i = 0; i < h.size(); i++) h[i] = __float2half(t->v[i]);
         text_embd = (__half *) P.dev(h.data(), h.size() * 2);
@@ -491,7 +494,10 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     int Nmax = 0, ntot = 0;
     std::vector<int> ntok(B), tok_off(B);
     for (int b = 0; b < B; b++) {
-        if (n_tokens[b] < 3 || n_tokens[b] > 512 || n_tokens[b] - 3 >= n_vrows) { set_error("utterance %d: n_tokens=%d out of range [3,%d]", b, n_tokens[b], std::min(512, n_vrows + 2)); return 1; }
+        const int cap = std::min(std::min(512, n_positions), n_vrows + 2);
+        if (n_tokens[b] < 3 || n_tokens[b] > cap) { set_error("utterance %d: n_tokens=%d out of range [3,%d]", b, n_tokens[b], cap); return 1; }
+        for (int i = 0; i < n_tokens[b]; i++)                                      // the ids index albert.token_embd and text_encoder.embedding_weight on the device
+            if (tokens[ntot + i] >= (uint32_t) n_vocab) { set_error("utterance %d: token %d is %u, the model's vocabulary has %d entries", b, i, tokens[ntot + i], n_vocab); return 1; }
         ntok[b] = n_tokens[b]; tok_off[b] = ntot; ntot += ntok[b]; Nmax = std::max(Nmax, ntok[b]);
     }
     taps.clear();

@@ -69,6 +69,7 @@ struct Kokoro {
     std::vector<void *> dev_allocs;
 
     // ALBERT
+    int n_vocab = 0, n_positions = 512;      // rows of the token / position tables (ids are validated against them before they reach the device)
     float * tok_embd = nullptr, * pos_embd = nullptr, * type_embd = nullptr, * in_nw = nullptr, * in_nb = nullptr;
     float * embd_w = nullptr, * embd_b = nullptr;
     W16 qkv, o, ffn, ffn_out;
