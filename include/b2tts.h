@@ -226,6 +226,12 @@ int   b2tts_parler_generate_teacher_forced(b2tts_parler * m, int n_sequences, co
                                            const int32_t * teacher, int32_t * out_tokens, float * out_logits);
 float b2tts_parler_last_ms(const b2tts_parler * m);
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m);   /* bytes of the matrices, tables and norms resident in HBM (F16 matrices count 2 bytes) */
+/* W_step of SURVEY 8(d): bytes of every weight tensor ONE decode step touches, each once, in its stored dtype (decoder matrices, norms, the stored cross K / V,
+ * the output heads; not the embedding tables, of which a step reads nine rows) -- the weight term of the decode-step roofline */
+size_t b2tts_parler_step_weight_bytes(const b2tts_parler * m);
+/* how many launches of the persistent decode kernel (csrc/pdk.cuh) this model has issued and how many decode steps they covered; 0 / 0 = every step so far took the
+ * launch-per-op path (sampling, > 16 sequences, F32 or block-quantised matrices, B2TTS_AR_PDK=0) */
+void  b2tts_parler_pdk_stats(const b2tts_parler * m, uint64_t * launches, uint64_t * steps);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dia autoregressive decode, FIRST CORRECT PATH, same status as Orpheus / Parler above (emulation-checked: identical token

@@ -36,7 +36,7 @@ b2emu_switch:
 namespace b2emu {
 
 Fiber * g_cur = nullptr;
-dim3 g_blockIdx, g_blockDim, g_gridDim;
+dim3 g_blockDim, g_gridDim;
 uint64_t g_launches = 0, g_blocks = 0;
 
 namespace {
@@ -45,10 +45,15 @@ void * g_sched_sp = nullptr;
 const std::function<void()> * g_body = nullptr;
 std::vector<Fiber> g_fibers;
 std::vector<char *> g_stacks;
-int g_alive = 0, g_arrived = 0; uint64_t g_gen = 0, g_progress = 0;
+// per-block barrier state.  Ordinary launches run their blocks one after another (one live Block); a cooperative launch (launch_coop) keeps every block of the grid
+// alive at once -- all their threads are fibers of one scheduler -- so that a grid-wide barrier in global memory can complete.
+struct NamedBar { int arrived = 0; uint64_t gen = 0; };
+struct Block { int alive = 0, arrived = 0; uint64_t gen = 0; std::vector<char> dyn; NamedBar nb[16]; };
+std::vector<Block> g_blk;
+int g_nt = 0;                                                     // threads per block of the running launch
+uint64_t g_progress = 0;
 struct Warp { int alive = 0, arrived = 0; uint64_t gen = 0; uint64_t slot[2][32]; unsigned wide[2][32][8]; };
 std::vector<Warp> g_warps;
-std::vector<char> g_dyn;
 
 void yield() { Fiber * f = g_cur; b2emu_switch(&f->sp, g_sched_sp); }
 int linear_tid(const Fiber * f) { return (int) (f - g_fibers.data()); }
@@ -72,19 +77,20 @@ void wait_pass_on(int lo, int hi, int & tries) {
     yield();
 }
 
-void release_if_complete() {      // a thread that exits while others wait at a barrier completes that barrier (CUDA leaves this undefined; be lenient)
-    if (g_alive > 0 && g_arrived == g_alive) { g_arrived = 0; g_gen++; }
+void release_if_complete(Block & b) {      // a thread that exits while others wait at a barrier completes that barrier (CUDA leaves this undefined; be lenient)
+    if (b.alive > 0 && b.arrived == b.alive) { b.arrived = 0; b.gen++; }
 }
 
 void fiber_entry() {
     (*g_body)();
     Fiber * f = g_cur;
     f->done = true; g_progress++;
-    g_alive--;
+    Block & b = g_blk[(size_t) f->blk];
+    b.alive--;
     Warp & w = g_warps[(size_t) linear_tid(f) >> 5];
     w.alive--;
     if (w.alive > 0 && w.arrived == w.alive) { w.arrived = 0; w.gen++; }
-    release_if_complete();
+    release_if_complete(b);
     yield();
     abort();   // a finished fiber is never resumed
 }
@@ -100,11 +106,30 @@ void warp_barrier() {
 }  // namespace
 
 void sync_block() {
-    const uint64_t gen = g_gen; g_progress++;
-    if (++g_arrived == g_alive) { g_arrived = 0; g_gen++; return; }
+    Block & b = g_blk[(size_t) g_cur->blk];
+    const uint64_t gen = b.gen; g_progress++;
+    if (++b.arrived == b.alive) { b.arrived = 0; b.gen++; return; }
+    const int lo = g_cur->blk * g_nt;
     int tries = 0;
-    while (g_gen == gen) wait_pass_on(0, (int) g_fibers.size(), tries);
+    while (b.gen == gen) wait_pass_on(lo, lo + g_nt, tries);
 }
+
+// bar.sync id, nthreads: the first `nthreads` arrivals at barrier `id` of this block release each other (which threads take part is the kernel's business)
+void named_bar(int id, int nthreads) {
+    if (id < 0 || id >= 16) { fprintf(stderr, "b2emu: named barrier %d\n", id); abort(); }
+    Block & b = g_blk[(size_t) g_cur->blk];
+    NamedBar & nb = b.nb[id];
+    const uint64_t gen = nb.gen; g_progress++;
+    if (++nb.arrived == nthreads) { nb.arrived = 0; nb.gen++; return; }
+    const int lo = g_cur->blk * g_nt;
+    int tries = 0;
+    while (nb.gen == gen) wait_pass_on(lo, lo + g_nt, tries);
+}
+
+// a thread that polls memory another thread will write (mbarrier phase, grid-barrier counter) gives the CPU away; writers call note_progress so that the
+// scheduler's deadlock detector can tell "everybody polls and nothing changes" from work in flight
+void yield_spin() { yield(); }
+void note_progress() { g_progress++; }
 
 uint64_t shfl(uint64_t v, int src_lane) {
     const int t = linear_tid(g_cur);
@@ -117,7 +142,7 @@ uint64_t shfl(uint64_t v, int src_lane) {
     return w.slot[buf][src_lane & 31];
 }
 
-void * dyn_smem() { return g_dyn.data(); }
+void * dyn_smem() { return g_blk[(size_t) g_cur->blk].dyn.data(); }
 
 void warp_exchange(const unsigned * mine, int nwords, unsigned * all) {
     if (nwords > 8) { fprintf(stderr, "b2emu: warp_exchange of %d words\n", nwords); abort(); }
@@ -136,36 +161,47 @@ namespace b2emu {
 static b2emu_graph * g_capture = nullptr;
 uint64_t g_replays = 0;
 
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body) {
+static void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body, bool coop) {
     if (g_cur) { fprintf(stderr, "b2emu: nested launch\n"); abort(); }
-    if (g_capture) { g_capture->nodes.push_back(Recorded{grid, block, smem, body}); return; }   // captured, not executed -- like a real stream capture
+    if (g_capture) { if (coop) { fprintf(stderr, "b2emu: cooperative launch during capture\n"); abort(); } g_capture->nodes.push_back(Recorded{grid, block, smem, body}); return; }   // captured, not executed -- like a real stream capture
     const int nt = (int) (block.x * block.y * block.z);
     if (nt <= 0 || nt > 1024) { fprintf(stderr, "b2emu: %d threads per block\n", nt); abort(); }
     if (smem > 227 * 1024) { fprintf(stderr, "b2emu: %zu bytes of dynamic shared memory\n", smem); abort(); }
+    const int nblocks = (int) (grid.x * grid.y * grid.z);
+    const int live_blocks = coop ? nblocks : 1;                     // blocks alive at once
+    if (coop && nt % 32) { fprintf(stderr, "b2emu: cooperative launch with %d threads per block\n", nt); abort(); }
     g_launches++;
-    g_body = &body; g_blockDim = block; g_gridDim = grid;
-    while ((int) g_stacks.size() < nt) g_stacks.push_back((char *) aligned_alloc(64, STACK));
-    g_fibers.assign((size_t) nt, Fiber{});
-    g_dyn.assign(smem + 64, 0);
-    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
-        g_blockIdx = dim3(bx, by, bz); g_blocks++;
-        g_alive = nt; g_arrived = 0;
-        g_warps.assign((size_t) (nt + 31) / 32, Warp{});
-        for (int t = 0; t < nt; t++) {
-            Fiber & f = g_fibers[(size_t) t];
-            f.tid = uint3{(unsigned) t % block.x, (unsigned) t / block.x % block.y, (unsigned) t / (block.x * block.y)};
-            f.done = false; f.stack = g_stacks[(size_t) t];
-            g_warps[(size_t) t >> 5].alive++;
-            void ** sp = (void **) (f.stack + STACK - 64);   // 6 callee-saved slots, then the entry address `ret` pops: rsp % 16 == 8 at entry
-            for (int i = 0; i < 6; i++) sp[i] = nullptr;
-            sp[6] = (void *) &fiber_entry; sp[7] = nullptr;
-            f.sp = sp;
+    g_body = &body; g_blockDim = block; g_gridDim = grid; g_nt = nt;
+    const int nf = nt * live_blocks;
+    while ((int) g_stacks.size() < nf) g_stacks.push_back((char *) aligned_alloc(64, STACK));
+    g_fibers.assign((size_t) nf, Fiber{});
+    g_blk.assign((size_t) live_blocks, Block{});
+    for (int first = 0; first < nblocks; first += live_blocks) {
+        g_warps.assign((size_t) (nf + 31) / 32, Warp{});
+        for (int lb = 0; lb < live_blocks; lb++) {
+            const int bi = first + lb;
+            const dim3 bidx((unsigned) bi % grid.x, (unsigned) bi / grid.x % grid.y, (unsigned) bi / (grid.x * grid.y));
+            g_blocks++;
+            Block & b = g_blk[(size_t) lb];
+            b.alive = nt; b.arrived = 0; b.gen = 0; b.dyn.assign(smem + 64, 0);
+            for (auto & nb : b.nb) nb = NamedBar{};
+            for (int t = 0; t < nt; t++) {
+                Fiber & f = g_fibers[(size_t) lb * nt + t];
+                f.tid = uint3{(unsigned) t % block.x, (unsigned) t / block.x % block.y, (unsigned) t / (block.x * block.y)};
+                f.bidx = bidx; f.blk = lb;
+                f.done = false; f.stack = g_stacks[(size_t) lb * nt + t];
+                g_warps[((size_t) lb * nt + t) >> 5].alive++;
+                void ** sp = (void **) (f.stack + STACK - 64);   // 6 callee-saved slots, then the entry address `ret` pops: rsp % 16 == 8 at entry
+                for (int i = 0; i < 6; i++) sp[i] = nullptr;
+                sp[6] = (void *) &fiber_entry; sp[7] = nullptr;
+                f.sp = sp;
+            }
         }
-        int live = nt;
+        int live = nf, stalls = 0;
         while (live > 0) {
             const uint64_t before = g_progress;
-            for (int tt = 0; tt < nt; tt++) {
-                const int t = g_reverse ? nt - 1 - tt : tt;
+            for (int tt = 0; tt < nf; tt++) {
+                const int t = g_reverse ? nf - 1 - tt : tt;
                 Fiber & f = g_fibers[(size_t) t];
                 if (f.done) continue;
                 g_cur = &f;
@@ -173,12 +209,19 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & bo
                 g_cur = nullptr;
             }
             live = 0;                                           // threads hand the CPU to each other directly, so any of them may have finished in this round
-            for (int t = 0; t < nt; t++) if (!g_fibers[(size_t) t].done) live++;
-            if (live > 0 && g_progress == before) { fprintf(stderr, "b2emu: deadlock -- %d threads of block (%u,%u,%u) wait at a barrier not all reach\n", live, bx, by, bz); abort(); }
+            for (int t = 0; t < nf; t++) if (!g_fibers[(size_t) t].done) live++;
+            stalls = (live > 0 && g_progress == before) ? stalls + 1 : 0;
+            if (stalls > (coop ? 4 : 0)) {
+                const Fiber & f0 = *std::find_if(g_fibers.begin(), g_fibers.end(), [](const Fiber & f) { return !f.done; });
+                fprintf(stderr, "b2emu: deadlock -- %d threads wait at a barrier not all reach (first: block (%u,%u,%u) thread %u)\n", live, f0.bidx.x, f0.bidx.y, f0.bidx.z, f0.tid.x);
+                abort();
+            }
         }
     }
     g_body = nullptr;
 }
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body) { launch_impl(grid, block, smem, body, false); }
+void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body) { launch_impl(grid, block, smem, body, true); }
 
 }  // namespace b2emu
 

@@ -36,6 +36,7 @@ struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(8) uint2 { unsigned x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorUnknown = 999 };
@@ -78,19 +79,23 @@ cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e);
 cudaError_t cudaGraphDestroy(cudaGraph_t g);
 
 namespace b2emu {
-struct Fiber { uint3 tid; void * sp; char * stack; bool done; };
+struct Fiber { uint3 tid; void * sp; char * stack; bool done; dim3 bidx; int blk; };     // bidx: blockIdx of the thread's block; blk: its slot among the blocks alive at once
 extern Fiber * g_cur;
-extern dim3 g_blockIdx, g_blockDim, g_gridDim;
+extern dim3 g_blockDim, g_gridDim;
 extern uint64_t g_launches, g_blocks, g_replays;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body);
+void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()> & body);   // every block of the grid alive at once (cudaLaunchCooperativeKernel)
 void sync_block();
+void named_bar(int id, int nthreads);      // bar.sync id, nthreads
+void yield_spin();                         // inside a polling loop on memory another thread writes
+void note_progress();                      // by the writer of such memory
 uint64_t shfl(uint64_t v, int src_lane);   // every live lane of the warp calls it; returns the value lane src_lane passed
 void * dyn_smem();
 void warp_exchange(const unsigned * mine, int nwords, unsigned * all /* [32][nwords] */);   // every live lane publishes nwords and receives the whole warp's
 }  // namespace b2emu
 
 #define threadIdx (b2emu::g_cur->tid)
-#define blockIdx  (b2emu::g_blockIdx)
+#define blockIdx  (b2emu::g_cur->bidx)
 #define blockDim  (b2emu::g_blockDim)
 #define gridDim   (b2emu::g_gridDim)
 
@@ -116,9 +121,11 @@ static inline int __dp4a(int a, int b, int c) { for (int i = 0; i < 4; i++) c +=
 static inline unsigned __vsub4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i); return r; }
 static inline int __float2int_rn(float x) { return (int) nearbyintf(x); }      // round-to-nearest-even (the default rounding mode)
 // fibers are cooperative (a thread runs until its next barrier / shuffle), so a read-modify-write is atomic as it stands
-static inline unsigned atomicAdd(unsigned * p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
-static inline int atomicAdd(int * p, int v) { const int o = *p; *p = o + v; return o; }
+static inline unsigned atomicAdd(unsigned * p, unsigned v) { const unsigned o = *p; *p = o + v; b2emu::note_progress(); return o; }
+static inline int atomicAdd(int * p, int v) { const int o = *p; *p = o + v; b2emu::note_progress(); return o; }
+static inline void __threadfence() {}
+template <class T> static inline T __ldcg(const T * p) { return *p; }
+template <class T> static inline void __stcg(T * p, T v) { *p = v; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
-static inline float __ldg(const float * p) { return *p; }
-static inline int __ldg(const int * p) { return *p; }
+template <class T> static inline T __ldg(const T * p) { return *p; }

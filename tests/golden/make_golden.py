@@ -185,23 +185,25 @@ def orpheus_vectors(wide: bool = False):
     print("orpheus wide vectors:" if wide else "orpheus vectors:", {k: v.shape for k, v in out.items()})
 
 
-def parler_vectors(f16: bool = False, quant: str | None = None):
-    from tts_cpp_b200.synth import cached_parler_gguf
-    gguf = cached_parler_gguf(seed=0, f16=f16, quant=quant)
+def parler_vectors(f16: bool = False, quant: str | None = None, mini: bool = False):
+    """mini: BASELINE config 3's model size (Parler-TTS-Mini-shaped F16 decoder: 24 layers x 1024, 16 heads x 64, ffn 4096), two prompts of 24 / 13 ids, 24 greedy
+    frames -- the reference's tokens and logits at the size the benchmark runs (parler_mini_vectors.npz)."""
+    from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_parler_gguf
+    gguf = cached_parler_gguf(seed=0, f16=f16, quant=quant, **(PARLER_MINI_SHAPE if mini else {}))
     rng = np.random.default_rng(7)
-    prompts = [rng.integers(1, 500, size=n) for n in (5, 9)]
+    prompts = [rng.integers(1, 500, size=n) for n in ((24, 13) if mini else (5, 9))]
     tmp = tempfile.mkdtemp()
     pf = os.path.join(tmp, "prompts.txt")
     open(pf, "w").write("\n".join(" ".join(map(str, q)) for q in prompts) + "\n")
     pre = os.path.join(tmp, "p")
-    steps = 5
+    steps = 24 if mini else 5
     run([os.path.join(REF, "parler_ref"), gguf, pf, pre, "--steps", str(steps), "--threads", "4", "--quiet"])
     out = {}
     for u, q in enumerate(prompts):
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(steps, 9)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, 9, -1)
-    tag = f"_{quant.lower()}" if quant else ("_f16" if f16 else "")
+    tag = "_mini" if mini else (f"_{quant.lower()}" if quant else ("_f16" if f16 else ""))
     np.savez_compressed(os.path.join(OUT, f"parler{tag}_vectors.npz"), **out)
     print(f"parler{tag} vectors:", {k: v.shape for k, v in out.items()})
 
@@ -321,6 +323,7 @@ if __name__ == "__main__":
     if "sampler" in which: sampler_vectors()
     if "orpheus_wide" in which: orpheus_vectors(wide=True)
     if "parler_f16" in which: parler_vectors(f16=True)
+    if "parler_mini" in which: parler_vectors(f16=True, mini=True)      # (not in the default list: ~2 minutes of CPU and a 1.5 GB GGUF)
     for q in ("Q8_0", "Q5_0", "Q4_0"):
         if f"parler_{q.lower()}" in which: parler_vectors(quant=q)
     if "dia_f16" in which: dia_vectors(f16=True)

@@ -1,55 +1,102 @@
 """GPU: the Dia decode loop (tts_cpp_b200/csrc/dia.cu) against the token ids and logits the compiled UNMODIFIED reference produced
-(tests/golden/dia_vectors.npz: two byte-token prompts, 5 greedy frames of 9 codebooks each with the CFG-combined logits, small synthetic Dia GGUF).
+(tests/golden/dia*_vectors.npz: two byte-token prompts, 5 greedy frames of 9 codebooks each with the CFG-combined logits, small synthetic Dia GGUFs).
 
-Written after round 1's GPU budget was spent: never run on a B200 (its logic is checked under the CPU emulation, tests/test_emu_cpu.py), hence
-xfail(strict=False) and a CHILD PROCESS, so that a fault in an unvalidated kernel cannot poison the CUDA context of the tests that follow.
-Round 2 removes both once it has passed on hardware.
-
-Update (end of round 1): the default greedy path ran on a B200 through scripts/rowb_first_contact.py and reproduced the reference's tokens (profiles/
-r1i_rowb_first_contact.log); its test below is a plain test now, the variants that have not run yet keep xfail(strict=False) (UNRUN)."""
-import os
-import subprocess
-import sys
-
+F32: free-running tokens bit-exact, logits 2e-2.  F16 (BASELINE config 4's dtype): every F16 product rounds its activations to fp16, Dia's softmax has no 1/sqrt(d)
+and cfg_scale multiplies the difference of two passes by 4, so rounding-boundary flips reach 0.1-0.6 in the logits (std 12-14) between two correct implementations --
+the reference's own F16 and F32 builds differ by 0.03-0.19 RMS.  On a B200 (gpurun_out/r2a/dia_triage_*.log; compute-sanitizer memcheck and racecheck clean) the one
+token that differs from the reference (prompt 1, step 2, head 7) sits on a reference top-2 gap of 0.099 with a logit difference of 0.19 at that step.  So F16 parity is
+TEACHER-FORCED with a decision-margin rule: logits within 0.15 RMS / 1.0 max at every step and identical tokens wherever the reference's top-2 gap exceeds twice
+that step's largest logit difference; free-running, the tokens must be identical up to the first such near-tie.  The per-step margins are printed (TIE-MARGIN lines)."""
 import pytest
 
-pytestmark = pytest.mark.gpu
-# the F32 model on the default path (fused launches) has run on a B200 (profiles/r1i_rowb_first_contact.log: reference tokens, logits 3.5e-3); the other variants have not
-UNRUN = pytest.mark.xfail(strict=False, reason="this variant of the Dia decode path has not run on a B200 yet (round 1 GPU budget exhausted)")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from conftest import run_snippet
 
-CHILD = r'''
+pytestmark = pytest.mark.gpu
+
+BODY = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from conftest import tie_report
+from tts_cpp_b200.binding import dia_runner_from_file
+from tts_cpp_b200.synth import cached_dia_gguf
+f16 = sys.argv[2] == "f16"
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "dia_f16_vectors.npz" if f16 else "dia_vectors.npz"))
+dia = dia_runner_from_file(cached_dia_gguf(seed=0, f16=f16))
+prompts = [g["prompt0"], g["prompt1"]]
+steps = g["tokens0"].shape[0]
+toks, ngen, logits = dia.generate_greedy(prompts, steps, want_logits=True)           # one ragged batch of both prompts
+ok = True
+if not f16:
+    for u in range(2):
+        d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
+        print(f"PARITY dia f32 prompt {u}: tokens {'EQUAL' if np.array_equal(toks[u], g[f'tokens{u}']) else 'DIFFER'}  max |logit diff| {d:.3e}")
+        tie_report(f"dia f32 prompt {u}", g[f"logits{u}"], g[f"tokens{u}"], logits[u], toks[u])
+        ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < 2e-2           # bit-exact ids at temperature 0; logits: CFG multiplies summation noise by 4 at std ~13
+else:
+    tf_t, tf_l = dia.generate_teacher_forced(prompts, np.stack([g["tokens0"], g["tokens1"]]))
+    for u in range(2):
+        rl, rt = g[f"logits{u}"], g[f"tokens{u}"]
+        rms = np.sqrt(((tf_l[u] - rl) ** 2).mean(axis=(1, 2)))
+        mx = np.abs(tf_l[u] - rl).max(axis=(1, 2))
+        print(f"PARITY dia f16 prompt {u} teacher-forced: per-step logit rms {np.round(rms, 4).tolist()} max {np.round(mx, 3).tolist()}; tokens equal {int((tf_t[u] == rt).sum())}/{rt.size}")
+        ok &= float(rms.max()) < 0.15 and float(mx.max()) < 1.0
+        ok &= tie_report(f"dia f16 prompt {u} (teacher-forced)", rl, rt, tf_l[u], tf_t[u])       # clear decisions must agree
+        # free-running: identical until the first step that holds a near-tie (reference gap below twice the step's logit difference); after it the streams may part ways
+        top2 = np.sort(rl, axis=-1)[..., -2:]
+        gap = (top2[..., 1] - top2[..., 0]).min(axis=1)
+        first_tie = next((s for s in range(steps) if gap[s] <= 2.0 * mx[s]), steps)
+        same = bool(np.array_equal(toks[u][:first_tie], rt[:first_tie]))
+        print(f"PARITY dia f16 prompt {u} free-running: identical through step {first_tie - 1} (first near-tie at step {first_tie}): {same}; all {steps} steps equal: {bool(np.array_equal(toks[u], rt))}")
+        ok &= same
+single, _ = dia.generate_greedy([prompts[1]], steps)
+ok &= bool(np.array_equal(single[0], toks[1])) and bool((ngen == steps).all())                                   # batching does not change a sequence
+dia.close()
+sys.exit(0 if ok else 1)
+'''
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_dia_tokens_and_logits_match_reference(dtype):
+    assert run_snippet(BODY, [dtype]) == 0
+
+
+def test_dia_f16_plain_kernels_match_reference():
+    """the same F16 check on the plain CUDA-core GEMV with direct launches (B2TTS_AR_MMA=0, B2TTS_AR_GRAPH=0): the rounding model, not the kernel family, sets the margins"""
+    assert run_snippet(BODY, ["f16"], env={"B2TTS_AR_MMA": "0", "B2TTS_AR_GRAPH": "0"}) == 0
+
+
+STOP_BODY = r'''
 import os, sys
 import numpy as np
 sys.path.insert(0, sys.argv[1])
 from tts_cpp_b200.binding import dia_runner_from_file
 from tts_cpp_b200.synth import cached_dia_gguf
-f16 = sys.argv[2] == "f16"
-g = np.load(os.path.join(sys.argv[1], "tests", "golden", "dia_f16_vectors.npz" if f16 else "dia_vectors.npz"))
-par = dia_runner_from_file(cached_dia_gguf(seed=0, f16=f16))
-prompts = [g["prompt0"], g["prompt1"]]
-steps = g["tokens0"].shape[0]
-toks, ngen, logits = par.generate_greedy(prompts, steps, want_logits=True)           # one ragged batch of both prompts
-ok = True
-for u in range(2):
-    d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
-    print(f"PARITY dia prompt {u}: tokens {toks[u].tolist()}  max |logit diff| {d:.3e}")
-    ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < (1.0 if f16 else 2e-2)   # bit-exact ids at temperature 0; logits: CFG multiplies summation noise by 4 at std ~13 (f16: + rounding-boundary flips)
-single, _ = par.generate_greedy([prompts[1]], steps)
-ok &= bool(np.array_equal(single[0], toks[1])) and bool((ngen == steps).all())                                   # batching does not change a sequence
-sys.exit(0 if ok else 1)
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "dia_stop_vectors.npz"))
+dia = dia_runner_from_file(cached_dia_gguf(seed=0))
+ref = g["tokens0"]
+cap = int(g["step_cap"])
+for logits_too in (True, False):                                               # without logits the CUDA graph of a step is replayed and the stop flags are polled every 32 steps
+    out = dia.generate_greedy([g["prompt0"]], cap, want_logits=logits_too)
+    toks, ngen = out[0], out[1]
+    good = int(ngen[0]) == ref.shape[0] and bool(np.array_equal(toks[0, :ref.shape[0]], ref)) and not toks[0, ref.shape[0]:].any()
+    if logits_too:
+        d = float(np.abs(out[2][0, ref.shape[0] - 1].reshape(-1) - g["logits_last0"].reshape(-1)).max())
+        good = good and d < 2e-2 and not out[2][0, ref.shape[0]:].any()
+    print(f"PARITY dia check_stopping (logits {logits_too}): frames {int(ngen[0])} vs {ref.shape[0]} ->", good)
+    if not good: sys.exit(1)
+dia.close()
+sys.exit(0)
 '''
 
 
-@pytest.mark.parametrize("dtype", ["f32", pytest.param("f16", marks=UNRUN)])
-def test_dia_greedy_tokens_and_logits_match_reference(dtype):
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=150)
-    print(r.stdout[-2000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
+def test_dia_check_stopping_matches_reference():
+    """check_stopping (EOS on channel 0 -> the delay pattern's 15-step flush with EOS / PAD injection; reference src/models/dia/model.cpp:806-823) on the device against
+    the reference run to completion (tests/golden/dia_stop_vectors.npz: 63 frames)."""
+    assert run_snippet(STOP_BODY, []) == 0
 
 
-QUANT_CHILD = r'''
+QUANT_BODY = r'''
 import os, sys
 import numpy as np
 sys.path.insert(0, sys.argv[1])
@@ -64,14 +111,11 @@ for u in range(2):
     agree = float((toks[u] == g[f"tokens{u}"]).mean())
     print(f"PARITY dia Q8_0 prompt {u}: per-step logit rms {np.round(rms, 3).tolist()}, tokens equal {agree:.2f}")
     ok &= float(rms.max()) < 4.0 and agree >= 0.8
+dia.close()
 sys.exit(0 if ok else 1)
 '''
 
 
-@UNRUN
 def test_dia_quantised_teacher_forced():
     """Q8_0 matrices (gemv_rows_q_kernel), teacher-forced on the reference's tokens; smoke-level bar (Dia amplifies re-quantisation noise: see tests/test_emu_cpu.py)."""
-    r = subprocess.run([sys.executable, "-c", QUANT_CHILD, ROOT], capture_output=True, text=True, timeout=150)
-    print(r.stdout[-2000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
+    assert run_snippet(QUANT_BODY, []) == 0

@@ -442,3 +442,58 @@ def test_address_sanitizer_emulated(tmp_path, case):
                        env=dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0", **env))
     assert r.returncode == 0, r.stderr[-3000:]
     assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr
+
+
+# ---- the persistent decode kernel (tts_cpp_b200/csrc/pdk.cuh): one cooperative launch runs up to 32 decode steps; under emulation every block of the grid is alive at
+# once (b2emu::launch_coop), mbarriers / bulk copies / the grid barrier have functional models.  F16 Parler GGUFs take this path by default (B2TTS_AR_PDK=0: per-op path).
+@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "1"}, {"B2TTS_PDK_GRID": "3", "B2TTS_AR_EXIT_EVERY": "2"}, {"B2TTS_PDK_GRID": "5", "B2EMU_REVERSE": "1"},
+                                 {"B2TTS_PDK_GRID": "7", "B2TTS_AR_EXIT_EVERY": "1", "B2TTS_KV": "f32"}], ids=["grid1", "grid3_chunks_of_2", "grid5_reversed", "grid7_kv_f32_chunks_of_1"])
+def test_persistent_decode_kernel_emulated_matches_reference(tmp_path, env):
+    """the reference's F16 tokens and logits (tests/golden/parler_f16_vectors.npz) from the persistent kernel with its paged fp16 (or fp32) KV cache, for several grid sizes
+    (different unit -> CTA distributions; grid 1 = no concurrency), several launches per generation (step counter / ring / page state carried across launches) and both
+    fiber schedules; the run must really have gone through the persistent kernel (launch count)."""
+    g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    tok, logits, err = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "pk", env=env, want_stderr=True)
+    _, _, err0 = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "op", env={"B2TTS_AR_PDK": "0"}, want_stderr=True)
+    n_pk, n_op = (int(e.split("emulated ")[1].split(" launches")[0]) for e in (err, err0))
+    assert n_pk < n_op - (steps - 1) * 50, (n_pk, n_op)          # the per-op path launches ~126 kernels per step of the 8-layer test model
+    for u in range(2):
+        ref = g[f"logits{u}"].reshape(steps, -1)
+        d = float(np.abs(logits[u] - ref).max())
+        print(f"PARITY(emulated, persistent kernel {env}) parler f16 prompt {u}: max |logit diff| {d:.3e}")
+        assert np.array_equal(tok[u], g[f"tokens{u}"])
+        assert d < 3e-2
+
+
+def test_persistent_decode_kernel_emulated_stop_rule_and_teacher(tmp_path):
+    """the delay pattern's stop bookkeeping (eos_seen, check_stopping) and teacher forcing inside the persistent kernel against the per-op path on an EOS-boosted F16 GGUF:
+    same tokens, same frame count, zero rows past the stop; teacher-forced: same tokens, logits within the F16 floor."""
+    g = np.load(os.path.join(GOLD, "parler_stop_vectors.npz"))
+    prompt, boost = g["all_eos.prompt"], float(g["all_eos.boost"])
+    cap = int(g["all_eos.tokens"].shape[0]) + 6
+    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
+    gguf = cached_parler_gguf(seed=0, eos_boost=boost, f16=True)
+    outs = {}
+    for tag, env in (("pk", {"B2TTS_PDK_GRID": "3"}), ("op", {"B2TTS_AR_PDK": "0"})):
+        pin, pout = str(tmp_path / f"p{tag}.bin"), str(tmp_path / f"o{tag}.bin")
+        with open(pin, "wb") as f:
+            f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompt.size)); f.write(prompt.astype(np.uint32).tobytes())
+        r = subprocess.run([exe, "parler", gguf, pin, pout], capture_output=True, text=True, timeout=900, env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1", B2TTS_AR_EXIT_EVERY="4", **env))
+        assert r.returncode == 0, r.stderr[-2000:]
+        raw = open(pout, "rb").read()
+        W, V = struct.unpack("ii", raw[:8])
+        outs[tag] = (np.frombuffer(raw, np.int32, cap * W, 8).reshape(cap, W), int(np.frombuffer(raw[-4:], np.int32)[0]))
+    assert outs["pk"][1] == outs["op"][1] and 0 < outs["pk"][1] < cap, (outs["pk"][1], outs["op"][1])
+    assert np.array_equal(outs["pk"][0], outs["op"][0]) and not outs["pk"][0][outs["pk"][1]:].any()
+    # teacher-forced on the reference's F16 tokens
+    g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].shape[0])
+    tf = str(tmp_path / "teacher.bin")
+    np.stack([g["tokens0"], g["tokens1"]]).astype(np.int32).tofile(tf)
+    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "tf", env={"B2EMU_TEACHER": tf, "B2TTS_PDK_GRID": "4"})
+    for u in range(2):
+        assert np.array_equal(tok[u], g[f"tokens{u}"])
+        assert float(np.abs(logits[u] - g[f"logits{u}"].reshape(steps, -1)).max()) < 3e-2

@@ -108,8 +108,8 @@ def test_stagewise_teacher_forced(runner, port):
         assert np.array_equal(durs[b], lens)
         # PCM given identical generator inputs up to stage 0: the north-star tolerance
         dp = rms(pcms[b] - ppcm)
-        print(f"u{b} teacher-forced PCM diff rms = {dp:.3g} (target 1e-4)")
-        assert dp < 1e-3
+        print(f"u{b} teacher-forced PCM diff rms = {dp:.3g} vs the PORT (itself 8.6e-5 from the reference; CUDA vs the reference directly: 1e-4 asserted in test_golden_gpu / test_bench_size_gpu)")
+        assert dp < 2e-4
     print("WORST", worst)
 
 

@@ -1,30 +1,24 @@
-"""GPU: the Parler decode loop (tts_cpp_b200/csrc/parler.cu) against the token ids and logits the compiled UNMODIFIED reference produced
-(tests/golden/parler_vectors.npz: two prompts, 5 greedy frames of 9 codebooks each, small synthetic Parler GGUF).
+"""GPU: the Parler decode loop (tts_cpp_b200/csrc/parler.cu, pdk.cuh) against the token ids and logits the compiled UNMODIFIED reference produced
+(tests/golden/parler*_vectors.npz: two prompts, 5 greedy frames of 9 codebooks each, small synthetic Parler GGUFs in F32 / F16 / Q8_0 / Q5_0 / Q4_0).
 
-Written after round 1's GPU budget was spent: never run on a B200 (its logic is checked under the CPU emulation, tests/test_emu_cpu.py), hence
-xfail(strict=False) and a CHILD PROCESS, so that a fault in an unvalidated kernel cannot poison the CUDA context of the tests that follow.
-Round 2 removes both once it has passed on hardware.
-
-Update (end of round 1): the default greedy path ran on a B200 through scripts/rowb_first_contact.py and reproduced the reference's tokens (profiles/
-r1i_rowb_first_contact.log); its test below is a plain test now, the variants that have not run yet keep xfail(strict=False) (UNRUN)."""
-import os
-import subprocess
-import sys
-
+Paths: F16 GGUFs take the PERSISTENT DECODE KERNEL (one cooperative launch per 32 steps, paged fp16 KV cache) by default; F32 and block-quantised GGUFs, sampling and
+batches above 16 take the launch-per-op path (CUDA-graph replay, tensor-core GEMV for F16 matrices).  Every variant below has passed on a B200 (gpurun_out/r2a, r2b):
+plain tests.  A variant that needs a different B2TTS_* switch than the default runs in a child process (the library reads its switches once per process)."""
 import pytest
 
-pytestmark = pytest.mark.gpu
-# the F32 model on the default path (fused launches) has run on a B200 (profiles/r1i_rowb_first_contact.log: reference tokens, logits 1.5e-3); the other variants have not
-UNRUN = pytest.mark.xfail(strict=False, reason="this variant of the Parler decode path has not run on a B200 yet (round 1 GPU budget exhausted)")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from conftest import run_snippet
 
-CHILD = r'''
+pytestmark = pytest.mark.gpu
+
+BODY = r'''
 import os, sys
 import numpy as np
-sys.path.insert(0, sys.argv[1])
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from conftest import tie_report
 from tts_cpp_b200.binding import parler_runner_from_file
 from tts_cpp_b200.synth import cached_parler_gguf
 f16 = sys.argv[2] == "f16"
+want_pdk = sys.argv[3] == "pdk"
 g = np.load(os.path.join(sys.argv[1], "tests", "golden", "parler_f16_vectors.npz" if f16 else "parler_vectors.npz"))
 par = parler_runner_from_file(cached_parler_gguf(seed=0, f16=f16))
 prompts = [g["prompt0"], g["prompt1"]]
@@ -33,35 +27,30 @@ toks, logits = par.generate_greedy(prompts, steps, want_logits=True)           #
 ok = True
 for u in range(2):
     d = float(np.abs(logits[u] - g[f"logits{u}"]).max())
-    print(f"PARITY parler prompt {u}: tokens {toks[u].tolist()}  max |logit diff| {d:.3e}")
+    print(f"PARITY parler {'f16' if f16 else 'f32'} prompt {u}: tokens {'EQUAL' if np.array_equal(toks[u], g[f'tokens{u}']) else 'DIFFER'}  max |logit diff| {d:.3e}")
+    tie_report(f"parler prompt {u}", g[f"logits{u}"], g[f"tokens{u}"], logits[u], toks[u])
     ok &= bool(np.array_equal(toks[u], g[f"tokens{u}"])) and d < (3e-2 if f16 else 1e-2)   # bit-exact ids at temperature 0; logits: ggml's fp16 GELU table (+ fp16 activation rounding for F16 weights)
-single = par.generate_greedy([prompts[1]], steps)
+single = par.generate_greedy([prompts[1]], steps)                              # (no logits: the launch-per-op path replays its CUDA graph here)
 ok &= bool(np.array_equal(single[0], toks[1]))                                   # batching does not change a sequence
+launches, psteps = par.pdk_stats()
+print("persistent-kernel launches / steps:", launches, psteps)
+ok &= (psteps == 2 * steps) if want_pdk else (psteps == 0)                      # the path this variant is about is the one that ran
+par.close()
 sys.exit(0 if ok else 1)
 '''
 
 
-@pytest.mark.parametrize("dtype", ["f32", pytest.param("f16", marks=UNRUN)])
-def test_parler_greedy_tokens_and_logits_match_reference(dtype):
-    """f16: the GGUF `quantize --quantized-type F16` writes (decoder matrices F16, activations rounded to fp16 before each such product).  Two runs
-    of that model that differ only in summation order already differ by 1.5e-3 RMS / 6e-3 max in the logits (rounding boundaries), so the bar there
-    is identical token ids + 3e-2."""
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, dtype], capture_output=True, text=True, timeout=150)
-    print(r.stdout[-2000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
+@pytest.mark.parametrize("variant", ["f32", "f16_persistent_kernel", "f16_persistent_kernel_kv_f32", "f16_persistent_kernel_small_grid_chunks_of_2", "f16_per_op_tensor_core", "f16_per_op_plain"])
+def test_parler_greedy_tokens_and_logits_match_reference(variant):
+    """f16: the GGUF `quantize --quantized-type F16` writes (decoder matrices F16, activations rounded to fp16 before each such product).  Two runs of that model that
+    differ only in summation order already differ by 1.5e-3 RMS / 6e-3 max in the logits (rounding boundaries), so the bar there is identical token ids + 3e-2."""
+    env = {"f32": None, "f16_persistent_kernel": None, "f16_persistent_kernel_kv_f32": {"B2TTS_KV": "f32"},
+           "f16_persistent_kernel_small_grid_chunks_of_2": {"B2TTS_PDK_GRID": "37", "B2TTS_AR_EXIT_EVERY": "2"},
+           "f16_per_op_tensor_core": {"B2TTS_AR_PDK": "0"}, "f16_per_op_plain": {"B2TTS_AR_PDK": "0", "B2TTS_AR_MMA": "0", "B2TTS_AR_GRAPH": "0"}}[variant]
+    assert run_snippet(BODY, ["f32" if variant == "f32" else "f16", "pdk" if "persistent" in variant else "ops"], env=env) == 0
 
 
-@UNRUN
-def test_parler_tensor_core_gemv_f16_matches_reference_tokens():
-    """B2TTS_AR_MMA=1: the F16 matrices through gemv_mma_kernel<false> (mma.sync with the batch as M) -- same token ids as the F16 reference."""
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, "f16"], capture_output=True, text=True, timeout=150, env=dict(os.environ, B2TTS_AR_MMA="1"))
-    print(r.stdout[-2000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
-
-
-STOP_CHILD = r'''
+STOP_BODY = r'''
 import os, sys
 import numpy as np
 sys.path.insert(0, sys.argv[1])
@@ -69,28 +58,42 @@ from tts_cpp_b200.binding import parler_runner_from_file
 from tts_cpp_b200.synth import cached_parler_gguf
 g = np.load(os.path.join(sys.argv[1], "tests", "golden", "parler_stop_vectors.npz"))
 ok = True
-for case in ("all_eos", "max_generation"):
-    par = parler_runner_from_file(cached_parler_gguf(seed=0, eos_boost=float(g[f"{case}.boost"])))
-    ref = g[f"{case}.tokens"]
-    toks, ngen = par.generate([g[f"{case}.prompt"]], int(g["step_cap"]))            # greedy, with the reference's stop rule
-    good = int(ngen[0]) == ref.shape[0] and bool(np.array_equal(toks[0, :ref.shape[0]], ref)) and not toks[0, ref.shape[0]:].any()
-    print(f"PARITY parler stop rule {case}: frames {int(ngen[0])} vs {ref.shape[0]} ->", good)
-    ok &= good
+if sys.argv[2] == "reference":
+    for case in ("all_eos", "max_generation"):
+        par = parler_runner_from_file(cached_parler_gguf(seed=0, eos_boost=float(g[f"{case}.boost"])))
+        ref = g[f"{case}.tokens"]
+        toks, ngen = par.generate([g[f"{case}.prompt"]], int(g["step_cap"]))            # greedy, with the reference's stop rule
+        good = int(ngen[0]) == ref.shape[0] and bool(np.array_equal(toks[0, :ref.shape[0]], ref)) and not toks[0, ref.shape[0]:].any()
+        print(f"PARITY parler stop rule {case}: frames {int(ngen[0])} vs {ref.shape[0]} ->", good)
+        ok &= good
+        par.close()
+else:                                                                           # the same bookkeeping inside the persistent kernel (F16 GGUF) against the per-op path's dump
+    par = parler_runner_from_file(cached_parler_gguf(seed=0, eos_boost=float(g["all_eos.boost"]), f16=True))
+    toks, ngen = par.generate([g["all_eos.prompt"], g["max_generation.prompt"][:9]], int(g["step_cap"]))
+    print("frames", ngen.tolist(), "pdk", par.pdk_stats())
+    if sys.argv[2] == "dump":
+        np.savez(sys.argv[3], toks=toks, ngen=ngen)
+    else:
+        want = np.load(sys.argv[3])
+        ok &= par.pdk_stats()[1] > 0 and bool(np.array_equal(toks, want["toks"])) and bool(np.array_equal(ngen, want["ngen"])) and bool((ngen < int(g["step_cap"])).any())
     par.close()
 sys.exit(0 if ok else 1)
 '''
 
 
-@UNRUN
 def test_parler_stop_rule_matches_reference():
-    """eos_seen feeding + check_stopping on the device against the reference run to completion (tests/golden/parler_stop_vectors.npz)."""
-    r = subprocess.run([sys.executable, "-c", STOP_CHILD, ROOT], capture_output=True, text=True, timeout=150)
-    print(r.stdout[-2000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
+    """eos_seen feeding + check_stopping on the device against the reference run to completion (tests/golden/parler_stop_vectors.npz; F32 GGUF: launch-per-op path)."""
+    assert run_snippet(STOP_BODY, ["reference"]) == 0
 
 
-QUANT_CHILD = r'''
+def test_parler_stop_rule_inside_persistent_kernel(tmp_path):
+    """the same stop bookkeeping inside the persistent kernel (EOS-boosted F16 GGUF, two sequences, early exit between launches) = the launch-per-op path's result."""
+    f = str(tmp_path / "ops.npz")
+    assert run_snippet(STOP_BODY, ["dump", f], env={"B2TTS_AR_PDK": "0"}) == 0
+    assert run_snippet(STOP_BODY, ["check", f]) == 0
+
+
+QUANT_BODY = r'''
 import os, sys
 import numpy as np
 sys.path.insert(0, sys.argv[1])
@@ -110,16 +113,13 @@ for u in range(2):
     clear = (top2[:, :, 1] - top2[:, :, 0]) > 0.5
     print(f"PARITY parler {quant} prompt {u}: per-step logit rms {np.round(rms, 4).tolist()}, tokens equal {int((toks[u] == ref_t).sum())}/{ref_t.size}")
     ok &= float(rms.max()) < 0.1 and bool(np.array_equal(toks[u][clear], ref_t[clear]))
+par.close()
 sys.exit(0 if ok else 1)
 '''
 
 
-@UNRUN
 @pytest.mark.parametrize("quant", ["Q8_0", "Q5_0", "Q4_0"])
 def test_parler_quantised_teacher_forced(quant):
     """Block-quantised decoder matrices (gemv_rows_q_kernel), teacher-forced on the reference's tokens: logits within 0.1 RMS at every step, the same token wherever
     the reference's top-2 gap exceeds 0.5 (two correct implementations differ by ~0.04 RMS here: activation re-quantisation amplifies summation-order noise)."""
-    r = subprocess.run([sys.executable, "-c", QUANT_CHILD, ROOT, quant], capture_output=True, text=True, timeout=150)
-    print(r.stdout[-2000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
+    assert run_snippet(QUANT_BODY, [quant]) == 0

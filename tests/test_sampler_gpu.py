@@ -2,15 +2,12 @@
 reference sampler stage by stage and by a histogram of its draws (tests/test_oracle_port.py).  The port is fed the uniforms the kernel derives from
 (seed, row, step): tokens and repetition state must be identical over consecutive steps.
 
-Written after round 1's GPU budget was spent (logic checked under tests/emu): xfail(strict=False) in a child process until it has run on a B200."""
-import os
-import subprocess
-import sys
-
+Passed on a B200 (GPUTEST_r01, gpurun_out/r2a), including the 156 940-wide rows: a plain in-process test."""
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="sampler kernel not yet run on a B200 (round 1 GPU budget exhausted)")]
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from conftest import run_snippet
+
+pytestmark = pytest.mark.gpu
 
 CHILD = r'''
 import ctypes as C, os, sys
@@ -58,7 +55,4 @@ sys.exit(0 if ok else 1)
 
 @pytest.mark.parametrize("shape", ["small", "wide"])
 def test_sampler_matches_port_over_steps(shape):
-    r = subprocess.run([sys.executable, "-c", CHILD, ROOT, shape], capture_output=True, text=True, timeout=150)
-    print(r.stdout[-3000:])
-    print(r.stderr[-2000:])
-    assert r.returncode == 0
+    assert run_snippet(CHILD, [shape]) == 0

@@ -445,6 +445,17 @@ class ParlerRunner:
         lib().b2tts_parler_weight_bytes.restype = C.c_size_t
         return int(lib().b2tts_parler_weight_bytes(self.h))
 
+    def step_weight_bytes(self) -> int:
+        """W_step: bytes of the weight tensors one decode step touches, each once"""
+        lib().b2tts_parler_step_weight_bytes.restype = C.c_size_t
+        return int(lib().b2tts_parler_step_weight_bytes(self.h))
+
+    def pdk_stats(self):
+        """-> (launches of the persistent decode kernel, decode steps they covered)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().b2tts_parler_pdk_stats(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def close(self):
         if self.h:
             lib().b2tts_parler_free(self.h)

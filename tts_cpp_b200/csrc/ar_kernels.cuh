@@ -291,8 +291,10 @@ static inline bool gemv_mma_ok(int K, int N, int R) { (void) R; return K % 256 =
 // MT = m16 tiles per block (batch rows / 16): the weight fragment of a k-step is reused for all of them, so a batch of 64 still streams W once
 static inline int gemv_mma_kc(int K, int mt) { const int kc = GM_KC / mt; return K < kc ? K : kc; }
 static inline size_t gemv_mma_smem(int K, bool split, int mt) { return (size_t) 16 * mt * (gemv_mma_kc(K, mt) + GM_PAD) * 2 * (split ? 2 : 1) + (size_t) 8 * 16 * mt * 8 * 4; }
-// off until it has run on hardware (B2TTS_AR_MMA=1 turns it on): the plain kernels are the emulation- and (from round 2) GPU-checked baseline
-static inline bool gemv_mma_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_MMA"); return e && e[0] == '1'; }(); return on; }
+// F16 matrices: on by default since it reproduced the reference's tokens on a B200 (round 2: 9.0 -> 4.0 ms per Parler-Mini step); B2TTS_AR_MMA=0 selects the plain kernels.
+// The split (fp32-faithful) form for F32 matrices (Orpheus) doubles the resident weight bytes and stays opt-in: B2TTS_AR_MMA=1.
+static inline bool gemv_mma_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_MMA"); return !(e && e[0] == '0'); }(); return on; }
+static inline bool gemv_split_mma_enabled() { static const bool on = [] { const char * e = getenv("B2TTS_AR_MMA"); return e && e[0] == '1'; }(); return on; }
 
 // D k-steps of 32: all D weight loads are issued before the first mma so that a lane keeps D x 16 B (SPLIT: 2 x D x 16 B) of the weight stream in flight
 // (read once: streaming hint).  SPLIT: the fp32-faithful product of an F32 matrix -- x = xh + xl, W = Wh + Wl in fp16 pairs, x.W ~ xh.Wh + (xl.Wh + xh.Wl)

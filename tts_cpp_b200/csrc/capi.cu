@@ -38,7 +38,8 @@ struct Dev {
     std::vector<void *> ptrs;
     ~Dev() { for (void * p : ptrs) cudaFree(p); }
     template <class T> T * get(size_t n) { void * p = nullptr; if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed"); return nullptr; } ptrs.push_back(p); return (T *) p; }
-    template <class T> T * put(const T * h, size_t n) { T * d = get<T>(n); if (d && n) cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice); return d; }
+    // blocking copy on the legacy stream, then a device-wide sync: the kernels that read it run on ctx->stream (non-blocking), which does not order itself after the legacy stream
+    template <class T> T * put(const T * h, size_t n) { T * d = get<T>(n); if (d && n) { cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice); cudaDeviceSynchronize(); } return d; }
 };
 int finish(Ctx * c, void * dst, const void * src, size_t bytes) {
     B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -267,6 +268,19 @@ int b2tts_parler_set_text_encoding(b2tts_parler * m, const float * encoding, int
 }
 float b2tts_parler_last_ms(const b2tts_parler * m) { return m ? m->p.timing_ms : 0.f; }
 size_t b2tts_parler_weight_bytes(const b2tts_parler * m) { return m ? m->p.weight_bytes : 0; }
+size_t b2tts_parler_step_weight_bytes(const b2tts_parler * m) {
+    if (!m) return 0;
+    const Parler & p = m->p;
+    auto wb = [](const ArW & w, size_t n) { return w.qtype ? n * (w.qtype == 2 ? 18 : w.qtype == 6 ? 22 : 34) / 32 : n * (w.f16 ? 2 : 4); };
+    const size_t H = (size_t) p.hidden, F = (size_t) p.ffn;
+    size_t b = 0;
+    for (const ParlerLayer & L : p.layers)
+        b += wb(L.wq, H * H) + wb(L.wk, H * H) + wb(L.wv, H * H) + wb(L.wo, H * H) + wb(L.cq, H * H) + wb(L.co, H * H) + wb(L.fc1, F * H) + wb(L.fc2, H * F) + 6 * H * 4 +
+             2 * (size_t) p.n_enc * H * 4;                                   // + the layer's cross K / V store (fp32, shared by the batch)
+    b += wb(p.heads_w, (size_t) p.n_out * p.vocab * H) + 2 * H * 4;
+    return b;
+}
+void b2tts_parler_pdk_stats(const b2tts_parler * m, uint64_t * launches, uint64_t * steps) { if (launches) *launches = m ? m->p.pdk_launches : 0; if (steps) *steps = m ? m->p.pdk_steps : 0; }
 // ---- Dia AR decode (first correct path)
 int b2tts_dia_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_dia ** out) {
     if (!ctx) { set_error("null context"); return 1; }

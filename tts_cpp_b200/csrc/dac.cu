@@ -310,6 +310,7 @@ int Dac::prepare() {
     if (!P.ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     host.clear();
+    cudaDeviceSynchronize();               // legacy-stream uploads above vs kernels on the non-blocking ctx->stream
     prepared = true;
     return 0;
 }
@@ -589,6 +590,7 @@ int Snac::prepare() {
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     noise_engine = new NormalGen();
     host.clear();
+    cudaDeviceSynchronize();               // legacy-stream uploads above vs kernels on the non-blocking ctx->stream
     prepared = true;
     return 0;
 }

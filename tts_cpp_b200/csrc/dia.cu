@@ -115,6 +115,7 @@ int Dia::prepare() {
     if (!ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     host.clear();
+    B2_CUDA(cudaDeviceSynchronize());      // the uploads above are blocking copies on the legacy stream; kernels run on ctx->stream (non-blocking), which does not wait for it by itself
     prepared = true;
     return 0;
 }
@@ -346,7 +347,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     };
     // B2TTS_AR_GRAPH=1: capture one decoder step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    if (ge && ge[0] == '1' && !out_logits && n_steps > 1) {
+    if (!(ge && ge[0] == '0') && !out_logits && n_steps > 1) {      // on by default (reproduced the reference's tokens on a B200, round 2); B2TTS_AR_GRAPH=0 for A/B runs
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         if (run_step()) return 1;                               // step 0 runs directly: every kernel instantiation has its attributes set before the capture
         const uint64_t l0 = ctx->launches;

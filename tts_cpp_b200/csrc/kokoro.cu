@@ -326,6 +326,7 @@ int Kokoro::prepare() {
     if (!P.ok) return 1;
     host.clear();
     for (int i = 0; i < 4; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+    cudaDeviceSynchronize();               // legacy-stream uploads above vs kernels on the non-blocking ctx->stream
     prepared = true;
     return 0;
 }

@@ -36,7 +36,7 @@ int Orpheus::prepare() {
         if (cudaMalloc(&d, it->second.v.size() * 4) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed for orpheus.%s", n.c_str()); ok = false; return nullptr; }
         cudaMemcpy(d, it->second.v.data(), it->second.v.size() * 4, cudaMemcpyHostToDevice);
         dev_allocs.push_back(d); weight_bytes += it->second.v.size() * 4;
-        if (gemv_mma_enabled() && it->second.shape.size() == 2) {                     // the split copy of a matrix: W = hi + lo, lo carried scaled by 2^11
+        if (gemv_split_mma_enabled() && it->second.shape.size() == 2) {                     // the split copy of a matrix: W = hi + lo, lo carried scaled by 2^11
             const size_t cnt = it->second.v.size();
             std::vector<__half> hi(cnt), lo(cnt);
             for (size_t i = 0; i < cnt; i++) { const float w = it->second.v[i]; hi[i] = __float2half_rn(w); lo[i] = __float2half_rn((w - __half2float(hi[i])) * GM_LO_SCALE); }
@@ -71,6 +71,7 @@ int Orpheus::prepare() {
     if (!ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     host.clear();
+    B2_CUDA(cudaDeviceSynchronize());      // the uploads above are blocking copies on the legacy stream; kernels run on ctx->stream (non-blocking), which does not wait for it by itself
     prepared = true;
     return 0;
 }
@@ -91,7 +92,7 @@ struct OFwd : ArLaunch {
     // up to 3 F32 matrices against the same rows in one launch (tensor-core path: when every one of them has its fp16 split and an eligible shape)
     int gemv_group_f32(const float * X, int ldx, int K, int R, const float * const * W, const int * N, float * const * Y, int n) {
         GemvItem it[3];
-        bool mma = gemv_mma_enabled();
+        bool mma = gemv_split_mma_enabled();
         for (int i = 0; i < n && mma; i++) mma = gemv_mma_ok(K, N[i], 16) && m->split.find(W[i]) != m->split.end();
         for (int i = 0; i < n; i++) {
             it[i] = GemvItem{W[i], nullptr, nullptr, N[i], GemvOut{nullptr, Y[i], nullptr, N[i], 0}};
@@ -101,7 +102,7 @@ struct OFwd : ArLaunch {
     }
     // an F32 matrix by its device pointer (fp32-faithful tensor-core path when its fp16 split exists)
     int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        if (gemv_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
+        if (gemv_split_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
             auto it = m->split.find(W);
             if (it != m->split.end()) return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) it->second.first, (const __half *) it->second.second, K, N, R, res, Y, ldy);
         }
@@ -224,7 +225,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     if (run_pass(R0, true) || copy_logits(0)) return 1;                                   // step 0: the whole ragged batch of prompts
     // B2TTS_AR_GRAPH=1: capture one decode step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    if (ge && ge[0] == '1' && !out_logits && n_steps > 2) {
+    if (!(ge && ge[0] == '0') && !out_logits && n_steps > 2) {      // on by default since it reproduced the reference's tokens on a B200 (round 2); B2TTS_AR_GRAPH=0 for A/B runs
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         if (run_decode()) return 1;                             // step 1 runs directly: every kernel instantiation has its attributes set before the capture
         const uint64_t l0 = ctx->launches;

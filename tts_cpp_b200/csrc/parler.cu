@@ -1,11 +1,13 @@
 // parler.cu -- Parler-TTS autoregressive decode, first correct CUDA path.  See parler.h for what it replaces.
 #include "parler.h"
 #include "ar_kernels.cuh"
+#include "pdk.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 namespace b2 {
 
@@ -100,6 +102,17 @@ int Parler::prepare() {
         }
         if (ok && heads_any_f16 != heads_f16) { set_error("parler: the output heads mix F16 and F32 tensors"); ok = false; }
         if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev_mat(hw.data(), hw.size(), heads_f16); }   // tables: ggml_get_rows widens F16 rows to fp32 exactly
+        if (ok && !heads_f16) {   // F32 heads (the quantize tool leaves them F32): fp16 (hi, 2^11-scaled lo) planes for the persistent decode kernel's split tensor-core product
+            std::vector<__half> hi(hw.size()), lo(hw.size());
+            for (size_t i = 0; i < hw.size(); i++) { hi[i] = __float2half_rn(hw[i]); lo[i] = __float2half_rn((hw[i] - __half2float(hi[i])) * GM_LO_SCALE); }
+            for (int pl = 0; pl < 2 && ok; pl++) {
+                void * d = nullptr;
+                if (cudaMalloc(&d, hw.size() * 2) != cudaSuccess) { cudaGetLastError(); set_error("parler: cudaMalloc of %zu bytes failed", hw.size() * 2); ok = false; break; }
+                cudaMemcpy(d, pl ? lo.data() : hi.data(), hw.size() * 2, cudaMemcpyHostToDevice);
+                dev_allocs.push_back(d); weight_bytes += hw.size() * 2;
+                (pl ? heads_lo : heads_hi) = (__half *) d;
+            }
+        }
     }
     {
         const HostTensor * t = find("layers.0.fc1.weight", 0);
@@ -123,11 +136,15 @@ int Parler::prepare() {
         L.wck = upw(b + ".encoder_attn.k_proj.weight", HH); L.wcv = upw(b + ".encoder_attn.v_proj.weight", HH);
         L.cross_k = dev(nullptr, (size_t) n_enc * hidden); L.cross_v = dev(nullptr, (size_t) n_enc * hidden);
         if (!ok) break;
+        B2_CUDA(cudaDeviceSynchronize());    // the blocking uploads above went through the legacy stream; ctx->stream is non-blocking and does not wait for it by itself
         if (Fw.gemv(d_enc, hidden, L.wck, hidden, hidden, n_enc, nullptr, L.cross_k, hidden)) return 1;
         if (Fw.gemv(d_enc, hidden, L.wcv, hidden, hidden, n_enc, nullptr, L.cross_v, hidden)) return 1;
     }
     if (!ok) return 1;
-    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2_CUDA(cudaDeviceSynchronize());      // the uploads above are blocking copies on the legacy stream, the kernels run on ctx->stream (non-blocking): order them once
+#ifndef B2EMU
+    B2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+#endif
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     host.clear();
     prepared = true;
@@ -141,6 +158,7 @@ int Parler::set_text_encoding(const float * enc, int n_rows) {
     float * d_enc = nullptr;
     B2_CUDA(cudaMalloc(&d_enc, (size_t) n_rows * hidden * 4));
     B2_CUDA(cudaMemcpy(d_enc, enc, (size_t) n_rows * hidden * 4, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaDeviceSynchronize());        // legacy-stream upload before kernels on the non-blocking ctx->stream
     PFwd Fw{this, ctx, ctx->stream};
     int rc = 0;
     for (int l = 0; l < n_layers && !rc; l++) {
@@ -179,12 +197,31 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     }
     const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, F = ffn, NV = n_out * vocab;
     if (Tmax > max_ctx) { set_error("parler: %d positions exceed the model's context of %d", Tmax, max_ctx); return 1; }
-    const size_t cache = (size_t) n_layers * B * Tmax * H * 4;
+    // ---- the persistent decode kernel (pdk.cuh) takes the decode steps when the model and the request fit it: greedy / teacher-forced, <= 16 sequences, F16 decoder
+    // matrices (the BASELINE config; F32 and block-quantised GGUFs stay on the launch-per-op path below), shapes in whole 256-column k-slices.  B2TTS_AR_PDK=0 turns it off.
+    static const bool pdk_env = [] { const char * e = getenv("B2TTS_AR_PDK"); return !(e && e[0] == '0'); }();
+    static const bool kv_f32 = [] { const char * e = getenv("B2TTS_KV"); return e && (e[0] == 'f' || e[0] == 'F') && e[1] == '3'; }();     // B2TTS_KV=f32: fp32 pages (default fp16)
+#ifdef B2EMU
+    const int pk_grid = [] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 3; return v > 0 ? v : 3; }();
+#else
+    const int pk_grid = [&] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 0; return v > 0 && v <= sm_count ? v : sm_count; }();
+#endif
+    bool use_pdk = pdk_env && !samp.do_sample && B <= 16 && H % 256 == 0 && F % 256 == 0 && (head_dim == 8 || head_dim == 64 || head_dim == 128) && (heads_w.f16 || heads_hi) && !heads_w.qtype &&
+                   pk_grid > 0 && (F <= PK_AK || H / 8 <= 3 * pk_grid) && (!out_logits || (size_t) n_steps * B * NV * 4 <= ((size_t) 1 << 30));
+    for (const ParlerLayer & L : layers) for (const ArW * w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.cq, &L.co, &L.fc1, &L.fc2}) use_pdk = use_pdk && w->f16 && !w->qtype;
+    const int Tst = use_pdk ? Pmax : Tmax;                          // positions per sequence in the contiguous fp32 cache: the persistent path keeps only the prompt pass there
+    const int pk_max_pages = cdiv(Tmax, PK_PAGE);
+    int pk_pages = 0;
+    for (int b = 0; b < B; b++) pk_pages += cdiv(n_prompt[b] + n_steps, PK_PAGE);
+    const size_t pk_layer_bytes = (size_t) pk_pages * 2 * H * PK_PAGE * (kv_f32 ? 4 : 2);
+    const size_t pk_need = use_pdk ? (size_t) n_layers * pk_layer_bytes + (size_t) B * pk_max_pages * 4 + (size_t) (8 * n_layers + 8) * sizeof(PkOp) + (size_t) R0 * 4 + 4096 + (size_t) PK_REP * 16 * ((size_t) 10 * H + 2 * F) + 4096 +
+                                     (out_logits ? (size_t) n_steps * B * NV * 4 : 0) : 0;
+    const size_t cache = (size_t) n_layers * B * Tst * H * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 6 * H + F) * 4 + (size_t) B * NV * 4 + (size_t) n_steps * B * n_out * 4 + (size_t) B * n_out * 4 +
-                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 12 + (size_t) B * 4 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
+                        (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * n_out * 12 + (size_t) B * 4 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0) + pk_need;
     if (arena.reserve(need)) return 1;
     PFwd Fw(this, ctx, st);
-    float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * H);
+    float * Kc = Fw.al<float>((size_t) n_layers * B * Tst * H), * Vc = Fw.al<float>((size_t) n_layers * B * Tst * H);
     float * x = Fw.al<float>((size_t) Rmax * H), * xn = Fw.al<float>((size_t) Rmax * H), * q = Fw.al<float>((size_t) Rmax * H), * att = Fw.al<float>((size_t) Rmax * H);
     float * kbuf = Fw.al<float>((size_t) Rmax * H), * vbuf = Fw.al<float>((size_t) Rmax * H), * g = Fw.al<float>((size_t) Rmax * F);
     float * logits = Fw.al<float>((size_t) B * NV);
@@ -205,7 +242,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
         int r = 0;
         for (int b = 0; b < B; b++) {
             hnp[(size_t) b] = n_prompt[b];
-            for (int i = 0; i < n_prompt[b]; i++, r++) { ht[(size_t) r] = (int) prompts[b][i]; hp[(size_t) r] = i; hb[(size_t) r] = b * Tmax; hl[(size_t) r] = i + 1; hd[(size_t) r] = b * Tmax + i; }
+            for (int i = 0; i < n_prompt[b]; i++, r++) { ht[(size_t) r] = (int) prompts[b][i]; hp[(size_t) r] = i; hb[(size_t) r] = b * Tst; hl[(size_t) r] = i + 1; hd[(size_t) r] = b * Tst + i; }
         }
     }
     B2_CUDA(cudaEventRecord(ev[0], st));
@@ -234,7 +271,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     auto run_layers = [&](int R) -> int {
         for (int l = 0; l < n_layers; l++) {
             const ParlerLayer & L = layers[(size_t) l];
-            float * Kl = Kc + (size_t) l * B * Tmax * H, * Vl = Vc + (size_t) l * B * Tmax * H;
+            float * Kl = Kc + (size_t) l * B * Tst * H, * Vl = Vc + (size_t) l * B * Tst * H;
             if (Fw.ln(x, L.ln1_w, L.ln1_b, H, R, xn)) return 1;
             if (fuse) {                                                                        // q, k, v in one launch; the k / v rows go straight to their cache slots
                 const ArW * W3[3] = {&L.wq, &L.wk, &L.wv}; const int N3[3] = {H, H, H};
@@ -267,6 +304,147 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     // the prompt pass: its logits are never read (generate_from_batch only samples after audio decodes)
     embed_pos_kernel<<<R0, 256, 0, st>>>(row_tok, row_pos, embed_prompts, pos_embed, H, x); B2_LAUNCH_CHECK(ctx);
     if (run_layers(R0)) return 1;
+    const int exit_every = [] { const char * e = getenv("B2TTS_AR_EXIT_EVERY"); const int v = e ? atoi(e) : 32; return v > 0 ? v : 32; }();
+    const bool track_stop = n_generated != nullptr;
+    std::vector<int32_t> hflags((size_t) B);
+    auto all_stopped = [&]() -> int {          // 1 all stopped, 0 not yet, -1 error
+        if (cudaMemcpyAsync(hflags.data(), stopped, (size_t) B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { set_error("parler: reading the stop flags failed"); return -1; }
+        for (int b = 0; b < B; b++) if (hflags[(size_t) b] < 0) return 0;
+        return 1;
+    };
+    float * logits_all = nullptr;
+    if (use_pdk) {
+        // ---- paged KV cache: a page table per sequence over one pool per layer; pages are handed out in sequence order for the positions this call can reach
+        // (ragged prompts take what they need, not Pmax + n_steps each)
+        unsigned char * pool = (unsigned char *) arena.alloc((size_t) n_layers * pk_layer_bytes);
+        int * page_table = Fw.al<int>((size_t) B * pk_max_pages), * row_seq = Fw.al<int>((size_t) R0);
+        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (8 * n_layers + 8) * sizeof(PkOp));
+        unsigned * d_bar = (unsigned *) arena.alloc(256);
+        if (out_logits) logits_all = Fw.al<float>((size_t) n_steps * B * NV);
+        // PK_REP copies of every buffer all CTAs read at a phase start (pdk.cuh): the residual stream x / xn (fp32) and the fp16 hand-offs attention -> o-projection, GELU(fc1) -> fc2
+        const size_t xrep = (size_t) 16 * H, grep = (size_t) 16 * F;
+        float * px = Fw.al<float>(PK_REP * xrep), * pxn = Fw.al<float>(PK_REP * xrep);
+        __half * att16 = Fw.al<__half>(PK_REP * xrep), * g16 = Fw.al<__half>(PK_REP * grep);
+        if (!pool || !d_ops || !d_bar || Fw.fail) return 1;
+        std::vector<int> hpt((size_t) B * pk_max_pages, 0), hrs((size_t) R0);
+        { int next = 0, r = 0; for (int b = 0; b < B; b++) { const int np = cdiv(n_prompt[b] + n_steps, PK_PAGE); for (int i = 0; i < np; i++) hpt[(size_t) b * pk_max_pages + i] = next++; for (int i = 0; i < n_prompt[b]; i++) hrs[(size_t) r++] = b; } }
+        std::vector<PkOp> ops;
+        auto seg = [&](const __half * W, const __half * Wl, int N, int epi, float * Y, const float * res, int ldy, int kvsel) { PkSeg sg; memset(&sg, 0, sizeof sg); sg.W = W; sg.Wl = Wl; sg.N = N; sg.epi = epi; sg.Y = Y; sg.res = res; sg.ldy = ldy; sg.kv = kvsel; return sg; };
+        auto gemv_op = [&](int layer, const float * X, int ldx, int K, const float * nw, const float * nb, std::initializer_list<PkSeg> segs) {
+            PkOp op; memset(&op, 0, sizeof op);
+            op.kind = PK_GEMV; op.layer = layer; op.X = X; op.ldx = ldx; op.K = K; op.norm = nw ? PKN_LAYER : PKN_NONE; op.nw = nw; op.nb = nb; op.eps = 1e-5f;
+            int u = 0;
+            for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; u += cdiv(sg.N, 8); op.nseg++; }
+            op.n_units = u;
+            ops.push_back(op);
+        };
+        auto attn_op = [&](int layer, const float * qv, __half * outv, const float * ckp, const float * cvp, int cross_len) {
+            PkOp op; memset(&op, 0, sizeof op);
+            op.kind = PK_ATTN; op.layer = layer; op.q = qv; op.out16 = outv; op.ck = ckp; op.cv = cvp; op.cross = ckp ? 1 : 0; op.cross_len = cross_len; op.scale = scale;
+            ops.push_back(op);
+        };
+        { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ROWS; ops.push_back(op); }
+        auto rep_in = [&](size_t stride) { ops.back().xrep = stride; };
+        auto rep_out = [&](size_t stride) { ops.back().seg[0].yrep = stride; };
+        for (int l = 0; l < n_layers; l++) {
+            const ParlerLayer & L = layers[(size_t) l];
+            gemv_op(l, px, H, H, L.ln1_w, L.ln1_b, {seg((const __half *) L.wq.p, nullptr, H, PKE_STORE, q, nullptr, H, 0), seg((const __half *) L.wk.p, nullptr, H, PKE_KV, nullptr, nullptr, H, 0),
+                                                    seg((const __half *) L.wv.p, nullptr, H, PKE_KV, nullptr, nullptr, H, 1)});
+            ops.back().kv_prefetch = 1; rep_in(xrep);
+            attn_op(l, q, att16, nullptr, nullptr, 0); ops.back().orep = xrep;
+            gemv_op(l, nullptr, H, H, nullptr, nullptr, {seg((const __half *) L.wo.p, nullptr, H, PKE_RES, pxn, px, H, 0)});           // xn = self-attention + residual(x)
+            ops.back().X16 = att16; rep_in(xrep); rep_out(xrep);
+            gemv_op(l, pxn, H, H, L.ln2_w, L.ln2_b, {seg((const __half *) L.cq.p, nullptr, H, PKE_STORE, q, nullptr, H, 0)}); rep_in(xrep);
+            attn_op(l, q, att16, L.cross_k, L.cross_v, n_enc); ops.back().orep = xrep;
+            gemv_op(l, nullptr, H, H, nullptr, nullptr, {seg((const __half *) L.co.p, nullptr, H, PKE_RES, px, pxn, H, 0)});           // x = cross-attention + residual(xn)
+            ops.back().X16 = att16; rep_in(xrep); rep_out(xrep);
+            gemv_op(l, px, H, H, L.ln3_w, L.ln3_b, {seg((const __half *) L.fc1.p, nullptr, F, PKE_GELU, nullptr, nullptr, F, 0)});
+            ops.back().seg[0].Y16 = g16; rep_in(xrep); rep_out(grep);
+            gemv_op(l, nullptr, F, F, nullptr, nullptr, {seg((const __half *) L.fc2.p, nullptr, H, PKE_RES, px, px, H, 0)});           // x = mlp + residual(x), element-wise in place (every copy)
+            ops.back().X16 = g16; rep_in(grep); rep_out(xrep);
+        }
+        gemv_op(0, px, H, H, ln_w, ln_b, {seg(heads_w.f16 ? (const __half *) heads_w.p : heads_hi, heads_w.f16 ? nullptr : heads_lo, NV, PKE_LOGITS, logits, nullptr, NV, 0)}); rep_in(xrep);
+        { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ARGMAX; ops.push_back(op); }
+        B2_CUDA(cudaMemcpyAsync(page_table, hpt.data(), hpt.size() * 4, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(row_seq, hrs.data(), hrs.size() * 4, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * sizeof(PkOp), cudaMemcpyHostToDevice, st));
+        PkParams Pk; memset(&Pk, 0, sizeof Pk);
+        Pk.ops = d_ops; Pk.n_ops = (int) ops.size(); Pk.R = B; Pk.H = H; Pk.heads = heads; Pk.hd = head_dim; Pk.n_out = n_out; Pk.vocab = vocab;
+        const bool any_split = !heads_w.f16;
+        {   // shared memory: activation rows of the widest phase (twice for split matrices) or the attention scratch of two half-CTA groups, the rest is the weight ring
+            const int KA = std::min(std::max(H, F), PK_AK), KAs = std::min(H, PK_AK);
+            size_t a = (size_t) 16 * (KA + PK_PAD) * 2;
+            if (any_split) a = std::max(a, (size_t) 2 * 16 * (KAs + PK_PAD) * 2);
+            a = std::max(a, (size_t) 2 * ((PK_ATT_HDR + 1024) * 4 + (size_t) ((std::max(Tmax, n_enc) + 3) & ~3) * 4));
+            if (pk_max_pages > 256) { set_error("parler: %d positions exceed the persistent kernel's page-id scratch", Tmax); return 1; }
+            a = (a + 255) & ~(size_t) 255;
+            int ns = PK_MAXSTAGES;
+            while (ns > 2 && pk_smem_bytes(ns, (int) a, B * pk_max_pages) > (size_t) 227 * 1024) ns--;
+            if (pk_smem_bytes(ns, (int) a, B * pk_max_pages) > (size_t) 227 * 1024) { set_error("parler: the persistent decode kernel does not fit this shape in shared memory"); return 1; }
+            Pk.n_stages = ns; Pk.a_bytes = (int) a;
+        }
+        Pk.bar = d_bar; Pk.d_step = d_step;
+        Pk.first_pos = d_np; Pk.d_out = d_out; Pk.d_teacher = d_teacher; Pk.bos = bos; Pk.eos = eos; Pk.max_gen = max_generation; Pk.seen = seen; Pk.stopped = stopped; Pk.ids = ids; Pk.row_pos = row_pos;
+        Pk.tables = tables; Pk.tab_stride = (size_t) tab_rows * H; Pk.pos_embed = pos_embed; Pk.x0 = px; Pk.x0rep = xrep;
+        Pk.kv_pool = pool; Pk.kv_layer_bytes = pk_layer_bytes; Pk.page_table = page_table; Pk.max_pages = pk_max_pages;
+        Pk.logits = logits; Pk.logits_all = logits_all;
+        // B2TTS_PDK_PROF=<step>: %globaltimer timeline of that decode step (every op x every CTA), written as raw uint64 to $B2TTS_PDK_PROF_FILE after the run
+        const char * prof_env = getenv("B2TTS_PDK_PROF");
+        const size_t prof_words = (size_t) ops.size() * pk_grid * 8;
+        if (prof_env) {
+            B2_CUDA(cudaMalloc(&Pk.prof, prof_words * 8));
+            B2_CUDA(cudaMemsetAsync(Pk.prof, 0, prof_words * 8, st));
+            Pk.prof_step = atoi(prof_env);
+        }
+        {   // the prompt pass' K / V rows (fp32, contiguous) into the pages
+            dim3 grid(R0, n_layers);
+            if (kv_f32) pk_kv_import_kernel<float><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * H, row_dst, row_seq, row_pos, Pk);
+            else pk_kv_import_kernel<__half><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * H, row_dst, row_seq, row_pos, Pk);
+            B2_LAUNCH_CHECK(ctx);
+        }
+        const size_t smem = pk_smem_bytes(Pk.n_stages, Pk.a_bytes, B * pk_max_pages);
+        // one instantiation per (cache element type, head size)
+        const void * kfn = nullptr;
+#ifdef B2EMU
+        std::function<void(const PkParams &)> kemu;
+#define PK_PICK(T, D) { kemu = [](const PkParams & q) { pdk_kernel<T, D>(q); }; }
+#else
+#define PK_PICK(T, D) { kfn = (const void *) pdk_kernel<T, D>; }
+#endif
+        if (kv_f32) { if (head_dim == 8) PK_PICK(float, 8) else if (head_dim == 64) PK_PICK(float, 64) else PK_PICK(float, 128) }
+        else        { if (head_dim == 8) PK_PICK(__half, 8) else if (head_dim == 64) PK_PICK(__half, 64) else PK_PICK(__half, 128) }
+#undef PK_PICK
+#ifndef B2EMU
+        B2_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+#endif
+        for (int s0 = 0; s0 < n_steps; s0 += exit_every) {
+            if (track_stop && s0 > 0) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
+            Pk.step_begin = s0; Pk.n_steps = std::min(exit_every, n_steps - s0);
+            B2_CUDA(cudaMemsetAsync(d_bar, 0, 256, st));
+#ifdef B2EMU
+            (void) kfn;
+            b2emu::launch_coop(dim3(pk_grid), dim3(PK_THREADS), smem, [=]() { kemu(Pk); });
+#else
+            void * args[] = {(void *) &Pk};
+            B2_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(pk_grid), dim3(PK_THREADS), args, smem, st));
+#endif
+            ctx->launches++; pdk_launches++; pdk_steps += (uint64_t) Pk.n_steps;
+        }
+        if (Pk.prof) {
+            std::vector<unsigned long long> hp(prof_words);
+            B2_CUDA(cudaMemcpyAsync(hp.data(), Pk.prof, prof_words * 8, cudaMemcpyDeviceToHost, st));
+            B2_CUDA(cudaStreamSynchronize(st));
+            if (const char * pf = getenv("B2TTS_PDK_PROF_FILE")) {
+                if (FILE * f = fopen(pf, "wb")) {
+                    const int hdr[4] = {(int) ops.size(), pk_grid, 8, Pk.prof_step};
+                    fwrite(hdr, 4, 4, f);
+                    for (const PkOp & o : ops) { const int k[4] = {o.kind, o.layer, o.K, o.n_units}; fwrite(k, 4, 4, f); }
+                    fwrite(hp.data(), 8, hp.size(), f); fclose(f);
+                }
+            }
+            cudaFree(Pk.prof);
+        }
+    }
     // one audio step; the step number is device-resident (d_step), so the launches are identical for every step
     auto run_step = [&]() -> int {
         delay_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_teacher ? d_teacher : d_out, d_np, B, n_out, d_step, bos, eos, max_generation, Tmax, seen, stopped, ids, row_pos, row_base, row_len, row_dst); B2_LAUNCH_CHECK(ctx);
@@ -279,22 +457,20 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
         step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
         return 0;
     };
-    // every `exit_every` steps the per-sequence stop flags are read back (one small sync): when the reference's loop would have ended for EVERY sequence of the
-    // batch the remaining steps are skipped
-    const int exit_every = [] { const char * e = getenv("B2TTS_AR_EXIT_EVERY"); const int v = e ? atoi(e) : 32; return v > 0 ? v : 32; }();
-    const bool track_stop = n_generated != nullptr;
-    std::vector<int32_t> hflags((size_t) B);
-    auto all_stopped = [&]() -> int {          // 1 all stopped, 0 not yet, -1 error
-        if (cudaMemcpyAsync(hflags.data(), stopped, (size_t) B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { set_error("parler: reading the stop flags failed"); return -1; }
-        for (int b = 0; b < B; b++) if (hflags[(size_t) b] < 0) return 0;
-        return 1;
-    };
+    // (launch-per-op path) every `exit_every` steps the per-sequence stop flags are read back (one small sync): when the reference's loop would have ended for EVERY
+    // sequence of the batch the remaining steps are skipped
     // B2TTS_AR_GRAPH=1: capture one step into a CUDA graph and replay it (an audio step is ~15 launches per layer of microsecond kernels: launch-bound
     // otherwise).  Off by default until it has run on hardware; not used when the caller wants every step's logits (a host copy per step).
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    const bool use_graph = ge && ge[0] == '1' && !out_logits;
+    const bool use_graph = !(ge && ge[0] == '0') && !out_logits;      // on by default since it reproduced the reference's tokens on a B200 (round 2); B2TTS_AR_GRAPH=0 for A/B runs
     const uint64_t launches_before_step = ctx->launches;
-    if (use_graph && n_steps > 1) {
+    if (use_pdk) {
+        // the steps already ran inside the persistent kernel; every step's logits sit in logits_all [step][b][NV]
+        if (out_logits)
+            for (int s = 0; s < n_steps; s++)
+                for (int b = 0; b < B; b++)
+                    B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits_all + ((size_t) s * B + b) * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+    } else if (use_graph && n_steps > 1) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         if (run_step()) return 1;                               // step 0 runs directly: every kernel instantiation has its attributes set before the capture
         B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));

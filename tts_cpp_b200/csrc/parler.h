@@ -28,6 +28,9 @@ struct Parler {
     int bos = 1025, eos = 1024;
     float * embed_prompts = nullptr, * pos_embed = nullptr, * tables = nullptr /* [n_out][tab_rows][hidden] */;
     ArW heads_w;   // [n_out * vocab][hidden]
+    __half * heads_hi = nullptr, * heads_lo = nullptr;   // F32 output heads as fp16 (hi, 2^11-scaled lo) planes: the persistent decode kernel's fp32-faithful tensor-core product (pdk.cuh)
+    int sm_count = 0;
+    uint64_t pdk_launches = 0, pdk_steps = 0;             // persistent-kernel launches / decode steps they covered (b2tts_parler_pdk_stats)
     float * ln_w = nullptr, * ln_b = nullptr;
     std::vector<ParlerLayer> layers;
 

@@ -1,0 +1,800 @@
+// pdk.cuh -- the persistent decode kernel: a whole run of autoregressive decode steps in ONE cooperative launch (BASELINE north star:
+// "persistent ... decode kernels fed by TMA from a paged HBM KV cache, LayerNorm / GELU folded into the epilogues").
+//
+// What it replaces: the ~11 micro-launches per layer of parler.cu's launch-per-op path (reference build_parler_graph, src/models/parler/model.cpp:520-614, one GGML
+// graph per step).  Measured on a B200 (profiles/r2a_*): every one of those launches is a 10-20 us latency chain (one CTA per SM, a dozen dependent L2 round trips),
+// 3.97 ms per Parler-Mini step at batch 16 under CUDA-graph replay -- 4 % of the weight-streaming roofline.  Here one grid of (SM count) CTAs walks a device-resident
+// PROGRAM of the step -- rows/embedding, then per layer { [LN1] q|k|v GEMV -> self-attention -> o GEMV + residual -> [LN2] cross-q GEMV -> cross-attention -> o GEMV +
+// residual -> [LN3] fc1 GEMV + GELU -> fc2 GEMV + residual }, final [LN] heads GEMV, argmax -- separated by grid-wide barriers in global memory, for up to 32 steps
+// per launch:
+//
+//   * warp 8 of every CTA is a TMA PRODUCER: one lane streams the CTA's weight tiles (8 output rows x 1 024 k, fp16; `cp.async.bulk` global -> shared completing
+//     on an mbarrier) through a ring of ~9 stages IN PROGRAM ORDER.  Weights do not depend on activations, so the producer runs ahead across phases, layers and
+//     steps: while the consumers sit in a grid barrier or in an attention phase the ring fills with the next phase's tiles and HBM keeps streaming.
+//   * warps 0-7 are CONSUMERS: per GEMV phase they stage the <= 16 activation rows ONCE per CTA as fp16 in shared memory -- with the LayerNorm of the reference
+//     (ggml_norm: double-accumulated mean / variance) folded into that staging pass, so no norm kernel and no normalised tensor in HBM -- and run
+//     mma.sync.m16n8k16 (batch = M, exact fp16 products, fp32 accumulation: ggml_mul_mat's numerics for F16 matrices) on their k-slice of every tile; the eight
+//     partial 16 x 8 tiles are summed in a fixed order and the epilogue applies GELU (fp16 table, ggml-cpu.c:1816-1830) / the residual / the KV-cache append.
+//     F32 matrices (the output heads) go through the same pipeline as fp16 (hi, 2^11-scaled lo) plane pairs with the fp32-faithful three-product rule of
+//     ar_kernels.cuh (gemv_mma_body<SPLIT>).
+//   * the self-attention KV cache is PAGED: pages of 32 positions x all heads, fp16 (or fp32: template parameter), a page table per sequence; the new k / v rows
+//     are written by the q|k|v phase's epilogue straight into their page.  Attention runs one (row, head) item per half-CTA: 16-byte loads of K / V rows spread
+//     over the threads so that dozens are in flight, scores in shared memory, the reference's softmax (max, expf, double-accumulated sum).
+//
+// tcgen05 is deliberately not used: M = batch <= 16 rows, the step is HBM- and latency-bound; what matters is bytes in flight and the dependency chain.
+// Logic checked in the build container under tests/emu (cooperative launch = all blocks' threads alive at once as fibers; mbarriers, bulk copies and the grid
+// barrier have functional models below).
+#pragma once
+#include "ar_kernels.cuh"
+
+namespace b2 {
+namespace {
+
+constexpr int PK_CONS = 256;                      // consumer threads (8 warps)
+constexpr int PK_THREADS = 288;                   // + the producer warp
+constexpr int PK_TK = 1024;                       // k extent of a weight tile (halves)
+constexpr int PK_PAD = 32;                        // halves of padding per smem row: rows start 16 banks apart (conflict-free 128-bit fragment loads, see GM_PAD)
+constexpr int PK_ROWB = (PK_TK + PK_PAD) * 2;     // bytes per tile row in shared memory
+constexpr int PK_STAGE = 8 * PK_ROWB;             // bytes per ring stage (one tile: 8 output rows)
+constexpr int PK_AK = 2048;                       // activations are staged in k chunks of this many columns
+constexpr int PK_PAGE = 32;                       // positions per KV page
+constexpr int PK_MAXSTAGES = 12;
+constexpr int PK_RED_BYTES = 8 * 128 * 4;         // cross-warp reduction scratch / argmax scratch
+constexpr int PK_REP = 8;                         // copies of every activation buffer that ALL CTAs read at the start of a phase.  Measured on a B200: 148 SMs asking L2 for the
+                                                  // same 64 KB right after a grid barrier wait ~2 us (each line is served to 148 requesters one after the other); with 8 copies
+                                                  // (8x the tiny epilogue stores) a line has 18-19 requesters
+
+enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3 };
+enum { PKN_NONE = 0, PKN_LAYER = 1 };
+enum { PKE_STORE = 0, PKE_RES = 1, PKE_GELU = 2, PKE_KV = 3, PKE_LOGITS = 4 };
+
+struct PkSeg {                                    // one matrix of a GEMV phase; unit = 8 consecutive output rows
+    const __half * W;                             // [N][K] fp16 (split: the high plane)
+    const __half * Wl;                            // split: the low plane (scaled by 2^11), else null
+    float * Y; const float * res;                 // STORE / RES / LOGITS: Y[r * ldy + n] (+ res[r * ldy + n])
+    __half * Y16;                                 // GELU: the activated values as fp16 [r * ldy + n] (their only consumer, fc2, rounds its input rows to fp16 anyway)
+    size_t yrep;                                  // != 0: Y / Y16 (and res) exist in PK_REP copies this many elements apart; the epilogue writes them all, a CTA reads copy blockIdx % PK_REP
+    int N, unit0, epi, ldy, kv;                   // unit0: first unit of this segment within the phase; kv: 0 = K, 1 = V (PKE_KV)
+};
+struct alignas(16) PkOp {
+    int kind, layer;
+    // PK_GEMV
+    const float * X; const __half * X16;          // input rows: fp32 (residual stream, q) or, when X16 is set, fp16 written by the previous phase (attention output, GELU output)
+    size_t xrep;                                  // != 0: X / X16 exist in PK_REP copies this many elements apart
+    const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; PkSeg seg[3];      // kv_prefetch: L2-prefetch this layer's K / V rows first
+    // PK_ATTN: cross != 0 -> every row attends to the flat fp32 store ck / cv [cross_len][H]; else to its sequence's pages, positions [0, row_pos[r]]
+    const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale;      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
+};
+struct PkParams {
+    const PkOp * ops; int n_ops;
+    int R, H, heads, hd, n_out, vocab;
+    int n_stages, a_bytes;                        // shared-memory layout: ring stages, bytes of the activation / attention-scratch region
+    unsigned * bar;                               // grid-barrier arrival counter, zeroed before every launch
+    int * d_step; int step_begin, n_steps;        // steps [step_begin, step_begin + n_steps) run in this launch
+    // rows of a step under the delay pattern + codebook embedding (parler generate_audio_tokens / parler_build_inp_embd; see delay_rows_kernel, codebook_embed_kernel)
+    const int * first_pos; int * d_out; const int * d_teacher; int bos, eos, max_gen; int * seen; int * stopped; int * ids; int * row_pos;
+    const float * tables; size_t tab_stride; const float * pos_embed; float * x0; size_t x0rep;
+    // paged KV cache: layer l's pool at kv_pool + l * kv_layer_bytes; page p = [2 (k, v)][heads][PK_PAGE][hd] elements; page_table [R][max_pages]
+    unsigned char * kv_pool; size_t kv_layer_bytes; const int * page_table; int max_pages;
+    float * logits; float * logits_all;           // logits [R][n_out * vocab]; logits_all (optional) [n_steps_total][R][n_out * vocab]
+    unsigned long long * prof; int prof_step;     // optional timeline of step prof_step: [n_ops][gridDim.x][8] %globaltimer ns (op begin, activations staged, barrier entered, barrier left, ns spent waiting for weight tiles, norm tile ready, -, -)
+};
+
+// ---------------------------------------------------------------- primitives: mbarrier, bulk copy, named / grid barriers (PTX; functional models under B2EMU)
+#ifdef B2EMU
+struct PkBar { int pending, count, tx; unsigned phase; };
+static inline void pk_mbar_flip(PkBar * b) { if (b->pending == 0 && b->tx == 0) { b->phase ^= 1u; b->pending = b->count; } b2emu::note_progress(); }
+static inline void pk_mbar_init(PkBar * b, int count) { b->pending = b->count = count; b->tx = 0; b->phase = 0; }
+static inline void pk_mbar_arrive(PkBar * b) { b->pending--; pk_mbar_flip(b); }
+static inline void pk_mbar_expect_tx(PkBar * b, unsigned bytes) { b->tx += (int) bytes; b->pending--; pk_mbar_flip(b); }
+static inline void pk_mbar_wait(PkBar * b, unsigned parity) { while (b->phase == parity) b2emu::yield_spin(); }
+static inline void pk_bulk_g2s(void * dst, const void * src, unsigned bytes, PkBar * b) { memcpy(dst, src, bytes); b->tx -= (int) bytes; pk_mbar_flip(b); }
+static inline void pk_bar_sync(int id, int n) { b2emu::named_bar(id, n); }
+static inline unsigned pk_ld_acquire(const unsigned * p) { return *p; }
+static inline void pk_red_release(unsigned * p, unsigned v) { *p += v; b2emu::note_progress(); }
+static inline void pk_spin() { b2emu::yield_spin(); }
+static inline void pk_fence_init() {}
+#else
+typedef uint64_t PkBar;
+__device__ __forceinline__ uint32_t pk_smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pk_mbar_init(PkBar * b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pk_smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void pk_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void pk_mbar_arrive(PkBar * b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pk_smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void pk_mbar_expect_tx(PkBar * b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pk_smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void pk_mbar_wait(PkBar * b, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "PK_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra PK_DONE;\n\t"
+        "bra PK_WAIT;\n\t"
+        "PK_DONE:\n\t"
+        "}" ::"r"(pk_smem_u32(b)), "r"(parity) : "memory");
+}
+// TMA bulk copy (1-D): global -> this CTA's shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void pk_bulk_g2s(void * dst, const void * src, unsigned bytes, PkBar * b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pk_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pk_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void pk_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ unsigned pk_ld_acquire(const unsigned * p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void pk_red_release(unsigned * p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void pk_spin() {}
+#endif
+#ifdef B2EMU
+static inline unsigned long long pk_now() { return 0ull; }
+#else
+__device__ __forceinline__ unsigned long long pk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
+// every consumer thread of every CTA calls it; orders all global stores before it against all loads after it, grid-wide (the cooperative-groups pattern: block
+// barrier, one thread releases / acquires at gpu scope, block barrier).  The counter only grows: generation e is complete when it reaches e * gridDim.x.
+__device__ __forceinline__ void pk_grid_sync(unsigned * ctr, unsigned & epoch) {
+    pk_bar_sync(1, PK_CONS);
+    epoch++;
+    if (threadIdx.x == 0) {
+        pk_red_release(ctr, 1u);                              // release at gpu scope: orders every store the block made before the bar.sync above (cumulativity); no extra fence
+        const unsigned target = epoch * gridDim.x;
+        while (pk_ld_acquire(ctr) < target) pk_spin();
+    }
+    pk_bar_sync(1, PK_CONS);
+}
+
+// 8 consecutive cache elements as floats (one 16-byte load for fp16 pages, two for fp32 stores); L2-coherent loads: other CTAs wrote them earlier in this launch
+__device__ __forceinline__ void pk_load8(const __half * p, float * v) {
+    const uint4 u = __ldcg(reinterpret_cast<const uint4 *>(p));
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { __half2 h; memcpy(&h, &w[i], 4); const float2 f = __half22float2(h); v[2 * i] = f.x; v[2 * i + 1] = f.y; }      // (memcpy: no type-punned reads)
+}
+__device__ __forceinline__ void pk_load8(const float * p, float * v) {
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(p)), b = __ldcg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void pk_store1(__half * p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void pk_store1(float * p, float v) { *p = v; }
+
+template <typename KVT> __device__ __forceinline__ KVT * pk_page_row(const PkParams & P, int layer, int r, int pos, int kv, int h) {
+    const int pg = __ldg(P.page_table + (size_t) r * P.max_pages + (pos >> 5));
+    KVT * base = reinterpret_cast<KVT *>(P.kv_pool + (size_t) layer * P.kv_layer_bytes);
+    return base + ((((size_t) pg * 2 + kv) * P.heads + h) * PK_PAGE + (pos & (PK_PAGE - 1))) * P.hd;
+}
+
+// ---------------------------------------------------------------- the producer: this CTA's weight tiles of one op, in the order the consumers use them
+__device__ __forceinline__ void pk_produce_gemv(const PkOp & op, unsigned char * ring, PkBar * full, PkBar * empty, int S, unsigned & it) {      // op: the producer's own shared-memory copy
+    const int K = op.K, nA = (K + PK_AK - 1) / PK_AK;
+    if (op.norm != PKN_NONE) {                                 // the norm's weight | bias (K floats each) travel through the ring like a tile: in shared memory long before the op starts
+        const int s = (int) (it % (unsigned) S);
+        pk_mbar_wait(&empty[s], ((it / (unsigned) S) & 1u) ^ 1u);
+        pk_mbar_expect_tx(&full[s], (unsigned) (2 * K * 4));
+        pk_bulk_g2s(ring + (size_t) s * PK_STAGE, op.nw, (unsigned) (K * 4), &full[s]);
+        pk_bulk_g2s(ring + (size_t) s * PK_STAGE + (size_t) K * 4, op.nb, (unsigned) (K * 4), &full[s]);
+        it++;
+    }
+    for (int a = 0; a < nA; a++) {
+        const int kA0 = a * PK_AK, kAn = K - kA0 < PK_AK ? K - kA0 : PK_AK, ntile = (kAn + PK_TK - 1) / PK_TK;
+        for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
+            const int sj = (op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0);
+            const PkSeg & sg = op.seg[sj];
+            const int n0 = (u - sg.unit0) * 8;
+            for (int plane = 0; plane < (sg.Wl ? 2 : 1); plane++) {
+                const __half * Wp = plane ? sg.Wl : sg.W;
+                for (int t = 0; t < ntile; t++, it++) {
+                    const int s = (int) (it % (unsigned) S);
+                    const int kt0 = kA0 + t * PK_TK, ktn = K - kt0 < PK_TK ? K - kt0 : PK_TK;
+                    pk_mbar_wait(&empty[s], ((it / (unsigned) S) & 1u) ^ 1u);
+                    pk_mbar_expect_tx(&full[s], (unsigned) (8 * ktn * 2));
+                    unsigned char * dst = ring + (size_t) s * PK_STAGE;
+                    for (int row = 0; row < 8; row++) {
+                        const int n = n0 + row < sg.N ? n0 + row : sg.N - 1;           // rows past N re-read the last row and are never stored
+                        pk_bulk_g2s(dst + (size_t) row * PK_ROWB, Wp + (size_t) n * K + kt0, (unsigned) (ktn * 2), &full[s]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- consumers: GEMV phase
+// stage rows [0, 16) x columns [k0, k0 + kn) of X as fp16 into sA (pitch halves per row; rows >= R are zero), optionally LayerNorm'd (mean / rstd per row in
+// registers of the owning warp: warp w owns rows w and w + 8) and, for split matrices, their scaled low halves into sAl.
+__device__ __forceinline__ void pk_stage_rows(const PkOp & op, const float * X, const float * snw, int R, int k0, int kn, __half * sA, __half * sAl, int pitch, const float * mean, const float * rstd) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float * snb = snw ? snw + op.K : nullptr;
+    const int n4 = kn >> 2;                                   // float4 per row (kn % 256 == 0 -> n4 % 64 == 0)
+    for (int j0 = 0; j0 < n4; j0 += 32 * 8) {                 // 8 float4 per lane and row in flight, for both rows
+        float4 v[2][8];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int r = warp + 8 * rr;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int j = j0 + u * 32 + lane;
+                v[rr][u] = (r < R && j < n4) ? __ldcg(reinterpret_cast<const float4 *>(X + (size_t) r * op.ldx + k0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int r = warp + 8 * rr;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int j = j0 + u * 32 + lane;
+                if (j >= n4) continue;
+                float4 x = v[rr][u];
+                if (op.norm == PKN_LAYER && r < R) {           // ggml_norm then * weight + bias (parler build_norm): ((x - mean) * scale) * w + b
+                    const float4 w = reinterpret_cast<const float4 *>(snw + k0)[j], b = reinterpret_cast<const float4 *>(snb + k0)[j];
+                    x.x = ((x.x - mean[rr]) * rstd[rr]) * w.x + b.x; x.y = ((x.y - mean[rr]) * rstd[rr]) * w.y + b.y;
+                    x.z = ((x.z - mean[rr]) * rstd[rr]) * w.z + b.z; x.w = ((x.w - mean[rr]) * rstd[rr]) * w.w + b.w;
+                }
+                const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                __half2 * d = reinterpret_cast<__half2 *>(sA + (size_t) r * pitch + 4 * j);
+                d[0] = h01; d[1] = h23;
+                if (sAl) {
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    __half2 * dl = reinterpret_cast<__half2 *>(sAl + (size_t) r * pitch + 4 * j);
+                    dl[0] = __floats2half2_rn((x.x - f01.x) * GM_LO_SCALE, (x.y - f01.y) * GM_LO_SCALE);
+                    dl[1] = __floats2half2_rn((x.z - f23.x) * GM_LO_SCALE, (x.w - f23.y) * GM_LO_SCALE);
+                }
+            }
+        }
+    }
+}
+
+
+// The fast path of the two functions below for K <= 1 024 (every normalised GEMV of the models here): rows warp and warp + 8 are loaded ONCE (8 float4 per lane and row,
+// all in flight together with the norm's weight / bias), the statistics come from the registers, the normalised fp16 rows go to shared memory -- one L2 round trip
+// instead of three.  Statistics: ggml_norm accumulates float values in double; here the four values of a float4 are added in float first (error <= 2^-23 of the
+// partial), then double -- 4x fewer FP64 operations, the float mean / variance come out the same except in rare last-bit cases.
+__device__ __forceinline__ void pk_stage_fast(const PkOp & op, const float * X, const float * snw, int R, __half * sA, __half * sAl, int pitch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, K = op.K, n4 = K >> 2;
+    const float * snb = snw ? snw + K : nullptr;
+    const int r0 = warp, r1 = warp + 8;
+    const bool norm = op.norm == PKN_LAYER;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[2][8], w[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int j = u * 32 + lane;
+        const bool in = j < n4;
+        v[0][u] = (in && r0 < R) ? __ldcg(reinterpret_cast<const float4 *>(X + (size_t) r0 * op.ldx) + j) : z4;
+        v[1][u] = (in && r1 < R) ? __ldcg(reinterpret_cast<const float4 *>(X + (size_t) r1 * op.ldx) + j) : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {                              // the norm's weight / bias: from the ring stage the producer filled ahead of time
+        const int j = u * 32 + lane;
+        w[u] = (norm && j < n4) ? reinterpret_cast<const float4 *>(snw)[j] : z4;
+        b[u] = (norm && j < n4) ? reinterpret_cast<const float4 *>(snb)[j] : z4;
+    }
+    float m0 = 0.f, m1 = 0.f, i0 = 1.f, i1 = 1.f;
+    if (norm) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) { s0 += (double) ((v[0][u].x + v[0][u].y) + (v[0][u].z + v[0][u].w)); s1 += (double) ((v[1][u].x + v[1][u].y) + (v[1][u].z + v[1][u].w)); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        m0 = (float) (s0 / (double) K); m1 = (float) (s1 / (double) K);
+        double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (u * 32 + lane < n4) {
+                float a = v[0][u].x - m0, c = v[0][u].y - m0, d = v[0][u].z - m0, e = v[0][u].w - m0;
+                q0 += (double) ((a * a + c * c) + (d * d + e * e));
+                a = v[1][u].x - m1; c = v[1][u].y - m1; d = v[1][u].z - m1; e = v[1][u].w - m1;
+                q1 += (double) ((a * a + c * c) + (d * d + e * e));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+        i0 = 1.0f / sqrtf((float) (q0 / (double) K) + op.eps); i1 = 1.0f / sqrtf((float) (q1 / (double) K) + op.eps);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        if (half) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = (4 + u) * 32 + lane;
+                w[u] = (norm && j < n4) ? reinterpret_cast<const float4 *>(snw)[j] : z4;
+                b[u] = (norm && j < n4) ? reinterpret_cast<const float4 *>(snb)[j] : z4;
+            }
+        }
+#pragma unroll
+        for (int uu = 0; uu < 4; uu++) {
+            const int u = half * 4 + uu, j = u * 32 + lane;
+            if (j >= n4) continue;
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int r = warp + 8 * rr;
+                float4 x = v[rr][u];
+                if (norm) {                                    // ggml_norm then * weight + bias (parler build_norm): ((x - mean) * scale) * w + b
+                    const float m = rr ? m1 : m0, is = rr ? i1 : i0;
+                    x.x = ((x.x - m) * is) * w[uu].x + b[uu].x; x.y = ((x.y - m) * is) * w[uu].y + b[uu].y;
+                    x.z = ((x.z - m) * is) * w[uu].z + b[uu].z; x.w = ((x.w - m) * is) * w[uu].w + b[uu].w;
+                }
+                if (r >= R) x = z4;
+                const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                __half2 * d = reinterpret_cast<__half2 *>(sA + (size_t) r * pitch + 4 * j);
+                d[0] = h01; d[1] = h23;
+                if (sAl) {
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    __half2 * dl = reinterpret_cast<__half2 *>(sAl + (size_t) r * pitch + 4 * j);
+                    dl[0] = __floats2half2_rn((x.x - f01.x) * GM_LO_SCALE, (x.y - f01.y) * GM_LO_SCALE);
+                    dl[1] = __floats2half2_rn((x.z - f23.x) * GM_LO_SCALE, (x.w - f23.y) * GM_LO_SCALE);
+                }
+            }
+        }
+    }
+}
+
+// fp16 input rows (written by the previous phase): straight 16-byte copies into the operand buffer, 8 per thread in flight
+__device__ __forceinline__ void pk_stage_h16(const PkOp & op, const __half * X16, int R, int k0, int kn, __half * sA, int pitch) {
+    const int n8 = kn >> 3, total = 16 * n8;                   // uint4 (8 halves) per row, in all
+    for (int i0 = threadIdx.x; i0 < total; i0 += PK_CONS * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = i0 + u * PK_CONS, r = i / n8, j = i - r * n8;
+            v[u] = (i < total && r < R) ? __ldcg(reinterpret_cast<const uint4 *>(X16 + (size_t) r * op.ldx + k0) + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = i0 + u * PK_CONS, r = i / n8, j = i - r * n8;
+            if (i < total) *reinterpret_cast<uint4 *>(sA + (size_t) r * pitch + 8 * j) = v[u];
+        }
+    }
+}
+
+// mean and 1/sqrt(var + eps) of rows warp, warp + 8 over all K columns, ggml_norm's way: float values, double accumulators (ggml-cpu.c:7114-7163)
+__device__ __forceinline__ void pk_row_stats(const PkOp & op, const float * X, int R, float * mean, float * rstd) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n4 = op.K >> 2;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = warp + 8 * rr;
+        mean[rr] = 0.f; rstd[rr] = 0.f;
+        if (r >= R) continue;                                   // warp-uniform
+        const float4 * row = reinterpret_cast<const float4 *>(X + (size_t) r * op.ldx);
+        double s = 0.0;
+        for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = j0 + 32 * u < n4 ? __ldcg(row + j0 + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += (double) v[u].x + (double) v[u].y + (double) v[u].z + (double) v[u].w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float m = (float) (s / (double) op.K);
+        double s2 = 0.0;
+        for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = j0 + 32 * u < n4 ? __ldcg(row + j0 + 32 * u) : make_float4(m, m, m, m);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float a = v[u].x - m, b = v[u].y - m, c = v[u].z - m, d = v[u].w - m;
+                s2 += (double) (a * a) + (double) (b * b) + (double) (c * c) + (double) (d * d);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        const float var = (float) (s2 / (double) op.K);
+        mean[rr] = m; rstd[rr] = 1.0f / sqrtf(var + op.eps);
+    }
+}
+
+template <typename KVT>
+__device__ __forceinline__ void pk_epilogue(const PkParams & P, const PkOp & op, const PkSeg & sg, int r, int n, float a, float resv, int step_abs, const unsigned long long * skv) {
+    const int nrep = sg.yrep ? PK_REP : 1;
+    switch (sg.epi) {
+        case PKE_GELU: { const __half hv = __float2half_rn(gelu_f16lut(a)); for (int c = 0; c < nrep; c++) sg.Y16[sg.yrep * c + (size_t) r * sg.ldy + n] = hv; break; }
+        case PKE_RES:  { const float v = a + resv; for (int c = 0; c < nrep; c++) sg.Y[sg.yrep * c + (size_t) r * sg.ldy + n] = v; break; }
+        case PKE_KV: {                                         // skv[r]: element offset of (this row's page, its slot in the page), looked up once per op
+            const int h = n / P.hd, d = n - h * P.hd;
+            KVT * base = reinterpret_cast<KVT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes);
+            pk_store1(base + skv[r] + ((size_t) sg.kv * P.heads + h) * PK_PAGE * P.hd + d, a);
+            break;
+        }
+        case PKE_LOGITS:
+            sg.Y[(size_t) r * sg.ldy + n] = a;
+            if (P.logits_all) P.logits_all[((size_t) step_abs * P.R + r) * sg.ldy + n] = a;
+            break;
+        default: sg.Y[(size_t) r * sg.ldy + n] = a; break;
+    }
+}
+
+// one tile: this warp's k-slice of 8 output rows against the staged activation rows.  plane 0: c += xh.Wh (split: cl += xl.Wh too); plane 1 (low weights): cl += xh.Wl
+__device__ __forceinline__ void pk_tile_mma(float * c, float * cl, const __half * wt, const __half * xa, const __half * xb, const __half * xla, const __half * xlb, int ks, bool split, int plane) {
+    for (int k = 0; k < ks; k += 32) {
+        const uint4 wv = *reinterpret_cast<const uint4 *>(wt + k);
+        const uint4 a = *reinterpret_cast<const uint4 *>(xa + k), b = *reinterpret_cast<const uint4 *>(xb + k);
+        const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
+        if (plane == 0) {
+            mma16816_f16f32(c, f0, wv.x, wv.y);
+            mma16816_f16f32(c, f1, wv.z, wv.w);
+            if (split) {
+                const uint4 la = *reinterpret_cast<const uint4 *>(xla + k), lb = *reinterpret_cast<const uint4 *>(xlb + k);
+                const unsigned l0[4] = {la.x, lb.x, la.y, lb.y}, l1[4] = {la.z, lb.z, la.w, lb.w};
+                mma16816_f16f32(cl, l0, wv.x, wv.y);
+                mma16816_f16f32(cl, l1, wv.z, wv.w);
+            }
+        } else {
+            mma16816_f16f32(cl, f0, wv.x, wv.y);
+            mma16816_f16f32(cl, f1, wv.z, wv.w);
+        }
+    }
+}
+
+template <typename KVT> __device__ __forceinline__ void pk_prefetch_kv(const PkParams & P, int layer, int step, const int * sfp, const int * spt);
+
+template <typename KVT>
+__device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, unsigned char * ring, __half * sA, float * red, PkBar * full, PkBar * empty, unsigned & it, int step_abs,
+                                        unsigned long long * pr, unsigned long long * skv, const int * sfp, const int * spt) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t8 = (lane & 3) * 8;
+    const int K = op.K, R = P.R, S = P.n_stages;
+    const bool split = op.seg[0].Wl != nullptr;
+    const int nA = (K + PK_AK - 1) / PK_AK;
+    const int pitch = (K < PK_AK ? K : PK_AK) + PK_PAD;
+    __half * sAl = split ? sA + (size_t) 16 * pitch : nullptr;
+    float mean[2] = {0.f, 0.f}, rstd[2] = {0.f, 0.f};
+    unsigned long long kvoff = 0ull;                           // the cache slot of row tid (q|k|v phase): requested now, parked in shared memory behind the staging pass
+    if (op.kv_prefetch && tid < R) {
+        const int pos = sfp[tid] + step_abs;                    // the position this step appends (the page table and the first positions sit in shared memory: see pdk_kernel)
+        kvoff = (unsigned long long) spt[tid * P.max_pages + (pos >> 5)] * ((size_t) 2 * P.heads * PK_PAGE * P.hd) + (size_t) (pos & (PK_PAGE - 1)) * P.hd;
+    }
+    if (op.kv_prefetch) pk_prefetch_kv<KVT>(P, op.layer, step_abs, sfp, spt);
+    const bool fast = K <= 1024;                               // one chunk, rows in registers: load + statistics + normalise in one pass
+    const size_t xoff = op.xrep * (size_t) (blockIdx.x % PK_REP);      // this CTA's copy of the input rows
+    const float * X = op.X ? op.X + xoff : nullptr; const __half * X16 = op.X16 ? op.X16 + xoff : nullptr;
+    const float * snw = nullptr; int norm_stage = -1;
+    if (op.norm != PKN_NONE) {                                 // the op's first "tile": the norm's weight | bias
+        norm_stage = (int) (it % (unsigned) S);
+        pk_mbar_wait(&full[norm_stage], (it / (unsigned) S) & 1u);
+        snw = reinterpret_cast<const float *>(ring + (size_t) norm_stage * PK_STAGE);
+        it++;
+        if (pr) pr[5] = pk_now();
+    }
+    if (op.norm != PKN_NONE && !fast && !op.X16) pk_row_stats(op, X, R, mean, rstd);
+    float acc[3][4], accl[3][4];                               // nA > 1 (down projections: at most 3 units per CTA): one accumulator per unit across the chunks
+#pragma unroll
+    for (int i = 0; i < 3; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; accl[i][0] = accl[i][1] = accl[i][2] = accl[i][3] = 0.f; }
+    for (int a = 0; a < nA; a++) {
+        const int kA0 = a * PK_AK, kAn = K - kA0 < PK_AK ? K - kA0 : PK_AK, ntile = (kAn + PK_TK - 1) / PK_TK;
+        if (a) pk_bar_sync(1, PK_CONS);                        // every warp is done with the previous chunk
+        if (op.X16) pk_stage_h16(op, X16, R, kA0, kAn, sA, pitch);
+        else if (fast) pk_stage_fast(op, X, snw, R, sA, sAl, pitch);
+        else pk_stage_rows(op, X, snw, R, kA0, kAn, sA, sAl, pitch, mean, rstd);
+        if (a == 0 && op.kv_prefetch && tid < R) skv[tid] = kvoff;
+        if (norm_stage >= 0 && a + 1 == nA) { __syncwarp(); if (lane == 0) pk_mbar_arrive(&empty[norm_stage]); }      // this warp is done with the norm's weights
+        pk_bar_sync(1, PK_CONS);
+        if (pr && a == 0) pr[1] = pk_now();                    // (GEMV phases: activations staged)
+        int ui = 0;
+        for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x, ui++) {
+            const int sj = (op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0);
+            const PkSeg & sg = op.seg[sj];
+            const int n0 = (u - sg.unit0) * 8;
+            float resv = 0.f;                                   // the epilogue's residual element of thread tid < 128, requested before the tiles are consumed
+            if (a + 1 == nA && sg.epi == PKE_RES && tid < 128) { const int r = tid >> 3, n = n0 + (tid & 7); if (r < R && n < sg.N) resv = __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n); }
+            float c[4], cl[4];
+            if (nA > 1) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) if (i == ui) { for (int e = 0; e < 4; e++) { c[e] = acc[i][e]; cl[e] = accl[i][e]; } }
+            } else { c[0] = c[1] = c[2] = c[3] = 0.f; cl[0] = cl[1] = cl[2] = cl[3] = 0.f; }
+            for (int plane = 0; plane < (split ? 2 : 1); plane++) {
+                for (int t = 0; t < ntile; t++, it++) {
+                    const int s = (int) (it % (unsigned) S);
+                    const int kt0 = t * PK_TK, ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, kb = warp * ks;
+                    const unsigned long long tw0 = pr ? pk_now() : 0ull;
+                    pk_mbar_wait(&full[s], (it / (unsigned) S) & 1u);
+                    if (pr) pr[4] += pk_now() - tw0;
+                    const __half * wt = reinterpret_cast<const __half *>(ring + (size_t) s * PK_STAGE) + (size_t) g * (PK_TK + PK_PAD) + t8 + kb;
+                    const __half * xa = sA + (size_t) g * pitch + kt0 + kb + t8, * xb = xa + (size_t) 8 * pitch;
+                    const __half * xla = split ? sAl + (size_t) g * pitch + kt0 + kb + t8 : nullptr, * xlb = split ? xla + (size_t) 8 * pitch : nullptr;
+                    pk_tile_mma(c, cl, wt, xa, xb, xla, xlb, ks, split, plane);
+                    __syncwarp();
+                    if (lane == 0) pk_mbar_arrive(&empty[s]);  // this warp is done reading the stage
+                }
+            }
+            if (a + 1 < nA) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) if (i == ui) { for (int e = 0; e < 4; e++) { acc[i][e] = c[e]; accl[i][e] = cl[e]; } }
+                continue;
+            }
+            // the eight warps' partial 16 x 8 tiles summed in warp order, then the epilogue: c0, c1 = row g, columns 2t, 2t+1; c2, c3 = row g + 8
+            if (split) { for (int e = 0; e < 4; e++) c[e] += cl[e] * (1.0f / GM_LO_SCALE); }
+            float * my = red + warp * 128;
+            const int tq = lane & 3;
+            my[g * 8 + 2 * tq] = c[0]; my[g * 8 + 2 * tq + 1] = c[1]; my[(g + 8) * 8 + 2 * tq] = c[2]; my[(g + 8) * 8 + 2 * tq + 1] = c[3];
+            pk_bar_sync(1, PK_CONS);
+            if (tid < 128) {
+                const int r = tid >> 3, col = tid & 7;
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; w++) sum += red[w * 128 + tid];
+                if (r < R && n0 + col < sg.N) pk_epilogue<KVT>(P, op, sg, r, n0 + col, sum, resv, step_abs, skv);
+            }
+            pk_bar_sync(1, PK_CONS);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- consumers: attention phase.  One (row, head) item per half-CTA (128 threads, named barrier 2 + grp)
+// raw 8-element cache reads: issued in batches so that a thread has 8 independent 16-byte (fp32 store: 2 x 16-byte) loads in flight, converted on use
+struct PkRawH { uint4 a; };
+struct PkRawF { float4 a, b; };
+__device__ __forceinline__ void pk_raw_load(const __half * p, PkRawH & r) { r.a = __ldcg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ void pk_raw_load(const float * p, PkRawF & r) { r.a = __ldcg(reinterpret_cast<const float4 *>(p)); r.b = __ldcg(reinterpret_cast<const float4 *>(p) + 1); }
+__device__ __forceinline__ void pk_raw_zero(PkRawH & r) { r.a = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void pk_raw_zero(PkRawF & r) { r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; }
+__device__ __forceinline__ void pk_raw_f(const PkRawH & r, float * v) {
+    const unsigned w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { __half2 h; memcpy(&h, &w[i], 4); const float2 f = __half22float2(h); v[2 * i] = f.x; v[2 * i + 1] = f.y; }      // (memcpy: no type-punned reads)
+}
+__device__ __forceinline__ void pk_raw_f(const PkRawF & r, float * v) { v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w; }
+template <typename CT> struct PkRawOf { typedef PkRawF type; };
+template <> struct PkRawOf<__half> { typedef PkRawH type; };
+
+#ifdef B2EMU
+static inline void pk_prefetch_l2(const void *) {}
+#else
+__device__ __forceinline__ void pk_prefetch_l2(const void * p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
+template <typename CT> struct PkAttU { static constexpr int v = sizeof(CT) == 2 ? 16 : 8; };      // keys per thread in flight (16 bytes each for fp16 pages, 32 for fp32 stores)
+constexpr int PK_ATT_HDR = 1024;                               // floats of per-group scratch before the scores: q [128] | reduction [128] | (pad) | page offsets [256 x 8 bytes]
+
+// HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three unrolled shuffles that the scheduler interleaves across the keys
+// in flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue slots on a B200)
+template <typename KVT, typename CT, int HD>
+__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int T, const int * spt) {
+    typedef typename PkRawOf<CT>::type Raw;
+    constexpr int U = PkAttU<CT>::v, PARTS = HD / 8, KPP = 128 / PARTS;
+    const int gt = threadIdx.x & 127, gw = gt >> 5, H = P.H, part = gt % PARTS, kq = gt / PARTS;
+    float * qs = base; float * wredf = base + 128; double * wredd = reinterpret_cast<double *>(base + 136);
+    unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 512);      // element offset of each of this sequence's pages within the layer's pool
+    float * pvs = base + PK_ATT_HDR; float * sc = base + PK_ATT_HDR + 1024;
+    const size_t page_elems = (size_t) 2 * P.heads * PK_PAGE * HD;
+    if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
+    if (!op.cross) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) spt[r * P.max_pages + i] * page_elems;
+    pk_bar_sync(2 + grp, 128);
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q8[i] = qs[part * 8 + i];
+    const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + (size_t) h * HD + part * 8, * flat_v = reinterpret_cast<const CT *>(op.cv) + (size_t) h * HD + part * 8;
+    const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) h * PK_PAGE * HD + part * 8;
+    const CT * pool_v = pool_k + (size_t) P.heads * PK_PAGE * HD;
+    auto krow = [&](int t, int kv) -> const CT * {
+        if (op.cross) return (kv ? flat_v : flat_k) + (size_t) t * H;
+        return (kv ? pool_v : pool_k) + spo[t >> 5] + (t & (PK_PAGE - 1)) * HD;
+    };
+    // scores: PARTS threads per key (8 channels each), KPP keys per pass, U passes in flight
+    float mloc = -INFINITY;
+    for (int tb = 0; tb < T; tb += KPP * U) {
+        Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = tb + u * KPP + kq;
+            if (t < T) pk_raw_load(krow(t, 0), raw[u]); else pk_raw_zero(raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = tb + u * KPP + kq;
+            float k8[8];
+            pk_raw_f(raw[u], k8);
+            float a = fmaf(q8[3], k8[3], fmaf(q8[2], k8[2], fmaf(q8[1], k8[1], q8[0] * k8[0]))) + fmaf(q8[7], k8[7], fmaf(q8[6], k8[6], fmaf(q8[5], k8[5], q8[4] * k8[4])));
+#pragma unroll
+            for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            a *= op.scale;
+            if (t < T) { if (part == 0) sc[t] = a; mloc = fmaxf(mloc, a); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+    if ((gt & 31) == 0) wredf[gw] = mloc;
+    pk_bar_sync(2 + grp, 128);
+    const float m = fmaxf(fmaxf(wredf[0], wredf[1]), fmaxf(wredf[2], wredf[3]));
+    double sum = 0.0;                                           // ggml_soft_max: expf(s - max), the sum accumulated in double, scale by (float) (1 / sum)
+    for (int t = gt; t < T; t += 128) { const float e = expf(sc[t] - m); sc[t] = e; sum += (double) e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((gt & 31) == 0) wredd[gw] = sum;
+    pk_bar_sync(2 + grp, 128);
+    const float inv = (float) (1.0 / (((wredd[0] + wredd[1]) + wredd[2]) + wredd[3]));
+    // P.V: thread (slice kq, part) walks positions kq, kq + KPP, ... for its 8 channels with p = e * inv; slices summed in order afterwards
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int tb = 0; tb < T; tb += KPP * U) {
+        Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = tb + u * KPP + kq;
+            if (t < T) pk_raw_load(krow(t, 1), raw[u]); else pk_raw_zero(raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = tb + u * KPP + kq;
+            const float p = t < T ? sc[t] * inv : 0.f;
+            float v8[8];
+            pk_raw_f(raw[u], v8);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = fmaf(p, v8[i], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) pvs[(size_t) kq * HD + part * 8 + i] = acc[i];
+    pk_bar_sync(2 + grp, 128);
+    if (gt < HD) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int sl = 0; sl < KPP; sl++) a += pvs[(size_t) sl * HD + gt];
+        const __half hv = __float2half_rn(a);
+        for (int c = 0; c < (op.orep ? PK_REP : 1); c++) op.out16[op.orep * c + (size_t) r * H + (size_t) h * HD + gt] = hv;
+    }
+    pk_bar_sync(2 + grp, 128);                                  // the scratch is free for the group's next item
+}
+
+template <typename KVT, int HD>
+__device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, unsigned char * scratch, int step, const int * sfp, const int * spt) {
+    const int grp = threadIdx.x >> 7;
+    float * base = reinterpret_cast<float *>(scratch + (size_t) grp * (P.a_bytes / 2));
+    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
+        const int r = it / P.heads, h = it - r * P.heads;
+        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, op.cross_len, spt);
+        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, sfp[r] + step + 1, spt);
+    }
+}
+
+// ask L2 for the K / V rows this CTA's self-attention items of layer `layer` will read (all positions but the one this step appends): issued at the start of the layer's
+// q|k|v phase, so that HBM serves them while that phase runs and the attention phase finds them in L2
+template <typename KVT>
+__device__ __forceinline__ void pk_prefetch_kv(const PkParams & P, int layer, int step, const int * sfp, const int * spt) {
+    const int grp = threadIdx.x >> 7, gt = threadIdx.x & 127, hd = P.hd;
+    const size_t page_elems = (size_t) 2 * P.heads * PK_PAGE * hd, v_off = (size_t) P.heads * PK_PAGE * hd;
+    const int lines = (hd * (int) sizeof(KVT) + 127) / 128;     // 128-byte lines per cache row
+    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
+        const int r = it / P.heads, h = it - r * P.heads, T = sfp[r] + step;
+        const KVT * pool = reinterpret_cast<const KVT *>(P.kv_pool + (size_t) layer * P.kv_layer_bytes) + (size_t) h * PK_PAGE * hd;
+        for (int i = gt; i < T * lines; i += 128) {
+            const int t = i / lines, ln = i - t * lines;
+            const KVT * row = pool + (size_t) spt[r * P.max_pages + (t >> 5)] * page_elems + (size_t) (t & (PK_PAGE - 1)) * hd + ln * (128 / (int) sizeof(KVT));
+            pk_prefetch_l2(row); pk_prefetch_l2(row + v_off);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- consumers: rows + embedding, argmax
+__device__ __forceinline__ void pk_rows(const PkParams & P, int step, int * sids) {
+    const int tid = threadIdx.x, n_out = P.n_out, R = P.R, H = P.H;
+    for (int b = (int) blockIdx.x; b < R; b += (int) gridDim.x) {
+        const int pos = (P.first_pos ? P.first_pos[b] : 0) + step;
+        if (tid == 0) {                                        // delay_rows_kernel for sequence b
+            const int * last = (P.d_teacher ? P.d_teacher : P.d_out) + ((size_t) (step > 0 ? step - 1 : 0) * R + b) * n_out;
+            if (P.seen && step >= 1 && P.stopped[b] < 0) {
+                bool stop = pos >= P.max_gen;
+                if (!stop) { stop = true; for (int i = 0; i < n_out; i++) stop = stop && (P.seen[b * n_out + i] || __ldcg(last + i) == P.eos); }
+                if (stop) P.stopped[b] = step;
+            }
+            for (int i = 0; i < n_out; i++) {
+                const bool s = P.seen && P.seen[b * n_out + i];
+                const int lt = step > 0 ? __ldcg(last + i) : 0;
+                const int id = step > i ? (s ? P.eos : lt) : P.bos;
+                sids[i] = id; P.ids[b * n_out + i] = id;
+                if (P.seen && step >= 1 && lt == P.eos) P.seen[b * n_out + i] = 1;
+            }
+            P.row_pos[b] = pos;
+        }
+        pk_bar_sync(1, PK_CONS);
+        for (int c = tid; c < H; c += PK_CONS) {              // codebook_embed_kernel: the tables' rows summed in head order, then the positional row
+            float a = P.tables[(size_t) sids[0] * H + c];
+            for (int i = 1; i < n_out; i++) a = P.tables[(size_t) i * P.tab_stride + (size_t) sids[i] * H + c] + a;
+            if (P.pos_embed) a = a + P.pos_embed[(size_t) pos * H + c];
+            for (int cp = 0; cp < (P.x0rep ? PK_REP : 1); cp++) P.x0[P.x0rep * cp + (size_t) b * H + c] = a;
+        }
+        pk_bar_sync(1, PK_CONS);
+    }
+}
+
+__device__ __forceinline__ void pk_argmax(const PkParams & P, int step, float * red) {      // sampler::max per (row, head): the first maximum wins
+    float * sv = red; int * si = reinterpret_cast<int *>(red + 256);
+    const int tid = threadIdx.x, V = P.vocab, rows = P.R * P.n_out;
+    for (int b = (int) blockIdx.x; b < rows; b += (int) gridDim.x) {
+        const float * lg = P.logits + (size_t) b * V;
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int i = tid; i < V; i += PK_CONS) { const float v = __ldcg(lg + i); if (v > best) { best = v; bi = i; } }
+        sv[tid] = best; si[tid] = bi;
+        pk_bar_sync(1, PK_CONS);
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
+            pk_bar_sync(1, PK_CONS);
+        }
+        if (tid == 0) P.d_out[(size_t) step * rows + b] = si[0] == 0x7fffffff ? 0 : si[0];
+        pk_bar_sync(1, PK_CONS);
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <typename KVT, int HD>
+__global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
+    extern __shared__ __align__(128) unsigned char pk_smem[];
+    unsigned char * ring = pk_smem;
+    unsigned char * areg = pk_smem + (size_t) P.n_stages * PK_STAGE;           // activation rows (GEMV phases) / attention scratch
+    float * red = reinterpret_cast<float *>(areg + P.a_bytes);
+    int * sids = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(red) + PK_RED_BYTES);      // [16] ids of the row being embedded
+    PkBar * full = reinterpret_cast<PkBar *>(sids + 16);
+    PkBar * empty = full + PK_MAXSTAGES;
+    PkOp * sops = reinterpret_cast<PkOp *>((reinterpret_cast<uintptr_t>(empty + PK_MAXSTAGES) + 15) & ~(uintptr_t) 15);      // [2]: the running op's descriptor and the next one's
+    unsigned long long * skv = reinterpret_cast<unsigned long long *>(sops + 3);      // (sops[2] is the producer warp's copy)                                             // [16]: cache slots of the rows' new k / v
+    // first decode position of every sequence and the page table: constant for the launch, read by every CTA in every attention phase -- from shared memory (as
+    // global reads they were 148 requesters on a handful of L2 lines right after each barrier, and ld.acquire's L1 invalidation defeats caching them)
+    int * sfp = reinterpret_cast<int *>(skv + 16); int * spt = sfp + 16;
+    for (int i = (int) threadIdx.x; i < 16; i += PK_THREADS) sfp[i] = (i < P.R && P.first_pos) ? P.first_pos[i] : 0;
+    for (int i = (int) threadIdx.x; i < P.R * P.max_pages; i += PK_THREADS) spt[i] = P.page_table[i];
+    const int tid = threadIdx.x, warp = tid >> 5, S = P.n_stages;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) { pk_mbar_init(&full[s], 1); pk_mbar_init(&empty[s], 8); }
+        pk_fence_init();
+    }
+    __syncthreads();
+    unsigned it = 0;
+    if (warp == 8) {                                           // ---- producer: one lane streams this CTA's weight tiles in program order, as far ahead as the ring allows
+        // the descriptor of the op being produced is copied to shared memory first (17 independent 16-byte loads: one L2 round trip per op instead of one per field
+        // and tile -- the mbarrier / bulk-copy instructions are compiler barriers, so every field read from global memory was re-issued after each of them)
+        PkOp * pop = sops + 2;
+        const int lane = tid & 31;
+        for (int st = 0; st < P.n_steps; st++)
+            for (int oi = 0; oi < P.n_ops; oi++) {
+                __syncwarp();
+                for (int w = lane; w < (int) (sizeof(PkOp) / 16); w += 32) reinterpret_cast<uint4 *>(pop)[w] = __ldg(reinterpret_cast<const uint4 *>(&P.ops[oi]) + w);
+                __syncwarp();
+                if (lane == 0 && pop->kind == PK_GEMV) pk_produce_gemv(*pop, ring, full, empty, S, it);
+            }
+        return;
+    }
+    unsigned epoch = 0;
+    // op descriptors are read from shared memory: the next op's descriptor is requested from global memory when an op starts and parked in the other slot before the
+    // grid barrier (a descriptor read at op start would put one more L2 round trip on every phase's critical path)
+    constexpr int OPW = (int) (sizeof(PkOp) / 16);
+    if (tid < OPW) reinterpret_cast<uint4 *>(&sops[0])[tid] = __ldg(reinterpret_cast<const uint4 *>(&P.ops[0]) + tid);
+    pk_bar_sync(1, PK_CONS);
+    unsigned opn = 0;
+    for (int st = 0; st < P.n_steps; st++) {
+        const int step = P.step_begin + st;
+        const bool prof = P.prof && step == P.prof_step && tid == 0;
+        for (int oi = 0; oi < P.n_ops; oi++, opn++) {
+            const PkOp & op = sops[opn & 1u];
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (tid < OPW) nxt = __ldg(reinterpret_cast<const uint4 *>(&P.ops[oi + 1 < P.n_ops ? oi + 1 : 0]) + tid);
+            unsigned long long * pr = prof ? P.prof + ((size_t) oi * gridDim.x + blockIdx.x) * 8 : nullptr;
+            if (pr) pr[0] = pk_now();
+            switch (op.kind) {
+                case PK_ROWS:   pk_rows(P, step, sids); break;
+                case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, it, step, pr, skv, sfp, spt); break;
+                case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
+                case PK_ARGMAX: pk_argmax(P, step, red); break;
+            }
+            if (pr) pr[2] = pk_now();
+            if (tid < OPW) reinterpret_cast<uint4 *>(&sops[(opn & 1u) ^ 1u])[tid] = nxt;
+            pk_grid_sync(P.bar, epoch);
+            if (pr) pr[3] = pk_now();
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) *P.d_step = P.step_begin + P.n_steps;
+}
+
+// prompt-pass K / V rows (fp32, [R0 rows][H] per layer, row r of sequence seq at position pos) -> the pages
+template <typename KVT>
+__global__ void pk_kv_import_kernel(const float * __restrict__ Kc, const float * __restrict__ Vc, size_t layer_stride, const int * __restrict__ row_src, const int * __restrict__ row_seq,
+                                    const int * __restrict__ row_pos, const PkParams P) {
+    const int r = blockIdx.x, l = blockIdx.y, seq = row_seq[r], pos = row_pos[r];
+    const float * k = Kc + (size_t) l * layer_stride + (size_t) row_src[r] * P.H, * v = Vc + (size_t) l * layer_stride + (size_t) row_src[r] * P.H;
+    for (int c = threadIdx.x; c < P.H; c += blockDim.x) {
+        const int h = c / P.hd, d = c - h * P.hd;
+        pk_store1(pk_page_row<KVT>(P, l, seq, pos, 0, h) + d, k[c]);
+        pk_store1(pk_page_row<KVT>(P, l, seq, pos, 1, h) + d, v[c]);
+    }
+}
+
+static inline size_t pk_smem_bytes(int n_stages, int a_bytes, int pt_ints) { return (size_t) (16 + pt_ints) * 4 + (size_t) n_stages * PK_STAGE + (size_t) a_bytes + PK_RED_BYTES + 64 + 2 * PK_MAXSTAGES * sizeof(PkBar) + 3 * sizeof(PkOp) + 16 + 128 + 128; }
+
+}  // namespace
+}  // namespace b2
