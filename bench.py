@@ -508,6 +508,52 @@ def run_parler(args):
     return 0
 
 
+def decode_step_record(ctx):
+    """The metric's second half, "decode-step HBM % peak": one decode step of BASELINE config 3's model (Parler-TTS-Mini-shaped F16 decoder, batch 16) around position 450,
+    through the persistent decode kernel, against SURVEY 8(d)'s algorithmic bytes (W_step + per sequence the KV cache read up to the position and one row written, 2 B per
+    element, + the logits).  Timed as the difference of two greedy generations (416 and 480 steps, CUDA events inside the library), i.e. over steps 416..479."""
+    from tts_cpp_b200.binding import parler_runner_from_file
+    from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_parler_gguf
+    par = parler_runner_from_file(cached_parler_gguf(seed=0, f16=True, **PARLER_MINI_SHAPE), ctx=ctx)
+    B, n_prompt, n0, n1 = 16, 24, 416, 480
+    rng = np.random.default_rng(5)
+    prompts = [rng.integers(1, 500, size=n_prompt).astype(np.uint32) for _ in range(B)]
+    par.generate_greedy(prompts, 64)                          # warm-up
+    t = []
+    for n in (n0, n1, n0, n1):
+        par.generate_greedy(prompts, n)
+        t.append(par.last_ms())
+    ms = ((t[1] - t[0]) + (t[3] - t[2])) / 2.0 / (n1 - n0)
+    L, H = par.n_layers, par.hidden_size
+    pos = n_prompt + (n0 + n1 - 1) / 2.0
+    w_step = par.step_weight_bytes()
+    kv_read, kv_write, lg = 2 * L * pos * H * 2, 2 * L * H * 2, par.n_heads * par.out_vocab * 4
+    alg = w_step + B * (kv_read + kv_write + lg)
+    _, hbm, peak_src = _peaks()
+    launches, steps = par.pdk_stats()
+    rec = {"workload": "Parler-TTS-Mini-sized F16 decoder (synthetic), batch 16, greedy, decode steps 416..479 (positions ~440-504)", "ms_per_decode_step": ms,
+           "algorithmic_bytes_per_step": alg, "terms": {"W_step": w_step, "kv_read_per_seq": kv_read, "kv_write_per_seq": kv_write, "logits_per_seq": lg, "batch": B, "position": pos},
+           "achieved_gbs": alg / (ms * 1e-3) / 1e9, "peak_gbs": hbm, "frac": alg / (ms * 1e-3) / 1e9 / hbm, "peak_source": peak_src,
+           "kernel": "pdk_kernel (persistent cooperative decode kernel: TMA weight ring, paged fp16 KV cache)" if steps else "launch-per-op decode path",
+           "persistent_kernel": {"launches": launches, "decode_steps": steps}, "audio_s_per_s_ar_only": B * 512 / 44100.0 / (ms * 1e-3),
+           "dram_traffic_per_step_ncu": _decode_traffic()}
+    par.close()
+    return rec
+
+
+def _decode_traffic():
+    """DRAM bytes per decode step from the committed ncu capture of the persistent kernel (profiles/*_pdk_traffic.json), or None"""
+    try:
+        import glob
+        cand = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_pdk_traffic.json")))
+        if cand:
+            tj = json.load(open(cand[-1]))
+            return {"bytes": tj["dram_bytes_per_step"], "source": os.path.basename(cand[-1])}
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -515,6 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode-step", action="store_true", help="skip the decode-step HBM record of the default line (Parler-Mini F16, batch 16; ~30 s incl. writing its synthetic GGUF)")
     ap.add_argument("--parler-dtype", default="f16", choices=["f16", "q8_0", "q5_0", "q4_0"],
                     help="--workload parler: dtype of the decoder matrices (f16 = BASELINE config 3; q5_0 is what the reference's published Parler numbers use)")
     ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "snac", "parler"],
@@ -640,6 +687,12 @@ def main():
         "device_ms_per_step": dev_ms / args.steps,
         "pass_ms_per_step": {"duration_pass": pass_ms[0] / args.steps, "generation_pass": pass_ms[1] / args.steps},
     }
+    if world == 1 and not args.no_decode_step:
+        try:
+            runner.close()                                     # free the Kokoro workspace (5.6 GB) before the decode model's
+            line["decode_step"] = decode_step_record(ctx)
+        except Exception as e:      # noqa: BLE001 -- the headline line must still be printed
+            line["decode_step"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu_baseline:
         base, why = reference_throughput(n_timed=1, n_warm=1)
         line["cpu_baseline"] = base if base else {"value": None, "unavailable": why}

@@ -80,6 +80,12 @@ size_t b2tts_kokoro_weight_bytes(const b2tts_kokoro * m);
  */
 int b2tts_kokoro_run_batch(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice,
                            const uint64_t * noise_skip, const float ** pcm, int64_t * n_samples, const float ** durations);
+/* The same forward for utterances that are CONSECUTIVE generate() calls of one reference process -- the chunks kokoro_runner::generate makes of a long prompt
+ * (model.cpp:1430-1447, run one after another there) or a drained request queue: utterance b's noise continues the process-wide uniform stream where utterance
+ * b-1 left it (9 * 600 * T_b draws each), the first at noise_skip_first.  The offsets depend on the durations, so the library sets them between its two passes.
+ * Everything else as b2tts_kokoro_run_batch. */
+int b2tts_kokoro_run_chunks(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, uint64_t noise_skip_first,
+                            const float ** pcm, int64_t * n_samples, const float ** durations);
 
 /* Stage timings of the last run_batch in milliseconds (CUDA events on the launching stream):
  * [0] duration pass, [1] generation pass (device), [2] whole call incl. H2D/D2H.  */

@@ -15,7 +15,10 @@
 #include "util.h"
 
 #include "b2tts.h"
+#include "tts_b200.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -74,50 +77,80 @@ struct kokoro_b200_runner : tts_generation_runner {
         }
     }
 
-    // kokoro_runner::run for all chunks at once
-    void run_chunks(const std::vector<std::vector<uint32_t>> & chunks, const std::string & voice, tts_response & out) {
+    // kokoro_runner::run for all chunks at once.  The chunks are consecutive run() calls in the reference (model.cpp:1430-1447): chunk b's noise continues the
+    // process-wide uniform stream where chunk b-1 left it; the library chains the offsets itself once it knows the durations (b2tts_kokoro_run_chunks).
+    void run_chunks(const std::vector<std::vector<uint32_t>> & chunks, const std::string & voice, std::vector<const float *> & pcm, std::vector<int64_t> & ns) {
         std::vector<uint32_t> toks;
         std::vector<int32_t>  n;
         for (auto & c : chunks) { toks.insert(toks.end(), c.begin(), c.end()); n.push_back((int32_t) c.size()); }
-        std::vector<const float *> pcm(chunks.size());
-        std::vector<int64_t>       ns(chunks.size());
-        // chunk b's noise starts after the draws of chunks 0..b-1; their lengths are only known after the call, so multi-chunk prompts
-        // share the starting offset here (single-chunk prompts reproduce the reference's stream exactly)
-        std::vector<uint64_t> skip(chunks.size(), noise_draws);
-        if (b2tts_kokoro_run_batch(model, (int) chunks.size(), toks.data(), n.data(), voice.c_str(), skip.data(), pcm.data(), ns.data(), nullptr))
-            TTS_ABORT("%s\n", b2tts_last_error());
-        size_t total = 0;
-        for (auto v : ns) total += (size_t) v;
-        if (chunks.size() == 1) {
-            out.data = const_cast<float *>(pcm[0]);           // borrowed, valid until the next generate (like kokoro_runner, model.cpp:1299)
-        } else {
-            joined.clear();
-            for (size_t b = 0; b < chunks.size(); b++) joined.insert(joined.end(), pcm[b], pcm[b] + ns[b]);
-            out.data = joined.data();
+        pcm.assign(chunks.size(), nullptr);
+        ns.assign(chunks.size(), 0);
+        if (const char * dump = getenv("B2TTS_DUMP_TOKENS")) {      // parity tests: the token ids the reference's front end produced for this call, one chunk per line
+            if (FILE * f = fopen(dump, "a")) { for (auto & c : chunks) { for (uint32_t t : c) fprintf(f, "%u ", t); fprintf(f, "\n"); } fclose(f); }
         }
-        out.n_outputs = total;
-        noise_draws += 9ull * total;
+        if (b2tts_kokoro_run_chunks(model, (int) chunks.size(), toks.data(), n.data(), voice.c_str(), noise_draws, pcm.data(), ns.data(), nullptr))
+            TTS_ABORT("%s\n", b2tts_last_error());
+        for (auto v : ns) noise_draws += 9ull * (uint64_t) v;
     }
 
-    void generate(const char * prompt, tts_response & response, const generation_configuration & config) override {
-        const std::string voice = config.voice.empty() ? "af_heart" : config.voice;
+    // the reference's flow from text to chunks (kokoro_runner::generate, model.cpp:1409-1450)
+    void chunks_of(const char * prompt, std::vector<std::vector<uint32_t>> & chunks) {
         std::string normalized = replace_any(prompt, "\n", " ");
         std::string phonemes   = phmzr->text_to_phonemes(normalized);
-        std::vector<std::vector<uint32_t>> chunks;
         std::vector<uint32_t> space;
         tokenizer->tokenize(" ", space);
         const uint32_t space_id = space.empty() ? 0xffffffffu : space[0];
         if (phonemes.size() < (size_t) max_context_length - 2) {
             phonemes = strip(replace_any(phonemes, ".!?", ""));
-            if (phonemes.empty()) return;
-            chunk_clause(phonemes, space_id, chunks);
+            if (!phonemes.empty()) chunk_clause(phonemes, space_id, chunks);
         } else {
             for (auto clause : split(phonemes, ".!?")) {
                 clause = strip(clause);
                 if (!clause.empty()) chunk_clause(clause, space_id, chunks);
             }
         }
-        if (!chunks.empty()) run_chunks(chunks, voice, response);
+    }
+
+    void generate(const char * prompt, tts_response & response, const generation_configuration & config) override {
+        const std::string voice = config.voice.empty() ? "af_heart" : config.voice;
+        std::vector<std::vector<uint32_t>> chunks;
+        chunks_of(prompt, chunks);
+        if (chunks.empty()) return;
+        std::vector<const float *> pcm; std::vector<int64_t> ns;
+        run_chunks(chunks, voice, pcm, ns);
+        size_t total = 0;
+        for (auto v : ns) total += (size_t) v;
+        if (chunks.size() == 1) {
+            response.data = const_cast<float *>(pcm[0]);      // borrowed, valid until the next generate (like kokoro_runner, model.cpp:1299)
+        } else {
+            joined.clear();
+            for (size_t b = 0; b < chunks.size(); b++) joined.insert(joined.end(), pcm[b], pcm[b] + ns[b]);
+            response.data = joined.data();
+        }
+        response.n_outputs = total;
+    }
+
+    // Non-breaking addition (SURVEY 8b "Batch"): several prompts in ONE forward, with the outputs the reference would give for generate(prompts[0]), generate(prompts[1]), ...
+    // in this order on this runner (the noise stream runs through all chunks of all prompts).  responses[i].data points into a runner-owned buffer valid until the
+    // next call; a server worker drains its queue into one call of this.
+    void generate_batch(const std::vector<const char *> & prompts, std::vector<tts_response> & responses, const generation_configuration & config) {
+        const std::string voice = config.voice.empty() ? "af_heart" : config.voice;
+        std::vector<std::vector<uint32_t>> chunks;
+        std::vector<size_t> first(prompts.size() + 1, 0);
+        for (size_t i = 0; i < prompts.size(); i++) { chunks_of(prompts[i], chunks); first[i + 1] = chunks.size(); }
+        responses.assign(prompts.size(), tts_response{});
+        if (chunks.empty()) return;
+        std::vector<const float *> pcm; std::vector<int64_t> ns;
+        run_chunks(chunks, voice, pcm, ns);
+        size_t total = 0;
+        for (auto v : ns) total += (size_t) v;
+        joined.clear(); joined.reserve(total);
+        std::vector<size_t> at(prompts.size() + 1, 0);
+        for (size_t i = 0; i < prompts.size(); i++) {
+            for (size_t b = first[i]; b < first[i + 1]; b++) joined.insert(joined.end(), pcm[b], pcm[b] + ns[b]);
+            at[i + 1] = joined.size();
+        }
+        for (size_t i = 0; i < prompts.size(); i++) { responses[i].data = joined.data() + at[i]; responses[i].n_outputs = at[i + 1] - at[i]; }
     }
 };
 
@@ -143,3 +176,10 @@ struct kokoro_b200_loader final : tts_model_loader {
 const kokoro_b200_loader kokoro_b200_loader_instance{};
 
 }  // namespace
+
+bool tts_b200_generate_batch(tts_generation_runner & runner, const std::vector<const char *> & prompts, std::vector<tts_response> & outputs, const generation_configuration & config) {
+    auto * k = dynamic_cast<kokoro_b200_runner *>(&runner);
+    if (!k) return false;
+    k->generate_batch(prompts, outputs, config);
+    return true;
+}

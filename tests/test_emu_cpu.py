@@ -22,6 +22,9 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "sampler.cu"]
+# The library's defaults are the fast paths (persistent decode kernel for F16 Parler, tensor-core GEMV for F16 matrices, CUDA-graph replay); most tests below are about
+# one specific kernel family, so they start from the plain launch-per-op configuration and switch on what they test.
+EMU_DEFAULTS = {"B2TTS_AR_PDK": "0", "B2TTS_AR_MMA": "0", "B2TTS_AR_GRAPH": "0"}
 
 
 def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag, env=None, want_stderr=False):
@@ -33,7 +36,7 @@ def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag, env=None, want_stde
         for p in prompts:
             f.write(struct.pack("i", p.size))
             f.write(np.asarray(p, np.uint32).tobytes())
-    r = subprocess.run([exe, model, gguf_path, pin, pout], capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
+    r = subprocess.run([exe, model, gguf_path, pin, pout], capture_output=True, text=True, timeout=900, env={**os.environ, **EMU_DEFAULTS, **(env or {})})
     assert r.returncode == 0, r.stderr[-2000:]
     raw = open(pout, "rb").read()
     W, V = struct.unpack("ii", raw[:8])
@@ -307,7 +310,7 @@ def test_parler_stop_rule_emulated(tmp_path, case):
     with open(pin, "wb") as f:
         f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompt.size)); f.write(prompt.astype(np.uint32).tobytes())
     r = subprocess.run([exe, "parler", cached_parler_gguf(seed=0, eos_boost=boost), pin, pout], capture_output=True, text=True, timeout=900,
-                       env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1", B2TTS_AR_EXIT_EVERY="4"))
+                       env={**os.environ, **EMU_DEFAULTS, "B2EMU_STOP": "1", "B2EMU_NO_LOGITS": "1", "B2TTS_AR_EXIT_EVERY": "4"})
     assert r.returncode == 0, r.stderr[-2000:]
     launches = int(r.stderr.split("emulated ")[1].split(" launches")[0])
     # the stop flags are read back every 4 steps here, so the batch stops stepping at most 4 steps after every sequence has ended: 16 launches of prepare, 121 of
@@ -420,6 +423,8 @@ ASAN_CASES = {
     "parler_f16_mma_sampling_stop": ("parler", lambda: cached_parler_gguf(seed=0, f16=True), "parler_f16_vectors", {"B2TTS_AR_MMA": "1", "B2EMU_SAMPLE": "20 0.9 0.8 1.2 5", "B2EMU_STOP": "1"}),
     "parler_q5_0": ("parler", lambda: cached_parler_gguf(seed=0, quant="Q5_0"), "parler_q5_0_vectors", {}),
     "dia_q8_0_plain_attention": ("dia", lambda: cached_dia_gguf(seed=0, quant="Q8_0"), "dia_q8_0_vectors", {"B2TTS_AR_ATT": "plain"}),
+    # the persistent decode kernel: ring stages, activation / attention scratch, page pool, page table, replicated hand-off buffers -- one exact-size allocation each
+    "parler_f16_persistent_kernel": ("parler", lambda: cached_parler_gguf(seed=0, f16=True), "parler_f16_vectors", {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "3", "B2TTS_AR_EXIT_EVERY": "2"}),
 }
 
 
@@ -439,15 +444,15 @@ def test_address_sanitizer_emulated(tmp_path, case):
         for p in prompts:
             f.write(struct.pack("i", p.size)); f.write(p.astype(np.uint32).tobytes())
     r = subprocess.run([exe, model, gguf(), pin, pout], capture_output=True, text=True, timeout=900,
-                       env=dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0", **env))
+                       env={**os.environ, **EMU_DEFAULTS, "ASAN_OPTIONS": "detect_stack_use_after_return=0:detect_leaks=0", **env})
     assert r.returncode == 0, r.stderr[-3000:]
     assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr
 
 
 # ---- the persistent decode kernel (tts_cpp_b200/csrc/pdk.cuh): one cooperative launch runs up to 32 decode steps; under emulation every block of the grid is alive at
 # once (b2emu::launch_coop), mbarriers / bulk copies / the grid barrier have functional models.  F16 Parler GGUFs take this path by default (B2TTS_AR_PDK=0: per-op path).
-@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "1"}, {"B2TTS_PDK_GRID": "3", "B2TTS_AR_EXIT_EVERY": "2"}, {"B2TTS_PDK_GRID": "5", "B2EMU_REVERSE": "1"},
-                                 {"B2TTS_PDK_GRID": "7", "B2TTS_AR_EXIT_EVERY": "1", "B2TTS_KV": "f32"}], ids=["grid1", "grid3_chunks_of_2", "grid5_reversed", "grid7_kv_f32_chunks_of_1"])
+@pytest.mark.parametrize("env", [{"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "1"}, {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "3", "B2TTS_AR_EXIT_EVERY": "2"}, {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "5", "B2EMU_REVERSE": "1"},
+                                 {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "7", "B2TTS_AR_EXIT_EVERY": "1", "B2TTS_KV": "f32"}], ids=["grid1", "grid3_chunks_of_2", "grid5_reversed", "grid7_kv_f32_chunks_of_1"])
 def test_persistent_decode_kernel_emulated_matches_reference(tmp_path, env):
     """the reference's F16 tokens and logits (tests/golden/parler_f16_vectors.npz) from the persistent kernel with its paged fp16 (or fp32) KV cache, for several grid sizes
     (different unit -> CTA distributions; grid 1 = no concurrency), several launches per generation (step counter / ring / page state carried across launches) and both
@@ -476,11 +481,11 @@ def test_persistent_decode_kernel_emulated_stop_rule_and_teacher(tmp_path):
     exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
     gguf = cached_parler_gguf(seed=0, eos_boost=boost, f16=True)
     outs = {}
-    for tag, env in (("pk", {"B2TTS_PDK_GRID": "3"}), ("op", {"B2TTS_AR_PDK": "0"})):
+    for tag, env in (("pk", {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "3"}), ("op", {"B2TTS_AR_PDK": "0"})):
         pin, pout = str(tmp_path / f"p{tag}.bin"), str(tmp_path / f"o{tag}.bin")
         with open(pin, "wb") as f:
             f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompt.size)); f.write(prompt.astype(np.uint32).tobytes())
-        r = subprocess.run([exe, "parler", gguf, pin, pout], capture_output=True, text=True, timeout=900, env=dict(os.environ, B2EMU_STOP="1", B2EMU_NO_LOGITS="1", B2TTS_AR_EXIT_EVERY="4", **env))
+        r = subprocess.run([exe, "parler", gguf, pin, pout], capture_output=True, text=True, timeout=900, env={**os.environ, **EMU_DEFAULTS, "B2EMU_STOP": "1", "B2EMU_NO_LOGITS": "1", "B2TTS_AR_EXIT_EVERY": "4", **env})
         assert r.returncode == 0, r.stderr[-2000:]
         raw = open(pout, "rb").read()
         W, V = struct.unpack("ii", raw[:8])
@@ -493,7 +498,7 @@ def test_persistent_decode_kernel_emulated_stop_rule_and_teacher(tmp_path):
     steps = int(g["tokens0"].shape[0])
     tf = str(tmp_path / "teacher.bin")
     np.stack([g["tokens0"], g["tokens1"]]).astype(np.int32).tofile(tf)
-    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "tf", env={"B2EMU_TEACHER": tf, "B2TTS_PDK_GRID": "4"})
+    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "tf", env={"B2EMU_TEACHER": tf, "B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "4"})
     for u in range(2):
         assert np.array_equal(tok[u], g[f"tokens{u}"])
         assert float(np.abs(logits[u] - g[f"logits{u}"].reshape(steps, -1)).max()) < 3e-2

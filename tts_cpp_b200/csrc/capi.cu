@@ -335,6 +335,14 @@ int b2tts_kokoro_run_batch(b2tts_kokoro * m, int batch, const uint32_t * tokens,
     B2_CUDA(cudaSetDevice(m->k.ctx->device));
     return m->k.run_batch(batch, tokens, n_tokens, voice, noise_skip, pcm, n_samples, durations);
 }
+int b2tts_kokoro_run_chunks(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, uint64_t noise_skip_first,
+                            const float ** pcm, int64_t * n_samples, const float ** durations) {
+    B2_CUDA(cudaSetDevice(m->k.ctx->device));
+    m->k.chain_noise = true; m->k.chain_noise_start = noise_skip_first;
+    const int rc = m->k.run_batch(batch, tokens, n_tokens, voice, nullptr, pcm, n_samples, durations);
+    m->k.chain_noise = false;
+    return rc;
+}
 int b2tts_kokoro_last_timings(const b2tts_kokoro * m, float ms[3]) { for (int i = 0; i < 3; i++) ms[i] = m->k.timings[i]; return 0; }
 
 int b2tts_kokoro_set_taps(b2tts_kokoro * m, int enable) { m->k.taps_on = enable != 0; return 0; }

@@ -82,11 +82,16 @@ struct PrepT {
         return w;
     }
     // Conv1d kernel [Cout][Cin][K] (+ bias).  F32 storage -> split form over 3*Cin operand channels (x hi | x lo | x hi) x (W hi | W hi | W lo)
-    DacConv conv(const std::string & base, int dil, int pad) {
+    DacConv conv(const std::string & base, int dil, int pad, int k_hint = 0) {
         DacConv c;
         auto t = get(base + ".weight");
         if (!t) return c;
-        c.Cout = (int) t->shape[0]; c.Cin = (int) t->shape[1]; c.K = t->shape.size() > 2 ? (int) t->shape[2] : 1; c.dil = dil; c.pad = pad;
+        // a caller that hands over ggml tensors reports ggml_n_dims(), which drops outermost dimensions of size 1: the final [1][96][7] kernel arrives as [96][7].
+        // Conv1d kernels are rank 3 in the file unless they are 1x1 projections stored as [Cout][Cin]: a rank-2 shape whose second extent is the kernel width of a
+        // unit-output conv is told apart by the caller's `k_hint`
+        std::vector<int64_t> sh = t->shape;
+        if (k_hint > 1 && sh.size() == 2 && sh[1] == k_hint) sh.insert(sh.begin(), 1);
+        c.Cout = (int) sh[0]; c.Cin = (int) sh[1]; c.K = sh.size() > 2 ? (int) sh[2] : 1; c.dil = dil; c.pad = pad;
         c.split = !t->f16;
         if (c.split) {
             const int C3 = 3 * c.Cin;
@@ -306,7 +311,7 @@ int Dac::prepare() {
         }
     }
     final_alpha = P.f32("final.alpha");
-    final_conv = P.conv("final", 1, 3);
+    final_conv = P.conv("final", 1, 3, 7);
     if (!P.ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     host.clear();
@@ -585,7 +590,7 @@ int Snac::prepare() {
         }
     }
     final_alpha = P.f32("alpha_out");
-    final_conv = P.conv("final", 1, 3);
+    final_conv = P.conv("final", 1, 3, 7);
     if (!P.ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     noise_engine = new NormalGen();

@@ -90,10 +90,14 @@ struct Prep {
         w.w = (__half *) dev(h.data(), h.size() * 2);
         return w;
     }
-    W16 w16(const std::string & n) {
+    // rank: the tensor's rank in the GGUF file when it may arrive with fewer dimensions -- a caller that hands over ggml tensors reports ggml_n_dims(), which drops
+    // outermost dimensions of size 1 (a [1][256][1] conv kernel arrives as [256][1]); missing leading dimensions are 1
+    W16 w16(const std::string & n, int rank = 0) {
         auto t = get(n);
         if (!t) return W16();
-        const int N = (int) t->shape[0], Cin = (int) t->shape[1], K = t->shape.size() > 2 ? (int) t->shape[2] : 1;
+        std::vector<int64_t> sh = t->shape;
+        while ((int) sh.size() < rank) sh.insert(sh.begin(), 1);
+        const int N = (int) sh[0], Cin = (int) sh[1], K = sh.size() > 2 ? (int) sh[2] : 1;
         return w16_from(t->v, N, Cin, K);
     }
     Lstm lstm(const std::string & base) {
@@ -218,8 +222,8 @@ int Kokoro::prepare() {
         f0_blocks[i] = P.ada("duration_predictor.f0_blocks." + std::to_string(i), 0);
         n_blocks[i] = P.ada("duration_predictor.n_blocks." + std::to_string(i), 0);
     }
-    f0_proj = P.w16("duration_predictor.f0_proj_kernel"); f0_proj_b = P.f32("duration_predictor.f0_proj_bias");
-    n_proj = P.w16("duration_predictor.n_proj_kernel"); n_proj_b = P.f32("duration_predictor.n_proj_bias");
+    f0_proj = P.w16("duration_predictor.f0_proj_kernel", 3); f0_proj_b = P.f32("duration_predictor.f0_proj_bias");
+    n_proj = P.w16("duration_predictor.n_proj_kernel", 3); n_proj_b = P.f32("duration_predictor.n_proj_bias");
     // text encoder
     if (auto t = P.get("text_encoder.embedding_weight")) {
         n_vocab = std::min(n_vocab, (int) (t->v.size() / 512));
@@ -604,6 +608,12 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     float * dur_out = lens_pinned + rows1 + B;
     for (int b = 0; b < B; b++) memcpy(dur_out + tok_off[b], lens_pinned + (size_t) b * Nmax, (size_t) ntok[b] * 4);
     if (durations) *durations = dur_out;
+    if (chain_noise) {                                          // consecutive calls of one reference process: each utterance continues the uniform stream of the one before
+        chain_skips.assign((size_t) B, 0ull);
+        unsigned long long at = chain_noise_start;
+        for (int b = 0; b < B; b++) { chain_skips[(size_t) b] = at; at += 9ull * 600ull * (unsigned long long) T[b]; }
+        B2_CUDA(cudaMemcpyAsync(d_skip, chain_skips.data(), (size_t) B * 8, cudaMemcpyHostToDevice, st));      // (member vector: alive until the next synchronisation below)
+    }
 
     // ================================================================ pass 2: generation (model.cpp:1141-1242)
     const int L1 = Tmax, L2 = 2 * Tmax, L4 = 120 * Tmax + 1, S = 600 * Tmax;

@@ -124,6 +124,11 @@ struct Kokoro {
     int prepare();
     int run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, const uint64_t * noise_skip, const float ** pcm,
                   int64_t * n_samples, const float ** durations);
+    // chain_noise: the utterances are consecutive generate() calls of ONE reference process (the chunks of a long prompt, kokoro/model.cpp:1430-1447, or a drained
+    // queue): utterance b's noise starts where utterance b-1's ended (9 * 600 * T draws each, util.cpp:66-72,140-172), the first one at chain_noise_start.  The
+    // offsets need the durations, so they are set between the two passes.
+    bool chain_noise = false; uint64_t chain_noise_start = 0;
+    std::vector<unsigned long long> chain_skips;
     void free_all();
 };
 

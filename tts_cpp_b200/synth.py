@@ -190,8 +190,10 @@ def kokoro_metadata(ctx_len: int = 512):
     return kv
 
 
-def write_kokoro_gguf(path: str, seed: int = 0, dtype: str = "f16", ctx_len: int = 512, **kw) -> dict:
-    """Write the synthetic model; returns {"tensors": n, "params": n, "bytes": n}."""
+def write_kokoro_gguf(path: str, seed: int = 0, dtype: str = "f16", ctx_len: int = 512, text_vocab: bool = False, **kw) -> dict:
+    """Write the synthetic model; returns {"tensors": n, "params": n, "bytes": n}.
+    text_vocab: a GGUF the reference's own TEXT front end can drive (examples/cli, generate("some text")): the built-in rule phonemizer (phonemizer.type 0) with one
+    rule per letter (a -> a ...) and a token vocabulary of the printable ASCII characters, so that plain lower-case text phonemizes to itself and tokenizes 1:1."""
     import gguf
 
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
@@ -209,12 +211,22 @@ def write_kokoro_gguf(path: str, seed: int = 0, dtype: str = "f16", ctx_len: int
     # the reference loader aborts without a (possibly trivial) rule phonemizer and tokenizer vocabulary
     w.add_uint32("phonemizer.type", 0)
     w.add_uint32("phonemizer.phoneme_type", 1)
-    w.add_array("phonemizer.graphemes", ["a", "b"])
-    w.add_array("phonemizer.rules.keys", ["a"])
-    w.add_array("phonemizer.rules.phonemes", ["a"])
-    w.add_array("phonemizer.dictionary.keys", ["a"])
-    w.add_array("phonemizer.dictionary.values", ["a"])
-    w.add_array("tokenizer.ggml.tokens", [""] + [chr(0x100 + i) for i in range(177)])
+    if text_vocab:
+        letters = [chr(c) for c in range(ord("a"), ord("z") + 1)]
+        w.add_array("phonemizer.graphemes", letters)
+        w.add_array("phonemizer.rules.keys", letters)
+        w.add_array("phonemizer.rules.phonemes", letters)
+        w.add_array("phonemizer.dictionary.keys", ["a"])
+        w.add_array("phonemizer.dictionary.values", ["a"])
+        ascii_tokens = [chr(c) for c in range(32, 127)]
+        w.add_array("tokenizer.ggml.tokens", [""] + ascii_tokens + [chr(0x100 + i) for i in range(177 - len(ascii_tokens))])
+    else:
+        w.add_array("phonemizer.graphemes", ["a", "b"])
+        w.add_array("phonemizer.rules.keys", ["a"])
+        w.add_array("phonemizer.rules.phonemes", ["a"])
+        w.add_array("phonemizer.dictionary.keys", ["a"])
+        w.add_array("phonemizer.dictionary.values", ["a"])
+        w.add_array("tokenizer.ggml.tokens", [""] + [chr(0x100 + i) for i in range(177)])
     w.add_array("kokoro.voices", ["af_heart"])
     w.write_header_to_file()
     w.write_kv_data_to_file()
@@ -231,7 +243,7 @@ def cached_gguf(dtype: str = "f16", ctx_len: int = 128, seed: int = 0, cache_dir
     path = os.path.join(cache_dir, f"kokoro_{dtype}_c{ctx_len}_s{seed}_{tag}.gguf")
     if not os.path.exists(path):
         tmp = f"{path}.{os.getpid()}.tmp"
-        write_kokoro_gguf(tmp, seed=seed, dtype=dtype, ctx_len=ctx_len, **kw)
+        write_kokoro_gguf(tmp, seed=seed, dtype=dtype, ctx_len=ctx_len, **kw)      # (kw may carry text_vocab=True)
         os.replace(tmp, path)
     return path
 
