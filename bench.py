@@ -541,6 +541,67 @@ def decode_step_record(ctx):
     return rec
 
 
+def strong_scaling_record(args, torch, dist, runner, rank, world, local):
+    """SURVEY 8(d)/(e), the north star's multi-GPU sentence: a FIXED job of 32 utterances on rank 0's host -> NCCL scatter of the prompts -> every rank's batched forward
+    (PCM stays in device memory) -> NCCL gather of the PCM to rank 0 -> one device-to-pinned-host copy there; everything inside the timed region, barrier + synchronize on
+    both sides, max over ranks.  At N = 1 the same path without the collectives (the table's first row)."""
+    from tts_cpp_b200 import sharding
+    device = torch.device("cuda", local)
+    counts = [BATCH // world + (1 if r < BATCH % world else 0) for r in range(world)]
+    all_prompts = _prompts(0) if rank == 0 else None
+    host_out = torch.empty(BATCH * 600 * 260, dtype=torch.float32).pin_memory() if rank == 0 else None
+    split = [0.0, 0.0, 0.0]
+    result = {}
+
+    def step(timed):
+        t0 = time.perf_counter()
+        if dist is not None:
+            mine = sharding.scatter_tokens_nccl(dist, torch, device, all_prompts, counts, src=0)
+        else:
+            mine = all_prompts
+        t1 = time.perf_counter()
+        ptr, stride, ns = runner.run_batch_device(mine) if mine else (0, 0, [])
+        t2 = time.perf_counter()
+        block = sharding.device_block(torch, device, ptr, len(ns), stride) if ns else None
+        if dist is not None:
+            got = sharding.gather_pcm_nccl(dist, torch, device, block, ns, counts, dst=0, host_out=host_out)
+        else:
+            packed = torch.cat([block[b, :n] for b, n in enumerate(ns)])
+            host_out[:packed.numel()].copy_(packed, non_blocking=True)
+            torch.cuda.synchronize()
+            got = (host_out[:packed.numel()], ns)
+        t3 = time.perf_counter()
+        if timed:
+            split[0] += t1 - t0; split[1] += t2 - t1; split[2] += t3 - t2
+        if rank == 0:
+            result["samples"] = int(sum(got[1])); result["utterances"] = len(got[1])
+        return got
+
+    for _ in range(2):
+        step(False)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([wall], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0])
+    if rank != 0:
+        return None
+    audio_s = result["samples"] / 24000.0
+    return {"scaling": "strong", "utterances_total": result["utterances"], "utterances_per_gpu": counts, "value": audio_s * args.steps / wall, "unit": "audio-s/s", "ms_per_step": wall * 1e3 / args.steps,
+            "rank0_ms_per_step": {"scatter": split[0] * 1e3 / args.steps, "forward": split[1] * 1e3 / args.steps, "gather_and_d2h": split[2] * 1e3 / args.steps},
+            "h2d_bytes_per_step": BATCH * (N_PHON + 2 + 1) * 8, "d2h_bytes_per_step": result["samples"] * 4,
+            "collectives": None if dist is None else "NCCL: broadcast of the packed prompts (lengths + ids), all_gather of the PCM lengths, exact-length send/recv of the PCM from device memory to rank 0"}
+
+
 def _decode_traffic():
     """DRAM bytes per decode step from the committed ncu capture of the persistent kernel (profiles/*_pdk_traffic.json), or None"""
     try:
@@ -561,6 +622,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (32 utterances in total: NCCL scatter of the prompts, forward, NCCL gather of the PCM to rank 0)")
     ap.add_argument("--no-decode-step", action="store_true", help="skip the decode-step HBM record of the default line (Parler-Mini F16, batch 16; ~30 s incl. writing its synthetic GGUF)")
     ap.add_argument("--parler-dtype", default="f16", choices=["f16", "q8_0", "q5_0", "q4_0"],
                     help="--workload parler: dtype of the decoder matrices (f16 = BASELINE config 3; q5_0 is what the reference's published Parler numbers use)")
@@ -648,6 +710,12 @@ def main():
         audio_total = float(a[0])
     else:
         audio_total = audio_s
+    strong = None
+    if not args.no_strong:
+        try:
+            strong = strong_scaling_record(args, torch, dist, runner, rank, world, local)     # every rank takes part; rank 0 gets the record
+        except Exception as e:      # noqa: BLE001 -- the weak-scaling headline must still be printed
+            strong = {"unavailable": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -687,6 +755,8 @@ def main():
         "device_ms_per_step": dev_ms / args.steps,
         "pass_ms_per_step": {"duration_pass": pass_ms[0] / args.steps, "generation_pass": pass_ms[1] / args.steps},
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
     if world == 1 and not args.no_decode_step:
         try:
             runner.close()                                     # free the Kokoro workspace (5.6 GB) before the decode model's

@@ -80,6 +80,12 @@ size_t b2tts_kokoro_weight_bytes(const b2tts_kokoro * m);
  */
 int b2tts_kokoro_run_batch(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice,
                            const uint64_t * noise_skip, const float ** pcm, int64_t * n_samples, const float ** durations);
+/* The same forward with the PCM LEFT IN DEVICE MEMORY: *pcm_device points at a [batch][*row_stride] float32 block on the context's device (utterance b occupies the
+ * first n_samples[b] floats of row b), owned by the model and valid until its next call; the forward is complete when the call returns.  The one entry point where a
+ * device pointer crosses the ABI: it exists for the multi-GPU gather ("NCCL/NVLink used only to scatter prompts and gather PCM"), which sends the audio to
+ * the gathering rank straight from device memory instead of through two host copies. */
+int b2tts_kokoro_run_batch_device(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, const uint64_t * noise_skip,
+                                  const float ** pcm_device, int64_t * row_stride, int64_t * n_samples);
 /* The same forward for utterances that are CONSECUTIVE generate() calls of one reference process -- the chunks kokoro_runner::generate makes of a long prompt
  * (model.cpp:1430-1447, run one after another there) or a drained request queue: utterance b's noise continues the process-wide uniform stream where utterance
  * b-1 left it (9 * 600 * T_b draws each), the first at noise_skip_first.  The offsets depend on the durations, so the library sets them between its two passes.

@@ -110,6 +110,52 @@ def test_scatter_gather_world2_gloo():
     assert q.get(timeout=5) is True
 
 
+def _worker_dev(rank, world, port, q):
+    """the tensor-collective forms bench.py's strong-scaling step uses (broadcast of the packed prompts, all_gather of lengths, exact-length send / grouped irecv),
+    here over gloo with CPU tensors"""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from tts_cpp_b200.sharding import scatter_tokens_nccl, gather_pcm_nccl
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    device = torch.device("cpu")
+    counts = [4, 3]
+    prompts = None
+    if rank == 0:
+        rng = np.random.default_rng(6)
+        prompts = [[0] + [int(v) for v in rng.integers(1, 178, size=int(n))] + [0] for n in rng.integers(1, 40, size=7)]
+    mine = scatter_tokens_nccl(dist, torch, device, prompts, counts, src=0)
+    assert len(mine) == counts[rank]
+    # stand-in for the forward: a padded [utterances][stride] block, utterance b = 10 samples per token with the token id as value
+    ns = [10 * len(p) for p in mine]
+    stride = max(ns) + 7
+    block = torch.full((len(mine), stride), -1.0)
+    for b, p in enumerate(mine):
+        block[b, :ns[b]] = torch.from_numpy(np.repeat(np.asarray(p, np.float32), 10))
+    got = gather_pcm_nccl(dist, torch, device, block, ns, counts, dst=0)
+    if rank == 0:
+        flat, lens = got
+        want = np.concatenate([np.repeat(np.asarray(p, np.float32), 10) for p in prompts])
+        q.put(bool(np.array_equal(flat.numpy(), want)) and lens == [10 * len(p) for p in prompts])
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+def test_device_scatter_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_dev, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_polyphase_identity_of_the_strided_noise_conv():
     """The strided noise conv (K = 12, stride 6, pad 3) runs on the tcgen05 kernel as a stride-1 conv over rows of `stride` input
     frames (tts_cpp_b200/csrc/kokoro.cu, Kokoro::prepare).  This restates that re-indexing in numpy and checks it against the plain

@@ -188,6 +188,17 @@ class KokoroRunner:
         p, d = self.run_batch([tokens], voice, [noise_skip])
         return p[0], d[0]
 
+    def run_batch_device(self, utterances, voice: str | None = None):
+        """the forward with the PCM left on the device (b2tts_kokoro_run_batch_device) -> (device pointer, row stride in floats, n_samples per utterance);
+        valid until the runner's next call.  For the multi-GPU gather (tts_cpp_b200/sharding.py)."""
+        B = len(utterances)
+        ntok = np.array([len(u) for u in utterances], np.int32)
+        toks = np.ascontiguousarray(np.concatenate([np.asarray(u, np.uint32) for u in utterances]))
+        ptr, stride, ns = C.POINTER(C.c_float)(), C.c_int64(), (C.c_int64 * B)()
+        _chk(lib().b2tts_kokoro_run_batch_device(self.h, B, toks.ctypes.data_as(C.POINTER(C.c_uint32)), ntok.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 voice.encode() if voice else None, None, C.byref(ptr), C.byref(stride), ns))
+        return C.cast(ptr, C.c_void_p).value, int(stride.value), [int(v) for v in ns]
+
     def timings(self):
         ms = (C.c_float * 3)()
         lib().b2tts_kokoro_last_timings(self.h, ms)

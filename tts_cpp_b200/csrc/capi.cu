@@ -335,6 +335,15 @@ int b2tts_kokoro_run_batch(b2tts_kokoro * m, int batch, const uint32_t * tokens,
     B2_CUDA(cudaSetDevice(m->k.ctx->device));
     return m->k.run_batch(batch, tokens, n_tokens, voice, noise_skip, pcm, n_samples, durations);
 }
+int b2tts_kokoro_run_batch_device(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, const uint64_t * noise_skip,
+                                  const float ** pcm_device, int64_t * row_stride, int64_t * n_samples) {
+    B2_CUDA(cudaSetDevice(m->k.ctx->device));
+    m->k.keep_on_device = true;
+    const int rc = m->k.run_batch(batch, tokens, n_tokens, voice, noise_skip, nullptr, n_samples, nullptr);
+    m->k.keep_on_device = false;
+    if (!rc) { if (pcm_device) *pcm_device = m->k.last_pcm_dev; if (row_stride) *row_stride = m->k.last_pcm_stride; }
+    return rc;
+}
 int b2tts_kokoro_run_chunks(b2tts_kokoro * m, int batch, const uint32_t * tokens, const int32_t * n_tokens, const char * voice, uint64_t noise_skip_first,
                             const float ** pcm, int64_t * n_samples, const float ** durations) {
     B2_CUDA(cudaSetDevice(m->k.ctx->device));

@@ -804,6 +804,16 @@ int Kokoro::run_batch(int B, const uint32_t * tokens, const int32_t * n_tokens, 
     // ---- D2H into the runner-owned pinned buffer (borrowed by the caller until the next call, like tts_response.data)
     // one copy of the padded [B][S] block when the padding is small (a copy per utterance costs ~10 us of launch overhead each);
     // ragged batches whose padding would add > 25 % bytes are copied utterance by utterance, packed
+    last_pcm_dev = pcm_d; last_pcm_stride = S;
+    if (keep_on_device) {                                       // the caller takes the PCM from device memory (NCCL gather): no host copy
+        for (int b = 0; b < B; b++) { if (pcm) pcm[b] = nullptr; if (n_samples) n_samples[b] = (int64_t) T[b] * 600; }
+        B2_CUDA(cudaEventRecord(ev[3], st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&timings[0], ev[0], ev[1]);
+        cudaEventElapsedTime(&timings[1], ev[1], ev[2]);
+        cudaEventElapsedTime(&timings[2], ev[0], ev[3]);
+        return 0;
+    }
     const bool one_copy = (size_t) B * S <= Ssum + Ssum / 4;
     const size_t need_pinned = one_copy ? (size_t) B * S : Ssum;
     if (pcm_pinned_cap < need_pinned) {

@@ -127,6 +127,9 @@ struct Kokoro {
     // chain_noise: the utterances are consecutive generate() calls of ONE reference process (the chunks of a long prompt, kokoro/model.cpp:1430-1447, or a drained
     // queue): utterance b's noise starts where utterance b-1's ended (9 * 600 * T draws each, util.cpp:66-72,140-172), the first one at chain_noise_start.  The
     // offsets need the durations, so they are set between the two passes.
+    // keep_on_device: skip the device -> host copy of the PCM (the multi-GPU gather sends it over NCCL from device memory); last_pcm_dev [B][last_pcm_stride] stays
+    // valid until the next call on this model
+    bool keep_on_device = false; const float * last_pcm_dev = nullptr; int64_t last_pcm_stride = 0;
     bool chain_noise = false; uint64_t chain_noise_start = 0;
     std::vector<unsigned long long> chain_skips;
     void free_all();
