@@ -508,6 +508,98 @@ def run_parler(args):
     return 0
 
 
+def run_orpheus(args):
+    """Secondary line: BASELINE config 5's model on ONE GPU of the 8 -- an Orpheus-3B-shaped decoder (28 layers x 3072, 24 / 8 heads x 128, ffn 8192, vocab 156 940) with
+    Q8_0 matrices (our own writer: the reference's quantize tool refuses Orpheus and its runtime is F32-only), random weights handed over tensor by tensor (no GGUF file),
+    greedy, launch-per-op path (dp4a block GEMV, CUDA-graph replay).  Sweep of the per-GPU batch {1, 2, 4, 8, 16} (config 5: 64 utterances over 8 GPUs = 8 per GPU);
+    a "step" = `n_tokens` decode steps of the whole batch (7 tokens = one 85.3 ms SNAC frame)."""
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "workload": "orpheus", "unavailable": "the reference runs Orpheus in F32 only (README.md:25): 13 GB of weights per CPU worker, minutes per second of audio; not timed here"}))
+        return 0
+    import torch  # noqa: F401
+    from tts_cpp_b200.binding import Context
+    from tts_cpp_b200.synth import build_orpheus_direct
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    t0 = time.perf_counter()
+    orph = build_orpheus_direct(ctx, dtype=args.orpheus_dtype)
+    load_s = time.perf_counter() - t0
+    n_tokens = 7 * 24                                           # 24 SNAC frames = 2.05 s of audio per sequence per step
+    rng = np.random.default_rng(9)
+    _, hbm, peak_src = _peaks()
+    w_step = orph.step_weight_bytes()
+    L, KV = orph.n_layers, 1024
+    sweep = []
+    for B in (1, 2, 4, 8, 16):
+        prompts = [rng.integers(1, 100000, size=40).astype(np.uint32) for _ in range(B)]
+        orph.generate_greedy(prompts, 16)                       # warm-up (graph instantiation, arena)
+        ms = []
+        for _ in range(max(1, min(args.steps, 3))):
+            orph.generate_greedy(prompts, n_tokens)
+            ms.append(orph.last_ms())
+        step_ms = min(ms) / n_tokens
+        pos = 40 + n_tokens / 2.0
+        alg = w_step + B * (2 * L * pos * KV * 2 + 2 * L * KV * 2 + orph.vocab_size * 4)
+        sweep.append({"batch_per_gpu": B, "ms_per_decode_step": step_ms, "audio_s_per_s": B * (n_tokens / 7) * (2048 / 24000.0) / (min(ms) * 1e-3),
+                      "algorithmic_bytes_per_step": alg, "achieved_gbs": alg / (step_ms * 1e-3) / 1e9, "frac": alg / (step_ms * 1e-3) / 1e9 / hbm})
+    best = next(x for x in sweep if x["batch_per_gpu"] == 8)
+    print(json.dumps({"metric": "audio_seconds_per_second", "workload": f"Orpheus-3B-shaped {args.orpheus_dtype} decoder (synthetic), greedy AR decode, per-GPU batch sweep (BASELINE config 5: 8 per GPU x 8 GPUs); SNAC decode measured by --workload snac",
+                      "value": best["audio_s_per_s"], "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": best["ms_per_decode_step"] * n_tokens,
+                      "sweep": sweep, "roofline": {"bound": "hbm", "kernel": "launch-per-op decode step (gemv_rows_q_kernel dp4a / attention_gqa_kernel)", "achieved": best["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                                                   "frac": best["frac"], "traffic": None, "peak_source": peak_src, "W_step": w_step},
+                      "load_s": load_s, "weight_bytes": orph.weight_bytes(), "dtype": f"{args.orpheus_dtype} matrices (Q8_0: Q8_0-requantised activations, int32 block dots, f32 accumulate)", "data": "synthetic",
+                      "config": {"workload": "orpheus-3b shape, 40-token prompts, 168 decode steps per timed generation, greedy"}}))
+    return 0
+
+
+def run_dia(args):
+    """Secondary line: BASELINE config 4's model on ONE GPU of the 4 -- a Dia-1.6B-shaped F16 model (encoder 12 x 1024, decoder 18 x 2048, 16 q / 4 kv heads x 128, ffn 8192),
+    2 utterances per GPU (8 over 4 GPUs), each a CFG pair, 128-byte two-speaker prompts padded to the 1 024-position encoder context, 10 s of audio (861 frames + the
+    15-step delay tail), greedy, launch-per-op path (tensor-core GEMV, CUDA-graph replay), then the DAC decode of the frames."""
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "workload": "dia", "unavailable": "not timed: a 1.6 B-parameter CPU decode of 876 steps per worker takes tens of minutes; the Parler arm (--workload parler --impl reference) is the timed AR reference"}))
+        return 0
+    import torch  # noqa: F401
+    from tts_cpp_b200.ar_host import dia_adjust_output_tokens
+    from tts_cpp_b200.binding import Context, dac_runner_from_file
+    from tts_cpp_b200.synth import build_dia_direct, cached_dac_gguf
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    t0 = time.perf_counter()
+    dia = build_dia_direct(ctx, dtype="f16")
+    load_s = time.perf_counter() - t0
+    dac = dac_runner_from_file(cached_dac_gguf(seed=0, max_frames=64), ctx=ctx)
+    B, frames = 2, 861
+    n_steps = frames + 15
+    rng = np.random.default_rng(4)
+    prompts = [np.concatenate([[1], rng.integers(32, 127, size=62), [2], rng.integers(32, 127, size=64)]).astype(np.uint32) for _ in range(B)]
+
+    def step():
+        toks, ngen = dia.generate_greedy(prompts, n_steps)
+        t_ar = dia.last_ms()
+        codes = [dia_adjust_output_tokens(t % 1024, 1024) for t in toks]
+        pcm = dac.run_batch(codes, copy=False)
+        return t_ar, dac.last_ms(), sum(p.shape[0] for p in pcm) / 44100.0, int(ngen.min())
+
+    step()
+    ar_ms = dac_ms = audio_s = 0.0
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        a, d, au, ng = step()
+        ar_ms += a; dac_ms += d; audio_s += au
+    n = max(1, min(args.steps, 3))
+    wall = time.perf_counter() - t0
+    _, hbm, peak_src = _peaks()
+    step_ms = ar_ms / n / n_steps
+    print(json.dumps({"metric": "audio_seconds_per_second", "workload": "Dia-1.6B-shaped F16 model (synthetic), 2 utterances (CFG pairs) per GPU, 10 s each, greedy AR decode + DAC decode (BASELINE config 4, one of its 4 GPUs)",
+                      "value": audio_s / ((ar_ms + dac_ms) * 1e-3), "unit": "audio-s/s", "n_gpus": 1, "steps": n, "ms_per_step": (ar_ms + dac_ms) / n, "ar_ms_per_step": ar_ms / n, "dac_ms_per_step": dac_ms / n,
+                      "decode_step_ms": step_ms, "frames_generated_min": ng, "e2e": {"value": audio_s / wall, "unit": "audio-s/s"},
+                      "roofline": {"bound": "hbm", "kernel": "launch-per-op decode step (gemv_mma_kernel / attention_gqa_kernel)", "achieved": dia.weight_bytes() / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                   "frac": dia.weight_bytes() / (step_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": peak_src,
+                                   "note": "algorithmic bytes = the resident weights once per step (encoder weights included: an upper bound of W_step by ~10 %); KV excluded"},
+                      "load_s": load_s, "weight_bytes": dia.weight_bytes(), "dtype": "f16 matrices x fp16-rounded activations, f32 accumulate", "data": "synthetic",
+                      "config": {"workload": "dia-1.6b shape, 128-byte prompts, 876 decode steps, EOS / PAD rows of the heads zeroed so that every generation runs its full length"}}))
+    return 0
+
+
 def decode_step_record(ctx):
     """The metric's second half, "decode-step HBM % peak": one decode step of BASELINE config 3's model (Parler-TTS-Mini-shaped F16 decoder, batch 16) around position 450,
     through the persistent decode kernel, against SURVEY 8(d)'s algorithmic bytes (W_step + per sequence the KV cache read up to the position and one row written, 2 B per
@@ -626,7 +718,8 @@ def main():
     ap.add_argument("--no-decode-step", action="store_true", help="skip the decode-step HBM record of the default line (Parler-Mini F16, batch 16; ~30 s incl. writing its synthetic GGUF)")
     ap.add_argument("--parler-dtype", default="f16", choices=["f16", "q8_0", "q5_0", "q4_0"],
                     help="--workload parler: dtype of the decoder matrices (f16 = BASELINE config 3; q5_0 is what the reference's published Parler numbers use)")
-    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "snac", "parler"],
+    ap.add_argument("--orpheus-dtype", default="q8_0", choices=["q8_0", "f16", "f32"], help="--workload orpheus: dtype of the matrices (q8_0 = BASELINE config 5)")
+    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "snac", "parler", "orpheus", "dia"],
                     help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
                          "parler: config 3 end to end (AR decode + DAC), plain first path")
     args = ap.parse_args()
@@ -640,6 +733,10 @@ def main():
         return run_dac(args)
     if args.workload == "parler":
         return run_parler(args)
+    if args.workload == "orpheus":
+        return run_orpheus(args)
+    if args.workload == "dia":
+        return run_dia(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 

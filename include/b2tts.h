@@ -204,6 +204,13 @@ int   b2tts_orpheus_generate_greedy(b2tts_orpheus * m, int n_sequences, const ui
 /* the same loop under the reference sampler's settings (sampler.cpp on the device, sampler.cu); sampling == NULL is the greedy call above */
 int   b2tts_orpheus_generate(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
                              int32_t * out_tokens, float * out_logits);
+/* generate_from_batch's loop WITH its stop condition (model.cpp:389-398: stop at orpheus.stopping_token_id or after max_steps tokens): per sequence n_generated[b]
+ * tokens were produced, the last of them the stopping token when it came (tokens past it are zero); the batch stops stepping once every sequence has ended (checked
+ * every 32 steps).  Matrices may be F32 (the reference's only Orpheus dtype), F16 or Q4_0 / Q5_0 / Q8_0 blocks (BASELINE config 5 runs q8_0). */
+int   b2tts_orpheus_generate_until_stop(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int max_steps,
+                                        const b2tts_sampling * sampling, int32_t * out_tokens, int32_t * n_generated);
+int   b2tts_orpheus_set_stopping_token(b2tts_orpheus * m, int token_id);   /* overrides orpheus.stopping_token_id of the GGUF (model.h:43: 128258) */
+size_t b2tts_orpheus_step_weight_bytes(const b2tts_orpheus * m);   /* W_step of SURVEY 8(d): bytes of the weight tensors one decode step touches, each once, stored dtype */
 size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m);   /* bytes resident in HBM (B2TTS_AR_MMA=1 adds the fp16 split copies of the matrices) */
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 

@@ -68,11 +68,12 @@ struct orpheus_b200_runner : tts_generation_runner {
         b2tts_sampling s;
         s.do_sample = config.sample; s.top_k = config.top_k; s.top_p = config.top_p; s.temperature = config.temperature; s.repetition_penalty = config.repetition_penalty;
         s.seed = ((uint64_t) std::random_device{}() << 32) | std::random_device{}();
+        // generate_from_batch's exit test runs on the device: the stream ends right after the stopping token (kept) or at max_generation, and the decode loop stops
+        // stepping there (a short utterance no longer pays for max_generation steps)
         std::vector<int32_t> stream(max_generation);
-        if (b2tts_orpheus_generate(decoder, 1, prompts, n_prompt, (int) max_generation, &s, stream.data(), nullptr)) TTS_ABORT("%s\n", b2tts_last_error());
-        // generate_from_batch's exit test: the stream ends right after the stopping token (kept) or at max_generation
-        size_t n = stream.size();
-        for (size_t i = 0; i < stream.size(); i++) if ((uint32_t) stream[i] == stopping_token) { n = i + 1; break; }
+        int32_t n_gen = 0;
+        if (b2tts_orpheus_generate_until_stop(decoder, 1, prompts, n_prompt, (int) max_generation, &s, stream.data(), &n_gen)) TTS_ABORT("%s\n", b2tts_last_error());
+        const size_t n = (size_t) n_gen;
         // prepare_output_tokens: whole 7-token frames; token ii of a frame minus 128266 + ii * 4096 goes to SNAC level heads[ii]
         std::vector<uint32_t> level[3];
         for (size_t i = 0; i < n / 7; i++)

@@ -502,3 +502,23 @@ def test_persistent_decode_kernel_emulated_stop_rule_and_teacher(tmp_path):
     for u in range(2):
         assert np.array_equal(tok[u], g[f"tokens{u}"])
         assert float(np.abs(logits[u] - g[f"logits{u}"].reshape(steps, -1)).max()) < 3e-2
+
+
+@pytest.mark.parametrize("kind", ["q8_0", "f16"])
+def test_orpheus_quantised_and_f16_matrices_emulated(tmp_path, kind):
+    """Orpheus with Q8_0 (BASELINE config 5's dtype; our own writer -- the reference's quantize tool refuses Orpheus and its runtime is F32-only) or F16 matrices through
+    the block-quantised / F16 GEMV kernels: no reference output exists for these files, so the yardstick is the reference's F32 run of the same weights
+    (tests/golden/orpheus_vectors.npz): logits within the storage format's noise and the same greedy token wherever the F32 top-2 gap is clear."""
+    g = np.load(os.path.join(GOLD, "orpheus_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].size)
+    gguf = cached_orpheus_gguf(seed=0, quant="Q8_0") if kind == "q8_0" else cached_orpheus_gguf(seed=0, f16=True)
+    tok, logits = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, kind)
+    for u in range(2):
+        ref = g[f"logits{u}"].reshape(steps, -1)
+        rel = float(np.sqrt(((logits[u] - ref) ** 2).mean()) / ref.std())
+        top2 = np.sort(ref, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 8.0 * np.abs(logits[u] - ref).max(axis=1)
+        print(f"PARITY(emulated) orpheus {kind} prompt {u}: logit rms / std {rel:.3e}; tokens equal {int((tok[u, :, 0] == g[f'tokens{u}']).sum())}/{steps}, clear decisions {int(clear.sum())}")
+        assert rel < (0.05 if kind == "q8_0" else 0.01)
+        assert np.array_equal(tok[u, :, 0][clear], g[f"tokens{u}"][clear])

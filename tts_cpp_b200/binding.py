@@ -384,6 +384,22 @@ class OrpheusRunner:
                                           toks.ctypes.data_as(C.POINTER(C.c_int32)), None))
         return toks
 
+    def generate_until_stop(self, prompts, max_steps: int, sampling: "Sampling | None" = None):
+        """-> (tokens [B][max_steps], n_generated [B]): the reference's loop with its stop condition (stopping token or max_steps)"""
+        B, arrs, npr, ptrs = _prompt_args(prompts)
+        toks = np.empty((B, max_steps), np.int32)
+        ngen = np.empty(B, np.int32)
+        _chk(lib().b2tts_orpheus_generate_until_stop(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), int(max_steps), C.byref(sampling) if sampling is not None else None,
+                                                     toks.ctypes.data_as(C.POINTER(C.c_int32)), ngen.ctypes.data_as(C.POINTER(C.c_int32))))
+        return toks, ngen
+
+    def set_stopping_token(self, token_id: int):
+        _chk(lib().b2tts_orpheus_set_stopping_token(self.h, int(token_id)))
+
+    def step_weight_bytes(self) -> int:
+        lib().b2tts_orpheus_step_weight_bytes.restype = C.c_size_t
+        return int(lib().b2tts_orpheus_step_weight_bytes(self.h))
+
     def last_ms(self) -> float:
         lib().b2tts_orpheus_last_ms.restype = C.c_float
         return float(lib().b2tts_orpheus_last_ms(self.h))

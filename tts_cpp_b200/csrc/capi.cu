@@ -224,6 +224,23 @@ int b2tts_orpheus_generate(b2tts_orpheus * m, int n_sequences, const uint32_t * 
     const ArSampling a = to_sampling(sampling);
     return m->o.generate(n_sequences, prompts, n_prompt, n_steps, &a, out_tokens, out_logits);
 }
+int b2tts_orpheus_generate_until_stop(b2tts_orpheus * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int max_steps, const b2tts_sampling * sampling,
+                                      int32_t * out_tokens, int32_t * n_generated) {
+    if (!m) { set_error("null model"); return 1; }
+    if (!n_generated) { set_error("n_generated must not be null"); return 1; }
+    const ArSampling a = to_sampling(sampling);
+    return m->o.generate(n_sequences, prompts, n_prompt, max_steps, &a, out_tokens, nullptr, n_generated);
+}
+int b2tts_orpheus_set_stopping_token(b2tts_orpheus * m, int token_id) { if (!m) { set_error("null model"); return 1; } m->o.stopping_token = token_id; return 0; }
+size_t b2tts_orpheus_step_weight_bytes(const b2tts_orpheus * m) {
+    if (!m) return 0;
+    const Orpheus & o = m->o;
+    auto wb = [](const ArW & w, size_t n) { return w.qtype ? n * (w.qtype == 2 ? 18 : w.qtype == 6 ? 22 : 34) / 32 : n * (w.f16 ? 2 : 4); };
+    const size_t H = (size_t) o.hidden, KV = (size_t) o.kv_hidden, F = (size_t) o.ffn;
+    size_t b = 0;
+    for (const OrpheusLayer & L : o.layers) b += wb(L.wq, H * H) + wb(L.wk, KV * H) + wb(L.wv, KV * H) + wb(L.wo, H * H) + wb(L.wgate, F * H) + wb(L.wup, F * H) + wb(L.wdown, H * F) + 2 * H * 4;
+    return b + wb(o.head, (size_t) o.vocab * H) + H * 4;
+}
 size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m) { return m ? m->o.weight_bytes : 0; }
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m) { return m ? m->o.timing_ms : 0.f; }
 // ---- Parler AR decode (first correct path)

@@ -14,7 +14,7 @@ int Orpheus::assign(const char * name, int type, int n_dims, const int64_t * ne,
     std::string nm(name);
     if (nm.rfind("orpheus.", 0) == 0) nm = nm.substr(8);
     HostTensor t;
-    if (host_tensor_from_gguf(t, name, type, n_dims, ne, data, nbytes, false)) return 1;
+    if (host_tensor_from_gguf(t, name, type, n_dims, ne, data, nbytes, true)) return 1;
     host[nm] = std::move(t);
     return 0;
 }
@@ -27,30 +27,46 @@ int Orpheus::prepare() {
         kvreq("orpheus.head_dim", head_dim) || kvreq("orpheus.hidden_size", hidden) || kvreq("orpheus.kv_hidden_size", kv_hidden)) return 1;
     { auto it = kv.find("orpheus.stopping_token_id"); stopping_token = it != kv.end() ? (int) it->second : 128258; }
     if (hidden != heads * head_dim || kv_hidden != kv_heads * head_dim || heads % kv_heads || head_dim % 4 || hidden % 4) { set_error("orpheus: inconsistent head configuration"); return 1; }
+    { auto it = kv.find("orpheus.context_length"); max_context = it != kv.end() ? (int) it->second : 0; }
     bool ok = true;
-    auto up = [&](const std::string & n, int64_t expect) -> float * {
+    auto find = [&](const std::string & n, int64_t expect) -> const HostTensor * {
         auto it = host.find(n);
         if (it == host.end()) { set_error("missing tensor orpheus.%s", n.c_str()); ok = false; return nullptr; }
         if (expect && (int64_t) it->second.v.size() != expect) { set_error("tensor orpheus.%s has %zu elements, expected %lld", n.c_str(), it->second.v.size(), (long long) expect); ok = false; return nullptr; }
+        return &it->second;
+    };
+    auto dev = [&](const void * src, size_t bytes) -> void * {
         void * d = nullptr;
-        if (cudaMalloc(&d, it->second.v.size() * 4) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed for orpheus.%s", n.c_str()); ok = false; return nullptr; }
-        cudaMemcpy(d, it->second.v.data(), it->second.v.size() * 4, cudaMemcpyHostToDevice);
-        dev_allocs.push_back(d); weight_bytes += it->second.v.size() * 4;
-        if (gemv_split_mma_enabled() && it->second.shape.size() == 2) {                     // the split copy of a matrix: W = hi + lo, lo carried scaled by 2^11
-            const size_t cnt = it->second.v.size();
-            std::vector<__half> hi(cnt), lo(cnt);
-            for (size_t i = 0; i < cnt; i++) { const float w = it->second.v[i]; hi[i] = __float2half_rn(w); lo[i] = __float2half_rn((w - __half2float(hi[i])) * GM_LO_SCALE); }
-            void * dh = nullptr, * dl = nullptr;
-            if (cudaMalloc(&dh, cnt * 2) != cudaSuccess || cudaMalloc(&dl, cnt * 2) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed for the split of orpheus.%s", n.c_str()); ok = false; return nullptr; }
-            cudaMemcpy(dh, hi.data(), cnt * 2, cudaMemcpyHostToDevice); cudaMemcpy(dl, lo.data(), cnt * 2, cudaMemcpyHostToDevice);
-            dev_allocs.push_back(dh); dev_allocs.push_back(dl); weight_bytes += cnt * 4;
-            split[(const float *) d] = {dh, dl};
+        if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); set_error("orpheus: cudaMalloc of %zu bytes failed", bytes); ok = false; return nullptr; }
+        cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+        dev_allocs.push_back(d); weight_bytes += bytes;
+        return d;
+    };
+    auto up = [&](const std::string & n, int64_t expect) -> float * { const HostTensor * t = find(n, expect); return t ? (float *) dev(t->v.data(), t->v.size() * 4) : nullptr; };   // fp32 values (F16 / blocks widened exactly like ggml_get_rows)
+    auto upw = [&](const std::string & n, int64_t expect) -> ArW {      // a matrix in its stored form
+        ArW w;
+        const HostTensor * t = find(n, expect);
+        if (!t) return w;
+        if (t->qtype) { if (!upload_quant_planes(*t, w, dev_allocs, weight_bytes)) ok = false; return w; }
+        if (t->f16) {
+            std::vector<__half> h(t->v.size());
+            for (size_t i = 0; i < h.size(); i++) h[i] = __float2half_rn(t->v[i]);
+            w.f16 = true; w.p = dev(h.data(), h.size() * 2);
+            return w;
         }
-        return (float *) d;
+        w.p = dev(t->v.data(), t->v.size() * 4);
+        if (gemv_split_mma_enabled() && t->shape.size() == 2 && w.p) {                   // the split copy of an F32 matrix: W = hi + lo, lo carried scaled by 2^11
+            const size_t cnt = t->v.size();
+            std::vector<__half> hi(cnt), lo(cnt);
+            for (size_t i = 0; i < cnt; i++) { const float x = t->v[i]; hi[i] = __float2half_rn(x); lo[i] = __float2half_rn((x - __half2float(hi[i])) * GM_LO_SCALE); }
+            const void * dh = dev(hi.data(), cnt * 2), * dl = dev(lo.data(), cnt * 2);
+            if (dh && dl) split[(const float *) w.p] = {dh, dl};
+        }
+        return w;
     };
     embed = up("embed_tokens", (int64_t) vocab * hidden);
     out_norm = up("norm", hidden);
-    head = up("lm_head", (int64_t) vocab * hidden);
+    head = upw("lm_head", (int64_t) vocab * hidden);
     rope_ff = up("rope_frequencies", head_dim / 2);
     {
         auto it = host.find("layers.0.mlp.gate_proj");
@@ -63,10 +79,13 @@ int Orpheus::prepare() {
         const std::string b = "layers." + std::to_string(l);
         OrpheusLayer & L = layers[(size_t) l];
         L.in_norm = up(b + ".input_layernorm", hidden);  L.post_norm = up(b + ".post_attention_layernorm", hidden);
-        L.wq = up(b + ".self_attn.q_proj", (int64_t) hidden * hidden);    L.wk = up(b + ".self_attn.k_proj", (int64_t) kv_hidden * hidden);
-        L.wv = up(b + ".self_attn.v_proj", (int64_t) kv_hidden * hidden); L.wo = up(b + ".self_attn.o_proj", (int64_t) hidden * hidden);
-        L.wgate = up(b + ".mlp.gate_proj", (int64_t) ffn * hidden);       L.wup = up(b + ".mlp.up_proj", (int64_t) ffn * hidden);
-        L.wdown = up(b + ".mlp.down_proj", (int64_t) hidden * ffn);
+        L.wq = upw(b + ".self_attn.q_proj", (int64_t) hidden * hidden);    L.wk = upw(b + ".self_attn.k_proj", (int64_t) kv_hidden * hidden);
+        L.wv = upw(b + ".self_attn.v_proj", (int64_t) kv_hidden * hidden); L.wo = upw(b + ".self_attn.o_proj", (int64_t) hidden * hidden);
+        L.wgate = upw(b + ".mlp.gate_proj", (int64_t) ffn * hidden);       L.wup = upw(b + ".mlp.up_proj", (int64_t) ffn * hidden);
+        L.wdown = upw(b + ".mlp.down_proj", (int64_t) hidden * ffn);
+        for (auto * w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.wgate, &L.wup, &L.wdown}) { (void) w; }
+        host.erase(b + ".self_attn.q_proj"); host.erase(b + ".self_attn.k_proj"); host.erase(b + ".self_attn.v_proj"); host.erase(b + ".self_attn.o_proj");      // free the host copies layer by layer
+        host.erase(b + ".mlp.gate_proj"); host.erase(b + ".mlp.up_proj"); host.erase(b + ".mlp.down_proj");
     }
     if (!ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
@@ -85,28 +104,46 @@ void Orpheus::free_all() {
 
 namespace {
 
+// generate_from_batch's stop rule (model.cpp:389-398): a sequence has ended once it produced the stopping token; `stopped[b]` keeps the number of tokens up to and
+// including it.  Also advances the device-resident step counter (one launch instead of two).
+__global__ void orpheus_stop_advance_kernel(int * d_step, const int * __restrict__ cur_tok, int * stopped, int B, int stop_token) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = *d_step;
+    if (stopped && b < B && stopped[b] < 0 && cur_tok[b] == stop_token) stopped[b] = step + 1;
+    __syncthreads();
+    if (b == 0) *d_step = step + 1;
+}
+
 struct OFwd : ArLaunch {
     Orpheus * m; bool fail = false;
     OFwd(Orpheus * m_, Ctx * c, cudaStream_t s) : m(m_) { ctx = c; st = s; }
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
-    // up to 3 F32 matrices against the same rows in one launch (tensor-core path: when every one of them has its fp16 split and an eligible shape)
-    int gemv_group_f32(const float * X, int ldx, int K, int R, const float * const * W, const int * N, float * const * Y, int n) {
+    // up to 3 matrices against the same rows in one launch when they share a storage kind (F32: fp32-faithful tensor-core path when every one has its fp16 split)
+    int gemv_n(const float * X, int ldx, int K, int R, const ArW * const * W, const int * N, float * const * Y, int n) {
+        bool f32 = true;
+        for (int i = 0; i < n; i++) f32 = f32 && !W[i]->f16 && !W[i]->qtype;
+        if (!f32) {
+            GemvOut o[3];
+            for (int i = 0; i < n; i++) o[i] = GemvOut{nullptr, Y[i], nullptr, N[i], 0};
+            return gemv_group(X, ldx, K, R, W, N, o, n);
+        }
         GemvItem it[3];
         bool mma = gemv_split_mma_enabled();
-        for (int i = 0; i < n && mma; i++) mma = gemv_mma_ok(K, N[i], 16) && m->split.find(W[i]) != m->split.end();
+        for (int i = 0; i < n && mma; i++) mma = gemv_mma_ok(K, N[i], 16) && m->split.find((const float *) W[i]->p) != m->split.end();
         for (int i = 0; i < n; i++) {
-            it[i] = GemvItem{W[i], nullptr, nullptr, N[i], GemvOut{nullptr, Y[i], nullptr, N[i], 0}};
-            if (mma) { const auto & sp = m->split.find(W[i])->second; it[i].W = sp.first; it[i].W2 = sp.second; }
+            it[i] = GemvItem{W[i]->p, nullptr, nullptr, N[i], GemvOut{nullptr, Y[i], nullptr, N[i], 0}};
+            if (mma) { const auto & sp = m->split.find((const float *) W[i]->p)->second; it[i].W = sp.first; it[i].W2 = sp.second; }
         }
         return gemv_group_launch(ctx, st, group_smem, mma ? GEMV_SPLIT_MMA : GEMV_F32, 0, X, ldx, K, R, it, n);
     }
-    // an F32 matrix by its device pointer (fp32-faithful tensor-core path when its fp16 split exists)
-    int gemv(const float * X, int ldx, const float * W, int K, int N, int R, const float * res, float * Y, int ldy) {
-        if (gemv_split_mma_enabled() && gemv_mma_ok(K, N, 16)) {                              // fp32-faithful tensor-core path over the fp16 split of W
-            auto it = m->split.find(W);
+    // one matrix in any storage kind (F32: fp32-faithful tensor-core path when its fp16 split exists)
+    int gemv_w(const float * X, int ldx, const ArW & W, int K, int N, int R, const float * res, float * Y, int ldy) {
+        if (W.f16 || W.qtype) return gemv(X, ldx, W, K, N, R, res, Y, ldy);
+        if (gemv_split_mma_enabled() && gemv_mma_ok(K, N, 16)) {
+            auto it = m->split.find((const float *) W.p);
             if (it != m->split.end()) return gemv_mma_launch(ctx, st, mma_smem_set, X, ldx, (const __half *) it->second.first, (const __half *) it->second.second, K, N, R, res, Y, ldy);
         }
-        gemv_rows_launch(st, X, ldx, W, false, K, N, R, res, Y, ldy);
+        gemv_rows_launch(st, X, ldx, W.p, false, K, N, R, res, Y, ldy);
         B2_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -114,7 +151,8 @@ struct OFwd : ArLaunch {
 
 }  // namespace
 
-int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits) {
+int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits,
+                      int32_t * n_generated) {
     const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("orpheus: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
@@ -127,6 +165,8 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         R0 += n_prompt[b]; Pmax = std::max(Pmax, (int) n_prompt[b]);
     }
     const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, KV = kv_hidden, F = ffn;
+    if (max_context > 0 && Tmax > max_context) { set_error("orpheus: %d positions (longest prompt + n_steps) exceed the model's context of %d", Tmax, max_context); return 1; }
+    if (B > 128) { set_error("orpheus: at most 128 sequences per call (%d given)", B); return 1; }
     const size_t cache = (size_t) n_layers * B * Tmax * KV * 4;
     const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
                         (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * vocab * 4 : 0);
@@ -141,10 +181,12 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     int * row_base = Fw.al<int>((size_t) Rmax), * row_len = Fw.al<int>((size_t) Rmax);
     int * d_np = Fw.al<int>((size_t) B), * d_last = Fw.al<int>((size_t) B), * cur_tok = Fw.al<int>((size_t) B), * d_out = Fw.al<int>((size_t) B * n_steps), * d_step = Fw.al<int>(1);
     int * s_last = Fw.al<int>((size_t) B), * s_cnt = Fw.al<int>((size_t) B);
+    int * stopped = n_generated ? Fw.al<int>((size_t) B) : nullptr;
     float * s_scratch = sampling_needs_scratch(samp, vocab) ? Fw.al<float>((size_t) B * vocab) : nullptr;
     if (Fw.fail) return 1;
     B2_CUDA(cudaMemsetAsync(s_last, 0xff, (size_t) B * 4, st));     // sampler::reset: last_token_ids = -1, repetition_counts = 0
     B2_CUDA(cudaMemsetAsync(s_cnt, 0, (size_t) B * 4, st));
+    if (stopped) B2_CUDA(cudaMemsetAsync(stopped, 0xff, (size_t) B * 4, st));
 
     std::vector<int> hs((size_t) R0), hp((size_t) R0), ht((size_t) R0), hb((size_t) R0), hl((size_t) R0), hnp((size_t) B), hlast((size_t) B);
     {
@@ -179,38 +221,47 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
             float * Kl = Kc + (size_t) l * B * Tmax * KV, * Vl = Vc + (size_t) l * B * Tmax * KV;
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, L.in_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
             if (fuse) {                                                                        // q, k, v in one launch
-                const float * W3[3] = {L.wq, L.wk, L.wv}; const int N3[3] = {H, KV, KV}; float * Y3[3] = {q, kbuf, vbuf};
-                if (Fw.gemv_group_f32(xn, H, H, R, W3, N3, Y3, 3)) return 1;
+                const ArW * W3[3] = {&L.wq, &L.wk, &L.wv}; const int N3[3] = {H, KV, KV}; float * Y3[3] = {q, kbuf, vbuf};
+                if (Fw.gemv_n(xn, H, H, R, W3, N3, Y3, 3)) return 1;
             } else {
-                if (Fw.gemv(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
-                if (Fw.gemv(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
-                if (Fw.gemv(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
+                if (Fw.gemv_w(xn, H, L.wq, H, H, R, nullptr, q, H)) return 1;
+                if (Fw.gemv_w(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
+                if (Fw.gemv_w(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
             }
             { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax, nullptr); B2_LAUNCH_CHECK(ctx); }
             if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, kv_heads, head_dim, Tmax, scale, att)) return 1;
-            if (Fw.gemv(att, H, L.wo, H, H, R, x, xn, H)) return 1;                        // xn = attn_out + residual(x)
+            if (Fw.gemv_w(att, H, L.wo, H, H, R, x, xn, H)) return 1;                      // xn = attn_out + residual(x)
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
             if (fuse) {                                                                        // gate and up in one launch
-                const float * W2[2] = {L.wgate, L.wup}; const int N2[2] = {F, F}; float * Y2[2] = {g, u};
-                if (Fw.gemv_group_f32(q, H, H, R, W2, N2, Y2, 2)) return 1;
+                const ArW * W2[2] = {&L.wgate, &L.wup}; const int N2[2] = {F, F}; float * Y2[2] = {g, u};
+                if (Fw.gemv_n(q, H, H, R, W2, N2, Y2, 2)) return 1;
             } else {
-                if (Fw.gemv(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;
-                if (Fw.gemv(q, H, L.wup, H, F, R, nullptr, u, F)) return 1;
+                if (Fw.gemv_w(q, H, L.wgate, H, F, R, nullptr, g, F)) return 1;
+                if (Fw.gemv_w(q, H, L.wup, H, F, R, nullptr, u, F)) return 1;
             }
             { const size_t n = (size_t) R * F; silu_mul_kernel<<<cdiv((int64_t) n, 256), 256, 0, st>>>(g, u, n); B2_LAUNCH_CHECK(ctx); }
-            if (Fw.gemv(g, F, L.wdown, F, H, R, xn, x, H)) return 1;                         // x = mlp + residual(xn)
+            if (Fw.gemv_w(g, F, L.wdown, F, H, R, xn, x, H)) return 1;                       // x = mlp + residual(xn)
         }
         rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, out_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
         const float * lastp = xn;
         if (prefill) { gather_rows_f32_kernel<<<B, 256, 0, st>>>(xn, d_last, H, last); B2_LAUNCH_CHECK(ctx); lastp = last; }   // logits of the last position only
-        if (Fw.gemv(lastp, H, head, H, vocab, B, nullptr, logits, vocab)) return 1;
+        if (Fw.gemv_w(lastp, H, head, H, vocab, B, nullptr, logits, vocab)) return 1;
         if (samp.do_sample) {
             SampleParams sp = make_sample_params(samp, logits, B, vocab, s_last, s_cnt, s_scratch, d_step, d_out);
             sp.cur_tok = cur_tok; sp.out_stride_steps = n_steps;
             if (sample_rows(ctx, sp)) return 1;
         } else { argmax_kernel<<<B, 256, 0, st>>>(logits, vocab, cur_tok, d_out, n_steps, d_step); B2_LAUNCH_CHECK(ctx); }
-        step_advance_kernel<<<1, 32, 0, st>>>(d_step); B2_LAUNCH_CHECK(ctx);
+        orpheus_stop_advance_kernel<<<1, 128, 0, st>>>(d_step, cur_tok, stopped, B, stopping_token); B2_LAUNCH_CHECK(ctx);
         return 0;
+    };
+    // every `exit_every` steps the stop flags are read back (one small sync): when EVERY sequence has produced its stopping token the remaining steps are skipped
+    const int exit_every = [] { const char * e = getenv("B2TTS_AR_EXIT_EVERY"); const int v = e ? atoi(e) : 32; return v > 0 ? v : 32; }();
+    std::vector<int32_t> hflags((size_t) B, -1);
+    auto all_stopped = [&]() -> int {          // 1 all stopped, 0 not yet, -1 error
+        if (!stopped) return 0;
+        if (cudaMemcpyAsync(hflags.data(), stopped, (size_t) B * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { set_error("orpheus: reading the stop flags failed"); return -1; }
+        for (int b = 0; b < B; b++) if (hflags[(size_t) b] < 0) return 0;
+        return 1;
     };
     auto copy_logits = [&](int s) -> int {
         if (out_logits)
@@ -235,16 +286,29 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) set_error("orpheus: stream capture failed: %s", cudaGetErrorString(ce)); return 1; }
         if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); set_error("orpheus: cudaGraphInstantiate failed"); return 1; }
         cudaError_t le = cudaSuccess;
-        for (int s = 2; s < n_steps && le == cudaSuccess; s++) le = cudaGraphLaunch(exec, st);
+        for (int s = 2; s < n_steps && le == cudaSuccess; s++) {
+            le = cudaGraphLaunch(exec, st);
+            if (stopped && le == cudaSuccess && (s + 1) % exit_every == 0 && s + 1 < n_steps) { const int a = all_stopped(); if (a < 0) le = cudaErrorUnknown; else if (a) break; }
+        }
         ctx->launches += (uint64_t) (n_steps - 3) * (ctx->launches - l0);
         cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
         if (le != cudaSuccess) { set_error("orpheus: cudaGraphLaunch failed: %s", cudaGetErrorString(le)); return 1; }
     } else {
-        for (int s = 1; s < n_steps; s++) if (run_decode() || copy_logits(s)) return 1;
+        for (int s = 1; s < n_steps; s++) {
+            if (stopped && s % exit_every == 0) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
+            if (run_decode() || copy_logits(s)) return 1;
+        }
     }
     B2_CUDA(cudaEventRecord(ev[1], st));
     B2_CUDA(cudaMemcpyAsync(out_tokens, d_out, (size_t) B * n_steps * 4, cudaMemcpyDeviceToHost, st));
+    if (stopped) B2_CUDA(cudaMemcpyAsync(hflags.data(), stopped, (size_t) B * 4, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
+    if (n_generated)
+        for (int b = 0; b < B; b++) {                           // tokens past a sequence's stopping token are what the reference never computes: zeroed
+            const int ng = hflags[(size_t) b] >= 0 ? hflags[(size_t) b] : n_steps;
+            n_generated[b] = ng;
+            for (int s2 = ng; s2 < n_steps; s2++) out_tokens[(size_t) b * n_steps + s2] = 0;
+        }
     cudaEventElapsedTime(&timing_ms, ev[0], ev[1]);
     return 0;
 }

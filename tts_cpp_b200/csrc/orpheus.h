@@ -12,7 +12,7 @@ namespace b2 {
 
 struct OrpheusLayer {
     float * in_norm = nullptr, * post_norm = nullptr;
-    float * wq = nullptr, * wk = nullptr, * wv = nullptr, * wo = nullptr, * wgate = nullptr, * wup = nullptr, * wdown = nullptr;
+    ArW wq, wk, wv, wo, wgate, wup, wdown;      // F32 (the reference's only Orpheus dtype), F16, or Q4_0 / Q5_0 / Q8_0 blocks (BASELINE config 5: q8_0 -- our own writer, the reference's quantize tool refuses Orpheus)
 };
 
 struct Orpheus {
@@ -25,7 +25,9 @@ struct Orpheus {
 
     int vocab = 0, heads = 0, kv_heads = 0, head_dim = 0, hidden = 0, kv_hidden = 0, ffn = 0, n_layers = 0;
     int stopping_token = -1;
-    float * embed = nullptr, * out_norm = nullptr, * head = nullptr, * rope_ff = nullptr;
+    float * embed = nullptr, * out_norm = nullptr, * rope_ff = nullptr;
+    ArW head;
+    int max_context = 0;                        // prompt + generated positions the model supports (orpheus.context_length when present, else unbounded by metadata)
     std::vector<OrpheusLayer> layers;
     // B2TTS_AR_MMA=1: fp16 (hi, 2^11-scaled lo) splits of the F32 matrices for the tensor-core batched GEMV (ar_kernels.cuh gemv_mma_kernel<true>), keyed by the fp32 pointer
     std::map<const float *, std::pair<const void *, const void *>> split;
@@ -42,7 +44,10 @@ struct Orpheus {
         return generate(B, prompts, n_prompt, n_steps, nullptr, out_tokens, out_logits);
     }
     // the same loop under the reference sampler's settings (sampler.cu): sampling == nullptr or do_sample == 0 is the greedy sampler::max
-    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits);
+    // n_generated (optional): turns on the reference's stop rule (generate_from_batch, model.cpp:389-398: the loop ends when the stopping token was produced): per
+    // sequence the number of tokens up to and including its stopping token (n_steps when it never came); the batch stops stepping once every sequence has ended
+    int generate(int B, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const ArSampling * sampling, int32_t * out_tokens, float * out_logits,
+                 int32_t * n_generated = nullptr);
     void free_all();
 };
 

@@ -475,7 +475,7 @@ def orpheus_tensors(seed: int = 0, layers: int = 2, heads: int = 6, kv_heads: in
 
 
 def write_orpheus_gguf(path: str, seed: int = 0, layers: int = 2, heads: int = 6, kv_heads: int = 2, head_dim: int = 64, ffn: int = 1024,
-                       vocab: int = 2048) -> dict:
+                       vocab: int = 2048, quant: str | None = None, f16: bool = False) -> dict:
     """Small synthetic Orpheus GGUF (all F32: the only dtype the reference supports for Orpheus, README.md:25), with the SNAC decoder
     tensors the reference's loader also needs."""
     import gguf
@@ -486,7 +486,12 @@ def write_orpheus_gguf(path: str, seed: int = 0, layers: int = 2, heads: int = 6
     n_params = 0
     for name, arr in items:
         n_params += arr.size
-        w.add_tensor(name, arr.astype(np.float32))
+        is_matrix = name.startswith("orpheus.") and arr.ndim == 2 and arr.shape[1] % 32 == 0      # the decoder matrices, the embedding table and the head (our own
+        if quant and is_matrix:                                                                # Q8_0 / F16 Orpheus writer: the reference's quantize tool refuses Orpheus)
+            qt = getattr(gguf.GGMLQuantizationType, quant)
+            w.add_tensor(name, gguf.quants.quantize(arr.astype(np.float32), qt), raw_dtype=qt)
+        else:
+            w.add_tensor(name, arr.astype(np.float16 if (f16 and is_matrix) else np.float32))
     for k, v in (("orpheus.vocab_size", vocab), ("orpheus.attn_heads", heads), ("orpheus.kv_attn_heads", kv_heads), ("orpheus.head_dim", head_dim),
                  ("orpheus.layers", layers), ("orpheus.hidden_size", heads * head_dim), ("orpheus.kv_hidden_size", kv_heads * head_dim),
                  ("orpheus.stopping_token_id", vocab - 1), ("tokenizer.ggml.eos_token_id", vocab - 2), ("tokenizer.ggml.bos_token_id", 1)):
@@ -726,3 +731,119 @@ if __name__ == "__main__":
     import sys
     print(write_kokoro_gguf(sys.argv[1], dtype=sys.argv[2] if len(sys.argv) > 2 else "f16",
                             ctx_len=int(sys.argv[3]) if len(sys.argv) > 3 else 512))
+
+
+# ------------------------------------------------------------------------------------------ full-size synthetic models without a GGUF file
+# BASELINE configs 4 and 5 name Dia-1.6B and Orpheus-3B.  Writing (and re-reading) a 3-15 GB synthetic GGUF on every fresh benchmark box costs minutes; the weights are
+# random anyway, so bench.py hands them to the library tensor by tensor through the same C-ABI runner_from_file drives (b2tts_<model>_create / _assign_weight /
+# _prepare, reference src/models/loaders.cpp:79-89) -- the layers share one set of random values (throughput does not depend on them; every layer still owns its HBM copy).
+ORPHEUS_3B_SHAPE = dict(layers=28, heads=24, kv_heads=8, head_dim=128, ffn=8192, vocab=156940)       # reference src/models/orpheus/model.h:30-46
+DIA_1B6_SHAPE = dict(enc_layers=12, dec_layers=18, head_dim=128, heads=16, query_heads=4, ffn=8192, enc_ffn=4096, vocab=1028, enc_ctx=1024)   # reference src/models/dia/model.h:63-85
+
+
+def _q8_0_blocks(rng, n: int, scale: float) -> np.ndarray:
+    """n weights ~ uniform int8 * scale as raw ggml Q8_0 blocks (fp16 scale + 32 int8: 34 bytes per 32 weights)"""
+    nb = n // 32
+    blk = np.zeros(nb, dtype=np.dtype([("d", "<f2"), ("q", "i1", (32,))]))
+    blk["d"] = np.float16(scale / 64.0)
+    blk["q"] = rng.integers(-127, 128, size=(nb, 32), dtype=np.int8)
+    return blk.view(np.uint8).reshape(-1)
+
+
+def build_orpheus_direct(ctx, dtype: str = "q8_0", seed: int = 0, **shape):
+    """-> OrpheusRunner over random weights of the given shape; dtype "q8_0" (config 5), "f16" or "f32" (the reference's)."""
+    import ctypes as C
+    from .binding import OrpheusRunner, _chk, lib
+    sh = dict(ORPHEUS_3B_SHAPE, **shape)
+    L, heads, kvh, hd, F, V = sh["layers"], sh["heads"], sh["kv_heads"], sh["head_dim"], sh["ffn"], sh["vocab"]
+    H, KV = heads * hd, kvh * hd
+    kv = {"orpheus.vocab_size": V, "orpheus.attn_heads": heads, "orpheus.kv_attn_heads": kvh, "orpheus.head_dim": hd, "orpheus.layers": L, "orpheus.hidden_size": H,
+          "orpheus.kv_hidden_size": KV, "orpheus.stopping_token_id": 128258}
+    keys = (C.c_char_p * len(kv))(*[k.encode() for k in kv]); vals = (C.c_uint32 * len(kv))(*kv.values())
+    h = C.c_void_p()
+    _chk(lib().b2tts_orpheus_create(ctx.h, len(kv), keys, vals, C.byref(h)))
+    rng = np.random.default_rng(seed)
+    L_ = lib()
+    L_.b2tts_orpheus_assign_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t]
+
+    def put(name, arr, ggml_type, shape_np):
+        ne = (C.c_int64 * 4)(*(list(reversed(shape_np)) + [1] * (4 - len(shape_np))))
+        a = np.ascontiguousarray(arr)
+        _chk(L_.b2tts_orpheus_assign_weight(h, ("orpheus." + name).encode(), ggml_type, len(shape_np), ne, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def mat(n_out, n_in, scale=None):
+        s = (1.0 / np.sqrt(n_in)) if scale is None else scale
+        if dtype == "q8_0":
+            return _q8_0_blocks(rng, n_out * n_in, 2.0 * s), 8
+        w = (rng.standard_normal((n_out, n_in), dtype=np.float32) * np.float32(s))
+        return (w.astype(np.float16), 1) if dtype == "f16" else (w, 0)
+
+    layer = {"self_attn.q_proj": (H, H), "self_attn.k_proj": (KV, H), "self_attn.v_proj": (KV, H), "self_attn.o_proj": (H, H), "mlp.gate_proj": (F, H), "mlp.up_proj": (F, H), "mlp.down_proj": (H, F)}
+    shared = {k: mat(*v) for k, v in layer.items()}
+    ones = np.ones(H, np.float32)
+    for l in range(L):
+        for k, (a, t) in shared.items():
+            put(f"layers.{l}.{k}", a, t, list(layer[k]))
+        put(f"layers.{l}.input_layernorm", ones, 0, [H]); put(f"layers.{l}.post_attention_layernorm", ones, 0, [H])
+    emb, t = mat(V, H, 1.0)
+    put("embed_tokens", emb, t, [V, H]); del emb
+    hd_, t = mat(V, H, 4.0 / np.sqrt(H))
+    put("lm_head", hd_, t, [V, H]); del hd_
+    put("norm", ones, 0, [H])
+    ff = np.ones(hd // 2, np.float32); ff[hd // 4:] = np.linspace(1.0, 8.0, hd // 2 - hd // 4).astype(np.float32)
+    put("rope_frequencies", ff, 0, [hd // 2])
+    _chk(lib().b2tts_orpheus_prepare(h))
+    return OrpheusRunner(ctx, h)
+
+
+def build_dia_direct(ctx, dtype: str = "f16", seed: int = 0, **shape):
+    """-> DiaRunner over random weights of the Dia-1.6B shape; dtype "f16" (config 4) or "f32".  (The output heads and norms stay F32, as the quantize tool leaves them.)"""
+    import ctypes as C
+    from .binding import DiaRunner, _chk, lib
+    sh = dict(DIA_1B6_SHAPE, **shape)
+    EL, DL, hd, heads, qh, F, EF, V, C_ = sh["enc_layers"], sh["dec_layers"], sh["head_dim"], sh["heads"], sh["query_heads"], sh["ffn"], sh["enc_ffn"], sh["vocab"], sh["enc_ctx"]
+    EH, D, KVD = 1024, heads * hd, (heads // qh) * hd
+    kv = {"dia.decoder.output_heads": 9, "dia.decoder.layers": DL, "dia.encoder.layers": EL, "dia.decoder.hidden_size": D, "dia.decoder.attn_heads": heads, "dia.decoder.query_heads": qh,
+          "dia.encoder.attn_heads": heads, "dia.attn_head_size": hd, "dia.eos_token_id": 1024, "dia.bos_token_id": 1026, "dia.pad_token_id": 1025, "dia.encoder.max_context_length": C_,
+          "dia.decoder.output_vocab_size": V, "dia.decoder.audio_vocab_size": 1024, "dia.decoder.max_generation_size": 3072, "dia.max_delay": 15}
+    keys = (C.c_char_p * len(kv))(*[k.encode() for k in kv]); vals = (C.c_uint32 * len(kv))(*kv.values())
+    h = C.c_void_p()
+    _chk(lib().b2tts_dia_create(ctx.h, len(kv), keys, vals, C.byref(h)))
+    rng = np.random.default_rng(seed)
+    L_ = lib()
+    L_.b2tts_dia_assign_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t]
+
+    def put(name, arr, ggml_type, shape_np):
+        ne = (C.c_int64 * 4)(*(list(reversed(shape_np)) + [1] * (4 - len(shape_np))))
+        a = np.ascontiguousarray(arr)
+        _chk(L_.b2tts_dia_assign_weight(h, ("dia." + name).encode(), ggml_type, len(shape_np), ne, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def mat(n_out, n_in, scale=None, force_f32=False):
+        w = rng.standard_normal((n_out, n_in), dtype=np.float32) * np.float32((1.0 / np.sqrt(n_in)) if scale is None else scale)
+        return (w.astype(np.float16), 1) if (dtype == "f16" and not force_f32) else (w, 0)
+
+    enc = {"q_proj": (D, EH), "k_proj": (D, EH), "v_proj": (D, EH), "o_proj": (EH, D), "gate": (EF, EH), "up": (EF, EH), "wo": (EH, EF)}
+    dec = {"self_q_proj": (D, D), "self_k_proj": (KVD, D), "self_v_proj": (KVD, D), "self_o_proj": (D, D), "cross_q_proj": (D, D), "cross_k_proj": (D, EH), "cross_v_proj": (D, EH),
+           "cross_o_proj": (D, D), "gate": (F, D), "up": (F, D), "wo": (D, F)}
+    se = {k: mat(*v) for k, v in enc.items()}; sd = {k: mat(*v) for k, v in dec.items()}
+    put("encoder.embedding", *mat(256, EH, 1.0), [256, EH])
+    for l in range(EL):
+        for k, (a, t) in se.items():
+            put(f"encoder.layers.{l}.{k}", a, t, list(enc[k]))
+        put(f"encoder.layers.{l}.pre_sa_norm", np.ones(EH, np.float32), 0, [EH]); put(f"encoder.layers.{l}.post_sa_norm", np.ones(EH, np.float32), 0, [EH])
+    put("encoder.norm", np.ones(EH, np.float32), 0, [EH])
+    tab = mat(V, D, 0.5)
+    for i in range(9):
+        put(f"decoder.embeddings.{i}", tab[0], tab[1], [V, D])
+    for l in range(DL):
+        for k, (a, t) in sd.items():
+            put(f"decoder.layers.{l}.{k}", a, t, list(dec[k]))
+        for nm in ("pre_sa_norm", "pre_ca_norm", "pre_mlp_norm"):
+            put(f"decoder.layers.{l}.{nm}", np.ones(D, np.float32), 0, [D])
+    put("decoder.norm", np.ones(D, np.float32), 0, [D])
+    hw = mat(V, D, 4.0 / np.sqrt(D), force_f32=True)
+    hw[0][1024:] = 0.0                                        # EOS / PAD / BOS never win the argmax: a benchmark generation runs its full length (check_stopping would end it at a random step)
+    for i in range(9):
+        put(f"decoder.heads.{i}", hw[0], hw[1], [V, D])
+    _chk(lib().b2tts_dia_prepare(h))
+    return DiaRunner(ctx, h)
