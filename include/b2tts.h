@@ -181,11 +181,11 @@ float b2tts_snac_last_ms(const b2tts_snac * m);   /* device time of the last dec
 int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Orpheus autoregressive decode, FIRST CORRECT PATH: fp32 CUDA-core GEMVs, compact GQA KV cache, device argmax.
- * On a B200 its default greedy path reproduces the reference's token ids exactly, logits 5.2e-6 (one short run at the end of round 1,
- * profiles/r1i_rowb_first_contact.log; the tensor-core and graph-replay variants have not run on hardware).  Its logic is checked in the build container: the unmodified .cu file,
- * compiled against a CPU emulation of the CUDA subset it uses (tests/emu), reproduces the reference's greedy token ids exactly and its logits
- * to 4.5e-6 (tests/test_emu_cpu.py).  No performance claims are made for it.
+ * Orpheus autoregressive decode, launch-per-op path: batched GEMVs over F32 (the reference's only Orpheus dtype), F16 or Q4_0 / Q5_0 / Q8_0 matrices,
+ * compact GQA KV cache, device argmax / sampler / stop rule, CUDA-graph replay of a decode step.  Hardware status (B200, tests/test_orpheus_gpu.py, all green): F32 -- the
+ * reference's token ids exactly, logits 5e-6, plain and fp32-faithful tensor-core (B2TTS_AR_MMA=1) variants; F16 / Q8_0 -- no reference output exists (its runtime is
+ * F32-only), they track the reference's F32 run within the storage format's noise (4e-4 / 1.7e-2 of the logit std, same greedy tokens).  Orpheus-3B-shaped q8_0
+ * (BASELINE config 5) measured by `bench.py --workload orpheus`.  The same .cu file is also checked under the CPU emulation of tests/emu.
  *   b2tts_orpheus_load_gguf      : orpheus_model::setup_from_file + assign_weight loop over "orpheus.*" (reference
  *                                  src/models/orpheus/model.h:59-63, model.cpp:11-120; loader.cpp:8-23)
  *   b2tts_orpheus_generate_greedy: generate_from_batch's decode + sampler loop (model.cpp:230-353,389-398; sampler::max) for n_sequences
@@ -215,9 +215,12 @@ size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m);   /* bytes resident 
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Parler-TTS autoregressive decode, FIRST CORRECT PATH, same status as Orpheus above (emulation-checked: identical token
- * ids, logits within 1.7e-3 of the reference at a logit std of 4 -- ggml's fp16 GELU table; on a B200: the F32 greedy path gives the reference's
- * token ids, logits 1.5e-3 -- the F16 / quantised / graph-replay / tensor-core variants have not run on hardware).
+ * Parler-TTS autoregressive decode.  Two paths behind the same calls: F16 GGUFs (BASELINE config 3), greedy or teacher-forced, <= 16 sequences run
+ * the PERSISTENT DECODE KERNEL (csrc/pdk.cuh: one cooperative launch per 32 decode steps, TMA weight ring, paged fp16 KV cache, LayerNorm / GELU / residual / KV append
+ * folded into the GEMV phases); everything else (F32 / Q8_0 / Q5_0 / Q4_0 matrices, sampling, larger batches, B2TTS_AR_PDK=0) the launch-per-op path (tensor-core GEMV,
+ * CUDA-graph replay).  Hardware status (B200, tests/test_parler_gpu.py + test_ar_fullsize_gpu.py, all green): the reference's token ids exactly on every F32 / F16
+ * variant of either path (logits 1.5e-3 / 9e-3 at a logit std of 4 -- ggml's fp16 GELU table and F16 activation rounding), at the Parler-Mini size too
+ * (tests/golden/parler_mini_vectors.npz); quantised GGUFs teacher-forced within 0.1 RMS; the stop rule against reference runs to completion.
  *   b2tts_parler_load_gguf      : parler_tts_model::setup_from_file + assign_weight loop over "decoder.*" + prep_cross_key_values (reference
  *                                 src/models/parler/model.cpp:3-28,110-173,271-318; parler/loader.cpp)
  *   b2tts_parler_generate_greedy: generate_from_batch's prompt decode, then the audio decode + sampler loop with the delay pattern
@@ -253,9 +256,10 @@ size_t b2tts_parler_step_weight_bytes(const b2tts_parler * m);
 void  b2tts_parler_pdk_stats(const b2tts_parler * m, uint64_t * launches, uint64_t * steps);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Dia autoregressive decode, FIRST CORRECT PATH, same status as Orpheus / Parler above (emulation-checked: identical token
- * ids, CFG-combined logits within 2.4e-3 of the reference at a logit std of 13; on a B200: the F32 greedy path gives the reference's token ids,
- * logits 3.5e-3 -- the other variants have not run on hardware).
+ * Dia autoregressive decode, launch-per-op path (tensor-core GEMV for F16 matrices, CUDA-graph replay).  Hardware status (B200,
+ * tests/test_dia_gpu.py, all green): F32 -- the reference's token ids exactly, CFG-combined logits 3.5e-3 at a logit std of 13, check_stopping's 63-frame run; F16
+ * (BASELINE config 4's dtype) -- teacher-forced logits within 0.15 RMS and identical tokens wherever the reference's top-2 gap exceeds twice the step's logit
+ * difference (the one free-running difference on a B200 sits on a 0.099 gap: rounding-boundary noise x the CFG gain, see the test's header); Q8_0 teacher-forced.
  *   b2tts_dia_load_gguf      : dia_model::setup_from_file + assign_weight loop over "dia.*" (reference src/models/dia/model.cpp:3-132,200-262;
  *                              dia/loader.cpp:8-22)
  *   b2tts_dia_generate_greedy: dia_runner::decode -- the encoder pass over the conditional and the all-zero unconditional sequence, the cross K/V

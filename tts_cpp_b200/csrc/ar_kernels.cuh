@@ -33,7 +33,19 @@ __global__ void rmsnorm_kernel(const float * __restrict__ x, const float * __res
     if (r >= R) return;
     const float * row = x + (size_t) r * H;
     double s = 0.0;
-    for (int c = lane; c < H; c += 32) s += (double) (row[c] * row[c]);
+    if ((H & 3) == 0) {                                         // 16-byte loads, 8 in flight per lane (the scalar lane-strided loop was a chain of H / 32 dependent round trips)
+        const float4 * row4 = reinterpret_cast<const float4 *>(row);
+        const int n4 = H >> 2;
+        for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = j0 + 32 * u < n4 ? row4[j0 + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += (double) (v[u].x * v[u].x) + (double) (v[u].y * v[u].y) + (double) (v[u].z * v[u].z) + (double) (v[u].w * v[u].w);
+        }
+    } else {
+        for (int c = lane; c < H; c += 32) s += (double) (row[c] * row[c]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = (float) (s / (double) H);
@@ -347,18 +359,29 @@ __device__ __forceinline__ void gemv_mma_body(const float * __restrict__ X, int 
     for (int k0 = 0; k0 < K; k0 += kc) {
         const int kn = K - k0 < kc ? K - k0 : kc;                                         // a multiple of 256, like K and GM_KC / MT
         if (k0) __syncthreads();                                                         // every warp is done with the previous chunk
-        for (int i = tid * 4; i < ROWS * kn; i += 256 * 4) {
-            const int r = i / kn, k = i - r * kn;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < R) v = *reinterpret_cast<const float4 *>(X + (size_t) r * ldx + k0 + k);
-            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-            __half2 * d = reinterpret_cast<__half2 *>(sX + (size_t) r * pitch + k);
-            d[0] = h01; d[1] = h23;
-            if constexpr (SPLIT) {
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                __half2 * dl = reinterpret_cast<__half2 *>(sXl + (size_t) r * pitch + k);
-                dl[0] = __floats2half2_rn((v.x - f01.x) * GM_LO_SCALE, (v.y - f01.y) * GM_LO_SCALE);
-                dl[1] = __floats2half2_rn((v.z - f23.x) * GM_LO_SCALE, (v.w - f23.y) * GM_LO_SCALE);
+        // 8 independent 16-byte loads per thread in flight (measured on a B200: one load per iteration made this staging pass a chain of 16 dependent L2 round
+        // trips, ~9 of the kernel's ~14 us at batch 16)
+        for (int i0 = tid * 4; i0 < ROWS * kn; i0 += 256 * 4 * 8) {
+            float4 vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * 256 * 4, r = i / kn, k = i - r * kn;
+                vv[u] = (i < ROWS * kn && r < R) ? *reinterpret_cast<const float4 *>(X + (size_t) r * ldx + k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * 256 * 4, r = i / kn, k = i - r * kn;
+                if (i >= ROWS * kn) continue;
+                const float4 v = vv[u];
+                const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                __half2 * d = reinterpret_cast<__half2 *>(sX + (size_t) r * pitch + k);
+                d[0] = h01; d[1] = h23;
+                if constexpr (SPLIT) {
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    __half2 * dl = reinterpret_cast<__half2 *>(sXl + (size_t) r * pitch + k);
+                    dl[0] = __floats2half2_rn((v.x - f01.x) * GM_LO_SCALE, (v.y - f01.y) * GM_LO_SCALE);
+                    dl[1] = __floats2half2_rn((v.z - f23.x) * GM_LO_SCALE, (v.w - f23.y) * GM_LO_SCALE);
+                }
             }
         }
         __syncthreads();
@@ -623,13 +646,39 @@ __global__ void layernorm_kernel(const float * __restrict__ x, const float * __r
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r >= R) return;
     const float * row = x + (size_t) r * H;
+    const bool vec = (H & 3) == 0;
+    const float4 * row4 = reinterpret_cast<const float4 *>(row);
+    const int n4 = H >> 2;
     double s = 0.0;
-    for (int c = lane; c < H; c += 32) s += (double) row[c];
+    if (vec) {                                                  // 16-byte loads, 8 in flight per lane
+        for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = j0 + 32 * u < n4 ? row4[j0 + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += (double) v[u].x + (double) v[u].y + (double) v[u].z + (double) v[u].w;
+        }
+    } else {
+        for (int c = lane; c < H; c += 32) s += (double) row[c];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = (float) (s / (double) H);
     double s2 = 0.0;
-    for (int c = lane; c < H; c += 32) { const float v = row[c] - mean; s2 += (double) (v * v); }
+    if (vec) {
+        for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = j0 + 32 * u < n4 ? row4[j0 + 32 * u] : make_float4(mean, mean, mean, mean);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+                s2 += (double) (a * a) + (double) (b * b) + (double) (c * c) + (double) (d * d);
+            }
+        }
+    } else {
+        for (int c = lane; c < H; c += 32) { const float v = row[c] - mean; s2 += (double) (v * v); }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     const float var = (float) (s2 / (double) H);
