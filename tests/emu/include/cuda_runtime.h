@@ -124,6 +124,7 @@ static inline int __float2int_rn(float x) { return (int) nearbyintf(x); }      /
 static inline unsigned atomicAdd(unsigned * p, unsigned v) { const unsigned o = *p; *p = o + v; b2emu::note_progress(); return o; }
 static inline int atomicAdd(int * p, int v) { const int o = *p; *p = o + v; b2emu::note_progress(); return o; }
 static inline void __threadfence() {}
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned) x) : 32; }
 template <class T> static inline T __ldcg(const T * p) { return *p; }
 template <class T> static inline void __stcg(T * p, T v) { *p = v; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }

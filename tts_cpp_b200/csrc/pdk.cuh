@@ -328,16 +328,18 @@ __device__ __forceinline__ void pk_stage_fast(const PkOp & op, const float * X, 
 // fp16 input rows (written by the previous phase): straight 16-byte copies into the operand buffer, 8 per thread in flight
 __device__ __forceinline__ void pk_stage_h16(const PkOp & op, const __half * X16, int R, int k0, int kn, __half * sA, int pitch) {
     const int n8 = kn >> 3, total = 16 * n8;                   // uint4 (8 halves) per row, in all
+    const bool p2 = (n8 & (n8 - 1)) == 0;
+    const int sh = 31 - __clz(n8);                             // row = i >> sh when n8 is a power of two (1 024 / 2 048-column chunks): no integer division per load
     for (int i0 = threadIdx.x; i0 < total; i0 += PK_CONS * 8) {
         uint4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int i = i0 + u * PK_CONS, r = i / n8, j = i - r * n8;
+            const int i = i0 + u * PK_CONS, r = p2 ? i >> sh : i / n8, j = i - r * n8;
             v[u] = (i < total && r < R) ? __ldcg(reinterpret_cast<const uint4 *>(X16 + (size_t) r * op.ldx + k0) + j) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const int i = i0 + u * PK_CONS, r = i / n8, j = i - r * n8;
+            const int i = i0 + u * PK_CONS, r = p2 ? i >> sh : i / n8, j = i - r * n8;
             if (i < total) *reinterpret_cast<uint4 *>(sA + (size_t) r * pitch + 8 * j) = v[u];
         }
     }
