@@ -211,6 +211,9 @@ int   b2tts_orpheus_generate_until_stop(b2tts_orpheus * m, int n_sequences, cons
                                         const b2tts_sampling * sampling, int32_t * out_tokens, int32_t * n_generated);
 int   b2tts_orpheus_set_stopping_token(b2tts_orpheus * m, int token_id);   /* overrides orpheus.stopping_token_id of the GGUF (model.h:43: 128258) */
 size_t b2tts_orpheus_step_weight_bytes(const b2tts_orpheus * m);   /* W_step of SURVEY 8(d): bytes of the weight tensors one decode step touches, each once, stored dtype */
+/* F16 GGUFs, greedy, <= 16 sequences, hidden <= 3 072: decode steps 1 .. n-1 run inside the persistent decode kernel (csrc/pdk.cuh; B2TTS_AR_PDK=0: launch per op);
+ * -> cooperative launches so far and the decode steps they covered */
+void  b2tts_orpheus_pdk_stats(const b2tts_orpheus * m, uint64_t * launches, uint64_t * steps);
 size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m);   /* bytes resident in HBM (B2TTS_AR_MMA=1 adds the fp16 split copies of the matrices) */
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 

@@ -25,6 +25,7 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       GGUFs: one ends at max_generation, one because every head produced EOS; from oracle/ref_parler_driver.cpp --stop
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
   orpheus_wide_vectors.npz : as orpheus_vectors.npz for a GGUF with head size 128 (hidden 768)
+  orpheus_wide_long_vectors.npz : the same GGUF, prompts of 7 and 40 ids, 72 greedy steps (crosses KV-page and persistent-kernel launch boundaries)
   sampler_vectors.npz      : the reference sampler (src/sampler.cpp) on fixed logits under four configurations: nucleus, probabilities, max_head_probs and a
       histogram of 20 000 draws each, from oracle/ref_sampler_driver.cpp
   dia_q8_0_vectors.npz     : as dia_vectors.npz for the Q8_0 GGUF of the quantize tool
@@ -164,24 +165,26 @@ def snac_vectors():
     print("snac vectors:", pcm.shape, "rms", float(np.sqrt((pcm ** 2).mean())))
 
 
-def orpheus_vectors(wide: bool = False):
-    """wide: head size 128 (hidden 768, a multiple of 256): the shape the tensor-core GEMV of the CUDA path accepts for every matrix"""
+def orpheus_vectors(wide: bool = False, long: bool = False):
+    """wide: head size 128 (hidden 768, a multiple of 256): the shape the tensor-core GEMV of the CUDA path accepts for every matrix.
+    long (orpheus_wide_long_vectors.npz): the wide GGUF, prompts of 7 and 40 ids, 72 greedy steps -- the run crosses KV-page (32 positions) and persistent-kernel launch
+    (32 steps) boundaries; the yardstick for the F16 file of the same (fp16-representable) weights through the persistent decode kernel."""
     from tts_cpp_b200.synth import cached_orpheus_gguf
     gguf = cached_orpheus_gguf(seed=0, head_dim=128) if wide else cached_orpheus_gguf(seed=0)
     rng = np.random.default_rng(5)
-    prompts = [rng.integers(2, 2000, size=n) for n in (7, 12)]
+    prompts = [rng.integers(2, 2000, size=n) for n in ((7, 40) if long else (7, 12))]
     tmp = tempfile.mkdtemp()
     pf = os.path.join(tmp, "prompts.txt")
     open(pf, "w").write("\n".join(" ".join(map(str, q)) for q in prompts) + "\n")
     pre = os.path.join(tmp, "o")
-    steps = 6
+    steps = 72 if long else 6
     run([os.path.join(REF, "orpheus_ref"), gguf, pf, pre, "--steps", str(steps), "--threads", "4", "--quiet"])
     out = {}
     for u, q in enumerate(prompts):
         out[f"prompt{u}"] = np.asarray(q, np.int32)
         out[f"tokens{u}"] = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32)
         out[f"logits{u}"] = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(steps, -1)
-    np.savez_compressed(os.path.join(OUT, "orpheus_wide_vectors.npz" if wide else "orpheus_vectors.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "orpheus_wide_long_vectors.npz" if long else "orpheus_wide_vectors.npz" if wide else "orpheus_vectors.npz"), **out)
     print("orpheus wide vectors:" if wide else "orpheus vectors:", {k: v.shape for k, v in out.items()})
 
 
@@ -322,6 +325,7 @@ if __name__ == "__main__":
     if "parler_encoding" in which: parler_encoding_vectors()
     if "sampler" in which: sampler_vectors()
     if "orpheus_wide" in which: orpheus_vectors(wide=True)
+    if "orpheus_wide_long" in which: orpheus_vectors(wide=True, long=True)
     if "parler_f16" in which: parler_vectors(f16=True)
     if "parler_mini" in which: parler_vectors(f16=True, mini=True)      # (not in the default list: ~2 minutes of CPU and a 1.5 GB GGUF)
     for q in ("Q8_0", "Q5_0", "Q4_0"):

@@ -106,3 +106,68 @@ def test_orpheus_stop_rule():
     """generate_from_batch's stop condition (reference src/models/orpheus/model.cpp:389-398) on the device: the loop ends at the stopping token per sequence, the batch
     stops stepping once every sequence has ended, tokens up to the stop are the reference's."""
     assert run_snippet(STOP_BODY, []) == 0
+
+
+PDK_BODY = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import orpheus_runner_from_file
+from tts_cpp_b200.synth import cached_orpheus_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "orpheus_wide_long_vectors.npz"))
+orph = orpheus_runner_from_file(cached_orpheus_gguf(seed=0, head_dim=128, f16=True))
+pdk_on = os.environ.get("B2TTS_AR_PDK") != "0"
+prompts = [g["prompt0"], g["prompt1"]]
+steps = int(g["tokens0"].size)
+toks_b, logits_b = orph.generate_greedy(prompts, steps, want_logits=True)     # one ragged batch: 7- and 40-token prompts
+launches, psteps = orph.pdk_stats()
+print("persistent-kernel launches / steps", launches, psteps)
+ok = (psteps == steps - 1 and launches == -(-(steps - 1) // 32)) if pdk_on else psteps == 0
+for u in range(2):
+    ref_t, ref_l = g[f"tokens{u}"], g[f"logits{u}"]
+    # free-running greedy decoding against the reference's F32 run of the same weights: the first differing token must be a near-tie of the reference (top-2 gap within
+    # 2x the step's largest logit difference); the run is then re-anchored on the reference's tokens (prompt + its tokens so far) and the comparison continues
+    done, prompt, got_t, got_l, anchors, worst = 0, prompts[u], toks_b[u], logits_b[u], 0, 0.0
+    while done < steps:
+        n = steps - done
+        d = np.abs(got_l[:n] - ref_l[done:]).max(axis=1)
+        neq = np.nonzero(got_t[:n] != ref_t[done:])[0]
+        upto = int(neq[0]) if neq.size else n - 1
+        worst = max(worst, float(d[:upto + 1].max()))
+        if not neq.size: break
+        s = done + upto
+        top2 = np.sort(ref_l[s])[-2:]
+        gap = float(top2[1] - top2[0])
+        print(f"TIE-MARGIN orpheus f16 pdk={int(pdk_on)} prompt {u} step {s}: token {int(got_t[upto])} vs {int(ref_t[s])}, reference top-2 gap {gap:.3e}, max |logit diff| {float(d[upto]):.3e}")
+        if gap > 2.0 * float(d[upto]): ok = False; print("  CLEAR DECISION DIFFERS"); break
+        anchors += 1
+        done = s + 1
+        if done >= steps - 1: break
+        prompt = np.concatenate([prompts[u], ref_t[:done]]).astype(np.uint32)
+        t2, l2 = orph.generate_greedy([prompt], steps - done, want_logits=True)
+        got_t, got_l = t2[0], l2[0]
+    print(f"PARITY orpheus wide F16 pdk={int(pdk_on)} prompt {u}: {steps} steps, {anchors} near-tie re-anchorings, max |logit diff| vs the reference's F32 run {worst:.3e}")
+    ok &= worst < 5e-2 and anchors <= 4
+    single = orph.generate_greedy([prompts[u]], steps)                          # batching does not change a sequence
+    ok &= bool(np.array_equal(single[0], toks_b[u]))
+# the stop rule inside the persistent kernel: sequence 0's third token becomes the stopping token
+stop = int(toks_b[0][2])
+orph.set_stopping_token(stop)
+toks, ngen = orph.generate_until_stop(prompts, steps)
+want = [next((i + 1 for i, t in enumerate(toks_b[u]) if t == stop), steps) for u in range(2)]
+print("n_generated", ngen.tolist(), "expected", want)
+for u in range(2):
+    ok &= int(ngen[u]) == want[u] and bool(np.array_equal(toks[u, :want[u]], toks_b[u][:want[u]])) and not toks[u, want[u]:].any()
+orph.close()
+sys.exit(0 if ok else 1)
+'''
+
+
+@pytest.mark.parametrize("variant", ["pdk_f16kv", "pdk_f32kv", "per_op"])
+def test_orpheus_f16_persistent_kernel_tracks_the_reference(variant):
+    """The F16 file of the wide GGUF (its weights are fp16-representable, so the reference's F32 run of the same values is the yardstick:
+    tests/golden/orpheus_wide_long_vectors.npz, 72 greedy steps, prompts of 7 and 40 ids) through the persistent decode kernel (pdk.cuh: RMSNorm in the staging, NeoX RoPE +
+    cache append and SwiGLU in the epilogues, GQA attention over fp16 / fp32 pages, argmax partials), across KV-page and launch boundaries; the launch-per-op path under
+    the same rule; the stop rule; batch invariance."""
+    env = {"pdk_f16kv": None, "pdk_f32kv": {"B2TTS_KV": "f32"}, "per_op": {"B2TTS_AR_PDK": "0"}}[variant]
+    assert run_snippet(PDK_BODY, [], env=env) == 0

@@ -400,6 +400,12 @@ class OrpheusRunner:
         lib().b2tts_orpheus_step_weight_bytes.restype = C.c_size_t
         return int(lib().b2tts_orpheus_step_weight_bytes(self.h))
 
+    def pdk_stats(self):
+        """-> (launches of the persistent decode kernel, decode steps they covered)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().b2tts_orpheus_pdk_stats(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def last_ms(self) -> float:
         lib().b2tts_orpheus_last_ms.restype = C.c_float
         return float(lib().b2tts_orpheus_last_ms(self.h))

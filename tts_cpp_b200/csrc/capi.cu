@@ -232,6 +232,7 @@ int b2tts_orpheus_generate_until_stop(b2tts_orpheus * m, int n_sequences, const 
     return m->o.generate(n_sequences, prompts, n_prompt, max_steps, &a, out_tokens, nullptr, n_generated);
 }
 int b2tts_orpheus_set_stopping_token(b2tts_orpheus * m, int token_id) { if (!m) { set_error("null model"); return 1; } m->o.stopping_token = token_id; return 0; }
+void b2tts_orpheus_pdk_stats(const b2tts_orpheus * m, uint64_t * launches, uint64_t * steps) { if (launches) *launches = m ? m->o.pdk_launches : 0; if (steps) *steps = m ? m->o.pdk_steps : 0; }
 size_t b2tts_orpheus_step_weight_bytes(const b2tts_orpheus * m) {
     if (!m) return 0;
     const Orpheus & o = m->o;

@@ -1,6 +1,7 @@
 // orpheus.cu -- Orpheus autoregressive decode (llama-3 style), first correct CUDA path.  See orpheus.h for what it replaces and why it is plain.
 #include "orpheus.h"
 #include "ar_kernels.cuh"
+#include "pdk.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -89,6 +90,9 @@ int Orpheus::prepare() {
     }
     if (!ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+#ifndef B2EMU
+    B2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+#endif
     host.clear();
     B2_CUDA(cudaDeviceSynchronize());      // the uploads above are blocking copies on the legacy stream; kernels run on ctx->stream (non-blocking), which does not wait for it by itself
     prepared = true;
@@ -167,12 +171,33 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     const int Tmax = Pmax + n_steps, Rmax = std::max(R0, B), H = hidden, KV = kv_hidden, F = ffn;
     if (max_context > 0 && Tmax > max_context) { set_error("orpheus: %d positions (longest prompt + n_steps) exceed the model's context of %d", Tmax, max_context); return 1; }
     if (B > 128) { set_error("orpheus: at most 128 sequences per call (%d given)", B); return 1; }
-    const size_t cache = (size_t) n_layers * B * Tmax * KV * 4;
-    const size_t need = 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
+    // ---- the persistent decode kernel (pdk.cuh) takes decode steps 1 .. n_steps - 1 when the model and the request fit it: greedy, <= 16 sequences, every matrix F16
+    // (block-quantised and F32 GGUFs stay on the launch-per-op path below), hidden size <= 3 072 in whole 256-column k-slices.  B2TTS_AR_PDK=0 turns it off.
+    static const bool pdk_env = [] { const char * e = getenv("B2TTS_AR_PDK"); return !(e && e[0] == '0'); }();
+    static const bool kv_f32 = [] { const char * e = getenv("B2TTS_KV"); return e && (e[0] == 'f' || e[0] == 'F') && e[1] == '3'; }();     // B2TTS_KV=f32: fp32 pages (default fp16)
+#ifdef B2EMU
+    const int pk_grid = [] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 3; return v > 0 ? v : 3; }();
+#else
+    const int pk_grid = [&] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 0; return v > 0 && v <= sm_count ? v : sm_count; }();
+#endif
+    const int pk_ak = [&] { const char * e = getenv("B2TTS_PDK_AK"); const int v = e ? atoi(e) : 0; return v >= 256 && v % 256 == 0 && v <= PK_AK_MAX && v >= H ? v : (H <= 2048 ? 2048 : PK_AK_MAX); }();
+    bool use_pdk = pdk_env && !samp.do_sample && B <= 16 && n_steps >= 2 && H % 256 == 0 && F % 256 == 0 && H <= pk_ak && (head_dim == 64 || head_dim == 128) && head.f16 && pk_grid > 0 &&
+                   (F <= pk_ak || cdiv(H / 8, pk_grid) <= 3) && (!out_logits || (size_t) n_steps * B * vocab * 4 <= ((size_t) 1 << 30));
+    for (const OrpheusLayer & L : layers) for (const ArW * w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.wgate, &L.wup, &L.wdown}) use_pdk = use_pdk && w->f16 && !w->qtype;
+    const int Tst = use_pdk ? Pmax : Tmax;                          // positions per sequence in the contiguous fp32 cache: the persistent path keeps only the prompt pass there
+    const int pk_max_pages = cdiv(Tmax, PK_PAGE);
+    int pk_pages = 0;
+    for (int b = 0; b < B; b++) pk_pages += cdiv(n_prompt[b] + n_steps, PK_PAGE);
+    const size_t pk_layer_bytes = (size_t) pk_pages * 2 * KV * PK_PAGE * (kv_f32 ? 4 : 2);
+    const int pk_amax = std::max(1, std::min(256, pk_grid / B));     // chunks a row's argmax is cut into: about one (row, chunk) item per CTA
+    const size_t pk_need = use_pdk ? (size_t) n_layers * pk_layer_bytes + (size_t) B * pk_max_pages * 4 + (size_t) (6 * n_layers + 8) * sizeof(PkOp) + (size_t) R0 * 8 + 8192 + (size_t) PK_REP * 16 * ((size_t) 8 * H + 2 * F) + 4096 +
+                                     (size_t) 16 * head_dim * 4 + (size_t) B * pk_amax * 8 + (out_logits ? (size_t) n_steps * B * vocab * 4 : 0) : 0;
+    const size_t cache = (size_t) n_layers * B * Tst * KV * 4;
+    const size_t need = pk_need + 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
                         (size_t) Rmax * 32 + (size_t) B * 16 + (32 << 20) + (size_t) B * 8 + (sampling_needs_scratch(samp, vocab) ? (size_t) B * vocab * 4 : 0);
     if (arena.reserve(need)) return 1;
     OFwd Fw(this, ctx, st);
-    float * Kc = Fw.al<float>((size_t) n_layers * B * Tmax * KV), * Vc = Fw.al<float>((size_t) n_layers * B * Tmax * KV);
+    float * Kc = Fw.al<float>((size_t) n_layers * B * Tst * KV), * Vc = Fw.al<float>((size_t) n_layers * B * Tst * KV);
     float * x = Fw.al<float>((size_t) Rmax * H), * xn = Fw.al<float>((size_t) Rmax * H), * q = Fw.al<float>((size_t) Rmax * H), * att = Fw.al<float>((size_t) Rmax * H);
     float * kbuf = Fw.al<float>((size_t) Rmax * KV), * vbuf = Fw.al<float>((size_t) Rmax * KV);
     float * g = Fw.al<float>((size_t) Rmax * F), * u = Fw.al<float>((size_t) Rmax * F);
@@ -193,7 +218,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         int r = 0;
         for (int b = 0; b < B; b++) {
             hnp[(size_t) b] = n_prompt[b];
-            for (int i = 0; i < n_prompt[b]; i++, r++) { hs[(size_t) r] = b; hp[(size_t) r] = i; ht[(size_t) r] = (int) prompts[b][i]; hb[(size_t) r] = b * (Pmax + n_steps); hl[(size_t) r] = i + 1; }
+            for (int i = 0; i < n_prompt[b]; i++, r++) { hs[(size_t) r] = b; hp[(size_t) r] = i; ht[(size_t) r] = (int) prompts[b][i]; hb[(size_t) r] = b * Tst; hl[(size_t) r] = i + 1; }
             hlast[(size_t) b] = r - 1;
         }
     }
@@ -218,7 +243,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         B2_LAUNCH_CHECK(ctx);
         for (int l = 0; l < n_layers; l++) {
             const OrpheusLayer & L = layers[(size_t) l];
-            float * Kl = Kc + (size_t) l * B * Tmax * KV, * Vl = Vc + (size_t) l * B * Tmax * KV;
+            float * Kl = Kc + (size_t) l * B * Tst * KV, * Vl = Vc + (size_t) l * B * Tst * KV;
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, L.in_norm, H, R, xn); B2_LAUNCH_CHECK(ctx);
             if (fuse) {                                                                        // q, k, v in one launch
                 const ArW * W3[3] = {&L.wq, &L.wk, &L.wv}; const int N3[3] = {H, KV, KV}; float * Y3[3] = {q, kbuf, vbuf};
@@ -228,8 +253,8 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
                 if (Fw.gemv_w(xn, H, L.wk, H, KV, R, nullptr, kbuf, KV)) return 1;
                 if (Fw.gemv_w(xn, H, L.wv, H, KV, R, nullptr, vbuf, KV)) return 1;
             }
-            { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tmax, nullptr); B2_LAUNCH_CHECK(ctx); }
-            if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, kv_heads, head_dim, Tmax, scale, att)) return 1;
+            { dim3 grid(R, heads + kv_heads); rope_append_kernel<<<grid, 64, 0, st>>>(q, kbuf, vbuf, rope_ff, row_seq, row_pos, heads, kv_heads, head_dim, theta_scale, Kl, Vl, Tst, nullptr); B2_LAUNCH_CHECK(ctx); }
+            if (Fw.attend(q, Kl, Vl, row_base, row_len, R, heads, kv_heads, head_dim, Tst, scale, att)) return 1;
             if (Fw.gemv_w(att, H, L.wo, H, H, R, x, xn, H)) return 1;                      // xn = attn_out + residual(x)
             rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(xn, L.post_norm, H, R, q); B2_LAUNCH_CHECK(ctx);   // q reused as the normalised MLP input
             if (fuse) {                                                                        // gate and up in one launch
@@ -270,13 +295,90 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         return 0;
     };
     auto run_decode = [&]() -> int {
-        decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, d_step, Tmax, row_seq, row_pos, row_tok, row_base, row_len); B2_LAUNCH_CHECK(ctx);
+        decode_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(d_np, cur_tok, B, d_step, Tst, row_seq, row_pos, row_tok, row_base, row_len); B2_LAUNCH_CHECK(ctx);
         return run_pass(B, false);
     };
     if (run_pass(R0, true) || copy_logits(0)) return 1;                                   // step 0: the whole ragged batch of prompts
+    if (use_pdk) {
+        // ---- steps 1 .. n_steps - 1 inside the persistent kernel.  Program of a step: rows (token of the previous step -> embedding row, RoPE table) | per layer
+        // { [RMSNorm] q|k|v GEMV with the NeoX rotation and the cache append in its epilogue -> GQA attention over the pages -> o GEMV + residual -> [RMSNorm] gate|up
+        // GEMV with SwiGLU in its epilogue -> down GEMV + residual } | [RMSNorm] lm_head GEMV | argmax partials (combined by the next step's rows phase)
+        unsigned char * pool = (unsigned char *) arena.alloc((size_t) n_layers * pk_layer_bytes);
+        int * page_table = Fw.al<int>((size_t) B * pk_max_pages), * row_src = Fw.al<int>((size_t) R0), * pk_pos = Fw.al<int>(16);
+        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (6 * n_layers + 8) * sizeof(PkOp));
+        unsigned * d_bar = (unsigned *) arena.alloc(256);
+        float * logits_all = out_logits ? Fw.al<float>((size_t) n_steps * B * vocab) : nullptr;
+        const size_t xrep = (size_t) 16 * H, grep = (size_t) 16 * F;
+        float * px = Fw.al<float>(PK_REP * xrep), * pxn = Fw.al<float>(PK_REP * xrep);
+        __half * att16 = Fw.al<__half>(PK_REP * xrep), * g16 = Fw.al<__half>(PK_REP * grep);
+        float2 * rope_cs = (float2 *) arena.alloc((size_t) 16 * (head_dim / 2) * sizeof(float2));
+        float * amax_v = Fw.al<float>((size_t) B * pk_amax); int * amax_i = Fw.al<int>((size_t) B * pk_amax);
+        if (!pool || !d_ops || !d_bar || !rope_cs || Fw.fail) return 1;
+        std::vector<int> hpt((size_t) B * pk_max_pages, 0), hsrc((size_t) R0);
+        { int next = 0, r = 0; for (int b = 0; b < B; b++) { const int np = cdiv(n_prompt[b] + n_steps, PK_PAGE); for (int i = 0; i < np; i++) hpt[(size_t) b * pk_max_pages + i] = next++; for (int i = 0; i < n_prompt[b]; i++) hsrc[(size_t) r++] = b * Tst + i; } }
+        std::vector<PkOp> ops;
+        auto seg = [&](const ArW & W, int N, int epi, int pair, int n_units) { PkSeg sg; memset(&sg, 0, sizeof sg); sg.W = (const __half *) W.p; sg.Wp = sg.W; sg.N = N; sg.epi = epi; sg.ldy = N; sg.pair = pair; sg.n_units = n_units; return sg; };
+        auto gemv_op = [&](int layer, const float * X, const __half * X16, size_t xr, int K, const float * nw, std::initializer_list<PkSeg> segs) {
+            PkOp op; memset(&op, 0, sizeof op);
+            op.kind = PK_GEMV; op.layer = layer; op.X = X; op.X16 = X16; op.xrep = xr; op.ldx = K; op.K = K; op.norm = nw ? PKN_RMS : PKN_NONE; op.nw = nw; op.eps = 1e-5f;
+            int u = 0;
+            for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; u += sg.n_units; op.nseg++; }
+            op.n_units = u;
+            ops.push_back(op);
+        };
+        { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ROWS; ops.push_back(op); }
+        const int rope_units_q = heads * (head_dim / 16), rope_units_k = kv_heads * (head_dim / 16);      // a unit = 8 rows of a head's first half + their partners in the second half
+        for (int l = 0; l < n_layers; l++) {
+            const OrpheusLayer & L = layers[(size_t) l];
+            PkSeg sq = seg(L.wq, H, PKE_ROPE_Q, PKP_ROPE, rope_units_q); sq.Y = q;
+            PkSeg sk = seg(L.wk, KV, PKE_ROPE_K, PKP_ROPE, rope_units_k);
+            PkSeg sv = seg(L.wv, KV, PKE_KV, PKP_NONE, KV / 8); sv.kv = 1;
+            gemv_op(l, px, nullptr, xrep, H, L.in_norm, {sq, sk, sv}); ops.back().kv_prefetch = 1;
+            { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ATTN; op.layer = l; op.q = q; op.out16 = att16; op.orep = xrep; op.scale = scale; ops.push_back(op); }
+            PkSeg so = seg(L.wo, H, PKE_RES, PKP_NONE, H / 8); so.Y = pxn; so.res = px; so.yrep = xrep;                 // xn = attention + residual(x)
+            gemv_op(l, nullptr, att16, xrep, H, nullptr, {so});
+            PkSeg sg2 = seg(L.wgate, F, PKE_SWIGLU, PKP_SWIGLU, F / 8); sg2.Wp = (const __half *) L.wup.p; sg2.Y16 = g16; sg2.yrep = grep;
+            gemv_op(l, pxn, nullptr, xrep, H, L.post_norm, {sg2});
+            PkSeg sd = seg(L.wdown, H, PKE_RES, PKP_NONE, H / 8); sd.Y = px; sd.res = pxn; sd.yrep = xrep;               // x = mlp + residual(xn)
+            gemv_op(l, nullptr, g16, grep, F, nullptr, {sd});
+        }
+        { PkSeg sh = seg(head, vocab, PKE_LOGITS, PKP_NONE, cdiv(vocab, 8)); sh.Y = logits; gemv_op(0, px, nullptr, xrep, H, out_norm, {sh}); }
+        { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ARGMAX; ops.push_back(op); }
+        B2_CUDA(cudaMemcpyAsync(page_table, hpt.data(), hpt.size() * 4, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(row_src, hsrc.data(), hsrc.size() * 4, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * sizeof(PkOp), cudaMemcpyHostToDevice, st));
+        PkParams Pk; memset(&Pk, 0, sizeof Pk);
+        Pk.ops = d_ops; Pk.n_ops = (int) ops.size(); Pk.R = B; Pk.H = H; Pk.heads = heads; Pk.kv_heads = kv_heads; Pk.hd = head_dim; Pk.n_out = 1; Pk.vocab = vocab;
+        Pk.model = PKM_ORPHEUS; Pk.ak = pk_ak; Pk.pos_off = 1; Pk.n_steps_total = n_steps; Pk.stop_token = stopping_token;
+        Pk.embed = embed; Pk.rope_ff = rope_ff; Pk.rope_cs = rope_cs; Pk.theta_scale = theta_scale; Pk.amax_v = amax_v; Pk.amax_i = amax_i; Pk.amax_ch = pk_amax;
+        Pk.bar = d_bar; Pk.d_step = d_step; Pk.first_pos = d_np; Pk.d_out = d_out; Pk.stopped = stopped; Pk.row_pos = pk_pos; Pk.x0 = px; Pk.x0rep = xrep;
+        Pk.kv_pool = pool; Pk.kv_layer_bytes = pk_layer_bytes; Pk.page_table = page_table; Pk.max_pages = pk_max_pages;
+        Pk.logits = logits; Pk.logits_all = logits_all;
+        PkLaunch pkl;
+        if (pk_configure(Pk, kv_f32, std::min(std::max(H, F), pk_ak), 0, Tmax, pkl)) { set_error("orpheus: the persistent decode kernel does not fit this shape (%d positions) in shared memory", Tmax); return 1; }
+        pk_prof_begin(Pk, ops.size(), pk_grid, st);
+        {   // the prompt pass' K / V rows (fp32, compact GQA rows) into the pages
+            dim3 grid(R0, n_layers);
+            if (kv_f32) pk_kv_import_kernel<float><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * KV, row_src, row_seq, row_pos, Pk);
+            else pk_kv_import_kernel<__half><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * KV, row_src, row_seq, row_pos, Pk);
+            B2_LAUNCH_CHECK(ctx);
+        }
+        for (int s0 = 1; s0 < n_steps; s0 += exit_every) {
+            if (stopped && s0 > 1) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
+            Pk.step_begin = s0; Pk.n_steps = std::min(exit_every, n_steps - s0);
+            B2_CUDA(pk_launch(pkl, Pk, pk_grid, st));
+            ctx->launches++; pdk_launches++; pdk_steps += (uint64_t) Pk.n_steps;
+        }
+        pk_prof_end(Pk, ops, pk_grid, st);
+        if (out_logits)
+            for (int s = 1; s < n_steps; s++)
+                for (int b = 0; b < B; b++)
+                    B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * vocab, logits_all + ((size_t) s * B + b) * vocab, (size_t) vocab * 4, cudaMemcpyDeviceToHost, st));
+    }
     // B2TTS_AR_GRAPH=1: capture one decode step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    if (!(ge && ge[0] == '0') && !out_logits && n_steps > 2) {      // on by default since it reproduced the reference's tokens on a B200 (round 2); B2TTS_AR_GRAPH=0 for A/B runs
+    if (use_pdk) {
+    } else if (!(ge && ge[0] == '0') && !out_logits && n_steps > 2) {      // on by default since it reproduced the reference's tokens on a B200 (round 2); B2TTS_AR_GRAPH=0 for A/B runs
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         if (run_decode()) return 1;                             // step 1 runs directly: every kernel instantiation has its attributes set before the capture
         const uint64_t l0 = ctx->launches;

@@ -27,6 +27,8 @@ struct Orpheus {
     int stopping_token = -1;
     float * embed = nullptr, * out_norm = nullptr, * rope_ff = nullptr;
     ArW head;
+    int sm_count = 0;
+    uint64_t pdk_launches = 0, pdk_steps = 0;   // cooperative launches of the persistent decode kernel (pdk.cuh) and the decode steps they covered
     int max_context = 0;                        // prompt + generated positions the model supports (orpheus.context_length when present, else unbounded by metadata)
     std::vector<OrpheusLayer> layers;
     // B2TTS_AR_MMA=1: fp16 (hi, 2^11-scaled lo) splits of the F32 matrices for the tensor-core batched GEMV (ar_kernels.cuh gemv_mma_kernel<true>), keyed by the fp32 pointer

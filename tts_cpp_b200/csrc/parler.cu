@@ -206,8 +206,9 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
 #else
     const int pk_grid = [&] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 0; return v > 0 && v <= sm_count ? v : sm_count; }();
 #endif
+    const int pk_ak = 2048;                                         // activation chunk (columns): LayerNorm weight + bias of a 2 048-wide row fill one ring stage
     bool use_pdk = pdk_env && !samp.do_sample && B <= 16 && H % 256 == 0 && F % 256 == 0 && (head_dim == 8 || head_dim == 64 || head_dim == 128) && (heads_w.f16 || heads_hi) && !heads_w.qtype &&
-                   pk_grid > 0 && (F <= PK_AK || H / 8 <= 3 * pk_grid) && (!out_logits || (size_t) n_steps * B * NV * 4 <= ((size_t) 1 << 30));
+                   pk_grid > 0 && (F <= pk_ak || H / 8 <= 3 * pk_grid) && (!out_logits || (size_t) n_steps * B * NV * 4 <= ((size_t) 1 << 30));
     for (const ParlerLayer & L : layers) for (const ArW * w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.cq, &L.co, &L.fc1, &L.fc2}) use_pdk = use_pdk && w->f16 && !w->qtype;
     const int Tst = use_pdk ? Pmax : Tmax;                          // positions per sequence in the contiguous fp32 cache: the persistent path keeps only the prompt pass there
     const int pk_max_pages = cdiv(Tmax, PK_PAGE);
@@ -334,7 +335,7 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
             PkOp op; memset(&op, 0, sizeof op);
             op.kind = PK_GEMV; op.layer = layer; op.X = X; op.ldx = ldx; op.K = K; op.norm = nw ? PKN_LAYER : PKN_NONE; op.nw = nw; op.nb = nb; op.eps = 1e-5f;
             int u = 0;
-            for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; u += cdiv(sg.N, 8); op.nseg++; }
+            for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; op.seg[op.nseg].n_units = cdiv(sg.N, 8); u += cdiv(sg.N, 8); op.nseg++; }
             op.n_units = u;
             ops.push_back(op);
         };
@@ -369,81 +370,30 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
         B2_CUDA(cudaMemcpyAsync(row_seq, hrs.data(), hrs.size() * 4, cudaMemcpyHostToDevice, st));
         B2_CUDA(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * sizeof(PkOp), cudaMemcpyHostToDevice, st));
         PkParams Pk; memset(&Pk, 0, sizeof Pk);
-        Pk.ops = d_ops; Pk.n_ops = (int) ops.size(); Pk.R = B; Pk.H = H; Pk.heads = heads; Pk.hd = head_dim; Pk.n_out = n_out; Pk.vocab = vocab;
-        const bool any_split = !heads_w.f16;
-        {   // shared memory: activation rows of the widest phase (twice for split matrices) or the attention scratch of two half-CTA groups, the rest is the weight ring
-            const int KA = std::min(std::max(H, F), PK_AK), KAs = std::min(H, PK_AK);
-            size_t a = (size_t) 16 * (KA + PK_PAD) * 2;
-            if (any_split) a = std::max(a, (size_t) 2 * 16 * (KAs + PK_PAD) * 2);
-            a = std::max(a, (size_t) 2 * ((PK_ATT_HDR + 1024) * 4 + (size_t) ((std::max(Tmax, n_enc) + 3) & ~3) * 4));
-            if (pk_max_pages > 256) { set_error("parler: %d positions exceed the persistent kernel's page-id scratch", Tmax); return 1; }
-            a = (a + 255) & ~(size_t) 255;
-            int ns = PK_MAXSTAGES;
-            while (ns > 2 && pk_smem_bytes(ns, (int) a, B * pk_max_pages) > (size_t) 227 * 1024) ns--;
-            if (pk_smem_bytes(ns, (int) a, B * pk_max_pages) > (size_t) 227 * 1024) { set_error("parler: the persistent decode kernel does not fit this shape in shared memory"); return 1; }
-            Pk.n_stages = ns; Pk.a_bytes = (int) a;
-        }
+        Pk.ops = d_ops; Pk.n_ops = (int) ops.size(); Pk.R = B; Pk.H = H; Pk.heads = heads; Pk.kv_heads = heads; Pk.hd = head_dim; Pk.n_out = n_out; Pk.vocab = vocab;
+        Pk.model = PKM_PARLER; Pk.ak = pk_ak; Pk.pos_off = 0; Pk.n_steps_total = n_steps;
         Pk.bar = d_bar; Pk.d_step = d_step;
         Pk.first_pos = d_np; Pk.d_out = d_out; Pk.d_teacher = d_teacher; Pk.bos = bos; Pk.eos = eos; Pk.max_gen = max_generation; Pk.seen = seen; Pk.stopped = stopped; Pk.ids = ids; Pk.row_pos = row_pos;
         Pk.tables = tables; Pk.tab_stride = (size_t) tab_rows * H; Pk.pos_embed = pos_embed; Pk.x0 = px; Pk.x0rep = xrep;
         Pk.kv_pool = pool; Pk.kv_layer_bytes = pk_layer_bytes; Pk.page_table = page_table; Pk.max_pages = pk_max_pages;
         Pk.logits = logits; Pk.logits_all = logits_all;
-        // B2TTS_PDK_PROF=<step>: %globaltimer timeline of that decode step (every op x every CTA), written as raw uint64 to $B2TTS_PDK_PROF_FILE after the run
-        const char * prof_env = getenv("B2TTS_PDK_PROF");
-        const size_t prof_words = (size_t) ops.size() * pk_grid * 8;
-        if (prof_env) {
-            B2_CUDA(cudaMalloc(&Pk.prof, prof_words * 8));
-            B2_CUDA(cudaMemsetAsync(Pk.prof, 0, prof_words * 8, st));
-            Pk.prof_step = atoi(prof_env);
-        }
+        // shared memory: activation rows of the widest phase (twice for split matrices) or the attention scratch of two half-CTA groups, the rest is the weight ring
+        PkLaunch pkl;
+        if (pk_configure(Pk, kv_f32, std::min(std::max(H, F), pk_ak), heads_w.f16 ? 0 : std::min(H, pk_ak), std::max(Tmax, n_enc), pkl)) { set_error("parler: the persistent decode kernel does not fit this shape (%d positions) in shared memory", Tmax); return 1; }
+        pk_prof_begin(Pk, ops.size(), pk_grid, st);
         {   // the prompt pass' K / V rows (fp32, contiguous) into the pages
             dim3 grid(R0, n_layers);
             if (kv_f32) pk_kv_import_kernel<float><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * H, row_dst, row_seq, row_pos, Pk);
             else pk_kv_import_kernel<__half><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * H, row_dst, row_seq, row_pos, Pk);
             B2_LAUNCH_CHECK(ctx);
         }
-        const size_t smem = pk_smem_bytes(Pk.n_stages, Pk.a_bytes, B * pk_max_pages);
-        // one instantiation per (cache element type, head size)
-        const void * kfn = nullptr;
-#ifdef B2EMU
-        std::function<void(const PkParams &)> kemu;
-#define PK_PICK(T, D) { kemu = [](const PkParams & q) { pdk_kernel<T, D>(q); }; }
-#else
-#define PK_PICK(T, D) { kfn = (const void *) pdk_kernel<T, D>; }
-#endif
-        if (kv_f32) { if (head_dim == 8) PK_PICK(float, 8) else if (head_dim == 64) PK_PICK(float, 64) else PK_PICK(float, 128) }
-        else        { if (head_dim == 8) PK_PICK(__half, 8) else if (head_dim == 64) PK_PICK(__half, 64) else PK_PICK(__half, 128) }
-#undef PK_PICK
-#ifndef B2EMU
-        B2_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-#endif
         for (int s0 = 0; s0 < n_steps; s0 += exit_every) {
             if (track_stop && s0 > 0) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
             Pk.step_begin = s0; Pk.n_steps = std::min(exit_every, n_steps - s0);
-            B2_CUDA(cudaMemsetAsync(d_bar, 0, 256, st));
-#ifdef B2EMU
-            (void) kfn;
-            b2emu::launch_coop(dim3(pk_grid), dim3(PK_THREADS), smem, [=]() { kemu(Pk); });
-#else
-            void * args[] = {(void *) &Pk};
-            B2_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(pk_grid), dim3(PK_THREADS), args, smem, st));
-#endif
+            B2_CUDA(pk_launch(pkl, Pk, pk_grid, st));
             ctx->launches++; pdk_launches++; pdk_steps += (uint64_t) Pk.n_steps;
         }
-        if (Pk.prof) {
-            std::vector<unsigned long long> hp(prof_words);
-            B2_CUDA(cudaMemcpyAsync(hp.data(), Pk.prof, prof_words * 8, cudaMemcpyDeviceToHost, st));
-            B2_CUDA(cudaStreamSynchronize(st));
-            if (const char * pf = getenv("B2TTS_PDK_PROF_FILE")) {
-                if (FILE * f = fopen(pf, "wb")) {
-                    const int hdr[4] = {(int) ops.size(), pk_grid, 8, Pk.prof_step};
-                    fwrite(hdr, 4, 4, f);
-                    for (const PkOp & o : ops) { const int k[4] = {o.kind, o.layer, o.K, o.n_units}; fwrite(k, 4, 4, f); }
-                    fwrite(hp.data(), 8, hp.size(), f); fclose(f);
-                }
-            }
-            cudaFree(Pk.prof);
-        }
+        pk_prof_end(Pk, ops, pk_grid, st);
     }
     // one audio step; the step number is device-resident (d_step), so the launches are identical for every step
     auto run_step = [&]() -> int {

@@ -27,6 +27,11 @@
 #pragma once
 #include "ar_kernels.cuh"
 
+#include <algorithm>
+#include <cstdio>
+#include <functional>
+#include <vector>
+
 namespace b2 {
 namespace {
 
@@ -36,17 +41,19 @@ constexpr int PK_TK = 1024;                       // k extent of a weight tile (
 constexpr int PK_PAD = 32;                        // halves of padding per smem row: rows start 16 banks apart (conflict-free 128-bit fragment loads, see GM_PAD)
 constexpr int PK_ROWB = (PK_TK + PK_PAD) * 2;     // bytes per tile row in shared memory
 constexpr int PK_STAGE = 8 * PK_ROWB;             // bytes per ring stage (one tile: 8 output rows)
-constexpr int PK_AK = 2048;                       // activations are staged in k chunks of this many columns
+constexpr int PK_AK_MAX = 3072;                   // activations are staged in k chunks of P.ak columns (2 048, or 3 072 for models whose hidden size is 3 072: one chunk for their q|k|v, gate|up phases)
 constexpr int PK_PAGE = 32;                       // positions per KV page
 constexpr int PK_MAXSTAGES = 12;
-constexpr int PK_RED_BYTES = 8 * 128 * 4;         // cross-warp reduction scratch / argmax scratch
+constexpr int PK_RED_BYTES = 2 * 8 * 128 * 4;     // cross-warp reduction scratch (two 16 x 8 tiles of a paired unit) / argmax scratch
 constexpr int PK_REP = 8;                         // copies of every activation buffer that ALL CTAs read at the start of a phase.  Measured on a B200: 148 SMs asking L2 for the
                                                   // same 64 KB right after a grid barrier wait ~2 us (each line is served to 148 requesters one after the other); with 8 copies
                                                   // (8x the tiny epilogue stores) a line has 18-19 requesters
 
 enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3 };
-enum { PKN_NONE = 0, PKN_LAYER = 1 };
-enum { PKE_STORE = 0, PKE_RES = 1, PKE_GELU = 2, PKE_KV = 3, PKE_LOGITS = 4 };
+enum { PKN_NONE = 0, PKN_LAYER = 1, PKN_RMS = 2 };
+enum { PKE_STORE = 0, PKE_RES = 1, PKE_GELU = 2, PKE_KV = 3, PKE_LOGITS = 4, PKE_ROPE_Q = 5, PKE_ROPE_K = 6, PKE_SWIGLU = 7 };
+enum { PKP_NONE = 0, PKP_ROPE = 1, PKP_SWIGLU = 2 };      // paired units: two tiles per k-tile (the two NeoX halves of a head's rows; the gate and the up rows of the same columns), one joint epilogue
+enum { PKM_PARLER = 0, PKM_ORPHEUS = 1 };
 
 struct PkSeg {                                    // one matrix of a GEMV phase; unit = 8 consecutive output rows
     const __half * W;                             // [N][K] fp16 (split: the high plane)
@@ -54,7 +61,8 @@ struct PkSeg {                                    // one matrix of a GEMV phase;
     float * Y; const float * res;                 // STORE / RES / LOGITS: Y[r * ldy + n] (+ res[r * ldy + n])
     __half * Y16;                                 // GELU: the activated values as fp16 [r * ldy + n] (their only consumer, fc2, rounds its input rows to fp16 anyway)
     size_t yrep;                                  // != 0: Y / Y16 (and res) exist in PK_REP copies this many elements apart; the epilogue writes them all, a CTA reads copy blockIdx % PK_REP
-    int N, unit0, epi, ldy, kv;                   // unit0: first unit of this segment within the phase; kv: 0 = K, 1 = V (PKE_KV)
+    const __half * Wp;                            // paired units: the partner tile's matrix (PKP_ROPE: W itself, rows + hd / 2; PKP_SWIGLU: the up matrix, same rows)
+    int N, unit0, epi, ldy, kv, pair, n_units;    // unit0: first unit of this segment within the phase; kv: 0 = K, 1 = V; pair: PKP_*; n_units of this segment
 };
 struct alignas(16) PkOp {
     int kind, layer;
@@ -67,7 +75,12 @@ struct alignas(16) PkOp {
 };
 struct PkParams {
     const PkOp * ops; int n_ops;
-    int R, H, heads, hd, n_out, vocab;
+    int R, H, heads, kv_heads, hd, n_out, vocab;
+    int model, ak, pos_off;                       // PKM_*; activation chunk columns; position of a row = first_pos + step - pos_off
+    // PKM_ORPHEUS rows: x0 = embed[token produced one step earlier]; NeoX RoPE table of the step rope_cs [R][hd / 2] (cos, sin) with ggml's iterated theta and the
+    // llama-3 frequency factors; d_out is [R][n_steps_total]; a sequence stops at stop_token
+    const float * embed; const float * rope_ff; float2 * rope_cs; float theta_scale; int n_steps_total, stop_token;
+    float * amax_v; int * amax_i; int amax_ch;    // PKM_ORPHEUS argmax over a 150k vocabulary: amax_ch partial (value, index) pairs per row, combined by the row's next rows phase
     int n_stages, a_bytes;                        // shared-memory layout: ring stages, bytes of the activation / attention-scratch region
     unsigned * bar;                               // grid-barrier arrival counter, zeroed before every launch
     int * d_step; int step_begin, n_steps;        // steps [step_begin, step_begin + n_steps) run in this launch
@@ -157,37 +170,47 @@ __device__ __forceinline__ void pk_store1(float * p, float v) { *p = v; }
 template <typename KVT> __device__ __forceinline__ KVT * pk_page_row(const PkParams & P, int layer, int r, int pos, int kv, int h) {
     const int pg = __ldg(P.page_table + (size_t) r * P.max_pages + (pos >> 5));
     KVT * base = reinterpret_cast<KVT *>(P.kv_pool + (size_t) layer * P.kv_layer_bytes);
-    return base + ((((size_t) pg * 2 + kv) * P.heads + h) * PK_PAGE + (pos & (PK_PAGE - 1))) * P.hd;
+    return base + ((((size_t) pg * 2 + kv) * P.kv_heads + h) * PK_PAGE + (pos & (PK_PAGE - 1))) * P.hd;      // h: kv head
 }
 
 // ---------------------------------------------------------------- the producer: this CTA's weight tiles of one op, in the order the consumers use them
-__device__ __forceinline__ void pk_produce_gemv(const PkOp & op, unsigned char * ring, PkBar * full, PkBar * empty, int S, unsigned & it) {      // op: the producer's own shared-memory copy
-    const int K = op.K, nA = (K + PK_AK - 1) / PK_AK;
+// unit u of segment sg -> first output row of its primary tile (and, for paired units, of the partner tile)
+__device__ __forceinline__ void pk_unit_rows(const PkSeg & sg, int u, int hd, int & n0, int & n1) {
+    const int lu = u - sg.unit0;
+    if (sg.pair == PKP_ROPE) { const int per = hd >> 4, head = lu / per, j = lu - head * per; n0 = head * hd + j * 8; n1 = n0 + (hd >> 1); }     // hd / 2 rows of a head in units of 8
+    else { n0 = lu * 8; n1 = n0; }
+}
+
+__device__ __forceinline__ void pk_produce_gemv(const PkOp & op, unsigned char * ring, PkBar * full, PkBar * empty, int S, unsigned & it, int ak, int hd) {      // op: the producer's own shared-memory copy
+    const int K = op.K, nA = (K + ak - 1) / ak;
     if (op.norm != PKN_NONE) {                                 // the norm's weight | bias (K floats each) travel through the ring like a tile: in shared memory long before the op starts
         const int s = (int) (it % (unsigned) S);
         pk_mbar_wait(&empty[s], ((it / (unsigned) S) & 1u) ^ 1u);
-        pk_mbar_expect_tx(&full[s], (unsigned) (2 * K * 4));
+        pk_mbar_expect_tx(&full[s], (unsigned) ((op.nb ? 2 : 1) * K * 4));
         pk_bulk_g2s(ring + (size_t) s * PK_STAGE, op.nw, (unsigned) (K * 4), &full[s]);
-        pk_bulk_g2s(ring + (size_t) s * PK_STAGE + (size_t) K * 4, op.nb, (unsigned) (K * 4), &full[s]);
+        if (op.nb) pk_bulk_g2s(ring + (size_t) s * PK_STAGE + (size_t) K * 4, op.nb, (unsigned) (K * 4), &full[s]);
         it++;
     }
     for (int a = 0; a < nA; a++) {
-        const int kA0 = a * PK_AK, kAn = K - kA0 < PK_AK ? K - kA0 : PK_AK, ntile = (kAn + PK_TK - 1) / PK_TK;
+        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak, ntile = (kAn + PK_TK - 1) / PK_TK;
         for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
             const int sj = (op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0);
             const PkSeg & sg = op.seg[sj];
-            const int n0 = (u - sg.unit0) * 8;
-            for (int plane = 0; plane < (sg.Wl ? 2 : 1); plane++) {
-                const __half * Wp = plane ? sg.Wl : sg.W;
-                for (int t = 0; t < ntile; t++, it++) {
+            int n0, n1;
+            pk_unit_rows(sg, u, hd, n0, n1);
+            const int nparts = sg.pair ? 2 : (sg.Wl ? 2 : 1);                          // paired unit: primary + partner tile; split matrix: high + low plane
+            for (int t = 0; t < ntile; t++) {
+                for (int part = 0; part < nparts; part++, it++) {
+                    const __half * Wsrc = sg.pair ? (part ? sg.Wp : sg.W) : (part ? sg.Wl : sg.W);
+                    const int nb = (sg.pair && part) ? n1 : n0;
                     const int s = (int) (it % (unsigned) S);
                     const int kt0 = kA0 + t * PK_TK, ktn = K - kt0 < PK_TK ? K - kt0 : PK_TK;
                     pk_mbar_wait(&empty[s], ((it / (unsigned) S) & 1u) ^ 1u);
                     pk_mbar_expect_tx(&full[s], (unsigned) (8 * ktn * 2));
                     unsigned char * dst = ring + (size_t) s * PK_STAGE;
                     for (int row = 0; row < 8; row++) {
-                        const int n = n0 + row < sg.N ? n0 + row : sg.N - 1;           // rows past N re-read the last row and are never stored
-                        pk_bulk_g2s(dst + (size_t) row * PK_ROWB, Wp + (size_t) n * K + kt0, (unsigned) (ktn * 2), &full[s]);
+                        const int n = nb + row < sg.N ? nb + row : sg.N - 1;           // rows past N re-read the last row and are never stored
+                        pk_bulk_g2s(dst + (size_t) row * PK_ROWB, Wsrc + (size_t) n * K + kt0, (unsigned) (ktn * 2), &full[s]);
                     }
                 }
             }
@@ -221,7 +244,10 @@ __device__ __forceinline__ void pk_stage_rows(const PkOp & op, const float * X, 
                 const int j = j0 + u * 32 + lane;
                 if (j >= n4) continue;
                 float4 x = v[rr][u];
-                if (op.norm == PKN_LAYER && r < R) {           // ggml_norm then * weight + bias (parler build_norm): ((x - mean) * scale) * w + b
+                if (op.norm == PKN_RMS && r < R) {             // ggml_rms_norm then * weight: (x * scale) * w
+                    const float4 w = reinterpret_cast<const float4 *>(snw + k0)[j];
+                    x.x = (x.x * rstd[rr]) * w.x; x.y = (x.y * rstd[rr]) * w.y; x.z = (x.z * rstd[rr]) * w.z; x.w = (x.w * rstd[rr]) * w.w;
+                } else if (op.norm == PKN_LAYER && r < R) {    // ggml_norm then * weight + bias (parler build_norm): ((x - mean) * scale) * w + b
                     const float4 w = reinterpret_cast<const float4 *>(snw + k0)[j], b = reinterpret_cast<const float4 *>(snb + k0)[j];
                     x.x = ((x.x - mean[rr]) * rstd[rr]) * w.x + b.x; x.y = ((x.y - mean[rr]) * rstd[rr]) * w.y + b.y;
                     x.z = ((x.z - mean[rr]) * rstd[rr]) * w.z + b.z; x.w = ((x.w - mean[rr]) * rstd[rr]) * w.w + b.w;
@@ -325,6 +351,36 @@ __device__ __forceinline__ void pk_stage_fast(const PkOp & op, const float * X, 
     }
 }
 
+// RMSNorm'd rows of up to NV * 128 columns (llama-style models: the whole hidden row), one row of the warp at a time: the row's NV float4 per lane are all in
+// flight at once and stay in registers for the statistics and the normalisation -- one L2 round trip per row.  ggml_rms_norm: float squares accumulated in double,
+// scale = 1 / sqrtf(mean + eps), then (x * scale) * weight (orpheus model.cpp:122-125).
+template <int NV>
+__device__ __forceinline__ void pk_stage_rms(const PkOp & op, const float * X, const float * snw, int R, __half * sA, int pitch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, K = op.K, n4 = K >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = warp + 8 * rr;
+        float4 v[NV];
+#pragma unroll
+        for (int u = 0; u < NV; u++) { const int j = u * 32 + lane; v[u] = (j < n4 && r < R) ? __ldcg(reinterpret_cast<const float4 *>(X + (size_t) r * op.ldx) + j) : z4; }
+        double ss = 0.0;
+#pragma unroll
+        for (int u = 0; u < NV; u++) ss += (double) (v[u].x * v[u].x) + (double) (v[u].y * v[u].y) + (double) (v[u].z * v[u].z) + (double) (v[u].w * v[u].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float sc = 1.0f / sqrtf((float) (ss / (double) K) + op.eps);
+#pragma unroll
+        for (int u = 0; u < NV; u++) {
+            const int j = u * 32 + lane;
+            if (j >= n4) continue;
+            const float4 w = reinterpret_cast<const float4 *>(snw)[j];
+            __half2 * d = reinterpret_cast<__half2 *>(sA + (size_t) r * pitch + 4 * j);
+            d[0] = __floats2half2_rn((v[u].x * sc) * w.x, (v[u].y * sc) * w.y); d[1] = __floats2half2_rn((v[u].z * sc) * w.z, (v[u].w * sc) * w.w);
+        }
+    }
+}
+
 // fp16 input rows (written by the previous phase): straight 16-byte copies into the operand buffer, 8 per thread in flight
 __device__ __forceinline__ void pk_stage_h16(const PkOp & op, const __half * X16, int R, int k0, int kn, __half * sA, int pitch) {
     const int n8 = kn >> 3, total = 16 * n8;                   // uint4 (8 halves) per row, in all
@@ -354,6 +410,20 @@ __device__ __forceinline__ void pk_row_stats(const PkOp & op, const float * X, i
         mean[rr] = 0.f; rstd[rr] = 0.f;
         if (r >= R) continue;                                   // warp-uniform
         const float4 * row = reinterpret_cast<const float4 *>(X + (size_t) r * op.ldx);
+        if (op.norm == PKN_RMS) {                               // ggml_rms_norm: float squares accumulated in double, scale = 1 / sqrtf(mean + eps)
+            double ss = 0.0;
+            for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = j0 + 32 * u < n4 ? __ldcg(row + j0 + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; u++) ss += (double) (v[u].x * v[u].x) + (double) (v[u].y * v[u].y) + (double) (v[u].z * v[u].z) + (double) (v[u].w * v[u].w);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            mean[rr] = 0.f; rstd[rr] = 1.0f / sqrtf((float) (ss / (double) op.K) + op.eps);
+            continue;
+        }
         double s = 0.0;
         for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
             float4 v[8];
@@ -392,7 +462,7 @@ __device__ __forceinline__ void pk_epilogue(const PkParams & P, const PkOp & op,
         case PKE_KV: {                                         // skv[r]: element offset of (this row's page, its slot in the page), looked up once per op
             const int h = n / P.hd, d = n - h * P.hd;
             KVT * base = reinterpret_cast<KVT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes);
-            pk_store1(base + skv[r] + ((size_t) sg.kv * P.heads + h) * PK_PAGE * P.hd + d, a);
+            pk_store1(base + skv[r] + ((size_t) sg.kv * P.kv_heads + h) * PK_PAGE * P.hd + d, a);
             break;
         }
         case PKE_LOGITS:
@@ -400,6 +470,25 @@ __device__ __forceinline__ void pk_epilogue(const PkParams & P, const PkOp & op,
             if (P.logits_all) P.logits_all[((size_t) step_abs * P.R + r) * sg.ldy + n] = a;
             break;
         default: sg.Y[(size_t) r * sg.ldy + n] = a; break;
+    }
+}
+
+// joint epilogue of a paired unit.  PKP_ROPE: a0 = the row's value at in-head index i < hd / 2 (output n_lo), a1 = its partner at i + hd / 2 (output n_hi): NeoX rotation with
+// the step's (cos, sin) table (ggml_rope_ext mode 2: rope_append_kernel), q to Y, k into the row's cache slot.  PKP_SWIGLU: a0 = gate, a1 = up: ggml_silu(gate) * up as fp16.
+template <typename KVT>
+__device__ __forceinline__ void pk_epilogue_pair(const PkParams & P, const PkOp & op, const PkSeg & sg, int r, int n_lo, int n_hi, float a0, float a1, const unsigned long long * skv) {
+    if (sg.epi == PKE_SWIGLU) {
+        const __half hv = __float2half_rn((a0 / (1.0f + expf(-a0))) * a1);
+        for (int c = 0; c < (sg.yrep ? PK_REP : 1); c++) sg.Y16[sg.yrep * c + (size_t) r * sg.ldy + n_lo] = hv;
+        return;
+    }
+    const int hd = P.hd, half = hd >> 1, h = n_lo / hd, i = n_lo - h * hd;
+    const float2 cs = __ldcg(P.rope_cs + (size_t) r * half + i);
+    const float y0 = a0 * cs.x - a1 * cs.y, y1 = a0 * cs.y + a1 * cs.x;
+    if (sg.epi == PKE_ROPE_Q) { sg.Y[(size_t) r * sg.ldy + n_lo] = y0; sg.Y[(size_t) r * sg.ldy + n_hi] = y1; }
+    else {
+        KVT * dst = reinterpret_cast<KVT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + skv[r] + (size_t) h * PK_PAGE * hd;      // K plane (kv = 0) of the row's page slot
+        pk_store1(dst + i, y0); pk_store1(dst + i + half, y1);
     }
 }
 
@@ -431,19 +520,19 @@ template <typename KVT>
 __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, unsigned char * ring, __half * sA, float * red, PkBar * full, PkBar * empty, unsigned & it, int step_abs,
                                         unsigned long long * pr, unsigned long long * skv, const int * sfp, const int * spt) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t8 = (lane & 3) * 8;
-    const int K = op.K, R = P.R, S = P.n_stages;
+    const int K = op.K, R = P.R, S = P.n_stages, ak = P.ak;
     const bool split = op.seg[0].Wl != nullptr;
-    const int nA = (K + PK_AK - 1) / PK_AK;
-    const int pitch = (K < PK_AK ? K : PK_AK) + PK_PAD;
+    const int nA = (K + ak - 1) / ak;
+    const int pitch = (K < ak ? K : ak) + PK_PAD;
     __half * sAl = split ? sA + (size_t) 16 * pitch : nullptr;
     float mean[2] = {0.f, 0.f}, rstd[2] = {0.f, 0.f};
     unsigned long long kvoff = 0ull;                           // the cache slot of row tid (q|k|v phase): requested now, parked in shared memory behind the staging pass
     if (op.kv_prefetch && tid < R) {
-        const int pos = sfp[tid] + step_abs;                    // the position this step appends (the page table and the first positions sit in shared memory: see pdk_kernel)
-        kvoff = (unsigned long long) spt[tid * P.max_pages + (pos >> 5)] * ((size_t) 2 * P.heads * PK_PAGE * P.hd) + (size_t) (pos & (PK_PAGE - 1)) * P.hd;
+        const int pos = sfp[tid] + step_abs - P.pos_off;        // the position this step appends (the page table and the first positions sit in shared memory: see pdk_kernel)
+        kvoff = (unsigned long long) spt[tid * P.max_pages + (pos >> 5)] * ((size_t) 2 * P.kv_heads * PK_PAGE * P.hd) + (size_t) (pos & (PK_PAGE - 1)) * P.hd;
     }
     if (op.kv_prefetch) pk_prefetch_kv<KVT>(P, op.layer, step_abs, sfp, spt);
-    const bool fast = K <= 1024;                               // one chunk, rows in registers: load + statistics + normalise in one pass
+    const bool fast = K <= 1024 && op.norm != PKN_RMS;         // one chunk, rows in registers: load + statistics + normalise in one pass
     const size_t xoff = op.xrep * (size_t) (blockIdx.x % PK_REP);      // this CTA's copy of the input rows
     const float * X = op.X ? op.X + xoff : nullptr; const __half * X16 = op.X16 ? op.X16 + xoff : nullptr;
     const float * snw = nullptr; int norm_stage = -1;
@@ -454,15 +543,17 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
         it++;
         if (pr) pr[5] = pk_now();
     }
-    if (op.norm != PKN_NONE && !fast && !op.X16) pk_row_stats(op, X, R, mean, rstd);
+    const bool fast_rms = op.norm == PKN_RMS && !op.X16 && !split && K <= 3072 && K <= ak;      // the whole row in one chunk, in registers
+    if (op.norm != PKN_NONE && !fast && !fast_rms && !op.X16) pk_row_stats(op, X, R, mean, rstd);
     float acc[3][4], accl[3][4];                               // nA > 1 (down projections: at most 3 units per CTA): one accumulator per unit across the chunks
 #pragma unroll
     for (int i = 0; i < 3; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; accl[i][0] = accl[i][1] = accl[i][2] = accl[i][3] = 0.f; }
     for (int a = 0; a < nA; a++) {
-        const int kA0 = a * PK_AK, kAn = K - kA0 < PK_AK ? K - kA0 : PK_AK, ntile = (kAn + PK_TK - 1) / PK_TK;
+        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak, ntile = (kAn + PK_TK - 1) / PK_TK;
         if (a) pk_bar_sync(1, PK_CONS);                        // every warp is done with the previous chunk
         if (op.X16) pk_stage_h16(op, X16, R, kA0, kAn, sA, pitch);
         else if (fast) pk_stage_fast(op, X, snw, R, sA, sAl, pitch);
+        else if (fast_rms) { if (K <= 1024) pk_stage_rms<8>(op, X, snw, R, sA, pitch); else pk_stage_rms<24>(op, X, snw, R, sA, pitch); }
         else pk_stage_rows(op, X, snw, R, kA0, kAn, sA, sAl, pitch, mean, rstd);
         if (a == 0 && op.kv_prefetch && tid < R) skv[tid] = kvoff;
         if (norm_stage >= 0 && a + 1 == nA) { __syncwarp(); if (lane == 0) pk_mbar_arrive(&empty[norm_stage]); }      // this warp is done with the norm's weights
@@ -472,16 +563,19 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
         for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x, ui++) {
             const int sj = (op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0);
             const PkSeg & sg = op.seg[sj];
-            const int n0 = (u - sg.unit0) * 8;
+            int n0, n1;
+            pk_unit_rows(sg, u, P.hd, n0, n1);
+            const bool paired = sg.pair != PKP_NONE;            // (paired units only in single-chunk phases: host-checked)
             float resv = 0.f;                                   // the epilogue's residual element of thread tid < 128, requested before the tiles are consumed
             if (a + 1 == nA && sg.epi == PKE_RES && tid < 128) { const int r = tid >> 3, n = n0 + (tid & 7); if (r < R && n < sg.N) resv = __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n); }
-            float c[4], cl[4];
+            float c[4], cl[4];                                  // cl: the split matrix's cross terms, or the partner tile of a paired unit
             if (nA > 1) {
 #pragma unroll
                 for (int i = 0; i < 3; i++) if (i == ui) { for (int e = 0; e < 4; e++) { c[e] = acc[i][e]; cl[e] = accl[i][e]; } }
             } else { c[0] = c[1] = c[2] = c[3] = 0.f; cl[0] = cl[1] = cl[2] = cl[3] = 0.f; }
-            for (int plane = 0; plane < (split ? 2 : 1); plane++) {
-                for (int t = 0; t < ntile; t++, it++) {
+            const int nparts = paired ? 2 : (split ? 2 : 1);
+            for (int t = 0; t < ntile; t++) {
+                for (int part = 0; part < nparts; part++, it++) {
                     const int s = (int) (it % (unsigned) S);
                     const int kt0 = t * PK_TK, ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, kb = warp * ks;
                     const unsigned long long tw0 = pr ? pk_now() : 0ull;
@@ -490,7 +584,8 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
                     const __half * wt = reinterpret_cast<const __half *>(ring + (size_t) s * PK_STAGE) + (size_t) g * (PK_TK + PK_PAD) + t8 + kb;
                     const __half * xa = sA + (size_t) g * pitch + kt0 + kb + t8, * xb = xa + (size_t) 8 * pitch;
                     const __half * xla = split ? sAl + (size_t) g * pitch + kt0 + kb + t8 : nullptr, * xlb = split ? xla + (size_t) 8 * pitch : nullptr;
-                    pk_tile_mma(c, cl, wt, xa, xb, xla, xlb, ks, split, plane);
+                    if (paired) pk_tile_mma(part ? cl : c, nullptr, wt, xa, xb, nullptr, nullptr, ks, false, 0);      // two plain tiles, one accumulator each
+                    else pk_tile_mma(c, cl, wt, xa, xb, xla, xlb, ks, split, part);
                     __syncwarp();
                     if (lane == 0) pk_mbar_arrive(&empty[s]);  // this warp is done reading the stage
                 }
@@ -501,17 +596,25 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
                 continue;
             }
             // the eight warps' partial 16 x 8 tiles summed in warp order, then the epilogue: c0, c1 = row g, columns 2t, 2t+1; c2, c3 = row g + 8
-            if (split) { for (int e = 0; e < 4; e++) c[e] += cl[e] * (1.0f / GM_LO_SCALE); }
+            if (split && !paired) { for (int e = 0; e < 4; e++) c[e] += cl[e] * (1.0f / GM_LO_SCALE); }
             float * my = red + warp * 128;
             const int tq = lane & 3;
             my[g * 8 + 2 * tq] = c[0]; my[g * 8 + 2 * tq + 1] = c[1]; my[(g + 8) * 8 + 2 * tq] = c[2]; my[(g + 8) * 8 + 2 * tq + 1] = c[3];
+            if (paired) { float * my2 = my + 8 * 128; my2[g * 8 + 2 * tq] = cl[0]; my2[g * 8 + 2 * tq + 1] = cl[1]; my2[(g + 8) * 8 + 2 * tq] = cl[2]; my2[(g + 8) * 8 + 2 * tq + 1] = cl[3]; }
             pk_bar_sync(1, PK_CONS);
             if (tid < 128) {
                 const int r = tid >> 3, col = tid & 7;
-                float sum = 0.f;
+                float sum = 0.f, sum2 = 0.f;
 #pragma unroll
                 for (int w = 0; w < 8; w++) sum += red[w * 128 + tid];
-                if (r < R && n0 + col < sg.N) pk_epilogue<KVT>(P, op, sg, r, n0 + col, sum, resv, step_abs, skv);
+                if (paired) {
+#pragma unroll
+                    for (int w = 0; w < 8; w++) sum2 += red[8 * 128 + w * 128 + tid];
+                }
+                if (r < R && n0 + col < sg.N) {
+                    if (paired) pk_epilogue_pair<KVT>(P, op, sg, r, n0 + col, n1 + col, sum, sum2, skv);
+                    else pk_epilogue<KVT>(P, op, sg, r, n0 + col, sum, resv, step_abs, skv);
+                }
             }
             pk_bar_sync(1, PK_CONS);
         }
@@ -547,14 +650,14 @@ constexpr int PK_ATT_HDR = 1024;                               // floats of per-
 // HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three unrolled shuffles that the scheduler interleaves across the keys
 // in flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue slots on a B200)
 template <typename KVT, typename CT, int HD>
-__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int T, const int * spt) {
+__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int kh, int T, const int * spt) {      // kh: the kv head query head h reads
     typedef typename PkRawOf<CT>::type Raw;
     constexpr int U = PkAttU<CT>::v, PARTS = HD / 8, KPP = 128 / PARTS;
     const int gt = threadIdx.x & 127, gw = gt >> 5, H = P.H, part = gt % PARTS, kq = gt / PARTS;
     float * qs = base; float * wredf = base + 128; double * wredd = reinterpret_cast<double *>(base + 136);
     unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 512);      // element offset of each of this sequence's pages within the layer's pool
     float * pvs = base + PK_ATT_HDR; float * sc = base + PK_ATT_HDR + 1024;
-    const size_t page_elems = (size_t) 2 * P.heads * PK_PAGE * HD;
+    const size_t page_elems = (size_t) 2 * P.kv_heads * PK_PAGE * HD;
     if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
     if (!op.cross) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) spt[r * P.max_pages + i] * page_elems;
     pk_bar_sync(2 + grp, 128);
@@ -562,8 +665,8 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
 #pragma unroll
     for (int i = 0; i < 8; i++) q8[i] = qs[part * 8 + i];
     const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + (size_t) h * HD + part * 8, * flat_v = reinterpret_cast<const CT *>(op.cv) + (size_t) h * HD + part * 8;
-    const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) h * PK_PAGE * HD + part * 8;
-    const CT * pool_v = pool_k + (size_t) P.heads * PK_PAGE * HD;
+    const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) kh * PK_PAGE * HD + part * 8;
+    const CT * pool_v = pool_k + (size_t) P.kv_heads * PK_PAGE * HD;
     auto krow = [&](int t, int kv) -> const CT * {
         if (op.cross) return (kv ? flat_v : flat_k) + (size_t) t * H;
         return (kv ? pool_v : pool_k) + spo[t >> 5] + (t & (PK_PAGE - 1)) * HD;
@@ -641,8 +744,8 @@ __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, uns
     float * base = reinterpret_cast<float *>(scratch + (size_t) grp * (P.a_bytes / 2));
     for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
         const int r = it / P.heads, h = it - r * P.heads;
-        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, op.cross_len, spt);
-        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, sfp[r] + step + 1, spt);
+        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, op.cross_len, spt);
+        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, h / (P.heads / P.kv_heads), sfp[r] + step - P.pos_off + 1, spt);      // the reference's repeat-interleaved GQA cache by indexing
     }
 }
 
@@ -651,10 +754,10 @@ __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, uns
 template <typename KVT>
 __device__ __forceinline__ void pk_prefetch_kv(const PkParams & P, int layer, int step, const int * sfp, const int * spt) {
     const int grp = threadIdx.x >> 7, gt = threadIdx.x & 127, hd = P.hd;
-    const size_t page_elems = (size_t) 2 * P.heads * PK_PAGE * hd, v_off = (size_t) P.heads * PK_PAGE * hd;
+    const size_t page_elems = (size_t) 2 * P.kv_heads * PK_PAGE * hd, v_off = (size_t) P.kv_heads * PK_PAGE * hd;
     const int lines = (hd * (int) sizeof(KVT) + 127) / 128;     // 128-byte lines per cache row
-    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
-        const int r = it / P.heads, h = it - r * P.heads, T = sfp[r] + step;
+    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.kv_heads; it += 2 * (int) gridDim.x) {
+        const int r = it / P.kv_heads, h = it - r * P.kv_heads, T = sfp[r] + step - P.pos_off;
         const KVT * pool = reinterpret_cast<const KVT *>(P.kv_pool + (size_t) layer * P.kv_layer_bytes) + (size_t) h * PK_PAGE * hd;
         for (int i = gt; i < T * lines; i += 128) {
             const int t = i / lines, ln = i - t * lines;
@@ -714,6 +817,76 @@ __device__ __forceinline__ void pk_argmax(const PkParams & P, int step, float * 
     }
 }
 
+// ---- PKM_ORPHEUS (llama-3 style: orpheus_runner::build_orpheus_graph, reference src/models/orpheus/model.cpp:231-353)
+// the token row b produced at step s: its amax_ch partial maxima combined (first maximum wins: sampler::max), written to d_out, checked against the stopping token
+// (generate_from_batch's stop rule, model.cpp:389-398); every consumer thread returns it
+__device__ __forceinline__ int pk_orpheus_token(const PkParams & P, int s, int b, float * red) {
+    float * sv = red; int * si = reinterpret_cast<int *>(red + 256);
+    const int tid = threadIdx.x;
+    sv[tid] = tid < P.amax_ch ? __ldcg(P.amax_v + (size_t) b * P.amax_ch + tid) : -INFINITY;
+    si[tid] = tid < P.amax_ch ? __ldcg(P.amax_i + (size_t) b * P.amax_ch + tid) : 0x7fffffff;
+    pk_bar_sync(1, PK_CONS);
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
+        pk_bar_sync(1, PK_CONS);
+    }
+    const int tok = si[0] == 0x7fffffff ? 0 : si[0];
+    pk_bar_sync(1, PK_CONS);                                   // (red is reused right away)
+    if (tid == 0) {
+        P.d_out[(size_t) b * P.n_steps_total + s] = tok;
+        if (P.stopped && P.stopped[b] < 0 && tok == P.stop_token) P.stopped[b] = s + 1;
+    }
+    return tok;
+}
+
+// rows of a decode step: x0[b] = embed[token of step - 1] (ggml_get_rows), position = prompt length + step - 1, and the step's NeoX RoPE table for that position
+// (ggml rope cache: theta starts at the position and is multiplied by theta_scale pair after pair; llama-3 frequency factors divide it)
+__device__ __forceinline__ void pk_rows_orpheus(const PkParams & P, int step, bool first_in_launch, float * red) {
+    const int tid = threadIdx.x, R = P.R, H = P.H, half = P.hd >> 1;
+    for (int b = (int) blockIdx.x; b < R; b += (int) gridDim.x) {
+        const int tok = first_in_launch ? __ldcg(P.d_out + (size_t) b * P.n_steps_total + step - 1) : pk_orpheus_token(P, step - 1, b, red);
+        const int pos = P.first_pos[b] + step - P.pos_off;
+        const float4 * src = reinterpret_cast<const float4 *>(P.embed + (size_t) tok * H);
+        for (int c = tid; c < (H >> 2); c += PK_CONS) {
+            const float4 v = __ldg(src + c);
+            for (int cp = 0; cp < (P.x0rep ? PK_REP : 1); cp++) reinterpret_cast<float4 *>(P.x0 + P.x0rep * cp + (size_t) b * H)[c] = v;
+        }
+        for (int i = tid; i < half; i += PK_CONS) {
+            float theta = (float) pos;
+            for (int j = 0; j < i; j++) theta *= P.theta_scale;
+            const float th = P.rope_ff ? theta / P.rope_ff[i] : theta;
+            P.rope_cs[(size_t) b * half + i] = make_float2(cosf(th), sinf(th));
+        }
+        if (tid == 0) P.row_pos[b] = pos;
+    }
+}
+
+// partial maxima of the step's logits: item (row b, chunk c) scans [c * len, (c + 1) * len) of the row
+__device__ __forceinline__ void pk_argmax_partial(const PkParams & P, float * red) {
+    float * sv = red; int * si = reinterpret_cast<int *>(red + 256);
+    const int tid = threadIdx.x, V = P.vocab, nch = P.amax_ch, len = (V + nch - 1) / nch;
+    for (int item = (int) blockIdx.x; item < P.R * nch; item += (int) gridDim.x) {
+        const int b = item / nch, c = item - b * nch, lo = c * len, hi = lo + len < V ? lo + len : V;
+        const float * lg = P.logits + (size_t) b * V;
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int i0 = lo + tid; i0 < hi; i0 += PK_CONS * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = i0 + u * PK_CONS < hi ? __ldcg(lg + i0 + u * PK_CONS) : -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (v[u] > best) { best = v[u]; bi = i0 + u * PK_CONS; }      // ascending indices per thread: the first maximum stays
+        }
+        sv[tid] = best; si[tid] = bi;
+        pk_bar_sync(1, PK_CONS);
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
+            pk_bar_sync(1, PK_CONS);
+        }
+        if (tid == 0) { P.amax_v[item] = sv[0]; P.amax_i[item] = si[0]; }
+        pk_bar_sync(1, PK_CONS);
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <typename KVT, int HD>
 __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
@@ -748,7 +921,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
                 __syncwarp();
                 for (int w = lane; w < (int) (sizeof(PkOp) / 16); w += 32) reinterpret_cast<uint4 *>(pop)[w] = __ldg(reinterpret_cast<const uint4 *>(&P.ops[oi]) + w);
                 __syncwarp();
-                if (lane == 0 && pop->kind == PK_GEMV) pk_produce_gemv(*pop, ring, full, empty, S, it);
+                if (lane == 0 && pop->kind == PK_GEMV) pk_produce_gemv(*pop, ring, full, empty, S, it, P.ak, P.hd);
             }
         return;
     }
@@ -769,10 +942,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
             unsigned long long * pr = prof ? P.prof + ((size_t) oi * gridDim.x + blockIdx.x) * 8 : nullptr;
             if (pr) pr[0] = pk_now();
             switch (op.kind) {
-                case PK_ROWS:   pk_rows(P, step, sids); break;
+                case PK_ROWS:   if (P.model == PKM_ORPHEUS) pk_rows_orpheus(P, step, st == 0, red); else pk_rows(P, step, sids); break;
                 case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, it, step, pr, skv, sfp, spt); break;
                 case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
-                case PK_ARGMAX: pk_argmax(P, step, red); break;
+                case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else pk_argmax(P, step, red); break;
             }
             if (pr) pr[2] = pk_now();
             if (tid < OPW) reinterpret_cast<uint4 *>(&sops[(opn & 1u) ^ 1u])[tid] = nxt;
@@ -780,6 +953,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
             if (pr) pr[3] = pk_now();
         }
     }
+    if (P.model == PKM_ORPHEUS)                                // the launch's last token (the other steps' tokens were combined by the following step's rows phase)
+        for (int b = (int) blockIdx.x; b < P.R; b += (int) gridDim.x) pk_orpheus_token(P, P.step_begin + P.n_steps - 1, b, red);
     if (blockIdx.x == 0 && tid == 0) *P.d_step = P.step_begin + P.n_steps;
 }
 
@@ -788,8 +963,9 @@ template <typename KVT>
 __global__ void pk_kv_import_kernel(const float * __restrict__ Kc, const float * __restrict__ Vc, size_t layer_stride, const int * __restrict__ row_src, const int * __restrict__ row_seq,
                                     const int * __restrict__ row_pos, const PkParams P) {
     const int r = blockIdx.x, l = blockIdx.y, seq = row_seq[r], pos = row_pos[r];
-    const float * k = Kc + (size_t) l * layer_stride + (size_t) row_src[r] * P.H, * v = Vc + (size_t) l * layer_stride + (size_t) row_src[r] * P.H;
-    for (int c = threadIdx.x; c < P.H; c += blockDim.x) {
+    const int KVW = P.kv_heads * P.hd;                           // floats per cache row (compact: kv heads, not query heads)
+    const float * k = Kc + (size_t) l * layer_stride + (size_t) row_src[r] * KVW, * v = Vc + (size_t) l * layer_stride + (size_t) row_src[r] * KVW;
+    for (int c = threadIdx.x; c < KVW; c += blockDim.x) {
         const int h = c / P.hd, d = c - h * P.hd;
         pk_store1(pk_page_row<KVT>(P, l, seq, pos, 0, h) + d, k[c]);
         pk_store1(pk_page_row<KVT>(P, l, seq, pos, 1, h) + d, v[c]);
@@ -797,6 +973,80 @@ __global__ void pk_kv_import_kernel(const float * __restrict__ Kc, const float *
 }
 
 static inline size_t pk_smem_bytes(int n_stages, int a_bytes, int pt_ints) { return (size_t) (16 + pt_ints) * 4 + (size_t) n_stages * PK_STAGE + (size_t) a_bytes + PK_RED_BYTES + 64 + 2 * PK_MAXSTAGES * sizeof(PkBar) + 3 * sizeof(PkOp) + 16 + 128 + 128; }
+
+// ---------------------------------------------------------------- host side shared by the models' generate() functions
+struct PkLaunch {
+    const void * kfn = nullptr; size_t smem = 0;
+#ifdef B2EMU
+    std::function<void(const PkParams &)> kemu;
+#endif
+};
+// shared-memory layout for a program whose widest activation chunk has KA columns (KAs: widest chunk of a split-matrix phase, 0 = none) and whose attention sees at
+// most Tscore positions; picks the kernel instantiation for (cache element type, head size).  Returns 1 when the shape does not fit.
+static inline int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int Tscore, PkLaunch & L) {
+    size_t a = (size_t) 16 * (KA + PK_PAD) * 2;
+    if (KAs) a = std::max(a, (size_t) 2 * 16 * (KAs + PK_PAD) * 2);
+    a = std::max(a, (size_t) 2 * ((PK_ATT_HDR + 1024) * 4 + (size_t) ((Tscore + 3) & ~3) * 4));
+    a = (a + 255) & ~(size_t) 255;
+    const int pt = Pk.R * Pk.max_pages;
+    if (Pk.max_pages > 256) return 1;                          // page offsets of a sequence sit in a 256-entry scratch (pk_attn_item)
+    int ns = PK_MAXSTAGES;
+    while (ns > 2 && pk_smem_bytes(ns, (int) a, pt) > (size_t) 227 * 1024) ns--;
+    if (pk_smem_bytes(ns, (int) a, pt) > (size_t) 227 * 1024) return 1;
+    Pk.n_stages = ns; Pk.a_bytes = (int) a;
+    L.smem = pk_smem_bytes(ns, (int) a, pt);
+#ifdef B2EMU
+#define PK_PICK(T, D) { L.kemu = [](const PkParams & q) { pdk_kernel<T, D>(q); }; }
+#else
+#define PK_PICK(T, D) { L.kfn = (const void *) pdk_kernel<T, D>; }
+#endif
+    const int hd = Pk.hd;
+    if (hd != 8 && hd != 64 && hd != 128) return 1;
+    if (kv_f32) { if (hd == 8) PK_PICK(float, 8) else if (hd == 64) PK_PICK(float, 64) else PK_PICK(float, 128) }
+    else        { if (hd == 8) PK_PICK(__half, 8) else if (hd == 64) PK_PICK(__half, 64) else PK_PICK(__half, 128) }
+#undef PK_PICK
+#ifndef B2EMU
+    if (cudaFuncSetAttribute(L.kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.smem) != cudaSuccess) { cudaGetLastError(); return 1; }
+#endif
+    return 0;
+}
+// one cooperative launch of steps [Pk.step_begin, Pk.step_begin + Pk.n_steps)
+static inline cudaError_t pk_launch(const PkLaunch & L, const PkParams & Pk, int grid, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(Pk.bar, 0, 256, st);
+    if (e != cudaSuccess) return e;
+#ifdef B2EMU
+    const PkParams q = Pk;
+    b2emu::launch_coop(dim3(grid), dim3(PK_THREADS), L.smem, [=]() { L.kemu(q); });
+    return cudaSuccess;
+#else
+    void * args[] = {(void *) &Pk};
+    return cudaLaunchCooperativeKernel(L.kfn, dim3(grid), dim3(PK_THREADS), args, L.smem, st);
+#endif
+}
+// B2TTS_PDK_PROF=<step>: %globaltimer timeline of that decode step (every op x every CTA), written as raw uint64 to $B2TTS_PDK_PROF_FILE after the run
+static inline void pk_prof_begin(PkParams & Pk, size_t n_ops, int grid, cudaStream_t st) {
+    const char * e = getenv("B2TTS_PDK_PROF");
+    if (!e) return;
+    const size_t words = n_ops * (size_t) grid * 8;
+    if (cudaMalloc(&Pk.prof, words * 8) != cudaSuccess) { cudaGetLastError(); Pk.prof = nullptr; return; }
+    cudaMemsetAsync(Pk.prof, 0, words * 8, st);
+    Pk.prof_step = atoi(e);
+}
+static inline void pk_prof_end(PkParams & Pk, const std::vector<PkOp> & ops, int grid, cudaStream_t st) {
+    if (!Pk.prof) return;
+    std::vector<unsigned long long> hp(ops.size() * (size_t) grid * 8);
+    cudaMemcpyAsync(hp.data(), Pk.prof, hp.size() * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (const char * pf = getenv("B2TTS_PDK_PROF_FILE")) {
+        if (FILE * f = fopen(pf, "wb")) {
+            const int hdr[4] = {(int) ops.size(), grid, 8, Pk.prof_step};
+            fwrite(hdr, 4, 4, f);
+            for (const PkOp & o : ops) { const int k[4] = {o.kind, o.layer, o.K, o.n_units}; fwrite(k, 4, 4, f); }
+            fwrite(hp.data(), 8, hp.size(), f); fclose(f);
+        }
+    }
+    cudaFree(Pk.prof); Pk.prof = nullptr;
+}
 
 }  // namespace
 }  // namespace b2
