@@ -425,6 +425,7 @@ ASAN_CASES = {
     "dia_q8_0_plain_attention": ("dia", lambda: cached_dia_gguf(seed=0, quant="Q8_0"), "dia_q8_0_vectors", {"B2TTS_AR_ATT": "plain"}),
     # the persistent decode kernel: ring stages, activation / attention scratch, page pool, page table, replicated hand-off buffers -- one exact-size allocation each
     "parler_f16_persistent_kernel": ("parler", lambda: cached_parler_gguf(seed=0, f16=True), "parler_f16_vectors", {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "3", "B2TTS_AR_EXIT_EVERY": "2"}),
+    "orpheus_f16_persistent_kernel": ("orpheus", lambda: cached_orpheus_gguf(seed=0, head_dim=128, f16=True), "orpheus_wide_vectors", {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "3", "B2TTS_AR_EXIT_EVERY": "1"}),
 }
 
 
@@ -522,3 +523,31 @@ def test_orpheus_quantised_and_f16_matrices_emulated(tmp_path, kind):
         print(f"PARITY(emulated) orpheus {kind} prompt {u}: logit rms / std {rel:.3e}; tokens equal {int((tok[u, :, 0] == g[f'tokens{u}']).sum())}/{steps}, clear decisions {int(clear.sum())}")
         assert rel < (0.05 if kind == "q8_0" else 0.01)
         assert np.array_equal(tok[u, :, 0][clear], g[f"tokens{u}"][clear])
+
+
+@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "3"}, {"B2TTS_PDK_GRID": "32", "B2TTS_KV": "f32", "B2TTS_PDK_AK": "768"}, {"B2TTS_PDK_GRID": "7", "B2EMU_REVERSE": "1"}],
+                         ids=["grid3_f16kv", "grid32_f32kv_two_k_chunks", "grid7_reverse"])
+def test_persistent_decode_kernel_emulated_orpheus(tmp_path, env):
+    """Orpheus (llama-3 style) through the persistent kernel under emulation: RMSNorm folded into the staging, paired units (NeoX RoPE halves of q / k, gate + up for SwiGLU)
+    with their joint epilogues, GQA attention over the pages, argmax partials combined by the next step's rows phase, three launches per generation
+    (B2TTS_AR_EXIT_EVERY=16), the down projection in one or two k-chunks.  Yardstick: the reference's F32 run of the same (fp16-representable) weights
+    (tests/golden/orpheus_wide_long_vectors.npz): same tokens up to the first near-tie, logits within the F16 floor."""
+    g = np.load(os.path.join(GOLD, "orpheus_wide_long_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = 36
+    gguf = cached_orpheus_gguf(seed=0, head_dim=128, f16=True)
+    tok, logits, err = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, "pk", env={"B2TTS_AR_PDK": "1", "B2TTS_AR_EXIT_EVERY": "16", **env}, want_stderr=True)
+    _, _, err0 = _run_ar(tmp_path, "orpheus", gguf, prompts, 4, "op", env={"B2TTS_AR_PDK": "0"}, want_stderr=True)
+    n_pk, n_op = (int(e.split("emulated ")[1].split(" launches")[0]) for e in (err, err0))
+    assert n_pk < n_op + 8, (n_pk, n_op)                         # prompt pass + 3 cooperative launches vs prompt pass + 3 steps of ~25 launches
+    for u in range(2):
+        ref_t, ref_l = g[f"tokens{u}"][:steps], g[f"logits{u}"][:steps]
+        neq = np.nonzero(tok[u, :, 0] != ref_t)[0]
+        upto = int(neq[0]) if neq.size else steps - 1
+        d = np.abs(logits[u][:upto + 1] - ref_l[:upto + 1]).max(axis=1)
+        print(f"PARITY(emulated, persistent kernel {env}) orpheus wide f16 prompt {u}: tokens equal for {upto + (0 if neq.size else 1)}/{steps} steps, max |logit diff| {float(d.max()):.3e}")
+        assert float(d.max()) < 3e-2
+        if neq.size:                                            # a differing token must be a near-tie of the reference
+            top2 = np.sort(ref_l[upto])[-2:]
+            assert float(top2[1] - top2[0]) <= 2.0 * float(d[upto]), (upto, float(top2[1] - top2[0]), float(d[upto]))
+        assert upto >= 20
