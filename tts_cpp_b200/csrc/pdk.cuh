@@ -8,7 +8,7 @@
 // residual -> [LN3] fc1 GEMV + GELU -> fc2 GEMV + residual }, final [LN] heads GEMV, argmax -- separated by grid-wide barriers in global memory, for up to 32 steps
 // per launch:
 //
-//   * warp 8 of every CTA is a TMA PRODUCER: one lane streams the CTA's weight tiles (8 output rows x 1 024 k, fp16; `cp.async.bulk` global -> shared completing
+//   * warp 8 of every CTA is a TMA PRODUCER: eight lanes stream the CTA's weight tiles (8 output rows x 1 024 k, fp16; `cp.async.bulk` global -> shared completing
 //     on an mbarrier) through a ring of ~9 stages IN PROGRAM ORDER.  Weights do not depend on activations, so the producer runs ahead across phases, layers and
 //     steps: while the consumers sit in a grid barrier or in an attention phase the ring fills with the next phase's tiles and HBM keeps streaming.
 //   * warps 0-7 are CONSUMERS: per GEMV phase they stage the <= 16 activation rows ONCE per CTA as fp16 in shared memory -- with the LayerNorm of the reference
@@ -44,7 +44,8 @@ constexpr int PK_STAGE = 8 * PK_ROWB;             // bytes per ring stage (one t
 constexpr int PK_AK_MAX = 3072;                   // activations are staged in k chunks of P.ak columns (2 048, or 3 072 for models whose hidden size is 3 072: one chunk for their q|k|v, gate|up phases)
 constexpr int PK_PAGE = 32;                       // positions per KV page
 constexpr int PK_MAXSTAGES = 12;
-constexpr int PK_RED_BYTES = 2 * 8 * 128 * 4;     // cross-warp reduction scratch (two 16 x 8 tiles of a paired unit) / argmax scratch
+constexpr int PK_RED_FLOATS = 2 * 8 * 128;        // cross-warp reduction scratch of one unit: eight warps' partial 16 x 8 tiles, twice for a paired unit
+constexpr int PK_RED_BYTES = 2 * PK_RED_FLOATS * 4;   // two such buffers used alternately (one block barrier per unit instead of two) / argmax scratch
 constexpr int PK_REP = 8;                         // copies of every activation buffer that ALL CTAs read at the start of a phase.  Measured on a B200: 148 SMs asking L2 for the
                                                   // same 64 KB right after a grid barrier wait ~2 us (each line is served to 148 requesters one after the other); with 8 copies
                                                   // (8x the tiny epilogue stores) a line has 18-19 requesters
@@ -140,6 +141,21 @@ static inline unsigned long long pk_now() { return 0ull; }
 __device__ __forceinline__ unsigned long long pk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
+// position in the weight ring: stage index and the parity of its current use (producer and consumers walk the same sequence of tiles)
+struct PkRingPos { int s; unsigned ph; };
+__device__ __forceinline__ void pk_ring_next(PkRingPos & p, int S) { if (++p.s == S) { p.s = 0; p.ph ^= 1u; } }
+// 16-byte shared-memory load as ld.shared (the operand pointers are derived from the dynamic shared array through several inlined calls: left to itself the compiler
+// emitted generic loads for part of them)
+#ifdef B2EMU
+static inline uint4 pk_lds128(const void * p) { uint4 v; memcpy(&v, p, 16); return v; }
+#else
+__device__ __forceinline__ uint4 pk_lds128(const void * p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(pk_smem_u32(p)));
+    return v;
+}
+#endif
+
 // every consumer thread of every CTA calls it; orders all global stores before it against all loads after it, grid-wide (the cooperative-groups pattern: block
 // barrier, one thread releases / acquires at gpu scope, block barrier).  The counter only grows: generation e is complete when it reaches e * gridDim.x.
 __device__ __forceinline__ void pk_grid_sync(unsigned * ctr, unsigned & epoch) {
@@ -181,37 +197,44 @@ __device__ __forceinline__ void pk_unit_rows(const PkSeg & sg, int u, int hd, in
     else { n0 = lu * 8; n1 = n0; }
 }
 
-__device__ __forceinline__ void pk_produce_gemv(const PkOp & op, unsigned char * ring, PkBar * full, PkBar * empty, int S, unsigned & it, int ak, int hd) {      // op: the producer's own shared-memory copy
+// The whole producer warp runs it: lane 0 waits for the stage and posts the byte count, lanes 0-7 each copy one row of the tile.  (One lane issuing all eight copies
+// spent ~200 dependent instructions per tile on addresses and the per-copy uniform-register hand-off: 0.6 us per 16 KB tile, a 2.7 TB/s cap on a B200 whose copy
+// engines stream 6.9 TB/s in this shape -- scripts/probes/tma_stream_probe.cu.)
+__device__ __forceinline__ void pk_produce_gemv(const PkOp & op, unsigned char * ring, PkBar * full, PkBar * empty, int S, PkRingPos & rp, int ak, int hd) {      // op: the producer's own shared-memory copy
+    const int lane = threadIdx.x & 31, row = lane & 7;
     const int K = op.K, nA = (K + ak - 1) / ak;
     if (op.norm != PKN_NONE) {                                 // the norm's weight | bias (K floats each) travel through the ring like a tile: in shared memory long before the op starts
-        const int s = (int) (it % (unsigned) S);
-        pk_mbar_wait(&empty[s], ((it / (unsigned) S) & 1u) ^ 1u);
-        pk_mbar_expect_tx(&full[s], (unsigned) ((op.nb ? 2 : 1) * K * 4));
-        pk_bulk_g2s(ring + (size_t) s * PK_STAGE, op.nw, (unsigned) (K * 4), &full[s]);
-        if (op.nb) pk_bulk_g2s(ring + (size_t) s * PK_STAGE + (size_t) K * 4, op.nb, (unsigned) (K * 4), &full[s]);
-        it++;
+        if (lane == 0) {
+            pk_mbar_wait(&empty[rp.s], rp.ph ^ 1u);
+            pk_mbar_expect_tx(&full[rp.s], (unsigned) ((op.nb ? 2 : 1) * K * 4));
+            pk_bulk_g2s(ring + (size_t) rp.s * PK_STAGE, op.nw, (unsigned) (K * 4), &full[rp.s]);
+            if (op.nb) pk_bulk_g2s(ring + (size_t) rp.s * PK_STAGE + (size_t) K * 4, op.nb, (unsigned) (K * 4), &full[rp.s]);
+        }
+        pk_ring_next(rp, S);
     }
     for (int a = 0; a < nA; a++) {
-        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak, ntile = (kAn + PK_TK - 1) / PK_TK;
+        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak;
         for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
             const int sj = (op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0);
             const PkSeg & sg = op.seg[sj];
             int n0, n1;
             pk_unit_rows(sg, u, hd, n0, n1);
-            const int nparts = sg.pair ? 2 : (sg.Wl ? 2 : 1);                          // paired unit: primary + partner tile; split matrix: high + low plane
-            for (int t = 0; t < ntile; t++) {
-                for (int part = 0; part < nparts; part++, it++) {
-                    const __half * Wsrc = sg.pair ? (part ? sg.Wp : sg.W) : (part ? sg.Wl : sg.W);
-                    const int nb = (sg.pair && part) ? n1 : n0;
-                    const int s = (int) (it % (unsigned) S);
-                    const int kt0 = kA0 + t * PK_TK, ktn = K - kt0 < PK_TK ? K - kt0 : PK_TK;
-                    pk_mbar_wait(&empty[s], ((it / (unsigned) S) & 1u) ^ 1u);
-                    pk_mbar_expect_tx(&full[s], (unsigned) (8 * ktn * 2));
-                    unsigned char * dst = ring + (size_t) s * PK_STAGE;
-                    for (int row = 0; row < 8; row++) {
-                        const int n = nb + row < sg.N ? nb + row : sg.N - 1;           // rows past N re-read the last row and are never stored
-                        pk_bulk_g2s(dst + (size_t) row * PK_ROWB, Wsrc + (size_t) n * K + kt0, (unsigned) (ktn * 2), &full[s]);
+            const int N = sg.N, pair = sg.pair;
+            const __half * Wl = sg.Wl;
+            const int nparts = pair ? 2 : (Wl ? 2 : 1);         // paired unit: primary + partner tile; split matrix: high + low plane
+            // this lane's row of the two tiles (rows past N re-read the last row and are never stored)
+            const int r0 = n0 + row < N ? n0 + row : N - 1, r1 = pair ? (n1 + row < N ? n1 + row : N - 1) : r0;
+            const __half * p0 = sg.W + (size_t) r0 * K + kA0, * p1 = (pair ? sg.Wp : (Wl ? Wl : sg.W)) + (size_t) r1 * K + kA0;
+            for (int kl = 0; kl < kAn; kl += PK_TK) {
+                const unsigned bytes = (unsigned) ((kAn - kl < PK_TK ? kAn - kl : PK_TK) * 2);      // within the chunk the consumers have staged
+                for (int part = 0; part < nparts; part++) {
+                    if (lane == 0) {
+                        pk_mbar_wait(&empty[rp.s], rp.ph ^ 1u);
+                        pk_mbar_expect_tx(&full[rp.s], 8u * bytes);
                     }
+                    __syncwarp();                               // the stage is free and its byte count posted before any row lands
+                    if (lane < 8) pk_bulk_g2s(ring + (size_t) rp.s * PK_STAGE + (size_t) row * PK_ROWB, (part ? p1 : p0) + kl, bytes, &full[rp.s]);
+                    pk_ring_next(rp, S);
                 }
             }
         }
@@ -352,8 +375,8 @@ __device__ __forceinline__ void pk_stage_fast(const PkOp & op, const float * X, 
 }
 
 // RMSNorm'd rows of up to NV * 128 columns (llama-style models: the whole hidden row), one row of the warp at a time: the row's NV float4 per lane are all in
-// flight at once and stay in registers for the statistics and the normalisation -- one L2 round trip per row.  ggml_rms_norm: float squares accumulated in double,
-// scale = 1 / sqrtf(mean + eps), then (x * scale) * weight (orpheus model.cpp:122-125).
+// flight at once and stay in registers for the statistics and the normalisation -- one L2 round trip per row.  ggml_rms_norm: float squares accumulated in double
+// (here: the four squares of a float4 are added in float first, as in pk_stage_fast), scale = 1 / sqrtf(mean + eps), then (x * scale) * weight (orpheus model.cpp:122-125).
 template <int NV>
 __device__ __forceinline__ void pk_stage_rms(const PkOp & op, const float * X, const float * snw, int R, __half * sA, int pitch) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, K = op.K, n4 = K >> 2;
@@ -366,7 +389,7 @@ __device__ __forceinline__ void pk_stage_rms(const PkOp & op, const float * X, c
         for (int u = 0; u < NV; u++) { const int j = u * 32 + lane; v[u] = (j < n4 && r < R) ? __ldcg(reinterpret_cast<const float4 *>(X + (size_t) r * op.ldx) + j) : z4; }
         double ss = 0.0;
 #pragma unroll
-        for (int u = 0; u < NV; u++) ss += (double) (v[u].x * v[u].x) + (double) (v[u].y * v[u].y) + (double) (v[u].z * v[u].z) + (double) (v[u].w * v[u].w);
+        for (int u = 0; u < NV; u++) ss += (double) ((v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w));      // four squares in float, then double (see pk_stage_fast)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         const float sc = 1.0f / sqrtf((float) (ss / (double) K) + op.eps);
@@ -375,29 +398,27 @@ __device__ __forceinline__ void pk_stage_rms(const PkOp & op, const float * X, c
             const int j = u * 32 + lane;
             if (j >= n4) continue;
             const float4 w = reinterpret_cast<const float4 *>(snw)[j];
-            __half2 * d = reinterpret_cast<__half2 *>(sA + (size_t) r * pitch + 4 * j);
-            d[0] = __floats2half2_rn((v[u].x * sc) * w.x, (v[u].y * sc) * w.y); d[1] = __floats2half2_rn((v[u].z * sc) * w.z, (v[u].w * sc) * w.w);
+            const __half2 h01 = __floats2half2_rn((v[u].x * sc) * w.x, (v[u].y * sc) * w.y), h23 = __floats2half2_rn((v[u].z * sc) * w.z, (v[u].w * sc) * w.w);
+            uint2 pk; memcpy(&pk.x, &h01, 4); memcpy(&pk.y, &h23, 4);
+            *reinterpret_cast<uint2 *>(sA + (size_t) r * pitch + 4 * j) = pk;      // one 8-byte store per lane: consecutive lanes, no bank conflict
         }
     }
 }
 
-// fp16 input rows (written by the previous phase): straight 16-byte copies into the operand buffer, 8 per thread in flight
+// fp16 input rows (written by the previous phase): straight 16-byte copies into the operand buffer; warp w copies rows w and w + 8, up to 12 loads per row and lane
+// all in flight (no index arithmetic per load: the row / column split by division was a quarter of the staging pass' instructions)
 __device__ __forceinline__ void pk_stage_h16(const PkOp & op, const __half * X16, int R, int k0, int kn, __half * sA, int pitch) {
-    const int n8 = kn >> 3, total = 16 * n8;                   // uint4 (8 halves) per row, in all
-    const bool p2 = (n8 & (n8 - 1)) == 0;
-    const int sh = 31 - __clz(n8);                             // row = i >> sh when n8 is a power of two (1 024 / 2 048-column chunks): no integer division per load
-    for (int i0 = threadIdx.x; i0 < total; i0 += PK_CONS * 8) {
-        uint4 v[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n8 = kn >> 3;      // uint4 (8 halves) per row
+    const uint4 * src0 = reinterpret_cast<const uint4 *>(X16 + (size_t) warp * op.ldx + k0), * src1 = reinterpret_cast<const uint4 *>(X16 + (size_t) (warp + 8) * op.ldx + k0);
+    uint4 * dst0 = reinterpret_cast<uint4 *>(sA + (size_t) warp * pitch), * dst1 = reinterpret_cast<uint4 *>(sA + (size_t) (warp + 8) * pitch);
+    const bool in0 = warp < R, in1 = warp + 8 < R;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int j0 = lane; j0 < n8; j0 += 32 * 12) {
+        uint4 v0[12], v1[12];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int i = i0 + u * PK_CONS, r = p2 ? i >> sh : i / n8, j = i - r * n8;
-            v[u] = (i < total && r < R) ? __ldcg(reinterpret_cast<const uint4 *>(X16 + (size_t) r * op.ldx + k0) + j) : make_uint4(0u, 0u, 0u, 0u);
-        }
+        for (int u = 0; u < 12; u++) { const int j = j0 + 32 * u; v0[u] = (in0 && j < n8) ? __ldcg(src0 + j) : z; v1[u] = (in1 && j < n8) ? __ldcg(src1 + j) : z; }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int i = i0 + u * PK_CONS, r = p2 ? i >> sh : i / n8, j = i - r * n8;
-            if (i < total) *reinterpret_cast<uint4 *>(sA + (size_t) r * pitch + 8 * j) = v[u];
-        }
+        for (int u = 0; u < 12; u++) { const int j = j0 + 32 * u; if (j < n8) { dst0[j] = v0[u]; dst1[j] = v1[u]; } }
     }
 }
 
@@ -492,24 +513,97 @@ __device__ __forceinline__ void pk_epilogue_pair(const PkParams & P, const PkOp 
     }
 }
 
-// one tile: this warp's k-slice of 8 output rows against the staged activation rows.  plane 0: c += xh.Wh (split: cl += xl.Wh too); plane 1 (low weights): cl += xh.Wl
-__device__ __forceinline__ void pk_tile_mma(float * c, float * cl, const __half * wt, const __half * xa, const __half * xb, const __half * xla, const __half * xlb, int ks, bool split, int plane) {
+// ---- one tile: this warp's k-slice (ks halves) of 8 output rows against the staged activation rows.  Fragments: 16 bytes per lane of the weight row g = lane / 4 and of
+// the activation rows g, g + 8 feed two m16n8k16 MMAs (see gemv_mma_body in ar_kernels.cuh for the layout argument).
+// plain: the two MMAs of a 32-column step go to two accumulators (half the dependent chain), added when the unit is done
+__device__ __forceinline__ void pk_mma_plain(float * cA, float * cB, const __half * wt, const __half * xa, const __half * xb, int ks) {
+#pragma unroll 4
     for (int k = 0; k < ks; k += 32) {
-        const uint4 wv = *reinterpret_cast<const uint4 *>(wt + k);
-        const uint4 a = *reinterpret_cast<const uint4 *>(xa + k), b = *reinterpret_cast<const uint4 *>(xb + k);
+        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = pk_lds128(xb + k);
         const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
-        if (plane == 0) {
-            mma16816_f16f32(c, f0, wv.x, wv.y);
-            mma16816_f16f32(c, f1, wv.z, wv.w);
-            if (split) {
-                const uint4 la = *reinterpret_cast<const uint4 *>(xla + k), lb = *reinterpret_cast<const uint4 *>(xlb + k);
-                const unsigned l0[4] = {la.x, lb.x, la.y, lb.y}, l1[4] = {la.z, lb.z, la.w, lb.w};
-                mma16816_f16f32(cl, l0, wv.x, wv.y);
-                mma16816_f16f32(cl, l1, wv.z, wv.w);
-            }
-        } else {
-            mma16816_f16f32(cl, f0, wv.x, wv.y);
-            mma16816_f16f32(cl, f1, wv.z, wv.w);
+        mma16816_f16f32(cA, f0, wv.x, wv.y);
+        mma16816_f16f32(cB, f1, wv.z, wv.w);
+    }
+}
+// split matrices (W = hi + lo / 2^11, x = xh + xl / 2^11), high plane: c += xh.Wh, cl += xl.Wh; the low plane's cl += xh.Wl goes through pk_mma_one
+__device__ __forceinline__ void pk_mma_split_hi(float * c, float * cl, const __half * wt, const __half * xa, const __half * xb, const __half * xla, const __half * xlb, int ks) {
+#pragma unroll 2
+    for (int k = 0; k < ks; k += 32) {
+        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = pk_lds128(xb + k), la = pk_lds128(xla + k), lb = pk_lds128(xlb + k);
+        const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w}, l0[4] = {la.x, lb.x, la.y, lb.y}, l1[4] = {la.z, lb.z, la.w, lb.w};
+        mma16816_f16f32(c, f0, wv.x, wv.y);
+        mma16816_f16f32(cl, l0, wv.x, wv.y);
+        mma16816_f16f32(c, f1, wv.z, wv.w);
+        mma16816_f16f32(cl, l1, wv.z, wv.w);
+    }
+}
+__device__ __forceinline__ void pk_mma_one(float * c, const __half * wt, const __half * xa, const __half * xb, int ks) {
+#pragma unroll 4
+    for (int k = 0; k < ks; k += 32) {
+        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = pk_lds128(xb + k);
+        const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
+        mma16816_f16f32(c, f0, wv.x, wv.y);
+        mma16816_f16f32(c, f1, wv.z, wv.w);
+    }
+}
+
+enum { PKT_PLAIN = 0, PKT_SPLIT = 1, PKT_PAIR = 2 };
+// all tiles of one unit within the staged activation chunk of kAn columns.  c / cl: PLAIN two partial accumulators of the same sums; SPLIT main and cross terms; PAIR the
+// unit's primary and partner tile
+template <int MODE>
+__device__ __forceinline__ void pk_unit_tiles(float * c, float * cl, unsigned char * ring, const __half * sA, const __half * sAl, int pitch, PkBar * full, PkBar * empty, PkRingPos & rp, int S, int kAn, unsigned long long * pr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t8 = (lane & 3) * 8;
+    for (int kt0 = 0; kt0 < kAn; kt0 += PK_TK) {
+        const int ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, ko = kt0 + warp * ks + t8;
+        const __half * xa = sA + (size_t) g * pitch + ko, * xb = xa + (size_t) 8 * pitch;
+#pragma unroll
+        for (int part = 0; part < (MODE == PKT_PLAIN ? 1 : 2); part++) {
+            if (pr) { const unsigned long long t0 = pk_now(); pk_mbar_wait(&full[rp.s], rp.ph); pr[4] += pk_now() - t0; }      // (timeline: ns thread 0 waited for weight tiles)
+            else pk_mbar_wait(&full[rp.s], rp.ph);
+            const __half * wt = reinterpret_cast<const __half *>(ring + (size_t) rp.s * PK_STAGE) + (size_t) g * (PK_TK + PK_PAD) + t8 + warp * ks;
+            if (MODE == PKT_PLAIN) pk_mma_plain(c, cl, wt, xa, xb, ks);
+            else if (MODE == PKT_PAIR) pk_mma_one(part ? cl : c, wt, xa, xb, ks);
+            else if (part == 0) pk_mma_split_hi(c, cl, wt, xa, xb, sAl + (size_t) g * pitch + ko, sAl + (size_t) (g + 8) * pitch + ko, ks);
+            else pk_mma_one(cl, wt, xa, xb, ks);
+            __syncwarp();
+            if (lane == 0) pk_mbar_arrive(&empty[rp.s]);       // this warp is done reading the stage
+            pk_ring_next(rp, S);
+        }
+    }
+}
+
+// the eight warps' partial 16 x 8 tiles of a unit summed in warp order, then the epilogue.  c0, c1 = row g, columns 2t, 2t + 1; c2, c3 = row g + 8.  The scratch
+// alternates between two buffers, so one block barrier per unit is enough: a warp that writes buffer b again has passed the next unit's barrier, which every warp
+// reaches only after its reads of b.
+template <typename KVT>
+__device__ __forceinline__ void pk_unit_finish(const PkParams & P, const PkOp & op, const PkSeg & sg, float * c, float * cl, int mode, float * red, unsigned & rb, int n0, int n1, float resv, int step_abs,
+                                               const unsigned long long * skv) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    if (mode == PKT_PLAIN) { for (int e = 0; e < 4; e++) c[e] += cl[e]; }
+    else if (mode == PKT_SPLIT) { for (int e = 0; e < 4; e++) c[e] += cl[e] * (1.0f / GM_LO_SCALE); }
+    float * buf = red + rb * PK_RED_FLOATS;
+    rb ^= 1u;
+    float * my = buf + warp * 128;
+    *reinterpret_cast<float2 *>(my + g * 8 + 2 * tq) = make_float2(c[0], c[1]);
+    *reinterpret_cast<float2 *>(my + (g + 8) * 8 + 2 * tq) = make_float2(c[2], c[3]);
+    if (mode == PKT_PAIR) {
+        float * my2 = my + 8 * 128;
+        *reinterpret_cast<float2 *>(my2 + g * 8 + 2 * tq) = make_float2(cl[0], cl[1]);
+        *reinterpret_cast<float2 *>(my2 + (g + 8) * 8 + 2 * tq) = make_float2(cl[2], cl[3]);
+    }
+    pk_bar_sync(1, PK_CONS);
+    if (tid < 128) {
+        const int r = tid >> 3, col = tid & 7;
+        float sum = 0.f, sum2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) sum += buf[w * 128 + tid];
+        if (mode == PKT_PAIR) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) sum2 += buf[8 * 128 + w * 128 + tid];
+        }
+        if (r < P.R && n0 + col < sg.N) {
+            if (mode == PKT_PAIR) pk_epilogue_pair<KVT>(P, op, sg, r, n0 + col, n1 + col, sum, sum2, skv);
+            else pk_epilogue<KVT>(P, op, sg, r, n0 + col, sum, resv, step_abs, skv);
         }
     }
 }
@@ -517,9 +611,9 @@ __device__ __forceinline__ void pk_tile_mma(float * c, float * cl, const __half 
 template <typename KVT> __device__ __forceinline__ void pk_prefetch_kv(const PkParams & P, int layer, int step, const int * sfp, const int * spt);
 
 template <typename KVT>
-__device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, unsigned char * ring, __half * sA, float * red, PkBar * full, PkBar * empty, unsigned & it, int step_abs,
+__device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, unsigned char * ring, __half * sA, float * red, PkBar * full, PkBar * empty, PkRingPos & rp, int step_abs,
                                         unsigned long long * pr, unsigned long long * skv, const int * sfp, const int * spt) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t8 = (lane & 3) * 8;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int K = op.K, R = P.R, S = P.n_stages, ak = P.ak;
     const bool split = op.seg[0].Wl != nullptr;
     const int nA = (K + ak - 1) / ak;
@@ -537,20 +631,16 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
     const float * X = op.X ? op.X + xoff : nullptr; const __half * X16 = op.X16 ? op.X16 + xoff : nullptr;
     const float * snw = nullptr; int norm_stage = -1;
     if (op.norm != PKN_NONE) {                                 // the op's first "tile": the norm's weight | bias
-        norm_stage = (int) (it % (unsigned) S);
-        pk_mbar_wait(&full[norm_stage], (it / (unsigned) S) & 1u);
+        norm_stage = rp.s;
+        pk_mbar_wait(&full[norm_stage], rp.ph);
         snw = reinterpret_cast<const float *>(ring + (size_t) norm_stage * PK_STAGE);
-        it++;
+        pk_ring_next(rp, S);
         if (pr) pr[5] = pk_now();
     }
     const bool fast_rms = op.norm == PKN_RMS && !op.X16 && !split && K <= 3072 && K <= ak;      // the whole row in one chunk, in registers
     if (op.norm != PKN_NONE && !fast && !fast_rms && !op.X16) pk_row_stats(op, X, R, mean, rstd);
-    float acc[3][4], accl[3][4];                               // nA > 1 (down projections: at most 3 units per CTA): one accumulator per unit across the chunks
-#pragma unroll
-    for (int i = 0; i < 3; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; accl[i][0] = accl[i][1] = accl[i][2] = accl[i][3] = 0.f; }
-    for (int a = 0; a < nA; a++) {
-        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak, ntile = (kAn + PK_TK - 1) / PK_TK;
-        if (a) pk_bar_sync(1, PK_CONS);                        // every warp is done with the previous chunk
+    auto stage = [&](int a) {
+        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak;
         if (op.X16) pk_stage_h16(op, X16, R, kA0, kAn, sA, pitch);
         else if (fast) pk_stage_fast(op, X, snw, R, sA, sAl, pitch);
         else if (fast_rms) { if (K <= 1024) pk_stage_rms<8>(op, X, snw, R, sA, pitch); else pk_stage_rms<24>(op, X, snw, R, sA, pitch); }
@@ -559,64 +649,48 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
         if (norm_stage >= 0 && a + 1 == nA) { __syncwarp(); if (lane == 0) pk_mbar_arrive(&empty[norm_stage]); }      // this warp is done with the norm's weights
         pk_bar_sync(1, PK_CONS);
         if (pr && a == 0) pr[1] = pk_now();                    // (GEMV phases: activations staged)
-        int ui = 0;
-        for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x, ui++) {
-            const int sj = (op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0);
-            const PkSeg & sg = op.seg[sj];
+        return kAn;
+    };
+    auto seg_of = [&](int u) -> const PkSeg & { return op.seg[(op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0)]; };
+    auto res_of = [&](const PkSeg & sg, int n0) -> float {      // the epilogue's residual element of thread tid < 128, requested before the tiles are consumed
+        if (sg.epi != PKE_RES || tid >= 128) return 0.f;
+        const int r = tid >> 3, n = n0 + (tid & 7);
+        return (r < R && n < sg.N) ? __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n) : 0.f;
+    };
+    unsigned rb = 0;
+    if (nA == 1) {                                             // the whole k extent staged at once: units one after the other
+        const int kAn = stage(0);
+        for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
+            const PkSeg & sg = seg_of(u);
             int n0, n1;
             pk_unit_rows(sg, u, P.hd, n0, n1);
-            const bool paired = sg.pair != PKP_NONE;            // (paired units only in single-chunk phases: host-checked)
-            float resv = 0.f;                                   // the epilogue's residual element of thread tid < 128, requested before the tiles are consumed
-            if (a + 1 == nA && sg.epi == PKE_RES && tid < 128) { const int r = tid >> 3, n = n0 + (tid & 7); if (r < R && n < sg.N) resv = __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n); }
-            float c[4], cl[4];                                  // cl: the split matrix's cross terms, or the partner tile of a paired unit
-            if (nA > 1) {
+            const float resv = res_of(sg, n0);
+            float c[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
+            const int mode = sg.pair != PKP_NONE ? PKT_PAIR : (split ? PKT_SPLIT : PKT_PLAIN);
+            if (mode == PKT_PAIR) pk_unit_tiles<PKT_PAIR>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+            else if (mode == PKT_SPLIT) pk_unit_tiles<PKT_SPLIT>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+            else pk_unit_tiles<PKT_PLAIN>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+            pk_unit_finish<KVT>(P, op, sg, c, cl, mode, red, rb, n0, n1, resv, step_abs, skv);
+        }
+    } else {                                                   // several k chunks (down projections): at most 3 units per CTA (host-checked), their accumulators live across the chunks
+        float acc[3][4], accl[3][4];
 #pragma unroll
-                for (int i = 0; i < 3; i++) if (i == ui) { for (int e = 0; e < 4; e++) { c[e] = acc[i][e]; cl[e] = accl[i][e]; } }
-            } else { c[0] = c[1] = c[2] = c[3] = 0.f; cl[0] = cl[1] = cl[2] = cl[3] = 0.f; }
-            const int nparts = paired ? 2 : (split ? 2 : 1);
-            for (int t = 0; t < ntile; t++) {
-                for (int part = 0; part < nparts; part++, it++) {
-                    const int s = (int) (it % (unsigned) S);
-                    const int kt0 = t * PK_TK, ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, kb = warp * ks;
-                    const unsigned long long tw0 = pr ? pk_now() : 0ull;
-                    pk_mbar_wait(&full[s], (it / (unsigned) S) & 1u);
-                    if (pr) pr[4] += pk_now() - tw0;
-                    const __half * wt = reinterpret_cast<const __half *>(ring + (size_t) s * PK_STAGE) + (size_t) g * (PK_TK + PK_PAD) + t8 + kb;
-                    const __half * xa = sA + (size_t) g * pitch + kt0 + kb + t8, * xb = xa + (size_t) 8 * pitch;
-                    const __half * xla = split ? sAl + (size_t) g * pitch + kt0 + kb + t8 : nullptr, * xlb = split ? xla + (size_t) 8 * pitch : nullptr;
-                    if (paired) pk_tile_mma(part ? cl : c, nullptr, wt, xa, xb, nullptr, nullptr, ks, false, 0);      // two plain tiles, one accumulator each
-                    else pk_tile_mma(c, cl, wt, xa, xb, xla, xlb, ks, split, part);
-                    __syncwarp();
-                    if (lane == 0) pk_mbar_arrive(&empty[s]);  // this warp is done reading the stage
+        for (int i = 0; i < 3; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; accl[i][0] = accl[i][1] = accl[i][2] = accl[i][3] = 0.f; }
+        for (int a = 0; a < nA; a++) {
+            if (a) pk_bar_sync(1, PK_CONS);                    // every warp is done with the previous chunk
+            const int kAn = stage(a);
+#pragma unroll
+            for (int ui = 0; ui < 3; ui++) {
+                const int u = (int) blockIdx.x + ui * (int) gridDim.x;
+                if (u < op.n_units) {
+                    const PkSeg & sg = seg_of(u);
+                    const int n0 = (u - sg.unit0) * 8;          // (paired units only in single-chunk phases: host-checked)
+                    const float resv = a + 1 == nA ? res_of(sg, n0) : 0.f;
+                    if (split) pk_unit_tiles<PKT_SPLIT>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                    else pk_unit_tiles<PKT_PLAIN>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                    if (a + 1 == nA) pk_unit_finish<KVT>(P, op, sg, acc[ui], accl[ui], split ? PKT_SPLIT : PKT_PLAIN, red, rb, n0, n0, resv, step_abs, skv);
                 }
             }
-            if (a + 1 < nA) {
-#pragma unroll
-                for (int i = 0; i < 3; i++) if (i == ui) { for (int e = 0; e < 4; e++) { acc[i][e] = c[e]; accl[i][e] = cl[e]; } }
-                continue;
-            }
-            // the eight warps' partial 16 x 8 tiles summed in warp order, then the epilogue: c0, c1 = row g, columns 2t, 2t+1; c2, c3 = row g + 8
-            if (split && !paired) { for (int e = 0; e < 4; e++) c[e] += cl[e] * (1.0f / GM_LO_SCALE); }
-            float * my = red + warp * 128;
-            const int tq = lane & 3;
-            my[g * 8 + 2 * tq] = c[0]; my[g * 8 + 2 * tq + 1] = c[1]; my[(g + 8) * 8 + 2 * tq] = c[2]; my[(g + 8) * 8 + 2 * tq + 1] = c[3];
-            if (paired) { float * my2 = my + 8 * 128; my2[g * 8 + 2 * tq] = cl[0]; my2[g * 8 + 2 * tq + 1] = cl[1]; my2[(g + 8) * 8 + 2 * tq] = cl[2]; my2[(g + 8) * 8 + 2 * tq + 1] = cl[3]; }
-            pk_bar_sync(1, PK_CONS);
-            if (tid < 128) {
-                const int r = tid >> 3, col = tid & 7;
-                float sum = 0.f, sum2 = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; w++) sum += red[w * 128 + tid];
-                if (paired) {
-#pragma unroll
-                    for (int w = 0; w < 8; w++) sum2 += red[8 * 128 + w * 128 + tid];
-                }
-                if (r < R && n0 + col < sg.N) {
-                    if (paired) pk_epilogue_pair<KVT>(P, op, sg, r, n0 + col, n1 + col, sum, sum2, skv);
-                    else pk_epilogue<KVT>(P, op, sg, r, n0 + col, sum, resv, step_abs, skv);
-                }
-            }
-            pk_bar_sync(1, PK_CONS);
         }
     }
 }
@@ -645,26 +719,33 @@ __device__ __forceinline__ void pk_prefetch_l2(const void * p) { asm volatile("p
 #endif
 
 template <typename CT> struct PkAttU { static constexpr int v = sizeof(CT) == 2 ? 16 : 8; };      // keys per thread in flight (16 bytes each for fp16 pages, 32 for fp32 stores)
-constexpr int PK_ATT_HDR = 1024;                               // floats of per-group scratch before the scores: q [128] | reduction [128] | (pad) | page offsets [256 x 8 bytes]
+constexpr int PK_ATT_MAXREP = 4;                               // query heads per kv head handled by one item (GQA: Orpheus 3, Dia 4)
+constexpr int PK_ATT_HDR = 1536;                               // floats of per-group scratch before the P.V partials: q [4 x 128] | float reduction [32] | double reduction [16] | (pad) | page offsets [256 x 8 bytes] at 1024
+static inline size_t pk_att_bytes(int rep, int T) { return (size_t) (PK_ATT_HDR + rep * 1024) * 4 + (size_t) rep * ((T + 3) & ~3) * 4; }      // per half-CTA group
 
-// HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three unrolled shuffles that the scheduler interleaves across the keys
-// in flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue slots on a B200)
-template <typename KVT, typename CT, int HD>
-__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int kh, int T, const int * spt) {      // kh: the kv head query head h reads
+// One item = one row x one kv head: the REP query heads that share the kv head (the reference's repeat-interleaved GQA cache, orpheus model.cpp:196-228, by indexing)
+// are computed together, so every K / V row is fetched once per step.  HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three
+// unrolled shuffles that the scheduler interleaves across the keys in flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue
+// slots on a B200).  h0 = first query head of the group; kh = the kv head (cross attention: h0, flat stores).
+template <typename KVT, typename CT, int HD, int REP>
+__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h0, int kh, int T, const int * spt) {
     typedef typename PkRawOf<CT>::type Raw;
     constexpr int U = PkAttU<CT>::v, PARTS = HD / 8, KPP = 128 / PARTS;
     const int gt = threadIdx.x & 127, gw = gt >> 5, H = P.H, part = gt % PARTS, kq = gt / PARTS;
-    float * qs = base; float * wredf = base + 128; double * wredd = reinterpret_cast<double *>(base + 136);
-    unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 512);      // element offset of each of this sequence's pages within the layer's pool
-    float * pvs = base + PK_ATT_HDR; float * sc = base + PK_ATT_HDR + 1024;
+    const int Tp = (T + 3) & ~3;
+    float * qs = base; float * wredf = base + 512; double * wredd = reinterpret_cast<double *>(base + 544);
+    unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 1024);      // element offset of each of this sequence's pages within the layer's pool
+    float * pvs = base + PK_ATT_HDR; float * sc = pvs + REP * 1024;
     const size_t page_elems = (size_t) 2 * P.kv_heads * PK_PAGE * HD;
-    if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
+    for (int i = gt; i < REP * HD; i += 128) qs[i] = __ldcg(op.q + (size_t) r * H + (size_t) h0 * HD + i);      // the REP heads' q rows are contiguous
     if (!op.cross) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) spt[r * P.max_pages + i] * page_elems;
     pk_bar_sync(2 + grp, 128);
-    float q8[8];
+    float q8[REP][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) q8[i] = qs[part * 8 + i];
-    const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + (size_t) h * HD + part * 8, * flat_v = reinterpret_cast<const CT *>(op.cv) + (size_t) h * HD + part * 8;
+    for (int j = 0; j < REP; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) q8[j][i] = qs[j * HD + part * 8 + i];
+    const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + (size_t) kh * HD + part * 8, * flat_v = reinterpret_cast<const CT *>(op.cv) + (size_t) kh * HD + part * 8;
     const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) kh * PK_PAGE * HD + part * 8;
     const CT * pool_v = pool_k + (size_t) P.kv_heads * PK_PAGE * HD;
     auto krow = [&](int t, int kv) -> const CT * {
@@ -672,7 +753,9 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
         return (kv ? pool_v : pool_k) + spo[t >> 5] + (t & (PK_PAGE - 1)) * HD;
     };
     // scores: PARTS threads per key (8 channels each), KPP keys per pass, U passes in flight
-    float mloc = -INFINITY;
+    float mloc[REP];
+#pragma unroll
+    for (int j = 0; j < REP; j++) mloc[j] = -INFINITY;
     for (int tb = 0; tb < T; tb += KPP * U) {
         Raw raw[U];
 #pragma unroll
@@ -685,29 +768,45 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
             const int t = tb + u * KPP + kq;
             float k8[8];
             pk_raw_f(raw[u], k8);
-            float a = fmaf(q8[3], k8[3], fmaf(q8[2], k8[2], fmaf(q8[1], k8[1], q8[0] * k8[0]))) + fmaf(q8[7], k8[7], fmaf(q8[6], k8[6], fmaf(q8[5], k8[5], q8[4] * k8[4])));
 #pragma unroll
-            for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            a *= op.scale;
-            if (t < T) { if (part == 0) sc[t] = a; mloc = fmaxf(mloc, a); }
+            for (int j = 0; j < REP; j++) {
+                float a = fmaf(q8[j][3], k8[3], fmaf(q8[j][2], k8[2], fmaf(q8[j][1], k8[1], q8[j][0] * k8[0]))) + fmaf(q8[j][7], k8[7], fmaf(q8[j][6], k8[6], fmaf(q8[j][5], k8[5], q8[j][4] * k8[4])));
+#pragma unroll
+                for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                a *= op.scale;
+                if (t < T) { if (part == 0) sc[j * Tp + t] = a; mloc[j] = fmaxf(mloc[j], a); }
+            }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
-    if ((gt & 31) == 0) wredf[gw] = mloc;
-    pk_bar_sync(2 + grp, 128);
-    const float m = fmaxf(fmaxf(wredf[0], wredf[1]), fmaxf(wredf[2], wredf[3]));
-    double sum = 0.0;                                           // ggml_soft_max: expf(s - max), the sum accumulated in double, scale by (float) (1 / sum)
-    for (int t = gt; t < T; t += 128) { const float e = expf(sc[t] - m); sc[t] = e; sum += (double) e; }
+    for (int j = 0; j < REP; j++) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((gt & 31) == 0) wredd[gw] = sum;
+        for (int o = 16; o > 0; o >>= 1) mloc[j] = fmaxf(mloc[j], __shfl_xor_sync(0xffffffffu, mloc[j], o));
+        if ((gt & 31) == 0) wredf[j * 4 + gw] = mloc[j];
+    }
     pk_bar_sync(2 + grp, 128);
-    const float inv = (float) (1.0 / (((wredd[0] + wredd[1]) + wredd[2]) + wredd[3]));
+    float inv[REP];
+    {
+        double sum[REP];                                        // ggml_soft_max: expf(s - max), the sum accumulated in double, scale by (float) (1 / sum)
+#pragma unroll
+        for (int j = 0; j < REP; j++) {
+            const float m = fmaxf(fmaxf(wredf[j * 4], wredf[j * 4 + 1]), fmaxf(wredf[j * 4 + 2], wredf[j * 4 + 3]));
+            sum[j] = 0.0;
+            for (int t = gt; t < T; t += 128) { const float e = expf(sc[j * Tp + t] - m); sc[j * Tp + t] = e; sum[j] += (double) e; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], o);
+            if ((gt & 31) == 0) wredd[j * 4 + gw] = sum[j];
+        }
+        pk_bar_sync(2 + grp, 128);
+#pragma unroll
+        for (int j = 0; j < REP; j++) inv[j] = (float) (1.0 / (((wredd[j * 4] + wredd[j * 4 + 1]) + wredd[j * 4 + 2]) + wredd[j * 4 + 3]));
+    }
     // P.V: thread (slice kq, part) walks positions kq, kq + KPP, ... for its 8 channels with p = e * inv; slices summed in order afterwards
-    float acc[8];
+    float acc[REP][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int j = 0; j < REP; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[j][i] = 0.f;
     for (int tb = 0; tb < T; tb += KPP * U) {
         Raw raw[U];
 #pragma unroll
@@ -718,22 +817,28 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int t = tb + u * KPP + kq;
-            const float p = t < T ? sc[t] * inv : 0.f;
             float v8[8];
             pk_raw_f(raw[u], v8);
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = fmaf(p, v8[i], acc[i]);
+            for (int j = 0; j < REP; j++) {
+                const float p = t < T ? sc[j * Tp + t] * inv[j] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[j][i] = fmaf(p, v8[i], acc[j][i]);
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++) pvs[(size_t) kq * HD + part * 8 + i] = acc[i];
+    for (int j = 0; j < REP; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) pvs[j * 1024 + (size_t) kq * HD + part * 8 + i] = acc[j][i];
     pk_bar_sync(2 + grp, 128);
-    if (gt < HD) {
+    for (int o = gt; o < REP * HD; o += 128) {
+        const int j = o / HD, c = o - j * HD;
         float a = 0.f;
 #pragma unroll 8
-        for (int sl = 0; sl < KPP; sl++) a += pvs[(size_t) sl * HD + gt];
+        for (int sl = 0; sl < KPP; sl++) a += pvs[j * 1024 + (size_t) sl * HD + c];
         const __half hv = __float2half_rn(a);
-        for (int c = 0; c < (op.orep ? PK_REP : 1); c++) op.out16[op.orep * c + (size_t) r * H + (size_t) h * HD + gt] = hv;
+        for (int cp = 0; cp < (op.orep ? PK_REP : 1); cp++) op.out16[op.orep * cp + (size_t) r * H + (size_t) h0 * HD + o] = hv;
     }
     pk_bar_sync(2 + grp, 128);                                  // the scratch is free for the group's next item
 }
@@ -742,10 +847,14 @@ template <typename KVT, int HD>
 __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, unsigned char * scratch, int step, const int * sfp, const int * spt) {
     const int grp = threadIdx.x >> 7;
     float * base = reinterpret_cast<float *>(scratch + (size_t) grp * (P.a_bytes / 2));
-    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
-        const int r = it / P.heads, h = it - r * P.heads;
-        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, op.cross_len, spt);
-        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, h / (P.heads / P.kv_heads), sfp[r] + step - P.pos_off + 1, spt);      // the reference's repeat-interleaved GQA cache by indexing
+    const int rep = op.cross ? 1 : P.heads / P.kv_heads, groups = P.heads / rep;
+    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * groups; it += 2 * (int) gridDim.x) {
+        const int r = it / groups, kh = it - r * groups;
+        if (op.cross) { pk_attn_item<KVT, float, HD, 1>(P, op, base, grp, r, kh, kh, op.cross_len, spt); continue; }
+        const int T = sfp[r] + step - P.pos_off + 1;
+        if (rep == 1) pk_attn_item<KVT, KVT, HD, 1>(P, op, base, grp, r, kh, kh, T, spt);
+        else if (rep == 3) pk_attn_item<KVT, KVT, HD, 3>(P, op, base, grp, r, kh * 3, kh, T, spt);
+        else pk_attn_item<KVT, KVT, HD, 4>(P, op, base, grp, r, kh * 4, kh, T, spt);      // (host-checked: rep is 1, 3 or 4)
     }
 }
 
@@ -910,8 +1019,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
         pk_fence_init();
     }
     __syncthreads();
-    unsigned it = 0;
-    if (warp == 8) {                                           // ---- producer: one lane streams this CTA's weight tiles in program order, as far ahead as the ring allows
+    PkRingPos rp; rp.s = 0; rp.ph = 0u;
+    if (warp == 8) {                                           // ---- producer warp: streams this CTA's weight tiles in program order, as far ahead as the ring allows
         // the descriptor of the op being produced is copied to shared memory first (17 independent 16-byte loads: one L2 round trip per op instead of one per field
         // and tile -- the mbarrier / bulk-copy instructions are compiler barriers, so every field read from global memory was re-issued after each of them)
         PkOp * pop = sops + 2;
@@ -921,7 +1030,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
                 __syncwarp();
                 for (int w = lane; w < (int) (sizeof(PkOp) / 16); w += 32) reinterpret_cast<uint4 *>(pop)[w] = __ldg(reinterpret_cast<const uint4 *>(&P.ops[oi]) + w);
                 __syncwarp();
-                if (lane == 0 && pop->kind == PK_GEMV) pk_produce_gemv(*pop, ring, full, empty, S, it, P.ak, P.hd);
+                if (pop->kind == PK_GEMV) pk_produce_gemv(*pop, ring, full, empty, S, rp, P.ak, P.hd);
             }
         return;
     }
@@ -943,7 +1052,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
             if (pr) pr[0] = pk_now();
             switch (op.kind) {
                 case PK_ROWS:   if (P.model == PKM_ORPHEUS) pk_rows_orpheus(P, step, st == 0, red); else pk_rows(P, step, sids); break;
-                case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, it, step, pr, skv, sfp, spt); break;
+                case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, rp, step, pr, skv, sfp, spt); break;
                 case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
                 case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else pk_argmax(P, step, red); break;
             }
@@ -986,7 +1095,9 @@ struct PkLaunch {
 static inline int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int Tscore, PkLaunch & L) {
     size_t a = (size_t) 16 * (KA + PK_PAD) * 2;
     if (KAs) a = std::max(a, (size_t) 2 * 16 * (KAs + PK_PAD) * 2);
-    a = std::max(a, (size_t) 2 * ((PK_ATT_HDR + 1024) * 4 + (size_t) ((Tscore + 3) & ~3) * 4));
+    const int rep = Pk.kv_heads > 0 ? Pk.heads / Pk.kv_heads : 1;
+    if (rep != 1 && rep != 3 && rep != 4) return 1;            // query heads per kv head the attention phase is instantiated for
+    a = std::max(a, 2 * pk_att_bytes(rep, Tscore));
     a = (a + 255) & ~(size_t) 255;
     const int pt = Pk.R * Pk.max_pages;
     if (Pk.max_pages > 256) return 1;                          // page offsets of a sequence sit in a 256-entry scratch (pk_attn_item)
