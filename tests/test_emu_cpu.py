@@ -551,3 +551,25 @@ def test_persistent_decode_kernel_emulated_orpheus(tmp_path, env):
             top2 = np.sort(ref_l[upto])[-2:]
             assert float(top2[1] - top2[0]) <= 2.0 * float(d[upto]), (upto, float(top2[1] - top2[0]), float(d[upto]))
         assert upto >= 20
+
+
+def test_persistent_decode_kernel_emulated_multi_tile_units(tmp_path):
+    """k extents of several weight tiles (ffn 2 560: the down projection's units are 1 024 + 1 024 + 512 columns -- the two-tiles-at-a-time loop and its odd tail; K = 768
+    elsewhere): no reference output exists for this shape, so the persistent kernel is held against the launch-per-op path on the same F16 GGUF: same tokens (or a near-tie
+    of the per-op logits), logits within twice the F16 floor the two paths show against the reference elsewhere."""
+    g = np.load(os.path.join(GOLD, "orpheus_wide_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = 8
+    gguf = cached_orpheus_gguf(seed=0, head_dim=128, ffn=2560, f16=True)
+    tok, logits = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, "pk", env={"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "5", "B2TTS_AR_EXIT_EVERY": "3"})
+    tok0, logits0 = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, "op", env={"B2TTS_AR_PDK": "0"})
+    for u in range(2):
+        neq = np.nonzero(tok[u, :, 0] != tok0[u, :, 0])[0]
+        upto = int(neq[0]) if neq.size else steps - 1
+        d = np.abs(logits[u][:upto + 1] - logits0[u][:upto + 1]).max(axis=1)
+        print(f"PARITY(emulated, persistent kernel vs per-op, ffn 2560) prompt {u}: tokens equal for {upto + (0 if neq.size else 1)}/{steps} steps, max |logit diff| {float(d.max()):.3e}")
+        assert float(d.max()) < 3e-2
+        if neq.size:
+            top2 = np.sort(logits0[u][upto])[-2:]
+            assert float(top2[1] - top2[0]) <= 2.0 * float(d[upto])
+        assert upto >= 4

@@ -549,25 +549,53 @@ __device__ __forceinline__ void pk_mma_one(float * c, const __half * wt, const _
 
 enum { PKT_PLAIN = 0, PKT_SPLIT = 1, PKT_PAIR = 2 };
 // all tiles of one unit within the staged activation chunk of kAn columns.  c / cl: PLAIN two partial accumulators of the same sums; SPLIT main and cross terms; PAIR the
-// unit's primary and partner tile
+// unit's primary and partner tile.  Two tiles are worked on at a time (PLAIN: two consecutive k tiles; SPLIT / PAIR: the two tiles of one k tile): with 2 consumer
+// warps per scheduler a single tile's chain of shared-memory loads and dependent MMAs left the tensor pipe idle most of the time (issue slots 22 % busy, ncu r2h).
 template <int MODE>
 __device__ __forceinline__ void pk_unit_tiles(float * c, float * cl, unsigned char * ring, const __half * sA, const __half * sAl, int pitch, PkBar * full, PkBar * empty, PkRingPos & rp, int S, int kAn, unsigned long long * pr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t8 = (lane & 3) * 8;
-    for (int kt0 = 0; kt0 < kAn; kt0 += PK_TK) {
-        const int ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, ko = kt0 + warp * ks + t8;
-        const __half * xa = sA + (size_t) g * pitch + ko, * xb = xa + (size_t) 8 * pitch;
-#pragma unroll
-        for (int part = 0; part < (MODE == PKT_PLAIN ? 1 : 2); part++) {
-            if (pr) { const unsigned long long t0 = pk_now(); pk_mbar_wait(&full[rp.s], rp.ph); pr[4] += pk_now() - t0; }      // (timeline: ns thread 0 waited for weight tiles)
-            else pk_mbar_wait(&full[rp.s], rp.ph);
-            const __half * wt = reinterpret_cast<const __half *>(ring + (size_t) rp.s * PK_STAGE) + (size_t) g * (PK_TK + PK_PAD) + t8 + warp * ks;
-            if (MODE == PKT_PLAIN) pk_mma_plain(c, cl, wt, xa, xb, ks);
-            else if (MODE == PKT_PAIR) pk_mma_one(part ? cl : c, wt, xa, xb, ks);
-            else if (part == 0) pk_mma_split_hi(c, cl, wt, xa, xb, sAl + (size_t) g * pitch + ko, sAl + (size_t) (g + 8) * pitch + ko, ks);
-            else pk_mma_one(cl, wt, xa, xb, ks);
+    auto wait_full = [&](const PkRingPos & q) {
+        if (pr) { const unsigned long long t0 = pk_now(); pk_mbar_wait(&full[q.s], q.ph); pr[4] += pk_now() - t0; }      // (timeline: ns thread 0 waited for weight tiles)
+        else pk_mbar_wait(&full[q.s], q.ph);
+    };
+    auto wtile = [&](const PkRingPos & q, int ks) { return reinterpret_cast<const __half *>(ring + (size_t) q.s * PK_STAGE) + (size_t) g * (PK_TK + PK_PAD) + t8 + warp * ks; };
+    auto release = [&](const PkRingPos & q) { if (lane == 0) pk_mbar_arrive(&empty[q.s]); };      // (after a __syncwarp: this warp is done reading the stage)
+    if (MODE == PKT_PLAIN) {
+        float c2[4] = {0.f, 0.f, 0.f, 0.f}, cl2[4] = {0.f, 0.f, 0.f, 0.f};
+        int kt0 = 0;
+        for (; kt0 + PK_TK < kAn; kt0 += 2 * PK_TK) {           // two k tiles at a time: the first is a full tile
+            const int ktn1 = kAn - kt0 - PK_TK < PK_TK ? kAn - kt0 - PK_TK : PK_TK, ks0 = PK_TK >> 3, ks1 = ktn1 >> 3;
+            const PkRingPos q0 = rp; pk_ring_next(rp, S);
+            const PkRingPos q1 = rp; pk_ring_next(rp, S);
+            const __half * xa0 = sA + (size_t) g * pitch + kt0 + warp * ks0 + t8, * xa1 = sA + (size_t) g * pitch + kt0 + PK_TK + warp * ks1 + t8;
+            wait_full(q0); wait_full(q1);
+            pk_mma_plain(c, cl, wtile(q0, ks0), xa0, xa0 + (size_t) 8 * pitch, ks0);
+            pk_mma_plain(c2, cl2, wtile(q1, ks1), xa1, xa1 + (size_t) 8 * pitch, ks1);
             __syncwarp();
-            if (lane == 0) pk_mbar_arrive(&empty[rp.s]);       // this warp is done reading the stage
-            pk_ring_next(rp, S);
+            release(q0); release(q1);
+        }
+        if (kt0 < kAn) {                                        // an odd tile left
+            const int ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3;
+            const PkRingPos q0 = rp; pk_ring_next(rp, S);
+            const __half * xa = sA + (size_t) g * pitch + kt0 + warp * ks + t8;
+            wait_full(q0);
+            pk_mma_plain(c, cl, wtile(q0, ks), xa, xa + (size_t) 8 * pitch, ks);
+            __syncwarp();
+            release(q0);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) { c[e] += c2[e]; cl[e] += cl2[e]; }
+    } else {
+        for (int kt0 = 0; kt0 < kAn; kt0 += PK_TK) {
+            const int ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, ko = kt0 + warp * ks + t8;
+            const PkRingPos q0 = rp; pk_ring_next(rp, S);
+            const PkRingPos q1 = rp; pk_ring_next(rp, S);
+            const __half * xa = sA + (size_t) g * pitch + ko, * xb = xa + (size_t) 8 * pitch;
+            wait_full(q0); wait_full(q1);
+            if (MODE == PKT_PAIR) { pk_mma_one(c, wtile(q0, ks), xa, xb, ks); pk_mma_one(cl, wtile(q1, ks), xa, xb, ks); }
+            else { pk_mma_split_hi(c, cl, wtile(q0, ks), xa, xb, sAl + (size_t) g * pitch + ko, sAl + (size_t) (g + 8) * pitch + ko, ks); pk_mma_one(cl, wtile(q1, ks), xa, xb, ks); }
+            __syncwarp();
+            release(q0); release(q1);
         }
     }
 }
@@ -719,126 +747,119 @@ __device__ __forceinline__ void pk_prefetch_l2(const void * p) { asm volatile("p
 #endif
 
 template <typename CT> struct PkAttU { static constexpr int v = sizeof(CT) == 2 ? 16 : 8; };      // keys per thread in flight (16 bytes each for fp16 pages, 32 for fp32 stores)
-constexpr int PK_ATT_MAXREP = 4;                               // query heads per kv head handled by one item (GQA: Orpheus 3, Dia 4)
-constexpr int PK_ATT_HDR = 1536;                               // floats of per-group scratch before the P.V partials: q [4 x 128] | float reduction [32] | double reduction [16] | (pad) | page offsets [256 x 8 bytes] at 1024
-static inline size_t pk_att_bytes(int rep, int T) { return (size_t) (PK_ATT_HDR + rep * 1024) * 4 + (size_t) rep * ((T + 3) & ~3) * 4; }      // per half-CTA group
+constexpr int PK_ATT_HDR = 1024;                               // floats of per-group scratch before the P.V partials: q [128] | reduction [128] | (pad) | page offsets [256 x 8 bytes] at 512
+static inline size_t pk_att_bytes(int T) { return (size_t) (PK_ATT_HDR + 1024) * 4 + (size_t) ((T + 3) & ~3) * 4; }      // per half-CTA group
 
-// One item = one row x one kv head: the REP query heads that share the kv head (the reference's repeat-interleaved GQA cache, orpheus model.cpp:196-228, by indexing)
-// are computed together, so every K / V row is fetched once per step.  HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three
-// unrolled shuffles that the scheduler interleaves across the keys in flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue
-// slots on a B200).  h0 = first query head of the group; kh = the kv head (cross attention: h0, flat stores).
-template <typename KVT, typename CT, int HD, int REP>
-__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h0, int kh, int T, const int * spt) {
+// One item = one (row, query head); kh = the kv head it reads (the reference's repeat-interleaved GQA cache, orpheus model.cpp:196-228, by indexing).
+// HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three unrolled shuffles that the scheduler interleaves across the keys in
+// flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue slots on a B200).
+// The item is a chain of L2 round trips (q row written by the previous phase, K rows, V rows: ~1-2 us each on a B200), so the loads are issued as early as their
+// addresses are known: the first batch of K rows before q (they do not depend on it), the first batch of V rows before the softmax reductions.
+// (Tried: one item per kv head with its 3 query heads sharing the K / V loads -- 2.6x slower per item, the scores / P.V arithmetic of three heads per thread is not
+// free at 128 threads; r2g timeline.)
+template <typename KVT, typename CT, int HD>
+__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int kh, int T, const int * spt) {
     typedef typename PkRawOf<CT>::type Raw;
     constexpr int U = PkAttU<CT>::v, PARTS = HD / 8, KPP = 128 / PARTS;
     const int gt = threadIdx.x & 127, gw = gt >> 5, H = P.H, part = gt % PARTS, kq = gt / PARTS;
-    const int Tp = (T + 3) & ~3;
-    float * qs = base; float * wredf = base + 512; double * wredd = reinterpret_cast<double *>(base + 544);
-    unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 1024);      // element offset of each of this sequence's pages within the layer's pool
-    float * pvs = base + PK_ATT_HDR; float * sc = pvs + REP * 1024;
+    float * qs = base; float * wredf = base + 128; double * wredd = reinterpret_cast<double *>(base + 136);
+    unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 512);      // element offset of each of this sequence's pages within the layer's pool
+    float * pvs = base + PK_ATT_HDR; float * sc = base + PK_ATT_HDR + 1024;
     const size_t page_elems = (size_t) 2 * P.kv_heads * PK_PAGE * HD;
-    for (int i = gt; i < REP * HD; i += 128) qs[i] = __ldcg(op.q + (size_t) r * H + (size_t) h0 * HD + i);      // the REP heads' q rows are contiguous
-    if (!op.cross) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) spt[r * P.max_pages + i] * page_elems;
-    pk_bar_sync(2 + grp, 128);
-    float q8[REP][8];
-#pragma unroll
-    for (int j = 0; j < REP; j++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) q8[j][i] = qs[j * HD + part * 8 + i];
     const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + (size_t) kh * HD + part * 8, * flat_v = reinterpret_cast<const CT *>(op.cv) + (size_t) kh * HD + part * 8;
     const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) kh * PK_PAGE * HD + part * 8;
     const CT * pool_v = pool_k + (size_t) P.kv_heads * PK_PAGE * HD;
+    const int * pt = spt + r * P.max_pages;
+    auto krow0 = [&](int t, int kv) -> const CT * {             // first batch: page offsets straight from the page table (the spo scratch is not written yet)
+        if (op.cross) return (kv ? flat_v : flat_k) + (size_t) t * H;
+        return (kv ? pool_v : pool_k) + (size_t) pt[t >> 5] * page_elems + (t & (PK_PAGE - 1)) * HD;
+    };
     auto krow = [&](int t, int kv) -> const CT * {
         if (op.cross) return (kv ? flat_v : flat_k) + (size_t) t * H;
         return (kv ? pool_v : pool_k) + spo[t >> 5] + (t & (PK_PAGE - 1)) * HD;
     };
+    Raw raw[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {                               // K rows of the first batch: in flight while q arrives
+        const int t = u * KPP + kq;
+        if (t < T) pk_raw_load(krow0(t, 0), raw[u]); else pk_raw_zero(raw[u]);
+    }
+    if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
+    if (!op.cross && T > KPP * U) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) pt[i] * page_elems;
+    pk_bar_sync(2 + grp, 128);
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q8[i] = qs[part * 8 + i];
     // scores: PARTS threads per key (8 channels each), KPP keys per pass, U passes in flight
-    float mloc[REP];
-#pragma unroll
-    for (int j = 0; j < REP; j++) mloc[j] = -INFINITY;
+    float mloc = -INFINITY;
     for (int tb = 0; tb < T; tb += KPP * U) {
-        Raw raw[U];
+        if (tb) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int t = tb + u * KPP + kq;
-            if (t < T) pk_raw_load(krow(t, 0), raw[u]); else pk_raw_zero(raw[u]);
+            for (int u = 0; u < U; u++) {
+                const int t = tb + u * KPP + kq;
+                if (t < T) pk_raw_load(krow(t, 0), raw[u]); else pk_raw_zero(raw[u]);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int t = tb + u * KPP + kq;
             float k8[8];
             pk_raw_f(raw[u], k8);
+            float a = fmaf(q8[3], k8[3], fmaf(q8[2], k8[2], fmaf(q8[1], k8[1], q8[0] * k8[0]))) + fmaf(q8[7], k8[7], fmaf(q8[6], k8[6], fmaf(q8[5], k8[5], q8[4] * k8[4])));
 #pragma unroll
-            for (int j = 0; j < REP; j++) {
-                float a = fmaf(q8[j][3], k8[3], fmaf(q8[j][2], k8[2], fmaf(q8[j][1], k8[1], q8[j][0] * k8[0]))) + fmaf(q8[j][7], k8[7], fmaf(q8[j][6], k8[6], fmaf(q8[j][5], k8[5], q8[j][4] * k8[4])));
+            for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            a *= op.scale;
+            if (t < T) { if (part == 0) sc[t] = a; mloc = fmaxf(mloc, a); }
+        }
+    }
 #pragma unroll
-                for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                a *= op.scale;
-                if (t < T) { if (part == 0) sc[j * Tp + t] = a; mloc[j] = fmaxf(mloc[j], a); }
+    for (int u = 0; u < U; u++) {                               // V rows of the first batch: in flight during the softmax reductions
+        const int t = u * KPP + kq;
+        if (t < T) pk_raw_load(krow0(t, 1), raw[u]); else pk_raw_zero(raw[u]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+    if ((gt & 31) == 0) wredf[gw] = mloc;
+    pk_bar_sync(2 + grp, 128);
+    const float m = fmaxf(fmaxf(wredf[0], wredf[1]), fmaxf(wredf[2], wredf[3]));
+    double sum = 0.0;                                           // ggml_soft_max: expf(s - max), the sum accumulated in double, scale by (float) (1 / sum)
+    for (int t = gt; t < T; t += 128) { const float e = expf(sc[t] - m); sc[t] = e; sum += (double) e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((gt & 31) == 0) wredd[gw] = sum;
+    pk_bar_sync(2 + grp, 128);
+    const float inv = (float) (1.0 / (((wredd[0] + wredd[1]) + wredd[2]) + wredd[3]));
+    // P.V: thread (slice kq, part) walks positions kq, kq + KPP, ... for its 8 channels with p = e * inv; slices summed in order afterwards
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int tb = 0; tb < T; tb += KPP * U) {
+        if (tb) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int t = tb + u * KPP + kq;
+                if (t < T) pk_raw_load(krow(t, 1), raw[u]); else pk_raw_zero(raw[u]);
             }
         }
-    }
-#pragma unroll
-    for (int j = 0; j < REP; j++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mloc[j] = fmaxf(mloc[j], __shfl_xor_sync(0xffffffffu, mloc[j], o));
-        if ((gt & 31) == 0) wredf[j * 4 + gw] = mloc[j];
-    }
-    pk_bar_sync(2 + grp, 128);
-    float inv[REP];
-    {
-        double sum[REP];                                        // ggml_soft_max: expf(s - max), the sum accumulated in double, scale by (float) (1 / sum)
-#pragma unroll
-        for (int j = 0; j < REP; j++) {
-            const float m = fmaxf(fmaxf(wredf[j * 4], wredf[j * 4 + 1]), fmaxf(wredf[j * 4 + 2], wredf[j * 4 + 3]));
-            sum[j] = 0.0;
-            for (int t = gt; t < T; t += 128) { const float e = expf(sc[j * Tp + t] - m); sc[j * Tp + t] = e; sum[j] += (double) e; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], o);
-            if ((gt & 31) == 0) wredd[j * 4 + gw] = sum[j];
-        }
-        pk_bar_sync(2 + grp, 128);
-#pragma unroll
-        for (int j = 0; j < REP; j++) inv[j] = (float) (1.0 / (((wredd[j * 4] + wredd[j * 4 + 1]) + wredd[j * 4 + 2]) + wredd[j * 4 + 3]));
-    }
-    // P.V: thread (slice kq, part) walks positions kq, kq + KPP, ... for its 8 channels with p = e * inv; slices summed in order afterwards
-    float acc[REP][8];
-#pragma unroll
-    for (int j = 0; j < REP; j++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[j][i] = 0.f;
-    for (int tb = 0; tb < T; tb += KPP * U) {
-        Raw raw[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int t = tb + u * KPP + kq;
-            if (t < T) pk_raw_load(krow(t, 1), raw[u]); else pk_raw_zero(raw[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int t = tb + u * KPP + kq;
+            const float p = t < T ? sc[t] * inv : 0.f;
             float v8[8];
             pk_raw_f(raw[u], v8);
 #pragma unroll
-            for (int j = 0; j < REP; j++) {
-                const float p = t < T ? sc[j * Tp + t] * inv[j] : 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; i++) acc[j][i] = fmaf(p, v8[i], acc[j][i]);
-            }
+            for (int i = 0; i < 8; i++) acc[i] = fmaf(p, v8[i], acc[i]);
         }
     }
 #pragma unroll
-    for (int j = 0; j < REP; j++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) pvs[j * 1024 + (size_t) kq * HD + part * 8 + i] = acc[j][i];
+    for (int i = 0; i < 8; i++) pvs[(size_t) kq * HD + part * 8 + i] = acc[i];
     pk_bar_sync(2 + grp, 128);
-    for (int o = gt; o < REP * HD; o += 128) {
-        const int j = o / HD, c = o - j * HD;
+    if (gt < HD) {
         float a = 0.f;
 #pragma unroll 8
-        for (int sl = 0; sl < KPP; sl++) a += pvs[j * 1024 + (size_t) sl * HD + c];
+        for (int sl = 0; sl < KPP; sl++) a += pvs[(size_t) sl * HD + gt];
         const __half hv = __float2half_rn(a);
-        for (int cp = 0; cp < (op.orep ? PK_REP : 1); cp++) op.out16[op.orep * cp + (size_t) r * H + (size_t) h0 * HD + o] = hv;
+        for (int c = 0; c < (op.orep ? PK_REP : 1); c++) op.out16[op.orep * c + (size_t) r * H + (size_t) h * HD + gt] = hv;
     }
     pk_bar_sync(2 + grp, 128);                                  // the scratch is free for the group's next item
 }
@@ -847,14 +868,11 @@ template <typename KVT, int HD>
 __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, unsigned char * scratch, int step, const int * sfp, const int * spt) {
     const int grp = threadIdx.x >> 7;
     float * base = reinterpret_cast<float *>(scratch + (size_t) grp * (P.a_bytes / 2));
-    const int rep = op.cross ? 1 : P.heads / P.kv_heads, groups = P.heads / rep;
-    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * groups; it += 2 * (int) gridDim.x) {
-        const int r = it / groups, kh = it - r * groups;
-        if (op.cross) { pk_attn_item<KVT, float, HD, 1>(P, op, base, grp, r, kh, kh, op.cross_len, spt); continue; }
-        const int T = sfp[r] + step - P.pos_off + 1;
-        if (rep == 1) pk_attn_item<KVT, KVT, HD, 1>(P, op, base, grp, r, kh, kh, T, spt);
-        else if (rep == 3) pk_attn_item<KVT, KVT, HD, 3>(P, op, base, grp, r, kh * 3, kh, T, spt);
-        else pk_attn_item<KVT, KVT, HD, 4>(P, op, base, grp, r, kh * 4, kh, T, spt);      // (host-checked: rep is 1, 3 or 4)
+    const int rep = P.heads / P.kv_heads;
+    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
+        const int r = it / P.heads, h = it - r * P.heads;
+        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, op.cross_len, spt);
+        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, h / rep, sfp[r] + step - P.pos_off + 1, spt);
     }
 }
 
@@ -1095,9 +1113,7 @@ struct PkLaunch {
 static inline int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int Tscore, PkLaunch & L) {
     size_t a = (size_t) 16 * (KA + PK_PAD) * 2;
     if (KAs) a = std::max(a, (size_t) 2 * 16 * (KAs + PK_PAD) * 2);
-    const int rep = Pk.kv_heads > 0 ? Pk.heads / Pk.kv_heads : 1;
-    if (rep != 1 && rep != 3 && rep != 4) return 1;            // query heads per kv head the attention phase is instantiated for
-    a = std::max(a, 2 * pk_att_bytes(rep, Tscore));
+    a = std::max(a, 2 * pk_att_bytes(Tscore));
     a = (a + 255) & ~(size_t) 255;
     const int pt = Pk.R * Pk.max_pages;
     if (Pk.max_pages > 256) return 1;                          // page offsets of a sequence sit in a 256-entry scratch (pk_attn_item)
