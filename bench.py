@@ -512,7 +512,8 @@ def run_orpheus(args):
     """Secondary line: BASELINE config 5's model on ONE GPU of the 8 -- an Orpheus-3B-shaped decoder (28 layers x 3072, 24 / 8 heads x 128, ffn 8192, vocab 156 940) with
     Q8_0 matrices (our own writer: the reference's quantize tool refuses Orpheus and its runtime is F32-only), random weights handed over tensor by tensor (no GGUF file),
     greedy, launch-per-op path (dp4a block GEMV, CUDA-graph replay).  Sweep of the per-GPU batch {1, 2, 4, 8, 16} (config 5: 64 utterances over 8 GPUs = 8 per GPU);
-    a "step" = `n_tokens` decode steps of the whole batch (7 tokens = one 85.3 ms SNAC frame)."""
+    a "step" = `n_tokens` decode steps of the whole batch (7 tokens = one 85.3 ms SNAC frame).  --orpheus-dtype f16: the same shape with F16 matrices, whose decode
+    steps run inside the persistent decode kernel (pdk.cuh)."""
     if args.impl == "reference":
         print(json.dumps({"impl": "reference", "workload": "orpheus", "unavailable": "the reference runs Orpheus in F32 only (README.md:25): 13 GB of weights per CPU worker, minutes per second of audio; not timed here"}))
         return 0
@@ -544,7 +545,8 @@ def run_orpheus(args):
     best = next(x for x in sweep if x["batch_per_gpu"] == 8)
     print(json.dumps({"metric": "audio_seconds_per_second", "workload": f"Orpheus-3B-shaped {args.orpheus_dtype} decoder (synthetic), greedy AR decode, per-GPU batch sweep (BASELINE config 5: 8 per GPU x 8 GPUs); SNAC decode measured by --workload snac",
                       "value": best["audio_s_per_s"], "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": best["ms_per_decode_step"] * n_tokens,
-                      "sweep": sweep, "roofline": {"bound": "hbm", "kernel": "launch-per-op decode step (gemv_rows_q_kernel dp4a / attention_gqa_kernel)", "achieved": best["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                      "persistent_kernel": dict(zip(("launches", "steps"), orph.pdk_stats())),
+                      "sweep": sweep, "roofline": {"bound": "hbm", "kernel": "pdk_kernel (persistent decode kernel)" if orph.pdk_stats()[1] else "launch-per-op decode step (gemv_rows_q_kernel dp4a / attention_gqa_kernel)", "achieved": best["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                                                    "frac": best["frac"], "traffic": None, "peak_source": peak_src, "W_step": w_step},
                       "load_s": load_s, "weight_bytes": orph.weight_bytes(), "dtype": f"{args.orpheus_dtype} matrices (Q8_0: Q8_0-requantised activations, int32 block dots, f32 accumulate)", "data": "synthetic",
                       "config": {"workload": "orpheus-3b shape, 40-token prompts, 168 decode steps per timed generation, greedy"}}))
@@ -592,7 +594,9 @@ def run_dia(args):
     print(json.dumps({"metric": "audio_seconds_per_second", "workload": "Dia-1.6B-shaped F16 model (synthetic), 2 utterances (CFG pairs) per GPU, 10 s each, greedy AR decode + DAC decode (BASELINE config 4, one of its 4 GPUs)",
                       "value": audio_s / ((ar_ms + dac_ms) * 1e-3), "unit": "audio-s/s", "n_gpus": 1, "steps": n, "ms_per_step": (ar_ms + dac_ms) / n, "ar_ms_per_step": ar_ms / n, "dac_ms_per_step": dac_ms / n,
                       "decode_step_ms": step_ms, "frames_generated_min": ng, "e2e": {"value": audio_s / wall, "unit": "audio-s/s"},
-                      "roofline": {"bound": "hbm", "kernel": "launch-per-op decode step (gemv_mma_kernel / attention_gqa_kernel)", "achieved": dia.weight_bytes() / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                      "persistent_kernel": dict(zip(("launches", "steps"), dia.pdk_stats())),
+                      "roofline": {"bound": "hbm", "kernel": "pdk_kernel (persistent decode kernel)" if dia.pdk_stats()[1] else "launch-per-op decode step (gemv_mma_kernel / attention_gqa_kernel)",
+                                   "achieved": dia.weight_bytes() / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": dia.weight_bytes() / (step_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": peak_src,
                                    "note": "algorithmic bytes = the resident weights once per step (encoder weights included: an upper bound of W_step by ~10 %); KV excluded"},
                       "load_s": load_s, "weight_bytes": dia.weight_bytes(), "dtype": "f16 matrices x fp16-rounded activations, f32 accumulate", "data": "synthetic",

@@ -284,6 +284,9 @@ int   b2tts_dia_generate_teacher_forced(b2tts_dia * m, int n_sequences, const ui
                                         const int32_t * teacher, int32_t * out_tokens, float * out_logits);
 /* generation_configuration::max_tokens (dia_runner::generate, model.cpp:873-879): replaces the model's max_generation_size in check_stopping when > max_delay */
 int   b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens);
+/* F16 GGUFs, greedy / teacher-forced, <= 8 utterances, decoder width <= 2 048: the decoder loop runs inside the persistent decode kernel (csrc/pdk.cuh;
+ * B2TTS_AR_PDK=0: launch per op); -> cooperative launches so far and the decode steps they covered */
+void  b2tts_dia_pdk_stats(const b2tts_dia * m, uint64_t * launches, uint64_t * steps);
 size_t b2tts_dia_weight_bytes(const b2tts_dia * m);
 float b2tts_dia_last_ms(const b2tts_dia * m);
 

@@ -48,7 +48,8 @@ static int gen(b2::Dia & m, int B, const uint32_t * const * pp, const int32_t * 
         if (!f || fread(teacher.data(), 4, teacher.size(), f) != teacher.size()) return 2;
         fclose(f);
     }
-    return m.generate(B, pp, np, steps, s, tok, lg, nullptr, teacher.empty() ? nullptr : teacher.data());
+    if (getenv("B2EMU_STOP")) g_ngen.assign((size_t) B, 0);
+    return m.generate(B, pp, np, steps, s, tok, lg, g_ngen.empty() ? nullptr : g_ngen.data(), teacher.empty() ? nullptr : teacher.data());
 }
 
 template <class M> static int run(int argc, char ** argv) {

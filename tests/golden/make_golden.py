@@ -25,6 +25,7 @@ The vectors pin oracle/kokoro_port.py (tests/test_oracle_port.py, CPU) and, thro
       GGUFs: one ends at max_generation, one because every head produced EOS; from oracle/ref_parler_driver.cpp --stop
   dia_f16_vectors.npz      : as dia_vectors.npz for the F16 GGUF of the quantize tool (all matrices and embeddings but the output heads F16)
   orpheus_wide_vectors.npz : as orpheus_vectors.npz for a GGUF with head size 128 (hidden 768)
+  dia_wide_f16_vectors.npz : Dia F16 with decoder width 256, two prompts, all 64 frames of the reference's loop (tokens, top-2 gaps, logits of 16 frames)
   orpheus_wide_long_vectors.npz : the same GGUF, prompts of 7 and 40 ids, 72 greedy steps (crosses KV-page and persistent-kernel launch boundaries)
   sampler_vectors.npz      : the reference sampler (src/sampler.cpp) on fixed logits under four configurations: nucleus, probabilities, max_head_probs and a
       histogram of 20 000 draws each, from oracle/ref_sampler_driver.cpp
@@ -271,6 +272,30 @@ def dia_vectors(f16: bool = False, quant: str | None = None):
     print(f"dia{tag} vectors:", {k: v.shape for k, v in out.items()})
 
 
+def dia_wide_vectors():
+    """dia_wide_f16_vectors.npz: the F16 GGUF with decoder width 256 (head size 64: the shape the persistent decode kernel accepts), two prompts, the whole of
+    generate_from_batch's loop (64 frames: check_stopping's countdown from position 49): tokens of every frame, the reference's top-2 logit gap per (frame, head), and
+    the logits of frames 0-7 and 28-35 (around the first KV-page boundary)."""
+    from tts_cpp_b200.synth import cached_dia_gguf
+    gguf = cached_dia_gguf(seed=0, f16=True, head_dim=64)
+    rng = np.random.default_rng(13)
+    prompts = [np.concatenate([[1], rng.integers(32, 127, size=n)]) for n in (9, 17)]
+    tmp = tempfile.mkdtemp()
+    pf = os.path.join(tmp, "prompts.txt")
+    open(pf, "w").write("\n".join(" ".join(map(str, q)) for q in prompts) + "\n")
+    pre = os.path.join(tmp, "d")
+    run([os.path.join(REF, "dia_ref"), gguf, pf, pre, "--steps", "80", "--threads", "4", "--quiet"])
+    keep = list(range(0, 8)) + list(range(28, 36))
+    out = {"logit_steps": np.asarray(keep, np.int32), "step_cap": np.int32(80)}
+    for u, q in enumerate(prompts):
+        toks = np.fromfile(f"{pre}.u{u}.tokens.i32", np.int32).reshape(-1, 9)
+        lg = np.fromfile(f"{pre}.u{u}.logits.f32", np.float32).reshape(toks.shape[0], 9, -1)
+        top2 = np.sort(lg, axis=-1)[:, :, -2:]
+        out[f"prompt{u}"] = np.asarray(q, np.int32); out[f"tokens{u}"] = toks; out[f"gap{u}"] = (top2[:, :, 1] - top2[:, :, 0]).astype(np.float32); out[f"logits{u}"] = lg[keep]
+    np.savez_compressed(os.path.join(OUT, "dia_wide_f16_vectors.npz"), **out)
+    print("dia wide f16 vectors:", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 def dia_stop_vectors():
     """The whole of generate_from_batch's loop: with dia.decoder.max_generation_size = 64 and max_delay = 15 check_stopping starts the end-of-stream
     countdown at position 49 (EOS / PAD injected head by head along the delay pattern) and ends the loop after 64 frames."""
@@ -325,6 +350,7 @@ if __name__ == "__main__":
     if "parler_encoding" in which: parler_encoding_vectors()
     if "sampler" in which: sampler_vectors()
     if "orpheus_wide" in which: orpheus_vectors(wide=True)
+    if "dia_wide" in which: dia_wide_vectors()
     if "orpheus_wide_long" in which: orpheus_vectors(wide=True, long=True)
     if "parler_f16" in which: parler_vectors(f16=True)
     if "parler_mini" in which: parler_vectors(f16=True, mini=True)      # (not in the default list: ~2 minutes of CPU and a 1.5 GB GGUF)

@@ -119,3 +119,57 @@ sys.exit(0 if ok else 1)
 def test_dia_quantised_teacher_forced():
     """Q8_0 matrices (gemv_rows_q_kernel), teacher-forced on the reference's tokens; smoke-level bar (Dia amplifies re-quantisation noise: see tests/test_emu_cpu.py)."""
     assert run_snippet(QUANT_BODY, []) == 0
+
+
+PDK_BODY = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from tts_cpp_b200.binding import dia_runner_from_file
+from tts_cpp_b200.synth import cached_dia_gguf
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "dia_wide_f16_vectors.npz"))
+dia = dia_runner_from_file(cached_dia_gguf(seed=0, f16=True, head_dim=64))
+pdk_on = os.environ.get("B2TTS_AR_PDK") != "0"
+prompts = [g["prompt0"], g["prompt1"]]
+frames = int(g["tokens0"].shape[0])
+keep = [int(s) for s in g["logit_steps"]]
+ok = True
+tf_t, tf_l = dia.generate_teacher_forced(prompts, np.stack([g["tokens0"], g["tokens1"]]))      # all 63 frames of the reference's loop, fed back from the reference
+launches, psteps = dia.pdk_stats()
+print("persistent-kernel launches / steps", launches, psteps)
+ok &= (psteps == frames and launches == -(-frames // 32)) if pdk_on else psteps == 0
+dmax = 0.0
+for u in range(2):
+    ref = g[f"logits{u}"]
+    d = np.abs(tf_l[u][keep] - ref).max(axis=(1, 2))
+    rms = np.sqrt(((tf_l[u][keep] - ref) ** 2).mean(axis=(1, 2)))
+    dmax = max(dmax, float(d.max()))
+    clear = g[f"gap{u}"] > 4.0 * float(d.max())
+    print(f"PARITY dia wide F16 pdk={int(pdk_on)} prompt {u} teacher-forced: logit rms {np.round(rms, 3).tolist()} max {np.round(d, 3).tolist()}; tokens equal "
+          f"{int((tf_t[u] == g[f'tokens{u}']).sum())}/{frames * 9}, clear decisions {int(clear.sum())}/{clear.size}")
+    ok &= float(rms.max()) < 0.25 and float(d.max()) < 1.5 and bool(np.array_equal(tf_t[u][clear], g[f"tokens{u}"][clear]))
+# free-running with check_stopping: the reference's frame count; identical tokens up to the first difference, which must sit within the F16 floor measured above
+toks, ngen = dia.generate_greedy(prompts, int(g["step_cap"]))
+print("frames", ngen.tolist(), "reference", frames)
+for u in range(2):
+    rt = g[f"tokens{u}"]
+    ok &= int(ngen[u]) == frames and not toks[u][frames:].any()
+    neq = np.argwhere(toks[u][:frames] != rt)
+    first = int(neq[0][0]) if neq.size else frames
+    near = all(float(g[f"gap{u}"][s, h]) < 2.0 * dmax for s, h in neq if s == first)
+    print(f"PARITY dia wide F16 pdk={int(pdk_on)} prompt {u} free-running: identical through frame {first - 1} of {frames}; first difference within the floor: {near}")
+    ok &= near and first >= 8
+dia.close()
+sys.exit(0 if ok else 1)
+'''
+
+
+@pytest.mark.parametrize("variant", ["pdk", "pdk_f16kv", "per_op"])
+def test_dia_f16_persistent_kernel_tracks_the_reference(variant):
+    """The F16 GGUF with decoder width 256 (the smallest shape the persistent decode kernel takes) against the reference's own F16 run of all 63 frames
+    (tests/golden/dia_wide_f16_vectors.npz): encoder per op, then the whole CFG decoder loop in the persistent kernel -- delay pattern and check_stopping in the rows
+    phase, RoPE'd self / cross queries, GQA pages (fp32 by default for Dia, fp16 under B2TTS_KV=f16), cross-attention over each row's encoding, cfg_scale + argmax --
+    teacher-forced logits at 16 frames around the first page boundary within Dia's F16 floor, the reference's token wherever its top-2 gap is clear, the reference's frame
+    count free-running; the launch-per-op path under the same rule."""
+    env = {"pdk": None, "pdk_f16kv": {"B2TTS_KV": "f16"}, "per_op": {"B2TTS_AR_PDK": "0"}}[variant]
+    assert run_snippet(PDK_BODY, [], env=env) == 0

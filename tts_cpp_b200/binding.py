@@ -551,6 +551,12 @@ class DiaRunner:
         lib().b2tts_dia_last_ms.restype = C.c_float
         return float(lib().b2tts_dia_last_ms(self.h))
 
+    def pdk_stats(self):
+        """-> (launches of the persistent decode kernel, decode steps they covered)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().b2tts_dia_pdk_stats(self.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def weight_bytes(self) -> int:
         lib().b2tts_dia_weight_bytes.restype = C.c_size_t
         return int(lib().b2tts_dia_weight_bytes(self.h))

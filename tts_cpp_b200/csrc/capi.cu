@@ -340,6 +340,7 @@ int b2tts_dia_set_max_generation(b2tts_dia * m, int max_tokens) {
     if (max_tokens > m->d.max_delay) m->d.max_gen = max_tokens;
     return 0;
 }
+void b2tts_dia_pdk_stats(const b2tts_dia * m, uint64_t * launches, uint64_t * steps) { if (launches) *launches = m ? m->d.pdk_launches : 0; if (steps) *steps = m ? m->d.pdk_steps : 0; }
 size_t b2tts_dia_weight_bytes(const b2tts_dia * m) { return m ? m->d.weight_bytes : 0; }
 float b2tts_dia_last_ms(const b2tts_dia * m) { return m ? m->d.timing_ms : 0.f; }
 

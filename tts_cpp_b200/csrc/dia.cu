@@ -1,6 +1,7 @@
 // dia.cu -- Dia autoregressive decode (encoder pass + CFG-paired decoder loop), first correct CUDA path.  See dia.h for what it replaces.
 #include "dia.h"
 #include "ar_kernels.cuh"
+#include "pdk.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -111,11 +112,25 @@ int Dia::prepare() {
         }
         if (ok && heads_any_f16 != heads_f16) { set_error("dia: the output heads mix F16 and F32 tensors"); ok = false; }
         if (ok) { tables = dev(tab.data(), tab.size()); heads_w = dev_mat(hw.data(), hw.size(), heads_f16); }   // tables: ggml_get_rows widens F16 rows to fp32 exactly
+        if (ok && !heads_f16) {   // F32 heads (dia_is_quantizable leaves them F32): fp16 (hi, 2^11-scaled lo) planes for the persistent decode kernel's split tensor-core product
+            std::vector<__half> hi(hw.size()), lo(hw.size());
+            for (size_t i = 0; i < hw.size(); i++) { hi[i] = __float2half_rn(hw[i]); lo[i] = __float2half_rn((hw[i] - __half2float(hi[i])) * GM_LO_SCALE); }
+            for (int pl = 0; pl < 2 && ok; pl++) {
+                void * d = nullptr;
+                if (cudaMalloc(&d, hw.size() * 2) != cudaSuccess) { cudaGetLastError(); set_error("dia: cudaMalloc of %zu bytes failed", hw.size() * 2); ok = false; break; }
+                cudaMemcpy(d, pl ? lo.data() : hi.data(), hw.size() * 2, cudaMemcpyHostToDevice);
+                dev_allocs.push_back(d); weight_bytes += hw.size() * 2;
+                (pl ? heads_lo : heads_hi) = (__half *) d;
+            }
+        }
     }
     if (!ok) return 1;
     for (int i = 0; i < 2; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     host.clear();
     B2_CUDA(cudaDeviceSynchronize());      // the uploads above are blocking copies on the legacy stream; kernels run on ctx->stream (non-blocking), which does not wait for it by itself
+#ifndef B2EMU
+    B2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+#endif
     prepared = true;
     return 0;
 }
@@ -207,17 +222,36 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         if (n_prompt[b] <= 0 || n_prompt[b] > C) { set_error("dia: prompt %d has %d tokens (1 .. %d supported)", b, n_prompt[b], C); return 1; }
         for (int i = 0; i < n_prompt[b]; i++) if (prompts[b][i] >= (uint32_t) enc_vocab) { set_error("dia: prompt %d token %u >= encoder vocabulary %d", b, prompts[b][i], enc_vocab); return 1; }
     }
+    // ---- the persistent decode kernel (pdk.cuh) runs the decoder loop when the model and the request fit it: greedy / teacher-forced, <= 8 utterances (16 rows with
+    // their unconditional twins), F16 decoder matrices (BASELINE config 4), decoder width <= 2 048 in whole 256-column k-slices.  B2TTS_AR_PDK=0 turns it off.
+    static const bool pdk_env = [] { const char * e = getenv("B2TTS_AR_PDK"); return !(e && e[0] == '0'); }();
+    // fp32 pages by default for Dia (B2TTS_KV=f16: fp16 pages): its decoder attends with softmax scale 1.0 and amplifies the cache's rounding -- fp16 pages moved the
+    // logits of the test model by up to 2.5 at a logit std of 13 (fp32 pages: 0.05, the summation-order floor); the cache is a small share of the step's traffic here
+    static const bool kv_f32 = [] { const char * e = getenv("B2TTS_KV"); return !(e && (e[0] == 'f' || e[0] == 'F') && e[1] == '1'); }();
+#ifdef B2EMU
+    const int pk_grid = [] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 3; return v > 0 ? v : 3; }();
+#else
+    const int pk_grid = [&] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 0; return v > 0 && v <= sm_count ? v : sm_count; }();
+#endif
+    const int pk_ak = [&] { const char * e = getenv("B2TTS_PDK_AK"); const int v = e ? atoi(e) : 0; return v >= 256 && v % 256 == 0 && v <= PK_AK_MAX && v >= D ? v : (D <= 2048 ? 2048 : PK_AK_MAX); }();
+    bool use_pdk = pdk_env && !samp.do_sample && S2 <= 16 && D % 256 == 0 && ffn % 256 == 0 && D <= pk_ak && heads * head_dim == D && (head_dim == 64 || head_dim == 128) && (heads_w.f16 || heads_hi) && !heads_w.qtype && n_out <= 9 &&
+                   pk_grid > 0 && (ffn <= pk_ak || cdiv(D / 8, pk_grid) <= 3) && (!out_logits || (size_t) n_steps * B * NV * 4 <= ((size_t) 1 << 30));
+    for (const DiaDecLayer & L : dec) for (const ArW * w : {&L.sq, &L.sk, &L.sv, &L.so, &L.cq, &L.co, &L.gate, &L.up, &L.down}) use_pdk = use_pdk && w->f16 && !w->qtype;
+    const int pk_max_pages = cdiv(Tmax, PK_PAGE);
+    const size_t pk_layer_bytes = (size_t) S2 * pk_max_pages * 2 * KVD * PK_PAGE * (kv_f32 ? 4 : 2);
+    const size_t pk_need = use_pdk ? (size_t) dec_layers * pk_layer_bytes + (size_t) S2 * pk_max_pages * 4 + (size_t) (8 * dec_layers + 8) * sizeof(PkOp) + 8192 + (size_t) PK_REP * 16 * ((size_t) 8 * D + 2 * ffn) + 4096 +
+                                     (size_t) 16 * head_dim * 4 + (out_logits ? (size_t) n_steps * B * NV * 4 : 0) : 0;
     const size_t enc_ws = (size_t) RE * ((size_t) 3 * EH + 4 * EI + 2 * enc_ffn) * 4;
     const size_t cross = (size_t) 2 * dec_layers * RE * D * 4;
-    const size_t self_cache = (size_t) 2 * dec_layers * S2 * Tmax * KVD * 4;
+    const size_t self_cache = use_pdk ? 0 : (size_t) 2 * dec_layers * S2 * Tmax * KVD * 4;      // the persistent kernel keeps the self-attention cache in its pages
     const size_t dec_ws = (size_t) S2 * ((size_t) 4 * D + 2 * KVD + 2 * ffn + NV) * 4 + (size_t) B * NV * 4;
-    const size_t need = enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20) +
+    const size_t need = pk_need + enc_ws + cross + self_cache + dec_ws + (size_t) RE * 16 + (size_t) S2 * (32 + 4 * n_out) + (size_t) n_steps * B * n_out * 4 + (size_t) B * 16 + (32 << 20) +
                         (size_t) B * n_out * 8 + (teacher ? (size_t) n_steps * B * n_out * 4 : 0) + (sampling_needs_scratch(samp, vocab) ? (size_t) B * NV * 4 : 0);
     if (arena.reserve(need)) return 1;
     DFwd Fw(this, ctx, st);
     // ---- buffers
     float * ck = Fw.al<float>((size_t) dec_layers * RE * D), * cv = Fw.al<float>((size_t) dec_layers * RE * D);
-    float * Kc = Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD), * Vc = Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD);
+    float * Kc = use_pdk ? nullptr : Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD), * Vc = use_pdk ? nullptr : Fw.al<float>((size_t) dec_layers * S2 * Tmax * KVD);
     int * e_tok = Fw.al<int>((size_t) RE), * e_pos = Fw.al<int>((size_t) RE), * e_base = Fw.al<int>((size_t) RE), * e_len = Fw.al<int>((size_t) RE);
     int * seq_len = Fw.al<int>((size_t) S2), * cross_base = Fw.al<int>((size_t) S2), * cross_len = Fw.al<int>((size_t) S2);
     int * ids = Fw.al<int>((size_t) S2 * n_out), * row_pos = Fw.al<int>((size_t) S2), * row_base = Fw.al<int>((size_t) S2), * row_len = Fw.al<int>((size_t) S2), * row_dst = Fw.al<int>((size_t) S2);
@@ -345,9 +379,96 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         for (int b = 0; b < B; b++) if (hflags[(size_t) b] < 0) return 0;
         return 1;
     };
+    if (use_pdk) {
+        // ---- the whole decoder loop inside the persistent kernel.  Program of a step: rows (delay pattern + end-of-stream injection, codebook embeddings of the row
+        // pair, RoPE table) | per layer { [RMSNorm] q|k|v GEMV with NeoX rotation + cache append in the epilogue -> GQA self-attention over the pages -> o GEMV +
+        // residual -> [RMSNorm] cross-q GEMV with rotation -> cross-attention over the row's encoding -> o GEMV + residual -> [RMSNorm] gate|up GEMV with SwiGLU ->
+        // down GEMV + residual } | [RMSNorm] heads GEMV | cfg_scale + argmax
+        const float scale = 1.0f;
+        unsigned char * pool = (unsigned char *) arena.alloc((size_t) dec_layers * pk_layer_bytes);
+        int * page_table = Fw.al<int>((size_t) S2 * pk_max_pages), * first_pos = Fw.al<int>(16);
+        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (8 * dec_layers + 8) * sizeof(PkOp));
+        unsigned * d_bar = (unsigned *) arena.alloc(256);
+        float * logits_all = out_logits ? Fw.al<float>((size_t) n_steps * B * NV) : nullptr;
+        const size_t xrep = (size_t) 16 * D, grep = (size_t) 16 * ffn;
+        float * px = Fw.al<float>(PK_REP * xrep), * pxn = Fw.al<float>(PK_REP * xrep);
+        __half * att16 = Fw.al<__half>(PK_REP * xrep), * g16 = Fw.al<__half>(PK_REP * grep);
+        float2 * rope_cs = (float2 *) arena.alloc((size_t) 16 * (head_dim / 2) * sizeof(float2));
+        if (!pool || !d_ops || !d_bar || !rope_cs || Fw.fail) return 1;
+        std::vector<int> hpt((size_t) S2 * pk_max_pages);
+        for (size_t i = 0; i < hpt.size(); i++) hpt[i] = (int) i;                            // every row takes its pages in order
+        std::vector<PkOp> ops;
+        auto seg = [&](const ArW & W, int N, int epi, int pair, int n_units) { PkSeg sg; memset(&sg, 0, sizeof sg); sg.W = (const __half *) W.p; sg.Wp = sg.W; sg.N = N; sg.epi = epi; sg.ldy = N; sg.pair = pair; sg.n_units = n_units; return sg; };
+        auto gemv_op = [&](int layer, const float * X, const __half * X16, size_t xr, int K, const float * nw, std::initializer_list<PkSeg> segs) {
+            PkOp op; memset(&op, 0, sizeof op);
+            op.kind = PK_GEMV; op.layer = layer; op.X = X; op.X16 = X16; op.xrep = xr; op.ldx = K; op.K = K; op.norm = nw ? PKN_RMS : PKN_NONE; op.nw = nw; op.eps = 1e-5f;
+            int u = 0;
+            for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; u += sg.n_units; op.nseg++; }
+            op.n_units = u;
+            ops.push_back(op);
+        };
+        auto attn_op = [&](int layer, const float * ckp, const float * cvp) {
+            PkOp op; memset(&op, 0, sizeof op);
+            op.kind = PK_ATTN; op.layer = layer; op.q = q; op.out16 = att16; op.orep = xrep; op.scale = scale; op.ck = ckp; op.cv = cvp; op.cross = ckp ? 1 : 0; op.cross_len = C; op.cross_row_stride = ckp ? (size_t) C * D : 0;
+            ops.push_back(op);
+        };
+        { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ROWS; ops.push_back(op); }
+        const int kv_heads = heads / rep, rope_units_q = heads * (head_dim / 16), rope_units_k = kv_heads * (head_dim / 16);
+        for (int l = 0; l < dec_layers; l++) {
+            const DiaDecLayer & L = dec[(size_t) l];
+            PkSeg sq = seg(L.sq, D, PKE_ROPE_Q, PKP_ROPE, rope_units_q); sq.Y = q;
+            PkSeg sk = seg(L.sk, KVD, PKE_ROPE_K, PKP_ROPE, rope_units_k);
+            PkSeg sv = seg(L.sv, KVD, PKE_KV, PKP_NONE, KVD / 8); sv.kv = 1;
+            gemv_op(l, px, nullptr, xrep, D, L.pre_sa, {sq, sk, sv}); ops.back().kv_prefetch = 1;
+            attn_op(l, nullptr, nullptr);
+            PkSeg so = seg(L.so, D, PKE_RES, PKP_NONE, D / 8); so.Y = pxn; so.res = px; so.yrep = xrep;                    // xn = self-attention + residual(x)
+            gemv_op(l, nullptr, att16, xrep, D, nullptr, {so});
+            PkSeg scq = seg(L.cq, D, PKE_ROPE_Q, PKP_ROPE, rope_units_q); scq.Y = q;                                      // the cross query is RoPE'd with the decode position
+            gemv_op(l, pxn, nullptr, xrep, D, L.pre_ca, {scq});
+            attn_op(l, ck + (size_t) l * RE * D, cv + (size_t) l * RE * D);
+            PkSeg sco = seg(L.co, D, PKE_RES, PKP_NONE, D / 8); sco.Y = px; sco.res = pxn; sco.yrep = xrep;                // x = cross-attention + residual(xn)
+            gemv_op(l, nullptr, att16, xrep, D, nullptr, {sco});
+            PkSeg sg2 = seg(L.gate, ffn, PKE_SWIGLU, PKP_SWIGLU, ffn / 8); sg2.Wp = (const __half *) L.up.p; sg2.Y16 = g16; sg2.yrep = grep;
+            gemv_op(l, px, nullptr, xrep, D, L.pre_mlp, {sg2});
+            PkSeg sd = seg(L.down, D, PKE_RES, PKP_NONE, D / 8); sd.Y = px; sd.res = px; sd.yrep = xrep;                   // x = mlp + residual(x), element-wise in place (every copy)
+            gemv_op(l, nullptr, g16, grep, ffn, nullptr, {sd});
+        }
+        {
+            PkSeg sh = seg(heads_w, NV, PKE_LOGITS, PKP_NONE, cdiv(NV, 8)); sh.Y = logits2;
+            if (!heads_w.f16) { sh.W = heads_hi; sh.Wp = heads_hi; sh.Wl = heads_lo; }
+            gemv_op(0, px, nullptr, xrep, D, dec_norm, {sh});
+        }
+        { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ARGMAX; ops.push_back(op); }
+        B2_CUDA(cudaMemcpyAsync(page_table, hpt.data(), hpt.size() * 4, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * sizeof(PkOp), cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemsetAsync(first_pos, 0, 64, st));
+        PkParams Pk; memset(&Pk, 0, sizeof Pk);
+        Pk.ops = d_ops; Pk.n_ops = (int) ops.size(); Pk.R = S2; Pk.H = D; Pk.heads = heads; Pk.kv_heads = kv_heads; Pk.hd = head_dim; Pk.n_out = n_out; Pk.vocab = vocab;
+        Pk.model = PKM_DIA; Pk.ak = pk_ak; Pk.pos_off = 0; Pk.n_steps_total = n_steps;
+        Pk.rope_cs = rope_cs; Pk.theta_scale = theta_scale; Pk.pad = pad; Pk.max_delay = max_delay; Pk.cfg = cfg; Pk.delay = delay; Pk.logits_cfg = logits;
+        Pk.bar = d_bar; Pk.d_step = d_step; Pk.first_pos = first_pos; Pk.d_out = d_out; Pk.d_teacher = d_teacher; Pk.bos = bos; Pk.eos = eos; Pk.max_gen = max_gen; Pk.stopped = stopped; Pk.ids = ids; Pk.row_pos = row_pos;
+        Pk.tables = tables; Pk.tab_stride = (size_t) vocab * D; Pk.x0 = px; Pk.x0rep = xrep;
+        Pk.kv_pool = pool; Pk.kv_layer_bytes = pk_layer_bytes; Pk.page_table = page_table; Pk.max_pages = pk_max_pages;
+        Pk.logits = logits2; Pk.logits_all = logits_all;
+        PkLaunch pkl;
+        if (pk_configure(Pk, kv_f32, std::min(std::max(D, ffn), pk_ak), heads_w.f16 ? 0 : std::min(D, pk_ak), std::max(Tmax, C), pkl)) { set_error("dia: the persistent decode kernel does not fit this shape (%d positions) in shared memory", Tmax); return 1; }
+        pk_prof_begin(Pk, ops.size(), pk_grid, st);
+        for (int s0 = 0; s0 < n_steps; s0 += exit_every) {
+            if (s0 > 0) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
+            Pk.step_begin = s0; Pk.n_steps = std::min(exit_every, n_steps - s0);
+            B2_CUDA(pk_launch(pkl, Pk, pk_grid, st));
+            ctx->launches++; pdk_launches++; pdk_steps += (uint64_t) Pk.n_steps;
+        }
+        pk_prof_end(Pk, ops, pk_grid, st);
+        if (out_logits)
+            for (int s = 0; s < n_steps; s++)
+                for (int b = 0; b < B; b++)
+                    B2_CUDA(cudaMemcpyAsync(out_logits + ((size_t) b * n_steps + s) * NV, logits_all + ((size_t) s * B + b) * NV, (size_t) NV * 4, cudaMemcpyDeviceToHost, st));
+    }
     // B2TTS_AR_GRAPH=1: capture one decoder step into a CUDA graph and replay it (see parler.cu); not used when every step's logits go to the host
     const char * ge = getenv("B2TTS_AR_GRAPH");
-    if (!(ge && ge[0] == '0') && !out_logits && n_steps > 1) {      // on by default (reproduced the reference's tokens on a B200, round 2); B2TTS_AR_GRAPH=0 for A/B runs
+    if (use_pdk) {
+    } else if (!(ge && ge[0] == '0') && !out_logits && n_steps > 1) {      // on by default (reproduced the reference's tokens on a B200, round 2); B2TTS_AR_GRAPH=0 for A/B runs
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         if (run_step()) return 1;                               // step 0 runs directly: every kernel instantiation has its attributes set before the capture
         const uint64_t l0 = ctx->launches;

@@ -27,9 +27,12 @@ struct Dia {
     int enc_layers = 0, dec_layers = 0, heads = 0, rep = 1, enc_heads = 0, head_dim = 0, enc_ctx = 0, n_out = 0, vocab = 0, max_gen = 0, max_delay = 15;
     int enc_hidden = 0, hidden = 0, kv_hidden = 0, enc_inner = 0, enc_ffn = 0, ffn = 0, enc_vocab = 0;
     int bos = 1026, eos = 1024, pad = 1025;
+    int sm_count = 0;
+    uint64_t pdk_launches = 0, pdk_steps = 0;   // cooperative launches of the persistent decode kernel (pdk.cuh) and the decode steps they covered
     float cfg = 3.0f;
     float * enc_embed = nullptr, * enc_norm = nullptr, * tables = nullptr /* [n_out][vocab][hidden] */, * dec_norm = nullptr;
     ArW heads_w;   // [n_out * vocab][hidden]
+    __half * heads_hi = nullptr, * heads_lo = nullptr;   // F32 heads (what the quantize tool leaves): fp16 (hi, 2^11-scaled lo) planes for the persistent decode kernel
     std::vector<DiaEncLayer> enc;
     std::vector<DiaDecLayer> dec;
 

@@ -54,7 +54,7 @@ enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3 };
 enum { PKN_NONE = 0, PKN_LAYER = 1, PKN_RMS = 2 };
 enum { PKE_STORE = 0, PKE_RES = 1, PKE_GELU = 2, PKE_KV = 3, PKE_LOGITS = 4, PKE_ROPE_Q = 5, PKE_ROPE_K = 6, PKE_SWIGLU = 7 };
 enum { PKP_NONE = 0, PKP_ROPE = 1, PKP_SWIGLU = 2 };      // paired units: two tiles per k-tile (the two NeoX halves of a head's rows; the gate and the up rows of the same columns), one joint epilogue
-enum { PKM_PARLER = 0, PKM_ORPHEUS = 1 };
+enum { PKM_PARLER = 0, PKM_ORPHEUS = 1, PKM_DIA = 2 };
 
 struct PkSeg {                                    // one matrix of a GEMV phase; unit = 8 consecutive output rows
     const __half * W;                             // [N][K] fp16 (split: the high plane)
@@ -72,7 +72,7 @@ struct alignas(16) PkOp {
     size_t xrep;                                  // != 0: X / X16 exist in PK_REP copies this many elements apart
     const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; PkSeg seg[3];      // kv_prefetch: L2-prefetch this layer's K / V rows first
     // PK_ATTN: cross != 0 -> every row attends to the flat fp32 store ck / cv [cross_len][H]; else to its sequence's pages, positions [0, row_pos[r]]
-    const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale;      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
+    const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale; size_t cross_row_stride;      // cross_row_stride: elements between the stores of consecutive rows (Dia: one encoding per sequence; 0: all rows share one)      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
 };
 struct PkParams {
     const PkOp * ops; int n_ops;
@@ -81,7 +81,10 @@ struct PkParams {
     // PKM_ORPHEUS rows: x0 = embed[token produced one step earlier]; NeoX RoPE table of the step rope_cs [R][hd / 2] (cos, sin) with ggml's iterated theta and the
     // llama-3 frequency factors; d_out is [R][n_steps_total]; a sequence stops at stop_token
     const float * embed; const float * rope_ff; float2 * rope_cs; float theta_scale; int n_steps_total, stop_token;
-    float * amax_v; int * amax_i; int amax_ch;    // PKM_ORPHEUS argmax over a 150k vocabulary: amax_ch partial (value, index) pairs per row, combined by the row's next rows phase
+    float * amax_v; int * amax_i; int amax_ch;
+    // PKM_DIA (reference src/models/dia/model.cpp:806-858): rows 2u (conditional) and 2u + 1 (unconditional) of utterance u share the step's ids; check_stopping's
+    // end-of-stream countdown `delay` [R / 2]; logits [R][n_out * vocab] per row, combined by cfg_scale (src/util.cpp:175-200) into logits_cfg [R / 2][n_out * vocab]
+    int pad, max_delay; float cfg; int * delay; float * logits_cfg;    // PKM_ORPHEUS argmax over a 150k vocabulary: amax_ch partial (value, index) pairs per row, combined by the row's next rows phase
     int n_stages, a_bytes;                        // shared-memory layout: ring stages, bytes of the activation / attention-scratch region
     unsigned * bar;                               // grid-barrier arrival counter, zeroed before every launch
     int * d_step; int step_begin, n_steps;        // steps [step_begin, step_begin + n_steps) run in this launch
@@ -488,7 +491,7 @@ __device__ __forceinline__ void pk_epilogue(const PkParams & P, const PkOp & op,
         }
         case PKE_LOGITS:
             sg.Y[(size_t) r * sg.ldy + n] = a;
-            if (P.logits_all) P.logits_all[((size_t) step_abs * P.R + r) * sg.ldy + n] = a;
+            if (P.logits_all && P.model != PKM_DIA) P.logits_all[((size_t) step_abs * P.R + r) * sg.ldy + n] = a;      // (Dia keeps the cfg-combined logits: pk_argmax_dia)
             break;
         default: sg.Y[(size_t) r * sg.ldy + n] = a; break;
     }
@@ -766,7 +769,8 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
     unsigned long long * spo = reinterpret_cast<unsigned long long *>(base + 512);      // element offset of each of this sequence's pages within the layer's pool
     float * pvs = base + PK_ATT_HDR; float * sc = base + PK_ATT_HDR + 1024;
     const size_t page_elems = (size_t) 2 * P.kv_heads * PK_PAGE * HD;
-    const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + (size_t) kh * HD + part * 8, * flat_v = reinterpret_cast<const CT *>(op.cv) + (size_t) kh * HD + part * 8;
+    const CT * flat_k = reinterpret_cast<const CT *>(op.ck) + op.cross_row_stride * (size_t) r + (size_t) kh * HD + part * 8;
+    const CT * flat_v = reinterpret_cast<const CT *>(op.cv) + op.cross_row_stride * (size_t) r + (size_t) kh * HD + part * 8;
     const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) kh * PK_PAGE * HD + part * 8;
     const CT * pool_v = pool_k + (size_t) P.kv_heads * PK_PAGE * HD;
     const int * pt = spt + r * P.max_pages;
@@ -1014,6 +1018,73 @@ __device__ __forceinline__ void pk_argmax_partial(const PkParams & P, float * re
     }
 }
 
+// ---- PKM_DIA (dia_runner::generate_from_batch / check_stopping, reference src/models/dia/model.cpp:806-858; build_dia_decoder :580-700)
+// rows of a step: utterance u's ids under the delay pattern with the end-of-stream injection (dia_step_rows_kernel), the summed codebook embeddings for its two rows
+// (codebook_embed_kernel) and the NeoX RoPE table of position `step` (no frequency factors)
+__device__ __forceinline__ void pk_rows_dia(const PkParams & P, int step, int * sids) {
+    const int tid = threadIdx.x, n_out = P.n_out, Bu = P.R >> 1, H = P.H, half = P.hd >> 1;
+    for (int u = (int) blockIdx.x; u < Bu; u += (int) gridDim.x) {
+        if (tid == 0) {
+            const int * last = (P.d_teacher ? P.d_teacher : P.d_out) + ((size_t) (step > 0 ? step - 1 : 0) * Bu + u) * n_out;
+            const int pattern[9] = {0, 8, 9, 10, 11, 12, 13, 14, 15};     // dia_model::delay_pattern (model.h:85)
+            int audio[9];
+            for (int i = 0; i < n_out; i++) audio[i] = step > i ? __ldcg(last + i) : P.bos;
+            int d = P.delay[u];
+            if (d == -1 && (audio[0] == P.eos || step >= P.max_gen - P.max_delay)) d = P.max_delay;
+            if (d > 0) {
+                const int after = P.max_delay - d;
+                for (int i = 0; i < n_out; i++) {
+                    if (after == pattern[i]) audio[i] = P.eos;
+                    else if (after > pattern[i]) audio[i] = P.pad;
+                }
+                d -= 1;
+            }
+            P.delay[u] = d;
+            if (d == 0 && P.stopped[u] < 0) P.stopped[u] = step;
+            for (int i = 0; i < n_out; i++) { sids[i] = audio[i]; P.ids[(2 * u) * n_out + i] = audio[i]; P.ids[(2 * u + 1) * n_out + i] = audio[i]; }
+            P.row_pos[2 * u] = step; P.row_pos[2 * u + 1] = step;
+        }
+        pk_bar_sync(1, PK_CONS);
+        for (int c = tid; c < H; c += PK_CONS) {              // the tables' rows summed in head order
+            float a = P.tables[(size_t) sids[0] * H + c];
+            for (int i = 1; i < n_out; i++) a = P.tables[(size_t) i * P.tab_stride + (size_t) sids[i] * H + c] + a;
+            for (int cp = 0; cp < (P.x0rep ? PK_REP : 1); cp++) { P.x0[P.x0rep * cp + (size_t) (2 * u) * H + c] = a; P.x0[P.x0rep * cp + (size_t) (2 * u + 1) * H + c] = a; }
+        }
+        for (int i = tid; i < half; i += PK_CONS) {
+            float theta = (float) step;
+            for (int j = 0; j < i; j++) theta *= P.theta_scale;
+            const float2 cs = make_float2(cosf(theta), sinf(theta));
+            P.rope_cs[(size_t) (2 * u) * half + i] = cs; P.rope_cs[(size_t) (2 * u + 1) * half + i] = cs;
+        }
+        pk_bar_sync(1, PK_CONS);
+    }
+}
+
+// cfg_scale then sampler::max per (utterance, head): out = cond + scale * (cond - uncond); the first maximum wins
+__device__ __forceinline__ void pk_argmax_dia(const PkParams & P, int step, float * red) {
+    float * sv = red; int * si = reinterpret_cast<int *>(red + 256);
+    const int tid = threadIdx.x, V = P.vocab, n_out = P.n_out, NV = n_out * V, Bu = P.R >> 1;
+    for (int b = (int) blockIdx.x; b < Bu * n_out; b += (int) gridDim.x) {
+        const int u = b / n_out, i = b - u * n_out;
+        const float * lc = P.logits + (size_t) (2 * u) * NV + (size_t) i * V, * lu = lc + NV;
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int j = tid; j < V; j += PK_CONS) {
+            const float cr = __ldcg(lc + j), ur = __ldcg(lu + j), v = cr + P.cfg * (cr - ur);
+            P.logits_cfg[(size_t) u * NV + (size_t) i * V + j] = v;
+            if (P.logits_all) P.logits_all[((size_t) step * Bu + u) * NV + (size_t) i * V + j] = v;
+            if (v > best) { best = v; bi = j; }
+        }
+        sv[tid] = best; si[tid] = bi;
+        pk_bar_sync(1, PK_CONS);
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) { if (sv[tid + o] > sv[tid] || (sv[tid + o] == sv[tid] && si[tid + o] < si[tid])) { sv[tid] = sv[tid + o]; si[tid] = si[tid + o]; } }
+            pk_bar_sync(1, PK_CONS);
+        }
+        if (tid == 0) P.d_out[(size_t) step * Bu * n_out + b] = si[0] == 0x7fffffff ? 0 : si[0];
+        pk_bar_sync(1, PK_CONS);
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <typename KVT, int HD>
 __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
@@ -1069,10 +1140,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
             unsigned long long * pr = prof ? P.prof + ((size_t) oi * gridDim.x + blockIdx.x) * 8 : nullptr;
             if (pr) pr[0] = pk_now();
             switch (op.kind) {
-                case PK_ROWS:   if (P.model == PKM_ORPHEUS) pk_rows_orpheus(P, step, st == 0, red); else pk_rows(P, step, sids); break;
+                case PK_ROWS:   if (P.model == PKM_ORPHEUS) pk_rows_orpheus(P, step, st == 0, red); else if (P.model == PKM_DIA) pk_rows_dia(P, step, sids); else pk_rows(P, step, sids); break;
                 case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, rp, step, pr, skv, sfp, spt); break;
                 case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
-                case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else pk_argmax(P, step, red); break;
+                case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else if (P.model == PKM_DIA) pk_argmax_dia(P, step, red); else pk_argmax(P, step, red); break;
             }
             if (pr) pr[2] = pk_now();
             if (tid < OPW) reinterpret_cast<uint4 *>(&sops[(opn & 1u) ^ 1u])[tid] = nxt;

@@ -707,13 +707,14 @@ def write_dia_gguf(path: str, seed: int = 0, enc_layers: int = 2, dec_layers: in
     return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
 
 
-def cached_dia_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, quant: str | None = None) -> str:
+def cached_dia_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, quant: str | None = None, head_dim: int = 32) -> str:
+    """head_dim 64: decoder width 256 -- the smallest shape the persistent decode kernel accepts (whole 256-column k-slices, head size 64 / 128)"""
     cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, f"dia_{quant.lower() if quant else ('f16' if f16 else 'f32')}_s{seed}.gguf")
+    path = os.path.join(cache_dir, f"dia_{quant.lower() if quant else ('f16' if f16 else 'f32')}{'' if head_dim == 32 else f'_hd{head_dim}'}_s{seed}.gguf")
     if not os.path.exists(path):
         tmp = f"{path}.{os.getpid()}.tmp"
-        write_dia_gguf(tmp, seed=seed, f16=f16, quant=quant)
+        write_dia_gguf(tmp, seed=seed, f16=f16, quant=quant, head_dim=head_dim)
         os.replace(tmp, path)
     return path
 
