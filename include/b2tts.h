@@ -181,7 +181,10 @@ float b2tts_snac_last_ms(const b2tts_snac * m);   /* device time of the last dec
 int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Orpheus autoregressive decode, launch-per-op path: batched GEMVs over F32 (the reference's only Orpheus dtype), F16 or Q4_0 / Q5_0 / Q8_0 matrices,
+ * Orpheus autoregressive decode.  Two paths behind the same calls: F16 GGUFs, greedy, <= 16 sequences, hidden <= 3 072 run decode steps 1 .. n-1 inside
+ * the PERSISTENT DECODE KERNEL (csrc/pdk.cuh: RMSNorm folded into the staging, NeoX RoPE + cache append and SwiGLU in the GEMV epilogues, paged fp16 GQA cache, chunked
+ * argmax; on a B200 the reference's tokens over 72 steps, logits 7.5e-3; Orpheus-3B shape 3.3-5.0 ms per step at 1-16 sequences); everything else runs the launch-per-op
+ * path: batched GEMVs over F32 (the reference's only Orpheus dtype), F16 or Q4_0 / Q5_0 / Q8_0 matrices,
  * compact GQA KV cache, device argmax / sampler / stop rule, CUDA-graph replay of a decode step.  Hardware status (B200, tests/test_orpheus_gpu.py, all green): F32 -- the
  * reference's token ids exactly, logits 5e-6, plain and fp32-faithful tensor-core (B2TTS_AR_MMA=1) variants; F16 / Q8_0 -- no reference output exists (its runtime is
  * F32-only), they track the reference's F32 run within the storage format's noise (4e-4 / 1.7e-2 of the logit std, same greedy tokens).  Orpheus-3B-shaped q8_0
@@ -259,7 +262,10 @@ size_t b2tts_parler_step_weight_bytes(const b2tts_parler * m);
 void  b2tts_parler_pdk_stats(const b2tts_parler * m, uint64_t * launches, uint64_t * steps);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Dia autoregressive decode, launch-per-op path (tensor-core GEMV for F16 matrices, CUDA-graph replay).  Hardware status (B200,
+ * Dia autoregressive decode.  The encoder pass runs launch per op; for F16 GGUFs (greedy / teacher-forced, <= 8 utterances) the whole CFG decoder loop
+ * runs inside the PERSISTENT DECODE KERNEL (csrc/pdk.cuh: delay pattern + check_stopping in the rows phase, RoPE'd self / cross queries, fp32 GQA pages, cross-attention
+ * over each row's encoding, cfg_scale + argmax phase; Dia-1.6B shape on a B200: 4.4 ms per step against 9.6 on the launch-per-op path); other dtypes / sampling use the
+ * launch-per-op path (tensor-core GEMV for F16 matrices, CUDA-graph replay).  Hardware status (B200,
  * tests/test_dia_gpu.py, all green): F32 -- the reference's token ids exactly, CFG-combined logits 3.5e-3 at a logit std of 13, check_stopping's 63-frame run; F16
  * (BASELINE config 4's dtype) -- teacher-forced logits within 0.15 RMS and identical tokens wherever the reference's top-2 gap exceeds twice the step's logit
  * difference (the one free-running difference on a B200 sits on a 0.099 gap: rounding-boundary noise x the CFG gain, see the test's header); Q8_0 teacher-forced.

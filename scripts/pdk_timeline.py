@@ -1,6 +1,6 @@
 """scripts/pdk_timeline.py -- where one decode step of the persistent kernel spends its time: run Parler-Mini F16 (BASELINE config 3 shape, batch 16) for N steps with
 B2TTS_PDK_PROF=<step> and summarise the %globaltimer timeline (every op x every CTA: op begin, activations staged, barrier entered, barrier left).
-    python scripts/pdk_timeline.py [steps=480] [prof_step=450] [parler|orpheus] [batch=16] > profiles/r2x_pdk_timeline.txt"""
+    python scripts/pdk_timeline.py [steps=480] [prof_step=450] [parler|orpheus|dia] [batch=16] > profiles/r2x_pdk_timeline.txt"""
 import os
 import struct
 import sys
@@ -24,6 +24,11 @@ def main():
         from tts_cpp_b200.synth import build_orpheus_direct
         par = build_orpheus_direct(Context(0), dtype="f16")
         prompts = [rng.integers(1, 100000, size=40).astype(np.uint32) for _ in range(batch)]
+    elif model == "dia":                                   # BASELINE config 4's model shape, F16, `batch` utterances (each a CFG row pair)
+        from tts_cpp_b200.binding import Context
+        from tts_cpp_b200.synth import build_dia_direct
+        par = build_dia_direct(Context(0), dtype="f16")
+        prompts = [np.concatenate([[1], rng.integers(32, 127, size=62), [2], rng.integers(32, 127, size=64)]).astype(np.uint32) for _ in range(batch)]
     else:
         from tts_cpp_b200.binding import parler_runner_from_file
         from tts_cpp_b200.synth import PARLER_MINI_SHAPE, cached_parler_gguf
@@ -31,7 +36,7 @@ def main():
         prompts = [rng.integers(1, 500, size=24).astype(np.uint32) for _ in range(batch)]
     par.generate_greedy(prompts, 40)                       # warm-up
     par.generate_greedy(prompts, steps)
-    print(f"# {'Orpheus-3B-shaped' if model == 'orpheus' else 'Parler-Mini'} F16, batch {batch}, {steps} steps: {par.last_ms() / steps:.4f} ms per step (incl. the prompt pass); timeline of step {pstep}; switches "
+    print(f"# { {'orpheus': 'Orpheus-3B-shaped', 'dia': 'Dia-1.6B-shaped'}.get(model, 'Parler-Mini') } F16, batch {batch}, {steps} steps: {par.last_ms() / steps:.4f} ms per step (incl. the prompt pass); timeline of step {pstep}; switches "
           f"{ {k: os.environ.get(k) for k in ('B2TTS_KV', 'B2TTS_PDK_GRID')} }")
     raw = open(pf, "rb").read()
     n_ops, G, W, ps = struct.unpack("iiii", raw[:16])

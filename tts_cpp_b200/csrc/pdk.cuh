@@ -519,20 +519,24 @@ __device__ __forceinline__ void pk_epilogue_pair(const PkParams & P, const PkOp 
 // ---- one tile: this warp's k-slice (ks halves) of 8 output rows against the staged activation rows.  Fragments: 16 bytes per lane of the weight row g = lane / 4 and of
 // the activation rows g, g + 8 feed two m16n8k16 MMAs (see gemv_mma_body in ar_kernels.cuh for the layout argument).
 // plain: the two MMAs of a 32-column step go to two accumulators (half the dependent chain), added when the unit is done
+// HI = false: at most 8 activation rows (rows 8 .. 15 of the M = 16 operand are zero): their fragments are not loaded -- a third less shared-memory traffic per tile
+template <bool HI>
 __device__ __forceinline__ void pk_mma_plain(float * cA, float * cB, const __half * wt, const __half * xa, const __half * xb, int ks) {
 #pragma unroll 4
     for (int k = 0; k < ks; k += 32) {
-        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = pk_lds128(xb + k);
+        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = HI ? pk_lds128(xb + k) : make_uint4(0u, 0u, 0u, 0u);
         const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
         mma16816_f16f32(cA, f0, wv.x, wv.y);
         mma16816_f16f32(cB, f1, wv.z, wv.w);
     }
 }
 // split matrices (W = hi + lo / 2^11, x = xh + xl / 2^11), high plane: c += xh.Wh, cl += xl.Wh; the low plane's cl += xh.Wl goes through pk_mma_one
+template <bool HI>
 __device__ __forceinline__ void pk_mma_split_hi(float * c, float * cl, const __half * wt, const __half * xa, const __half * xb, const __half * xla, const __half * xlb, int ks) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 2
     for (int k = 0; k < ks; k += 32) {
-        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = pk_lds128(xb + k), la = pk_lds128(xla + k), lb = pk_lds128(xlb + k);
+        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = HI ? pk_lds128(xb + k) : z, la = pk_lds128(xla + k), lb = HI ? pk_lds128(xlb + k) : z;
         const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w}, l0[4] = {la.x, lb.x, la.y, lb.y}, l1[4] = {la.z, lb.z, la.w, lb.w};
         mma16816_f16f32(c, f0, wv.x, wv.y);
         mma16816_f16f32(cl, l0, wv.x, wv.y);
@@ -540,10 +544,11 @@ __device__ __forceinline__ void pk_mma_split_hi(float * c, float * cl, const __h
         mma16816_f16f32(cl, l1, wv.z, wv.w);
     }
 }
+template <bool HI>
 __device__ __forceinline__ void pk_mma_one(float * c, const __half * wt, const __half * xa, const __half * xb, int ks) {
 #pragma unroll 4
     for (int k = 0; k < ks; k += 32) {
-        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = pk_lds128(xb + k);
+        const uint4 wv = pk_lds128(wt + k), a = pk_lds128(xa + k), b = HI ? pk_lds128(xb + k) : make_uint4(0u, 0u, 0u, 0u);
         const unsigned f0[4] = {a.x, b.x, a.y, b.y}, f1[4] = {a.z, b.z, a.w, b.w};
         mma16816_f16f32(c, f0, wv.x, wv.y);
         mma16816_f16f32(c, f1, wv.z, wv.w);
@@ -554,7 +559,7 @@ enum { PKT_PLAIN = 0, PKT_SPLIT = 1, PKT_PAIR = 2 };
 // all tiles of one unit within the staged activation chunk of kAn columns.  c / cl: PLAIN two partial accumulators of the same sums; SPLIT main and cross terms; PAIR the
 // unit's primary and partner tile.  Two tiles are worked on at a time (PLAIN: two consecutive k tiles; SPLIT / PAIR: the two tiles of one k tile): with 2 consumer
 // warps per scheduler a single tile's chain of shared-memory loads and dependent MMAs left the tensor pipe idle most of the time (issue slots 22 % busy, ncu r2h).
-template <int MODE>
+template <int MODE, bool HI>
 __device__ __forceinline__ void pk_unit_tiles(float * c, float * cl, unsigned char * ring, const __half * sA, const __half * sAl, int pitch, PkBar * full, PkBar * empty, PkRingPos & rp, int S, int kAn, unsigned long long * pr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t8 = (lane & 3) * 8;
     auto wait_full = [&](const PkRingPos & q) {
@@ -572,8 +577,8 @@ __device__ __forceinline__ void pk_unit_tiles(float * c, float * cl, unsigned ch
             const PkRingPos q1 = rp; pk_ring_next(rp, S);
             const __half * xa0 = sA + (size_t) g * pitch + kt0 + warp * ks0 + t8, * xa1 = sA + (size_t) g * pitch + kt0 + PK_TK + warp * ks1 + t8;
             wait_full(q0); wait_full(q1);
-            pk_mma_plain(c, cl, wtile(q0, ks0), xa0, xa0 + (size_t) 8 * pitch, ks0);
-            pk_mma_plain(c2, cl2, wtile(q1, ks1), xa1, xa1 + (size_t) 8 * pitch, ks1);
+            pk_mma_plain<HI>(c, cl, wtile(q0, ks0), xa0, xa0 + (size_t) 8 * pitch, ks0);
+            pk_mma_plain<HI>(c2, cl2, wtile(q1, ks1), xa1, xa1 + (size_t) 8 * pitch, ks1);
             __syncwarp();
             release(q0); release(q1);
         }
@@ -582,7 +587,7 @@ __device__ __forceinline__ void pk_unit_tiles(float * c, float * cl, unsigned ch
             const PkRingPos q0 = rp; pk_ring_next(rp, S);
             const __half * xa = sA + (size_t) g * pitch + kt0 + warp * ks + t8;
             wait_full(q0);
-            pk_mma_plain(c, cl, wtile(q0, ks), xa, xa + (size_t) 8 * pitch, ks);
+            pk_mma_plain<HI>(c, cl, wtile(q0, ks), xa, xa + (size_t) 8 * pitch, ks);
             __syncwarp();
             release(q0);
         }
@@ -595,8 +600,8 @@ __device__ __forceinline__ void pk_unit_tiles(float * c, float * cl, unsigned ch
             const PkRingPos q1 = rp; pk_ring_next(rp, S);
             const __half * xa = sA + (size_t) g * pitch + ko, * xb = xa + (size_t) 8 * pitch;
             wait_full(q0); wait_full(q1);
-            if (MODE == PKT_PAIR) { pk_mma_one(c, wtile(q0, ks), xa, xb, ks); pk_mma_one(cl, wtile(q1, ks), xa, xb, ks); }
-            else { pk_mma_split_hi(c, cl, wtile(q0, ks), xa, xb, sAl + (size_t) g * pitch + ko, sAl + (size_t) (g + 8) * pitch + ko, ks); pk_mma_one(cl, wtile(q1, ks), xa, xb, ks); }
+            if (MODE == PKT_PAIR) { pk_mma_one<HI>(c, wtile(q0, ks), xa, xb, ks); pk_mma_one<HI>(cl, wtile(q1, ks), xa, xb, ks); }
+            else { pk_mma_split_hi<HI>(c, cl, wtile(q0, ks), xa, xb, sAl + (size_t) g * pitch + ko, sAl + (size_t) (g + 8) * pitch + ko, ks); pk_mma_one<HI>(cl, wtile(q1, ks), xa, xb, ks); }
             __syncwarp();
             release(q0); release(q1);
         }
@@ -689,6 +694,7 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
         return (r < R && n < sg.N) ? __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n) : 0.f;
     };
     unsigned rb = 0;
+    const bool hi = R > 8;                                     // rows 8 .. 15 of the MMA's M = 16 exist
     if (nA == 1) {                                             // the whole k extent staged at once: units one after the other
         const int kAn = stage(0);
         for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
@@ -698,9 +704,15 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
             const float resv = res_of(sg, n0);
             float c[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
             const int mode = sg.pair != PKP_NONE ? PKT_PAIR : (split ? PKT_SPLIT : PKT_PLAIN);
-            if (mode == PKT_PAIR) pk_unit_tiles<PKT_PAIR>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
-            else if (mode == PKT_SPLIT) pk_unit_tiles<PKT_SPLIT>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
-            else pk_unit_tiles<PKT_PLAIN>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+            if (hi) {
+                if (mode == PKT_PAIR) pk_unit_tiles<PKT_PAIR, true>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                else if (mode == PKT_SPLIT) pk_unit_tiles<PKT_SPLIT, true>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                else pk_unit_tiles<PKT_PLAIN, true>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+            } else {
+                if (mode == PKT_PAIR) pk_unit_tiles<PKT_PAIR, false>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                else if (mode == PKT_SPLIT) pk_unit_tiles<PKT_SPLIT, false>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                else pk_unit_tiles<PKT_PLAIN, false>(c, cl, ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+            }
             pk_unit_finish<KVT>(P, op, sg, c, cl, mode, red, rb, n0, n1, resv, step_abs, skv);
         }
     } else {                                                   // several k chunks (down projections): at most 3 units per CTA (host-checked), their accumulators live across the chunks
@@ -717,8 +729,9 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
                     const PkSeg & sg = seg_of(u);
                     const int n0 = (u - sg.unit0) * 8;          // (paired units only in single-chunk phases: host-checked)
                     const float resv = a + 1 == nA ? res_of(sg, n0) : 0.f;
-                    if (split) pk_unit_tiles<PKT_SPLIT>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
-                    else pk_unit_tiles<PKT_PLAIN>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                    if (split) pk_unit_tiles<PKT_SPLIT, true>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                    else if (hi) pk_unit_tiles<PKT_PLAIN, true>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
+                    else pk_unit_tiles<PKT_PLAIN, false>(acc[ui], accl[ui], ring, sA, sAl, pitch, full, empty, rp, S, kAn, pr);
                     if (a + 1 == nA) pk_unit_finish<KVT>(P, op, sg, acc[ui], accl[ui], split ? PKT_SPLIT : PKT_PLAIN, red, rb, n0, n0, resv, step_abs, skv);
                 }
             }
