@@ -575,7 +575,7 @@ def test_persistent_decode_kernel_emulated_multi_tile_units(tmp_path):
         assert upto >= 4
 
 
-@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "3"}, {"B2TTS_PDK_GRID": "6", "B2EMU_REVERSE": "1"}], ids=["grid3", "grid6_reverse"])
+@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "3", "B2TTS_PDK_TSPLIT": "1"}, {"B2TTS_PDK_GRID": "6", "B2EMU_REVERSE": "1", "B2TTS_PDK_TSPLIT": "3"}], ids=["grid3", "grid6_reverse_split_attention"])
 def test_persistent_decode_kernel_emulated_dia(tmp_path, env):
     """Dia (encoder per op, then the whole CFG decoder loop inside the persistent kernel: delay pattern + end-of-stream injection in the rows phase, RoPE'd self and cross
     queries, GQA self-attention over the pages, cross-attention over each row's own encoding, SwiGLU, cfg_scale + argmax) against the reference's F16 run

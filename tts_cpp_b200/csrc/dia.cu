@@ -239,7 +239,9 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
     for (const DiaDecLayer & L : dec) for (const ArW * w : {&L.sq, &L.sk, &L.sv, &L.so, &L.cq, &L.co, &L.gate, &L.up, &L.down}) use_pdk = use_pdk && w->f16 && !w->qtype;
     const int pk_max_pages = cdiv(Tmax, PK_PAGE);
     const size_t pk_layer_bytes = (size_t) S2 * pk_max_pages * 2 * KVD * PK_PAGE * (kv_f32 ? 4 : 2);
-    const size_t pk_need = use_pdk ? (size_t) dec_layers * pk_layer_bytes + (size_t) S2 * pk_max_pages * 4 + (size_t) (8 * dec_layers + 8) * sizeof(PkOp) + 8192 + (size_t) PK_REP * 16 * ((size_t) 8 * D + 2 * ffn) + 4096 +
+    // few (row, head) items and long contexts (the 1 024-position encodings): every attention item is cut into position chunks spread over the idle CTAs, then combined
+    const int pk_tsplit = [&] { const char * e = getenv("B2TTS_PDK_TSPLIT"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : std::max(1, std::min(8, 2 * pk_grid / std::max(1, S2 * heads))); }();
+    const size_t pk_need = use_pdk ? (size_t) dec_layers * pk_layer_bytes + (size_t) S2 * pk_max_pages * 4 + (size_t) (10 * dec_layers + 8) * sizeof(PkOp) + 8192 + (size_t) S2 * heads * pk_tsplit * (head_dim + 4) * 4 + (size_t) PK_REP * 16 * ((size_t) 8 * D + 2 * ffn) + 4096 +
                                      (size_t) 16 * head_dim * 4 + (out_logits ? (size_t) n_steps * B * NV * 4 : 0) : 0;
     const size_t enc_ws = (size_t) RE * ((size_t) 3 * EH + 4 * EI + 2 * enc_ffn) * 4;
     const size_t cross = (size_t) 2 * dec_layers * RE * D * 4;
@@ -387,7 +389,8 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         const float scale = 1.0f;
         unsigned char * pool = (unsigned char *) arena.alloc((size_t) dec_layers * pk_layer_bytes);
         int * page_table = Fw.al<int>((size_t) S2 * pk_max_pages), * first_pos = Fw.al<int>(16);
-        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (8 * dec_layers + 8) * sizeof(PkOp));
+        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (10 * dec_layers + 8) * sizeof(PkOp));
+        float * att_part = pk_tsplit > 1 ? Fw.al<float>((size_t) S2 * heads * pk_tsplit * (head_dim + 4)) : nullptr;
         unsigned * d_bar = (unsigned *) arena.alloc(256);
         float * logits_all = out_logits ? Fw.al<float>((size_t) n_steps * B * NV) : nullptr;
         const size_t xrep = (size_t) 16 * D, grep = (size_t) 16 * ffn;
@@ -410,7 +413,9 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         auto attn_op = [&](int layer, const float * ckp, const float * cvp) {
             PkOp op; memset(&op, 0, sizeof op);
             op.kind = PK_ATTN; op.layer = layer; op.q = q; op.out16 = att16; op.orep = xrep; op.scale = scale; op.ck = ckp; op.cv = cvp; op.cross = ckp ? 1 : 0; op.cross_len = C; op.cross_row_stride = ckp ? (size_t) C * D : 0;
+            op.tsplit = pk_tsplit;
             ops.push_back(op);
+            if (pk_tsplit > 1) { op.kind = PK_ATTNC; ops.push_back(op); }
         };
         { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ROWS; ops.push_back(op); }
         const int kv_heads = heads / rep, rope_units_q = heads * (head_dim / 16), rope_units_k = kv_heads * (head_dim / 16);
@@ -445,7 +450,7 @@ int Dia::generate(int B, const uint32_t * const * prompts, const int32_t * n_pro
         PkParams Pk; memset(&Pk, 0, sizeof Pk);
         Pk.ops = d_ops; Pk.n_ops = (int) ops.size(); Pk.R = S2; Pk.H = D; Pk.heads = heads; Pk.kv_heads = kv_heads; Pk.hd = head_dim; Pk.n_out = n_out; Pk.vocab = vocab;
         Pk.model = PKM_DIA; Pk.ak = pk_ak; Pk.pos_off = 0; Pk.n_steps_total = n_steps;
-        Pk.rope_cs = rope_cs; Pk.theta_scale = theta_scale; Pk.pad = pad; Pk.max_delay = max_delay; Pk.cfg = cfg; Pk.delay = delay; Pk.logits_cfg = logits;
+        Pk.rope_cs = rope_cs; Pk.theta_scale = theta_scale; Pk.pad = pad; Pk.max_delay = max_delay; Pk.cfg = cfg; Pk.delay = delay; Pk.logits_cfg = logits; Pk.att_part = att_part;
         Pk.bar = d_bar; Pk.d_step = d_step; Pk.first_pos = first_pos; Pk.d_out = d_out; Pk.d_teacher = d_teacher; Pk.bos = bos; Pk.eos = eos; Pk.max_gen = max_gen; Pk.stopped = stopped; Pk.ids = ids; Pk.row_pos = row_pos;
         Pk.tables = tables; Pk.tab_stride = (size_t) vocab * D; Pk.x0 = px; Pk.x0rep = xrep;
         Pk.kv_pool = pool; Pk.kv_layer_bytes = pk_layer_bytes; Pk.page_table = page_table; Pk.max_pages = pk_max_pages;

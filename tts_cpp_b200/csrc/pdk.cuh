@@ -50,7 +50,7 @@ constexpr int PK_REP = 8;                         // copies of every activation 
                                                   // same 64 KB right after a grid barrier wait ~2 us (each line is served to 148 requesters one after the other); with 8 copies
                                                   // (8x the tiny epilogue stores) a line has 18-19 requesters
 
-enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3 };
+enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3, PK_ATTNC = 4 };      // PK_ATTNC: combine the position chunks of a split attention phase
 enum { PKN_NONE = 0, PKN_LAYER = 1, PKN_RMS = 2 };
 enum { PKE_STORE = 0, PKE_RES = 1, PKE_GELU = 2, PKE_KV = 3, PKE_LOGITS = 4, PKE_ROPE_Q = 5, PKE_ROPE_K = 6, PKE_SWIGLU = 7 };
 enum { PKP_NONE = 0, PKP_ROPE = 1, PKP_SWIGLU = 2 };      // paired units: two tiles per k-tile (the two NeoX halves of a head's rows; the gate and the up rows of the same columns), one joint epilogue
@@ -72,7 +72,7 @@ struct alignas(16) PkOp {
     size_t xrep;                                  // != 0: X / X16 exist in PK_REP copies this many elements apart
     const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; PkSeg seg[3];      // kv_prefetch: L2-prefetch this layer's K / V rows first
     // PK_ATTN: cross != 0 -> every row attends to the flat fp32 store ck / cv [cross_len][H]; else to its sequence's pages, positions [0, row_pos[r]]
-    const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale; size_t cross_row_stride;      // cross_row_stride: elements between the stores of consecutive rows (Dia: one encoding per sequence; 0: all rows share one)      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
+    const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale; size_t cross_row_stride; int tsplit;      // tsplit > 1: every (row, head) item is cut into tsplit position chunks (few items, long contexts), combined by a PK_ATTNC op      // cross_row_stride: elements between the stores of consecutive rows (Dia: one encoding per sequence; 0: all rows share one)      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
 };
 struct PkParams {
     const PkOp * ops; int n_ops;
@@ -84,7 +84,8 @@ struct PkParams {
     float * amax_v; int * amax_i; int amax_ch;
     // PKM_DIA (reference src/models/dia/model.cpp:806-858): rows 2u (conditional) and 2u + 1 (unconditional) of utterance u share the step's ids; check_stopping's
     // end-of-stream countdown `delay` [R / 2]; logits [R][n_out * vocab] per row, combined by cfg_scale (src/util.cpp:175-200) into logits_cfg [R / 2][n_out * vocab]
-    int pad, max_delay; float cfg; int * delay; float * logits_cfg;    // PKM_ORPHEUS argmax over a 150k vocabulary: amax_ch partial (value, index) pairs per row, combined by the row's next rows phase
+    int pad, max_delay; float cfg; int * delay; float * logits_cfg;
+    float * att_part;                             // split attention: per (row, head, chunk) hd + 4 floats: max, sum of exps, (pad), unnormalised P.V    // PKM_ORPHEUS argmax over a 150k vocabulary: amax_ch partial (value, index) pairs per row, combined by the row's next rows phase
     int n_stages, a_bytes;                        // shared-memory layout: ring stages, bytes of the activation / attention-scratch region
     unsigned * bar;                               // grid-barrier arrival counter, zeroed before every launch
     int * d_step; int step_begin, n_steps;        // steps [step_begin, step_begin + n_steps) run in this launch
@@ -774,7 +775,7 @@ static inline size_t pk_att_bytes(int T) { return (size_t) (PK_ATT_HDR + 1024) *
 // (Tried: one item per kv head with its 3 query heads sharing the K / V loads -- 2.6x slower per item, the scores / P.V arithmetic of three heads per thread is not
 // free at 128 threads; r2g timeline.)
 template <typename KVT, typename CT, int HD>
-__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int kh, int T, const int * spt) {
+__device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int kh, int t0, int T, float * chunk, const int * spt) {      // positions [t0, T); chunk != null: one position chunk of a split item
     typedef typename PkRawOf<CT>::type Raw;
     constexpr int U = PkAttU<CT>::v, PARTS = HD / 8, KPP = 128 / PARTS;
     const int gt = threadIdx.x & 127, gw = gt >> 5, H = P.H, part = gt % PARTS, kq = gt / PARTS;
@@ -798,19 +799,19 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
     Raw raw[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {                               // K rows of the first batch: in flight while q arrives
-        const int t = u * KPP + kq;
+        const int t = t0 + u * KPP + kq;
         if (t < T) pk_raw_load(krow0(t, 0), raw[u]); else pk_raw_zero(raw[u]);
     }
     if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
-    if (!op.cross && T > KPP * U) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) pt[i] * page_elems;
+    if (!op.cross && T - t0 > KPP * U) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) pt[i] * page_elems;
     pk_bar_sync(2 + grp, 128);
     float q8[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) q8[i] = qs[part * 8 + i];
     // scores: PARTS threads per key (8 channels each), KPP keys per pass, U passes in flight
     float mloc = -INFINITY;
-    for (int tb = 0; tb < T; tb += KPP * U) {
-        if (tb) {
+    for (int tb = t0; tb < T; tb += KPP * U) {
+        if (tb != t0) {
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int t = tb + u * KPP + kq;
@@ -826,12 +827,12 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
 #pragma unroll
             for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
             a *= op.scale;
-            if (t < T) { if (part == 0) sc[t] = a; mloc = fmaxf(mloc, a); }
+            if (t < T) { if (part == 0) sc[t - t0] = a; mloc = fmaxf(mloc, a); }
         }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {                               // V rows of the first batch: in flight during the softmax reductions
-        const int t = u * KPP + kq;
+        const int t = t0 + u * KPP + kq;
         if (t < T) pk_raw_load(krow0(t, 1), raw[u]); else pk_raw_zero(raw[u]);
     }
 #pragma unroll
@@ -840,18 +841,19 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
     pk_bar_sync(2 + grp, 128);
     const float m = fmaxf(fmaxf(wredf[0], wredf[1]), fmaxf(wredf[2], wredf[3]));
     double sum = 0.0;                                           // ggml_soft_max: expf(s - max), the sum accumulated in double, scale by (float) (1 / sum)
-    for (int t = gt; t < T; t += 128) { const float e = expf(sc[t] - m); sc[t] = e; sum += (double) e; }
+    for (int t = gt; t < T - t0; t += 128) { const float e = expf(sc[t] - m); sc[t] = e; sum += (double) e; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if ((gt & 31) == 0) wredd[gw] = sum;
     pk_bar_sync(2 + grp, 128);
-    const float inv = (float) (1.0 / (((wredd[0] + wredd[1]) + wredd[2]) + wredd[3]));
+    const double total = ((wredd[0] + wredd[1]) + wredd[2]) + wredd[3];
+    const float inv = chunk ? 1.0f : (float) (1.0 / total);      // a chunk keeps its exps unnormalised: pk_attn_combine divides by the sum over all chunks
     // P.V: thread (slice kq, part) walks positions kq, kq + KPP, ... for its 8 channels with p = e * inv; slices summed in order afterwards
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    for (int tb = 0; tb < T; tb += KPP * U) {
-        if (tb) {
+    for (int tb = t0; tb < T; tb += KPP * U) {
+        if (tb != t0) {
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int t = tb + u * KPP + kq;
@@ -861,7 +863,7 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int t = tb + u * KPP + kq;
-            const float p = t < T ? sc[t] * inv : 0.f;
+            const float p = t < T ? sc[t - t0] * inv : 0.f;
             float v8[8];
             pk_raw_f(raw[u], v8);
 #pragma unroll
@@ -875,8 +877,13 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
         float a = 0.f;
 #pragma unroll 8
         for (int sl = 0; sl < KPP; sl++) a += pvs[(size_t) sl * HD + gt];
-        const __half hv = __float2half_rn(a);
-        for (int c = 0; c < (op.orep ? PK_REP : 1); c++) op.out16[op.orep * c + (size_t) r * H + (size_t) h * HD + gt] = hv;
+        if (chunk) {
+            chunk[4 + gt] = a;
+            if (gt == 0) { chunk[0] = m; chunk[1] = (float) total; }
+        } else {
+            const __half hv = __float2half_rn(a);
+            for (int c = 0; c < (op.orep ? PK_REP : 1); c++) op.out16[op.orep * c + (size_t) r * H + (size_t) h * HD + gt] = hv;
+        }
     }
     pk_bar_sync(2 + grp, 128);                                  // the scratch is free for the group's next item
 }
@@ -885,11 +892,44 @@ template <typename KVT, int HD>
 __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, unsigned char * scratch, int step, const int * sfp, const int * spt) {
     const int grp = threadIdx.x >> 7;
     float * base = reinterpret_cast<float *>(scratch + (size_t) grp * (P.a_bytes / 2));
-    const int rep = P.heads / P.kv_heads;
-    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads; it += 2 * (int) gridDim.x) {
-        const int r = it / P.heads, h = it - r * P.heads;
-        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, op.cross_len, spt);
-        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, h / rep, sfp[r] + step - P.pos_off + 1, spt);
+    const int rep = P.heads / P.kv_heads, ns = op.tsplit > 1 ? op.tsplit : 1;
+    for (int it = (int) blockIdx.x * 2 + grp; it < P.R * P.heads * ns; it += 2 * (int) gridDim.x) {
+        const int item = it / ns, c = it - item * ns, r = item / P.heads, h = item - r * P.heads;
+        const int T = op.cross ? op.cross_len : sfp[r] + step - P.pos_off + 1;
+        int t0 = 0, t1 = T;
+        float * part = nullptr;
+        if (ns > 1) {                                           // chunk c of the item's positions, in whole pages
+            const int per = (((T + ns - 1) / ns) + PK_PAGE - 1) & ~(PK_PAGE - 1);
+            t0 = c * per; t1 = t0 + per < T ? t0 + per : T;
+            part = P.att_part + ((size_t) item * ns + c) * (HD + 4);
+            if (t0 >= T) { if ((threadIdx.x & 127) == 0) { part[0] = -INFINITY; part[1] = 0.f; } continue; }      // an empty chunk (short context): weight 0 in the combination
+        }
+        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, t0, t1, part, spt);
+        else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, h / rep, t0, t1, part, spt);
+    }
+}
+
+// the chunks of a split attention phase combined: out = sum_c w_c acc_c / sum_c w_c sum_c with w_c = exp(max_c - max) -- the reference's softmax(max, expf, double sum)
+// followed by P.V, evaluated chunk by chunk
+template <int HD>
+__device__ __forceinline__ void pk_attn_combine(const PkParams & P, const PkOp & op) {
+    const int grp = threadIdx.x >> 7, gt = threadIdx.x & 127, ns = op.tsplit, H = P.H;
+    for (int item = (int) blockIdx.x * 2 + grp; item < P.R * P.heads; item += 2 * (int) gridDim.x) {
+        const int r = item / P.heads, h = item - r * P.heads;
+        const float * part = P.att_part + (size_t) item * ns * (HD + 4);
+        float M = -INFINITY;
+        for (int c = 0; c < ns; c++) M = fmaxf(M, __ldcg(part + (size_t) c * (HD + 4)));
+        double den = 0.0; float a = 0.f;
+        for (int c = 0; c < ns; c++) {
+            const float * pc = part + (size_t) c * (HD + 4);
+            const float mc = __ldcg(pc), w = mc == -INFINITY ? 0.f : expf(mc - M);
+            den += (double) (w * __ldcg(pc + 1));
+            if (gt < HD && w != 0.f) a = fmaf(w, __ldcg(pc + 4 + gt), a);
+        }
+        if (gt < HD) {
+            const __half hv = __float2half_rn(a * (float) (1.0 / den));
+            for (int cp = 0; cp < (op.orep ? PK_REP : 1); cp++) op.out16[op.orep * cp + (size_t) r * H + (size_t) h * HD + gt] = hv;
+        }
     }
 }
 
@@ -1156,6 +1196,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
                 case PK_ROWS:   if (P.model == PKM_ORPHEUS) pk_rows_orpheus(P, step, st == 0, red); else if (P.model == PKM_DIA) pk_rows_dia(P, step, sids); else pk_rows(P, step, sids); break;
                 case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, rp, step, pr, skv, sfp, spt); break;
                 case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
+                case PK_ATTNC:  pk_attn_combine<HD>(P, op); break;
                 case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else if (P.model == PKM_DIA) pk_argmax_dia(P, step, red); else pk_argmax(P, step, red); break;
             }
             if (pr) pr[2] = pk_now();
