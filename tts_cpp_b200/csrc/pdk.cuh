@@ -770,8 +770,8 @@ static inline size_t pk_att_bytes(int T) { return (size_t) (PK_ATT_HDR + 1024) *
 // One item = one (row, query head); kh = the kv head it reads (the reference's repeat-interleaved GQA cache, orpheus model.cpp:196-228, by indexing).
 // HD = head size (compile time: the per-key reduction over the HD / 8 threads of a key is three unrolled shuffles that the scheduler interleaves across the keys in
 // flight; with a run-time head size it was a serial loop per key -- 20 % of the kernel's issue slots on a B200).
-// The item is a chain of L2 round trips (q row written by the previous phase, K rows, V rows: ~1-2 us each on a B200), so the loads are issued as early as their
-// addresses are known: the first batch of K rows before q (they do not depend on it), the first batch of V rows before the softmax reductions.
+// (Tried: the first batch of K rows issued before q arrives and the first batch of V rows before the softmax reductions, to overlap the item's chain of L2 round trips:
+// the load registers then live across the block barriers and the item became 1.5-2x slower -- r2h / r2k2 timelines.)
 // (Tried: one item per kv head with its 3 query heads sharing the K / V loads -- 2.6x slower per item, the scores / P.V arithmetic of three heads per thread is not
 // free at 128 threads; r2g timeline.)
 template <typename KVT, typename CT, int HD>
@@ -788,22 +788,12 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
     const CT * pool_k = reinterpret_cast<const CT *>(P.kv_pool + (size_t) op.layer * P.kv_layer_bytes) + (size_t) kh * PK_PAGE * HD + part * 8;
     const CT * pool_v = pool_k + (size_t) P.kv_heads * PK_PAGE * HD;
     const int * pt = spt + r * P.max_pages;
-    auto krow0 = [&](int t, int kv) -> const CT * {             // first batch: page offsets straight from the page table (the spo scratch is not written yet)
-        if (op.cross) return (kv ? flat_v : flat_k) + (size_t) t * H;
-        return (kv ? pool_v : pool_k) + (size_t) pt[t >> 5] * page_elems + (t & (PK_PAGE - 1)) * HD;
-    };
     auto krow = [&](int t, int kv) -> const CT * {
         if (op.cross) return (kv ? flat_v : flat_k) + (size_t) t * H;
         return (kv ? pool_v : pool_k) + spo[t >> 5] + (t & (PK_PAGE - 1)) * HD;
     };
-    Raw raw[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {                               // K rows of the first batch: in flight while q arrives
-        const int t = t0 + u * KPP + kq;
-        if (t < T) pk_raw_load(krow0(t, 0), raw[u]); else pk_raw_zero(raw[u]);
-    }
     if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
-    if (!op.cross && T - t0 > KPP * U) for (int i = gt; i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) pt[i] * page_elems;
+    if (!op.cross) for (int i = gt + (t0 >> 5); i * PK_PAGE < T; i += 128) spo[i] = (unsigned long long) pt[i] * page_elems;
     pk_bar_sync(2 + grp, 128);
     float q8[8];
 #pragma unroll
@@ -811,12 +801,11 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
     // scores: PARTS threads per key (8 channels each), KPP keys per pass, U passes in flight
     float mloc = -INFINITY;
     for (int tb = t0; tb < T; tb += KPP * U) {
-        if (tb != t0) {
+        Raw raw[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int t = tb + u * KPP + kq;
-                if (t < T) pk_raw_load(krow(t, 0), raw[u]); else pk_raw_zero(raw[u]);
-            }
+        for (int u = 0; u < U; u++) {
+            const int t = tb + u * KPP + kq;
+            if (t < T) pk_raw_load(krow(t, 0), raw[u]); else pk_raw_zero(raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -829,11 +818,6 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
             a *= op.scale;
             if (t < T) { if (part == 0) sc[t - t0] = a; mloc = fmaxf(mloc, a); }
         }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {                               // V rows of the first batch: in flight during the softmax reductions
-        const int t = t0 + u * KPP + kq;
-        if (t < T) pk_raw_load(krow0(t, 1), raw[u]); else pk_raw_zero(raw[u]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
@@ -853,12 +837,11 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
     for (int tb = t0; tb < T; tb += KPP * U) {
-        if (tb != t0) {
+        Raw raw[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int t = tb + u * KPP + kq;
-                if (t < T) pk_raw_load(krow(t, 1), raw[u]); else pk_raw_zero(raw[u]);
-            }
+        for (int u = 0; u < U; u++) {
+            const int t = tb + u * KPP + kq;
+            if (t < T) pk_raw_load(krow(t, 1), raw[u]); else pk_raw_zero(raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
