@@ -625,3 +625,33 @@ def test_persistent_decode_kernel_emulated_dia(tmp_path, env):
     dmax0 = float(np.abs(logits[0][keep] - g["logits0"][:len(keep)].reshape(len(keep), -1)).max())
     assert all(g["gap0"][s, h] < 2.0 * dmax0 for s, h in neq if s == first)      # the first difference, if any, is within the F16 floor measured above on the reference's own tokens
     assert first >= 20
+
+
+def test_gguf_reader_rejects_hostile_files(tmp_path):
+    """csrc/gguf_reader.cpp on corrupt / hostile input: counts and string lengths beyond the file, a truncated file, a tensor directory pointing past the
+    end, an impossible shape -- every one must come back as a load error from the reader (exit code 1 of the emulation driver), never a crash or an exception."""
+    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
+    good = open(cached_orpheus_gguf(seed=0), "rb").read()
+    hdr = struct.pack("<II", 0x46554747, 3)
+    cases = {
+        "huge_counts": hdr + struct.pack("<QQ", 1 << 60, 1 << 60) + b"\0" * 64,
+        "huge_tensor_count": hdr + struct.pack("<QQ", 1 << 40, 0) + b"\0" * 64,
+        "huge_string": hdr + struct.pack("<QQ", 0, 1) + struct.pack("<Q", (1 << 64) - 8) + b"x" * 64,
+        "huge_array": hdr + struct.pack("<QQ", 0, 1) + struct.pack("<Q", 1) + b"k" + struct.pack("<IIQ", 9, 4, 1 << 62) + b"\0" * 64,
+        "truncated_directory": good[:len(good) // 200],
+        "truncated_data": good[:len(good) // 10],
+        "too_short": hdr,
+    }
+    # a tensor whose shape overflows: patch the first dimension of the first "orpheus." tensor of the good file
+    at = good.find(b"orpheus.")
+    name_len = struct.unpack("<Q", good[at - 8:at])[0]
+    dims_at = at + name_len + 4
+    cases["impossible_shape"] = good[:dims_at] + struct.pack("<q", -7) + good[dims_at + 8:]
+    pin, pout = str(tmp_path / "p.bin"), str(tmp_path / "o.bin")
+    with open(pin, "wb") as f:
+        f.write(struct.pack("iii", 1, 2, 1)); f.write(struct.pack("I", 5))
+    for tag, blob in cases.items():
+        path = str(tmp_path / f"{tag}.gguf")
+        open(path, "wb").write(blob)
+        r = subprocess.run([exe, "orpheus", path, pin, pout], capture_output=True, text=True, timeout=120, env={**os.environ, **EMU_DEFAULTS})
+        assert r.returncode == 1 and "load:" in r.stderr, (tag, r.returncode, r.stderr[-300:])

@@ -11,6 +11,7 @@
 #include "parler.h"
 #include "dia.h"
 
+#include <exception>
 #include <functional>
 
 #include <cstdio>
@@ -24,17 +25,20 @@
 namespace b2 {
 namespace {
 
+// every length read from the file is checked against the bytes that are left (by subtraction: a huge value cannot wrap a pointer past the check)
 struct Cursor {
     const uint8_t * p; const uint8_t * end; bool ok = true;
+    size_t left() const { return (size_t) (end - p); }
     template <class T> T rd() {
         T v{};
-        if (p + sizeof(T) > end) { ok = false; return v; }
+        if (!ok || sizeof(T) > left()) { ok = false; return v; }
         memcpy(&v, p, sizeof(T)); p += sizeof(T);
         return v;
     }
+    bool skip(size_t n) { if (!ok || n > left()) { ok = false; return false; } p += n; return true; }
     std::string str() {
         uint64_t n = rd<uint64_t>();
-        if (!ok || p + n > end) { ok = false; return std::string(); }
+        if (!ok || n > (uint64_t) left()) { ok = false; return std::string(); }
         std::string s((const char *) p, (size_t) n); p += n;
         return s;
     }
@@ -55,18 +59,19 @@ bool read_value(Cursor & c, uint32_t t, uint32_t * u32_out, std::string * str_ou
     if (t == 8) { std::string s = c.str(); if (str_out) *str_out = s; return c.ok; }
     if (t == 9) {
         uint32_t et = c.rd<uint32_t>(); uint64_t n = c.rd<uint64_t>();
-        for (uint64_t i = 0; i < n && c.ok; i++) {
-            if (et == 8) { std::string s = c.str(); if (arr_out) arr_out->push_back(s); }
-            else { size_t sz = scalar_size(et); if (!sz) return false; c.p += sz; if (c.p > c.end) c.ok = false; }
+        if (et != 8) {                                            // scalars: one bounds check for the whole array
+            const size_t sz = scalar_size(et);
+            if (!sz || n > (uint64_t) c.left() / sz) { c.ok = false; return false; }
+            return c.skip((size_t) n * sz);
         }
+        if (n > (uint64_t) c.left() / 8) { c.ok = false; return false; }      // every string costs at least its 8-byte length
+        for (uint64_t i = 0; i < n && c.ok; i++) { std::string s = c.str(); if (arr_out && c.ok) arr_out->push_back(s); }
         return c.ok;
     }
     size_t sz = scalar_size(t);
     if (!sz) return false;
     if ((t == 4 || t == 6) && u32_out) { *u32_out = c.rd<uint32_t>(); return c.ok; }   // f32 values are captured as their bit pattern
-    c.p += sz;
-    if (c.p > c.end) c.ok = false;
-    return c.ok;
+    return c.skip(sz);
 }
 
 }  // namespace
@@ -80,18 +85,21 @@ int read_gguf(const char * path, const char * prefix, const char * arch_required
     int fd = open(path, O_RDONLY);
     if (fd < 0) { set_error("cannot open '%s'", path); return 1; }
     struct stat st;
-    fstat(fd, &st);
+    if (fstat(fd, &st) != 0 || st.st_size < 24) { close(fd); set_error("%s: cannot stat, or too short to be a GGUF file", path); return 1; }
     void * map = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (map == MAP_FAILED) { set_error("mmap of '%s' failed", path); return 1; }
     const uint8_t * base = (const uint8_t *) map;
     Cursor c{base, base + st.st_size};
     int rc = 1;
+    try {
     do {
         if (c.rd<uint32_t>() != 0x46554747u) { set_error("%s: not a GGUF file", path); break; }
         uint32_t ver = c.rd<uint32_t>();
         if (ver < 2 || ver > 3) { set_error("%s: unsupported GGUF version %u", path, ver); break; }
         uint64_t n_tensors = c.rd<uint64_t>(), n_kv = c.rd<uint64_t>();
+        // counts from an untrusted header: a key / value record is at least 12 bytes, a tensor record at least 24
+        if (!c.ok || n_kv > (uint64_t) c.left() / 12 || n_tensors > (uint64_t) c.left() / 24) { set_error("%s: corrupt GGUF header (counts exceed the file size)", path); break; }
         uint32_t alignment = 32;
         std::string arch;
         bool bad = false;
@@ -102,6 +110,7 @@ int read_gguf(const char * path, const char * prefix, const char * arch_required
             const bool is_f32 = (t == 6);
             if (!read_value(c, t, &u, &s, nullptr)) { bad = true; break; }
             if (is_u32) { kv[key] = u; if (key == "general.alignment") alignment = u; }
+            if (alignment == 0 || alignment > (1u << 20) || (alignment & (alignment - 1))) { bad = true; break; }
             if (is_f32) kv[key + "#f32"] = u;   // e.g. dia.cfg_scale: the bit pattern of the float under a suffixed key
             if (key == "general.architecture") arch = s;
         }
@@ -115,24 +124,31 @@ int read_gguf(const char * path, const char * prefix, const char * arch_required
             for (int d = 0; d < 4; d++) t.ne[d] = 1;
             for (int d = 0; d < t.nd; d++) t.ne[d] = (int64_t) c.rd<uint64_t>();
             t.type = c.rd<uint32_t>(); t.off = c.rd<uint64_t>();
+            if (!c.ok) break;
         }
         if (bad || !c.ok) { set_error("%s: corrupt GGUF tensor directory", path); break; }
         size_t data0 = (size_t) (c.p - base);
         data0 = (data0 + alignment - 1) / alignment * alignment;
         for (auto & t : tis) {
             if (t.name.rfind(prefix, 0) != 0) continue;
-            int64_t n = 1; for (int d = 0; d < t.nd; d++) n *= t.ne[d];
+            const size_t fsize = (size_t) st.st_size;
+            if (data0 > fsize || t.off > fsize - data0) { set_error("%s: tensor '%s' starts past the end of the file", path, t.name.c_str()); bad = true; break; }
+            const size_t avail = fsize - data0 - (size_t) t.off;
+            int64_t n = 1;                                        // element count with overflow / sign checks: no tensor has more elements than the file has bytes x 2 (Q4_0)
+            for (int d = 0; d < t.nd && !bad; d++) { if (t.ne[d] <= 0 || t.ne[d] > (int64_t) (2 * fsize) || n > (int64_t) (2 * fsize) / t.ne[d]) bad = true; else n *= t.ne[d]; }
+            if (bad) { set_error("%s: tensor '%s' has an impossible shape", path, t.name.c_str()); break; }
             // F32, F16, or 32-value blocks: Q4_0 (18 bytes), Q5_0 (22), Q8_0 (34) -- ggml-common.h; the model decides whether it accepts a quantised tensor
             const size_t blk = t.type == 2 ? 18 : t.type == 6 ? 22 : t.type == 8 ? 34 : 0;
             size_t nbytes = t.type == 0 ? (size_t) n * 4 : t.type == 1 ? (size_t) n * 2 : 0;
             if (blk) { if (t.ne[0] % 32) { set_error("%s: quantised tensor '%s' has a row length that is not a multiple of 32", path, t.name.c_str()); bad = true; break; } nbytes = (size_t) n / 32 * blk; }
             if (!nbytes) { set_error("%s: tensor '%s' has ggml type %u; F32, F16, Q4_0, Q5_0 and Q8_0 are supported", path, t.name.c_str(), t.type); bad = true; break; }
-            if (data0 + t.off + nbytes > (size_t) st.st_size) { set_error("%s: tensor '%s' runs past the end of the file", path, t.name.c_str()); bad = true; break; }
+            if (nbytes > avail) { set_error("%s: tensor '%s' runs past the end of the file", path, t.name.c_str()); bad = true; break; }
             if (on_tensor(t.name.c_str(), (int) t.type, t.nd, t.ne, base + data0 + t.off, nbytes)) { bad = true; break; }
         }
         if (bad) break;
         rc = 0;
     } while (false);
+    } catch (const std::exception & e) { set_error("%s: %s while reading the file", path, e.what()); rc = 1; }      // (bad_alloc on a hostile header: never across the extern "C" boundary)
     munmap(map, (size_t) st.st_size);
     return rc;
 }
