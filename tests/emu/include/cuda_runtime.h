@@ -37,6 +37,7 @@ struct alignas(8) uint2 { unsigned x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorUnknown = 999 };

@@ -655,3 +655,26 @@ def test_gguf_reader_rejects_hostile_files(tmp_path):
         open(path, "wb").write(blob)
         r = subprocess.run([exe, "orpheus", path, pin, pout], capture_output=True, text=True, timeout=120, env={**os.environ, **EMU_DEFAULTS})
         assert r.returncode == 1 and "load:" in r.stderr, (tag, r.returncode, r.stderr[-300:])
+
+
+def test_persistent_decode_kernel_emulated_orpheus_q8_0(tmp_path):
+    """Orpheus with Q8_0 matrices (BASELINE config 5's dtype) through the persistent kernel: activations quantised per 32-block while they are staged (RMSNorm'd fp32 rows
+    and the fp16 hand-offs), int8 MMA per block, fp32 scale products -- ggml_vec_dot_q8_0_q8_0's arithmetic.  No reference output exists for Q8_0 Orpheus (its runtime is
+    F32-only): the yardsticks are the reference's F32 run of the same weights (format noise, as for the launch-per-op Q8_0 path) and the launch-per-op Q8_0 path itself."""
+    g = np.load(os.path.join(GOLD, "orpheus_wide_vectors.npz"))
+    prompts = [g["prompt0"], g["prompt1"]]
+    steps = int(g["tokens0"].size)
+    gguf = cached_orpheus_gguf(seed=0, head_dim=128, quant="Q8_0")
+    tok, logits, err = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, "pk", env={"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "4", "B2TTS_AR_EXIT_EVERY": "2"}, want_stderr=True)
+    tok0, logits0, err0 = _run_ar(tmp_path, "orpheus", gguf, prompts, steps, "op", env={"B2TTS_AR_PDK": "0"}, want_stderr=True)
+    n_pk, n_op = (int(e.split("emulated ")[1].split(" launches")[0]) for e in (err, err0))
+    assert n_pk < n_op - (steps - 2) * 15, (n_pk, n_op)
+    for u in range(2):
+        ref = g[f"logits{u}"].reshape(steps, -1)
+        rel = float(np.sqrt(((logits[u] - ref) ** 2).mean()) / ref.std()), float(np.sqrt(((logits0[u] - ref) ** 2).mean()) / ref.std())
+        top2 = np.sort(ref, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 8.0 * np.abs(logits[u] - ref).max(axis=1)
+        print(f"PARITY(emulated, persistent kernel) orpheus wide Q8_0 prompt {u}: logit rms / std vs the F32 reference {rel[0]:.3e} (launch-per-op Q8_0: {rel[1]:.3e}); "
+              f"tokens equal {int((tok[u, :, 0] == g[f'tokens{u}']).sum())}/{steps}, clear decisions {int(clear.sum())}")
+        assert rel[0] < 0.05 and rel[0] < 1.5 * rel[1] + 1e-3
+        assert np.array_equal(tok[u, :, 0][clear], g[f"tokens{u}"][clear])

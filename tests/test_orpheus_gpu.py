@@ -115,7 +115,8 @@ sys.path.insert(0, sys.argv[1])
 from tts_cpp_b200.binding import orpheus_runner_from_file
 from tts_cpp_b200.synth import cached_orpheus_gguf
 g = np.load(os.path.join(sys.argv[1], "tests", "golden", "orpheus_wide_long_vectors.npz"))
-orph = orpheus_runner_from_file(cached_orpheus_gguf(seed=0, head_dim=128, f16=True))
+q8 = len(sys.argv) > 2 and sys.argv[2] == "q8_0"
+orph = orpheus_runner_from_file(cached_orpheus_gguf(seed=0, head_dim=128, quant="Q8_0") if q8 else cached_orpheus_gguf(seed=0, head_dim=128, f16=True))
 pdk_on = os.environ.get("B2TTS_AR_PDK") != "0"
 prompts = [g["prompt0"], g["prompt1"]]
 steps = int(g["tokens0"].size)
@@ -147,7 +148,7 @@ for u in range(2):
         t2, l2 = orph.generate_greedy([prompt], steps - done, want_logits=True)
         got_t, got_l = t2[0], l2[0]
     print(f"PARITY orpheus wide F16 pdk={int(pdk_on)} prompt {u}: {steps} steps, {anchors} near-tie re-anchorings, max |logit diff| vs the reference's F32 run {worst:.3e}")
-    ok &= worst < 5e-2 and anchors <= 4
+    ok &= worst < (0.8 if q8 else 5e-2) and anchors <= (24 if q8 else 4)      # Q8_0: format noise ~2 % of the logit std (4) on both paths, near-ties are frequent
     single = orph.generate_greedy([prompts[u]], steps)                          # batching does not change a sequence
     ok &= bool(np.array_equal(single[0], toks_b[u]))
 # the stop rule inside the persistent kernel: sequence 0's third token becomes the stopping token
@@ -171,3 +172,11 @@ def test_orpheus_f16_persistent_kernel_tracks_the_reference(variant):
     the same rule; the stop rule; batch invariance."""
     env = {"pdk_f16kv": None, "pdk_f32kv": {"B2TTS_KV": "f32"}, "per_op": {"B2TTS_AR_PDK": "0"}}[variant]
     assert run_snippet(PDK_BODY, [], env=env) == 0
+
+
+@pytest.mark.parametrize("variant", ["pdk", "per_op"])
+def test_orpheus_q8_0_persistent_kernel_tracks_the_reference(variant):
+    """BASELINE config 5's dtype through the persistent decode kernel (int8 MMA over Q8_0-quantised activations: ggml_vec_dot_q8_0_q8_0's arithmetic) and through the
+    launch-per-op dp4a path, 72 greedy steps each against the reference's F32 run of the same weights: logits within the Q8_0 format noise, every differing token a near-tie
+    of the reference (the run is re-anchored on the reference's tokens after each), stop rule, batch invariance."""
+    assert run_snippet(PDK_BODY, ["q8_0"], env=None if variant == "pdk" else {"B2TTS_AR_PDK": "0"}) == 0

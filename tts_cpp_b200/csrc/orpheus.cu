@@ -181,9 +181,11 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     const int pk_grid = [&] { const char * e = getenv("B2TTS_PDK_GRID"); const int v = e ? atoi(e) : 0; return v > 0 && v <= sm_count ? v : sm_count; }();
 #endif
     const int pk_ak = [&] { const char * e = getenv("B2TTS_PDK_AK"); const int v = e ? atoi(e) : 0; return v >= 256 && v % 256 == 0 && v <= PK_AK_MAX && v >= H ? v : (H <= 2048 ? 2048 : PK_AK_MAX); }();
-    bool use_pdk = pdk_env && !samp.do_sample && B <= 16 && n_steps >= 2 && H % 256 == 0 && F % 256 == 0 && H <= pk_ak && (head_dim == 64 || head_dim == 128) && head.f16 && pk_grid > 0 &&
+    bool use_pdk = pdk_env && !samp.do_sample && B <= 16 && n_steps >= 2 && H % 256 == 0 && F % 256 == 0 && H <= pk_ak && (head_dim == 64 || head_dim == 128) && (head.f16 || head.qtype == 8) && pk_grid > 0 &&
                    (F <= pk_ak || cdiv(H / 8, pk_grid) <= 3) && (!out_logits || (size_t) n_steps * B * vocab * 4 <= ((size_t) 1 << 30));
-    for (const OrpheusLayer & L : layers) for (const ArW * w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.wgate, &L.wup, &L.wdown}) use_pdk = use_pdk && w->f16 && !w->qtype;
+    // every matrix F16, or every matrix Q8_0 (BASELINE config 5's dtype: int8 MMA over Q8_0-quantised activations, ggml_vec_dot_q8_0_q8_0's arithmetic)
+    const bool pk_q8 = head.qtype == 8;
+    for (const OrpheusLayer & L : layers) for (const ArW * w : {&L.wq, &L.wk, &L.wv, &L.wo, &L.wgate, &L.wup, &L.wdown}) use_pdk = use_pdk && (pk_q8 ? w->qtype == 8 : (w->f16 && !w->qtype));
     const int Tst = use_pdk ? Pmax : Tmax;                          // positions per sequence in the contiguous fp32 cache: the persistent path keeps only the prompt pass there
     const int pk_max_pages = cdiv(Tmax, PK_PAGE);
     int pk_pages = 0;
@@ -317,10 +319,10 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         std::vector<int> hpt((size_t) B * pk_max_pages, 0), hsrc((size_t) R0);
         { int next = 0, r = 0; for (int b = 0; b < B; b++) { const int np = cdiv(n_prompt[b] + n_steps, PK_PAGE); for (int i = 0; i < np; i++) hpt[(size_t) b * pk_max_pages + i] = next++; for (int i = 0; i < n_prompt[b]; i++) hsrc[(size_t) r++] = b * Tst + i; } }
         std::vector<PkOp> ops;
-        auto seg = [&](const ArW & W, int N, int epi, int pair, int n_units) { PkSeg sg; memset(&sg, 0, sizeof sg); sg.W = (const __half *) W.p; sg.Wp = sg.W; sg.N = N; sg.epi = epi; sg.ldy = N; sg.pair = pair; sg.n_units = n_units; return sg; };
+        auto seg = [&](const ArW & W, int N, int epi, int pair, int n_units) { PkSeg sg; memset(&sg, 0, sizeof sg); sg.W = (const __half *) W.p; sg.Wp = sg.W; sg.Ws = (const __half *) W.scales; sg.Wps = sg.Ws; sg.N = N; sg.epi = epi; sg.ldy = N; sg.pair = pair; sg.n_units = n_units; return sg; };
         auto gemv_op = [&](int layer, const float * X, const __half * X16, size_t xr, int K, const float * nw, std::initializer_list<PkSeg> segs) {
             PkOp op; memset(&op, 0, sizeof op);
-            op.kind = PK_GEMV; op.layer = layer; op.X = X; op.X16 = X16; op.xrep = xr; op.ldx = K; op.K = K; op.norm = nw ? PKN_RMS : PKN_NONE; op.nw = nw; op.eps = 1e-5f;
+            op.kind = PK_GEMV; op.layer = layer; op.X = X; op.X16 = X16; op.xrep = xr; op.ldx = K; op.K = K; op.norm = nw ? PKN_RMS : PKN_NONE; op.nw = nw; op.eps = 1e-5f; op.q8 = pk_q8 ? 1 : 0;
             int u = 0;
             for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; u += sg.n_units; op.nseg++; }
             op.n_units = u;
@@ -337,7 +339,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
             { PkOp op; memset(&op, 0, sizeof op); op.kind = PK_ATTN; op.layer = l; op.q = q; op.out16 = att16; op.orep = xrep; op.scale = scale; ops.push_back(op); }
             PkSeg so = seg(L.wo, H, PKE_RES, PKP_NONE, H / 8); so.Y = pxn; so.res = px; so.yrep = xrep;                 // xn = attention + residual(x)
             gemv_op(l, nullptr, att16, xrep, H, nullptr, {so});
-            PkSeg sg2 = seg(L.wgate, F, PKE_SWIGLU, PKP_SWIGLU, F / 8); sg2.Wp = (const __half *) L.wup.p; sg2.Y16 = g16; sg2.yrep = grep;
+            PkSeg sg2 = seg(L.wgate, F, PKE_SWIGLU, PKP_SWIGLU, F / 8); sg2.Wp = (const __half *) L.wup.p; sg2.Wps = (const __half *) L.wup.scales; sg2.Y16 = g16; sg2.yrep = grep;
             gemv_op(l, pxn, nullptr, xrep, H, L.post_norm, {sg2});
             PkSeg sd = seg(L.wdown, H, PKE_RES, PKP_NONE, H / 8); sd.Y = px; sd.res = pxn; sd.yrep = xrep;               // x = mlp + residual(xn)
             gemv_op(l, nullptr, g16, grep, F, nullptr, {sd});

@@ -42,6 +42,8 @@ constexpr int PK_PAD = 32;                        // halves of padding per smem 
 constexpr int PK_ROWB = (PK_TK + PK_PAD) * 2;     // bytes per tile row in shared memory
 constexpr int PK_STAGE = 8 * PK_ROWB;             // bytes per ring stage (one tile: 8 output rows)
 constexpr int PK_AK_MAX = 3072;                   // activations are staged in k chunks of P.ak columns (2 048, or 3 072 for models whose hidden size is 3 072: one chunk for their q|k|v, gate|up phases)
+constexpr int PK_ROWQ = PK_TK + 32;               // bytes per row of a Q8_0 tile's values in shared memory (rows 8 banks apart: conflict-free 8-byte fragment loads)
+constexpr int PK_QSC = 8 * PK_ROWQ;               // byte offset of a Q8_0 tile's block scales within its stage: [8 rows][32 blocks] fp16
 constexpr int PK_PAGE = 32;                       // positions per KV page
 constexpr int PK_MAXSTAGES = 12;
 constexpr int PK_RED_FLOATS = 2 * 8 * 128;        // cross-warp reduction scratch of one unit: eight warps' partial 16 x 8 tiles, twice for a paired unit
@@ -62,6 +64,7 @@ struct PkSeg {                                    // one matrix of a GEMV phase;
     float * Y; const float * res;                 // STORE / RES / LOGITS: Y[r * ldy + n] (+ res[r * ldy + n])
     __half * Y16;                                 // GELU: the activated values as fp16 [r * ldy + n] (their only consumer, fc2, rounds its input rows to fp16 anyway)
     size_t yrep;                                  // != 0: Y / Y16 (and res) exist in PK_REP copies this many elements apart; the epilogue writes them all, a CTA reads copy blockIdx % PK_REP
+    const __half * Ws; const __half * Wps;        // Q8_0 phases (op.q8): W / Wp point at int8 values [N][K], Ws / Wps at their fp16 block scales [N][K / 32]
     const __half * Wp;                            // paired units: the partner tile's matrix (PKP_ROPE: W itself, rows + hd / 2; PKP_SWIGLU: the up matrix, same rows)
     int N, unit0, epi, ldy, kv, pair, n_units;    // unit0: first unit of this segment within the phase; kv: 0 = K, 1 = V; pair: PKP_*; n_units of this segment
 };
@@ -70,7 +73,7 @@ struct alignas(16) PkOp {
     // PK_GEMV
     const float * X; const __half * X16;          // input rows: fp32 (residual stream, q) or, when X16 is set, fp16 written by the previous phase (attention output, GELU output)
     size_t xrep;                                  // != 0: X / X16 exist in PK_REP copies this many elements apart
-    const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; PkSeg seg[3];      // kv_prefetch: L2-prefetch this layer's K / V rows first
+    const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; int q8; PkSeg seg[3];      // q8: the matrices are Q8_0 blocks (ggml_vec_dot_q8_0_q8_0 arithmetic: activations quantised per 32-block, int8 MMA, fp32 scale products)      // kv_prefetch: L2-prefetch this layer's K / V rows first
     // PK_ATTN: cross != 0 -> every row attends to the flat fp32 store ck / cv [cross_len][H]; else to its sequence's pages, positions [0, row_pos[r]]
     const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale; size_t cross_row_stride; int tsplit;      // tsplit > 1: every (row, head) item is cut into tsplit position chunks (few items, long contexts), combined by a PK_ATTNC op      // cross_row_stride: elements between the stores of consecutive rows (Dia: one encoding per sequence; 0: all rows share one)      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
 };
@@ -160,6 +163,35 @@ __device__ __forceinline__ uint4 pk_lds128(const void * p) {
 }
 #endif
 
+#ifdef B2EMU
+static inline uint2 pk_lds64(const void * p) { uint2 v; memcpy(&v, p, 8); return v; }
+// functional model of mma.sync.m16n8k32.s8: a0 / a1 = rows g / g + 8, k slots 4t .. 4t+3; a2 / a3 the same rows, slots 16 + 4t ..; b0 / b1 = column g, the same slots
+static inline void pk_imma16832(int * c, unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    unsigned mine[6] = {a0, a1, a2, a3, b0, b1}, all[32][6];
+    b2emu::warp_exchange(mine, 6, &all[0][0]);
+    const int lane = b2emu_lane(), g = lane >> 2, t = lane & 3;
+    auto by = [](unsigned v, int i) { return (int) (signed char) ((v >> (8 * i)) & 0xffu); };
+    for (int ci = 0; ci < 4; ci++) {
+        const int row = g + (ci >> 1) * 8, col = 2 * t + (ci & 1);
+        int acc = c[ci];
+        for (int tp = 0; tp < 4; tp++)
+            for (int hi = 0; hi < 2; hi++)
+                for (int i = 0; i < 4; i++) acc += by(all[(row & 7) * 4 + tp][(row >> 3) + 2 * hi], i) * by(all[col * 4 + tp][4 + hi], i);
+        c[ci] = acc;
+    }
+}
+#else
+__device__ __forceinline__ uint2 pk_lds64(const void * p) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(pk_smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void pk_imma16832(int * c, unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+#endif
+
 // every consumer thread of every CTA calls it; orders all global stores before it against all loads after it, grid-wide (the cooperative-groups pattern: block
 // barrier, one thread releases / acquires at gpu scope, block barrier).  The counter only grows: generation e is complete when it reaches e * gridDim.x.
 __device__ __forceinline__ void pk_grid_sync(unsigned * ctr, unsigned & epoch) {
@@ -224,6 +256,26 @@ __device__ __forceinline__ void pk_produce_gemv(const PkOp & op, unsigned char *
             int n0, n1;
             pk_unit_rows(sg, u, hd, n0, n1);
             const int N = sg.N, pair = sg.pair;
+            if (op.q8) {                                        // Q8_0: a tile = 8 rows x <= 1 024 int8 values (lanes 0-7) + their <= 32 fp16 block scales per row (lanes 8-15)
+                const int r0q = n0 + row < N ? n0 + row : N - 1, r1q = pair ? (n1 + row < N ? n1 + row : N - 1) : r0q;
+                const unsigned char * v0 = reinterpret_cast<const unsigned char *>(sg.W) + (size_t) r0q * K + kA0, * v1 = reinterpret_cast<const unsigned char *>(pair ? sg.Wp : sg.W) + (size_t) r1q * K + kA0;
+                const __half * s0 = sg.Ws + (size_t) r0q * (K >> 5) + (kA0 >> 5), * s1 = (pair ? sg.Wps : sg.Ws) + (size_t) r1q * (K >> 5) + (kA0 >> 5);
+                for (int kl = 0; kl < kAn; kl += PK_TK) {
+                    const unsigned bytes = (unsigned) (kAn - kl < PK_TK ? kAn - kl : PK_TK), sbytes = bytes >> 4;      // (bytes / 32 blocks x 2 bytes)
+                    for (int part = 0; part < (pair ? 2 : 1); part++) {
+                        if (lane == 0) {
+                            pk_mbar_wait(&empty[rp.s], rp.ph ^ 1u);
+                            pk_mbar_expect_tx(&full[rp.s], 8u * (bytes + sbytes));
+                        }
+                        __syncwarp();
+                        unsigned char * st = ring + (size_t) rp.s * PK_STAGE;
+                        if (lane < 8) pk_bulk_g2s(st + (size_t) row * PK_ROWQ, (part ? v1 : v0) + kl, bytes, &full[rp.s]);
+                        else if (lane < 16) pk_bulk_g2s(st + PK_QSC + (size_t) row * 64, (part ? s1 : s0) + (kl >> 5), sbytes, &full[rp.s]);
+                        pk_ring_next(rp, S);
+                    }
+                }
+                continue;
+            }
             const __half * Wl = sg.Wl;
             const int nparts = pair ? 2 : (Wl ? 2 : 1);         // paired unit: primary + partner tile; split matrix: high + low plane
             // this lane's row of the two tiles (rows past N re-read the last row and are never stored)
@@ -740,6 +792,196 @@ __device__ __forceinline__ void pk_gemv(const PkParams & P, const PkOp & op, uns
     }
 }
 
+// ---------------------------------------------------------------- consumers: GEMV phase over Q8_0 matrices
+// ggml's Q8_0 x Q8_0 product (ggml_vec_dot_q8_0_q8_0; gemv_rows_q_body in ar_kernels.cuh is the launch-per-op form): the activation row is quantised per 32-value block
+// (quantize_row_q8_0: d = fp16(amax / 127), q = round(x * 127 / amax)), the block's integer dot product is scaled by d_w * d_x in fp32.  Here the integer dot products of
+// 16 rows x 8 output rows x one block are ONE mma.sync.m16n8k32.s8 (every lane loads 8 consecutive bytes of its row: k slots permuted the same way on both operands).
+// RMSNorm'd fp32 rows -> int8 rows + block scales in shared memory; the row stays in registers (see pk_stage_rms)
+template <int NV>
+__device__ __forceinline__ void pk_stage_q8_rms(const PkOp & op, const float * X, const float * snw, int R, unsigned char * sQ, float * sD, int pitchq, int nbk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, K = op.K, n4 = K >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = warp + 8 * rr;
+        float4 v[NV];
+#pragma unroll
+        for (int u = 0; u < NV; u++) { const int j = u * 32 + lane; v[u] = (j < n4 && r < R) ? __ldcg(reinterpret_cast<const float4 *>(X + (size_t) r * op.ldx) + j) : z4; }
+        float sc = 1.f;
+        if (op.norm == PKN_RMS) {
+            double ss = 0.0;
+#pragma unroll
+            for (int u = 0; u < NV; u++) ss += (double) ((v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            sc = 1.0f / sqrtf((float) (ss / (double) K) + op.eps);
+        }
+#pragma unroll
+        for (int u = 0; u < NV; u++) {
+            if (u * 32 >= n4) continue;                         // (n4 is a multiple of 32: the whole warp takes the same branch)
+            const int j = u * 32 + lane;
+            float4 x = v[u];
+            if (op.norm == PKN_RMS) { const float4 w = reinterpret_cast<const float4 *>(snw)[j]; x.x = (x.x * sc) * w.x; x.y = (x.y * sc) * w.y; x.z = (x.z * sc) * w.z; x.w = (x.w * sc) * w.w; }
+            float amax = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));      // a block = the 8 float4 of lanes 8m .. 8m + 7
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            const float id = amax != 0.f ? 127.f / amax : 0.f;
+            const int a0 = __float2int_rn(x.x * id), a1 = __float2int_rn(x.y * id), a2 = __float2int_rn(x.z * id), a3 = __float2int_rn(x.w * id);
+            reinterpret_cast<int *>(sQ + (size_t) r * pitchq)[j] = (a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24);
+            if ((lane & 7) == 0) sD[(size_t) r * nbk + (j >> 3)] = __half2float(__float2half_rn(amax / 127.f));
+        }
+    }
+}
+// fp16 rows written by the previous phase (attention output, SwiGLU output) -> int8 rows + block scales: a block = the 4 uint4 of lanes 4m .. 4m + 3
+__device__ __forceinline__ void pk_stage_q8_h16(const PkOp & op, const __half * X16, int R, int k0, int kn, unsigned char * sQ, float * sD, int pitchq, int nbk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n8 = kn >> 3;
+#pragma unroll 1
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = warp + 8 * rr;
+        const uint4 * src = reinterpret_cast<const uint4 *>(X16 + (size_t) r * op.ldx + k0);
+        for (int j0 = 0; j0 < n8; j0 += 32 * 12) {
+            uint4 v[12];
+#pragma unroll
+            for (int u = 0; u < 12; u++) { const int j = j0 + 32 * u + lane; v[u] = (r < R && j < n8) ? __ldcg(src + j) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                if (j0 + 32 * u >= n8) continue;                // (n8 is a multiple of 32: warp-uniform)
+                const int j = j0 + 32 * u + lane;
+                float x[8];
+                {
+                    const unsigned wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { __half2 h; memcpy(&h, &wv[i], 4); const float2 f = __half22float2(h); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+                }
+                float amax = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(x[i]));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                const float id = amax != 0.f ? 127.f / amax : 0.f;
+                unsigned w[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int a0 = __float2int_rn(x[4 * h] * id), a1 = __float2int_rn(x[4 * h + 1] * id), a2 = __float2int_rn(x[4 * h + 2] * id), a3 = __float2int_rn(x[4 * h + 3] * id);
+                    w[h] = (unsigned) ((a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24));
+                }
+                *reinterpret_cast<uint2 *>(sQ + (size_t) r * pitchq + 8 * j) = make_uint2(w[0], w[1]);
+                if ((lane & 3) == 0) sD[(size_t) r * nbk + (j >> 2)] = __half2float(__float2half_rn(amax / 127.f));
+            }
+        }
+    }
+}
+
+// all tiles of one unit within the staged chunk; c: the unit's sums, cl: the partner tile's (paired units)
+template <bool PAIR>
+__device__ __forceinline__ void pk_unit_tiles_q8(float * c, float * cl, unsigned char * ring, const unsigned char * sQ, const float * sD, int pitchq, int nbk, PkBar * full, PkBar * empty, PkRingPos & rp, int S,
+                                                 int kAn, unsigned long long * pr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    for (int kt0 = 0; kt0 < kAn; kt0 += PK_TK) {
+        const int ktn = kAn - kt0 < PK_TK ? kAn - kt0 : PK_TK, ks = ktn >> 3, nb = ks >> 5, tb0 = (warp * ks) >> 5, cb0 = (kt0 >> 5) + tb0;      // this warp's blocks: tb0.. within the tile, cb0.. within the chunk
+        const unsigned char * xa = sQ + (size_t) g * pitchq + kt0 + warp * ks + 8 * tq, * xb = xa + (size_t) 8 * pitchq;
+        const float * da = sD + (size_t) g * nbk + cb0, * db = da + (size_t) 8 * nbk;
+#pragma unroll
+        for (int part = 0; part < (PAIR ? 2 : 1); part++) {
+            if (pr) { const unsigned long long t0 = pk_now(); pk_mbar_wait(&full[rp.s], rp.ph); pr[4] += pk_now() - t0; }
+            else pk_mbar_wait(&full[rp.s], rp.ph);
+            const unsigned char * st = ring + (size_t) rp.s * PK_STAGE, * wr = st + (size_t) g * PK_ROWQ + warp * ks + 8 * tq;
+            const __half * ws = reinterpret_cast<const __half *>(st + PK_QSC) + tb0;
+            float * acc = part ? cl : c;
+#pragma unroll 4
+            for (int i = 0; i < nb; i++) {
+                const uint2 w = pk_lds64(wr + 32 * i), a = pk_lds64(xa + 32 * i), b = pk_lds64(xb + 32 * i);
+                int ci[4] = {0, 0, 0, 0};
+                pk_imma16832(ci, a.x, b.x, a.y, b.y, w.x, w.y);
+                const float dxa = da[i], dxb = db[i], dw0 = __half2float(ws[(2 * tq) * 32 + i]), dw1 = __half2float(ws[(2 * tq + 1) * 32 + i]);
+                acc[0] = fmaf((float) ci[0], dw0 * dxa, acc[0]); acc[1] = fmaf((float) ci[1], dw1 * dxa, acc[1]);
+                acc[2] = fmaf((float) ci[2], dw0 * dxb, acc[2]); acc[3] = fmaf((float) ci[3], dw1 * dxb, acc[3]);
+            }
+            __syncwarp();
+            if (lane == 0) pk_mbar_arrive(&empty[rp.s]);
+            pk_ring_next(rp, S);
+        }
+    }
+}
+
+template <typename KVT> __device__ __forceinline__ void pk_prefetch_kv(const PkParams & P, int layer, int step, const int * sfp, const int * spt);
+template <typename KVT>
+__device__ __forceinline__ void pk_unit_finish(const PkParams & P, const PkOp & op, const PkSeg & sg, float * c, float * cl, int mode, float * red, unsigned & rb, int n0, int n1, float resv, int step_abs,
+                                               const unsigned long long * skv);
+
+template <typename KVT>
+__device__ __forceinline__ void pk_gemv_q8(const PkParams & P, const PkOp & op, unsigned char * ring, unsigned char * sQ, float * red, PkBar * full, PkBar * empty, PkRingPos & rp, int step_abs,
+                                           unsigned long long * pr, unsigned long long * skv, const int * sfp, const int * spt) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int K = op.K, R = P.R, S = P.n_stages, ak = P.ak;
+    const int nA = (K + ak - 1) / ak, kc = K < ak ? K : ak, pitchq = kc + 32, nbk = kc >> 5;
+    float * sD = reinterpret_cast<float *>(sQ + (size_t) 16 * pitchq);
+    unsigned long long kvoff = 0ull;
+    if (op.kv_prefetch && tid < R) {
+        const int pos = sfp[tid] + step_abs - P.pos_off;
+        kvoff = (unsigned long long) spt[tid * P.max_pages + (pos >> 5)] * ((size_t) 2 * P.kv_heads * PK_PAGE * P.hd) + (size_t) (pos & (PK_PAGE - 1)) * P.hd;
+    }
+    if (op.kv_prefetch) pk_prefetch_kv<KVT>(P, op.layer, step_abs, sfp, spt);
+    const size_t xoff = op.xrep * (size_t) (blockIdx.x % PK_REP);
+    const float * X = op.X ? op.X + xoff : nullptr; const __half * X16 = op.X16 ? op.X16 + xoff : nullptr;
+    const float * snw = nullptr; int norm_stage = -1;
+    if (op.norm != PKN_NONE) {
+        norm_stage = rp.s;
+        pk_mbar_wait(&full[norm_stage], rp.ph);
+        snw = reinterpret_cast<const float *>(ring + (size_t) norm_stage * PK_STAGE);
+        pk_ring_next(rp, S);
+        if (pr) pr[5] = pk_now();
+    }
+    auto stage = [&](int a) {
+        const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak;
+        if (X16) pk_stage_q8_h16(op, X16, R, kA0, kAn, sQ, sD, pitchq, nbk);
+        else if (K <= 1024) pk_stage_q8_rms<8>(op, X, snw, R, sQ, sD, pitchq, nbk);      // (fp32 rows are staged whole: host-checked K <= ak <= 3 072)
+        else pk_stage_q8_rms<24>(op, X, snw, R, sQ, sD, pitchq, nbk);
+        if (a == 0 && op.kv_prefetch && tid < R) skv[tid] = kvoff;
+        if (norm_stage >= 0 && a + 1 == nA) { __syncwarp(); if (lane == 0) pk_mbar_arrive(&empty[norm_stage]); }
+        pk_bar_sync(1, PK_CONS);
+        if (pr && a == 0) pr[1] = pk_now();
+        return kAn;
+    };
+    auto seg_of = [&](int u) -> const PkSeg & { return op.seg[(op.nseg > 2 && u >= op.seg[2].unit0) ? 2 : ((op.nseg > 1 && u >= op.seg[1].unit0) ? 1 : 0)]; };
+    auto res_of = [&](const PkSeg & sg, int n0) -> float {
+        if (sg.epi != PKE_RES || tid >= 128) return 0.f;
+        const int r = tid >> 3, n = n0 + (tid & 7);
+        return (r < R && n < sg.N) ? __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n) : 0.f;
+    };
+    unsigned rb = 0;
+    if (nA == 1) {
+        const int kAn = stage(0);
+        for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
+            const PkSeg & sg = seg_of(u);
+            int n0, n1;
+            pk_unit_rows(sg, u, P.hd, n0, n1);
+            const float resv = res_of(sg, n0);
+            float c[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
+            if (sg.pair != PKP_NONE) pk_unit_tiles_q8<true>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+            else pk_unit_tiles_q8<false>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+            pk_unit_finish<KVT>(P, op, sg, c, cl, sg.pair != PKP_NONE ? PKT_PAIR : PKT_PLAIN, red, rb, n0, n1, resv, step_abs, skv);
+        }
+    } else {
+        float acc[3][4], zero[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int a = 0; a < nA; a++) {
+            if (a) pk_bar_sync(1, PK_CONS);
+            const int kAn = stage(a);
+#pragma unroll
+            for (int ui = 0; ui < 3; ui++) {
+                const int u = (int) blockIdx.x + ui * (int) gridDim.x;
+                if (u < op.n_units) {
+                    const PkSeg & sg = seg_of(u);
+                    const int n0 = (u - sg.unit0) * 8;
+                    const float resv = a + 1 == nA ? res_of(sg, n0) : 0.f;
+                    pk_unit_tiles_q8<false>(acc[ui], zero, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+                    if (a + 1 == nA) pk_unit_finish<KVT>(P, op, sg, acc[ui], zero, PKT_PLAIN, red, rb, n0, n0, resv, step_abs, skv);
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- consumers: attention phase.  One (row, head) item per half-CTA (128 threads, named barrier 2 + grp)
 // raw 8-element cache reads: issued in batches so that a thread has 8 independent 16-byte (fp32 store: 2 x 16-byte) loads in flight, converted on use
 struct PkRawH { uint4 a; };
@@ -1177,7 +1419,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
             if (pr) pr[0] = pk_now();
             switch (op.kind) {
                 case PK_ROWS:   if (P.model == PKM_ORPHEUS) pk_rows_orpheus(P, step, st == 0, red); else if (P.model == PKM_DIA) pk_rows_dia(P, step, sids); else pk_rows(P, step, sids); break;
-                case PK_GEMV:   pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, rp, step, pr, skv, sfp, spt); break;
+                case PK_GEMV:   if (op.q8) pk_gemv_q8<KVT>(P, op, ring, areg, red, full, empty, rp, step, pr, skv, sfp, spt);
+                                else pk_gemv<KVT>(P, op, ring, reinterpret_cast<__half *>(areg), red, full, empty, rp, step, pr, skv, sfp, spt);
+                                break;
                 case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
                 case PK_ATTNC:  pk_attn_combine<HD>(P, op); break;
                 case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else if (P.model == PKM_DIA) pk_argmax_dia(P, step, red); else pk_argmax(P, step, red); break;
