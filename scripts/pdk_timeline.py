@@ -22,7 +22,7 @@ def main():
     if model == "orpheus":                                 # BASELINE config 5's decoder shape, F16 matrices, random weights handed over tensor by tensor
         from tts_cpp_b200.binding import Context
         from tts_cpp_b200.synth import build_orpheus_direct
-        par = build_orpheus_direct(Context(0), dtype="f16")
+        par = build_orpheus_direct(Context(0), dtype=os.environ.get("B2TTS_TIMELINE_DTYPE", "f16"))
         prompts = [rng.integers(1, 100000, size=40).astype(np.uint32) for _ in range(batch)]
     elif model == "dia":                                   # BASELINE config 4's model shape, F16, `batch` utterances (each a CFG row pair)
         from tts_cpp_b200.binding import Context

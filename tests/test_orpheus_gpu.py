@@ -139,7 +139,7 @@ for u in range(2):
         s = done + upto
         top2 = np.sort(ref_l[s])[-2:]
         gap = float(top2[1] - top2[0])
-        print(f"TIE-MARGIN orpheus f16 pdk={int(pdk_on)} prompt {u} step {s}: token {int(got_t[upto])} vs {int(ref_t[s])}, reference top-2 gap {gap:.3e}, max |logit diff| {float(d[upto]):.3e}")
+        print(f"TIE-MARGIN orpheus {'q8_0' if q8 else 'f16'} pdk={int(pdk_on)} prompt {u} step {s}: token {int(got_t[upto])} vs {int(ref_t[s])}, reference top-2 gap {gap:.3e}, max |logit diff| {float(d[upto]):.3e}")
         if gap > 2.0 * float(d[upto]): ok = False; print("  CLEAR DECISION DIFFERS"); break
         anchors += 1
         done = s + 1
@@ -147,7 +147,7 @@ for u in range(2):
         prompt = np.concatenate([prompts[u], ref_t[:done]]).astype(np.uint32)
         t2, l2 = orph.generate_greedy([prompt], steps - done, want_logits=True)
         got_t, got_l = t2[0], l2[0]
-    print(f"PARITY orpheus wide F16 pdk={int(pdk_on)} prompt {u}: {steps} steps, {anchors} near-tie re-anchorings, max |logit diff| vs the reference's F32 run {worst:.3e}")
+    print(f"PARITY orpheus wide {'Q8_0' if q8 else 'F16'} pdk={int(pdk_on)} prompt {u}: {steps} steps, {anchors} near-tie re-anchorings, max |logit diff| vs the reference's F32 run {worst:.3e}")
     ok &= worst < (0.8 if q8 else 5e-2) and anchors <= (24 if q8 else 4)      # Q8_0: format noise ~2 % of the logit std (4) on both paths, near-ties are frequent
     single = orph.generate_greedy([prompts[u]], steps)                          # batching does not change a sequence
     ok &= bool(np.array_equal(single[0], toks_b[u]))

@@ -192,7 +192,7 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     for (int b = 0; b < B; b++) pk_pages += cdiv(n_prompt[b] + n_steps, PK_PAGE);
     const size_t pk_layer_bytes = (size_t) pk_pages * 2 * KV * PK_PAGE * (kv_f32 ? 4 : 2);
     const int pk_amax = std::max(1, std::min(256, pk_grid / B));     // chunks a row's argmax is cut into: about one (row, chunk) item per CTA
-    const size_t pk_need = use_pdk ? (size_t) n_layers * pk_layer_bytes + (size_t) B * pk_max_pages * 4 + (size_t) (6 * n_layers + 8) * sizeof(PkOp) + (size_t) R0 * 8 + 8192 + (size_t) PK_REP * 16 * ((size_t) 8 * H + 2 * F) + 4096 +
+    const size_t pk_need = use_pdk ? (size_t) n_layers * pk_layer_bytes + (size_t) B * pk_max_pages * 4 + (size_t) (10 * n_layers + 8) * sizeof(PkOp) + (size_t) PK_REP * 16 * std::max(H, F) * 2 + (size_t) R0 * 8 + 8192 + (size_t) PK_REP * 16 * ((size_t) 8 * H + 2 * F) + 4096 +
                                      (size_t) 16 * head_dim * 4 + (size_t) B * pk_amax * 8 + (out_logits ? (size_t) n_steps * B * vocab * 4 : 0) : 0;
     const size_t cache = (size_t) n_layers * B * Tst * KV * 4;
     const size_t need = pk_need + 2 * cache + (size_t) Rmax * ((size_t) 4 * H + 2 * KV + 2 * F) * 4 + (size_t) B * ((size_t) vocab + H) * 4 + (size_t) B * n_steps * 4 +
@@ -307,7 +307,13 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         // GEMV with SwiGLU in its epilogue -> down GEMV + residual } | [RMSNorm] lm_head GEMV | argmax partials (combined by the next step's rows phase)
         unsigned char * pool = (unsigned char *) arena.alloc((size_t) n_layers * pk_layer_bytes);
         int * page_table = Fw.al<int>((size_t) B * pk_max_pages), * row_src = Fw.al<int>((size_t) R0), * pk_pos = Fw.al<int>(16);
-        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (6 * n_layers + 8) * sizeof(PkOp));
+        PkOp * d_ops = (PkOp *) arena.alloc((size_t) (10 * n_layers + 8) * sizeof(PkOp));
+        // Q8_0: the phase inputs are quantised ONCE per phase by a PK_QUANT op into these (replicated) buffers; the GEMV phases copy them into shared memory
+        const int Kq = std::max(H, F);
+        const size_t qrep = (size_t) 16 * Kq, qdrep = (size_t) 16 * (Kq / 32);
+        unsigned char * xq = pk_q8 ? (unsigned char *) arena.alloc(PK_REP * qrep) : nullptr;
+        float * xqd = pk_q8 ? Fw.al<float>(PK_REP * qdrep) : nullptr;
+        if (pk_q8 && (!xq || !xqd)) return 1;
         unsigned * d_bar = (unsigned *) arena.alloc(256);
         float * logits_all = out_logits ? Fw.al<float>((size_t) n_steps * B * vocab) : nullptr;
         const size_t xrep = (size_t) 16 * H, grep = (size_t) 16 * F;
@@ -322,6 +328,13 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         auto seg = [&](const ArW & W, int N, int epi, int pair, int n_units) { PkSeg sg; memset(&sg, 0, sizeof sg); sg.W = (const __half *) W.p; sg.Wp = sg.W; sg.Ws = (const __half *) W.scales; sg.Wps = sg.Ws; sg.N = N; sg.epi = epi; sg.ldy = N; sg.pair = pair; sg.n_units = n_units; return sg; };
         auto gemv_op = [&](int layer, const float * X, const __half * X16, size_t xr, int K, const float * nw, std::initializer_list<PkSeg> segs) {
             PkOp op; memset(&op, 0, sizeof op);
+            if (pk_q8) {                                        // first the quantisation of this phase's input rows (with the RMSNorm, if any) ...
+                op.kind = PK_QUANT; op.layer = layer; op.X = X; op.X16 = X16; op.xrep = 0; op.ldx = K; op.K = K; op.norm = nw ? PKN_RMS : PKN_NONE; op.nw = nw; op.eps = 1e-5f;
+                op.QY = xq; op.QD = xqd; op.qrep = qrep; op.qdrep = qdrep;
+                ops.push_back(op);
+                memset(&op, 0, sizeof op);
+                op.XQ = xq; op.XD = xqd; op.qrep = qrep; op.qdrep = qdrep; nw = nullptr;      // ... then the GEMV over the quantised rows
+            }
             op.kind = PK_GEMV; op.layer = layer; op.X = X; op.X16 = X16; op.xrep = xr; op.ldx = K; op.K = K; op.norm = nw ? PKN_RMS : PKN_NONE; op.nw = nw; op.eps = 1e-5f; op.q8 = pk_q8 ? 1 : 0;
             int u = 0;
             for (const PkSeg & sg : segs) { op.seg[op.nseg] = sg; op.seg[op.nseg].unit0 = u; u += sg.n_units; op.nseg++; }

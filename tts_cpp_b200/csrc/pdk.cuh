@@ -52,7 +52,7 @@ constexpr int PK_REP = 8;                         // copies of every activation 
                                                   // same 64 KB right after a grid barrier wait ~2 us (each line is served to 148 requesters one after the other); with 8 copies
                                                   // (8x the tiny epilogue stores) a line has 18-19 requesters
 
-enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3, PK_ATTNC = 4 };      // PK_ATTNC: combine the position chunks of a split attention phase
+enum { PK_ROWS = 0, PK_GEMV = 1, PK_ATTN = 2, PK_ARGMAX = 3, PK_ATTNC = 4, PK_QUANT = 5 };      // PK_QUANT: Q8_0-quantise the activation rows once for the whole grid      // PK_ATTNC: combine the position chunks of a split attention phase
 enum { PKN_NONE = 0, PKN_LAYER = 1, PKN_RMS = 2 };
 enum { PKE_STORE = 0, PKE_RES = 1, PKE_GELU = 2, PKE_KV = 3, PKE_LOGITS = 4, PKE_ROPE_Q = 5, PKE_ROPE_K = 6, PKE_SWIGLU = 7 };
 enum { PKP_NONE = 0, PKP_ROPE = 1, PKP_SWIGLU = 2 };      // paired units: two tiles per k-tile (the two NeoX halves of a head's rows; the gate and the up rows of the same columns), one joint epilogue
@@ -73,7 +73,11 @@ struct alignas(16) PkOp {
     // PK_GEMV
     const float * X; const __half * X16;          // input rows: fp32 (residual stream, q) or, when X16 is set, fp16 written by the previous phase (attention output, GELU output)
     size_t xrep;                                  // != 0: X / X16 exist in PK_REP copies this many elements apart
-    const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; int q8; PkSeg seg[3];      // q8: the matrices are Q8_0 blocks (ggml_vec_dot_q8_0_q8_0 arithmetic: activations quantised per 32-block, int8 MMA, fp32 scale products)      // kv_prefetch: L2-prefetch this layer's K / V rows first
+    const float * nw; const float * nb; int ldx, K, norm; float eps; int nseg, n_units; int kv_prefetch; int q8;
+    // Q8_0 phases: XQ / XD (GEMV: input rows already quantised by a PK_QUANT op: int8 [16][K] + block scales [16][K / 32], PK_REP copies qrep bytes / qdrep floats apart);
+    // QY / QD (PK_QUANT: where to put them).  Quantising inside every CTA's staging pass cost 20-26 us per phase on a B200 -- 148 CTAs repeating the same 16 rows
+    const unsigned char * XQ; const float * XD; unsigned char * QY; float * QD; size_t qrep, qdrep;
+    PkSeg seg[3];      // q8: the matrices are Q8_0 blocks (ggml_vec_dot_q8_0_q8_0 arithmetic: activations quantised per 32-block, int8 MMA, fp32 scale products)      // kv_prefetch: L2-prefetch this layer's K / V rows first
     // PK_ATTN: cross != 0 -> every row attends to the flat fp32 store ck / cv [cross_len][H]; else to its sequence's pages, positions [0, row_pos[r]]
     const float * q; __half * out16; size_t orep; const float * ck; const float * cv; int cross, cross_len; float scale; size_t cross_row_stride; int tsplit;      // tsplit > 1: every (row, head) item is cut into tsplit position chunks (few items, long contexts), combined by a PK_ATTNC op      // cross_row_stride: elements between the stores of consecutive rows (Dia: one encoding per sequence; 0: all rows share one)      // out16 [R][H] fp16: consumed only by the o-projection, which rounds to fp16
 };
@@ -870,8 +874,107 @@ __device__ __forceinline__ void pk_stage_q8_h16(const PkOp & op, const __half * 
     }
 }
 
-// all tiles of one unit within the staged chunk; c: the unit's sums, cl: the partner tile's (paired units)
-template <bool PAIR>
+// rows quantised by a PK_QUANT op -> shared memory: plain 16-byte copies (int8 values: K / 16 per row; scales: K / 128 per row)
+__device__ __forceinline__ void pk_stage_q8_copy(const unsigned char * XQ, const float * XD, int K, int R, int k0, int kn, unsigned char * sQ, float * sD, int pitchq, int nbk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n16 = kn >> 4, nd4 = kn >> 7;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = warp + 8 * rr;
+        const uint4 * src = reinterpret_cast<const uint4 *>(XQ + (size_t) r * K + k0);
+        uint4 * dst = reinterpret_cast<uint4 *>(sQ + (size_t) r * pitchq);
+        uint4 v[6];
+#pragma unroll
+        for (int u = 0; u < 6; u++) { const int j = u * 32 + lane; v[u] = (r < R && j < n16) ? __ldcg(src + j) : z; }      // (kn <= 3 072: at most 6 per lane)
+        const uint4 d = (r < R && lane < nd4) ? __ldcg(reinterpret_cast<const uint4 *>(XD + (size_t) r * (K >> 5) + (k0 >> 5)) + lane) : z;
+#pragma unroll
+        for (int u = 0; u < 6; u++) { const int j = u * 32 + lane; if (j < n16) dst[j] = v[u]; }
+        if (lane < nd4) reinterpret_cast<uint4 *>(sD + (size_t) r * nbk)[lane] = d;
+    }
+}
+
+// PK_QUANT: quantize_row_q8_0 of the phase's input rows (after ggml_rms_norm x weight when op.norm says so), once for the whole grid
+__device__ __forceinline__ void pk_quant(const PkParams & P, const PkOp & op, float * red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K = op.K, R = P.R, nrep = op.qrep ? PK_REP : 1;
+    if (op.X) {                                                 // fp32 rows (the residual stream): one row per CTA turn, K <= 3 072 -> at most 3 float4 per thread
+        const int n4 = K >> 2;
+        double * redd = reinterpret_cast<double *>(red);
+        for (int r = (int) blockIdx.x; r < R; r += (int) gridDim.x) {
+            const float4 * row = reinterpret_cast<const float4 *>(op.X + (size_t) r * op.ldx);
+            float4 v[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) { const int j = u * PK_CONS + tid; v[u] = j < n4 ? __ldcg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f); }
+            float sc = 1.f;
+            if (op.norm == PKN_RMS) {
+                double ss = 0.0;
+#pragma unroll
+                for (int u = 0; u < 3; u++) ss += (double) ((v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0) redd[warp] = ss;
+                pk_bar_sync(1, PK_CONS);
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) tot += redd[w];
+                sc = 1.0f / sqrtf((float) (tot / (double) K) + op.eps);
+                pk_bar_sync(1, PK_CONS);                        // (redd is reused by the CTA's next row)
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                if (u * PK_CONS >= n4) continue;                // (n4 is a multiple of 64 and the tail of a partial pass is handled per lane below)
+                const int j = u * PK_CONS + tid;
+                float4 x = v[u];
+                if (op.norm == PKN_RMS && j < n4) { const float4 w = __ldg(reinterpret_cast<const float4 *>(op.nw) + j); x.x = (x.x * sc) * w.x; x.y = (x.y * sc) * w.y; x.z = (x.z * sc) * w.z; x.w = (x.w * sc) * w.w; }
+                float amax = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));      // a block = the 8 float4 of lanes 8m .. 8m + 7 (whole or absent: n4 % 8 == 0)
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                if (j >= n4) continue;
+                const float id = amax != 0.f ? 127.f / amax : 0.f;
+                const int a0 = __float2int_rn(x.x * id), a1 = __float2int_rn(x.y * id), a2 = __float2int_rn(x.z * id), a3 = __float2int_rn(x.w * id);
+                const int word = (a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24);
+                const float d = __half2float(__float2half_rn(amax / 127.f));
+                for (int c = 0; c < nrep; c++) {
+                    reinterpret_cast<int *>(op.QY + op.qrep * c + (size_t) r * K)[j] = word;
+                    if ((lane & 7) == 0) op.QD[op.qdrep * c + (size_t) r * (K >> 5) + (j >> 3)] = d;
+                }
+            }
+        }
+    } else {                                                    // fp16 rows written by the previous phase: item = (row, 2 048 columns), one uint4 (8 halves) per thread
+        const int nch = (K + 2047) >> 11;
+        for (int it = (int) blockIdx.x; it < R * nch; it += (int) gridDim.x) {
+            const int r = it / nch, k0 = (it - r * nch) << 11, j = tid, col = k0 + 8 * j;
+            const bool in = col < K;
+            const uint4 v = in ? __ldcg(reinterpret_cast<const uint4 *>(op.X16 + (size_t) r * op.ldx + k0) + j) : make_uint4(0u, 0u, 0u, 0u);
+            float x[8];
+            {
+                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) { __half2 h; memcpy(&h, &wv[i], 4); const float2 f = __half22float2(h); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+            }
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(x[i]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));      // a block = 4 threads (K % 32 == 0: whole or absent)
+            if (!in) continue;
+            const float id = amax != 0.f ? 127.f / amax : 0.f;
+            unsigned w[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int a0 = __float2int_rn(x[4 * h] * id), a1 = __float2int_rn(x[4 * h + 1] * id), a2 = __float2int_rn(x[4 * h + 2] * id), a3 = __float2int_rn(x[4 * h + 3] * id);
+                w[h] = (unsigned) ((a0 & 0xff) | ((a1 & 0xff) << 8) | ((a2 & 0xff) << 16) | ((a3 & 0xff) << 24));
+            }
+            const float d = __half2float(__float2half_rn(amax / 127.f));
+            for (int c = 0; c < nrep; c++) {
+                *reinterpret_cast<uint2 *>(op.QY + op.qrep * c + (size_t) r * K + col) = make_uint2(w[0], w[1]);
+                if ((lane & 3) == 0) op.QD[op.qdrep * c + (size_t) r * (K >> 5) + (col >> 5)] = d;
+            }
+        }
+    }
+}
+
+// all tiles of one unit within the staged chunk; c: the unit's sums, cl: the partner tile's (paired units).  A warp's k-slice of a tile is ks / 32 blocks (4 for a full
+// tile): their scales come in one 8-byte (weights, per output column) / 16-byte (activations, per row) load each.  HI = false: at most 8 activation rows -- the
+// fragments, scale products and sums of rows 8 .. 15 are skipped.
+template <bool PAIR, bool HI>
 __device__ __forceinline__ void pk_unit_tiles_q8(float * c, float * cl, unsigned char * ring, const unsigned char * sQ, const float * sD, int pitchq, int nbk, PkBar * full, PkBar * empty, PkRingPos & rp, int S,
                                                  int kAn, unsigned long long * pr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
@@ -886,14 +989,38 @@ __device__ __forceinline__ void pk_unit_tiles_q8(float * c, float * cl, unsigned
             const unsigned char * st = ring + (size_t) rp.s * PK_STAGE, * wr = st + (size_t) g * PK_ROWQ + warp * ks + 8 * tq;
             const __half * ws = reinterpret_cast<const __half *>(st + PK_QSC) + tb0;
             float * acc = part ? cl : c;
-#pragma unroll 4
-            for (int i = 0; i < nb; i++) {
-                const uint2 w = pk_lds64(wr + 32 * i), a = pk_lds64(xa + 32 * i), b = pk_lds64(xb + 32 * i);
-                int ci[4] = {0, 0, 0, 0};
-                pk_imma16832(ci, a.x, b.x, a.y, b.y, w.x, w.y);
-                const float dxa = da[i], dxb = db[i], dw0 = __half2float(ws[(2 * tq) * 32 + i]), dw1 = __half2float(ws[(2 * tq + 1) * 32 + i]);
-                acc[0] = fmaf((float) ci[0], dw0 * dxa, acc[0]); acc[1] = fmaf((float) ci[1], dw1 * dxa, acc[1]);
-                acc[2] = fmaf((float) ci[2], dw0 * dxb, acc[2]); acc[3] = fmaf((float) ci[3], dw1 * dxb, acc[3]);
+            if (nb == 4) {                                      // a full tile: 4 blocks per warp, vector scale loads
+                const uint2 s0 = pk_lds64(ws + (2 * tq) * 32), s1 = pk_lds64(ws + (2 * tq + 1) * 32);
+                const uint4 ua = pk_lds128(da), ub = HI ? pk_lds128(db) : make_uint4(0u, 0u, 0u, 0u);
+                float dw0[4], dw1[4], dxa[4], dxb[4];
+                {
+                    const unsigned w0[2] = {s0.x, s0.y}, w1[2] = {s1.x, s1.y}, fa[4] = {ua.x, ua.y, ua.z, ua.w}, fb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        __half2 h; float2 f;
+                        memcpy(&h, &w0[i], 4); f = __half22float2(h); dw0[2 * i] = f.x; dw0[2 * i + 1] = f.y;
+                        memcpy(&h, &w1[i], 4); f = __half22float2(h); dw1[2 * i] = f.x; dw1[2 * i + 1] = f.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { memcpy(&dxa[i], &fa[i], 4); memcpy(&dxb[i], &fb[i], 4); }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint2 w = pk_lds64(wr + 32 * i), a = pk_lds64(xa + 32 * i), b = HI ? pk_lds64(xb + 32 * i) : make_uint2(0u, 0u);
+                    int ci[4] = {0, 0, 0, 0};
+                    pk_imma16832(ci, a.x, b.x, a.y, b.y, w.x, w.y);
+                    acc[0] = fmaf((float) ci[0], dw0[i] * dxa[i], acc[0]); acc[1] = fmaf((float) ci[1], dw1[i] * dxa[i], acc[1]);
+                    if (HI) { acc[2] = fmaf((float) ci[2], dw0[i] * dxb[i], acc[2]); acc[3] = fmaf((float) ci[3], dw1[i] * dxb[i], acc[3]); }
+                }
+            } else {
+                for (int i = 0; i < nb; i++) {
+                    const uint2 w = pk_lds64(wr + 32 * i), a = pk_lds64(xa + 32 * i), b = HI ? pk_lds64(xb + 32 * i) : make_uint2(0u, 0u);
+                    int ci[4] = {0, 0, 0, 0};
+                    pk_imma16832(ci, a.x, b.x, a.y, b.y, w.x, w.y);
+                    const float dxa = da[i], dxb = HI ? db[i] : 0.f, dw0 = __half2float(ws[(2 * tq) * 32 + i]), dw1 = __half2float(ws[(2 * tq + 1) * 32 + i]);
+                    acc[0] = fmaf((float) ci[0], dw0 * dxa, acc[0]); acc[1] = fmaf((float) ci[1], dw1 * dxa, acc[1]);
+                    if (HI) { acc[2] = fmaf((float) ci[2], dw0 * dxb, acc[2]); acc[3] = fmaf((float) ci[3], dw1 * dxb, acc[3]); }
+                }
             }
             __syncwarp();
             if (lane == 0) pk_mbar_arrive(&empty[rp.s]);
@@ -932,7 +1059,8 @@ __device__ __forceinline__ void pk_gemv_q8(const PkParams & P, const PkOp & op, 
     }
     auto stage = [&](int a) {
         const int kA0 = a * ak, kAn = K - kA0 < ak ? K - kA0 : ak;
-        if (X16) pk_stage_q8_h16(op, X16, R, kA0, kAn, sQ, sD, pitchq, nbk);
+        if (op.XQ) pk_stage_q8_copy(op.XQ + op.qrep * (size_t) (blockIdx.x % PK_REP), op.XD + op.qdrep * (size_t) (blockIdx.x % PK_REP), K, R, kA0, kAn, sQ, sD, pitchq, nbk);
+        else if (X16) pk_stage_q8_h16(op, X16, R, kA0, kAn, sQ, sD, pitchq, nbk);
         else if (K <= 1024) pk_stage_q8_rms<8>(op, X, snw, R, sQ, sD, pitchq, nbk);      // (fp32 rows are staged whole: host-checked K <= ak <= 3 072)
         else pk_stage_q8_rms<24>(op, X, snw, R, sQ, sD, pitchq, nbk);
         if (a == 0 && op.kv_prefetch && tid < R) skv[tid] = kvoff;
@@ -948,6 +1076,7 @@ __device__ __forceinline__ void pk_gemv_q8(const PkParams & P, const PkOp & op, 
         return (r < R && n < sg.N) ? __ldcg(sg.res + sg.yrep * (size_t) (blockIdx.x % PK_REP) + (size_t) r * sg.ldy + n) : 0.f;
     };
     unsigned rb = 0;
+    const bool hi = R > 8;
     if (nA == 1) {
         const int kAn = stage(0);
         for (int u = (int) blockIdx.x; u < op.n_units; u += (int) gridDim.x) {
@@ -956,8 +1085,13 @@ __device__ __forceinline__ void pk_gemv_q8(const PkParams & P, const PkOp & op, 
             pk_unit_rows(sg, u, P.hd, n0, n1);
             const float resv = res_of(sg, n0);
             float c[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
-            if (sg.pair != PKP_NONE) pk_unit_tiles_q8<true>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
-            else pk_unit_tiles_q8<false>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+            if (hi) {
+                if (sg.pair != PKP_NONE) pk_unit_tiles_q8<true, true>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+                else pk_unit_tiles_q8<false, true>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+            } else {
+                if (sg.pair != PKP_NONE) pk_unit_tiles_q8<true, false>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+                else pk_unit_tiles_q8<false, false>(c, cl, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+            }
             pk_unit_finish<KVT>(P, op, sg, c, cl, sg.pair != PKP_NONE ? PKT_PAIR : PKT_PLAIN, red, rb, n0, n1, resv, step_abs, skv);
         }
     } else {
@@ -974,7 +1108,8 @@ __device__ __forceinline__ void pk_gemv_q8(const PkParams & P, const PkOp & op, 
                     const PkSeg & sg = seg_of(u);
                     const int n0 = (u - sg.unit0) * 8;
                     const float resv = a + 1 == nA ? res_of(sg, n0) : 0.f;
-                    pk_unit_tiles_q8<false>(acc[ui], zero, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+                    if (hi) pk_unit_tiles_q8<false, true>(acc[ui], zero, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
+                    else pk_unit_tiles_q8<false, false>(acc[ui], zero, ring, sQ, sD, pitchq, nbk, full, empty, rp, S, kAn, pr);
                     if (a + 1 == nA) pk_unit_finish<KVT>(P, op, sg, acc[ui], zero, PKT_PLAIN, red, rb, n0, n0, resv, step_abs, skv);
                 }
             }
@@ -1424,6 +1559,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) pdk_kernel(const PkParams P) {
                                 break;
                 case PK_ATTN:   pk_attn<KVT, HD>(P, op, areg, step, sfp, spt); break;
                 case PK_ATTNC:  pk_attn_combine<HD>(P, op); break;
+                case PK_QUANT:  pk_quant(P, op, red); break;
                 case PK_ARGMAX: if (P.model == PKM_ORPHEUS) pk_argmax_partial(P, red); else if (P.model == PKM_DIA) pk_argmax_dia(P, step, red); else pk_argmax(P, step, red); break;
             }
             if (pr) pr[2] = pk_now();
