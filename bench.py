@@ -511,7 +511,8 @@ def run_parler(args):
 def run_orpheus(args):
     """Secondary line: BASELINE config 5's model on ONE GPU of the 8 -- an Orpheus-3B-shaped decoder (28 layers x 3072, 24 / 8 heads x 128, ffn 8192, vocab 156 940) with
     Q8_0 matrices (our own writer: the reference's quantize tool refuses Orpheus and its runtime is F32-only), random weights handed over tensor by tensor (no GGUF file),
-    greedy, launch-per-op path (dp4a block GEMV, CUDA-graph replay).  Sweep of the per-GPU batch {1, 2, 4, 8, 16} (config 5: 64 utterances over 8 GPUs = 8 per GPU);
+    greedy, decode steps inside the persistent decode kernel (pdk.cuh: int8 MMA over activations quantised per 32-block, ggml_vec_dot_q8_0_q8_0's arithmetic;
+    B2TTS_AR_PDK=0: launch-per-op dp4a path under CUDA-graph replay).  Sweep of the per-GPU batch {1, 2, 4, 8, 16} (config 5: 64 utterances over 8 GPUs = 8 per GPU);
     a "step" = `n_tokens` decode steps of the whole batch (7 tokens = one 85.3 ms SNAC frame).  --orpheus-dtype f16: the same shape with F16 matrices, whose decode
     steps run inside the persistent decode kernel (pdk.cuh)."""
     if args.impl == "reference":

@@ -181,9 +181,10 @@ float b2tts_snac_last_ms(const b2tts_snac * m);   /* device time of the last dec
 int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Orpheus autoregressive decode.  Two paths behind the same calls: F16 GGUFs, greedy, <= 16 sequences, hidden <= 3 072 run decode steps 1 .. n-1 inside
+ * Orpheus autoregressive decode.  Two paths behind the same calls: F16 or Q8_0 matrices (all of one kind), greedy, <= 16 sequences, hidden <= 3 072 run decode steps 1 .. n-1 inside
  * the PERSISTENT DECODE KERNEL (csrc/pdk.cuh: RMSNorm folded into the staging, NeoX RoPE + cache append and SwiGLU in the GEMV epilogues, paged fp16 GQA cache, chunked
- * argmax; on a B200 the reference's tokens over 72 steps, logits 7.5e-3; Orpheus-3B shape 3.3-5.0 ms per step at 1-16 sequences); everything else runs the launch-per-op
+ * argmax; Q8_0: activations quantised per 32-block once per phase, int8 MMA, fp32 scale products = ggml_vec_dot_q8_0_q8_0; on a B200 the reference's tokens over 72
+ * steps, logits 7.5e-3 (F16); Orpheus-3B shape F16 3.3-5.0 ms per step at 1-16 sequences); everything else runs the launch-per-op
  * path: batched GEMVs over F32 (the reference's only Orpheus dtype), F16 or Q4_0 / Q5_0 / Q8_0 matrices,
  * compact GQA KV cache, device argmax / sampler / stop rule, CUDA-graph replay of a decode step.  Hardware status (B200, tests/test_orpheus_gpu.py, all green): F32 -- the
  * reference's token ids exactly, logits 5e-6, plain and fp32-faithful tensor-core (B2TTS_AR_MMA=1) variants; F16 / Q8_0 -- no reference output exists (its runtime is

@@ -42,7 +42,7 @@ def main():
     n_ops, G, W, ps = struct.unpack("iiii", raw[:16])
     kinds = np.frombuffer(raw, np.int32, n_ops * 4, 16).reshape(n_ops, 4)
     t = np.frombuffer(raw, np.uint64, n_ops * G * W, 16 + n_ops * 16).reshape(n_ops, G, W).astype(np.int64)
-    names = {0: "rows+embed", 1: "gemv", 2: "attention", 3: "argmax", 4: "attn-combine"}
+    names = {0: "rows+embed", 1: "gemv", 2: "attention", 3: "argmax", 4: "attn-combine", 5: "quantise"}
     t0 = t[:, :, 0].min()
     print(f"# step wall (first op begin -> last barrier left): {(t[:, :, 3].max() - t0) / 1e3:.1f} us over {n_ops} ops on {G} CTAs")
     print("# per op: wall = max_cta(barrier left) - min_cta(op begin); work = median over CTAs of (barrier entered - op begin); stage = median(staged - begin) [gemv]; "
