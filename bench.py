@@ -508,6 +508,59 @@ def run_parler(args):
     return 0
 
 
+def _sharded(args):
+    """-> (rank, world, dist or None): configs 4 / 5 shard independent utterances over the GPUs of a box: one process per GPU under torchrun, every rank runs
+    its own per-GPU batch, no data-path collective; NCCL carries the barriers and the max-over-ranks of the device-timed milliseconds."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return 0, 1, None
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, dist
+
+
+def _max_over_ranks(dist, ms: float) -> float:
+    if dist is None:
+        return ms
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_orpheus_sharded(args):
+    """BASELINE config 5 as it is stated -- Orpheus-3B q8_0, 64 utterances sharded over 8 GPUs = 8 per GPU (N GPUs: 8 N utterances, weak scaling): every rank decodes its 8
+    sequences for 168 steps (24 SNAC frames each) inside the persistent kernel; barrier + synchronize on both sides, device-timed, max over ranks."""
+    import torch
+    from tts_cpp_b200.binding import Context
+    from tts_cpp_b200.synth import build_orpheus_direct
+    rank, world, dist = _sharded(args)
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    orph = build_orpheus_direct(ctx, dtype=args.orpheus_dtype)
+    B, n_tokens = 8, 7 * 24
+    rng = np.random.default_rng(9 + rank)
+    prompts = [rng.integers(1, 100000, size=40).astype(np.uint32) for _ in range(B)]
+    orph.generate_greedy(prompts, 16)
+    ms = []
+    for _ in range(max(1, min(args.steps, 3))):
+        if dist is not None: dist.barrier()
+        torch.cuda.synchronize()
+        orph.generate_greedy(prompts, n_tokens)
+        torch.cuda.synchronize()
+        ms.append(_max_over_ranks(dist, orph.last_ms()))
+    if rank == 0:
+        best = min(ms)
+        audio = world * B * (n_tokens / 7) * (2048 / 24000.0)
+        print(json.dumps({"metric": "audio_seconds_per_second", "workload": f"Orpheus-3B-shaped {args.orpheus_dtype} decoder (synthetic), greedy AR decode, {world * B} utterances sharded over {world} GPU(s), 8 per GPU (BASELINE config 5)",
+                          "value": audio / (best * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": len(ms), "ms_per_step": best, "ms_per_decode_step": best / n_tokens, "scaling": "weak", "collectives": None,
+                          "persistent_kernel": dict(zip(("launches", "steps"), orph.pdk_stats())), "data": "synthetic", "config": {"workload": "orpheus-3b shape, 40-token prompts, 168 decode steps, 8 sequences per GPU"}}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
 def run_orpheus(args):
     """Secondary line: BASELINE config 5's model on ONE GPU of the 8 -- an Orpheus-3B-shaped decoder (28 layers x 3072, 24 / 8 heads x 128, ffn 8192, vocab 156 940) with
     Q8_0 matrices (our own writer: the reference's quantize tool refuses Orpheus and its runtime is F32-only), random weights handed over tensor by tensor (no GGUF file),
@@ -554,10 +607,53 @@ def run_orpheus(args):
     return 0
 
 
+def run_dia_sharded(args):
+    """BASELINE config 4 as it is stated -- Dia-1.6B F16, 8 utterances sharded over 4 GPUs = 2 per GPU (N GPUs: 2 N utterances, weak scaling): every rank generates 10 s for
+    its two CFG pairs inside the persistent kernel and decodes the frames with its DAC; device-timed per rank, max over ranks, barriers on both sides."""
+    import torch
+    from tts_cpp_b200.ar_host import dia_adjust_output_tokens
+    from tts_cpp_b200.binding import Context, dac_runner_from_file
+    from tts_cpp_b200.synth import build_dia_direct, cached_dac_gguf
+    rank, world, dist = _sharded(args)
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    dia = build_dia_direct(ctx, dtype="f16")
+    if rank == 0: cached_dac_gguf(seed=0, max_frames=64)
+    if dist is not None: dist.barrier()
+    dac = dac_runner_from_file(cached_dac_gguf(seed=0, max_frames=64), ctx=ctx)
+    B, frames = 2, 861
+    n_steps = frames + 15
+    rng = np.random.default_rng(4 + rank)
+    prompts = [np.concatenate([[1], rng.integers(32, 127, size=62), [2], rng.integers(32, 127, size=64)]).astype(np.uint32) for _ in range(B)]
+
+    def step():
+        toks, ngen = dia.generate_greedy(prompts, n_steps)
+        t_ar = dia.last_ms()
+        codes = [dia_adjust_output_tokens(t % 1024, 1024) for t in toks]
+        pcm = dac.run_batch(codes, copy=False)
+        return t_ar + dac.last_ms(), sum(p.shape[0] for p in pcm) / 44100.0
+
+    step()
+    ms, audio = [], 0.0
+    for _ in range(max(1, min(args.steps, 3))):
+        if dist is not None: dist.barrier()
+        torch.cuda.synchronize()
+        t, audio = step()
+        ms.append(_max_over_ranks(dist, t))
+    if rank == 0:
+        best = min(ms)
+        print(json.dumps({"metric": "audio_seconds_per_second", "workload": f"Dia-1.6B-shaped F16 model (synthetic), {world * B} utterances (CFG pairs) sharded over {world} GPU(s), 2 per GPU, 10 s each, greedy AR decode + DAC decode (BASELINE config 4)",
+                          "value": world * audio / (best * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": len(ms), "ms_per_step": best, "scaling": "weak", "collectives": None,
+                          "persistent_kernel": dict(zip(("launches", "steps"), dia.pdk_stats())), "data": "synthetic", "config": {"workload": "dia-1.6b shape, 128-byte prompts, 876 decode steps, 2 utterances per GPU"}}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
 def run_dia(args):
     """Secondary line: BASELINE config 4's model on ONE GPU of the 4 -- a Dia-1.6B-shaped F16 model (encoder 12 x 1024, decoder 18 x 2048, 16 q / 4 kv heads x 128, ffn 8192),
     2 utterances per GPU (8 over 4 GPUs), each a CFG pair, 128-byte two-speaker prompts padded to the 1 024-position encoder context, 10 s of audio (861 frames + the
-    15-step delay tail), greedy, launch-per-op path (tensor-core GEMV, CUDA-graph replay), then the DAC decode of the frames."""
+    15-step delay tail), greedy, the decoder loop inside the persistent decode kernel (B2TTS_AR_PDK=0: launch-per-op path), then the DAC decode of the frames.  Under torchrun:
+    run_dia_sharded."""
     if args.impl == "reference":
         print(json.dumps({"impl": "reference", "workload": "dia", "unavailable": "not timed: a 1.6 B-parameter CPU decode of 876 steps per worker takes tens of minutes; the Parler arm (--workload parler --impl reference) is the timed AR reference"}))
         return 0
@@ -728,8 +824,12 @@ def main():
                     help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
                          "parler: config 3 end to end (AR decode + DAC), plain first path")
     args = ap.parse_args()
+    if args.workload == "orpheus" and int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference":
+        return run_orpheus_sharded(args)
+    if args.workload == "dia" and int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference":
+        return run_dia_sharded(args)
     if args.workload != "kokoro" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        if int(os.environ.get("RANK", "0")) == 0:       # the secondary lines are single-GPU measurements; the headline workload is the one that shards
+        if int(os.environ.get("RANK", "0")) == 0:       # the other secondary lines are single-GPU measurements; the headline workload is the one that shards
             print(json.dumps({"workload": args.workload, "unavailable": "secondary workloads are measured on one GPU (run without torchrun)"}))
         return 0
     if args.workload == "snac":
