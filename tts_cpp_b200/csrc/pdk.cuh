@@ -1248,6 +1248,75 @@ __device__ __forceinline__ void pk_attn_item(const PkParams & P, const PkOp & op
     pk_bar_sync(2 + grp, 128);                                  // the scratch is free for the group's next item
 }
 
+// Cross-attention over a SHORT flat store (T <= 4 x 128 / (HD / 8) keys: Parler's text encoding): the same arithmetic in the same order as pk_attn_item, but the K and the
+// V rows (at most 4 + 4 per thread) are requested together with q, so the item is one L2 round trip plus arithmetic instead of three dependent ones.
+template <int HD>
+__device__ __forceinline__ void pk_attn_cross_short(const PkParams & P, const PkOp & op, float * base, int grp, int r, int h, int T) {
+    constexpr int US = 4, PARTS = HD / 8, KPP = 128 / PARTS;
+    const int gt = threadIdx.x & 127, gw = gt >> 5, H = P.H, part = gt % PARTS, kq = gt / PARTS;
+    float * qs = base; float * wredf = base + 128; double * wredd = reinterpret_cast<double *>(base + 136);
+    float * pvs = base + PK_ATT_HDR; float * sc = base + PK_ATT_HDR + 1024;
+    const float * flat_k = op.ck + op.cross_row_stride * (size_t) r + (size_t) h * HD + part * 8, * flat_v = op.cv + op.cross_row_stride * (size_t) r + (size_t) h * HD + part * 8;
+    PkRawF rk[US], rv[US];
+#pragma unroll
+    for (int u = 0; u < US; u++) {
+        const int t = u * KPP + kq;
+        if (t < T) { pk_raw_load(flat_k + (size_t) t * H, rk[u]); pk_raw_load(flat_v + (size_t) t * H, rv[u]); } else { pk_raw_zero(rk[u]); pk_raw_zero(rv[u]); }
+    }
+    if (gt < HD) qs[gt] = __ldcg(op.q + (size_t) r * H + (size_t) h * HD + gt);
+    pk_bar_sync(2 + grp, 128);
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q8[i] = qs[part * 8 + i];
+    float mloc = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < US; u++) {
+        const int t = u * KPP + kq;
+        float k8[8];
+        pk_raw_f(rk[u], k8);
+        float a = fmaf(q8[3], k8[3], fmaf(q8[2], k8[2], fmaf(q8[1], k8[1], q8[0] * k8[0]))) + fmaf(q8[7], k8[7], fmaf(q8[6], k8[6], fmaf(q8[5], k8[5], q8[4] * k8[4])));
+#pragma unroll
+        for (int o = PARTS >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        a *= op.scale;
+        if (t < T) { if (part == 0) sc[t] = a; mloc = fmaxf(mloc, a); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+    if ((gt & 31) == 0) wredf[gw] = mloc;
+    pk_bar_sync(2 + grp, 128);
+    const float m = fmaxf(fmaxf(wredf[0], wredf[1]), fmaxf(wredf[2], wredf[3]));
+    double sum = 0.0;
+    for (int t = gt; t < T; t += 128) { const float e = expf(sc[t] - m); sc[t] = e; sum += (double) e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((gt & 31) == 0) wredd[gw] = sum;
+    pk_bar_sync(2 + grp, 128);
+    const float inv = (float) (1.0 / (((wredd[0] + wredd[1]) + wredd[2]) + wredd[3]));
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int u = 0; u < US; u++) {
+        const int t = u * KPP + kq;
+        const float p = t < T ? sc[t] * inv : 0.f;
+        float v8[8];
+        pk_raw_f(rv[u], v8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fmaf(p, v8[i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) pvs[(size_t) kq * HD + part * 8 + i] = acc[i];
+    pk_bar_sync(2 + grp, 128);
+    if (gt < HD) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int sl = 0; sl < KPP; sl++) a += pvs[(size_t) sl * HD + gt];
+        const __half hv = __float2half_rn(a);
+        for (int c = 0; c < (op.orep ? PK_REP : 1); c++) op.out16[op.orep * c + (size_t) r * H + (size_t) h * HD + gt] = hv;
+    }
+    pk_bar_sync(2 + grp, 128);
+}
+
 template <typename KVT, int HD>
 __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, unsigned char * scratch, int step, const int * sfp, const int * spt) {
     const int grp = threadIdx.x >> 7;
@@ -1264,7 +1333,8 @@ __device__ __forceinline__ void pk_attn(const PkParams & P, const PkOp & op, uns
             part = P.att_part + ((size_t) item * ns + c) * (HD + 4);
             if (t0 >= T) { if ((threadIdx.x & 127) == 0) { part[0] = -INFINITY; part[1] = 0.f; } continue; }      // an empty chunk (short context): weight 0 in the combination
         }
-        if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, t0, t1, part, spt);
+        if (op.cross && ns == 1 && T <= 4 * (128 / (HD / 8))) pk_attn_cross_short<HD>(P, op, base, grp, r, h, T);
+        else if (op.cross) pk_attn_item<KVT, float, HD>(P, op, base, grp, r, h, h, t0, t1, part, spt);
         else pk_attn_item<KVT, KVT, HD>(P, op, base, grp, r, h, h / rep, t0, t1, part, spt);
     }
 }
