@@ -151,6 +151,10 @@ for u in range(2):
     ok &= worst < (0.8 if q8 else 5e-2) and anchors <= (24 if q8 else 4)      # Q8_0: format noise ~2 % of the logit std (4) on both paths, near-ties are frequent
     single = orph.generate_greedy([prompts[u]], steps)                          # batching does not change a sequence
     ok &= bool(np.array_equal(single[0], toks_b[u]))
+# 18 sequences: two groups (16 + 2) through the persistent kernel, each sequence as in the batch of two
+big = orph.generate_greedy([prompts[i % 2] for i in range(18)], 12)
+ok &= all(bool(np.array_equal(big[i], toks_b[i % 2][:12])) for i in range(18))
+print("18-sequence call equals the 2-sequence batch per sequence:", ok)
 # the stop rule inside the persistent kernel: sequence 0's third token becomes the stopping token
 stop = int(toks_b[0][2])
 orph.set_stopping_token(stop)

@@ -35,6 +35,8 @@ ok &= bool(np.array_equal(single[0], toks[1]))                                  
 launches, psteps = par.pdk_stats()
 print("persistent-kernel launches / steps:", launches, psteps)
 ok &= (psteps == 2 * steps) if want_pdk else (psteps == 0)                      # the path this variant is about is the one that ran
+big = par.generate_greedy([prompts[i % 2] for i in range(18)], steps)            # 18 sequences: on the persistent path two groups (16 + 2); every sequence as in the batch of two
+ok &= all(bool(np.array_equal(big[i], toks[i % 2])) for i in range(18))
 par.close()
 sys.exit(0 if ok else 1)
 '''

@@ -160,6 +160,18 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
     const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("orpheus: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
+    // more than 16 sequences, greedy, F16 or Q8_0 matrices: groups of 16, each inside the persistent decode kernel (sequences are independent)
+    if (B > 16 && !samp.do_sample && (head.f16 || head.qtype == 8) && !(getenv("B2TTS_AR_PDK") && getenv("B2TTS_AR_PDK")[0] == '0')) {
+        float total_ms = 0.f;
+        for (int b0 = 0; b0 < B; b0 += 16) {
+            const int nb = std::min(16, B - b0);
+            if (generate(nb, prompts + b0, n_prompt + b0, n_steps, sampling, out_tokens + (size_t) b0 * n_steps, out_logits ? out_logits + (size_t) b0 * n_steps * vocab : nullptr,
+                         n_generated ? n_generated + b0 : nullptr)) return 1;
+            total_ms += timing_ms;
+        }
+        timing_ms = total_ms;
+        return 0;
+    }
     B2_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int R0 = 0, Pmax = 0;

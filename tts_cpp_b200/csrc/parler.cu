@@ -187,6 +187,20 @@ int Parler::generate(int B, const uint32_t * const * prompts, const int32_t * n_
     const ArSampling samp = sampling ? *sampling : ArSampling();
     if (!prepared) { set_error("parler: model not prepared"); return 1; }
     if (B <= 0 || n_steps <= 0) return 0;
+    // more than 16 sequences, greedy / teacher-forced, F16 matrices: groups of 16, each inside the persistent decode kernel (rows are independent: the same tokens as
+    // one large batch on the launch-per-op path, at the persistent kernel's step time)
+    if (B > 16 && !samp.do_sample && heads_w.f16 + (heads_hi != nullptr) > 0 && !layers.empty() && layers[0].wq.f16 && !(getenv("B2TTS_AR_PDK") && getenv("B2TTS_AR_PDK")[0] == '0')) {
+        const int NV_ = n_out * vocab;
+        float total_ms = 0.f;
+        for (int b0 = 0; b0 < B; b0 += 16) {
+            const int nb = std::min(16, B - b0);
+            if (generate(nb, prompts + b0, n_prompt + b0, n_steps, sampling, out_tokens + (size_t) b0 * n_steps * n_out, out_logits ? out_logits + (size_t) b0 * n_steps * NV_ : nullptr,
+                         n_generated ? n_generated + b0 : nullptr, teacher ? teacher + (size_t) b0 * n_steps * n_out : nullptr)) return 1;
+            total_ms += timing_ms;
+        }
+        timing_ms = total_ms;
+        return 0;
+    }
     B2_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int R0 = 0, Pmax = 0;
