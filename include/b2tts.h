@@ -181,7 +181,7 @@ float b2tts_snac_last_ms(const b2tts_snac * m);   /* device time of the last dec
 int   b2tts_snac_reset_noise(b2tts_snac * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Orpheus autoregressive decode.  Two paths behind the same calls: F16 or Q8_0 matrices (all of one kind), greedy, <= 16 sequences, hidden <= 3 072 run decode steps 1 .. n-1 inside
+ * Orpheus autoregressive decode.  Two paths behind the same calls: F16 or Q8_0 matrices (all of one kind), greedy (calls with more than 16 sequences run as groups of 16), hidden <= 3 072 run decode steps 1 .. n-1 inside
  * the PERSISTENT DECODE KERNEL (csrc/pdk.cuh: RMSNorm folded into the staging, NeoX RoPE + cache append and SwiGLU in the GEMV epilogues, paged fp16 GQA cache, chunked
  * argmax; Q8_0: activations quantised per 32-block once per phase, int8 MMA, fp32 scale products = ggml_vec_dot_q8_0_q8_0; on a B200 the reference's tokens over 72
  * steps, logits 7.5e-3 (F16); Orpheus-3B shape F16 3.3-5.0 ms per step at 1-16 sequences); everything else runs the launch-per-op
@@ -215,14 +215,14 @@ int   b2tts_orpheus_generate_until_stop(b2tts_orpheus * m, int n_sequences, cons
                                         const b2tts_sampling * sampling, int32_t * out_tokens, int32_t * n_generated);
 int   b2tts_orpheus_set_stopping_token(b2tts_orpheus * m, int token_id);   /* overrides orpheus.stopping_token_id of the GGUF (model.h:43: 128258) */
 size_t b2tts_orpheus_step_weight_bytes(const b2tts_orpheus * m);   /* W_step of SURVEY 8(d): bytes of the weight tensors one decode step touches, each once, stored dtype */
-/* F16 GGUFs, greedy, <= 16 sequences, hidden <= 3 072: decode steps 1 .. n-1 run inside the persistent decode kernel (csrc/pdk.cuh; B2TTS_AR_PDK=0: launch per op);
+/* F16 or Q8_0 GGUFs, greedy (groups of 16 sequences), hidden <= 3 072: decode steps 1 .. n-1 run inside the persistent decode kernel (csrc/pdk.cuh; B2TTS_AR_PDK=0: launch per op);
  * -> cooperative launches so far and the decode steps they covered */
 void  b2tts_orpheus_pdk_stats(const b2tts_orpheus * m, uint64_t * launches, uint64_t * steps);
 size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m);   /* bytes resident in HBM (B2TTS_AR_MMA=1 adds the fp16 split copies of the matrices) */
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Parler-TTS autoregressive decode.  Two paths behind the same calls: F16 GGUFs (BASELINE config 3), greedy or teacher-forced, <= 16 sequences run
+ * Parler-TTS autoregressive decode.  Two paths behind the same calls: F16 GGUFs (BASELINE config 3), greedy or teacher-forced (calls with more than 16 sequences run as groups of 16) run
  * the PERSISTENT DECODE KERNEL (csrc/pdk.cuh: one cooperative launch per 32 decode steps, TMA weight ring, paged fp16 KV cache, LayerNorm / GELU / residual / KV append
  * folded into the GEMV phases); everything else (F32 / Q8_0 / Q5_0 / Q4_0 matrices, sampling, larger batches, B2TTS_AR_PDK=0) the launch-per-op path (tensor-core GEMV,
  * CUDA-graph replay).  Hardware status (B200, tests/test_parler_gpu.py + test_ar_fullsize_gpu.py, all green): the reference's token ids exactly on every F32 / F16
