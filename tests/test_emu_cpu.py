@@ -21,7 +21,7 @@ from tts_cpp_b200.synth import cached_dia_gguf, cached_orpheus_gguf, cached_parl
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "sampler.cu"]
+AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "pdk.cu", "sampler.cu"]
 # The library's defaults are the fast paths (persistent decode kernel for F16 Parler, tensor-core GEMV for F16 matrices, CUDA-graph replay); most tests below are about
 # one specific kernel family, so they start from the plain launch-per-op configuration and switch on what they test.
 EMU_DEFAULTS = {"B2TTS_AR_PDK": "0", "B2TTS_AR_MMA": "0", "B2TTS_AR_GRAPH": "0"}

@@ -384,12 +384,8 @@ int Orpheus::generate(int B, const uint32_t * const * prompts, const int32_t * n
         PkLaunch pkl;
         if (pk_configure(Pk, kv_f32, std::min(std::max(H, F), pk_ak), 0, Tmax, pkl)) { set_error("orpheus: the persistent decode kernel does not fit this shape (%d positions) in shared memory", Tmax); return 1; }
         pk_prof_begin(Pk, ops.size(), pk_grid, st);
-        {   // the prompt pass' K / V rows (fp32, compact GQA rows) into the pages
-            dim3 grid(R0, n_layers);
-            if (kv_f32) pk_kv_import_kernel<float><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * KV, row_src, row_seq, row_pos, Pk);
-            else pk_kv_import_kernel<__half><<<grid, 256, 0, st>>>(Kc, Vc, (size_t) B * Tst * KV, row_src, row_seq, row_pos, Pk);
-            B2_LAUNCH_CHECK(ctx);
-        }
+        pk_kv_import(kv_f32, Kc, Vc, (size_t) B * Tst * KV, row_src, row_seq, row_pos, Pk, R0, n_layers, st);      // the prompt pass' K / V rows (fp32, compact GQA rows) into the pages
+        B2_LAUNCH_CHECK(ctx);
         for (int s0 = 1; s0 < n_steps; s0 += exit_every) {
             if (stopped && s0 > 1) { const int a = all_stopped(); if (a < 0) return 1; if (a) break; }
             Pk.step_begin = s0; Pk.n_steps = std::min(exit_every, n_steps - s0);

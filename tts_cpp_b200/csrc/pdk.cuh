@@ -25,15 +25,18 @@
 // Logic checked in the build container under tests/emu (cooperative launch = all blocks' threads alive at once as fibers; mbarriers, bulk copies and the grid
 // barrier have functional models below).
 #pragma once
-#include "ar_kernels.cuh"
+#include "kokoro.h"   // CUDA types, HostTensor, ArW
 
 #include <algorithm>
 #include <cstdio>
 #include <functional>
 #include <vector>
 
+// This header has two faces.  Included plainly (parler.cu, orpheus.cu, dia.cu) it declares the program types and the host entry points; pdk.cu defines
+// B2_PDK_IMPLEMENTATION before including it and is the one translation unit that carries the kernel (six instantiations) -- compiled into every model file it was 3 x 7 MB
+// of identical device code.
 namespace b2 {
-namespace {
+
 
 constexpr int PK_CONS = 256;                      // consumer threads (8 warps)
 constexpr int PK_THREADS = 288;                   // + the producer warp
@@ -104,6 +107,27 @@ struct PkParams {
     float * logits; float * logits_all;           // logits [R][n_out * vocab]; logits_all (optional) [n_steps_total][R][n_out * vocab]
     unsigned long long * prof; int prof_step;     // optional timeline of step prof_step: [n_ops][gridDim.x][8] %globaltimer ns (op begin, activations staged, barrier entered, barrier left, ns spent waiting for weight tiles, norm tile ready, -, -)
 };
+
+struct PkLaunch {
+    const void * kfn = nullptr; size_t smem = 0;
+#ifdef B2EMU
+    std::function<void(const PkParams &)> kemu;
+#endif
+};
+// shared-memory layout + kernel instantiation for a program; one cooperative launch of Pk.n_steps steps; the %globaltimer timeline; the prompt pass' K / V rows -> pages
+int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int Tscore, PkLaunch & L);
+cudaError_t pk_launch(const PkLaunch & L, const PkParams & Pk, int grid, cudaStream_t st);
+void pk_prof_begin(PkParams & Pk, size_t n_ops, int grid, cudaStream_t st);
+void pk_prof_end(PkParams & Pk, const std::vector<PkOp> & ops, int grid, cudaStream_t st);
+void pk_kv_import(bool kv_f32, const float * Kc, const float * Vc, size_t layer_stride, const int * row_src, const int * row_seq, const int * row_pos, const PkParams & P, int n_rows, int n_layers, cudaStream_t st);
+
+}  // namespace b2
+
+#ifdef B2_PDK_IMPLEMENTATION
+#include "ar_kernels.cuh"
+
+namespace b2 {
+namespace {
 
 // ---------------------------------------------------------------- primitives: mbarrier, bulk copy, named / grid barriers (PTX; functional models under B2EMU)
 #ifdef B2EMU
@@ -1657,18 +1681,15 @@ __global__ void pk_kv_import_kernel(const float * __restrict__ Kc, const float *
     }
 }
 
+}  // namespace
+
 static inline size_t pk_smem_bytes(int n_stages, int a_bytes, int pt_ints) { return (size_t) (16 + pt_ints) * 4 + (size_t) n_stages * PK_STAGE + (size_t) a_bytes + PK_RED_BYTES + 64 + 2 * PK_MAXSTAGES * sizeof(PkBar) + 3 * sizeof(PkOp) + 16 + 128 + 128; }
 
 // ---------------------------------------------------------------- host side shared by the models' generate() functions
-struct PkLaunch {
-    const void * kfn = nullptr; size_t smem = 0;
-#ifdef B2EMU
-    std::function<void(const PkParams &)> kemu;
-#endif
-};
+
 // shared-memory layout for a program whose widest activation chunk has KA columns (KAs: widest chunk of a split-matrix phase, 0 = none) and whose attention sees at
 // most Tscore positions; picks the kernel instantiation for (cache element type, head size).  Returns 1 when the shape does not fit.
-static inline int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int Tscore, PkLaunch & L) {
+int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int Tscore, PkLaunch & L) {
     size_t a = (size_t) 16 * (KA + PK_PAD) * 2;
     if (KAs) a = std::max(a, (size_t) 2 * 16 * (KAs + PK_PAD) * 2);
     a = std::max(a, 2 * pk_att_bytes(Tscore));
@@ -1696,7 +1717,7 @@ static inline int pk_configure(PkParams & Pk, bool kv_f32, int KA, int KAs, int 
     return 0;
 }
 // one cooperative launch of steps [Pk.step_begin, Pk.step_begin + Pk.n_steps)
-static inline cudaError_t pk_launch(const PkLaunch & L, const PkParams & Pk, int grid, cudaStream_t st) {
+cudaError_t pk_launch(const PkLaunch & L, const PkParams & Pk, int grid, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(Pk.bar, 0, 256, st);
     if (e != cudaSuccess) return e;
 #ifdef B2EMU
@@ -1709,7 +1730,7 @@ static inline cudaError_t pk_launch(const PkLaunch & L, const PkParams & Pk, int
 #endif
 }
 // B2TTS_PDK_PROF=<step>: %globaltimer timeline of that decode step (every op x every CTA), written as raw uint64 to $B2TTS_PDK_PROF_FILE after the run
-static inline void pk_prof_begin(PkParams & Pk, size_t n_ops, int grid, cudaStream_t st) {
+void pk_prof_begin(PkParams & Pk, size_t n_ops, int grid, cudaStream_t st) {
     const char * e = getenv("B2TTS_PDK_PROF");
     if (!e) return;
     const size_t words = n_ops * (size_t) grid * 8;
@@ -1717,7 +1738,7 @@ static inline void pk_prof_begin(PkParams & Pk, size_t n_ops, int grid, cudaStre
     cudaMemsetAsync(Pk.prof, 0, words * 8, st);
     Pk.prof_step = atoi(e);
 }
-static inline void pk_prof_end(PkParams & Pk, const std::vector<PkOp> & ops, int grid, cudaStream_t st) {
+void pk_prof_end(PkParams & Pk, const std::vector<PkOp> & ops, int grid, cudaStream_t st) {
     if (!Pk.prof) return;
     std::vector<unsigned long long> hp(ops.size() * (size_t) grid * 8);
     cudaMemcpyAsync(hp.data(), Pk.prof, hp.size() * 8, cudaMemcpyDeviceToHost, st);
@@ -1733,5 +1754,12 @@ static inline void pk_prof_end(PkParams & Pk, const std::vector<PkOp> & ops, int
     cudaFree(Pk.prof); Pk.prof = nullptr;
 }
 
-}  // namespace
+
+void pk_kv_import(bool kv_f32, const float * Kc, const float * Vc, size_t layer_stride, const int * row_src, const int * row_seq, const int * row_pos, const PkParams & P, int n_rows, int n_layers, cudaStream_t st) {
+    dim3 grid(n_rows, n_layers);
+    if (kv_f32) pk_kv_import_kernel<float><<<grid, 256, 0, st>>>(Kc, Vc, layer_stride, row_src, row_seq, row_pos, P);
+    else pk_kv_import_kernel<__half><<<grid, 256, 0, st>>>(Kc, Vc, layer_stride, row_src, row_seq, row_pos, P);
+}
+
 }  // namespace b2
+#endif  // B2_PDK_IMPLEMENTATION
