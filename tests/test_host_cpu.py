@@ -201,6 +201,19 @@ def test_reference_side_binding_type_checks_against_the_reference_headers():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_batch_draining_worker_selftest():
+    """integration/b200_batch_worker.h behind a server-shaped queue with the reference's own dummy_runner: compatible tasks share one forward,
+    the others keep their place and order, max_batch, timed-out tasks, the one-by-one fallback, task-owned PCM.  The binary is built by build() where the reference
+    checkout exists (integration/Makefile) and needs no GPU."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "integration", "_build", "worker_demo")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build/worker_demo not built (no reference checkout)")
+    r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "worker selftest OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
 def test_delay_pattern_undo_matches_the_reference_indexing():
     """ar_host.{parler,dia}_adjust_output_tokens against a literal restatement of the reference's flat-index loops
     (parler model.cpp:734-760, dia model.cpp:825-847) on random token streams with special ids mixed in."""
