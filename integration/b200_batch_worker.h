@@ -19,6 +19,7 @@
 #include "tts_b200.h"
 
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -101,6 +102,7 @@ void batch_loop(std::atomic<bool> & running, Queue & q, Map & responses, int tas
         std::vector<decltype(head)> batch{ head };
         if (max_batch > 1) drain_compatible(q, head, tts_kind, max_batch, batch);
         if (batch_sizes) batch_sizes->push_back(batch.size());
+        if (std::getenv("B2TTS_WORKER_LOG")) { fprintf(stderr, "b200 worker: forward of %zu task(s)\n", batch.size()); fflush(stderr); }
         process_batch(batch, runner_of(head), responses, task_timeout, generate_batch);
     }
 }

@@ -107,3 +107,72 @@ def tie_report(name, ref_logits, ref_tokens, got_logits, got_tokens, margin_fact
               + (f"  CLEAR DECISIONS DIFFER: {clear}" if clear else ""))
         ok &= not clear
     return ok
+
+
+class patched_server:
+    """integration/_build/tts-server-b200 (the reference's server.cpp with the batch-draining worker patched in at build time) on 127.0.0.1.
+    `with patched_server(model_path) as url:`; the process is ended by PID.  `.log()` = its stderr (B2TTS_WORKER_LOG=1: one line per batched forward)."""
+
+    def __init__(self, model_path, max_batch=32, extra=()):
+        self.exe = os.path.join(ROOT, "integration", "_build", "tts-server-b200")
+        self.model_path, self.max_batch, self.extra = model_path, max_batch, list(extra)
+
+    def __enter__(self):
+        import socket
+        import subprocess
+        import tempfile
+        import time
+        import requests
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        self.errf = tempfile.NamedTemporaryFile(prefix="b2srv_", suffix=".log", delete=False)
+        env = dict(os.environ, B2TTS_WORKER_LOG="1", B2TTS_SERVER_MAX_BATCH=str(self.max_batch))
+        self.p = subprocess.Popen([self.exe, "--model-path", self.model_path, "--port", str(port), "--n-threads", "4"] + self.extra, stdout=subprocess.DEVNULL,
+                                  stderr=self.errf, env=env, cwd=tempfile.gettempdir())
+        self.url = f"http://127.0.0.1:{port}"
+        for _ in range(600):                                   # model load + CUDA context on a fresh box can take a while
+            if self.p.poll() is not None:
+                raise RuntimeError("server exited: " + self.log()[-2000:])
+            try:
+                if requests.get(self.url + "/health", timeout=1).status_code == 200:
+                    return self
+            except requests.RequestException:
+                pass
+            time.sleep(0.25)
+        self.__exit__(None, None, None)
+        raise RuntimeError("server did not come up: " + self.log()[-2000:])
+
+    def speech(self, prompts, threads=8, **fields):
+        """POST /v1/audio/speech for every prompt, `threads` at a time -> list of (status, int16 samples, frame rate)."""
+        import concurrent.futures as cf
+        import io
+        import wave
+        import requests
+
+        def one(p):
+            r = requests.post(self.url + "/v1/audio/speech", json=dict(input=p, **fields), timeout=300)
+            if r.status_code != 200:
+                return r.status_code, np.zeros(0, np.int16), 0
+            with wave.open(io.BytesIO(r.content), "rb") as w:
+                return 200, np.frombuffer(w.readframes(w.getnframes()), np.int16), w.getframerate()
+        with cf.ThreadPoolExecutor(threads) as ex:
+            return list(ex.map(one, prompts))
+
+    def log(self):
+        self.errf.flush()
+        return open(self.errf.name, errors="replace").read()
+
+    def forwards(self):
+        import re
+        return [int(m) for m in re.findall(r"b200 worker: forward of (\d+) task", self.log())]
+
+    def __exit__(self, *a):
+        import subprocess
+        if self.p.poll() is None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+                self.p.wait()

@@ -214,6 +214,30 @@ def test_batch_draining_worker_selftest():
     assert r.returncode == 0 and "worker selftest OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
+def test_patched_reference_server_serves_http_with_the_batch_worker():
+    """The reference's examples/server/server.cpp with the three edits of INTEGRATION.md section 5 applied at build time (integration/patch_server.py), over real HTTP
+    with the reference's `test:dummy` model (one second of a per-character tone per prompt character, src/models/dummy/model.cpp): every concurrent request gets ITS
+    OWN audio (the worker hands every task a copy; upstream hands out a pointer into the runner's buffer), and every task went through b200::batch_loop."""
+    from conftest import patched_server
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "integration", "_build", "tts-server-b200")):
+        pytest.skip("integration/_build/tts-server-b200 not built (no reference checkout)")
+    prompts = ["a", "bb", "ccc", "dd", "e", "ff", "ggg", "h", "ab", "ba"]
+    with patched_server("test:dummy", max_batch=4) as srv:
+        out = srv.speech(prompts, threads=10)
+        fw = srv.forwards()
+    sr = 44100
+    j = np.arange(sr, dtype=np.float32)
+    for p, (code, pcm, rate) in zip(prompts, out):
+        assert code == 200 and rate == sr and pcm.size == len(p) * sr, (p, code, rate, pcm.size)
+        for i, ch in enumerate(p):                             # the dummy model's tone for this character: 16-bit WAV of sin(j pi / sr) * sin(j / wavelength)
+            wl = np.float32(np.float32(sr / np.pi / 2) / np.float32(200 + ord(ch)))
+            want = np.sin(j * np.float32(np.pi / sr)) * np.sin(j / wl)
+            got = pcm[i * sr:(i + 1) * sr].astype(np.float32) / 32768.0
+            assert np.abs(got - want).max() < 2e-3, (p, i, float(np.abs(got - want).max()))
+    assert sum(fw) == len(prompts) and max(fw) <= 4, fw       # every task through the batch loop, never more than max_batch per forward
+
+
 def test_delay_pattern_undo_matches_the_reference_indexing():
     """ar_host.{parler,dia}_adjust_output_tokens against a literal restatement of the reference's flat-index loops
     (parler model.cpp:734-760, dia model.cpp:825-847) on random token streams with special ids mixed in."""
