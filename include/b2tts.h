@@ -129,6 +129,13 @@ int b2tts_op_cumsum(b2tts_ctx * ctx, const float * x, int L, int rows, float * y
 int   b2tts_op_sample(b2tts_ctx * ctx, const float * logits, int rows, int vocab, int do_sample, int top_k, float top_p, float temperature, float repetition_penalty,
                       int32_t * last_ids, int32_t * rep_counts, uint64_t seed, int step, int32_t * tokens);
 float b2tts_sample_uniform(uint64_t seed, uint64_t row, uint64_t step);
+/* apply_energy_voice_inactivity_detection (reference examples/cli/vad.cpp:11-68, the `tts-cli --vad` trailing-silence trim) for a batch of B utterances laid back to
+ * back in `pcm` (n_samples[b] floats each): n_out[b] = the data.n_outputs the reference leaves behind (its size_t as int64 two's complement).  The argument list is
+ * the reference function's (vad.h:13-22, same defaults: 44100, 10, 20, 0.01, 5, 3, 0.1).  energies_out (may be NULL): the frame energies (vad.cpp:3-9), per
+ * utterance n_samples[b] / samples_per_frame floats, back to back.  Errors where the reference divides by zero (ms_per_frame <= 0, samples_per_frame < 1). */
+int b2tts_op_vad_trim(b2tts_ctx * ctx, const float * pcm, const int64_t * n_samples, int B, float sample_rate, int ms_per_frame, int frame_threshold,
+                      float normalized_energy_threshold, int trailing_silent_frames, int early_cutoff_seconds_threshold, float early_cutoff_energy_threshold,
+                      int64_t * n_out, float * energies_out);
 int b2tts_op_mod(b2tts_ctx * ctx, const float * x, int64_t n, float mod_val, float * y);      /* ggml_mod: fmod */
 int b2tts_op_round(b2tts_ctx * ctx, const float * x, int64_t n, float * y);                   /* ggml_round: (float)(int)(x+0.5f) */
 int b2tts_op_reciprocal(b2tts_ctx * ctx, const float * x, int64_t n, float * y);              /* ggml_reciprocal */

@@ -120,6 +120,11 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 template <class T> static inline T __ldcs(const T * p) { return *p; }
 static inline int __dp4a(int a, int b, int c) { for (int i = 0; i < 4; i++) c += (int) (int8_t) (a >> (8 * i)) * (int) (int8_t) (b >> (8 * i)); return c; }
 static inline unsigned __vsub4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i); return r; }
+// the explicitly rounded forms: one IEEE operation each, never contracted into an FMA by the host compiler (the volatile result pins the rounding)
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline int __float2int_rn(float x) { return (int) nearbyintf(x); }      // round-to-nearest-even (the default rounding mode)
 // fibers are cooperative (a thread runs until its next barrier / shuffle), so a read-modify-write is atomic as it stands
 static inline unsigned atomicAdd(unsigned * p, unsigned v) { const unsigned o = *p; *p = o + v; b2emu::note_progress(); return o; }

@@ -678,3 +678,27 @@ def test_persistent_decode_kernel_emulated_orpheus_q8_0(tmp_path):
               f"tokens equal {int((tok[u, :, 0] == g[f'tokens{u}']).sum())}/{steps}, clear decisions {int(clear.sum())}")
         assert rel[0] < 0.05 and rel[0] < 1.5 * rel[1] + 1e-3
         assert np.array_equal(tok[u, :, 0][clear], g[f"tokens{u}"][clear])
+
+
+def test_vad_kernels_emulated_match_reference(tmp_path):
+    """vad.cu (vad_energy_kernel + vad_decide_kernel through vad_trim_rows) under emulation against the compiled unmodified examples/cli/vad.cpp
+    (tests/golden/vad_vectors.npz): trimmed lengths and frame energies bit for bit on every case of vad_cases.py, in both thread orders and under AddressSanitizer
+    (exact-size PCM / energy buffers: a read past an utterance's last whole frame or a write past the energy array is reported)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden")); sys.path.insert(0, ROOT)
+    import vad_cases
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vad_vectors.npz"))
+    exe = emu_build.build("vad_emu", ["vad.cu"], ["vad_main.cpp"])
+    exe_asan = emu_build.build("vad_emu_asan", ["vad.cu"], ["vad_main.cpp"], asan=True)
+    for name, kw, utts in vad_cases.cases():
+        pin, pout = str(tmp_path / f"{name}.in"), str(tmp_path / f"{name}.out")
+        open(pin, "wb").write(vad_cases.pack_input(kw, utts))
+        raws = []
+        for e, env in ((exe, {}), (exe, {"B2EMU_REVERSE": "1"}), (exe_asan, {"ASAN_OPTIONS": "detect_stack_use_after_return=0:detect_leaks=0"})):
+            r = subprocess.run([e, pin, pout], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+            assert r.returncode == 0, (name, r.stderr[-3000:])
+            raws.append(open(pout, "rb").read())
+        assert raws[0] == raws[1] == raws[2]
+        n_out, en = vad_cases.unpack_output(raws[0], kw, utts)
+        assert np.array_equal(n_out, g[name + ".n_out"]), (name, n_out, g[name + ".n_out"])
+        for b in range(len(utts)):
+            assert np.array_equal(en[b], g[f"{name}.energies.{b}"]), (name, b)

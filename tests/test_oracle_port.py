@@ -301,3 +301,21 @@ def test_parler_port_replacement_text_encoding():
     port.set_text_encoding(g["encoding"])
     toks, logits = port.greedy(g["prompt0"], g["tokens0"].shape[0])
     assert np.array_equal(toks, g["tokens0"]) and float(np.abs(logits - g["logits0"]).max()) < 1e-2
+
+
+def test_vad_port_against_reference():
+    """oracle/vad_port.py against the compiled unmodified examples/cli/vad.cpp (tests/golden/vad_vectors.npz, made by make_golden_vad.py from the generated inputs of
+    vad_cases.py): trimmed lengths AND frame energies bit for bit -- trailing trim, early cut-off, ragged tails, empty / sub-frame / constant inputs, the
+    negative-trim quirk (n_outputs grows), frame lengths with every fused-tail length of the reference build."""
+    sys.path.insert(0, GOLD)
+    import vad_cases
+    from oracle.vad_port import vad_trim
+    g = np.load(os.path.join(GOLD, "vad_vectors.npz"))
+    for name, kw, utts in vad_cases.cases():
+        assert [u.size for u in utts] == g[name + ".n_in"].tolist()
+        for b, u in enumerate(utts):
+            n, e = vad_trim(u, **kw)
+            assert n == int(g[name + ".n_out"][b]), (name, b, n, int(g[name + ".n_out"][b]))
+            assert np.array_equal(e, g[f"{name}.energies.{b}"]), (name, b)
+    assert int(g["kokoro_rate_negative_trim.n_out"][0]) > int(g["kokoro_rate_negative_trim.n_in"][0])      # the quirk is in the vectors
+    assert int(g["defaults.n_out"][3]) < 44100                                                                # so is the early cut-off

@@ -85,6 +85,23 @@ class Context:
         _chk(lib().b2tts_op_conv_1d(self.h, _fp(k), K, cin, cout, _fp(xx), L, stride, pad, dil, 1, _fp(y)))
         return y
 
+    def vad_trim(self, utterances, sample_rate=44100.0, ms_per_frame=10, frame_threshold=20, normalized_energy_threshold=0.01, trailing_silent_frames=5,
+                 early_cutoff_seconds_threshold=3, early_cutoff_energy_threshold=0.1):
+        """apply_energy_voice_inactivity_detection (examples/cli/vad.cpp:11-68) for a batch -> (n_outputs[B] int64, [energies per utterance])"""
+        utts = [np.ascontiguousarray(u, np.float32).ravel() for u in utterances]
+        n = np.asarray([u.size for u in utts], np.int64)
+        pcm = np.concatenate(utts) if utts else np.zeros(0, np.float32)
+        spf = int(np.float32(ms_per_frame) * np.float32(sample_rate) / np.float32(1000.0)) if ms_per_frame > 0 else 0
+        nf = (n // spf) if spf > 0 else np.zeros_like(n)
+        en = np.zeros(max(int(nf.sum()), 1), np.float32)
+        out = np.zeros(max(len(utts), 1), np.int64)
+        L = lib()
+        L.b2tts_op_vad_trim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        _chk(L.b2tts_op_vad_trim(self.h, pcm.ctypes.data, n.ctypes.data, len(utts), sample_rate, ms_per_frame, frame_threshold, normalized_energy_threshold,
+                                 trailing_silent_frames, early_cutoff_seconds_threshold, early_cutoff_energy_threshold, out.ctypes.data, en.ctypes.data))
+        cuts = np.concatenate([[0], np.cumsum(nf)]).astype(np.int64)
+        return out[:len(utts)], [en[cuts[b]:cuts[b + 1]].copy() for b in range(len(utts))]
+
     def cumsum(self, x):
         xx = np.ascontiguousarray(x, np.float32); y = np.empty_like(xx)
         _chk(lib().b2tts_op_cumsum(self.h, _fp(xx), xx.shape[-1], int(xx.size // xx.shape[-1]), _fp(y)))

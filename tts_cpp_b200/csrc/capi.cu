@@ -451,6 +451,35 @@ int b2tts_op_cumsum(b2tts_ctx * ctx, const float * x, int L, int rows, float * y
     if (!dx || !dy || op_cumsum(c, dx, L, rows, dy)) return 1;
     return finish(c, y, dy, (size_t) L * rows * 4);
 }
+int b2tts_op_vad_trim(b2tts_ctx * ctx, const float * pcm, const int64_t * n_samples, int B, float sample_rate, int ms_per_frame, int frame_threshold,
+                      float normalized_energy_threshold, int trailing_silent_frames, int early_cutoff_seconds_threshold, float early_cutoff_energy_threshold,
+                      int64_t * n_out, float * energies_out) {
+    Ctx * c = &ctx->c;
+    if (B <= 0) return 0;
+    if (ms_per_frame <= 0) { set_error("vad: ms_per_frame must be positive (the reference divides by it)"); return 1; }
+    const int spf = (int) (ms_per_frame * sample_rate / 1000.0f);                                  // vad.cpp:20
+    if (spf <= 0) { set_error("vad: ms_per_frame * sample_rate / 1000 < 1 (the reference divides by zero here)"); return 1; }
+    const int early_frames = (int) ((early_cutoff_seconds_threshold * 1000) / ms_per_frame);       // vad.cpp:22
+    std::vector<long long> off((size_t) B + 1, 0), eoff((size_t) B + 1, 0);
+    int max_frames = 0;
+    for (int b = 0; b < B; b++) {
+        if (n_samples[b] < 0) { set_error("vad: utterance %d has a negative length", b); return 1; }
+        const long long nf = n_samples[b] / spf;
+        if (nf > 0x7fffffff) { set_error("vad: utterance %d has more frames than the reference's int can count", b); return 1; }
+        off[(size_t) b + 1] = off[(size_t) b] + n_samples[b]; eoff[(size_t) b + 1] = eoff[(size_t) b] + nf;
+        max_frames = std::max(max_frames, (int) nf);
+    }
+    Dev d;
+    float * dp = d.put(pcm, (size_t) off[(size_t) B]); long long * doff = d.put(off.data(), off.size()), * deoff = d.put(eoff.data(), eoff.size());
+    float * de = d.get<float>((size_t) eoff[(size_t) B]); long long * dn = d.get<long long>((size_t) B);
+    if (!dp || !doff || !deoff || !de || !dn) return 1;
+    if (vad_trim_rows(c, dp, doff, deoff, B, max_frames, spf, frame_threshold, normalized_energy_threshold, trailing_silent_frames, early_frames,
+                      early_cutoff_energy_threshold, de, dn)) return 1;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t");
+    if (finish(c, n_out, dn, (size_t) B * 8)) return 1;
+    if (energies_out && eoff[(size_t) B]) B2_CUDA(cudaMemcpy(energies_out, de, (size_t) eoff[(size_t) B] * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
 static int unary(b2tts_ctx * ctx, int which, const float * x, int64_t n, float arg, float * y) {
     Ctx * c = &ctx->c; Dev d; float * dx = d.put(x, (size_t) n); float * dy = d.get<float>((size_t) n);
     if (!dx || !dy || op_unary(c, which, dx, n, arg, dy)) return 1;

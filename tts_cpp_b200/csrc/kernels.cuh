@@ -114,6 +114,12 @@ int op_conv_transpose_1d(Ctx * ctx, const float * w, int K, int coutg, int cin, 
 int convt_cl(Ctx * ctx, const float * x, int ldx, int Cin, int B, int LmaxIn, const int * lenIn, const float * w, const float * bias, int K,
              int Cout, int stride, int pad, float ns, int reflect1, float * y, int ldy, int LmaxOut, const int * lenOut);
 
+// vad.cu -- apply_energy_voice_inactivity_detection (reference examples/cli/vad.cpp:11-68) for B utterances resident in HBM, back to back in d_pcm.
+// d_off[B + 1]: sample offsets; d_eoff[B + 1]: offsets into d_energies (n_b / spf whole frames each); max_frames = the largest frame count; spf, early_frames: the
+// reference's samples_per_frame / early_cuttoff_frames (computed by the caller as vad.cpp:20,22 does); d_n_out[b] = the trimmed n_outputs
+int vad_trim_rows(Ctx * ctx, const float * d_pcm, const long long * d_off, const long long * d_eoff, int B, int max_frames, int spf, int frame_threshold,
+                  float norm_threshold, int trailing, int early_frames, float early_threshold, float * d_energies, long long * d_n_out);
+
 // sampler.cu -- the reference sampler (src/sampler.cpp) on the device for `rows` independent heads: repetition penalty, temperature, top-k, top-p, one draw each.
 // temperature <= 0 or do_sample == 0 is sampler::max.  The uniform of a row comes from (seed, row, *d_step) by a counter-based hash, so a captured graph of a
 // decode step can be replayed; out[*d_step * rows + row] receives the token (d_step == nullptr: step 0).
