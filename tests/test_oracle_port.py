@@ -319,3 +319,21 @@ def test_vad_port_against_reference():
             assert np.array_equal(e, g[f"{name}.energies.{b}"]), (name, b)
     assert int(g["kokoro_rate_negative_trim.n_out"][0]) > int(g["kokoro_rate_negative_trim.n_in"][0])      # the quirk is in the vectors
     assert int(g["defaults.n_out"][3]) < 44100                                                                # so is the early cut-off
+
+
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide"])
+def test_t5_port_against_reference(case):
+    """oracle/t5_port.py against the compiled unmodified T5 encoder (t5_runner::run; tests/golden/t5_vectors.npz from make_golden_t5.py): 2- to 88-token prompts
+    (every relative-position bucket incl. the log-spaced ones and the reference's integer division inside the logarithm), with / without the down projection,
+    F32 and F16 matrices.  Floor: the fp16 GELU table (an input on a rounding boundary moves an activation by 1e-3) -- and fp16 activation rounding for F16."""
+    sys.path.insert(0, GOLD)
+    import make_golden_t5 as M
+    from oracle.t5_port import T5Port
+    from tts_cpp_b200.synth import cached_t5_gguf
+    g = np.load(os.path.join(GOLD, "t5_vectors.npz"))
+    kw, prompts = M.CASES[case]
+    port = T5Port(cached_t5_gguf(**kw))
+    for i, p in enumerate(prompts):
+        assert g[f"{case}.tokens.{i}"].tolist() == p
+        d, r, mx = report(f"t5 port {case}.{i}", port.run(p), g[f"{case}.encoding.{i}"])
+        assert d < (1.5e-3 if case == "f16" else 1e-4) * r, (case, i, d, r)

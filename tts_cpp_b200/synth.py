@@ -848,3 +848,72 @@ def build_dia_direct(ctx, dtype: str = "f16", seed: int = 0, **shape):
         put(f"decoder.heads.{i}", hw[0], hw[1], [V, D])
     _chk(lib().b2tts_dia_prepare(h))
     return DiaRunner(ctx, h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------------
+# T5 conditional-prompt encoder: the text encoder Parler-TTS conditions on (reference src/models/parler/t5/model.cpp)
+def t5_tensors(seed: int = 0, layers: int = 3, heads: int = 2, ffn: int = 192, vocab: int = 96, out_size: int = 256, down_proj: bool = True):
+    """Synthetic weights in the reference's T5-encoder schema (T5_TENSOR_GGUF_LOOKUP, src/models/parler/t5/model.cpp:3-19; hyper-parameter keys
+    :118-158).  The head size is fixed at 64 upstream (model.h:46), so hidden = 64 * heads."""
+    rng = np.random.default_rng(seed + 7700)
+    hidden = 64 * heads
+    items: list[tuple[str, np.ndarray]] = []
+
+    def rand(name, shape, scale):
+        items.append((name, (rng.standard_normal(shape).astype(np.float32) * np.float32(scale)).astype(np.float16).astype(np.float32)))
+
+    def norm(name, c):
+        items.append((name, (1.0 + 0.1 * rng.standard_normal(c)).astype(np.float32).astype(np.float16).astype(np.float32)))
+
+    rand("t5encoder.token_embd", (vocab, hidden), 1.0)
+    for l in range(layers):
+        b = f"t5encoder.enc.blk.{l}"        # parse_layer_count(name, 2) takes the layer index from the fourth dot-separated field (src/util.cpp)
+        norm(b + ".attn_norm", hidden)
+        # T5 attends WITHOUT 1/sqrt(d) (softmax scale 1.0, model.cpp:262): keep the scores O(1)
+        rand(b + ".attn_q", (hidden, hidden), 0.6 / np.sqrt(hidden)); rand(b + ".attn_k", (hidden, hidden), 0.6 / np.sqrt(hidden))
+        rand(b + ".attn_v", (hidden, hidden), 1.0 / np.sqrt(hidden)); rand(b + ".attn_o", (hidden, hidden), 1.0 / np.sqrt(hidden))
+        if l == 0:
+            rand(b + ".attn_rel_b", (32, heads), 0.5)         # [relative_attn_buckets][heads]: rows are fetched by bucket (ggml_get_rows, model.cpp:196)
+        norm(b + ".ffn_norm", hidden)
+        rand(b + ".ffn_gate", (ffn, hidden), 1.0 / np.sqrt(hidden)); rand(b + ".ffn_up", (ffn, hidden), 1.0 / np.sqrt(hidden))
+        rand(b + ".ffn_down", (hidden, ffn), 1.0 / np.sqrt(ffn))
+    norm("t5encoder.enc.final_layer_norm", hidden)
+    if down_proj:
+        rand("t5encoder.down_proj", (out_size, hidden), 1.0 / np.sqrt(hidden))
+        rand("t5encoder.down_proj_bias", (out_size,), 0.1)
+    return items
+
+
+def write_t5_gguf(path: str, seed: int = 0, layers: int = 3, heads: int = 2, ffn: int = 192, vocab: int = 96, out_size: int = 256, down_proj: bool = True,
+                  context_length: int = 64, f16: bool = False) -> dict:
+    """Small synthetic T5-encoder GGUF.  f16: the layer matrices as F16 (what `quantize --quantized-type F16` does to a text encoder)."""
+    import gguf
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    w = gguf.GGUFWriter(path, arch="t5encoder")
+    items = t5_tensors(seed, layers, heads, ffn, vocab, out_size, down_proj)
+    n_params = 0
+    for name, arr in items:
+        n_params += arr.size
+        mat = arr.ndim == 2 and ".attn_rel_b" not in name and "token_embd" not in name and name != "t5encoder.down_proj"
+        w.add_tensor(name, arr.astype(np.float16 if f16 and mat else np.float32))
+    for k, v in (("t5encoder.block_count", layers), ("t5encoder.embedding_length", 64 * heads), ("t5encoder.attention.head_count", heads),
+                 ("t5encoder.context_length", context_length), ("t5encoder.vocab_size", vocab), ("t5encoder.output_size", out_size if down_proj else 64 * heads),
+                 ("tokenizer.ggml.bos_token_id", 0), ("tokenizer.ggml.eos_token_id", 1)):
+        w.add_uint32(k, int(v))
+    w.write_header_to_file()
+    w.write_kv_data_to_file()
+    w.write_tensors_to_file()
+    w.close()
+    return {"tensors": len(items), "params": int(n_params), "bytes": os.path.getsize(path)}
+
+
+def cached_t5_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, **shape) -> str:
+    cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
+    tag = "_".join(f"{k}{v}" for k, v in sorted(shape.items()))
+    path = os.path.join(cache_dir, f"t5_{'f16' if f16 else 'f32'}_s{seed}{('_' + tag) if tag else ''}.gguf")
+    if not os.path.exists(path):
+        tmp = path + f".tmp{os.getpid()}"
+        write_t5_gguf(tmp, seed=seed, f16=f16, **shape)
+        os.replace(tmp, path)
+    return path
