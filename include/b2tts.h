@@ -241,6 +241,21 @@ float b2tts_orpheus_last_ms(const b2tts_orpheus * m);
  *                                 (model.cpp:387-470,520-614,762-786; sampler::max per output head) for n_sequences independent prompts of token
  *                                 ids sharing the model's stored conditional-prompt encoding, n_steps frames each, without check_stopping.
  *                                 out_tokens [n_sequences][n_steps][n_heads]; out_logits (may be NULL) [n_sequences][n_steps][n_heads][out_vocab]. */
+/* ---- T5 conditional-prompt encoder (reference src/models/parler/t5/model.cpp): the pass parler_tts_runner::update_conditional_prompt makes before
+ * prep_cross_key_values (src/models/parler/model.cpp:510-518), on the GPU.
+ *   b2tts_t5_load_gguf : text_encoder_from_file (t5/model.cpp:365-400) below the tokenizer: hyper-parameters (prep_constants, :118-158), the assign_weight loop over
+ *                        the "t5encoder.*" tensors (F32, F16, Q8_0 / Q5_0 / Q4_0 matrices), prepare_post_load
+ *   b2tts_t5_encode    : t5_runner::run (t5/model.cpp:336-363) = build_t5_graph + set_inputs (:214-334) for a ragged batch of prompts: tokens[b][0 .. n_tokens[b])
+ *                        (the caller appends EOS = eos_token_id, as t5_runner::generate does, :365-371) -> encodings = the prompts' [n_tokens[b]][output_size] rows
+ *                        back to back; one prompt's rows are what b2tts_parler_set_text_encoding takes.  Errors: n_tokens outside 1 .. context_length, id >= vocab. */
+typedef struct b2tts_t5 b2tts_t5;
+int    b2tts_t5_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_t5 ** out);
+void   b2tts_t5_free(b2tts_t5 * m);
+int    b2tts_t5_info(const b2tts_t5 * m, int * n_layers, int * hidden_size, int * output_size, int * vocab_size, int * context_length, int * eos_token_id);
+int    b2tts_t5_encode(b2tts_t5 * m, int n_prompts, const uint32_t * const * tokens, const int32_t * n_tokens, float * encodings);
+float  b2tts_t5_last_ms(const b2tts_t5 * m);          /* device time of the last encode (CUDA events around the forward) */
+size_t b2tts_t5_weight_bytes(const b2tts_t5 * m);
+
 typedef struct b2tts_parler b2tts_parler;
 int   b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out);
 void  b2tts_parler_free(b2tts_parler * m);

@@ -9,7 +9,7 @@
 // loader registry (src/models/loaders.cpp:11-31,79-89), unigram_tokenizer (src/tokenizer.h:35-53).  Behaviour mirrored: parler_model_loader::from_file
 // (src/models/parler/loader.cpp:8-26), batch_from_sentence (model.cpp:473-498: tokens + EOS), parler_tts_runner::generate / generate_from_batch /
 // adjust_output_tokens (model.cpp:734-792,838-861), assign_weight's routing of "audio_encoder.*" to the DAC (model.cpp:499-512).
-// update_conditional_prompt runs the reference's own T5 encoder on the host and hands its output to b2tts_parler_set_text_encoding (cross K / V recomputed on the
+// update_conditional_prompt runs the T5 encoder on the GPU (b2tts_t5_*) and hands its output to b2tts_parler_set_text_encoding (cross K / V recomputed on the
 // device).  Not supported: use_cross_attn = false.
 #include "models/loaders.h"
 #include "models/parler/t5/model.h"
@@ -27,6 +27,8 @@ struct parler_b200_runner : tts_generation_runner {
     b2tts_ctx *         ctx       = nullptr;
     b2tts_parler *      decoder   = nullptr;
     b2tts_dac *         dac       = nullptr;
+    b2tts_t5 *          t5        = nullptr;      // the conditional-prompt encoder, loaded on the first update_conditional_prompt
+    std::string         t5_path;
     unigram_tokenizer * tokenizer = nullptr;
     uint32_t n_output_heads = 9, audio_vocab_size = 1024, max_generation = 2580;
     int n_threads = 4;
@@ -37,6 +39,7 @@ struct parler_b200_runner : tts_generation_runner {
     }
     ~parler_b200_runner() override {
         b2tts_parler_free(decoder);
+        b2tts_t5_free(t5);
         b2tts_dac_free(dac);
         b2tts_ctx_destroy(ctx);
         delete tokenizer;
@@ -53,14 +56,25 @@ struct parler_b200_runner : tts_generation_runner {
     void prepare_post_load() override {
         if (b2tts_parler_prepare(decoder) || b2tts_dac_prepare(dac)) TTS_ABORT("%s\n", b2tts_last_error());
     }
-    // the reference's own T5 encoder pass on the host (parler_tts_runner::update_conditional_prompt, model.cpp:510-518; the T5 encoder is a "next" row of the B200
-    // path), then the cross-attention K / V of every layer recomputed on the device from its output
+    // parler_tts_runner::update_conditional_prompt (model.cpp:510-518) entirely on the device: the reference's own unigram tokenizer (host string work, kept), EOS
+    // appended as t5_runner::generate does (t5/model.cpp:365-371), the T5 encoder pass on the GPU (b2tts_t5_encode; the GGUF stays loaded between calls), then the
+    // cross-attention K / V of every layer recomputed from its output (b2tts_parler_set_text_encoding = prep_cross_key_values)
     void update_conditional_prompt(const char * file_path, const char * prompt) override {
-        t5_runner *    text_encoder = text_encoder_from_file(file_path, n_threads, tokenizer, /*cpu_only*/ true);
-        tts_response * response     = nullptr;
-        text_encoder->generate(prompt, response);
-        if (!response || b2tts_parler_set_text_encoding(decoder, response->data, (int) response->n_outputs)) TTS_ABORT("%s\n", b2tts_last_error());
-        delete text_encoder;
+        if (!t5 || t5_path != file_path) {
+            b2tts_t5_free(t5); t5 = nullptr;
+            if (b2tts_t5_load_gguf(ctx, file_path, &t5)) TTS_ABORT("%s\n", b2tts_last_error());
+            t5_path = file_path;
+        }
+        int out_size = 0, eos = 1;
+        if (b2tts_t5_info(t5, nullptr, nullptr, &out_size, nullptr, nullptr, &eos)) TTS_ABORT("%s\n", b2tts_last_error());
+        if (!tokenizer->init) tokenizer->initialize_tokenizer();              // text_encoder_from_file does this for the shared tokenizer (t5/model.cpp:385-387)
+        std::vector<uint32_t> ids;
+        tokenizer->tokenize(prompt, ids);
+        ids.push_back((uint32_t) eos);
+        std::vector<float> enc(ids.size() * (size_t) out_size);
+        const uint32_t * pp = ids.data();
+        const int32_t    n  = (int32_t) ids.size();
+        if (b2tts_t5_encode(t5, 1, &pp, &n, enc.data()) || b2tts_parler_set_text_encoding(decoder, enc.data(), n)) TTS_ABORT("%s\n", b2tts_last_error());
     }
 
     // parler_tts_runner::adjust_output_tokens (model.cpp:734-760): undo the delay pattern (head h lags h steps) and drop frames holding a special id

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 
 # GPU runs use -x: the rows that carry the headline (Kokoro, the patched ops, the codecs) are collected first, the autoregressive decode paths after them.
-_LATE = ("test_orpheus_gpu", "test_parler_gpu", "test_dia_gpu", "test_sampler_gpu", "test_ar_graph_gpu", "test_ar_fullsize_gpu", "test_vad_gpu", "test_server_gpu")
+_LATE = ("test_orpheus_gpu", "test_parler_gpu", "test_dia_gpu", "test_sampler_gpu", "test_ar_graph_gpu", "test_ar_fullsize_gpu", "test_vad_gpu", "test_server_gpu", "test_t5_gpu")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -6,6 +6,7 @@
 #include "orpheus.h"
 #include "parler.h"
 #include "dia.h"
+#include "t5.h"
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
@@ -84,8 +85,33 @@ template <class M> static int run(int argc, char ** argv) {
     return 0;
 }
 
+// ar_emu t5 <t5.gguf> <prompts.bin> <out.bin>: prompts.bin as above (n_steps ignored); out.bin: int32 output_size, then the encodings back to back
+static int run_t5(char ** argv) {
+    b2::Ctx ctx;
+    b2::T5 m; m.ctx = &ctx;
+    if (b2::load_gguf_into(&m, argv[2])) { fprintf(stderr, "load: %s\n", b2::emu_last_error()); return 1; }
+    FILE * f = fopen(argv[3], "rb");
+    if (!f) return 2;
+    int32_t B = 0, steps = 0;
+    if (fread(&B, 4, 1, f) != 1 || fread(&steps, 4, 1, f) != 1) return 2;
+    std::vector<std::vector<uint32_t>> pr((size_t) B);
+    std::vector<const uint32_t *> pp; std::vector<int32_t> np;
+    size_t rows = 0;
+    for (auto & p : pr) { int32_t n = 0; if (fread(&n, 4, 1, f) != 1) return 2; p.resize((size_t) n); if (fread(p.data(), 4, (size_t) n, f) != (size_t) n) return 2; pp.push_back(p.data()); np.push_back(n); rows += (size_t) n; }
+    fclose(f);
+    const int32_t O = m.output_size();
+    std::vector<float> enc(rows * (size_t) O);                // exact size: AddressSanitizer sees a row too many
+    if (m.encode(B, pp.data(), np.data(), enc.data())) { fprintf(stderr, "encode: %s\n", b2::emu_last_error()); return 1; }
+    f = fopen(argv[4], "wb");
+    fwrite(&O, 4, 1, f); fwrite(enc.data(), 4, enc.size(), f);
+    fclose(f);
+    fprintf(stderr, "emulated %llu launches, %llu blocks\n", (unsigned long long) b2emu::g_launches, (unsigned long long) b2emu::g_blocks);
+    return 0;
+}
+
 int main(int argc, char ** argv) {
     if (argc < 5) return 2;
+    if (!strcmp(argv[1], "t5")) return run_t5(argv);
     if (!strcmp(argv[1], "orpheus")) return run<b2::Orpheus>(argc, argv);
     if (!strcmp(argv[1], "parler")) return run<b2::Parler>(argc, argv);
     if (!strcmp(argv[1], "dia")) return run<b2::Dia>(argc, argv);

@@ -21,7 +21,7 @@ from tts_cpp_b200.synth import cached_dia_gguf, cached_orpheus_gguf, cached_parl
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "pdk.cu", "sampler.cu"]
+AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "t5.cu", "pdk.cu", "sampler.cu"]
 # The library's defaults are the fast paths (persistent decode kernel for F16 Parler, tensor-core GEMV for F16 matrices, CUDA-graph replay); most tests below are about
 # one specific kernel family, so they start from the plain launch-per-op configuration and switch on what they test.
 EMU_DEFAULTS = {"B2TTS_AR_PDK": "0", "B2TTS_AR_MMA": "0", "B2TTS_AR_GRAPH": "0"}
@@ -702,3 +702,41 @@ def test_vad_kernels_emulated_match_reference(tmp_path):
         assert np.array_equal(n_out, g[name + ".n_out"]), (name, n_out, g[name + ".n_out"])
         for b in range(len(utts)):
             assert np.array_equal(en[b], g[f"{name}.energies.{b}"]), (name, b)
+
+
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide"])
+def test_t5_encoder_cuda_path_emulated_matches_reference(tmp_path, case):
+    """T5::encode (t5.cu: embedding rows, RMS norm eps 1e-6, the storage-aware GEMVs, bidirectional attention with the relative-position bias table, gated GELU, down
+    projection + bias) under emulation against the compiled unmodified t5_runner::run (tests/golden/t5_vectors.npz), the prompts of a case as ONE ragged batch:
+    at the port's own distance from the reference (fp16 GELU table; fp16 activation rounding for F16 matrices).  The "wide" 88-token prompt hits every
+    relative-position bucket, incl. the log-spaced ones with the reference's integer division."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden")); sys.path.insert(0, ROOT)
+    import make_golden_t5 as M
+    from tts_cpp_b200.synth import cached_t5_gguf
+    g = np.load(os.path.join(ROOT, "tests", "golden", "t5_vectors.npz"))
+    kw, prompts = M.CASES[case]
+    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
+    pin, pout = str(tmp_path / "p.bin"), str(tmp_path / "o.bin")
+    with open(pin, "wb") as f:
+        f.write(struct.pack("<ii", len(prompts), 0))
+        for p in prompts:
+            f.write(struct.pack("<i", len(p))); f.write(np.asarray(p, np.uint32).tobytes())
+    r = subprocess.run([exe, "t5", cached_t5_gguf(**kw), pin, pout], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = open(pout, "rb").read()
+    O = struct.unpack("<i", raw[:4])[0]
+    enc = np.frombuffer(raw[4:], np.float32).reshape(-1, O)
+    assert enc.shape[0] == sum(len(p) for p in prompts)
+    at = 0
+    for i, p in enumerate(prompts):
+        ref = g[f"{case}.encoding.{i}"]
+        got = enc[at:at + len(p)]; at += len(p)
+        d = float(np.sqrt(((got - ref) ** 2).mean())); rr = float(np.sqrt((ref ** 2).mean()))
+        print(f"PARITY t5 emulated {case}.{i}: rms {d:.3g} of {rr:.3g}, max {float(np.abs(got - ref).max()):.3g}")
+        assert d < (1.5e-3 if case == "f16" else 1e-4) * rr, (case, i, d, rr)
+    if case == "f32":      # a wrong prompt is refused, not read out of bounds: token id >= vocabulary, an empty prompt
+        for bad in ([5, 96, 1], []):
+            with open(pin, "wb") as f:
+                f.write(struct.pack("<ii", 1, 0)); f.write(struct.pack("<i", len(bad))); f.write(np.asarray(bad, np.uint32).tobytes())
+            r = subprocess.run([exe, "t5", cached_t5_gguf(**kw), pin, pout], capture_output=True, text=True, timeout=900)
+            assert r.returncode == 1 and "t5: prompt 0" in r.stderr, r.stderr[-500:]

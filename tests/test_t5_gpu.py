@@ -1,0 +1,56 @@
+"""GPU: the T5 conditional-prompt encoder (t5.cu) through the C-ABI (b2tts_t5_load_gguf / b2tts_t5_encode) against the compiled unmodified
+reference (t5_runner::run; tests/golden/t5_vectors.npz made by tests/golden/make_golden_t5.py), and chained into Parler: T5 encoding -> b2tts_parler_set_text_encoding.
+Collected last (conftest._LATE): new in this round's last session; validated under tests/emu before its first hardware run."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import CACHE, ROOT, report
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide"])
+def test_t5_encode_matches_reference(gpu_ctx, case):
+    import make_golden_t5 as M
+    from tts_cpp_b200.binding import t5_runner_from_file
+    from tts_cpp_b200.synth import cached_t5_gguf
+    g = np.load(os.path.join(ROOT, "tests", "golden", "t5_vectors.npz"))
+    kw, prompts = M.CASES[case]
+    t5 = t5_runner_from_file(cached_t5_gguf(cache_dir=CACHE, **kw), ctx=gpu_ctx)
+    try:
+        batch = t5.run(prompts)                                # the case's prompts as one ragged batch
+        for i, p in enumerate(prompts):
+            ref = g[f"{case}.encoding.{i}"]
+            d, r, mx = report(f"t5 {case}.{i} (batched)", batch[i], ref)
+            assert batch[i].shape == ref.shape and d < (1.5e-3 if case == "f16" else 1e-4) * r, (case, i, d, r)
+            one = t5.run([p])[0]                               # and alone: a prompt's encoding does not depend on its batch
+            assert np.array_equal(one, batch[i]), (case, i)
+        with pytest.raises(RuntimeError):
+            t5.run([[5, t5.vocab_size, 1]])
+        with pytest.raises(RuntimeError):
+            t5.run([list(range(2, 2 + t5.context_length)) + [1]])
+    finally:
+        t5.close()
+
+
+def test_t5_encoding_feeds_parler_cross_attention(gpu_ctx):
+    """update_conditional_prompt as a whole on the device: T5 encode -> b2tts_parler_set_text_encoding -> decode.  The tokens equal those of the same decode with
+    the same encoding handed over from the host (the path tests/test_parler_gpu.py pins to the reference), and differ from the stored-encoding run."""
+    from tts_cpp_b200.binding import parler_runner_from_file, t5_runner_from_file
+    from tts_cpp_b200.synth import cached_parler_gguf, cached_t5_gguf
+    t5 = t5_runner_from_file(cached_t5_gguf(cache_dir=CACHE), ctx=gpu_ctx)          # output_size 256 = the toy Parler's hidden (32 heads x 8)
+    parler = parler_runner_from_file(cached_parler_gguf(cache_dir=CACHE), ctx=gpu_ctx)
+    assert t5.output_size == parler.hidden_size
+    prompts = [[3, 17, 250, 9], [44, 2, 300]]
+    base = parler.generate_greedy(prompts, 6)
+    enc = t5.run([[5, 17, 3, 90, 60, 61, 62, 1]])[0]
+    parler.set_text_encoding(enc)
+    a = parler.generate_greedy(prompts, 6)
+    parler.set_text_encoding(enc.copy())
+    b = parler.generate_greedy(prompts, 6)
+    assert np.array_equal(a, b) and not np.array_equal(a, base)
+    t5.close()

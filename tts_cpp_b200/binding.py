@@ -454,6 +454,12 @@ class ParlerRunner:
         _chk(lib().b2tts_parler_info(self.h, C.byref(nh), C.byref(v), C.byref(l), C.byref(hd)))
         self.n_heads, self.out_vocab, self.n_layers, self.hidden_size = nh.value, v.value, l.value, hd.value
 
+    def set_text_encoding(self, encoding):
+        """update_conditional_prompt's second half (prep_cross_key_values with a new [rows, hidden] encoding, e.g. T5Runner.run's output)"""
+        e = np.ascontiguousarray(encoding, np.float32)
+        assert e.ndim == 2 and e.shape[1] == self.hidden_size, (e.shape, self.hidden_size)
+        _chk(lib().b2tts_parler_set_text_encoding(self.h, e.ctypes.data_as(C.POINTER(C.c_float)), int(e.shape[0])))
+
     def generate_greedy(self, prompts, n_steps: int, want_logits: bool = False):
         """-> tokens [B][n_steps][n_heads] (and logits [B][n_steps][n_heads][out_vocab])"""
         B = len(prompts)
@@ -510,6 +516,45 @@ class ParlerRunner:
         if self.h:
             lib().b2tts_parler_free(self.h)
             self.h = None
+
+
+class T5Runner:
+    """t5_runner::run (reference src/models/parler/t5/model.cpp:336-363) below the tokenizer, for a ragged batch of prompts."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        v = [C.c_int() for _ in range(6)]
+        _chk(lib().b2tts_t5_info(self.h, *[C.byref(x) for x in v]))
+        self.n_layers, self.hidden_size, self.output_size, self.vocab_size, self.context_length, self.eos_token_id = [x.value for x in v]
+
+    def run(self, prompts):
+        """prompts: token-id lists (EOS appended by the caller, like t5_runner::generate) -> list of [n_tokens, output_size] encodings"""
+        B = len(prompts)
+        arrs = [np.ascontiguousarray(np.asarray(p, np.uint32)) for p in prompts]
+        npr = np.array([a.size for a in arrs], np.int32)
+        ptrs = (C.POINTER(C.c_uint32) * B)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        out = np.empty((int(npr.sum()), self.output_size), np.float32)
+        _chk(lib().b2tts_t5_encode(self.h, B, ptrs, npr.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.POINTER(C.c_float))))
+        cuts = np.concatenate([[0], np.cumsum(npr)])
+        return [out[cuts[b]:cuts[b + 1]].copy() for b in range(B)]
+
+    def last_ms(self) -> float:
+        lib().b2tts_t5_last_ms.restype = C.c_float
+        return float(lib().b2tts_t5_last_ms(self.h))
+
+    def close(self):
+        if self.h:
+            lib().b2tts_t5_free(self.h)
+            self.h = C.c_void_p()
+
+
+def t5_runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> T5Runner:
+    """text_encoder_from_file (reference src/models/parler/t5/model.cpp:373-400) below the tokenizer"""
+    ctx = ctx or Context(device)
+    h = C.c_void_p()
+    _chk(lib().b2tts_t5_load_gguf(ctx.h, path.encode(), C.byref(h)))
+    return T5Runner(ctx, h)
 
 
 def parler_runner_from_file(path: str, device: int = 0, ctx: Context | None = None) -> ParlerRunner:

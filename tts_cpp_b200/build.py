@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2tts.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["capi.cu", "kokoro.cu", "dac.cu", "orpheus.cu", "parler.cu", "dia.cu", "pdk.cu", "gemm_conv.cu", "gemm_umma.cu", "lstm.cu", "elementwise.cu", "source.cu", "sampler.cu", "vad.cu", "gguf_reader.cpp"]
+SOURCES = ["capi.cu", "kokoro.cu", "dac.cu", "orpheus.cu", "parler.cu", "dia.cu", "t5.cu", "pdk.cu", "gemm_conv.cu", "gemm_umma.cu", "lstm.cu", "elementwise.cu", "source.cu", "sampler.cu", "vad.cu", "gguf_reader.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

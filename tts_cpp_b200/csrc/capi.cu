@@ -4,6 +4,7 @@
 #include "dac.h"
 #include "orpheus.h"
 #include "parler.h"
+#include "t5.h"
 #include "dia.h"
 
 #include <cstdarg>
@@ -30,6 +31,7 @@ struct b2tts_dac { Dac d; };
 struct b2tts_snac { Snac s; };
 struct b2tts_orpheus { Orpheus o; };
 struct b2tts_parler { Parler p; };
+struct b2tts_t5 { T5 t; };
 struct b2tts_dia { Dia d; };
 
 namespace {
@@ -244,6 +246,33 @@ size_t b2tts_orpheus_step_weight_bytes(const b2tts_orpheus * m) {
 }
 size_t b2tts_orpheus_weight_bytes(const b2tts_orpheus * m) { return m ? m->o.weight_bytes : 0; }
 float b2tts_orpheus_last_ms(const b2tts_orpheus * m) { return m ? m->o.timing_ms : 0.f; }
+// ---- T5 conditional-prompt encoder (the pass before Parler's decode loop)
+int b2tts_t5_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_t5 ** out) {
+    if (!ctx) { set_error("null context"); return 1; }
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    b2tts_t5 * m = new b2tts_t5();
+    m->t.ctx = &ctx->c;
+    if (load_gguf_into(&m->t, path)) { m->t.free_all(); delete m; return 1; }
+    *out = m;
+    return 0;
+}
+void b2tts_t5_free(b2tts_t5 * m) { if (m) { m->t.free_all(); delete m; } }
+int b2tts_t5_info(const b2tts_t5 * m, int * n_layers, int * hidden_size, int * output_size, int * vocab_size, int * context_length, int * eos_token_id) {
+    if (!m) { set_error("null model"); return 1; }
+    if (n_layers) *n_layers = m->t.n_layers;
+    if (hidden_size) *hidden_size = m->t.hidden;
+    if (output_size) *output_size = m->t.output_size();
+    if (vocab_size) *vocab_size = m->t.vocab;
+    if (context_length) *context_length = m->t.max_ctx;
+    if (eos_token_id) *eos_token_id = m->t.eos;
+    return 0;
+}
+int b2tts_t5_encode(b2tts_t5 * m, int n_prompts, const uint32_t * const * tokens, const int32_t * n_tokens, float * encodings) {
+    if (!m) { set_error("null model"); return 1; }
+    return m->t.encode(n_prompts, tokens, n_tokens, encodings);
+}
+float b2tts_t5_last_ms(const b2tts_t5 * m) { return m ? m->t.timing_ms : 0.f; }
+size_t b2tts_t5_weight_bytes(const b2tts_t5 * m) { return m ? m->t.weight_bytes : 0; }
 // ---- Parler AR decode (first correct path)
 int b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out) {
     if (!ctx) { set_error("null context"); return 1; }

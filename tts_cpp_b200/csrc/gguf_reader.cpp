@@ -10,6 +10,7 @@
 #include "orpheus.h"
 #include "parler.h"
 #include "dia.h"
+#include "t5.h"
 
 #include <exception>
 #include <functional>
@@ -186,6 +187,12 @@ int load_gguf_into(Parler * m, const char * path) {
 // Dia's encoder + decoder tensors live under "dia." (reference src/models/dia/model.cpp:3-132); its DAC under "audio_encoder."
 int load_gguf_into(Dia * m, const char * path) {
     if (read_gguf(path, "dia.", "dia", m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
+    return m->prepare();
+}
+
+// the T5 conditional-prompt encoder is its own GGUF (--text-encoder-path; reference src/models/parler/t5/model.cpp:373-400), tensors under "t5encoder."
+int load_gguf_into(T5 * m, const char * path) {
+    if (read_gguf(path, "t5encoder.", nullptr, m->kv, [m](const char * n, int ty, int nd, const int64_t * ne, const void * d, size_t nb) { return m->assign(n, ty, nd, ne, d, nb); })) return 1;
     return m->prepare();
 }
 
