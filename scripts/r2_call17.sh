@@ -5,8 +5,8 @@ cd "$(dirname "$0")/.."
 OUT=gpurun_out/${1:-r2x}
 mkdir -p "$OUT"
 run() { local name=$1 t=$2; shift 2; echo "=== $name" | tee -a "$OUT/index.log"; local t0=$(date +%s); timeout -s KILL "$t" "$@" > "$OUT/$name.log" 2>&1; echo "rc=$? $name ($(( $(date +%s) - t0 )) s)" | tee -a "$OUT/index.log"; }
-run t5_tests 70 python -m pytest tests/test_t5_gpu.py -q -s -m gpu
+run t5_tests 80 python -m pytest tests/test_t5_gpu.py -q -s -m gpu
 tail -n 25 "$OUT/t5_tests.log"
-run t5_timing 75 python scripts/t5_timing.py
+run t5_timing 80 python scripts/t5_timing.py
 tail -n 6 "$OUT/t5_timing.log"
 tail -n 3 "$OUT/index.log"

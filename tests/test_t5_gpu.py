@@ -13,10 +13,13 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
-@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide"])
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide"])
 def test_t5_encode_matches_reference(gpu_ctx, case):
+    """Every golden case as one ragged batch and prompt by prompt.  "f16" (40 rows batched) and "f16_wide" (148 rows, 88 and 60 alone) reach the row count at which
+    F16 matrices go through the tensor-core GEMM (t5.cu T5_GEMM_MIN_ROWS): the same numerics class as the reference's F16 mul_mat (fp16-rounded activations, exact
+    products, fp32 accumulation), another summation order."""
     import make_golden_t5 as M
-    from tts_cpp_b200.binding import t5_runner_from_file
+    from tts_cpp_b200.binding import lib, t5_runner_from_file
     from tts_cpp_b200.synth import cached_t5_gguf
     g = np.load(os.path.join(ROOT, "tests", "golden", "t5_vectors.npz"))
     kw, prompts = M.CASES[case]
@@ -26,15 +29,42 @@ def test_t5_encode_matches_reference(gpu_ctx, case):
         for i, p in enumerate(prompts):
             ref = g[f"{case}.encoding.{i}"]
             d, r, mx = report(f"t5 {case}.{i} (batched)", batch[i], ref)
-            assert batch[i].shape == ref.shape and d < (1.5e-3 if case == "f16" else 1e-4) * r, (case, i, d, r)
+            assert batch[i].shape == ref.shape and d < (1.5e-3 if case.startswith("f16") else 1e-4) * r, (case, i, d, r)
             one = t5.run([p])[0]                               # and alone: a prompt's encoding does not depend on its batch
-            assert np.array_equal(one, batch[i]), (case, i)
+            if case.startswith("f16"):                         # ... up to the summation order where the row count picks the GEMV or the GEMM kernel
+                d1, r1, _ = report(f"t5 {case}.{i} (alone)", one, ref)
+                assert d1 < 1.5e-3 * r1, (case, i, d1, r1)
+            else:
+                assert np.array_equal(one, batch[i]), (case, i)
+        if case == "f16_wide":
+            assert lib().b2tts_t5_last_used_gemm(t5.h) == 1    # 60 rows alone: the GEMM path ran
         with pytest.raises(RuntimeError):
             t5.run([[5, t5.vocab_size, 1]])
         with pytest.raises(RuntimeError):
             t5.run([list(range(2, 2 + t5.context_length)) + [1]])
     finally:
         t5.close()
+
+
+def test_t5_gemm_path_agrees_with_gemv_path_at_the_flan_t5_large_width(gpu_ctx):
+    """No reference run at this size in the goldens (hidden 1024, ffn 2816: the tile shapes the real text encoder uses), so a size-independent property: the same
+    200-token prompt through the tensor-core GEMM and -- B2TTS_T5_GEMM=0, read at every call -- through the GEMV family, two implementations of the same F16 numerics
+    that share no matrix kernel, agree at the F16 rounding floor."""
+    from tts_cpp_b200.binding import lib, t5_runner_from_file
+    from tts_cpp_b200.synth import cached_t5_gguf
+    t5 = t5_runner_from_file(cached_t5_gguf(cache_dir=CACHE, f16=True, layers=2, heads=16, ffn=2816, vocab=512, out_size=1024, context_length=256), ctx=gpu_ctx)
+    prompt = [(13 * i) % 500 + 2 for i in range(199)] + [1]
+    try:
+        a = t5.run([prompt])[0]
+        assert lib().b2tts_t5_last_used_gemm(t5.h) == 1
+        os.environ["B2TTS_T5_GEMM"] = "0"
+        b = t5.run([prompt])[0]
+        assert lib().b2tts_t5_last_used_gemm(t5.h) == 0
+    finally:
+        os.environ.pop("B2TTS_T5_GEMM", None)
+        t5.close()
+    d, r, mx = report("t5 GEMM vs GEMV path, 200 x 1024", a, b)
+    assert np.isfinite(a).all() and d < 1.5e-3 * r, (d, r)
 
 
 def test_t5_encoding_feeds_parler_cross_attention(gpu_ctx):

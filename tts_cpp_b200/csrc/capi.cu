@@ -272,6 +272,7 @@ int b2tts_t5_encode(b2tts_t5 * m, int n_prompts, const uint32_t * const * tokens
     return m->t.encode(n_prompts, tokens, n_tokens, encodings);
 }
 float b2tts_t5_last_ms(const b2tts_t5 * m) { return m ? m->t.timing_ms : 0.f; }
+int b2tts_t5_last_used_gemm(const b2tts_t5 * m) { return m && m->t.last_used_gemm ? 1 : 0; }
 size_t b2tts_t5_weight_bytes(const b2tts_t5 * m) { return m ? m->t.weight_bytes : 0; }
 // ---- Parler AR decode (first correct path)
 int b2tts_parler_load_gguf(b2tts_ctx * ctx, const char * path, b2tts_parler ** out) {

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2 {
@@ -73,6 +74,12 @@ __global__ void t5_gated_gelu_kernel(float * __restrict__ up, const float * __re
     if (i < n) up[i] = gelu_f16lut(up[i]) * gate[i];
 }
 
+// fp32 rows -> the fp16 operand of the tensor-core GEMM: the rounding ggml_mul_mat applies to the activations of an F16 matrix (vec_dot_type F16)
+__global__ void t5_cast_h_kernel(const float * __restrict__ x, size_t n4, __half2 * __restrict__ y) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) { const float4 v = reinterpret_cast<const float4 *>(x)[i]; y[2 * i] = __floats2half2_rn(v.x, v.y); y[2 * i + 1] = __floats2half2_rn(v.z, v.w); }
+}
+
 __global__ void t5_add_bias_kernel(float * __restrict__ y, const float * __restrict__ b, int N, size_t n) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += b[i % (size_t) N];
@@ -86,11 +93,36 @@ int t5_bucket(int key_pos, int query_pos, int relative_attn_buckets) {
     return (rpos > 0 ? n_buckets : 0) + (ab_rpos < max_exact ? ab_rpos : std::min(n_buckets - 1, max_exact + (int) ((log((double) (ab_rpos / max_exact)) / logarithmic_denominator) * max_exact)));
 }
 
+// From this many rows on an F16 matrix goes through the tensor-core GEMM (conv_gemm: the tcgen05 + TMA kernel of gemm_umma.cu as a K = 1 "convolution", the
+// mma.sync kernel for shapes it does not take): ONE pass over the matrix for all rows, where the GEMV family -- built for decode batches -- streams it once per 64 rows.
+constexpr int T5_GEMM_MIN_ROWS = 32;
+
 struct TFwd : ArLaunch {
-    T5 * m; bool fail = false;
+    T5 * m; bool fail = false, use_gemm = false;
+    __half * xh = nullptr;                                     // [R][max(hidden, ffn)] fp16 operand scratch
     TFwd(T5 * m_, Ctx * c, cudaStream_t s) : m(m_) { ctx = c; st = s; }
     template <class T> T * al(size_t n) { T * p = (T *) m->arena.alloc(n * sizeof(T)); if (!p) fail = true; return p; }
     int rms(const float * x, const float * w, int H, int R, float * y) { t5_rmsnorm_kernel<<<cdiv(R, 8), 256, 0, st>>>(x, w, H, R, y); B2_LAUNCH_CHECK(ctx); return 0; }
+    static bool gemm_shape(const ArW & W, int K, int N) { return W.f16 && !W.qtype && K % 64 == 0 && N % 128 == 0; }
+    int cast(const float * x, int K, int R) {                  // xh = fp16(x), once per group of matrices that share the rows
+        const size_t n4 = (size_t) R * K / 4;
+        t5_cast_h_kernel<<<cdiv((int64_t) n4, 256), 256, 0, st>>>(x, n4, reinterpret_cast<__half2 *>(xh)); B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    // Y = X . W^T (+ res); `casted`: xh already holds fp16(X)
+    int linear(const float * X, const ArW & W, int K, int N, int R, const float * res, float * Y, bool casted = false) {
+#ifndef B2EMU
+        if (use_gemm && gemm_shape(W, K, N)) {
+            if (!casted && cast(X, K, R)) return 1;
+            ConvGemmParams p;
+            p.A = xh; p.lda = K; p.W = (const __half *) W.p; p.N = N; p.Npad = N; p.KW = 1; p.CinPad = K; p.CinTrue = K;
+            p.B = 1; p.LmaxIn = R; p.LmaxOut = R; p.outF = Y; p.ldo = N; p.add1 = res; p.ldadd1 = N;
+            return conv_gemm(ctx, p);
+        }
+#endif
+        (void) casted;
+        return gemv(X, K, W, K, N, R, res, Y, N);
+    }
 };
 
 }  // namespace
@@ -211,14 +243,17 @@ int T5::encode(int B, const uint32_t * const * tokens, const int32_t * n_tokens,
         R += n_tokens[b]; Tmax = std::max(Tmax, n_tokens[b]);
     }
     const int H = hidden, F = ffn, O = output_size();
-    const size_t need = (size_t) R * ((size_t) 6 * H + 2 * (size_t) F + (size_t) O) * 4 + (size_t) R * 16 + (1 << 20);
+    const size_t need = (size_t) R * ((size_t) 6 * H + 2 * (size_t) F + (size_t) O) * 4 + (size_t) R * std::max(H, F) * 2 + (size_t) R * 16 + (1 << 20);
     if (arena.reserve(need)) return 1;
     TFwd Fw(this, ctx, st);
     float * x = Fw.al<float>((size_t) R * H), * xn = Fw.al<float>((size_t) R * H), * q = Fw.al<float>((size_t) R * H), * k = Fw.al<float>((size_t) R * H),
           * v = Fw.al<float>((size_t) R * H), * att = Fw.al<float>((size_t) R * H), * g = Fw.al<float>((size_t) R * F), * u = Fw.al<float>((size_t) R * F),
           * y = Fw.al<float>((size_t) R * O);
     int * row_tok = Fw.al<int>((size_t) R), * row_base = Fw.al<int>((size_t) R), * row_len = Fw.al<int>((size_t) R), * row_pos = Fw.al<int>((size_t) R);
+    Fw.xh = Fw.al<__half>((size_t) R * std::max(H, F));
     if (Fw.fail) return 1;
+    { const char * e = getenv("B2TTS_T5_GEMM"); Fw.use_gemm = R >= T5_GEMM_MIN_ROWS && !(e && e[0] == '0'); }      // B2TTS_T5_GEMM=0: the GEMV family at every row count (A/B runs)
+    last_used_gemm = false;
     {
         std::vector<int> ht((size_t) R), hb((size_t) R), hl((size_t) R), hp((size_t) R);
         int at = 0;
@@ -235,19 +270,23 @@ int T5::encode(int B, const uint32_t * const * tokens, const int32_t * n_tokens,
     for (int l = 0; l < n_layers; l++) {
         const T5Layer & L = layers[(size_t) l];
         if (Fw.rms(x, L.attn_norm, H, R, xn)) return 1;
-        if (Fw.gemv(xn, H, L.q, H, H, R, nullptr, q, H) || Fw.gemv(xn, H, L.k, H, H, R, nullptr, k, H) || Fw.gemv(xn, H, L.v, H, H, R, nullptr, v, H)) return 1;
+        const bool g3 = Fw.use_gemm && TFwd::gemm_shape(L.q, H, H) && TFwd::gemm_shape(L.k, H, H) && TFwd::gemm_shape(L.v, H, H);      // one cast for q, k and v
+        if (g3) { if (Fw.cast(xn, H, R)) return 1; last_used_gemm = true; }
+        if (Fw.linear(xn, L.q, H, H, R, nullptr, q, g3) || Fw.linear(xn, L.k, H, H, R, nullptr, k, g3) || Fw.linear(xn, L.v, H, H, R, nullptr, v, g3)) return 1;
         t5_attention_kernel<<<dim3((unsigned) R, (unsigned) heads), 128, att_smem, st>>>(q, k, v, row_base, row_len, row_pos, bias_lut, max_ctx, heads, head_dim, Tmax, att);
         B2_LAUNCH_CHECK(ctx);
-        if (Fw.gemv(att, H, L.o, H, H, R, x, xn, H)) return 1;                      // xn = attention output + residual(x)
+        if (Fw.linear(att, L.o, H, H, R, x, xn)) return 1;                          // xn = attention output + residual(x)
         if (Fw.rms(xn, L.ffn_norm, H, R, x)) return 1;
-        if (Fw.gemv(x, H, L.wi0, H, F, R, nullptr, u, F) || Fw.gemv(x, H, L.wi1, H, F, R, nullptr, g, F)) return 1;
+        const bool g2 = Fw.use_gemm && TFwd::gemm_shape(L.wi0, H, F) && TFwd::gemm_shape(L.wi1, H, F);
+        if (g2 && Fw.cast(x, H, R)) return 1;
+        if (Fw.linear(x, L.wi0, H, F, R, nullptr, u, g2) || Fw.linear(x, L.wi1, H, F, R, nullptr, g, g2)) return 1;
         t5_gated_gelu_kernel<<<cdiv((int64_t) R * F, 256), 256, 0, st>>>(u, g, (size_t) R * F); B2_LAUNCH_CHECK(ctx);
-        if (Fw.gemv(u, F, L.wo, F, H, R, xn, x, H)) return 1;                        // x = mlp + residual(xn)
+        if (Fw.linear(u, L.wo, F, H, R, xn, x)) return 1;                            // x = mlp + residual(xn)
     }
     if (Fw.rms(x, out_norm, H, R, xn)) return 1;
     const float * res = xn;
     if (has_down) {
-        if (Fw.gemv(xn, H, down, H, O, R, nullptr, y, O)) return 1;
+        if (Fw.linear(xn, down, H, O, R, nullptr, y)) return 1;
         if (down_bias) { t5_add_bias_kernel<<<cdiv((int64_t) R * O, 256), 256, 0, st>>>(y, down_bias, O, (size_t) R * O); B2_LAUNCH_CHECK(ctx); }
         res = y;
     }
