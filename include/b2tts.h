@@ -254,7 +254,7 @@ void   b2tts_t5_free(b2tts_t5 * m);
 int    b2tts_t5_info(const b2tts_t5 * m, int * n_layers, int * hidden_size, int * output_size, int * vocab_size, int * context_length, int * eos_token_id);
 int    b2tts_t5_encode(b2tts_t5 * m, int n_prompts, const uint32_t * const * tokens, const int32_t * n_tokens, float * encodings);
 float  b2tts_t5_last_ms(const b2tts_t5 * m);          /* device time of the last encode (CUDA events around the forward) */
-int    b2tts_t5_last_used_gemm(const b2tts_t5 * m);   /* 1: the last encode had >= 32 rows and sent its F16 matrices through the tensor-core GEMM (B2TTS_T5_GEMM=0 disables) */
+int    b2tts_t5_last_used_gemm(const b2tts_t5 * m);   /* 1: the last encode had more than 32 rows and sent its F16 matrices through the tensor-core GEMM (B2TTS_T5_GEMM=0 disables) */
 size_t b2tts_t5_weight_bytes(const b2tts_t5 * m);
 
 typedef struct b2tts_parler b2tts_parler;

@@ -28,7 +28,7 @@ def main():
     for B, n in ((1, 16), (1, 32), (1, 64), (8, 32), (1, 256)):
         prompts = [list(rng.integers(2, 2048, n - 1)) + [1] for _ in range(B)]
         res = {}
-        for path, env in (("default", None), ("gemv_only", "0")):      # B2TTS_T5_GEMM is read at every encode: >= 32 rows take the tensor-core GEMM unless it is "0"
+        for path, env in (("default", None), ("gemv_only", "0")):      # B2TTS_T5_GEMM is read at every encode: > 32 rows take the tensor-core GEMM unless it is "0"
             if env is None:
                 os.environ.pop("B2TTS_T5_GEMM", None)
             else:

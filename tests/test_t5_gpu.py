@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 @pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide"])
 def test_t5_encode_matches_reference(gpu_ctx, case):
-    """Every golden case as one ragged batch and prompt by prompt.  "f16" (40 rows batched) and "f16_wide" (148 rows, 88 and 60 alone) reach the row count at which
+    """Every golden case as one ragged batch and prompt by prompt.  "f16" (40 rows batched) and "f16_wide" (148 rows, 88 and 60 alone) exceed the 32 rows above which
     F16 matrices go through the tensor-core GEMM (t5.cu T5_GEMM_MIN_ROWS): the same numerics class as the reference's F16 mul_mat (fp16-rounded activations, exact
     products, fp32 accumulation), another summation order."""
     import make_golden_t5 as M

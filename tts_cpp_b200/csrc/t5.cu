@@ -95,7 +95,7 @@ int t5_bucket(int key_pos, int query_pos, int relative_attn_buckets) {
 
 // From this many rows on an F16 matrix goes through the tensor-core GEMM (conv_gemm: the tcgen05 + TMA kernel of gemm_umma.cu as a K = 1 "convolution", the
 // mma.sync kernel for shapes it does not take): ONE pass over the matrix for all rows, where the GEMV family -- built for decode batches -- streams it once per 64 rows.
-constexpr int T5_GEMM_MIN_ROWS = 32;
+constexpr int T5_GEMM_MIN_ROWS = 33;      // measured (profiles/r2x_t5.txt): 32 rows 2.66 ms GEMV vs 3.65 ms GEMM; 64 rows 4.49 vs 3.84 (the GEMV kernels run 33-64 rows as one 64-row tile)
 
 struct TFwd : ArLaunch {
     T5 * m; bool fail = false, use_gemm = false;

@@ -4,7 +4,7 @@
 // independent prompts: token ids in, the [n_tokens][output_size] encoding out -- what parler_tts_runner::update_conditional_prompt hands to
 // prep_cross_key_values (src/models/parler/model.cpp:510-518), i.e. the input of b2tts_parler_set_text_encoding.  Launch-per-op over the kernels of
 // ar_kernels.cuh (the storage-aware GEMV family: F32, F16 with fp16-rounded activations, Q8_0 / Q5_0 / Q4_0) plus its own (t5.cu): RMS norm with T5's
-// eps, bidirectional attention with the relative-position bias, gated GELU; from 32 rows on, F16 matrices go through the tcgen05 GEMM of gemm_umma.cu instead.  An encoder pass runs once per voice description, not per audio frame: it is latency-,
+// eps, bidirectional attention with the relative-position bias, gated GELU; above 32 rows, F16 matrices go through the tcgen05 GEMM of gemm_umma.cu instead.  An encoder pass runs once per voice description, not per audio frame: it is latency-,
 // not bandwidth-critical, so the first correct path is the product here (tests/emu runs it on the CPU; GPU parity: tests/test_t5_gpu.py).
 #pragma once
 #include "kokoro.h"   // HostTensor, Arena, ArW
@@ -32,7 +32,7 @@ struct T5 {
 
     Arena arena;
     float timing_ms = 0.f;
-    bool  last_used_gemm = false;   // the last encode sent its F16 projections through the tensor-core GEMM (>= 32 rows; t5.cu)
+    bool  last_used_gemm = false;   // the last encode sent its F16 projections through the tensor-core GEMM (> 32 rows; t5.cu)
     cudaEvent_t ev[2] = {nullptr, nullptr};
 
     int assign(const char * name, int type, int n_dims, const int64_t * ne, const void * data, size_t nbytes);
