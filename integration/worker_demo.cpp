@@ -4,6 +4,8 @@
 //       no GPU: the reference's own dummy_runner (src/models/dummy) behind a server-shaped queue; checks what the drain promises -- compatible tasks share one forward,
 //       incompatible ones keep their place and order, max_batch is respected, timed-out tasks get no response, a runner without generate_batch is driven one by one and
 //       every task owns its PCM.  Prints "worker selftest OK".
+//   worker_demo stress
+//       no GPU: four producers and two workers on one queue (built a second time with -fsanitize=thread: worker_demo_tsan).
 //   worker_demo <model.gguf> <prompts.txt> <out_prefix> <max_batch>
 //       GPU: all prompts of the file are queued (as the HTTP handlers would), ONE worker thread runs b200::batch_loop over the B200 runner, every response is dumped as
 //       <out_prefix>.worker.<i>.f32; then the same prompts go one by one through generate() on a second runner -> <out_prefix>.single.<i>.f32.  Prints the batch sizes
@@ -132,6 +134,64 @@ static int selftest() {
     return 0;
 }
 
+// worker_demo stress: 4 producers x 100 tasks (3 voices, 2 models, a few non-TTS tasks) against 2 workers draining the same queue with max_batch 8, each with its own
+// dummy_runner; every task must be answered exactly once with ITS OWN audio.  The test runs this under ThreadSanitizer (integration/Makefile: worker_demo_tsan).
+static int stress() {
+    queue_t q; map_t done;
+    constexpr int P = 4, N = 100;
+    std::vector<std::unique_ptr<task_t>> tasks((size_t) P * N);
+    std::atomic<bool> running{ true };
+    std::atomic<int> others{ 0 }, forwards{ 0 }, max_seen{ 0 };
+    auto fake_batch = [&](tts_generation_runner & r, const std::vector<const char *> & prompts, std::vector<tts_response> & outs, const generation_configuration & cfg) {
+        static thread_local std::vector<std::vector<float>> keep;                      // "runner-owned" buffers of this worker, overwritten by its next forward
+        keep.assign(prompts.size(), {});
+        outs.assign(prompts.size(), tts_response{});
+        for (size_t i = 0; i < prompts.size(); i++) {
+            keep[i].assign(64, (float) atoi(prompts[i]) + (cfg.voice == "v1" ? 0.25f : cfg.voice == "v2" ? 0.5f : 0.0f));
+            outs[i].data = keep[i].data(); outs[i].n_outputs = keep[i].size();
+        }
+        r.sampling_rate = 24000.0f;
+        forwards++;
+        int m = max_seen.load(); while ((int) prompts.size() > m && !max_seen.compare_exchange_weak(m, (int) prompts.size())) {}
+        return true;
+    };
+    std::vector<std::thread> workers;
+    std::vector<std::unique_ptr<dummy_runner>> runners;
+    for (int w = 0; w < 2; w++) runners.push_back(std::make_unique<dummy_runner>());
+    for (int w = 0; w < 2; w++) workers.emplace_back([&, w] {
+        b200::batch_loop(running, q, done, 300, 8, TTS_KIND, [&, w](task_t *) -> tts_generation_runner & { return *runners[(size_t) w]; },
+                         [&](task_t * t) { others++; t->success = true; done.push(t); }, fake_batch);
+    });
+    std::vector<std::thread> producers;
+    for (int p = 0; p < P; p++) producers.emplace_back([&, p] {
+        for (int i = 0; i < N; i++) {
+            const int id = p * N + i;
+            auto t = std::make_unique<task_t>();
+            t->id = id; t->prompt = std::to_string(id); t->model = (id % 7 == 0) ? "m2" : "m"; t->task = (id % 23 == 0) ? OTHER_KIND : TTS_KIND;
+            t->gen_config.voice = id % 3 == 0 ? "v0" : id % 3 == 1 ? "v1" : "v2";
+            task_t * raw = t.get();
+            tasks[(size_t) id] = std::move(t);
+            q.push(raw);
+        }
+    });
+    for (auto & t : producers) t.join();
+    done.wait_for((size_t) P * N);
+    running = false; q.terminate();
+    for (auto & t : workers) t.join();
+    int n_other = 0;
+    for (int id = 0; id < P * N; id++) {
+        task_t * t = tasks[(size_t) id].get();
+        if (t->task == OTHER_KIND) { n_other++; CHECK(t->success); continue; }
+        const float want = (float) id + (id % 3 == 1 ? 0.25f : id % 3 == 2 ? 0.5f : 0.0f);
+        CHECK(t->success && t->length == 64 && t->sample_rate == 24000.0f);
+        for (int k = 0; k < 64; k++) CHECK(((float *) t->response)[k] == want);
+        b200::release(t);
+    }
+    CHECK(others.load() == n_other && (int) done.completed.size() == P * N && max_seen.load() <= 8);
+    printf("worker stress OK: %d tasks, %d forwards (largest %d), %d non-TTS\n", P * N, forwards.load(), max_seen.load(), n_other);
+    return 0;
+}
+
 static void dump(const std::string & path, const float * d, size_t n) {
     FILE * f = fopen(path.c_str(), "wb");
     if (f) { fwrite(d, sizeof(float), n, f); fclose(f); }
@@ -139,6 +199,7 @@ static void dump(const std::string & path, const float * d, size_t n) {
 
 int main(int argc, char ** argv) {
     if (argc == 2 && std::string(argv[1]) == "selftest") return selftest();
+    if (argc == 2 && std::string(argv[1]) == "stress") return stress();
     if (argc < 5) { fprintf(stderr, "usage: %s selftest | model.gguf prompts.txt out_prefix max_batch\n", argv[0]); return 2; }
     std::vector<std::string> lines;
     { std::ifstream in(argv[2]); std::string l; while (std::getline(in, l)) if (!l.empty()) lines.push_back(l); }

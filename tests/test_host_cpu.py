@@ -214,6 +214,19 @@ def test_batch_draining_worker_selftest():
     assert r.returncode == 0 and "worker selftest OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
+def test_batch_draining_worker_two_workers_under_thread_sanitizer():
+    """Four producers and two workers (each with its own runner) on ONE queue, max_batch 8, mixed voices / models / non-TTS tasks: every one of 400 tasks is answered
+    exactly once with its own audio -- natively and under ThreadSanitizer (worker_demo_tsan: the worker header and the queue are instrumented; no report allowed)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for exe, env in (("worker_demo", {}), ("worker_demo_tsan", {"TSAN_OPTIONS": "halt_on_error=1 exitcode=66"})):
+        path = os.path.join(root, "integration", "_build", exe)
+        if not os.path.exists(path):
+            pytest.skip(f"integration/_build/{exe} not built (no reference checkout)")
+        r = subprocess.run([path, "stress"], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+        assert r.returncode == 0 and "worker stress OK: 400 tasks" in r.stdout and "ThreadSanitizer" not in r.stderr, (exe, r.stdout[-500:], r.stderr[-2000:])
+
+
 def test_patched_reference_server_serves_http_with_the_batch_worker():
     """The reference's examples/server/server.cpp with the three edits of INTEGRATION.md section 5 applied at build time (integration/patch_server.py), over real HTTP
     with the reference's `test:dummy` model (one second of a per-character tone per prompt character, src/models/dummy/model.cpp): every concurrent request gets ITS
