@@ -16,8 +16,10 @@ import torch
 
 try:
     from .kokoro_port import gelu_f16_lut
+    from .parler_port import quant_mm, unpack_blocks
 except ImportError:
     from kokoro_port import gelu_f16_lut
+    from parler_port import quant_mm, unpack_blocks
 
 
 def relative_bucket(key_pos: int, query_pos: int, relative_attn_buckets: int = 32) -> int:
@@ -39,8 +41,12 @@ class T5Port:
         import gguf
         torch.set_num_threads(threads)
         rd = gguf.GGUFReader(gguf_path)
-        self.w, self.f16 = {}, set()
+        self.w, self.f16, self.q = {}, set(), {}
         for t in rd.tensors:
+            if t.tensor_type.name in ("Q8_0", "Q5_0", "Q4_0"):            # block-quantised matrix: (scales, integer values), see parler_port.quant_mm
+                d, qv = unpack_blocks(np.array(t.data), t.tensor_type.name)
+                self.q[t.name] = (torch.from_numpy(d), torch.from_numpy(qv))
+                continue
             self.w[t.name] = torch.from_numpy(np.array(t.data).astype(np.float32))
             if t.tensor_type.name == "F16":
                 self.f16.add(t.name)
@@ -53,6 +59,8 @@ class T5Port:
         assert self.heads * self.hd == self.hidden
 
     def mm(self, x, name):
+        if name in self.q:
+            return quant_mm(x, *self.q[name])
         if name in self.f16:
             x = x.half().float()
         return x @ self.w[name].t()

@@ -20,6 +20,9 @@ CASES = {
     "f16": (dict(f16=True), [[5, 17, 3, 90, 1], list(range(7, 41)) + [1]]),
     "no_down_proj": (dict(down_proj=False, layers=2), [[11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 1]]),
     "wide": (dict(heads=4, ffn=512, layers=2, out_size=128, context_length=128), [list(range(3, 90)) + [1]]),      # 88 tokens: every log-spaced bucket is hit
+    # block-quantised layer matrices: activations re-quantised to Q8_0 per 32 columns by ggml_mul_mat (vec_dot_type), integer dot products
+    "q8_0": (dict(quant="Q8_0"), [[5, 17, 3, 90, 1], list(range(7, 41)) + [1]]),
+    "q4_0": (dict(quant="Q4_0"), [list(range(7, 41)) + [1]]),
     # F16 matrices whose shapes the tensor-core GEMM takes (K % 64 == 0, N % 128 == 0) with enough rows to be routed there (> 32 per encode, t5.cu)
     "f16_wide": (dict(f16=True, heads=4, ffn=512, layers=2, out_size=128, context_length=128), [list(range(3, 90)) + [1], [(7 * i) % 90 + 2 for i in range(59)] + [1]]),
 }

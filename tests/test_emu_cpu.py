@@ -20,6 +20,12 @@ from tts_cpp_b200.synth import cached_dia_gguf, cached_orpheus_gguf, cached_parl
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
+def _T5_TOL(case):
+    """relative RMS bar of a T5 golden case: F32 1e-4 (fp16 GELU table); F16 1.5e-3 (fp16 activation rounding); block-quantised 3e-2 -- ggml_mul_mat re-quantises the
+    activations to Q8_0 per 32 columns, so 1e-7 of summation-order noise moves whole quantisation steps (two correct implementations: 1e-7 on one prompt, 1e-2 on the next)"""
+    return 3e-2 if case.startswith("q") else 1.5e-3 if case.startswith("f16") else 1e-4
+
+
 
 AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "t5.cu", "pdk.cu", "sampler.cu"]
 # The library's defaults are the fast paths (persistent decode kernel for F16 Parler, tensor-core GEMV for F16 matrices, CUDA-graph replay); most tests below are about
@@ -704,7 +710,7 @@ def test_vad_kernels_emulated_match_reference(tmp_path):
             assert np.array_equal(en[b], g[f"{name}.energies.{b}"]), (name, b)
 
 
-@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide"])
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q4_0"])
 def test_t5_encoder_cuda_path_emulated_matches_reference(tmp_path, case):
     """T5::encode (t5.cu: embedding rows, RMS norm eps 1e-6, the storage-aware GEMVs, bidirectional attention with the relative-position bias table, gated GELU, down
     projection + bias) under emulation against the compiled unmodified t5_runner::run (tests/golden/t5_vectors.npz), the prompts of a case as ONE ragged batch:
@@ -733,7 +739,7 @@ def test_t5_encoder_cuda_path_emulated_matches_reference(tmp_path, case):
         got = enc[at:at + len(p)]; at += len(p)
         d = float(np.sqrt(((got - ref) ** 2).mean())); rr = float(np.sqrt((ref ** 2).mean()))
         print(f"PARITY t5 emulated {case}.{i}: rms {d:.3g} of {rr:.3g}, max {float(np.abs(got - ref).max()):.3g}")
-        assert d < (1.5e-3 if case.startswith("f16") else 1e-4) * rr, (case, i, d, rr)
+        assert d < _T5_TOL(case) * rr, (case, i, d, rr)
     if case == "f32":      # a wrong prompt is refused, not read out of bounds: token id >= vocabulary, an empty prompt
         for bad in ([5, 96, 1], []):
             with open(pin, "wb") as f:

@@ -11,6 +11,12 @@ from conftest import report, rms
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+def _T5_TOL(case):
+    """relative RMS bar of a T5 golden case: F32 1e-4 (fp16 GELU table); F16 1.5e-3 (fp16 activation rounding); block-quantised 3e-2 -- ggml_mul_mat re-quantises the
+    activations to Q8_0 per 32 columns, so 1e-7 of summation-order noise moves whole quantisation steps (two correct implementations: 1e-7 on one prompt, 1e-2 on the next)"""
+    return 3e-2 if case.startswith("q") else 1.5e-3 if case.startswith("f16") else 1e-4
+
+
 
 @pytest.fixture(scope="module")
 def ops():
@@ -321,7 +327,7 @@ def test_vad_port_against_reference():
     assert int(g["defaults.n_out"][3]) < 44100                                                                # so is the early cut-off
 
 
-@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide"])
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q4_0"])
 def test_t5_port_against_reference(case):
     """oracle/t5_port.py against the compiled unmodified T5 encoder (t5_runner::run; tests/golden/t5_vectors.npz from make_golden_t5.py): 2- to 88-token prompts
     (every relative-position bucket incl. the log-spaced ones and the reference's integer division inside the logarithm), with / without the down projection,
@@ -336,4 +342,4 @@ def test_t5_port_against_reference(case):
     for i, p in enumerate(prompts):
         assert g[f"{case}.tokens.{i}"].tolist() == p
         d, r, mx = report(f"t5 port {case}.{i}", port.run(p), g[f"{case}.encoding.{i}"])
-        assert d < (1.5e-3 if case.startswith("f16") else 1e-4) * r, (case, i, d, r)
+        assert d < _T5_TOL(case) * r, (case, i, d, r)

@@ -885,8 +885,9 @@ def t5_tensors(seed: int = 0, layers: int = 3, heads: int = 2, ffn: int = 192, v
 
 
 def write_t5_gguf(path: str, seed: int = 0, layers: int = 3, heads: int = 2, ffn: int = 192, vocab: int = 96, out_size: int = 256, down_proj: bool = True,
-                  context_length: int = 64, f16: bool = False) -> dict:
-    """Small synthetic T5-encoder GGUF.  f16: the layer matrices as F16 (what `quantize --quantized-type F16` does to a text encoder)."""
+                  context_length: int = 64, f16: bool = False, quant: str | None = None) -> dict:
+    """Small synthetic T5-encoder GGUF.  f16: the layer matrices as F16; quant ("Q8_0" / "Q5_0" / "Q4_0"): the layer matrices as ggml blocks (the reference's
+    quantize tool does not handle text encoders, but its graph takes whatever type the file holds: ggml_mul_mat)."""
     import gguf
 
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
@@ -896,7 +897,11 @@ def write_t5_gguf(path: str, seed: int = 0, layers: int = 3, heads: int = 2, ffn
     for name, arr in items:
         n_params += arr.size
         mat = arr.ndim == 2 and ".attn_rel_b" not in name and "token_embd" not in name and name != "t5encoder.down_proj"
-        w.add_tensor(name, arr.astype(np.float16 if f16 and mat else np.float32))
+        if quant and mat and arr.shape[1] % 32 == 0:
+            qt = getattr(gguf.GGMLQuantizationType, quant)
+            w.add_tensor(name, gguf.quants.quantize(arr.astype(np.float32), qt), raw_dtype=qt)
+        else:
+            w.add_tensor(name, arr.astype(np.float16 if f16 and mat else np.float32))
     for k, v in (("t5encoder.block_count", layers), ("t5encoder.embedding_length", 64 * heads), ("t5encoder.attention.head_count", heads),
                  ("t5encoder.context_length", context_length), ("t5encoder.vocab_size", vocab), ("t5encoder.output_size", out_size if down_proj else 64 * heads),
                  ("tokenizer.ggml.bos_token_id", 0), ("tokenizer.ggml.eos_token_id", 1)):
@@ -910,7 +915,8 @@ def write_t5_gguf(path: str, seed: int = 0, layers: int = 3, heads: int = 2, ffn
 
 def cached_t5_gguf(seed: int = 0, cache_dir: str | None = None, f16: bool = False, **shape) -> str:
     cache_dir = cache_dir or os.environ.get("B2TTS_CACHE", "/tmp/b2tts_cache")
-    tag = "_".join(f"{k}{v}" for k, v in sorted(shape.items()))
+    os.makedirs(cache_dir, exist_ok=True)
+    tag = "_".join(f"{k}{v}" for k, v in sorted(shape.items()) if v is not None)
     path = os.path.join(cache_dir, f"t5_{'f16' if f16 else 'f32'}_s{seed}{('_' + tag) if tag else ''}.gguf")
     if not os.path.exists(path):
         tmp = path + f".tmp{os.getpid()}"
