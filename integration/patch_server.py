@@ -24,7 +24,15 @@ def main() -> None:
     src_path, out_path, html_path, hpp_path = sys.argv[1:5]
     s = open(src_path).read()
     s = once(s, r'#include "\.\./\.\./src/models/loaders\.h"', '#include "models/loaders.h"\n#include "b200_batch_worker.h"', "loaders include")
-    s = once(s, r'    void loop\(\) \{\n        while \(running\) \{.*?\n        \}\n    \}\n',
+    loop_upstream = ("    void loop() {\n"
+                     "        while (running) {\n"
+                     "            struct simple_server_task * task = task_queue->get_next();\n"
+                     "            if (task) {\n"
+                     "                process_task(task);\n"
+                     "            }\n"
+                     "        }\n"
+                     "    }\n")                                          # the worker loop as upstream has it (server.cpp:247-254), matched literally
+    s = once(s, re.escape(loop_upstream),
              '    void loop() {\n'
              '        const char * mb = getenv("B2TTS_SERVER_MAX_BATCH");\n'
              '        b200::batch_loop(running, *task_queue, *response_map, task_timeout, (size_t) (mb ? atoi(mb) : 32), TTS,\n'

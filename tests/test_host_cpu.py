@@ -227,6 +227,26 @@ def test_batch_draining_worker_two_workers_under_thread_sanitizer():
         assert r.returncode == 0 and "worker stress OK: 400 tasks" in r.stdout and "ThreadSanitizer" not in r.stderr, (exe, r.stdout[-500:], r.stderr[-2000:])
 
 
+def test_server_patch_fails_loudly_when_upstream_moves(tmp_path):
+    """integration/patch_server.py applies three edits to the reference's server.cpp at build time; each must match exactly once.  A server.cpp whose worker loop
+    reads differently must stop the build with a message, not produce a server that silently keeps the one-task-at-a-time loop."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = "/root/reference/examples/server/server.cpp"
+    if not os.path.exists(src):
+        pytest.skip("reference checkout not present")
+    html = "/root/reference/examples/server/public/index.html"
+    script = os.path.join(root, "integration", "patch_server.py")
+    ok = subprocess.run([sys.executable, script, src, str(tmp_path / "ok.cpp"), html, str(tmp_path / "ok.hpp")], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr
+    out = open(tmp_path / "ok.cpp").read()
+    assert out.count("b200::batch_loop(") == 1 and out.count("b200::release(rtask)") == 1 and "task_queue->get_next()" not in out
+    moved = open(src).read().replace("struct simple_server_task * task = task_queue->get_next();", "auto * task = task_queue->next();")
+    (tmp_path / "moved.cpp").write_text(moved)
+    bad = subprocess.run([sys.executable, script, str(tmp_path / "moved.cpp"), str(tmp_path / "bad.cpp"), html, str(tmp_path / "bad.hpp")], capture_output=True, text=True)
+    assert bad.returncode != 0 and "worker::loop" in bad.stderr and not os.path.exists(tmp_path / "bad.cpp"), (bad.returncode, bad.stderr)
+
+
 def test_patched_reference_server_serves_http_with_the_batch_worker():
     """The reference's examples/server/server.cpp with the three edits of INTEGRATION.md section 5 applied at build time (integration/patch_server.py), over real HTTP
     with the reference's `test:dummy` model (one second of a per-character tone per prompt character, src/models/dummy/model.cpp): every concurrent request gets ITS
