@@ -33,6 +33,15 @@ AR_SOURCES = ["orpheus.cu", "parler.cu", "dia.cu", "t5.cu", "pdk.cu", "sampler.c
 EMU_DEFAULTS = {"B2TTS_AR_PDK": "0", "B2TTS_AR_MMA": "0", "B2TTS_AR_GRAPH": "0"}
 
 
+# independent emulator runs of one test go to the host's other cores (each is a single-threaded subprocess; subprocess.run releases the GIL): same runs, same checks
+from concurrent.futures import ThreadPoolExecutor  # noqa: E402
+_POOL = ThreadPoolExecutor(3)
+
+
+def _bg(fn, *a, **k):
+    return _POOL.submit(fn, *a, **k)
+
+
 def _run_ar(tmp_path, model, gguf_path, prompts, steps, tag, env=None, want_stderr=False):
     """-> (tokens [B][steps][W], logits [B][steps][V]) from the library's generate_greedy under emulation"""
     exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
@@ -487,12 +496,21 @@ def test_persistent_decode_kernel_emulated_stop_rule_and_teacher(tmp_path):
     cap = int(g["all_eos.tokens"].shape[0]) + 6
     exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
     gguf = cached_parler_gguf(seed=0, eos_boost=boost, f16=True)
-    outs = {}
+    # the teacher-forced run of the second half is independent of the two stop-rule runs: all three go to separate cores
+    g16 = np.load(os.path.join(GOLD, "parler_f16_vectors.npz"))
+    tf = str(tmp_path / "teacher.bin")
+    np.stack([g16["tokens0"], g16["tokens1"]]).astype(np.int32).tofile(tf)
+    f_tf = _bg(_run_ar, tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), [g16["prompt0"], g16["prompt1"]], int(g16["tokens0"].shape[0]), "tf",
+               env={"B2EMU_TEACHER": tf, "B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "4"})
+    outs, runs = {}, {}
     for tag, env in (("pk", {"B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "3"}), ("op", {"B2TTS_AR_PDK": "0"})):
         pin, pout = str(tmp_path / f"p{tag}.bin"), str(tmp_path / f"o{tag}.bin")
         with open(pin, "wb") as f:
             f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompt.size)); f.write(prompt.astype(np.uint32).tobytes())
-        r = subprocess.run([exe, "parler", gguf, pin, pout], capture_output=True, text=True, timeout=900, env={**os.environ, **EMU_DEFAULTS, "B2EMU_STOP": "1", "B2EMU_NO_LOGITS": "1", "B2TTS_AR_EXIT_EVERY": "4", **env})
+        runs[tag] = (pout, _bg(subprocess.run, [exe, "parler", gguf, pin, pout], capture_output=True, text=True, timeout=900,
+                               env={**os.environ, **EMU_DEFAULTS, "B2EMU_STOP": "1", "B2EMU_NO_LOGITS": "1", "B2TTS_AR_EXIT_EVERY": "4", **env}))
+    for tag, (pout, fut) in runs.items():
+        r = fut.result()
         assert r.returncode == 0, r.stderr[-2000:]
         raw = open(pout, "rb").read()
         W, V = struct.unpack("ii", raw[:8])
@@ -503,9 +521,7 @@ def test_persistent_decode_kernel_emulated_stop_rule_and_teacher(tmp_path):
     g = np.load(os.path.join(GOLD, "parler_f16_vectors.npz"))
     prompts = [g["prompt0"], g["prompt1"]]
     steps = int(g["tokens0"].shape[0])
-    tf = str(tmp_path / "teacher.bin")
-    np.stack([g["tokens0"], g["tokens1"]]).astype(np.int32).tofile(tf)
-    tok, logits = _run_ar(tmp_path, "parler", cached_parler_gguf(seed=0, f16=True), prompts, steps, "tf", env={"B2EMU_TEACHER": tf, "B2TTS_AR_PDK": "1", "B2TTS_PDK_GRID": "4"})
+    tok, logits = f_tf.result()
     for u in range(2):
         assert np.array_equal(tok[u], g[f"tokens{u}"])
         assert float(np.abs(logits[u] - g[f"logits{u}"].reshape(steps, -1)).max()) < 3e-2
@@ -592,10 +608,21 @@ def test_persistent_decode_kernel_emulated_dia(tmp_path, env):
     gguf = cached_dia_gguf(seed=0, f16=True, head_dim=64)
     tf = str(tmp_path / "teacher.bin")
     np.stack([g["tokens0"][:steps], g["tokens1"][:steps]]).astype(np.int32).tofile(tf)
-    tok, logits, err = _run_ar(tmp_path, "dia", gguf, prompts, steps, "pk", env={"B2TTS_AR_PDK": "1", "B2TTS_AR_EXIT_EVERY": "16", "B2EMU_TEACHER": tf, **env}, want_stderr=True)
+    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])      # built before the concurrent runs below
+    f_pk = _bg(_run_ar, tmp_path, "dia", gguf, prompts, steps, "pk", env={"B2TTS_AR_PDK": "1", "B2TTS_AR_EXIT_EVERY": "16", "B2EMU_TEACHER": tf, **env}, want_stderr=True)
     tf2 = str(tmp_path / "teacher_op.bin")
     np.stack([g["tokens0"][:steps_op], g["tokens1"][:steps_op]]).astype(np.int32).tofile(tf2)
-    tok0, logits0, err0 = _run_ar(tmp_path, "dia", gguf, prompts, steps_op, "op", env={"B2TTS_AR_PDK": "0", "B2EMU_TEACHER": tf2}, want_stderr=True)
+    f_op = _bg(_run_ar, tmp_path, "dia", gguf, prompts, steps_op, "op", env={"B2TTS_AR_PDK": "0", "B2EMU_TEACHER": tf2}, want_stderr=True)
+    f_free = None
+    cap = int(g["step_cap"])
+    pin, pout = str(tmp_path / "ps.bin"), str(tmp_path / "os.bin")
+    if "B2EMU_REVERSE" not in env:      # free-running with the stop rule (checked at the end), started now
+        with open(pin, "wb") as f:
+            f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompts[0].size)); f.write(prompts[0].astype(np.uint32).tobytes())
+        f_free = _bg(subprocess.run, [exe, "dia", gguf, pin, pout], capture_output=True, text=True, timeout=900,
+                     env={**os.environ, **EMU_DEFAULTS, "B2TTS_AR_PDK": "1", "B2EMU_STOP": "1", "B2EMU_NO_LOGITS": "1", "B2TTS_AR_EXIT_EVERY": "16", **env})
+    tok, logits, err = f_pk.result()
+    tok0, logits0, err0 = f_op.result()
     n_pk, n_op = (int(e.split("emulated ")[1].split(" launches")[0]) for e in (err, err0))
     assert n_pk < n_op - (steps_op - 1) * 30, (n_pk, n_op)       # encoder pass + 3 cooperative launches (34 steps) vs ~45 launches per decoder step of the 2-layer test model (10 steps)
     keep = [int(s) for s in g["logit_steps"] if s < steps]
@@ -610,14 +637,9 @@ def test_persistent_decode_kernel_emulated_dia(tmp_path, env):
               f"tokens equal {int((tok[u] == g[f'tokens{u}'][:steps]).sum())}/{steps * 9}, clear decisions {int(clear.sum())}")
         assert float(d.max()) < 1.5 and dp < 0.2                 # (fp32 pages, Dia's default: with fp16 pages the cache's rounding alone moves these logits by up to 2.5)
         assert np.array_equal(tok[u][clear], g[f"tokens{u}"][:steps][clear])
-    if "B2EMU_REVERSE" in env: return
+    if f_free is None: return
     # free-running with the stop rule: the loop ends after the reference's number of frames
-    exe = emu_build.build("ar_emu", AR_SOURCES, ["ar_main.cpp", os.path.join(emu_build.CSRC, "gguf_reader.cpp")])
-    cap = int(g["step_cap"])
-    pin, pout = str(tmp_path / "ps.bin"), str(tmp_path / "os.bin")
-    with open(pin, "wb") as f:
-        f.write(struct.pack("ii", 1, cap)); f.write(struct.pack("i", prompts[0].size)); f.write(prompts[0].astype(np.uint32).tobytes())
-    r = subprocess.run([exe, "dia", gguf, pin, pout], capture_output=True, text=True, timeout=900, env={**os.environ, **EMU_DEFAULTS, "B2TTS_AR_PDK": "1", "B2EMU_STOP": "1", "B2EMU_NO_LOGITS": "1", "B2TTS_AR_EXIT_EVERY": "16", **env})
+    r = f_free.result()
     assert r.returncode == 0, r.stderr[-2000:]
     raw = open(pout, "rb").read()
     W, V = struct.unpack("ii", raw[:8])
