@@ -269,6 +269,8 @@ int b2tts_t5_info(const b2tts_t5 * m, int * n_layers, int * hidden_size, int * o
 }
 int b2tts_t5_encode(b2tts_t5 * m, int n_prompts, const uint32_t * const * tokens, const int32_t * n_tokens, float * encodings) {
     if (!m) { set_error("null model"); return 1; }
+    if (n_prompts > 0 && (!tokens || !n_tokens || !encodings)) { set_error("t5: null argument"); return 1; }
+    for (int b = 0; b < n_prompts; b++) if (!tokens[b]) { set_error("t5: prompt %d is a null pointer", b); return 1; }
     return m->t.encode(n_prompts, tokens, n_tokens, encodings);
 }
 float b2tts_t5_last_ms(const b2tts_t5 * m) { return m ? m->t.timing_ms : 0.f; }
@@ -484,8 +486,10 @@ int b2tts_op_cumsum(b2tts_ctx * ctx, const float * x, int L, int rows, float * y
 int b2tts_op_vad_trim(b2tts_ctx * ctx, const float * pcm, const int64_t * n_samples, int B, float sample_rate, int ms_per_frame, int frame_threshold,
                       float normalized_energy_threshold, int trailing_silent_frames, int early_cutoff_seconds_threshold, float early_cutoff_energy_threshold,
                       int64_t * n_out, float * energies_out) {
+    if (!ctx) { set_error("null context"); return 1; }
     Ctx * c = &ctx->c;
     if (B <= 0) return 0;
+    if (!pcm || !n_samples || !n_out) { set_error("vad: null argument"); return 1; }
     if (ms_per_frame <= 0) { set_error("vad: ms_per_frame must be positive (the reference divides by it)"); return 1; }
     const int spf = (int) (ms_per_frame * sample_rate / 1000.0f);                                  // vad.cpp:20
     if (spf <= 0) { set_error("vad: ms_per_frame * sample_rate / 1000 < 1 (the reference divides by zero here)"); return 1; }
