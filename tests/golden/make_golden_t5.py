@@ -23,6 +23,7 @@ CASES = {
     # block-quantised layer matrices: activations re-quantised to Q8_0 per 32 columns by ggml_mul_mat (vec_dot_type), integer dot products
     "q8_0": (dict(quant="Q8_0"), [[5, 17, 3, 90, 1], list(range(7, 41)) + [1]]),
     "q4_0": (dict(quant="Q4_0"), [list(range(7, 41)) + [1]]),
+    "q5_0": (dict(quant="Q5_0"), [list(range(7, 41)) + [1]]),
     # F16 matrices whose shapes the tensor-core GEMM takes (K % 64 == 0, N % 128 == 0) with enough rows to be routed there (> 32 per encode, t5.cu)
     "f16_wide": (dict(f16=True, heads=4, ffn=512, layers=2, out_size=128, context_length=128), [list(range(3, 90)) + [1], [(7 * i) % 90 + 2 for i in range(59)] + [1]]),
 }

@@ -732,7 +732,7 @@ def test_vad_kernels_emulated_match_reference(tmp_path):
             assert np.array_equal(en[b], g[f"{name}.energies.{b}"]), (name, b)
 
 
-@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q4_0"])
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q5_0", "q4_0"])
 def test_t5_encoder_cuda_path_emulated_matches_reference(tmp_path, case):
     """T5::encode (t5.cu: embedding rows, RMS norm eps 1e-6, the storage-aware GEMVs, bidirectional attention with the relative-position bias table, gated GELU, down
     projection + bias) under emulation against the compiled unmodified t5_runner::run (tests/golden/t5_vectors.npz), the prompts of a case as ONE ragged batch:

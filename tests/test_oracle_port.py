@@ -327,7 +327,7 @@ def test_vad_port_against_reference():
     assert int(g["defaults.n_out"][3]) < 44100                                                                # so is the early cut-off
 
 
-@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q4_0"])
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q5_0", "q4_0"])
 def test_t5_port_against_reference(case):
     """oracle/t5_port.py against the compiled unmodified T5 encoder (t5_runner::run; tests/golden/t5_vectors.npz from make_golden_t5.py): 2- to 88-token prompts
     (every relative-position bucket incl. the log-spaced ones and the reference's integer division inside the logarithm), with / without the down projection,

@@ -19,7 +19,7 @@ def _T5_TOL(case):
 
 
 
-@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q4_0"])
+@pytest.mark.parametrize("case", ["f32", "f16", "no_down_proj", "wide", "f16_wide", "q8_0", "q5_0", "q4_0"])
 def test_t5_encode_matches_reference(gpu_ctx, case):
     """Every golden case as one ragged batch and prompt by prompt.  "f16" (40 rows batched) and "f16_wide" (148 rows, 88 and 60 alone) exceed the 32 rows above which
     F16 matrices go through the tensor-core GEMM (t5.cu T5_GEMM_MIN_ROWS): the same numerics class as the reference's F16 mul_mat (fp16-rounded activations, exact
