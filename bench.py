@@ -14,6 +14,10 @@ used only for the barrier and the max-over-ranks of the timings.
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref/kokoro_ref, built from /root/reference by
                oracle/Makefile) on the host cores, as P worker processes x 4 ggml threads (its own server's
                n-parallelism model, examples/server/server.cpp:225-321), on a bounded sample of the same prompts.
+
+Secondary lines (`--workload dac | snac | parler | orpheus | dia | t5`; never the headline): the codecs, BASELINE configs 3 / 4 / 5 and the T5 conditional-prompt
+encoder pass, each with its own `--impl reference` arm.  (`--workload t5` was added after the round's GPU budget ended: its reference arm has run, its CUDA arm
+has not -- the T5 numbers in DESIGN section 7.3 come from scripts/t5_timing.py, which makes the same calls.)
 """
 from __future__ import annotations
 
@@ -808,6 +812,76 @@ def _decode_traffic():
     return None
 
 
+T5_SHAPE = dict(f16=True, layers=24, heads=16, ffn=2816, vocab=2048, out_size=1024, context_length=512)      # flan-t5-large's encoder + the projection to Parler-Mini's width
+
+
+def _t5_prompts(B: int, n: int):
+    import numpy as np
+    rng = np.random.default_rng(0)
+    return [[int(t) for t in rng.integers(2, 2048, n - 1)] + [1] for _ in range(B)]
+
+
+def run_t5_reference(args, threads: int = 8, n_tokens: int = 16):
+    """CPU arm of --workload t5: the unmodified t5_runner::run (oracle/_ref/t5_ref) on the same GGUF and prompt; per-pass time = (5 passes - 1 pass) / 4 of one process
+    (removes the load).  A reported baseline."""
+    from tts_cpp_b200.synth import cached_t5_gguf
+    exe, build = ref_bin("t5_ref")
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "workload": "t5", "unavailable": "oracle/_ref/t5_ref not built"}))
+        return 0
+    g = cached_t5_gguf(**T5_SHAPE)
+    p = ",".join(str(t) for t in _t5_prompts(1, n_tokens)[0])
+    out = os.path.join(tempfile.gettempdir(), f"t5_ref_{os.getpid()}.bin")
+    subprocess.run([exe, g, out, str(threads), p], check=True, stdout=subprocess.DEVNULL)          # warm the page cache
+    t0 = time.perf_counter(); subprocess.run([exe, g, out, str(threads), p], check=True, stdout=subprocess.DEVNULL); t1 = time.perf_counter() - t0
+    t0 = time.perf_counter(); subprocess.run([exe, g, out, str(threads)] + [p] * 5, check=True, stdout=subprocess.DEVNULL); t5 = time.perf_counter() - t0
+    os.remove(out)
+    ms = max((t5 - t1) / 4 * 1e3, 1e-3)
+    cpu = {"value": 1e3 / ms, "unit": "encodings/s", "cores": threads, "kind": "reference", "build": build,
+           "sample": f"one {n_tokens}-token prompt, 4 timed passes of t5_runner::run inside one process ({threads} ggml threads)"}
+    print(json.dumps({"impl": "reference", "metric": "t5_prompt_encodings_per_second", "workload": f"T5 conditional-prompt encoder pass, flan-t5-large shape, F16 layer matrices, {n_tokens}-token prompt",
+                      "value": 1e3 / ms, "unit": "encodings/s", "n_gpus": 1, "steps": 4, "ms_per_step": ms, "higher_is_better": True, "data": "synthetic", "cpu_baseline": cpu,
+                      "e2e": {"value": 1e3 / ms, "unit": "encodings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def run_t5(args, n_tokens: int = 16):
+    """Secondary line: one T5 conditional-prompt encoder pass (b2tts_t5_encode) at the flan-t5-large shape; value = passes per second of a 16-token voice
+    description (device time, CUDA events around the forward); e2e = the same through the C-ABI with host token ids in and the host encoding out."""
+    if args.impl == "reference":
+        return run_t5_reference(args, n_tokens=n_tokens)
+    import ctypes as C
+    from tts_cpp_b200.binding import Context, lib, t5_runner_from_file
+    from tts_cpp_b200.synth import cached_t5_gguf
+    ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    t5 = t5_runner_from_file(cached_t5_gguf(**T5_SHAPE), ctx=ctx)
+    lib().b2tts_t5_weight_bytes.restype = C.c_size_t
+    wbytes = int(lib().b2tts_t5_weight_bytes(t5.h))
+    prompts = _t5_prompts(1, n_tokens)
+    for _ in range(max(args.warmup, 3)):
+        t5.run(prompts)
+    l0 = ctx.launches()
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        t5.run(prompts)
+        dev_ms += t5.last_ms()
+    wall = time.perf_counter() - t0
+    ms = dev_ms / args.steps
+    act_bytes = n_tokens * (6 * 1024 + 2 * 2816 + 1024) * 4
+    _, hbm, peak_src = _peaks()
+    ach = (wbytes + act_bytes) / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "t5_prompt_encodings_per_second", "workload": f"T5 conditional-prompt encoder pass (SURVEY 8f row 3), flan-t5-large shape, F16 layer matrices, {n_tokens}-token prompt",
+        "value": 1e3 / ms, "unit": "encodings/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "e2e": {"value": args.steps / wall, "unit": "encodings/s", "h2d_bytes_per_step": n_tokens * 4, "d2h_bytes_per_step": n_tokens * 1024 * 4},
+        "gpu_launches": int(ctx.launches() - l0), "tensor_core_gemm": bool(lib().b2tts_t5_last_used_gemm(t5.h)),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                     "algorithmic_bytes": wbytes + act_bytes, "peak_source": peak_src, "note": "every weight once per pass + rows x (6 hidden + 2 ffn + out) x 4 B of activations"},
+        "dtype": "f16 weights, fp16-rounded activations into exact products, f32 accumulate (the reference's F16 mul_mat numerics)", "data": "synthetic"}))
+    t5.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -820,7 +894,7 @@ def main():
     ap.add_argument("--parler-dtype", default="f16", choices=["f16", "q8_0", "q5_0", "q4_0"],
                     help="--workload parler: dtype of the decoder matrices (f16 = BASELINE config 3; q5_0 is what the reference's published Parler numbers use)")
     ap.add_argument("--orpheus-dtype", default="q8_0", choices=["q8_0", "f16", "f32"], help="--workload orpheus: dtype of the matrices (q8_0 = BASELINE config 5)")
-    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "snac", "parler", "orpheus", "dia"],
+    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "dac", "snac", "parler", "orpheus", "dia", "t5"],
                     help="kokoro (default, the headline metric) | dac: codec decode of BASELINE config 3's shape (batch 16 x 10 s), a secondary line | "
                          "parler: config 3 end to end (AR decode + DAC), plain first path")
     args = ap.parse_args()
@@ -842,6 +916,8 @@ def main():
         return run_orpheus(args)
     if args.workload == "dia":
         return run_dia(args)
+    if args.workload == "t5":
+        return run_t5(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 
