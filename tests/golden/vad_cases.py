@@ -61,6 +61,16 @@ def cases():
     out.append(("frame_160", m, [pcm_of([(0.5, 0.5), (0.4, 0.001)], 16000.0, 11)]))
     t = dict(DEFAULTS, sample_rate=44300.0, ms_per_frame=10)          # 443 samples per frame
     out.append(("frame_443", t, [pcm_of([(0.5, 0.5), (0.4, 0.001)], 44300.0, 12)]))
+    # 5. BASELINE config 3's codec output size: 16 utterances x ~10 s at 44.1 kHz (7 M samples), ragged, each with its own quiet tail (0.3 .. 1.8 s); one is cut
+    #    early by three seconds of digital silence in the middle
+    big = []
+    for b in range(16):
+        tail = 0.3 + 0.1 * b
+        if b == 5:
+            big.append(pcm_of([(3.0, 0.4), (3.1, 0.0), (3.0, 0.4), (0.9, 0.0004)], 44100.0, 100 + b))
+        else:
+            big.append(pcm_of([(10.0 - tail - 0.003 * b, 0.2 + 0.02 * b), (tail, 0.0004)], 44100.0, 100 + b, extra_samples=17 * b))
+    out.append(("config3_size", d, big))
     return out
 
 
