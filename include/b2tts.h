@@ -268,7 +268,7 @@ int   b2tts_parler_generate_greedy(b2tts_parler * m, int n_sequences, const uint
 int   b2tts_parler_generate(b2tts_parler * m, int n_sequences, const uint32_t * const * prompts, const int32_t * n_prompt, int n_steps, const b2tts_sampling * sampling,
                             int32_t * out_tokens, float * out_logits, int32_t * n_generated);
 /* parler_tts_runner::update_conditional_prompt's second half (model.cpp:510-518 -> prep_cross_key_values, model.cpp:110-173): replace the stored conditional-prompt
- * encoding by `encoding` [n_rows][hidden] (the T5 encoder's output for a new voice description -- computed by the caller, e.g. by the reference's own t5_runner)
+ * encoding by `encoding` [n_rows][hidden] (the T5 encoder's output for a new voice description: b2tts_t5_encode above, or any other caller-side encoder)
  * and recompute the cross-attention K / V of every layer on the device. */
 int   b2tts_parler_set_text_encoding(b2tts_parler * m, const float * encoding, int n_rows);
 /* parity helper: greedy, fixed length, but the tokens fed back through the delay pattern are `teacher` ([n_sequences][n_steps][n_heads], e.g. the reference's own
